@@ -1,0 +1,331 @@
+"""Oracle: scheduler inner loops, denoiser wrappers, CFG and RNG contract restated (TEST ONLY).
+
+Follows (all under /root/reference):
+  gyre/src/k-diffusion/k_diffusion/external.py:43-113,141-167   DiscreteSchedule / Eps / V denoisers
+  gyre/src/k-diffusion/k_diffusion/sampling.py:12-58,118-215    schedules, to_d, ancestral step, samplers
+  gyre/pipeline/schedulers/sample_dpmpp_2m.py:6-50              gyre's DPM++ 2M
+  gyre/pipeline/schedulers/scheduling_ddim.py:189-321           DDIM set_timesteps / step
+  gyre/pipeline/common_scheduler.py:410-428,430-541,555-623     KDiffusionScheduler
+  gyre/pipeline/unet/cfg.py:41-57                               CFGUNet_Parallel
+  gyre/pipeline/randtools.py:39-64                              batched_randn
+Pinned against the vendored k-diffusion sources by scripts/make_golden.py -> tests/golden.
+"""
+from __future__ import annotations
+
+import torch
+
+
+# ----------------------------------------------------------------------------- RNG contract
+
+def batched_randn(shape, generators, device, dtype):
+    """randtools.py:39-64: ONE randn of shape (1, *shape[1:]) per generator, on the generator's
+    device, concatenated, then moved to `device`."""
+    if shape[0] % len(generators) != 0:
+        raise ValueError(f"shape[0] ({shape[0]}) needs to be a multiple of len(generators) ({len(generators)})")
+    lat = torch.cat([
+        torch.randn((1, *shape[1:]), generator=g, device=g.device, dtype=dtype)
+        for g in generators * (shape[0] // len(generators))
+    ], dim=0)
+    return lat.to(device)
+
+
+# ----------------------------------------------------------------------------- schedule
+
+def sd_alphas_cumprod(device="cpu", n=1000, beta_start=0.00085, beta_end=0.012):
+    """common_scheduler.py:410-428 (scaled-linear betas)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, n, device=device) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+class DiscreteSchedule:
+    """external.py:43-84 with quantize=True (KDiffusionUNetWrapper, common_scheduler.py:342-355)."""
+
+    def __init__(self, alphas_cumprod):
+        self.sigmas = ((1 - alphas_cumprod) / alphas_cumprod) ** 0.5
+        self.log_sigmas = self.sigmas.log()
+
+    @property
+    def sigma_min(self):
+        return self.sigmas[0]
+
+    @property
+    def sigma_max(self):
+        return self.sigmas[-1]
+
+    def sigma_to_t(self, sigma):
+        log_sigma = sigma.log()
+        dists = log_sigma - self.log_sigmas[:, None]
+        return dists.abs().argmin(dim=0).view(sigma.shape)
+
+    def t_to_sigma(self, t):
+        t = t.float()
+        low_idx, high_idx, w = t.floor().long(), t.ceil().long(), t.frac()
+        log_sigma = (1 - w) * self.log_sigmas[low_idx] + w * self.log_sigmas[high_idx]
+        return log_sigma.exp()
+
+
+def append_dims(x, n):
+    return x[(...,) + (None,) * (n - x.ndim)]
+
+
+class EpsDenoiser(DiscreteSchedule):
+    """external.py:87-113: denoised = x + eps(x*c_in, t)*c_out, c_out=-sigma, c_in=1/sqrt(sigma^2+1)."""
+
+    def __init__(self, eps_unet, alphas_cumprod):
+        super().__init__(alphas_cumprod)
+        self.inner_model = eps_unet
+
+    def __call__(self, x, sigma):
+        c_out = append_dims(-sigma, x.ndim)
+        c_in = append_dims(1 / (sigma ** 2 + 1.0) ** 0.5, x.ndim)
+        eps = self.inner_model(x * c_in, self.sigma_to_t(sigma))
+        return x + eps * c_out
+
+
+class VDenoiser(DiscreteSchedule):
+    """external.py:141-167: denoised = v(x*c_in, t)*c_out + x*c_skip."""
+
+    def __init__(self, v_unet, alphas_cumprod):
+        super().__init__(alphas_cumprod)
+        self.inner_model = v_unet
+
+    def __call__(self, x, sigma):
+        c_skip = append_dims(1.0 / (sigma ** 2 + 1.0), x.ndim)
+        c_out = append_dims(-sigma / (sigma ** 2 + 1.0) ** 0.5, x.ndim)
+        c_in = append_dims(1 / (sigma ** 2 + 1.0) ** 0.5, x.ndim)
+        return self.inner_model(x * c_in, self.sigma_to_t(sigma)) * c_out + x * c_skip
+
+
+def append_zero(x):
+    return torch.cat([x, x.new_zeros([1])])
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
+    """sampling.py:16-22."""
+    ramp = torch.linspace(0, 1, n)
+    min_inv_rho = sigma_min ** (1 / rho)
+    max_inv_rho = sigma_max ** (1 / rho)
+    sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    return append_zero(sigmas).to(device)
+
+
+def k_sigmas(schedule: DiscreteSchedule, n: int, karras_rho=None, device="cpu"):
+    """common_scheduler.py:485-514: Karras schedule if rho given, else linear-in-t + [0]."""
+    if karras_rho is not None:
+        return get_sigmas_karras(n, schedule.sigma_min.to("cpu"), schedule.sigma_max.to("cpu"), karras_rho, device)
+    t = torch.linspace(len(schedule.sigmas) - 1, 0, n, device=device)
+    return append_zero(schedule.t_to_sigma(t))
+
+
+# ----------------------------------------------------------------------------- CFG
+
+class CFGParallel:
+    """cfg.py:41-57 + core.py:242-274: duplicate latents, ONE unet call on [uncond, cond], u + s*(g-u)."""
+
+    def __init__(self, unet, uncond_emb, cond_emb, guidance_scale):
+        self.unet = unet
+        self.emb = torch.cat([uncond_emb, cond_emb])
+        self.guidance_scale = guidance_scale
+
+    def __call__(self, latents, t):
+        latents = torch.cat([latents, latents])
+        if isinstance(t, torch.Tensor) and t.shape:
+            t = torch.cat([t, t])
+        noise_pred = self.unet(latents, t, encoder_hidden_states=self.emb).sample
+        u, g = noise_pred.chunk(2)
+        return u + self.guidance_scale * (g - u)
+
+
+# ----------------------------------------------------------------------------- k samplers
+
+def to_d(x, sigma, denoised):
+    return (x - denoised) / append_dims(sigma, x.ndim)
+
+
+def get_ancestral_step(sigma_from, sigma_to, eta=1.0):
+    """sampling.py:51-58."""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+def sample_euler_ancestral(model, x, sigmas, noise_sampler, eta=1.0, s_noise=1.0, callback=None):
+    """sampling.py:139-155."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "denoised": denoised})
+        d = to_d(x, sigmas[i], denoised)
+        dt = sigma_down - sigmas[i]
+        x = x + d * dt
+        if sigmas[i + 1] > 0:
+            x = x + noise_sampler(sigmas[i], sigmas[i + 1]) * s_noise * sigma_up
+    return x
+
+
+def sample_euler(model, x, sigmas, randn_like, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
+    """sampling.py:118-135.  `randn_like` is drawn EVERY step even when churn==0 (advances generators)."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        eps = randn_like(x) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(x, sigma_hat * s_in)
+        d = to_d(x, sigma_hat, denoised)
+        dt = sigmas[i + 1] - sigma_hat
+        x = x + d * dt
+    return x
+
+
+def sample_heun(model, x, sigmas, randn_like, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
+    """sampling.py:159-184."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        eps = randn_like(x) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(x, sigma_hat * s_in)
+        d = to_d(x, sigma_hat, denoised)
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            denoised_2 = model(x_2, sigmas[i + 1] * s_in)
+            d_2 = to_d(x_2, sigmas[i + 1], denoised_2)
+            x = x + (d + d_2) / 2 * dt
+    return x
+
+
+def sample_dpmpp_2m(model, x, sigmas, warmup_lms=False, ddim_cutoff=0.0):
+    """gyre/pipeline/schedulers/sample_dpmpp_2m.py:6-50 (samplers.py:58-60 passes warmup_lms=True, ddim_cutoff=0.1)."""
+    s_in = x.new_ones([x.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()
+    t_fn = lambda sigma: sigma.log().neg()
+    old_denoised = None
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+        h = t_next - t
+        if old_denoised is None and warmup_lms:
+            r = 1 / 2
+            s = t + r * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * denoised
+            denoised_i = model(x_2, sigma_fn(s) * s_in)
+        elif sigmas[i + 1] <= ddim_cutoff or old_denoised is None:
+            denoised_i = denoised
+        else:
+            h_last = t - t_fn(sigmas[i - 1])
+            r = h_last / h
+            denoised_i = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old_denoised
+        x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * denoised_i
+        old_denoised = denoised
+    return x
+
+
+# ----------------------------------------------------------------------------- DDIM
+
+def ddim_timesteps(n, num_train=1000, steps_offset=1):
+    """scheduling_ddim.py:189-203 with the SD config (ckpt_utils.py:244-255): steps_offset=1."""
+    ratio = num_train // n
+    ts = (torch.arange(0, n, dtype=torch.float64) * ratio).round().flip(0).to(torch.int64)
+    return ts + steps_offset
+
+
+def ddim_step(eps, t, x, alphas_cumprod, n, eta=0.0, noise=None, prediction_type="epsilon", num_train=1000):
+    """scheduling_ddim.py:259-316: set_alpha_to_one=False => final alpha_prev = alphas_cumprod[0];
+    clip_sample=False."""
+    prev_t = t - num_train // n
+    a_t = alphas_cumprod[t]
+    a_prev = alphas_cumprod[prev_t] if prev_t >= 0 else alphas_cumprod[0]
+    b_t = 1 - a_t
+    if prediction_type == "epsilon":
+        x0 = (x - b_t ** 0.5 * eps) / a_t ** 0.5
+    else:  # v_prediction
+        x0 = (a_t ** 0.5) * x - (b_t ** 0.5) * eps
+        eps = (a_t ** 0.5) * eps + (b_t ** 0.5) * x
+    var = ((1 - a_prev) / (1 - a_t)) * (1 - a_t / a_prev)
+    std = eta * var ** 0.5
+    prev = a_prev ** 0.5 * x0 + (1 - a_prev - std ** 2) ** 0.5 * eps
+    if eta > 0:
+        prev = prev + var ** 0.5 * eta * noise
+    return prev, x0
+
+
+def sample_ddim(eps_unet, x, n, alphas_cumprod, eta=0.0, generator=None, prediction_type="epsilon"):
+    """DiffusersSchedulerBase.loop + wrap_unet (common_scheduler.py:261-301); DDIM scale_model_input is
+    identity, init_noise_sigma 1.0; eta>0 noise comes from generators[0] only (:265-266)."""
+    for t in ddim_timesteps(n).to(x.device):
+        eps = eps_unet(x, t)
+        noise = None
+        if eta > 0:
+            noise = torch.randn(eps.shape, dtype=eps.dtype, generator=generator, device=generator.device).to(eps.device)
+        x, _ = ddim_step(eps, int(t), x, alphas_cumprod, n, eta, noise, prediction_type)
+    return x
+
+
+# ----------------------------------------------------------------------------- pipeline hot segment
+
+def txt2img_latents(eps_unet_cfg, *, batch, in_channels, height, width, sample_size, seeds, steps, sampler,
+                    device="cpu", latent_dtype=torch.float32, prediction_type="epsilon", eta=None,
+                    karras_rho=None, trace=None):
+    """UnifiedPipeline.__call__ hot segment up to the final latents
+    (unified_pipeline.py:2478-2483; Txt2imgMode.generateLatents :193-237; KDiffusionScheduler.loop
+    common_scheduler.py:555-623).  `latent_dtype` reproduces the reference's sigma cast
+    (`self.sigmas[...].to(self.dtype)`, :560) and the dtype of every drawn noise tensor."""
+    generators = [torch.Generator(device="cpu").manual_seed(s) for s in seeds]
+    h, w = height // 8, width // 8
+    shape = (batch, in_channels, h, w)
+    mid = batched_randn([batch, in_channels, sample_size, sample_size], generators, device, latent_dtype)
+    off2, off3 = (sample_size - h) // 2, (sample_size - w) // 2
+    if off2 > 0:
+        mid = mid[:, :, off2:off2 + h, :]
+    if off3 > 0:
+        mid = mid[:, :, :, off3:off3 + w]
+    if off2 >= 0 and off3 >= 0:
+        latents = mid
+    else:
+        latents = batched_randn(shape, generators, device, latent_dtype)
+        o2, o3 = (latents.shape[2] - mid.shape[2]) // 2, (latents.shape[3] - mid.shape[3]) // 2
+        latents[:, :, o2:o2 + mid.shape[2], o3:o3 + mid.shape[3]] = mid
+
+    acp = sd_alphas_cumprod(device)
+    if sampler == "ddim":
+        latents = latents * 1.0
+        return sample_ddim(eps_unet_cfg, latents.float(), steps, acp, eta or 0.0, generators[0], prediction_type)
+
+    den = (VDenoiser if prediction_type == "v_prediction" else EpsDenoiser)(eps_unet_cfg, acp)
+    sigmas_full = k_sigmas(den, steps, karras_rho, device)
+    latents = latents * sigmas_full[0]                       # prepare_initial_latents (:540-541)
+    sigmas = sigmas_full.to(latent_dtype)                    # loop(): sigmas.to(self.dtype) (:560)
+    # arithmetic itself stays fp32 in the oracle; only the quantisation points are reproduced
+    sigmas = sigmas.float()
+    latents = latents.float()
+    noise = lambda *_: batched_randn(shape, generators, device, latent_dtype).float()
+    randn_like = lambda x: batched_randn(shape, generators, device, latent_dtype).float()
+    cb = None
+    if trace is not None:
+        cb = lambda d: trace.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()})
+    if sampler == "euler_a":
+        return sample_euler_ancestral(den, latents, sigmas, noise, eta=1.0 if eta is None else eta, callback=cb)
+    if sampler == "euler":
+        return sample_euler(den, latents, sigmas, randn_like)
+    if sampler == "heun":
+        return sample_heun(den, latents, sigmas, randn_like)
+    if sampler == "dpmpp_2m":
+        return sample_dpmpp_2m(den, latents, sigmas, warmup_lms=True, ddim_cutoff=0.1)
+    raise ValueError(sampler)
+
+
+def decode_image(vae, latents, scaling=0.18215):
+    """unified_pipeline.py:2488-2491."""
+    img = vae.decode(1 / scaling * latents).sample
+    return (img / 2 + 0.5).clamp(0, 1)

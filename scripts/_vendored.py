@@ -1,0 +1,101 @@
+"""Import the reference's *vendored* k-diffusion and ToMe sources from /root/reference (this container
+only; the GPU box has no /root/reference).  Same stub trick gyre uses (gyre/src/__init__.py:52-71)."""
+import importlib.util
+import os
+import sys
+import types
+
+REF = os.environ.get("GYRE_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "gyre/src/k-diffusion/k_diffusion"))
+
+
+def _load(pkg, base, name):
+    if pkg not in sys.modules:
+        m = types.ModuleType(pkg)
+        m.__path__ = [base]
+        sys.modules[pkg] = m
+    full = f"{pkg}.{name}"
+    if full in sys.modules:
+        return sys.modules[full]
+    spec = importlib.util.spec_from_file_location(full, os.path.join(base, f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[full] = mod
+    spec.loader.exec_module(mod)
+    setattr(sys.modules[pkg], name, mod)
+    return mod
+
+
+def k_diffusion():
+    for stub in ("torchsde", "torchdiffeq"):
+        if stub not in sys.modules:
+            sys.modules[stub] = types.ModuleType(stub)
+    sys.modules["torchdiffeq"].odeint = None
+    base = os.path.join(REF, "gyre/src/k-diffusion/k_diffusion")
+    utils = _load("k_diffusion", base, "utils")
+    sampling = _load("k_diffusion", base, "sampling")
+    external = _load("k_diffusion", base, "external")
+    return utils, sampling, external
+
+
+def tome_merge():
+    base = os.path.join(REF, "nonfree/ToMe/tome")
+    return _load("tome", base, "merge")
+
+
+def gyre_dpmpp_2m():
+    p = os.path.join(REF, "gyre/pipeline/schedulers/sample_dpmpp_2m.py")
+    spec = importlib.util.spec_from_file_location("_gyre_sample_dpmpp_2m", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gyre_ddim():
+    """The in-tree DDIM copy (gyre/pipeline/schedulers/scheduling_ddim.py) with a minimal `diffusers` stub
+    (ConfigMixin / register_to_config / BaseOutput / SchedulerMixin are plumbing, not arithmetic)."""
+    import functools
+    import inspect
+
+    if "diffusers" not in sys.modules:
+        d = types.ModuleType("diffusers")
+        cu = types.ModuleType("diffusers.configuration_utils")
+        ut = types.ModuleType("diffusers.utils")
+        sc = types.ModuleType("diffusers.schedulers")
+        su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+
+        class _Cfg(dict):
+            __getattr__ = dict.__getitem__
+
+        class ConfigMixin:
+            pass
+
+        def register_to_config(init):
+            @functools.wraps(init)
+            def inner(self, *a, **kw):
+                sig = inspect.signature(init)
+                b = sig.bind(self, *a, **kw)
+                b.apply_defaults()
+                self.config = _Cfg({k: v for k, v in b.arguments.items() if k != "self"})
+                init(self, *a, **kw)
+            return inner
+
+        class BaseOutput:
+            pass
+
+        class SchedulerMixin:
+            pass
+
+        cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+        ut.BaseOutput, ut.deprecate = BaseOutput, (lambda *a, **k: None)
+        su.SchedulerMixin = SchedulerMixin
+        for n, m in (("diffusers", d), ("diffusers.configuration_utils", cu), ("diffusers.utils", ut),
+                     ("diffusers.schedulers", sc), ("diffusers.schedulers.scheduling_utils", su)):
+            sys.modules[n] = m
+    p = os.path.join(REF, "gyre/pipeline/schedulers/scheduling_ddim.py")
+    spec = importlib.util.spec_from_file_location("_gyre_scheduling_ddim", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -1,0 +1,222 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.pt (run in the build container, where /root/reference is mounted).
+
+Part 1 PINS the oracle: it imports the reference's own vendored k-diffusion, ToMe and DDIM sources,
+runs them on seeded inputs, asserts that the oracle restatement reproduces them, and stores the
+REFERENCE outputs as golden vectors.
+Part 2 stores oracle outputs for the UNet / VAE / pipeline (no reference implementation of those is
+importable: diffusers is an absent third-party dependency -> "parity unpinned" there).
+
+    python scripts/make_golden.py [--full]     (--full adds the SD1.5-size C1 fixture, ~5 min of CPU)
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+import _vendored  # noqa: E402
+from oracle import sampling as osamp  # noqa: E402
+from oracle import tome as otome  # noqa: E402
+from oracle.unet import UNetConfig, OracleUNet, synth_params, unet_forward, unet_param_shapes  # noqa: E402
+from oracle.vae import VAEConfig, OracleVAE, vae_decode, vae_encode_moments, vae_param_shapes  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def toy_eps(x, t):
+    t = t if torch.is_tensor(t) else torch.tensor(t)
+    tt = t.float().reshape(-1, *([1] * (x.ndim - 1)))
+    return 0.7 * torch.tanh(x) + 0.001 * tt * x.roll(1, -1)
+
+
+def pin_samplers():
+    _, ks, kext = _vendored.k_diffusion()
+    dpmpp = _vendored.gyre_dpmpp_2m()
+    acp = osamp.sd_alphas_cumprod()
+    out = {}
+    for dtype_name, ldt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        for name in ("euler_a", "euler", "heun", "dpmpp_2m"):
+            for steps in (7, 20):
+                shape = (2, 4, 8, 8)
+                seeds = [420420420, 420420421]
+                # ---- reference (vendored) run, following KDiffusionScheduler.set_timesteps/loop
+                gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+                ref_den = kext.DiscreteEpsDDPMDenoiser(toy_eps, acp, quantize=True)
+                t = torch.linspace(len(ref_den.sigmas) - 1, 0, steps)
+                sig_full = ks.append_zero(ref_den.t_to_sigma(t))
+                x0 = osamp.batched_randn(shape, gens, "cpu", ldt) * sig_full[0]
+                sig = sig_full.to(ldt).float()
+                x0 = x0.float()
+                ns = lambda *_: osamp.batched_randn(shape, gens, "cpu", ldt).float()
+                orig_randn_like = ks.torch.randn_like
+                if name == "euler_a":
+                    ref = ks.sample_euler_ancestral(ref_den, x0, sig, noise_sampler=ns, disable=True)
+                elif name in ("euler", "heun"):
+                    class _T:  # TorchRandOverride (randtools.py:67-90) restated for the patch
+                        def __getattr__(self, k):
+                            return getattr(torch, k)
+
+                        def randn_like(self, inp, **kw):
+                            return ns()
+                    ks.torch = _T()
+                    try:
+                        fn = ks.sample_euler if name == "euler" else ks.sample_heun
+                        ref = fn(ref_den, x0, sig, disable=True)
+                    finally:
+                        ks.torch = torch
+                else:
+                    ref = dpmpp.sample_dpmpp_2m(ref_den, x0, sig, disable=True, warmup_lms=True, ddim_cutoff=0.1)
+                assert ks.torch.randn_like is orig_randn_like
+                # ---- oracle restatement
+                gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+                den = osamp.EpsDenoiser(toy_eps, acp)
+                sig2 = osamp.k_sigmas(den, steps)
+                assert torch.equal(sig2, sig_full), "sigma schedule mismatch"
+                y0 = (osamp.batched_randn(shape, gens, "cpu", ldt) * sig2[0]).float()
+                ns2 = lambda *_: osamp.batched_randn(shape, gens, "cpu", ldt).float()
+                s2 = sig2.to(ldt).float()
+                if name == "euler_a":
+                    got = osamp.sample_euler_ancestral(den, y0, s2, ns2)
+                elif name == "euler":
+                    got = osamp.sample_euler(den, y0, s2, lambda x: ns2())
+                elif name == "heun":
+                    got = osamp.sample_heun(den, y0, s2, lambda x: ns2())
+                else:
+                    got = osamp.sample_dpmpp_2m(den, y0, s2, warmup_lms=True, ddim_cutoff=0.1)
+                err = (got - ref).abs().max().item()
+                assert err == 0.0, f"{name}/{steps}/{dtype_name}: oracle != vendored k-diffusion ({err})"
+                out[f"{name}/{steps}/{dtype_name}"] = {"seeds": seeds, "shape": shape, "sigmas": sig_full,
+                                                        "result": ref}
+    # v-prediction denoiser
+    x = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1))
+    s = torch.tensor([3.3, 0.7])
+    refv = kext.DiscreteVDDPMDenoiser(toy_eps, acp, quantize=True)(x, s)
+    gotv = osamp.VDenoiser(toy_eps, acp)(x, s)
+    assert torch.equal(refv, gotv)
+    out["vdenoiser"] = {"x": x, "sigma": s, "result": refv}
+    # karras
+    kk = ks.get_sigmas_karras(11, ref_den.sigma_min, ref_den.sigma_max, rho=7.0)
+    assert torch.equal(kk, osamp.get_sigmas_karras(11, den.sigma_min, den.sigma_max, 7.0))
+    out["karras/11"] = kk
+    # sigma_to_t on fp16-quantised sigmas
+    sg = sig_full[:-1].to(torch.float16).float()
+    assert torch.equal(ref_den.sigma_to_t(sg), den.sigma_to_t(sg))
+    out["sigma_to_t"] = {"sigma": sg, "t": ref_den.sigma_to_t(sg)}
+    torch.save(out, os.path.join(GOLD, "samplers.pt"))
+    print("samplers pinned:", len(out))
+
+
+def pin_ddim():
+    mod = _vendored.gyre_ddim()
+    out = {}
+    for pred in ("epsilon", "v_prediction"):
+        for eta in (0.0, 0.6):
+            sch = mod.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                    clip_sample=False, set_alpha_to_one=False, steps_offset=1,
+                                    prediction_type=pred)        # ckpt_utils.py:244-255
+            n = 10
+            sch.set_timesteps(n)
+            assert torch.equal(sch.timesteps, osamp.ddim_timesteps(n))
+            g = torch.Generator("cpu").manual_seed(7)
+            x = torch.randn(2, 4, 8, 8, generator=g)
+            xr = x.clone()
+            gr = torch.Generator("cpu").manual_seed(99)
+            for t in sch.timesteps:
+                eps = toy_eps(xr, t)
+                xr = sch.step(eps, t, xr, eta=eta, generator=gr).prev_sample
+            go = torch.Generator("cpu").manual_seed(99)
+            got = osamp.sample_ddim(toy_eps, x.clone(), n, osamp.sd_alphas_cumprod(), eta, go, pred)
+            err = (got - xr).abs().max().item()
+            assert err < 1e-6, f"ddim {pred} eta={eta}: {err}"
+            out[f"{pred}/{eta}"] = {"x": x, "result": xr}
+    torch.save(out, os.path.join(GOLD, "ddim.pt"))
+    print("ddim pinned:", len(out))
+
+
+def pin_tome():
+    tm = _vendored.tome_merge()
+    out = {}
+    g = torch.Generator("cpu").manual_seed(3)
+    for (B, N, C, r) in ((2, 64, 32, 16), (2, 64, 32, 40), (1, 256, 64, 128), (3, 30, 16, 7)):
+        k = torch.randn(B, N, C, generator=g)
+        v = torch.randn(B, N, C, generator=g)
+        merge, _ = tm.bipartite_soft_matching(k, r, False, False)
+        km, _ = tm.merge_wavg(merge, k)
+        vm, _ = tm.merge_wavg(merge, v)
+        plan = otome.bipartite_soft_matching_plan(k, r)
+        assert torch.equal(otome.merge_mean(plan, k), km) and torch.equal(otome.merge_mean(plan, v), vm)
+        out[f"{B}x{N}x{C}/r{r}"] = {"k": k, "v": v, "r": r, "k_merged": km, "v_merged": vm}
+    sys.path.insert(0, os.path.join(_vendored.REF, "nonfree/ToMe"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_tome_utils_src", os.path.join(_vendored.REF, "nonfree/ToMe/tome/utils.py"))
+    src = open(spec.origin).read()
+    ns = {}
+    start = src.index("def parse_r")
+    exec("from typing import List, Tuple, Union\n" + src[start:], ns)
+    for arg in (8, (8, -1.0), (100, 0.5), [3, 2, 1]):
+        assert ns["parse_r"](16, arg if not isinstance(arg, list) else list(arg)) == otome.parse_r(16, arg if not isinstance(arg, list) else list(arg))
+    out["parse_r"] = {"(100,0.5)": ns["parse_r"](16, (100, 0.5))}
+    torch.save(out, os.path.join(GOLD, "tome.pt"))
+    print("tome pinned:", len(out))
+
+
+def oracle_fixtures(full: bool):
+    """Oracle self-fixtures (unpinned at the diffusers boundary)."""
+    out = {}
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    g = torch.Generator("cpu").manual_seed(5)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    t = torch.tensor([981, 21])
+    with torch.no_grad():
+        out["unet_tiny"] = {"x": x, "ctx": ctx, "t": t, "eps": unet_forward(P, cfg, x, t, ctx)}
+        out["unet_tiny_tome"] = {"r": 48, "eps": unet_forward(P, cfg, x, t, ctx, tome_r=48)}
+        vcfg = VAEConfig.tiny()
+        VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+        z = torch.randn(1, 4, 8, 8, generator=g)
+        out["vae_tiny"] = {"z": z, "img": vae_decode(VP, vcfg, z)}
+        img = torch.rand(1, 3, 32, 32, generator=g) * 2 - 1
+        out["vae_tiny_enc"] = {"img": img, "moments": vae_encode_moments(VP, vcfg, img)}
+        unet = OracleUNet(cfg, P)
+        emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(11))
+        unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1)
+        cfgu = osamp.CFGParallel(unet, unc, emb, 7.5)
+        for sampler, steps in (("ddim", 10), ("euler_a", 12), ("euler", 8), ("dpmpp_2m", 8)):
+            lat = osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=128, width=128, sample_size=16,
+                                        seeds=[420420420, 420420421], steps=steps, sampler=sampler)
+            out[f"pipe_tiny/{sampler}"] = {"steps": steps, "latents": lat}
+    torch.save(out, os.path.join(GOLD, "oracle_tiny.pt"))
+    print("oracle tiny fixtures:", list(out))
+    if full:
+        import time
+        cfg = UNetConfig.sd15()
+        P = synth_params(unet_param_shapes(cfg), seed=1234)
+        unet = OracleUNet(cfg, P)
+        emb = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(11))
+        unc = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(12))
+        cfgu = osamp.CFGParallel(unet, unc, emb, 7.5)
+        t0 = time.time()
+        with torch.no_grad():
+            lat = osamp.txt2img_latents(cfgu, batch=1, in_channels=4, height=512, width=512, sample_size=64,
+                                        seeds=[420420420], steps=10, sampler="ddim")
+        print("C1 full-size oracle run: %.1fs" % (time.time() - t0))
+        torch.save({"latents": lat, "steps": 10, "sampler": "ddim", "seed": 420420420, "weights_seed": 1234},
+                   os.path.join(GOLD, "c1_sd15_ddim10.pt"))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    pin_samplers()
+    pin_ddim()
+    pin_tome()
+    oracle_fixtures(a.full)
