@@ -1,0 +1,265 @@
+"""ctypes binding of libgyre_b200.so (include/gyre_b200.h).  PyTorch is plumbing here: it owns device
+memory and the stream; every arithmetic step goes through the C ABI.  There is NO fallback: a missing
+library, a failing build or a non-zero status raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libgyre_b200.so")
+_lock = threading.Lock()
+_lib = None
+
+
+class Epilogue(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p), ("rowgroup_bias", C.c_void_p), ("rows_per_group", C.c_int32), ("rgb_ld", C.c_int32),
+        ("residual", C.c_void_p), ("ldr", C.c_int32), ("act", C.c_int32), ("out_f32", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int32),
+    ]
+
+
+class Step(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("v_pred", C.c_int32), ("cfg", C.c_int32), ("guidance", C.c_float),
+        ("sigma", C.c_float), ("c_in_next", C.c_float), ("dt", C.c_float), ("sigma_up", C.c_float),
+        ("sqrt_a_t", C.c_float), ("sqrt_1m_a_t", C.c_float), ("sqrt_a_prev", C.c_float), ("dir_coef", C.c_float),
+        ("noise_coef", C.c_float),
+    ]
+
+
+class UNetConfigC(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int32), ("out_channels", C.c_int32), ("num_levels", C.c_int32),
+        ("block_out_channels", C.c_int32 * 4), ("num_heads", C.c_int32 * 4), ("attn_levels", C.c_int32 * 4),
+        ("layers_per_block", C.c_int32), ("cross_attention_dim", C.c_int32), ("norm_num_groups", C.c_int32),
+        ("norm_eps", C.c_float), ("use_linear_projection", C.c_int32), ("upcast_attention", C.c_int32),
+    ]
+
+
+class VAEConfigC(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int32), ("out_channels", C.c_int32), ("latent_channels", C.c_int32),
+        ("num_levels", C.c_int32), ("block_out_channels", C.c_int32 * 4), ("layers_per_block", C.c_int32),
+        ("norm_num_groups", C.c_int32),
+    ]
+
+
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gyre_b200.h one to one
+SIGNATURES = {
+    "gyre_b200_abi_version": (_i, []),
+    "gyre_b200_last_error": (_i, [C.c_char_p, _sz]),
+    "gyre_b200_unet_create": (_i, [C.POINTER(UNetConfigC), C.POINTER(_vp)]),
+    "gyre_b200_load_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i, _vp]),
+    "gyre_b200_finalize": (_i, [_vp]),
+    "gyre_b200_unet_workspace_bytes": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_sz)]),
+    "gyre_b200_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
+    "gyre_b200_vae_create": (_i, [C.POINTER(VAEConfigC), C.POINTER(_vp)]),
+    "gyre_b200_vae_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
+    "gyre_b200_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "gyre_b200_vae_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "gyre_b200_destroy": (_i, [_vp]),
+    "gyre_b200_sched_step": (_i, [C.POINTER(Step), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "gyre_b200_scale_latents": (_i, [_vp, _f, _i, _i, _i64, _vp, _vp]),
+    "gyre_b200_tome_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "gyre_b200_tome_merge_kv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "gyre_b200_gemm": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, C.POINTER(Epilogue), _vp]),
+    "gyre_b200_pack_geglu": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "gyre_b200_conv3x3": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, C.POINTER(Epilogue), _vp]),
+    "gyre_b200_conv3x3_packed_elems": (_sz, [_i, _i]),
+    "gyre_b200_pack_conv3x3": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "gyre_b200_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),
+    "gyre_b200_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "gyre_b200_layernorm": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "gyre_b200_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
+}
+
+
+class NativeError(RuntimeError):
+    """Non-zero status from libgyre_b200 (the reference surfaces failures as Python exceptions that
+    gyre/services/exception_to_grpc.py maps to gRPC codes; we keep that contract)."""
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Loads (building first if the .so is absent) and type-annotates the library."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            if not build_if_missing:
+                raise NativeError(f"{_LIB_PATH} is missing; run `python -m gyre_b200.build`")
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)     # AttributeError here == header/library drift: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.gyre_b200_abi_version() != 1:
+            raise NativeError("libgyre_b200 ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(2048)
+    load().gyre_b200_last_error(buf, 2048)
+    return buf.value.decode(errors="replace")
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise NativeError(f"{what} failed ({status}): {last_error()}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NativeError("gyre_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+_DT = {torch.float16: 0, torch.float32: 1}
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise NativeError(f"unsupported parameter dtype {t.dtype}") from None
+
+
+# ----------------------------------------------------------------------------------------------------
+# building-block wrappers (used by the per-kernel parity tests and the attention patcher)
+
+def _epilogue(out, bias=None, residual=None, act=0, rowgroup_bias=None, rows_per_group=1):
+    e = Epilogue()
+    e.bias = ptr(bias)
+    e.rowgroup_bias = ptr(rowgroup_bias)
+    e.rows_per_group = rows_per_group
+    e.rgb_ld = rowgroup_bias.stride(0) if rowgroup_bias is not None else 0
+    e.residual = ptr(residual)
+    e.ldr = residual.stride(0) if residual is not None else 0
+    e.act = act
+    e.out_f32 = 1 if out.dtype == torch.float32 else 0
+    e.out = ptr(out)
+    e.ldo = out.stride(0)
+    return e
+
+
+def gemm(a, w, bias=None, residual=None, act=0, a2=None, out_dtype=torch.float16, rowgroup_bias=None,
+         rows_per_group=1):
+    """out = epilogue([a | a2] @ w.T); a [M, K1] fp16, w [N, K1+K2] fp16 (GEGLU: pre-packed), bias fp32."""
+    require_cuda(a, w)
+    M, K1 = a.shape
+    K2 = a2.shape[1] if a2 is not None else 0
+    N = w.shape[0]
+    n_out = N // 2 if act == 1 else N
+    out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
+    e = _epilogue(out, bias, residual, act, rowgroup_bias, rows_per_group)
+    check(load().gyre_b200_gemm(ptr(a), a.stride(0), K1, ptr(a2), a2.stride(0) if a2 is not None else 0, K2, ptr(w),
+                                w.stride(0), M, N, C.byref(e), stream_ptr(a.device)), "gemm")
+    return out
+
+
+def pack_geglu(w, bias):
+    require_cuda(w)
+    F2, K = w.shape
+    wp = torch.empty((F2, K), device=w.device, dtype=torch.float16)
+    bp = torch.empty((F2,), device=w.device, dtype=torch.float32) if bias is not None else None
+    w = w.contiguous()
+    if bias is not None:
+        bias = bias.contiguous()
+    check(load().gyre_b200_pack_geglu(ptr(w), dtype_code(w), F2 // 2, K, ptr(bias),
+                                      dtype_code(bias) if bias is not None else 0, ptr(wp), ptr(bp),
+                                      stream_ptr(w.device)), "pack_geglu")
+    return wp, bp
+
+
+def pack_conv3x3(w):
+    require_cuda(w)
+    cout, cin = w.shape[0], w.shape[1]
+    n = load().gyre_b200_conv3x3_packed_elems(cin, cout)
+    wp = torch.empty((n,), device=w.device, dtype=torch.float16)
+    w = w.contiguous()
+    check(load().gyre_b200_pack_conv3x3(ptr(w), dtype_code(w), cin, cout, ptr(wp), stream_ptr(w.device)), "pack_conv3x3")
+    return wp
+
+
+def conv3x3(x_nhwc, wp, cout, bias=None, residual=None, stride=1, pad=1, act=0, rowgroup_bias=None,
+            rows_per_group=1):
+    """x [B, H, W, Cin] fp16 NHWC -> [B, Ho, Wo, Cout] fp16 NHWC."""
+    require_cuda(x_nhwc, wp)
+    B, H, W, Cin = x_nhwc.shape
+    if stride == 1:
+        Ho, Wo = H, W
+    elif pad == 1:
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    else:
+        Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
+    out = torch.empty((B * Ho * Wo, cout), device=x_nhwc.device, dtype=torch.float16)
+    e = _epilogue(out, bias, residual, act, rowgroup_bias, rows_per_group)
+    check(load().gyre_b200_conv3x3(ptr(x_nhwc), Cin, B, H, W, Cin, ptr(wp), cout, stride, pad, C.byref(e),
+                                   stream_ptr(x_nhwc.device)), "conv3x3")
+    return out.view(B, Ho, Wo, cout)
+
+
+def groupnorm(x1, gamma, beta, groups, eps, silu, x2=None):
+    """x1 [B, HW, C1] (+ x2 [B, HW, C2]) fp16 -> [B, HW, C1+C2] fp16."""
+    require_cuda(x1, gamma, beta)
+    B, HW, C1 = x1.shape
+    C2 = x2.shape[2] if x2 is not None else 0
+    out = torch.empty((B, HW, C1 + C2), device=x1.device, dtype=torch.float16)
+    scratch = torch.empty((load().gyre_b200_groupnorm_scratch_floats(B, HW, groups),), device=x1.device,
+                          dtype=torch.float32)
+    check(load().gyre_b200_groupnorm(ptr(x1), C1, ptr(x2), C2, B, HW, groups, eps, ptr(gamma), ptr(beta),
+                                     1 if silu else 0, ptr(out), ptr(scratch), stream_ptr(x1.device)), "groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    require_cuda(x, gamma, beta)
+    rows, Cc = x.shape
+    out = torch.empty_like(x)
+    check(load().gyre_b200_layernorm(ptr(x), rows, Cc, eps, ptr(gamma), ptr(beta), ptr(out), stream_ptr(x.device)),
+          "layernorm")
+    return out
+
+
+def attention(q, k, v, heads, scale=None):
+    """q [B, Nq, C(+)] / k, v [B, Nk, C(+)] fp16 token-major views (last-dim stride 1) -> [B, Nq, C]."""
+    require_cuda(q, k, v)
+    B, Nq, _ = q.shape
+    Nk = k.shape[1]
+    Cc = v.shape[2]
+    d = Cc // heads
+    if scale is None:
+        scale = d ** -0.5
+    out = torch.empty((B, Nq, Cc), device=q.device, dtype=torch.float16)
+    for t in (q, k, v):
+        if t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise NativeError("attention operands must be [B, N, *] views with dense batch stride")
+    check(load().gyre_b200_attention(ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1), B, heads, Nq, Nk,
+                                     d, scale, ptr(out), Cc, stream_ptr(q.device)), "attention")
+    return out

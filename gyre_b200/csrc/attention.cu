@@ -1,0 +1,335 @@
+// K5: flash-style attention on tcgen05 for sm_100a.
+//
+// One CTA owns 128 query rows of one (batch, head).  Q, K and V are read IN PLACE from the token-major
+// projection outputs ([B, N, ld], head h at columns h*d) through 4-D TMA tensor maps, so no head-split /
+// transpose pass exists: K tiles land as K-major operands, V tiles as MN-major operands (keys are the
+// MMA K dimension, d is contiguous), both with the 128B swizzle; the head dimension is zero-padded to the
+// next 64 by the TMA unit's out-of-bounds fill (d = 40/80/160 in SD1.x).
+//
+//   warp 0      TMA producer (Q once, then K/V tiles through a STAGES-deep full/empty ring)
+//   warp 1      TMEM owner + tcgen05.mma issuer:  S = Q K^T  (TMEM cols [0,128)),  O += P V (cols [128, ..))
+//   warps 2..5  softmax: one query row per thread (tcgen05.ld 32x32b), online max/sum in fp32 with exp2,
+//               P written as fp16 into a swizzled K-major smem tile, lazy rescale of O in TMEM
+//               (only when the running max grows by more than 2^8), final O / l -> global.
+#include "common.cuh"
+#include "ops.h"
+
+namespace gyre {
+
+constexpr int kAttThreads = 192;
+constexpr int kBQ = 128;
+constexpr int kBKeys = 128;
+constexpr int kChunkBytes = 128 * 128;   // one 64-wide (128 B) column chunk of a 128-row tile
+
+struct AttnParams {
+  int Nq, Nk, heads, d;
+  int n_kv_tiles;
+  int ksteps_qk;     // ceil(d / 16)
+  int npv;           // round_up(d, 16): accumulator columns of O
+  int q_tiles;
+  float scale_log2;  // scale * log2(e)
+  __half* out;
+  int ldo;
+};
+
+template <int DCH>
+struct AttnCfg {
+  static constexpr int STAGES = DCH >= 3 ? 1 : 2;   // d > 128: one K/V stage keeps the CTA under 227 KB
+  static constexpr int Q_BYTES = DCH * kChunkBytes;
+  static constexpr int KV_BYTES = DCH * kChunkBytes;          // per operand per stage
+  static constexpr int P_BYTES = 2 * kChunkBytes;
+  static constexpr int SMEM = Q_BYTES + P_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = (128 + DCH * 64 <= 256) ? 256 : 512;
+};
+
+template <int DCH>
+__global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                const __grid_constant__ CUtensorMap tmK,
+                                                                const __grid_constant__ CUtensorMap tmV,
+                                                                const AttnParams p) {
+  using Cfg = AttnCfg<DCH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + Cfg::Q_BYTES;
+  uint8_t* sK = sP + Cfg::P_BYTES;
+  uint8_t* sV = sK + Cfg::STAGES * Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::STAGES * Cfg::KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + Cfg::STAGES;
+  uint64_t* s_full = kv_empty + Cfg::STAGES;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_done = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x % p.q_tiles;
+  const int bh = blockIdx.x / p.q_tiles;
+  const int h = bh % p.heads;
+  const int b = bh / p.heads;
+  const int q0 = q_tile * kBQ;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * kChunkBytes, &tmQ, q_full, c * 64, q0, h, b);
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int s = j % Cfg::STAGES;
+        const uint32_t ph = (j / Cfg::STAGES) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) {
+          tma_load_4d(sK + s * Cfg::KV_BYTES + c * kChunkBytes, &tmK, &kv_full[s], c * 64, j * kBKeys, h, b);
+          tma_load_4d(sV + s * Cfg::KV_BYTES + c * kChunkBytes, &tmV, &kv_full[s], c * 64, j * kBKeys, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int s = j % Cfg::STAGES;
+        const uint32_t ph = (j / Cfg::STAGES) & 1;
+        const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+        const int n_s = (nk_tile + 15) & ~15;
+        mbar_wait(&kv_full[s], ph);
+        tc_fence_after();
+        {
+          const uint32_t idesc = umma_idesc_f16(kBQ, n_s);
+          const uint32_t qa = smem_u32(sQ);
+          const uint32_t ka = smem_u32(sK + s * Cfg::KV_BYTES);
+          for (int ks = 0; ks < p.ksteps_qk; ++ks) {
+            const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+            umma_f16_ss(tmem_S, umma_desc_kmajor_sw128(qa + off), umma_desc_kmajor_sw128(ka + off), idesc,
+                        ks != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        {
+          const uint32_t idesc = umma_idesc_f16(kBQ, p.npv, /*b_mn_major=*/1);
+          const uint32_t pa = smem_u32(sP);
+          const uint32_t va = smem_u32(sV + s * Cfg::KV_BYTES);
+          const int ksteps = n_s >> 4;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
+            const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+            umma_f16_ss(tmem_O, da, db, idesc, (j | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                       // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float c = p.scale_log2;
+    float m_ref = -INFINITY;
+    float l = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int rx = r & 7;
+
+    for (int j = 0; j < p.n_kv_tiles; ++j) {
+      const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+      const int n_s = (nk_tile + 15) & ~15;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max over the valid keys of this tile
+      float mt = -INFINITY;
+      for (int c0 = 0; c0 < n_s; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_S + lane_off + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < nk_tile) mt = fmaxf(mt, __uint_as_float(v[i]));
+      }
+      if (j == 0) {
+        m_ref = mt;
+      } else {
+        // P and O are free once PV(j-1) retired (it always has by now: the tensor pipe runs in order)
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        const bool grow = (mt - m_ref) * c > 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = fmaxf(m_ref, mt);
+          const float alpha = ex2_approx((m_ref - m_new) * c);
+          m_ref = m_new;
+          l *= alpha;
+          int c0 = 0;
+          for (; c0 + 32 <= p.npv; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_O + lane_off + c0, o);
+          }
+          if (c0 < p.npv) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tmem_O + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_O + lane_off + c0, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: p = exp2((s - m_ref) * c) -> fp16, swizzled K-major store
+      const float mc = m_ref * c;
+      for (int c0 = 0; c0 < n_s; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_S + lane_off + c0, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c0 + i < nk_tile) ? ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          float p1 = (c0 + i + 1 < nk_tile) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc)) : 0.f;
+          const __half2 hh = __floats2half2_rn(p0, p1);
+          // the sum uses the rounded values the tensor core will actually multiply
+          const float2 back = __half22float2(hh);
+          l += back.x + back.y;
+          packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        uint8_t* pchunk = prow + (c0 >> 6) * kChunkBytes;
+        const int u0 = (c0 & 63) >> 3;                   // first 16-byte unit of this 32-column group
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+          *reinterpret_cast<uint4*>(pchunk + (((u0 + u) ^ rx) << 4)) = w;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> out[b, q0 + r, h*d + :]
+    mbar_wait(pv_done, (p.n_kv_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const bool valid = q0 + r < p.Nq;
+    __half* dst = p.out + (static_cast<int64_t>(b) * p.Nq + q0 + r) * p.ldo + h * p.d;
+    for (int c0 = 0; c0 < p.npv; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld_32x32b_x16(tmem_O + lane_off + c0, o);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = c0 + g * 8;
+          if (col < p.d) {    // d % 8 == 0
+            __align__(16) __half2 hh[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              hh[i] = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv,
+                                        __uint_as_float(o[g * 8 + 2 * i + 1]) * inv);
+            *reinterpret_cast<uint4*>(dst + col) = *reinterpret_cast<uint4*>(hh);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int DCH>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                       long long blocks, cudaStream_t st) {
+  using Cfg = AttnCfg<DCH>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    GYRE_CHECK_CUDA(
+        cudaFuncSetAttribute(attention_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_done = true;
+  }
+  attention_kernel<DCH><<<static_cast<unsigned>(blocks), kAttThreads, Cfg::SMEM, st>>>(tq, tk, tv, p);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int make_head_map(CUtensorMap* m, const __half* base, int ld, int N, int heads, int d, int B, int box_rows) {
+  uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(N), static_cast<uint64_t>(heads),
+                      static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(d) * 2,
+                         static_cast<uint64_t>(N) * ld * 2};
+  uint32_t box[4] = {64, static_cast<uint32_t>(box_rows), 1, 1};
+  uint32_t es[4] = {1, 1, 1, 1};
+  return encode_tmap_f16(m, base, 4, dims, strides, box, es, true);
+}
+
+int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, int B, int heads,
+                  int Nq, int Nk, int d, float scale, __half* out, int ldo, cudaStream_t st) {
+  GYRE_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: empty problem");
+  GYRE_REQUIRE(d >= 8 && d % 8 == 0 && d <= 192, "attention: head dim %d must be a multiple of 8 in [8, 192]", d);
+  GYRE_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: pitches must be multiples of 8");
+  GYRE_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                 reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "attention: operands must be 16B aligned");
+  GYRE_REQUIRE(ldq >= heads * d && ldk >= heads * d && ldv >= heads * d && ldo >= heads * d,
+               "attention: pitch smaller than heads*d");
+  AttnParams p{};
+  p.Nq = Nq;
+  p.Nk = Nk;
+  p.heads = heads;
+  p.d = d;
+  p.n_kv_tiles = (Nk + kBKeys - 1) / kBKeys;
+  p.ksteps_qk = (d + 15) / 16;
+  p.npv = (d + 15) & ~15;
+  p.q_tiles = (Nq + kBQ - 1) / kBQ;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = out;
+  p.ldo = ldo;
+  CUtensorMap tq, tk, tv;
+  GYRE_TRY(make_head_map(&tq, q, ldq, Nq, heads, d, B, kBQ));
+  GYRE_TRY(make_head_map(&tk, k, ldk, Nk, heads, d, B, kBKeys));
+  GYRE_TRY(make_head_map(&tv, v, ldv, Nk, heads, d, B, kBKeys));
+  const long long blocks = static_cast<long long>(B) * heads * p.q_tiles;
+  GYRE_REQUIRE(blocks < (1ll << 31), "attention: grid too large");
+  const int dch = (d + 63) / 64;
+  switch (dch) {
+    case 1: return launch_attn<1>(tq, tk, tv, p, blocks, st);
+    case 2: return launch_attn<2>(tq, tk, tv, p, blocks, st);
+    case 3: return launch_attn<3>(tq, tk, tv, p, blocks, st);
+  }
+  set_last_error("attention: unsupported head dim %d", d);
+  return -2;
+}
+
+}  // namespace gyre

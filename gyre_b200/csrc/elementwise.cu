@@ -1,0 +1,286 @@
+// Layout shuffles, tiny-channel convolutions, timestep embedding, the fused scheduler step (K7) and the
+// VAE image tail (K8).  All HBM/latency-bound: coalesced, vectorised where the layout allows.
+#include "common.cuh"
+#include "ops.h"
+
+namespace gyre {
+
+static inline unsigned blocks_for(int64_t n, int threads) {
+  return static_cast<unsigned>((n + threads - 1) / threads);
+}
+
+// ------------------------------------------------------------------ NCHW <-> NHWC (small C: latents / images)
+__global__ void nchw_to_nhwc_kernel(const __half* __restrict__ x, int C, int HW, __half* __restrict__ out, int ldo,
+                                    int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over b*HW*C (NHWC order)
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const int64_t bp = i / C;
+  const int p = static_cast<int>(bp % HW);
+  const int64_t b = bp / HW;
+  out[bp * ldo + c] = x[(b * C + c) * HW + p];
+}
+int nchw_to_nhwc_f16(const __half* x, int B, int C, int H, int W, __half* out, int ldo, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(B) * C * H * W;
+  GYRE_REQUIRE(total > 0, "nchw_to_nhwc: empty");
+  nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, C, H * W, out, ldo, total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int ldx, int C, int HW, __half* __restrict__ out,
+                                    int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over b*C*HW (NCHW order)
+  if (i >= total) return;
+  const int p = static_cast<int>(i % HW);
+  const int64_t bc = i / HW;
+  const int c = static_cast<int>(bc % C);
+  const int64_t b = bc / C;
+  out[i] = x[(b * HW + p) * ldx + c];
+}
+int nhwc_to_nchw_f16(const __half* x, int ldx, int B, int C, int H, int W, __half* out, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(B) * C * H * W;
+  GYRE_REQUIRE(total > 0, "nhwc_to_nchw: empty");
+  nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, C, H * W, out, total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ nearest 2x upsample, NHWC, 16B vectors
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int H, int W, int nvec, uint4* __restrict__ out,
+                                  int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over output vectors
+  if (i >= total) return;
+  const int v = static_cast<int>(i % nvec);
+  int64_t p = i / nvec;
+  const int xo = static_cast<int>(p % (2 * W));
+  p /= (2 * W);
+  const int yo = static_cast<int>(p % (2 * H));
+  const int64_t b = p / (2 * H);
+  out[i] = x[((b * H + (yo >> 1)) * W + (xo >> 1)) * nvec + v];
+}
+int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(C % 8 == 0, "upsample2x: C must be a multiple of 8");
+  const int64_t total = static_cast<int64_t>(B) * 4 * H * W * (C / 8);
+  GYRE_REQUIRE(total > 0, "upsample2x: empty");
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), H, W, C / 8,
+                                                            reinterpret_cast<uint4*>(out), total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ channel concat (rows x (Ca+Cb))
+__global__ void concat_kernel(const uint4* __restrict__ a, int na, const uint4* __restrict__ b, int nb,
+                              uint4* __restrict__ out, int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int n = na + nb;
+  const int v = static_cast<int>(i % n);
+  const int64_t r = i / n;
+  out[i] = v < na ? a[r * na + v] : b[r * nb + (v - na)];
+}
+int concat_channels(const __half* a, int Ca, const __half* b, int Cb, int64_t rows, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat: channel counts must be multiples of 8");
+  const int64_t total = rows * ((Ca + Cb) / 8);
+  GYRE_REQUIRE(total > 0, "concat: empty");
+  concat_kernel<<<blocks_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a), Ca / 8,
+                                                        reinterpret_cast<const uint4*>(b), Cb / 8,
+                                                        reinterpret_cast<uint4*>(out), total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ timestep embedding [cos | sin], fp16
+__global__ void timestep_embed_kernel(const int64_t* __restrict__ t, int dim, __half* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int half = dim / 2;
+  const float tv = static_cast<float>(t[b]);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+    const float e = tv * freq;
+    out[static_cast<int64_t>(b) * dim + i] = __float2half_rn(cosf(e));
+    out[static_cast<int64_t>(b) * dim + half + i] = __float2half_rn(sinf(e));
+  }
+}
+int timestep_embed(const int64_t* t, int B, int dim, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, "timestep_embed: bad shape");
+  timestep_embed_kernel<<<B, 128, 0, st>>>(t, dim, out);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void silu_kernel(const __half* __restrict__ x, int64_t n, __half* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float v = __half2float(x[i]);
+  out[i] = __float2half_rn(v / (1.0f + __expf(-v)));
+}
+int silu_f16(const __half* x, int64_t n, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(n > 0, "silu: empty");
+  silu_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, n, out);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ direct 3x3 conv, tiny Cin (conv_in)
+// thread -> (pixel, group of 8 output channels); weights fp32 [Cout, 3, 3, Cin]
+__global__ void conv3x3_small_kernel(const __half* __restrict__ X, int H, int W, int Cin, const float* __restrict__ Wt,
+                                     const float* __restrict__ bias, int Cout, __half* __restrict__ out,
+                                     int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int ng = Cout >> 3;
+  const int g = static_cast<int>(i % ng);
+  int64_t p = i / ng;
+  const int x = static_cast<int>(p % W);
+  p /= W;
+  const int y = static_cast<int>(p % H);
+  const int64_t b = p / H;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = bias ? bias[g * 8 + o] : 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int yy = y + kh - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int xx = x + kw - 1;
+      if (xx < 0 || xx >= W) continue;
+      const __half* px = X + ((b * H + yy) * W + xx) * Cin;
+      for (int c = 0; c < Cin; ++c) {
+        const float xv = __half2float(px[c]);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = fmaf(xv, Wt[((g * 8 + o) * 9 + kh * 3 + kw) * Cin + c], acc[o]);
+      }
+    }
+  }
+  __align__(16) __half2 h[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) h[o] = __floats2half2_rn(acc[2 * o], acc[2 * o + 1]);
+  *reinterpret_cast<uint4*>(out + ((b * H + y) * W + x) * Cout + g * 8) = *reinterpret_cast<uint4*>(h);
+}
+int conv3x3_small_cin(const __half* X, int B, int H, int W, int Cin, const float* Wt, const float* bias, int Cout,
+                      __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(Cout % 8 == 0 && Cin > 0 && Cin <= 16, "conv3x3_small: Cin<=16, Cout%%8==0 (got %d,%d)", Cin, Cout);
+  const int64_t total = static_cast<int64_t>(B) * H * W * (Cout / 8);
+  GYRE_REQUIRE(total > 0, "conv3x3_small: empty");
+  conv3x3_small_kernel<<<blocks_for(total, 128), 128, 0, st>>>(X, H, W, Cin, Wt, bias, Cout, out, total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void conv1x1_small_kernel(const __half* __restrict__ X, int64_t rows, int Cin, const float* __restrict__ Wt,
+                                     const float* __restrict__ bias, int Cout, __half* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= rows * Cout) return;
+  const int o = static_cast<int>(i % Cout);
+  const int64_t r = i / Cout;
+  float acc = bias ? bias[o] : 0.f;
+  for (int c = 0; c < Cin; ++c) acc = fmaf(__half2float(X[r * Cin + c]), Wt[o * Cin + c], acc);
+  out[i] = __float2half_rn(acc);
+}
+int conv1x1_small(const __half* X, int64_t rows, int Cin, const float* Wt, const float* bias, int Cout, __half* out,
+                  cudaStream_t st) {
+  GYRE_REQUIRE(rows > 0 && Cin > 0 && Cout > 0, "conv1x1_small: empty");
+  conv1x1_small_kernel<<<blocks_for(rows * Cout, 256), 256, 0, st>>>(X, rows, Cin, Wt, bias, Cout, out);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ K7: fused scheduler step
+// One launch does: CFG combine (u + s*(g-u)), denoiser scalings (eps: x - sigma*eps ; v: c_out*v + c_skip*x),
+// to_d + Euler update (x + (x-den)/sigma * dt), ancestral noise add (+ noise*sigma_up) - or the DDIM update -
+// and emits the NEXT step's CFG-duplicated, c_in-scaled fp16 UNet input.  Latents stay fp32 across steps.
+__global__ void sched_step_kernel(StepScalars s, const float* __restrict__ x, const __half* __restrict__ mo,
+                                  const float* __restrict__ noise, float* __restrict__ x_out,
+                                  float* __restrict__ den_out, __half* __restrict__ x_in_next, int64_t n_total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_total) return;
+  float m;
+  if (s.cfg) {
+    const float u = __half2float(mo[i]);
+    const float g = __half2float(mo[n_total + i]);
+    m = u + s.guidance * (g - u);
+  } else {
+    m = __half2float(mo[i]);
+  }
+  const float xv = x[i];
+  float xn, den;
+  if (s.kind == 0) {
+    if (s.v_pred) {
+      const float q = s.sigma * s.sigma + 1.0f;
+      den = m * (-s.sigma * rsqrtf(q)) + xv * (1.0f / q);
+    } else {
+      den = xv - s.sigma * m;
+    }
+    const float d = (xv - den) / s.sigma;
+    xn = xv + d * s.dt;
+    if (s.sigma_up != 0.f) xn += noise[i] * s.sigma_up;
+  } else {
+    float eps = m;
+    if (s.v_pred) {
+      den = s.sqrt_a_t * xv - s.sqrt_1m_a_t * m;
+      eps = s.sqrt_a_t * m + s.sqrt_1m_a_t * xv;
+    } else {
+      den = (xv - s.sqrt_1m_a_t * m) / s.sqrt_a_t;
+    }
+    xn = s.sqrt_a_prev * den + s.dir_coef * eps;
+    if (s.noise_coef != 0.f) xn += s.noise_coef * noise[i];
+  }
+  x_out[i] = xn;
+  if (den_out) den_out[i] = den;
+  if (x_in_next) {
+    const __half h = __float2half_rn(xn * s.c_in_next);
+    x_in_next[i] = h;
+    if (s.cfg) x_in_next[n_total + i] = h;
+  }
+}
+int sched_step(const StepScalars& s, const float* x, const __half* model_out, const float* noise, float* x_out,
+               float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(B) * per_sample;
+  GYRE_REQUIRE(n > 0, "sched_step: empty");
+  GYRE_REQUIRE(!((s.sigma_up != 0.f || (s.kind == 1 && s.noise_coef != 0.f)) && noise == nullptr),
+               "sched_step: noise required");
+  sched_step_kernel<<<blocks_for(n, 256), 256, 0, st>>>(s, x, model_out, noise, x_out, denoised_out,
+                                                        s.c_in_next != 0.f ? x_in_next : nullptr, n);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void scale_dup_kernel(const float* __restrict__ x, float c_in, int dup, int64_t n, __half* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const __half h = __float2half_rn(x[i] * c_in);
+  out[i] = h;
+  if (dup) out[n + i] = h;
+}
+int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sample, __half* out, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(B) * per_sample;
+  GYRE_REQUIRE(n > 0, "scale_dup: empty");
+  scale_dup_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, c_in, dup, n, out);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ K8: VAE tail  (x/2+0.5).clamp(0,1), NHWC -> NCHW
+__global__ void vae_tail_kernel(const __half* __restrict__ x, int ldx, int HW, __half* __restrict__ out,
+                                uint8_t* __restrict__ u8, int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over b*HW pixels
+  if (i >= total) return;
+  const int64_t b = i / HW;
+  const int p = static_cast<int>(i % HW);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = __half2float(x[i * ldx + c]) * 0.5f + 0.5f;
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    out[(b * 3 + c) * HW + p] = __float2half_rn(v);
+    if (u8) u8[i * 3 + c] = static_cast<uint8_t>(__float2int_rn(v * 255.0f));
+  }
+}
+int vae_tail(const __half* x, int ldx, int B, int H, int W, __half* out_nchw, uint8_t* out_u8_nhwc, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(B) * H * W;
+  GYRE_REQUIRE(total > 0, "vae_tail: empty");
+  vae_tail_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, H * W, out_nchw, out_u8_nhwc, total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gyre

@@ -1,0 +1,120 @@
+// Internal op layer of libgyre_b200: every function enqueues sm_100a kernels on the given stream and
+// returns 0 or a negative status (message via gyre::set_last_error).  Activations are NHWC fp16
+// ("token-major": [B, H*W, C]); weights are pre-packed K-major fp16.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gyre {
+
+enum OutMode { OUT_F16 = 0, OUT_F32 = 1, OUT_SECTIONS = 4 };
+enum SecMode { SEC_ROWMAJOR = 0, SEC_HEADSPLIT = 2, SEC_HEADSPLIT_T = 3 };
+enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2 };
+
+struct OutSection {
+  void* ptr;   // fp16
+  int mode;    // SecMode
+  int ld;      // row pitch (elements) for SEC_ROWMAJOR
+};
+
+// Epilogue description shared by the GEMM and the implicit-GEMM conv.
+struct Epilogue {
+  const float* bias = nullptr;            // [N] fp32, indexed by accumulator column
+  const __half* rowgroup_bias = nullptr;  // [groups, rgb_ld] added per (row / rows_per_group), e.g. temb projection
+  int rows_per_group = 1;
+  int rgb_ld = 0;
+  const __half* residual = nullptr;       // [rows, ldr] fp16 added after bias/activation
+  int ldr = 0;
+  void* out = nullptr;                    // OUT_F16 / OUT_F32 destination
+  int ldo = 0;
+  int out_mode = OUT_F16;
+  int act = ACT_NONE;
+  // OUT_SECTIONS: column c belongs to section c / sec_width; head layouts use the hs_* fields
+  OutSection sec[3] = {};
+  int sec_width = 0;
+  int hs_tokens = 0, hs_heads = 0, hs_d = 0, hs_dpad = 0, hs_tpad = 0;
+};
+
+// out[M, N] = epilogue(A[M, K] @ W[N, K]^T).  A: fp16 row pitch lda; W: packed fp16 [N, Kp] row pitch ldw.
+// For ACT_GEGLU the packed W interleaves value/gate rows per 256-column tile and N counts both.
+int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const Epilogue& ep,
+             cudaStream_t st);
+// Same with the K dimension split over two sources: out = [A | A2] @ W^T  (UNet skip-concat feeding a 1x1
+// shortcut without materialising the concatenation).  K1 must be a multiple of 64.
+int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int K2, const __half* W, int ldw, int M,
+              int N, const Epilogue& ep, cudaStream_t st);
+
+// 3x3 convolution as implicit GEMM.  X: [B, H, W, Cin] fp16 NHWC with channel pitch ldx; Wp: packed
+// [Cout, 9*cin_pad] (tap-major, cin_pad = round_up(Cin, 64)); output rows are pixels of [B, Ho, Wo].
+// stride 1|2; pad 1 (symmetric) or 0 (diffusers Downsample2D padding=0: zero pad right/bottom only).
+int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp, int Cout, int stride,
+                int pad, const Epilogue& ep, cudaStream_t st);
+
+// GroupNorm (+optional SiLU) over NHWC fp16.  Input may be the channel-concatenation of two tensors
+// (x1 [.., C1] ++ x2 [.., C2]); output is one dense [B, HW, C1+C2] tensor.  `partials` is fp32 scratch
+// of at least gn_partials_floats(B, HW, G) floats.
+size_t gn_partials_floats(int B, int HW, int G);
+int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, int G, float eps,
+                   const float* gamma, const float* beta, bool silu, __half* out, float* partials, cudaStream_t st);
+
+// LayerNorm over the last dim of [rows, C] fp16 (fp32 statistics, affine).
+int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gamma, const float* beta, __half* out,
+                   cudaStream_t st);
+
+// Flash attention reading Q/K/V in place from token-major projections: q [B, Nq, ldq] (head h at columns
+// h*d), k/v [B, Nk, ldk/ldv]; writes out [B, Nq, ldo] (head h at columns h*d).  d % 8 == 0, d <= 192.
+int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, int B, int heads,
+                  int Nq, int Nk, int d, float scale, __half* out, int ldo, cudaStream_t st);
+
+// Row softmax on fp32 scores [rows, n] -> fp16 probs [rows, ldp] (VAE single-head attention).
+int softmax_rows_f32(const float* s, int rows, int n, float scale, __half* p, int ldp, cudaStream_t st);
+
+// Layout / elementwise helpers
+int nchw_to_nhwc_f16(const __half* x, int B, int C, int H, int W, __half* out, int ldo, cudaStream_t st);
+int nhwc_to_nchw_f16(const __half* x, int ldx, int B, int C, int H, int W, __half* out, cudaStream_t st);
+int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t st);
+int concat_channels(const __half* a, int Ca, const __half* b, int Cb, int64_t rows, __half* out, cudaStream_t st);
+int transpose_rows_f16(const __half* x, int rows, int cols, int batch, __half* out, cudaStream_t st);
+int timestep_embed(const int64_t* t, int B, int dim, __half* out, cudaStream_t st);
+int silu_f16(const __half* x, int64_t n, __half* out, cudaStream_t st);
+// Direct 3x3 conv for tiny channel counts (conv_in: Cin 4/9, VAE conv_in): X NCHW-agnostic NHWC with
+// Cin <= 16, weights fp32 [Cout, 3, 3, Cin], output NHWC fp16.
+int conv3x3_small_cin(const __half* X, int B, int H, int W, int Cin, const float* Wt, const float* bias, int Cout,
+                      __half* out, cudaStream_t st);
+// 1x1 conv on tiny channel counts (post_quant_conv 4->4, quant_conv 8->8): NHWC fp16.
+int conv1x1_small(const __half* X, int64_t rows, int Cin, const float* Wt, const float* bias, int Cout, __half* out,
+                  cudaStream_t st);
+
+// Scheduler-step fusions (fp32 latents NCHW [B,4,h,w]; eps fp16 NCHW [2B or B, ...]).
+struct StepScalars {
+  int kind;            // 0 euler/euler-a style (k-diffusion eps or v denoiser), 1 ddim
+  int v_pred;          // 1: model output is v
+  int cfg;             // 1: model_out holds [uncond; cond] halves
+  float guidance;      // CFG scale
+  float sigma;         // current sigma (k) ; unused for ddim
+  float c_in_next;     // scaling of x for the NEXT unet call (written to x_in_next), 0 to skip
+  float dt;            // sigma_down - sigma
+  float sigma_up;      // ancestral noise scale (0: no noise)
+  // ddim
+  float sqrt_a_t, sqrt_1m_a_t, sqrt_a_prev, dir_coef, noise_coef;
+};
+int sched_step(const StepScalars& s, const float* x, const __half* model_out, const float* noise, float* x_out,
+               float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st);
+// unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)
+int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sample, __half* out, cudaStream_t st);
+// VAE tail: img = clamp(x/2+0.5, 0, 1): NHWC fp16 [B,H,W,ldx>=3] -> NCHW fp16 [B,3,H,W] (+ optional uint8 copy)
+int vae_tail(const __half* x, int ldx, int B, int H, int W, __half* out_nchw, uint8_t* out_u8_nhwc, cudaStream_t st);
+
+}  // namespace gyre
+
+namespace gyre {
+// ---- weight packing (pack.cu); dtype: 0 fp16, 1 fp32
+size_t conv3x3_packed_elems(int Cin, int Cout);
+int pack_conv3x3(const void* w, int dtype, int Cin, int Cout, __half* out, cudaStream_t st);
+int cast_to_f16(const void* src, int dtype, int64_t rows, int cols, __half* dst, int ldd, cudaStream_t st);
+int cast_to_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st);
+int pack_geglu(const void* w, int dtype, int F, int K, const void* bias, int bias_dtype, __half* wp, float* bias_p,
+               cudaStream_t st);
+const char* last_error();
+}  // namespace gyre

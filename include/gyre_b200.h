@@ -1,0 +1,209 @@
+/* gyre_b200 -- C ABI of the Blackwell-native (sm_100a) diffusion sampling path.
+ *
+ * This is the drop-in boundary for the hot path of stablecabal/gyre.  The
+ * reference has no native code: its hot path is Python calling third-party libraries.  Each entry
+ * point below cites the reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative status on failure; the message is
+ *     available (per calling thread) from gyre_b200_last_error();
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the library never allocates
+ *     or frees caller memory; it owns only the packed weights behind a handle;
+ *   - all work is enqueued on the caller-supplied CUDA stream (a cudaStream_t passed as void*);
+ *     nothing synchronises the device;
+ *   - activations handed across this boundary use the reference's layouts (NCHW latents / images,
+ *     [B, L, C] token tensors); the token-major NHWC fp16 layout the kernels use is internal;
+ *   - handles are bound to the device that was current at creation; functions are re-entrant
+ *     across handles; one handle must not be entered by two threads at once (same rule as the
+ *     reference: gyre/manager.py:2047-2103 hands one pipeline clone to one thread).
+ */
+#ifndef GYRE_B200_H
+#define GYRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GYRE_B200_ABI_VERSION 1
+
+typedef void* gyre_b200_stream;  /* cudaStream_t */
+typedef struct gyre_b200_model* gyre_b200_handle;
+
+enum { GYRE_B200_F16 = 0, GYRE_B200_F32 = 1, GYRE_B200_BF16 = 2 };
+
+int gyre_b200_abi_version(void);
+/* Copies the calling thread's last error message; returns its length. */
+int gyre_b200_last_error(char* buf, size_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * UNet  (replaces diffusers UNet2DConditionModel.forward as called from
+ *        gyre/pipeline/unet/core.py:274 through the DiffusersUNet protocol,
+ *        gyre/pipeline/unet/types.py:30-39; ToMe variant nonfree/tome_unet.py:229-247)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gyre_b200_unet_config {
+  int32_t in_channels;             /* 4, 9 (inpaint), 5 (depth)  unified_pipeline.py:186          */
+  int32_t out_channels;            /* 4                                                            */
+  int32_t num_levels;              /* <= 4                                                         */
+  int32_t block_out_channels[4];   /* (320,640,1280,1280)        gyre/ldm_config/v1-inference.yaml */
+  int32_t num_heads[4];            /* diffusers-0.16 `attention_head_dim` == number of heads       */
+  int32_t attn_levels[4];          /* 1: CrossAttn block at this level                             */
+  int32_t layers_per_block;        /* 2                                                            */
+  int32_t cross_attention_dim;     /* 768 / 1024                                                   */
+  int32_t norm_num_groups;         /* 32                                                           */
+  float norm_eps;                  /* 1e-5                                                         */
+  int32_t use_linear_projection;   /* SD2.x                                                        */
+  int32_t upcast_attention;        /* SD2.1-768 (softmax/QK^T are fp32 in this library regardless) */
+} gyre_b200_unet_config;
+
+int gyre_b200_unet_create(const gyre_b200_unet_config* cfg, gyre_b200_handle* out);
+
+/* Hands one parameter to the library under its diffusers state-dict key,
+ * e.g. "down_blocks.0.resnets.0.conv1.weight".  `data` is a device pointer to a dense tensor of
+ * `dtype` (GYRE_B200_F16/F32); the library packs its own copy (K-major fp16, tap-major convs) on
+ * `stream`.  Replaces the parameter ownership of the nn.Module the reference clones to the GPU
+ * (gyre/pipeline/model_utils.py:172-259); call again with the same key to re-pack after a
+ * LoRA-style weight edit. */
+int gyre_b200_load_weight(gyre_b200_handle h, const char* key, const void* data, int dtype,
+                          const int64_t* shape, int ndim, gyre_b200_stream stream);
+/* Verifies that every parameter the architecture needs has been loaded. */
+int gyre_b200_finalize(gyre_b200_handle h);
+
+/* Scratch bytes one forward needs for a CFG-doubled batch `batch`, latent height/width, context
+ * length.  The caller allocates (torch.empty) and passes it to every forward. */
+int gyre_b200_unet_workspace_bytes(gyre_b200_handle h, int batch, int height, int width, int ctx_len,
+                                   size_t* bytes);
+
+/* eps = unet(sample, timestep, encoder_hidden_states)
+ *   sample  [batch, in_channels, height, width]  fp16 NCHW
+ *   timestep[batch]                               int64 (the reference broadcasts scalars first)
+ *   ctx     [batch, ctx_len, cross_attention_dim] fp16
+ *   tome_r  NULL, or one int32 per transformer block in module execution order: the number of
+ *           K/V tokens to merge (nonfree/tome_memory_efficient_cross_attention.py:28-50; the list
+ *           parse_r builds, nonfree/ToMe/tome/utils.py:80-105) -- HOST pointer
+ *   out     [batch, out_channels, height, width]  fp16 NCHW */
+int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx,
+                           int batch, int height, int width, int ctx_len, const int32_t* tome_r_host,
+                           void* out, void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * AutoencoderKL  (replaces vae.decode(x).sample, gyre/pipeline/unified_pipeline.py:1523-1536,
+ *                 and vae.encode(img).latent_dist, :305-318)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gyre_b200_vae_config {
+  int32_t in_channels;             /* 3 */
+  int32_t out_channels;            /* 3 */
+  int32_t latent_channels;         /* 4 */
+  int32_t num_levels;              /* 4 */
+  int32_t block_out_channels[4];   /* (128,256,512,512)  gyre/ldm_config/v1-inference.yaml:46-67 */
+  int32_t layers_per_block;        /* 2 */
+  int32_t norm_num_groups;         /* 32 */
+} gyre_b200_vae_config;
+
+int gyre_b200_vae_create(const gyre_b200_vae_config* cfg, gyre_b200_handle* out);
+int gyre_b200_vae_workspace_bytes(gyre_b200_handle h, int batch, int latent_h, int latent_w, size_t* bytes);
+/* z [batch, 4, h, w] fp16 NCHW (already divided by the scaling factor, as the reference passes it)
+ * -> img [batch, 3, 8h, 8w] fp16 NCHW.  postprocess != 0 additionally applies the pipeline tail
+ * (img/2+0.5).clamp(0,1) (unified_pipeline.py:2491); img_u8 (optional, may be NULL) receives the
+ * same image as [batch, 8h, 8w, 3] uint8 for the multi-GPU gather. */
+int gyre_b200_vae_decode(gyre_b200_handle h, const void* z, int batch, int latent_h, int latent_w, int postprocess,
+                         void* img, uint8_t* img_u8, void* workspace, size_t workspace_bytes,
+                         gyre_b200_stream stream);
+/* img [batch, 3, H, W] fp16 NCHW -> moments [batch, 8, H/8, W/8] fp16 NCHW (mean | logvar), the
+ * parameters of the reference's DiagonalGaussianDistribution. */
+int gyre_b200_vae_encode(gyre_b200_handle h, const void* img, int batch, int height, int width, void* moments,
+                         void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+
+int gyre_b200_destroy(gyre_b200_handle h);
+
+/* ------------------------------------------------------------------------------------------
+ * Scheduler inner loop  (replaces the per-step elementwise chain of
+ *   k_diffusion/external.py:96-113,149-167 (denoiser scalings), gyre/pipeline/unet/cfg.py:47-57 (CFG),
+ *   k_diffusion/sampling.py:46-58,139-155 (to_d / Euler / Euler-ancestral update) and
+ *   gyre/pipeline/schedulers/scheduling_ddim.py:259-316 (DDIM step) -- one launch per step)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gyre_b200_step {
+  int32_t kind;        /* 0: k-diffusion Euler family   1: DDIM                                    */
+  int32_t v_pred;      /* model predicts v (SD2.1-768)                                              */
+  int32_t cfg;         /* model_out holds [uncond ; cond] halves (CFGUNet_Parallel)                 */
+  float guidance;      /* CFG scale                                                                 */
+  float sigma;         /* k: sigma_i (after fp16 quantisation, common_scheduler.py:560)             */
+  float c_in_next;     /* k: 1/sqrt(sigma_{i+1}^2+1) -- scale of the NEXT unet input; 0: skip       */
+  float dt;            /* k: sigma_down - sigma_i                                                   */
+  float sigma_up;      /* k: ancestral noise scale (0: none)                                        */
+  float sqrt_a_t, sqrt_1m_a_t, sqrt_a_prev, dir_coef, noise_coef; /* DDIM coefficients             */
+} gyre_b200_step;
+
+/* x, x_out, denoised_out: fp32 [B, C, h, w]; model_out: fp16 [2B or B, C, h, w]; noise fp32 or NULL;
+ * x_in_next: fp16 [2B or B, ...] = x_out * c_in_next (duplicated for CFG) or NULL. */
+int gyre_b200_sched_step(const gyre_b200_step* s, const float* x, const void* model_out, const float* noise,
+                         float* x_out, float* denoised_out, void* x_in_next, int batch, int64_t per_sample,
+                         gyre_b200_stream stream);
+/* out_f16[(dup?2:1) * B, ...] = x * c_in  (first unet input of a run) */
+int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
+                            gyre_b200_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention patcher  (replaces ToMeMemoryEfficientCrossAttention.forward's merge,
+ *   nonfree/tome_memory_efficient_cross_attention.py:28-50, i.e. tome/merge.py:18-97,210-224)
+ * k, v [B, N, C] fp16 -> k_out, v_out [B, N - r, C] fp16 with the reference's token order
+ * ([unmerged even tokens in descending-score order ..., odd tokens ...]).
+ * ------------------------------------------------------------------------------------------ */
+int gyre_b200_tome_workspace_bytes(int batch, int tokens, int channels, size_t* bytes);
+int gyre_b200_tome_merge_kv(const void* k, const void* v, int batch, int tokens, int channels, int r, void* k_out,
+                            void* v_out, void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Building-block kernels, exported for the per-kernel parity tests and for callers that patch a
+ * single module (the reference's attention patcher swaps one module's forward:
+ * nonfree/tome_patcher.py:14-52).  Token-major fp16 tensors ([rows, C], C contiguous).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gyre_b200_epilogue {
+  const float* bias;          /* [N] fp32 or NULL                                                    */
+  const void* rowgroup_bias;  /* fp16 [rows / rows_per_group, rgb_ld] added per row group or NULL    */
+  int32_t rows_per_group;
+  int32_t rgb_ld;
+  const void* residual;       /* fp16 [rows, ldr] or NULL                                            */
+  int32_t ldr;
+  int32_t act;                /* 0 none, 1 GEGLU (value*gelu(gate); W holds [value rows ; gate rows]), 2 SiLU */
+  int32_t out_f32;            /* 1: out is fp32                                                      */
+  void* out;                  /* [rows, ldo]                                                         */
+  int32_t ldo;
+} gyre_b200_epilogue;
+
+/* out = epilogue([A | A2] @ W^T): A [M, K1] pitch lda, A2 [M, K2] pitch lda2 (may be NULL/0),
+ * W [N, K1+K2] pitch ldw; fp16, fp32 accumulate (replaces F.linear / 1x1 conv: cuBLAS HGEMM). */
+int gyre_b200_gemm(const void* A, int lda, int K1, const void* A2, int lda2, int K2, const void* W, int ldw, int M,
+                   int N, const gyre_b200_epilogue* ep, gyre_b200_stream stream);
+/* GEGLU weights must be re-ordered so that each 256-row tile holds 128 value rows then their 128
+ * gate rows: packs W [2*F, K] (diffusers ff.net.0.proj layout) into Wp [2*F, K]. F % 128 == 0. */
+int gyre_b200_pack_geglu(const void* W, int dtype, int F, int K, const void* bias, int bias_dtype, void* Wp,
+                         float* bias_p, gyre_b200_stream stream);
+/* 3x3 convolution, implicit GEMM: X [B, H, W, Cin] NHWC fp16 (pitch ldx), Wp packed by
+ * gyre_b200_pack_conv3x3 -> out rows = output pixels (replaces F.conv2d: cuDNN). */
+int gyre_b200_conv3x3(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wp, int Cout, int stride,
+                      int pad, const gyre_b200_epilogue* ep, gyre_b200_stream stream);
+/* W [Cout, Cin, 3, 3] (dtype f16/f32) -> Wp fp16 [Cout, 9, round_up(Cin, 64)], tap = kh*3+kw. */
+size_t gyre_b200_conv3x3_packed_elems(int Cin, int Cout);
+int gyre_b200_pack_conv3x3(const void* W, int dtype, int Cin, int Cout, void* Wp, gyre_b200_stream stream);
+/* GroupNorm (+SiLU) over NHWC fp16; the input may be the channel concatenation x1 ++ x2
+ * (replaces at::native_group_norm + silu).  scratch: fp32, gyre_b200_groupnorm_scratch_floats. */
+size_t gyre_b200_groupnorm_scratch_floats(int B, int HW, int G);
+int gyre_b200_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int G, float eps,
+                        const float* gamma, const float* beta, int silu, void* out, float* scratch,
+                        gyre_b200_stream stream);
+int gyre_b200_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
+                        gyre_b200_stream stream);
+/* softmax(Q K^T * scale) V per head, reading Q/K/V in place from token-major projections:
+ * q [B, Nq, ldq] (head h at columns h*d), k / v [B, Nk, ldk / ldv]; out [B, Nq, heads*d]
+ * (replaces xformers.ops.memory_efficient_attention,
+ *  gyre/pipeline/models/memory_efficient_cross_attention.py:39-60). */
+int gyre_b200_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int B, int heads,
+                        int Nq, int Nk, int d, float scale, void* out, int ldo, gyre_b200_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYRE_B200_H */

@@ -1,0 +1,150 @@
+"""Per-kernel parity: every building-block CUDA kernel, called through the C ABI, against a plain PyTorch
+fp32 evaluation of the same op on the same (fp16-rounded) inputs.  Tolerances are stated per test: the
+kernels accumulate in fp32 and round once to fp16 on output, so the bound is fp16 output rounding
+(2^-11 relative) plus accumulation-order noise."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from gyre_b200 import _native
+    _native.load()
+    return _native
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float16):
+    g = torch.Generator("cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def assert_close(got, ref, atol, rtol, what):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} out of tolerance, max abs err {err.max().item():.4g} " \
+                          f"(ref max {ref.abs().max().item():.4g}) first bad idx {bad.nonzero()[0].tolist()}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (100, 64, 128), (4096, 320, 320), (300, 1280, 1280),
+                                   (77 * 2, 640, 768), (16, 1280, 320), (512, 4, 320), (130, 160, 72)])
+def test_gemm_shapes(nat, M, N, K):
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=1 / math.sqrt(K))
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    out = nat.gemm(a, w, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    assert_close(out, ref, 2e-3, 2e-3, f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_residual_f32_out(nat):
+    M, N, K = 384, 320, 1280
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K))
+    res = rnd(M, N, seed=4)
+    out = nat.gemm(a, w, residual=res)
+    ref = a.float() @ w.float().t() + res.float()
+    assert_close(out, ref, 2e-3, 2e-3, "gemm+residual")
+    out32 = nat.gemm(a, w, out_dtype=torch.float32)
+    assert_close(out32, a.float() @ w.float().t(), 2e-4, 1e-4, "gemm f32 out")
+
+
+def test_gemm_two_sources(nat):
+    M, K1, K2, N = 300, 128, 64, 192
+    a1, a2 = rnd(M, K1, seed=1), rnd(M, K2, seed=5)
+    w = rnd(N, K1 + K2, seed=2, scale=0.1)
+    out = nat.gemm(a1, w, a2=a2)
+    ref = torch.cat([a1, a2], 1).float() @ w.float().t()
+    assert_close(out, ref, 2e-3, 2e-3, "gemm two-source")
+
+
+def test_gemm_geglu(nat):
+    M, C = 200, 128
+    a = rnd(M, C, seed=1)
+    w = rnd(8 * C, C, seed=2, scale=1 / math.sqrt(C))
+    b = rnd(8 * C, seed=3, dtype=torch.float32)
+    wp, bp = nat.pack_geglu(w, b)
+    out = nat.gemm(a, wp, bias=bp, act=1)
+    h = a.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    assert_close(out, ref, 3e-3, 3e-3, "geglu")
+
+
+def test_gemm_rowgroup_bias_silu(nat):
+    M, N, K = 256, 64, 64
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.125)
+    rgb = rnd(4, N, seed=7)
+    out = nat.gemm(a, w, rowgroup_bias=rgb, rows_per_group=64)
+    ref = a.float() @ w.float().t() + rgb.float().repeat_interleave(64, 0)
+    assert_close(out, ref, 2e-3, 2e-3, "rowgroup bias")
+    out = nat.gemm(a, w, act=2)
+    assert_close(out, F.silu(a.float() @ w.float().t()), 2e-3, 2e-3, "silu epilogue")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,pad", [
+    (1, 16, 16, 64, 64, 1, 1), (2, 8, 8, 128, 96, 1, 1), (2, 64, 64, 320, 320, 1, 1), (1, 32, 32, 640, 320, 1, 1),
+    (3, 8, 8, 1280, 1280, 1, 1), (2, 16, 16, 64, 64, 2, 1), (2, 32, 32, 320, 320, 2, 1), (1, 16, 16, 128, 128, 2, 0),
+    (1, 64, 64, 320, 4, 1, 1), (1, 12, 20, 64, 32, 1, 1), (2, 24, 24, 192, 160, 1, 1), (1, 96, 96, 128, 128, 1, 1),
+])
+def test_conv3x3(nat, B, H, W, Cin, Cout, stride, pad):
+    x = rnd(B, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=1 / math.sqrt(9 * Cin))
+    bias = rnd(Cout, seed=3, dtype=torch.float32)
+    wp = nat.pack_conv3x3(w)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = nat.conv3x3(x_nhwc, wp, Cout, bias=bias, stride=stride, pad=pad)
+    xin = x.float()
+    if pad == 0:
+        xin = F.pad(xin, (0, 1, 0, 1))
+    ref = F.conv2d(xin, w.float(), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert_close(out, ref, 3e-3, 3e-3, f"conv {B}x{H}x{W} {Cin}->{Cout} s{stride} p{pad}")
+
+
+def test_conv3x3_fused_epilogue(nat):
+    B, H, W, Cin, Cout = 2, 16, 16, 64, 128
+    x = rnd(B, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=1 / math.sqrt(9 * Cin))
+    bias = rnd(Cout, seed=3, dtype=torch.float32)
+    temb = rnd(B, Cout, seed=4)
+    res = rnd(B * H * W, Cout, seed=5)
+    wp = nat.pack_conv3x3(w)
+    out = nat.conv3x3(x.permute(0, 2, 3, 1).contiguous(), wp, Cout, bias=bias, residual=res, rowgroup_bias=temb,
+                      rows_per_group=H * W)
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1) + temb.float()[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout) + res.float()
+    assert_close(out.reshape(B * H * W, Cout), ref, 3e-3, 3e-3, "conv fused epilogue")
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,G,silu", [(2, 256, 64, 0, 32, True), (2, 4096, 320, 0, 32, True),
+                                               (1, 1024, 640, 320, 32, True), (3, 64, 1280, 1280, 32, False),
+                                               (1, 100, 128, 0, 32, False), (1, 65536, 128, 0, 32, True)])
+def test_groupnorm(nat, B, HW, C1, C2, G, silu):
+    x1 = rnd(B, HW, C1, seed=1) + 0.5
+    x2 = rnd(B, HW, C2, seed=2, scale=2.0) if C2 else None
+    C = C1 + C2
+    gamma = 1 + 0.1 * rnd(C, seed=3, dtype=torch.float32)
+    beta = 0.1 * rnd(C, seed=4, dtype=torch.float32)
+    out = nat.groupnorm(x1, gamma, beta, G, 1e-5, silu, x2=x2)
+    xin = x1 if x2 is None else torch.cat([x1, x2], dim=2)
+    ref = F.group_norm(xin.float().permute(0, 2, 1), G, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert_close(out, ref.permute(0, 2, 1), 2e-3, 2e-3, "groupnorm")
+
+
+@pytest.mark.parametrize("rows,C", [(77, 64), (4096, 320), (1000, 640), (257, 1280)])
+def test_layernorm(nat, rows, C):
+    x = rnd(rows, C, seed=1) * 2 + 0.3
+    gamma = 1 + 0.1 * rnd(C, seed=3, dtype=torch.float32)
+    beta = 0.1 * rnd(C, seed=4, dtype=torch.float32)
+    out = nat.layernorm(x, gamma, beta)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    assert_close(out, ref, 2e-3, 2e-3, "layernorm")
