@@ -57,6 +57,7 @@ SIGNATURES = {
     "gyre_b200_abi_version": (_i, []),
     "gyre_b200_last_error": (_i, [C.c_char_p, _sz]),
     "gyre_b200_unet_create": (_i, [C.POINTER(UNetConfigC), C.POINTER(_vp)]),
+    "gyre_b200_unet_num_transformer_blocks": (_i, [_vp]),
     "gyre_b200_load_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i, _vp]),
     "gyre_b200_finalize": (_i, [_vp]),
     "gyre_b200_unet_workspace_bytes": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_sz)]),

@@ -1,6 +1,7 @@
 // extern "C" surface of libgyre_b200.so (include/gyre_b200.h): argument checking + forwarding to the op
 // layer.  Nothing here throws; every failure becomes a negative status + thread-local message.
 #include <cstring>
+#include <new>
 
 #include "../../include/gyre_b200.h"
 #include "common.cuh"
@@ -118,19 +119,156 @@ int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int6
 
 }  // extern "C"
 
-// ---- TEMPORARY stubs (replaced by model.cu / tome.cu)
-extern "C" {
-#define GYRE_NOT_YET(name) do { set_last_error(name ": not implemented yet"); return -100; } while (0)
-int gyre_b200_unet_create(const gyre_b200_unet_config*, gyre_b200_handle*) { GYRE_NOT_YET("unet_create"); }
-int gyre_b200_load_weight(gyre_b200_handle, const char*, const void*, int, const int64_t*, int, gyre_b200_stream) { GYRE_NOT_YET("load_weight"); }
-int gyre_b200_finalize(gyre_b200_handle) { GYRE_NOT_YET("finalize"); }
-int gyre_b200_unet_workspace_bytes(gyre_b200_handle, int, int, int, int, size_t*) { GYRE_NOT_YET("unet_workspace_bytes"); }
-int gyre_b200_unet_forward(gyre_b200_handle, const void*, const int64_t*, const void*, int, int, int, int, const int32_t*, void*, void*, size_t, gyre_b200_stream) { GYRE_NOT_YET("unet_forward"); }
-int gyre_b200_vae_create(const gyre_b200_vae_config*, gyre_b200_handle*) { GYRE_NOT_YET("vae_create"); }
-int gyre_b200_vae_workspace_bytes(gyre_b200_handle, int, int, int, size_t*) { GYRE_NOT_YET("vae_workspace_bytes"); }
-int gyre_b200_vae_decode(gyre_b200_handle, const void*, int, int, int, int, void*, uint8_t*, void*, size_t, gyre_b200_stream) { GYRE_NOT_YET("vae_decode"); }
-int gyre_b200_vae_encode(gyre_b200_handle, const void*, int, int, int, void*, void*, size_t, gyre_b200_stream) { GYRE_NOT_YET("vae_encode"); }
-int gyre_b200_destroy(gyre_b200_handle) { GYRE_NOT_YET("destroy"); }
-int gyre_b200_tome_workspace_bytes(int, int, int, size_t*) { GYRE_NOT_YET("tome_workspace_bytes"); }
-int gyre_b200_tome_merge_kv(const void*, const void*, int, int, int, int, void*, void*, void*, size_t, gyre_b200_stream) { GYRE_NOT_YET("tome_merge_kv"); }
+// ------------------------------------------------------------------------------------------ models
+namespace {
+inline Model* M(gyre_b200_handle h) { return reinterpret_cast<Model*>(h); }
+
+int make_exec(Exec* ex, void* workspace, size_t bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(workspace != nullptr, "null workspace");
+  GYRE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  ex->st = S(stream);
+  ex->dry = false;
+  ex->base = static_cast<uint8_t*>(workspace);
+  ex->cap = bytes & ~static_cast<size_t>(1023);
+  return 0;
 }
+}  // namespace
+
+extern "C" {
+
+int gyre_b200_unet_create(const gyre_b200_unet_config* cfg, gyre_b200_handle* out) {
+  GYRE_REQUIRE(cfg && out, "unet_create: null argument");
+  GYRE_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= 4 && cfg->layers_per_block >= 1, "unet_create: bad topology");
+  for (int i = 0; i < cfg->num_levels; ++i) {
+    const int c = cfg->block_out_channels[i];
+    GYRE_REQUIRE(c > 0 && c % 64 == 0, "unet_create: block_out_channels[%d]=%d must be a multiple of 64", i, c);
+    GYRE_REQUIRE(c % cfg->norm_num_groups == 0, "unet_create: channels %d not divisible by %d groups", c,
+                 cfg->norm_num_groups);
+    if (cfg->attn_levels[i]) {
+      const int hds = cfg->num_heads[i];
+      GYRE_REQUIRE(hds > 0 && c % hds == 0 && (c / hds) % 8 == 0 && c / hds <= 192,
+                   "unet_create: level %d head dim %d unsupported", i, hds > 0 ? c / hds : -1);
+    }
+  }
+  GYRE_REQUIRE(cfg->in_channels >= 1 && cfg->in_channels <= 16, "unet_create: in_channels %d", cfg->in_channels);
+  GYRE_REQUIRE(cfg->cross_attention_dim > 0 && cfg->cross_attention_dim % 8 == 0, "unet_create: cross_attention_dim");
+  GYRE_REQUIRE(cfg->norm_num_groups > 0 && cfg->norm_num_groups <= 32, "unet_create: norm_num_groups");
+  UNetModel* m = new (std::nothrow) UNetModel(*cfg);
+  GYRE_REQUIRE(m != nullptr, "unet_create: out of host memory");
+  *out = reinterpret_cast<gyre_b200_handle>(static_cast<Model*>(m));
+  return 0;
+}
+
+int gyre_b200_load_weight(gyre_b200_handle h, const char* key, const void* data, int dtype, const int64_t* shape,
+                          int ndim, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h, "load_weight: null handle");
+  return M(h)->load(key, data, dtype, shape, ndim, S(stream));
+}
+
+int gyre_b200_finalize(gyre_b200_handle h) {
+  GYRE_REQUIRE(h, "finalize: null handle");
+  return M(h)->finalize();
+}
+
+int gyre_b200_unet_workspace_bytes(gyre_b200_handle h, int batch, int height, int width, int ctx_len, size_t* bytes) {
+  GYRE_REQUIRE(h && bytes, "unet_workspace_bytes: null argument");
+  GYRE_REQUIRE(M(h)->is_unet(), "unet_workspace_bytes: handle is not a UNet");
+  Exec ex;
+  ex.dry = true;
+  ex.cap = static_cast<size_t>(1) << 60;
+  // sized for the no-merge case, which is the larger one (ToMe only shrinks K/V)
+  GYRE_TRY(static_cast<UNetModel*>(M(h))->forward(ex, nullptr, nullptr, nullptr, batch, height, width, ctx_len, nullptr,
+                                                  nullptr));
+  *bytes = ex.peak + (64u << 20);   // headroom for ToMe scratch
+  return 0;
+}
+
+int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx, int batch,
+                           int height, int width, int ctx_len, const int32_t* tome_r_host, void* out, void* workspace,
+                           size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && sample && timestep && ctx && out, "unet_forward: null argument");
+  GYRE_REQUIRE(M(h)->is_unet(), "unet_forward: handle is not a UNet");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return static_cast<UNetModel*>(M(h))->forward(ex, static_cast<const __half*>(sample), timestep,
+                                                static_cast<const __half*>(ctx), batch, height, width, ctx_len,
+                                                tome_r_host, static_cast<__half*>(out));
+}
+
+int gyre_b200_unet_num_transformer_blocks(gyre_b200_handle h) {
+  if (!h || !M(h)->is_unet()) return -1;
+  return static_cast<UNetModel*>(M(h))->num_transformer_blocks();
+}
+
+int gyre_b200_vae_create(const gyre_b200_vae_config* cfg, gyre_b200_handle* out) {
+  GYRE_REQUIRE(cfg && out, "vae_create: null argument");
+  GYRE_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= 4 && cfg->layers_per_block >= 1, "vae_create: bad topology");
+  for (int i = 0; i < cfg->num_levels; ++i) {
+    const int c = cfg->block_out_channels[i];
+    GYRE_REQUIRE(c > 0 && c % 64 == 0 && c % cfg->norm_num_groups == 0,
+                 "vae_create: block_out_channels[%d]=%d must be a multiple of 64 and of the group count", i, c);
+  }
+  GYRE_REQUIRE(cfg->in_channels == 3 && cfg->out_channels == 3, "vae_create: RGB only");
+  GYRE_REQUIRE(cfg->latent_channels >= 1 && cfg->latent_channels <= 8, "vae_create: latent_channels");
+  VAEModel* m = new (std::nothrow) VAEModel(*cfg);
+  GYRE_REQUIRE(m != nullptr, "vae_create: out of host memory");
+  *out = reinterpret_cast<gyre_b200_handle>(static_cast<Model*>(m));
+  return 0;
+}
+
+int gyre_b200_vae_workspace_bytes(gyre_b200_handle h, int batch, int latent_h, int latent_w, size_t* bytes) {
+  GYRE_REQUIRE(h && bytes, "vae_workspace_bytes: null argument");
+  GYRE_REQUIRE(!M(h)->is_unet(), "vae_workspace_bytes: handle is not a VAE");
+  VAEModel* v = static_cast<VAEModel*>(M(h));
+  Exec ex;
+  ex.dry = true;
+  ex.cap = static_cast<size_t>(1) << 60;
+  GYRE_TRY(v->decode(ex, nullptr, batch, latent_h, latent_w, true, reinterpret_cast<__half*>(16), nullptr));
+  const size_t dec = ex.peak;
+  Exec ex2;
+  ex2.dry = true;
+  ex2.cap = static_cast<size_t>(1) << 60;
+  GYRE_TRY(v->encode(ex2, nullptr, batch, latent_h * 8, latent_w * 8, nullptr));
+  *bytes = (dec > ex2.peak ? dec : ex2.peak) + 4096;
+  return 0;
+}
+
+int gyre_b200_vae_decode(gyre_b200_handle h, const void* z, int batch, int latent_h, int latent_w, int postprocess,
+                         void* img, uint8_t* img_u8, void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && z, "vae_decode: null argument");
+  GYRE_REQUIRE(!M(h)->is_unet(), "vae_decode: handle is not a VAE");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return static_cast<VAEModel*>(M(h))->decode(ex, static_cast<const __half*>(z), batch, latent_h, latent_w,
+                                              postprocess != 0, static_cast<__half*>(img), img_u8);
+}
+
+int gyre_b200_vae_encode(gyre_b200_handle h, const void* img, int batch, int height, int width, void* moments,
+                         void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && img && moments, "vae_encode: null argument");
+  GYRE_REQUIRE(!M(h)->is_unet(), "vae_encode: handle is not a VAE");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return static_cast<VAEModel*>(M(h))->encode(ex, static_cast<const __half*>(img), batch, height, width,
+                                              static_cast<__half*>(moments));
+}
+
+int gyre_b200_destroy(gyre_b200_handle h) {
+  if (h) delete M(h);
+  return 0;
+}
+
+int gyre_b200_tome_workspace_bytes(int batch, int tokens, int channels, size_t* bytes) {
+  GYRE_REQUIRE(bytes, "tome_workspace_bytes: null argument");
+  return tome_workspace_bytes(batch, tokens, channels, bytes);
+}
+
+int gyre_b200_tome_merge_kv(const void* k, const void* v, int batch, int tokens, int channels, int r, void* k_out,
+                            void* v_out, void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(k && v && k_out && v_out, "tome_merge_kv: null operand");
+  return tome_merge_kv(static_cast<const __half*>(k), static_cast<const __half*>(v), channels, batch, tokens, channels,
+                       r, static_cast<__half*>(k_out), static_cast<__half*>(v_out), workspace, workspace_bytes,
+                       S(stream));
+}
+
+}  // extern "C"

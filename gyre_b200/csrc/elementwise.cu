@@ -261,7 +261,7 @@ int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sa
 }
 
 // ------------------------------------------------------------------ K8: VAE tail  (x/2+0.5).clamp(0,1), NHWC -> NCHW
-__global__ void vae_tail_kernel(const __half* __restrict__ x, int ldx, int HW, __half* __restrict__ out,
+__global__ void vae_tail_kernel(const __half* __restrict__ x, int ldx, int HW, int post, __half* __restrict__ out,
                                 uint8_t* __restrict__ u8, int64_t total) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over b*HW pixels
   if (i >= total) return;
@@ -269,16 +269,17 @@ __global__ void vae_tail_kernel(const __half* __restrict__ x, int ldx, int HW, _
   const int p = static_cast<int>(i % HW);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float v = __half2float(x[i * ldx + c]) * 0.5f + 0.5f;
-    v = fminf(fmaxf(v, 0.f), 1.f);
-    out[(b * 3 + c) * HW + p] = __float2half_rn(v);
+    const float raw = __half2float(x[i * ldx + c]);
+    const float v = fminf(fmaxf(raw * 0.5f + 0.5f, 0.f), 1.f);
+    if (out) out[(b * 3 + c) * HW + p] = post ? __float2half_rn(v) : x[i * ldx + c];
     if (u8) u8[i * 3 + c] = static_cast<uint8_t>(__float2int_rn(v * 255.0f));
   }
 }
-int vae_tail(const __half* x, int ldx, int B, int H, int W, __half* out_nchw, uint8_t* out_u8_nhwc, cudaStream_t st) {
+int vae_tail(const __half* x, int ldx, int B, int H, int W, bool postprocess, __half* out_nchw, uint8_t* out_u8_nhwc,
+             cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(B) * H * W;
   GYRE_REQUIRE(total > 0, "vae_tail: empty");
-  vae_tail_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, H * W, out_nchw, out_u8_nhwc, total);
+  vae_tail_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, H * W, postprocess ? 1 : 0, out_nchw, out_u8_nhwc, total);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,830 @@
+// UNet2DCondition / AutoencoderKL op graphs over the sm_100a kernels (see model.h).
+//
+// Architecture follows SURVEY.md Appendix A (diffusers-0.16 modules as used by
+// gyre/pipeline/unet/core.py:274 and gyre/pipeline/unified_pipeline.py:1523-1536); parameter keys are the
+// diffusers state-dict names so that real checkpoints drop in.  Internal activation layout: token-major
+// NHWC fp16 ([B, H*W, C]); a 1x1 conv and a Linear are the same GEMM, the SD1 "conv projection" and the SD2
+// "linear projection" transformer variants coincide, and no permute exists anywhere inside the network.
+#include "model.h"
+
+#include <cstring>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace gyre {
+
+// ------------------------------------------------------------------------------------------ Exec
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void* Exec::alloc_p(size_t bytes) {
+  bytes = align_up(bytes, 1024);
+  const size_t off = bottom;
+  bottom += bytes;
+  if (bottom + top > peak) peak = bottom + top;
+  if (!dry && bottom + top > cap) overflow = true;
+  return dry ? nullptr : base + off;
+}
+
+void* Exec::alloc_s(size_t bytes) {
+  bytes = align_up(bytes, 1024);
+  top += bytes;
+  if (bottom + top > peak) peak = bottom + top;
+  if (!dry && bottom + top > cap) {
+    overflow = true;
+    return base;   // never used: callers check ex.overflow before launching
+  }
+  return dry ? nullptr : base + cap - top;
+}
+
+#define EX_CHECK(ex)                                                                         \
+  do {                                                                                       \
+    if ((ex).overflow) {                                                                     \
+      set_last_error("workspace too small: need > %zu bytes, have %zu", (ex).peak, (ex).cap); \
+      return -4;                                                                             \
+    }                                                                                        \
+  } while (0)
+// launch helper: skipped entirely in a dry (sizing) run
+#define RUN(ex, call)          \
+  do {                         \
+    EX_CHECK(ex);              \
+    if (!(ex).dry) GYRE_TRY(call); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ Model base
+Model::Model() { cudaGetDevice(&device_); }
+
+Model::~Model() {
+  for (void* p : allocs_) cudaFree(p);
+}
+
+void* Model::dalloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes > 0 ? bytes : 16) != cudaSuccess) {
+    alloc_failed_ = true;
+    cudaGetLastError();
+    return nullptr;
+  }
+  cudaMemset(p, 0, bytes);
+  allocs_.push_back(p);
+  return p;
+}
+
+void Model::reg(const std::string& key, int kind, void* dst, std::initializer_list<int64_t> shape, int ld) {
+  ParamSlot s;
+  s.kind = kind;
+  s.dst = dst;
+  s.ndim = static_cast<int>(shape.size());
+  int i = 0;
+  for (int64_t v : shape) s.shape[i++] = v;
+  s.ld = ld;
+  slots_[key] = s;
+}
+
+void Model::reg_norm(const std::string& p, int C, NormW* n) {
+  n->C = C;
+  n->g = static_cast<float*>(dalloc(sizeof(float) * C));
+  n->b = static_cast<float*>(dalloc(sizeof(float) * C));
+  reg(p + ".weight", P_F32, n->g, {C});
+  reg(p + ".bias", P_F32, n->b, {C});
+}
+
+void Model::reg_linear(const std::string& p, int N, int K, bool bias, LinW* l) {
+  l->N = N;
+  l->K = K;
+  l->w = static_cast<__half*>(dalloc(sizeof(__half) * N * K));
+  reg(p + ".weight", P_LINEAR, l->w, {N, K}, K);
+  if (bias) {
+    l->bias = static_cast<float*>(dalloc(sizeof(float) * N));
+    reg(p + ".bias", P_F32, l->bias, {N});
+  }
+}
+
+void Model::reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c) {
+  c->Cin = Cin;
+  c->Cout = Cout;
+  c->wp = static_cast<__half*>(dalloc(sizeof(__half) * conv3x3_packed_elems(Cin, Cout)));
+  c->bias = static_cast<float*>(dalloc(sizeof(float) * Cout));
+  reg(p + ".weight", P_CONV3, c->wp, {Cout, Cin, 3, 3});
+  reg(p + ".bias", P_F32, c->bias, {Cout});
+}
+
+void Model::reg_smallconv(const std::string& p, int Cin, int Cout, SmallConvW* c) {
+  c->Cin = Cin;
+  c->Cout = Cout;
+  c->w = static_cast<float*>(dalloc(sizeof(float) * Cout * 9 * Cin));
+  c->bias = static_cast<float*>(dalloc(sizeof(float) * Cout));
+  reg(p + ".weight", P_SMALLCONV, c->w, {Cout, Cin, 3, 3});
+  reg(p + ".bias", P_F32, c->bias, {Cout});
+}
+
+void Model::reg_resnet(const std::string& p, int cin, int cout, bool temb, ResnetW* r) {
+  r->cin = cin;
+  r->cout = cout;
+  reg_norm(p + ".norm1", cin, &r->n1);
+  reg_conv3(p + ".conv1", cin, cout, &r->c1);
+  reg_norm(p + ".norm2", cout, &r->n2);
+  reg_conv3(p + ".conv2", cout, cout, &r->c2);
+  r->has_sc = cin != cout;
+  if (r->has_sc) reg_linear(p + ".conv_shortcut", cout, cin, true, &r->sc);
+  if (temb) {
+    // rows [temb_off, temb_off+cout) of the fused projection; registered once temb_proj_ is allocated
+    r->temb_off = temb_total_;
+    temb_total_ += cout;
+  }
+}
+
+int Model::ensure_device() {
+  int cur = -1;
+  GYRE_CHECK_CUDA(cudaGetDevice(&cur));
+  GYRE_REQUIRE(cur == device_, "handle belongs to device %d but device %d is current", device_, cur);
+  return 0;
+}
+
+int Model::load(const char* key, const void* data, int dtype, const int64_t* shape, int ndim, cudaStream_t st) {
+  GYRE_TRY(ensure_device());
+  GYRE_REQUIRE(key && data && shape, "load_weight: null argument");
+  GYRE_REQUIRE(dtype == 0 || dtype == 1, "load_weight(%s): dtype %d (want fp16=0 / fp32=1)", key, dtype);
+  auto it = slots_.find(key);
+  GYRE_REQUIRE(it != slots_.end(), "load_weight: unknown parameter '%s'", key);
+  ParamSlot& s = it->second;
+  // a Linear weight may arrive as a 1x1 conv [N, K, 1, 1] (SD1 proj_in / conv_shortcut) or as [N, K]
+  bool ok = false;
+  if (ndim == s.ndim) {
+    ok = true;
+    for (int i = 0; i < ndim; ++i) ok = ok && shape[i] == s.shape[i];
+  } else if ((s.kind == P_LINEAR || s.kind == P_F32MAT) && s.ndim == 2 && ndim == 4) {
+    ok = shape[0] == s.shape[0] && shape[1] == s.shape[1] && shape[2] == 1 && shape[3] == 1;
+  }
+  GYRE_REQUIRE(ok, "load_weight(%s): shape mismatch (got ndim %d [%lld,%lld,..], want ndim %d [%lld,%lld,..])", key,
+               ndim, (long long)shape[0], (long long)(ndim > 1 ? shape[1] : 0), s.ndim, (long long)s.shape[0],
+               (long long)(s.ndim > 1 ? s.shape[1] : 0));
+  switch (s.kind) {
+    case P_F32:
+      GYRE_TRY(cast_to_f32(data, dtype, s.shape[0], static_cast<float*>(s.dst), st));
+      break;
+    case P_F32MAT:
+      GYRE_TRY(cast_to_f32(data, dtype, s.shape[0] * s.shape[1], static_cast<float*>(s.dst), st));
+      break;
+    case P_LINEAR:
+      GYRE_TRY(cast_to_f16(data, dtype, s.shape[0], static_cast<int>(s.shape[1]), static_cast<__half*>(s.dst), s.ld, st));
+      break;
+    case P_CONV3:
+      GYRE_TRY(pack_conv3x3(data, dtype, static_cast<int>(s.shape[1]), static_cast<int>(s.shape[0]),
+                            static_cast<__half*>(s.dst), st));
+      break;
+    case P_GEGLU_W:
+      GYRE_TRY(pack_geglu(data, dtype, static_cast<int>(s.shape[0] / 2), static_cast<int>(s.shape[1]), nullptr, 0,
+                          static_cast<__half*>(s.dst), nullptr, st));
+      break;
+    case P_GEGLU_B:
+      GYRE_TRY(pack_geglu(nullptr, 0, static_cast<int>(s.shape[0] / 2), 1, data, dtype, nullptr,
+                          static_cast<float*>(s.dst), st));
+      break;
+    case P_SMALLCONV:
+      GYRE_TRY(pack_smallconv(data, dtype, static_cast<int>(s.shape[1]), static_cast<int>(s.shape[0]),
+                              static_cast<float*>(s.dst), st));
+      break;
+    default:
+      GYRE_REQUIRE(false, "load_weight(%s): bad slot", key);
+  }
+  s.loaded = true;
+  return 0;
+}
+
+int Model::finalize() {
+  GYRE_REQUIRE(!alloc_failed_, "device allocation failed while creating the model");
+  int missing = 0;
+  std::string first;
+  for (auto& kv : slots_)
+    if (!kv.second.loaded) {
+      if (missing == 0 || kv.first < first) first = kv.first;
+      ++missing;
+    }
+  GYRE_REQUIRE(missing == 0, "finalize: %d parameter(s) not loaded, e.g. '%s'", missing, first.c_str());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ shared blocks
+// pointer offset that stays null in a dry run
+template <typename T>
+static inline T* off(T* p, size_t n) { return p ? p + n : nullptr; }
+
+static Epilogue ep_out(__half* out, int ldo, const float* bias = nullptr, const __half* residual = nullptr,
+                       int ldr = 0, int act = ACT_NONE) {
+  Epilogue e;
+  e.out = out;
+  e.ldo = ldo;
+  e.bias = bias;
+  e.residual = residual;
+  e.ldr = ldr;
+  e.act = act;
+  return e;
+}
+
+// ResnetBlock2D: GN+SiLU -> conv3x3 (+bias +temb) -> GN+SiLU -> conv3x3 (+bias) + shortcut(x)
+// The input may be the channel concatenation x1 ++ x2 (UNet up path): GroupNorm and the 1x1 shortcut read
+// both sources directly, so the concatenation is never written to memory.
+int Model::resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __half* x2, int C2, int B, int H, int W,
+                  float eps, const __half* temb_all, int temb_ld, __half* out) {
+  const int HW = H * W;
+  const size_t rows = static_cast<size_t>(B) * HW;
+  GYRE_REQUIRE(C1 + C2 == r.cin, "resnet: input channels %d+%d != %d", C1, C2, r.cin);
+  float* gn_scratch = ex.s32(gn_partials_floats(B, HW, groups_));
+  __half* t1 = ex.s16(rows * r.cin);
+  RUN(ex, groupnorm_nhwc(x1, C1, x2, C2, B, HW, groups_, eps, r.n1.g, r.n1.b, true, t1, gn_scratch, ex.st));
+  __half* t2 = ex.s16(rows * r.cout);
+  {
+    Epilogue e = ep_out(t2, r.cout, r.c1.bias);
+    if (r.temb_off >= 0) {
+      e.rowgroup_bias = off(temb_all, r.temb_off);
+      e.rgb_ld = temb_ld;
+      e.rows_per_group = HW;
+    }
+    RUN(ex, conv3x3_f16(t1, r.cin, B, H, W, r.cin, r.c1.wp, r.cout, 1, 1, e, ex.st));
+  }
+  __half* t3 = ex.s16(rows * r.cout);
+  RUN(ex, groupnorm_nhwc(t2, r.cout, nullptr, 0, B, HW, groups_, eps, r.n2.g, r.n2.b, true, t3, gn_scratch, ex.st));
+  const __half* res = x1;
+  if (r.has_sc) {
+    __half* t4 = ex.s16(rows * r.cout);
+    Epilogue e = ep_out(t4, r.cout, r.sc.bias);
+    RUN(ex, gemm2_f16(x1, C1, C1, x2, C2, C2, r.sc.w, r.cin, static_cast<int>(rows), r.cout, e, ex.st));
+    res = t4;
+  } else {
+    GYRE_REQUIRE(C2 == 0, "resnet: concatenated input needs a shortcut conv");
+  }
+  {
+    Epilogue e = ep_out(out, r.cout, r.c2.bias, res, r.cout);
+    RUN(ex, conv3x3_f16(t3, r.cout, B, H, W, r.cout, r.c2.wp, r.cout, 1, 1, e, ex.st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ UNet
+UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
+  groups_ = cfg.norm_num_groups;
+  const int L = cfg.num_levels;
+  const int* ch = cfg.block_out_channels;
+  temb_dim_ = ch[0] * 4;
+  reg_smallconv("conv_in", cfg.in_channels, ch[0], &conv_in_);
+  reg_linear("time_embedding.linear_1", temb_dim_, ch[0], true, &time1_);
+  reg_linear("time_embedding.linear_2", temb_dim_, temb_dim_, true, &time2_);
+
+  auto add_transformer = [&](const std::string& p, int C, int heads) {
+    tblocks_.emplace_back();
+    TransformerW* t = &tblocks_.back();
+    t->C = C;
+    t->heads = heads;
+    const int ctx = cfg.cross_attention_dim;
+    reg_norm(p + ".norm", C, &t->gn);
+    reg_linear(p + ".proj_in", C, C, true, &t->proj_in);
+    reg_linear(p + ".proj_out", C, C, true, &t->proj_out);
+    const std::string b = p + ".transformer_blocks.0";
+    reg_norm(b + ".norm1", C, &t->ln1);
+    reg_norm(b + ".norm2", C, &t->ln2);
+    reg_norm(b + ".norm3", C, &t->ln3);
+    // attn1: fused [to_q ; to_k ; to_v] -> one GEMM with N = 3C
+    t->qkv.N = 3 * C;
+    t->qkv.K = C;
+    t->qkv.w = static_cast<__half*>(dalloc(sizeof(__half) * 3 * C * C));
+    reg(b + ".attn1.to_q.weight", P_LINEAR, t->qkv.w, {C, C}, C);
+    reg(b + ".attn1.to_k.weight", P_LINEAR, t->qkv.w ? t->qkv.w + static_cast<size_t>(C) * C : nullptr, {C, C}, C);
+    reg(b + ".attn1.to_v.weight", P_LINEAR, t->qkv.w ? t->qkv.w + static_cast<size_t>(2) * C * C : nullptr, {C, C}, C);
+    reg_linear(b + ".attn1.to_out.0", C, C, true, &t->o1);
+    // attn2: q from tokens, fused [to_k ; to_v] from the text context
+    reg_linear(b + ".attn2.to_q", C, C, false, &t->q2);
+    t->kv2.N = 2 * C;
+    t->kv2.K = ctx;
+    t->kv2.w = static_cast<__half*>(dalloc(sizeof(__half) * 2 * C * ctx));
+    reg(b + ".attn2.to_k.weight", P_LINEAR, t->kv2.w, {C, ctx}, ctx);
+    reg(b + ".attn2.to_v.weight", P_LINEAR, t->kv2.w ? t->kv2.w + static_cast<size_t>(C) * ctx : nullptr, {C, ctx}, ctx);
+    reg_linear(b + ".attn2.to_out.0", C, C, true, &t->o2);
+    // GEGLU feed-forward
+    t->geglu.N = 8 * C;
+    t->geglu.K = C;
+    t->geglu.w = static_cast<__half*>(dalloc(sizeof(__half) * 8 * C * C));
+    t->geglu.bias = static_cast<float*>(dalloc(sizeof(float) * 8 * C));
+    reg(b + ".ff.net.0.proj.weight", P_GEGLU_W, t->geglu.w, {8 * C, C});
+    reg(b + ".ff.net.0.proj.bias", P_GEGLU_B, t->geglu.bias, {8 * C});
+    reg_linear(b + ".ff.net.2", C, 4 * C, true, &t->ff2);
+  };
+  auto add_resnet = [&](const std::string& p, int cin, int cout) {
+    resnets_.emplace_back();
+    reg_resnet(p, cin, cout, true, &resnets_.back());
+  };
+  // reserve so that emplace_back never moves already-registered blocks (slots hold raw pointers into
+  // device memory only, but ResnetW/TransformerW copies must stay stable for the lambdas above)
+  resnets_.reserve(64);
+  tblocks_.reserve(64);
+  downs_.reserve(8);
+  ups_.reserve(8);
+
+  std::vector<int> skips{ch[0]};
+  int cin = ch[0];
+  for (int i = 0; i < L; ++i) {
+    for (int j = 0; j < cfg.layers_per_block; ++j) {
+      const std::string p = "down_blocks." + std::to_string(i);
+      add_resnet(p + ".resnets." + std::to_string(j), cin, ch[i]);
+      cin = ch[i];
+      if (cfg.attn_levels[i]) add_transformer(p + ".attentions." + std::to_string(j), ch[i], cfg.num_heads[i]);
+      skips.push_back(ch[i]);
+    }
+    if (i < L - 1) {
+      downs_.emplace_back();
+      reg_conv3("down_blocks." + std::to_string(i) + ".downsamplers.0.conv", ch[i], ch[i], &downs_.back());
+      skips.push_back(ch[i]);
+    }
+  }
+  add_resnet("mid_block.resnets.0", cin, cin);
+  add_transformer("mid_block.attentions.0", cin, cfg.num_heads[L - 1]);
+  add_resnet("mid_block.resnets.1", cin, cin);
+  for (int i = 0; i < L; ++i) {
+    const int lvl = L - 1 - i;
+    const int c = ch[lvl];
+    for (int j = 0; j < cfg.layers_per_block + 1; ++j) {
+      const int s = skips.back();
+      skips.pop_back();
+      const std::string p = "up_blocks." + std::to_string(i);
+      add_resnet(p + ".resnets." + std::to_string(j), cin + s, c);
+      cin = c;
+      if (cfg.attn_levels[lvl]) add_transformer(p + ".attentions." + std::to_string(j), c, cfg.num_heads[lvl]);
+    }
+    if (i < L - 1) {
+      ups_.emplace_back();
+      reg_conv3("up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, &ups_.back());
+    }
+  }
+  reg_norm("conv_norm_out", ch[0], &norm_out_);
+  reg_conv3("conv_out", ch[0], cfg.out_channels, &conv_out_);
+
+  // fused time_emb_proj: one [sum(cout), temb_dim] GEMM per forward instead of 22 M=batch GEMMs
+  temb_proj_.N = temb_total_;
+  temb_proj_.K = temb_dim_;
+  temb_proj_.w = static_cast<__half*>(dalloc(sizeof(__half) * temb_total_ * temb_dim_));
+  temb_proj_.bias = static_cast<float*>(dalloc(sizeof(float) * temb_total_));
+  {
+    // re-walk the resnet names in the same order to register the slices
+    size_t idx = 0;
+    auto reg_temb = [&](const std::string& p) {
+      const ResnetW& r = resnets_[idx++];
+      reg(p + ".time_emb_proj.weight", P_LINEAR,
+          temb_proj_.w ? temb_proj_.w + static_cast<size_t>(r.temb_off) * temb_dim_ : nullptr, {r.cout, temb_dim_},
+          temb_dim_);
+      reg(p + ".time_emb_proj.bias", P_F32, temb_proj_.bias ? temb_proj_.bias + r.temb_off : nullptr, {r.cout});
+    };
+    for (int i = 0; i < L; ++i)
+      for (int j = 0; j < cfg.layers_per_block; ++j)
+        reg_temb("down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
+    reg_temb("mid_block.resnets.0");
+    reg_temb("mid_block.resnets.1");
+    for (int i = 0; i < L; ++i)
+      for (int j = 0; j < cfg.layers_per_block + 1; ++j)
+        reg_temb("up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
+  }
+}
+
+// Transformer2DModel + BasicTransformerBlock (nonfree/tome_unet.py:114-136)
+int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int B, int HW, const __half* ctx, int L,
+                           int r, __half* out) {
+  const int C = t.C;
+  const int M = B * HW;
+  const size_t n = static_cast<size_t>(M) * C;
+  const int d = C / t.heads;
+  const float scale = 1.0f / sqrtf(static_cast<float>(d));
+  float* gn_scratch = ex.s32(gn_partials_floats(B, HW, groups_));
+  __half* tn = ex.s16(n);
+  RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, B, HW, groups_, 1e-6f, t.gn.g, t.gn.b, false, tn, gn_scratch, ex.st));
+  __half* h = ex.s16(n);
+  RUN(ex, gemm_f16(tn, C, t.proj_in.w, C, M, C, C, ep_out(h, C, t.proj_in.bias), ex.st));
+  // ---- self-attention
+  __half* nrm = tn;   // the GroupNorm output is dead after proj_in: reuse it for the LayerNorm outputs
+  RUN(ex, layernorm_rows(h, M, C, 1e-5f, t.ln1.g, t.ln1.b, nrm, ex.st));
+  __half* qkv = ex.s16(n * 3);
+  RUN(ex, gemm_f16(nrm, C, t.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C), ex.st));
+  __half* o = ex.s16(n);
+  if (r > 0) {
+    // ToMe (nonfree/tome_memory_efficient_cross_attention.py:28-50): merge K and V with one plan built from K
+    const int rr = r < HW / 2 ? r : HW / 2;
+    const int nk = HW - rr;
+    size_t tome_bytes = 0;
+    GYRE_TRY(tome_workspace_bytes(B, HW, C, &tome_bytes));
+    void* tws = ex.alloc_s(tome_bytes);
+    __half* km = ex.s16(static_cast<size_t>(B) * nk * C);
+    __half* vm = ex.s16(static_cast<size_t>(B) * nk * C);
+    RUN(ex, tome_merge_kv(off(qkv, C), off(qkv, 2 * C), 3 * C, B, HW, C, rr, km, vm, tws, tome_bytes, ex.st));
+    RUN(ex, attention_f16(qkv, 3 * C, km, C, vm, C, B, t.heads, HW, nk, d, scale, o, C, ex.st));
+  } else {
+    RUN(ex, attention_f16(qkv, 3 * C, off(qkv, C), 3 * C, off(qkv, 2 * C), 3 * C, B, t.heads, HW, HW, d, scale, o, C, ex.st));
+  }
+  __half* h2 = ex.s16(n);
+  RUN(ex, gemm_f16(o, C, t.o1.w, C, M, C, C, ep_out(h2, C, t.o1.bias, h, C), ex.st));
+  // ---- cross-attention
+  RUN(ex, layernorm_rows(h2, M, C, 1e-5f, t.ln2.g, t.ln2.b, nrm, ex.st));
+  __half* q = qkv;   // dead after self-attention
+  RUN(ex, gemm_f16(nrm, C, t.q2.w, C, M, C, C, ep_out(q, C), ex.st));
+  __half* kv = ex.s16(static_cast<size_t>(B) * L * 2 * C);
+  RUN(ex, gemm_f16(ctx, t.kv2.K, t.kv2.w, t.kv2.K, B * L, 2 * C, t.kv2.K, ep_out(kv, 2 * C), ex.st));
+  RUN(ex, attention_f16(q, C, kv, 2 * C, off(kv, C), 2 * C, B, t.heads, HW, L, d, scale, o, C, ex.st));
+  RUN(ex, gemm_f16(o, C, t.o2.w, C, M, C, C, ep_out(h, C, t.o2.bias, h2, C), ex.st));   // h <- h2 + attn2
+  // ---- GEGLU feed-forward
+  RUN(ex, layernorm_rows(h, M, C, 1e-5f, t.ln3.g, t.ln3.b, nrm, ex.st));
+  __half* g = ex.s16(n * 4);
+  RUN(ex, gemm_f16(nrm, C, t.geglu.w, C, M, 8 * C, C, ep_out(g, 4 * C, t.geglu.bias, nullptr, 0, ACT_GEGLU), ex.st));
+  RUN(ex, gemm_f16(g, 4 * C, t.ff2.w, 4 * C, M, C, 4 * C, ep_out(h2, C, t.ff2.bias, h, C), ex.st));   // h2 <- h + ff
+  RUN(ex, gemm_f16(h2, C, t.proj_out.w, C, M, C, C, ep_out(out, C, t.proj_out.bias, x, C), ex.st));
+  return 0;
+}
+
+int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, int B, int H, int W, int L,
+                       const int32_t* tome_r, __half* out) {
+  GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && L > 0, "unet_forward: empty problem");
+  const int nl = cfg_.num_levels;
+  GYRE_REQUIRE(H % (1 << (nl - 1)) == 0 && W % (1 << (nl - 1)) == 0,
+               "unet_forward: latent %dx%d must be divisible by %d", H, W, 1 << (nl - 1));
+  const int* ch = cfg_.block_out_channels;
+  const float eps = cfg_.norm_eps;
+  if (!ex.dry) GYRE_TRY(ensure_device());
+
+  // ---- time embedding: sinusoid -> Linear -> SiLU -> Linear ; every consumer applies SiLU first, so the
+  // second Linear's epilogue applies it once; then ONE fused GEMM produces all 22 resnet projections.
+  __half* te0 = ex.p16(static_cast<size_t>(B) * ch[0]);
+  RUN(ex, timestep_embed(t, B, ch[0], te0, ex.st));
+  __half* te1 = ex.p16(static_cast<size_t>(B) * temb_dim_);
+  RUN(ex, gemm_f16(te0, ch[0], time1_.w, ch[0], B, temb_dim_, ch[0],
+                   ep_out(te1, temb_dim_, time1_.bias, nullptr, 0, ACT_SILU), ex.st));
+  __half* te2 = ex.p16(static_cast<size_t>(B) * temb_dim_);
+  RUN(ex, gemm_f16(te1, temb_dim_, time2_.w, temb_dim_, B, temb_dim_, temb_dim_,
+                   ep_out(te2, temb_dim_, time2_.bias, nullptr, 0, ACT_SILU), ex.st));
+  __half* temb_all = ex.p16(static_cast<size_t>(B) * temb_total_);
+  RUN(ex, gemm_f16(te2, temb_dim_, temb_proj_.w, temb_dim_, B, temb_total_, temb_dim_,
+                   ep_out(temb_all, temb_total_, temb_proj_.bias), ex.st));
+
+  // ---- conv_in
+  int h_ = H, w_ = W;
+  __half* x_nhwc = ex.p16(static_cast<size_t>(B) * H * W * cfg_.in_channels);
+  RUN(ex, nchw_to_nhwc_f16(sample, B, cfg_.in_channels, H, W, x_nhwc, cfg_.in_channels, ex.st));
+  __half* hcur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
+  RUN(ex, conv3x3_small_cin(x_nhwc, B, H, W, cfg_.in_channels, conv_in_.w, conv_in_.bias, ch[0], hcur, ex.st));
+
+  struct Skip { const __half* p; int C; };
+  std::vector<Skip> skips;
+  skips.push_back({hcur, ch[0]});
+  size_t ri = 0, ti = 0, di = 0, ui = 0;
+  int ccur = ch[0];
+  auto r_of = [&](size_t idx) { return tome_r ? tome_r[idx] : 0; };
+
+  for (int i = 0; i < nl; ++i) {
+    for (int j = 0; j < cfg_.layers_per_block; ++j) {
+      ex.reset_scratch();
+      __half* o = ex.p16(static_cast<size_t>(B) * h_ * w_ * ch[i]);
+      GYRE_TRY(resnet(ex, resnets_[ri++], hcur, ccur, nullptr, 0, B, h_, w_, eps, temb_all, temb_total_, o));
+      hcur = o;
+      ccur = ch[i];
+      if (cfg_.attn_levels[i]) {
+        ex.reset_scratch();
+        __half* o2 = ex.p16(static_cast<size_t>(B) * h_ * w_ * ccur);
+        GYRE_TRY(transformer(ex, tblocks_[ti], hcur, B, h_ * w_, ctx, L, r_of(ti), o2));
+        ++ti;
+        hcur = o2;
+      }
+      skips.push_back({hcur, ccur});
+    }
+    if (i < nl - 1) {
+      ex.reset_scratch();
+      const int ho = (h_ - 1) / 2 + 1, wo = (w_ - 1) / 2 + 1;
+      __half* o = ex.p16(static_cast<size_t>(B) * ho * wo * ccur);
+      RUN(ex, conv3x3_f16(hcur, ccur, B, h_, w_, ccur, downs_[di].wp, ccur, 2, 1, ep_out(o, ccur, downs_[di].bias),
+                          ex.st));
+      ++di;
+      hcur = o;
+      h_ = ho;
+      w_ = wo;
+      skips.push_back({hcur, ccur});
+    }
+  }
+  // ---- mid
+  {
+    ex.reset_scratch();
+    __half* o = ex.p16(static_cast<size_t>(B) * h_ * w_ * ccur);
+    GYRE_TRY(resnet(ex, resnets_[ri++], hcur, ccur, nullptr, 0, B, h_, w_, eps, temb_all, temb_total_, o));
+    ex.reset_scratch();
+    __half* o2 = ex.p16(static_cast<size_t>(B) * h_ * w_ * ccur);
+    GYRE_TRY(transformer(ex, tblocks_[ti], o, B, h_ * w_, ctx, L, r_of(ti), o2));
+    ++ti;
+    ex.reset_scratch();
+    __half* o3 = ex.p16(static_cast<size_t>(B) * h_ * w_ * ccur);
+    GYRE_TRY(resnet(ex, resnets_[ri++], o2, ccur, nullptr, 0, B, h_, w_, eps, temb_all, temb_total_, o3));
+    hcur = o3;
+  }
+  // ---- up
+  for (int i = 0; i < nl; ++i) {
+    const int lvl = nl - 1 - i;
+    const int c = ch[lvl];
+    for (int j = 0; j < cfg_.layers_per_block + 1; ++j) {
+      const Skip s = skips.back();
+      skips.pop_back();
+      ex.reset_scratch();
+      __half* o = ex.p16(static_cast<size_t>(B) * h_ * w_ * c);
+      GYRE_TRY(resnet(ex, resnets_[ri++], hcur, ccur, s.p, s.C, B, h_, w_, eps, temb_all, temb_total_, o));
+      hcur = o;
+      ccur = c;
+      if (cfg_.attn_levels[lvl]) {
+        ex.reset_scratch();
+        __half* o2 = ex.p16(static_cast<size_t>(B) * h_ * w_ * c);
+        GYRE_TRY(transformer(ex, tblocks_[ti], hcur, B, h_ * w_, ctx, L, r_of(ti), o2));
+        ++ti;
+        hcur = o2;
+      }
+    }
+    if (i < nl - 1) {
+      ex.reset_scratch();
+      __half* up = ex.s16(static_cast<size_t>(B) * 4 * h_ * w_ * c);
+      RUN(ex, upsample2x_nhwc(hcur, B, h_, w_, c, up, ex.st));
+      h_ *= 2;
+      w_ *= 2;
+      __half* o = ex.p16(static_cast<size_t>(B) * h_ * w_ * c);
+      RUN(ex, conv3x3_f16(up, c, B, h_, w_, c, ups_[ui].wp, c, 1, 1, ep_out(o, c, ups_[ui].bias), ex.st));
+      ++ui;
+      hcur = o;
+    }
+  }
+  // ---- out
+  ex.reset_scratch();
+  {
+    const size_t rows = static_cast<size_t>(B) * h_ * w_;
+    float* gn_scratch = ex.s32(gn_partials_floats(B, h_ * w_, groups_));
+    __half* tn = ex.s16(rows * ccur);
+    RUN(ex, groupnorm_nhwc(hcur, ccur, nullptr, 0, B, h_ * w_, groups_, eps, norm_out_.g, norm_out_.b, true, tn,
+                           gn_scratch, ex.st));
+    const int oc = cfg_.out_channels;
+    __half* eps_nhwc = ex.s16(rows * oc);
+    RUN(ex, conv3x3_f16(tn, ccur, B, h_, w_, ccur, conv_out_.wp, oc, 1, 1, ep_out(eps_nhwc, oc, conv_out_.bias),
+                        ex.st));
+    RUN(ex, nhwc_to_nchw_f16(eps_nhwc, oc, B, oc, h_, w_, out, ex.st));
+  }
+  EX_CHECK(ex);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ VAE
+VAEModel::VAEModel(const gyre_b200_vae_config& cfg) : cfg_(cfg) {
+  groups_ = cfg.norm_num_groups;
+  const int L = cfg.num_levels;
+  const int* ch = cfg.block_out_channels;
+  const int z = cfg.latent_channels;
+  const int top = ch[L - 1];
+  dec_res_.reserve(32);
+  enc_res_.reserve(32);
+  dec_ups_.reserve(8);
+  enc_downs_.reserve(8);
+
+  auto reg_attn = [&](const std::string& p, int C, VaeAttnW* a) {
+    a->C = C;
+    reg_norm(p + ".group_norm", C, &a->gn);
+    a->qk.N = 2 * C;
+    a->qk.K = C;
+    a->qk.w = static_cast<__half*>(dalloc(sizeof(__half) * 2 * C * C));
+    a->qk.bias = static_cast<float*>(dalloc(sizeof(float) * 2 * C));
+    reg(p + ".query.weight", P_LINEAR, a->qk.w, {C, C}, C);
+    reg(p + ".key.weight", P_LINEAR, a->qk.w ? a->qk.w + static_cast<size_t>(C) * C : nullptr, {C, C}, C);
+    reg(p + ".query.bias", P_F32, a->qk.bias, {C});
+    reg(p + ".key.bias", P_F32, a->qk.bias ? a->qk.bias + C : nullptr, {C});
+    a->v.N = C;
+    a->v.K = C;
+    a->v.w = static_cast<__half*>(dalloc(sizeof(__half) * C * C));
+    a->v_bias = static_cast<float*>(dalloc(sizeof(float) * C));
+    reg(p + ".value.weight", P_LINEAR, a->v.w, {C, C}, C);
+    reg(p + ".value.bias", P_F32, a->v_bias, {C});
+    reg_linear(p + ".proj_attn", C, C, true, &a->proj);
+  };
+
+  // ---- decoder
+  post_quant_.Cin = z;
+  post_quant_.Cout = z;
+  post_quant_.w = static_cast<float*>(dalloc(sizeof(float) * z * z));
+  post_quant_.bias = static_cast<float*>(dalloc(sizeof(float) * z));
+  reg("post_quant_conv.weight", P_F32MAT, post_quant_.w, {z, z});
+  reg("post_quant_conv.bias", P_F32, post_quant_.bias, {z});
+  reg_smallconv("decoder.conv_in", z, top, &dec_conv_in_);
+  reg_resnet("decoder.mid_block.resnets.0", top, top, false, &dec_mid_[0]);
+  reg_attn("decoder.mid_block.attentions.0", top, &dec_attn_);
+  reg_resnet("decoder.mid_block.resnets.1", top, top, false, &dec_mid_[1]);
+  int cin = top;
+  for (int i = 0; i < L; ++i) {
+    const int c = ch[L - 1 - i];
+    for (int j = 0; j < cfg.layers_per_block + 1; ++j) {
+      dec_res_.emplace_back();
+      reg_resnet("decoder.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), cin, c, false,
+                 &dec_res_.back());
+      cin = c;
+    }
+    if (i < L - 1) {
+      dec_ups_.emplace_back();
+      reg_conv3("decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, &dec_ups_.back());
+    }
+  }
+  reg_norm("decoder.conv_norm_out", ch[0], &dec_norm_out_);
+  reg_conv3("decoder.conv_out", ch[0], cfg.out_channels, &dec_conv_out_);
+
+  // ---- encoder
+  reg_smallconv("encoder.conv_in", cfg.in_channels, ch[0], &enc_conv_in_);
+  cin = ch[0];
+  for (int i = 0; i < L; ++i) {
+    for (int j = 0; j < cfg.layers_per_block; ++j) {
+      enc_res_.emplace_back();
+      reg_resnet("encoder.down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), cin, ch[i], false,
+                 &enc_res_.back());
+      cin = ch[i];
+    }
+    if (i < L - 1) {
+      enc_downs_.emplace_back();
+      reg_conv3("encoder.down_blocks." + std::to_string(i) + ".downsamplers.0.conv", ch[i], ch[i], &enc_downs_.back());
+    }
+  }
+  reg_resnet("encoder.mid_block.resnets.0", cin, cin, false, &enc_mid_[0]);
+  reg_attn("encoder.mid_block.attentions.0", cin, &enc_attn_);
+  reg_resnet("encoder.mid_block.resnets.1", cin, cin, false, &enc_mid_[1]);
+  reg_norm("encoder.conv_norm_out", cin, &enc_norm_out_);
+  reg_conv3("encoder.conv_out", cin, 2 * z, &enc_conv_out_);
+  quant_.Cin = 2 * z;
+  quant_.Cout = 2 * z;
+  quant_.w = static_cast<float*>(dalloc(sizeof(float) * 4 * z * z));
+  quant_.bias = static_cast<float*>(dalloc(sizeof(float) * 2 * z));
+  reg("quant_conv.weight", P_F32MAT, quant_.w, {2 * z, 2 * z});
+  reg("quant_conv.bias", P_F32, quant_.bias, {2 * z});
+}
+
+// Legacy single-head AttentionBlock: d = C = 512 exceeds the flash kernel's TMEM budget, so
+// the scores are materialised: S = Q K^T (fp32) -> row softmax -> P (fp16) -> O = P V.  V^T is produced
+// directly by a GEMM (W_v X^T); its bias is added after P.V because softmax rows sum to one.
+int VAEModel::attn(Exec& ex, const VaeAttnW& a, const __half* x, int B, int HW, __half* out) {
+  const int C = a.C;
+  const int M = B * HW;
+  const size_t n = static_cast<size_t>(M) * C;
+  float* gn_scratch = ex.s32(gn_partials_floats(B, HW, groups_));
+  __half* tn = ex.s16(n);
+  RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, B, HW, groups_, 1e-6f, a.gn.g, a.gn.b, false, tn, gn_scratch, ex.st));
+  __half* qk = ex.s16(n * 2);
+  RUN(ex, gemm_f16(tn, C, a.qk.w, C, M, 2 * C, C, ep_out(qk, 2 * C, a.qk.bias), ex.st));
+  __half* o = ex.s16(n);
+  __half* vt = ex.s16(static_cast<size_t>(C) * HW);
+  float* s = ex.s32(static_cast<size_t>(HW) * HW);
+  __half* p = ex.s16(static_cast<size_t>(HW) * HW);
+  const float scale = 1.0f / sqrtf(static_cast<float>(C));
+  for (int b = 0; b < B; ++b) {
+    const __half* tb = off(tn, static_cast<size_t>(b) * HW * C);
+    const __half* qb = off(qk, static_cast<size_t>(b) * HW * 2 * C);
+    RUN(ex, gemm_f16(a.v.w, C, tb, C, C, HW, C, ep_out(vt, HW), ex.st));                      // V^T [C, HW]
+    {
+      Epilogue e;
+      e.out = s;
+      e.ldo = HW;
+      e.out_mode = OUT_F32;
+      RUN(ex, gemm_f16(qb, 2 * C, off(qb, C), 2 * C, HW, HW, C, e, ex.st));                      // S = Q K^T
+    }
+    RUN(ex, softmax_rows_f32(s, HW, HW, scale, p, HW, ex.st));
+    RUN(ex, gemm_f16(p, HW, vt, HW, HW, C, HW, ep_out(off(o, static_cast<size_t>(b) * HW * C), C, a.v_bias),
+                     ex.st));
+  }
+  RUN(ex, gemm_f16(o, C, a.proj.w, C, M, C, C, ep_out(out, C, a.proj.bias, x, C), ex.st));
+  return 0;
+}
+
+int VAEModel::decode(Exec& ex, const __half* z, int B, int h, int w, bool postprocess, __half* img, uint8_t* img_u8) {
+  GYRE_REQUIRE(B > 0 && h > 0 && w > 0, "vae_decode: empty problem");
+  GYRE_REQUIRE(img != nullptr || img_u8 != nullptr, "vae_decode: no output requested");
+  if (!ex.dry) GYRE_TRY(ensure_device());
+  const int L = cfg_.num_levels;
+  const int* ch = cfg_.block_out_channels;
+  const int zc = cfg_.latent_channels;
+  const int top = ch[L - 1];
+  const float eps = 1e-6f;
+  const size_t px = static_cast<size_t>(B) * h * w;
+  // block outputs are simply stacked in the persistent region (the decoder is a chain; the dry run sizes
+  // the workspace, a few GB at batch 8 / 512x512 -- small against 180 GB of HBM)
+  __half* z_nhwc = ex.p16(px * zc);
+  RUN(ex, nchw_to_nhwc_f16(z, B, zc, h, w, z_nhwc, zc, ex.st));
+  __half* z2 = ex.p16(px * zc);
+  RUN(ex, conv1x1_small(z_nhwc, static_cast<int64_t>(px), zc, post_quant_.w, post_quant_.bias, zc, z2, ex.st));
+  __half* cur = ex.p16(px * top);
+  RUN(ex, conv3x3_small_cin(z2, B, h, w, zc, dec_conv_in_.w, dec_conv_in_.bias, top, cur, ex.st));
+  int H = h, W = w, C = top;
+  auto block_out = [&](size_t elems) { return ex.p16(elems); };
+  {
+    ex.reset_scratch();
+    __half* o = block_out(px * top);
+    GYRE_TRY(resnet(ex, dec_mid_[0], cur, C, nullptr, 0, B, H, W, eps, nullptr, 0, o));
+    ex.reset_scratch();
+    __half* o2 = block_out(px * top);
+    GYRE_TRY(attn(ex, dec_attn_, o, B, H * W, o2));
+    ex.reset_scratch();
+    __half* o3 = block_out(px * top);
+    GYRE_TRY(resnet(ex, dec_mid_[1], o2, C, nullptr, 0, B, H, W, eps, nullptr, 0, o3));
+    cur = o3;
+  }
+  size_t ri = 0;
+  for (int i = 0; i < L; ++i) {
+    const int c = ch[L - 1 - i];
+    for (int j = 0; j < cfg_.layers_per_block + 1; ++j) {
+      ex.reset_scratch();
+      __half* o = block_out(static_cast<size_t>(B) * H * W * c);
+      GYRE_TRY(resnet(ex, dec_res_[ri++], cur, C, nullptr, 0, B, H, W, eps, nullptr, 0, o));
+      cur = o;
+      C = c;
+    }
+    if (i < L - 1) {
+      ex.reset_scratch();
+      __half* up = ex.s16(static_cast<size_t>(B) * 4 * H * W * c);
+      RUN(ex, upsample2x_nhwc(cur, B, H, W, c, up, ex.st));
+      H *= 2;
+      W *= 2;
+      __half* o = block_out(static_cast<size_t>(B) * H * W * c);
+      RUN(ex, conv3x3_f16(up, c, B, H, W, c, dec_ups_[i].wp, c, 1, 1, ep_out(o, c, dec_ups_[i].bias), ex.st));
+      cur = o;
+    }
+  }
+  ex.reset_scratch();
+  {
+    const size_t rows = static_cast<size_t>(B) * H * W;
+    float* gn_scratch = ex.s32(gn_partials_floats(B, H * W, groups_));
+    __half* tn = ex.s16(rows * C);
+    RUN(ex, groupnorm_nhwc(cur, C, nullptr, 0, B, H * W, groups_, eps, dec_norm_out_.g, dec_norm_out_.b, true, tn,
+                           gn_scratch, ex.st));
+    const int oc = cfg_.out_channels;
+    GYRE_REQUIRE(oc == 3, "vae_decode: out_channels must be 3");
+    __half* rgb = ex.s16(rows * 4);
+    RUN(ex, conv3x3_f16(tn, C, B, H, W, C, dec_conv_out_.wp, oc, 1, 1, ep_out(rgb, 4, dec_conv_out_.bias), ex.st));
+    RUN(ex, vae_tail(rgb, 4, B, H, W, postprocess, img, img_u8, ex.st));
+  }
+  EX_CHECK(ex);
+  return 0;
+}
+
+int VAEModel::encode(Exec& ex, const __half* img, int B, int H, int W, __half* moments) {
+  GYRE_REQUIRE(B > 0 && H > 0 && W > 0, "vae_encode: empty problem");
+  const int L = cfg_.num_levels;
+  GYRE_REQUIRE(H % (1 << (L - 1)) == 0 && W % (1 << (L - 1)) == 0, "vae_encode: image %dx%d not divisible by %d", H, W,
+               1 << (L - 1));
+  if (!ex.dry) GYRE_TRY(ensure_device());
+  const int* ch = cfg_.block_out_channels;
+  const int zc = cfg_.latent_channels;
+  const int ic = cfg_.in_channels;
+  const float eps = 1e-6f;
+  __half* x = ex.p16(static_cast<size_t>(B) * H * W * ic);
+  RUN(ex, nchw_to_nhwc_f16(img, B, ic, H, W, x, ic, ex.st));
+  __half* cur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
+  RUN(ex, conv3x3_small_cin(x, B, H, W, ic, enc_conv_in_.w, enc_conv_in_.bias, ch[0], cur, ex.st));
+  int C = ch[0];
+  size_t ri = 0;
+  for (int i = 0; i < L; ++i) {
+    for (int j = 0; j < cfg_.layers_per_block; ++j) {
+      ex.reset_scratch();
+      __half* o = ex.p16(static_cast<size_t>(B) * H * W * ch[i]);
+      GYRE_TRY(resnet(ex, enc_res_[ri++], cur, C, nullptr, 0, B, H, W, eps, nullptr, 0, o));
+      cur = o;
+      C = ch[i];
+    }
+    if (i < L - 1) {
+      ex.reset_scratch();
+      // Downsample2D(padding=0): F.pad(x, (0,1,0,1)) + conv3x3 stride 2 -- the asymmetric zero pad is the
+      // TMA out-of-bounds fill on the right/bottom edge
+      const int ho = (H + 1 - 3) / 2 + 1, wo = (W + 1 - 3) / 2 + 1;
+      __half* o = ex.p16(static_cast<size_t>(B) * ho * wo * C);
+      RUN(ex, conv3x3_f16(cur, C, B, H, W, C, enc_downs_[i].wp, C, 2, 0, ep_out(o, C, enc_downs_[i].bias), ex.st));
+      cur = o;
+      H = ho;
+      W = wo;
+    }
+  }
+  {
+    ex.reset_scratch();
+    __half* o = ex.p16(static_cast<size_t>(B) * H * W * C);
+    GYRE_TRY(resnet(ex, enc_mid_[0], cur, C, nullptr, 0, B, H, W, eps, nullptr, 0, o));
+    ex.reset_scratch();
+    __half* o2 = ex.p16(static_cast<size_t>(B) * H * W * C);
+    GYRE_TRY(attn(ex, enc_attn_, o, B, H * W, o2));
+    ex.reset_scratch();
+    __half* o3 = ex.p16(static_cast<size_t>(B) * H * W * C);
+    GYRE_TRY(resnet(ex, enc_mid_[1], o2, C, nullptr, 0, B, H, W, eps, nullptr, 0, o3));
+    cur = o3;
+  }
+  ex.reset_scratch();
+  {
+    const size_t rows = static_cast<size_t>(B) * H * W;
+    float* gn_scratch = ex.s32(gn_partials_floats(B, H * W, groups_));
+    __half* tn = ex.s16(rows * C);
+    RUN(ex, groupnorm_nhwc(cur, C, nullptr, 0, B, H * W, groups_, eps, enc_norm_out_.g, enc_norm_out_.b, true, tn,
+                           gn_scratch, ex.st));
+    __half* m0 = ex.s16(rows * 2 * zc);
+    RUN(ex, conv3x3_f16(tn, C, B, H, W, C, enc_conv_out_.wp, 2 * zc, 1, 1, ep_out(m0, 2 * zc, enc_conv_out_.bias),
+                        ex.st));
+    __half* m1 = ex.s16(rows * 2 * zc);
+    RUN(ex, conv1x1_small(m0, static_cast<int64_t>(rows), 2 * zc, quant_.w, quant_.bias, 2 * zc, m1, ex.st));
+    RUN(ex, nhwc_to_nchw_f16(m1, 2 * zc, B, 2 * zc, H, W, moments, ex.st));
+  }
+  EX_CHECK(ex);
+  return 0;
+}
+
+}  // namespace gyre

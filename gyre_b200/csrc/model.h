@@ -1,2 +1,156 @@
-// placeholder until the model runner lands
+// Model runner: the UNet2DCondition / AutoencoderKL op graphs expressed as sequences of the sm_100a
+// kernels in ops.h.  A model owns its packed weights (device memory) and nothing else; activations live
+// in a caller-provided workspace carved by a two-ended bump allocator (persistent block outputs grow
+// from the bottom, per-block temporaries from the top).  The same code path runs "dry" to size the
+// workspace, so the plan and the execution cannot drift.
 #pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/gyre_b200.h"
+
+namespace gyre {
+
+struct Exec {
+  cudaStream_t st = nullptr;
+  bool dry = false;
+  uint8_t* base = nullptr;
+  size_t cap = 0;
+  size_t bottom = 0;     // persistent bytes used
+  size_t top = 0;        // scratch bytes used (from the end)
+  size_t peak = 0;
+  bool overflow = false;
+  void* alloc_p(size_t bytes);
+  void* alloc_s(size_t bytes);
+  void reset_scratch() { top = 0; }
+  __half* p16(size_t elems) { return static_cast<__half*>(alloc_p(elems * 2)); }
+  __half* s16(size_t elems) { return static_cast<__half*>(alloc_s(elems * 2)); }
+  float* s32(size_t elems) { return static_cast<float*>(alloc_s(elems * 4)); }
+};
+
+struct NormW { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct LinW { __half* w = nullptr; float* bias = nullptr; int N = 0, K = 0; };
+struct Conv3W { __half* wp = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0; };
+struct SmallConvW { float* w = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0; };
+
+struct ResnetW {
+  NormW n1, n2;
+  Conv3W c1, c2;
+  LinW sc;
+  bool has_sc = false;
+  int cin = 0, cout = 0;
+  int temb_off = -1;    // column offset into the fused time_emb_proj output (-1: no temb)
+};
+
+struct TransformerW {
+  NormW gn, ln1, ln2, ln3;
+  LinW proj_in, qkv, o1, q2, kv2, o2, geglu, ff2, proj_out;
+  int C = 0, heads = 0;
+};
+
+struct VaeAttnW {
+  NormW gn;
+  LinW qk, v, proj;      // qk fused [2C, C]; v [C, C] (its bias is applied after P.V: softmax rows sum to 1)
+  float* v_bias = nullptr;
+  int C = 0;
+};
+
+enum ParamKind { P_F32 = 0, P_LINEAR, P_CONV3, P_GEGLU_W, P_GEGLU_B, P_SMALLCONV, P_F32MAT };
+
+struct ParamSlot {
+  int kind = P_F32;
+  void* dst = nullptr;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int ndim = 0;
+  int ld = 0;            // P_LINEAR: destination row pitch (elements)
+  bool loaded = false;
+};
+
+class Model {
+ public:
+  virtual ~Model();
+  int load(const char* key, const void* data, int dtype, const int64_t* shape, int ndim, cudaStream_t st);
+  int finalize();
+  int device() const { return device_; }
+  virtual bool is_unet() const = 0;
+
+ protected:
+  Model();
+  void* dalloc(size_t bytes);
+  void reg(const std::string& key, int kind, void* dst, std::initializer_list<int64_t> shape, int ld = 0);
+  void reg_norm(const std::string& p, int C, NormW* n);
+  void reg_linear(const std::string& p, int N, int K, bool bias, LinW* l);
+  void reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c);
+  void reg_smallconv(const std::string& p, int Cin, int Cout, SmallConvW* c);
+  void reg_resnet(const std::string& p, int cin, int cout, bool temb, ResnetW* r);
+  int resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __half* x2, int C2, int B, int H, int W,
+             float eps, const __half* temb_all, int temb_ld, __half* out);
+  int ensure_device();
+
+  std::unordered_map<std::string, ParamSlot> slots_;
+  std::vector<void*> allocs_;
+  int device_ = 0;
+  int groups_ = 32;
+  bool alloc_failed_ = false;
+  // fused time_emb_proj of every resnet: [temb_total, temb_dim] + bias
+  LinW temb_proj_;
+  int temb_total_ = 0;
+  int temb_dim_ = 0;
+};
+
+class UNetModel : public Model {
+ public:
+  explicit UNetModel(const gyre_b200_unet_config& cfg);
+  bool is_unet() const override { return true; }
+  int num_transformer_blocks() const { return static_cast<int>(tblocks_.size()); }
+  // dry == true sizes the workspace (ex.peak) without launching anything
+  int forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, int B, int H, int W, int L,
+              const int32_t* tome_r, __half* out);
+
+ private:
+  int transformer(Exec& ex, const TransformerW& t, const __half* x, int B, int HW, const __half* ctx, int L, int r,
+                  __half* out);
+  gyre_b200_unet_config cfg_;
+  SmallConvW conv_in_;
+  LinW time1_, time2_;
+  std::vector<ResnetW> resnets_;        // in module execution order
+  std::vector<TransformerW> tblocks_;   // in module execution order (== ToMe r-list order)
+  std::vector<Conv3W> downs_, ups_;
+  NormW norm_out_;
+  Conv3W conv_out_;
+};
+
+class VAEModel : public Model {
+ public:
+  explicit VAEModel(const gyre_b200_vae_config& cfg);
+  bool is_unet() const override { return false; }
+  int decode(Exec& ex, const __half* z, int B, int h, int w, bool postprocess, __half* img, uint8_t* img_u8);
+  int encode(Exec& ex, const __half* img, int B, int H, int W, __half* moments);
+
+ private:
+  int attn(Exec& ex, const VaeAttnW& a, const __half* x, int B, int HW, __half* out);
+  gyre_b200_vae_config cfg_;
+  // decoder
+  SmallConvW post_quant_, dec_conv_in_;
+  ResnetW dec_mid_[2];
+  VaeAttnW dec_attn_;
+  std::vector<ResnetW> dec_res_;
+  std::vector<Conv3W> dec_ups_;
+  NormW dec_norm_out_;
+  Conv3W dec_conv_out_;
+  // encoder
+  SmallConvW enc_conv_in_, quant_;
+  std::vector<ResnetW> enc_res_;
+  std::vector<Conv3W> enc_downs_;
+  ResnetW enc_mid_[2];
+  VaeAttnW enc_attn_;
+  NormW enc_norm_out_;
+  Conv3W enc_conv_out_;
+};
+
+}  // namespace gyre

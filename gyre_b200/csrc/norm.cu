@@ -62,29 +62,31 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __h
       ss[i] += xv[i] * xv[i];
     }
   }
-  __shared__ float sh[kMaxGroups * 2];
-  if (threadIdx.x < 2 * kMaxGroups) sh[threadIdx.x] = 0.f;
-  __syncthreads();
-  // fold the 8 channels into (at most a few) groups, then shared atomics (once per thread)
-  int g_prev = c0 / cpg;
-  float a = 0.f, q = 0.f;
+  // Deterministic fold: per-thread channel sums go to shared memory, then one thread per group adds its
+  // channels x row-lanes in a fixed order (no float atomics: results are bit-reproducible, which the
+  // reference's batch-independence contract, tests/batch_independance.py, is checked against).
+  extern __shared__ float sh[];            // [rpar][C][2]
+  float* mine = sh + (static_cast<size_t>(ty) * C + c0) * 2;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int g = (c0 + i) / cpg;
-    if (g != g_prev) {
-      atomicAdd(&sh[2 * g_prev], a);
-      atomicAdd(&sh[2 * g_prev + 1], q);
-      a = q = 0.f;
-      g_prev = g;
-    }
-    a += s[i];
-    q += ss[i];
+    mine[2 * i] = s[i];
+    mine[2 * i + 1] = ss[i];
   }
-  atomicAdd(&sh[2 * g_prev], a);
-  atomicAdd(&sh[2 * g_prev + 1], q);
   __syncthreads();
-  if (threadIdx.x < 2 * G)
-    partials[(static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * (2 * G) + threadIdx.x] = sh[threadIdx.x];
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float a = 0.f, q = 0.f;
+    for (int t = 0; t < rpar; ++t) {
+      const float* row = sh + (static_cast<size_t>(t) * C + g * cpg) * 2;
+      for (int c = 0; c < cpg; ++c) {
+        a += row[2 * c];
+        q += row[2 * c + 1];
+      }
+    }
+    float* dst = partials + (static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * (2 * G) + 2 * g;
+    dst[0] = a;
+    dst[1] = q;
+  }
 }
 
 // one CTA per (sample, group): merges the per-chunk (sum, sumsq) partials in fp64 -> (mean, rstd)
@@ -175,11 +177,12 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   int rpar = 256 / nvec;
   if (rpar < 1) rpar = 1;
   const int threads = nvec * rpar;
-  GYRE_REQUIRE(threads >= 2 * G, "groupnorm: too few threads for %d groups", G);
+  GYRE_REQUIRE(threads >= G, "groupnorm: too few threads for %d groups", G);
   const int chunks = (HW + kGnRows - 1) / kGnRows;
   dim3 grid(chunks, B);
   float* stats = partials + static_cast<size_t>(B) * chunks * G * 2;
-  gn_stats_kernel<<<grid, threads, 0, st>>>(x1, C1, x2, C2, HW, G, rpar, partials);
+  gn_stats_kernel<<<grid, threads, static_cast<size_t>(rpar) * C * 2 * sizeof(float), st>>>(x1, C1, x2, C2, HW, G, rpar,
+                                                                                          partials);
   gn_finalize_kernel<<<dim3(G, B), 128, 0, st>>>(partials, chunks, G, HW, C / G, eps, stats);
   gn_apply_kernel<<<grid, threads, 0, st>>>(x1, C1, x2, C2, HW, G, rpar, gamma, beta, silu ? 1 : 0, stats, out);
   GYRE_CHECK_CUDA(cudaGetLastError());

@@ -75,7 +75,6 @@ int nchw_to_nhwc_f16(const __half* x, int B, int C, int H, int W, __half* out, i
 int nhwc_to_nchw_f16(const __half* x, int ldx, int B, int C, int H, int W, __half* out, cudaStream_t st);
 int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t st);
 int concat_channels(const __half* a, int Ca, const __half* b, int Cb, int64_t rows, __half* out, cudaStream_t st);
-int transpose_rows_f16(const __half* x, int rows, int cols, int batch, __half* out, cudaStream_t st);
 int timestep_embed(const int64_t* t, int B, int dim, __half* out, cudaStream_t st);
 int silu_f16(const __half* x, int64_t n, __half* out, cudaStream_t st);
 // Direct 3x3 conv for tiny channel counts (conv_in: Cin 4/9, VAE conv_in): X NCHW-agnostic NHWC with
@@ -104,7 +103,9 @@ int sched_step(const StepScalars& s, const float* x, const __half* model_out, co
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)
 int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sample, __half* out, cudaStream_t st);
 // VAE tail: img = clamp(x/2+0.5, 0, 1): NHWC fp16 [B,H,W,ldx>=3] -> NCHW fp16 [B,3,H,W] (+ optional uint8 copy)
-int vae_tail(const __half* x, int ldx, int B, int H, int W, __half* out_nchw, uint8_t* out_u8_nhwc, cudaStream_t st);
+// postprocess=false: plain NHWC->NCHW copy of the 3 channels (the u8 copy, if requested, is always post-processed)
+int vae_tail(const __half* x, int ldx, int B, int H, int W, bool postprocess, __half* out_nchw, uint8_t* out_u8_nhwc,
+             cudaStream_t st);
 
 }  // namespace gyre
 
@@ -116,5 +117,11 @@ int cast_to_f16(const void* src, int dtype, int64_t rows, int cols, __half* dst,
 int cast_to_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st);
 int pack_geglu(const void* w, int dtype, int F, int K, const void* bias, int bias_dtype, __half* wp, float* bias_p,
                cudaStream_t st);
+// [Cout, Cin, 3, 3] -> fp32 [Cout, 3, 3, Cin] for the direct small-Cin conv
+int pack_smallconv(const void* w, int dtype, int Cin, int Cout, float* out, cudaStream_t st);
 const char* last_error();
+// ---- ToMe K/V merge (tome.cu): k, v [B, N, C] with row pitch ld -> k_out, v_out [B, N-r, C] dense
+int tome_workspace_bytes(int B, int N, int C, size_t* bytes);
+int tome_merge_kv(const __half* k, const __half* v, int ld, int B, int N, int C, int r, __half* k_out, __half* v_out,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace gyre

@@ -1,0 +1,160 @@
+"""Host-side mirror of the UNet the reference pipeline drives: an object satisfying the `DiffusersUNet`
+protocol (reference: gyre/pipeline/unet/types.py:30-39; sole call site gyre/pipeline/unet/core.py:274)
+whose forward is ONE call into libgyre_b200 (gyre_b200_unet_forward).  PyTorch only owns the memory."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _native as N
+from .config import UNetConfig
+
+
+@dataclass
+class UNetOutput:
+    """What `unet(...)` returns in the reference: an object with `.sample` (core.py:274)."""
+    sample: torch.Tensor
+
+
+def parse_r(num_layers: int, r):
+    """ToMe r expansion (reference: nonfree/ToMe/tome/utils.py:80-105, called by ToMeUNet.forward,
+    nonfree/tome_unet.py:229-247): int -> constant list; (r, inflect) -> linear ramp; list -> padded."""
+    inflect = 0
+    if isinstance(r, list):
+        if len(r) < num_layers:
+            r = r + [0] * (num_layers - len(r))
+        return list(r)
+    elif isinstance(r, tuple):
+        r, inflect = r
+    min_val = int(r * (1.0 - inflect))
+    max_val = 2 * r - min_val
+    step = (max_val - min_val) / (num_layers - 1)
+    return [int(min_val + step * i) for i in range(num_layers)]
+
+
+class B200UNet:
+    """UNet2DConditionModel replacement.  `unet(latents, t, encoder_hidden_states=ctx).sample`."""
+
+    def __init__(self, config, device=None):
+        self.config = UNetConfig.from_any(config)
+        if not torch.cuda.is_available():
+            raise N.NativeError("B200UNet needs a CUDA device: there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = torch.float16
+        self.r = 0                      # ToMe: `unet.r = int(value)` (unified_pipeline.py:1582-1584)
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        self._ws = {}
+        self._loaded = False
+        cfg = self.config
+        c = N.UNetConfigC()
+        c.in_channels, c.out_channels = cfg.in_channels, cfg.out_channels
+        c.num_levels = len(cfg.block_out_channels)
+        for i, v in enumerate(cfg.block_out_channels):
+            c.block_out_channels[i] = v
+            c.num_heads[i] = cfg.num_heads[i]
+            c.attn_levels[i] = 1 if cfg.attn_levels[i] else 0
+        c.layers_per_block = cfg.layers_per_block
+        c.cross_attention_dim = cfg.cross_attention_dim
+        c.norm_num_groups = cfg.norm_num_groups
+        c.norm_eps = cfg.norm_eps
+        c.use_linear_projection = int(cfg.use_linear_projection)
+        c.upcast_attention = int(cfg.upcast_attention)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gyre_b200_unet_create(C.byref(c), C.byref(self._h)), "unet_create")
+        self.num_transformer_blocks = self._lib.gyre_b200_unet_num_transformer_blocks(self._h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.gyre_b200_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- parameters ---------------------------------------------------------------------------------
+    def load_weight(self, key: str, tensor: torch.Tensor):
+        t = tensor.detach()
+        if t.dtype not in (torch.float16, torch.float32):
+            t = t.float()
+        t = t.to(self.device).contiguous()
+        shape = (C.c_int64 * t.ndim)(*t.shape)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gyre_b200_load_weight(self._h, key.encode(), N.ptr(t), N.dtype_code(t), shape, t.ndim,
+                                                    N.stream_ptr(self.device)), f"load_weight({key})")
+            # the packing kernels read `t` asynchronously; keep it alive until they are done
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        for k, v in state_dict.items():
+            self.load_weight(k, v)
+        if strict:
+            N.check(self._lib.gyre_b200_finalize(self._h), "finalize")
+        self._loaded = True
+        return self
+
+    # -- forward ------------------------------------------------------------------------------------
+    def _workspace(self, B, H, W, L):
+        key = (B, H, W, L)
+        ws = self._ws.get(key)
+        if ws is None:
+            n = C.c_size_t()
+            N.check(self._lib.gyre_b200_unet_workspace_bytes(self._h, B, H, W, L, C.byref(n)), "unet_workspace_bytes")
+            self._ws.clear()            # one live shape at a time is the pipeline's usage pattern
+            ws = torch.empty((n.value,), device=self.device, dtype=torch.uint8)
+            self._ws[key] = ws
+        return ws
+
+    def _timesteps(self, t, B):
+        if not torch.is_tensor(t):
+            t = torch.tensor([t], device=self.device)
+        if t.ndim == 0:
+            t = t[None]
+        if t.is_floating_point():
+            ti = t.round()
+            if not torch.equal(ti, t):
+                raise NotImplementedError("fractional timesteps are not supported (the reference quantises, "
+                                          "common_scheduler.py:342-355)")
+            t = ti
+        return t.to(device=self.device, dtype=torch.int64).expand(B).contiguous()
+
+    def tome_r_list(self):
+        if not self.r:
+            return None
+        return parse_r(self.num_transformer_blocks, self.r)
+
+    def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None):
+        """No conversions: fp16 NCHW sample, int64 [B] timesteps, fp16 [B, L, Cc] context, all on device."""
+        if not self._loaded:
+            raise N.NativeError("B200UNet: weights not loaded")
+        B, Cin, H, W = sample_f16.shape
+        L = ctx_f16.shape[1]
+        if out is None:
+            out = torch.empty((B, self.config.out_channels, H, W), device=self.device, dtype=torch.float16)
+        ws = self._workspace(B, H, W, L)
+        r_list = self.tome_r_list()
+        r_arr = (C.c_int32 * len(r_list))(*r_list) if r_list else None
+        N.check(self._lib.gyre_b200_unet_forward(self._h, N.ptr(sample_f16), N.ptr(t_i64), N.ptr(ctx_f16), B, H, W, L,
+                                                 r_arr, N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr(self.device)),
+                "unet_forward")
+        return out
+
+    def __call__(self, latents, t, *, encoder_hidden_states, down_block_additional_residuals=None,
+                 mid_block_additional_residual=None, adapter_states=None, **kwargs):
+        if down_block_additional_residuals is not None or mid_block_additional_residual is not None \
+                or adapter_states is not None:
+            # ControlNet / T2I residual injection (core.py:45-64,213-239) is a "next" row
+            raise NotImplementedError("ControlNet / T2I-adapter residuals are not supported by the B200 UNet")
+        N.require_cuda(latents, encoder_hidden_states)
+        B = latents.shape[0]
+        if latents.shape[1] != self.config.in_channels:
+            raise ValueError(f"expected {self.config.in_channels} input channels, got {latents.shape[1]}")
+        x = latents.to(torch.float16).contiguous()
+        ctx = encoder_hidden_states.to(torch.float16).contiguous()
+        if ctx.shape[0] != B:
+            raise ValueError("encoder_hidden_states batch does not match latents")
+        out = self.forward_raw(x, self._timesteps(t, B), ctx)
+        return UNetOutput(sample=out.to(latents.dtype) if latents.dtype != torch.float16 else out)

@@ -1,0 +1,135 @@
+"""Host-side mirror of AutoencoderKL as the reference pipeline uses it: `vae.decode(x).sample`
+(reference: gyre/pipeline/unified_pipeline.py:1523-1536) and
+`vae.encode(img).latent_dist.sample(generator=g)` (:305-318)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _native as N
+from .config import VAEConfig
+
+
+@dataclass
+class DecoderOutput:
+    sample: torch.Tensor
+
+
+class DiagonalGaussianDistribution:
+    """mean | logvar split, logvar clamped to [-30, 20]; sample = mean + std * randn(generator)
+    (diffusers-0.16 semantics; the draw happens on the generator's device)."""
+
+    def __init__(self, moments: torch.Tensor):
+        self.parameters = moments
+        self.mean, logvar = moments.float().chunk(2, dim=1)
+        self.logvar = logvar.clamp(-30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def sample(self, generator=None):
+        dev = generator.device if generator is not None else self.mean.device
+        noise = torch.randn(self.mean.shape, generator=generator, device=dev, dtype=self.parameters.dtype)
+        return (self.mean + self.std * noise.to(self.mean.device).float()).to(self.parameters.dtype)
+
+    def mode(self):
+        return self.mean.to(self.parameters.dtype)
+
+
+@dataclass
+class EncoderOutput:
+    latent_dist: DiagonalGaussianDistribution
+
+
+class B200VAE:
+    def __init__(self, config, device=None):
+        self.config = VAEConfig.from_any(config)
+        if not torch.cuda.is_available():
+            raise N.NativeError("B200VAE needs a CUDA device: there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = torch.float16
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        self._ws = {}
+        self._loaded = False
+        cfg = self.config
+        c = N.VAEConfigC()
+        c.in_channels, c.out_channels, c.latent_channels = cfg.in_channels, cfg.out_channels, cfg.latent_channels
+        c.num_levels = len(cfg.block_out_channels)
+        for i, v in enumerate(cfg.block_out_channels):
+            c.block_out_channels[i] = v
+        c.layers_per_block = cfg.layers_per_block
+        c.norm_num_groups = cfg.norm_num_groups
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gyre_b200_vae_create(C.byref(c), C.byref(self._h)), "vae_create")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.gyre_b200_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def load_weight(self, key, tensor):
+        t = tensor.detach()
+        if t.dtype not in (torch.float16, torch.float32):
+            t = t.float()
+        t = t.to(self.device).contiguous()
+        shape = (C.c_int64 * t.ndim)(*t.shape)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gyre_b200_load_weight(self._h, key.encode(), N.ptr(t), N.dtype_code(t), shape, t.ndim,
+                                                    N.stream_ptr(self.device)), f"load_weight({key})")
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        for k, v in state_dict.items():
+            self.load_weight(k, v)
+        if strict:
+            N.check(self._lib.gyre_b200_finalize(self._h), "finalize")
+        self._loaded = True
+        return self
+
+    def _workspace(self, B, h, w):
+        key = (B, h, w)
+        ws = self._ws.get(key)
+        if ws is None:
+            n = C.c_size_t()
+            N.check(self._lib.gyre_b200_vae_workspace_bytes(self._h, B, h, w, C.byref(n)), "vae_workspace_bytes")
+            self._ws.clear()
+            ws = torch.empty((n.value,), device=self.device, dtype=torch.uint8)
+            self._ws[key] = ws
+        return ws
+
+    def decode_raw(self, z_f16, postprocess=False, want_u8=False):
+        if not self._loaded:
+            raise N.NativeError("B200VAE: weights not loaded")
+        B, _, h, w = z_f16.shape
+        img = torch.empty((B, 3, 8 * h, 8 * w), device=self.device, dtype=torch.float16)
+        u8 = torch.empty((B, 8 * h, 8 * w, 3), device=self.device, dtype=torch.uint8) if want_u8 else None
+        ws = self._workspace(B, h, w)
+        N.check(self._lib.gyre_b200_vae_decode(self._h, N.ptr(z_f16), B, h, w, 1 if postprocess else 0, N.ptr(img),
+                                               N.ptr(u8), N.ptr(ws), ws.numel(), N.stream_ptr(self.device)),
+                "vae_decode")
+        return img, u8
+
+    def decode(self, z):
+        N.require_cuda(z)
+        img, _ = self.decode_raw(z.to(torch.float16).contiguous())
+        return DecoderOutput(sample=img if z.dtype == torch.float16 else img.to(z.dtype))
+
+    def encode(self, image):
+        if not self._loaded:
+            raise N.NativeError("B200VAE: weights not loaded")
+        N.require_cuda(image)
+        B, _, H, W = image.shape
+        if H % 8 or W % 8:
+            raise ValueError("image size must be a multiple of 8")
+        x = image.to(torch.float16).contiguous()
+        mom = torch.empty((B, 2 * self.config.latent_channels, H // 8, W // 8), device=self.device,
+                          dtype=torch.float16)
+        ws = self._workspace(B, H // 8, W // 8)
+        N.check(self._lib.gyre_b200_vae_encode(self._h, N.ptr(x), B, H, W, N.ptr(mom), N.ptr(ws), ws.numel(),
+                                               N.stream_ptr(self.device)), "vae_encode")
+        return EncoderOutput(latent_dist=DiagonalGaussianDistribution(mom.to(image.dtype)))

@@ -59,6 +59,8 @@ typedef struct gyre_b200_unet_config {
 } gyre_b200_unet_config;
 
 int gyre_b200_unet_create(const gyre_b200_unet_config* cfg, gyre_b200_handle* out);
+/* Number of transformer blocks == length of the ToMe r-list (nonfree/tome_unet.py:243). */
+int gyre_b200_unet_num_transformer_blocks(gyre_b200_handle h);
 
 /* Hands one parameter to the library under its diffusers state-dict key,
  * e.g. "down_blocks.0.resnets.0.conv1.weight".  `data` is a device pointer to a dense tensor of

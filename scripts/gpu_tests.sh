@@ -6,10 +6,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 rc=0
 for f in "$@"; do
   name=$(basename "$f" .py)
-  timeout 600 python -m pytest "$f" -m gpu -q --tb=short > "gpurun_out/$name.log" 2>&1
+  timeout 600 python -m pytest "$f" -m gpu -q -rP --tb=short > "gpurun_out/$name.log" 2>&1
   r=$?
   echo "== $f -> exit $r"
-  tail -n 25 "gpurun_out/$name.log"
+  grep -E "rel err|max abs|passed|failed|Error|error|img/s" "gpurun_out/$name.log" | tail -n 40
   [ $r -ne 0 ] && rc=$r
 done
 exit $rc

@@ -1,0 +1,175 @@
+"""UNet / VAE forward parity through the C ABI against the oracle (fp32 restatement of the reference's
+diffusers op graph) on identical synthetic weights and inputs.
+
+Tolerance model: the CUDA path keeps activations in fp16 between kernels (fp32 accumulation, fp32
+norm/softmax statistics), exactly like the reference's own fp16 GPU path, so it cannot match an fp32
+evaluation bit for bit.  The bound asserted is relative to the output scale, and the same oracle evaluated in
+fp16 by PyTorch's library kernels is reported next to it as the noise floor of fp16 evaluation."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.fixture(scope="module")
+def tiny_unet():
+    from oracle.unet import UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    unet = B200UNet(cfg).load_state_dict(P)
+    return cfg, P, unet
+
+
+def test_unet_tiny_vs_golden(tiny_unet):
+    cfg, P, unet = tiny_unet
+    g = torch.load(os.path.join(GOLD, "oracle_tiny.pt"))["unet_tiny"]
+    out = unet(g["x"].cuda().half(), g["t"].cuda(), encoder_hidden_states=g["ctx"].cuda().half()).sample
+    err = rel_err(out.cpu(), g["eps"])
+    print("tiny unet rel err vs fp32 golden:", err)
+    assert err < 2e-2
+
+
+def test_unet_tiny_taps(tiny_unet):
+    """Same forward against the oracle evaluated on the fp16-rounded inputs (isolates kernel error)."""
+    from oracle.unet import unet_forward
+    cfg, P, unet = tiny_unet
+    _no_tf32()
+    gen = torch.Generator("cpu").manual_seed(9)
+    x = torch.randn(3, 4, 16, 16, generator=gen).half()
+    ctx = torch.randn(3, 77, cfg.cross_attention_dim, generator=gen).half()
+    t = torch.tensor([999, 500, 1])
+    with torch.no_grad():
+        ref = unet_forward(P, cfg, x.float(), t, ctx.float())
+    out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample
+    err = rel_err(out.cpu(), ref)
+    print("tiny unet B=3 rel err:", err)
+    assert err < 2e-2
+    # scalar / 0-dim timesteps broadcast like the reference (`t.expand(B)`)
+    out2 = unet(x.cuda(), 500, encoder_hidden_states=ctx.cuda()).sample
+    with torch.no_grad():
+        ref2 = unet_forward(P, cfg, x.float(), 500, ctx.float())
+    assert rel_err(out2.cpu(), ref2) < 2e-2
+
+
+def test_unet_batch_independence(tiny_unet):
+    """reference tests/batch_independance.py: a sample's result must not depend on its batch mates."""
+    cfg, P, unet = tiny_unet
+    gen = torch.Generator("cpu").manual_seed(10)
+    x = torch.randn(4, 4, 16, 16, generator=gen).half().cuda()
+    ctx = torch.randn(4, 77, cfg.cross_attention_dim, generator=gen).half().cuda()
+    t = torch.tensor([10, 200, 600, 900]).cuda()
+    full = unet(x, t, encoder_hidden_states=ctx).sample.clone()
+    for i in range(4):
+        one = unet(x[i:i + 1], t[i:i + 1], encoder_hidden_states=ctx[i:i + 1]).sample
+        assert torch.equal(one[0], full[i]), f"sample {i} differs between batch 1 and batch 4"
+
+
+def test_unet_rejects_bad_input(tiny_unet):
+    cfg, P, unet = tiny_unet
+    x = torch.zeros(1, 5, 16, 16).half().cuda()
+    with pytest.raises(ValueError):
+        unet(x, 1, encoder_hidden_states=torch.zeros(1, 77, cfg.cross_attention_dim).half().cuda())
+    with pytest.raises(NotImplementedError):
+        unet(torch.zeros(1, 4, 16, 16).half().cuda(), 1,
+             encoder_hidden_states=torch.zeros(1, 77, cfg.cross_attention_dim).half().cuda(),
+             mid_block_additional_residual=torch.zeros(1))
+
+
+def test_unet_sd15_full_size():
+    """SD1.5 architecture at 64x64 latents, CFG-shaped batch of 2, against the fp32 oracle on the GPU."""
+    from oracle.unet import UNetConfig, synth_params, unet_forward, unet_param_shapes
+    from gyre_b200.unet import B200UNet
+    _no_tf32()
+    cfg = UNetConfig.sd15()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    unet = B200UNet(cfg).load_state_dict(P)
+    gen = torch.Generator("cpu").manual_seed(21)
+    x = torch.randn(2, 4, 64, 64, generator=gen).half()
+    ctx = torch.randn(2, 77, 768, generator=gen).half()
+    t = torch.tensor([981, 981])
+    Pc = {k: v.cuda() for k, v in P.items()}
+    with torch.no_grad():
+        ref = unet_forward(Pc, cfg, x.cuda().float(), t.cuda(), ctx.cuda().float())
+        Ph = {k: v.half() for k, v in Pc.items()}
+        ref16 = unet_forward(Ph, cfg, x.cuda(), t.cuda(), ctx.cuda())
+    out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample
+    err = rel_err(out, ref)
+    floor = rel_err(ref16, ref)
+    print(f"SD1.5 64x64 forward: gyre_b200 rel err {err:.3e}; torch-fp16 oracle rel err (noise floor) {floor:.3e}; "
+          f"|eps|max {ref.abs().max().item():.3f}")
+    assert torch.isfinite(out).all()
+    assert err < 2e-2
+    assert err < 4 * floor + 2e-3
+
+
+@pytest.fixture(scope="module")
+def tiny_vae():
+    from oracle.unet import synth_params
+    from oracle.vae import VAEConfig, vae_param_shapes
+    from gyre_b200.vae import B200VAE
+    cfg = VAEConfig.tiny()
+    P = synth_params(vae_param_shapes(cfg), seed=4321)
+    return cfg, P, B200VAE(cfg).load_state_dict(P)
+
+
+def test_vae_tiny_decode_vs_golden(tiny_vae):
+    cfg, P, vae = tiny_vae
+    g = torch.load(os.path.join(GOLD, "oracle_tiny.pt"))["vae_tiny"]
+    img = vae.decode(g["z"].cuda().half()).sample
+    err = rel_err(img.cpu(), g["img"])
+    print("tiny vae decode rel err:", err)
+    assert err < 2e-2
+
+
+def test_vae_tiny_encode_vs_golden(tiny_vae):
+    cfg, P, vae = tiny_vae
+    g = torch.load(os.path.join(GOLD, "oracle_tiny.pt"))["vae_tiny_enc"]
+    dist = vae.encode(g["img"].cuda().half()).latent_dist
+    err = rel_err(dist.parameters.cpu(), g["moments"])
+    print("tiny vae encode rel err:", err)
+    assert err < 2e-2
+    # sampling draws on the generator's device like the reference (unified_pipeline.py:309-313)
+    g1 = torch.Generator("cpu").manual_seed(3)
+    s1 = dist.sample(generator=g1)
+    g2 = torch.Generator("cpu").manual_seed(3)
+    noise = torch.randn(dist.mean.shape, generator=g2, dtype=dist.parameters.dtype)
+    ref = dist.mean.cpu() + dist.std.cpu() * noise.float()
+    assert (s1.cpu().float() - ref).abs().max().item() < 2e-3
+
+
+def test_vae_sd_decode_full_size():
+    """SD VAE decoder, 64x64 latent -> 512x512 image, batch 1, vs the fp32 oracle on the GPU."""
+    from oracle.unet import synth_params
+    from oracle.vae import VAEConfig, vae_decode, vae_param_shapes
+    from gyre_b200.vae import B200VAE
+    _no_tf32()
+    cfg = VAEConfig.sd()
+    P = synth_params(vae_param_shapes(cfg, encoder=True, decoder=True), seed=4321)
+    vae = B200VAE(cfg).load_state_dict(P)
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(2)).half()
+    Pc = {k: v.cuda() for k, v in P.items()}
+    with torch.no_grad():
+        ref = vae_decode(Pc, cfg, z.cuda().float())
+    img = vae.decode(z.cuda()).sample
+    err = rel_err(img, ref)
+    print(f"SD VAE decode 512x512 rel err {err:.3e}, |img|max {ref.abs().max().item():.3f}")
+    assert torch.isfinite(img).all()
+    assert err < 2e-2
+    # pipeline tail (unified_pipeline.py:2491) fused into the last kernel
+    post, u8 = vae.decode_raw(z.cuda(), postprocess=True, want_u8=True)
+    ref_post = (ref / 2 + 0.5).clamp(0, 1)
+    assert (post.float() - ref_post).abs().max().item() < 2e-2
+    assert (u8.permute(0, 3, 1, 2).float() / 255 - ref_post).abs().max().item() < 2e-2 + 1 / 255
