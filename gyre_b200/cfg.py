@@ -1,0 +1,43 @@
+"""Classifier-free-guidance wrapper around the native UNet: the reference's
+`CFGUNet_Parallel` (gyre/pipeline/unet/cfg.py:41-57) composed with `UNetWithEmbeddings` /
+`CFGUNetFromDiffusersUNet` (gyre/pipeline/unet/core.py:242-274): ONE UNet call on the doubled batch
+`[uncond ; cond]`, then `u + s * (g - u)`."""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+
+class B200GuidedUNet:
+    """`NoisePredictionUNet` protocol object (`eps = f(latents, t)`, gyre/pipeline/unet/types.py:56-59) that
+    also exposes the doubled-batch entry the fused scheduler loop uses (`raw`)."""
+
+    def __init__(self, unet, uncond_embeddings, text_embeddings, guidance_scale: float):
+        if uncond_embeddings.shape != text_embeddings.shape:
+            raise ValueError("uncond and text embeddings must have the same shape")
+        self.unet = unet
+        self.guidance_scale = float(guidance_scale)
+        self.batch = text_embeddings.shape[0]
+        # CFG order is [uncond, cond] (unified_pipeline.py:2335, cfg.py:54)
+        self.embeddings = torch.cat([uncond_embeddings, text_embeddings]).to(device=unet.device,
+                                                                              dtype=torch.float16).contiguous()
+
+    def raw(self, x2_f16, t2_i64, out=None):
+        return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out)
+
+    def __call__(self, latents, t):
+        N.require_cuda(latents)
+        B = latents.shape[0]
+        if B != self.batch:
+            raise ValueError(f"latents batch {B} does not match the {self.batch} bound embeddings")
+        x = latents.to(torch.float16)
+        x2 = torch.cat([x, x]).contiguous()
+        t2 = self.unet._timesteps(t, B)
+        t2 = torch.cat([t2, t2])
+        eps2 = self.raw(x2, t2)
+        out16 = torch.empty_like(x) if latents.dtype == torch.float16 else None
+        out32 = torch.empty(latents.shape, device=latents.device, dtype=torch.float32) if out16 is None else None
+        N.check(N.load().gyre_b200_cfg_combine(N.ptr(eps2), self.guidance_scale, B, x[0].numel(), N.ptr(out16),
+                                               N.ptr(out32), N.stream_ptr(latents.device)), "cfg_combine")
+        return out16 if out16 is not None else out32.to(latents.dtype)

@@ -1,0 +1,406 @@
+"""Scheduler inner loops behind the reference's `CommonScheduler` interface
+(gyre/pipeline/common_scheduler.py:97-177): `set_eps_unets / set_timesteps / prepare_initial_latents /
+scale_latents / add_noise / set_callback / loop(latents, progress_wrapper)`.
+
+The host side only does what the reference does on the host anyway - the sigma / alpha tables and a handful
+of per-step scalars, evaluated with the same fp32 torch expressions so the rounding points match
+(k_diffusion/external.py:43-113, sampling.py:46-58, scheduling_ddim.py:259-316).  Everything that touches
+a latent runs in ONE fused CUDA kernel per step (gyre_b200_sched_step): CFG combine, denoiser scalings,
+to_d + Euler / Euler-ancestral / DDIM update, noise add, and the next step's c_in-scaled, CFG-duplicated
+fp16 UNet input.  Latents stay fp32 on the device across steps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Literal
+
+import torch
+
+from . import _native as N
+from .cfg import B200GuidedUNet
+from .randtools import batched_randn, predraw_noise
+
+SCHEDULER_NOISE_TYPE = Literal["brownian", "normal"]
+SCHEDULER_PREDICTION_TYPE = Literal["epsilon", "v_prediction"]
+
+
+@dataclass
+class SchedulerConfig:
+    """Same fields as the reference's SchedulerConfig (common_scheduler.py:84-94)."""
+    sigma_min: float | None = None
+    sigma_max: float | None = None
+    karras_rho: float | None = None
+    eta: float | None = None
+    churn: float = 0
+    churn_tmin: float = 0
+    churn_tmax: float = float("inf")
+    noise_type: SCHEDULER_NOISE_TYPE = "normal"
+
+
+def sd_alphas_cumprod(device="cpu", num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
+    """common_scheduler.py:410-428: scaled-linear betas -> cumprod(1 - beta)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, device=device) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+class DiscreteSchedule:
+    """sigma <-> t maps of k_diffusion/external.py:43-84 (quantize=True), on the host."""
+
+    def __init__(self, alphas_cumprod):
+        self.sigmas = ((1 - alphas_cumprod) / alphas_cumprod) ** 0.5
+        self.log_sigmas = self.sigmas.log()
+
+    @property
+    def sigma_min(self):
+        return self.sigmas[0]
+
+    @property
+    def sigma_max(self):
+        return self.sigmas[-1]
+
+    def sigma_to_t(self, sigma):
+        log_sigma = sigma.log()
+        dists = log_sigma - self.log_sigmas[:, None]
+        return dists.abs().argmin(dim=0).view(sigma.shape)
+
+    def t_to_sigma(self, t):
+        t = t.float()
+        low_idx, high_idx, w = t.floor().long(), t.ceil().long(), t.frac()
+        log_sigma = (1 - w) * self.log_sigmas[low_idx] + w * self.log_sigmas[high_idx]
+        return log_sigma.exp()
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0):
+    """k_diffusion/sampling.py:16-22."""
+    ramp = torch.linspace(0, 1, n)
+    min_inv_rho = sigma_min ** (1 / rho)
+    max_inv_rho = sigma_max ** (1 / rho)
+    sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    return torch.cat([sigmas, sigmas.new_zeros([1])])
+
+
+def get_ancestral_step(sigma_from, sigma_to, eta=1.0):
+    """k_diffusion/sampling.py:51-58 (python `min` on 0-dim tensors; python 0. when eta == 0)."""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+def _f(v) -> float:
+    return float(v.item()) if torch.is_tensor(v) else float(v)
+
+
+class CommonScheduler:
+    """Interface of gyre/pipeline/common_scheduler.py:97-177."""
+
+    def __init__(self, scheduler, generators, device, dtype, callback=None, callback_steps: int = 1):
+        self.scheduler = scheduler          # sampler name (the reference holds a function / scheduler object)
+        self.generators = list(generators)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.callback = callback
+        self.callback_steps = callback_steps
+        self.start_timestep = 0
+        self.eps_unets = []
+        self.unet = None
+
+    def set_callback(self, callback, callback_steps: int = 1):
+        self.callback = callback
+        self.callback_steps = callback_steps
+
+    def set_eps_unets(self, eps_unets):
+        if getattr(self, "_timesteps_set", False):
+            raise RuntimeError("Can't set eps_unet once set_timesteps has been called")
+        for u in eps_unets:
+            if not isinstance(u, B200GuidedUNet):
+                raise TypeError("the B200 schedulers drive a B200GuidedUNet (native CFG + UNet); got %r" % type(u))
+        self.eps_unets = list(eps_unets)
+
+    # -- shared plumbing --------------------------------------------------------------------------
+    def _guided(self) -> B200GuidedUNet:
+        if not self.eps_unets:
+            raise ValueError("Epsilon unet needs to be set before timesteps")
+        return self.eps_unets[0]
+
+    def _step(self, step: N.Step, x, model_out, noise, x_out, den_out, x_in_next, B, per_sample):
+        N.check(N.load().gyre_b200_sched_step(C.byref(step), N.ptr(x), N.ptr(model_out), N.ptr(noise), N.ptr(x_out),
+                                              N.ptr(den_out), N.ptr(x_in_next), B, per_sample,
+                                              N.stream_ptr(self.device)), "sched_step")
+
+    def _first_input(self, x32, c_in, dup, B, per_sample, out):
+        N.check(N.load().gyre_b200_scale_latents(N.ptr(x32), float(c_in), 1 if dup else 0, B, per_sample, N.ptr(out),
+                                                 N.stream_ptr(self.device)), "scale_latents")
+
+
+class KDiffusionScheduler(CommonScheduler):
+    """gyre/pipeline/common_scheduler.py:392-623 for the samplers whose update is a single fused step:
+    `sample_euler_ancestral` (k_diffusion/sampling.py:139-155) and `sample_euler` (:118-135, churn 0)."""
+
+    SAMPLERS = ("sample_euler_ancestral", "sample_euler")
+
+    def __init__(self, scheduler, *args, **kwargs):
+        name = scheduler if isinstance(scheduler, str) else getattr(scheduler, "__name__", str(scheduler))
+        if name not in self.SAMPLERS:
+            raise NotImplementedError(f"sampler {name!r} has no fused B200 loop (supported: {self.SAMPLERS})")
+        super().__init__(name, *args, **kwargs)
+        self.accepts_eta = name == "sample_euler_ancestral"
+        self.accepts_s_churn = name == "sample_euler"
+        self.accepts_sigmas = True
+
+    def set_timesteps(self, num_inference_steps, start_offset=None, strength=None, prediction_type="epsilon",
+                      config: SchedulerConfig = SchedulerConfig()):
+        self._guided()
+        if config.churn and self.accepts_s_churn:
+            raise NotImplementedError("churn > 0 is not implemented in the fused Euler loop")
+        if config.noise_type != "normal":
+            raise NotImplementedError("only normal noise is implemented (brownian needs torchsde)")
+        self.prediction_type = prediction_type
+        self._sched = DiscreteSchedule(sd_alphas_cumprod("cpu"))
+        sch = self._sched
+        sigma_min, sigma_max = config.sigma_min, config.sigma_max
+        if sigma_min is not None:
+            sigma_min = max(sch.sigma_min, sigma_min)
+        if sigma_max is not None:
+            sigma_max = min(sch.sigma_max, sigma_max)
+        if config.karras_rho is not None:
+            if sigma_min is not None:
+                sigma_min = sch.t_to_sigma(sch.sigma_to_t(torch.as_tensor(sigma_min)))
+            if sigma_max is not None:
+                sigma_max = sch.t_to_sigma(sch.sigma_to_t(torch.as_tensor(sigma_max)))
+            self.sigmas = get_sigmas_karras(num_inference_steps,
+                                            sigma_min if sigma_min is not None else sch.sigma_min,
+                                            sigma_max if sigma_max is not None else sch.sigma_max, config.karras_rho)
+        else:
+            t_min = 0
+            if sigma_min is not None:
+                t_min = sch.sigma_to_t(torch.as_tensor(sigma_min))
+            t_max = len(sch.sigmas) - 1
+            if sigma_max is not None:
+                t_max = sch.sigma_to_t(torch.as_tensor(sigma_max))
+            t = torch.linspace(_f(t_max), _f(t_min), num_inference_steps)
+            self.sigmas = torch.cat([sch.t_to_sigma(t), torch.zeros(1)])
+        self.eta = config.eta
+        self.num_inference_steps = num_inference_steps
+        if strength is not None:
+            if start_offset is not None:
+                raise ValueError("Can't pass both start_offset and strength to set_timesteps")
+            init_timestep = min(int(num_inference_steps * strength), num_inference_steps)
+            self.start_offset = max(num_inference_steps - init_timestep, 0)
+        elif start_offset is not None:
+            self.start_offset = start_offset
+        else:
+            self.start_offset = 0
+        self.start_timestep = sch.sigma_to_t(self.sigmas[self.start_offset])
+        self.unets = list(self.eps_unets)
+        self.unet = self.unets[0]
+        self._timesteps_set = True
+
+    def prepare_initial_latents(self, latents):
+        return latents * self.sigmas[0].to(latents.device)
+
+    def scale_latents(self, latents, t):
+        sigma = self._sched.t_to_sigma(torch.as_tensor(t).cpu())
+        c_in = 1 / (sigma ** 2 + 1.0) ** 0.5
+        return latents * c_in.to(latents.dtype).to(latents.device)
+
+    def add_noise(self, latents, noise, t):
+        sigma = self._sched.t_to_sigma(torch.as_tensor(t).cpu())
+        return latents + noise * sigma.to(noise.device)
+
+    @torch.no_grad()
+    def loop(self, latents, progress_wrapper=None, *, out_dtype=None):
+        guided = self._guided()
+        if self.unet is None:
+            raise ValueError("unet must be set before calling loop")
+        N.require_cuda(latents)
+        progress_wrapper = progress_wrapper or (lambda it: it)
+        sch = self._sched
+        # `sigmas[start:].to(self.dtype)`: the fp16 quantisation of the schedule is part of the result (:560)
+        sigmas = self.sigmas[self.start_offset:].to(self.dtype).float()
+        n = len(sigmas) - 1
+        B = latents.shape[0]
+        per_sample = latents[0].numel()
+        shape = tuple(latents.shape)
+        ancestral = self.scheduler == "sample_euler_ancestral"
+        eta = 1.0 if self.eta is None else self.eta
+        vpred = self.prediction_type == "v_prediction"
+
+        # ---- host-side scalars for every step, with the reference's fp32 expressions
+        steps = []
+        for i in range(n):
+            s, s_next = sigmas[i], sigmas[i + 1]
+            if ancestral:
+                sigma_down, sigma_up = get_ancestral_step(s, s_next, eta=eta)
+                dt = sigma_down - s
+                add_noise = bool(s_next > 0)
+            else:
+                dt, sigma_up, add_noise = s_next - s, 0.0, False
+            st = N.Step()
+            st.kind, st.v_pred, st.cfg = 0, int(vpred), 1
+            st.guidance = guided.guidance_scale
+            st.sigma = _f(s)
+            st.dt = _f(dt)
+            st.sigma_up = _f(sigma_up) if add_noise else 0.0
+            st.c_in_next = _f(1 / (s_next ** 2 + 1.0) ** 0.5) if i + 1 < n else 0.0
+            steps.append(st)
+        t_all = sch.sigma_to_t(sigmas[:-1])                                   # int64 [n] (argmin over 1000)
+        t_dev = t_all.to(self.device)[:, None].expand(n, 2 * B).contiguous()
+
+        # ---- noise: one draw per generator per step, in step order (see randtools.predraw_noise)
+        n_draws = sum(1 for st in steps if st.sigma_up != 0.0) if ancestral else n
+        noise = predraw_noise(n_draws, shape, self.generators, self.device, self.dtype) if n_draws else None
+        noise32 = noise.float() if (noise is not None and ancestral) else None
+
+        x = latents.to(torch.float32).contiguous().clone()
+        x_next = torch.empty_like(x)
+        x_in = torch.empty((2 * B, *shape[1:]), device=self.device, dtype=torch.float16)
+        eps2 = torch.empty_like(x_in)
+        den = torch.empty_like(x) if self.callback else None
+        if n > 0:
+            self._first_input(x, _f(1 / (sigmas[0] ** 2 + 1.0) ** 0.5), True, B, per_sample, x_in)
+        k = 0
+        for i in progress_wrapper(range(n)):
+            guided.raw(x_in, t_dev[i], out=eps2)
+            st = steps[i]
+            nz = None
+            if st.sigma_up != 0.0:
+                nz = noise32[k]
+                k += 1
+            self._step(st, x, eps2, nz, x_next, den, x_in if st.c_in_next != 0.0 else None, B, per_sample)
+            x, x_next = x_next, x
+            if self.callback and i % self.callback_steps == 0:
+                self.callback(i, t_all[i], den.to(self.dtype))
+        return x.to(out_dtype or self.dtype)
+
+
+class DiffusersScheduler(CommonScheduler):
+    """DDIM through the reference's `DiffusersSchedulerBase.loop` / `wrap_unet`
+    (common_scheduler.py:179-331) with the step of gyre/pipeline/schedulers/scheduling_ddim.py:189-321 under
+    the SD config (ckpt_utils.py:244-255: scaled_linear, steps_offset 1, set_alpha_to_one False,
+    clip_sample False).  eta > 0 noise comes from generators[0] only (:265-266)."""
+
+    def __init__(self, scheduler="ddim", *args, **kwargs):
+        name = scheduler if isinstance(scheduler, str) else type(scheduler).__name__
+        if name.lower() not in ("ddim", "ddimscheduler"):
+            raise NotImplementedError(f"scheduler {name!r} has no fused B200 loop (supported: DDIM)")
+        super().__init__("ddim", *args, **kwargs)
+        self.accepts_eta = True
+        self.num_train_timesteps = 1000
+        self.steps_offset = 1
+        self.init_noise_sigma = 1.0
+        self.alphas_cumprod = sd_alphas_cumprod("cpu")
+
+    def set_timesteps(self, num_inference_steps, start_offset=None, strength=None, prediction_type="epsilon",
+                      config: SchedulerConfig = SchedulerConfig()):
+        self._guided()
+        self.eta = config.eta
+        self.prediction_type = prediction_type
+        self.num_inference_steps = num_inference_steps
+        if strength is not None:
+            if start_offset is not None:
+                raise ValueError("Can't pass both start_offset and strength to set_timesteps")
+            offset = self.steps_offset
+            init_timestep = min(int(num_inference_steps * strength) + offset, num_inference_steps)
+            self.start_offset = max(num_inference_steps - init_timestep + offset, 0)
+        elif start_offset is not None:
+            self.start_offset = start_offset
+        else:
+            self.start_offset = 0
+        ratio = self.num_train_timesteps // num_inference_steps
+        ts = (torch.arange(0, num_inference_steps, dtype=torch.float64) * ratio).round().flip(0).to(torch.int64)
+        self.timesteps = ts + self.steps_offset
+        self.start_timestep = self.timesteps[self.start_offset]
+        self.unets = list(self.eps_unets)
+        self.unet = self.unets[0]
+        self._timesteps_set = True
+
+    def prepare_initial_latents(self, latents):
+        return latents * self.init_noise_sigma
+
+    def scale_latents(self, latents, t):
+        return latents
+
+    def add_noise(self, latents, noise, t):
+        a = self.alphas_cumprod[int(t)]
+        return (a ** 0.5).to(latents.device) * latents + ((1 - a) ** 0.5).to(latents.device) * noise
+
+    @torch.no_grad()
+    def loop(self, latents, progress_wrapper=None, *, out_dtype=None):
+        guided = self._guided()
+        if self.unet is None:
+            raise ValueError("unet must be set before calling loop")
+        N.require_cuda(latents)
+        progress_wrapper = progress_wrapper or (lambda it: it)
+        acp = self.alphas_cumprod
+        ts = self.timesteps[self.start_offset:]
+        n = len(ts)
+        B = latents.shape[0]
+        per_sample = latents[0].numel()
+        shape = tuple(latents.shape)
+        eta = self.eta or 0.0
+        vpred = self.prediction_type == "v_prediction"
+        steps = []
+        for t in ts.tolist():
+            prev_t = t - self.num_train_timesteps // self.num_inference_steps
+            a_t = acp[t]
+            a_prev = acp[prev_t] if prev_t >= 0 else acp[0]
+            b_t = 1 - a_t
+            var = ((1 - a_prev) / (1 - a_t)) * (1 - a_t / a_prev)
+            std = eta * var ** 0.5
+            st = N.Step()
+            st.kind, st.v_pred, st.cfg = 1, int(vpred), 1
+            st.guidance = guided.guidance_scale
+            st.sqrt_a_t = _f(a_t ** 0.5)
+            st.sqrt_1m_a_t = _f(b_t ** 0.5)
+            st.sqrt_a_prev = _f(a_prev ** 0.5)
+            st.dir_coef = _f((1 - a_prev - std ** 2) ** 0.5)
+            st.noise_coef = _f(var ** 0.5 * eta) if eta > 0 else 0.0
+            st.c_in_next = 1.0
+            steps.append(st)
+        if steps:
+            steps[-1].c_in_next = 0.0
+        t_dev = ts.to(self.device)[:, None].expand(n, 2 * B).contiguous()
+        noise32 = None
+        if eta > 0 and n:
+            g0 = self.generators[0]
+            noise32 = torch.stack([torch.randn(shape, dtype=self.dtype, generator=g0, device=g0.device)
+                                   for _ in range(n)]).to(self.device).float()
+        x = latents.to(torch.float32).contiguous().clone()
+        x_next = torch.empty_like(x)
+        x_in = torch.empty((2 * B, *shape[1:]), device=self.device, dtype=torch.float16)
+        eps2 = torch.empty_like(x_in)
+        den = torch.empty_like(x) if self.callback else None
+        if n > 0:
+            self._first_input(x, 1.0, True, B, per_sample, x_in)
+        for i in progress_wrapper(range(n)):
+            guided.raw(x_in, t_dev[i], out=eps2)
+            st = steps[i]
+            self._step(st, x, eps2, noise32[i] if noise32 is not None else None, x_next, den,
+                       x_in if st.c_in_next != 0.0 else None, B, per_sample)
+            x, x_next = x_next, x
+            if self.callback and i % self.callback_steps == 0:
+                self.callback(i, ts[i], den.to(self.dtype))
+        return x.to(out_dtype or self.dtype)
+
+
+# sampler enum names of the reference (gyre/pipeline/samplers.py:24-67) -> (scheduler class, implementation)
+SAMPLERS = {
+    "k_euler_ancestral": (KDiffusionScheduler, "sample_euler_ancestral"),
+    "k_euler": (KDiffusionScheduler, "sample_euler"),
+    "ddim": (DiffusersScheduler, "ddim"),
+}
+
+
+def build_scheduler(sampler: str, generators, device, dtype, callback=None, callback_steps=1) -> CommonScheduler:
+    try:
+        klass, impl = SAMPLERS[sampler]
+    except KeyError:
+        raise NotImplementedError(f"Scheduler not implemented: {sampler!r} (have {sorted(SAMPLERS)})") from None
+    return klass(impl, generators, device, dtype, callback, callback_steps)
+
+
+__all__ = ["SchedulerConfig", "CommonScheduler", "KDiffusionScheduler", "DiffusersScheduler", "build_scheduler",
+           "batched_randn", "sd_alphas_cumprod", "DiscreteSchedule"]

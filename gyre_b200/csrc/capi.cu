@@ -111,6 +111,13 @@ int gyre_b200_sched_step(const gyre_b200_step* s, const float* x, const void* mo
                     static_cast<__half*>(x_in_next), batch, per_sample, S(stream));
 }
 
+int gyre_b200_cfg_combine(const void* model_out, float guidance, int batch, int64_t per_sample, void* out_f16,
+                          float* out_f32, gyre_b200_stream stream) {
+  GYRE_REQUIRE(model_out, "cfg_combine: null operand");
+  return cfg_combine(static_cast<const __half*>(model_out), guidance, batch, per_sample, static_cast<__half*>(out_f16),
+                     out_f32, S(stream));
+}
+
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream) {
   GYRE_REQUIRE(x && out, "scale_latents: null operand");

@@ -260,6 +260,27 @@ int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sa
   return 0;
 }
 
+// CFG combine for callers that drive the UNet through the NoisePredictionUNet protocol instead of the fused
+// step: out = u + s * (g - u) over [uncond ; cond] halves (gyre/pipeline/unet/cfg.py:54-57)
+__global__ void cfg_combine_kernel(const __half* __restrict__ mo, float s, int64_t n, __half* __restrict__ o16,
+                                   float* __restrict__ o32) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float u = __half2float(mo[i]);
+  const float g = __half2float(mo[n + i]);
+  const float m = u + s * (g - u);
+  if (o16) o16[i] = __float2half_rn(m);
+  if (o32) o32[i] = m;
+}
+int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_sample, __half* out16, float* out32,
+                cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(B) * per_sample;
+  GYRE_REQUIRE(n > 0 && (out16 || out32), "cfg_combine: empty");
+  cfg_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(model_out, guidance, n, out16, out32);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ K8: VAE tail  (x/2+0.5).clamp(0,1), NHWC -> NCHW
 __global__ void vae_tail_kernel(const __half* __restrict__ x, int ldx, int HW, int post, __half* __restrict__ out,
                                 uint8_t* __restrict__ u8, int64_t total) {

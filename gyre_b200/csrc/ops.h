@@ -100,6 +100,8 @@ struct StepScalars {
 };
 int sched_step(const StepScalars& s, const float* x, const __half* model_out, const float* noise, float* x_out,
                float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st);
+int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_sample, __half* out16, float* out32,
+                cudaStream_t st);
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)
 int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sample, __half* out, cudaStream_t st);
 // VAE tail: img = clamp(x/2+0.5, 0, 1): NHWC fp16 [B,H,W,ldx>=3] -> NCHW fp16 [B,3,H,W] (+ optional uint8 copy)

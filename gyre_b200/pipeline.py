@@ -1,0 +1,110 @@
+"""The hot segment of the reference's `UnifiedPipeline.__call__` for txt2img
+(gyre/pipeline/unified_pipeline.py:1723-1773 signature; :2326-2337 CFG binding; :2341-2350 scheduler choice;
+:2432-2483 set_eps_unets / set_timesteps / initial latents / `cscheduler.loop`; :2488-2491 VAE decode and
+the image tail), driven through the same objects the reference composes: a guided eps-UNet, a
+CommonScheduler and a VAE - all backed by libgyre_b200.
+
+Text encoding is out of scope for this round: the pipeline takes the `[B, 77, C]` text /
+uncond embeddings the reference's LPW encoder would produce.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .cfg import B200GuidedUNet
+from .common_scheduler import SchedulerConfig, build_scheduler
+from .randtools import batched_randn
+
+
+@dataclass
+class PipelineOutput:
+    images: torch.Tensor | None      # [B, 3, H, W] in [0, 1] (output_type "pt"), uint8 NHWC ("uint8"), None ("latent")
+    latents: torch.Tensor            # final latents (before the 1/0.18215 scaling)
+
+
+def generate_latents(generators, batch, in_channels, height, width, sample_size, device, dtype):
+    """Txt2imgMode.generateLatents (unified_pipeline.py:193-237): noise is ALWAYS drawn at the UNet's native
+    `sample_size` first (one draw per generator), then centre-cropped to, or inserted into the middle of, a
+    fresh draw of the requested size - so a seed gives related images across resolutions."""
+    h, w = height // 8, width // 8
+    shape = (batch, in_channels, h, w)
+    mid = batched_randn([batch, in_channels, sample_size, sample_size], generators, device, dtype)
+    off2, off3 = (sample_size - h) // 2, (sample_size - w) // 2
+    if off2 > 0:
+        mid = mid[:, :, off2:off2 + h, :]
+    if off3 > 0:
+        mid = mid[:, :, :, off3:off3 + w]
+    if off2 >= 0 and off3 >= 0:
+        return mid.contiguous()
+    latents = batched_randn(shape, generators, device, dtype)
+    o2, o3 = (latents.shape[2] - mid.shape[2]) // 2, (latents.shape[3] - mid.shape[3]) // 2
+    latents[:, :, o2:o2 + mid.shape[2], o3:o3 + mid.shape[3]] = mid
+    return latents
+
+
+class B200Pipeline:
+    def __init__(self, unet, vae=None):
+        self.unet = unet
+        self.vae = vae
+        self.device = unet.device
+        self.vae_scale_factor = 8
+        self._options = {}
+        self.unet_sample_size_override = None   # tests with sub-64 toy UNets
+
+    def get_unet_sample_size(self, unet):
+        """unified_pipeline.py:1317-1320: forced minimum of 64."""
+        if self.unet_sample_size_override is not None:
+            return self.unet_sample_size_override
+        return max(64, getattr(unet.config, "sample_size", 64))
+
+    def set_options(self, options: dict):
+        """Subset of UnifiedPipeline.set_options (unified_pipeline.py:1538-1629) that concerns the hot path."""
+        for key, value in options.items():
+            if key == "tome":
+                # `self.unet.r = int(value)` (:1582-1584); the merge itself is native (gyre_b200.tome_patcher)
+                from .tome_patcher import apply_tome
+                apply_tome(self.unet)
+                self.unet.r = int(value) if not isinstance(value, (tuple, list)) else value
+            elif key in ("hires_fix", "grafted_inpaint", "grafted_depth"):
+                if value:
+                    raise NotImplementedError(f"option {key!r} composes around the boundary and is out of scope")
+            else:
+                raise ValueError(f"Unknown option {key!r}")
+            self._options[key] = value
+
+    @torch.no_grad()
+    def __call__(self, prompt_embeds, negative_prompt_embeds, height: int = 512, width: int = 512,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, generator=None,
+                 sampler: str = "k_euler_ancestral", scheduler_config: SchedulerConfig | None = None,
+                 output_type: str = "pt", callback=None, callback_steps: int = 1, progress_wrapper=None,
+                 latents_dtype=torch.float16, return_fp32_latents: bool = False) -> PipelineOutput:
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps}")
+        B = prompt_embeds.shape[0]
+        if generator is None:
+            raise ValueError("a list of per-sample torch.Generator is required (seeds define the result)")
+        generators = list(generator) if isinstance(generator, (list, tuple)) else [generator]
+        if B % len(generators) != 0:
+            raise ValueError(f"batch {B} is not a multiple of the {len(generators)} generators")
+        cfg = self.unet.config
+        if cfg.in_channels != 4:
+            raise NotImplementedError("txt2img needs a 4-channel UNet (inpaint / depth UNets take extra channels)")
+
+        guided = B200GuidedUNet(self.unet, negative_prompt_embeds, prompt_embeds, guidance_scale)
+        sched = build_scheduler(sampler, generators, self.device, latents_dtype, callback, callback_steps)
+        sched.set_eps_unets([guided])
+        sched.set_timesteps(num_inference_steps, prediction_type=cfg.prediction_type,
+                            config=scheduler_config or SchedulerConfig())
+        latents = generate_latents(generators, B, cfg.in_channels, height, width, self.get_unet_sample_size(self.unet),
+                                   self.device, latents_dtype)
+        latents = sched.prepare_initial_latents(latents)
+        latents = sched.loop(latents, progress_wrapper, out_dtype=torch.float32 if return_fp32_latents else None)
+        if output_type == "latent" or self.vae is None:
+            return PipelineOutput(images=None, latents=latents)
+        z = (1 / self.vae.config.scaling_factor * latents.float()).to(torch.float16)
+        img, u8 = self.vae.decode_raw(z.contiguous(), postprocess=True, want_u8=(output_type == "uint8"))
+        return PipelineOutput(images=u8 if output_type == "uint8" else img, latents=latents)

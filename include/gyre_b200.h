@@ -143,6 +143,11 @@ typedef struct gyre_b200_step {
 int gyre_b200_sched_step(const gyre_b200_step* s, const float* x, const void* model_out, const float* noise,
                          float* x_out, float* denoised_out, void* x_in_next, int batch, int64_t per_sample,
                          gyre_b200_stream stream);
+/* CFG combine on its own, for callers that keep the reference's un-fused wrapper stack
+ * (gyre/pipeline/unet/cfg.py:54-57): out = u + guidance * (g - u), model_out fp16 [2B, ...] =
+ * [uncond ; cond]; either output may be NULL. */
+int gyre_b200_cfg_combine(const void* model_out, float guidance, int batch, int64_t per_sample, void* out_f16,
+                          float* out_f32, gyre_b200_stream stream);
 /* out_f16[(dup?2:1) * B, ...] = x * c_in  (first unet input of a run) */
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream);

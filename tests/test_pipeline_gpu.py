@@ -1,0 +1,126 @@
+"""Scheduler loop + pipeline parity: the native path (fused step kernel + native UNet) against the oracle's
+restatement of the reference loop on identical seeds.  The oracle runs fp32; the CUDA path runs fp16
+activations, so final-latent tolerances are stated relative to the latent scale."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from oracle.unet import UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    unet = B200UNet(cfg).load_state_dict(P)
+    pipe = B200Pipeline(unet, None)
+    pipe.unet_sample_size_override = 16
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(11))
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1)
+    return cfg, P, pipe, emb, unc
+
+
+@pytest.mark.parametrize("sampler,name,steps", [("ddim", "ddim", 10), ("k_euler_ancestral", "euler_a", 12),
+                                                ("k_euler", "euler", 8)])
+def test_pipeline_tiny_vs_golden(tiny, sampler, name, steps):
+    """Golden latents were produced by the oracle with fp32 latents / schedule (scripts/make_golden.py)."""
+    cfg, P, pipe, emb, unc = tiny
+    g = torch.load(os.path.join(GOLD, "oracle_tiny.pt"))[f"pipe_tiny/{name}"]
+    gens = [torch.Generator("cpu").manual_seed(s) for s in (420420420, 420420421)]
+    out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
+               generator=gens, sampler=sampler, output_type="latent", latents_dtype=torch.float32,
+               return_fp32_latents=True)
+    ref = g["latents"]
+    err = (out.latents.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"pipeline tiny {sampler}: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
+    assert err < 2e-2 * scale
+
+
+def test_scheduler_step_kernel_matches_vendored_loop():
+    """Euler-a with an analytic eps model: the fused step kernel reproduces the golden vectors that
+    scripts/make_golden.py took from the reference's vendored k-diffusion `sample_euler_ancestral`."""
+    import ctypes as C
+    from gyre_b200 import _native as N
+    from gyre_b200.common_scheduler import DiscreteSchedule, get_ancestral_step, sd_alphas_cumprod
+    from gyre_b200.randtools import batched_randn
+    g = torch.load(os.path.join(GOLD, "samplers.pt"))
+    for dtype_name, ldt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        rec = g[f"euler_a/20/{dtype_name}"]
+        shape, seeds, sig_full = rec["shape"], rec["seeds"], rec["sigmas"]
+        gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+        sch = DiscreteSchedule(sd_alphas_cumprod())
+        x = (batched_randn(shape, gens, "cpu", ldt) * sig_full[0]).float().cuda()
+        sig = sig_full.to(ldt).float()
+        B, per = shape[0], shape[1] * shape[2] * shape[3]
+        for i in range(len(sig) - 1):
+            s, sn = sig[i], sig[i + 1]
+            c_in = 1 / (s ** 2 + 1.0) ** 0.5
+            t = sch.sigma_to_t(s * torch.ones(B))
+            xin = x * c_in.cuda()
+            tt = t.float().reshape(-1, 1, 1, 1).cuda()
+            eps = 0.7 * torch.tanh(xin) + 0.001 * tt * xin.roll(1, -1)          # toy_eps of make_golden.py
+            sd, su = get_ancestral_step(s, sn)
+            st = N.Step()
+            st.kind, st.cfg, st.v_pred, st.guidance = 0, 0, 0, 1.0
+            st.sigma, st.dt = float(s), float(sd - s)
+            st.sigma_up = float(su) if sn > 0 else 0.0
+            st.c_in_next = 0.0
+            noise = batched_randn(shape, gens, "cuda", ldt).float() if sn > 0 else None
+            # the kernel takes the model output in fp16; feed eps through an fp32->fp16 split to keep the
+            # comparison about the step arithmetic: run twice (hi + lo parts) is overkill - use tolerance
+            out = torch.empty_like(x)
+            N.check(N.load().gyre_b200_sched_step(C.byref(st), N.ptr(x), N.ptr(eps.half()), N.ptr(noise), N.ptr(out),
+                                                  None, None, B, per, N.stream_ptr()), "sched_step")
+            x = out
+        err = (x.cpu() - rec["result"]).abs().max().item()
+        print(f"euler_a/20/{dtype_name}: step-kernel loop max abs err vs vendored k-diffusion {err:.3e}")
+        assert err < 5e-2   # eps is rounded to fp16 on entry (~5e-4 relative on sigma<=14.6 scaled terms)
+
+
+def test_pipeline_callback_and_cancel(tiny):
+    cfg, P, pipe, emb, unc = tiny
+    gens = [torch.Generator("cpu").manual_seed(s) for s in (1, 2)]
+    seen = []
+    pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=6, generator=gens,
+         sampler="k_euler_ancestral", output_type="latent", callback=lambda i, t, x0: seen.append((i, int(t), x0.shape)),
+         callback_steps=2)
+    assert [s[0] for s in seen] == [0, 2, 4]
+
+    class Abort(Exception):
+        pass
+
+    def wrapper(it):       # the reference cancels by raising from the progress iterator (pipeline_wrapper.py:34-47)
+        for j in it:
+            if j == 3:
+                raise Abort()
+            yield j
+    gens = [torch.Generator("cpu").manual_seed(s) for s in (1, 2)]
+    with pytest.raises(Abort):
+        pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=6, generator=gens,
+             sampler="k_euler_ancestral", output_type="latent", progress_wrapper=wrapper)
+    # and the pipeline is still usable afterwards
+    gens = [torch.Generator("cpu").manual_seed(s) for s in (1, 2)]
+    out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=2, generator=gens,
+               sampler="ddim", output_type="latent")
+    assert torch.isfinite(out.latents).all()
+
+
+def test_pipeline_batch_independence(tiny):
+    """reference tests/batch_independance.py:16-26: seeds [1,2] together == seed 1 alone, seed 2 alone."""
+    cfg, P, pipe, emb, unc = tiny
+
+    def run(idx):
+        gens = [torch.Generator("cpu").manual_seed(100 + i) for i in idx]
+        e = emb[idx].cuda()
+        u = unc[idx].cuda()
+        return pipe(e, u, height=128, width=128, num_inference_steps=5, generator=gens, sampler="k_euler_ancestral",
+                    output_type="latent", return_fp32_latents=True).latents
+    both = run([0, 1])
+    assert torch.equal(run([0])[0], both[0])
+    assert torch.equal(run([1])[0], both[1])
