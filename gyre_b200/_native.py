@@ -56,6 +56,11 @@ _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 SIGNATURES = {
     "gyre_b200_abi_version": (_i, []),
     "gyre_b200_last_error": (_i, [C.c_char_p, _sz]),
+    "gyre_b200_launch_count": (C.c_ulonglong, []),
+    "gyre_b200_prof_enable": (_i, [_i]),
+    "gyre_b200_prof_reset": (_i, []),
+    "gyre_b200_prof_read": (_i, [_i, C.POINTER(C.c_ulonglong), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double)]),
     "gyre_b200_unet_create": (_i, [C.POINTER(UNetConfigC), C.POINTER(_vp)]),
     "gyre_b200_unet_num_transformer_blocks": (_i, [_vp]),
     "gyre_b200_load_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i, _vp]),
@@ -264,4 +269,29 @@ def attention(q, k, v, heads, scale=None):
             raise NativeError("attention operands must be [B, N, *] views with dense batch stride")
     check(load().gyre_b200_attention(ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1), B, heads, Nq, Nk,
                                      d, scale, ptr(out), Cc, stream_ptr(q.device)), "attention")
+    return out
+
+
+FAMILIES = ("gemm", "conv3x3", "attention", "groupnorm", "layernorm", "softmax", "elementwise", "tome")
+
+
+def launch_count() -> int:
+    return int(load().gyre_b200_launch_count())
+
+
+def prof_enable(on: bool):
+    load().gyre_b200_prof_enable(1 if on else 0)
+
+
+def prof_reset():
+    load().gyre_b200_prof_reset()
+
+
+def prof_read() -> dict:
+    """{family: {count, ms, flops, bytes}} since the last reset (synchronises the device)."""
+    out = {}
+    for i, name in enumerate(FAMILIES):
+        c, ms, fl, by = C.c_ulonglong(), C.c_double(), C.c_double(), C.c_double()
+        check(load().gyre_b200_prof_read(i, C.byref(c), C.byref(ms), C.byref(fl), C.byref(by)), "prof_read")
+        out[name] = {"count": c.value, "ms": ms.value, "flops": fl.value, "bytes": by.value}
     return out

@@ -323,6 +323,8 @@ int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __ha
   const long long blocks = static_cast<long long>(B) * heads * p.q_tiles;
   GYRE_REQUIRE(blocks < (1ll << 31), "attention: grid too large");
   const int dch = (d + 63) / 64;
+  prof::Scope ps(prof::F_ATTN, 4.0 * B * heads * static_cast<double>(Nq) * Nk * d,
+                 2.0 * B * heads * d * (2.0 * Nq + 2.0 * Nk), st);
   switch (dch) {
     case 1: return launch_attn<1>(tq, tk, tv, p, blocks, st);
     case 2: return launch_attn<2>(tq, tk, tv, p, blocks, st);

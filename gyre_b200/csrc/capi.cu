@@ -44,6 +44,20 @@ int gyre_b200_last_error(char* buf, size_t n) {
   return static_cast<int>(len);
 }
 
+unsigned long long gyre_b200_launch_count(void) { return prof::launch_count(); }
+int gyre_b200_prof_enable(int on) {
+  prof::enable(on);
+  return 0;
+}
+int gyre_b200_prof_reset(void) {
+  prof::reset();
+  return 0;
+}
+int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, double* flops, double* bytes) {
+  GYRE_REQUIRE(family >= 0 && family < prof::F_COUNT, "prof_read: family %d", family);
+  return prof::read(family, count, ms, flops, bytes);
+}
+
 int gyre_b200_gemm(const void* A, int lda, int K1, const void* A2, int lda2, int K2, const void* W, int ldw, int M,
                    int N, const gyre_b200_epilogue* ep, gyre_b200_stream stream) {
   Epilogue e;

@@ -23,6 +23,7 @@ __global__ void nchw_to_nhwc_kernel(const __half* __restrict__ x, int C, int HW,
 int nchw_to_nhwc_f16(const __half* x, int B, int C, int H, int W, __half* out, int ldo, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(B) * C * H * W;
   GYRE_REQUIRE(total > 0, "nchw_to_nhwc: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, C, H * W, out, ldo, total);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -40,6 +41,7 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int ldx, int C
 int nhwc_to_nchw_f16(const __half* x, int ldx, int B, int C, int H, int W, __half* out, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(B) * C * H * W;
   GYRE_REQUIRE(total > 0, "nhwc_to_nchw: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, C, H * W, out, total);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -62,6 +64,7 @@ int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cu
   GYRE_REQUIRE(C % 8 == 0, "upsample2x: C must be a multiple of 8");
   const int64_t total = static_cast<int64_t>(B) * 4 * H * W * (C / 8);
   GYRE_REQUIRE(total > 0, "upsample2x: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   upsample2x_kernel<<<blocks_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), H, W, C / 8,
                                                             reinterpret_cast<uint4*>(out), total);
   GYRE_CHECK_CUDA(cudaGetLastError());
@@ -82,6 +85,7 @@ int concat_channels(const __half* a, int Ca, const __half* b, int Cb, int64_t ro
   GYRE_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat: channel counts must be multiples of 8");
   const int64_t total = rows * ((Ca + Cb) / 8);
   GYRE_REQUIRE(total > 0, "concat: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   concat_kernel<<<blocks_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a), Ca / 8,
                                                         reinterpret_cast<const uint4*>(b), Cb / 8,
                                                         reinterpret_cast<uint4*>(out), total);
@@ -103,6 +107,7 @@ __global__ void timestep_embed_kernel(const int64_t* __restrict__ t, int dim, __
 }
 int timestep_embed(const int64_t* t, int B, int dim, __half* out, cudaStream_t st) {
   GYRE_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, "timestep_embed: bad shape");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   timestep_embed_kernel<<<B, 128, 0, st>>>(t, dim, out);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -116,6 +121,7 @@ __global__ void silu_kernel(const __half* __restrict__ x, int64_t n, __half* __r
 }
 int silu_f16(const __half* x, int64_t n, __half* out, cudaStream_t st) {
   GYRE_REQUIRE(n > 0, "silu: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   silu_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, n, out);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -162,6 +168,7 @@ int conv3x3_small_cin(const __half* X, int B, int H, int W, int Cin, const float
   GYRE_REQUIRE(Cout % 8 == 0 && Cin > 0 && Cin <= 16, "conv3x3_small: Cin<=16, Cout%%8==0 (got %d,%d)", Cin, Cout);
   const int64_t total = static_cast<int64_t>(B) * H * W * (Cout / 8);
   GYRE_REQUIRE(total > 0, "conv3x3_small: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   conv3x3_small_kernel<<<blocks_for(total, 128), 128, 0, st>>>(X, H, W, Cin, Wt, bias, Cout, out, total);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -180,6 +187,7 @@ __global__ void conv1x1_small_kernel(const __half* __restrict__ X, int64_t rows,
 int conv1x1_small(const __half* X, int64_t rows, int Cin, const float* Wt, const float* bias, int Cout, __half* out,
                   cudaStream_t st) {
   GYRE_REQUIRE(rows > 0 && Cin > 0 && Cout > 0, "conv1x1_small: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   conv1x1_small_kernel<<<blocks_for(rows * Cout, 256), 256, 0, st>>>(X, rows, Cin, Wt, bias, Cout, out);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -239,6 +247,7 @@ int sched_step(const StepScalars& s, const float* x, const __half* model_out, co
   GYRE_REQUIRE(n > 0, "sched_step: empty");
   GYRE_REQUIRE(!((s.sigma_up != 0.f || (s.kind == 1 && s.noise_coef != 0.f)) && noise == nullptr),
                "sched_step: noise required");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   sched_step_kernel<<<blocks_for(n, 256), 256, 0, st>>>(s, x, model_out, noise, x_out, denoised_out,
                                                         s.c_in_next != 0.f ? x_in_next : nullptr, n);
   GYRE_CHECK_CUDA(cudaGetLastError());
@@ -255,6 +264,7 @@ __global__ void scale_dup_kernel(const float* __restrict__ x, float c_in, int du
 int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sample, __half* out, cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(B) * per_sample;
   GYRE_REQUIRE(n > 0, "scale_dup: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   scale_dup_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, c_in, dup, n, out);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -276,6 +286,7 @@ int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_samp
                 cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(B) * per_sample;
   GYRE_REQUIRE(n > 0 && (out16 || out32), "cfg_combine: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   cfg_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(model_out, guidance, n, out16, out32);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -300,6 +311,7 @@ int vae_tail(const __half* x, int ldx, int B, int H, int W, bool postprocess, __
              cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(B) * H * W;
   GYRE_REQUIRE(total > 0, "vae_tail: empty");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   vae_tail_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, H * W, postprocess ? 1 : 0, out_nchw, out_u8_nhwc, total);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;

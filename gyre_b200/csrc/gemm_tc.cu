@@ -412,6 +412,8 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
     uint32_t es[2] = {1, 1};
     GYRE_TRY(encode_tmap_f16(&tmB, W, 2, dims, strides, box, es, true));
   }
+  prof::Scope ps(prof::F_GEMM, 2.0 * M * (ep.act == ACT_GEGLU ? N : N) * K,
+                 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * (ep.act == ACT_GEGLU ? N / 2 : N)), st);
   return dispatch(bn, tmA, tmA2, tmB, p, (M + kBM - 1) / kBM, st);
 }
 
@@ -491,6 +493,8 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
     GYRE_TRY(encode_tmap_f16(&tmB, Wp, 2, dims, strides, box, es, true));
   }
   const int m_tiles = p.tiles_x * p.tiles_y * ((B + best_n - 1) / best_n);
+  prof::Scope ps(prof::F_CONV, 2.0 * 9 * Cin * Cout * static_cast<double>(B) * Ho * Wo,
+                 2.0 * (static_cast<double>(B) * H * W * Cin + 9.0 * Cin * Cout + static_cast<double>(B) * Ho * Wo * Cout), st);
   return dispatch(bn, tmA, tmA, tmB, p, m_tiles, st);
 }
 

@@ -181,6 +181,7 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   const int chunks = (HW + kGnRows - 1) / kGnRows;
   dim3 grid(chunks, B);
   float* stats = partials + static_cast<size_t>(B) * chunks * G * 2;
+  prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 3);
   gn_stats_kernel<<<grid, threads, static_cast<size_t>(rpar) * C * 2 * sizeof(float), st>>>(x1, C1, x2, C2, HW, G, rpar,
                                                                                           partials);
   gn_finalize_kernel<<<dim3(G, B), 128, 0, st>>>(partials, chunks, G, HW, C / G, eps, stats);
@@ -247,6 +248,7 @@ int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gam
                    cudaStream_t st) {
   GYRE_REQUIRE(rows > 0 && C > 0, "layernorm: empty input");
   GYRE_REQUIRE(C % 8 == 0 && C <= 2048, "layernorm: C=%d must be a multiple of 8 and <= 2048", C);
+  prof::Scope ps(prof::F_LAYERNORM, 0.0, 2.0 * 2.0 * rows * C, st);
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 
 int softmax_rows_f32(const float* s, int rows, int n, float scale, __half* p, int ldp, cudaStream_t st) {
   GYRE_REQUIRE(rows > 0 && n > 0 && ldp >= n, "softmax: bad shape");
+  prof::Scope ps(prof::F_SOFTMAX, 0.0, static_cast<double>(rows) * n * 6.0, st);
   softmax_rows_kernel<<<rows, 256, 0, st>>>(s, n, scale, p, ldp);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -127,3 +127,27 @@ int tome_workspace_bytes(int B, int N, int C, size_t* bytes);
 int tome_merge_kv(const __half* k, const __half* v, int ld, int B, int N, int C, int r, __half* k_out, __half* v_out,
                   void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace gyre
+
+namespace gyre {
+namespace prof {
+// Kernel families for the launch counter and the optional CUDA-event profiler (bench.py's roofline leg).
+enum Family { F_GEMM = 0, F_CONV = 1, F_ATTN = 2, F_GROUPNORM = 3, F_LAYERNORM = 4, F_SOFTMAX = 5, F_ELEMENTWISE = 6,
+              F_TOME = 7, F_COUNT = 8 };
+unsigned long long launch_count();
+void enable(int on);
+bool enabled();
+void reset();
+int read(int family, unsigned long long* count, double* ms, double* flops, double* bytes);
+// RAII: counts `kernels` launches; when profiling is enabled brackets them with events on `st`.
+class Scope {
+ public:
+  Scope(int family, double flops, double bytes, cudaStream_t st, int kernels = 1);
+  ~Scope();
+ private:
+  int family_;
+  double flops_, bytes_;
+  cudaStream_t st_;
+  void* e0_;
+};
+}  // namespace prof
+}  // namespace gyre

@@ -3,9 +3,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
+#include "ops.h"
 
 namespace gyre {
 
@@ -62,4 +65,83 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
   return 0;
 }
 
+
+// ------------------------------------------------------------------ launch counter + per-family event profiler
+namespace prof {
+
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_enabled{0};
+struct Rec {
+  int family;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_mu;
+static std::vector<Rec> g_recs;
+static std::vector<cudaEvent_t> g_pool;
+
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) {
+    cudaEvent_t e = g_pool.back();
+    g_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+unsigned long long launch_count() { return g_launches.load(); }
+void enable(int on) { g_enabled.store(on); }
+bool enabled() { return g_enabled.load() != 0; }
+
+void reset() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& r : g_recs) {
+    g_pool.push_back(r.e0);
+    g_pool.push_back(r.e1);
+  }
+  g_recs.clear();
+}
+
+Scope::Scope(int family, double flops, double bytes, cudaStream_t st, int kernels)
+    : family_(family), flops_(flops), bytes_(bytes), st_(st), e0_(nullptr) {
+  g_launches.fetch_add(static_cast<unsigned long long>(kernels));
+  if (enabled()) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    e0_ = get_event();
+    cudaEventRecord(static_cast<cudaEvent_t>(e0_), st_);
+  }
+}
+
+Scope::~Scope() {
+  if (e0_) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaEvent_t e1 = get_event();
+    cudaEventRecord(e1, st_);
+    g_recs.push_back(Rec{family_, flops_, bytes_, static_cast<cudaEvent_t>(e0_), e1});
+  }
+}
+
+int read(int family, unsigned long long* count, double* ms, double* flops, double* bytes) {
+  GYRE_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_mu);
+  unsigned long long c = 0;
+  double t = 0, f = 0, b = 0;
+  for (auto& r : g_recs) {
+    if (r.family != family) continue;
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, r.e0, r.e1) == cudaSuccess) t += e;
+    ++c;
+    f += r.flops;
+    b += r.bytes;
+  }
+  if (count) *count = c;
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (bytes) *bytes = b;
+  return 0;
+}
+
+}  // namespace prof
 }  // namespace gyre

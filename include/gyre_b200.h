@@ -39,6 +39,19 @@ int gyre_b200_abi_version(void);
 int gyre_b200_last_error(char* buf, size_t n);
 
 /* ------------------------------------------------------------------------------------------
+ * Measurement hooks (no reference counterpart: the reference only prints wall time and peak VRAM,
+ * tests/test_harness.py:155-166).  launch_count: kernels this library has launched in this process.
+ * prof_*: when enabled, every op brackets its kernels with CUDA events on the launching stream;
+ * prof_read synchronises the device and returns, per kernel family (0 gemm, 1 conv3x3, 2 attention,
+ * 3 groupnorm, 4 layernorm, 5 softmax, 6 elementwise, 7 tome), the launch-group count, summed
+ * device milliseconds, algorithmic FLOPs and algorithmic bytes.  Not for use under graph capture.
+ * ------------------------------------------------------------------------------------------ */
+unsigned long long gyre_b200_launch_count(void);
+int gyre_b200_prof_enable(int on);
+int gyre_b200_prof_reset(void);
+int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, double* flops, double* bytes);
+
+/* ------------------------------------------------------------------------------------------
  * UNet  (replaces diffusers UNet2DConditionModel.forward as called from
  *        gyre/pipeline/unet/core.py:274 through the DiffusersUNet protocol,
  *        gyre/pipeline/unet/types.py:30-39; ToMe variant nonfree/tome_unet.py:229-247)
