@@ -12,17 +12,17 @@ static inline unsigned blocks_for(int64_t n, int threads) {
 // ------------------------------------------------------------------ NCHW <-> NHWC (small C: latents / images)
 __global__ void nchw_to_nhwc_kernel(const __half* __restrict__ x, int C, int HW, __half* __restrict__ out, int ldo,
                                     int64_t total) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over b*HW*C (NHWC order)
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over b*HW*ldo (padded NHWC)
   if (i >= total) return;
-  const int c = static_cast<int>(i % C);
-  const int64_t bp = i / C;
+  const int c = static_cast<int>(i % ldo);
+  const int64_t bp = i / ldo;
   const int p = static_cast<int>(bp % HW);
   const int64_t b = bp / HW;
-  out[bp * ldo + c] = x[(b * C + c) * HW + p];
+  out[i] = c < C ? x[(b * C + c) * HW + p] : __float2half_rn(0.f);   // pad channels are written as zeros
 }
 int nchw_to_nhwc_f16(const __half* x, int B, int C, int H, int W, __half* out, int ldo, cudaStream_t st) {
-  const int64_t total = static_cast<int64_t>(B) * C * H * W;
-  GYRE_REQUIRE(total > 0, "nchw_to_nhwc: empty");
+  const int64_t total = static_cast<int64_t>(B) * ldo * H * W;
+  GYRE_REQUIRE(total > 0 && ldo >= C, "nchw_to_nhwc: bad shape");
   prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, C, H * W, out, ldo, total);
   GYRE_CHECK_CUDA(cudaGetLastError());
@@ -127,68 +127,24 @@ int silu_f16(const __half* x, int64_t n, __half* out, cudaStream_t st) {
   return 0;
 }
 
-// ------------------------------------------------------------------ direct 3x3 conv, tiny Cin (conv_in)
-// thread -> (pixel, group of 8 output channels); weights fp32 [Cout, 3, 3, Cin]
-__global__ void conv3x3_small_kernel(const __half* __restrict__ X, int H, int W, int Cin, const float* __restrict__ Wt,
-                                     const float* __restrict__ bias, int Cout, __half* __restrict__ out,
-                                     int64_t total) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int ng = Cout >> 3;
-  const int g = static_cast<int>(i % ng);
-  int64_t p = i / ng;
-  const int x = static_cast<int>(p % W);
-  p /= W;
-  const int y = static_cast<int>(p % H);
-  const int64_t b = p / H;
-  float acc[8];
-#pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = bias ? bias[g * 8 + o] : 0.f;
-  for (int kh = 0; kh < 3; ++kh) {
-    const int yy = y + kh - 1;
-    if (yy < 0 || yy >= H) continue;
-    for (int kw = 0; kw < 3; ++kw) {
-      const int xx = x + kw - 1;
-      if (xx < 0 || xx >= W) continue;
-      const __half* px = X + ((b * H + yy) * W + xx) * Cin;
-      for (int c = 0; c < Cin; ++c) {
-        const float xv = __half2float(px[c]);
-#pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = fmaf(xv, Wt[((g * 8 + o) * 9 + kh * 3 + kw) * Cin + c], acc[o]);
-      }
-    }
-  }
-  __align__(16) __half2 h[4];
-#pragma unroll
-  for (int o = 0; o < 4; ++o) h[o] = __floats2half2_rn(acc[2 * o], acc[2 * o + 1]);
-  *reinterpret_cast<uint4*>(out + ((b * H + y) * W + x) * Cout + g * 8) = *reinterpret_cast<uint4*>(h);
-}
-int conv3x3_small_cin(const __half* X, int B, int H, int W, int Cin, const float* Wt, const float* bias, int Cout,
-                      __half* out, cudaStream_t st) {
-  GYRE_REQUIRE(Cout % 8 == 0 && Cin > 0 && Cin <= 16, "conv3x3_small: Cin<=16, Cout%%8==0 (got %d,%d)", Cin, Cout);
-  const int64_t total = static_cast<int64_t>(B) * H * W * (Cout / 8);
-  GYRE_REQUIRE(total > 0, "conv3x3_small: empty");
-  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
-  conv3x3_small_kernel<<<blocks_for(total, 128), 128, 0, st>>>(X, H, W, Cin, Wt, bias, Cout, out, total);
-  GYRE_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 __global__ void conv1x1_small_kernel(const __half* __restrict__ X, int64_t rows, int Cin, const float* __restrict__ Wt,
-                                     const float* __restrict__ bias, int Cout, __half* __restrict__ out) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= rows * Cout) return;
-  const int o = static_cast<int>(i % Cout);
-  const int64_t r = i / Cout;
-  float acc = bias ? bias[o] : 0.f;
-  for (int c = 0; c < Cin; ++c) acc = fmaf(__half2float(X[r * Cin + c]), Wt[o * Cin + c], acc);
-  out[i] = __float2half_rn(acc);
+                                     const float* __restrict__ bias, int Cout, __half* __restrict__ out, int ldo) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over rows * ldo
+  if (i >= rows * ldo) return;
+  const int o = static_cast<int>(i % ldo);
+  const int64_t r = i / ldo;
+  float acc = 0.f;
+  if (o < Cout) {
+    acc = bias ? bias[o] : 0.f;
+    for (int c = 0; c < Cin; ++c) acc = fmaf(__half2float(X[r * Cin + c]), Wt[o * Cin + c], acc);
+  }
+  out[i] = __float2half_rn(acc);   // columns [Cout, ldo) are zero padding for a following TMA-fed conv
 }
 int conv1x1_small(const __half* X, int64_t rows, int Cin, const float* Wt, const float* bias, int Cout, __half* out,
-                  cudaStream_t st) {
-  GYRE_REQUIRE(rows > 0 && Cin > 0 && Cout > 0, "conv1x1_small: empty");
+                  int ldo, cudaStream_t st) {
+  GYRE_REQUIRE(rows > 0 && Cin > 0 && Cout > 0 && ldo >= Cout, "conv1x1_small: bad shape");
   prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
-  conv1x1_small_kernel<<<blocks_for(rows * Cout, 256), 256, 0, st>>>(X, rows, Cin, Wt, bias, Cout, out);
+  conv1x1_small_kernel<<<blocks_for(rows * ldo, 256), 256, 0, st>>>(X, rows, Cin, Wt, bias, Cout, out, ldo);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

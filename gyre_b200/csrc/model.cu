@@ -109,15 +109,6 @@ void Model::reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c) {
   reg(p + ".bias", P_F32, c->bias, {Cout});
 }
 
-void Model::reg_smallconv(const std::string& p, int Cin, int Cout, SmallConvW* c) {
-  c->Cin = Cin;
-  c->Cout = Cout;
-  c->w = static_cast<float*>(dalloc(sizeof(float) * Cout * 9 * Cin));
-  c->bias = static_cast<float*>(dalloc(sizeof(float) * Cout));
-  reg(p + ".weight", P_SMALLCONV, c->w, {Cout, Cin, 3, 3});
-  reg(p + ".bias", P_F32, c->bias, {Cout});
-}
-
 void Model::reg_resnet(const std::string& p, int cin, int cout, bool temb, ResnetW* r) {
   r->cin = cin;
   r->cout = cout;
@@ -180,10 +171,6 @@ int Model::load(const char* key, const void* data, int dtype, const int64_t* sha
     case P_GEGLU_B:
       GYRE_TRY(pack_geglu(nullptr, 0, static_cast<int>(s.shape[0] / 2), 1, data, dtype, nullptr,
                           static_cast<float*>(s.dst), st));
-      break;
-    case P_SMALLCONV:
-      GYRE_TRY(pack_smallconv(data, dtype, static_cast<int>(s.shape[1]), static_cast<int>(s.shape[0]),
-                              static_cast<float*>(s.dst), st));
       break;
     default:
       GYRE_REQUIRE(false, "load_weight(%s): bad slot", key);
@@ -267,7 +254,7 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
   const int L = cfg.num_levels;
   const int* ch = cfg.block_out_channels;
   temb_dim_ = ch[0] * 4;
-  reg_smallconv("conv_in", cfg.in_channels, ch[0], &conv_in_);
+  reg_conv3("conv_in", cfg.in_channels, ch[0], &conv_in_);
   reg_linear("time_embedding.linear_1", temb_dim_, ch[0], true, &time1_);
   reg_linear("time_embedding.linear_2", temb_dim_, temb_dim_, true, &time2_);
 
@@ -462,10 +449,13 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
 
   // ---- conv_in
   int h_ = H, w_ = W;
-  __half* x_nhwc = ex.p16(static_cast<size_t>(B) * H * W * cfg_.in_channels);
-  RUN(ex, nchw_to_nhwc_f16(sample, B, cfg_.in_channels, H, W, x_nhwc, cfg_.in_channels, ex.st));
+  // conv_in on the tensor cores too: the 4/9-channel latent is staged NHWC with a zero-padded channel pitch of
+  // 8/16 (TMA needs 16-byte pixel rows); the padded K slice costs nothing measurable
+  const int cin8 = (cfg_.in_channels + 7) & ~7;
+  __half* x_nhwc = ex.p16(static_cast<size_t>(B) * H * W * cin8);
+  RUN(ex, nchw_to_nhwc_f16(sample, B, cfg_.in_channels, H, W, x_nhwc, cin8, ex.st));
   __half* hcur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
-  RUN(ex, conv3x3_small_cin(x_nhwc, B, H, W, cfg_.in_channels, conv_in_.w, conv_in_.bias, ch[0], hcur, ex.st));
+  RUN(ex, conv3x3_f16(x_nhwc, cin8, B, H, W, cin8, conv_in_.wp, ch[0], 1, 1, ep_out(hcur, ch[0], conv_in_.bias), ex.st));
 
   struct Skip { const __half* p; int C; };
   std::vector<Skip> skips;
@@ -606,7 +596,7 @@ VAEModel::VAEModel(const gyre_b200_vae_config& cfg) : cfg_(cfg) {
   post_quant_.bias = static_cast<float*>(dalloc(sizeof(float) * z));
   reg("post_quant_conv.weight", P_F32MAT, post_quant_.w, {z, z});
   reg("post_quant_conv.bias", P_F32, post_quant_.bias, {z});
-  reg_smallconv("decoder.conv_in", z, top, &dec_conv_in_);
+  reg_conv3("decoder.conv_in", z, top, &dec_conv_in_);
   reg_resnet("decoder.mid_block.resnets.0", top, top, false, &dec_mid_[0]);
   reg_attn("decoder.mid_block.attentions.0", top, &dec_attn_);
   reg_resnet("decoder.mid_block.resnets.1", top, top, false, &dec_mid_[1]);
@@ -628,7 +618,7 @@ VAEModel::VAEModel(const gyre_b200_vae_config& cfg) : cfg_(cfg) {
   reg_conv3("decoder.conv_out", ch[0], cfg.out_channels, &dec_conv_out_);
 
   // ---- encoder
-  reg_smallconv("encoder.conv_in", cfg.in_channels, ch[0], &enc_conv_in_);
+  reg_conv3("encoder.conv_in", cfg.in_channels, ch[0], &enc_conv_in_);
   cin = ch[0];
   for (int i = 0; i < L; ++i) {
     for (int j = 0; j < cfg.layers_per_block; ++j) {
@@ -705,10 +695,11 @@ int VAEModel::decode(Exec& ex, const __half* z, int B, int h, int w, bool postpr
   // the workspace, a few GB at batch 8 / 512x512 -- small against 180 GB of HBM)
   __half* z_nhwc = ex.p16(px * zc);
   RUN(ex, nchw_to_nhwc_f16(z, B, zc, h, w, z_nhwc, zc, ex.st));
-  __half* z2 = ex.p16(px * zc);
-  RUN(ex, conv1x1_small(z_nhwc, static_cast<int64_t>(px), zc, post_quant_.w, post_quant_.bias, zc, z2, ex.st));
+  const int zc8 = (zc + 7) & ~7;
+  __half* z2 = ex.p16(px * zc8);
+  RUN(ex, conv1x1_small(z_nhwc, static_cast<int64_t>(px), zc, post_quant_.w, post_quant_.bias, zc, z2, zc8, ex.st));
   __half* cur = ex.p16(px * top);
-  RUN(ex, conv3x3_small_cin(z2, B, h, w, zc, dec_conv_in_.w, dec_conv_in_.bias, top, cur, ex.st));
+  RUN(ex, conv3x3_f16(z2, zc8, B, h, w, zc8, dec_conv_in_.wp, top, 1, 1, ep_out(cur, top, dec_conv_in_.bias), ex.st));
   int H = h, W = w, C = top;
   auto block_out = [&](size_t elems) { return ex.p16(elems); };
   {
@@ -771,10 +762,11 @@ int VAEModel::encode(Exec& ex, const __half* img, int B, int H, int W, __half* m
   const int zc = cfg_.latent_channels;
   const int ic = cfg_.in_channels;
   const float eps = 1e-6f;
-  __half* x = ex.p16(static_cast<size_t>(B) * H * W * ic);
-  RUN(ex, nchw_to_nhwc_f16(img, B, ic, H, W, x, ic, ex.st));
+  const int ic8 = (ic + 7) & ~7;
+  __half* x = ex.p16(static_cast<size_t>(B) * H * W * ic8);
+  RUN(ex, nchw_to_nhwc_f16(img, B, ic, H, W, x, ic8, ex.st));
   __half* cur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
-  RUN(ex, conv3x3_small_cin(x, B, H, W, ic, enc_conv_in_.w, enc_conv_in_.bias, ch[0], cur, ex.st));
+  RUN(ex, conv3x3_f16(x, ic8, B, H, W, ic8, enc_conv_in_.wp, ch[0], 1, 1, ep_out(cur, ch[0], enc_conv_in_.bias), ex.st));
   int C = ch[0];
   size_t ri = 0;
   for (int i = 0; i < L; ++i) {
@@ -820,7 +812,7 @@ int VAEModel::encode(Exec& ex, const __half* img, int B, int H, int W, __half* m
     RUN(ex, conv3x3_f16(tn, C, B, H, W, C, enc_conv_out_.wp, 2 * zc, 1, 1, ep_out(m0, 2 * zc, enc_conv_out_.bias),
                         ex.st));
     __half* m1 = ex.s16(rows * 2 * zc);
-    RUN(ex, conv1x1_small(m0, static_cast<int64_t>(rows), 2 * zc, quant_.w, quant_.bias, 2 * zc, m1, ex.st));
+    RUN(ex, conv1x1_small(m0, static_cast<int64_t>(rows), 2 * zc, quant_.w, quant_.bias, 2 * zc, m1, 2 * zc, ex.st));
     RUN(ex, nhwc_to_nchw_f16(m1, 2 * zc, B, 2 * zc, H, W, moments, ex.st));
   }
   EX_CHECK(ex);

@@ -36,7 +36,7 @@ struct Exec {
 struct NormW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct LinW { __half* w = nullptr; float* bias = nullptr; int N = 0, K = 0; };
 struct Conv3W { __half* wp = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0; };
-struct SmallConvW { float* w = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0; };
+struct SmallConvW { float* w = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0; };   // fp32 1x1 on <= 8 channels
 
 struct ResnetW {
   NormW n1, n2;
@@ -60,7 +60,7 @@ struct VaeAttnW {
   int C = 0;
 };
 
-enum ParamKind { P_F32 = 0, P_LINEAR, P_CONV3, P_GEGLU_W, P_GEGLU_B, P_SMALLCONV, P_F32MAT };
+enum ParamKind { P_F32 = 0, P_LINEAR, P_CONV3, P_GEGLU_W, P_GEGLU_B, P_F32MAT };
 
 struct ParamSlot {
   int kind = P_F32;
@@ -86,7 +86,6 @@ class Model {
   void reg_norm(const std::string& p, int C, NormW* n);
   void reg_linear(const std::string& p, int N, int K, bool bias, LinW* l);
   void reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c);
-  void reg_smallconv(const std::string& p, int Cin, int Cout, SmallConvW* c);
   void reg_resnet(const std::string& p, int cin, int cout, bool temb, ResnetW* r);
   int resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __half* x2, int C2, int B, int H, int W,
              float eps, const __half* temb_all, int temb_ld, __half* out);
@@ -116,7 +115,7 @@ class UNetModel : public Model {
   int transformer(Exec& ex, const TransformerW& t, const __half* x, int B, int HW, const __half* ctx, int L, int r,
                   __half* out);
   gyre_b200_unet_config cfg_;
-  SmallConvW conv_in_;
+  Conv3W conv_in_;      // Cin = in_channels (4/5/9): the input is staged NHWC with the channel pitch padded to 8
   LinW time1_, time2_;
   std::vector<ResnetW> resnets_;        // in module execution order
   std::vector<TransformerW> tblocks_;   // in module execution order (== ToMe r-list order)
@@ -136,7 +135,8 @@ class VAEModel : public Model {
   int attn(Exec& ex, const VaeAttnW& a, const __half* x, int B, int HW, __half* out);
   gyre_b200_vae_config cfg_;
   // decoder
-  SmallConvW post_quant_, dec_conv_in_;
+  SmallConvW post_quant_;
+  Conv3W dec_conv_in_;
   ResnetW dec_mid_[2];
   VaeAttnW dec_attn_;
   std::vector<ResnetW> dec_res_;
@@ -144,7 +144,8 @@ class VAEModel : public Model {
   NormW dec_norm_out_;
   Conv3W dec_conv_out_;
   // encoder
-  SmallConvW enc_conv_in_, quant_;
+  Conv3W enc_conv_in_;
+  SmallConvW quant_;
   std::vector<ResnetW> enc_res_;
   std::vector<Conv3W> enc_downs_;
   ResnetW enc_mid_[2];

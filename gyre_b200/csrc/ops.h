@@ -77,13 +77,9 @@ int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cu
 int concat_channels(const __half* a, int Ca, const __half* b, int Cb, int64_t rows, __half* out, cudaStream_t st);
 int timestep_embed(const int64_t* t, int B, int dim, __half* out, cudaStream_t st);
 int silu_f16(const __half* x, int64_t n, __half* out, cudaStream_t st);
-// Direct 3x3 conv for tiny channel counts (conv_in: Cin 4/9, VAE conv_in): X NCHW-agnostic NHWC with
-// Cin <= 16, weights fp32 [Cout, 3, 3, Cin], output NHWC fp16.
-int conv3x3_small_cin(const __half* X, int B, int H, int W, int Cin, const float* Wt, const float* bias, int Cout,
-                      __half* out, cudaStream_t st);
 // 1x1 conv on tiny channel counts (post_quant_conv 4->4, quant_conv 8->8): NHWC fp16.
 int conv1x1_small(const __half* X, int64_t rows, int Cin, const float* Wt, const float* bias, int Cout, __half* out,
-                  cudaStream_t st);
+                  int ldo, cudaStream_t st);
 
 // Scheduler-step fusions (fp32 latents NCHW [B,4,h,w]; eps fp16 NCHW [2B or B, ...]).
 struct StepScalars {
@@ -119,8 +115,6 @@ int cast_to_f16(const void* src, int dtype, int64_t rows, int cols, __half* dst,
 int cast_to_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st);
 int pack_geglu(const void* w, int dtype, int F, int K, const void* bias, int bias_dtype, __half* wp, float* bias_p,
                cudaStream_t st);
-// [Cout, Cin, 3, 3] -> fp32 [Cout, 3, 3, Cin] for the direct small-Cin conv
-int pack_smallconv(const void* w, int dtype, int Cin, int Cout, float* out, cudaStream_t st);
 const char* last_error();
 // ---- ToMe K/V merge (tome.cu): k, v [B, N, C] with row pitch ld -> k_out, v_out [B, N-r, C] dense
 int tome_workspace_bytes(int B, int N, int C, size_t* bytes);

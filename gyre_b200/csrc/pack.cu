@@ -85,30 +85,6 @@ int cast_to_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t 
   return 0;
 }
 
-template <typename T>
-__global__ void pack_smallconv_kernel(const T* __restrict__ w, int Cin, int64_t total, float* __restrict__ out) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over [Cout, 9, Cin]
-  if (i >= total) return;
-  const int c = static_cast<int>(i % Cin);
-  const int64_t r = i / Cin;
-  const int tap = static_cast<int>(r % 9);
-  const int64_t o = r / 9;
-  out[i] = to_f32(w[(o * Cin + c) * 9 + tap]);
-}
-int pack_smallconv(const void* w, int dtype, int Cin, int Cout, float* out, cudaStream_t st) {
-  const int64_t total = static_cast<int64_t>(Cout) * 9 * Cin;
-  GYRE_REQUIRE(total > 0, "pack_smallconv: empty");
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (dtype == 0)
-    pack_smallconv_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(w), Cin, total, out);
-  else if (dtype == 1)
-    pack_smallconv_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(w), Cin, total, out);
-  else
-    GYRE_REQUIRE(false, "pack_smallconv: dtype %d", dtype);
-  GYRE_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 // GEGLU: W [2F, K] = [value rows ; gate rows]  ->  per 256-row tile: 128 value rows then their 128 gate rows
 template <typename T>
 __global__ void pack_geglu_kernel(const T* __restrict__ w, int F, int K, int64_t total, __half* __restrict__ out) {
