@@ -1,6 +1,6 @@
 // K4 / K1: tcgen05 GEMM and 3x3 implicit-GEMM convolution for sm_100a.
 //
-// One CTA computes a 128 x BN output tile.  Warp 0 is the TMA producer, warp 1 owns TMEM and issues
+// One CTA (persistent, one per SM) computes 128 x BN output tiles.  Warp 0 is the TMA producer, warp 1 owns TMEM and issues
 // tcgen05.mma (one elected lane), warps 2..5 are the epilogue (one accumulator row per thread, read
 // with tcgen05.ld 32x32b).  Operands are staged by TMA into 128B-swizzled K-major shared-memory tiles
 // (64 halfs = one swizzle span per row), STAGES deep, handed over with full/empty mbarriers; the
@@ -21,6 +21,7 @@ struct GemmParams {
   int k_iters;
   int k1_iters;   // k-iterations served by the first A source (tmA); the rest come from tmA2 (skip-concat inputs)
   int n_tiles;
+  int m_tiles;
   // conv
   int conv, cin_chunks, cin_pad;
   int tile_w, tile_h, tile_n;
@@ -32,15 +33,21 @@ struct GemmParams {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
+constexpr int kEpiThreads = 256;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  // as many stages as fit in ~200 KB (one persistent CTA per SM)
+  static constexpr int STAGES_RAW = (200 * 1024) / (A_BYTES + B_BYTES);
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  // two accumulator buffers so that the epilogue of tile i overlaps the main loop of tile i+1
+  static constexpr int BUF_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = 2 * BUF_COLS;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ +
+                              2 * BN * 4 /*per-tile column bias, double buffered*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -100,11 +107,15 @@ __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col,
   }
 }
 
+// Persistent kernel: grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+// (n fastest, so CTAs sharing an A tile run concurrently and hit in L2).  The smem ring and the two TMEM
+// accumulator buffers run continuously across tiles: while the epilogue warps drain buffer b, the MMA
+// warp is already accumulating the next tile into buffer b^1.
 template <int BN>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmA2,
-                                                           const __grid_constant__ CUtensorMap tmB,
-                                                           const GemmParams p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmA2,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -112,25 +123,13 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + Cfg::STAGES * Cfg::B_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* accum_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;    // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int n_tile = blockIdx.x % p.n_tiles;   // N fastest: CTAs sharing an A tile are co-resident (L2 reuse)
-  const int m_tile = blockIdx.x / p.n_tiles;
-
-  // conv tile origin
-  int x0 = 0, y0 = 0, n0 = 0;
-  if (p.conv) {
-    const int tx = m_tile % p.tiles_x;
-    const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-    const int tn = m_tile / (p.tiles_x * p.tiles_y);
-    x0 = tx * p.tile_w;
-    y0 = ty * p.tile_h;
-    n0 = tn * p.tile_n;
-  }
+  const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -140,7 +139,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kEpiThreads);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -152,24 +154,35 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      for (int it = 0; it < p.k_iters; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (it / Cfg::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+      uint32_t g = 0;   // k-iterations issued so far (ring position)
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % p.n_tiles;
+        const int m_tile = t / p.n_tiles;
+        int x0 = 0, y0 = 0, n0 = 0;
         if (p.conv) {
-          const int tap = it / p.cin_chunks;
-          const int cc = it - tap * p.cin_chunks;
-          const int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], cc * kBK, x0 * p.stride + kw - p.pad,
-                      y0 * p.stride + kh - p.pad, n0);
-          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], tap * p.cin_pad + cc * kBK, n_tile * BN);
-        } else {
-          if (it < p.k1_iters)
-            tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], it * kBK, m_tile * kBM);
-          else
-            tma_load_2d(sA + s * Cfg::A_BYTES, &tmA2, &full_bar[s], (it - p.k1_iters) * kBK, m_tile * kBM);
-          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], it * kBK, n_tile * BN);
+          x0 = (m_tile % p.tiles_x) * p.tile_w;
+          y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.tile_h;
+          n0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tile_n;
+        }
+        for (int it = 0; it < p.k_iters; ++it, ++g) {
+          const int s = g % Cfg::STAGES;
+          const uint32_t ph = (g / Cfg::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+          if (p.conv) {
+            const int tap = it / p.cin_chunks;
+            const int cc = it - tap * p.cin_chunks;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], cc * kBK, x0 * p.stride + kw - p.pad,
+                        y0 * p.stride + kh - p.pad, n0);
+            tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], tap * p.cin_pad + cc * kBK, n_tile * BN);
+          } else {
+            if (it < p.k1_iters)
+              tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], it * kBK, m_tile * kBM);
+            else
+              tma_load_2d(sA + s * Cfg::A_BYTES, &tmA2, &full_bar[s], (it - p.k1_iters) * kBK, m_tile * kBM);
+            tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], it * kBK, n_tile * BN);
+          }
         }
       }
     }
@@ -177,126 +190,182 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
-      for (int it = 0; it < p.k_iters; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (it / Cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t g = 0;
+      uint32_t lt = 0;   // local tile counter
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1;
+        const uint32_t use = lt >> 1;
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this buffer's previous tile
         tc_fence_after();
-        const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * Cfg::A_BYTES));
-        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + s * Cfg::B_BYTES));
+        const uint32_t tmem_d = tmem_base + buf * Cfg::BUF_COLS;
+        for (int it = 0; it < p.k_iters; ++it, ++g) {
+          const int s = g % Cfg::STAGES;
+          const uint32_t ph = (g / Cfg::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * Cfg::A_BYTES));
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + s * Cfg::B_BYTES));
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
+        }
+        umma_commit(&tfull_bar[buf]);   // accumulator complete
       }
-      umma_commit(accum_bar);         // accumulator complete
     }
   } else {
     // ------------------------------------------------------------ epilogue: TMEM -> regs -> global
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    // 8 warps: warp w reads TMEM lane quadrant (w & 3); the two warps of a quadrant alternate over the
+    // 32-column chunks of the tile.  Per tile the column bias is staged once in shared memory; the row-wise
+    // operands (residual, per-sample temb bias) are fetched as 16-byte vectors one chunk AHEAD of their use,
+    // the first chunk before the accumulator is even ready, so their latency hides under the main loop.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;       // 0 | 1
     const int r = q * 32 + lane;            // accumulator row
-    bool valid;
-    int64_t out_row;
-    if (p.conv) {
-      const int dx = r % p.tile_w;
-      const int dy = (r / p.tile_w) % p.tile_h;
-      const int dn = r / (p.tile_w * p.tile_h);
-      const int x = x0 + dx, y = y0 + dy, n = n0 + dn;
-      valid = (x < p.Wo) && (y < p.Ho) && (n < p.Bn);
-      out_row = (static_cast<int64_t>(n) * p.Ho + y) * p.Wo + x;
-    } else {
-      out_row = static_cast<int64_t>(m_tile) * kBM + r;
-      valid = out_row < p.M;
-    }
+    const int etid = threadIdx.x - 64;      // 0..255
     const Epilogue& ep = p.ep;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [2][BN]
+    constexpr bool kGeglu = false;
+    (void)kGeglu;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const int n_tile = t % p.n_tiles;
+      const int m_tile = t / p.n_tiles;
+      bool valid;
+      int64_t out_row;
+      if (p.conv) {
+        const int x0 = (m_tile % p.tiles_x) * p.tile_w;
+        const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.tile_h;
+        const int n0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tile_n;
+        const int dx = r % p.tile_w;
+        const int dy = (r / p.tile_w) % p.tile_h;
+        const int dn = r / (p.tile_w * p.tile_h);
+        const int x = x0 + dx, y = y0 + dy, n = n0 + dn;
+        valid = (x < p.Wo) && (y < p.Ho) && (n < p.Bn);
+        out_row = (static_cast<int64_t>(n) * p.Ho + y) * p.Wo + x;
+      } else {
+        out_row = static_cast<int64_t>(m_tile) * kBM + r;
+        valid = out_row < p.M;
+      }
+      const uint32_t buf = lt & 1;
+      const uint32_t use = lt >> 1;
+      float* sb = sbias + buf * BN;
+      for (int c = etid; c < BN; c += kEpiThreads) {
+        const int col = n_tile * BN + c;
+        sb[c] = (ep.bias != nullptr && col < p.N) ? __ldg(ep.bias + col) : 0.f;
+      }
+      const __half* rgb = (valid && ep.rowgroup_bias) ? ep.rowgroup_bias + (out_row / ep.rows_per_group) * ep.rgb_ld
+                                                      : nullptr;
+      const __half* res = (valid && ep.residual) ? ep.residual + out_row * ep.ldr : nullptr;
+      const bool res_vec = res != nullptr && (ep.ldr & 7) == 0 && (p.N & 7) == 0;
+      const bool rgb_vec = rgb != nullptr && (ep.rgb_ld & 7) == 0 && (p.N & 7) == 0 &&
+                           ((reinterpret_cast<uintptr_t>(ep.rowgroup_bias) & 15) == 0);
+      const int col_base = n_tile * BN;
+      uint4 rv[4], gv[4];
+      auto fetch_rows = [&](int c0, uint4 (&rr)[4], uint4 (&gg)[4]) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int col = col_base + c0 + g8 * 8;
+          if (col + 8 <= p.N) {
+            if (res_vec) rr[g8] = *reinterpret_cast<const uint4*>(res + col);
+            if (rgb_vec) gg[g8] = __ldg(reinterpret_cast<const uint4*>(rgb + col));
+          }
+        }
+      };
+      if (ep.act != ACT_GEGLU) fetch_rows(half * 32, rv, gv);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // column bias staged (epilogue warps only)
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + buf * Cfg::BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
 
-    if (ep.act == ACT_GEGLU) {
-      // tile columns [0, BN/2) = value, [BN/2, BN) = gate (weights are packed that way)
-      constexpr int HALF = BN / 2;
-      const int n_out = p.N / 2;
+      if (ep.act == ACT_GEGLU) {
+        // tile columns [0, BN/2) = value, [BN/2, BN) = gate (weights are packed that way)
+        constexpr int HALF = BN / 2;
+        const int n_out = p.N / 2;
 #pragma unroll 1
-      for (int c0 = 0; c0 < HALF; c0 += 32) {
-        uint32_t ra[32], rg[32];
-        tmem_ld_32x32b_x32(lane_addr + c0, ra);
-        tmem_ld_32x32b_x32(lane_addr + HALF + c0, rg);
-        tmem_ld_wait();
-        if (valid) {
-          const int col_acc = n_tile * BN + c0;          // accumulator column (bias index, value half)
-          const int col_out = n_tile * HALF + c0;
+        for (int c0 = half * 32; c0 < HALF; c0 += 64) {
+          uint32_t ra[32], rg[32];
+          tmem_ld_32x32b_x32(lane_addr + c0, ra);
+          tmem_ld_32x32b_x32(lane_addr + HALF + c0, rg);
+          tmem_ld_wait();
+          if (valid) {
+            const int col_out = n_tile * HALF + c0;
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float v[8];
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = g8 * 8 + i;
-              float a = __uint_as_float(ra[j]);
-              float g = __uint_as_float(rg[j]);
-              if (ep.bias) {
-                a += __ldg(ep.bias + col_acc + j);
-                g += __ldg(ep.bias + col_acc + HALF + j);
+              for (int i = 0; i < 8; ++i) {
+                const int j = g8 * 8 + i;
+                const float a = __uint_as_float(ra[j]) + sb[c0 + j];
+                const float g = __uint_as_float(rg[j]) + sb[HALF + c0 + j];
+                v[i] = a * gelu_erf(g);
               }
-              v[i] = a * gelu_erf(g);
+              store8(ep, out_row, col_out + g8 * 8, n_out, v);
             }
-            store8(ep, out_row, col_out + g8 * 8, n_out, v);
           }
         }
-      }
-    } else {
+      } else {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t ra[32];
-        tmem_ld_32x32b_x32(lane_addr + c0, ra);
-        tmem_ld_wait();
-        const int col0 = n_tile * BN + c0;
-        if (valid && col0 < p.N) {
-          const __half* rgb = ep.rowgroup_bias
-                                  ? ep.rowgroup_bias + (out_row / ep.rows_per_group) * ep.rgb_ld
-                                  : nullptr;
-          const __half* res = ep.residual ? ep.residual + out_row * ep.ldr : nullptr;
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          uint32_t ra[32];
+          tmem_ld_32x32b_x32(lane_addr + c0, ra);
+          uint4 rnext[4], gnext[4];
+          if (c0 + 64 < BN) fetch_rows(c0 + 64, rnext, gnext);   // next chunk's row operands, before this chunk's stores
+          tmem_ld_wait();
+          const int col0 = col_base + c0;
+          if (valid && col0 < p.N) {
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int col = col0 + g8 * 8;
-            if (col >= p.N) break;
-            float v[8];
-            const bool full8 = col + 8 <= p.N;
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int col = col0 + g8 * 8;
+              if (col >= p.N) break;
+              float v[8];
+              const bool full8 = col + 8 <= p.N;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ra[g8 * 8 + i]);
-            if (ep.bias) {
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ra[g8 * 8 + i]) + sb[c0 + g8 * 8 + i];
+              if (rgb) {
+                if (full8 && rgb_vec) {
+                  const __half2* gh = reinterpret_cast<const __half2*>(&gv[g8]);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (full8 || col + i < p.N) v[i] += __ldg(ep.bias + col + i);
-            }
-            if (rgb) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (full8 || col + i < p.N) v[i] += __half2float(rgb[col + i]);
-            }
-            if (ep.act == ACT_SILU) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-            }
-            if (res) {
-              if (full8 && (ep.ldr & 7) == 0) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res + col);
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = __half22float2(rh[i]);
-                  v[2 * i] += f.x;
-                  v[2 * i + 1] += f.y;
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(gh[i]);
+                    v[2 * i] += f.x;
+                    v[2 * i + 1] += f.y;
+                  }
+                } else {
+                  for (int i = 0; i < 8; ++i)
+                    if (col + i < p.N) v[i] += __half2float(__ldg(rgb + col + i));
                 }
-              } else {
-                for (int i = 0; i < 8; ++i)
-                  if (col + i < p.N) v[i] += __half2float(res[col + i]);
               }
+              if (ep.act == ACT_SILU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+              }
+              if (res) {
+                if (full8 && res_vec) {
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[g8]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(rh[i]);
+                    v[2 * i] += f.x;
+                    v[2 * i + 1] += f.y;
+                  }
+                } else {
+                  for (int i = 0; i < 8; ++i)
+                    if (col + i < p.N) v[i] += __half2float(res[col + i]);
+                }
+              }
+              store8(ep, out_row, col, p.N, v);
             }
-            store8(ep, out_row, col, p.N, v);
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            rv[g8] = rnext[g8];
+            gv[g8] = gnext[g8];
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);
     }
   }
 
@@ -306,6 +375,16 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------ host
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
                   int m_tiles, cudaStream_t st) {
@@ -315,20 +394,41 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
     GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  const long long blocks = static_cast<long long>(m_tiles) * p.n_tiles;
-  GYRE_REQUIRE(blocks > 0 && blocks < (1ll << 31), "gemm: bad grid %lld", blocks);
-  gemm_tc_kernel<BN><<<static_cast<unsigned>(blocks), kThreads, Cfg::SMEM, st>>>(tmA, tmA2, tmB, p);
+  const long long tiles = static_cast<long long>(m_tiles) * p.n_tiles;
+  GYRE_REQUIRE(tiles > 0 && tiles < (1ll << 31), "gemm: bad tile count %lld", tiles);
+  GemmParams pp = p;
+  pp.m_tiles = m_tiles;
+  const int sms = sm_count();
+  const unsigned blocks = static_cast<unsigned>(tiles < sms ? tiles : sms);
+  gemm_tc_kernel<BN><<<blocks, kThreads, Cfg::SMEM, st>>>(tmA, tmA2, tmB, pp);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int pick_bn(int N, int act) {
+// Tile width: maximise (SM wave efficiency) x (1 - N padding) x (per-tile efficiency of the shape).
+static int pick_bn(long long m_tiles, int N, int act) {
   if (act == ACT_GEGLU) return 256;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N % 160 == 0 && N % 256 != 0) return 160;   // 320, 640, 960, 1920: exact tiles
-  if (N % 256 == 0 || N > 1024) return 256;
-  return 128;
+  const int cand[4] = {256, 160, 128, 64};
+  const double shape_eff[4] = {1.0, 0.96, 0.92, 0.78};
+  const int sms = sm_count();
+  int best = 128;
+  double best_score = -1.0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    const long long n_tiles = (N + bn - 1) / bn;
+    const long long tiles = m_tiles * n_tiles;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double wave_eff = static_cast<double>(tiles) / static_cast<double>(waves * sms);
+    const double pad_eff = static_cast<double>(N) / static_cast<double>(n_tiles * bn);
+    const double score = wave_eff * pad_eff * shape_eff[i];
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 static int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
@@ -379,7 +479,7 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
   GYRE_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                "gemm: operands must be 16B aligned");
   GYRE_TRY(check_epilogue(ep, ep.act == ACT_GEGLU ? N / 2 : N));
-  const int bn = pick_bn(N, ep.act);
+  const int bn = pick_bn((M + kBM - 1) / kBM, N, ep.act);
   if (ep.act == ACT_GEGLU) GYRE_REQUIRE(N % 256 == 0, "gemm: GEGLU needs N %% 256 == 0 (got %d)", N);
   GemmParams p{};
   p.M = M;
@@ -453,7 +553,9 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
     }
   }
   GYRE_REQUIRE(best_cost > 0, "conv3x3: no tile shape for %dx%d", Ho, Wo);
-  const int bn = pick_bn(Cout, ACT_NONE);
+  const int bn = pick_bn(static_cast<long long>((Wo + best_w - 1) / best_w) * ((Ho + best_h - 1) / best_h) *
+                             ((B + best_n - 1) / best_n),
+                         Cout, ACT_NONE);
   GemmParams p{};
   p.M = 0;
   p.N = Cout;
