@@ -53,7 +53,26 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __h
   float s[8], ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-  for (int r = row0 + ty; r < row1; r += rpar) {
+  // 4 independent 16-byte loads in flight per thread
+  int r = row0 + ty;
+  for (; r + 3 * rpar < row1; r += 4 * rpar) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r + k * rpar) * ld);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        s[2 * i] += f.x;
+        ss[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y;
+        ss[2 * i + 1] += f.y * f.y;
+      }
+    }
+  }
+  for (; r < row1; r += rpar) {
     float xv[8];
     load8(src + static_cast<int64_t>(r) * ld, xv);
 #pragma unroll
@@ -152,7 +171,31 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
     sc[i] = ga;
     sf[i] = beta[c0 + i] - s_mean[g] * ga;
   }
-  for (int r = row0 + ty; r < row1; r += rpar) {
+  int r = row0 + ty;
+  for (; r + 3 * rpar < row1; r += 4 * rpar) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r + k * rpar) * ld);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        xv[2 * i] = f.x;
+        xv[2 * i + 1] = f.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(xv[i], sc[i], sf[i]);
+        if (silu) y = y / (1.0f + __expf(-y));
+        xv[i] = y;
+      }
+      store8h(dst + static_cast<int64_t>(r + k * rpar) * C, xv);
+    }
+  }
+  for (; r < row1; r += rpar) {
     float xv[8];
     load8(src + static_cast<int64_t>(r) * ld, xv);
 #pragma unroll
@@ -165,6 +208,73 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
   }
 }
 
+// Small feature maps (UNet levels 2-3): ONE kernel, one CTA per (sample, group).  The group's HW x cpg slab
+// (<= 48 KB) is read once into shared memory, reduced in a fixed order (deterministic), normalised and
+// written back - a single pass over HBM and a single launch instead of three.
+__global__ void __launch_bounds__(256) gn_small_kernel(const __half* __restrict__ x1, int C1,
+                                                       const __half* __restrict__ x2, int C2, int HW, int G, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int silu, __half* __restrict__ out) {
+  extern __shared__ __half2 slab[];          // [HW][cpg / 2]
+  const int C = C1 + C2;
+  const int cpg = C / G;
+  const int hp = cpg >> 1;                   // half2 pairs per row (cpg is even)
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cbase = g * cpg;
+  const int total = HW * hp;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int row = i / hp;
+    const int c = cbase + 2 * (i - row * hp);
+    const __half* src = c < C1 ? x1 + (static_cast<int64_t>(b) * HW + row) * C1 + c
+                               : x2 + (static_cast<int64_t>(b) * HW + row) * C2 + (c - C1);
+    const __half2 v = *reinterpret_cast<const __half2*>(src);
+    slab[i] = v;
+    const float2 f = __half22float2(v);
+    s += f.x + f.y;
+    ss += f.x * f.x + f.y * f.y;
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  __shared__ float red[16];
+  __shared__ float stat[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp] = s;
+    red[8 + warp] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, q = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += static_cast<double>(red[w]);
+      q += static_cast<double>(red[8 + w]);
+    }
+    const double n = static_cast<double>(HW) * cpg;
+    const double mean = a / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[0] = static_cast<float>(mean);
+    stat[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const float mean = stat[0], rstd = stat[1];
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int row = i / hp;
+    const int cl = 2 * (i - row * hp);
+    const int c = cbase + cl;
+    const float2 f = __half22float2(slab[i]);
+    const float ga0 = gamma[c] * rstd, ga1 = gamma[c + 1] * rstd;
+    float y0 = fmaf(f.x - mean, ga0, beta[c]);
+    float y1 = fmaf(f.y - mean, ga1, beta[c + 1]);
+    if (silu) {
+      y0 = y0 / (1.0f + __expf(-y0));
+      y1 = y1 / (1.0f + __expf(-y1));
+    }
+    *reinterpret_cast<__half2*>(out + (static_cast<int64_t>(b) * HW + row) * C + c) = __floats2half2_rn(y0, y1);
+  }
+}
+
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, int G, float eps,
                    const float* gamma, const float* beta, bool silu, __half* out, float* partials, cudaStream_t st) {
   const int C = C1 + C2;
@@ -172,6 +282,16 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   GYRE_REQUIRE(G > 0 && G <= kMaxGroups && C % G == 0, "groupnorm: C=%d not divisible into %d groups", C, G);
   GYRE_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "groupnorm: channel counts must be multiples of 8");
   GYRE_REQUIRE(x2 != nullptr || C2 == 0, "groupnorm: missing second source");
+  {
+    const int cpg = C / G;
+    const size_t slab_bytes = static_cast<size_t>(HW) * cpg * sizeof(__half);
+    if ((cpg & 1) == 0 && HW <= 256 && slab_bytes <= 40 * 1024 && (C1 % 2 == 0)) {
+      prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 1);
+      gn_small_kernel<<<dim3(G, B), 256, slab_bytes, st>>>(x1, C1, x2, C2, HW, G, eps, gamma, beta, silu ? 1 : 0, out);
+      GYRE_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   const int nvec = C / 8;
   GYRE_REQUIRE(nvec <= 1024, "groupnorm: C=%d too large", C);
   int rpar = 256 / nvec;
@@ -191,7 +311,9 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm
-// one warp per row, the row lives in registers (<= 8 vectors of 8 per lane => C <= 2048)
+// one warp per row, the row lives in registers: NV 16-byte vectors per lane (C <= 256 * NV), sized per call so
+// that small C keeps the register count - and therefore the bytes in flight per SM - where HBM needs them
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int rows, int C, float eps,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __half* __restrict__ out) {
@@ -200,21 +322,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   if (row >= rows) return;
   const int nvec = C >> 3;
   const __half* src = x + static_cast<int64_t>(row) * C;
-  float v[8][8];
+  uint4 u[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int vi = lane + 32 * k;
+    if (vi < nvec) u[k] = *reinterpret_cast<const uint4*>(src + vi * 8);
+  }
+  float v[NV][8];
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = lane + 32 * k;
     if (vi < nvec) {
-      load8(src + vi * 8, v[k]);
+      const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sum += v[k][i];
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[k][2 * i] = f.x;
+        v[k][2 * i + 1] = f.y;
+        sum += f.x + f.y;
+      }
     }
   }
   const float mean = warp_sum(sum) / C;
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = lane + 32 * k;
     if (vi < nvec) {
 #pragma unroll
@@ -227,14 +360,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   const float rstd = rsqrtf(warp_sum(sq) / C + eps);
   __half* dst = out + static_cast<int64_t>(row) * C;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = lane + 32 * k;
     if (vi < nvec) {
       float y[8];
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8);
-      const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
       const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -249,7 +382,17 @@ int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gam
   GYRE_REQUIRE(rows > 0 && C > 0, "layernorm: empty input");
   GYRE_REQUIRE(C % 8 == 0 && C <= 2048, "layernorm: C=%d must be a multiple of 8 and <= 2048", C);
   prof::Scope ps(prof::F_LAYERNORM, 0.0, 2.0 * 2.0 * rows * C, st);
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out);
+  const int nv = (C + 255) / 256;
+  const unsigned grid = (rows + 7) / 8;
+  switch (nv) {
+    case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+    case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+    case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+    case 5: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+    case 6: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+    default: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+  }
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
