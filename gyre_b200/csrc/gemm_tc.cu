@@ -28,6 +28,9 @@ struct GemmParams {
   int Ho, Wo, Bn;
   int tiles_x, tiles_y;
   int stride, pad;
+  // epilogue routing
+  int tma_epi;        // 1: output (and residual) tiles move through swizzled smem slices with TMA
+  int rgb_rows;       // rows of a tile that share one rowgroup-bias vector (staged in smem); 0: per-thread loads
   Epilogue ep;
 };
 
@@ -35,25 +38,29 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kThreads = 320;        // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
 constexpr int kEpiThreads = 256;
+constexpr int kSliceBytes = kBM * 32 * 2;   // one 128-row x 32-column fp16 epilogue slice (64-byte rows)
+constexpr int kMaxBiasGroups = 2;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
-  // as many stages as fit in ~200 KB (one persistent CTA per SM)
-  static constexpr int STAGES_RAW = (200 * 1024) / (A_BYTES + B_BYTES);
+  // epilogue staging: per column-half 2 output + 2 residual slices; per-tile column bias (double buffered)
+  static constexpr int EPI_BYTES = 2 * 2 * 2 * kSliceBytes;
+  static constexpr int BIAS_BYTES = 2 * kMaxBiasGroups * BN * 4;
+  static constexpr int FIXED = EPI_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int STAGES_RAW = (227 * 1024 - FIXED) / (A_BYTES + B_BYTES);
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // two accumulator buffers so that the epilogue of tile i overlaps the main loop of tile i+1
   static constexpr int BUF_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * BUF_COLS;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ +
-                              2 * BN * 4 /*per-tile column bias, double buffered*/;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + FIXED;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-// Store 8 consecutive output columns (col .. col+7) of one row.
+// Direct store of 8 consecutive output columns of one row (fp32 outputs, unaligned pitches, tiny N).
 __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col, int n_valid_cols, const float* v) {
   if (ep.out_mode == OUT_F16) {
     __half* dst = reinterpret_cast<__half*>(ep.out) + row * ep.ldo + col;
@@ -66,7 +73,7 @@ __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col,
       for (int i = 0; i < 8; ++i)
         if (col + i < n_valid_cols) dst[i] = __float2half_rn(v[i]);
     }
-  } else if (ep.out_mode == OUT_F32) {
+  } else {
     float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col;
     if (col + 8 <= n_valid_cols && (ep.ldo & 3) == 0) {
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -75,35 +82,6 @@ __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col,
       for (int i = 0; i < 8; ++i)
         if (col + i < n_valid_cols) dst[i] = v[i];
     }
-  } else {  // OUT_SECTIONS; sec_width and hs_d are multiples of 8, so an 8-group never straddles
-    if (col >= n_valid_cols) return;
-    const int s = col / ep.sec_width;
-    const int c = col - s * ep.sec_width;
-    const OutSection sec = ep.sec[s];
-    if (sec.mode == SEC_ROWMAJOR) {
-      __half* dst = reinterpret_cast<__half*>(sec.ptr) + row * sec.ld + c;
-      __align__(16) __half2 h[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
-    } else {
-      const int b = static_cast<int>(row / ep.hs_tokens);
-      const int t = static_cast<int>(row - static_cast<int64_t>(b) * ep.hs_tokens);
-      const int hd = c / ep.hs_d;
-      const int j = c - hd * ep.hs_d;
-      const int64_t bh = static_cast<int64_t>(b) * ep.hs_heads + hd;
-      if (sec.mode == SEC_HEADSPLIT) {
-        __half* dst = reinterpret_cast<__half*>(sec.ptr) + (bh * ep.hs_tpad + t) * ep.hs_dpad + j;
-        __align__(16) __half2 h[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
-      } else {  // SEC_HEADSPLIT_T: [bh, dvpad(rows), tpad]; lanes hold consecutive tokens -> coalesced
-        __half* dst = reinterpret_cast<__half*>(sec.ptr) + (bh * ep.hs_dpad + j) * ep.hs_tpad + t;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dst[static_cast<int64_t>(i) * ep.hs_tpad] = __float2half_rn(v[i]);
-      }
-    }
   }
 }
 
@@ -111,21 +89,32 @@ __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col,
 // (n fastest, so CTAs sharing an A tile run concurrently and hit in L2).  The smem ring and the two TMEM
 // accumulator buffers run continuously across tiles: while the epilogue warps drain buffer b, the MMA
 // warp is already accumulating the next tile into buffer b^1.
+//
+// Epilogue (8 warps; warp w owns TMEM lane quadrant w&3, the two warps of a quadrant alternate over
+// 32-column slices).  Fast path: a slice is converted in registers, written to a 64B-swizzled shared-memory
+// slice and stored with ONE TMA bulk store per slice (full 64-byte row segments, clipped at the tensor
+// edges by the TMA unit); the residual slice arrives the same way, prefetched one slice ahead.  A thread
+// writing its own row 16 bytes at a time would be bound by L1/LSU request rate, not by HBM.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmA2,
                                                               const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmOut,
+                                                              const __grid_constant__ CUtensorMap tmRes,
                                                               const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + Cfg::STAGES * Cfg::B_BYTES);
+  uint8_t* sEpi = sB + Cfg::STAGES * Cfg::B_BYTES;            // [half][out0,out1,res0,res1][kSliceBytes]
+  float* sbias = reinterpret_cast<float*>(sEpi + Cfg::EPI_BYTES);   // [2 bufs][kMaxBiasGroups][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;    // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;               // [half][slot] residual slice landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,6 +124,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
+    if (p.tma_epi) {
+      prefetch_tmap(&tmOut);
+      prefetch_tmap(&tmRes);
+    }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -143,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], kEpiThreads);
     }
+    for (int b = 0; b < 4; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -214,29 +208,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue: TMEM -> regs -> global
-    // 8 warps: warp w reads TMEM lane quadrant (w & 3); the two warps of a quadrant alternate over the
-    // 32-column chunks of the tile.  Per tile the column bias is staged once in shared memory; the row-wise
-    // operands (residual, per-sample temb bias) are fetched as 16-byte vectors one chunk AHEAD of their use,
-    // the first chunk before the accumulator is even ready, so their latency hides under the main loop.
+    // ------------------------------------------------------------ epilogue
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;       // 0 | 1
-    const int r = q * 32 + lane;            // accumulator row
+    const int half = (warp - 2) >> 2;       // 0 | 1: which 32-column slices of the tile this warp handles
+    const int r = q * 32 + lane;            // accumulator row == TMEM lane
     const int etid = threadIdx.x - 64;      // 0..255
+    const bool leader = (threadIdx.x == 64 + 128 * half);
     const Epilogue& ep = p.ep;
-    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [2][BN]
-    constexpr bool kGeglu = false;
-    (void)kGeglu;
+    const bool geglu = ep.act == ACT_GEGLU;
+    const int bn_out = geglu ? BN / 2 : BN;           // output columns per tile
+    const int n_out = geglu ? p.N / 2 : p.N;          // output columns of the problem
+    uint8_t* sOut = sEpi + half * 4 * kSliceBytes;    // 2 slots
+    uint8_t* sRes = sOut + 2 * kSliceBytes;           // 2 slots
+    const int swz = (r >> 1) & 3;                     // 64B swizzle: 16-byte unit index ^= (row / 2) & 3
+    uint8_t* my_out_row = sOut + r * 64;
+    const uint8_t* my_res_row = sRes + r * 64;
+    uint32_t slice_cnt = 0;                           // slices processed by this half (slot = cnt & 1)
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int n_tile = t % p.n_tiles;
       const int m_tile = t / p.n_tiles;
+      int x0 = 0, y0 = 0, n0 = 0;
       bool valid;
       int64_t out_row;
       if (p.conv) {
-        const int x0 = (m_tile % p.tiles_x) * p.tile_w;
-        const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.tile_h;
-        const int n0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tile_n;
+        x0 = (m_tile % p.tiles_x) * p.tile_w;
+        y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.tile_h;
+        n0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tile_n;
         const int dx = r % p.tile_w;
         const int dy = (r / p.tile_w) % p.tile_h;
         const int dn = r / (p.tile_w * p.tile_h);
@@ -249,124 +247,161 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       const uint32_t buf = lt & 1;
       const uint32_t use = lt >> 1;
-      float* sb = sbias + buf * BN;
-      for (int c = etid; c < BN; c += kEpiThreads) {
-        const int col = n_tile * BN + c;
-        sb[c] = (ep.bias != nullptr && col < p.N) ? __ldg(ep.bias + col) : 0.f;
-      }
-      const __half* rgb = (valid && ep.rowgroup_bias) ? ep.rowgroup_bias + (out_row / ep.rows_per_group) * ep.rgb_ld
-                                                      : nullptr;
-      const __half* res = (valid && ep.residual) ? ep.residual + out_row * ep.ldr : nullptr;
-      const bool res_vec = res != nullptr && (ep.ldr & 7) == 0 && (p.N & 7) == 0;
-      const bool rgb_vec = rgb != nullptr && (ep.rgb_ld & 7) == 0 && (p.N & 7) == 0 &&
-                           ((reinterpret_cast<uintptr_t>(ep.rowgroup_bias) & 15) == 0);
-      const int col_base = n_tile * BN;
-      uint4 rv[4], gv[4];
-      auto fetch_rows = [&](int c0, uint4 (&rr)[4], uint4 (&gg)[4]) {
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int col = col_base + c0 + g8 * 8;
-          if (col + 8 <= p.N) {
-            if (res_vec) rr[g8] = *reinterpret_cast<const uint4*>(res + col);
-            if (rgb_vec) gg[g8] = __ldg(reinterpret_cast<const uint4*>(rgb + col));
+      const int col_base = n_tile * bn_out;                         // first OUTPUT column of the tile
+      const int nsl = (min(bn_out, n_out - col_base) + 31) >> 5;    // 32-column output slices in this tile
+
+      // ---- per-tile column bias (+ the per-sample temb vector when it is uniform over row blocks) -> smem
+      float* sb = sbias + buf * (kMaxBiasGroups * BN);
+      {
+        const int ngroups = p.rgb_rows > 0 ? (kBM / p.rgb_rows) : 1;
+        for (int i = etid; i < ngroups * BN; i += kEpiThreads) {
+          const int gi = i / BN;
+          const int c = i - gi * BN;
+          const int col = n_tile * BN + c;                          // accumulator column == bias index
+          float v = 0.f;
+          if (col < p.N) {
+            if (ep.bias) v = __ldg(ep.bias + col);
+            if (p.rgb_rows > 0 && n0 + gi < p.Bn)
+              v += __half2float(__ldg(ep.rowgroup_bias + static_cast<int64_t>(n0 + gi) * ep.rgb_ld + col));
           }
+          sb[i] = v;
         }
-      };
-      if (ep.act != ACT_GEGLU) fetch_rows(half * 32, rv, gv);
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // column bias staged (epilogue warps only)
-      mbar_wait(&tfull_bar[buf], use & 1);
-      tc_fence_after();
+      }
+      const float* sbr = sb + (p.rgb_rows > 0 ? (r / p.rgb_rows) * BN : 0);
       const uint32_t lane_addr = tmem_base + buf * Cfg::BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
 
-      if (ep.act == ACT_GEGLU) {
-        // tile columns [0, BN/2) = value, [BN/2, BN) = gate (weights are packed that way)
-        constexpr int HALF = BN / 2;
-        const int n_out = p.N / 2;
-#pragma unroll 1
-        for (int c0 = half * 32; c0 < HALF; c0 += 64) {
-          uint32_t ra[32], rg[32];
-          tmem_ld_32x32b_x32(lane_addr + c0, ra);
-          tmem_ld_32x32b_x32(lane_addr + HALF + c0, rg);
-          tmem_ld_wait();
-          if (valid) {
-            const int col_out = n_tile * HALF + c0;
+      if (p.tma_epi) {
+        // ================================================= fast path: smem slices + TMA
+        const bool has_res = ep.residual != nullptr;
+        auto issue_res = [&](int slice, uint32_t cnt) {       // leader only
+          const int slot = cnt & 1;
+          mbar_arrive_expect_tx(&res_bar[half * 2 + slot], kSliceBytes);
+          if (p.conv)
+            tma_load_4d(sRes + slot * kSliceBytes, &tmRes, &res_bar[half * 2 + slot], col_base + slice * 32, x0, y0, n0);
+          else
+            tma_load_2d(sRes + slot * kSliceBytes, &tmRes, &res_bar[half * 2 + slot], col_base + slice * 32,
+                        m_tile * kBM);
+        };
+        // the first residual slice of the tile is requested before the accumulator is ready
+        if (has_res && leader && half < nsl) issue_res(half, slice_cnt);
+        named_bar_sync(1, kEpiThreads);                        // column bias staged
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
+        for (int sl = half; sl < nsl; sl += 2, ++slice_cnt) {
+          const int slot = slice_cnt & 1;
+          if (leader) {
+            tma_store_wait_read<1>();                          // the store that last used this out slot has drained
+            if (has_res && sl + 2 < nsl) issue_res(sl + 2, slice_cnt + 1);
+          }
+          named_bar_sync(2 + half, 128);
+          float v[32];
+          if (geglu) {
+            uint32_t ra[32], rg[32];
+            tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
+            tmem_ld_32x32b_x32(lane_addr + BN / 2 + sl * 32, rg);
+            tmem_ld_wait();
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int j = g8 * 8 + i;
-                const float a = __uint_as_float(ra[j]) + sb[c0 + j];
-                const float g = __uint_as_float(rg[j]) + sb[HALF + c0 + j];
-                v[i] = a * gelu_erf(g);
-              }
-              store8(ep, out_row, col_out + g8 * 8, n_out, v);
+            for (int j = 0; j < 32; ++j) {
+              const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+              const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
+              v[j] = a * gelu_erf(gg);
             }
+          } else {
+            uint32_t ra[32];
+            tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+            if (ep.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            }
+          }
+          if (has_res) {
+            mbar_wait(&res_bar[half * 2 + slot], (slice_cnt >> 1) & 1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(my_res_row + slot * kSliceBytes + ((u ^ swz) << 4));
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(rh[i]);
+                v[u * 8 + 2 * i] += f.x;
+                v[u * 8 + 2 * i + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            __align__(16) __half2 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[u * 8 + 2 * i], v[u * 8 + 2 * i + 1]);
+            *reinterpret_cast<uint4*>(my_out_row + slot * kSliceBytes + ((u ^ swz) << 4)) = *reinterpret_cast<uint4*>(h);
+          }
+          fence_proxy_async();
+          named_bar_sync(2 + half, 128);
+          if (leader) {
+            if (p.conv)
+              tma_store_4d(&tmOut, sOut + slot * kSliceBytes, col_base + sl * 32, x0, y0, n0);
+            else
+              tma_store_2d(&tmOut, sOut + slot * kSliceBytes, col_base + sl * 32, m_tile * kBM);
+            tma_store_commit();
           }
         }
       } else {
+        // ================================================= direct path (fp32 out, unaligned pitches, tiny N)
+        const __half* rgb = (p.rgb_rows == 0 && valid && ep.rowgroup_bias)
+                                ? ep.rowgroup_bias + (out_row / ep.rows_per_group) * ep.rgb_ld
+                                : nullptr;
+        const __half* res = (valid && ep.residual) ? ep.residual + out_row * ep.ldr : nullptr;
+        named_bar_sync(1, kEpiThreads);
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
-          uint32_t ra[32];
-          tmem_ld_32x32b_x32(lane_addr + c0, ra);
-          uint4 rnext[4], gnext[4];
-          if (c0 + 64 < BN) fetch_rows(c0 + 64, rnext, gnext);   // next chunk's row operands, before this chunk's stores
-          tmem_ld_wait();
-          const int col0 = col_base + c0;
-          if (valid && col0 < p.N) {
+        for (int sl = half; sl < nsl; sl += 2) {
+          float v[32];
+          if (geglu) {
+            uint32_t ra[32], rg[32];
+            tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
+            tmem_ld_32x32b_x32(lane_addr + BN / 2 + sl * 32, rg);
+            tmem_ld_wait();
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int col = col0 + g8 * 8;
-              if (col >= p.N) break;
-              float v[8];
-              const bool full8 = col + 8 <= p.N;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ra[g8 * 8 + i]) + sb[c0 + g8 * 8 + i];
-              if (rgb) {
-                if (full8 && rgb_vec) {
-                  const __half2* gh = reinterpret_cast<const __half2*>(&gv[g8]);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(gh[i]);
-                    v[2 * i] += f.x;
-                    v[2 * i + 1] += f.y;
-                  }
-                } else {
-                  for (int i = 0; i < 8; ++i)
-                    if (col + i < p.N) v[i] += __half2float(__ldg(rgb + col + i));
-                }
-              }
-              if (ep.act == ACT_SILU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
-              }
-              if (res) {
-                if (full8 && res_vec) {
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[g8]);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(rh[i]);
-                    v[2 * i] += f.x;
-                    v[2 * i + 1] += f.y;
-                  }
-                } else {
-                  for (int i = 0; i < 8; ++i)
-                    if (col + i < p.N) v[i] += __half2float(res[col + i]);
-                }
-              }
-              store8(ep, out_row, col, p.N, v);
+            for (int j = 0; j < 32; ++j) {
+              const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+              const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
+              v[j] = a * gelu_erf(gg);
             }
-          }
+          } else {
+            uint32_t ra[32];
+            tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
+            tmem_ld_wait();
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            rv[g8] = rnext[g8];
-            gv[g8] = gnext[g8];
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+          }
+          if (valid) {
+            const int col0 = col_base + sl * 32;
+            if (rgb) {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < n_out) v[j] += __half2float(__ldg(rgb + col0 + j));
+            }
+            if (ep.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            }
+            if (res) {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < n_out) v[j] += __half2float(res[col0 + j]);
+            }
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8)
+              if (col0 + g8 * 8 < n_out) store8(ep, out_row, col0 + g8 * 8, n_out, v + g8 * 8);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
     }
+    if (leader) tma_store_wait_all();   // smem must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -386,21 +421,20 @@ static int sm_count() {
 }
 
 template <int BN>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const GemmParams& p,
-                  int m_tiles, cudaStream_t st) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                  const CUtensorMap& tmRes, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
+  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
   static bool attr_done = false;
   if (!attr_done) {
     GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  const long long tiles = static_cast<long long>(m_tiles) * p.n_tiles;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   GYRE_REQUIRE(tiles > 0 && tiles < (1ll << 31), "gemm: bad tile count %lld", tiles);
-  GemmParams pp = p;
-  pp.m_tiles = m_tiles;
   const int sms = sm_count();
   const unsigned blocks = static_cast<unsigned>(tiles < sms ? tiles : sms);
-  gemm_tc_kernel<BN><<<blocks, kThreads, Cfg::SMEM, st>>>(tmA, tmA2, tmB, pp);
+  gemm_tc_kernel<BN><<<blocks, kThreads, Cfg::SMEM, st>>>(tmA, tmA2, tmB, tmOut, tmRes, p);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -432,35 +466,25 @@ static int pick_bn(long long m_tiles, int N, int act) {
 }
 
 static int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
-                    const GemmParams& p, int m_tiles, cudaStream_t st) {
+                    const CUtensorMap& tmOut, const CUtensorMap& tmRes, const GemmParams& p, cudaStream_t st) {
   switch (bn) {
-    case 32: return launch<32>(tmA, tmA2, tmB, p, m_tiles, st);
-    case 64: return launch<64>(tmA, tmA2, tmB, p, m_tiles, st);
-    case 128: return launch<128>(tmA, tmA2, tmB, p, m_tiles, st);
-    case 160: return launch<160>(tmA, tmA2, tmB, p, m_tiles, st);
-    case 256: return launch<256>(tmA, tmA2, tmB, p, m_tiles, st);
+    case 32: return launch<32>(tmA, tmA2, tmB, tmOut, tmRes, p, st);
+    case 64: return launch<64>(tmA, tmA2, tmB, tmOut, tmRes, p, st);
+    case 128: return launch<128>(tmA, tmA2, tmB, tmOut, tmRes, p, st);
+    case 160: return launch<160>(tmA, tmA2, tmB, tmOut, tmRes, p, st);
+    case 256: return launch<256>(tmA, tmA2, tmB, tmOut, tmRes, p, st);
   }
   set_last_error("gemm: unsupported BN %d", bn);
   return -2;
 }
 
-static int check_epilogue(const Epilogue& ep, int N) {
-  if (ep.out_mode == OUT_SECTIONS) {
-    GYRE_REQUIRE(ep.sec_width > 0 && ep.sec_width % 8 == 0 && N % ep.sec_width == 0 && N / ep.sec_width <= 3,
-                 "gemm: bad sections (N=%d width=%d)", N, ep.sec_width);
-    for (int s = 0; s < N / ep.sec_width; ++s) {
-      GYRE_REQUIRE(ep.sec[s].ptr != nullptr, "gemm: null section %d", s);
-      if (ep.sec[s].mode != SEC_ROWMAJOR)
-        GYRE_REQUIRE(ep.hs_d % 8 == 0 && ep.hs_dpad % 8 == 0 && ep.hs_heads * ep.hs_d == ep.sec_width &&
-                         ep.hs_tokens > 0 && ep.hs_tpad >= ep.hs_tokens,
-                     "gemm: bad head-split geometry");
-      else
-        GYRE_REQUIRE(ep.sec[s].ld % 8 == 0, "gemm: section ld must be a multiple of 8");
-    }
-  } else {
-    GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "gemm: null output");
-  }
-  return 0;
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Can output / residual go through the TMA slices?  (fp16, 16-byte aligned rows)
+static bool tma_epilogue_ok(const Epilogue& ep, int n_out) {
+  if (ep.out_mode != OUT_F16 || ep.out == nullptr || (ep.ldo & 7) != 0 || !aligned16(ep.out)) return false;
+  if (ep.residual != nullptr && ((ep.ldr & 7) != 0 || !aligned16(ep.residual))) return false;
+  return n_out >= 8;
 }
 
 int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const Epilogue& ep,
@@ -472,29 +496,31 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
               int N, const Epilogue& ep, cudaStream_t st) {
   const int K = K1 + K2;
   GYRE_REQUIRE(M > 0 && N > 0 && K1 > 0 && K2 >= 0, "gemm: empty problem %dx%dx%d", M, N, K);
-  GYRE_REQUIRE(K2 == 0 || (A2 != nullptr && K1 % kBK == 0 && lda2 % 8 == 0 &&
-                           (reinterpret_cast<uintptr_t>(A2) & 15) == 0),
+  GYRE_REQUIRE(K2 == 0 || (A2 != nullptr && K1 % kBK == 0 && lda2 % 8 == 0 && aligned16(A2)),
                "gemm: two-source A needs K1 %% 64 == 0 and a 16B-aligned second source (K1=%d)", K1);
   GYRE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 halfs (TMA 16B pitch)");
-  GYRE_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
-               "gemm: operands must be 16B aligned");
-  GYRE_TRY(check_epilogue(ep, ep.act == ACT_GEGLU ? N / 2 : N));
+  GYRE_REQUIRE(aligned16(A) && aligned16(W), "gemm: operands must be 16B aligned");
+  GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "gemm: null output");
   const int bn = pick_bn((M + kBM - 1) / kBM, N, ep.act);
   if (ep.act == ACT_GEGLU) GYRE_REQUIRE(N % 256 == 0, "gemm: GEGLU needs N %% 256 == 0 (got %d)", N);
+  const int n_out = ep.act == ACT_GEGLU ? N / 2 : N;
   GemmParams p{};
   p.M = M;
   p.N = N;
   p.k1_iters = (K1 + kBK - 1) / kBK;
   p.k_iters = p.k1_iters + (K2 + kBK - 1) / kBK;
   p.n_tiles = (N + bn - 1) / bn;
+  p.m_tiles = (M + kBM - 1) / kBM;
   p.conv = 0;
   p.ep = ep;
-  CUtensorMap tmA, tmA2, tmB;
+  p.rgb_rows = 0;
+  p.tma_epi = (tma_epilogue_ok(ep, n_out) && ep.rowgroup_bias == nullptr) ? 1 : 0;
+  CUtensorMap tmA, tmA2, tmB, tmOut, tmRes;
+  uint32_t es[2] = {1, 1};
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K1), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
     uint32_t box[2] = {kBK, kBM};
-    uint32_t es[2] = {1, 1};
     GYRE_TRY(encode_tmap_f16(&tmA, A, 2, dims, strides, box, es, true));
     tmA2 = tmA;
   }
@@ -502,19 +528,32 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
     uint64_t dims[2] = {static_cast<uint64_t>(K2), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(lda2) * 2};
     uint32_t box[2] = {kBK, kBM};
-    uint32_t es[2] = {1, 1};
     GYRE_TRY(encode_tmap_f16(&tmA2, A2, 2, dims, strides, box, es, true));
   }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
     uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
-    uint32_t es[2] = {1, 1};
     GYRE_TRY(encode_tmap_f16(&tmB, W, 2, dims, strides, box, es, true));
   }
-  prof::Scope ps(prof::F_GEMM, 2.0 * M * (ep.act == ACT_GEGLU ? N : N) * K,
-                 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * (ep.act == ACT_GEGLU ? N / 2 : N)), st);
-  return dispatch(bn, tmA, tmA2, tmB, p, (M + kBM - 1) / kBM, st);
+  tmOut = tmA;
+  tmRes = tmA;
+  if (p.tma_epi) {
+    uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
+    uint32_t box[2] = {32, kBM};
+    uint64_t so[1] = {static_cast<uint64_t>(ep.ldo) * 2};
+    GYRE_TRY(encode_tmap_f16_sw(&tmOut, ep.out, 2, dims, so, box, es, 64));
+    tmRes = tmOut;
+    if (ep.residual) {
+      uint64_t sr[1] = {static_cast<uint64_t>(ep.ldr) * 2};
+      GYRE_TRY(encode_tmap_f16_sw(&tmRes, ep.residual, 2, dims, sr, box, es, 64));
+    }
+  }
+  prof::Scope ps(prof::F_GEMM, 2.0 * M * static_cast<double>(N) * K,
+                 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K +
+                        static_cast<double>(M) * n_out * (ep.residual ? 2 : 1)),
+                 st);
+  return dispatch(bn, tmA, tmA2, tmB, tmOut, tmRes, p, st);
 }
 
 static inline int pow2_ceil(int v) {
@@ -529,7 +568,7 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   GYRE_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d", stride);
   GYRE_REQUIRE(ldx % 8 == 0 && Cin % 8 == 0, "conv3x3: channel pitch must be a multiple of 8");
   GYRE_REQUIRE(ep.act != ACT_GEGLU, "conv3x3: GEGLU epilogue not supported");
-  GYRE_TRY(check_epilogue(ep, Cout));
+  GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "conv3x3: null output");
   const int Ho = (stride == 1) ? H : (pad == 1 ? (H - 1) / 2 + 1 : (H + 1 - 3) / 2 + 1);
   const int Wo = (stride == 1) ? W : (pad == 1 ? (W - 1) / 2 + 1 : (W + 1 - 3) / 2 + 1);
   // choose the 128-pixel patch shape with the least padded work
@@ -553,9 +592,8 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
     }
   }
   GYRE_REQUIRE(best_cost > 0, "conv3x3: no tile shape for %dx%d", Ho, Wo);
-  const int bn = pick_bn(static_cast<long long>((Wo + best_w - 1) / best_w) * ((Ho + best_h - 1) / best_h) *
-                             ((B + best_n - 1) / best_n),
-                         Cout, ACT_NONE);
+  const int m_tiles = ((Wo + best_w - 1) / best_w) * ((Ho + best_h - 1) / best_h) * ((B + best_n - 1) / best_n);
+  const int bn = pick_bn(m_tiles, Cout, ACT_NONE);
   GemmParams p{};
   p.M = 0;
   p.N = Cout;
@@ -564,6 +602,7 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   p.k_iters = 9 * p.cin_chunks;
   p.k1_iters = p.k_iters;
   p.n_tiles = (Cout + bn - 1) / bn;
+  p.m_tiles = m_tiles;
   p.conv = 1;
   p.tile_w = best_w;
   p.tile_h = best_h;
@@ -576,7 +615,13 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   p.stride = stride;
   p.pad = pad;
   p.ep = ep;
-  CUtensorMap tmA, tmB;
+  // the per-sample bias (temb projection) is uniform over the rows of one image inside a tile: stage it with
+  // the column bias when a tile holds at most kMaxBiasGroups images
+  p.rgb_rows = 0;
+  if (ep.rowgroup_bias != nullptr && ep.rows_per_group == Ho * Wo && best_n <= kMaxBiasGroups)
+    p.rgb_rows = best_w * best_h;
+  p.tma_epi = (tma_epilogue_ok(ep, Cout) && (ep.rowgroup_bias == nullptr || p.rgb_rows > 0)) ? 1 : 0;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                         static_cast<uint64_t>(B)};
@@ -594,10 +639,28 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
     uint32_t es[2] = {1, 1};
     GYRE_TRY(encode_tmap_f16(&tmB, Wp, 2, dims, strides, box, es, true));
   }
-  const int m_tiles = p.tiles_x * p.tiles_y * ((B + best_n - 1) / best_n);
+  tmOut = tmA;
+  tmRes = tmA;
+  if (p.tma_epi) {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                        static_cast<uint64_t>(B)};
+    uint32_t box[4] = {32, static_cast<uint32_t>(best_w), static_cast<uint32_t>(best_h), static_cast<uint32_t>(best_n)};
+    uint32_t es[4] = {1, 1, 1, 1};
+    uint64_t so[3] = {static_cast<uint64_t>(ep.ldo) * 2, static_cast<uint64_t>(ep.ldo) * 2 * Wo,
+                      static_cast<uint64_t>(ep.ldo) * 2 * Wo * Ho};
+    GYRE_TRY(encode_tmap_f16_sw(&tmOut, ep.out, 4, dims, so, box, es, 64));
+    tmRes = tmOut;
+    if (ep.residual) {
+      uint64_t sr[3] = {static_cast<uint64_t>(ep.ldr) * 2, static_cast<uint64_t>(ep.ldr) * 2 * Wo,
+                        static_cast<uint64_t>(ep.ldr) * 2 * Wo * Ho};
+      GYRE_TRY(encode_tmap_f16_sw(&tmRes, ep.residual, 4, dims, sr, box, es, 64));
+    }
+  }
   prof::Scope ps(prof::F_CONV, 2.0 * 9 * Cin * Cout * static_cast<double>(B) * Ho * Wo,
-                 2.0 * (static_cast<double>(B) * H * W * Cin + 9.0 * Cin * Cout + static_cast<double>(B) * Ho * Wo * Cout), st);
-  return dispatch(bn, tmA, tmA, tmB, p, m_tiles, st);
+                 2.0 * (static_cast<double>(B) * H * W * Cin + 9.0 * Cin * Cout +
+                        static_cast<double>(B) * Ho * Wo * Cout * (ep.residual ? 2 : 1)),
+                 st);
+  return dispatch(bn, tmA, tmA, tmB, tmOut, tmRes, p, st);
 }
 
 }  // namespace gyre

@@ -8,15 +8,8 @@
 
 namespace gyre {
 
-enum OutMode { OUT_F16 = 0, OUT_F32 = 1, OUT_SECTIONS = 4 };
-enum SecMode { SEC_ROWMAJOR = 0, SEC_HEADSPLIT = 2, SEC_HEADSPLIT_T = 3 };
+enum OutMode { OUT_F16 = 0, OUT_F32 = 1 };
 enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2 };
-
-struct OutSection {
-  void* ptr;   // fp16
-  int mode;    // SecMode
-  int ld;      // row pitch (elements) for SEC_ROWMAJOR
-};
 
 // Epilogue description shared by the GEMM and the implicit-GEMM conv.
 struct Epilogue {
@@ -30,10 +23,6 @@ struct Epilogue {
   int ldo = 0;
   int out_mode = OUT_F16;
   int act = ACT_NONE;
-  // OUT_SECTIONS: column c belongs to section c / sec_width; head layouts use the hs_* fields
-  OutSection sec[3] = {};
-  int sec_width = 0;
-  int hs_tokens = 0, hs_heads = 0, hs_d = 0, hs_dpad = 0, hs_tpad = 0;
 };
 
 // out[M, N] = epilogue(A[M, K] @ W[N, K]^T).  A: fp16 row pitch lda; W: packed fp16 [N, Kp] row pitch ldw.
