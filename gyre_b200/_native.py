@@ -272,6 +272,22 @@ def attention(q, k, v, heads, scale=None):
     return out
 
 
+def tome_merge_kv(k, v, r):
+    """k, v [B, N, C] fp16 (dense) -> merged [B, N - r, C] pair (reference: bipartite_soft_matching + merge_wavg)."""
+    require_cuda(k, v)
+    B, Nt, Cc = k.shape
+    r = min(r, Nt // 2)
+    n = C.c_size_t()
+    check(load().gyre_b200_tome_workspace_bytes(B, Nt, Cc, C.byref(n)), "tome_workspace_bytes")
+    ws = torch.empty((n.value,), device=k.device, dtype=torch.uint8)
+    ko = torch.empty((B, Nt - r, Cc), device=k.device, dtype=torch.float16)
+    vo = torch.empty_like(ko)
+    k, v = k.contiguous(), v.contiguous()
+    check(load().gyre_b200_tome_merge_kv(ptr(k), ptr(v), B, Nt, Cc, r, ptr(ko), ptr(vo), ptr(ws), ws.numel(),
+                                         stream_ptr(k.device)), "tome_merge_kv")
+    return ko, vo
+
+
 FAMILIES = ("gemm", "conv3x3", "attention", "groupnorm", "layernorm", "softmax", "elementwise", "tome")
 
 

@@ -357,6 +357,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         named_bar_sync(1, kEpiThreads);
         mbar_wait(&tfull_bar[buf], use & 1);
         tc_fence_after();
+        float best = -INFINITY;
+        int best_idx = 0x7fffffff;
 #pragma unroll 1
         for (int sl = half; sl < nsl; sl += 2) {
           float v[32];
@@ -378,7 +380,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
           }
-          if (valid) {
+          if (ep.act == ACT_ROWMAX) {
+            const int col0 = col_base + sl * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < n_out && v[j] > best) {     // strict: the first (lowest) column wins ties
+                best = v[j];
+                best_idx = col0 + j;
+              }
+          } else if (valid) {
             const int col0 = col_base + sl * 32;
             if (rgb) {
               for (int j = 0; j < 32; ++j)
@@ -396,6 +406,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int g8 = 0; g8 < 4; ++g8)
               if (col0 + g8 * 8 < n_out) store8(ep, out_row, col0 + g8 * 8, n_out, v + g8 * 8);
           }
+        }
+        if (ep.act == ACT_ROWMAX && valid) {
+          const int64_t o = out_row * ep.rowmax_ld + n_tile * 2 + half;
+          ep.rowmax_val[o] = best;
+          ep.rowmax_idx[o] = best_idx;
         }
       }
       tc_fence_before();
@@ -487,6 +502,11 @@ static bool tma_epilogue_ok(const Epilogue& ep, int n_out) {
   return n_out >= 8;
 }
 
+int gemm_rowmax_partials(int M, int N) {
+  const int bn = pick_bn((M + kBM - 1) / kBM, N, ACT_ROWMAX);
+  return 2 * ((N + bn - 1) / bn);
+}
+
 int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const Epilogue& ep,
              cudaStream_t st) {
   return gemm2_f16(A, lda, K, nullptr, 0, 0, W, ldw, M, N, ep, st);
@@ -500,7 +520,10 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
                "gemm: two-source A needs K1 %% 64 == 0 and a 16B-aligned second source (K1=%d)", K1);
   GYRE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 halfs (TMA 16B pitch)");
   GYRE_REQUIRE(aligned16(A) && aligned16(W), "gemm: operands must be 16B aligned");
-  GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "gemm: null output");
+  if (ep.act == ACT_ROWMAX)
+    GYRE_REQUIRE(ep.rowmax_val && ep.rowmax_idx && ep.rowmax_ld >= gemm_rowmax_partials(M, N), "gemm: bad rowmax buffers");
+  else
+    GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "gemm: null output");
   const int bn = pick_bn((M + kBM - 1) / kBM, N, ep.act);
   if (ep.act == ACT_GEGLU) GYRE_REQUIRE(N % 256 == 0, "gemm: GEGLU needs N %% 256 == 0 (got %d)", N);
   const int n_out = ep.act == ACT_GEGLU ? N / 2 : N;

@@ -9,7 +9,7 @@
 namespace gyre {
 
 enum OutMode { OUT_F16 = 0, OUT_F32 = 1 };
-enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2 };
+enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2, ACT_ROWMAX = 3 };
 
 // Epilogue description shared by the GEMM and the implicit-GEMM conv.
 struct Epilogue {
@@ -23,6 +23,11 @@ struct Epilogue {
   int ldo = 0;
   int out_mode = OUT_F16;
   int act = ACT_NONE;
+  // ACT_ROWMAX (ToMe scoring): nothing is stored but, per row, the max and argmax over each (n-tile, column-half)
+  // of the product: rowmax_val / rowmax_idx [rows, rowmax_ld], entry n_tile * 2 + half
+  float* rowmax_val = nullptr;
+  int* rowmax_idx = nullptr;
+  int rowmax_ld = 0;
 };
 
 // out[M, N] = epilogue(A[M, K] @ W[N, K]^T).  A: fp16 row pitch lda; W: packed fp16 [N, Kp] row pitch ldw.
@@ -33,6 +38,8 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
 // shortcut without materialising the concatenation).  K1 must be a multiple of 64.
 int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int K2, const __half* W, int ldw, int M,
               int N, const Epilogue& ep, cudaStream_t st);
+// number of (max, argmax) partials per row an ACT_ROWMAX GEMM of this shape writes
+int gemm_rowmax_partials(int M, int N);
 
 // 3x3 convolution as implicit GEMM.  X: [B, H, W, Cin] fp16 NHWC with channel pitch ldx; Wp: packed
 // [Cout, 9*cin_pad] (tap-major, cin_pad = round_up(Cin, 64)); output rows are pixels of [B, Ho, Wo].
