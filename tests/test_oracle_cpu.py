@@ -1,0 +1,118 @@
+"""The oracle against the committed golden vectors (tests/golden/*.pt).  samplers.pt / ddim.pt / tome.pt hold
+outputs of the REFERENCE's own vendored code (k-diffusion, in-tree DDIM copy, ToMe), produced by
+scripts/make_golden.py in the build container where /root/reference is mounted; oracle_tiny.pt pins the
+oracle's UNet / VAE / pipeline outputs against accidental drift."""
+import os
+
+import pytest
+import torch
+
+from oracle import sampling as osamp
+from oracle import tome as otome
+from oracle.unet import UNetConfig, OracleUNet, synth_params, unet_forward, unet_param_shapes
+from oracle.vae import VAEConfig, vae_decode, vae_encode_moments, vae_param_shapes
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def toy_eps(x, t):
+    t = t if torch.is_tensor(t) else torch.tensor(t)
+    tt = t.float().reshape(-1, *([1] * (x.ndim - 1)))
+    return 0.7 * torch.tanh(x) + 0.001 * tt * x.roll(1, -1)
+
+
+@pytest.mark.parametrize("name", ["euler_a", "euler", "heun", "dpmpp_2m"])
+@pytest.mark.parametrize("steps", [7, 20])
+@pytest.mark.parametrize("dtype_name,ldt", [("fp32", torch.float32), ("fp16", torch.float16)])
+def test_samplers_match_vendored_k_diffusion(name, steps, dtype_name, ldt):
+    rec = torch.load(os.path.join(GOLD, "samplers.pt"))[f"{name}/{steps}/{dtype_name}"]
+    shape, seeds = rec["shape"], rec["seeds"]
+    gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    den = osamp.EpsDenoiser(toy_eps, osamp.sd_alphas_cumprod())
+    sig = osamp.k_sigmas(den, steps)
+    assert torch.equal(sig, rec["sigmas"])
+    x = (osamp.batched_randn(shape, gens, "cpu", ldt) * sig[0]).float()
+    ns = lambda *_: osamp.batched_randn(shape, gens, "cpu", ldt).float()
+    s = sig.to(ldt).float()
+    if name == "euler_a":
+        got = osamp.sample_euler_ancestral(den, x, s, ns)
+    elif name == "euler":
+        got = osamp.sample_euler(den, x, s, lambda _x: ns())
+    elif name == "heun":
+        got = osamp.sample_heun(den, x, s, lambda _x: ns())
+    else:
+        got = osamp.sample_dpmpp_2m(den, x, s, warmup_lms=True, ddim_cutoff=0.1)
+    assert torch.equal(got, rec["result"]), f"{name}/{steps}/{dtype_name} drifted from the vendored k-diffusion output"
+
+
+def test_denoiser_wrappers_and_schedules():
+    g = torch.load(os.path.join(GOLD, "samplers.pt"))
+    acp = osamp.sd_alphas_cumprod()
+    v = g["vdenoiser"]
+    assert torch.equal(osamp.VDenoiser(toy_eps, acp)(v["x"], v["sigma"]), v["result"])
+    den = osamp.EpsDenoiser(toy_eps, acp)
+    assert torch.equal(osamp.get_sigmas_karras(11, den.sigma_min, den.sigma_max, 7.0), g["karras/11"])
+    st = g["sigma_to_t"]
+    assert torch.equal(den.sigma_to_t(st["sigma"]), st["t"])
+    # SD schedule end points
+    assert abs(float(den.sigma_min) - 0.0292) < 1e-3 and abs(float(den.sigma_max) - 14.6146) < 1e-3
+
+
+@pytest.mark.parametrize("pred", ["epsilon", "v_prediction"])
+@pytest.mark.parametrize("eta", [0.0, 0.6])
+def test_ddim_matches_in_tree_copy(pred, eta):
+    rec = torch.load(os.path.join(GOLD, "ddim.pt"))[f"{pred}/{eta}"]
+    gen = torch.Generator("cpu").manual_seed(99)
+    got = osamp.sample_ddim(toy_eps, rec["x"].clone(), 10, osamp.sd_alphas_cumprod(), eta, gen, pred)
+    assert (got - rec["result"]).abs().max().item() < 1e-6
+    assert osamp.ddim_timesteps(10).tolist() == [901, 801, 701, 601, 501, 401, 301, 201, 101, 1]
+
+
+def test_tome_matches_vendored_merge():
+    g = torch.load(os.path.join(GOLD, "tome.pt"))
+    for name, rec in g.items():
+        if name == "parse_r":
+            assert otome.parse_r(16, (100, 0.5)) == rec["(100,0.5)"]
+            continue
+        plan = otome.bipartite_soft_matching_plan(rec["k"], rec["r"])
+        assert torch.equal(otome.merge_mean(plan, rec["k"]), rec["k_merged"]), name
+        assert torch.equal(otome.merge_mean(plan, rec["v"]), rec["v_merged"]), name
+    # edge cases the reference handles: r == 0 / r larger than half (clamped) / odd token counts
+    k = torch.randn(1, 9, 8, generator=torch.Generator().manual_seed(0))
+    assert otome.bipartite_soft_matching_plan(k, 0) is None
+    plan = otome.bipartite_soft_matching_plan(k, 100)
+    assert otome.merge_mean(plan, k).shape == (1, 9 - 4, 8)
+    assert otome.parse_r(4, [3]) == [3, 0, 0, 0]
+    assert otome.parse_r(16, 8) == [8] * 16
+
+
+def test_oracle_unet_vae_pipeline_fixtures():
+    g = torch.load(os.path.join(GOLD, "oracle_tiny.pt"))
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    u = g["unet_tiny"]
+    with torch.no_grad():
+        assert (unet_forward(P, cfg, u["x"], u["t"], u["ctx"]) - u["eps"]).abs().max().item() < 1e-4
+        t = g["unet_tiny_tome"]
+        assert (unet_forward(P, cfg, u["x"], u["t"], u["ctx"], tome_r=t["r"]) - t["eps"]).abs().max().item() < 1e-4
+        vcfg = VAEConfig.tiny()
+        VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+        assert (vae_decode(VP, vcfg, g["vae_tiny"]["z"]) - g["vae_tiny"]["img"]).abs().max().item() < 1e-4
+        e = g["vae_tiny_enc"]
+        assert (vae_encode_moments(VP, vcfg, e["img"]) - e["moments"]).abs().max().item() < 1e-4
+        unet = OracleUNet(cfg, P)
+        emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(11))
+        unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1)
+        cfgu = osamp.CFGParallel(unet, unc, emb, 7.5)
+        rec = g["pipe_tiny/euler_a"]
+        lat = osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=128, width=128, sample_size=16,
+                                    seeds=[420420420, 420420421], steps=rec["steps"], sampler="euler_a")
+        assert (lat - rec["latents"]).abs().max().item() < 1e-3 * rec["latents"].abs().max().item()
+
+
+def test_c1_fixture_present_and_sane():
+    """The full-size C1 latents (SD1.5 arch, 10 DDIM steps, seed 420420420) are what the GPU parity test of
+    BASELINE config 1 compares against."""
+    rec = torch.load(os.path.join(GOLD, "c1_sd15_ddim10.pt"))
+    assert rec["latents"].shape == (1, 4, 64, 64) and rec["steps"] == 10 and rec["sampler"] == "ddim"
+    assert torch.isfinite(rec["latents"]).all()
