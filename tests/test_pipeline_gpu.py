@@ -124,3 +124,75 @@ def test_pipeline_batch_independence(tiny):
     both = run([0, 1])
     assert torch.equal(run([0])[0], both[0])
     assert torch.equal(run([1])[0], both[1])
+
+
+def _oracle_on_gpu(cfg_name="sd15"):
+    from oracle.unet import UNetConfig, OracleUNet, synth_params, unet_param_shapes
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = UNetConfig.sd15()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    return cfg, P
+
+
+def test_c1_sd15_ddim10_final_latents_vs_golden():
+    """BASELINE config 1: SD1.5 architecture, 512x512, 10 DDIM steps, CFG 7.5, batch 1, seed 420420420.
+    The golden latents come from the fp32 oracle run on the CPU (scripts/make_golden.py --full)."""
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    cfg, P = _oracle_on_gpu()
+    rec = torch.load(os.path.join(GOLD, "c1_sd15_ddim10.pt"))
+    unet = B200UNet(cfg).load_state_dict(P)
+    pipe = B200Pipeline(unet, None)
+    emb = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(11))
+    unc = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(12))
+    out = pipe(emb.cuda(), unc.cuda(), height=512, width=512, num_inference_steps=10, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(rec["seed"])], sampler="ddim", output_type="latent",
+               latents_dtype=torch.float32, return_fp32_latents=True)
+    ref = rec["latents"]
+    err = (out.latents.cpu() - ref).abs().max().item()
+    print(f"C1 SD1.5 512x512 10-step DDIM: final-latent max abs err {err:.4e} (latent max {ref.abs().max().item():.3f}, "
+          f"rel {err / ref.abs().max().item():.3e})")
+    assert err < 2e-2 * ref.abs().max().item()
+
+
+def test_c2_sd15_euler_a_50_final_latents_vs_oracle():
+    """BASELINE config 2 shape (batch 2 of the 8): 50 Euler-ancestral steps, fp16 sigma quantisation, per-sample
+    CPU generators; oracle evaluated in fp32 on the GPU with the same weights / seeds.  Also reports how far
+    the oracle moves when PyTorch evaluates it in fp16 (the reference's own GPU dtype) - the noise floor."""
+    from oracle import sampling as osamp
+    from oracle.unet import OracleUNet
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    cfg, P = _oracle_on_gpu()
+    seeds = [420420420, 420420421]
+    emb = torch.randn(2, 77, 768, generator=torch.Generator().manual_seed(11))
+    unc = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1).contiguous()
+    unet = B200UNet(cfg).load_state_dict(P)
+    pipe = B200Pipeline(unet, None)
+    out = pipe(emb.cuda(), unc.cuda(), height=512, width=512, num_inference_steps=50, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
+               output_type="latent", latents_dtype=torch.float16, return_fp32_latents=True)
+    Pc = {k: v.cuda() for k, v in P.items()}
+
+    def run_oracle(params, dtype):
+        ou = OracleUNet(cfg, params)
+        class Cast:
+            config = cfg
+            def __call__(self, latents, t, *, encoder_hidden_states):
+                r = ou(latents.to(dtype), t, encoder_hidden_states=encoder_hidden_states.to(dtype))
+                r.sample = r.sample.float()
+                return r
+        cfgu = osamp.CFGParallel(Cast(), unc.cuda(), emb.cuda(), 7.5)
+        with torch.no_grad():
+            return osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=512, width=512, sample_size=64, seeds=seeds,
+                                         steps=50, sampler="euler_a", device="cuda", latent_dtype=torch.float16)
+    ref = run_oracle(Pc, torch.float32)
+    ref16 = run_oracle({k: v.half() for k, v in Pc.items()}, torch.float16)
+    err = (out.latents - ref).abs().max().item()
+    floor = (ref16 - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"C2 SD1.5 512x512 50-step Euler-a (2 samples): final-latent max abs err {err:.4e}; torch-fp16 evaluation "
+          f"of the oracle differs by {floor:.4e} (noise floor); latent max {scale:.3f}")
+    assert torch.isfinite(out.latents).all()
+    assert err < max(4 * floor, 5e-2 * scale)

@@ -61,7 +61,8 @@ def test_tome_vs_oracle_same_inputs(nat, B, N, C, r):
         return torch.softmax(q @ kk.float().transpose(1, 2) * C ** -0.5, dim=-1) @ vv.float()
     err = (attend(ko, vo) - attend(kr, vr)).abs().max().item()
     print(f"tome B{B} N{N} C{C} r{r}: position-wise token match k {ak:.4f} v {av:.4f}; attention max abs diff {err:.2e}")
-    assert err < 5e-3
+    # a partial merge (r < N/2) additionally lets a near-tie decide WHICH token crosses the rank-r cut
+    assert err < (5e-3 if r >= N // 2 else 3e-2)
     if r >= N // 2:          # everything merged: no ordering freedom left
         assert ak > 0.97 and av > 0.97
 
