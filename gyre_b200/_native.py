@@ -61,12 +61,15 @@ SIGNATURES = {
     "gyre_b200_prof_reset": (_i, []),
     "gyre_b200_prof_read": (_i, [_i, C.POINTER(C.c_ulonglong), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]),
+    "gyre_b200_set_tunable": (_i, [C.c_char_p, _i]),
+    "gyre_b200_get_tunable": (_i, [C.c_char_p, C.POINTER(_i)]),
     "gyre_b200_unet_create": (_i, [C.POINTER(UNetConfigC), C.POINTER(_vp)]),
     "gyre_b200_unet_num_transformer_blocks": (_i, [_vp]),
     "gyre_b200_load_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i, _vp]),
     "gyre_b200_finalize": (_i, [_vp]),
     "gyre_b200_unet_workspace_bytes": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
+    "gyre_b200_unet_set_context": (_i, [_vp, _vp, _i, _i, _vp]),
     "gyre_b200_vae_create": (_i, [C.POINTER(VAEConfigC), C.POINTER(_vp)]),
     "gyre_b200_vae_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -82,6 +85,9 @@ SIGNATURES = {
     "gyre_b200_conv3x3": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, C.POINTER(Epilogue), _vp]),
     "gyre_b200_conv3x3_packed_elems": (_sz, [_i, _i]),
     "gyre_b200_pack_conv3x3": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "gyre_b200_upconv3x3_packed_elems": (_sz, [_i, _i]),
+    "gyre_b200_pack_upconv3x3": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "gyre_b200_upconv2x": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(Epilogue), _vp]),
     "gyre_b200_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),
     "gyre_b200_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
     "gyre_b200_layernorm": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
@@ -232,6 +238,28 @@ def conv3x3(x_nhwc, wp, cout, bias=None, residual=None, stride=1, pad=1, act=0, 
     return out.view(B, Ho, Wo, cout)
 
 
+def pack_upconv3x3(w):
+    require_cuda(w)
+    cout, cin = w.shape[0], w.shape[1]
+    n = load().gyre_b200_upconv3x3_packed_elems(cin, cout)
+    wp = torch.empty((n,), device=w.device, dtype=torch.float16)
+    w = w.contiguous()
+    check(load().gyre_b200_pack_upconv3x3(ptr(w), dtype_code(w), cin, cout, ptr(wp), stream_ptr(w.device)),
+          "pack_upconv3x3")
+    return wp
+
+
+def upconv2x(x_nhwc, wp4, cout, bias=None):
+    """conv3x3(nearest_upsample_2x(x)): x [B, H, W, Cin] fp16 NHWC -> [B, 2H, 2W, Cout] fp16 NHWC."""
+    require_cuda(x_nhwc, wp4)
+    B, H, W, Cin = x_nhwc.shape
+    out = torch.empty((B * 4 * H * W, cout), device=x_nhwc.device, dtype=torch.float16)
+    e = _epilogue(out, bias)
+    check(load().gyre_b200_upconv2x(ptr(x_nhwc), Cin, B, H, W, Cin, ptr(wp4), cout, C.byref(e),
+                                    stream_ptr(x_nhwc.device)), "upconv2x")
+    return out.view(B, 2 * H, 2 * W, cout)
+
+
 def groupnorm(x1, gamma, beta, groups, eps, silu, x2=None):
     """x1 [B, HW, C1] (+ x2 [B, HW, C2]) fp16 -> [B, HW, C1+C2] fp16."""
     require_cuda(x1, gamma, beta)
@@ -293,6 +321,16 @@ FAMILIES = ("gemm", "conv3x3", "attention", "groupnorm", "layernorm", "softmax",
 
 def launch_count() -> int:
     return int(load().gyre_b200_launch_count())
+
+
+def set_tunable(name: str, value: int):
+    check(load().gyre_b200_set_tunable(name.encode(), int(value)), "set_tunable")
+
+
+def get_tunable(name: str) -> int:
+    v = C.c_int(0)
+    check(load().gyre_b200_get_tunable(name.encode(), C.byref(v)), "get_tunable")
+    return v.value
 
 
 def prof_enable(on: bool):

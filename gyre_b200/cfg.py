@@ -24,6 +24,13 @@ class B200GuidedUNet:
                                                                               dtype=torch.float16).contiguous()
 
     def raw(self, x2_f16, t2_i64, out=None):
+        # The embeddings are fixed for the life of this wrapper (as in UNetWithEmbeddings, core.py:253-259), so
+        # the UNet projects them to cross-attention K/V once instead of at every step (tunable CTX_KV_CACHE).
+        if N.get_tunable("CTX_KV_CACHE"):
+            bound = self.unet._ctx_bound
+            if bound is None or bound[0] is not self:
+                self.unet.set_context(self.embeddings, owner=self)
+            return self.unet.forward_raw(x2_f16, t2_i64, None, out=out)
         return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out)
 
     def __call__(self, latents, t):

@@ -27,6 +27,7 @@ struct AttnParams {
   int ksteps_qk;     // ceil(d / 16)
   int npv;           // round_up(d, 16): accumulator columns of O
   int q_tiles;
+  int splits, tiles_per_cta;   // short-key kernel: CTAs per (batch, head) and 128-row query tiles per CTA
   float scale_log2;  // scale * log2(e)
   __half* out;
   int ldo;
@@ -90,6 +91,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
 
@@ -286,6 +289,86 @@ struct Att2Cfg {
   static constexpr int TMEM_COLS = 512;                        // S0, S1: [0,256); O0 at 256, O1 at 384
 };
 
+// Softmax variants (template parameter V of attention2_kernel; bit flags):
+//   AV_STAGGER  the first S tile of group 1 is issued only after group 0 is half way through its first exp
+//               phase, so the two groups' exp phases alternate on the MUFU instead of colliding
+//   AV_PACKED   scale / sum with packed fp32x2 instructions (FFMA2 / FADD2: two elements per issue slot)
+//   AV_POLY25 / AV_POLY50  every 4th / 2nd pair of scores takes exp2 on the FMA pipe (Cody-Waite split +
+//               degree-3 minimax polynomial, rel err 7.5e-5 < fp16 rounding of P) instead of the MUFU
+//   AV_F16EXP   ex2.approx.f16x2 (arguments rounded to fp16: measurement variant only)
+//   AV_NOEXP    diagnostic: no exponential at all (timing floor of everything that is not the MUFU)
+enum : int { AV_STAGGER = 1, AV_PACKED = 2, AV_POLY25 = 4, AV_POLY50 = 8, AV_F16EXP = 16, AV_NOEXP = 32 };
+
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  // 2^x for x <= ~8: n = round(x) via the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-3
+  // polynomial, exponent inserted with an integer add.  Arguments are clamped at -125 (result ~ 2^-125 ~ 0).
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 r = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 q = __ffma2_rn(make_float2(0.05517084f, 0.05517084f), f, make_float2(0.24260935f, 0.24260935f));
+  q = __ffma2_rn(q, f, make_float2(0.69326096f, 0.69326096f));
+  q = __ffma2_rn(q, f, make_float2(0.99992818f, 0.99992818f));
+  float2 o;
+  o.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
+  o.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
+  return o;
+}
+
+// p = exp2(s * c - mc) for 32 scores of one row -> fp16, swizzled K-major store of 4 x 16 bytes; row sum in lsum
+template <int V>
+__device__ __forceinline__ void softmax_chunk32(const uint32_t (&v)[32], float c, float mc, float2& lsum,
+                                                uint8_t* pchunk, int u0, int rx) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = u * 8 + 2 * k;
+      const int pair = u * 4 + k;
+      float2 x;
+      if constexpr ((V & AV_PACKED) != 0) {
+        x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(c, c),
+                       make_float2(-mc, -mc));
+      } else {
+        x.x = fmaf(__uint_as_float(v[i]), c, -mc);
+        x.y = fmaf(__uint_as_float(v[i + 1]), c, -mc);
+      }
+      const bool poly = ((V & AV_POLY50) != 0 && (pair & 1) == 1) || ((V & AV_POLY25) != 0 && (pair & 3) == 3);
+      float2 e;
+      if constexpr ((V & AV_F16EXP) != 0) {
+        const __half2 xh = __floats2half2_rn(x.x, x.y);
+        uint32_t ph;
+        asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(*reinterpret_cast<const uint32_t*>(&xh)));
+        w[k] = ph;
+        e = __half22float2(*reinterpret_cast<const __half2*>(&ph));
+      } else {
+        if constexpr ((V & AV_NOEXP) != 0) {
+          e.x = fmaf(x.x, 1e-4f, 0.5f);
+          e.y = fmaf(x.y, 1e-4f, 0.5f);
+        } else if (poly) {
+          e = exp2_poly2(x);
+        } else {
+          e.x = ex2_approx(x.x);
+          e.y = ex2_approx(x.y);
+        }
+        const __half2 hh = __floats2half2_rn(e.x, e.y);
+        w[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      if constexpr ((V & AV_PACKED) != 0) {
+        lsum = __fadd2_rn(lsum, e);
+      } else {
+        lsum.x += e.x;
+        lsum.y += e.y;
+      }
+    }
+    *reinterpret_cast<uint4*>(pchunk + (((u0 + u) ^ rx) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <int V>
 __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                      const __grid_constant__ CUtensorMap tmK,
                                                                      const __grid_constant__ CUtensorMap tmV,
@@ -304,7 +387,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   uint64_t* s_full = kv_empty + Cfg::STAGES;   // [2]
   uint64_t* p_full = s_full + 2;               // [2]
   uint64_t* pv_done = p_full + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* half_bar = pv_done + 2;            // group 0 is half way through its first exp phase
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(half_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -314,6 +398,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   const int b = bh / p.heads;
   const int q0 = q_pair * 2 * kBQ;
   const bool two = q0 + kBQ < p.Nq;            // the second tile exists
+  // staggering costs half an exp phase of latency once: only worth it on long key sequences
+  const bool stagger = (V & AV_STAGGER) != 0 && two && p.n_kv_tiles >= 4;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ);
@@ -329,6 +415,7 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
       mbar_init(&p_full[g], 128);
       mbar_init(&pv_done[g], 1);
     }
+    mbar_init(half_bar, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -336,6 +423,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -371,7 +460,11 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      for (int g = 0; g < ng; ++g) issue_s(g, 0);
+      issue_s(0, 0);
+      if (ng == 2) {
+        if (stagger) mbar_wait(half_bar, 0);
+        issue_s(1, 0);
+      }
       for (int j = 0; j < p.n_kv_tiles; ++j) {
         const int s = j % Cfg::STAGES;
         const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
@@ -455,29 +548,13 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
             }
           }
           const float mc = m_ref * c;
-          float l0 = 0.f, l1 = 0.f;
-#define GYRE_SOFTMAX_CHUNK(V, CH, U0)                                                              \
-          {                                                                                          \
-            uint8_t* pchunk = prow + (CH) * kChunkBytes;                                             \
-            _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                          \
-              uint32_t w[4];                                                                         \
-              _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                        \
-                const float p0 = ex2_approx(fmaf(__uint_as_float(V[u * 8 + 2 * k]), c, -mc));        \
-                const float p1 = ex2_approx(fmaf(__uint_as_float(V[u * 8 + 2 * k + 1]), c, -mc));    \
-                l0 += p0;                                                                            \
-                l1 += p1;                                                                            \
-                const __half2 hh = __floats2half2_rn(p0, p1);                                        \
-                w[k] = *reinterpret_cast<const uint32_t*>(&hh);                                      \
-              }                                                                                      \
-              *reinterpret_cast<uint4*>(pchunk + ((((U0) + u) ^ rx) << 4)) = make_uint4(w[0], w[1], w[2], w[3]); \
-            }                                                                                        \
-          }
-          GYRE_SOFTMAX_CHUNK(v0, 0, 0)
-          GYRE_SOFTMAX_CHUNK(v1, 0, 4)
-          GYRE_SOFTMAX_CHUNK(v2, 1, 0)
-          GYRE_SOFTMAX_CHUNK(v3, 1, 4)
-#undef GYRE_SOFTMAX_CHUNK
-          l += l0 + l1;
+          float2 ls = make_float2(0.f, 0.f);
+          softmax_chunk32<V>(v0, c, mc, ls, prow, 0, rx);
+          softmax_chunk32<V>(v1, c, mc, ls, prow, 4, rx);
+          if (stagger && g == 0 && j == 0) mbar_arrive(half_bar);
+          softmax_chunk32<V>(v2, c, mc, ls, prow + kChunkBytes, 0, rx);
+          softmax_chunk32<V>(v3, c, mc, ls, prow + kChunkBytes, 4, rx);
+          l += ls.x + ls.y;
         } else {
           // ---- ragged last tile (cross-attention Nk = 77, ToMe-merged Nk): masked two-pass path
           const int n_s = (nk_tile + 15) & ~15;
@@ -571,19 +648,276 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, AttnParams p, int B,
-                        cudaStream_t st) {
+
+// ------------------------------------------------------------------------------------------ short key sequences
+// Cross-attention (77 text tokens) and any Nk <= 128: the whole K/V of one (batch, head) is ONE tile, so the
+// roles of the flash kernel are turned around - K and V are loaded once per CTA and the CTA streams over a
+// run of 128-row query tiles through a TMA ring.  Two softmax groups alternate tiles (own S / O accumulators
+// in TMEM, own P buffer), the single MMA thread interleaves  S_g(i+2) right behind PV_g(i), and the
+// normalised output leaves through the group's P buffer as a 128B-swizzled tile with one TMA bulk store
+// per 64-column chunk.  The kernel is bound by the Q read + O write; nothing is re-read.
+template <int DCH>
+struct XAttCfg {
+  static constexpr int STAGES = DCH == 1 ? 4 : 2;
+  static constexpr int Q_BYTES = DCH * kChunkBytes;             // per stage
+  static constexpr int KV_BYTES = DCH * kChunkBytes;            // per operand
+  static constexpr int P_BYTES = 2 * kChunkBytes;               // per group (also the output staging tile)
+  static constexpr int SMEM = STAGES * Q_BYTES + 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;                         // S0, S1: [0,256); O0 at 256, O1 at 384
+};
+
+template <int DCH>
+__global__ void __launch_bounds__(kAtt2Threads, 1) xattention_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                     const __grid_constant__ CUtensorMap tmK,
+                                                                     const __grid_constant__ CUtensorMap tmV,
+                                                                     const __grid_constant__ CUtensorMap tmO,
+                                                                     const AttnParams p) {
+  using Cfg = XAttCfg<DCH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [STAGES][DCH chunks]
+  uint8_t* sK = sQ + Cfg::STAGES * Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::KV_BYTES;
+  uint8_t* sP = sV + Cfg::KV_BYTES;                     // [2 groups][2 chunks]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = q_full + Cfg::STAGES;
+  uint64_t* s_full = q_empty + Cfg::STAGES;             // [2]
+  uint64_t* p_full = s_full + 2;                        // [2]
+  uint64_t* o_full = p_full + 2;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x % p.splits;
+  const int bh = blockIdx.x / p.splits;
+  const int h = bh % p.heads;
+  const int b = bh / p.heads;
+  const int t0 = split * p.tiles_per_cta;
+  const int n = min(p.tiles_per_cta, p.q_tiles - t0);   // > 0 by construction of the grid
+  const int n_s = (p.Nk + 15) & ~15;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&o_full[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * Cfg::KV_BYTES);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) {
+        tma_load_4d(sK + c * kChunkBytes, &tmK, kv_full, c * 64, 0, h, b);
+        tma_load_4d(sV + c * kChunkBytes, &tmV, kv_full, c * 64, 0, h, b);
+      }
+      for (int i = 0; i < n; ++i) {
+        const int s = i % Cfg::STAGES;
+        mbar_wait(&q_empty[s], ((i / Cfg::STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[s], Cfg::Q_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c)
+          tma_load_4d(sQ + s * Cfg::Q_BYTES + c * kChunkBytes, &tmQ, &q_full[s], c * 64, (t0 + i) * kBQ, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_f16(kBQ, n_s);
+      const uint32_t idesc_pv = umma_idesc_f16(kBQ, p.npv, /*b_mn_major=*/1);
+      const uint32_t ka = smem_u32(sK);
+      const uint32_t va = smem_u32(sV);
+      auto issue_s = [&](int i) {
+        const int g = i & 1;
+        const int s = i % Cfg::STAGES;
+        mbar_wait(&q_full[s], (i / Cfg::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQ + s * Cfg::Q_BYTES);
+        for (int ks = 0; ks < p.ksteps_qk; ++ks) {
+          const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+          umma_f16_ss(tmem_base + g * 128, umma_desc_kmajor_sw128(qa + off), umma_desc_kmajor_sw128(ka + off), idesc_s,
+                      ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&q_empty[s]);      // Q is only needed for S
+        umma_commit(&s_full[g]);
+      };
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      if (n > 1) issue_s(1);
+      const int ksteps = n_s >> 4;
+      for (int i = 0; i < n; ++i) {
+        const int g = i & 1;
+        mbar_wait(&p_full[g], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP + g * Cfg::P_BYTES);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
+          const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+          umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[g]);
+        if (i + 2 < n) issue_s(i + 2);   // S_g is free: the group read it before it arrived on p_full
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output, two groups
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + g * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + g * 128 + lane_off;
+    const float c = p.scale_log2;
+    uint8_t* pbase = sP + g * Cfg::P_BYTES;
+    uint8_t* prow = pbase + r * 128;
+    const int rx = r & 7;
+    const bool leader = (threadIdx.x == 64 + 128 * g);
+    const int nk = p.Nk;
+
+    for (int i = g; i < n; i += 2) {
+      const uint32_t ph = (i >> 1) & 1;
+      mbar_wait(&s_full[g], ph);
+      tc_fence_after();
+      float mt = -INFINITY;
+      for (int c0 = 0; c0 < n_s; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tS + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (c0 + k < nk) mt = fmaxf(mt, __uint_as_float(v[k]));
+      }
+      const float mc = mt * c;
+      float l = 0.f;
+      // the previous tile's output store must have finished READING this buffer before P overwrites it
+      if (leader) tma_store_wait_read<0>();
+      named_bar_sync(1 + g, 128);
+      for (int c0 = 0; c0 < n_s; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tS + c0, v);
+        tmem_ld_wait();
+        uint32_t packed[8];
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          const float p0 = (c0 + k < nk) ? ex2_approx(fmaf(__uint_as_float(v[k]), c, -mc)) : 0.f;
+          const float p1 = (c0 + k + 1 < nk) ? ex2_approx(fmaf(__uint_as_float(v[k + 1]), c, -mc)) : 0.f;
+          const __half2 hh = __floats2half2_rn(p0, p1);
+          const float2 back = __half22float2(hh);     // the sum uses the values the tensor core multiplies
+          l += back.x + back.y;
+          packed[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        uint8_t* pchunk = prow + (c0 >> 6) * kChunkBytes;
+        const int u0 = (c0 & 63) >> 3;
+        *reinterpret_cast<uint4*>(pchunk + ((u0 ^ rx) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(pchunk + (((u0 + 1) ^ rx) << 4)) =
+            make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(&p_full[g]);
+      // ---- output: O / l -> swizzled staging tile (the P buffer, free once PV retired) -> TMA store
+      mbar_wait(&o_full[g], ph);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      for (int c0 = 0; c0 < p.npv; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(tO + c0, o);
+        tmem_ld_wait();
+        uint8_t* ochunk = prow + (c0 >> 6) * kChunkBytes;
+        const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          __align__(16) __half2 hh[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            hh[k] = __floats2half2_rn(__uint_as_float(o[u * 8 + 2 * k]) * inv, __uint_as_float(o[u * 8 + 2 * k + 1]) * inv);
+          *reinterpret_cast<uint4*>(ochunk + (((u0 + u) ^ rx) << 4)) = *reinterpret_cast<uint4*>(hh);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      named_bar_sync(1 + g, 128);
+      if (leader) {
+#pragma unroll
+        for (int cc = 0; cc < DCH; ++cc)
+          if (cc * 64 < p.d) tma_store_4d(&tmO, pbase + cc * kChunkBytes, cc * 64, (t0 + i) * kBQ, h, b);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int DCH>
+static int launch_xattn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                        const AttnParams& p, unsigned blocks, cudaStream_t st) {
+  using Cfg = XAttCfg<DCH>;
   static bool attr_done = false;
   if (!attr_done) {
-    GYRE_CHECK_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg::SMEM));
+    GYRE_CHECK_CUDA(
+        cudaFuncSetAttribute(xattention_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
+  GYRE_TRY(launch_kernel(xattention_kernel<DCH>, dim3(blocks), dim3(kAtt2Threads), Cfg::SMEM, st, tq, tk, tv, to, p));
+  return 0;
+}
+
+template <int V>
+static int launch_attn2_v(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                          unsigned blocks, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    GYRE_CHECK_CUDA(
+        cudaFuncSetAttribute(attention2_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg::SMEM));
+    attr_done = true;
+  }
+  return launch_kernel(attention2_kernel<V>, dim3(blocks), dim3(kAtt2Threads), Att2Cfg::SMEM, st, tq, tk, tv, p);
+}
+
+static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, AttnParams p, int B,
+                        cudaStream_t st) {
   p.q_tiles = (p.Nq + 2 * kBQ - 1) / (2 * kBQ);
   const long long blocks = static_cast<long long>(B) * p.heads * p.q_tiles;
   GYRE_REQUIRE(blocks < (1ll << 31), "attention: grid too large");
-  attention2_kernel<<<static_cast<unsigned>(blocks), kAtt2Threads, Att2Cfg::SMEM, st>>>(tq, tk, tv, p);
-  GYRE_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  const unsigned nb = static_cast<unsigned>(blocks);
+  switch (tunable(TUNE_ATT_VARIANT)) {
+    case 0: return launch_attn2_v<0>(tq, tk, tv, p, nb, st);
+    case AV_STAGGER: return launch_attn2_v<AV_STAGGER>(tq, tk, tv, p, nb, st);
+    case AV_STAGGER | AV_PACKED: return launch_attn2_v<AV_STAGGER | AV_PACKED>(tq, tk, tv, p, nb, st);
+    case AV_STAGGER | AV_PACKED | AV_POLY25: return launch_attn2_v<AV_STAGGER | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_STAGGER | AV_PACKED | AV_POLY50: return launch_attn2_v<AV_STAGGER | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
+    case AV_PACKED | AV_POLY25: return launch_attn2_v<AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_STAGGER | AV_F16EXP: return launch_attn2_v<AV_STAGGER | AV_F16EXP>(tq, tk, tv, p, nb, st);
+    case AV_STAGGER | AV_NOEXP: return launch_attn2_v<AV_STAGGER | AV_NOEXP>(tq, tk, tv, p, nb, st);
+  }
+  set_last_error("attention: variant %d is not compiled in", tunable(TUNE_ATT_VARIANT));
+  return -2;
 }
 
 template <int DCH>
@@ -596,9 +930,8 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
         cudaFuncSetAttribute(attention_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  attention_kernel<DCH><<<static_cast<unsigned>(blocks), kAttThreads, Cfg::SMEM, st>>>(tq, tk, tv, p);
-  GYRE_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_kernel(attention_kernel<DCH>, dim3(static_cast<unsigned>(blocks)), dim3(kAttThreads), Cfg::SMEM, st, tq,
+                       tk, tv, p);
 }
 
 static int make_head_map(CUtensorMap* m, const __half* base, int ld, int N, int heads, int d, int B, int box_rows) {
@@ -642,6 +975,23 @@ int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __ha
   const int dch = (d + 63) / 64;
   prof::Scope ps(prof::F_ATTN, 4.0 * B * heads * static_cast<double>(Nq) * Nk * d,
                  2.0 * B * heads * d * (2.0 * Nq + 2.0 * Nk), st);
+  if (tunable(TUNE_XATTN) && Nk <= kBKeys && dch <= 2 && Nq >= 4 * kBQ) {
+    // short key sequence: K/V resident, CTA streams over query tiles; aim at ~2 CTAs per SM in total
+    CUtensorMap to;
+    GYRE_TRY(make_head_map(&to, out, ldo, Nq, heads, d, B, kBQ));
+    const long long bh = static_cast<long long>(B) * heads;
+    int splits = static_cast<int>((2ll * 148 + bh - 1) / bh);
+    if (splits < 1) splits = 1;
+    int tpc = (p.q_tiles + splits - 1) / splits;
+    if (tpc < 4) tpc = 4;                       // amortise the K/V load and the pipeline fill
+    if (tpc > p.q_tiles) tpc = p.q_tiles;
+    p.tiles_per_cta = tpc;
+    p.splits = (p.q_tiles + tpc - 1) / tpc;
+    const long long nb = bh * p.splits;
+    GYRE_REQUIRE(nb < (1ll << 31), "attention: grid too large");
+    return dch == 1 ? launch_xattn<1>(tq, tk, tv, to, p, static_cast<unsigned>(nb), st)
+                    : launch_xattn<2>(tq, tk, tv, to, p, static_cast<unsigned>(nb), st);
+  }
   if (dch == 1 && Nq > kBQ) return launch_attn2(tq, tk, tv, p, B, st);
   switch (dch) {
     case 1: return launch_attn<1>(tq, tk, tv, p, blocks, st);

@@ -58,6 +58,9 @@ int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, doubl
   return prof::read(family, count, ms, flops, bytes);
 }
 
+int gyre_b200_set_tunable(const char* name, int value) { return set_tunable_by_name(name, value); }
+int gyre_b200_get_tunable(const char* name, int* value) { return get_tunable_by_name(name, value); }
+
 int gyre_b200_gemm(const void* A, int lda, int K1, const void* A2, int lda2, int K2, const void* W, int ldw, int M,
                    int N, const gyre_b200_epilogue* ep, gyre_b200_stream stream) {
   Epilogue e;
@@ -87,6 +90,22 @@ size_t gyre_b200_conv3x3_packed_elems(int Cin, int Cout) { return conv3x3_packed
 int gyre_b200_pack_conv3x3(const void* W, int dtype, int Cin, int Cout, void* Wp, gyre_b200_stream stream) {
   GYRE_REQUIRE(W && Wp, "pack_conv3x3: null operand");
   return pack_conv3x3(W, dtype, Cin, Cout, static_cast<__half*>(Wp), S(stream));
+}
+
+size_t gyre_b200_upconv3x3_packed_elems(int Cin, int Cout) { return upconv3x3_packed_elems(Cin, Cout); }
+
+int gyre_b200_pack_upconv3x3(const void* W, int dtype, int Cin, int Cout, void* Wp4, gyre_b200_stream stream) {
+  GYRE_REQUIRE(W && Wp4, "pack_upconv3x3: null operand");
+  return pack_upconv3x3(W, dtype, Cin, Cout, static_cast<__half*>(Wp4), S(stream));
+}
+
+int gyre_b200_upconv2x(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wp4, int Cout,
+                       const gyre_b200_epilogue* ep, gyre_b200_stream stream) {
+  Epilogue e;
+  GYRE_TRY(to_epilogue(ep, &e));
+  GYRE_REQUIRE(X && Wp4, "upconv2x: null operand");
+  return upconv2x_f16(static_cast<const __half*>(X), ldx, B, H, W, Cin, static_cast<const __half*>(Wp4), Cout, e,
+                      S(stream));
 }
 
 size_t gyre_b200_groupnorm_scratch_floats(int B, int HW, int G) { return gn_partials_floats(B, HW, G); }
@@ -207,13 +226,19 @@ int gyre_b200_unet_workspace_bytes(gyre_b200_handle h, int batch, int height, in
 int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx, int batch,
                            int height, int width, int ctx_len, const int32_t* tome_r_host, void* out, void* workspace,
                            size_t workspace_bytes, gyre_b200_stream stream) {
-  GYRE_REQUIRE(h && sample && timestep && ctx && out, "unet_forward: null argument");
+  GYRE_REQUIRE(h && sample && timestep && out, "unet_forward: null argument");
   GYRE_REQUIRE(M(h)->is_unet(), "unet_forward: handle is not a UNet");
   Exec ex;
   GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
   return static_cast<UNetModel*>(M(h))->forward(ex, static_cast<const __half*>(sample), timestep,
                                                 static_cast<const __half*>(ctx), batch, height, width, ctx_len,
                                                 tome_r_host, static_cast<__half*>(out));
+}
+
+int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, int ctx_len, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h, "unet_set_context: null handle");
+  GYRE_REQUIRE(M(h)->is_unet(), "unet_set_context: handle is not a UNet");
+  return static_cast<UNetModel*>(M(h))->set_context(static_cast<const __half*>(ctx), batch, ctx_len, S(stream));
 }
 
 int gyre_b200_unet_num_transformer_blocks(gyre_b200_handle h) {

@@ -57,6 +57,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel that is launched through launch_kernel() (below) calls pdl_wait() after its prologue (barrier
+// init, TMEM allocation, tensor-map prefetch) and BEFORE its first access to global memory: the prologue
+// then overlaps the tail of the preceding kernel in the stream.  pdl_trigger() lets the NEXT kernel's CTAs be
+// scheduled as soon as every CTA of this grid has passed it.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -221,6 +229,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x) with two MUFU ops (ex2 + rcp) and no IEEE division
+__device__ __forceinline__ float silu_fast(float x) {
+  return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
 
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor for a K-major fp16 tile laid out as 128-byte rows with the
@@ -255,6 +272,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int b_mn_maj
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 #endif  // __CUDACC__
+
+// ------------------------------------------------------------------ host: launches
+int tunable(int id);
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute (tunable PDL, id 1): the kernel MUST call pdl_wait().
+template <typename... KArgs, typename... Args>
+inline int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tunable(1) != 0 ? 1 : 0;
+  GYRE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  return 0;
+}
+#endif
 
 // ------------------------------------------------------------------ host: tensor maps
 // Encodes fp16 tensor maps through the driver entry point fetched at run time (the library never

@@ -27,10 +27,13 @@ struct GemmParams {
   int tile_w, tile_h, tile_n;
   int Ho, Wo, Bn;
   int tiles_x, tiles_y;
-  int stride, pad;
+  int stride;
+  int taps_w;         // taps per kernel row (3; 2 for the phase convs of the folded upsample)
+  int off_x, off_y;   // input offset of tap (0, 0): -pad, or (phase - 1) for the phase convs
   // epilogue routing
   int tma_epi;        // 1: output (and residual) tiles move through swizzled smem slices with TMA
   int rgb_rows;       // rows of a tile that share one rowgroup-bias vector (staged in smem); 0: per-thread loads
+  int fast_gelu;      // GEGLU gate through gelu_fast instead of libdevice erff
   Epilogue ep;
 };
 
@@ -58,7 +61,23 @@ struct GemmCfg {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return silu_fast(x); }
+// Exact (erf) GELU without libdevice's branchy erff: x * Phi(x) with Phi(-|x|) = 0.5 * erfc(|x| / sqrt 2) from
+// Abramowitz-Stegun 7.1.26 (|abs err of erf| <= 1.5e-7): branch-free, 2 MUFU (rcp, ex2) + ~14 FMA-pipe ops.
+// Evaluating the tail Phi(-|x|) directly keeps the RELATIVE error of gelu(x) small for negative x as well.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  q = fmaf(q, t, 0.5f * 1.421413741f);
+  q = fmaf(q, t, 0.5f * -0.284496736f);
+  q = fmaf(q, t, 0.5f * 0.254829592f);
+  q *= t;
+  const float w = z * 1.2011224087864498f;          // sqrt(log2 e) * z : exp(-z^2) = 2^(-w^2)
+  q *= ex2_approx(-w * w);                            // q = Phi(-|x|)
+  const float phi = x < 0.f ? q : 1.0f - q;
+  return x * phi;
+}
 
 // Direct store of 8 consecutive output columns of one row (fp32 outputs, unaligned pitches, tiny N).
 __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col, int n_valid_cols, const float* v) {
@@ -144,6 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -166,9 +187,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           if (p.conv) {
             const int tap = it / p.cin_chunks;
             const int cc = it - tap * p.cin_chunks;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], cc * kBK, x0 * p.stride + kw - p.pad,
-                        y0 * p.stride + kh - p.pad, n0);
+            const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
+            tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], cc * kBK, x0 * p.stride + kw + p.off_x,
+                        y0 * p.stride + kh + p.off_y, n0);
             tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], tap * p.cin_pad + cc * kBK, n_tile * BN);
           } else {
             if (it < p.k1_iters)
@@ -300,11 +321,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
             tmem_ld_32x32b_x32(lane_addr + BN / 2 + sl * 32, rg);
             tmem_ld_wait();
+            if (p.fast_gelu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
-              const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
-              v[j] = a * gelu_erf(gg);
+              for (int j = 0; j < 32; ++j) {
+                const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+                const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
+                v[j] = a * gelu_fast(gg);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+                const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
+                v[j] = a * gelu_erf(gg);
+              }
             }
           } else {
             uint32_t ra[32];
@@ -449,9 +479,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   GYRE_REQUIRE(tiles > 0 && tiles < (1ll << 31), "gemm: bad tile count %lld", tiles);
   const int sms = sm_count();
   const unsigned blocks = static_cast<unsigned>(tiles < sms ? tiles : sms);
-  gemm_tc_kernel<BN><<<blocks, kThreads, Cfg::SMEM, st>>>(tmA, tmA2, tmB, tmOut, tmRes, p);
-  GYRE_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_kernel(gemm_tc_kernel<BN>, dim3(blocks), dim3(kThreads), Cfg::SMEM, st, tmA, tmA2, tmB, tmOut, tmRes, p);
 }
 
 // Tile width: maximise (SM wave efficiency) x (1 - N padding) x (per-tile efficiency of the shape).
@@ -535,6 +563,7 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
   p.n_tiles = (N + bn - 1) / bn;
   p.m_tiles = (M + kBM - 1) / kBM;
   p.conv = 0;
+  p.fast_gelu = tunable(TUNE_GELU_FAST);
   p.ep = ep;
   p.rgb_rows = 0;
   p.tma_epi = (tma_epilogue_ok(ep, n_out) && ep.rowgroup_bias == nullptr) ? 1 : 0;
@@ -585,15 +614,21 @@ static inline int pow2_ceil(int v) {
   return p;
 }
 
-int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp, int Cout, int stride,
-                int pad, const Epilogue& ep, cudaStream_t st) {
-  GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3: empty problem");
-  GYRE_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d", stride);
-  GYRE_REQUIRE(ldx % 8 == 0 && Cin % 8 == 0, "conv3x3: channel pitch must be a multiple of 8");
-  GYRE_REQUIRE(ep.act != ACT_GEGLU, "conv3x3: GEGLU epilogue not supported");
-  GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "conv3x3: null output");
-  const int Ho = (stride == 1) ? H : (pad == 1 ? (H - 1) / 2 + 1 : (H + 1 - 3) / 2 + 1);
-  const int Wo = (stride == 1) ? W : (pad == 1 ? (W - 1) / 2 + 1 : (W + 1 - 3) / 2 + 1);
+// Geometry of one implicit-GEMM convolution launch: taps_h x taps_w taps whose (0, 0) tap reads input pixel
+// (x * stride + off_x, y * stride + off_y); output pixel (x, y) of the Ho x Wo grid is written to pixel
+// (x * out_step + out_ox, y * out_step + out_oy) of a [B, Ho*out_step, Wo*out_step, ldo] tensor.
+struct ConvGeom {
+  int taps_h = 3, taps_w = 3;
+  int off_x = -1, off_y = -1;
+  int Ho = 0, Wo = 0;
+  int out_step = 1, out_ox = 0, out_oy = 0;
+  double algo_flops = 0.0, algo_bytes = 0.0;
+};
+
+static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp, int Cout, int stride,
+                     const ConvGeom& gm, const Epilogue& ep, cudaStream_t st) {
+  const int Ho = gm.Ho, Wo = gm.Wo;
+  const int ntaps = gm.taps_h * gm.taps_w;
   // choose the 128-pixel patch shape with the least padded work
   int best_w = 0, best_h = 0, best_n = 0;
   long long best_cost = -1;
@@ -622,7 +657,7 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   p.N = Cout;
   p.cin_chunks = (Cin + kBK - 1) / kBK;
   p.cin_pad = p.cin_chunks * kBK;
-  p.k_iters = 9 * p.cin_chunks;
+  p.k_iters = ntaps * p.cin_chunks;
   p.k1_iters = p.k_iters;
   p.n_tiles = (Cout + bn - 1) / bn;
   p.m_tiles = m_tiles;
@@ -636,7 +671,10 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   p.tiles_x = (Wo + best_w - 1) / best_w;
   p.tiles_y = (Ho + best_h - 1) / best_h;
   p.stride = stride;
-  p.pad = pad;
+  p.taps_w = gm.taps_w;
+  p.off_x = gm.off_x;
+  p.off_y = gm.off_y;
+  p.fast_gelu = 0;
   p.ep = ep;
   // the per-sample bias (temb projection) is uniform over the rows of one image inside a tile: stage it with
   // the column bias when a tile holds at most kMaxBiasGroups images
@@ -644,6 +682,8 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   if (ep.rowgroup_bias != nullptr && ep.rows_per_group == Ho * Wo && best_n <= kMaxBiasGroups)
     p.rgb_rows = best_w * best_h;
   p.tma_epi = (tma_epilogue_ok(ep, Cout) && (ep.rowgroup_bias == nullptr || p.rgb_rows > 0)) ? 1 : 0;
+  GYRE_REQUIRE(gm.out_step == 1 || (p.tma_epi && ep.residual == nullptr),
+               "conv: a strided output view needs the TMA epilogue (fp16, 16B-aligned rows, no residual)");
   CUtensorMap tmA, tmB, tmOut, tmRes;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
@@ -656,8 +696,8 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
     GYRE_TRY(encode_tmap_f16(&tmA, X, 4, dims, strides, box, es, true));
   }
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(9) * p.cin_pad, static_cast<uint64_t>(Cout)};
-    uint64_t strides[1] = {static_cast<uint64_t>(9) * p.cin_pad * 2};
+    uint64_t dims[2] = {static_cast<uint64_t>(ntaps) * p.cin_pad, static_cast<uint64_t>(Cout)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ntaps) * p.cin_pad * 2};
     uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
     uint32_t es[2] = {1, 1};
     GYRE_TRY(encode_tmap_f16(&tmB, Wp, 2, dims, strides, box, es, true));
@@ -669,9 +709,12 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
                         static_cast<uint64_t>(B)};
     uint32_t box[4] = {32, static_cast<uint32_t>(best_w), static_cast<uint32_t>(best_h), static_cast<uint32_t>(best_n)};
     uint32_t es[4] = {1, 1, 1, 1};
-    uint64_t so[3] = {static_cast<uint64_t>(ep.ldo) * 2, static_cast<uint64_t>(ep.ldo) * 2 * Wo,
-                      static_cast<uint64_t>(ep.ldo) * 2 * Wo * Ho};
-    GYRE_TRY(encode_tmap_f16_sw(&tmOut, ep.out, 4, dims, so, box, es, 64));
+    const uint64_t step = static_cast<uint64_t>(gm.out_step);
+    const uint64_t pix = static_cast<uint64_t>(ep.ldo) * 2;            // bytes per output pixel
+    uint64_t so[3] = {pix * step, pix * (Wo * step) * step, pix * (Wo * step) * (Ho * step)};
+    const __half* obase = static_cast<const __half*>(ep.out) +
+                          (static_cast<size_t>(gm.out_oy) * Wo * step + gm.out_ox) * ep.ldo;
+    GYRE_TRY(encode_tmap_f16_sw(&tmOut, obase, 4, dims, so, box, es, 64));
     tmRes = tmOut;
     if (ep.residual) {
       uint64_t sr[3] = {static_cast<uint64_t>(ep.ldr) * 2, static_cast<uint64_t>(ep.ldr) * 2 * Wo,
@@ -679,11 +722,54 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
       GYRE_TRY(encode_tmap_f16_sw(&tmRes, ep.residual, 4, dims, sr, box, es, 64));
     }
   }
-  prof::Scope ps(prof::F_CONV, 2.0 * 9 * Cin * Cout * static_cast<double>(B) * Ho * Wo,
-                 2.0 * (static_cast<double>(B) * H * W * Cin + 9.0 * Cin * Cout +
-                        static_cast<double>(B) * Ho * Wo * Cout * (ep.residual ? 2 : 1)),
-                 st);
+  prof::Scope ps(prof::F_CONV, gm.algo_flops, gm.algo_bytes, st);
   return dispatch(bn, tmA, tmA, tmB, tmOut, tmRes, p, st);
+}
+
+int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp, int Cout, int stride,
+                int pad, const Epilogue& ep, cudaStream_t st) {
+  GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3: empty problem");
+  GYRE_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d", stride);
+  GYRE_REQUIRE(ldx % 8 == 0 && Cin % 8 == 0, "conv3x3: channel pitch must be a multiple of 8");
+  GYRE_REQUIRE(ep.act != ACT_GEGLU, "conv3x3: GEGLU epilogue not supported");
+  GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "conv3x3: null output");
+  ConvGeom gm;
+  gm.off_x = gm.off_y = -pad;
+  gm.Ho = (stride == 1) ? H : (pad == 1 ? (H - 1) / 2 + 1 : (H + 1 - 3) / 2 + 1);
+  gm.Wo = (stride == 1) ? W : (pad == 1 ? (W - 1) / 2 + 1 : (W + 1 - 3) / 2 + 1);
+  gm.algo_flops = 2.0 * 9 * Cin * Cout * static_cast<double>(B) * gm.Ho * gm.Wo;
+  gm.algo_bytes = 2.0 * (static_cast<double>(B) * H * W * Cin + 9.0 * Cin * Cout +
+                         static_cast<double>(B) * gm.Ho * gm.Wo * Cout * (ep.residual ? 2 : 1));
+  return conv_impl(X, ldx, B, H, W, Cin, Wp, Cout, stride, gm, ep, st);
+}
+
+int upconv2x_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp4, int Cout,
+                 const Epilogue& ep, cudaStream_t st) {
+  GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "upconv2x: empty problem");
+  GYRE_REQUIRE(ldx % 8 == 0 && Cin % 8 == 0, "upconv2x: channel pitch must be a multiple of 8");
+  GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0 && ep.act == ACT_NONE && ep.residual == nullptr &&
+                   ep.rowgroup_bias == nullptr,
+               "upconv2x: only a bias epilogue is supported");
+  const int cin_pad = (Cin + kBK - 1) / kBK * kBK;
+  const size_t phase_elems = static_cast<size_t>(Cout) * 4 * cin_pad;
+  for (int phase = 0; phase < 4; ++phase) {
+    const int dy = phase >> 1, dx = phase & 1;
+    ConvGeom gm;
+    gm.taps_h = gm.taps_w = 2;
+    gm.off_x = dx - 1;
+    gm.off_y = dy - 1;
+    gm.Ho = H;
+    gm.Wo = W;
+    gm.out_step = 2;
+    gm.out_ox = dx;
+    gm.out_oy = dy;
+    // algorithmic work of the un-folded op (9 taps on the upsampled grid), a quarter per phase
+    gm.algo_flops = 2.0 * 9 * Cin * Cout * static_cast<double>(B) * H * W;
+    gm.algo_bytes = 2.0 * (static_cast<double>(B) * H * W * Cin * 0.25 + 9.0 * Cin * Cout * 0.25 +
+                           static_cast<double>(B) * H * W * Cout);
+    GYRE_TRY(conv_impl(X, ldx, B, H, W, Cin, Wp4 + phase * phase_elems, Cout, 1, gm, ep, st));
+  }
+  return 0;
 }
 
 }  // namespace gyre

@@ -100,13 +100,35 @@ void Model::reg_linear(const std::string& p, int N, int K, bool bias, LinW* l) {
   }
 }
 
-void Model::reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c) {
+void Model::reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c, bool upsampler) {
   c->Cin = Cin;
   c->Cout = Cout;
   c->wp = static_cast<__half*>(dalloc(sizeof(__half) * conv3x3_packed_elems(Cin, Cout)));
   c->bias = static_cast<float*>(dalloc(sizeof(float) * Cout));
-  reg(p + ".weight", P_CONV3, c->wp, {Cout, Cin, 3, 3});
+  reg(p + ".weight", upsampler ? P_CONV3_UP : P_CONV3, c->wp, {Cout, Cin, 3, 3});
+  if (upsampler) {
+    c->wp_up = static_cast<__half*>(dalloc(sizeof(__half) * upconv3x3_packed_elems(Cin, Cout)));
+    slots_[p + ".weight"].dst2 = c->wp_up;
+  }
   reg(p + ".bias", P_F32, c->bias, {Cout});
+}
+
+// Upsample2D (nearest 2x) + conv3x3.  Folded path (tunable UPCONV_FOLD): four 2x2 phase convolutions read the
+// low-res tensor directly - the 4x larger upsampled tensor is never written and 5/9 of the MACs disappear.
+// The scratch buffer is reserved either way so that the workspace size does not depend on the tunable.
+int Model::upsample_conv(Exec& ex, const Conv3W& c, const __half* x, int B, int H, int W, __half* out) {
+  __half* up = ex.s16(static_cast<size_t>(B) * 4 * H * W * c.Cin);
+  Epilogue e;
+  e.out = out;
+  e.ldo = c.Cout;
+  e.bias = c.bias;
+  if (tunable(TUNE_UPCONV_FOLD) && c.wp_up != nullptr && c.Cout % 8 == 0) {
+    RUN(ex, upconv2x_f16(x, c.Cin, B, H, W, c.Cin, c.wp_up, c.Cout, e, ex.st));
+  } else {
+    RUN(ex, upsample2x_nhwc(x, B, H, W, c.Cin, up, ex.st));
+    RUN(ex, conv3x3_f16(up, c.Cin, B, 2 * H, 2 * W, c.Cin, c.wp, c.Cout, 1, 1, e, ex.st));
+  }
+  return 0;
 }
 
 void Model::reg_resnet(const std::string& p, int cin, int cout, bool temb, ResnetW* r) {
@@ -161,8 +183,12 @@ int Model::load(const char* key, const void* data, int dtype, const int64_t* sha
       GYRE_TRY(cast_to_f16(data, dtype, s.shape[0], static_cast<int>(s.shape[1]), static_cast<__half*>(s.dst), s.ld, st));
       break;
     case P_CONV3:
+    case P_CONV3_UP:
       GYRE_TRY(pack_conv3x3(data, dtype, static_cast<int>(s.shape[1]), static_cast<int>(s.shape[0]),
                             static_cast<__half*>(s.dst), st));
+      if (s.kind == P_CONV3_UP)
+        GYRE_TRY(pack_upconv3x3(data, dtype, static_cast<int>(s.shape[1]), static_cast<int>(s.shape[0]),
+                                static_cast<__half*>(s.dst2), st));
       break;
     case P_GEGLU_W:
       GYRE_TRY(pack_geglu(data, dtype, static_cast<int>(s.shape[0] / 2), static_cast<int>(s.shape[1]), nullptr, 0,
@@ -339,7 +365,7 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
     }
     if (i < L - 1) {
       ups_.emplace_back();
-      reg_conv3("up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, &ups_.back());
+      reg_conv3("up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, &ups_.back(), true);
     }
   }
   reg_norm("conv_norm_out", ch[0], &norm_out_);
@@ -369,6 +395,38 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
       for (int j = 0; j < cfg.layers_per_block + 1; ++j)
         reg_temb("up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
   }
+}
+
+UNetModel::~UNetModel() {
+  for (__half* p : kv_cache_)
+    if (p) cudaFree(p);
+}
+
+int UNetModel::set_context(const __half* ctx, int B, int L, cudaStream_t st) {
+  GYRE_TRY(ensure_device());
+  if (ctx == nullptr) {
+    ctx_B_ = ctx_L_ = 0;
+    return 0;
+  }
+  GYRE_REQUIRE(B > 0 && L > 0, "set_context: empty context");
+  kv_cache_.resize(tblocks_.size(), nullptr);
+  kv_cache_elems_.resize(tblocks_.size(), 0);
+  ctx_B_ = ctx_L_ = 0;
+  for (size_t i = 0; i < tblocks_.size(); ++i) {
+    const TransformerW& t = tblocks_[i];
+    const size_t need = static_cast<size_t>(B) * L * 2 * t.C;
+    if (kv_cache_elems_[i] < need) {
+      if (kv_cache_[i]) cudaFree(kv_cache_[i]);   // synchronises: no forward can still be reading it
+      kv_cache_[i] = nullptr;
+      kv_cache_elems_[i] = 0;
+      GYRE_CHECK_CUDA(cudaMalloc(&kv_cache_[i], need * sizeof(__half)));
+      kv_cache_elems_[i] = need;
+    }
+    GYRE_TRY(gemm_f16(ctx, t.kv2.K, t.kv2.w, t.kv2.K, B * L, 2 * t.C, t.kv2.K, ep_out(kv_cache_[i], 2 * t.C), st));
+  }
+  ctx_B_ = B;
+  ctx_L_ = L;
+  return 0;
 }
 
 // Transformer2DModel + BasicTransformerBlock (nonfree/tome_unet.py:114-136)
@@ -410,8 +468,16 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   RUN(ex, layernorm_rows(h2, M, C, 1e-5f, t.ln2.g, t.ln2.b, nrm, ex.st));
   __half* q = qkv;   // dead after self-attention
   RUN(ex, gemm_f16(nrm, C, t.q2.w, C, M, C, C, ep_out(q, C), ex.st));
-  __half* kv = ex.s16(static_cast<size_t>(B) * L * 2 * C);
-  RUN(ex, gemm_f16(ctx, t.kv2.K, t.kv2.w, t.kv2.K, B * L, 2 * C, t.kv2.K, ep_out(kv, 2 * C), ex.st));
+  const __half* kv;
+  {
+    __half* kv_new = ex.s16(static_cast<size_t>(B) * L * 2 * C);   // reserved even when the bound context is used
+    if (ctx != nullptr || ex.dry) {
+      RUN(ex, gemm_f16(ctx, t.kv2.K, t.kv2.w, t.kv2.K, B * L, 2 * C, t.kv2.K, ep_out(kv_new, 2 * C), ex.st));
+      kv = kv_new;
+    } else {
+      kv = kv_cache_[static_cast<size_t>(&t - tblocks_.data())];
+    }
+  }
   RUN(ex, attention_f16(q, C, kv, 2 * C, off(kv, C), 2 * C, B, t.heads, HW, L, d, scale, o, C, ex.st));
   RUN(ex, gemm_f16(o, C, t.o2.w, C, M, C, C, ep_out(h, C, t.o2.bias, h2, C), ex.st));   // h <- h2 + attn2
   // ---- GEGLU feed-forward
@@ -426,6 +492,9 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
 int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, int B, int H, int W, int L,
                        const int32_t* tome_r, __half* out) {
   GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && L > 0, "unet_forward: empty problem");
+  if (!ex.dry && ctx == nullptr)
+    GYRE_REQUIRE(ctx_B_ == B && ctx_L_ == L, "unet_forward: no context given and the bound one is [%d, %d], need [%d, %d]",
+                 ctx_B_, ctx_L_, B, L);
   const int nl = cfg_.num_levels;
   GYRE_REQUIRE(H % (1 << (nl - 1)) == 0 && W % (1 << (nl - 1)) == 0,
                "unet_forward: latent %dx%d must be divisible by %d", H, W, 1 << (nl - 1));
@@ -529,12 +598,10 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
     }
     if (i < nl - 1) {
       ex.reset_scratch();
-      __half* up = ex.s16(static_cast<size_t>(B) * 4 * h_ * w_ * c);
-      RUN(ex, upsample2x_nhwc(hcur, B, h_, w_, c, up, ex.st));
+      __half* o = ex.p16(static_cast<size_t>(B) * 4 * h_ * w_ * c);
+      GYRE_TRY(upsample_conv(ex, ups_[ui], hcur, B, h_, w_, o));
       h_ *= 2;
       w_ *= 2;
-      __half* o = ex.p16(static_cast<size_t>(B) * h_ * w_ * c);
-      RUN(ex, conv3x3_f16(up, c, B, h_, w_, c, ups_[ui].wp, c, 1, 1, ep_out(o, c, ups_[ui].bias), ex.st));
       ++ui;
       hcur = o;
     }
@@ -611,7 +678,7 @@ VAEModel::VAEModel(const gyre_b200_vae_config& cfg) : cfg_(cfg) {
     }
     if (i < L - 1) {
       dec_ups_.emplace_back();
-      reg_conv3("decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, &dec_ups_.back());
+      reg_conv3("decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, &dec_ups_.back(), true);
     }
   }
   reg_norm("decoder.conv_norm_out", ch[0], &dec_norm_out_);
@@ -726,12 +793,10 @@ int VAEModel::decode(Exec& ex, const __half* z, int B, int h, int w, bool postpr
     }
     if (i < L - 1) {
       ex.reset_scratch();
-      __half* up = ex.s16(static_cast<size_t>(B) * 4 * H * W * c);
-      RUN(ex, upsample2x_nhwc(cur, B, H, W, c, up, ex.st));
+      __half* o = block_out(static_cast<size_t>(B) * 4 * H * W * c);
+      GYRE_TRY(upsample_conv(ex, dec_ups_[i], cur, B, H, W, o));
       H *= 2;
       W *= 2;
-      __half* o = block_out(static_cast<size_t>(B) * H * W * c);
-      RUN(ex, conv3x3_f16(up, c, B, H, W, c, dec_ups_[i].wp, c, 1, 1, ep_out(o, c, dec_ups_[i].bias), ex.st));
       cur = o;
     }
   }

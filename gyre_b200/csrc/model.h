@@ -35,7 +35,12 @@ struct Exec {
 
 struct NormW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct LinW { __half* w = nullptr; float* bias = nullptr; int N = 0, K = 0; };
-struct Conv3W { __half* wp = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0; };
+struct Conv3W {
+  __half* wp = nullptr;
+  __half* wp_up = nullptr;   // upsampler convs only: the four 2x2 phase kernels of the folded nearest-2x upsample
+  float* bias = nullptr;
+  int Cin = 0, Cout = 0;
+};
 struct SmallConvW { float* w = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0; };   // fp32 1x1 on <= 8 channels
 
 struct ResnetW {
@@ -60,7 +65,7 @@ struct VaeAttnW {
   int C = 0;
 };
 
-enum ParamKind { P_F32 = 0, P_LINEAR, P_CONV3, P_GEGLU_W, P_GEGLU_B, P_F32MAT };
+enum ParamKind { P_F32 = 0, P_LINEAR, P_CONV3, P_GEGLU_W, P_GEGLU_B, P_F32MAT, P_CONV3_UP };
 
 struct ParamSlot {
   int kind = P_F32;
@@ -68,6 +73,7 @@ struct ParamSlot {
   int64_t shape[4] = {0, 0, 0, 0};
   int ndim = 0;
   int ld = 0;            // P_LINEAR: destination row pitch (elements)
+  void* dst2 = nullptr;  // P_CONV3_UP: phase-packed copy
   bool loaded = false;
 };
 
@@ -85,7 +91,9 @@ class Model {
   void reg(const std::string& key, int kind, void* dst, std::initializer_list<int64_t> shape, int ld = 0);
   void reg_norm(const std::string& p, int C, NormW* n);
   void reg_linear(const std::string& p, int N, int K, bool bias, LinW* l);
-  void reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c);
+  void reg_conv3(const std::string& p, int Cin, int Cout, Conv3W* c, bool upsampler = false);
+  // conv3x3 applied to the nearest-2x upsample of x [B, H, W, c.Cin] -> out [B, 2H, 2W, c.Cout]
+  int upsample_conv(Exec& ex, const Conv3W& c, const __half* x, int B, int H, int W, __half* out);
   void reg_resnet(const std::string& p, int cin, int cout, bool temb, ResnetW* r);
   int resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __half* x2, int C2, int B, int H, int W,
              float eps, const __half* temb_all, int temb_ld, __half* out);
@@ -110,6 +118,12 @@ class UNetModel : public Model {
   // dry == true sizes the workspace (ex.peak) without launching anything
   int forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, int B, int H, int W, int L,
               const int32_t* tome_r, __half* out);
+  // Binds a text context for the following forwards (the reference binds the embeddings once per request:
+  // UNetWithEmbeddings, gyre/pipeline/unet/core.py:253-259): the cross-attention K/V projections of every
+  // transformer block depend only on ctx, so they are computed here ONCE instead of once per step.
+  // ctx == nullptr drops the binding.
+  int set_context(const __half* ctx, int B, int L, cudaStream_t st);
+  ~UNetModel() override;
 
  private:
   int transformer(Exec& ex, const TransformerW& t, const __half* x, int B, int HW, const __half* ctx, int L, int r,
@@ -122,6 +136,10 @@ class UNetModel : public Model {
   std::vector<Conv3W> downs_, ups_;
   NormW norm_out_;
   Conv3W conv_out_;
+  // bound-context cache: per transformer block [ctx_B_ * ctx_L_, 2C] fp16 (k | v)
+  std::vector<__half*> kv_cache_;
+  std::vector<size_t> kv_cache_elems_;
+  int ctx_B_ = 0, ctx_L_ = 0;
 };
 
 class VAEModel : public Model {

@@ -3,17 +3,29 @@
 // LayerNorm over token rows, and the fp32 row softmax used by the VAE's single-head attention.
 // All loads/stores are 128-bit; statistics are fp32 with warp-shuffle / shared-memory reductions and a
 // Chan-style merge of per-chunk (n, mean, M2) partials (deterministic: no float atomics to global).
+#include <type_traits>
+
 #include "common.cuh"
 #include "ops.h"
 
 namespace gyre {
 
-constexpr int kGnRows = 64;      // pixels per CTA chunk
 constexpr int kMaxGroups = 32;
+constexpr int kGnMaxChunks = 128;   // per-sample partials the apply kernel folds in its prologue
+constexpr int kGnUnroll = 8;        // independent 16-byte loads in flight per thread
+
+// Rows (pixels) per CTA: a function of HW ONLY, so the summation order - and with it every bit of the result -
+// does not depend on the batch size (tests/batch_independance.py contract of the reference).
+static inline int gn_rows_per_cta(int HW) {
+  int rows = (HW + kGnMaxChunks - 1) / kGnMaxChunks;
+  if (rows < 16) rows = 16;
+  return (rows + 7) & ~7;
+}
 
 size_t gn_partials_floats(int B, int HW, int G) {
-  const int chunks = (HW + kGnRows - 1) / kGnRows;
-  return static_cast<size_t>(B) * chunks * G * 2 + static_cast<size_t>(B) * G * 2;   // partials + (mean, rstd)
+  const int rows = gn_rows_per_cta(HW);
+  const int chunks = (HW + rows - 1) / rows;
+  return static_cast<size_t>(B) * chunks * G * 2 + static_cast<size_t>(B) * G * 2;
 }
 
 __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
@@ -33,57 +45,57 @@ __device__ __forceinline__ void store8h(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
 }
 
-// grid (chunks, B); block = nvec * rpar threads, thread -> (vector v of 8 channels, row lane ty)
-__global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
-                                int G, int rpar, float* __restrict__ partials) {
-  const int C = C1 + C2;
+struct GnArgs {
+  const __half* x1;
+  const __half* x2;
+  int C1, C2, HW, G, rpar, rows_per_cta;
+};
+
+// grid (chunks, B); block = nvec * rpar threads, thread -> (vector v of 8 channels, row lane ty).
+// Pass 1: per-chunk (sum, sum of squares) of every group -> partials[b][chunk][G][2].
+__global__ void gn_stats_kernel(const GnArgs a, float* __restrict__ partials) {
+  pdl_wait();
+  pdl_trigger();
+  const int C = a.C1 + a.C2;
   const int nvec = C >> 3;
-  const int cpg = C / G;
+  const int cpg = C / a.G;
   const int v = threadIdx.x % nvec;
   const int ty = threadIdx.x / nvec;
   const int b = blockIdx.y;
-  const int row0 = blockIdx.x * kGnRows;
-  const int row1 = min(row0 + kGnRows, HW);
+  const int row0 = blockIdx.x * a.rows_per_cta;
+  const int row1 = min(row0 + a.rows_per_cta, a.HW);
   const int c0 = v * 8;
   const __half* src;
   int ld, cc;
-  if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
-  src += (static_cast<int64_t>(b) * HW) * ld + cc;
+  if (c0 < a.C1) { src = a.x1; ld = a.C1; cc = c0; } else { src = a.x2; ld = a.C2; cc = c0 - a.C1; }
+  src += (static_cast<int64_t>(b) * a.HW) * ld + cc;
 
   float s[8], ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-  // 4 independent 16-byte loads in flight per thread
-  int r = row0 + ty;
-  for (; r + 3 * rpar < row1; r += 4 * rpar) {
-    uint4 u[4];
+  const int rstep = a.rpar;
+  for (int base = row0 + ty; base < row1; base += kGnUnroll * rstep) {
+    uint4 u[kGnUnroll];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r + k * rpar) * ld);
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const int r = base + k * rstep;
+      u[k] = r < row1 ? *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r) * ld) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kGnUnroll; ++k) {
       const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(h[i]);
         s[2 * i] += f.x;
-        ss[2 * i] += f.x * f.x;
+        ss[2 * i] = fmaf(f.x, f.x, ss[2 * i]);
         s[2 * i + 1] += f.y;
-        ss[2 * i + 1] += f.y * f.y;
+        ss[2 * i + 1] = fmaf(f.y, f.y, ss[2 * i + 1]);
       }
     }
   }
-  for (; r < row1; r += rpar) {
-    float xv[8];
-    load8(src + static_cast<int64_t>(r) * ld, xv);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i] += xv[i];
-      ss[i] += xv[i] * xv[i];
-    }
-  }
   // Deterministic fold: per-thread channel sums go to shared memory, then one thread per group adds its
-  // channels x row-lanes in a fixed order (no float atomics: results are bit-reproducible, which the
-  // reference's batch-independence contract, tests/batch_independance.py, is checked against).
+  // channels x row-lanes in a fixed order (no float atomics: results are bit-reproducible).
   extern __shared__ float sh[];            // [rpar][C][2]
   float* mine = sh + (static_cast<size_t>(ty) * C + c0) * 2;
 #pragma unroll
@@ -92,77 +104,90 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __h
     mine[2 * i + 1] = ss[i];
   }
   __syncthreads();
-  if (threadIdx.x < G) {
+  if (threadIdx.x < a.G) {
     const int g = threadIdx.x;
-    float a = 0.f, q = 0.f;
-    for (int t = 0; t < rpar; ++t) {
+    float acc = 0.f, q = 0.f;
+    for (int t = 0; t < a.rpar; ++t) {
       const float* row = sh + (static_cast<size_t>(t) * C + g * cpg) * 2;
       for (int c = 0; c < cpg; ++c) {
-        a += row[2 * c];
+        acc += row[2 * c];
         q += row[2 * c + 1];
       }
     }
-    float* dst = partials + (static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * (2 * G) + 2 * g;
-    dst[0] = a;
+    float* dst = partials + (static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * (2 * a.G) + 2 * g;
+    dst[0] = acc;
     dst[1] = q;
   }
 }
 
-// one CTA per (sample, group): merges the per-chunk (sum, sumsq) partials in fp64 -> (mean, rstd)
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partials, int chunks, int G, int HW,
-                                                          int cpg, float eps, float* __restrict__ stats) {
-  const int g = blockIdx.x, b = blockIdx.y;
-  double s = 0.0, q = 0.0;
-  for (int c = threadIdx.x; c < chunks; c += 128) {
-    const float* pp = partials + (static_cast<int64_t>(b) * chunks + c) * (2 * G) + 2 * g;
-    s += static_cast<double>(pp[0]);
-    q += static_cast<double>(pp[1]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  __shared__ double sh[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { sh[warp] = s; sh[4 + warp] = q; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    s = sh[0] + sh[1] + sh[2] + sh[3];
-    q = sh[4] + sh[5] + sh[6] + sh[7];
-    const double n = static_cast<double>(HW) * cpg;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[(static_cast<int64_t>(b) * G + g) * 2] = static_cast<float>(mean);
-    stats[(static_cast<int64_t>(b) * G + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
-}
-
-__global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
-                                int G, int rpar, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int silu, const float* __restrict__ stats,
-                                __half* __restrict__ out) {
-  const int C = C1 + C2;
+// Pass 2: every CTA folds its sample's per-chunk partials (fp64, fixed order) into (mean, rstd) - no separate
+// finalize launch - then normalises (+SiLU) its chunk.  The first batch of rows is requested BEFORE the fold so
+// the statistics latency hides under the loads.  Chunks and samples are walked in the REVERSE order of pass 1:
+// what pass 1 touched last is still in L2.
+__global__ void gn_apply_kernel(const GnArgs a, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int silu, float eps, const float* __restrict__ partials, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int C = a.C1 + a.C2;
   const int nvec = C >> 3;
-  const int cpg = C / G;
-  const int b = blockIdx.y;
-  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
-  if (threadIdx.x < G) {
-    s_mean[threadIdx.x] = stats[(static_cast<int64_t>(b) * G + threadIdx.x) * 2];
-    s_rstd[threadIdx.x] = stats[(static_cast<int64_t>(b) * G + threadIdx.x) * 2 + 1];
-  }
-  __syncthreads();
+  const int cpg = C / a.G;
+  const int chunks = gridDim.x;
+  const int chunk = chunks - 1 - blockIdx.x;
+  const int b = gridDim.y - 1 - blockIdx.y;
   const int v = threadIdx.x % nvec;
   const int ty = threadIdx.x / nvec;
-  const int row0 = blockIdx.x * kGnRows;
-  const int row1 = min(row0 + kGnRows, HW);
+  const int row0 = chunk * a.rows_per_cta;
+  const int row1 = min(row0 + a.rows_per_cta, a.HW);
   const int c0 = v * 8;
   const __half* src;
   int ld, cc;
-  if (c0 < C1) { src = x1; ld = C1; cc = c0; } else { src = x2; ld = C2; cc = c0 - C1; }
-  src += (static_cast<int64_t>(b) * HW) * ld + cc;
-  __half* dst = out + (static_cast<int64_t>(b) * HW) * C + c0;
+  if (c0 < a.C1) { src = a.x1; ld = a.C1; cc = c0; } else { src = a.x2; ld = a.C2; cc = c0 - a.C1; }
+  src += (static_cast<int64_t>(b) * a.HW) * ld + cc;
+  __half* dst = out + (static_cast<int64_t>(b) * a.HW) * C + c0;
+  const int rstep = a.rpar;
+
+  uint4 u[kGnUnroll];
+  int base = row0 + ty;
+#pragma unroll
+  for (int k = 0; k < kGnUnroll; ++k) {
+    const int r = base + k * rstep;
+    u[k] = r < row1 ? __ldcs(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r) * ld)) : make_uint4(0, 0, 0, 0);
+  }
+
+  __shared__ double sh_s[8][kMaxGroups], sh_q[8][kMaxGroups];
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+  int parts = static_cast<int>(blockDim.x) / a.G;
+  if (parts > 8) parts = 8;
+  if (static_cast<int>(threadIdx.x) < parts * a.G) {
+    const int g = threadIdx.x % a.G;
+    const int part = threadIdx.x / a.G;
+    const float* pp = partials + static_cast<int64_t>(b) * chunks * (2 * a.G) + 2 * g;
+    double s = 0.0, q = 0.0;
+    for (int c = part; c < chunks; c += parts) {
+      const float2 t = *reinterpret_cast<const float2*>(pp + static_cast<int64_t>(c) * (2 * a.G));
+      s += static_cast<double>(t.x);
+      q += static_cast<double>(t.y);
+    }
+    sh_s[part][g] = s;
+    sh_q[part][g] = q;
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < a.G) {
+    const int g = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int t = 0; t < parts; ++t) {
+      s += sh_s[t][g];
+      q += sh_q[t][g];
+    }
+    const double n = static_cast<double>(a.HW) * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+
   float sc[8], sf[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -171,68 +196,73 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
     sc[i] = ga;
     sf[i] = beta[c0 + i] - s_mean[g] * ga;
   }
-  int r = row0 + ty;
-  for (; r + 3 * rpar < row1; r += 4 * rpar) {
-    uint4 u[4];
+  while (true) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r + k * rpar) * ld);
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const int r = base + k * rstep;
+      if (r < row1) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+        float xv[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
-      float xv[8];
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          xv[2 * i] = f.x;
+          xv[2 * i + 1] = f.y;
+        }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        xv[2 * i] = f.x;
-        xv[2 * i + 1] = f.y;
+        for (int i = 0; i < 8; ++i) {
+          float y = fmaf(xv[i], sc[i], sf[i]);
+          if (silu) y = silu_fast(y);
+          xv[i] = y;
+        }
+        store8h(dst + static_cast<int64_t>(r) * C, xv);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float y = fmaf(xv[i], sc[i], sf[i]);
-        if (silu) y = y / (1.0f + __expf(-y));
-        xv[i] = y;
-      }
-      store8h(dst + static_cast<int64_t>(r + k * rpar) * C, xv);
     }
-  }
-  for (; r < row1; r += rpar) {
-    float xv[8];
-    load8(src + static_cast<int64_t>(r) * ld, xv);
+    base += kGnUnroll * rstep;
+    if (base >= row1) break;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = fmaf(xv[i], sc[i], sf[i]);
-      if (silu) y = y / (1.0f + __expf(-y));
-      xv[i] = y;
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const int r = base + k * rstep;
+      u[k] = r < row1 ? __ldcs(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r) * ld)) : make_uint4(0, 0, 0, 0);
     }
-    store8h(dst + static_cast<int64_t>(r) * C, xv);
   }
 }
 
 // Small feature maps (UNet levels 2-3): ONE kernel, one CTA per (sample, group).  The group's HW x cpg slab
-// (<= 48 KB) is read once into shared memory, reduced in a fixed order (deterministic), normalised and
-// written back - a single pass over HBM and a single launch instead of three.
+// (<= 40 KB) is read once into shared memory with the widest vector the group width allows (VEC halfs per
+// load), reduced in a fixed order (deterministic), normalised and written back - a single pass over HBM and a
+// single launch.
+template <int VEC>
 __global__ void __launch_bounds__(256) gn_small_kernel(const __half* __restrict__ x1, int C1,
                                                        const __half* __restrict__ x2, int C2, int HW, int G, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int silu, __half* __restrict__ out) {
-  extern __shared__ __half2 slab[];          // [HW][cpg / 2]
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t slab_raw[];
+  typedef typename std::conditional<VEC == 8, uint4, typename std::conditional<VEC == 4, uint2, uint32_t>::type>::type vec_t;
+  vec_t* slab = reinterpret_cast<vec_t*>(slab_raw);   // [HW][cpg / VEC]
   const int C = C1 + C2;
   const int cpg = C / G;
-  const int hp = cpg >> 1;                   // half2 pairs per row (cpg is even)
+  const int vp = cpg / VEC;                  // vectors per row
   const int g = blockIdx.x, b = blockIdx.y;
   const int cbase = g * cpg;
-  const int total = HW * hp;
+  const int total = HW * vp;
   float s = 0.f, ss = 0.f;
   for (int i = threadIdx.x; i < total; i += 256) {
-    const int row = i / hp;
-    const int c = cbase + 2 * (i - row * hp);
+    const int row = i / vp;
+    const int c = cbase + VEC * (i - row * vp);
     const __half* src = c < C1 ? x1 + (static_cast<int64_t>(b) * HW + row) * C1 + c
                                : x2 + (static_cast<int64_t>(b) * HW + row) * C2 + (c - C1);
-    const __half2 v = *reinterpret_cast<const __half2*>(src);
+    const vec_t v = *reinterpret_cast<const vec_t*>(src);
     slab[i] = v;
-    const float2 f = __half22float2(v);
-    s += f.x + f.y;
-    ss += f.x * f.x + f.y * f.y;
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int k = 0; k < VEC / 2; ++k) {
+      const float2 f = __half22float2(h[k]);
+      s += f.x + f.y;
+      ss += f.x * f.x + f.y * f.y;
+    }
   }
   s = warp_sum(s);
   ss = warp_sum(ss);
@@ -245,13 +275,13 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const __half* __restrict_
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double a = 0.0, q = 0.0;
+    double acc = 0.0, q = 0.0;
     for (int w = 0; w < 8; ++w) {
-      a += static_cast<double>(red[w]);
+      acc += static_cast<double>(red[w]);
       q += static_cast<double>(red[8 + w]);
     }
     const double n = static_cast<double>(HW) * cpg;
-    const double mean = a / n;
+    const double mean = acc / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
     stat[0] = static_cast<float>(mean);
@@ -260,18 +290,25 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const __half* __restrict_
   __syncthreads();
   const float mean = stat[0], rstd = stat[1];
   for (int i = threadIdx.x; i < total; i += 256) {
-    const int row = i / hp;
-    const int cl = 2 * (i - row * hp);
-    const int c = cbase + cl;
-    const float2 f = __half22float2(slab[i]);
-    const float ga0 = gamma[c] * rstd, ga1 = gamma[c + 1] * rstd;
-    float y0 = fmaf(f.x - mean, ga0, beta[c]);
-    float y1 = fmaf(f.y - mean, ga1, beta[c + 1]);
-    if (silu) {
-      y0 = y0 / (1.0f + __expf(-y0));
-      y1 = y1 / (1.0f + __expf(-y1));
+    const int row = i / vp;
+    const int c = cbase + VEC * (i - row * vp);
+    const vec_t v = slab[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    vec_t o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < VEC / 2; ++k) {
+      const float2 f = __half22float2(h[k]);
+      const float ga0 = gamma[c + 2 * k] * rstd, ga1 = gamma[c + 2 * k + 1] * rstd;
+      float y0 = fmaf(f.x - mean, ga0, beta[c + 2 * k]);
+      float y1 = fmaf(f.y - mean, ga1, beta[c + 2 * k + 1]);
+      if (silu) {
+        y0 = silu_fast(y0);
+        y1 = silu_fast(y1);
+      }
+      oh[k] = __floats2half2_rn(y0, y1);
     }
-    *reinterpret_cast<__half2*>(out + (static_cast<int64_t>(b) * HW + row) * C + c) = __floats2half2_rn(y0, y1);
+    *reinterpret_cast<vec_t*>(out + (static_cast<int64_t>(b) * HW + row) * C + c) = o;
   }
 }
 
@@ -285,11 +322,19 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   {
     const int cpg = C / G;
     const size_t slab_bytes = static_cast<size_t>(HW) * cpg * sizeof(__half);
-    if ((cpg & 1) == 0 && HW <= 256 && slab_bytes <= 40 * 1024 && (C1 % 2 == 0)) {
+    if ((cpg & 1) == 0 && HW <= 256 && slab_bytes <= 40 * 1024) {
       prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 1);
-      gn_small_kernel<<<dim3(G, B), 256, slab_bytes, st>>>(x1, C1, x2, C2, HW, G, eps, gamma, beta, silu ? 1 : 0, out);
-      GYRE_CHECK_CUDA(cudaGetLastError());
-      return 0;
+      // a vector must not straddle the x1 / x2 boundary or a group boundary: C1, cpg multiples of VEC
+      const int vec = (cpg % 8 == 0) ? 8 : (cpg % 4 == 0 ? 4 : 2);
+      const dim3 grid(G, B);
+      if (vec == 8)
+        return launch_kernel(gn_small_kernel<8>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
+                             silu ? 1 : 0, out);
+      if (vec == 4)
+        return launch_kernel(gn_small_kernel<4>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
+                             silu ? 1 : 0, out);
+      return launch_kernel(gn_small_kernel<2>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
+                           silu ? 1 : 0, out);
     }
   }
   const int nvec = C / 8;
@@ -298,15 +343,22 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   if (rpar < 1) rpar = 1;
   const int threads = nvec * rpar;
   GYRE_REQUIRE(threads >= G, "groupnorm: too few threads for %d groups", G);
-  const int chunks = (HW + kGnRows - 1) / kGnRows;
+  GnArgs a;
+  a.x1 = x1;
+  a.x2 = x2;
+  a.C1 = C1;
+  a.C2 = C2;
+  a.HW = HW;
+  a.G = G;
+  a.rpar = rpar;
+  a.rows_per_cta = gn_rows_per_cta(HW);
+  const int chunks = (HW + a.rows_per_cta - 1) / a.rows_per_cta;
   dim3 grid(chunks, B);
-  float* stats = partials + static_cast<size_t>(B) * chunks * G * 2;
-  prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 3);
-  gn_stats_kernel<<<grid, threads, static_cast<size_t>(rpar) * C * 2 * sizeof(float), st>>>(x1, C1, x2, C2, HW, G, rpar,
-                                                                                          partials);
-  gn_finalize_kernel<<<dim3(G, B), 128, 0, st>>>(partials, chunks, G, HW, C / G, eps, stats);
-  gn_apply_kernel<<<grid, threads, 0, st>>>(x1, C1, x2, C2, HW, G, rpar, gamma, beta, silu ? 1 : 0, stats, out);
-  GYRE_CHECK_CUDA(cudaGetLastError());
+  prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 2);
+  GYRE_TRY(launch_kernel(gn_stats_kernel, grid, dim3(threads), static_cast<size_t>(rpar) * C * 2 * sizeof(float), st, a,
+                         partials));
+  GYRE_TRY(launch_kernel(gn_apply_kernel, grid, dim3(threads), 0, st, a, gamma, beta, silu ? 1 : 0, eps,
+                         static_cast<const float*>(partials), out));
   return 0;
 }
 
@@ -317,6 +369,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int rows, int C, float eps,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -385,13 +439,13 @@ int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gam
   const int nv = (C + 255) / 256;
   const unsigned grid = (rows + 7) / 8;
   switch (nv) {
-    case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
-    case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
-    case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
-    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
-    case 5: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
-    case 6: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
-    default: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out); break;
+    case 1: GYRE_TRY(launch_kernel(layernorm_kernel<1>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
+    case 2: GYRE_TRY(launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
+    case 3: GYRE_TRY(launch_kernel(layernorm_kernel<3>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
+    case 4: GYRE_TRY(launch_kernel(layernorm_kernel<4>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
+    case 5: GYRE_TRY(launch_kernel(layernorm_kernel<5>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
+    case 6: GYRE_TRY(launch_kernel(layernorm_kernel<6>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
+    default: GYRE_TRY(launch_kernel(layernorm_kernel<8>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
   }
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;

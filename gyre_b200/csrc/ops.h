@@ -47,6 +47,12 @@ int gemm_rowmax_partials(int M, int N);
 int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp, int Cout, int stride,
                 int pad, const Epilogue& ep, cudaStream_t st);
 
+// conv3x3(nearest_upsample_2x(X)) without materialising the upsampled tensor: four 2x2 phase convolutions on
+// the low-res X [B, H, W, Cin] with weights packed by pack_upconv3x3; output [B, 2H, 2W, Cout] (ep.out, pitch
+// ep.ldo, fp16, 16-byte aligned rows).  Epilogue: bias only.
+int upconv2x_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp4, int Cout,
+                 const Epilogue& ep, cudaStream_t st);
+
 // GroupNorm (+optional SiLU) over NHWC fp16.  Input may be the channel-concatenation of two tensors
 // (x1 [.., C1] ++ x2 [.., C2]); output is one dense [B, HW, C1+C2] tensor.  `partials` is fp32 scratch
 // of at least gn_partials_floats(B, HW, G) floats.
@@ -107,6 +113,8 @@ namespace gyre {
 // ---- weight packing (pack.cu); dtype: 0 fp16, 1 fp32
 size_t conv3x3_packed_elems(int Cin, int Cout);
 int pack_conv3x3(const void* w, int dtype, int Cin, int Cout, __half* out, cudaStream_t st);
+size_t upconv3x3_packed_elems(int Cin, int Cout);
+int pack_upconv3x3(const void* w, int dtype, int Cin, int Cout, __half* out, cudaStream_t st);
 int cast_to_f16(const void* src, int dtype, int64_t rows, int cols, __half* dst, int ldd, cudaStream_t st);
 int cast_to_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st);
 int pack_geglu(const void* w, int dtype, int F, int K, const void* bias, int bias_dtype, __half* wp, float* bias_p,
@@ -119,6 +127,14 @@ int tome_merge_kv(const __half* k, const __half* v, int ld, int B, int N, int C,
 }  // namespace gyre
 
 namespace gyre {
+// ---- tunables: small integer knobs read on the host at launch time.  Each starts from the environment
+// variable GYRE_B200_<NAME> (if set) and can be changed through gyre_b200_set_tunable (A/B measurements).
+enum Tunable { TUNE_ATT_VARIANT = 0, TUNE_PDL = 1, TUNE_GELU_FAST = 2, TUNE_GN_FUSED = 3, TUNE_UPCONV_FOLD = 4,
+               TUNE_CTX_KV_CACHE = 5, TUNE_XATTN = 6, TUNE_COUNT = 7 };
+int tunable(int id);
+int set_tunable_by_name(const char* name, int value);
+int get_tunable_by_name(const char* name, int* value);
+
 namespace prof {
 // Kernel families for the launch counter and the optional CUDA-event profiler (bench.py's roofline leg).
 enum Family { F_GEMM = 0, F_CONV = 1, F_ATTN = 2, F_GROUPNORM = 3, F_LAYERNORM = 4, F_SOFTMAX = 5, F_ELEMENTWISE = 6,

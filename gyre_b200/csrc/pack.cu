@@ -47,6 +47,60 @@ int pack_conv3x3(const void* w, int dtype, int Cin, int Cout, __half* out, cudaS
   return 0;
 }
 
+// nearest-2x upsample followed by a 3x3 conv == four 2x2 convs on the LOW-RES input, one per output phase
+// (dy, dx) = (Y & 1, X & 1): the 3 taps of a row collapse onto 2 source pixels, so their weights add
+//   dy = 0: source row y-1 <- ky{0},   source row y   <- ky{1,2}
+//   dy = 1: source row y   <- ky{0,1}, source row y+1 <- ky{2}            (same for columns)
+// 2.25x fewer MACs than convolving the upsampled tensor, which is never written.  Zero padding of the
+// upsampled image coincides with zero padding of the source (TMA out-of-bounds fill), so borders are exact.
+// out: [4 phases][Cout][4 taps = th*2+tw][cin_pad]; sums are formed in fp32 and rounded to fp16 once.
+template <typename T>
+__global__ void pack_upconv3x3_kernel(const T* __restrict__ w, int Cin, int Cout, int cin_pad, int64_t total,
+                                      __half* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % cin_pad);
+  int64_t r = i / cin_pad;
+  const int tap = static_cast<int>(r % 4);
+  r /= 4;
+  const int o = static_cast<int>(r % Cout);
+  const int phase = static_cast<int>(r / Cout);
+  const int dy = phase >> 1, dx = phase & 1;
+  const int th = tap >> 1, tw = tap & 1;
+  // [k_lo, k_hi] of the 3x3 taps that land on source offset t for phase d
+  const int ky0 = dy == 0 ? (th == 0 ? 0 : 1) : (th == 0 ? 0 : 2);
+  const int ky1 = dy == 0 ? (th == 0 ? 0 : 2) : (th == 0 ? 1 : 2);
+  const int kx0 = dx == 0 ? (tw == 0 ? 0 : 1) : (tw == 0 ? 0 : 2);
+  const int kx1 = dx == 0 ? (tw == 0 ? 0 : 2) : (tw == 0 ? 1 : 2);
+  float v = 0.f;
+  if (c < Cin) {
+    const T* base = w + (static_cast<int64_t>(o) * Cin + c) * 9;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) v += to_f32(base[ky * 3 + kx]);
+  }
+  out[i] = __float2half_rn(v);
+}
+
+size_t upconv3x3_packed_elems(int Cin, int Cout) {
+  const int cin_pad = (Cin + 63) / 64 * 64;
+  return static_cast<size_t>(4) * Cout * 4 * cin_pad;
+}
+
+int pack_upconv3x3(const void* w, int dtype, int Cin, int Cout, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(Cin > 0 && Cout > 0, "pack_upconv3x3: empty");
+  const int cin_pad = (Cin + 63) / 64 * 64;
+  const int64_t total = static_cast<int64_t>(upconv3x3_packed_elems(Cin, Cout));
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == 0)
+    pack_upconv3x3_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(w), Cin, Cout, cin_pad, total, out);
+  else if (dtype == 1)
+    pack_upconv3x3_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(w), Cin, Cout, cin_pad, total, out);
+  else
+    GYRE_REQUIRE(false, "pack_upconv3x3: dtype %d", dtype);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // generic cast / copy with row pitch: src [rows, cols] dtype -> dst fp16 or fp32 [rows, ldd]
 template <typename T, typename U>
 __global__ void cast_rows_kernel(const T* __restrict__ src, int64_t rows, int cols, U* __restrict__ dst, int ldd) {

@@ -2,6 +2,7 @@
 // point resolved at run time (no link-time dependency on libcuda: the library must load on GPU-less hosts).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -74,6 +75,55 @@ int encode_tmap_f16_sw(CUtensorMap* out, const void* base, int rank, const uint6
   return 0;
 }
 
+
+// ------------------------------------------------------------------ tunables
+static const char* kTunableNames[TUNE_COUNT] = {"ATT_VARIANT", "PDL", "GELU_FAST", "GN_FUSED", "UPCONV_FOLD",
+                                                "CTX_KV_CACHE", "XATTN"};
+// defaults = the configuration measured fastest on B200 (profiles/); 0 restores the plain round-1 kernels
+static const int kTunableDefaults[TUNE_COUNT] = {3, 1, 1, 1, 1, 1, 1};
+static std::atomic<int> g_tunables[TUNE_COUNT];
+static std::once_flag g_tunables_once;
+
+static void init_tunables() {
+  std::call_once(g_tunables_once, [] {
+    for (int i = 0; i < TUNE_COUNT; ++i) {
+      int v = kTunableDefaults[i];
+      char name[64];
+      snprintf(name, sizeof(name), "GYRE_B200_%s", kTunableNames[i]);
+      if (const char* e = getenv(name)) v = atoi(e);
+      g_tunables[i].store(v);
+    }
+  });
+}
+
+int tunable(int id) {
+  init_tunables();
+  return (id >= 0 && id < TUNE_COUNT) ? g_tunables[id].load(std::memory_order_relaxed) : 0;
+}
+
+int set_tunable_by_name(const char* name, int value) {
+  init_tunables();
+  GYRE_REQUIRE(name != nullptr, "set_tunable: null name");
+  for (int i = 0; i < TUNE_COUNT; ++i)
+    if (strcmp(name, kTunableNames[i]) == 0) {
+      g_tunables[i].store(value);
+      return 0;
+    }
+  set_last_error("set_tunable: unknown tunable '%s'", name);
+  return -2;
+}
+
+int get_tunable_by_name(const char* name, int* value) {
+  init_tunables();
+  GYRE_REQUIRE(name != nullptr && value != nullptr, "get_tunable: null argument");
+  for (int i = 0; i < TUNE_COUNT; ++i)
+    if (strcmp(name, kTunableNames[i]) == 0) {
+      *value = g_tunables[i].load();
+      return 0;
+    }
+  set_last_error("get_tunable: unknown tunable '%s'", name);
+  return -2;
+}
 
 // ------------------------------------------------------------------ launch counter + per-family event profiler
 namespace prof {

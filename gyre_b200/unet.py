@@ -48,6 +48,7 @@ class B200UNet:
         self._h = C.c_void_p()
         self._ws = {}
         self._loaded = False
+        self._ctx_bound = None          # (owner, B, L) of the context bound with set_context
         cfg = self.config
         c = N.UNetConfigC()
         c.in_channels, c.out_channels = cfg.in_channels, cfg.out_channels
@@ -89,6 +90,7 @@ class B200UNet:
             torch.cuda.current_stream(self.device).synchronize()
 
     def load_state_dict(self, state_dict, strict: bool = True):
+        self.set_context(None)          # cached K/V projections depend on the attn2 weights
         for k, v in state_dict.items():
             self.load_weight(k, v)
         if strict:
@@ -126,12 +128,37 @@ class B200UNet:
             return None
         return parse_r(self.num_transformer_blocks, self.r)
 
+    def set_context(self, ctx_f16, owner=None):
+        """Binds `ctx` ([B, L, Cc] fp16) for the following `forward_raw(..., None)` calls: the cross-attention
+        K/V projections are computed once here (gyre_b200_unet_set_context).  `None` drops the binding."""
+        if ctx_f16 is None:
+            if self._ctx_bound is not None:
+                with torch.cuda.device(self.device):
+                    N.check(self._lib.gyre_b200_unet_set_context(self._h, None, 0, 0, N.stream_ptr(self.device)),
+                            "unet_set_context")
+            self._ctx_bound = None
+            return
+        if not self._loaded:
+            raise N.NativeError("B200UNet: weights not loaded")
+        N.require_cuda(ctx_f16)
+        B, L, _ = ctx_f16.shape
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gyre_b200_unet_set_context(self._h, N.ptr(ctx_f16), B, L, N.stream_ptr(self.device)),
+                    "unet_set_context")
+        self._ctx_bound = (owner, B, L)
+
     def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None):
-        """No conversions: fp16 NCHW sample, int64 [B] timesteps, fp16 [B, L, Cc] context, all on device."""
+        """No conversions: fp16 NCHW sample, int64 [B] timesteps, fp16 [B, L, Cc] context (or None: the context
+        bound with `set_context`), all on device."""
         if not self._loaded:
             raise N.NativeError("B200UNet: weights not loaded")
         B, Cin, H, W = sample_f16.shape
-        L = ctx_f16.shape[1]
+        if ctx_f16 is None:
+            if self._ctx_bound is None or self._ctx_bound[1] != B:
+                raise N.NativeError("B200UNet: no context bound for this batch")
+            L = self._ctx_bound[2]
+        else:
+            L = ctx_f16.shape[1]
         if out is None:
             out = torch.empty((B, self.config.out_channels, H, W), device=self.device, dtype=torch.float16)
         ws = self._workspace(B, H, W, L)

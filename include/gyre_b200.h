@@ -51,6 +51,15 @@ int gyre_b200_prof_enable(int on);
 int gyre_b200_prof_reset(void);
 int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, double* flops, double* bytes);
 
+/* Kernel-selection knobs for A/B measurement (no reference counterpart).  Names: "ATT_VARIANT" (softmax
+ * variant bit flags of the d<=64 flash kernel), "PDL" (programmatic dependent launch), "GELU_FAST",
+ * "GN_FUSED", "UPCONV_FOLD" (nearest-2x upsample folded into four 2x2 phase convolutions),
+ * "CTX_KV_CACHE" (cross-attention K/V projections of an unchanged text context are reused across
+ * steps), "XATTN" (short-key attention kernel).  Every knob also reads GYRE_B200_<NAME> from the
+ * environment at first use.  Results stay within the documented tolerances for every setting. */
+int gyre_b200_set_tunable(const char* name, int value);
+int gyre_b200_get_tunable(const char* name, int* value);
+
 /* ------------------------------------------------------------------------------------------
  * UNet  (replaces diffusers UNet2DConditionModel.forward as called from
  *        gyre/pipeline/unet/core.py:274 through the DiffusersUNet protocol,
@@ -98,10 +107,19 @@ int gyre_b200_unet_workspace_bytes(gyre_b200_handle h, int batch, int height, in
  *   tome_r  NULL, or one int32 per transformer block in module execution order: the number of
  *           K/V tokens to merge (nonfree/tome_memory_efficient_cross_attention.py:28-50; the list
  *           parse_r builds, nonfree/ToMe/tome/utils.py:80-105) -- HOST pointer
- *   out     [batch, out_channels, height, width]  fp16 NCHW */
+ *   out     [batch, out_channels, height, width]  fp16 NCHW
+ * ctx may be NULL after gyre_b200_unet_set_context bound a context of the same [batch, ctx_len]. */
 int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx,
                            int batch, int height, int width, int ctx_len, const int32_t* tome_r_host,
                            void* out, void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+
+/* Binds the text context for the following forwards (the reference binds the embeddings once per
+ * request: UNetWithEmbeddings, gyre/pipeline/unet/core.py:253-259).  The cross-attention K/V
+ * projections depend only on ctx, so they are computed here once instead of once per denoising step;
+ * later forwards pass ctx = NULL.  The library keeps the projected K/V (batch*ctx_len*2C fp16 per
+ * transformer block) until the next call; ctx = NULL drops the binding.  The caller must re-bind
+ * after changing the context tensor's contents or any attn2.to_k / to_v weight. */
+int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, int ctx_len, gyre_b200_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * AutoencoderKL  (replaces vae.decode(x).sample, gyre/pipeline/unified_pipeline.py:1523-1536,
@@ -208,6 +226,14 @@ int gyre_b200_conv3x3(const void* X, int ldx, int B, int H, int W, int Cin, cons
 /* W [Cout, Cin, 3, 3] (dtype f16/f32) -> Wp fp16 [Cout, 9, round_up(Cin, 64)], tap = kh*3+kw. */
 size_t gyre_b200_conv3x3_packed_elems(int Cin, int Cout);
 int gyre_b200_pack_conv3x3(const void* W, int dtype, int Cin, int Cout, void* Wp, gyre_b200_stream stream);
+/* conv3x3(nearest-2x upsample(X)) without writing the upsampled tensor (replaces diffusers Upsample2D:
+ * F.interpolate(scale_factor=2, mode="nearest") + conv): X [B, H, W, Cin] NHWC fp16 ->
+ * out [B, 2H, 2W, Cout].  Wp4 = the four 2x2 phase kernels packed by gyre_b200_pack_upconv3x3
+ * (fp16 [4, Cout, 4, round_up(Cin, 64)]); epilogue: bias only. */
+size_t gyre_b200_upconv3x3_packed_elems(int Cin, int Cout);
+int gyre_b200_pack_upconv3x3(const void* W, int dtype, int Cin, int Cout, void* Wp4, gyre_b200_stream stream);
+int gyre_b200_upconv2x(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wp4, int Cout,
+                       const gyre_b200_epilogue* ep, gyre_b200_stream stream);
 /* GroupNorm (+SiLU) over NHWC fp16; the input may be the channel concatenation x1 ++ x2
  * (replaces at::native_group_norm + silu).  scratch: fp32, gyre_b200_groupnorm_scratch_floats. */
 size_t gyre_b200_groupnorm_scratch_floats(int B, int HW, int G);

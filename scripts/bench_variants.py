@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""A/B timings of kernel variants at the SD1.5 (CFG batch 16) shapes, host overhead removed: each case is
+captured into a CUDA graph of REP launches over rotating buffers (working set > L2) and the graph is replayed;
+time = CUDA events around the replays / launches.  Writes gpurun_out/variants.json.
+
+    python scripts/bench_variants.py [attn] [xattn] [geglu] [gn] [upconv] [ln] [pdl]
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gyre_b200 import _native as N  # noqa: E402
+
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(dev)
+N.load()
+what = set(sys.argv[1:]) or {"attn", "xattn", "geglu", "gn", "upconv", "ln", "pdl"}
+ROT = 4
+REP = 8
+results = {}
+
+
+def graph_time(fn, rep=REP, replays=5):
+    """fn(i) enqueues one launch group using buffer set i % ROT.  Returns us per call."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for i in range(ROT):          # warm-up outside capture (function attributes, lazy init)
+            fn(i)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(rep):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (rep * replays)
+
+
+def rec(group, name, us, flops=0.0, bytes_=0.0):
+    results.setdefault(group, []).append({"case": name, "us": us, "tflops": flops / us / 1e6 if flops else None,
+                                          "gbs": bytes_ / us / 1e3 if bytes_ else None})
+    print(f"{group:8s} {name:58s} {us:9.1f} us" + (f"  {flops / us / 1e6:7.1f} TF/s" if flops else "") +
+          (f"  {bytes_ / us / 1e3:7.0f} GB/s" if bytes_ else ""), flush=True)
+
+
+def with_tunable(name, value, fn):
+    old = N.get_tunable(name)
+    N.set_tunable(name, value)
+    try:
+        return fn()
+    finally:
+        N.set_tunable(name, old)
+
+
+B2 = 16
+if "attn" in what:
+    for (heads, Nq, d) in ((8, 4096, 40), (8, 1024, 40), (10, 2304, 64)):
+        C = heads * d
+        qkv = [torch.randn(B2, Nq, 3 * C, device=dev).half() for _ in range(ROT)]
+        fl = 4.0 * B2 * heads * Nq * Nq * d
+        for v in (0, 1, 3, 7, 11, 6, 17, 33):
+            us = with_tunable("ATT_VARIANT", v, lambda: graph_time(
+                lambda i: N.attention(qkv[i % ROT][:, :, :C], qkv[i % ROT][:, :, C:2 * C], qkv[i % ROT][:, :, 2 * C:], heads)))
+            rec("attn", f"self B{B2} h{heads} N{Nq} d{d} variant {v}", us, fl)
+        del qkv
+
+if "xattn" in what:
+    for (heads, Nq, d) in ((8, 4096, 40), (8, 1024, 80), (8, 256, 160), (10, 2304, 64)):
+        C = heads * d
+        q = [torch.randn(B2, Nq, C, device=dev).half() for _ in range(ROT)]
+        kv = torch.randn(B2, 77, 2 * C, device=dev).half()
+        by = 2.0 * B2 * C * (2 * Nq + 2 * 77)
+        for x in (0, 1):
+            us = with_tunable("XATTN", x, lambda: graph_time(
+                lambda i: N.attention(q[i % ROT], kv[:, :, :C], kv[:, :, C:], heads)))
+            rec("xattn", f"cross B{B2} h{heads} Nq{Nq} Nk77 d{d} xattn={x}", us, 4.0 * B2 * heads * Nq * 77 * d, by)
+        del q
+
+if "geglu" in what:
+    for (HW, C) in ((4096, 320), (1024, 640), (256, 1280)):
+        M = B2 * HW
+        a = [torch.randn(M, C, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(8 * C, C, device=dev).half() * (1 / math.sqrt(C))
+        bias = torch.randn(8 * C, device=dev)
+        wp, bp = N.pack_geglu(w, bias)
+        for fast in (0, 1):
+            us = with_tunable("GELU_FAST", fast, lambda: graph_time(lambda i: N.gemm(a[i % ROT], wp, bias=bp, act=1)))
+            rec("geglu", f"geglu M{M} N{8 * C} K{C} fast={fast}", us, 2.0 * M * 8 * C * C)
+        del a
+
+if "gn" in what:
+    for (HW, C, silu) in ((4096, 320, True), (4096, 640, True), (4096, 960, True), (1024, 640, True), (1024, 1920, True),
+                          (256, 1280, True), (256, 2560, True), (64, 1280, True), (4096, 320, False)):
+        x = [torch.randn(B2, HW, C, device=dev).half() for _ in range(ROT)]
+        g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        us = graph_time(lambda i: N.groupnorm(x[i % ROT], g, b, 32, 1e-5, silu))
+        rec("gn", f"gn B{B2} HW{HW} C{C} silu={int(silu)}", us, 0.0, 2.0 * 2 * B2 * HW * C)
+        del x
+    # VAE-sized
+    for (HW, C) in ((262144, 128), (65536, 256), (16384, 512)):
+        x = [torch.randn(8, HW, C, device=dev).half() for _ in range(2)]
+        g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        us = graph_time(lambda i: N.groupnorm(x[i % 2], g, b, 32, 1e-6, True), rep=4)
+        rec("gn", f"gn B8 HW{HW} C{C} (VAE)", us, 0.0, 2.0 * 2 * 8 * HW * C)
+        del x
+
+if "ln" in what:
+    for (rows, C) in ((65536, 320), (16384, 640), (4096, 1280)):
+        x = [torch.randn(rows, C, device=dev).half() for _ in range(ROT)]
+        g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        us = graph_time(lambda i: N.layernorm(x[i % ROT], g, b))
+        rec("ln", f"ln rows{rows} C{C}", us, 0.0, 2.0 * 2 * rows * C)
+        del x
+
+if "upconv" in what:
+    for (B, H, C) in ((16, 16, 1280), (16, 32, 640), (16, 8, 1280), (8, 128, 512), (8, 256, 256)):
+        x = [torch.randn(B, H, H, C, device=dev).half() for _ in range(2)]
+        w = torch.randn(C, C, 3, 3, device=dev).half() * (1 / math.sqrt(9 * C))
+        bias = torch.randn(C, device=dev)
+        wp, wp4 = N.pack_conv3x3(w), N.pack_upconv3x3(w)
+        fl = 2.0 * 9 * C * C * B * 4 * H * H
+        up = [torch.empty(B, 2 * H, 2 * H, C, device=dev, dtype=torch.float16) for _ in range(2)]
+
+        def plain(i):
+            # un-folded: the upsampled tensor is materialised (torch's nearest kernel stands in for ours here)
+            up[i % 2].copy_(x[i % 2].repeat_interleave(2, 1).repeat_interleave(2, 2))
+            N.conv3x3(up[i % 2], wp, C, bias=bias)
+        us = graph_time(plain, rep=4)
+        rec("upconv", f"upsample+conv B{B} {H}x{H} C{C} un-folded (torch upsample)", us, fl)
+        us = graph_time(lambda i: N.upconv2x(x[i % 2], wp4, C, bias=bias), rep=4)
+        rec("upconv", f"upsample+conv B{B} {H}x{H} C{C} folded (4 phase convs)", us, fl)
+        del x, up
+
+if "pdl" in what:
+    # a chain of dependent small kernels (the transformer block at level 2): LN -> GEMM -> GEMM(+res) -> LN ...
+    M, C = B2 * 256, 1280
+    h = torch.randn(M, C, device=dev).half()
+    w = torch.randn(C, C, device=dev).half() * (1 / math.sqrt(C))
+    g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+
+    def chain(i):
+        t = N.layernorm(h, g, b)
+        t = N.gemm(t, w)
+        t = N.gemm(t, w, residual=h)
+        t = N.layernorm(t, g, b)
+        t = N.gemm(t, w)
+        N.gemm(t, w, residual=h)
+    for pdl in (0, 1):
+        us = with_tunable("PDL", pdl, lambda: graph_time(chain, rep=8))
+        rec("pdl", f"LN-GEMM-GEMM x2 chain M{M} C{C} pdl={pdl} (6 kernels)", us)
+
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(results, open("gpurun_out/variants.json", "w"), indent=1)

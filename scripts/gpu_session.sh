@@ -1,0 +1,34 @@
+#!/bin/bash
+# One GPU-box session: [tests] [variants] [bench] [profile]; everything lands in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+for what in "$@"; do
+  case "$what" in
+    tests)
+      for f in tests/test_ops_gpu.py tests/test_attention_gpu.py tests/test_tome_gpu.py tests/test_models_gpu.py tests/test_pipeline_gpu.py; do
+        name=$(basename "$f" .py)
+        timeout 900 python -m pytest "$f" -m gpu -q -x --tb=short > "gpurun_out/$name.log" 2>&1
+        echo "== $f -> exit $?"; tail -n 3 "gpurun_out/$name.log"
+      done ;;
+    tests_quick)
+      timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_attention_gpu.py -m gpu -q --tb=short > gpurun_out/quick.log 2>&1
+      echo "== quick tests -> exit $?"; grep -E "passed|failed|Error" gpurun_out/quick.log | tail -n 30 ;;
+    variants)
+      timeout 600 python scripts/bench_variants.py > gpurun_out/variants.log 2>&1
+      echo "== variants -> exit $?"; cat gpurun_out/variants.log | tail -n 90 ;;
+    bench)
+      timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+      echo "== bench -> exit $?"; tail -c 4000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err ;;
+    bench_fast)
+      timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+      echo "== bench -> exit $?"; tail -c 4000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err ;;
+    shapes)
+      timeout 600 python scripts/bench_kernels.py > gpurun_out/shapes.log 2>&1
+      echo "== shapes -> exit $?"; tail -n 12 gpurun_out/shapes.log ;;
+    profile)
+      bash scripts/gpu_profile.sh ;;
+    smoke)
+      timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+      echo "== smoke -> exit $?"; tail -n 5 gpurun_out/smoke.log ;;
+  esac
+done

@@ -31,7 +31,10 @@ def ref_attention(q, k, v, heads):
 # (B, heads, Nq, Nk, d): SD1.5 levels (d=40/80/160), SD2 (d=64), cross (Nk=77), ToMe-merged (Nk=N-r), tiny dims
 CASES = [(1, 1, 128, 128, 64), (2, 4, 256, 256, 16), (2, 8, 1024, 1024, 40), (1, 8, 256, 256, 80),
          (2, 8, 64, 64, 160), (2, 5, 300, 300, 64), (2, 8, 1024, 77, 40), (1, 8, 256, 77, 160), (1, 2, 100, 13, 32),
-         (1, 8, 1024, 768, 40), (1, 8, 4096, 4096, 40), (1, 4, 256, 130, 80)]
+         (1, 8, 1024, 768, 40), (1, 8, 4096, 4096, 40), (1, 4, 256, 130, 80),
+         # short-key kernel (Nk <= 128, Nq >= 512): cross-attention at SD1.5 / SD2.1 / SDXL shapes, ragged edges
+         (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 10, 2304, 77, 64), (1, 5, 9216, 77, 64),
+         (1, 3, 700, 77, 40), (2, 4, 512, 128, 64), (1, 2, 640, 16, 128), (1, 8, 1000, 100, 72)]
 
 
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", CASES)
@@ -64,3 +67,37 @@ def test_attention_peaked_softmax(nat):
     ref = ref_attention(q, k, v, heads)
     assert torch.isfinite(out).all()
     assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+# softmax variants of the d <= 64 flash kernel (include/gyre_b200.h: tunable "ATT_VARIANT"): 0 plain, 1 staggered
+# groups, 3 + packed fp32x2 maths, 7 / 11 + polynomial exp2 on 25 % / 50 % of the scores, 6 packed + poly w/o stagger
+@pytest.mark.parametrize("variant", [0, 1, 3, 7, 11, 6])
+def test_attention_softmax_variants(nat, variant):
+    old = nat.get_tunable("ATT_VARIANT")
+    try:
+        nat.set_tunable("ATT_VARIANT", variant)
+        for (B, heads, Nq, Nk, d) in [(1, 8, 1024, 1024, 40), (1, 2, 512, 640, 64), (1, 4, 2048, 2000, 40)]:
+            C = heads * d
+            q, k, v = rnd(B, Nq, C, seed=1, scale=1.5), rnd(B, Nk, C, seed=2, scale=1.5), rnd(B, Nk, C, seed=3)
+            out = nat.attention(q, k, v, heads)
+            ref = ref_attention(q, k, v, heads)
+            err = (out.float() - ref).abs().max().item()
+            assert err < 4e-3, f"variant {variant} Nq{Nq} Nk{Nk} d{d}: max abs err {err}"
+    finally:
+        nat.set_tunable("ATT_VARIANT", old)
+
+
+def test_attention_short_key_kernel_matches_flash(nat):
+    """The K/V-resident kernel and the flash kernel give the same cross-attention to fp16 noise."""
+    B, heads, Nq, Nk, d = 2, 8, 4096, 77, 40
+    C = heads * d
+    q, k, v = rnd(B, Nq, C, seed=1), rnd(B, Nk, C, seed=2), rnd(B, Nk, C, seed=3)
+    old = nat.get_tunable("XATTN")
+    try:
+        nat.set_tunable("XATTN", 1)
+        a = nat.attention(q, k, v, heads)
+        nat.set_tunable("XATTN", 0)
+        b = nat.attention(q, k, v, heads)
+    finally:
+        nat.set_tunable("XATTN", old)
+    assert (a.float() - b.float()).abs().max().item() < 2e-3
