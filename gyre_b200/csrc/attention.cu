@@ -980,13 +980,23 @@ int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __ha
     CUtensorMap to;
     GYRE_TRY(make_head_map(&to, out, ldo, Nq, heads, d, B, kBQ));
     const long long bh = static_cast<long long>(B) * heads;
-    int splits = static_cast<int>((2ll * 148 + bh - 1) / bh);
-    if (splits < 1) splits = 1;
-    int tpc = (p.q_tiles + splits - 1) / splits;
-    if (tpc < 4) tpc = 4;                       // amortise the K/V load and the pipeline fill
-    if (tpc > p.q_tiles) tpc = p.q_tiles;
-    p.tiles_per_cta = tpc;
-    p.splits = (p.q_tiles + tpc - 1) / tpc;
+    // CTAs per (batch, head): minimise  waves x (tiles per CTA + fixed cost of ~6 tiles for the K/V load and the
+    // pipeline fill) over the split counts that leave every CTA at least 2 tiles
+    int best_split = 1;
+    long long best_cost = -1;
+    for (int sp = 1; sp <= p.q_tiles / 2 || sp == 1; ++sp) {
+      const int tpc = (p.q_tiles + sp - 1) / sp;
+      const int real = (p.q_tiles + tpc - 1) / tpc;
+      const long long waves = (bh * real + 147) / 148;
+      const long long cost = waves * (tpc + 6);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_split = real;
+      }
+      if (sp >= 64) break;
+    }
+    p.tiles_per_cta = (p.q_tiles + best_split - 1) / best_split;
+    p.splits = (p.q_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     const long long nb = bh * p.splits;
     GYRE_REQUIRE(nb < (1ll << 31), "attention: grid too large");
     return dch == 1 ? launch_xattn<1>(tq, tk, tv, to, p, static_cast<unsigned>(nb), st)

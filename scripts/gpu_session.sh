@@ -14,8 +14,12 @@ for what in "$@"; do
       timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_attention_gpu.py -m gpu -q --tb=short > gpurun_out/quick.log 2>&1
       echo "== quick tests -> exit $?"; grep -E "passed|failed|Error" gpurun_out/quick.log | tail -n 30 ;;
     variants)
-      timeout 600 python scripts/bench_variants.py > gpurun_out/variants.log 2>&1
-      echo "== variants -> exit $?"; cat gpurun_out/variants.log | tail -n 90 ;;
+      : > gpurun_out/variants.log
+      for grp in attn xattn geglu gn ln upconv pdl; do
+        timeout 300 python scripts/bench_variants.py $grp > gpurun_out/variants_$grp.log 2>&1
+        echo "== variants $grp -> exit $?"; cp gpurun_out/variants.json gpurun_out/variants_$grp.json 2>/dev/null
+        grep -E "us|Error|error" gpurun_out/variants_$grp.log | tail -n 30
+      done ;;
     bench)
       timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
       echo "== bench -> exit $?"; tail -c 4000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err ;;
