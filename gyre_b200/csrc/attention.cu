@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
 // The single MMA thread interleaves them (S0, S1, then per tile: PV_g, S_g(next)), so one group's QK^T / PV
 // runs on the tensor pipe while the other group is in its exp2 phase (the SFU is the bound at d = 40), and
 // every K/V tile is loaded once for 256 queries.  Scores are read from TMEM once and kept in registers.
-constexpr int kAtt2Threads = 320;   // TMA warp, MMA warp, 2 x 4 softmax warps
+constexpr int kAtt2Threads = 352;   // TMA warp, S-MMA warp, 2 x 4 softmax warps, PV-MMA warp
+constexpr int kXAttThreads = 320;   // TMA warp, MMA warp, 2 x 4 softmax warps
 
 struct Att2Cfg {
   static constexpr int STAGES = 3;
@@ -297,7 +298,10 @@ struct Att2Cfg {
 //               degree-3 minimax polynomial, rel err 7.5e-5 < fp16 rounding of P) instead of the MUFU
 //   AV_F16EXP   ex2.approx.f16x2 (arguments rounded to fp16: measurement variant only)
 //   AV_NOEXP    diagnostic: no exponential at all (timing floor of everything that is not the MUFU)
-enum : int { AV_STAGGER = 1, AV_PACKED = 2, AV_POLY25 = 4, AV_POLY50 = 8, AV_F16EXP = 16, AV_NOEXP = 32 };
+//   AV_SPLIT    S = Q K^T of tile j+1 is issued (by its own warp) as soon as the group has pulled tile j's scores
+//               out of TMEM, i.e. it runs UNDER the exp phase of tile j instead of after P V of tile j; a second
+//               issuing warp feeds P V.  Takes the MMA round trip out of the per-tile dependency chain.
+enum : int { AV_STAGGER = 1, AV_PACKED = 2, AV_POLY25 = 4, AV_POLY50 = 8, AV_F16EXP = 16, AV_NOEXP = 32, AV_SPLIT = 64 };
 
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   // 2^x for x <= ~8: n = round(x) via the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-3
@@ -388,7 +392,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   uint64_t* p_full = s_full + 2;               // [2]
   uint64_t* pv_done = p_full + 2;              // [2]
   uint64_t* half_bar = pv_done + 2;            // group 0 is half way through its first exp phase
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(half_bar + 1);
+  uint64_t* s_free = half_bar + 1;             // [2] the group holds tile j's scores in registers (AV_SPLIT)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -416,6 +421,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
       mbar_init(&pv_done[g], 1);
     }
     mbar_init(half_bar, 128);
+    mbar_init(&s_free[0], 128);
+    mbar_init(&s_free[1], 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -458,38 +465,84 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
         umma_commit(&s_full[g]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      if (ng == 2) {
-        if (stagger) mbar_wait(half_bar, 0);
-        issue_s(1, 0);
-      }
-      for (int j = 0; j < p.n_kv_tiles; ++j) {
-        const int s = j % Cfg::STAGES;
-        const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
-        const int ksteps = ((nk_tile + 15) & ~15) >> 4;
-        const uint32_t idesc_pv = umma_idesc_f16(kBQ, p.npv, /*b_mn_major=*/1);
-        const uint32_t va = smem_u32(sV + s * Cfg::KV_BYTES);
-        for (int g = 0; g < ng; ++g) {
-          mbar_wait(&p_full[g], j & 1);
+      if constexpr ((V & AV_SPLIT) != 0) {
+        // ---- S issuer only: tile j+1's scores as soon as the group has read tile j's out of TMEM
+        for (int j = 0; j < p.n_kv_tiles; ++j) {
+          const int s = j % Cfg::STAGES;
+          mbar_wait(&kv_full[s], (j / Cfg::STAGES) & 1);
           tc_fence_after();
-          const uint32_t pa = smem_u32(sP + g * 2 * kChunkBytes);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
-            const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
-            umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
-          }
-          umma_commit(&pv_done[g]);
-          if (g == ng - 1) umma_commit(&kv_empty[s]);
-          if (j + 1 < p.n_kv_tiles) {
-            if (g == 0) {
-              const int s1 = (j + 1) % Cfg::STAGES;
-              mbar_wait(&kv_full[s1], ((j + 1) / Cfg::STAGES) & 1);
+          for (int g = 0; g < ng; ++g) {
+            if (j > 0) {
+              mbar_wait(&s_free[g], (j - 1) & 1);
               tc_fence_after();
+            } else if (g == 1 && stagger) {
+              mbar_wait(half_bar, 0);
             }
-            issue_s(g, j + 1);
+            issue_s(g, j);
           }
+        }
+      } else {
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_s(0, 0);
+        if (ng == 2) {
+          if (stagger) mbar_wait(half_bar, 0);
+          issue_s(1, 0);
+        }
+        for (int j = 0; j < p.n_kv_tiles; ++j) {
+          const int s = j % Cfg::STAGES;
+          const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+          const int ksteps = ((nk_tile + 15) & ~15) >> 4;
+          const uint32_t idesc_pv = umma_idesc_f16(kBQ, p.npv, /*b_mn_major=*/1);
+          const uint32_t va = smem_u32(sV + s * Cfg::KV_BYTES);
+          for (int g = 0; g < ng; ++g) {
+            mbar_wait(&p_full[g], j & 1);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP + g * 2 * kChunkBytes);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
+              const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+              umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&pv_done[g]);
+            if (g == ng - 1) umma_commit(&kv_empty[s]);
+            if (j + 1 < p.n_kv_tiles) {
+              if (g == 0) {
+                const int s1 = (j + 1) % Cfg::STAGES;
+                mbar_wait(&kv_full[s1], ((j + 1) / Cfg::STAGES) & 1);
+                tc_fence_after();
+              }
+              issue_s(g, j + 1);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ P V issuer (AV_SPLIT)
+    if constexpr ((V & AV_SPLIT) != 0) {
+      if (elect_one()) {
+        const int ng = two ? 2 : 1;
+        const uint32_t idesc_pv = umma_idesc_f16(kBQ, p.npv, /*b_mn_major=*/1);
+        for (int j = 0; j < p.n_kv_tiles; ++j) {
+          const int s = j % Cfg::STAGES;
+          const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+          const int ksteps = ((nk_tile + 15) & ~15) >> 4;
+          const uint32_t va = smem_u32(sV + s * Cfg::KV_BYTES);
+          mbar_wait(&kv_full[s], (j / Cfg::STAGES) & 1);   // V tile j landed (this thread's own observation)
+          for (int g = 0; g < ng; ++g) {
+            mbar_wait(&p_full[g], j & 1);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP + g * 2 * kChunkBytes);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
+              const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+              umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&pv_done[g]);
+          }
+          // S(j) of both groups retired long ago (their P tiles exist), so this commit also covers K tile j
+          umma_commit(&kv_empty[s]);
         }
       }
     }
@@ -520,6 +573,10 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
           tmem_ld_32x32b_x32(tS + 64, v2);
           tmem_ld_32x32b_x32(tS + 96, v3);
           tmem_ld_wait();
+          if constexpr ((V & AV_SPLIT) != 0) {
+            tc_fence_before();
+            mbar_arrive(&s_free[g]);       // the S buffer may be overwritten by tile j+1
+          }
           float mt = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -667,7 +724,7 @@ struct XAttCfg {
 };
 
 template <int DCH>
-__global__ void __launch_bounds__(kAtt2Threads, 1) xattention_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(kXAttThreads, 1) xattention_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                      const __grid_constant__ CUtensorMap tmK,
                                                                      const __grid_constant__ CUtensorMap tmV,
                                                                      const __grid_constant__ CUtensorMap tmO,
@@ -884,7 +941,7 @@ static int launch_xattn(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
         cudaFuncSetAttribute(xattention_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  GYRE_TRY(launch_kernel(xattention_kernel<DCH>, dim3(blocks), dim3(kAtt2Threads), Cfg::SMEM, st, tq, tk, tv, to, p));
+  GYRE_TRY(launch_kernel(xattention_kernel<DCH>, dim3(blocks), dim3(kXAttThreads), Cfg::SMEM, st, tq, tk, tv, to, p));
   return 0;
 }
 
@@ -915,6 +972,15 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
     case AV_PACKED | AV_POLY25: return launch_attn2_v<AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
     case AV_STAGGER | AV_F16EXP: return launch_attn2_v<AV_STAGGER | AV_F16EXP>(tq, tk, tv, p, nb, st);
     case AV_STAGGER | AV_NOEXP: return launch_attn2_v<AV_STAGGER | AV_NOEXP>(tq, tk, tv, p, nb, st);
+    case AV_SPLIT: return launch_attn2_v<AV_SPLIT>(tq, tk, tv, p, nb, st);
+    case AV_SPLIT | AV_STAGGER: return launch_attn2_v<AV_SPLIT | AV_STAGGER>(tq, tk, tv, p, nb, st);
+    case AV_SPLIT | AV_STAGGER | AV_PACKED: return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_PACKED>(tq, tk, tv, p, nb, st);
+    case AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY25:
+      return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY50:
+      return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
+    case AV_SPLIT | AV_PACKED | AV_POLY25: return launch_attn2_v<AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_SPLIT | AV_STAGGER | AV_NOEXP: return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_NOEXP>(tq, tk, tv, p, nb, st);
   }
   set_last_error("attention: variant %d is not compiled in", tunable(TUNE_ATT_VARIANT));
   return -2;

@@ -11,21 +11,23 @@
 namespace gyre {
 
 constexpr int kMaxGroups = 32;
-constexpr int kGnMaxChunks = 128;   // per-sample partials the apply kernel folds in its prologue
+constexpr int kGnMaxChunks = 256;   // upper bound of per-sample partials (sizes the scratch)
 constexpr int kGnUnroll = 8;        // independent 16-byte loads in flight per thread
 
 // Rows (pixels) per CTA: a function of HW ONLY, so the summation order - and with it every bit of the result -
 // does not depend on the batch size (tests/batch_independance.py contract of the reference).
 static inline int gn_rows_per_cta(int HW) {
-  int rows = (HW + kGnMaxChunks - 1) / kGnMaxChunks;
+  int max_chunks = tunable(TUNE_GN_CHUNKS);   // per-sample partials the apply kernel folds in its prologue
+  if (max_chunks < 8) max_chunks = 8;
+  if (max_chunks > kGnMaxChunks) max_chunks = kGnMaxChunks;
+  int rows = (HW + max_chunks - 1) / max_chunks;
   if (rows < 16) rows = 16;
   return (rows + 7) & ~7;
 }
 
 size_t gn_partials_floats(int B, int HW, int G) {
-  const int rows = gn_rows_per_cta(HW);
-  const int chunks = (HW + rows - 1) / rows;
-  return static_cast<size_t>(B) * chunks * G * 2 + static_cast<size_t>(B) * G * 2;
+  (void)HW;
+  return static_cast<size_t>(B) * kGnMaxChunks * G * 2 + static_cast<size_t>(B) * G * 2;
 }
 
 __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
@@ -104,19 +106,29 @@ __global__ void gn_stats_kernel(const GnArgs a, float* __restrict__ partials) {
     mine[2 * i + 1] = ss[i];
   }
   __syncthreads();
-  if (threadIdx.x < a.G) {
-    const int g = threadIdx.x;
+  // four threads per group, each a fixed quarter of the (row-lane, channel) entries, then a fixed-order combine
+  if (threadIdx.x < 4 * a.G) {
+    const int g = threadIdx.x >> 2;
+    const int k = threadIdx.x & 3;
+    const int n = a.rpar * cpg;
     float acc = 0.f, q = 0.f;
-    for (int t = 0; t < a.rpar; ++t) {
-      const float* row = sh + (static_cast<size_t>(t) * C + g * cpg) * 2;
-      for (int c = 0; c < cpg; ++c) {
-        acc += row[2 * c];
-        q += row[2 * c + 1];
-      }
+    for (int e = k; e < n; e += 4) {
+      const int t = e / cpg;
+      const int c = e - t * cpg;
+      const float2 v2 = *reinterpret_cast<const float2*>(sh + (static_cast<size_t>(t) * C + g * cpg + c) * 2);
+      acc += v2.x;
+      q += v2.y;
     }
-    float* dst = partials + (static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * (2 * a.G) + 2 * g;
-    dst[0] = acc;
-    dst[1] = q;
+    const unsigned m = __activemask();   // whole quads: 4 * G threads take this branch
+    acc += __shfl_xor_sync(m, acc, 1);
+    q += __shfl_xor_sync(m, q, 1);
+    acc += __shfl_xor_sync(m, acc, 2);
+    q += __shfl_xor_sync(m, q, 2);
+    if (k == 0) {
+      float* dst = partials + (static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * (2 * a.G) + 2 * g;
+      dst[0] = acc;
+      dst[1] = q;
+    }
   }
 }
 
@@ -342,7 +354,7 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   int rpar = 256 / nvec;
   if (rpar < 1) rpar = 1;
   const int threads = nvec * rpar;
-  GYRE_REQUIRE(threads >= G, "groupnorm: too few threads for %d groups", G);
+  GYRE_REQUIRE(threads >= 4 * G, "groupnorm: too few threads for %d groups", G);
   GnArgs a;
   a.x1 = x1;
   a.x2 = x2;
@@ -355,10 +367,13 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   const int chunks = (HW + a.rows_per_cta - 1) / a.rows_per_cta;
   dim3 grid(chunks, B);
   prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 2);
-  GYRE_TRY(launch_kernel(gn_stats_kernel, grid, dim3(threads), static_cast<size_t>(rpar) * C * 2 * sizeof(float), st, a,
-                         partials));
-  GYRE_TRY(launch_kernel(gn_apply_kernel, grid, dim3(threads), 0, st, a, gamma, beta, silu ? 1 : 0, eps,
-                         static_cast<const float*>(partials), out));
+  const int phase = tunable(TUNE_GN_PHASE);   // measurement only: 1 = statistics pass alone, 2 = apply pass alone
+  if (phase != 2)
+    GYRE_TRY(launch_kernel(gn_stats_kernel, grid, dim3(threads), static_cast<size_t>(rpar) * C * 2 * sizeof(float), st, a,
+                           partials));
+  if (phase != 1)
+    GYRE_TRY(launch_kernel(gn_apply_kernel, grid, dim3(threads), 0, st, a, gamma, beta, silu ? 1 : 0, eps,
+                           static_cast<const float*>(partials), out));
   return 0;
 }
 

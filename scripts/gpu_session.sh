@@ -26,6 +26,16 @@ for what in "$@"; do
     bench_fast)
       timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
       echo "== bench -> exit $?"; tail -c 4000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err ;;
+    variants_sel)
+      for grp in $VARIANT_GROUPS; do
+        timeout 300 python scripts/bench_variants.py $grp > gpurun_out/variants_$grp.log 2>&1
+        echo "== variants $grp -> exit $?"; cp gpurun_out/variants.json gpurun_out/variants_$grp.json 2>/dev/null
+        grep -E " us|Error|error" gpurun_out/variants_$grp.log | tail -n 80
+      done ;;
+    ncu_gn)
+      ncu --set full --clock-control none -k regex:gn_ -c 12 -o gpurun_out/prof_gn -f python scripts/gn_only.py > gpurun_out/ncu_gn.log 2>&1
+      echo "== ncu gn -> exit $?"
+      ncu -i gpurun_out/prof_gn.ncu-rep --page raw --csv > gpurun_out/prof_gn_raw.csv 2>/dev/null ;;
     shapes)
       timeout 600 python scripts/bench_kernels.py > gpurun_out/shapes.log 2>&1
       echo "== shapes -> exit $?"; tail -n 12 gpurun_out/shapes.log ;;
