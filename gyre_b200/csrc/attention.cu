@@ -301,7 +301,10 @@ struct Att2Cfg {
 //   AV_SPLIT    S = Q K^T of tile j+1 is issued (by its own warp) as soon as the group has pulled tile j's scores
 //               out of TMEM, i.e. it runs UNDER the exp phase of tile j instead of after P V of tile j; a second
 //               issuing warp feeds P V.  Takes the MMA round trip out of the per-tile dependency chain.
-enum : int { AV_STAGGER = 1, AV_PACKED = 2, AV_POLY25 = 4, AV_POLY50 = 8, AV_F16EXP = 16, AV_NOEXP = 32, AV_SPLIT = 64 };
+//   AV_PTMEM    P stays in tensor memory: the softmax warps write fp16 P with tcgen05.st and P V takes its A operand
+//               from TMEM - P never crosses shared memory (no 64 KB/tile-pair of stores + 64 KB of operand reads)
+enum : int { AV_STAGGER = 1, AV_PACKED = 2, AV_POLY25 = 4, AV_POLY50 = 8, AV_F16EXP = 16, AV_NOEXP = 32, AV_SPLIT = 64,
+             AV_PTMEM = 128 };
 
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   // 2^x for x <= ~8: n = round(x) via the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-3
@@ -321,54 +324,57 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return o;
 }
 
-// p = exp2(s * c - mc) for 32 scores of one row -> fp16, swizzled K-major store of 4 x 16 bytes; row sum in lsum
+// p = exp2(s * c - mc) for 32 scores of one row -> fp16; row sum in lsum.  Destination: a swizzled K-major
+// shared-memory tile (4 x 16 bytes) or, with AV_PTMEM, 16 packed columns of the group's P region in TMEM.
 template <int V>
 __device__ __forceinline__ void softmax_chunk32(const uint32_t (&v)[32], float c, float mc, float2& lsum,
-                                                uint8_t* pchunk, int u0, int rx) {
+                                                uint8_t* pchunk, int u0, int rx, uint32_t tP) {
+  uint32_t w[16];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = u * 8 + 2 * k;
-      const int pair = u * 4 + k;
-      float2 x;
-      if constexpr ((V & AV_PACKED) != 0) {
-        x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(c, c),
-                       make_float2(-mc, -mc));
-      } else {
-        x.x = fmaf(__uint_as_float(v[i]), c, -mc);
-        x.y = fmaf(__uint_as_float(v[i + 1]), c, -mc);
-      }
-      const bool poly = ((V & AV_POLY50) != 0 && (pair & 1) == 1) || ((V & AV_POLY25) != 0 && (pair & 3) == 3);
-      float2 e;
-      if constexpr ((V & AV_F16EXP) != 0) {
-        const __half2 xh = __floats2half2_rn(x.x, x.y);
-        uint32_t ph;
-        asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(*reinterpret_cast<const uint32_t*>(&xh)));
-        w[k] = ph;
-        e = __half22float2(*reinterpret_cast<const __half2*>(&ph));
-      } else {
-        if constexpr ((V & AV_NOEXP) != 0) {
-          e.x = fmaf(x.x, 1e-4f, 0.5f);
-          e.y = fmaf(x.y, 1e-4f, 0.5f);
-        } else if (poly) {
-          e = exp2_poly2(x);
-        } else {
-          e.x = ex2_approx(x.x);
-          e.y = ex2_approx(x.y);
-        }
-        const __half2 hh = __floats2half2_rn(e.x, e.y);
-        w[k] = *reinterpret_cast<const uint32_t*>(&hh);
-      }
-      if constexpr ((V & AV_PACKED) != 0) {
-        lsum = __fadd2_rn(lsum, e);
-      } else {
-        lsum.x += e.x;
-        lsum.y += e.y;
-      }
+  for (int pair = 0; pair < 16; ++pair) {
+    const int i = 2 * pair;
+    float2 x;
+    if constexpr ((V & AV_PACKED) != 0) {
+      x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(c, c),
+                     make_float2(-mc, -mc));
+    } else {
+      x.x = fmaf(__uint_as_float(v[i]), c, -mc);
+      x.y = fmaf(__uint_as_float(v[i + 1]), c, -mc);
     }
-    *reinterpret_cast<uint4*>(pchunk + (((u0 + u) ^ rx) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    const bool poly = ((V & AV_POLY50) != 0 && (pair & 1) == 1) || ((V & AV_POLY25) != 0 && (pair & 3) == 3);
+    float2 e;
+    if constexpr ((V & AV_F16EXP) != 0) {
+      const __half2 xh = __floats2half2_rn(x.x, x.y);
+      uint32_t ph;
+      asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(*reinterpret_cast<const uint32_t*>(&xh)));
+      w[pair] = ph;
+      e = __half22float2(*reinterpret_cast<const __half2*>(&ph));
+    } else {
+      if constexpr ((V & AV_NOEXP) != 0) {
+        e.x = fmaf(x.x, 1e-4f, 0.5f);
+        e.y = fmaf(x.y, 1e-4f, 0.5f);
+      } else if (poly) {
+        e = exp2_poly2(x);
+      } else {
+        e.x = ex2_approx(x.x);
+        e.y = ex2_approx(x.y);
+      }
+      const __half2 hh = __floats2half2_rn(e.x, e.y);
+      w[pair] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    if constexpr ((V & AV_PACKED) != 0) {
+      lsum = __fadd2_rn(lsum, e);
+    } else {
+      lsum.x += e.x;
+      lsum.y += e.y;
+    }
+  }
+  if constexpr ((V & AV_PTMEM) != 0) {
+    tmem_st_32x32b_x16(tP, w);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<uint4*>(pchunk + (((u0 + u) ^ rx) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
   }
 }
 
@@ -533,11 +539,19 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
           for (int g = 0; g < ng; ++g) {
             mbar_wait(&p_full[g], j & 1);
             tc_fence_after();
-            const uint32_t pa = smem_u32(sP + g * 2 * kChunkBytes);
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
-              const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
-              umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            if constexpr ((V & AV_PTMEM) != 0) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+                umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + ks * 8, db, idesc_pv,
+                            (j | ks) != 0 ? 1u : 0u);
+              }
+            } else {
+              const uint32_t pa = smem_u32(sP + g * 2 * kChunkBytes);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
+                const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+                umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+              }
             }
             umma_commit(&pv_done[g]);
           }
@@ -554,7 +568,9 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
       const int r = q * 32 + lane;
       const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
       const uint32_t tS = tmem_base + g * 128 + lane_off;
-      const uint32_t tO = tmem_base + 256 + g * 128 + lane_off;
+      // AV_PTMEM: O0, O1 at 256 / 320 (npv <= 64), P0, P1 (64 packed columns each) at 384 / 448
+      const uint32_t tO = tmem_base + 256 + g * ((V & AV_PTMEM) != 0 ? 64 : 128) + lane_off;
+      const uint32_t tP = tmem_base + 384 + g * 64 + lane_off;
       const float c = p.scale_log2;
       float m_ref = -INFINITY;
       float l = 0.f;
@@ -606,11 +622,11 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
           }
           const float mc = m_ref * c;
           float2 ls = make_float2(0.f, 0.f);
-          softmax_chunk32<V>(v0, c, mc, ls, prow, 0, rx);
-          softmax_chunk32<V>(v1, c, mc, ls, prow, 4, rx);
+          softmax_chunk32<V>(v0, c, mc, ls, prow, 0, rx, tP);
+          softmax_chunk32<V>(v1, c, mc, ls, prow, 4, rx, tP + 16);
           if (stagger && g == 0 && j == 0) mbar_arrive(half_bar);
-          softmax_chunk32<V>(v2, c, mc, ls, prow + kChunkBytes, 0, rx);
-          softmax_chunk32<V>(v3, c, mc, ls, prow + kChunkBytes, 4, rx);
+          softmax_chunk32<V>(v2, c, mc, ls, prow + kChunkBytes, 0, rx, tP + 32);
+          softmax_chunk32<V>(v3, c, mc, ls, prow + kChunkBytes, 4, rx, tP + 48);
           l += ls.x + ls.y;
         } else {
           // ---- ragged last tile (cross-attention Nk = 77, ToMe-merged Nk): masked two-pass path
@@ -659,16 +675,25 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
               const __half2 hh = __floats2half2_rn(p0, p1);
               packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
             }
-            uint8_t* pchunk = prow + (c0 >> 6) * kChunkBytes;
-            const int u0 = (c0 & 63) >> 3;
+            if constexpr ((V & AV_PTMEM) != 0) {
+              tmem_st_32x32b_x16(tP + (c0 >> 1), packed);
+            } else {
+              uint8_t* pchunk = prow + (c0 >> 6) * kChunkBytes;
+              const int u0 = (c0 & 63) >> 3;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<uint4*>(pchunk + (((u0 + u) ^ rx) << 4)) =
-                  make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(pchunk + (((u0 + u) ^ rx) << 4)) =
+                    make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+            }
           }
         }
-        tc_fence_before();
-        fence_proxy_async();
+        if constexpr ((V & AV_PTMEM) != 0) {
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          tc_fence_before();
+          fence_proxy_async();
+        }
         mbar_arrive(&p_full[g]);
       }
       // ---- epilogue
@@ -981,6 +1006,17 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
       return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
     case AV_SPLIT | AV_PACKED | AV_POLY25: return launch_attn2_v<AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
     case AV_SPLIT | AV_STAGGER | AV_NOEXP: return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_NOEXP>(tq, tk, tv, p, nb, st);
+    case AV_PTMEM | AV_SPLIT: return launch_attn2_v<AV_PTMEM | AV_SPLIT>(tq, tk, tv, p, nb, st);
+    case AV_PTMEM | AV_SPLIT | AV_PACKED: return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED>(tq, tk, tv, p, nb, st);
+    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_STAGGER:
+      return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_STAGGER>(tq, tk, tv, p, nb, st);
+    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
+      return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50:
+      return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
+    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER:
+      return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER>(tq, tk, tv, p, nb, st);
+    case AV_PTMEM | AV_SPLIT | AV_NOEXP: return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_NOEXP>(tq, tk, tv, p, nb, st);
   }
   set_last_error("attention: variant %d is not compiled in", tunable(TUNE_ATT_VARIANT));
   return -2;

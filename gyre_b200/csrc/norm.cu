@@ -201,12 +201,21 @@ __global__ void gn_apply_kernel(const GnArgs a, const float* __restrict__ gamma,
   __syncthreads();
 
   float sc[8], sf[8];
+  {
+    // 16-byte loads: a scalar load per channel would cost one 32-byte sector per lane per instruction
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int g = (c0 + i) / cpg;
-    const float ga = gamma[c0 + i] * s_rstd[g];
-    sc[i] = ga;
-    sf[i] = beta[c0 + i] - s_mean[g] * ga;
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c0 + i) / cpg;
+      const float ga = gg[i] * s_rstd[g];
+      sc[i] = ga;
+      sf[i] = bb[i] - s_mean[g] * ga;
+    }
   }
   while (true) {
 #pragma unroll

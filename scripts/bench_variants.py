@@ -70,7 +70,7 @@ if "attn" in what:
         C = heads * d
         qkv = [torch.randn(B2, Nq, 3 * C, device=dev).half() for _ in range(ROT)]
         fl = 4.0 * B2 * heads * Nq * Nq * d
-        for v in (0, 3, 64, 65, 67, 71, 75, 70, 97):
+        for v in (0, 70, 192, 194, 195, 198, 202, 199, 224):
             us = with_tunable("ATT_VARIANT", v, lambda: graph_time(
                 lambda i: N.attention(qkv[i % ROT][:, :, :C], qkv[i % ROT][:, :, C:2 * C], qkv[i % ROT][:, :, 2 * C:], heads)))
             rec("attn", f"self B{B2} h{heads} N{Nq} d{d} variant {v}", us, fl)
@@ -116,19 +116,31 @@ if "gn" in what:
         rec("gn", f"gn B8 HW{HW} C{C} (VAE)", us, 0.0, 2.0 * 2 * 8 * HW * C)
         del x
 
+if "copy" in what:
+    # calibration: what a plain device copy / reduction achieves at these (small) sizes
+    for mb in (21, 42, 126, 537):
+        n = mb * 1024 * 1024 // 2
+        x = [torch.randn(n, device=dev).half() for _ in range(ROT)]
+        y = torch.empty(n, device=dev, dtype=torch.float16)
+        us = graph_time(lambda i: y.copy_(x[i % ROT]))
+        rec("copy", f"torch copy {mb} MB (read + write)", us, 0.0, 2.0 * n * 2)
+        us = graph_time(lambda i: x[i % ROT].sum(dtype=torch.float32))
+        rec("copy", f"torch sum  {mb} MB (read)", us, 0.0, 1.0 * n * 2)
+        del x, y
+
 if "gnx" in what:
     # GroupNorm dissection: each pass alone, and the chunk count (CTAs per sample)
     for (HW, C) in ((4096, 320), (4096, 960), (1024, 640)):
         x = [torch.randn(B2, HW, C, device=dev).half() for _ in range(ROT)]
         g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-        for chunks in (32, 64, 128, 256):
+        for chunks in (16, 32, 64):
             N.set_tunable("GN_CHUNKS", chunks)
             for phase in (0, 1, 2):
                 for silu in ((True, False) if phase != 1 else (True,)):
                     us = with_tunable("GN_PHASE", phase, lambda: graph_time(lambda i: N.groupnorm(x[i % ROT], g, b, 32, 1e-5, silu)))
                     rec("gnx", f"gn B{B2} HW{HW} C{C} chunks<={chunks} phase={phase} silu={int(silu)}", us, 0.0,
                         2.0 * B2 * HW * C * (1 if phase == 1 else 2))
-        N.set_tunable("GN_CHUNKS", 128)
+        N.set_tunable("GN_CHUNKS", 32)
         del x
 
 if "ln" in what:
