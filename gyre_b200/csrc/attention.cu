@@ -303,8 +303,11 @@ struct Att2Cfg {
 //               issuing warp feeds P V.  Takes the MMA round trip out of the per-tile dependency chain.
 //   AV_PTMEM    P stays in tensor memory: the softmax warps write fp16 P with tcgen05.st and P V takes its A operand
 //               from TMEM - P never crosses shared memory (no 64 KB/tile-pair of stores + 64 KB of operand reads)
+//   AV_LAZYMAX  optimistic softmax: a full tile is exponentiated against the RUNNING max while its own max is folded
+//               on the side (no max pass in front of the exp phase, second half of the scores still in flight
+//               from TMEM); only if the tile turns out to raise the max by more than 2^8 is it redone (rare)
 enum : int { AV_STAGGER = 1, AV_PACKED = 2, AV_POLY25 = 4, AV_POLY50 = 8, AV_F16EXP = 16, AV_NOEXP = 32, AV_SPLIT = 64,
-             AV_PTMEM = 128 };
+             AV_PTMEM = 128, AV_LAZYMAX = 256 };
 
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   // 2^x for x <= ~8: n = round(x) via the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-3
@@ -327,9 +330,8 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // p = exp2(s * c - mc) for 32 scores of one row -> fp16; row sum in lsum.  Destination: a swizzled K-major
 // shared-memory tile (4 x 16 bytes) or, with AV_PTMEM, 16 packed columns of the group's P region in TMEM.
 template <int V>
-__device__ __forceinline__ void softmax_chunk32(const uint32_t (&v)[32], float c, float mc, float2& lsum,
-                                                uint8_t* pchunk, int u0, int rx, uint32_t tP) {
-  uint32_t w[16];
+__device__ __forceinline__ void softmax_exp32(const uint32_t (&v)[32], float c, float mc, float2& lsum,
+                                              uint32_t (&w)[16]) {
 #pragma unroll
   for (int pair = 0; pair < 16; ++pair) {
     const int i = 2 * pair;
@@ -369,6 +371,10 @@ __device__ __forceinline__ void softmax_chunk32(const uint32_t (&v)[32], float c
       lsum.y += e.y;
     }
   }
+}
+
+template <int V>
+__device__ __forceinline__ void softmax_store32(const uint32_t (&w)[16], uint8_t* pchunk, int u0, int rx, uint32_t tP) {
   if constexpr ((V & AV_PTMEM) != 0) {
     tmem_st_32x32b_x16(tP, w);
   } else {
@@ -376,6 +382,26 @@ __device__ __forceinline__ void softmax_chunk32(const uint32_t (&v)[32], float c
     for (int u = 0; u < 4; ++u)
       *reinterpret_cast<uint4*>(pchunk + (((u0 + u) ^ rx) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
   }
+}
+
+template <int V>
+__device__ __forceinline__ void softmax_chunk32(const uint32_t (&v)[32], float c, float mc, float2& lsum,
+                                                uint8_t* pchunk, int u0, int rx, uint32_t tP) {
+  uint32_t w[16];
+  softmax_exp32<V>(v, c, mc, lsum, w);
+  softmax_store32<V>(w, pchunk, u0, rx, tP);
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+  for (int i = 4; i < 32; i += 4) {
+    m0 = fmaxf(m0, __uint_as_float(v[i]));
+    m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+    m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+    m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
 template <int V>
@@ -581,7 +607,65 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
         const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
         mbar_wait(&s_full[g], j & 1);
         tc_fence_after();
-        if (nk_tile == kBKeys) {
+        bool done = false;
+        if constexpr ((V & AV_LAZYMAX) != 0) {
+          if (nk_tile == kBKeys && j > 0) {
+            // ---- optimistic full tile: exponentiate against the running max, fold this tile's max on the side
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            tmem_ld_32x32b_x32(tS, v0);
+            tmem_ld_32x32b_x32(tS + 32, v1);
+            tmem_ld_wait_dep(v0);
+            reg_fence(v1);
+            tmem_ld_32x32b_x32(tS + 64, v2);      // second half stays in flight under the first exps
+            tmem_ld_32x32b_x32(tS + 96, v3);
+            const float l_before = l;
+            float mc = m_ref * c;
+            float2 ls = make_float2(0.f, 0.f);
+            float mt = fmaxf(max32(v0), max32(v1));
+            uint32_t w[16];
+            softmax_exp32<V>(v0, c, mc, ls, w);
+            mbar_wait(&pv_done[g], (j - 1) & 1);   // P (and O) are free once P V of the previous tile retired
+            tc_fence_after();
+            softmax_store32<V>(w, prow, 0, rx, tP);
+            softmax_chunk32<V>(v1, c, mc, ls, prow, 4, rx, tP + 16);
+            tmem_ld_wait_dep(v2);
+            reg_fence(v3);
+            if constexpr ((V & AV_SPLIT) != 0) {
+              tc_fence_before();
+              mbar_arrive(&s_free[g]);
+            }
+            mt = fmaxf(mt, fmaxf(max32(v2), max32(v3)));
+            softmax_chunk32<V>(v2, c, mc, ls, prow + kChunkBytes, 0, rx, tP + 32);
+            softmax_chunk32<V>(v3, c, mc, ls, prow + kChunkBytes, 4, rx, tP + 48);
+            if (__any_sync(0xffffffffu, (mt - m_ref) * c > 8.0f)) {
+              // the running max jumped: rescale O and redo the tile against the new max (overwrites P)
+              const float m_new = fmaxf(m_ref, mt);
+              const float alpha = ex2_approx((m_ref - m_new) * c);
+              m_ref = m_new;
+              l = l_before * alpha;
+              if constexpr ((V & AV_PTMEM) != 0) tmem_st_wait();
+              for (int c0 = 0; c0 < p.npv; c0 += 16) {
+                uint32_t o[16];
+                tmem_ld_32x32b_x16(tO + c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32b_x16(tO + c0, o);
+              }
+              tmem_st_wait();
+              mc = m_ref * c;
+              ls = make_float2(0.f, 0.f);
+              softmax_chunk32<V>(v0, c, mc, ls, prow, 0, rx, tP);
+              softmax_chunk32<V>(v1, c, mc, ls, prow, 4, rx, tP + 16);
+              softmax_chunk32<V>(v2, c, mc, ls, prow + kChunkBytes, 0, rx, tP + 32);
+              softmax_chunk32<V>(v3, c, mc, ls, prow + kChunkBytes, 4, rx, tP + 48);
+            }
+            l += ls.x + ls.y;
+            done = true;
+          }
+        }
+        if (done) {
+        } else if (nk_tile == kBKeys) {
           // ---- full tile: one TMEM read, scores stay in registers
           uint32_t v0[32], v1[32], v2[32], v3[32];
           tmem_ld_32x32b_x32(tS, v0);
@@ -1017,6 +1101,18 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
     case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER:
       return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER>(tq, tk, tv, p, nb, st);
     case AV_PTMEM | AV_SPLIT | AV_NOEXP: return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_NOEXP>(tq, tk, tv, p, nb, st);
+    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED:
+      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED>(tq, tk, tv, p, nb, st);
+    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
+      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50:
+      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
+    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER:
+      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER>(tq, tk, tv, p, nb, st);
+    case AV_LAZYMAX | AV_SPLIT | AV_PACKED | AV_POLY25:
+      return launch_attn2_v<AV_LAZYMAX | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_NOEXP:
+      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_NOEXP>(tq, tk, tv, p, nb, st);
   }
   set_last_error("attention: variant %d is not compiled in", tunable(TUNE_ATT_VARIANT));
   return -2;

@@ -36,6 +36,13 @@ for what in "$@"; do
       ncu --set full --clock-control none -k regex:gn_ -c 12 -o gpurun_out/prof_gn -f python scripts/gn_only.py > gpurun_out/ncu_gn.log 2>&1
       echo "== ncu gn -> exit $?"
       ncu -i gpurun_out/prof_gn.ncu-rep --page raw --csv > gpurun_out/prof_gn_raw.csv 2>/dev/null ;;
+    ncu_attn)
+      for v in $ATT_VARIANTS; do
+        ncu --set full --import-source on --clock-control none -k regex:attention2 -s 1 -c 1 -o gpurun_out/prof_attn_v$v -f python scripts/attn_only.py $v > gpurun_out/ncu_attn_$v.log 2>&1
+        echo "== ncu attn v$v -> exit $?"
+        ncu -i gpurun_out/prof_attn_v$v.ncu-rep --page source --csv > gpurun_out/prof_attn_v${v}_source.csv 2>/dev/null
+        ncu -i gpurun_out/prof_attn_v$v.ncu-rep --page raw --csv > gpurun_out/prof_attn_v${v}_raw.csv 2>/dev/null
+      done ;;
     shapes)
       timeout 600 python scripts/bench_kernels.py > gpurun_out/shapes.log 2>&1
       echo "== shapes -> exit $?"; tail -n 12 gpurun_out/shapes.log ;;

@@ -71,7 +71,7 @@ def test_attention_peaked_softmax(nat):
 
 # softmax variants of the d <= 64 flash kernel (include/gyre_b200.h: tunable "ATT_VARIANT"): 0 plain, 1 staggered
 # groups, 3 + packed fp32x2 maths, 7 / 11 + polynomial exp2 on 25 % / 50 % of the scores, 6 packed + poly w/o stagger
-@pytest.mark.parametrize("variant", [0, 1, 3, 7, 11, 6, 64, 65, 67, 71, 75, 70, 192, 194, 195, 198, 202, 199])
+@pytest.mark.parametrize("variant", [0, 1, 3, 7, 11, 6, 64, 65, 67, 71, 75, 70, 192, 194, 195, 198, 202, 199, 450, 454, 458, 455, 326])
 def test_attention_softmax_variants(nat, variant):
     old = nat.get_tunable("ATT_VARIANT")
     try:
@@ -83,6 +83,28 @@ def test_attention_softmax_variants(nat, variant):
             ref = ref_attention(q, k, v, heads)
             err = (out.float() - ref).abs().max().item()
             assert err < 4e-3, f"variant {variant} Nq{Nq} Nk{Nk} d{d}: max abs err {err}"
+    finally:
+        nat.set_tunable("ATT_VARIANT", old)
+
+
+def test_attention_optimistic_max_redo_path(nat):
+    """Optimistic softmax: logits that keep raising the running max by > 2^8 force the redo path on most tiles."""
+    B, N, heads, d = 1, 1024, 2, 64
+    C = heads * d
+    q, k, v = rnd(B, N, C, seed=1, scale=1.0), rnd(B, N, C, seed=2, scale=1.0), rnd(B, N, C, seed=3)
+    # keys grow along the sequence: every later tile dominates the earlier ones
+    ramp = torch.linspace(0.2, 12.0, N, device=k.device)[None, :, None]
+    k = (k.float() * ramp).half()
+    q = (q.float().abs() * 1.5).half()
+    old = nat.get_tunable("ATT_VARIANT")
+    try:
+        for variant in (454, 450, 326):
+            nat.set_tunable("ATT_VARIANT", variant)
+            out = nat.attention(q, k, v, heads)
+            ref = ref_attention(q, k, v, heads)
+            assert torch.isfinite(out).all()
+            err = (out.float() - ref).abs().max().item()
+            assert err < 2e-2, f"variant {variant}: max abs err {err}"
     finally:
         nat.set_tunable("ATT_VARIANT", old)
 
