@@ -61,6 +61,7 @@ SIGNATURES = {
     "gyre_b200_prof_reset": (_i, []),
     "gyre_b200_prof_read": (_i, [_i, C.POINTER(C.c_ulonglong), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]),
+    "gyre_b200_debug_mma_bench": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
     "gyre_b200_set_tunable": (_i, [C.c_char_p, _i]),
     "gyre_b200_get_tunable": (_i, [C.c_char_p, C.POINTER(_i)]),
     "gyre_b200_unet_create": (_i, [C.POINTER(UNetConfigC), C.POINTER(_vp)]),

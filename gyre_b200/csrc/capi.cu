@@ -58,6 +58,12 @@ int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, doubl
   return prof::read(family, count, ms, flops, bytes);
 }
 
+int gyre_b200_debug_mma_bench(int n, int naccs, int a_tmem, int reps, int blocks, long long* out_dev,
+                              gyre_b200_stream stream) {
+  GYRE_REQUIRE(out_dev, "mma_bench: null output");
+  return mma_bench(n, naccs, a_tmem, reps, blocks, out_dev, S(stream));
+}
+
 int gyre_b200_set_tunable(const char* name, int value) { return set_tunable_by_name(name, value); }
 int gyre_b200_get_tunable(const char* name, int* value) { return get_tunable_by_name(name, value); }
 

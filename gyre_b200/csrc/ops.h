@@ -127,6 +127,8 @@ int tome_merge_kv(const __half* k, const __half* v, int ld, int B, int N, int C,
 }  // namespace gyre
 
 namespace gyre {
+// measurement-only (microbench.cu)
+int mma_bench(int n, int naccs, int a_tmem, int reps, int blocks, long long* out_dev, cudaStream_t st);
 // ---- tunables: small integer knobs read on the host at launch time.  Each starts from the environment
 // variable GYRE_B200_<NAME> (if set) and can be changed through gyre_b200_set_tunable (A/B measurements).
 enum Tunable { TUNE_ATT_VARIANT = 0, TUNE_PDL = 1, TUNE_GELU_FAST = 2, TUNE_GN_CHUNKS = 3, TUNE_UPCONV_FOLD = 4,

@@ -58,6 +58,10 @@ int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, doubl
  * steps), "XATTN" (short-key attention kernel).  Every knob also reads GYRE_B200_<NAME> from the
  * environment at first use.  Results stay within the documented tolerances for every setting. */
 int gyre_b200_set_tunable(const char* name, int value);
+/* Measurement only: clocks one thread needs to issue and retire `reps` tcgen05.mma (M=128, K=16, N=n) round-robin
+ * over `naccs` TMEM accumulators, A from shared memory (a_tmem = 0) or TMEM; out_dev[blocks] (int64, device). */
+int gyre_b200_debug_mma_bench(int n, int naccs, int a_tmem, int reps, int blocks, long long* out_dev,
+                              gyre_b200_stream stream);
 int gyre_b200_get_tunable(const char* name, int* value);
 
 /* ------------------------------------------------------------------------------------------
