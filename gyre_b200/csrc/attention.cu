@@ -677,12 +677,7 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
             tc_fence_before();
             mbar_arrive(&s_free[g]);       // the S buffer may be overwritten by tile j+1
           }
-          float mt = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            mt = fmaxf(mt, fmaxf(fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])),
-                                 fmaxf(__uint_as_float(v2[i]), __uint_as_float(v3[i]))));
-          }
+          const float mt = fmaxf(fmaxf(max32(v0), max32(v1)), fmaxf(max32(v2), max32(v3)));
           if (j == 0) {
             m_ref = mt;
           } else {
@@ -708,9 +703,11 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
           float2 ls = make_float2(0.f, 0.f);
           softmax_chunk32<V>(v0, c, mc, ls, prow, 0, rx, tP);
           softmax_chunk32<V>(v1, c, mc, ls, prow, 4, rx, tP + 16);
-          if (stagger && g == 0 && j == 0) mbar_arrive(half_bar);
           softmax_chunk32<V>(v2, c, mc, ls, prow + kChunkBytes, 0, rx, tP + 32);
           softmax_chunk32<V>(v3, c, mc, ls, prow + kChunkBytes, 4, rx, tP + 48);
+          // group 1 starts its first tile when group 0 leaves its first exp phase: from then on one group's exp phase
+          // falls into the other's load / max / hand-over phase instead of both sharing the MUFU and then idling it
+          if (stagger && g == 0 && j == 0) mbar_arrive(half_bar);
           l += ls.x + ls.y;
         } else {
           // ---- ragged last tile (cross-attention Nk = 77, ToMe-merged Nk): masked two-pass path
