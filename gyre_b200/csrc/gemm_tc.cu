@@ -34,6 +34,7 @@ struct GemmParams {
   int tma_epi;        // 1: output (and residual) tiles move through swizzled smem slices with TMA
   int rgb_rows;       // rows of a tile that share one rowgroup-bias vector (staged in smem); 0: per-thread loads
   int fast_gelu;      // GEGLU gate through gelu_fast instead of libdevice erff
+  int mcast;          // 1: CTA pairs (cluster of 2 along M) share every B tile through TMA multicast
   Epilogue ep;
 };
 
@@ -114,6 +115,12 @@ __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col,
 // slice and stored with ONE TMA bulk store per slice (full 64-byte row segments, clipped at the tensor
 // edges by the TMA unit); the residual slice arrives the same way, prefetched one slice ahead.  A thread
 // writing its own row 16 bytes at a time would be bound by L1/LSU request rate, not by HBM.
+//
+// CTA pairs (p.mcast): the operand stream of a 128 x BN tile needs (128 + BN) x 128 B per 64-wide k step, and one
+// SM cannot pull more than ~100 GB/s out of L2 - that, not the tensor pipe, bounds the single-CTA kernel (measured:
+// the same ~96 GB/s per SM at BN = 128, 160 and 256).  In pair mode two CTAs of a cluster work on the two M tiles
+// of the same N tile; each loads its own A tile and HALF of the B tile, multicast into both CTAs' shared memory.
+// A slot is refilled only when both CTAs' MMAs have drained it (their commits arrive on both empty barriers).
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmA2,
@@ -137,7 +144,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // work units: tiles, or (pair mode) pairs of M tiles; worker = CTA or cluster
+  const int rank = p.mcast ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = p.mcast ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = p.mcast ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_tiles = (p.mcast ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], p.mcast ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -163,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.mcast) cluster_sync_all();   // the peer's barriers exist before anything can arrive on them
   pdl_wait();
   pdl_trigger();
 
@@ -170,9 +182,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t g = 0;   // k-iterations issued so far (ring position)
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = worker; t < num_tiles; t += n_workers) {
         const int n_tile = t % p.n_tiles;
-        const int m_tile = t / p.n_tiles;
+        const int m_tile = p.mcast ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
         int x0 = 0, y0 = 0, n0 = 0;
         if (p.conv) {
           x0 = (m_tile % p.tiles_x) * p.tile_w;
@@ -190,13 +202,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
             tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], cc * kBK, x0 * p.stride + kw + p.off_x,
                         y0 * p.stride + kh + p.off_y, n0);
-            tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], tap * p.cin_pad + cc * kBK, n_tile * BN);
+            if (p.mcast)
+              tma_load_2d_mcast(sB + s * Cfg::B_BYTES + rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[s],
+                                tap * p.cin_pad + cc * kBK, n_tile * BN + rank * (BN / 2), 3);
+            else
+              tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], tap * p.cin_pad + cc * kBK, n_tile * BN);
           } else {
             if (it < p.k1_iters)
               tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, &full_bar[s], it * kBK, m_tile * kBM);
             else
               tma_load_2d(sA + s * Cfg::A_BYTES, &tmA2, &full_bar[s], (it - p.k1_iters) * kBK, m_tile * kBM);
-            tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], it * kBK, n_tile * BN);
+            if (p.mcast)
+              tma_load_2d_mcast(sB + s * Cfg::B_BYTES + rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[s], it * kBK,
+                                n_tile * BN + rank * (BN / 2), 3);
+            else
+              tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], it * kBK, n_tile * BN);
           }
         }
       }
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
       uint32_t g = 0;
       uint32_t lt = 0;   // local tile counter
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      for (int t = worker; t < num_tiles; t += n_workers, ++lt) {
         const uint32_t buf = lt & 1;
         const uint32_t use = lt >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this buffer's previous tile
@@ -223,7 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
             umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (pair mode: in both CTAs - the peer refills half of it)
+          if (p.mcast) umma_commit_mcast(&empty_bar[s], 3);
+          else umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[buf]);   // accumulator complete
       }
@@ -246,9 +268,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint8_t* my_res_row = sRes + r * 64;
     uint32_t slice_cnt = 0;                           // slices processed by this half (slot = cnt & 1)
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+    for (int t = worker; t < num_tiles; t += n_workers, ++lt) {
       const int n_tile = t % p.n_tiles;
-      const int m_tile = t / p.n_tiles;
+      const int m_tile = p.mcast ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
       int x0 = 0, y0 = 0, n0 = 0;
       bool valid;
       int64_t out_row;
@@ -451,6 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (p.mcast) cluster_sync_all();   // neither CTA leaves while the other can still signal its barriers
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -465,19 +488,76 @@ static int sm_count() {
   return n;
 }
 
+// One-time per tile width: opt in to the large dynamic shared memory and ask how many 2-CTA clusters of this kernel
+// the device can hold at once (GPCs with an odd SM count strand one SM).
+template <int BN>
+static int prepare(int* max_clusters) {
+  using Cfg = GemmCfg<BN>;
+  static bool done = false;
+  static int clusters = 0;
+  if (!done) {
+    GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * sm_count());
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cudaLaunchAttribute a[1];
+    a[0].id = cudaLaunchAttributeClusterDimension;
+    a[0].val.clusterDim.x = 2;
+    a[0].val.clusterDim.y = 1;
+    a[0].val.clusterDim.z = 1;
+    cfg.attrs = a;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN>, &cfg) == cudaSuccess) clusters = n;
+    cudaGetLastError();
+    done = true;
+  }
+  *max_clusters = clusters;
+  return 0;
+}
+
+static int gemm_max_clusters(int bn, int* n) {
+  switch (bn) {
+    case 32: return prepare<32>(n);
+    case 64: return prepare<64>(n);
+    case 128: return prepare<128>(n);
+    case 160: return prepare<160>(n);
+    case 256: return prepare<256>(n);
+  }
+  *n = 0;
+  return 0;
+}
+
+// Pair mode (see the kernel comment) when the tunable allows it, there are at least two M tiles and the device can
+// co-schedule enough clusters.
+static int want_pair_mode(int bn, long long m_tiles, int* mcast) {
+  *mcast = 0;
+  if (!tunable(TUNE_MCAST) || m_tiles < 2 || bn < 64) return 0;
+  int n = 0;
+  GYRE_TRY(gemm_max_clusters(bn, &n));
+  if (n >= sm_count() / 4) *mcast = 1;
+  return 0;
+}
+
 template <int BN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                   const CUtensorMap& tmRes, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
-  static bool attr_done = false;
-  if (!attr_done) {
-    GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr_done = true;
+  int max_clusters = 0;
+  GYRE_TRY(prepare<BN>(&max_clusters));
+  const int sms = sm_count();
+  if (p.mcast) {
+    GYRE_REQUIRE(max_clusters > 0, "gemm: pair mode requested but clusters are unavailable");
+    const long long pairs = static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles;
+    GYRE_REQUIRE(pairs > 0 && pairs < (1ll << 30), "gemm: bad tile count %lld", pairs);
+    const unsigned clusters = static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
+    return launch_kernel_cluster(gemm_tc_kernel<BN>, dim3(2 * clusters), dim3(kThreads), Cfg::SMEM, st, 2, tmA, tmA2, tmB,
+                                 tmOut, tmRes, p);
   }
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   GYRE_REQUIRE(tiles > 0 && tiles < (1ll << 31), "gemm: bad tile count %lld", tiles);
-  const int sms = sm_count();
   const unsigned blocks = static_cast<unsigned>(tiles < sms ? tiles : sms);
   return launch_kernel(gemm_tc_kernel<BN>, dim3(blocks), dim3(kThreads), Cfg::SMEM, st, tmA, tmA2, tmB, tmOut, tmRes, p);
 }
@@ -564,6 +644,7 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
   p.m_tiles = (M + kBM - 1) / kBM;
   p.conv = 0;
   p.fast_gelu = tunable(TUNE_GELU_FAST);
+  GYRE_TRY(want_pair_mode(bn, p.m_tiles, &p.mcast));
   p.ep = ep;
   p.rgb_rows = 0;
   p.tma_epi = (tma_epilogue_ok(ep, n_out) && ep.rowgroup_bias == nullptr) ? 1 : 0;
@@ -585,7 +666,7 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(p.mcast ? bn / 2 : bn)};   // pair mode: each CTA fetches half a B tile
     GYRE_TRY(encode_tmap_f16(&tmB, W, 2, dims, strides, box, es, true));
   }
   tmOut = tmA;
@@ -675,6 +756,7 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
   p.off_x = gm.off_x;
   p.off_y = gm.off_y;
   p.fast_gelu = 0;
+  GYRE_TRY(want_pair_mode(bn, m_tiles, &p.mcast));
   p.ep = ep;
   // the per-sample bias (temb projection) is uniform over the rows of one image inside a tile: stage it with
   // the column bias when a tile holds at most kMaxBiasGroups images
@@ -698,7 +780,7 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ntaps) * p.cin_pad, static_cast<uint64_t>(Cout)};
     uint64_t strides[1] = {static_cast<uint64_t>(ntaps) * p.cin_pad * 2};
-    uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(p.mcast ? bn / 2 : bn)};
     uint32_t es[2] = {1, 1};
     GYRE_TRY(encode_tmap_f16(&tmB, Wp, 2, dims, strides, box, es, true));
   }

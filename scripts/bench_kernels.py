@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-shape kernel timings for the SD1.5 UNet at CFG batch 16 (8 images): every distinct GEMM / conv /
-attention / norm shape, CUDA-event timed with rotating buffers (working set > L2), next to its roofline
+attention / norm shape, timed by CUDA-graph replay (no host overhead) with rotating buffers, next to its roofline
 (max of FLOPs / measured tensor peak and algorithmic bytes / measured HBM copy bandwidth)."""
 import json
 import math
@@ -21,20 +21,31 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 N.load()
 B2 = 16
-ROT = 6
+ROT = 4
 
 
-def timeit(fn, iters=10):
-    for i in range(3):
-        fn(i)
+def timeit(fn, iters=8, replays=4):
+    """CUDA-graph replay of `iters` launches over rotating buffers: no host launch overhead in the number."""
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        for i in range(ROT):
+            fn(i)
+    torch.cuda.current_stream().wait_stream(st)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i)
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i)
+    for _ in range(replays):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3   # us
+    return e0.elapsed_time(e1) / (iters * replays) * 1e3   # us
 
 
 rows = []

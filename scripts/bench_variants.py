@@ -116,6 +116,31 @@ if "gn" in what:
         rec("gn", f"gn B8 HW{HW} C{C} (VAE)", us, 0.0, 2.0 * 2 * 8 * HW * C)
         del x
 
+if "mcast" in what:
+    cases = [("gemm", 65536, 2560, 320, True), ("gemm", 16384, 5120, 640, True), ("gemm", 4096, 10240, 1280, True),
+             ("gemm", 65536, 320, 320, False), ("gemm", 16384, 640, 640, False), ("gemm", 4096, 1280, 1280, False),
+             ("gemm", 65536, 960, 320, False), ("gemm", 4096, 1280, 5120, False), ("gemm", 65536, 320, 1280, False)]
+    for (_, M, Nn, K, geglu) in cases:
+        a = [torch.randn(M, K, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(Nn, K, device=dev).half() * (1 / math.sqrt(K))
+        bias = torch.randn(Nn, device=dev)
+        if geglu:
+            w, bias = N.pack_geglu(w, bias)
+        for mc in (0, 1):
+            us = with_tunable("MCAST", mc, lambda: graph_time(lambda i: N.gemm(a[i % ROT], w, bias=bias, act=1 if geglu else 0)))
+            rec("mcast", f"gemm M{M} N{Nn} K{K}{' geglu' if geglu else ''} mcast={mc}", us, 2.0 * M * Nn * K)
+        del a
+    for (B, H, cin, cout) in ((16, 64, 320, 320), (16, 32, 640, 640), (16, 16, 1280, 1280), (16, 8, 1280, 1280),
+                              (16, 8, 2560, 1280), (16, 64, 640, 320), (8, 256, 128, 128), (8, 512, 128, 128)):
+        x = [torch.randn(B, H, H, cin, device=dev).half() for _ in range(2)]
+        w = torch.randn(cout, cin, 3, 3, device=dev).half() * (1 / math.sqrt(9 * cin))
+        wp = N.pack_conv3x3(w)
+        bias = torch.randn(cout, device=dev)
+        for mc in (0, 1):
+            us = with_tunable("MCAST", mc, lambda: graph_time(lambda i: N.conv3x3(x[i % 2], wp, cout, bias=bias), rep=4))
+            rec("mcast", f"conv {B}x{H}x{H} {cin}->{cout} mcast={mc}", us, 2.0 * 9 * cin * cout * B * H * H)
+        del x
+
 if "copy" in what:
     # calibration: what a plain device copy / reduction achieves at these (small) sizes
     for mb in (21, 42, 126, 537):

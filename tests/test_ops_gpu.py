@@ -44,6 +44,43 @@ def test_gemm_shapes(nat, M, N, K):
     assert_close(out, ref, 2e-3, 2e-3, f"gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (300, 1280, 1280), (129, 640, 2560), (1000, 2560, 320), (128, 256, 64)])
+def test_gemm_pair_mode_bit_identical(nat, M, N, K):
+    """CTA-pair mode (B tiles multicast to two CTAs of a cluster) changes who loads what, not the arithmetic:
+    outputs are bit-identical to the single-CTA kernel, including an odd number of M tiles (phantom tile)."""
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K))
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    res = rnd(M, N, seed=4)
+    old = nat.get_tunable("MCAST")
+    try:
+        nat.set_tunable("MCAST", 1)
+        o1 = nat.gemm(a, w, bias=bias, residual=res)
+        nat.set_tunable("MCAST", 0)
+        o0 = nat.gemm(a, w, bias=bias, residual=res)
+    finally:
+        nat.set_tunable("MCAST", old)
+    assert torch.equal(o0, o1)
+    assert_close(o1, a.float() @ w.float().t() + bias + res.float(), 2e-3, 2e-3, "gemm pair mode")
+
+
+def test_conv_pair_mode_bit_identical(nat):
+    for (B, H, W, Cin, Cout, stride) in [(2, 32, 32, 320, 320, 1), (3, 8, 8, 1280, 1280, 1), (2, 32, 32, 320, 320, 2),
+                                         (1, 24, 24, 192, 160, 1)]:
+        x = rnd(B, H, W, Cin, seed=1)
+        w = rnd(Cout, Cin, 3, 3, seed=2, scale=1 / math.sqrt(9 * Cin))
+        bias = rnd(Cout, seed=3, dtype=torch.float32)
+        wp = nat.pack_conv3x3(w)
+        old = nat.get_tunable("MCAST")
+        try:
+            nat.set_tunable("MCAST", 1)
+            o1 = nat.conv3x3(x, wp, Cout, bias=bias, stride=stride)
+            nat.set_tunable("MCAST", 0)
+            o0 = nat.conv3x3(x, wp, Cout, bias=bias, stride=stride)
+        finally:
+            nat.set_tunable("MCAST", old)
+        assert torch.equal(o0, o1), f"conv {B}x{H}x{W} {Cin}->{Cout} s{stride}"
+
+
 def test_gemm_residual_f32_out(nat):
     M, N, K = 384, 320, 1280
     a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K))
