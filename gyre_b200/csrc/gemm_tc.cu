@@ -268,6 +268,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint8_t* my_res_row = sRes + r * 64;
     uint32_t slice_cnt = 0;                           // slices processed by this half (slot = cnt & 1)
     uint32_t lt = 0;
+    // bias (+ per-sample vector) entry i of tile tt: i = group * BN + column
+    const int nbias = (p.rgb_rows > 0 ? (kBM / p.rgb_rows) : 1) * BN;
+    auto bias_of = [&](int tt, int i) -> float {
+      if (i >= nbias) return 0.f;
+      const int gi = i / BN;
+      const int col = (tt % p.n_tiles) * BN + (i - gi * BN);        // accumulator column == bias index
+      if (col >= p.N) return 0.f;
+      float v = ep.bias ? __ldg(ep.bias + col) : 0.f;
+      if (p.rgb_rows > 0) {
+        const int mt = p.mcast ? 2 * (tt / p.n_tiles) + rank : tt / p.n_tiles;
+        const int nn = (mt / (p.tiles_x * p.tiles_y)) * p.tile_n + gi;
+        if (nn < p.Bn) v += __half2float(__ldg(ep.rowgroup_bias + static_cast<int64_t>(nn) * ep.rgb_ld + col));
+      }
+      return v;
+    };
+    float nb0 = 0.f, nb1 = 0.f;
+    if (worker < num_tiles) {
+      nb0 = bias_of(worker, etid);
+      nb1 = bias_of(worker, etid + kEpiThreads);
+    }
     for (int t = worker; t < num_tiles; t += n_workers, ++lt) {
       const int n_tile = t % p.n_tiles;
       const int m_tile = p.mcast ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
@@ -293,22 +313,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int col_base = n_tile * bn_out;                         // first OUTPUT column of the tile
       const int nsl = (min(bn_out, n_out - col_base) + 31) >> 5;    // 32-column output slices in this tile
 
-      // ---- per-tile column bias (+ the per-sample temb vector when it is uniform over row blocks) -> smem
+      // ---- per-tile column bias (+ the per-sample temb vector when it is uniform over row blocks) -> smem.
+      // The values were requested one tile ahead (nb0 / nb1): a global load at this point would put ~1 us of
+      // latency into every tile's epilogue, more than the main loop of a short-K tile takes.
       float* sb = sbias + buf * (kMaxBiasGroups * BN);
-      {
-        const int ngroups = p.rgb_rows > 0 ? (kBM / p.rgb_rows) : 1;
-        for (int i = etid; i < ngroups * BN; i += kEpiThreads) {
-          const int gi = i / BN;
-          const int c = i - gi * BN;
-          const int col = n_tile * BN + c;                          // accumulator column == bias index
-          float v = 0.f;
-          if (col < p.N) {
-            if (ep.bias) v = __ldg(ep.bias + col);
-            if (p.rgb_rows > 0 && n0 + gi < p.Bn)
-              v += __half2float(__ldg(ep.rowgroup_bias + static_cast<int64_t>(n0 + gi) * ep.rgb_ld + col));
-          }
-          sb[i] = v;
-        }
+      if (etid < nbias) sb[etid] = nb0;
+      if (etid + kEpiThreads < nbias) sb[etid + kEpiThreads] = nb1;
+      if (t + n_workers < num_tiles) {
+        nb0 = bias_of(t + n_workers, etid);
+        nb1 = bias_of(t + n_workers, etid + kEpiThreads);
       }
       const float* sbr = sb + (p.rgb_rows > 0 ? (r / p.rgb_rows) * BN : 0);
       const uint32_t lane_addr = tmem_base + buf * Cfg::BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
