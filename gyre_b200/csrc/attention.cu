@@ -281,13 +281,18 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
 constexpr int kAtt2Threads = 352;   // TMA warp, S-MMA warp, 2 x 4 softmax warps, PV-MMA warp
 constexpr int kXAttThreads = 320;   // TMA warp, MMA warp, 2 x 4 softmax warps
 
+// DCH = 64-wide chunks of the head dimension (1: d <= 64, 2: d <= 128).  With DCH = 2 the O accumulators take
+// 2 x 128 TMEM columns, so P cannot have columns of its own: it is written IN PLACE over the scores (packed fp16
+// in the first 64 columns of the group's S region) and P V reads it from there - which rules out issuing the
+// next S early (no AV_SPLIT), but also removes P from shared memory, making room for a second K/V stage.
+template <int DCH, bool P_IN_SMEM>
 struct Att2Cfg {
-  static constexpr int STAGES = 3;
-  static constexpr int Q_BYTES = 2 * kChunkBytes;
-  static constexpr int P_BYTES = 2 * 2 * kChunkBytes;
-  static constexpr int KV_BYTES = kChunkBytes;                 // per operand per stage
+  static constexpr int STAGES = DCH == 1 ? 3 : 2;
+  static constexpr int Q_BYTES = 2 * DCH * kChunkBytes;
+  static constexpr int P_BYTES = P_IN_SMEM ? 2 * 2 * kChunkBytes : 0;
+  static constexpr int KV_BYTES = DCH * kChunkBytes;           // per operand per stage
   static constexpr int SMEM = Q_BYTES + P_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 512;                        // S0, S1: [0,256); O0 at 256, O1 at 384
+  static constexpr int TMEM_COLS = 512;
 };
 
 // Softmax variants (template parameter V of attention2_kernel; bit flags):
@@ -404,16 +409,21 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-template <int V>
+template <int V, int DCH>
 __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                      const __grid_constant__ CUtensorMap tmK,
                                                                      const __grid_constant__ CUtensorMap tmV,
                                                                      const AttnParams p) {
-  using Cfg = Att2Cfg;
+  using Cfg = Att2Cfg<DCH, (V & AV_PTMEM) == 0>;
+  static_assert(DCH == 1 || ((V & AV_PTMEM) != 0 && (V & AV_SPLIT) == 0), "d > 64 needs P aliased onto S, no early S");
+  // TMEM map: S_g at g*128.  DCH 1 + AV_PTMEM: O_g at 256 + g*64, P_g at 384 + g*64.  Otherwise O_g at 256 + g*128
+  // and (DCH 2) P_g aliased onto S_g.
+  constexpr uint32_t kOBase = 256, kOStride = (DCH == 1 && (V & AV_PTMEM) != 0) ? 64 : 128;
+  constexpr uint32_t kPBase = DCH == 1 ? 384 : 0, kPStride = DCH == 1 ? 64 : 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                          // [2 tiles][128 x 128 B]
-  uint8_t* sP = sQ + Cfg::Q_BYTES;             // [2 groups][2 chunks][128 x 128 B]
+  uint8_t* sQ = smem;                          // [2 tiles][DCH chunks][128 x 128 B]
+  uint8_t* sP = sQ + Cfg::Q_BYTES;             // [2 groups][2 chunks][128 x 128 B] (absent with AV_PTMEM)
   uint8_t* sK = sP + Cfg::P_BYTES;
   uint8_t* sV = sK + Cfg::STAGES * Cfg::KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::STAGES * Cfg::KV_BYTES);
@@ -469,15 +479,21 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, two ? Cfg::Q_BYTES : Cfg::Q_BYTES / 2);
-      tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
-      if (two) tma_load_4d(sQ + kChunkBytes, &tmQ, q_full, 0, q0 + kBQ, h, b);
+#pragma unroll
+      for (int cc = 0; cc < DCH; ++cc) {
+        tma_load_4d(sQ + cc * kChunkBytes, &tmQ, q_full, cc * 64, q0, h, b);
+        if (two) tma_load_4d(sQ + (DCH + cc) * kChunkBytes, &tmQ, q_full, cc * 64, q0 + kBQ, h, b);
+      }
       for (int j = 0; j < p.n_kv_tiles; ++j) {
         const int s = j % Cfg::STAGES;
         const uint32_t ph = (j / Cfg::STAGES) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
-        tma_load_4d(sK + s * Cfg::KV_BYTES, &tmK, &kv_full[s], 0, j * kBKeys, h, b);
-        tma_load_4d(sV + s * Cfg::KV_BYTES, &tmV, &kv_full[s], 0, j * kBKeys, h, b);
+#pragma unroll
+        for (int cc = 0; cc < DCH; ++cc) {
+          tma_load_4d(sK + s * Cfg::KV_BYTES + cc * kChunkBytes, &tmK, &kv_full[s], cc * 64, j * kBKeys, h, b);
+          tma_load_4d(sV + s * Cfg::KV_BYTES + cc * kChunkBytes, &tmV, &kv_full[s], cc * 64, j * kBKeys, h, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -489,11 +505,13 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
         const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
         const int n_s = (nk_tile + 15) & ~15;
         const uint32_t idesc = umma_idesc_f16(kBQ, n_s);
-        const uint32_t qa = smem_u32(sQ + g * kChunkBytes);
+        const uint32_t qa = smem_u32(sQ + g * DCH * kChunkBytes);
         const uint32_t ka = smem_u32(sK + s * Cfg::KV_BYTES);
-        for (int ks = 0; ks < p.ksteps_qk; ++ks)
-          umma_f16_ss(tmem_base + g * 128, umma_desc_kmajor_sw128(qa + ks * 32), umma_desc_kmajor_sw128(ka + ks * 32),
-                      idesc, ks != 0 ? 1u : 0u);
+        for (int ks = 0; ks < p.ksteps_qk; ++ks) {
+          const uint32_t off = (ks >> 2) * kChunkBytes + (ks & 3) * 32;
+          umma_f16_ss(tmem_base + g * 128, umma_desc_kmajor_sw128(qa + off), umma_desc_kmajor_sw128(ka + off), idesc,
+                      ks != 0 ? 1u : 0u);
+        }
         umma_commit(&s_full[g]);
       };
       mbar_wait(q_full, 0);
@@ -530,11 +548,19 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
           for (int g = 0; g < ng; ++g) {
             mbar_wait(&p_full[g], j & 1);
             tc_fence_after();
-            const uint32_t pa = smem_u32(sP + g * 2 * kChunkBytes);
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
-              const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
-              umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            if constexpr ((V & AV_PTMEM) != 0) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+                umma_f16_ts(tmem_base + kOBase + g * kOStride, tmem_base + kPBase + g * kPStride + ks * 8, db, idesc_pv,
+                            (j | ks) != 0 ? 1u : 0u);
+              }
+            } else {
+              const uint32_t pa = smem_u32(sP + g * 2 * kChunkBytes);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
+                const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+                umma_f16_ss(tmem_base + kOBase + g * kOStride, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+              }
             }
             umma_commit(&pv_done[g]);
             if (g == ng - 1) umma_commit(&kv_empty[s]);
@@ -568,7 +594,7 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
             if constexpr ((V & AV_PTMEM) != 0) {
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
-                umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + ks * 8, db, idesc_pv,
+                umma_f16_ts(tmem_base + kOBase + g * kOStride, tmem_base + kPBase + g * kPStride + ks * 8, db, idesc_pv,
                             (j | ks) != 0 ? 1u : 0u);
               }
             } else {
@@ -576,7 +602,7 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t da = umma_desc_kmajor_sw128(pa + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
                 const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
-                umma_f16_ss(tmem_base + 256 + g * 128, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                umma_f16_ss(tmem_base + kOBase + g * kOStride, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
               }
             }
             umma_commit(&pv_done[g]);
@@ -594,13 +620,12 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
       const int r = q * 32 + lane;
       const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
       const uint32_t tS = tmem_base + g * 128 + lane_off;
-      // AV_PTMEM: O0, O1 at 256 / 320 (npv <= 64), P0, P1 (64 packed columns each) at 384 / 448
-      const uint32_t tO = tmem_base + 256 + g * ((V & AV_PTMEM) != 0 ? 64 : 128) + lane_off;
-      const uint32_t tP = tmem_base + 384 + g * 64 + lane_off;
+      const uint32_t tO = tmem_base + kOBase + g * kOStride + lane_off;
+      const uint32_t tP = tmem_base + kPBase + g * kPStride + lane_off;
       const float c = p.scale_log2;
       float m_ref = -INFINITY;
       float l = 0.f;
-      uint8_t* prow = sP + g * 2 * kChunkBytes + r * 128;
+      uint8_t* prow = sP + g * 2 * kChunkBytes + r * 128;   // only dereferenced without AV_PTMEM
       const int rx = r & 7;
 
       for (int j = 0; j < p.n_kv_tiles; ++j) {
@@ -1051,16 +1076,17 @@ static int launch_xattn(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   return 0;
 }
 
-template <int V>
+template <int V, int DCH = 1>
 static int launch_attn2_v(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                           unsigned blocks, cudaStream_t st) {
+  using Cfg = Att2Cfg<DCH, (V & AV_PTMEM) == 0>;
   static bool attr_done = false;
   if (!attr_done) {
     GYRE_CHECK_CUDA(
-        cudaFuncSetAttribute(attention2_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg::SMEM));
+        cudaFuncSetAttribute(attention2_kernel<V, DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done = true;
   }
-  return launch_kernel(attention2_kernel<V>, dim3(blocks), dim3(kAtt2Threads), Att2Cfg::SMEM, st, tq, tk, tv, p);
+  return launch_kernel(attention2_kernel<V, DCH>, dim3(blocks), dim3(kAtt2Threads), Cfg::SMEM, st, tq, tk, tv, p);
 }
 
 static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, AttnParams p, int B,
@@ -1069,6 +1095,7 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   const long long blocks = static_cast<long long>(B) * p.heads * p.q_tiles;
   GYRE_REQUIRE(blocks < (1ll << 31), "attention: grid too large");
   const unsigned nb = static_cast<unsigned>(blocks);
+  if (p.d > 64) return launch_attn2_v<AV_PTMEM | AV_PACKED | AV_POLY25, 2>(tq, tk, tv, p, nb, st);
   switch (tunable(TUNE_ATT_VARIANT)) {
     case 0: return launch_attn2_v<0>(tq, tk, tv, p, nb, st);
     case AV_STAGGER: return launch_attn2_v<AV_STAGGER>(tq, tk, tv, p, nb, st);
@@ -1198,6 +1225,7 @@ int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __ha
                     : launch_xattn<2>(tq, tk, tv, to, p, static_cast<unsigned>(nb), st);
   }
   if (dch == 1 && Nq > kBQ) return launch_attn2(tq, tk, tv, p, B, st);
+  if (dch == 2 && Nq > kBQ && tunable(TUNE_ATT_D128)) return launch_attn2(tq, tk, tv, p, B, st);
   switch (dch) {
     case 1: return launch_attn<1>(tq, tk, tv, p, blocks, st);
     case 2: return launch_attn<2>(tq, tk, tv, p, blocks, st);

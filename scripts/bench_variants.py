@@ -76,6 +76,17 @@ if "attn" in what:
             rec("attn", f"self B{B2} h{heads} N{Nq} d{d} variant {v}", us, fl)
         del qkv
 
+if "attn80" in what:
+    for (heads, Nq, d) in ((8, 1024, 80), (8, 4096, 80), (10, 2304, 128)):
+        C = heads * d
+        qkv = [torch.randn(B2, Nq, 3 * C, device=dev).half() for _ in range(ROT)]
+        fl = 4.0 * B2 * heads * Nq * Nq * d
+        for v in (0, 1):
+            us = with_tunable("ATT_D128", v, lambda: graph_time(
+                lambda i: N.attention(qkv[i % ROT][:, :, :C], qkv[i % ROT][:, :, C:2 * C], qkv[i % ROT][:, :, 2 * C:], heads)))
+            rec("attn80", f"self B{B2} h{heads} N{Nq} d{d} ping-pong={v}", us, fl)
+        del qkv
+
 if "xattn" in what:
     for (heads, Nq, d) in ((8, 4096, 40), (8, 1024, 80), (8, 256, 160), (10, 2304, 64)):
         C = heads * d

@@ -43,6 +43,11 @@ for what in "$@"; do
         ncu -i gpurun_out/prof_attn_v$v.ncu-rep --page source --csv > gpurun_out/prof_attn_v${v}_source.csv 2>/dev/null
         ncu -i gpurun_out/prof_attn_v$v.ncu-rep --page raw --csv > gpurun_out/prof_attn_v${v}_raw.csv 2>/dev/null
       done ;;
+    ncu_gemm)
+      ncu --set full --import-source on --clock-control none -k regex:gemm_tc -s 2 -c 1 -o gpurun_out/prof_gemm1 -f python scripts/gemm_only.py $GEMM_SHAPE > gpurun_out/ncu_gemm1.log 2>&1
+      echo "== ncu gemm -> exit $?"
+      ncu -i gpurun_out/prof_gemm1.ncu-rep --page source --csv > gpurun_out/prof_gemm1_source.csv 2>/dev/null
+      ncu -i gpurun_out/prof_gemm1.ncu-rep --page raw --csv > gpurun_out/prof_gemm1_raw.csv 2>/dev/null ;;
     shapes)
       timeout 600 python scripts/bench_kernels.py > gpurun_out/shapes.log 2>&1
       echo "== shapes -> exit $?"; tail -n 12 gpurun_out/shapes.log ;;

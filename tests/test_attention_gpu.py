@@ -34,7 +34,9 @@ CASES = [(1, 1, 128, 128, 64), (2, 4, 256, 256, 16), (2, 8, 1024, 1024, 40), (1,
          (1, 8, 1024, 768, 40), (1, 8, 4096, 4096, 40), (1, 4, 256, 130, 80),
          # short-key kernel (Nk <= 128, Nq >= 512): cross-attention at SD1.5 / SD2.1 / SDXL shapes, ragged edges
          (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 10, 2304, 77, 64), (1, 5, 9216, 77, 64),
-         (1, 3, 700, 77, 40), (2, 4, 512, 128, 64), (1, 2, 640, 16, 128), (1, 8, 1000, 100, 72)]
+         (1, 3, 700, 77, 40), (2, 4, 512, 128, 64), (1, 2, 640, 16, 128), (1, 8, 1000, 100, 72),
+         # ping-pong kernel at 64 < d <= 128 (P aliased onto S in TMEM): SD1.5 level 1, ragged keys, d = 128
+         (2, 8, 1024, 1024, 80), (1, 5, 640, 640, 128), (1, 4, 384, 300, 96), (1, 2, 2048, 1500, 104), (1, 8, 300, 290, 80)]
 
 
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", CASES)
@@ -107,6 +109,21 @@ def test_attention_optimistic_max_redo_path(nat):
             assert err < 2e-2, f"variant {variant}: max abs err {err}"
     finally:
         nat.set_tunable("ATT_VARIANT", old)
+
+
+def test_attention_d128_kernel_matches_single_tile_kernel(nat):
+    B, heads, N, d = 2, 8, 1024, 80
+    C = heads * d
+    q, k, v = rnd(B, N, C, seed=1), rnd(B, N, C, seed=2), rnd(B, N, C, seed=3)
+    old = nat.get_tunable("ATT_D128")
+    try:
+        nat.set_tunable("ATT_D128", 1)
+        a = nat.attention(q, k, v, heads)
+        nat.set_tunable("ATT_D128", 0)
+        b = nat.attention(q, k, v, heads)
+    finally:
+        nat.set_tunable("ATT_D128", old)
+    assert (a.float() - b.float()).abs().max().item() < 2e-3
 
 
 def test_attention_short_key_kernel_matches_flash(nat):
