@@ -984,44 +984,38 @@ __global__ void __launch_bounds__(kXAttThreads, 1) xattention_kernel(const __gri
     const bool leader = (threadIdx.x == 64 + 128 * g);
     const int nk = p.Nk;
 
+    constexpr int VX = AV_PACKED | AV_POLY25;   // softmax arithmetic of the flash kernel's default variant, P in smem
+    const int nchunks = (n_s + 31) >> 5;
     for (int i = g; i < n; i += 2) {
       const uint32_t ph = (i >> 1) & 1;
       mbar_wait(&s_full[g], ph);
       tc_fence_after();
-      float mt = -INFINITY;
-      for (int c0 = 0; c0 < n_s; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tS + c0, v);
-        tmem_ld_wait();
+      // one TMEM round trip for the whole score row: columns beyond n_s were never written by the MMA and are
+      // masked to -inf together with the ragged tail, so they fall out of the max and exponentiate to zero
+      uint32_t v0[32], v1[32], v2[32], v3[32];
+      tmem_ld_32x32b_x32(tS, v0);
+      tmem_ld_32x32b_x32(tS + 32, v1);
+      tmem_ld_32x32b_x32(tS + 64, v2);
+      if (nchunks > 3) tmem_ld_32x32b_x32(tS + 96, v3);
+      tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (c0 + k < nk) mt = fmaxf(mt, __uint_as_float(v[k]));
+      for (int k = 0; k < 32; ++k) {
+        if (k >= nk) v0[k] = 0xff800000u;
+        if (32 + k >= nk) v1[k] = 0xff800000u;
+        if (64 + k >= nk) v2[k] = 0xff800000u;
+        if (96 + k >= nk || nchunks <= 3) v3[k] = 0xff800000u;
       }
+      const float mt = fmaxf(fmaxf(max32(v0), max32(v1)), fmaxf(max32(v2), max32(v3)));
       const float mc = mt * c;
-      float l = 0.f;
+      float2 ls = make_float2(0.f, 0.f);
       // the previous tile's output store must have finished READING this buffer before P overwrites it
       if (leader) tma_store_wait_read<0>();
       named_bar_sync(1 + g, 128);
-      for (int c0 = 0; c0 < n_s; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tS + c0, v);
-        tmem_ld_wait();
-        uint32_t packed[8];
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-          const float p0 = (c0 + k < nk) ? ex2_approx(fmaf(__uint_as_float(v[k]), c, -mc)) : 0.f;
-          const float p1 = (c0 + k + 1 < nk) ? ex2_approx(fmaf(__uint_as_float(v[k + 1]), c, -mc)) : 0.f;
-          const __half2 hh = __floats2half2_rn(p0, p1);
-          const float2 back = __half22float2(hh);     // the sum uses the values the tensor core multiplies
-          l += back.x + back.y;
-          packed[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-        }
-        uint8_t* pchunk = prow + (c0 >> 6) * kChunkBytes;
-        const int u0 = (c0 & 63) >> 3;
-        *reinterpret_cast<uint4*>(pchunk + ((u0 ^ rx) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        *reinterpret_cast<uint4*>(pchunk + (((u0 + 1) ^ rx) << 4)) =
-            make_uint4(packed[4], packed[5], packed[6], packed[7]);
-      }
+      softmax_chunk32<VX>(v0, c, mc, ls, prow, 0, rx, 0);
+      if (nchunks > 1) softmax_chunk32<VX>(v1, c, mc, ls, prow, 4, rx, 0);
+      if (nchunks > 2) softmax_chunk32<VX>(v2, c, mc, ls, prow + kChunkBytes, 0, rx, 0);
+      if (nchunks > 3) softmax_chunk32<VX>(v3, c, mc, ls, prow + kChunkBytes, 4, rx, 0);
+      const float l = ls.x + ls.y;
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(&p_full[g]);

@@ -395,62 +395,72 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         const float* __restrict__ beta, __half* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
+  constexpr int R = NV <= 2 ? 2 : 1;   // rows per warp: narrow rows leave registers for a second row in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= rows) return;
+  const int row0 = (blockIdx.x * 8 + warp) * R;
+  if (row0 >= rows) return;
   const int nvec = C >> 3;
-  const __half* src = x + static_cast<int64_t>(row) * C;
-  uint4 u[NV];
+  uint4 u[R][NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < nvec) u[k] = *reinterpret_cast<const uint4*>(src + vi * 8);
-  }
-  float v[NV][8];
-  float sum = 0.f;
+  for (int rr = 0; rr < R; ++rr) {
+    const int row = min(row0 + rr, rows - 1);
+    const __half* src = x + static_cast<int64_t>(row) * C;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < nvec) {
-      const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        v[k][2 * i] = f.x;
-        v[k][2 * i + 1] = f.y;
-        sum += f.x + f.y;
-      }
+    for (int k = 0; k < NV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < nvec) u[rr][k] = *reinterpret_cast<const uint4*>(src + vi * 8);
     }
   }
-  const float mean = warp_sum(sum) / C;
-  float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < nvec) {
+  for (int rr = 0; rr < R; ++rr) {
+    const int row = row0 + rr;
+    if (row >= rows) break;
+    float v[NV][8];
+    float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = v[k][i] - mean;
-        sq += d * d;
+    for (int k = 0; k < NV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < nvec) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[rr][k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          v[k][2 * i] = f.x;
+          v[k][2 * i + 1] = f.y;
+          sum += f.x + f.y;
+        }
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
-  __half* dst = out + static_cast<int64_t>(row) * C;
+    const float mean = warp_sum(sum) / C;
+    float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < nvec) {
-      float y[8];
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int k = 0; k < NV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < nvec) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = (v[k][i] - mean) * rstd * gg[i] + bb[i];
-      store8h(dst + vi * 8, y);
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[k][i] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+    __half* dst = out + static_cast<int64_t>(row) * C;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < nvec) {
+        float y[8];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = (v[k][i] - mean) * rstd * gg[i] + bb[i];
+        store8h(dst + vi * 8, y);
+      }
     }
   }
 }
@@ -461,7 +471,8 @@ int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gam
   GYRE_REQUIRE(C % 8 == 0 && C <= 2048, "layernorm: C=%d must be a multiple of 8 and <= 2048", C);
   prof::Scope ps(prof::F_LAYERNORM, 0.0, 2.0 * 2.0 * rows * C, st);
   const int nv = (C + 255) / 256;
-  const unsigned grid = (rows + 7) / 8;
+  const int rows_per_cta = 8 * (nv <= 2 ? 2 : 1);
+  const unsigned grid = (rows + rows_per_cta - 1) / rows_per_cta;
   switch (nv) {
     case 1: GYRE_TRY(launch_kernel(layernorm_kernel<1>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
     case 2: GYRE_TRY(launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out)); break;
