@@ -136,18 +136,26 @@ class CommonScheduler:
 
 
 class KDiffusionScheduler(CommonScheduler):
-    """gyre/pipeline/common_scheduler.py:392-623 for the samplers whose update is a single fused step:
-    `sample_euler_ancestral` (k_diffusion/sampling.py:139-155) and `sample_euler` (:118-135, churn 0)."""
+    """gyre/pipeline/common_scheduler.py:392-623.  `sample_euler_ancestral` (k_diffusion/sampling.py:139-155) and
+    `sample_euler` (:118-135, churn 0) run as ONE fused kernel per step; the multi-evaluation samplers
+    (`sample_heun`, `sample_dpm_2`, `sample_dpm_2_ancestral`, `sample_lms`, `sample_dpmpp_2s_ancestral`,
+    `sample_dpmpp_sde`, gyre's `sample_dpmpp_2m`) run on two generic kernels - denoise and linear combination -
+    with the scalar coefficients computed on the host by the reference's own expressions."""
 
-    SAMPLERS = ("sample_euler_ancestral", "sample_euler")
+    FUSED = ("sample_euler_ancestral", "sample_euler")
+    GENERIC = ("sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_lms", "sample_dpmpp_2s_ancestral",
+               "sample_dpmpp_sde", "sample_dpmpp_2m")
+    SAMPLERS = FUSED + GENERIC
 
     def __init__(self, scheduler, *args, **kwargs):
         name = scheduler if isinstance(scheduler, str) else getattr(scheduler, "__name__", str(scheduler))
         if name not in self.SAMPLERS:
-            raise NotImplementedError(f"sampler {name!r} has no fused B200 loop (supported: {self.SAMPLERS})")
+            raise NotImplementedError(f"sampler {name!r} has no B200 loop (supported: {self.SAMPLERS})")
         super().__init__(name, *args, **kwargs)
-        self.accepts_eta = name == "sample_euler_ancestral"
-        self.accepts_s_churn = name == "sample_euler"
+        # which keyword arguments the reference's sampler function takes (common_scheduler.py:400-408 inspects them)
+        self.accepts_eta = name in ("sample_euler_ancestral", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral",
+                                    "sample_dpmpp_sde")
+        self.accepts_s_churn = name in ("sample_euler", "sample_heun", "sample_dpm_2")
         self.accepts_sigmas = True
 
     def set_timesteps(self, num_inference_steps, start_offset=None, strength=None, prediction_type="epsilon",
@@ -227,6 +235,8 @@ class KDiffusionScheduler(CommonScheduler):
         ancestral = self.scheduler == "sample_euler_ancestral"
         eta = 1.0 if self.eta is None else self.eta
         vpred = self.prediction_type == "v_prediction"
+        if self.scheduler in self.GENERIC:
+            return self._loop_generic(latents, sigmas, progress_wrapper, out_dtype, eta)
 
         # ---- host-side scalars for every step, with the reference's fp32 expressions
         steps = []
@@ -273,6 +283,200 @@ class KDiffusionScheduler(CommonScheduler):
             x, x_next = x_next, x
             if self.callback and i % self.callback_steps == 0:
                 self.callback(i, t_all[i], den.to(self.dtype))
+        return x.to(out_dtype or self.dtype)
+
+
+    # -- generic samplers -------------------------------------------------------------------------
+    class _Engine:
+        """Device-side state of one run: fp32 latents, the two generic kernels and the native UNet."""
+
+        def __init__(self, sched, latents):
+            self.s = sched
+            self.guided = sched._guided()
+            self.dev = sched.device
+            self.B = latents.shape[0]
+            self.shape = tuple(latents.shape)
+            self.per_sample = latents[0].numel()
+            self.vpred = sched.prediction_type == "v_prediction"
+            self.x_in = torch.empty((2 * self.B, *self.shape[1:]), device=self.dev, dtype=torch.float16)
+            self.eps2 = torch.empty_like(self.x_in)
+            self.lib = N.load()
+
+        def new(self):
+            return torch.empty(self.shape, device=self.dev, dtype=torch.float32)
+
+        def denoise(self, x, sigma):
+            """KDiffusionUNetWrapper + Discrete{Eps,V}DDPMDenoiser.forward (common_scheduler.py:342-355,
+            external.py:96-113,149-167): x0 = x * c_skip + unet(x * c_in, t(sigma)) * c_out, with CFG inside."""
+            sg = torch.as_tensor(sigma, dtype=torch.float32)
+            c_in = 1 / (sg ** 2 + 1.0) ** 0.5
+            if self.vpred:
+                c_skip, c_out = 1.0 / (sg ** 2 + 1.0), -sg / (sg ** 2 + 1.0) ** 0.5
+            else:
+                c_skip, c_out = torch.tensor(1.0), -sg
+            t = self.s._sched.sigma_to_t(sg.reshape(1))
+            t2 = t.to(self.dev).expand(2 * self.B).contiguous()
+            st = N.stream_ptr(self.dev)
+            N.check(self.lib.gyre_b200_scale_latents(N.ptr(x), _f(c_in), 1, self.B, self.per_sample, N.ptr(self.x_in), st),
+                    "scale_latents")
+            self.guided.raw(self.x_in, t2, out=self.eps2)
+            den = self.new()
+            N.check(self.lib.gyre_b200_denoise(N.ptr(x), N.ptr(self.eps2), 1, self.guided.guidance_scale, _f(c_skip),
+                                               _f(c_out), self.B, self.per_sample, N.ptr(den), st), "denoise")
+            return den
+
+        def lin(self, terms, out=None):
+            """out = sum(coef * tensor): every sampler update is one of these."""
+            terms = [(c, t) for c, t in terms if t is not None]
+            n = len(terms)
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for _, t in terms])
+            coefs = (C.c_float * n)(*[_f(c) for c, _ in terms])
+            out = self.new() if out is None else out
+            N.check(self.lib.gyre_b200_lincomb(n, ptrs, coefs, self.B, self.per_sample, N.ptr(out), None, 0.0, 0,
+                                               N.stream_ptr(self.dev)), "lincomb")
+            return out
+
+        def noise(self):
+            """One `batched_randn` draw (noise sampler for "normal" noise, common_scheduler.py:596-610; also what
+            TorchRandOverride.randn_like resolves to, randtools.py:67-90)."""
+            return batched_randn(self.shape, self.s.generators, self.dev, self.s.dtype).float()
+
+    def _make_engine(self, latents):
+        return self._Engine(self, latents)
+
+    def _loop_generic(self, latents, sigmas, progress_wrapper, out_dtype, eta):
+        """The reference's sampler functions with every tensor expression folded into scalar coefficients of
+        `lin` (the arithmetic is the same linear map; only the rounding points differ: fp32 state here, the
+        latent dtype in the reference)."""
+        E = self._make_engine(latents)
+        name = self.scheduler
+        n = len(sigmas) - 1
+        x = latents.to(torch.float32).contiguous().clone()
+        sigma_fn = lambda t: t.neg().exp()
+        t_fn = lambda sigma: sigma.log().neg()
+        ds = []                 # sample_lms history
+        old_denoised = None     # sample_dpmpp_2m
+        sig_np = sigmas.detach().cpu().numpy()
+
+        def cb(i, den):
+            if self.callback and i % self.callback_steps == 0:
+                self.callback(i, self._sched.sigma_to_t(sigmas[i].reshape(1))[0], den.to(self.dtype))
+
+        for i in progress_wrapper(range(n)):
+            s, s_next = sigmas[i], sigmas[i + 1]
+            if name in ("sample_heun", "sample_dpm_2"):
+                E.noise()                                   # `randn_like` is drawn every step (churn 0: unused)
+                den = E.denoise(x, s)
+                cb(i, den)
+                if s_next == 0:
+                    dt = s_next - s                          # Euler: x + (x - den) / s * dt
+                    x = E.lin([(1 + dt / s, x), (-dt / s, den)])
+                elif name == "sample_heun":
+                    dt = s_next - s
+                    x_2 = E.lin([(1 + dt / s, x), (-dt / s, den)])
+                    den_2 = E.denoise(x_2, s_next)
+                    # x + (d + d_2) / 2 * dt,  d = (x - den) / s,  d_2 = (x_2 - den_2) / s_next
+                    h = dt / 2
+                    x = E.lin([(1 + h / s, x), (-h / s, den), (h / s_next, x_2), (-h / s_next, den_2)])
+                else:
+                    s_mid = s.log().lerp(s_next.log(), 0.5).exp()
+                    dt_1, dt_2 = s_mid - s, s_next - s
+                    x_2 = E.lin([(1 + dt_1 / s, x), (-dt_1 / s, den)])
+                    den_2 = E.denoise(x_2, s_mid)
+                    x = E.lin([(1.0, x), (dt_2 / s_mid, x_2), (-dt_2 / s_mid, den_2)])
+            elif name == "sample_dpm_2_ancestral":
+                den = E.denoise(x, s)
+                cb(i, den)
+                s_down, s_up = get_ancestral_step(s, s_next, eta=eta)
+                if s_down == 0:
+                    dt = s_down - s
+                    x = E.lin([(1 + dt / s, x), (-dt / s, den)])
+                else:
+                    s_mid = s.log().lerp(s_down.log(), 0.5).exp()
+                    dt_1, dt_2 = s_mid - s, s_down - s
+                    x_2 = E.lin([(1 + dt_1 / s, x), (-dt_1 / s, den)])
+                    den_2 = E.denoise(x_2, s_mid)
+                    x = E.lin([(1.0, x), (dt_2 / s_mid, x_2), (-dt_2 / s_mid, den_2), (s_up, E.noise())])
+            elif name == "sample_lms":
+                from scipy import integrate
+                den = E.denoise(x, s)
+                cb(i, den)
+                ds.append(E.lin([(1 / s, x), (-1 / s, den)]))
+                if len(ds) > 4:
+                    ds.pop(0)
+                order = min(i + 1, 4)
+
+                def coeff(j, order=order, i=i):
+                    def fn(tau):
+                        prod = 1.0
+                        for k in range(order):
+                            if j == k:
+                                continue
+                            prod *= (tau - sig_np[i - k]) / (sig_np[i - j] - sig_np[i - k])
+                        return prod
+                    return integrate.quad(fn, sig_np[i], sig_np[i + 1], epsrel=1e-4)[0]
+                x = E.lin([(1.0, x)] + [(coeff(j), d) for j, d in zip(range(order), reversed(ds))])
+            elif name == "sample_dpmpp_2s_ancestral":
+                den = E.denoise(x, s)
+                cb(i, den)
+                s_down, s_up = get_ancestral_step(s, s_next, eta=eta)
+                nz = None
+                if s_down == 0:
+                    dt = s_down - s
+                    terms = [(1 + dt / s, x), (-dt / s, den)]
+                else:
+                    t, t_next = t_fn(s), t_fn(s_down)
+                    h = t_next - t
+                    sm = t + 0.5 * h
+                    x_2 = E.lin([(sigma_fn(sm) / sigma_fn(t), x), (-(-h * 0.5).expm1(), den)])
+                    den_2 = E.denoise(x_2, sigma_fn(sm))
+                    terms = [(sigma_fn(t_next) / sigma_fn(t), x), (-(-h).expm1(), den_2)]
+                if s_next > 0:
+                    terms.append((s_up, E.noise()))
+                x = E.lin(terms)
+            elif name == "sample_dpmpp_sde":
+                den = E.denoise(x, s)
+                cb(i, den)
+                if s_next == 0:
+                    dt = s_next - s
+                    x = E.lin([(1 + dt / s, x), (-dt / s, den)])
+                else:
+                    r = 0.5
+                    t, t_next = t_fn(s), t_fn(s_next)
+                    h = t_next - t
+                    sm = t + h * r
+                    fac = 1 / (2 * r)
+                    sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(sm), eta)
+                    s_ = t_fn(sd)
+                    x_2 = E.lin([(sigma_fn(s_) / sigma_fn(t), x), (-(t - s_).expm1(), den), (su, E.noise())])
+                    den_2 = E.denoise(x_2, sigma_fn(sm))
+                    sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(t_next), eta)
+                    t_next_ = t_fn(sd)
+                    e = -(t - t_next_).expm1()
+                    x = E.lin([(sigma_fn(t_next_) / sigma_fn(t), x), (e * (1 - fac), den), (e * fac, den_2),
+                               (su, E.noise())])
+            elif name == "sample_dpmpp_2m":
+                # gyre/pipeline/schedulers/sample_dpmpp_2m.py:6-50 with warmup_lms=True, ddim_cutoff=0.1
+                # (gyre/pipeline/samplers.py:58-60)
+                den = E.denoise(x, s)
+                cb(i, den)
+                t, t_next = t_fn(s), t_fn(s_next)
+                h = t_next - t
+                a, e = sigma_fn(t_next) / sigma_fn(t), -(-h).expm1()
+                if old_denoised is None:
+                    sm = t + 0.5 * h
+                    x_2 = E.lin([(sigma_fn(sm) / sigma_fn(t), x), (-(-h * 0.5).expm1(), den)])
+                    den_i = E.denoise(x_2, sigma_fn(sm))
+                    x = E.lin([(a, x), (e, den_i)])
+                elif s_next <= 0.1:
+                    x = E.lin([(a, x), (e, den)])
+                else:
+                    h_last = t - t_fn(sigmas[i - 1])
+                    r = h_last / h
+                    x = E.lin([(a, x), (e * (1 + 1 / (2 * r)), den), (-e / (2 * r), old_denoised)])
+                old_denoised = den
+            else:
+                raise NotImplementedError(name)
         return x.to(out_dtype or self.dtype)
 
 
@@ -390,6 +594,13 @@ class DiffusersScheduler(CommonScheduler):
 SAMPLERS = {
     "k_euler_ancestral": (KDiffusionScheduler, "sample_euler_ancestral"),
     "k_euler": (KDiffusionScheduler, "sample_euler"),
+    "k_heun": (KDiffusionScheduler, "sample_heun"),
+    "k_dpm_2": (KDiffusionScheduler, "sample_dpm_2"),
+    "k_dpm_2_ancestral": (KDiffusionScheduler, "sample_dpm_2_ancestral"),
+    "k_lms": (KDiffusionScheduler, "sample_lms"),
+    "k_dpmpp_2s_ancestral": (KDiffusionScheduler, "sample_dpmpp_2s_ancestral"),
+    "k_dpmpp_sde": (KDiffusionScheduler, "sample_dpmpp_sde"),
+    "k_dpmpp_2m": (KDiffusionScheduler, "sample_dpmpp_2m"),
     "ddim": (DiffusersScheduler, "ddim"),
 }
 

@@ -157,6 +157,20 @@ int gyre_b200_cfg_combine(const void* model_out, float guidance, int batch, int6
                      out_f32, S(stream));
 }
 
+int gyre_b200_denoise(const float* x, const void* model_out, int cfg, float guidance, float c_skip, float c_out,
+                      int batch, int64_t per_sample, float* denoised, gyre_b200_stream stream) {
+  GYRE_REQUIRE(x && model_out && denoised, "denoise: null operand");
+  return denoise_combine(x, static_cast<const __half*>(model_out), cfg, guidance, c_skip, c_out, batch, per_sample,
+                         denoised, S(stream));
+}
+
+int gyre_b200_lincomb(int n_terms, const float* const* inputs_host, const float* coefs_host, int batch,
+                      int64_t per_sample, float* out, void* x_in_next, float c_in, int dup, gyre_b200_stream stream) {
+  GYRE_REQUIRE(inputs_host && coefs_host, "lincomb: null operand");
+  return lincomb(n_terms, inputs_host, coefs_host, batch, per_sample, out, static_cast<__half*>(x_in_next), c_in, dup,
+                 S(stream));
+}
+
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream) {
   GYRE_REQUIRE(x && out, "scale_latents: null operand");

@@ -210,6 +210,75 @@ int sched_step(const StepScalars& s, const float* x, const __half* model_out, co
   return 0;
 }
 
+// ------------------------------------------------------------------ generic sampler building blocks
+// The multi-evaluation samplers (Heun, DPM-2, LMS, DPM++ ...) are sequences of "denoise" and of linear
+// combinations of latent-sized tensors with host-computed scalar coefficients; two kernels cover all of them.
+//
+// denoise: CFG combine + k-diffusion denoiser scalings (external.py:96-113 eps, :149-167 v):
+//   den = x * c_skip + model * c_out      (eps-prediction: c_skip = 1, c_out = -sigma)
+__global__ void denoise_kernel(const float* __restrict__ x, const __half* __restrict__ mo, int cfg, float guidance,
+                               float c_skip, float c_out, int64_t n, float* __restrict__ den) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float m;
+  if (cfg) {
+    const float u = __half2float(mo[i]);
+    const float g = __half2float(mo[n + i]);
+    m = u + guidance * (g - u);
+  } else {
+    m = __half2float(mo[i]);
+  }
+  den[i] = x[i] * c_skip + m * c_out;
+}
+int denoise_combine(const float* x, const __half* model_out, int cfg, float guidance, float c_skip, float c_out, int B,
+                    int64_t per_sample, float* den, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(B) * per_sample;
+  GYRE_REQUIRE(n > 0 && x && model_out && den, "denoise: bad arguments");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  denoise_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, model_out, cfg, guidance, c_skip, c_out, n, den);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out = sum_k coef[k] * in[k]  (k < n_terms <= 6, fp32); optionally also the next UNet input
+// x_in = fp16(out * c_in), duplicated for CFG.  `out` may alias any input (pure elementwise).
+struct LinArgs {
+  const float* in[6];
+  float coef[6];
+  int n_terms;
+};
+__global__ void lincomb_kernel(LinArgs a, int64_t n, float* __restrict__ out, __half* __restrict__ x_in, float c_in,
+                               int dup) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (k < a.n_terms) acc = fmaf(a.coef[k], a.in[k][i], acc);
+  if (out) out[i] = acc;
+  if (x_in) {
+    const __half h = __float2half_rn(acc * c_in);
+    x_in[i] = h;
+    if (dup) x_in[n + i] = h;
+  }
+}
+int lincomb(int n_terms, const float* const* in, const float* coef, int B, int64_t per_sample, float* out,
+            __half* x_in, float c_in, int dup, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(B) * per_sample;
+  GYRE_REQUIRE(n > 0 && n_terms >= 1 && n_terms <= 6 && in && coef && (out || x_in), "lincomb: bad arguments");
+  LinArgs a;
+  for (int k = 0; k < 6; ++k) {
+    a.in[k] = k < n_terms ? in[k] : nullptr;
+    a.coef[k] = k < n_terms ? coef[k] : 0.f;
+    GYRE_REQUIRE(k >= n_terms || in[k] != nullptr, "lincomb: null input %d", k);
+  }
+  a.n_terms = n_terms;
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  lincomb_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a, n, out, x_in, c_in, dup);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void scale_dup_kernel(const float* __restrict__ x, float c_in, int dup, int64_t n, __half* __restrict__ out) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;

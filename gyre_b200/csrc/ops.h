@@ -98,6 +98,11 @@ struct StepScalars {
 };
 int sched_step(const StepScalars& s, const float* x, const __half* model_out, const float* noise, float* x_out,
                float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st);
+// generic sampler blocks: den = x * c_skip + cfg(model_out) * c_out ; out = sum coef[k] * in[k] (+ next UNet input)
+int denoise_combine(const float* x, const __half* model_out, int cfg, float guidance, float c_skip, float c_out, int B,
+                    int64_t per_sample, float* den, cudaStream_t st);
+int lincomb(int n_terms, const float* const* in, const float* coef, int B, int64_t per_sample, float* out,
+            __half* x_in, float c_in, int dup, cudaStream_t st);
 int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_sample, __half* out16, float* out32,
                 cudaStream_t st);
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)

@@ -183,6 +183,18 @@ int gyre_b200_sched_step(const gyre_b200_step* s, const float* x, const void* mo
  * [uncond ; cond]; either output may be NULL. */
 int gyre_b200_cfg_combine(const void* model_out, float guidance, int batch, int64_t per_sample, void* out_f16,
                           float* out_f32, gyre_b200_stream stream);
+/* Building blocks of the multi-evaluation samplers (k_diffusion/sampling.py:159-278,509-581 Heun, DPM-2,
+ * DPM-2 ancestral, LMS, DPM++ 2S ancestral, DPM++ SDE; gyre/pipeline/schedulers/sample_dpmpp_2m.py:6-50):
+ * every update there is a denoiser call followed by a linear combination of latent-sized tensors whose
+ * scalar coefficients the host computes exactly as the reference does.
+ *   denoise: denoised = x * c_skip + cfg(model_out) * c_out   (external.py:96-113: eps c_skip=1, c_out=-sigma;
+ *            :149-167: v c_skip=1/(sigma^2+1), c_out=-sigma/sqrt(sigma^2+1)); cfg != 0: model_out = [uncond ; cond]
+ *   lincomb: out = sum_k coefs_host[k] * inputs_host[k]  (n_terms <= 6 device pointers in a HOST array, fp32);
+ *            x_in_next (optional) = fp16(out * c_in), duplicated when dup != 0; out may alias an input or be NULL */
+int gyre_b200_denoise(const float* x, const void* model_out, int cfg, float guidance, float c_skip, float c_out,
+                      int batch, int64_t per_sample, float* denoised, gyre_b200_stream stream);
+int gyre_b200_lincomb(int n_terms, const float* const* inputs_host, const float* coefs_host, int batch,
+                      int64_t per_sample, float* out, void* x_in_next, float c_in, int dup, gyre_b200_stream stream);
 /* out_f16[(dup?2:1) * B, ...] = x * c_in  (first unet input of a run) */
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream);

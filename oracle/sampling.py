@@ -2,7 +2,7 @@
 
 Follows (all under /root/reference):
   gyre/src/k-diffusion/k_diffusion/external.py:43-113,141-167   DiscreteSchedule / Eps / V denoisers
-  gyre/src/k-diffusion/k_diffusion/sampling.py:12-58,118-215    schedules, to_d, ancestral step, samplers
+  gyre/src/k-diffusion/k_diffusion/sampling.py:12-58,118-278,509-581   schedules, to_d, ancestral step, samplers
   gyre/pipeline/schedulers/sample_dpmpp_2m.py:6-50              gyre's DPM++ 2M
   gyre/pipeline/schedulers/scheduling_ddim.py:189-321           DDIM set_timesteps / step
   gyre/pipeline/common_scheduler.py:410-428,430-541,555-623     KDiffusionScheduler
@@ -205,6 +205,141 @@ def sample_heun(model, x, sigmas, randn_like, s_churn=0.0, s_tmin=0.0, s_tmax=fl
     return x
 
 
+def sample_dpm_2(model, x, sigmas, randn_like, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
+    """sampling.py:188-215."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        eps = randn_like(x) * s_noise
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(x, sigma_hat * s_in)
+        d = to_d(x, sigma_hat, denoised)
+        if sigmas[i + 1] == 0:
+            dt = sigmas[i + 1] - sigma_hat
+            x = x + d * dt
+        else:
+            sigma_mid = sigma_hat.log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            dt_1 = sigma_mid - sigma_hat
+            dt_2 = sigmas[i + 1] - sigma_hat
+            x_2 = x + d * dt_1
+            denoised_2 = model(x_2, sigma_mid * s_in)
+            d_2 = to_d(x_2, sigma_mid, denoised_2)
+            x = x + d_2 * dt_2
+    return x
+
+
+def sample_dpm_2_ancestral(model, x, sigmas, noise_sampler, eta=1.0, s_noise=1.0):
+    """sampling.py:219-245."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        d = to_d(x, sigmas[i], denoised)
+        if sigma_down == 0:
+            dt = sigma_down - sigmas[i]
+            x = x + d * dt
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigma_down.log(), 0.5).exp()
+            dt_1 = sigma_mid - sigmas[i]
+            dt_2 = sigma_down - sigmas[i]
+            x_2 = x + d * dt_1
+            denoised_2 = model(x_2, sigma_mid * s_in)
+            d_2 = to_d(x_2, sigma_mid, denoised_2)
+            x = x + d_2 * dt_2
+            x = x + noise_sampler(sigmas[i], sigmas[i + 1]) * s_noise * sigma_up
+    return x
+
+
+def linear_multistep_coeff(order, t, i, j):
+    """sampling.py:247-258 (scipy.integrate.quad on the host, epsrel 1e-4)."""
+    from scipy import integrate
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+def sample_lms(model, x, sigmas, order=4):
+    """sampling.py:261-278."""
+    s_in = x.new_ones([x.shape[0]])
+    sigmas_cpu = sigmas.detach().cpu().numpy()
+    ds = []
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        d = to_d(x, sigmas[i], denoised)
+        ds.append(d)
+        if len(ds) > order:
+            ds.pop(0)
+        cur_order = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur_order, sigmas_cpu, i, j) for j in range(cur_order)]
+        x = x + sum(coeff * d for coeff, d in zip(coeffs, reversed(ds)))
+    return x
+
+
+def sample_dpmpp_2s_ancestral(model, x, sigmas, noise_sampler, eta=1.0, s_noise=1.0):
+    """sampling.py:509-539."""
+    s_in = x.new_ones([x.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()
+    t_fn = lambda sigma: sigma.log().neg()
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        if sigma_down == 0:
+            d = to_d(x, sigmas[i], denoised)
+            dt = sigma_down - sigmas[i]
+            x = x + d * dt
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
+            r = 1 / 2
+            h = t_next - t
+            s = t + r * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * denoised
+            denoised_2 = model(x_2, sigma_fn(s) * s_in)
+            x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * denoised_2
+        if sigmas[i + 1] > 0:
+            x = x + noise_sampler(sigmas[i], sigmas[i + 1]) * s_noise * sigma_up
+    return x
+
+
+def sample_dpmpp_sde(model, x, sigmas, noise_sampler, eta=1.0, s_noise=1.0, r=1 / 2):
+    """sampling.py:543-581 with the caller's noise sampler (gyre passes its own for "normal" noise,
+    common_scheduler.py:596-610; the Brownian-tree default needs torchsde, absent here)."""
+    s_in = x.new_ones([x.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()
+    t_fn = lambda sigma: sigma.log().neg()
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        if sigmas[i + 1] == 0:
+            d = to_d(x, sigmas[i], denoised)
+            dt = sigmas[i + 1] - sigmas[i]
+            x = x + d * dt
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+            h = t_next - t
+            s = t + h * r
+            fac = 1 / (2 * r)
+            sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(s), eta)
+            s_ = t_fn(sd)
+            x_2 = (sigma_fn(s_) / sigma_fn(t)) * x - (t - s_).expm1() * denoised
+            x_2 = x_2 + noise_sampler(sigma_fn(t), sigma_fn(s)) * s_noise * su
+            denoised_2 = model(x_2, sigma_fn(s) * s_in)
+            sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(t_next), eta)
+            t_next_ = t_fn(sd)
+            denoised_d = (1 - fac) * denoised + fac * denoised_2
+            x = (sigma_fn(t_next_) / sigma_fn(t)) * x - (t - t_next_).expm1() * denoised_d
+            x = x + noise_sampler(sigma_fn(t), sigma_fn(t_next)) * s_noise * su
+    return x
+
+
 def sample_dpmpp_2m(model, x, sigmas, warmup_lms=False, ddim_cutoff=0.0):
     """gyre/pipeline/schedulers/sample_dpmpp_2m.py:6-50 (samplers.py:58-60 passes warmup_lms=True, ddim_cutoff=0.1)."""
     s_in = x.new_ones([x.shape[0]])
@@ -322,6 +457,16 @@ def txt2img_latents(eps_unet_cfg, *, batch, in_channels, height, width, sample_s
         return sample_heun(den, latents, sigmas, randn_like)
     if sampler == "dpmpp_2m":
         return sample_dpmpp_2m(den, latents, sigmas, warmup_lms=True, ddim_cutoff=0.1)
+    if sampler == "dpm_2":
+        return sample_dpm_2(den, latents, sigmas, randn_like)
+    if sampler == "dpm_2_a":
+        return sample_dpm_2_ancestral(den, latents, sigmas, noise, eta=1.0 if eta is None else eta)
+    if sampler == "lms":
+        return sample_lms(den, latents, sigmas)
+    if sampler == "dpmpp_2s_a":
+        return sample_dpmpp_2s_ancestral(den, latents, sigmas, noise, eta=1.0 if eta is None else eta)
+    if sampler == "dpmpp_sde":
+        return sample_dpmpp_sde(den, latents, sigmas, noise, eta=1.0 if eta is None else eta)
     raise ValueError(sampler)
 
 

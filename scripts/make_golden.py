@@ -40,7 +40,7 @@ def pin_samplers():
     acp = osamp.sd_alphas_cumprod()
     out = {}
     for dtype_name, ldt in (("fp32", torch.float32), ("fp16", torch.float16)):
-        for name in ("euler_a", "euler", "heun", "dpmpp_2m"):
+        for name in ("euler_a", "euler", "heun", "dpmpp_2m", "dpm_2", "dpm_2_a", "lms", "dpmpp_2s_a", "dpmpp_sde"):
             for steps in (7, 20):
                 shape = (2, 4, 8, 8)
                 seeds = [420420420, 420420421]
@@ -56,7 +56,15 @@ def pin_samplers():
                 orig_randn_like = ks.torch.randn_like
                 if name == "euler_a":
                     ref = ks.sample_euler_ancestral(ref_den, x0, sig, noise_sampler=ns, disable=True)
-                elif name in ("euler", "heun"):
+                elif name == "dpm_2_a":
+                    ref = ks.sample_dpm_2_ancestral(ref_den, x0, sig, noise_sampler=ns, disable=True)
+                elif name == "dpmpp_2s_a":
+                    ref = ks.sample_dpmpp_2s_ancestral(ref_den, x0, sig, noise_sampler=ns, disable=True)
+                elif name == "dpmpp_sde":
+                    ref = ks.sample_dpmpp_sde(ref_den, x0, sig, noise_sampler=ns, disable=True)
+                elif name == "lms":
+                    ref = ks.sample_lms(ref_den, x0, sig, disable=True)
+                elif name in ("euler", "heun", "dpm_2"):
                     class _T:  # TorchRandOverride (randtools.py:67-90) restated for the patch
                         def __getattr__(self, k):
                             return getattr(torch, k)
@@ -65,7 +73,7 @@ def pin_samplers():
                             return ns()
                     ks.torch = _T()
                     try:
-                        fn = ks.sample_euler if name == "euler" else ks.sample_heun
+                        fn = {"euler": ks.sample_euler, "heun": ks.sample_heun, "dpm_2": ks.sample_dpm_2}[name]
                         ref = fn(ref_den, x0, sig, disable=True)
                     finally:
                         ks.torch = torch
@@ -86,6 +94,16 @@ def pin_samplers():
                     got = osamp.sample_euler(den, y0, s2, lambda x: ns2())
                 elif name == "heun":
                     got = osamp.sample_heun(den, y0, s2, lambda x: ns2())
+                elif name == "dpm_2":
+                    got = osamp.sample_dpm_2(den, y0, s2, lambda x: ns2())
+                elif name == "dpm_2_a":
+                    got = osamp.sample_dpm_2_ancestral(den, y0, s2, ns2)
+                elif name == "lms":
+                    got = osamp.sample_lms(den, y0, s2)
+                elif name == "dpmpp_2s_a":
+                    got = osamp.sample_dpmpp_2s_ancestral(den, y0, s2, ns2)
+                elif name == "dpmpp_sde":
+                    got = osamp.sample_dpmpp_sde(den, y0, s2, ns2)
                 else:
                     got = osamp.sample_dpmpp_2m(den, y0, s2, warmup_lms=True, ddim_cutoff=0.1)
                 err = (got - ref).abs().max().item()
@@ -187,7 +205,8 @@ def oracle_fixtures(full: bool):
         emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(11))
         unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1)
         cfgu = osamp.CFGParallel(unet, unc, emb, 7.5)
-        for sampler, steps in (("ddim", 10), ("euler_a", 12), ("euler", 8), ("dpmpp_2m", 8)):
+        for sampler, steps in (("ddim", 10), ("euler_a", 12), ("euler", 8), ("dpmpp_2m", 8), ("heun", 7), ("dpm_2", 7),
+                               ("dpm_2_a", 7), ("lms", 9), ("dpmpp_2s_a", 7), ("dpmpp_sde", 7)):
             lat = osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=128, width=128, sample_size=16,
                                         seeds=[420420420, 420420421], steps=steps, sampler=sampler)
             out[f"pipe_tiny/{sampler}"] = {"steps": steps, "latents": lat}
