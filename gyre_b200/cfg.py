@@ -22,8 +22,34 @@ class B200GuidedUNet:
         # CFG order is [uncond, cond] (unified_pipeline.py:2335, cfg.py:54)
         self.embeddings = torch.cat([uncond_embeddings, text_embeddings]).to(device=unet.device,
                                                                               dtype=torch.float16).contiguous()
+        self.extra = None           # [B, Ce, h, w] fp16: mask + masked-image latents of the inpaint UNets
+        self._xcat = None
+
+    def set_extra_channels(self, extra):
+        """EnhancedRunwayInpaintMode.wrap_unet (unified_pipeline.py:668-690) / UnetWithExtraChannels (unet/core.py:21-37):
+        the same un-scaled extra channels are appended to the (CFG-doubled) latents at every step."""
+        if extra is not None:
+            N.require_cuda(extra)
+            if extra.shape[0] != self.batch:
+                raise ValueError("extra channels batch does not match the embeddings")
+            if extra.shape[1] + 4 != self.unet.config.in_channels:
+                raise ValueError(f"UNet takes {self.unet.config.in_channels} channels, got 4 + {extra.shape[1]}")
+            extra = extra.to(torch.float16).contiguous()
+        self.extra = extra
+
+    def _expand(self, x2_f16):
+        if self.extra is None:
+            return x2_f16
+        B2, Cx, h, w = x2_f16.shape
+        Ce = self.extra.shape[1]
+        if self._xcat is None or self._xcat.shape != (B2, Cx + Ce, h, w):
+            self._xcat = torch.empty((B2, Cx + Ce, h, w), device=x2_f16.device, dtype=torch.float16)
+        N.check(N.load().gyre_b200_cat_channels(N.ptr(x2_f16), Cx, N.ptr(self.extra), Ce, self.extra.shape[0], B2, h * w,
+                                                N.ptr(self._xcat), N.stream_ptr(x2_f16.device)), "cat_channels")
+        return self._xcat
 
     def raw(self, x2_f16, t2_i64, out=None):
+        x2_f16 = self._expand(x2_f16)
         # The embeddings are fixed for the life of this wrapper (as in UNetWithEmbeddings, core.py:253-259), so
         # the UNet projects them to cross-attention K/V once instead of at every step (tunable CTX_KV_CACHE).
         if N.get_tunable("CTX_KV_CACHE"):

@@ -106,6 +106,7 @@ class CommonScheduler:
         self.start_timestep = 0
         self.eps_unets = []
         self.unet = None
+        self._blend = None          # (orig fp32, mask fp32): legacy inpaint x0 blend (set_x0_blend)
 
     def set_callback(self, callback, callback_steps: int = 1):
         self.callback = callback
@@ -119,13 +120,29 @@ class CommonScheduler:
                 raise TypeError("the B200 schedulers drive a B200GuidedUNet (native CFG + UNet); got %r" % type(u))
         self.eps_unets = list(eps_unets)
 
+    def set_x0_blend(self, orig, mask):
+        """EnhancedInpaintMode.wrap_k_unet (unified_pipeline.py:627-636): x0 <- orig where mask > u."""
+        self._blend = None if orig is None else (orig.float().contiguous(), mask.float().contiguous())
+
+    def _u(self, i, i_max, n_sigmas_total):
+        """KDiffusionPositionTracker.get_u (common_scheduler.py:358-389)."""
+        u_off = self.start_offset / n_sigmas_total
+        u = u_off + (1 - u_off) * i / i_max
+        return max(min(u, 0.999), 0)
+
     # -- shared plumbing --------------------------------------------------------------------------
     def _guided(self) -> B200GuidedUNet:
         if not self.eps_unets:
             raise ValueError("Epsilon unet needs to be set before timesteps")
         return self.eps_unets[0]
 
-    def _step(self, step: N.Step, x, model_out, noise, x_out, den_out, x_in_next, B, per_sample):
+    def _step(self, step: N.Step, x, model_out, noise, x_out, den_out, x_in_next, B, per_sample, u=None):
+        if self._blend is not None and u is not None:
+            N.check(N.load().gyre_b200_sched_step_blend(C.byref(step), N.ptr(x), N.ptr(model_out), N.ptr(noise),
+                                                        N.ptr(x_out), N.ptr(den_out), N.ptr(x_in_next), B, per_sample,
+                                                        N.ptr(self._blend[0]), N.ptr(self._blend[1]), float(u),
+                                                        N.stream_ptr(self.device)), "sched_step_blend")
+            return
         N.check(N.load().gyre_b200_sched_step(C.byref(step), N.ptr(x), N.ptr(model_out), N.ptr(noise), N.ptr(x_out),
                                               N.ptr(den_out), N.ptr(x_in_next), B, per_sample,
                                               N.stream_ptr(self.device)), "sched_step")
@@ -279,7 +296,8 @@ class KDiffusionScheduler(CommonScheduler):
             if st.sigma_up != 0.0:
                 nz = noise32[k]
                 k += 1
-            self._step(st, x, eps2, nz, x_next, den, x_in if st.c_in_next != 0.0 else None, B, per_sample)
+            self._step(st, x, eps2, nz, x_next, den, x_in if st.c_in_next != 0.0 else None, B, per_sample,
+                       u=self._u(i, n, len(self.sigmas)))
             x, x_next = x_next, x
             if self.callback and i % self.callback_steps == 0:
                 self.callback(i, t_all[i], den.to(self.dtype))
@@ -301,6 +319,7 @@ class KDiffusionScheduler(CommonScheduler):
             self.x_in = torch.empty((2 * self.B, *self.shape[1:]), device=self.dev, dtype=torch.float16)
             self.eps2 = torch.empty_like(self.x_in)
             self.lib = N.load()
+            self.u = 0.0            # progress of the current step (legacy inpaint blend)
 
         def new(self):
             return torch.empty(self.shape, device=self.dev, dtype=torch.float32)
@@ -321,8 +340,14 @@ class KDiffusionScheduler(CommonScheduler):
                     "scale_latents")
             self.guided.raw(self.x_in, t2, out=self.eps2)
             den = self.new()
-            N.check(self.lib.gyre_b200_denoise(N.ptr(x), N.ptr(self.eps2), 1, self.guided.guidance_scale, _f(c_skip),
-                                               _f(c_out), self.B, self.per_sample, N.ptr(den), st), "denoise")
+            if self.s._blend is not None:
+                N.check(self.lib.gyre_b200_denoise_blend(N.ptr(x), N.ptr(self.eps2), 1, self.guided.guidance_scale,
+                                                         _f(c_skip), _f(c_out), self.B, self.per_sample, N.ptr(den),
+                                                         N.ptr(self.s._blend[0]), N.ptr(self.s._blend[1]), float(self.u),
+                                                         st), "denoise_blend")
+            else:
+                N.check(self.lib.gyre_b200_denoise(N.ptr(x), N.ptr(self.eps2), 1, self.guided.guidance_scale, _f(c_skip),
+                                                   _f(c_out), self.B, self.per_sample, N.ptr(den), st), "denoise")
             return den
 
         def lin(self, terms, out=None):
@@ -364,6 +389,7 @@ class KDiffusionScheduler(CommonScheduler):
 
         for i in progress_wrapper(range(n)):
             s, s_next = sigmas[i], sigmas[i + 1]
+            E.u = self._u(i, n, len(self.sigmas))
             if name in ("sample_heun", "sample_dpm_2"):
                 E.noise()                                   # `randn_like` is drawn every step (churn 0: unused)
                 den = E.denoise(x, s)

@@ -164,6 +164,32 @@ int gyre_b200_denoise(const float* x, const void* model_out, int cfg, float guid
                          denoised, S(stream));
 }
 
+int gyre_b200_denoise_blend(const float* x, const void* model_out, int cfg, float guidance, float c_skip, float c_out,
+                            int batch, int64_t per_sample, float* denoised, const float* blend_orig,
+                            const float* blend_mask, float blend_u, gyre_b200_stream stream) {
+  GYRE_REQUIRE(x && model_out && denoised && blend_orig && blend_mask, "denoise_blend: null operand");
+  return denoise_combine(x, static_cast<const __half*>(model_out), cfg, guidance, c_skip, c_out, batch, per_sample,
+                         denoised, S(stream), blend_orig, blend_mask, blend_u);
+}
+
+int gyre_b200_sched_step_blend(const gyre_b200_step* s, const float* x, const void* model_out, const float* noise,
+                               float* x_out, float* denoised_out, void* x_in_next, int batch, int64_t per_sample,
+                               const float* blend_orig, const float* blend_mask, float blend_u,
+                               gyre_b200_stream stream) {
+  GYRE_REQUIRE(s && x && model_out && x_out && blend_orig && blend_mask, "sched_step_blend: null operand");
+  StepScalars k;
+  static_assert(sizeof(StepScalars) == sizeof(gyre_b200_step), "step struct drift");
+  memcpy(&k, s, sizeof(k));
+  return sched_step(k, x, static_cast<const __half*>(model_out), noise, x_out, denoised_out,
+                    static_cast<__half*>(x_in_next), batch, per_sample, S(stream), blend_orig, blend_mask, blend_u);
+}
+
+int gyre_b200_cat_channels(const void* x, int channels, const void* extra, int extra_channels, int extra_batch, int batch,
+                           int64_t hw, void* out, gyre_b200_stream stream) {
+  return cat_channels_nchw(static_cast<const __half*>(x), channels, static_cast<const __half*>(extra), extra_channels,
+                           extra_batch, batch, hw, static_cast<__half*>(out), S(stream));
+}
+
 int gyre_b200_lincomb(int n_terms, const float* const* inputs_host, const float* coefs_host, int batch,
                       int64_t per_sample, float* out, void* x_in_next, float c_in, int dup, gyre_b200_stream stream) {
   GYRE_REQUIRE(inputs_host && coefs_host, "lincomb: null operand");

@@ -155,7 +155,9 @@ int conv1x1_small(const __half* X, int64_t rows, int Cin, const float* Wt, const
 // and emits the NEXT step's CFG-duplicated, c_in-scaled fp16 UNet input.  Latents stay fp32 across steps.
 __global__ void sched_step_kernel(StepScalars s, const float* __restrict__ x, const __half* __restrict__ mo,
                                   const float* __restrict__ noise, float* __restrict__ x_out,
-                                  float* __restrict__ den_out, __half* __restrict__ x_in_next, int64_t n_total) {
+                                  float* __restrict__ den_out, __half* __restrict__ x_in_next, int64_t n_total,
+                                  const float* __restrict__ blend_orig, const float* __restrict__ blend_mask,
+                                  float blend_u) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n_total) return;
   float m;
@@ -175,6 +177,9 @@ __global__ void sched_step_kernel(StepScalars s, const float* __restrict__ x, co
     } else {
       den = xv - s.sigma * m;
     }
+    // EnhancedInpaintMode.wrap_k_unet / _blend (unified_pipeline.py:620-636): where the mask still protects the
+    // original at progress u, the predicted x0 is replaced by the original latents
+    if (blend_mask != nullptr && blend_mask[i] > blend_u) den = blend_orig[i];
     const float d = (xv - den) / s.sigma;
     xn = xv + d * s.dt;
     if (s.sigma_up != 0.f) xn += noise[i] * s.sigma_up;
@@ -198,14 +203,18 @@ __global__ void sched_step_kernel(StepScalars s, const float* __restrict__ x, co
   }
 }
 int sched_step(const StepScalars& s, const float* x, const __half* model_out, const float* noise, float* x_out,
-               float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st) {
+               float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st,
+               const float* blend_orig, const float* blend_mask, float blend_u) {
   const int64_t n = static_cast<int64_t>(B) * per_sample;
   GYRE_REQUIRE(n > 0, "sched_step: empty");
+  GYRE_REQUIRE((blend_orig == nullptr) == (blend_mask == nullptr), "sched_step: blend needs both original and mask");
+  GYRE_REQUIRE(blend_mask == nullptr || s.kind == 0, "sched_step: x0 blending is defined for the k-diffusion step only");
   GYRE_REQUIRE(!((s.sigma_up != 0.f || (s.kind == 1 && s.noise_coef != 0.f)) && noise == nullptr),
                "sched_step: noise required");
   prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   sched_step_kernel<<<blocks_for(n, 256), 256, 0, st>>>(s, x, model_out, noise, x_out, denoised_out,
-                                                        s.c_in_next != 0.f ? x_in_next : nullptr, n);
+                                                        s.c_in_next != 0.f ? x_in_next : nullptr, n, blend_orig,
+                                                        blend_mask, blend_u);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -217,7 +226,9 @@ int sched_step(const StepScalars& s, const float* x, const __half* model_out, co
 // denoise: CFG combine + k-diffusion denoiser scalings (external.py:96-113 eps, :149-167 v):
 //   den = x * c_skip + model * c_out      (eps-prediction: c_skip = 1, c_out = -sigma)
 __global__ void denoise_kernel(const float* __restrict__ x, const __half* __restrict__ mo, int cfg, float guidance,
-                               float c_skip, float c_out, int64_t n, float* __restrict__ den) {
+                               float c_skip, float c_out, int64_t n, float* __restrict__ den,
+                               const float* __restrict__ blend_orig, const float* __restrict__ blend_mask,
+                               float blend_u) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   float m;
@@ -228,14 +239,19 @@ __global__ void denoise_kernel(const float* __restrict__ x, const __half* __rest
   } else {
     m = __half2float(mo[i]);
   }
-  den[i] = x[i] * c_skip + m * c_out;
+  float d = x[i] * c_skip + m * c_out;
+  if (blend_mask != nullptr && blend_mask[i] > blend_u) d = blend_orig[i];
+  den[i] = d;
 }
 int denoise_combine(const float* x, const __half* model_out, int cfg, float guidance, float c_skip, float c_out, int B,
-                    int64_t per_sample, float* den, cudaStream_t st) {
+                    int64_t per_sample, float* den, cudaStream_t st, const float* blend_orig, const float* blend_mask,
+                    float blend_u) {
   const int64_t n = static_cast<int64_t>(B) * per_sample;
   GYRE_REQUIRE(n > 0 && x && model_out && den, "denoise: bad arguments");
   prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
-  denoise_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, model_out, cfg, guidance, c_skip, c_out, n, den);
+  GYRE_REQUIRE((blend_orig == nullptr) == (blend_mask == nullptr), "denoise: blend needs both original and mask");
+  denoise_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, model_out, cfg, guidance, c_skip, c_out, n, den, blend_orig,
+                                                     blend_mask, blend_u);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -275,6 +291,30 @@ int lincomb(int n_terms, const float* const* in, const float* coef, int B, int64
   a.n_terms = n_terms;
   prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
   lincomb_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a, n, out, x_in, c_in, dup);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// UNet input of the inpaint / depth models (EnhancedRunwayInpaintMode.wrap_unet, unified_pipeline.py:668-690;
+// UnetWithExtraChannels, unet/core.py:21-37): out[b] = cat([x[b], extra[b % extra_batch]], dim=channel), NCHW fp16.
+// The extra channels (mask + masked-image latents) are NOT scaled by c_in (see the reference's comment there).
+__global__ void cat_channels_nchw_kernel(const __half* __restrict__ x, int Cx, const __half* __restrict__ extra, int Ce,
+                                         int extra_batch, int64_t hw, int64_t total, __half* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int C = Cx + Ce;
+  const int64_t p = i % hw;
+  const int64_t bc = i / hw;
+  const int c = static_cast<int>(bc % C);
+  const int64_t b = bc / C;
+  out[i] = c < Cx ? x[(b * Cx + c) * hw + p] : extra[((b % extra_batch) * Ce + (c - Cx)) * hw + p];
+}
+int cat_channels_nchw(const __half* x, int Cx, const __half* extra, int Ce, int extra_batch, int B, int64_t hw,
+                      __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(x && extra && out && B > 0 && Cx > 0 && Ce > 0 && extra_batch > 0 && hw > 0, "cat_channels: bad arguments");
+  const int64_t total = static_cast<int64_t>(B) * (Cx + Ce) * hw;
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  cat_channels_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, Cx, extra, Ce, extra_batch, hw, total, out);
   GYRE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

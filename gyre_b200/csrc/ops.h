@@ -97,10 +97,14 @@ struct StepScalars {
   float sqrt_a_t, sqrt_1m_a_t, sqrt_a_prev, dir_coef, noise_coef;
 };
 int sched_step(const StepScalars& s, const float* x, const __half* model_out, const float* noise, float* x_out,
-               float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st);
+               float* denoised_out, __half* x_in_next, int B, int64_t per_sample, cudaStream_t st,
+               const float* blend_orig = nullptr, const float* blend_mask = nullptr, float blend_u = 0.f);
+int cat_channels_nchw(const __half* x, int Cx, const __half* extra, int Ce, int extra_batch, int B, int64_t hw,
+                      __half* out, cudaStream_t st);
 // generic sampler blocks: den = x * c_skip + cfg(model_out) * c_out ; out = sum coef[k] * in[k] (+ next UNet input)
 int denoise_combine(const float* x, const __half* model_out, int cfg, float guidance, float c_skip, float c_out, int B,
-                    int64_t per_sample, float* den, cudaStream_t st);
+                    int64_t per_sample, float* den, cudaStream_t st, const float* blend_orig = nullptr,
+                    const float* blend_mask = nullptr, float blend_u = 0.f);
 int lincomb(int n_terms, const float* const* in, const float* coef, int B, int64_t per_sample, float* out,
             __half* x_in, float c_in, int dup, cudaStream_t st);
 int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_sample, __half* out16, float* out32,

@@ -14,7 +14,8 @@ from dataclasses import dataclass
 import torch
 
 from .cfg import B200GuidedUNet
-from .common_scheduler import SchedulerConfig, build_scheduler
+from .common_scheduler import KDiffusionScheduler, SchedulerConfig, build_scheduler
+from .modes import EnhancedInpaintMode, EnhancedRunwayInpaintMode, Img2imgMode
 from .randtools import batched_randn
 
 
@@ -79,7 +80,12 @@ class B200Pipeline:
                  num_inference_steps: int = 50, guidance_scale: float = 7.5, generator=None,
                  sampler: str = "k_euler_ancestral", scheduler_config: SchedulerConfig | None = None,
                  output_type: str = "pt", callback=None, callback_steps: int = 1, progress_wrapper=None,
-                 latents_dtype=torch.float16, return_fp32_latents: bool = False) -> PipelineOutput:
+                 latents_dtype=torch.float16, return_fp32_latents: bool = False, image=None, mask_image=None,
+                 strength: float = 0.8) -> PipelineOutput:
+        """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
+        EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
+        unified_pipeline.py:2100-2181.  `image` / `mask_image` are [1, C, H, W] tensors in [0, 1]; the mask is white =
+        repaint (the reference's default input convention, preprocess_mask_tensor(inputIs0K1D=True))."""
         if height % 8 != 0 or width % 8 != 0:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
         if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
@@ -91,17 +97,44 @@ class B200Pipeline:
         if B % len(generators) != 0:
             raise ValueError(f"batch {B} is not a multiple of the {len(generators)} generators")
         cfg = self.unet.config
-        if cfg.in_channels != 4:
-            raise NotImplementedError("txt2img needs a 4-channel UNet (inpaint / depth UNets take extra channels)")
+        if image is None and mask_image is not None:
+            raise ValueError("Can't pass a mask without an image")
+        runway = cfg.in_channels == 9
+        if cfg.in_channels not in (4, 9):
+            raise NotImplementedError(f"in_channels={cfg.in_channels}: only the 4- and 9-channel UNets are wired up")
+        if runway and mask_image is None:
+            raise ValueError("an inpainting UNet (in_channels=9) needs image + mask_image")
+        if image is not None and self.vae is None:
+            raise ValueError("img2img / inpaint need the VAE (encode)")
 
         guided = B200GuidedUNet(self.unet, negative_prompt_embeds, prompt_embeds, guidance_scale)
         sched = build_scheduler(sampler, generators, self.device, latents_dtype, callback, callback_steps)
         sched.set_eps_unets([guided])
+        ts_args = {"strength": min(strength, 1.0)} if image is not None else {}
         sched.set_timesteps(num_inference_steps, prediction_type=cfg.prediction_type,
-                            config=scheduler_config or SchedulerConfig())
-        latents = generate_latents(generators, B, cfg.in_channels, height, width, self.get_unet_sample_size(self.unet),
-                                   self.device, latents_dtype)
-        latents = sched.prepare_initial_latents(latents)
+                            config=scheduler_config or SchedulerConfig(), **ts_args)
+        if image is None:
+            latents = generate_latents(generators, B, 4, height, width, self.get_unet_sample_size(self.unet),
+                                       self.device, latents_dtype)
+            latents = sched.prepare_initial_latents(latents)
+        else:
+            if tuple(image.shape[-2:]) != (height, width):
+                raise ValueError(f"image is {tuple(image.shape[-2:])}, expected ({height}, {width})")
+            common = dict(pipeline=self, scheduler=sched, generators=generators, image=image,
+                          latents_dtype=latents_dtype, batch_total=B)
+            if mask_image is None:
+                mode = Img2imgMode(strength=strength, **common)
+            elif runway:
+                mode = EnhancedRunwayInpaintMode(mask_image=mask_image, strength=strength, **common)
+            else:
+                if not isinstance(sched, KDiffusionScheduler):
+                    raise NotImplementedError("legacy (4-channel) inpainting is wired for the k-diffusion samplers")
+                mode = EnhancedInpaintMode(mask_image=mask_image, strength=strength, **common)
+            latents = mode.generate_latents()
+            guided.set_extra_channels(mode.unet_extra_channels())
+            blend = mode.x0_blend()
+            if blend is not None:
+                sched.set_x0_blend(*blend)
         latents = sched.loop(latents, progress_wrapper, out_dtype=torch.float32 if return_fp32_latents else None)
         if output_type == "latent" or self.vae is None:
             return PipelineOutput(images=None, latents=latents)

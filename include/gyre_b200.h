@@ -195,6 +195,22 @@ int gyre_b200_denoise(const float* x, const void* model_out, int cfg, float guid
                       int batch, int64_t per_sample, float* denoised, gyre_b200_stream stream);
 int gyre_b200_lincomb(int n_terms, const float* const* inputs_host, const float* coefs_host, int batch,
                       int64_t per_sample, float* out, void* x_in_next, float c_in, int dup, gyre_b200_stream stream);
+/* Legacy (4-channel UNet) inpainting: EnhancedInpaintMode.wrap_k_unet / _blend
+ * (gyre/pipeline/unified_pipeline.py:620-636) replaces the predicted x0 by the original image latents
+ * wherever blend_mask > u (u = progress in [0, 1), common_scheduler.py:358-389).  Same as the functions
+ * above with that substitution applied to `denoised` before the update. */
+int gyre_b200_denoise_blend(const float* x, const void* model_out, int cfg, float guidance, float c_skip, float c_out,
+                            int batch, int64_t per_sample, float* denoised, const float* blend_orig,
+                            const float* blend_mask, float blend_u, gyre_b200_stream stream);
+int gyre_b200_sched_step_blend(const gyre_b200_step* s, const float* x, const void* model_out, const float* noise,
+                               float* x_out, float* denoised_out, void* x_in_next, int batch, int64_t per_sample,
+                               const float* blend_orig, const float* blend_mask, float blend_u,
+                               gyre_b200_stream stream);
+/* UNet input of the inpaint (9-channel) / depth (5-channel) models: out[b] = cat([x[b], extra[b % extra_batch]], dim=1),
+ * NCHW fp16 (EnhancedRunwayInpaintMode.wrap_unet, unified_pipeline.py:668-690; UnetWithExtraChannels,
+ * gyre/pipeline/unet/core.py:21-37).  The extra channels are not scaled by c_in. */
+int gyre_b200_cat_channels(const void* x, int channels, const void* extra, int extra_channels, int extra_batch, int batch,
+                           int64_t hw, void* out, gyre_b200_stream stream);
 /* out_f16[(dup?2:1) * B, ...] = x * c_in  (first unet input of a run) */
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream);

@@ -470,6 +470,128 @@ def txt2img_latents(eps_unet_cfg, *, batch, in_channels, height, width, sample_s
     raise ValueError(sampler)
 
 
+# ----------------------------------------------------------------------------- img2img / inpaint modes
+
+def _downscale_boxop_2d(inp, scale=8, op="max"):
+    """unified_pipeline.py:335-343."""
+    def one(t):
+        shape = t.shape[:-1] + (t.shape[-1] // scale, scale)
+        return getattr(t.reshape(shape), op)(dim=-1).values
+    return one(one(inp).transpose(-2, -1)).transpose(-2, -1)
+
+
+def _round_mask(mask, threshold):
+    mask = mask.clone()
+    mask[mask >= threshold] = 1
+    mask[mask < 1] = 0
+    return mask
+
+
+def image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image, mask_image=None, seeds, steps,
+                       strength, sampler="euler_a", latent_dtype=torch.float32, prediction_type="epsilon", eta=None):
+    """Img2imgMode / EnhancedInpaintMode / EnhancedRunwayInpaintMode + KDiffusionScheduler on the CPU
+    (unified_pipeline.py:240-337, 400-696; common_scheduler.py:430-623), k-diffusion samplers only.
+    `unet.cfg.in_channels == 9` selects the Runway path (mask + masked-image latents appended to the UNet input,
+    un-scaled); a mask with a 4-channel UNet selects the legacy x0 blend."""
+    import numpy as np
+    generators = [torch.Generator(device="cpu").manual_seed(s) for s in seeds]
+    B = len(seeds)
+    acp = sd_alphas_cumprod()
+    img = image if image.ndim == 4 else image[None]
+    img = 2.0 * img[:, [0, 1, 2]] - 1.0
+
+    def to_latents(im, mask=None):
+        if mask is not None:
+            im = im * (mask > 0.5)
+        dist = vae.encode(im).latent_dist
+        return 0.18215 * torch.cat([dist.sample(generator=g) for g in generators], dim=0).to(latent_dtype)
+
+    runway = getattr(unet, "config", None) is not None and unet.config.in_channels == 9
+    fill = False
+    sns = 1.0
+    if mask_image is not None:
+        fill = strength >= 1.0
+        sns = min(2 - strength, 1)
+        strength = min(strength, 1)
+        m = mask_image if mask_image.ndim == 4 else mask_image[None]
+        mask = (1 - m[:, [0]]).to(latent_dtype)
+        init_orig = to_latents(img, _round_mask(mask, 0.001))
+        latent_mask = torch.cat([_downscale_boxop_2d(mask, 8, "min")[:, [0, 0, 0, 0]]] * B)
+        high = _round_mask(latent_mask, 0.001)
+
+    # schedule (set_timesteps with strength, common_scheduler.py:516-538)
+    den_probe = EpsDenoiser(None, acp)
+    sigmas_full = k_sigmas(den_probe, steps)
+    init_timestep = min(int(steps * strength), steps)
+    start_offset = max(steps - init_timestep, 0)
+    start_t = den_probe.sigma_to_t(sigmas_full[start_offset])
+
+    init = to_latents(img)
+    if mask_image is not None and fill:
+        masked = init * high
+        batch_noise = []
+        for g, split in zip(generators, masked.split(1)):
+            npseed = torch.randint(low=0, high=torch.iinfo(torch.int32).max, size=[1], generator=g, device=g.device,
+                                   dtype=torch.int32).cpu()
+            npgen = np.random.default_rng(npseed.numpy())
+            keep = high[[0], [0]].ge(0.5)
+            chans = []
+            for ch in split.split(1, dim=1):
+                good = ch.masked_select(keep)
+                chans.append(torch.from_numpy(npgen.choice(good.float().numpy(), tuple(ch.shape))).to(split.dtype))
+            nz = torch.zeros_like(split).normal_(generator=g)
+            batch_noise.append(nz * (1 - sns) + torch.cat(chans, dim=1) * sns)
+        init = init * latent_mask + torch.cat(batch_noise, dim=0) * (1 - latent_mask)
+    image_noise = batched_randn(init.shape, generators, "cpu", latent_dtype)
+    sigma_start = den_probe.t_to_sigma(start_t)
+    latents = (init + image_noise * sigma_start).to(latent_dtype)
+
+    # eps model with CFG (+ the Runway extra channels)
+    emb = torch.cat([uncond_emb, cond_emb])
+    if runway:
+        extra = torch.cat([1 - high[:, [0]], init_orig], dim=1)
+
+    def eps_cfg(x, t):
+        x2 = torch.cat([x, x])
+        if runway:
+            x2 = torch.cat([x2, torch.cat([extra, extra]).to(x2.dtype)], dim=1)
+        t2 = torch.cat([t, t]) if (torch.is_tensor(t) and t.shape) else t
+        out = unet(x2, t2, encoder_hidden_states=emb).sample
+        u, g = out.chunk(2)
+        return u + guidance_scale * (g - u)
+
+    den = (VDenoiser if prediction_type == "v_prediction" else EpsDenoiser)(eps_cfg, acp)
+    sigmas = sigmas_full[start_offset:].to(latent_dtype).float()
+    n = len(sigmas) - 1
+    state = {"i": 0}
+    model = den
+    if mask_image is not None and not runway:
+        u_off = start_offset / len(sigmas_full)
+
+        def model(x, sigma):                                   # wrap_k_unet + KDiffusionPositionTracker.get_u
+            u = max(min(u_off + (1 - u_off) * state["i"] / n, 0.999), 0)
+            px0 = den(x, sigma)
+            keep_orig = latent_mask.gt(u).to(px0.dtype)
+            return init_orig.to(px0.dtype) * keep_orig + px0 * (1 - keep_orig)
+    latents = latents.float()
+    shape = tuple(latents.shape)
+    noise = lambda *_: batched_randn(shape, generators, "cpu", latent_dtype).float()
+    if sampler != "euler_a":
+        raise ValueError("image_mode_latents restates the Euler-ancestral loop only")
+    x = latents
+    s_in = x.new_ones([x.shape[0]])
+    e = 1.0 if eta is None else eta
+    for i in range(n):                                         # sample_euler_ancestral with the step index exposed
+        state["i"] = i
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=e)
+        d = to_d(x, sigmas[i], denoised)
+        x = x + d * (sigma_down - sigmas[i])
+        if sigmas[i + 1] > 0:
+            x = x + noise() * sigma_up
+    return x
+
+
 def decode_image(vae, latents, scaling=0.18215):
     """unified_pipeline.py:2488-2491."""
     img = vae.decode(1 / scaling * latents).sample

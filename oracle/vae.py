@@ -189,3 +189,24 @@ class OracleVAE:
     def decode(self, z):
         with torch.no_grad():
             return self._Out(vae_decode(self.params, self.config, z))
+
+    class _Dist:
+        """diffusers-0.16 DiagonalGaussianDistribution: logvar clamped to [-30, 20],
+        sample = mean + std * randn(generator) drawn on the generator's device."""
+
+        def __init__(self, moments):
+            self.mean, logvar = moments.chunk(2, dim=1)
+            self.std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
+
+        def sample(self, generator=None):
+            dev = generator.device if generator is not None else self.mean.device
+            noise = torch.randn(self.mean.shape, generator=generator, device=dev, dtype=self.mean.dtype)
+            return self.mean + self.std * noise.to(self.mean.device)
+
+    class _Enc:
+        def __init__(self, dist):
+            self.latent_dist = dist
+
+    def encode(self, x):
+        with torch.no_grad():
+            return self._Enc(self._Dist(vae_encode_moments(self.params, self.config, x)))

@@ -248,3 +248,73 @@ def test_c2_sd15_euler_a_50_final_latents_vs_oracle():
           f"of the oracle differs by {floor:.4e} (noise floor); latent max {scale:.3f}")
     assert torch.isfinite(out.latents).all()
     assert err < max(4 * floor, 5e-2 * scale)
+
+
+@pytest.mark.parametrize("kind", ["img2img", "runway_inpaint", "runway_inpaint_strength1", "legacy_inpaint"])
+def test_image_modes_vs_oracle(kind):
+    """img2img / inpaint modes (VAE encode -> posterior sample -> start-timestep noise -> loop; the 9-channel UNet's
+    extra input channels; the legacy x0 blend) against the oracle's restatement of the reference modes on the CPU."""
+    from oracle import sampling as osamp
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_param_shapes
+    from oracle.vae import OracleVAE, VAEConfig, vae_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    from gyre_b200.vae import B200VAE
+    runway = kind.startswith("runway")
+    cfg = UNetConfig.tiny(in_channels=9) if runway else UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    vcfg = VAEConfig.tiny()
+    VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+    pipe = B200Pipeline(B200UNet(cfg).load_state_dict(P), B200VAE(vcfg).load_state_dict(VP))
+    pipe.unet_sample_size_override = 16
+    g = torch.Generator().manual_seed(21)
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).expand(2, -1, -1).contiguous()
+    image = torch.rand(1, 3, 128, 128, generator=g)
+    mask = torch.zeros(1, 1, 128, 128)
+    mask[:, :, 32:96, 40:104] = 1.0                     # white = repaint
+    strength = {"img2img": 0.6, "runway_inpaint": 0.75, "runway_inpaint_strength1": 1.0, "legacy_inpaint": 0.8}[kind]
+    seeds = [420420420, 420420421]
+    steps = 10
+    kw = {} if kind == "img2img" else {"mask_image": mask.cuda()}
+    out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
+               output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True, image=image.cuda(),
+               strength=strength, **kw)
+    ref = osamp.image_mode_latents(OracleUNet(cfg, P), OracleVAE(vcfg, VP), unc, emb, 7.5, image=image,
+                                   mask_image=None if kind == "img2img" else mask, seeds=seeds, steps=steps,
+                                   strength=strength)
+    err = (out.latents.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"{kind}: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
+    assert err < 2e-2 * scale
+
+
+def test_c4_shape_vprediction_linear_proj_tome():
+    """Config 4 in miniature: SD2.1-style UNet (linear projections, v-prediction through DiscreteVDDPMDenoiser
+    scalings, head dim 64) with ToMe K/V merging set through `set_options({"tome": r})`, 12 Euler-a steps."""
+    from oracle import sampling as osamp
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny(use_linear_projection=True, prediction_type="v_prediction", num_heads=(1, 2, 4, 4))
+    P = synth_params(unet_param_shapes(cfg), seed=77)
+    pipe = B200Pipeline(B200UNet(cfg).load_state_dict(P), None)
+    pipe.unet_sample_size_override = 16
+    pipe.set_options({"tome": 40})
+    g = torch.Generator().manual_seed(5)
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).expand(2, -1, -1).contiguous()
+    seeds = [420420420, 420420421]
+    out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=12, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
+               output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True)
+    ounet = OracleUNet(cfg, P)
+    ounet.r = 40
+    ref = osamp.txt2img_latents(osamp.CFGParallel(ounet, unc, emb, 7.5), batch=2, in_channels=4, height=128, width=128,
+                                sample_size=16, seeds=seeds, steps=12, sampler="euler_a", prediction_type="v_prediction")
+    err = (out.latents.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"C4-mini v-pred + ToMe: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
+    # ToMe's argsort can flip near-ties under fp16 scores; the bound allows for a few flipped merges
+    assert err < 5e-2 * scale
