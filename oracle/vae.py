@@ -182,9 +182,10 @@ class OracleVAE:
         def __init__(self, sample):
             self.sample = sample
 
-    def __init__(self, cfg: VAEConfig, params: dict):
+    def __init__(self, cfg: VAEConfig, params: dict, sample_dtype=None):
         self.config = cfg
         self.params = params
+        self.sample_dtype = sample_dtype
 
     def decode(self, z):
         with torch.no_grad():
@@ -194,14 +195,17 @@ class OracleVAE:
         """diffusers-0.16 DiagonalGaussianDistribution: logvar clamped to [-30, 20],
         sample = mean + std * randn(generator) drawn on the generator's device."""
 
-        def __init__(self, moments):
+        def __init__(self, moments, sample_dtype=None):
             self.mean, logvar = moments.chunk(2, dim=1)
             self.std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
+            # the draw happens in the VAE's dtype (fp16 on the GPU path, unified_pipeline.py:305-313): a
+            # torch.randn in fp16 is a different stream from one in fp32, so the dtype is part of the seed contract
+            self.sample_dtype = sample_dtype or self.mean.dtype
 
         def sample(self, generator=None):
             dev = generator.device if generator is not None else self.mean.device
-            noise = torch.randn(self.mean.shape, generator=generator, device=dev, dtype=self.mean.dtype)
-            return self.mean + self.std * noise.to(self.mean.device)
+            noise = torch.randn(self.mean.shape, generator=generator, device=dev, dtype=self.sample_dtype)
+            return self.mean + self.std * noise.to(self.mean.device).to(self.mean.dtype)
 
     class _Enc:
         def __init__(self, dist):
@@ -209,4 +213,4 @@ class OracleVAE:
 
     def encode(self, x):
         with torch.no_grad():
-            return self._Enc(self._Dist(vae_encode_moments(self.params, self.config, x)))
+            return self._Enc(self._Dist(vae_encode_moments(self.params, self.config, x), self.sample_dtype))

@@ -281,7 +281,8 @@ def test_image_modes_vs_oracle(kind):
                generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
                output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True, image=image.cuda(),
                strength=strength, **kw)
-    ref = osamp.image_mode_latents(OracleUNet(cfg, P), OracleVAE(vcfg, VP), unc, emb, 7.5, image=image,
+    ref = osamp.image_mode_latents(OracleUNet(cfg, P), OracleVAE(vcfg, VP, sample_dtype=torch.float16), unc, emb, 7.5,
+                                   image=image,
                                    mask_image=None if kind == "img2img" else mask, seeds=seeds, steps=steps,
                                    strength=strength)
     err = (out.latents.cpu() - ref).abs().max().item()
