@@ -275,8 +275,19 @@ def main():
         tc = {k: v for k, v in families.items() if v["flops"] > 0 and v["ms"] > 0}
         dom = max(tc, key=lambda k: tc[k]["ms"])
         ach = tc[dom]["flops"] / (tc[dom]["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if dom in tj:
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this family from the committed ncu launch
+                # list of the same workload (scripts/gpu_profile.sh), weighted like one step (50 forwards + 1 decode)
+                traffic = tj[dom]["dram_bytes_per_launch"]
+                traffic_src = "profiles/r01_traffic.json (ncu, cold L2 per launch)"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tflops_sustained"], "traffic": None, "peak_source": peaks["source"] +
+                    "frac": ach / peaks["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": tc[dom]["bytes"] / tc[dom]["count"],
+                    "peak_source": peaks["source"] +
                     ", sustained figure (kernel timed inside a long step)",
                     "launches": tc[dom]["count"], "avg_launch_ms": tc[dom]["ms"] / tc[dom]["count"],
                     "algorithmic_gflop_per_launch": tc[dom]["flops"] / tc[dom]["count"] / 1e9,
