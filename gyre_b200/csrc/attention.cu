@@ -312,7 +312,10 @@ struct Att2Cfg {
 //               on the side (no max pass in front of the exp phase, second half of the scores still in flight
 //               from TMEM); only if the tile turns out to raise the max by more than 2^8 is it redone (rare)
 enum : int { AV_STAGGER = 1, AV_PACKED = 2, AV_POLY25 = 4, AV_POLY50 = 8, AV_F16EXP = 16, AV_NOEXP = 32, AV_SPLIT = 64,
-             AV_PTMEM = 128, AV_LAZYMAX = 256 };
+             AV_PTMEM = 128, AV_LAZYMAX = 256, AV_TURNS = 512 };
+//   AV_TURNS    the two groups take turns in the exponential phase (an mbarrier hand-off each way): one group's exps
+//               run at the full MUFU rate while the other loads / maxes / hands over, instead of both sharing the
+//               MUFU and then leaving it idle together
 
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   // 2^x for x <= ~8: n = round(x) via the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-3
@@ -435,7 +438,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   uint64_t* pv_done = p_full + 2;              // [2]
   uint64_t* half_bar = pv_done + 2;            // group 0 is half way through its first exp phase
   uint64_t* s_free = half_bar + 1;             // [2] the group holds tile j's scores in registers (AV_SPLIT)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* exp_turn = s_free + 2;             // [2] group g may enter its exp phase (AV_TURNS)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(exp_turn + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -465,6 +469,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
     mbar_init(half_bar, 128);
     mbar_init(&s_free[0], 128);
     mbar_init(&s_free[1], 128);
+    mbar_init(&exp_turn[0], 128);
+    mbar_init(&exp_turn[1], 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -726,10 +732,17 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
           }
           const float mc = m_ref * c;
           float2 ls = make_float2(0.f, 0.f);
+          if constexpr ((V & AV_TURNS) != 0) {
+            // group 0 enters tile j's exps after group 1 left tile j-1's; group 1 after group 0 left tile j's
+            if (two && (g == 1 || j > 0)) mbar_wait(&exp_turn[g], (g == 1 ? j : j - 1) & 1);
+          }
           softmax_chunk32<V>(v0, c, mc, ls, prow, 0, rx, tP);
           softmax_chunk32<V>(v1, c, mc, ls, prow, 4, rx, tP + 16);
           softmax_chunk32<V>(v2, c, mc, ls, prow + kChunkBytes, 0, rx, tP + 32);
           softmax_chunk32<V>(v3, c, mc, ls, prow + kChunkBytes, 4, rx, tP + 48);
+          if constexpr ((V & AV_TURNS) != 0) {
+            if (two) mbar_arrive(&exp_turn[g ^ 1]);
+          }
           // group 1 starts its first tile when group 0 leaves its first exp phase: from then on one group's exp phase
           // falls into the other's load / max / hand-over phase instead of both sharing the MUFU and then idling it
           if (stagger && g == 0 && j == 0) mbar_arrive(half_bar);
@@ -768,6 +781,10 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
             }
           }
           const float mc = m_ref * c;
+          if constexpr ((V & AV_TURNS) != 0) {
+            if (two && (g == 1 || j > 0)) mbar_wait(&exp_turn[g], (g == 1 ? j : j - 1) & 1);
+            if (two) mbar_arrive(&exp_turn[g ^ 1]);   // short tile: hand the turn on right away
+          }
           for (int c0 = 0; c0 < n_s; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tS + c0, v);
@@ -836,6 +853,295 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------ d <= 64, 16 softmax warps
+// Same pipeline as attention2 (two 128-row query tiles per CTA, S of tile j+1 issued under tile j's exps, P kept in
+// TMEM, P V issued by its own warp) but every score tile is shared by TWO warps per TMEM lane quadrant, each taking 64
+// of its 128 columns: 16 softmax warps = 4 per SM sub-partition instead of 2.  Measured on B200 the two-warp version
+// is bound by how fast ONE warp can issue its ~4 instructions per score (issue slots half empty, MUFU half idle,
+// forcing the groups to alternate made it slower), so the cure is more warps, not less MUFU work.  The two warps of
+// a row pair exchange their partial row max / row sum through shared memory (one 64-thread named barrier per tile).
+// Scores are read from TMEM twice (max pass, exp pass) to keep the live registers under the 96 a 640-thread CTA allows.
+constexpr int kAtt4Threads = 640;   // warp 0 TMA, 1 S issuer, 2 P V issuer, 3 idle, 4..19 softmax
+
+struct Att4Cfg {
+  static constexpr int STAGES = 4;
+  static constexpr int Q_BYTES = 2 * kChunkBytes;
+  static constexpr int KV_BYTES = kChunkBytes;
+  static constexpr int XCH_BYTES = 2 /*parity*/ * 2 /*groups*/ * 2 /*halves*/ * 128 * 4;
+  static constexpr int SMEM = Q_BYTES + STAGES * 2 * KV_BYTES + 2 * XCH_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;   // S0, S1 at 0 / 128; O0, O1 at 256 / 320; P0, P1 at 384 / 448
+};
+
+template <int V>
+__global__ void __launch_bounds__(kAtt4Threads, 1) attention4_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                     const __grid_constant__ CUtensorMap tmK,
+                                                                     const __grid_constant__ CUtensorMap tmV,
+                                                                     const AttnParams p) {
+  using Cfg = Att4Cfg;
+  constexpr int VS = V | AV_PTMEM;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::STAGES * Cfg::KV_BYTES;
+  float* xmax = reinterpret_cast<float*>(sV + Cfg::STAGES * Cfg::KV_BYTES);   // [parity][group][half][128]
+  float* xsum = xmax + 2 * 2 * 2 * 128;                                       // [group][half][128] (+ unused)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + 2 * Cfg::XCH_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + Cfg::STAGES;
+  uint64_t* s_full = kv_empty + Cfg::STAGES;   // [2]
+  uint64_t* s_free = s_full + 2;               // [2] all 256 threads of the group hold / are done with the scores
+  uint64_t* p_full = s_free + 2;               // [2]
+  uint64_t* pv_done = p_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x % p.q_tiles;
+  const int bh = blockIdx.x / p.q_tiles;
+  const int h = bh % p.heads;
+  const int b = bh / p.heads;
+  const int q0 = q_pair * 2 * kBQ;
+  const bool two = q0 + kBQ < p.Nq;
+  const int ng = two ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 256);
+      mbar_init(&p_full[g], 256);
+      mbar_init(&pv_done[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, two ? Cfg::Q_BYTES : Cfg::Q_BYTES / 2);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+      if (two) tma_load_4d(sQ + kChunkBytes, &tmQ, q_full, 0, q0 + kBQ, h, b);
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int s = j % Cfg::STAGES;
+        mbar_wait(&kv_empty[s], ((j / Cfg::STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+        tma_load_4d(sK + s * Cfg::KV_BYTES, &tmK, &kv_full[s], 0, j * kBKeys, h, b);
+        tma_load_4d(sV + s * Cfg::KV_BYTES, &tmV, &kv_full[s], 0, j * kBKeys, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ S issuer
+    if (elect_one()) {
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int s = j % Cfg::STAGES;
+        const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+        const uint32_t idesc = umma_idesc_f16(kBQ, (nk_tile + 15) & ~15);
+        mbar_wait(&kv_full[s], (j / Cfg::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sK + s * Cfg::KV_BYTES);
+        for (int g = 0; g < ng; ++g) {
+          if (j > 0) {
+            mbar_wait(&s_free[g], (j - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t qa = smem_u32(sQ + g * kChunkBytes);
+          for (int ks = 0; ks < p.ksteps_qk; ++ks)
+            umma_f16_ss(tmem_base + g * 128, umma_desc_kmajor_sw128(qa + ks * 32), umma_desc_kmajor_sw128(ka + ks * 32),
+                        idesc, ks != 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ P V issuer
+    if (elect_one()) {
+      const uint32_t idesc_pv = umma_idesc_f16(kBQ, p.npv, /*b_mn_major=*/1);
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int s = j % Cfg::STAGES;
+        const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+        const int ksteps = ((nk_tile + 15) & ~15) >> 4;
+        const uint32_t va = smem_u32(sV + s * Cfg::KV_BYTES);
+        mbar_wait(&kv_full[s], (j / Cfg::STAGES) & 1);
+        for (int g = 0; g < ng; ++g) {
+          mbar_wait(&p_full[g], j & 1);
+          tc_fence_after();
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+            umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + ks * 8, db, idesc_pv,
+                        (j | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&pv_done[g]);
+        }
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax: 2 groups x 2 column halves x 4 quadrants
+    const int sw = warp - 4;
+    const int g = sw >> 3;
+    if (g < ng) {
+      const int hh = (sw >> 2) & 1;
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t tS = tmem_base + g * 128 + hh * 64 + lane_off;
+      const uint32_t tP = tmem_base + 384 + g * 64 + hh * 32 + lane_off;
+      const uint32_t tO = tmem_base + 256 + g * 64 + lane_off;
+      const int pair_bar = 1 + g * 4 + q;           // named barrier of the two warps that share these 32 rows
+      const float c = p.scale_log2;
+      float m_ref = -INFINITY;
+      float l = 0.f;
+      const int col0 = hh * 64;
+
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+        const bool ragged = nk_tile < kBKeys;
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        // ---- pass 1: max of my 64 columns, then of the row
+        float mt;
+        {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS, v);
+          tmem_ld_wait();
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i >= nk_tile) v[i] = 0xff800000u;
+          }
+          mt = max32(v);
+          tmem_ld_32x32b_x32(tS + 32, v);
+          tmem_ld_wait();
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + 32 + i >= nk_tile) v[i] = 0xff800000u;
+          }
+          mt = fmaxf(mt, max32(v));
+        }
+        float* xm = xmax + ((j & 1) * 4 + g * 2) * 128;
+        xm[hh * 128 + r] = mt;
+        named_bar_sync(pair_bar, 64);
+        mt = fmaxf(mt, xm[(hh ^ 1) * 128 + r]);
+        if (j == 0) {
+          m_ref = mt;
+        } else {
+          mbar_wait(&pv_done[g], (j - 1) & 1);   // P and O are free once P V of the previous tile retired
+          tc_fence_after();
+          // both warps of the pair see the same row maxima, so they take the same decision
+          if (__any_sync(0xffffffffu, (mt - m_ref) * c > 8.0f)) {
+            const float m_new = fmaxf(m_ref, mt);
+            const float alpha = ex2_approx((m_ref - m_new) * c);
+            m_ref = m_new;
+            l *= alpha;
+            for (int c0 = hh * 16; c0 < p.npv; c0 += 32) {   // the pair splits O's 16-column chunks
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(tO + c0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x16(tO + c0, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        // ---- pass 2: exponentials of my 64 columns -> packed fp16 P in TMEM
+        const float mc = m_ref * c;
+        float2 ls = make_float2(0.f, 0.f);
+        {
+          uint32_t v[32], w[16];
+          tmem_ld_32x32b_x32(tS, v);
+          tmem_ld_wait();
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i >= nk_tile) v[i] = 0xff800000u;
+          }
+          softmax_exp32<VS>(v, c, mc, ls, w);
+          softmax_store32<VS>(w, nullptr, 0, 0, tP);
+          tmem_ld_32x32b_x32(tS + 32, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&s_free[g]);                 // the S buffer may be overwritten by tile j+1
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + 32 + i >= nk_tile) v[i] = 0xff800000u;
+          }
+          softmax_exp32<VS>(v, c, mc, ls, w);
+          softmax_store32<VS>(w, nullptr, 0, 0, tP + 16);
+        }
+        l += ls.x + ls.y;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[g]);
+      }
+      // ---- epilogue: total row sum from both halves, then each warp normalises its share of O's columns
+      float* xs = xsum + g * 2 * 128;
+      xs[hh * 128 + r] = l;
+      named_bar_sync(pair_bar, 64);
+      const float inv = 1.0f / (l + xs[(hh ^ 1) * 128 + r]);
+      mbar_wait(&pv_done[g], (p.n_kv_tiles - 1) & 1);
+      tc_fence_after();
+      const int row = q0 + g * kBQ + r;
+      const bool valid = row < p.Nq;
+      __half* dst = p.out + (static_cast<int64_t>(b) * p.Nq + row) * p.ldo + h * p.d;
+      for (int c0 = hh * 16; c0 < p.npv; c0 += 32) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(tO + c0, o);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int gg = 0; gg < 2; ++gg) {
+            const int col = c0 + gg * 8;
+            if (col < p.d) {
+              __align__(16) __half2 hv[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                hv[i] = __floats2half2_rn(__uint_as_float(o[gg * 8 + 2 * i]) * inv,
+                                          __uint_as_float(o[gg * 8 + 2 * i + 1]) * inv);
+              *reinterpret_cast<uint4*>(dst + col) = *reinterpret_cast<uint4*>(hv);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int V>
+static int launch_attn4_v(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                          unsigned blocks, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    GYRE_CHECK_CUDA(
+        cudaFuncSetAttribute(attention4_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att4Cfg::SMEM));
+    attr_done = true;
+  }
+  return launch_kernel(attention4_kernel<V>, dim3(blocks), dim3(kAtt4Threads), Att4Cfg::SMEM, st, tq, tk, tv, p);
+}
 
 // ------------------------------------------------------------------------------------------ short key sequences
 // Cross-attention (77 text tokens) and any Nk <= 128: the whole K/V of one (batch, head) is ONE tile, so the
@@ -1091,6 +1397,12 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   const unsigned nb = static_cast<unsigned>(blocks);
   if (p.d > 64) return launch_attn2_v<AV_PTMEM | AV_PACKED | AV_POLY25, 2>(tq, tk, tv, p, nb, st);
   switch (tunable(TUNE_ATT_VARIANT)) {
+    // 1000+: the 16-softmax-warp kernel (attention4); low bits select the arithmetic of the exponentials
+    case 1000: return launch_attn4_v<0>(tq, tk, tv, p, nb, st);
+    case 1000 + AV_PACKED: return launch_attn4_v<AV_PACKED>(tq, tk, tv, p, nb, st);
+    case 1000 + (AV_PACKED | AV_POLY25): return launch_attn4_v<AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case 1000 + (AV_PACKED | AV_POLY50): return launch_attn4_v<AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
+    case 1000 + (AV_PACKED | AV_NOEXP): return launch_attn4_v<AV_PACKED | AV_NOEXP>(tq, tk, tv, p, nb, st);
     case 0: return launch_attn2_v<0>(tq, tk, tv, p, nb, st);
     case AV_STAGGER: return launch_attn2_v<AV_STAGGER>(tq, tk, tv, p, nb, st);
     case AV_STAGGER | AV_PACKED: return launch_attn2_v<AV_STAGGER | AV_PACKED>(tq, tk, tv, p, nb, st);
@@ -1119,6 +1431,14 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
     case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER:
       return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER>(tq, tk, tv, p, nb, st);
     case AV_PTMEM | AV_SPLIT | AV_NOEXP: return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_NOEXP>(tq, tk, tv, p, nb, st);
+    case AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED:
+      return launch_attn2_v<AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED>(tq, tk, tv, p, nb, st);
+    case AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
+      return launch_attn2_v<AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50:
+      return launch_attn2_v<AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
+    case AV_TURNS | AV_SPLIT | AV_PACKED | AV_POLY25:
+      return launch_attn2_v<AV_TURNS | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
     case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED:
       return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED>(tq, tk, tv, p, nb, st);
     case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
