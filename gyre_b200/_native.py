@@ -21,6 +21,7 @@ class Epilogue(C.Structure):
         ("bias", C.c_void_p), ("rowgroup_bias", C.c_void_p), ("rows_per_group", C.c_int32), ("rgb_ld", C.c_int32),
         ("residual", C.c_void_p), ("ldr", C.c_int32), ("act", C.c_int32), ("out_f32", C.c_int32),
         ("out", C.c_void_p), ("ldo", C.c_int32),
+        ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t), ("sk_flags", C.c_void_p), ("sk_flags_count", C.c_int32),
     ]
 
 
@@ -172,8 +173,22 @@ def dtype_code(t: torch.Tensor) -> int:
 # ----------------------------------------------------------------------------------------------------
 # building-block wrappers (used by the per-kernel parity tests and the attention patcher)
 
+_sk_scratch = {}
+
+
+def stream_k_scratch(device):
+    """Per-device stream-K scratch for the standalone building-block calls (a model owns its own)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _sk_scratch:
+        _sk_scratch[key] = (torch.empty((48 << 20,), device=device, dtype=torch.uint8),
+                            torch.zeros((256,), device=device, dtype=torch.int32))
+    return _sk_scratch[key]
+
+
 def _epilogue(out, bias=None, residual=None, act=0, rowgroup_bias=None, rows_per_group=1):
     e = Epilogue()
+    ws, flags = stream_k_scratch(out.device)
+    e.sk_ws, e.sk_ws_bytes, e.sk_flags, e.sk_flags_count = ptr(ws), ws.numel(), ptr(flags), flags.numel()
     e.bias = ptr(bias)
     e.rowgroup_bias = ptr(rowgroup_bias)
     e.rows_per_group = rows_per_group

@@ -25,6 +25,10 @@ int to_epilogue(const gyre_b200_epilogue* e, Epilogue* out) {
   out->out = e->out;
   out->ldo = e->ldo;
   out->out_mode = e->out_f32 ? OUT_F32 : OUT_F16;
+  out->sk_ws = e->sk_ws;
+  out->sk_ws_bytes = e->sk_ws_bytes;
+  out->sk_flags = e->sk_flags;
+  out->sk_flags_count = e->sk_flags_count;
   return 0;
 }
 }  // namespace

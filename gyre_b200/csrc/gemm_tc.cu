@@ -35,6 +35,12 @@ struct GemmParams {
   int rgb_rows;       // rows of a tile that share one rowgroup-bias vector (staged in smem); 0: per-thread loads
   int fast_gelu;      // GEGLU gate through gelu_fast instead of libdevice erff
   int mcast;          // 1: CTA pairs (cluster of 2 along M) share every B tile through TMA multicast
+  // stream-K over the tiles of the last, partial wave (sk_tiles == 0: off)
+  int sk_first;       // first tile index handled by stream-K; tiles below it are dealt round-robin as whole tiles
+  int sk_tiles;       // number of stream-K tiles (< grid size)
+  int sk_maxp;        // partial-accumulator slots per stream-K tile
+  float* sk_ws;       // [sk_tiles][sk_maxp][128][BN] fp32 partial accumulators
+  int* sk_flags;      // [sk_tiles] partials delivered (zero between launches)
   Epilogue ep;
 };
 
@@ -150,6 +156,62 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int n_workers = p.mcast ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_tiles = (p.mcast ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
 
+  // ---- work items.  Whole tiles are dealt round-robin; the tiles of the last, partial wave (p.sk_tiles of them) are
+  // cut along K instead: the sk_tiles * k_iters k-iterations are divided evenly over ALL CTAs, every CTA gets one
+  // contiguous range (at most two segments in adjacent tiles).  A segment that does not reach the end of its tile's K
+  // range dumps its fp32 accumulator to a workspace slot and raises the tile's flag; the CTA holding the last segment
+  // (the owner) waits for the flag, adds the slots in a fixed order (deterministic) and runs the normal epilogue.
+  // Segments are processed FIRST and partial-producing ones before owned ones, so no CTA ever waits on work that
+  // is queued behind another wait.
+  struct Item { int t, k0, k1, kind, aux; };          // kind 0 whole tile, 1 partial producer (aux = slot), 2 owner (aux = #partials)
+  Item sk_item[2];
+  int n_sk = 0;
+  const int n_whole = p.sk_tiles > 0 ? p.sk_first : num_tiles;
+  if (p.sk_tiles > 0) {
+    const long long W = static_cast<long long>(p.sk_tiles) * p.k_iters;
+    const long long G = n_workers;
+    const long long it0 = worker * W / G, it1 = (worker + 1) * W / G;
+    auto make = [&](long long a, long long b) {          // iterations [a, b) inside one tile
+      Item it;
+      const int tt = static_cast<int>(a / p.k_iters);
+      it.t = p.sk_first + tt;
+      it.k0 = static_cast<int>(a - static_cast<long long>(tt) * p.k_iters);
+      it.k1 = static_cast<int>(b - static_cast<long long>(tt) * p.k_iters);
+      int cf = worker;                                    // first CTA whose range reaches into this tile
+      while (cf > 0 && cf * W / G > static_cast<long long>(tt) * p.k_iters) --cf;
+      it.aux = worker - cf;
+      it.kind = it.k1 < p.k_iters ? 1 : (it.k0 > 0 ? 2 : 0);
+      return it;
+    };
+    if (it1 > it0) {
+      const long long endA = min(it1, (it0 / p.k_iters + 1) * static_cast<long long>(p.k_iters));
+      const Item a = make(it0, endA);
+      if (it1 > endA) {
+        const Item b2 = make(endA, it1);
+        // the segment that produces a partial goes first
+        if (b2.kind == 1) { sk_item[0] = b2; sk_item[1] = a; } else { sk_item[0] = a; sk_item[1] = b2; }
+        n_sk = 2;
+      } else {
+        sk_item[0] = a;
+        n_sk = 1;
+      }
+    }
+  }
+  auto get_item = [&](int idx, Item& it) -> bool {
+    if (idx < n_sk) {
+      it = sk_item[idx];
+      return true;
+    }
+    const int t = worker + (idx - n_sk) * n_workers;
+    if (t >= n_whole) return false;
+    it.t = t;
+    it.k0 = 0;
+    it.k1 = p.k_iters;
+    it.kind = 0;
+    it.aux = 0;
+    return true;
+  };
+
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmA2);
@@ -182,7 +244,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t g = 0;   // k-iterations issued so far (ring position)
-      for (int t = worker; t < num_tiles; t += n_workers) {
+      Item wi;
+      for (int idx = 0; get_item(idx, wi); ++idx) {
+        const int t = wi.t;
         const int n_tile = t % p.n_tiles;
         const int m_tile = p.mcast ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
         int x0 = 0, y0 = 0, n0 = 0;
@@ -191,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.tile_h;
           n0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tile_n;
         }
-        for (int it = 0; it < p.k_iters; ++it, ++g) {
+        for (int it = wi.k0; it < wi.k1; ++it, ++g) {
           const int s = g % Cfg::STAGES;
           const uint32_t ph = (g / Cfg::STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -227,13 +291,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
       uint32_t g = 0;
       uint32_t lt = 0;   // local tile counter
-      for (int t = worker; t < num_tiles; t += n_workers, ++lt) {
+      Item wi;
+      for (int idx = 0; get_item(idx, wi); ++idx, ++lt) {
         const uint32_t buf = lt & 1;
         const uint32_t use = lt >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this buffer's previous tile
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * Cfg::BUF_COLS;
-        for (int it = 0; it < p.k_iters; ++it, ++g) {
+        for (int it = wi.k0; it < wi.k1; ++it, ++g) {
           const int s = g % Cfg::STAGES;
           const uint32_t ph = (g / Cfg::STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -242,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + s * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > wi.k0 || k != 0) ? 1u : 0u);
           // frees the smem slot when these MMAs retire (pair mode: in both CTAs - the peer refills half of it)
           if (p.mcast) umma_commit_mcast(&empty_bar[s], 3);
           else umma_commit(&empty_bar[s]);
@@ -284,11 +349,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       return v;
     };
     float nb0 = 0.f, nb1 = 0.f;
-    if (worker < num_tiles) {
-      nb0 = bias_of(worker, etid);
-      nb1 = bias_of(worker, etid + kEpiThreads);
+    Item wi, wnext;
+    bool have = get_item(0, wi);
+    if (have) {
+      nb0 = bias_of(wi.t, etid);
+      nb1 = bias_of(wi.t, etid + kEpiThreads);
     }
-    for (int t = worker; t < num_tiles; t += n_workers, ++lt) {
+    for (int idx = 0; have; ++idx, ++lt) {
+      const bool have_next = get_item(idx + 1, wnext);
+      const int t = wi.t;
       const int n_tile = t % p.n_tiles;
       const int m_tile = p.mcast ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
       int x0 = 0, y0 = 0, n0 = 0;
@@ -319,12 +388,68 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       float* sb = sbias + buf * (kMaxBiasGroups * BN);
       if (etid < nbias) sb[etid] = nb0;
       if (etid + kEpiThreads < nbias) sb[etid + kEpiThreads] = nb1;
-      if (t + n_workers < num_tiles) {
-        nb0 = bias_of(t + n_workers, etid);
-        nb1 = bias_of(t + n_workers, etid + kEpiThreads);
+      if (have_next) {
+        nb0 = bias_of(wnext.t, etid);
+        nb1 = bias_of(wnext.t, etid + kEpiThreads);
       }
       const float* sbr = sb + (p.rgb_rows > 0 ? (r / p.rgb_rows) * BN : 0);
       const uint32_t lane_addr = tmem_base + buf * Cfg::BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
+
+      // ---- stream-K bookkeeping of this item
+      const int sk_tt = wi.t - p.sk_first;                    // index among the stream-K tiles (kind != 0 only)
+      const float* sk_part = nullptr;                         // owner: slot 0 of this tile's partial accumulators
+      if (wi.kind == 1) {
+        // partial producer: dump the raw fp32 accumulator (all BN columns of my row) and raise the tile's flag
+        float* dst = p.sk_ws + ((static_cast<size_t>(sk_tt) * p.sk_maxp + wi.aux) * kBM + r) * BN;
+        named_bar_sync(1, kEpiThreads);
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
+        for (int sl = half; sl < BN / 32; sl += 2) {
+          uint32_t ra[32];
+          tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<uint4*>(dst + sl * 32 + u * 4) = make_uint4(ra[4 * u], ra[4 * u + 1], ra[4 * u + 2], ra[4 * u + 3]);
+        }
+        __threadfence();
+        named_bar_sync(1, kEpiThreads);
+        if (etid == 0) atomicAdd(p.sk_flags + sk_tt, 1);
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
+        wi = wnext;
+        have = have_next;
+        continue;
+      }
+      if (wi.kind == 2) {
+        // owner: the earlier segments of this tile were queued before anything their CTAs could wait on
+        if (etid == 0) {
+          const volatile int* f = p.sk_flags + sk_tt;
+          uint32_t spins = 0;
+          while (*f < wi.aux) {
+            if (++spins > (1u << 27)) {
+              printf("gyre_b200: stream-K flag timeout block %d tile %d\n", blockIdx.x, wi.t);
+              __trap();
+            }
+          }
+          __threadfence();
+        }
+        sk_part = p.sk_ws + ((static_cast<size_t>(sk_tt) * p.sk_maxp) * kBM + r) * BN;
+      }
+      // adds the partial accumulators of this row, columns [c, c + 32), in slot order
+      auto add_partials = [&](uint32_t (&acc)[32], int c) {
+        for (int s2 = 0; s2 < wi.aux; ++s2) {
+          const float* src = sk_part + static_cast<size_t>(s2) * kBM * BN + c;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + u * 4));
+            acc[4 * u] = __float_as_uint(__uint_as_float(acc[4 * u]) + v4.x);
+            acc[4 * u + 1] = __float_as_uint(__uint_as_float(acc[4 * u + 1]) + v4.y);
+            acc[4 * u + 2] = __float_as_uint(__uint_as_float(acc[4 * u + 2]) + v4.z);
+            acc[4 * u + 3] = __float_as_uint(__uint_as_float(acc[4 * u + 3]) + v4.w);
+          }
+        }
+      };
 
       if (p.tma_epi) {
         // ================================================= fast path: smem slices + TMA
@@ -356,6 +481,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
             tmem_ld_32x32b_x32(lane_addr + BN / 2 + sl * 32, rg);
             tmem_ld_wait();
+            if (sk_part) {
+              add_partials(ra, sl * 32);
+              add_partials(rg, BN / 2 + sl * 32);
+            }
             if (p.fast_gelu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -375,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             uint32_t ra[32];
             tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
             tmem_ld_wait();
+            if (sk_part) add_partials(ra, sl * 32);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
             if (ep.act == ACT_SILU) {
@@ -478,8 +608,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           ep.rowmax_idx[o] = best_idx;
         }
       }
+      if (wi.kind == 2 && etid == 0) p.sk_flags[sk_tt] = 0;   // zero again for the next launch
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
+      wi = wnext;
+      have = have_next;
     }
     if (leader) tma_store_wait_all();   // smem must outlive the last bulk stores
   }
@@ -556,6 +689,37 @@ static int want_pair_mode(int bn, long long m_tiles, int* mcast) {
   return 0;
 }
 
+// Stream-K over the last, partial wave: worth it when the wave is far from full and K is long enough to cut.
+static void plan_stream_k(GemmParams* p, int bn) {
+  p->sk_tiles = 0;
+  p->sk_first = 0;
+  p->sk_maxp = 0;
+  p->sk_ws = nullptr;
+  p->sk_flags = nullptr;
+  const Epilogue& ep = p->ep;
+  if (!tunable(TUNE_STREAMK) || p->mcast || !p->tma_epi || ep.sk_ws == nullptr || ep.sk_flags == nullptr) return;
+  if (ep.act == ACT_ROWMAX || p->k_iters < 8) return;
+  const long long T = static_cast<long long>(p->m_tiles) * p->n_tiles;
+  const int G = sm_count();
+  const long long full_waves = T / G;
+  const int R = static_cast<int>(T % G);
+  if (R == 0) return;
+  // time in tile units: ceil(T/G) without, T/G with; require >= 6 % gain
+  const double without = static_cast<double>(full_waves + 1), with = static_cast<double>(T) / G;
+  if ((without - with) / without < 0.06) return;
+  const long long W = static_cast<long long>(R) * p->k_iters;
+  const long long per = W / G;
+  if (per < 4) return;                                   // segments too short to be worth a hand-off
+  const int maxp = static_cast<int>(p->k_iters / per) + 2;
+  const size_t need = static_cast<size_t>(R) * maxp * kBM * bn * sizeof(float);
+  if (need > ep.sk_ws_bytes || R > ep.sk_flags_count) return;
+  p->sk_tiles = R;
+  p->sk_first = static_cast<int>(T - R);
+  p->sk_maxp = maxp;
+  p->sk_ws = static_cast<float*>(ep.sk_ws);
+  p->sk_flags = ep.sk_flags;
+}
+
 template <int BN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                   const CUtensorMap& tmRes, const GemmParams& p, cudaStream_t st) {
@@ -577,7 +741,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   }
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   GYRE_REQUIRE(tiles > 0 && tiles < (1ll << 31), "gemm: bad tile count %lld", tiles);
-  const unsigned blocks = static_cast<unsigned>(tiles < sms ? tiles : sms);
+  // stream-K needs every CTA resident at once (owners spin on flags other CTAs raise): one CTA per SM, whole device
+  const unsigned blocks = p.sk_tiles > 0 ? static_cast<unsigned>(sms) : static_cast<unsigned>(tiles < sms ? tiles : sms);
   // the implicit-GEMM convolution is its own instantiation (no run-time branches in the producer / epilogue, and a
   // distinct kernel name in profiles)
   if (p.conv)
@@ -707,6 +872,7 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
       GYRE_TRY(encode_tmap_f16_sw(&tmRes, ep.residual, 2, dims, sr, box, es, 64));
     }
   }
+  plan_stream_k(&p, bn);
   prof::Scope ps(prof::F_GEMM, 2.0 * M * static_cast<double>(N) * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K +
                         static_cast<double>(M) * n_out * (ep.residual ? 2 : 1)),
@@ -829,6 +995,7 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
       GYRE_TRY(encode_tmap_f16_sw(&tmRes, ep.residual, 4, dims, sr, box, es, 64));
     }
   }
+  plan_stream_k(&p, bn);
   prof::Scope ps(prof::F_CONV, gm.algo_flops, gm.algo_bytes, st);
   return dispatch(bn, tmA, tmA, tmB, tmOut, tmRes, p, st);
 }

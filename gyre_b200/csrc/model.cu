@@ -52,7 +52,15 @@ void* Exec::alloc_s(size_t bytes) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------ Model base
-Model::Model() { cudaGetDevice(&device_); }
+constexpr size_t kStreamKBytes = 48u << 20;
+constexpr int kStreamKFlags = 256;
+
+Model::Model() {
+  cudaGetDevice(&device_);
+  sk_ws_ = dalloc(kStreamKBytes);
+  sk_flags_ = static_cast<int*>(dalloc(kStreamKFlags * sizeof(int)));   // dalloc zero-fills
+  sk_ws_bytes_ = sk_ws_ ? kStreamKBytes : 0;
+}
 
 Model::~Model() {
   for (void* p : allocs_) cudaFree(p);
@@ -223,9 +231,12 @@ int Model::finalize() {
 template <typename T>
 static inline T* off(T* p, size_t n) { return p ? p + n : nullptr; }
 
-static Epilogue ep_out(__half* out, int ldo, const float* bias = nullptr, const __half* residual = nullptr,
-                       int ldr = 0, int act = ACT_NONE) {
+Epilogue Model::ep_out(__half* out, int ldo, const float* bias, const __half* residual, int ldr, int act) const {
   Epilogue e;
+  e.sk_ws = sk_ws_;
+  e.sk_ws_bytes = sk_ws_bytes_;
+  e.sk_flags = sk_flags_;
+  e.sk_flags_count = sk_flags_ ? kStreamKFlags : 0;
   e.out = out;
   e.ldo = ldo;
   e.bias = bias;

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/gyre_b200.h"
+#include "ops.h"
 
 namespace gyre {
 
@@ -98,6 +99,9 @@ class Model {
   int resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __half* x2, int C2, int B, int H, int W,
              float eps, const __half* temb_all, int temb_ld, __half* out);
   int ensure_device();
+  // epilogue descriptor carrying this model's stream-K scratch
+  Epilogue ep_out(__half* out, int ldo, const float* bias = nullptr, const __half* residual = nullptr, int ldr = 0,
+                  int act = 0) const;
 
   std::unordered_map<std::string, ParamSlot> slots_;
   std::vector<void*> allocs_;
@@ -108,6 +112,10 @@ class Model {
   LinW temb_proj_;
   int temb_total_ = 0;
   int temb_dim_ = 0;
+  // stream-K scratch shared by all GEMM / conv launches of this model (they are serialised on one stream)
+  void* sk_ws_ = nullptr;
+  size_t sk_ws_bytes_ = 0;
+  int* sk_flags_ = nullptr;
 };
 
 class UNetModel : public Model {

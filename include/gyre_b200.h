@@ -241,6 +241,14 @@ typedef struct gyre_b200_epilogue {
   int32_t out_f32;            /* 1: out is fp32                                                      */
   void* out;                  /* [rows, ldo]                                                         */
   int32_t ldo;
+  /* optional stream-K scratch (NULL: whole tiles only).  When the last wave of 128 x BN tiles would leave most
+   * SMs idle, its tiles are cut along K across ALL SMs; partial fp32 accumulators travel through sk_ws and are
+   * summed in a fixed order (deterministic).  sk_flags: >= 148 int32, zero before the first use (the kernel
+   * leaves them zero); both may be shared by every launch on one stream. */
+  void* sk_ws;
+  size_t sk_ws_bytes;
+  int32_t* sk_flags;
+  int32_t sk_flags_count;
 } gyre_b200_epilogue;
 
 /* out = epilogue([A | A2] @ W^T): A [M, K1] pitch lda, A2 [M, K2] pitch lda2 (may be NULL/0),

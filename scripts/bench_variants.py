@@ -152,6 +152,28 @@ if "mcast" in what:
             rec("mcast", f"conv {B}x{H}x{H} {cin}->{cout} mcast={mc}", us, 2.0 * 9 * cin * cout * B * H * H)
         del x
 
+if "streamk" in what:
+    for (M, Nn, K) in ((4096, 1280, 1280), (16384, 640, 640), (16384, 640, 2560), (4096, 1280, 5120), (4096, 3840, 1280),
+                       (65536, 320, 320)):
+        a = [torch.randn(M, K, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(Nn, K, device=dev).half() * (1 / math.sqrt(K))
+        bias = torch.randn(Nn, device=dev)
+        r = [torch.randn(M, Nn, device=dev).half() for _ in range(ROT)]
+        for sk in (0, 1):
+            us = with_tunable("STREAMK", sk, lambda: graph_time(lambda i: N.gemm(a[i % ROT], w, bias=bias, residual=r[i % ROT])))
+            rec("streamk", f"gemm M{M} N{Nn} K{K} +res streamk={sk}", us, 2.0 * M * Nn * K)
+        del a, r
+    for (B, H, cin, cout) in ((16, 8, 1280, 1280), (16, 8, 2560, 1280), (16, 16, 1280, 1280), (16, 32, 640, 640),
+                              (16, 16, 2560, 1280), (16, 32, 1920, 640), (16, 64, 320, 320)):
+        x = [torch.randn(B, H, H, cin, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(cout, cin, 3, 3, device=dev).half() * (1 / math.sqrt(9 * cin))
+        wp = N.pack_conv3x3(w)
+        bias = torch.randn(cout, device=dev)
+        for sk in (0, 1):
+            us = with_tunable("STREAMK", sk, lambda: graph_time(lambda i: N.conv3x3(x[i % ROT], wp, cout, bias=bias)))
+            rec("streamk", f"conv {B}x{H}x{H} {cin}->{cout} streamk={sk}", us, 2.0 * 9 * cin * cout * B * H * H)
+        del x
+
 if "copy" in what:
     # calibration: what a plain device copy / reduction achieves at these (small) sizes
     for mb in (21, 42, 126, 537):

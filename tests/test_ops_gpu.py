@@ -63,6 +63,51 @@ def test_gemm_pair_mode_bit_identical(nat, M, N, K):
     assert_close(o1, a.float() @ w.float().t() + bias + res.float(), 2e-3, 2e-3, "gemm pair mode")
 
 
+@pytest.mark.parametrize("M,N,K,res", [(4096, 1280, 1280, True), (16384, 640, 2560, True), (1024, 1280, 1280, False),
+                                         (4096, 3840, 1280, False), (16384, 640, 640, True), (2000, 1280, 5120, True)])
+def test_gemm_stream_k(nat, M, N, K, res):
+    """Stream-K over the partial last wave: same result as whole-tile scheduling up to fp32 summation order
+    (partials are added in a fixed slot order, so repeated runs are bit-identical)."""
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K))
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    r = rnd(M, N, seed=4) if res else None
+    old = nat.get_tunable("STREAMK")
+    try:
+        nat.set_tunable("STREAMK", 1)
+        o1 = nat.gemm(a, w, bias=bias, residual=r)
+        o1b = nat.gemm(a, w, bias=bias, residual=r)
+        nat.set_tunable("STREAMK", 0)
+        o0 = nat.gemm(a, w, bias=bias, residual=r)
+    finally:
+        nat.set_tunable("STREAMK", old)
+    assert torch.equal(o1, o1b), "stream-K must be deterministic"
+    ref = a.float() @ w.float().t() + bias + (r.float() if res else 0)
+    assert_close(o1, ref, 2e-3, 2e-3, "gemm stream-K")
+    assert (o1.float() - o0.float()).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_stream_k(nat):
+    for (B, H, W, Cin, Cout) in [(16, 8, 8, 1280, 1280), (16, 16, 16, 1280, 1280), (16, 32, 32, 640, 640), (4, 8, 8, 2560, 1280)]:
+        x = rnd(B, H, W, Cin, seed=1)
+        w = rnd(Cout, Cin, 3, 3, seed=2, scale=1 / math.sqrt(9 * Cin))
+        bias = rnd(Cout, seed=3, dtype=torch.float32)
+        temb = rnd(B, Cout, seed=4)
+        res = rnd(B * H * W, Cout, seed=5)
+        wp = nat.pack_conv3x3(w)
+        old = nat.get_tunable("STREAMK")
+        try:
+            nat.set_tunable("STREAMK", 1)
+            o1 = nat.conv3x3(x, wp, Cout, bias=bias, residual=res, rowgroup_bias=temb, rows_per_group=H * W)
+            nat.set_tunable("STREAMK", 0)
+            o0 = nat.conv3x3(x, wp, Cout, bias=bias, residual=res, rowgroup_bias=temb, rows_per_group=H * W)
+        finally:
+            nat.set_tunable("STREAMK", old)
+        ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + temb.float()[:, :, None, None]
+        ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout) + res.float()
+        assert_close(o1.reshape(B * H * W, Cout), ref, 4e-3, 4e-3, f"conv stream-K {B}x{H}x{W} {Cin}->{Cout}")
+        assert (o1.float() - o0.float()).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_conv_pair_mode_bit_identical(nat):
     for (B, H, W, Cin, Cout, stride) in [(2, 32, 32, 320, 320, 1), (3, 8, 8, 1280, 1280, 1), (2, 32, 32, 320, 320, 2),
                                          (1, 24, 24, 192, 160, 1)]:
