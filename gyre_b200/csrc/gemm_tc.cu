@@ -698,7 +698,10 @@ static void plan_stream_k(GemmParams* p, int bn) {
   p->sk_flags = nullptr;
   const Epilogue& ep = p->ep;
   if (!tunable(TUNE_STREAMK) || p->mcast || !p->tma_epi || ep.sk_ws == nullptr || ep.sk_flags == nullptr) return;
-  if (ep.act == ACT_ROWMAX || p->k_iters < 8) return;
+  // The hand-off costs ~5-10 us of epilogue time per launch (partial dump + fence + flag, then latency-bound partial
+  // loads in the owner's epilogue - measured on B200), so only tiles whose main loop runs for tens of us qualify:
+  // the 3x3 convolutions at 32x32 and below, not the transformer GEMMs (their 3-15 us tiles got slower).
+  if (ep.act == ACT_ROWMAX || static_cast<long long>(p->k_iters) * bn < 14000) return;
   const long long T = static_cast<long long>(p->m_tiles) * p->n_tiles;
   const int G = sm_count();
   const long long full_waves = T / G;
