@@ -177,6 +177,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
+        # NCCL's own banner ("NCCL version ...") must not land on stdout: the contract is ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from gyre_b200 import _native as N
