@@ -40,6 +40,7 @@ class UNetConfigC(C.Structure):
         ("block_out_channels", C.c_int32 * 4), ("num_heads", C.c_int32 * 4), ("attn_levels", C.c_int32 * 4),
         ("layers_per_block", C.c_int32), ("cross_attention_dim", C.c_int32), ("norm_num_groups", C.c_int32),
         ("norm_eps", C.c_float), ("use_linear_projection", C.c_int32), ("upcast_attention", C.c_int32),
+        ("transformer_depth", C.c_int32 * 4), ("addition_embed_dim", C.c_int32),
     ]
 
 
@@ -72,6 +73,7 @@ SIGNATURES = {
     "gyre_b200_unet_workspace_bytes": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
     "gyre_b200_unet_set_context": (_i, [_vp, _vp, _i, _i, _vp]),
+    "gyre_b200_unet_forward_cond": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
     "gyre_b200_vae_create": (_i, [C.POINTER(VAEConfigC), C.POINTER(_vp)]),
     "gyre_b200_vae_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -24,6 +24,16 @@ class B200GuidedUNet:
                                                                               dtype=torch.float16).contiguous()
         self.extra = None           # [B, Ce, h, w] fp16: mask + masked-image latents of the inpaint UNets
         self._xcat = None
+        self.add_cond = None        # [2B, proj_in] fp16: text_time conditioning of SDXL-style UNets ([uncond ; cond])
+
+    def set_added_cond(self, uncond_kwargs, cond_kwargs):
+        """`added_cond_kwargs` of text_time models ({text_embeds [B, P], time_ids [B, 6]}), for the uncond and the
+        cond half of the CFG batch."""
+        te = torch.cat([uncond_kwargs["text_embeds"], cond_kwargs["text_embeds"]])
+        ti = torch.cat([uncond_kwargs["time_ids"], cond_kwargs["time_ids"]])
+        if te.shape[0] != 2 * self.batch:
+            raise ValueError("added_cond_kwargs batch does not match the embeddings")
+        self.add_cond = self.unet.added_cond_vector(te, ti)
 
     def set_extra_channels(self, extra):
         """EnhancedRunwayInpaintMode.wrap_unet (unified_pipeline.py:668-690) / UnetWithExtraChannels (unet/core.py:21-37):
@@ -56,8 +66,8 @@ class B200GuidedUNet:
             bound = self.unet._ctx_bound
             if bound is None or bound[0] is not self:
                 self.unet.set_context(self.embeddings, owner=self)
-            return self.unet.forward_raw(x2_f16, t2_i64, None, out=out)
-        return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out)
+            return self.unet.forward_raw(x2_f16, t2_i64, None, out=out, add_cond=self.add_cond)
+        return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out, add_cond=self.add_cond)
 
     def __call__(self, latents, t):
         N.require_cuda(latents)

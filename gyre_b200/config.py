@@ -21,6 +21,17 @@ class UNetConfig:
     sample_size: int = 64
     prediction_type: str = "epsilon"
     upcast_attention: bool = False
+    # SDXL-style topologies (BASELINE config 5): BasicTransformerBlocks per Transformer2DModel per level, and the
+    # text_time additional conditioning (pooled text embedding ++ 256-dim sinusoids of the 6 time ids)
+    transformer_layers_per_block: tuple = (1, 1, 1, 1)
+    addition_time_embed_dim: int = 0
+    projection_class_embeddings_input_dim: int = 0
+
+    @staticmethod
+    def sdxl(**kw):
+        return UNetConfig(block_out_channels=(320, 640, 1280), num_heads=(5, 10, 20), attn_levels=(False, True, True),
+                          transformer_layers_per_block=(1, 2, 10), cross_attention_dim=2048, use_linear_projection=True,
+                          sample_size=128, addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816, **kw)
 
     @staticmethod
     def sd15(**kw):

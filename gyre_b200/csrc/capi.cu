@@ -242,6 +242,9 @@ int gyre_b200_unet_create(const gyre_b200_unet_config* cfg, gyre_b200_handle* ou
   }
   GYRE_REQUIRE(cfg->in_channels >= 1 && cfg->in_channels <= 16, "unet_create: in_channels %d", cfg->in_channels);
   GYRE_REQUIRE(cfg->cross_attention_dim > 0 && cfg->cross_attention_dim % 8 == 0, "unet_create: cross_attention_dim");
+  GYRE_REQUIRE(cfg->addition_embed_dim >= 0 && cfg->addition_embed_dim % 8 == 0, "unet_create: addition_embed_dim");
+  for (int i = 0; i < cfg->num_levels; ++i)
+    GYRE_REQUIRE(cfg->transformer_depth[i] >= 0 && cfg->transformer_depth[i] <= 16, "unet_create: transformer_depth");
   GYRE_REQUIRE(cfg->norm_num_groups > 0 && cfg->norm_num_groups <= 32, "unet_create: norm_num_groups");
   UNetModel* m = new (std::nothrow) UNetModel(*cfg);
   GYRE_REQUIRE(m != nullptr, "unet_create: out of host memory");
@@ -267,22 +270,30 @@ int gyre_b200_unet_workspace_bytes(gyre_b200_handle h, int batch, int height, in
   ex.dry = true;
   ex.cap = static_cast<size_t>(1) << 60;
   // sized for the no-merge case, which is the larger one (ToMe only shrinks K/V)
-  GYRE_TRY(static_cast<UNetModel*>(M(h))->forward(ex, nullptr, nullptr, nullptr, batch, height, width, ctx_len, nullptr,
-                                                  nullptr));
+  GYRE_TRY(static_cast<UNetModel*>(M(h))->forward(ex, nullptr, nullptr, nullptr, nullptr, batch, height, width, ctx_len,
+                                                  nullptr, nullptr));
   *bytes = ex.peak + (64u << 20);   // headroom for ToMe scratch
   return 0;
 }
 
-int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx, int batch,
-                           int height, int width, int ctx_len, const int32_t* tome_r_host, void* out, void* workspace,
-                           size_t workspace_bytes, gyre_b200_stream stream) {
+int gyre_b200_unet_forward_cond(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx,
+                                const void* add_cond, int batch, int height, int width, int ctx_len,
+                                const int32_t* tome_r_host, void* out, void* workspace, size_t workspace_bytes,
+                                gyre_b200_stream stream) {
   GYRE_REQUIRE(h && sample && timestep && out, "unet_forward: null argument");
   GYRE_REQUIRE(M(h)->is_unet(), "unet_forward: handle is not a UNet");
   Exec ex;
   GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
   return static_cast<UNetModel*>(M(h))->forward(ex, static_cast<const __half*>(sample), timestep,
-                                                static_cast<const __half*>(ctx), batch, height, width, ctx_len,
-                                                tome_r_host, static_cast<__half*>(out));
+                                                static_cast<const __half*>(ctx), static_cast<const __half*>(add_cond),
+                                                batch, height, width, ctx_len, tome_r_host, static_cast<__half*>(out));
+}
+
+int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx, int batch,
+                           int height, int width, int ctx_len, const int32_t* tome_r_host, void* out, void* workspace,
+                           size_t workspace_bytes, gyre_b200_stream stream) {
+  return gyre_b200_unet_forward_cond(h, sample, timestep, ctx, nullptr, batch, height, width, ctx_len, tome_r_host, out,
+                                     workspace, workspace_bytes, stream);
 }
 
 int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, int ctx_len, gyre_b200_stream stream) {

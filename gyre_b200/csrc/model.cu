@@ -295,7 +295,12 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
   reg_linear("time_embedding.linear_1", temb_dim_, ch[0], true, &time1_);
   reg_linear("time_embedding.linear_2", temb_dim_, temb_dim_, true, &time2_);
 
-  auto add_transformer = [&](const std::string& p, int C, int heads) {
+  if (cfg.addition_embed_dim > 0) {
+    reg_linear("add_embedding.linear_1", temb_dim_, cfg.addition_embed_dim, true, &add1_);
+    reg_linear("add_embedding.linear_2", temb_dim_, temb_dim_, true, &add2_);
+  }
+
+  auto add_transformer = [&](const std::string& p, int C, int heads, int depth) {
     tblocks_.emplace_back();
     TransformerW* t = &tblocks_.back();
     t->C = C;
@@ -304,35 +309,41 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
     reg_norm(p + ".norm", C, &t->gn);
     reg_linear(p + ".proj_in", C, C, true, &t->proj_in);
     reg_linear(p + ".proj_out", C, C, true, &t->proj_out);
-    const std::string b = p + ".transformer_blocks.0";
-    reg_norm(b + ".norm1", C, &t->ln1);
-    reg_norm(b + ".norm2", C, &t->ln2);
-    reg_norm(b + ".norm3", C, &t->ln3);
-    // attn1: fused [to_q ; to_k ; to_v] -> one GEMM with N = 3C
-    t->qkv.N = 3 * C;
-    t->qkv.K = C;
-    t->qkv.w = static_cast<__half*>(dalloc(sizeof(__half) * 3 * C * C));
-    reg(b + ".attn1.to_q.weight", P_LINEAR, t->qkv.w, {C, C}, C);
-    reg(b + ".attn1.to_k.weight", P_LINEAR, t->qkv.w ? t->qkv.w + static_cast<size_t>(C) * C : nullptr, {C, C}, C);
-    reg(b + ".attn1.to_v.weight", P_LINEAR, t->qkv.w ? t->qkv.w + static_cast<size_t>(2) * C * C : nullptr, {C, C}, C);
-    reg_linear(b + ".attn1.to_out.0", C, C, true, &t->o1);
-    // attn2: q from tokens, fused [to_k ; to_v] from the text context
-    reg_linear(b + ".attn2.to_q", C, C, false, &t->q2);
-    t->kv2.N = 2 * C;
-    t->kv2.K = ctx;
-    t->kv2.w = static_cast<__half*>(dalloc(sizeof(__half) * 2 * C * ctx));
-    reg(b + ".attn2.to_k.weight", P_LINEAR, t->kv2.w, {C, ctx}, ctx);
-    reg(b + ".attn2.to_v.weight", P_LINEAR, t->kv2.w ? t->kv2.w + static_cast<size_t>(C) * ctx : nullptr, {C, ctx}, ctx);
-    reg_linear(b + ".attn2.to_out.0", C, C, true, &t->o2);
-    // GEGLU feed-forward
-    t->geglu.N = 8 * C;
-    t->geglu.K = C;
-    t->geglu.w = static_cast<__half*>(dalloc(sizeof(__half) * 8 * C * C));
-    t->geglu.bias = static_cast<float*>(dalloc(sizeof(float) * 8 * C));
-    reg(b + ".ff.net.0.proj.weight", P_GEGLU_W, t->geglu.w, {8 * C, C});
-    reg(b + ".ff.net.0.proj.bias", P_GEGLU_B, t->geglu.bias, {8 * C});
-    reg_linear(b + ".ff.net.2", C, 4 * C, true, &t->ff2);
+    t->blocks.resize(depth < 1 ? 1 : depth);
+    for (size_t bi = 0; bi < t->blocks.size(); ++bi) {
+      TBlockW* k = &t->blocks[bi];
+      k->flat = n_tblocks_flat_++;
+      const std::string b = p + ".transformer_blocks." + std::to_string(bi);
+      reg_norm(b + ".norm1", C, &k->ln1);
+      reg_norm(b + ".norm2", C, &k->ln2);
+      reg_norm(b + ".norm3", C, &k->ln3);
+      // attn1: fused [to_q ; to_k ; to_v] -> one GEMM with N = 3C
+      k->qkv.N = 3 * C;
+      k->qkv.K = C;
+      k->qkv.w = static_cast<__half*>(dalloc(sizeof(__half) * 3 * C * C));
+      reg(b + ".attn1.to_q.weight", P_LINEAR, k->qkv.w, {C, C}, C);
+      reg(b + ".attn1.to_k.weight", P_LINEAR, k->qkv.w ? k->qkv.w + static_cast<size_t>(C) * C : nullptr, {C, C}, C);
+      reg(b + ".attn1.to_v.weight", P_LINEAR, k->qkv.w ? k->qkv.w + static_cast<size_t>(2) * C * C : nullptr, {C, C}, C);
+      reg_linear(b + ".attn1.to_out.0", C, C, true, &k->o1);
+      // attn2: q from tokens, fused [to_k ; to_v] from the text context
+      reg_linear(b + ".attn2.to_q", C, C, false, &k->q2);
+      k->kv2.N = 2 * C;
+      k->kv2.K = ctx;
+      k->kv2.w = static_cast<__half*>(dalloc(sizeof(__half) * 2 * C * ctx));
+      reg(b + ".attn2.to_k.weight", P_LINEAR, k->kv2.w, {C, ctx}, ctx);
+      reg(b + ".attn2.to_v.weight", P_LINEAR, k->kv2.w ? k->kv2.w + static_cast<size_t>(C) * ctx : nullptr, {C, ctx}, ctx);
+      reg_linear(b + ".attn2.to_out.0", C, C, true, &k->o2);
+      // GEGLU feed-forward
+      k->geglu.N = 8 * C;
+      k->geglu.K = C;
+      k->geglu.w = static_cast<__half*>(dalloc(sizeof(__half) * 8 * C * C));
+      k->geglu.bias = static_cast<float*>(dalloc(sizeof(float) * 8 * C));
+      reg(b + ".ff.net.0.proj.weight", P_GEGLU_W, k->geglu.w, {8 * C, C});
+      reg(b + ".ff.net.0.proj.bias", P_GEGLU_B, k->geglu.bias, {8 * C});
+      reg_linear(b + ".ff.net.2", C, 4 * C, true, &k->ff2);
+    }
   };
+  auto depth_of = [&](int lvl) { return cfg.transformer_depth[lvl] > 0 ? cfg.transformer_depth[lvl] : 1; };
   auto add_resnet = [&](const std::string& p, int cin, int cout) {
     resnets_.emplace_back();
     reg_resnet(p, cin, cout, true, &resnets_.back());
@@ -351,7 +362,7 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
       const std::string p = "down_blocks." + std::to_string(i);
       add_resnet(p + ".resnets." + std::to_string(j), cin, ch[i]);
       cin = ch[i];
-      if (cfg.attn_levels[i]) add_transformer(p + ".attentions." + std::to_string(j), ch[i], cfg.num_heads[i]);
+      if (cfg.attn_levels[i]) add_transformer(p + ".attentions." + std::to_string(j), ch[i], cfg.num_heads[i], depth_of(i));
       skips.push_back(ch[i]);
     }
     if (i < L - 1) {
@@ -361,7 +372,7 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
     }
   }
   add_resnet("mid_block.resnets.0", cin, cin);
-  add_transformer("mid_block.attentions.0", cin, cfg.num_heads[L - 1]);
+  add_transformer("mid_block.attentions.0", cin, cfg.num_heads[L - 1], depth_of(L - 1));
   add_resnet("mid_block.resnets.1", cin, cin);
   for (int i = 0; i < L; ++i) {
     const int lvl = L - 1 - i;
@@ -372,7 +383,7 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
       const std::string p = "up_blocks." + std::to_string(i);
       add_resnet(p + ".resnets." + std::to_string(j), cin + s, c);
       cin = c;
-      if (cfg.attn_levels[lvl]) add_transformer(p + ".attentions." + std::to_string(j), c, cfg.num_heads[lvl]);
+      if (cfg.attn_levels[lvl]) add_transformer(p + ".attentions." + std::to_string(j), c, cfg.num_heads[lvl], depth_of(lvl));
     }
     if (i < L - 1) {
       ups_.emplace_back();
@@ -420,20 +431,22 @@ int UNetModel::set_context(const __half* ctx, int B, int L, cudaStream_t st) {
     return 0;
   }
   GYRE_REQUIRE(B > 0 && L > 0, "set_context: empty context");
-  kv_cache_.resize(tblocks_.size(), nullptr);
-  kv_cache_elems_.resize(tblocks_.size(), 0);
+  kv_cache_.resize(n_tblocks_flat_, nullptr);
+  kv_cache_elems_.resize(n_tblocks_flat_, 0);
   ctx_B_ = ctx_L_ = 0;
-  for (size_t i = 0; i < tblocks_.size(); ++i) {
-    const TransformerW& t = tblocks_[i];
-    const size_t need = static_cast<size_t>(B) * L * 2 * t.C;
-    if (kv_cache_elems_[i] < need) {
-      if (kv_cache_[i]) cudaFree(kv_cache_[i]);   // synchronises: no forward can still be reading it
-      kv_cache_[i] = nullptr;
-      kv_cache_elems_[i] = 0;
-      GYRE_CHECK_CUDA(cudaMalloc(&kv_cache_[i], need * sizeof(__half)));
-      kv_cache_elems_[i] = need;
+  for (const TransformerW& t : tblocks_) {
+    for (const TBlockW& k : t.blocks) {
+      const size_t i = static_cast<size_t>(k.flat);
+      const size_t need = static_cast<size_t>(B) * L * 2 * t.C;
+      if (kv_cache_elems_[i] < need) {
+        if (kv_cache_[i]) cudaFree(kv_cache_[i]);   // synchronises: no forward can still be reading it
+        kv_cache_[i] = nullptr;
+        kv_cache_elems_[i] = 0;
+        GYRE_CHECK_CUDA(cudaMalloc(&kv_cache_[i], need * sizeof(__half)));
+        kv_cache_elems_[i] = need;
+      }
+      GYRE_TRY(gemm_f16(ctx, k.kv2.K, k.kv2.w, k.kv2.K, B * L, 2 * t.C, k.kv2.K, ep_out(kv_cache_[i], 2 * t.C), st));
     }
-    GYRE_TRY(gemm_f16(ctx, t.kv2.K, t.kv2.w, t.kv2.K, B * L, 2 * t.C, t.kv2.K, ep_out(kv_cache_[i], 2 * t.C), st));
   }
   ctx_B_ = B;
   ctx_L_ = L;
@@ -453,56 +466,69 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, B, HW, groups_, 1e-6f, t.gn.g, t.gn.b, false, tn, gn_scratch, ex.st));
   __half* h = ex.s16(n);
   RUN(ex, gemm_f16(tn, C, t.proj_in.w, C, M, C, C, ep_out(h, C, t.proj_in.bias), ex.st));
-  // ---- self-attention
   __half* nrm = tn;   // the GroupNorm output is dead after proj_in: reuse it for the LayerNorm outputs
-  RUN(ex, layernorm_rows(h, M, C, 1e-5f, t.ln1.g, t.ln1.b, nrm, ex.st));
   __half* qkv = ex.s16(n * 3);
-  RUN(ex, gemm_f16(nrm, C, t.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C), ex.st));
   __half* o = ex.s16(n);
-  if (r > 0) {
-    // ToMe (nonfree/tome_memory_efficient_cross_attention.py:28-50): merge K and V with one plan built from K
-    const int rr = r < HW / 2 ? r : HW / 2;
-    const int nk = HW - rr;
-    size_t tome_bytes = 0;
-    GYRE_TRY(tome_workspace_bytes(B, HW, C, &tome_bytes));
-    void* tws = ex.alloc_s(tome_bytes);
-    __half* km = ex.s16(static_cast<size_t>(B) * nk * C);
-    __half* vm = ex.s16(static_cast<size_t>(B) * nk * C);
-    RUN(ex, tome_merge_kv(off(qkv, C), off(qkv, 2 * C), 3 * C, B, HW, C, rr, km, vm, tws, tome_bytes, ex.st));
-    RUN(ex, attention_f16(qkv, 3 * C, km, C, vm, C, B, t.heads, HW, nk, d, scale, o, C, ex.st));
-  } else {
-    RUN(ex, attention_f16(qkv, 3 * C, off(qkv, C), 3 * C, off(qkv, 2 * C), 3 * C, B, t.heads, HW, HW, d, scale, o, C, ex.st));
-  }
   __half* h2 = ex.s16(n);
-  RUN(ex, gemm_f16(o, C, t.o1.w, C, M, C, C, ep_out(h2, C, t.o1.bias, h, C), ex.st));
-  // ---- cross-attention
-  RUN(ex, layernorm_rows(h2, M, C, 1e-5f, t.ln2.g, t.ln2.b, nrm, ex.st));
-  __half* q = qkv;   // dead after self-attention
-  RUN(ex, gemm_f16(nrm, C, t.q2.w, C, M, C, C, ep_out(q, C), ex.st));
-  const __half* kv;
-  {
-    __half* kv_new = ex.s16(static_cast<size_t>(B) * L * 2 * C);   // reserved even when the bound context is used
+  __half* g = ex.s16(n * 4);
+  __half* kv_new = ex.s16(static_cast<size_t>(B) * L * 2 * C);   // reserved even when the bound context is used
+  __half *km = nullptr, *vm = nullptr;
+  void* tws = nullptr;
+  size_t tome_bytes = 0;
+  const int rr = r > 0 ? (r < HW / 2 ? r : HW / 2) : 0;
+  if (rr > 0) {
+    GYRE_REQUIRE(t.blocks.size() == 1, "ToMe is wired for transformer depth 1");
+    GYRE_TRY(tome_workspace_bytes(B, HW, C, &tome_bytes));
+    tws = ex.alloc_s(tome_bytes);
+    km = ex.s16(static_cast<size_t>(B) * (HW - rr) * C);
+    vm = ex.s16(static_cast<size_t>(B) * (HW - rr) * C);
+  }
+  // h holds the residual stream on entry to every block and again on exit (h -> h2 -> h -> h2 -> copy-free swap)
+  for (size_t bi = 0; bi < t.blocks.size(); ++bi) {
+    const TBlockW& k = t.blocks[bi];
+    // ---- self-attention
+    RUN(ex, layernorm_rows(h, M, C, 1e-5f, k.ln1.g, k.ln1.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, C, k.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C), ex.st));
+    if (rr > 0) {
+      // ToMe (nonfree/tome_memory_efficient_cross_attention.py:28-50): merge K and V with one plan built from K
+      const int nk = HW - rr;
+      RUN(ex, tome_merge_kv(off(qkv, C), off(qkv, 2 * C), 3 * C, B, HW, C, rr, km, vm, tws, tome_bytes, ex.st));
+      RUN(ex, attention_f16(qkv, 3 * C, km, C, vm, C, B, t.heads, HW, nk, d, scale, o, C, ex.st));
+    } else {
+      RUN(ex, attention_f16(qkv, 3 * C, off(qkv, C), 3 * C, off(qkv, 2 * C), 3 * C, B, t.heads, HW, HW, d, scale, o, C, ex.st));
+    }
+    RUN(ex, gemm_f16(o, C, k.o1.w, C, M, C, C, ep_out(h2, C, k.o1.bias, h, C), ex.st));
+    // ---- cross-attention
+    RUN(ex, layernorm_rows(h2, M, C, 1e-5f, k.ln2.g, k.ln2.b, nrm, ex.st));
+    __half* q = qkv;   // dead after self-attention
+    RUN(ex, gemm_f16(nrm, C, k.q2.w, C, M, C, C, ep_out(q, C), ex.st));
+    const __half* kv;
     if (ctx != nullptr || ex.dry) {
-      RUN(ex, gemm_f16(ctx, t.kv2.K, t.kv2.w, t.kv2.K, B * L, 2 * C, t.kv2.K, ep_out(kv_new, 2 * C), ex.st));
+      RUN(ex, gemm_f16(ctx, k.kv2.K, k.kv2.w, k.kv2.K, B * L, 2 * C, k.kv2.K, ep_out(kv_new, 2 * C), ex.st));
       kv = kv_new;
     } else {
-      kv = kv_cache_[static_cast<size_t>(&t - tblocks_.data())];
+      kv = kv_cache_[static_cast<size_t>(k.flat)];
     }
+    RUN(ex, attention_f16(q, C, kv, 2 * C, off(kv, C), 2 * C, B, t.heads, HW, L, d, scale, o, C, ex.st));
+    RUN(ex, gemm_f16(o, C, k.o2.w, C, M, C, C, ep_out(h, C, k.o2.bias, h2, C), ex.st));   // h <- h2 + attn2
+    // ---- GEGLU feed-forward
+    RUN(ex, layernorm_rows(h, M, C, 1e-5f, k.ln3.g, k.ln3.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, C, k.geglu.w, C, M, 8 * C, C, ep_out(g, 4 * C, k.geglu.bias, nullptr, 0, ACT_GEGLU), ex.st));
+    RUN(ex, gemm_f16(g, 4 * C, k.ff2.w, 4 * C, M, C, 4 * C, ep_out(h2, C, k.ff2.bias, h, C), ex.st));   // h2 <- h + ff
+    std::swap(h, h2);   // the block's output becomes the next block's residual stream
   }
-  RUN(ex, attention_f16(q, C, kv, 2 * C, off(kv, C), 2 * C, B, t.heads, HW, L, d, scale, o, C, ex.st));
-  RUN(ex, gemm_f16(o, C, t.o2.w, C, M, C, C, ep_out(h, C, t.o2.bias, h2, C), ex.st));   // h <- h2 + attn2
-  // ---- GEGLU feed-forward
-  RUN(ex, layernorm_rows(h, M, C, 1e-5f, t.ln3.g, t.ln3.b, nrm, ex.st));
-  __half* g = ex.s16(n * 4);
-  RUN(ex, gemm_f16(nrm, C, t.geglu.w, C, M, 8 * C, C, ep_out(g, 4 * C, t.geglu.bias, nullptr, 0, ACT_GEGLU), ex.st));
-  RUN(ex, gemm_f16(g, 4 * C, t.ff2.w, 4 * C, M, C, 4 * C, ep_out(h2, C, t.ff2.bias, h, C), ex.st));   // h2 <- h + ff
+  h2 = h;
   RUN(ex, gemm_f16(h2, C, t.proj_out.w, C, M, C, C, ep_out(out, C, t.proj_out.bias, x, C), ex.st));
   return 0;
 }
 
-int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, int B, int H, int W, int L,
-                       const int32_t* tome_r, __half* out) {
+int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B,
+                       int H, int W, int L, const int32_t* tome_r, __half* out) {
   GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && L > 0, "unet_forward: empty problem");
+  if (!ex.dry)
+    GYRE_REQUIRE((cfg_.addition_embed_dim > 0) == (add_cond != nullptr),
+                 "unet_forward: this model %s an additional conditioning vector (addition_embed_dim = %d)",
+                 cfg_.addition_embed_dim > 0 ? "needs" : "does not take", cfg_.addition_embed_dim);
   if (!ex.dry && ctx == nullptr)
     GYRE_REQUIRE(ctx_B_ == B && ctx_L_ == L, "unet_forward: no context given and the bound one is [%d, %d], need [%d, %d]",
                  ctx_B_, ctx_L_, B, L);
@@ -521,8 +547,23 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   RUN(ex, gemm_f16(te0, ch[0], time1_.w, ch[0], B, temb_dim_, ch[0],
                    ep_out(te1, temb_dim_, time1_.bias, nullptr, 0, ACT_SILU), ex.st));
   __half* te2 = ex.p16(static_cast<size_t>(B) * temb_dim_);
-  RUN(ex, gemm_f16(te1, temb_dim_, time2_.w, temb_dim_, B, temb_dim_, temb_dim_,
-                   ep_out(te2, temb_dim_, time2_.bias, nullptr, 0, ACT_SILU), ex.st));
+  if (cfg_.addition_embed_dim > 0) {
+    // text_time conditioning: emb = time_embedding(t) + add_embedding(add_cond); SiLU comes after the sum
+    const int ad = cfg_.addition_embed_dim;
+    __half* traw = ex.p16(static_cast<size_t>(B) * temb_dim_);
+    RUN(ex, gemm_f16(te1, temb_dim_, time2_.w, temb_dim_, B, temb_dim_, temb_dim_, ep_out(traw, temb_dim_, time2_.bias),
+                     ex.st));
+    __half* a1 = ex.p16(static_cast<size_t>(B) * temb_dim_);
+    RUN(ex, gemm_f16(add_cond, ad, add1_.w, ad, B, temb_dim_, ad, ep_out(a1, temb_dim_, add1_.bias, nullptr, 0, ACT_SILU),
+                     ex.st));
+    __half* esum = ex.p16(static_cast<size_t>(B) * temb_dim_);
+    RUN(ex, gemm_f16(a1, temb_dim_, add2_.w, temb_dim_, B, temb_dim_, temb_dim_,
+                     ep_out(esum, temb_dim_, add2_.bias, traw, temb_dim_), ex.st));
+    RUN(ex, silu_f16(esum, static_cast<int64_t>(B) * temb_dim_, te2, ex.st));
+  } else {
+    RUN(ex, gemm_f16(te1, temb_dim_, time2_.w, temb_dim_, B, temb_dim_, temb_dim_,
+                     ep_out(te2, temb_dim_, time2_.bias, nullptr, 0, ACT_SILU), ex.st));
+  }
   __half* temb_all = ex.p16(static_cast<size_t>(B) * temb_total_);
   RUN(ex, gemm_f16(te2, temb_dim_, temb_proj_.w, temb_dim_, B, temb_total_, temb_dim_,
                    ep_out(temb_all, temb_total_, temb_proj_.bias), ex.st));

@@ -53,9 +53,16 @@ struct ResnetW {
   int temb_off = -1;    // column offset into the fused time_emb_proj output (-1: no temb)
 };
 
-struct TransformerW {
-  NormW gn, ln1, ln2, ln3;
-  LinW proj_in, qkv, o1, q2, kv2, o2, geglu, ff2, proj_out;
+struct TBlockW {          // one BasicTransformerBlock
+  NormW ln1, ln2, ln3;
+  LinW qkv, o1, q2, kv2, o2, geglu, ff2;
+  int flat = 0;           // index among all BasicTransformerBlocks of the model (bound-context cache slot)
+};
+
+struct TransformerW {     // Transformer2DModel: GroupNorm, proj_in, `depth` blocks, proj_out
+  NormW gn;
+  LinW proj_in, proj_out;
+  std::vector<TBlockW> blocks;
   int C = 0, heads = 0;
 };
 
@@ -124,8 +131,8 @@ class UNetModel : public Model {
   bool is_unet() const override { return true; }
   int num_transformer_blocks() const { return static_cast<int>(tblocks_.size()); }
   // dry == true sizes the workspace (ex.peak) without launching anything
-  int forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, int B, int H, int W, int L,
-              const int32_t* tome_r, __half* out);
+  int forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B, int H,
+              int W, int L, const int32_t* tome_r, __half* out);
   // Binds a text context for the following forwards (the reference binds the embeddings once per request:
   // UNetWithEmbeddings, gyre/pipeline/unet/core.py:253-259): the cross-attention K/V projections of every
   // transformer block depend only on ctx, so they are computed here ONCE instead of once per step.
@@ -139,6 +146,8 @@ class UNetModel : public Model {
   gyre_b200_unet_config cfg_;
   Conv3W conv_in_;      // Cin = in_channels (4/5/9): the input is staged NHWC with the channel pitch padded to 8
   LinW time1_, time2_;
+  LinW add1_, add2_;    // add_embedding (text_time conditioning), only when cfg_.addition_embed_dim > 0
+  int n_tblocks_flat_ = 0;
   std::vector<ResnetW> resnets_;        // in module execution order
   std::vector<TransformerW> tblocks_;   // in module execution order (== ToMe r-list order)
   std::vector<Conv3W> downs_, ups_;

@@ -63,6 +63,9 @@ class B200UNet:
         c.norm_eps = cfg.norm_eps
         c.use_linear_projection = int(cfg.use_linear_projection)
         c.upcast_attention = int(cfg.upcast_attention)
+        for i, v in enumerate(cfg.transformer_layers_per_block[:len(cfg.block_out_channels)]):
+            c.transformer_depth[i] = int(v)
+        c.addition_embed_dim = int(cfg.projection_class_embeddings_input_dim if cfg.addition_time_embed_dim else 0)
         with torch.cuda.device(self.device):
             N.check(self._lib.gyre_b200_unet_create(C.byref(c), C.byref(self._h)), "unet_create")
         self.num_transformer_blocks = self._lib.gyre_b200_unet_num_transformer_blocks(self._h)
@@ -147,7 +150,18 @@ class B200UNet:
                     "unet_set_context")
         self._ctx_bound = (owner, B, L)
 
-    def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None):
+    def added_cond_vector(self, text_embeds, time_ids):
+        """`addition_embed_type == "text_time"`: cat([text_embeds, sinusoid(time_ids).flatten(1)]) -> [B, proj_in] fp16.
+        The sinusoid layout is the timestep embedding's ([cos | sin], flip_sin_to_cos, shift 0)."""
+        import math
+        dim = self.config.addition_time_embed_dim
+        half = dim // 2
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=self.device) / half)
+        ang = time_ids.to(self.device).float().reshape(-1)[:, None] * freqs[None]
+        emb = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).reshape(time_ids.shape[0], -1)
+        return torch.cat([text_embeds.to(self.device).float(), emb], dim=-1).to(torch.float16).contiguous()
+
+    def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None, add_cond=None):
         """No conversions: fp16 NCHW sample, int64 [B] timesteps, fp16 [B, L, Cc] context (or None: the context
         bound with `set_context`), all on device."""
         if not self._loaded:
@@ -164,13 +178,13 @@ class B200UNet:
         ws = self._workspace(B, H, W, L)
         r_list = self.tome_r_list()
         r_arr = (C.c_int32 * len(r_list))(*r_list) if r_list else None
-        N.check(self._lib.gyre_b200_unet_forward(self._h, N.ptr(sample_f16), N.ptr(t_i64), N.ptr(ctx_f16), B, H, W, L,
-                                                 r_arr, N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr(self.device)),
-                "unet_forward")
+        N.check(self._lib.gyre_b200_unet_forward_cond(self._h, N.ptr(sample_f16), N.ptr(t_i64), N.ptr(ctx_f16),
+                                                      N.ptr(add_cond), B, H, W, L, r_arr, N.ptr(out), N.ptr(ws),
+                                                      ws.numel(), N.stream_ptr(self.device)), "unet_forward")
         return out
 
     def __call__(self, latents, t, *, encoder_hidden_states, down_block_additional_residuals=None,
-                 mid_block_additional_residual=None, adapter_states=None, **kwargs):
+                 mid_block_additional_residual=None, adapter_states=None, added_cond_kwargs=None, **kwargs):
         if down_block_additional_residuals is not None or mid_block_additional_residual is not None \
                 or adapter_states is not None:
             # ControlNet / T2I residual injection (core.py:45-64,213-239) is a "next" row
@@ -183,5 +197,10 @@ class B200UNet:
         ctx = encoder_hidden_states.to(torch.float16).contiguous()
         if ctx.shape[0] != B:
             raise ValueError("encoder_hidden_states batch does not match latents")
-        out = self.forward_raw(x, self._timesteps(t, B), ctx)
+        add = None
+        if self.config.addition_time_embed_dim:
+            if not added_cond_kwargs or "text_embeds" not in added_cond_kwargs or "time_ids" not in added_cond_kwargs:
+                raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")
+            add = self.added_cond_vector(added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"])
+        out = self.forward_raw(x, self._timesteps(t, B), ctx, add_cond=add)
         return UNetOutput(sample=out.to(latents.dtype) if latents.dtype != torch.float16 else out)

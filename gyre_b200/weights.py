@@ -28,28 +28,34 @@ def _resnet_keys(p, cin, cout, temb):
     return ks
 
 
-def _transformer_keys(p, c, ctx, linear):
+def _transformer_keys(p, c, ctx, linear, depth=1):
     ks = {f"{p}.norm.weight": (c,), f"{p}.norm.bias": (c,)}
     proj = (c, c) if linear else (c, c, 1, 1)
     ks[f"{p}.proj_in.weight"] = proj
     ks[f"{p}.proj_out.weight"] = proj
     ks[f"{p}.proj_in.bias"] = (c,)
     ks[f"{p}.proj_out.bias"] = (c,)
-    b = f"{p}.transformer_blocks.0"
-    for n in ("norm1", "norm2", "norm3"):
-        ks[f"{b}.{n}.weight"] = (c,)
-        ks[f"{b}.{n}.bias"] = (c,)
-    for a, kd in (("attn1", c), ("attn2", ctx)):
-        ks[f"{b}.{a}.to_q.weight"] = (c, c)
-        ks[f"{b}.{a}.to_k.weight"] = (c, kd)
-        ks[f"{b}.{a}.to_v.weight"] = (c, kd)
-        ks[f"{b}.{a}.to_out.0.weight"] = (c, c)
-        ks[f"{b}.{a}.to_out.0.bias"] = (c,)
-    ks[f"{b}.ff.net.0.proj.weight"] = (8 * c, c)
-    ks[f"{b}.ff.net.0.proj.bias"] = (8 * c,)
-    ks[f"{b}.ff.net.2.weight"] = (c, 4 * c)
-    ks[f"{b}.ff.net.2.bias"] = (c,)
+    for bi in range(depth):
+        b = f"{p}.transformer_blocks.{bi}"
+        for n in ("norm1", "norm2", "norm3"):
+            ks[f"{b}.{n}.weight"] = (c,)
+            ks[f"{b}.{n}.bias"] = (c,)
+        for a, kd in (("attn1", c), ("attn2", ctx)):
+            ks[f"{b}.{a}.to_q.weight"] = (c, c)
+            ks[f"{b}.{a}.to_k.weight"] = (c, kd)
+            ks[f"{b}.{a}.to_v.weight"] = (c, kd)
+            ks[f"{b}.{a}.to_out.0.weight"] = (c, c)
+            ks[f"{b}.{a}.to_out.0.bias"] = (c,)
+        ks[f"{b}.ff.net.0.proj.weight"] = (8 * c, c)
+        ks[f"{b}.ff.net.0.proj.bias"] = (8 * c,)
+        ks[f"{b}.ff.net.2.weight"] = (c, 4 * c)
+        ks[f"{b}.ff.net.2.bias"] = (c,)
     return ks
+
+
+def _depth(cfg, level):
+    d = getattr(cfg, "transformer_layers_per_block", None)
+    return int(d[level]) if d else 1
 
 
 def unet_param_shapes(cfg) -> dict:
@@ -61,6 +67,10 @@ def unet_param_shapes(cfg) -> dict:
         "time_embedding.linear_1.weight": (T, ch[0]), "time_embedding.linear_1.bias": (T,),
         "time_embedding.linear_2.weight": (T, T), "time_embedding.linear_2.bias": (T,),
     }
+    if getattr(cfg, "addition_time_embed_dim", 0):
+        pin = cfg.projection_class_embeddings_input_dim
+        ks.update({"add_embedding.linear_1.weight": (T, pin), "add_embedding.linear_1.bias": (T,),
+                   "add_embedding.linear_2.weight": (T, T), "add_embedding.linear_2.bias": (T,)})
     skips = [ch[0]]
     cin = ch[0]
     for i, c in enumerate(ch):
@@ -69,14 +79,15 @@ def unet_param_shapes(cfg) -> dict:
             cin = c
             if cfg.attn_levels[i]:
                 ks.update(_transformer_keys(f"down_blocks.{i}.attentions.{j}", c, cfg.cross_attention_dim,
-                                            cfg.use_linear_projection))
+                                            cfg.use_linear_projection, _depth(cfg, i)))
             skips.append(c)
         if i < len(ch) - 1:
             ks[f"down_blocks.{i}.downsamplers.0.conv.weight"] = (c, c, 3, 3)
             ks[f"down_blocks.{i}.downsamplers.0.conv.bias"] = (c,)
             skips.append(c)
     ks.update(_resnet_keys("mid_block.resnets.0", cin, cin, T))
-    ks.update(_transformer_keys("mid_block.attentions.0", cin, cfg.cross_attention_dim, cfg.use_linear_projection))
+    ks.update(_transformer_keys("mid_block.attentions.0", cin, cfg.cross_attention_dim, cfg.use_linear_projection,
+                                _depth(cfg, len(ch) - 1)))
     ks.update(_resnet_keys("mid_block.resnets.1", cin, cin, T))
     rch = list(reversed(ch))
     rattn = list(reversed(cfg.attn_levels))
@@ -87,7 +98,7 @@ def unet_param_shapes(cfg) -> dict:
             cin = c
             if rattn[i]:
                 ks.update(_transformer_keys(f"up_blocks.{i}.attentions.{j}", c, cfg.cross_attention_dim,
-                                            cfg.use_linear_projection))
+                                            cfg.use_linear_projection, _depth(cfg, len(ch) - 1 - i)))
         if i < len(ch) - 1:
             ks[f"up_blocks.{i}.upsamplers.0.conv.weight"] = (c, c, 3, 3)
             ks[f"up_blocks.{i}.upsamplers.0.conv.bias"] = (c,)

@@ -82,6 +82,11 @@ typedef struct gyre_b200_unet_config {
   float norm_eps;                  /* 1e-5                                                         */
   int32_t use_linear_projection;   /* SD2.x                                                        */
   int32_t upcast_attention;        /* SD2.1-768 (softmax/QK^T are fp32 in this library regardless) */
+  /* SDXL-style topologies (BASELINE config 5; no counterpart in the reference, public diffusers config names): */
+  int32_t transformer_depth[4];    /* `transformer_layers_per_block` per level; 0 is read as 1; the mid block
+                                      uses the last level's value                                            */
+  int32_t addition_embed_dim;      /* 0: none.  > 0: input width of `add_embedding.linear_1` (text_time
+                                      conditioning: pooled text embedding ++ sinusoids of the 6 time ids)    */
 } gyre_b200_unet_config;
 
 int gyre_b200_unet_create(const gyre_b200_unet_config* cfg, gyre_b200_handle* out);
@@ -116,6 +121,12 @@ int gyre_b200_unet_workspace_bytes(gyre_b200_handle h, int batch, int height, in
 int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx,
                            int batch, int height, int width, int ctx_len, const int32_t* tome_r_host,
                            void* out, void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+/* Same with the additional conditioning vector of `addition_embed_type = "text_time"` models:
+ * add_cond [batch, addition_embed_dim] fp16 = cat([text_embeds, sinusoid_256(time_ids).flatten(1)]). */
+int gyre_b200_unet_forward_cond(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx,
+                                const void* add_cond, int batch, int height, int width, int ctx_len,
+                                const int32_t* tome_r_host, void* out, void* workspace, size_t workspace_bytes,
+                                gyre_b200_stream stream);
 
 /* Binds the text context for the following forwards (the reference binds the embeddings once per
  * request: UNetWithEmbeddings, gyre/pipeline/unet/core.py:253-259).  The cross-attention K/V

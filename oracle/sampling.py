@@ -122,16 +122,18 @@ def k_sigmas(schedule: DiscreteSchedule, n: int, karras_rho=None, device="cpu"):
 class CFGParallel:
     """cfg.py:41-57 + core.py:242-274: duplicate latents, ONE unet call on [uncond, cond], u + s*(g-u)."""
 
-    def __init__(self, unet, uncond_emb, cond_emb, guidance_scale):
+    def __init__(self, unet, uncond_emb, cond_emb, guidance_scale, added_cond_kwargs=None):
         self.unet = unet
         self.emb = torch.cat([uncond_emb, cond_emb])
         self.guidance_scale = guidance_scale
+        self.added = added_cond_kwargs       # already [uncond ; cond] (text_time models only)
 
     def __call__(self, latents, t):
         latents = torch.cat([latents, latents])
         if isinstance(t, torch.Tensor) and t.shape:
             t = torch.cat([t, t])
-        noise_pred = self.unet(latents, t, encoder_hidden_states=self.emb).sample
+        kw = {"added_cond_kwargs": self.added} if self.added is not None else {}
+        noise_pred = self.unet(latents, t, encoder_hidden_states=self.emb, **kw).sample
         u, g = noise_pred.chunk(2)
         return u + self.guidance_scale * (g - u)
 

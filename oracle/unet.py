@@ -35,6 +35,10 @@ class UNetConfig:
     sample_size: int = 64
     prediction_type: str = "epsilon"
     upcast_attention: bool = False
+    # SDXL-style topologies (BASELINE config 5; public diffusers config names, not in the reference)
+    transformer_layers_per_block: tuple = (1, 1, 1, 1)
+    addition_time_embed_dim: int = 0
+    projection_class_embeddings_input_dim: int = 0
 
     @property
     def time_embed_dim(self):
@@ -53,6 +57,22 @@ class UNetConfig:
         # gyre/ldm_config/v2-inference-v.yaml: num_head_channels 64, context_dim 1024, linear proj, v-pred
         return UNetConfig(num_heads=(5, 10, 20, 20), cross_attention_dim=1024, use_linear_projection=True,
                           sample_size=96, prediction_type="v_prediction", upcast_attention=True, **kw)
+
+    @staticmethod
+    def sdxl(**kw):
+        return UNetConfig(block_out_channels=(320, 640, 1280), num_heads=(5, 10, 20), attn_levels=(False, True, True),
+                          transformer_layers_per_block=(1, 2, 10), cross_attention_dim=2048, use_linear_projection=True,
+                          sample_size=128, addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816, **kw)
+
+    @staticmethod
+    def tiny_xl(**kw):
+        """SDXL topology in miniature: 3 levels, no attention at level 0, transformer depth (1, 2, 3), head dim 32,
+        text_time conditioning (pooled 32 + 6 x 16 sinusoids = 128)."""
+        d = dict(block_out_channels=(64, 128, 256), num_heads=(2, 4, 8), attn_levels=(False, True, True),
+                 transformer_layers_per_block=(1, 2, 3), cross_attention_dim=64, use_linear_projection=True,
+                 sample_size=16, addition_time_embed_dim=16, projection_class_embeddings_input_dim=128)
+        d.update(kw)
+        return UNetConfig(**d)
 
     @staticmethod
     def tiny(**kw):
@@ -81,7 +101,7 @@ def _resnet_keys(p, cin, cout, temb):
     return ks
 
 
-def _transformer_keys(p, c, ctx, linear):
+def _transformer_keys(p, c, ctx, linear, depth=1):
     ks = {f"{p}.norm.weight": (c,), f"{p}.norm.bias": (c,)}
     if linear:
         ks[f"{p}.proj_in.weight"] = (c, c)
@@ -91,21 +111,27 @@ def _transformer_keys(p, c, ctx, linear):
         ks[f"{p}.proj_out.weight"] = (c, c, 1, 1)
     ks[f"{p}.proj_in.bias"] = (c,)
     ks[f"{p}.proj_out.bias"] = (c,)
-    b = f"{p}.transformer_blocks.0"
-    for n in ("norm1", "norm2", "norm3"):
-        ks[f"{b}.{n}.weight"] = (c,)
-        ks[f"{b}.{n}.bias"] = (c,)
-    for a, kd in (("attn1", c), ("attn2", ctx)):
-        ks[f"{b}.{a}.to_q.weight"] = (c, c)
-        ks[f"{b}.{a}.to_k.weight"] = (c, kd)
-        ks[f"{b}.{a}.to_v.weight"] = (c, kd)
-        ks[f"{b}.{a}.to_out.0.weight"] = (c, c)
-        ks[f"{b}.{a}.to_out.0.bias"] = (c,)
-    ks[f"{b}.ff.net.0.proj.weight"] = (8 * c, c)
-    ks[f"{b}.ff.net.0.proj.bias"] = (8 * c,)
-    ks[f"{b}.ff.net.2.weight"] = (c, 4 * c)
-    ks[f"{b}.ff.net.2.bias"] = (c,)
+    for bi in range(depth):
+        b = f"{p}.transformer_blocks.{bi}"
+        for n in ("norm1", "norm2", "norm3"):
+            ks[f"{b}.{n}.weight"] = (c,)
+            ks[f"{b}.{n}.bias"] = (c,)
+        for a, kd in (("attn1", c), ("attn2", ctx)):
+            ks[f"{b}.{a}.to_q.weight"] = (c, c)
+            ks[f"{b}.{a}.to_k.weight"] = (c, kd)
+            ks[f"{b}.{a}.to_v.weight"] = (c, kd)
+            ks[f"{b}.{a}.to_out.0.weight"] = (c, c)
+            ks[f"{b}.{a}.to_out.0.bias"] = (c,)
+        ks[f"{b}.ff.net.0.proj.weight"] = (8 * c, c)
+        ks[f"{b}.ff.net.0.proj.bias"] = (8 * c,)
+        ks[f"{b}.ff.net.2.weight"] = (c, 4 * c)
+        ks[f"{b}.ff.net.2.bias"] = (c,)
     return ks
+
+
+def _depth(cfg, level):
+    d = getattr(cfg, "transformer_layers_per_block", None)
+    return int(d[level]) if d else 1
 
 
 def unet_param_shapes(cfg: UNetConfig) -> dict:
@@ -117,6 +143,10 @@ def unet_param_shapes(cfg: UNetConfig) -> dict:
         "time_embedding.linear_1.weight": (T, ch[0]), "time_embedding.linear_1.bias": (T,),
         "time_embedding.linear_2.weight": (T, T), "time_embedding.linear_2.bias": (T,),
     }
+    if getattr(cfg, "addition_time_embed_dim", 0):
+        pin = cfg.projection_class_embeddings_input_dim
+        ks.update({"add_embedding.linear_1.weight": (T, pin), "add_embedding.linear_1.bias": (T,),
+                   "add_embedding.linear_2.weight": (T, T), "add_embedding.linear_2.bias": (T,)})
     skips = [ch[0]]
     cin = ch[0]
     for i, c in enumerate(ch):
@@ -125,14 +155,15 @@ def unet_param_shapes(cfg: UNetConfig) -> dict:
             cin = c
             if cfg.attn_levels[i]:
                 ks.update(_transformer_keys(f"down_blocks.{i}.attentions.{j}", c, cfg.cross_attention_dim,
-                                            cfg.use_linear_projection))
+                                            cfg.use_linear_projection, _depth(cfg, i)))
             skips.append(c)
         if i < len(ch) - 1:
             ks[f"down_blocks.{i}.downsamplers.0.conv.weight"] = (c, c, 3, 3)
             ks[f"down_blocks.{i}.downsamplers.0.conv.bias"] = (c,)
             skips.append(c)
     ks.update(_resnet_keys("mid_block.resnets.0", cin, cin, T))
-    ks.update(_transformer_keys("mid_block.attentions.0", cin, cfg.cross_attention_dim, cfg.use_linear_projection))
+    ks.update(_transformer_keys("mid_block.attentions.0", cin, cfg.cross_attention_dim, cfg.use_linear_projection,
+                                _depth(cfg, len(ch) - 1)))
     ks.update(_resnet_keys("mid_block.resnets.1", cin, cin, T))
     rch = list(reversed(ch))
     rattn = list(reversed(cfg.attn_levels))
@@ -143,7 +174,7 @@ def unet_param_shapes(cfg: UNetConfig) -> dict:
             cin = c
             if rattn[i]:
                 ks.update(_transformer_keys(f"up_blocks.{i}.attentions.{j}", c, cfg.cross_attention_dim,
-                                            cfg.use_linear_projection))
+                                            cfg.use_linear_projection, _depth(cfg, len(ch) - 1 - i)))
         if i < len(ch) - 1:
             ks[f"up_blocks.{i}.upsamplers.0.conv.weight"] = (c, c, 3, 3)
             ks[f"up_blocks.{i}.upsamplers.0.conv.bias"] = (c,)
@@ -242,14 +273,17 @@ def transformer_2d(P, p, x, ctx, heads, groups, linear, tome_r=0):
     else:
         h = F.conv2d(h, P[f"{p}.proj_in.weight"], P[f"{p}.proj_in.bias"])
         h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
-    b = f"{p}.transformer_blocks.0"
-    h = attention(P, f"{b}.attn1", F.layer_norm(h, (C,), P[f"{b}.norm1.weight"], P[f"{b}.norm1.bias"], 1e-5),
-                  None, heads, tome_r) + h
-    h = attention(P, f"{b}.attn2", F.layer_norm(h, (C,), P[f"{b}.norm2.weight"], P[f"{b}.norm2.bias"], 1e-5),
-                  ctx, heads) + h
-    n = F.layer_norm(h, (C,), P[f"{b}.norm3.weight"], P[f"{b}.norm3.bias"], 1e-5)
-    a, g = F.linear(n, P[f"{b}.ff.net.0.proj.weight"], P[f"{b}.ff.net.0.proj.bias"]).chunk(2, dim=-1)
-    h = F.linear(a * F.gelu(g), P[f"{b}.ff.net.2.weight"], P[f"{b}.ff.net.2.bias"]) + h
+    bi = 0
+    while f"{p}.transformer_blocks.{bi}.norm1.weight" in P:
+        b = f"{p}.transformer_blocks.{bi}"
+        h = attention(P, f"{b}.attn1", F.layer_norm(h, (C,), P[f"{b}.norm1.weight"], P[f"{b}.norm1.bias"], 1e-5),
+                      None, heads, tome_r) + h
+        h = attention(P, f"{b}.attn2", F.layer_norm(h, (C,), P[f"{b}.norm2.weight"], P[f"{b}.norm2.bias"], 1e-5),
+                      ctx, heads) + h
+        n = F.layer_norm(h, (C,), P[f"{b}.norm3.weight"], P[f"{b}.norm3.bias"], 1e-5)
+        a, g = F.linear(n, P[f"{b}.ff.net.0.proj.weight"], P[f"{b}.ff.net.0.proj.bias"]).chunk(2, dim=-1)
+        h = F.linear(a * F.gelu(g), P[f"{b}.ff.net.2.weight"], P[f"{b}.ff.net.2.bias"]) + h
+        bi += 1
     if linear:
         h = F.linear(h, P[f"{p}.proj_out.weight"], P[f"{p}.proj_out.bias"])
         h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
@@ -265,7 +299,8 @@ def num_transformer_blocks(cfg: UNetConfig) -> int:
     return n
 
 
-def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_states, tome_r=0, taps=None):
+def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_states, tome_r=0, taps=None,
+                 added_cond_kwargs=None):
     """UNet2DConditionModel.forward (call site gyre/pipeline/unet/core.py:274; encoder-half wiring
     cf. gyre/pipeline/controlnet/models.py:446-511; up path cf. nonfree/tome_unet.py:34-70).
     `tome_r`: int | (r, inflect) | list, expanded by parse_r over the transformer blocks in module
@@ -287,6 +322,15 @@ def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_stat
     temb = timestep_embedding(t, ch[0]).to(sample.dtype)
     temb = F.linear(temb, P["time_embedding.linear_1.weight"], P["time_embedding.linear_1.bias"])
     temb = F.linear(F.silu(temb), P["time_embedding.linear_2.weight"], P["time_embedding.linear_2.bias"])
+    if cfg.addition_time_embed_dim:
+        # addition_embed_type == "text_time" (public diffusers UNet2DConditionModel): emb += add_embedding(cat(
+        # [text_embeds, add_time_proj(time_ids.flatten()).reshape(B, -1)]))
+        te, tid = added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]
+        tproj = timestep_embedding(tid.flatten(), cfg.addition_time_embed_dim).reshape(B, -1)
+        aug = torch.cat([te.to(sample.dtype), tproj.to(sample.dtype)], dim=-1)
+        aug = F.linear(aug, P["add_embedding.linear_1.weight"], P["add_embedding.linear_1.bias"])
+        aug = F.linear(F.silu(aug), P["add_embedding.linear_2.weight"], P["add_embedding.linear_2.bias"])
+        temb = temb + aug
 
     def tap(name, v):
         if taps is not None:
@@ -343,6 +387,7 @@ class OracleUNet:
         self.params = params
         self.r = 0  # ToMe: set like `unet.r = int(value)` (gyre/pipeline/unified_pipeline.py:1582-1584)
 
-    def __call__(self, latents, t, *, encoder_hidden_states, **_):
+    def __call__(self, latents, t, *, encoder_hidden_states, added_cond_kwargs=None, **_):
         with torch.no_grad():
-            return self._Out(unet_forward(self.params, self.config, latents, t, encoder_hidden_states, self.r))
+            return self._Out(unet_forward(self.params, self.config, latents, t, encoder_hidden_states, self.r,
+                                          added_cond_kwargs=added_cond_kwargs))

@@ -173,3 +173,46 @@ def test_vae_sd_decode_full_size():
     ref_post = (ref / 2 + 0.5).clamp(0, 1)
     assert (post.float() - ref_post).abs().max().item() < 2e-2
     assert (u8.permute(0, 3, 1, 2).float() / 255 - ref_post).abs().max().item() < 2e-2 + 1 / 255
+
+
+def test_unet_sdxl_topology_vs_oracle():
+    """Config 5's topology in miniature (3 levels, no attention at level 0, transformer depth 1 / 2 / 3, linear
+    projections, text_time additional conditioning): native forward vs the oracle, and through the pipeline."""
+    from oracle import sampling as osamp
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_forward, unet_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny_xl()
+    P = synth_params(unet_param_shapes(cfg), seed=99)
+    unet = B200UNet(cfg).load_state_dict(P)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    t = torch.tensor([801, 33])
+    added = {"text_embeds": torch.randn(2, 32, generator=g), "time_ids": torch.tensor([[128., 128, 0, 0, 128, 128]] * 2)}
+    ref = unet_forward(P, cfg, x, t, ctx, added_cond_kwargs=added)
+    out = unet(x.cuda().half(), t.cuda(), encoder_hidden_states=ctx.cuda().half(),
+               added_cond_kwargs={k: v.cuda() for k, v in added.items()}).sample
+    err = (out.float().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"SDXL-topology UNet forward rel err {err:.3e}")
+    assert err < 2e-2
+    with pytest.raises(ValueError):
+        unet(x.cuda().half(), t.cuda(), encoder_hidden_states=ctx.cuda().half())
+    # pipeline: 8 Euler-a steps with CFG (uncond half gets its own pooled embedding)
+    pipe = B200Pipeline(unet, None)
+    pipe.unet_sample_size_override = 16
+    unc = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    neg = {"text_embeds": torch.randn(2, 32, generator=g), "time_ids": added["time_ids"]}
+    seeds = [420420420, 420420421]
+    res = pipe(ctx.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=8, guidance_scale=5.0,
+               generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
+               output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True,
+               added_cond_kwargs={k: v.cuda() for k, v in added.items()},
+               negative_added_cond_kwargs={k: v.cuda() for k, v in neg.items()})
+    both = {"text_embeds": torch.cat([neg["text_embeds"], added["text_embeds"]]),
+            "time_ids": torch.cat([neg["time_ids"], added["time_ids"]])}
+    lat = osamp.txt2img_latents(osamp.CFGParallel(OracleUNet(cfg, P), unc, ctx, 5.0, both), batch=2, in_channels=4,
+                                height=128, width=128, sample_size=16, seeds=seeds, steps=8, sampler="euler_a")
+    e2 = (res.latents.cpu() - lat).abs().max().item() / lat.abs().max().item()
+    print(f"SDXL-topology pipeline final-latent rel err {e2:.3e}")
+    assert e2 < 2e-2
