@@ -269,10 +269,10 @@ int gyre_b200_unet_workspace_bytes(gyre_b200_handle h, int batch, int height, in
   Exec ex;
   ex.dry = true;
   ex.cap = static_cast<size_t>(1) << 60;
-  // sized for the no-merge case, which is the larger one (ToMe only shrinks K/V)
+  // the dry run reserves the ToMe scratch as well (see UNetModel::transformer)
   GYRE_TRY(static_cast<UNetModel*>(M(h))->forward(ex, nullptr, nullptr, nullptr, nullptr, batch, height, width, ctx_len,
                                                   nullptr, nullptr));
-  *bytes = ex.peak + (64u << 20);   // headroom for ToMe scratch
+  *bytes = ex.peak + (1u << 20);
   return 0;
 }
 

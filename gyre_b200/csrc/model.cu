@@ -476,12 +476,15 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   void* tws = nullptr;
   size_t tome_bytes = 0;
   const int rr = r > 0 ? (r < HW / 2 ? r : HW / 2) : 0;
-  if (rr > 0) {
-    GYRE_REQUIRE(t.blocks.size() == 1, "ToMe is wired for transformer depth 1");
+  if (rr > 0 || ex.dry) {
+    // the sizing (dry) run reserves the ToMe scratch for the smallest merge (largest K/V), so that a workspace sized
+    // once serves every r
+    GYRE_REQUIRE(ex.dry || t.blocks.size() == 1, "ToMe is wired for transformer depth 1");
     GYRE_TRY(tome_workspace_bytes(B, HW, C, &tome_bytes));
     tws = ex.alloc_s(tome_bytes);
-    km = ex.s16(static_cast<size_t>(B) * (HW - rr) * C);
-    vm = ex.s16(static_cast<size_t>(B) * (HW - rr) * C);
+    const int nk_max = ex.dry ? HW : HW - rr;
+    km = ex.s16(static_cast<size_t>(B) * nk_max * C);
+    vm = ex.s16(static_cast<size_t>(B) * nk_max * C);
   }
   // h holds the residual stream on entry to every block and again on exit (h -> h2 -> h -> h2 -> copy-free swap)
   for (size_t bi = 0; bi < t.blocks.size(); ++bi) {
