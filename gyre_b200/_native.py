@@ -44,6 +44,14 @@ class UNetConfigC(C.Structure):
     ]
 
 
+class ClipConfigC(C.Structure):
+    _fields_ = [
+        ("vocab_size", C.c_int32), ("hidden_size", C.c_int32), ("intermediate_size", C.c_int32),
+        ("num_layers", C.c_int32), ("num_heads", C.c_int32), ("max_positions", C.c_int32), ("hidden_act", C.c_int32),
+        ("layer_norm_eps", C.c_float),
+    ]
+
+
 class VAEConfigC(C.Structure):
     _fields_ = [
         ("in_channels", C.c_int32), ("out_channels", C.c_int32), ("latent_channels", C.c_int32),
@@ -78,6 +86,9 @@ SIGNATURES = {
     "gyre_b200_vae_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "gyre_b200_vae_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "gyre_b200_clip_create": (_i, [C.POINTER(ClipConfigC), C.POINTER(_vp)]),
+    "gyre_b200_clip_workspace_bytes": (_i, [_vp, _i, _i, C.POINTER(_sz)]),
+    "gyre_b200_clip_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "gyre_b200_destroy": (_i, [_vp]),
     "gyre_b200_sched_step": (_i, [C.POINTER(Step), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "gyre_b200_cfg_combine": (_i, [_vp, _f, _i, _i64, _vp, _vp, _vp]),

@@ -325,7 +325,7 @@ int gyre_b200_vae_create(const gyre_b200_vae_config* cfg, gyre_b200_handle* out)
 
 int gyre_b200_vae_workspace_bytes(gyre_b200_handle h, int batch, int latent_h, int latent_w, size_t* bytes) {
   GYRE_REQUIRE(h && bytes, "vae_workspace_bytes: null argument");
-  GYRE_REQUIRE(!M(h)->is_unet(), "vae_workspace_bytes: handle is not a VAE");
+  GYRE_REQUIRE(M(h)->kind() == 1, "vae_workspace_bytes: handle is not a VAE");
   VAEModel* v = static_cast<VAEModel*>(M(h));
   Exec ex;
   ex.dry = true;
@@ -343,7 +343,7 @@ int gyre_b200_vae_workspace_bytes(gyre_b200_handle h, int batch, int latent_h, i
 int gyre_b200_vae_decode(gyre_b200_handle h, const void* z, int batch, int latent_h, int latent_w, int postprocess,
                          void* img, uint8_t* img_u8, void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
   GYRE_REQUIRE(h && z, "vae_decode: null argument");
-  GYRE_REQUIRE(!M(h)->is_unet(), "vae_decode: handle is not a VAE");
+  GYRE_REQUIRE(M(h)->kind() == 1, "vae_decode: handle is not a VAE");
   Exec ex;
   GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
   return static_cast<VAEModel*>(M(h))->decode(ex, static_cast<const __half*>(z), batch, latent_h, latent_w,
@@ -353,11 +353,48 @@ int gyre_b200_vae_decode(gyre_b200_handle h, const void* z, int batch, int laten
 int gyre_b200_vae_encode(gyre_b200_handle h, const void* img, int batch, int height, int width, void* moments,
                          void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
   GYRE_REQUIRE(h && img && moments, "vae_encode: null argument");
-  GYRE_REQUIRE(!M(h)->is_unet(), "vae_encode: handle is not a VAE");
+  GYRE_REQUIRE(M(h)->kind() == 1, "vae_encode: handle is not a VAE");
   Exec ex;
   GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
   return static_cast<VAEModel*>(M(h))->encode(ex, static_cast<const __half*>(img), batch, height, width,
                                               static_cast<__half*>(moments));
+}
+
+int gyre_b200_clip_create(const gyre_b200_clip_config* cfg, gyre_b200_handle* out) {
+  GYRE_REQUIRE(cfg && out, "clip_create: null argument");
+  GYRE_REQUIRE(cfg->vocab_size > 0 && cfg->num_layers > 0 && cfg->num_heads > 0 && cfg->max_positions > 0 &&
+                   cfg->max_positions <= 128,
+               "clip_create: bad sizes");
+  GYRE_REQUIRE(cfg->hidden_size % 8 == 0 && cfg->intermediate_size % 8 == 0 && cfg->hidden_size % cfg->num_heads == 0 &&
+                   (cfg->hidden_size / cfg->num_heads) <= 128,
+               "clip_create: hidden %d / heads %d unsupported", cfg->hidden_size, cfg->num_heads);
+  GYRE_REQUIRE(cfg->hidden_act == 0 || cfg->hidden_act == 1, "clip_create: hidden_act must be quick_gelu (0) or gelu (1)");
+  ClipTextModel* m = new (std::nothrow) ClipTextModel(*cfg);
+  GYRE_REQUIRE(m != nullptr, "clip_create: out of host memory");
+  *out = reinterpret_cast<gyre_b200_handle>(static_cast<Model*>(m));
+  return 0;
+}
+
+int gyre_b200_clip_workspace_bytes(gyre_b200_handle h, int batch, int seq_len, size_t* bytes) {
+  GYRE_REQUIRE(h && bytes, "clip_workspace_bytes: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 2, "clip_workspace_bytes: handle is not a text encoder");
+  Exec ex;
+  ex.dry = true;
+  ex.cap = static_cast<size_t>(1) << 60;
+  GYRE_TRY(static_cast<ClipTextModel*>(M(h))->forward(ex, nullptr, batch, seq_len, 0, true, nullptr));
+  *bytes = ex.peak + 4096;
+  return 0;
+}
+
+int gyre_b200_clip_forward(gyre_b200_handle h, const int64_t* input_ids, int batch, int seq_len, int skip_last,
+                           int apply_final_ln, void* out, void* workspace, size_t workspace_bytes,
+                           gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && input_ids && out, "clip_forward: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 2, "clip_forward: handle is not a text encoder");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return static_cast<ClipTextModel*>(M(h))->forward(ex, input_ids, batch, seq_len, skip_last, apply_final_ln != 0,
+                                                    static_cast<__half*>(out));
 }
 
 int gyre_b200_destroy(gyre_b200_handle h) {

@@ -357,6 +357,116 @@ int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_samp
   return 0;
 }
 
+// ------------------------------------------------------------------ text encoder: embeddings + causal attention
+// hidden = token_embedding[ids] + position_embedding[pos]   (transformers CLIPTextEmbeddings.forward)
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const uint4* __restrict__ tok,
+                                    const uint4* __restrict__ pos, int L, int nvec, int vocab, uint4* __restrict__ out,
+                                    int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % nvec);
+  const int64_t row = i / nvec;
+  const int p = static_cast<int>(row % L);
+  int64_t id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const uint4 a = tok[id * nvec + v], b = pos[static_cast<int64_t>(p) * nvec + v];
+  const __half2* ah = reinterpret_cast<const __half2*>(&a);
+  const __half2* bh = reinterpret_cast<const __half2*>(&b);
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 x = __half22float2(ah[k]), y = __half22float2(bh[k]);
+    oh[k] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+  }
+  out[i] = o;
+}
+int embed_tokens(const int64_t* ids, const __half* tok_emb, const __half* pos_emb, int B, int L, int C, int vocab,
+                 __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(ids && tok_emb && pos_emb && out && B > 0 && L > 0 && C % 8 == 0, "embed_tokens: bad arguments");
+  const int64_t total = static_cast<int64_t>(B) * L * (C / 8);
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  embed_tokens_kernel<<<blocks_for(total, 256), 256, 0, st>>>(ids, reinterpret_cast<const uint4*>(tok_emb),
+                                                              reinterpret_cast<const uint4*>(pos_emb), L, C / 8, vocab,
+                                                              reinterpret_cast<uint4*>(out), total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Causal self-attention of one (batch, head) per CTA for L <= 128, d <= 128 (CLIP: L = 77, d = 64): 0.1 % of the
+// sampling path's work, so plain FMA code - K and V of the head sit in shared memory as fp32, one warp per query
+// row, lanes over keys for the scores and over channels for P.V.  (The tcgen05 flash kernels have no mask input.)
+__global__ void __launch_bounds__(128) causal_attn_kernel(const __half* __restrict__ qkv, int L, int heads, int d,
+                                                          float scale, __half* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int C = heads * d;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int dp = d + 1;
+  float* sK = sm;                     // [L][d + 1]
+  float* sV = sK + L * dp;            // [L][d + 1]
+  float* sQ = sV + L * dp;            // [4 warps][d]
+  float* sP = sQ + 4 * d;             // [4 warps][L]
+  const __half* base = qkv + static_cast<int64_t>(b) * L * 3 * C + h * d;
+  for (int i = threadIdx.x; i < L * d; i += 128) {
+    const int j = i / d, c = i - j * d;
+    sK[j * dp + c] = __half2float(base[static_cast<int64_t>(j) * 3 * C + C + c]);
+    sV[j * dp + c] = __half2float(base[static_cast<int64_t>(j) * 3 * C + 2 * C + c]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q = sQ + warp * d;
+  float* pr = sP + warp * L;
+  for (int i = warp; i < L; i += 4) {
+    for (int c = lane; c < d; c += 32) q[c] = __half2float(base[static_cast<int64_t>(i) * 3 * C + c]) * scale;
+    __syncwarp();
+    float sc[4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane + 32 * t;
+      float a = -INFINITY;
+      if (j <= i) {
+        a = 0.f;
+        for (int c = 0; c < d; ++c) a = fmaf(q[c], sK[j * dp + c], a);
+      }
+      sc[t] = a;
+      m = fmaxf(m, a);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane + 32 * t;
+      const float e = j <= i ? __expf(sc[t] - m) : 0.f;
+      if (j < L) pr[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    for (int c = lane; c < d; c += 32) {
+      float acc = 0.f;
+      for (int j = 0; j <= i; ++j) acc = fmaf(pr[j], sV[j * dp + c], acc);
+      out[(static_cast<int64_t>(b) * L + i) * C + h * d + c] = __float2half_rn(acc * inv);
+    }
+    __syncwarp();
+  }
+}
+int causal_attention_short(const __half* qkv, int B, int L, int heads, int d, float scale, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(qkv && out && B > 0 && heads > 0, "causal_attention: bad arguments");
+  GYRE_REQUIRE(L >= 1 && L <= 128 && d >= 8 && d <= 128, "causal_attention: L=%d (<= 128), d=%d (<= 128)", L, d);
+  const size_t smem = (static_cast<size_t>(2) * L * (d + 1) + 4 * d + 4 * L) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    GYRE_CHECK_CUDA(cudaFuncSetAttribute(causal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  prof::Scope ps(prof::F_ATTN, 2.0 * B * heads * static_cast<double>(L) * L * d, 2.0 * B * L * heads * d * 4.0, st);
+  causal_attn_kernel<<<dim3(heads, B), 128, smem, st>>>(qkv, L, heads, d, scale, out);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ K8: VAE tail  (x/2+0.5).clamp(0,1), NHWC -> NCHW
 __global__ void vae_tail_kernel(const __half* __restrict__ x, int ldx, int HW, int post, __half* __restrict__ out,
                                 uint8_t* __restrict__ u8, int64_t total) {

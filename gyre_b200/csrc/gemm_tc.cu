@@ -510,6 +510,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (ep.act == ACT_SILU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            } else if (ep.act == ACT_QUICKGELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * rcp_approx(1.0f + ex2_approx(-2.4554669595930156f * v[j]));
+            } else if (ep.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
             }
           }
           if (has_res) {
@@ -592,6 +598,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (ep.act == ACT_SILU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            } else if (ep.act == ACT_QUICKGELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * rcp_approx(1.0f + ex2_approx(-2.4554669595930156f * v[j]));
+            } else if (ep.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
             }
             if (res) {
               for (int j = 0; j < 32; ++j)

@@ -939,4 +939,75 @@ int VAEModel::encode(Exec& ex, const __half* img, int B, int H, int W, __half* m
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ CLIP text encoder
+// transformers CLIPTextModel (CLIPTextTransformer): embeddings -> num_layers x [LN1 -> causal self-attention
+// (q, k, v, out projections with bias) -> +res ; LN2 -> fc1 -> quick_gelu -> fc2 -> +res] -> final LayerNorm.
+ClipTextModel::ClipTextModel(const gyre_b200_clip_config& cfg) : cfg_(cfg) {
+  const int C = cfg.hidden_size, F = cfg.intermediate_size;
+  tok_emb_ = static_cast<__half*>(dalloc(sizeof(__half) * static_cast<size_t>(cfg.vocab_size) * C));
+  pos_emb_ = static_cast<__half*>(dalloc(sizeof(__half) * static_cast<size_t>(cfg.max_positions) * C));
+  reg("text_model.embeddings.token_embedding.weight", P_LINEAR, tok_emb_, {cfg.vocab_size, C}, C);
+  reg("text_model.embeddings.position_embedding.weight", P_LINEAR, pos_emb_, {cfg.max_positions, C}, C);
+  layers_.resize(cfg.num_layers);
+  for (int i = 0; i < cfg.num_layers; ++i) {
+    ClipLayerW* l = &layers_[i];
+    const std::string p = "text_model.encoder.layers." + std::to_string(i);
+    reg_norm(p + ".layer_norm1", C, &l->ln1);
+    reg_norm(p + ".layer_norm2", C, &l->ln2);
+    // fused [q ; k ; v] projection with its fused bias
+    l->qkv.N = 3 * C;
+    l->qkv.K = C;
+    l->qkv.w = static_cast<__half*>(dalloc(sizeof(__half) * 3 * C * C));
+    l->qkv.bias = static_cast<float*>(dalloc(sizeof(float) * 3 * C));
+    const char* names[3] = {"q_proj", "k_proj", "v_proj"};
+    for (int j = 0; j < 3; ++j) {
+      reg(p + ".self_attn." + names[j] + ".weight", P_LINEAR, l->qkv.w ? l->qkv.w + static_cast<size_t>(j) * C * C : nullptr,
+          {C, C}, C);
+      reg(p + ".self_attn." + names[j] + ".bias", P_F32, l->qkv.bias ? l->qkv.bias + j * C : nullptr, {C});
+    }
+    reg_linear(p + ".self_attn.out_proj", C, C, true, &l->out);
+    reg_linear(p + ".mlp.fc1", F, C, true, &l->fc1);
+    reg_linear(p + ".mlp.fc2", C, F, true, &l->fc2);
+  }
+  reg_norm("text_model.final_layer_norm", C, &final_ln_);
+}
+
+int ClipTextModel::forward(Exec& ex, const int64_t* ids, int B, int L, int skip_last, bool final_ln, __half* out) {
+  GYRE_REQUIRE(B > 0 && L > 0 && L <= cfg_.max_positions && L <= 128, "clip_forward: sequence length %d (max %d)", L,
+               cfg_.max_positions);
+  GYRE_REQUIRE(skip_last >= 0 && skip_last <= cfg_.num_layers, "clip_forward: skip_last %d", skip_last);
+  if (!ex.dry) GYRE_TRY(ensure_device());
+  const int C = cfg_.hidden_size, F = cfg_.intermediate_size, H = cfg_.num_heads;
+  const int d = C / H;
+  const int M = B * L;
+  const size_t n = static_cast<size_t>(M) * C;
+  const float eps = cfg_.layer_norm_eps;
+  const float scale = 1.0f / sqrtf(static_cast<float>(d));
+  __half* h = ex.p16(n);
+  __half* h2 = ex.p16(n);
+  __half* nrm = ex.p16(n);
+  __half* qkv = ex.p16(n * 3);
+  __half* att = ex.p16(n);
+  __half* mid = ex.p16(static_cast<size_t>(M) * F);
+  RUN(ex, embed_tokens(ids, tok_emb_, pos_emb_, B, L, C, cfg_.vocab_size, h, ex.st));
+  const int act = cfg_.hidden_act == 0 ? ACT_QUICKGELU : ACT_GELU;
+  for (int i = 0; i < cfg_.num_layers - skip_last; ++i) {
+    const ClipLayerW& l = layers_[i];
+    RUN(ex, layernorm_rows(h, M, C, eps, l.ln1.g, l.ln1.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, C, l.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C, l.qkv.bias), ex.st));
+    RUN(ex, causal_attention_short(qkv, B, L, H, d, scale, att, ex.st));
+    RUN(ex, gemm_f16(att, C, l.out.w, C, M, C, C, ep_out(h2, C, l.out.bias, h, C), ex.st));          // h2 = h + attn
+    RUN(ex, layernorm_rows(h2, M, C, eps, l.ln2.g, l.ln2.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, C, l.fc1.w, C, M, F, C, ep_out(mid, F, l.fc1.bias, nullptr, 0, act), ex.st));
+    RUN(ex, gemm_f16(mid, F, l.fc2.w, F, M, C, F, ep_out(h, C, l.fc2.bias, h2, C), ex.st));           // h = h2 + mlp
+  }
+  if (final_ln) {
+    RUN(ex, layernorm_rows(h, M, C, eps, final_ln_.g, final_ln_.b, out, ex.st));
+  } else if (!ex.dry) {
+    GYRE_CHECK_CUDA(cudaMemcpyAsync(out, h, n * sizeof(__half), cudaMemcpyDeviceToDevice, ex.st));
+  }
+  EX_CHECK(ex);
+  return 0;
+}
+
 }  // namespace gyre

@@ -92,6 +92,7 @@ class Model {
   int finalize();
   int device() const { return device_; }
   virtual bool is_unet() const = 0;
+  virtual int kind() const { return is_unet() ? 0 : 1; }   // 0 unet, 1 vae, 2 clip text encoder
 
  protected:
   Model();
@@ -187,6 +188,26 @@ class VAEModel : public Model {
   VaeAttnW enc_attn_;
   NormW enc_norm_out_;
   Conv3W enc_conv_out_;
+};
+
+struct ClipLayerW {
+  NormW ln1, ln2;
+  LinW qkv, out, fc1, fc2;
+};
+
+class ClipTextModel : public Model {
+ public:
+  explicit ClipTextModel(const gyre_b200_clip_config& cfg);
+  bool is_unet() const override { return false; }
+  int kind() const override { return 2; }
+  int forward(Exec& ex, const int64_t* ids, int B, int L, int skip_last, bool final_ln, __half* out);
+
+ private:
+  gyre_b200_clip_config cfg_;
+  __half* tok_emb_ = nullptr;   // [vocab, C]
+  __half* pos_emb_ = nullptr;   // [max_positions, C]
+  std::vector<ClipLayerW> layers_;
+  NormW final_ln_;
 };
 
 }  // namespace gyre

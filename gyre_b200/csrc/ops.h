@@ -9,7 +9,7 @@
 namespace gyre {
 
 enum OutMode { OUT_F16 = 0, OUT_F32 = 1 };
-enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2, ACT_ROWMAX = 3 };
+enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2, ACT_ROWMAX = 3, ACT_QUICKGELU = 4, ACT_GELU = 5 };
 
 // Epilogue description shared by the GEMM and the implicit-GEMM conv.
 struct Epilogue {
@@ -74,6 +74,12 @@ int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gam
 // h*d), k/v [B, Nk, ldk/ldv]; writes out [B, Nq, ldo] (head h at columns h*d).  d % 8 == 0, d <= 192.
 int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, int B, int heads,
                   int Nq, int Nk, int d, float scale, __half* out, int ldo, cudaStream_t st);
+
+// Text-encoder kernels (CLIP): token + position embedding gather, and causal self-attention over short sequences
+// (L <= 128) read in place from the fused q|k|v projection [B, L, 3C].
+int embed_tokens(const int64_t* ids, const __half* tok_emb, const __half* pos_emb, int B, int L, int C, int vocab,
+                 __half* out, cudaStream_t st);
+int causal_attention_short(const __half* qkv, int B, int L, int heads, int d, float scale, __half* out, cudaStream_t st);
 
 // Row softmax on fp32 scores [rows, n] -> fp16 probs [rows, ldp] (VAE single-head attention).
 int softmax_rows_f32(const float* s, int rows, int n, float scale, __half* p, int ldp, cudaStream_t st);

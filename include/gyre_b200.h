@@ -164,6 +164,35 @@ int gyre_b200_vae_decode(gyre_b200_handle h, const void* z, int batch, int laten
 int gyre_b200_vae_encode(gyre_b200_handle h, const void* img, int batch, int height, int width, void* moments,
                          void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CLIP text encoder  (the step right before the sampling path: replaces
+ *   transformers CLIPTextModel.forward as called through gyre's TextEncoderAltLayer,
+ *   gyre/pipeline/text_embedding/text_encoder_alt_layer.py:6-36, from the LPW embedding code,
+ *   gyre/pipeline/text_embedding/lpw_text_embedding.py:195-386)
+ * Parameter keys are the transformers state-dict names ("text_model.embeddings.token_embedding.weight",
+ * "text_model.encoder.layers.3.self_attn.q_proj.weight", ...), handed over with gyre_b200_load_weight.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gyre_b200_clip_config {
+  int32_t vocab_size;              /* 49408                          */
+  int32_t hidden_size;             /* 768 (CLIP-L) / 1024 (ViT-H)    */
+  int32_t intermediate_size;       /* 3072 / 4096                    */
+  int32_t num_layers;              /* 12 / 23-24                     */
+  int32_t num_heads;               /* 12 / 16                        */
+  int32_t max_positions;           /* 77                             */
+  int32_t hidden_act;              /* 0 quick_gelu, 1 gelu (erf)     */
+  float layer_norm_eps;            /* 1e-5                           */
+} gyre_b200_clip_config;
+
+int gyre_b200_clip_create(const gyre_b200_clip_config* cfg, gyre_b200_handle* out);
+int gyre_b200_clip_workspace_bytes(gyre_b200_handle h, int batch, int seq_len, size_t* bytes);
+/* input_ids [batch, seq_len] int64 -> out [batch, seq_len, hidden] fp16.
+ * skip_last = 0: last_hidden_state ("final").  skip_last = k > 0: final_layer_norm(hidden_states[-(k+1)]),
+ * i.e. TextEncoderAltLayer's "penultimate" (k = 1) / integer layer (k = layer - 1).
+ * apply_final_ln = 0 returns the selected hidden state without the final LayerNorm. */
+int gyre_b200_clip_forward(gyre_b200_handle h, const int64_t* input_ids, int batch, int seq_len, int skip_last,
+                           int apply_final_ln, void* out, void* workspace, size_t workspace_bytes,
+                           gyre_b200_stream stream);
+
 int gyre_b200_destroy(gyre_b200_handle h);
 
 /* ------------------------------------------------------------------------------------------

@@ -183,6 +183,39 @@ def pin_tome():
     print("tome pinned:", len(out))
 
 
+def pin_clip():
+    """The CLIP text-encoder oracle against the INSTALLED transformers CLIPTextModel (random-init, seeded)."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from oracle import clip as oclip
+    out = {}
+    for act in ("quick_gelu", "gelu"):
+        cfg = CLIPTextConfig(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=3,
+                             num_attention_heads=4, max_position_embeddings=77, hidden_act=act)
+        torch.manual_seed(7)
+        m = CLIPTextModel(cfg).eval()
+        sd = {k: v.clone() for k, v in m.state_dict().items() if not k.endswith("position_ids")}
+        g = torch.Generator().manual_seed(3)
+        # make the norms / biases non-trivial
+        for k in sd:
+            if k.endswith("bias") or "layer_norm" in k:
+                sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
+        m.load_state_dict(sd, strict=False)
+        ids = torch.randint(0, 1000, (2, 77), generator=g)
+        with torch.no_grad():
+            ref = m(ids, output_hidden_states=True)
+        last, hs = oclip.clip_text_forward(sd, ids, num_layers=3, num_heads=4, hidden_act=act)
+        err = (last - ref.last_hidden_state).abs().max().item()
+        assert err < 2e-5, f"clip oracle != transformers ({act}): {err}"
+        for a, b in zip(hs, ref.hidden_states):
+            assert (a - b).abs().max().item() < 2e-5
+        pen = m.text_model.final_layer_norm(ref.hidden_states[-2])
+        assert (oclip.alt_layer(sd, ids, "penultimate", num_layers=3, num_heads=4, hidden_act=act) - pen).abs().max() < 2e-5
+        out[act] = {"state_dict": sd, "ids": ids, "last_hidden_state": ref.last_hidden_state,
+                    "penultimate": pen.detach(), "hidden_states": [t.detach() for t in ref.hidden_states]}
+    torch.save(out, os.path.join(GOLD, "clip.pt"))
+    print("clip pinned against transformers", __import__("transformers").__version__)
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -238,4 +271,5 @@ if __name__ == "__main__":
     pin_samplers()
     pin_ddim()
     pin_tome()
+    pin_clip()
     oracle_fixtures(a.full)
