@@ -46,9 +46,10 @@ def generate_latents(generators, batch, in_channels, height, width, sample_size,
 
 
 class B200Pipeline:
-    def __init__(self, unet, vae=None):
+    def __init__(self, unet, vae=None, text_encoder=None):
         self.unet = unet
         self.vae = vae
+        self.text_encoder = text_encoder   # B200CLIPTextModel or None: embeddings are passed in
         self.device = unet.device
         self.vae_scale_factor = 8
         self._options = {}
@@ -59,6 +60,13 @@ class B200Pipeline:
         if self.unet_sample_size_override is not None:
             return self.unet_sample_size_override
         return max(64, getattr(unet.config, "sample_size", 64))
+
+    def encode_prompt(self, input_ids, clip_layer="final"):
+        """Token ids [B, 77] -> text embeddings [B, 77, C] on the native text encoder, with TextEncoderAltLayer's
+        layer choice (text_encoder_alt_layer.py:17-36).  Tokenisation and prompt weighting stay upstream."""
+        if self.text_encoder is None:
+            raise ValueError("no text encoder attached to this pipeline")
+        return self.text_encoder.encode(input_ids, clip_layer)
 
     def set_options(self, options: dict):
         """Subset of UnifiedPipeline.set_options (unified_pipeline.py:1538-1629) that concerns the hot path."""
