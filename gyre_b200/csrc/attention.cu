@@ -1396,61 +1396,28 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   GYRE_REQUIRE(blocks < (1ll << 31), "attention: grid too large");
   const unsigned nb = static_cast<unsigned>(blocks);
   if (p.d > 64) return launch_attn2_v<AV_PTMEM | AV_PACKED | AV_POLY25, 2>(tq, tk, tv, p, nb, st);
+  // Compiled-in variants = the ones the A/B record in profiles/r01_ab_attn.txt covers (each flag alone on top of its
+  // predecessor, the default, the negative results and the no-exp timing floor).
   switch (tunable(TUNE_ATT_VARIANT)) {
-    // 1000+: the 16-softmax-warp kernel (attention4); low bits select the arithmetic of the exponentials
-    case 1000: return launch_attn4_v<0>(tq, tk, tv, p, nb, st);
-    case 1000 + AV_PACKED: return launch_attn4_v<AV_PACKED>(tq, tk, tv, p, nb, st);
-    case 1000 + (AV_PACKED | AV_POLY25): return launch_attn4_v<AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case 1000 + (AV_PACKED | AV_POLY50): return launch_attn4_v<AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
-    case 1000 + (AV_PACKED | AV_NOEXP): return launch_attn4_v<AV_PACKED | AV_NOEXP>(tq, tk, tv, p, nb, st);
     case 0: return launch_attn2_v<0>(tq, tk, tv, p, nb, st);
     case AV_STAGGER: return launch_attn2_v<AV_STAGGER>(tq, tk, tv, p, nb, st);
     case AV_STAGGER | AV_PACKED: return launch_attn2_v<AV_STAGGER | AV_PACKED>(tq, tk, tv, p, nb, st);
     case AV_STAGGER | AV_PACKED | AV_POLY25: return launch_attn2_v<AV_STAGGER | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_STAGGER | AV_PACKED | AV_POLY50: return launch_attn2_v<AV_STAGGER | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
-    case AV_PACKED | AV_POLY25: return launch_attn2_v<AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_STAGGER | AV_F16EXP: return launch_attn2_v<AV_STAGGER | AV_F16EXP>(tq, tk, tv, p, nb, st);
-    case AV_STAGGER | AV_NOEXP: return launch_attn2_v<AV_STAGGER | AV_NOEXP>(tq, tk, tv, p, nb, st);
     case AV_SPLIT: return launch_attn2_v<AV_SPLIT>(tq, tk, tv, p, nb, st);
-    case AV_SPLIT | AV_STAGGER: return launch_attn2_v<AV_SPLIT | AV_STAGGER>(tq, tk, tv, p, nb, st);
-    case AV_SPLIT | AV_STAGGER | AV_PACKED: return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_PACKED>(tq, tk, tv, p, nb, st);
-    case AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY25:
-      return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY50:
-      return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
     case AV_SPLIT | AV_PACKED | AV_POLY25: return launch_attn2_v<AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_SPLIT | AV_STAGGER | AV_NOEXP: return launch_attn2_v<AV_SPLIT | AV_STAGGER | AV_NOEXP>(tq, tk, tv, p, nb, st);
     case AV_PTMEM | AV_SPLIT: return launch_attn2_v<AV_PTMEM | AV_SPLIT>(tq, tk, tv, p, nb, st);
-    case AV_PTMEM | AV_SPLIT | AV_PACKED: return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED>(tq, tk, tv, p, nb, st);
-    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_STAGGER:
-      return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_STAGGER>(tq, tk, tv, p, nb, st);
-    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
+    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:      // 198: default
       return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
     case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50:
       return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
-    case AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER:
-      return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER>(tq, tk, tv, p, nb, st);
     case AV_PTMEM | AV_SPLIT | AV_NOEXP: return launch_attn2_v<AV_PTMEM | AV_SPLIT | AV_NOEXP>(tq, tk, tv, p, nb, st);
-    case AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED:
-      return launch_attn2_v<AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED>(tq, tk, tv, p, nb, st);
-    case AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
-      return launch_attn2_v<AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50:
-      return launch_attn2_v<AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
-    case AV_TURNS | AV_SPLIT | AV_PACKED | AV_POLY25:
-      return launch_attn2_v<AV_TURNS | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED:
-      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED>(tq, tk, tv, p, nb, st);
     case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
       return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50:
-      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY50>(tq, tk, tv, p, nb, st);
-    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER:
-      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25 | AV_STAGGER>(tq, tk, tv, p, nb, st);
-    case AV_LAZYMAX | AV_SPLIT | AV_PACKED | AV_POLY25:
-      return launch_attn2_v<AV_LAZYMAX | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
-    case AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_NOEXP:
-      return launch_attn2_v<AV_LAZYMAX | AV_PTMEM | AV_SPLIT | AV_NOEXP>(tq, tk, tv, p, nb, st);
+    case AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25:
+      return launch_attn2_v<AV_TURNS | AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    // 1000+: the 16-softmax-warp kernel (attention4); low bits select the arithmetic of the exponentials
+    case 1000 + (AV_PACKED | AV_POLY25): return launch_attn4_v<AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
+    case 1000 + (AV_PACKED | AV_NOEXP): return launch_attn4_v<AV_PACKED | AV_NOEXP>(tq, tk, tv, p, nb, st);
   }
   set_last_error("attention: variant %d is not compiled in", tunable(TUNE_ATT_VARIANT));
   return -2;

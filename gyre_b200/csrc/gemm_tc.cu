@@ -770,6 +770,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
 // Tile width: maximise (SM wave efficiency) x (1 - N padding) x (per-tile efficiency of the shape).
 static int pick_bn(long long m_tiles, int N, int act) {
   if (act == ACT_GEGLU) return 256;
+  {
+    const int f = tunable(TUNE_FORCE_BN);   // measurement only
+    if (f == 32 || f == 64 || f == 128 || f == 160 || f == 256) return f;
+  }
   if (N <= 32) return 32;
   if (N <= 64) return 64;
   const int cand[4] = {256, 160, 128, 64};

@@ -70,7 +70,7 @@ if "attn" in what:
         C = heads * d
         qkv = [torch.randn(B2, Nq, 3 * C, device=dev).half() for _ in range(ROT)]
         fl = 4.0 * B2 * heads * Nq * Nq * d
-        for v in (198, 1000, 1002, 1006, 1010, 1034):
+        for v in (0, 1, 3, 7, 64, 70, 192, 198, 202, 224, 454, 710, 1006, 1034):
             us = with_tunable("ATT_VARIANT", v, lambda: graph_time(
                 lambda i: N.attention(qkv[i % ROT][:, :, :C], qkv[i % ROT][:, :, C:2 * C], qkv[i % ROT][:, :, 2 * C:], heads)))
             rec("attn", f"self B{B2} h{heads} N{Nq} d{d} variant {v}", us, fl)
@@ -173,6 +173,20 @@ if "streamk" in what:
             us = with_tunable("STREAMK", sk, lambda: graph_time(lambda i: N.conv3x3(x[i % ROT], wp, cout, bias=bias)))
             rec("streamk", f"conv {B}x{H}x{H} {cin}->{cout} streamk={sk}", us, 2.0 * 9 * cin * cout * B * H * H)
         del x
+
+if "bn" in what:
+    for (M, Nn, K, res) in ((65536, 320, 320, False), (65536, 320, 320, True), (65536, 960, 320, False), (65536, 320, 1280, True),
+                            (16384, 640, 640, True), (4096, 1280, 1280, True)):
+        a = [torch.randn(M, K, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(Nn, K, device=dev).half() * (1 / math.sqrt(K))
+        bias = torch.randn(Nn, device=dev)
+        r = [torch.randn(M, Nn, device=dev).half() for _ in range(ROT)] if res else None
+        for bn in (0, 64, 128, 160, 256):
+            us = with_tunable("FORCE_BN", bn, lambda: graph_time(
+                lambda i: N.gemm(a[i % ROT], w, bias=bias, residual=r[i % ROT] if res else None)))
+            rec("bn", f"gemm M{M} N{Nn} K{K}{' +res' if res else ''} BN={bn or 'auto'}", us, 2.0 * M * Nn * K,
+                2.0 * (M * K + Nn * K + M * Nn * (2 if res else 1)))
+        del a, r
 
 if "copy" in what:
     # calibration: what a plain device copy / reduction achieves at these (small) sizes

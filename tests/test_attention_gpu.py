@@ -73,7 +73,7 @@ def test_attention_peaked_softmax(nat):
 
 # softmax variants of the d <= 64 flash kernel (include/gyre_b200.h: tunable "ATT_VARIANT"): 0 plain, 1 staggered
 # groups, 3 + packed fp32x2 maths, 7 / 11 + polynomial exp2 on 25 % / 50 % of the scores, 6 packed + poly w/o stagger
-@pytest.mark.parametrize("variant", [0, 1, 3, 7, 11, 6, 64, 65, 67, 71, 75, 70, 192, 194, 195, 198, 202, 199, 450, 454, 458, 455, 326, 706, 710, 714, 582, 1000, 1002, 1006, 1010])
+@pytest.mark.parametrize("variant", [0, 1, 3, 7, 64, 70, 192, 198, 202, 454, 710, 1006])
 def test_attention_softmax_variants(nat, variant):
     old = nat.get_tunable("ATT_VARIANT")
     try:
@@ -100,7 +100,7 @@ def test_attention_optimistic_max_redo_path(nat):
     q = (q.float().abs() * 1.5).half()
     old = nat.get_tunable("ATT_VARIANT")
     try:
-        for variant in (454, 450, 326):
+        for variant in (454, 198, 1006):
             nat.set_tunable("ATT_VARIANT", variant)
             out = nat.attention(q, k, v, heads)
             ref = ref_attention(q, k, v, heads)
