@@ -319,3 +319,27 @@ def test_c4_shape_vprediction_linear_proj_tome():
     print(f"C4-mini v-pred + ToMe: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
     # ToMe's argsort can flip near-ties under fp16 scores; the bound allows for a few flipped merges
     assert err < 5e-2 * scale
+
+
+def test_full_size_run_to_run_determinism():
+    """SD1.5 size, 3 Euler-a steps, batch 4: two runs from the same seeds give bit-identical latents.  Every
+    cross-CTA hand-off on the path (stream-K partial sums, the ToMe-free attention pipelines, GroupNorm partials)
+    uses a fixed order, so any difference would be a race."""
+    from gyre_b200.config import UNetConfig
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    from gyre_b200.weights import synth_state_dict, unet_param_shapes
+    dev = torch.device("cuda", 0)
+    cfg = UNetConfig.sd15()
+    unet = B200UNet(cfg, dev).load_state_dict(synth_state_dict(unet_param_shapes(cfg), 1234, dtype=torch.float16, device=dev))
+    pipe = B200Pipeline(unet, None)
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(4, 77, 768, generator=g).half().to(dev)
+    unc = torch.randn(4, 77, 768, generator=g).half().to(dev)
+    outs = []
+    for _ in range(2):
+        gens = [torch.Generator("cpu").manual_seed(100 + i) for i in range(4)]
+        outs.append(pipe(emb, unc, height=512, width=512, num_inference_steps=3, guidance_scale=7.5, generator=gens,
+                         sampler="k_euler_ancestral", output_type="latent", return_fp32_latents=True).latents)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
