@@ -13,12 +13,15 @@ class B200GuidedUNet:
     """`NoisePredictionUNet` protocol object (`eps = f(latents, t)`, gyre/pipeline/unet/types.py:56-59) that
     also exposes the doubled-batch entry the fused scheduler loop uses (`raw`)."""
 
-    def __init__(self, unet, uncond_embeddings, text_embeddings, guidance_scale: float):
+    def __init__(self, unet, uncond_embeddings, text_embeddings, guidance_scale: float, parallel: bool = True):
         if uncond_embeddings.shape != text_embeddings.shape:
             raise ValueError("uncond and text embeddings must have the same shape")
         self.unet = unet
         self.guidance_scale = float(guidance_scale)
         self.batch = text_embeddings.shape[0]
+        # CFGUNet_Parallel (one UNet call on the doubled batch, cfg.py:41-57) or CFGUNet_Sequential (two calls of the
+        # single batch, cfg.py:26-38 - the reference's low-memory execution mode); same results, halves the workspace
+        self.parallel = parallel
         # CFG order is [uncond, cond] (unified_pipeline.py:2335, cfg.py:54)
         self.embeddings = torch.cat([uncond_embeddings, text_embeddings]).to(device=unet.device,
                                                                               dtype=torch.float16).contiguous()
@@ -59,6 +62,8 @@ class B200GuidedUNet:
         return self._xcat
 
     def raw(self, x2_f16, t2_i64, out=None):
+        if not self.parallel:
+            return self._raw_sequential(x2_f16, t2_i64, out)
         x2_f16 = self._expand(x2_f16)
         # The embeddings are fixed for the life of this wrapper (as in UNetWithEmbeddings, core.py:253-259), so
         # the UNet projects them to cross-attention K/V once instead of at every step (tunable CTX_KV_CACHE).
@@ -68,6 +73,20 @@ class B200GuidedUNet:
                 self.unet.set_context(self.embeddings, owner=self)
             return self.unet.forward_raw(x2_f16, t2_i64, None, out=out, add_cond=self.add_cond)
         return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out, add_cond=self.add_cond)
+
+    def _raw_sequential(self, x2_f16, t2_i64, out):
+        """[uncond ; cond] evaluated as two UNet calls of batch B (CFGUNet_Sequential)."""
+        B = self.batch
+        if out is None:
+            out = torch.empty((2 * B, self.unet.config.out_channels, *x2_f16.shape[2:]), device=x2_f16.device,
+                              dtype=torch.float16)
+        xe = self._expand(x2_f16)
+        for half in (0, 1):
+            sl = slice(half * B, (half + 1) * B)
+            add = self.add_cond[sl].contiguous() if self.add_cond is not None else None
+            self.unet.forward_raw(xe[sl].contiguous(), t2_i64[sl].contiguous(), self.embeddings[sl].contiguous(),
+                                  out=out[sl], add_cond=add)
+        return out
 
     def __call__(self, latents, t):
         N.require_cuda(latents)

@@ -178,8 +178,10 @@ class KDiffusionScheduler(CommonScheduler):
     def set_timesteps(self, num_inference_steps, start_offset=None, strength=None, prediction_type="epsilon",
                       config: SchedulerConfig = SchedulerConfig()):
         self._guided()
-        if config.churn and self.accepts_s_churn:
-            raise NotImplementedError("churn > 0 is not implemented in the fused Euler loop")
+        # churn (Karras et al. stochasticity, sampling.py:124-129): the fused Euler kernel has no churn input, so a
+        # churned Euler run takes the generic path like Heun / DPM-2
+        self.churn = config.churn if self.accepts_s_churn else 0
+        self.churn_tmin, self.churn_tmax = config.churn_tmin, config.churn_tmax
         if config.noise_type != "normal":
             raise NotImplementedError("only normal noise is implemented (brownian needs torchsde)")
         self.prediction_type = prediction_type
@@ -252,7 +254,7 @@ class KDiffusionScheduler(CommonScheduler):
         ancestral = self.scheduler == "sample_euler_ancestral"
         eta = 1.0 if self.eta is None else self.eta
         vpred = self.prediction_type == "v_prediction"
-        if self.scheduler in self.GENERIC:
+        if self.scheduler in self.GENERIC or (self.scheduler == "sample_euler" and self.churn):
             return self._loop_generic(latents, sigmas, progress_wrapper, out_dtype, eta)
 
         # ---- host-side scalars for every step, with the reference's fp32 expressions
@@ -390,10 +392,20 @@ class KDiffusionScheduler(CommonScheduler):
         for i in progress_wrapper(range(n)):
             s, s_next = sigmas[i], sigmas[i + 1]
             E.u = self._u(i, n, len(self.sigmas))
-            if name in ("sample_heun", "sample_dpm_2"):
-                E.noise()                                   # `randn_like` is drawn every step (churn 0: unused)
+            if name in ("sample_heun", "sample_dpm_2", "sample_euler"):
+                # sampling.py:124-129 / 165-170 / 194-199: gamma, eps = randn_like (drawn EVERY step), sigma_hat
+                gamma = min(self.churn / n, 2 ** 0.5 - 1) if self.churn_tmin <= s <= self.churn_tmax else 0.0
+                eps = E.noise()
+                s_hat = s * (gamma + 1)
+                if gamma > 0:
+                    x = E.lin([(1.0, x), ((s_hat ** 2 - s ** 2) ** 0.5, eps)])
+                s = s_hat
                 den = E.denoise(x, s)
                 cb(i, den)
+                if name == "sample_euler":
+                    dt = s_next - s
+                    x = E.lin([(1 + dt / s, x), (-dt / s, den)])
+                    continue
                 if s_next == 0:
                     dt = s_next - s                          # Euler: x + (x - den) / s * dt
                     x = E.lin([(1 + dt / s, x), (-dt / s, den)])

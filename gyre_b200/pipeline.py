@@ -89,7 +89,8 @@ class B200Pipeline:
                  sampler: str = "k_euler_ancestral", scheduler_config: SchedulerConfig | None = None,
                  output_type: str = "pt", callback=None, callback_steps: int = 1, progress_wrapper=None,
                  latents_dtype=torch.float16, return_fp32_latents: bool = False, image=None, mask_image=None,
-                 strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None) -> PipelineOutput:
+                 strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None,
+                 cfg_execution: str = "parallel") -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
         unified_pipeline.py:2100-2181.  `image` / `mask_image` are [1, C, H, W] tensors in [0, 1]; the mask is white =
@@ -115,7 +116,10 @@ class B200Pipeline:
         if image is not None and self.vae is None:
             raise ValueError("img2img / inpaint need the VAE (encode)")
 
-        guided = B200GuidedUNet(self.unet, negative_prompt_embeds, prompt_embeds, guidance_scale)
+        if cfg_execution not in ("parallel", "sequential"):
+            raise ValueError(f"cfg_execution must be 'parallel' or 'sequential', got {cfg_execution!r}")
+        guided = B200GuidedUNet(self.unet, negative_prompt_embeds, prompt_embeds, guidance_scale,
+                                parallel=cfg_execution == "parallel")
         if cfg.addition_time_embed_dim:
             if added_cond_kwargs is None:
                 raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")

@@ -110,6 +110,36 @@ def pin_samplers():
                 assert err == 0.0, f"{name}/{steps}/{dtype_name}: oracle != vendored k-diffusion ({err})"
                 out[f"{name}/{steps}/{dtype_name}"] = {"seeds": seeds, "shape": shape, "sigmas": sig_full,
                                                         "result": ref}
+    # churn > 0 (Karras stochasticity) for the samplers that take s_churn
+    for name in ("euler", "heun", "dpm_2"):
+        shape, seeds, steps = (2, 4, 8, 8), [420420420, 420420421], 12
+        gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+        ref_den = kext.DiscreteEpsDDPMDenoiser(toy_eps, acp, quantize=True)
+        sig = ks.append_zero(ref_den.t_to_sigma(torch.linspace(len(ref_den.sigmas) - 1, 0, steps)))
+        x0 = (osamp.batched_randn(shape, gens, "cpu", torch.float32) * sig[0])
+        ns = lambda *_: osamp.batched_randn(shape, gens, "cpu", torch.float32)
+
+        class _T:
+            def __getattr__(self, k):
+                return getattr(torch, k)
+
+            def randn_like(self, inp, **kw):
+                return ns()
+        ks.torch = _T()
+        try:
+            fn = {"euler": ks.sample_euler, "heun": ks.sample_heun, "dpm_2": ks.sample_dpm_2}[name]
+            ref = fn(ref_den, x0, sig, disable=True, s_churn=6.0, s_tmin=0.5, s_tmax=9.0)
+        finally:
+            ks.torch = torch
+        gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+        den = osamp.EpsDenoiser(toy_eps, acp)
+        y0 = osamp.batched_randn(shape, gens, "cpu", torch.float32) * sig[0]
+        ofn = {"euler": osamp.sample_euler, "heun": osamp.sample_heun, "dpm_2": osamp.sample_dpm_2}[name]
+        got = ofn(den, y0, sig, lambda x: osamp.batched_randn(shape, gens, "cpu", torch.float32), s_churn=6.0, s_tmin=0.5,
+                  s_tmax=9.0)
+        assert (got - ref).abs().max().item() == 0.0, f"{name} churn: oracle != vendored"
+        out[f"{name}_churn/12/fp32"] = {"seeds": seeds, "shape": shape, "sigmas": sig, "result": ref,
+                                         "churn": (6.0, 0.5, 9.0)}
     # v-prediction denoiser
     x = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1))
     s = torch.tensor([3.3, 0.7])

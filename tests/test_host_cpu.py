@@ -126,6 +126,23 @@ def test_generic_sampler_host_logic_vs_vendored_golden(enum_name, gold_name, ste
     assert err <= 2e-5 * max(scale, 1.0), f"{enum_name}/{steps}/{dtype_name}: {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("enum_name,gold_name", [("k_euler", "euler"), ("k_heun", "heun"), ("k_dpm_2", "dpm_2")])
+def test_churn_host_logic_vs_vendored_golden(enum_name, gold_name):
+    """s_churn > 0 (sampling.py:124-129): gamma / sigma_hat / the extra noise injection, against the vendored loops."""
+    import os
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "samplers.pt"))[f"{gold_name}_churn/12/fp32"]
+    gens = [torch.Generator("cpu").manual_seed(sd) for sd in gold["seeds"]]
+    sched = cs.build_scheduler(enum_name, gens, "cpu", torch.float32)
+    sched.set_eps_unets([_dummy_guided()])
+    churn, tmin, tmax = gold["churn"]
+    sched.set_timesteps(12, config=cs.SchedulerConfig(churn=churn, churn_tmin=tmin, churn_tmax=tmax))
+    x0 = sched.prepare_initial_latents(batched_randn(gold["shape"], gens, "cpu", torch.float32)).float()
+    sched._make_engine = lambda latents: _CpuEngine(sched, latents, _toy_eps)
+    out = sched._loop_generic(x0, sched.sigmas.float(), lambda it: it, torch.float32, 1.0)
+    err = (out - gold["result"]).abs().max().item()
+    assert err <= 2e-5 * max(gold["result"].abs().max().item(), 1.0), f"{enum_name} churn: {err}"
+
+
 def test_ddim_scheduler_host_state():
     sched = cs.build_scheduler("ddim", [torch.Generator()], "cpu", torch.float32)
     sched.set_eps_unets([_dummy_guided()])

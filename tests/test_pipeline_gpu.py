@@ -75,15 +75,23 @@ def test_generic_sampler_kernels_match_vendored_loops():
                                           N.ptr(den), N.stream_ptr(self.dev)), "denoise")
             return den
 
-    for enum_name, gold_name in (("k_heun", "heun"), ("k_dpm_2", "dpm_2"), ("k_dpm_2_ancestral", "dpm_2_a"), ("k_lms", "lms"),
-                                 ("k_dpmpp_2s_ancestral", "dpmpp_2s_a"), ("k_dpmpp_sde", "dpmpp_sde"), ("k_dpmpp_2m", "dpmpp_2m")):
-        rec = g[f"{gold_name}/20/fp32"]
+    cases = [(e, f"{n}/20/fp32", 20) for e, n in (("k_heun", "heun"), ("k_dpm_2", "dpm_2"), ("k_dpm_2_ancestral", "dpm_2_a"),
+                                                  ("k_lms", "lms"), ("k_dpmpp_2s_ancestral", "dpmpp_2s_a"),
+                                                  ("k_dpmpp_sde", "dpmpp_sde"), ("k_dpmpp_2m", "dpmpp_2m"))]
+    # s_churn > 0: gamma / sigma_hat / noise injection of sample_euler, sample_heun, sample_dpm_2
+    cases += [(e, f"{n}_churn/12/fp32", 12) for e, n in (("k_euler", "euler"), ("k_heun", "heun"), ("k_dpm_2", "dpm_2"))]
+    for enum_name, key, steps in cases:
+        rec = g[key]
         gens = [torch.Generator("cpu").manual_seed(sd) for sd in rec["seeds"]]
         sched = cs.build_scheduler(enum_name, gens, dev, torch.float32)
         guided = object.__new__(B200GuidedUNet)
         guided.guidance_scale = 7.5
         sched.set_eps_unets([guided])
-        sched.set_timesteps(20)
+        if "churn" in rec:
+            churn, tmin, tmax = rec["churn"]
+            sched.set_timesteps(steps, config=cs.SchedulerConfig(churn=churn, churn_tmin=tmin, churn_tmax=tmax))
+        else:
+            sched.set_timesteps(steps)
         x0 = sched.prepare_initial_latents(batched_randn(rec["shape"], gens, dev, torch.float32)).float()
         sched._make_engine = lambda latents, sched=sched: Engine(sched, latents)
         out = sched._loop_generic(x0, sched.sigmas.float(), lambda it: it, torch.float32, 1.0)
@@ -176,6 +184,21 @@ def test_pipeline_batch_independence(tiny):
     both = run([0, 1])
     assert torch.equal(run([0])[0], both[0])
     assert torch.equal(run([1])[0], both[1])
+
+
+def test_cfg_sequential_equals_parallel(tiny):
+    """CFGUNet_Sequential (cfg.py:26-38) == CFGUNet_Parallel (cfg.py:41-57): the kernels are batch-invariant, so two
+    UNet calls of batch B give the bits of one call of batch 2B."""
+    cfg, P, pipe, emb, unc = tiny
+    outs = []
+    for mode in ("parallel", "sequential"):
+        gens = [torch.Generator("cpu").manual_seed(s) for s in (7, 8)]
+        outs.append(pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=5, generator=gens,
+                         sampler="k_dpmpp_2m", output_type="latent", return_fp32_latents=True,
+                         cfg_execution=mode).latents)
+    assert torch.equal(outs[0], outs[1])
+    with pytest.raises(ValueError):
+        pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=1, generator=gens, cfg_execution="x")
 
 
 def _oracle_on_gpu(cfg_name="sd15"):
