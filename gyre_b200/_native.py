@@ -216,14 +216,15 @@ def _epilogue(out, bias=None, residual=None, act=0, rowgroup_bias=None, rows_per
 
 
 def gemm(a, w, bias=None, residual=None, act=0, a2=None, out_dtype=torch.float16, rowgroup_bias=None,
-         rows_per_group=1):
+         rows_per_group=1, out=None):
     """out = epilogue([a | a2] @ w.T); a [M, K1] fp16, w [N, K1+K2] fp16 (GEGLU: pre-packed), bias fp32."""
     require_cuda(a, w)
     M, K1 = a.shape
     K2 = a2.shape[1] if a2 is not None else 0
     N = w.shape[0]
     n_out = N // 2 if act == 1 else N
-    out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
     e = _epilogue(out, bias, residual, act, rowgroup_bias, rows_per_group)
     check(load().gyre_b200_gemm(ptr(a), a.stride(0), K1, ptr(a2), a2.stride(0) if a2 is not None else 0, K2, ptr(w),
                                 w.stride(0), M, N, C.byref(e), stream_ptr(a.device)), "gemm")

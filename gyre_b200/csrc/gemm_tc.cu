@@ -34,7 +34,10 @@ struct GemmParams {
   int tma_epi;        // 1: output (and residual) tiles move through swizzled smem slices with TMA
   int rgb_rows;       // rows of a tile that share one rowgroup-bias vector (staged in smem); 0: per-thread loads
   int fast_gelu;      // GEGLU gate through gelu_fast instead of libdevice erff
-  int mcast;          // 1: CTA pairs (cluster of 2 along M) share every B tile through TMA multicast
+  int stages;         // smem ring depth in use (tunable GEMM_STAGES caps it; measurement only)
+  int mcast;          // CTA pairs (cluster of 2 along M) on one N tile.  1: every B tile is fetched in halves and TMA-
+                      // multicast into both CTAs; 2: ONE tcgen05.mma.cta_group::2 (M = 256) per k step, each CTA holds
+                      // its A tile and half of the B tile only
   // stream-K over the tiles of the last, partial wave (sk_tiles == 0: off)
   int sk_first;       // first tile index handled by stream-K; tiles below it are dealt round-robin as whole tiles
   int sk_tiles;       // number of stream-K tiles (< grid size)
@@ -51,10 +54,11 @@ constexpr int kEpiThreads = 256;
 constexpr int kSliceBytes = kBM * 32 * 2;   // one 128-row x 32-column fp16 epilogue slice (64-byte rows)
 constexpr int kMaxBiasGroups = 2;
 
-template <int BN>
+template <int BN, bool PAIR2 = false>
 struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;
-  static constexpr int B_BYTES = BN * kBK * 2;
+  // B rows held per CTA and stage: the whole BN-row tile, or half of it under cta_group::2 (-> a deeper ring)
+  static constexpr int B_BYTES = (PAIR2 ? BN / 2 : BN) * kBK * 2;
   // epilogue staging: per column-half 2 output + 2 residual slices; per-tile column bias (double buffered)
   static constexpr int EPI_BYTES = 2 * 2 * 2 * kSliceBytes;
   static constexpr int BIAS_BYTES = 2 * kMaxBiasGroups * BN * 4;
@@ -127,14 +131,26 @@ __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col,
 // the same ~96 GB/s per SM at BN = 128, 160 and 256).  In pair mode two CTAs of a cluster work on the two M tiles
 // of the same N tile; each loads its own A tile and HALF of the B tile, multicast into both CTAs' shared memory.
 // A slot is refilled only when both CTAs' MMAs have drained it (their commits arrive on both empty barriers).
-template <int BN, bool CONV>
+//
+// cta_group::2 pairs (p.mcast == 2, the default for everything that is not stream-K): measured on B200, a CTA ingests
+// at most ~45-50 B/clk from L2 whatever the tile shape, so a 128 x BN tile with its (128 + BN) operand rows per k step
+// is ingest-bound at ~85 flop/B (BN = 256) = ~1.0 PFLOP/s - multicast does not help, both CTAs still receive all of B.
+// With cta_group::2 the pair computes a 256 x BN tile from ONE instruction stream: each CTA loads its own 128 A rows
+// and only BN/2 rows of B (the tensor core reads the other half from the peer's shared memory), i.e. 1.5x fewer bytes
+// per flop at BN = 256.  The leader CTA (rank 0) issues every MMA and owns the "stage full" / "accumulator drained"
+// barriers: the peer's TMA loads credit their bytes to the leader's full barrier, the peer's epilogue threads arrive
+// remotely on the leader's drained barrier; commits are multicast to both CTAs' "slot free" / "accumulator ready"
+// barriers.  Each CTA drains its own 128 accumulator rows exactly as in the single-CTA kernel.
+// PAIR2 is a template parameter, not a run-time mode: a kernel image that contains cta_group::2 instructions can only be
+// launched with an even cluster size ("cluster misconfiguration" otherwise), so the single-CTA kernel must not carry them.
+template <int BN, bool CONV, bool PAIR2 = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmA2,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmOut,
                                                               const __grid_constant__ CUtensorMap tmRes,
                                                               const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -152,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int lane = threadIdx.x & 31;
   // work units: tiles, or (pair mode) pairs of M tiles; worker = CTA or cluster
   const int rank = p.mcast ? static_cast<int>(cluster_ctarank()) : 0;
+  constexpr bool pair2 = PAIR2;
   const int worker = p.mcast ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int n_workers = p.mcast ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_tiles = (p.mcast ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
@@ -197,6 +214,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     }
   }
+  const int stages = p.stages;                          // ring depth in use (<= Cfg::STAGES)
+  auto ring_next = [&](int& s, uint32_t& ph) {
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1;
+    }
+  };
   auto get_item = [&](int idx, Item& it) -> bool {
     if (idx < n_sk) {
       it = sk_item[idx];
@@ -222,16 +246,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], p.mcast ? 2 : 1);
+      mbar_init(&empty_bar[s], p.mcast == 1 ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiThreads);
+      mbar_init(&tempty_bar[b], pair2 ? 2 * kEpiThreads : kEpiThreads);
     }
     for (int b = 0; b < 4; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR2) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -243,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      uint32_t g = 0;   // k-iterations issued so far (ring position)
+      int s = 0;          // ring position
+      uint32_t ph = 0;    // ring pass parity
       Item wi;
       for (int idx = 0; get_item(idx, wi); ++idx) {
         const int t = wi.t;
@@ -255,10 +283,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.tile_h;
           n0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tile_n;
         }
-        for (int it = wi.k0; it < wi.k1; ++it, ++g) {
-          const int s = g % Cfg::STAGES;
-          const uint32_t ph = (g / Cfg::STAGES) & 1;
+        for (int it = wi.k0; it < wi.k1; ++it, ring_next(s, ph)) {
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if constexpr (PAIR2) {
+            // both CTAs' loads of this stage are counted on the leader's barrier
+            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+            if (CONV) {
+              const int tap = it / p.cin_chunks;
+              const int cc = it - tap * p.cin_chunks;
+              const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
+              tma_load_4d_2cta(sA + s * Cfg::A_BYTES, &tmA, lead_full, cc * kBK, x0 * p.stride + kw + p.off_x,
+                               y0 * p.stride + kh + p.off_y, n0);
+              tma_load_2d_2cta(sB + s * Cfg::B_BYTES, &tmB, lead_full, tap * p.cin_pad + cc * kBK,
+                               n_tile * BN + rank * (BN / 2));
+            } else {
+              if (it < p.k1_iters)
+                tma_load_2d_2cta(sA + s * Cfg::A_BYTES, &tmA, lead_full, it * kBK, m_tile * kBM);
+              else
+                tma_load_2d_2cta(sA + s * Cfg::A_BYTES, &tmA2, lead_full, (it - p.k1_iters) * kBK, m_tile * kBM);
+              tma_load_2d_2cta(sB + s * Cfg::B_BYTES, &tmB, lead_full, it * kBK, n_tile * BN + rank * (BN / 2));
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
           if (CONV) {
             const int tap = it / p.cin_chunks;
@@ -287,9 +334,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    if constexpr (PAIR2) {
+      // one instruction stream for the pair: the leader issues 256 x BN MMAs over both CTAs' operands
+      if (rank == 0 && elect_one()) {
+        constexpr uint32_t idesc2 = umma_idesc_f16(2 * kBM, BN);
+        int s = 0;
+        uint32_t ph = 0;
+        uint32_t lt = 0;
+        Item wi;
+        for (int idx = 0; get_item(idx, wi); ++idx, ++lt) {
+          const uint32_t buf = lt & 1;
+          const uint32_t use = lt >> 1;
+          mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);   // both CTAs' epilogues have drained this buffer
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * Cfg::BUF_COLS;
+          for (int it = wi.k0; it < wi.k1; ++it, ring_next(s, ph)) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * Cfg::A_BYTES));
+            const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + s * Cfg::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_f16_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc2, (it > wi.k0 || k != 0) ? 1u : 0u);
+            umma_commit_2cta_mcast(&empty_bar[s], 3);     // the slot is free in both CTAs
+          }
+          umma_commit_2cta_mcast(&tfull_bar[buf], 3);     // accumulator halves complete in both CTAs
+        }
+      }
+    } else if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
-      uint32_t g = 0;
+      int s = 0;
+        uint32_t ph = 0;
       uint32_t lt = 0;   // local tile counter
       Item wi;
       for (int idx = 0; get_item(idx, wi); ++idx, ++lt) {
@@ -298,9 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);   // epilogue has drained this buffer's previous tile
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * Cfg::BUF_COLS;
-        for (int it = wi.k0; it < wi.k1; ++it, ++g) {
-          const int s = g % Cfg::STAGES;
-          const uint32_t ph = (g / Cfg::STAGES) & 1;
+        for (int it = wi.k0; it < wi.k1; ++it, ring_next(s, ph)) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * Cfg::A_BYTES));
@@ -622,7 +695,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       if (wi.kind == 2 && etid == 0) p.sk_flags[sk_tt] = 0;   // zero again for the next launch
       tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
+      if constexpr (PAIR2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader waits for both CTAs
+      else mbar_arrive(&tempty_bar[buf]);
       wi = wnext;
       have = have_next;
     }
@@ -632,7 +706,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (p.mcast) cluster_sync_all();   // neither CTA leaves while the other can still signal its barriers
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -658,6 +735,12 @@ static int prepare(int* max_clusters) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     GYRE_CHECK_CUDA(
         cudaFuncSetAttribute(gemm_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    if constexpr (BN >= 64) {
+      GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           GemmCfg<BN, true>::SMEM));
+      GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           GemmCfg<BN, true>::SMEM));
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * sm_count());
     cfg.blockDim = dim3(kThreads);
@@ -692,12 +775,16 @@ static int gemm_max_clusters(int bn, int* n) {
 
 // Pair mode (see the kernel comment) when the tunable allows it, there are at least two M tiles and the device can
 // co-schedule enough clusters.
-static int want_pair_mode(int bn, long long m_tiles, int* mcast) {
+static int want_pair_mode(int bn, long long m_tiles, int k_iters, int* mcast) {
   *mcast = 0;
-  if (!tunable(TUNE_MCAST) || m_tiles < 2 || bn < 64) return 0;
+  // 0 off, 1 multicast pairs, 2 cta_group::2 pairs where they win, 3 cta_group::2 pairs everywhere (measurement)
+  int mode = tunable(TUNE_MCAST);
+  if (mode <= 0 || mode > 3 || m_tiles < 2 || bn < 64) return 0;
+  if (mode == 2 && k_iters < 16) return 0;   // short-K tiles: the pair's per-tile hand-offs cost more than the B half saves
+  if (mode == 3) mode = 2;
   int n = 0;
   GYRE_TRY(gemm_max_clusters(bn, &n));
-  if (n >= sm_count() / 4) *mcast = 1;
+  if (n >= sm_count() / 4) *mcast = mode;
   return 0;
 }
 
@@ -737,17 +824,32 @@ static void plan_stream_k(GemmParams* p, int bn) {
 
 template <int BN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                  const CUtensorMap& tmRes, const GemmParams& p, cudaStream_t st) {
+                  const CUtensorMap& tmRes, const GemmParams& p_in, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
   int max_clusters = 0;
   GYRE_TRY(prepare<BN>(&max_clusters));
   const int sms = sm_count();
+  GemmParams p = p_in;
+  const int cap = tunable(TUNE_GEMM_STAGES);
+  p.stages = (cap >= 2 && cap < Cfg::STAGES) ? cap : Cfg::STAGES;
   if (p.mcast) {
     GYRE_REQUIRE(max_clusters > 0, "gemm: pair mode requested but clusters are unavailable");
     const long long pairs = static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles;
     GYRE_REQUIRE(pairs > 0 && pairs < (1ll << 30), "gemm: bad tile count %lld", pairs);
     const unsigned clusters = static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
+    if constexpr (BN >= 64) {
+      if (p.mcast == 2) {
+        using Cfg2 = GemmCfg<BN, true>;
+        p.stages = (cap >= 2 && cap < Cfg2::STAGES) ? cap : Cfg2::STAGES;
+        if (p.conv)
+          return launch_kernel_cluster(gemm_tc_kernel<BN, true, true>, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM, st,
+                                       2, tmA, tmA2, tmB, tmOut, tmRes, p);
+        return launch_kernel_cluster(gemm_tc_kernel<BN, false, true>, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM, st,
+                                     2, tmA, tmA2, tmB, tmOut, tmRes, p);
+      }
+    }
+    GYRE_REQUIRE(p.mcast == 1, "gemm: pair mode %d is not available at BN %d", p.mcast, BN);
     if (p.conv)
       return launch_kernel_cluster(gemm_tc_kernel<BN, true>, dim3(2 * clusters), dim3(kThreads), Cfg::SMEM, st, 2, tmA,
                                    tmA2, tmB, tmOut, tmRes, p);
@@ -853,10 +955,12 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
   p.m_tiles = (M + kBM - 1) / kBM;
   p.conv = 0;
   p.fast_gelu = tunable(TUNE_GELU_FAST);
-  GYRE_TRY(want_pair_mode(bn, p.m_tiles, &p.mcast));
+  p.mcast = 0;
   p.ep = ep;
   p.rgb_rows = 0;
   p.tma_epi = (tma_epilogue_ok(ep, n_out) && ep.rowgroup_bias == nullptr) ? 1 : 0;
+  plan_stream_k(&p, bn);                                   // stream-K tiles stay single-CTA
+  if (p.sk_tiles == 0) GYRE_TRY(want_pair_mode(bn, p.m_tiles, p.k_iters, &p.mcast));
   CUtensorMap tmA, tmA2, tmB, tmOut, tmRes;
   uint32_t es[2] = {1, 1};
   {
@@ -891,7 +995,6 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
       GYRE_TRY(encode_tmap_f16_sw(&tmRes, ep.residual, 2, dims, sr, box, es, 64));
     }
   }
-  plan_stream_k(&p, bn);
   prof::Scope ps(prof::F_GEMM, 2.0 * M * static_cast<double>(N) * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K +
                         static_cast<double>(M) * n_out * (ep.residual ? 2 : 1)),
@@ -966,7 +1069,7 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
   p.off_x = gm.off_x;
   p.off_y = gm.off_y;
   p.fast_gelu = 0;
-  GYRE_TRY(want_pair_mode(bn, m_tiles, &p.mcast));
+  p.mcast = 0;
   p.ep = ep;
   // the per-sample bias (temb projection) is uniform over the rows of one image inside a tile: stage it with
   // the column bias when a tile holds at most kMaxBiasGroups images
@@ -974,6 +1077,8 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
   if (ep.rowgroup_bias != nullptr && ep.rows_per_group == Ho * Wo && best_n <= kMaxBiasGroups)
     p.rgb_rows = best_w * best_h;
   p.tma_epi = (tma_epilogue_ok(ep, Cout) && (ep.rowgroup_bias == nullptr || p.rgb_rows > 0)) ? 1 : 0;
+  plan_stream_k(&p, bn);                                   // stream-K tiles stay single-CTA
+  if (p.sk_tiles == 0) GYRE_TRY(want_pair_mode(bn, m_tiles, p.k_iters, &p.mcast));
   GYRE_REQUIRE(gm.out_step == 1 || (p.tma_epi && ep.residual == nullptr),
                "conv: a strided output view needs the TMA epilogue (fp16, 16B-aligned rows, no residual)");
   CUtensorMap tmA, tmB, tmOut, tmRes;
@@ -1014,7 +1119,6 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
       GYRE_TRY(encode_tmap_f16_sw(&tmRes, ep.residual, 4, dims, sr, box, es, 64));
     }
   }
-  plan_stream_k(&p, bn);
   prof::Scope ps(prof::F_CONV, gm.algo_flops, gm.algo_bytes, st);
   return dispatch(bn, tmA, tmA, tmB, tmOut, tmRes, p, st);
 }

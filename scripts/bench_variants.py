@@ -137,7 +137,7 @@ if "mcast" in what:
         bias = torch.randn(Nn, device=dev)
         if geglu:
             w, bias = N.pack_geglu(w, bias)
-        for mc in (0, 1):
+        for mc in (0, 3):
             us = with_tunable("MCAST", mc, lambda: graph_time(lambda i: N.gemm(a[i % ROT], w, bias=bias, act=1 if geglu else 0)))
             rec("mcast", f"gemm M{M} N{Nn} K{K}{' geglu' if geglu else ''} mcast={mc}", us, 2.0 * M * Nn * K)
         del a
@@ -147,10 +147,27 @@ if "mcast" in what:
         w = torch.randn(cout, cin, 3, 3, device=dev).half() * (1 / math.sqrt(9 * cin))
         wp = N.pack_conv3x3(w)
         bias = torch.randn(cout, device=dev)
-        for mc in (0, 1):
+        for mc in (0, 3):
             us = with_tunable("MCAST", mc, lambda: graph_time(lambda i: N.conv3x3(x[i % 2], wp, cout, bias=bias), rep=4))
             rec("mcast", f"conv {B}x{H}x{H} {cin}->{cout} mcast={mc}", us, 2.0 * 9 * cin * cout * B * H * H)
         del x
+
+if "stages" in what:
+    # ring depth sweep (is the main loop bound by bytes in flight?) and L2-resident vs HBM-resident A (rot 1 vs 4)
+    for (M, Nn, K) in ((65536, 320, 320), (65536, 320, 1280), (16384, 640, 640), (16384, 320, 1280)):
+        a = [torch.randn(M, K, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(Nn, K, device=dev).half() * (1 / math.sqrt(K))
+        bias = torch.randn(Nn, device=dev)
+        o = [torch.empty(M, Nn, device=dev, dtype=torch.float16) for _ in range(ROT)]
+        for mc in (0, 3):
+            for st in (2, 3, 4, 0):
+                def run():
+                    return with_tunable("GEMM_STAGES", st, lambda: graph_time(lambda i: N.gemm(a[i % ROT], w, bias=bias, out=o[i % ROT])))
+                us = with_tunable("MCAST", mc, run)
+                rec("stages", f"gemm M{M} N{Nn} K{K} mcast={mc} stages={st}", us, 2.0 * M * Nn * K)
+            us = with_tunable("MCAST", mc, lambda: graph_time(lambda i: N.gemm(a[0], w, bias=bias, out=o[0])))
+            rec("stages", f"gemm M{M} N{Nn} K{K} mcast={mc} rot=1 (L2-resident when it fits)", us, 2.0 * M * Nn * K)
+        del a, o
 
 if "streamk" in what:
     for (M, Nn, K) in ((4096, 1280, 1280), (16384, 640, 640), (16384, 640, 2560), (4096, 1280, 5120), (4096, 3840, 1280),

@@ -44,17 +44,20 @@ def test_gemm_shapes(nat, M, N, K):
     assert_close(out, ref, 2e-3, 2e-3, f"gemm {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (300, 1280, 1280), (129, 640, 2560), (1000, 2560, 320), (128, 256, 64)])
-def test_gemm_pair_mode_bit_identical(nat, M, N, K):
-    """CTA-pair mode (B tiles multicast to two CTAs of a cluster) changes who loads what, not the arithmetic:
-    outputs are bit-identical to the single-CTA kernel, including an odd number of M tiles (phantom tile)."""
+@pytest.mark.parametrize("mode", [3, 1])
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (300, 1280, 1280), (129, 640, 2560), (1000, 2560, 320), (128, 256, 64),
+                                   (65536, 320, 320), (16384, 1920, 640)])
+def test_gemm_pair_mode_bit_identical(nat, M, N, K, mode):
+    """CTA-pair modes (2: one tcgen05.mma.cta_group::2 of M = 256 per k step, each CTA holding half of the B tile;
+    1: B tiles multicast to both CTAs) change who loads and issues what, not the arithmetic: outputs are bit-identical
+    to the single-CTA kernel, including an odd number of M tiles (phantom tile)."""
     a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K))
     bias = rnd(N, seed=3, dtype=torch.float32)
     res = rnd(M, N, seed=4)
     old, old_sk = nat.get_tunable("MCAST"), nat.get_tunable("STREAMK")
     try:
         nat.set_tunable("STREAMK", 0)           # stream-K changes the fp32 summation order
-        nat.set_tunable("MCAST", 1)
+        nat.set_tunable("MCAST", mode)
         o1 = nat.gemm(a, w, bias=bias, residual=res)
         nat.set_tunable("MCAST", 0)
         o0 = nat.gemm(a, w, bias=bias, residual=res)
@@ -110,9 +113,10 @@ def test_conv_stream_k(nat):
         assert (o1.float() - o0.float()).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
 
 
-def test_conv_pair_mode_bit_identical(nat):
+@pytest.mark.parametrize("mode", [3, 1])
+def test_conv_pair_mode_bit_identical(nat, mode):
     for (B, H, W, Cin, Cout, stride) in [(2, 32, 32, 320, 320, 1), (3, 8, 8, 1280, 1280, 1), (2, 32, 32, 320, 320, 2),
-                                         (1, 24, 24, 192, 160, 1)]:
+                                         (1, 24, 24, 192, 160, 1), (16, 32, 32, 640, 640, 1)]:
         x = rnd(B, H, W, Cin, seed=1)
         w = rnd(Cout, Cin, 3, 3, seed=2, scale=1 / math.sqrt(9 * Cin))
         bias = rnd(Cout, seed=3, dtype=torch.float32)
@@ -120,7 +124,7 @@ def test_conv_pair_mode_bit_identical(nat):
         old, old_sk = nat.get_tunable("MCAST"), nat.get_tunable("STREAMK")
         try:
             nat.set_tunable("STREAMK", 0)
-            nat.set_tunable("MCAST", 1)
+            nat.set_tunable("MCAST", mode)
             o1 = nat.conv3x3(x, wp, Cout, bias=bias, stride=stride)
             nat.set_tunable("MCAST", 0)
             o0 = nat.conv3x3(x, wp, Cout, bias=bias, stride=stride)
