@@ -470,10 +470,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
       // ---- stream-K bookkeeping of this item
       const int sk_tt = wi.t - p.sk_first;                    // index among the stream-K tiles (kind != 0 only)
+      const int npr = p.mcast ? 2 : 1;                        // CTAs per worker: each keeps its own partial slots / flag
       const float* sk_part = nullptr;                         // owner: slot 0 of this tile's partial accumulators
       if (wi.kind == 1) {
         // partial producer: dump the raw fp32 accumulator (all BN columns of my row) and raise the tile's flag
-        float* dst = p.sk_ws + ((static_cast<size_t>(sk_tt) * p.sk_maxp + wi.aux) * kBM + r) * BN;
+        float* dst = p.sk_ws + (((static_cast<size_t>(sk_tt) * p.sk_maxp + wi.aux) * npr + rank) * kBM + r) * BN;
         named_bar_sync(1, kEpiThreads);
         mbar_wait(&tfull_bar[buf], use & 1);
         tc_fence_after();
@@ -487,9 +488,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         __threadfence();
         named_bar_sync(1, kEpiThreads);
-        if (etid == 0) atomicAdd(p.sk_flags + sk_tt, 1);
+        if (etid == 0) atomicAdd(p.sk_flags + sk_tt * npr + rank, 1);
         tc_fence_before();
-        mbar_arrive(&tempty_bar[buf]);
+        if constexpr (PAIR2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+        else mbar_arrive(&tempty_bar[buf]);
         wi = wnext;
         have = have_next;
         continue;
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       if (wi.kind == 2) {
         // owner: the earlier segments of this tile were queued before anything their CTAs could wait on
         if (etid == 0) {
-          const volatile int* f = p.sk_flags + sk_tt;
+          const volatile int* f = p.sk_flags + sk_tt * npr + rank;
           uint32_t spins = 0;
           while (*f < wi.aux) {
             if (++spins > (1u << 27)) {
@@ -507,12 +509,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           __threadfence();
         }
-        sk_part = p.sk_ws + ((static_cast<size_t>(sk_tt) * p.sk_maxp) * kBM + r) * BN;
+        sk_part = p.sk_ws + (((static_cast<size_t>(sk_tt) * p.sk_maxp) * npr + rank) * kBM + r) * BN;
       }
       // adds the partial accumulators of this row, columns [c, c + 32), in slot order
       auto add_partials = [&](uint32_t (&acc)[32], int c) {
         for (int s2 = 0; s2 < wi.aux; ++s2) {
-          const float* src = sk_part + static_cast<size_t>(s2) * kBM * BN + c;
+          const float* src = sk_part + static_cast<size_t>(s2) * npr * kBM * BN + c;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + u * 4));
@@ -693,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           ep.rowmax_idx[o] = best_idx;
         }
       }
-      if (wi.kind == 2 && etid == 0) p.sk_flags[sk_tt] = 0;   // zero again for the next launch
+      if (wi.kind == 2 && etid == 0) p.sk_flags[sk_tt * npr + rank] = 0;   // zero again for the next launch
       tc_fence_before();
       if constexpr (PAIR2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader waits for both CTAs
       else mbar_arrive(&tempty_bar[buf]);
@@ -789,32 +791,35 @@ static int want_pair_mode(int bn, long long m_tiles, int k_iters, int* mcast) {
 }
 
 // Stream-K over the last, partial wave: worth it when the wave is far from full and K is long enough to cut.
-static void plan_stream_k(GemmParams* p, int bn) {
+static void plan_stream_k(GemmParams* p, int bn, int max_clusters) {
   p->sk_tiles = 0;
   p->sk_first = 0;
   p->sk_maxp = 0;
   p->sk_ws = nullptr;
   p->sk_flags = nullptr;
   const Epilogue& ep = p->ep;
-  if (!tunable(TUNE_STREAMK) || p->mcast || !p->tma_epi || ep.sk_ws == nullptr || ep.sk_flags == nullptr) return;
+  if (!tunable(TUNE_STREAMK) || p->mcast == 1 || !p->tma_epi || ep.sk_ws == nullptr || ep.sk_flags == nullptr) return;
+  const int npr = p->mcast ? 2 : 1;                          // cta_group::2 pairs: the worker is a cluster
   // The hand-off costs ~5-10 us of epilogue time per launch (partial dump + fence + flag, then latency-bound partial
   // loads in the owner's epilogue - measured on B200), so only tiles whose main loop runs for tens of us qualify:
   // the 3x3 convolutions at 32x32 and below, not the transformer GEMMs (their 3-15 us tiles got slower).
   if (ep.act == ACT_ROWMAX || static_cast<long long>(p->k_iters) * bn < 14000) return;
-  const long long T = static_cast<long long>(p->m_tiles) * p->n_tiles;
-  const int G = sm_count();
+  const long long T = static_cast<long long>(npr == 2 ? (p->m_tiles + 1) / 2 : p->m_tiles) * p->n_tiles;
+  const int G = npr == 2 ? max_clusters : sm_count();
+  if (G <= 0) return;
   const long long full_waves = T / G;
   const int R = static_cast<int>(T % G);
   if (R == 0) return;
   // time in tile units: ceil(T/G) without, T/G with; require >= 6 % gain
   const double without = static_cast<double>(full_waves + 1), with = static_cast<double>(T) / G;
-  if ((without - with) / without < 0.06) return;
+  // measured: the hand-off eats ~8 points of the theoretical gain, and with many waves the partial wave is a small share
+  if ((without - with) / without < (npr == 2 ? 0.10 : 0.06) || (npr == 2 && without > 4.0)) return;
   const long long W = static_cast<long long>(R) * p->k_iters;
   const long long per = W / G;
   if (per < 4) return;                                   // segments too short to be worth a hand-off
   const int maxp = static_cast<int>(p->k_iters / per) + 2;
-  const size_t need = static_cast<size_t>(R) * maxp * kBM * bn * sizeof(float);
-  if (need > ep.sk_ws_bytes || R > ep.sk_flags_count) return;
+  const size_t need = static_cast<size_t>(R) * maxp * npr * kBM * bn * sizeof(float);
+  if (need > ep.sk_ws_bytes || R * npr > ep.sk_flags_count) return;
   p->sk_tiles = R;
   p->sk_first = static_cast<int>(T - R);
   p->sk_maxp = maxp;
@@ -837,7 +842,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
     GYRE_REQUIRE(max_clusters > 0, "gemm: pair mode requested but clusters are unavailable");
     const long long pairs = static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles;
     GYRE_REQUIRE(pairs > 0 && pairs < (1ll << 30), "gemm: bad tile count %lld", pairs);
-    const unsigned clusters = static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
+    // stream-K needs every worker resident at once (owners spin on flags other workers raise)
+    const unsigned clusters = p.sk_tiles > 0 ? static_cast<unsigned>(max_clusters)
+                                             : static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
     if constexpr (BN >= 64) {
       if (p.mcast == 2) {
         using Cfg2 = GemmCfg<BN, true>;
@@ -959,8 +966,12 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
   p.ep = ep;
   p.rgb_rows = 0;
   p.tma_epi = (tma_epilogue_ok(ep, n_out) && ep.rowgroup_bias == nullptr) ? 1 : 0;
-  plan_stream_k(&p, bn);                                   // stream-K tiles stay single-CTA
-  if (p.sk_tiles == 0) GYRE_TRY(want_pair_mode(bn, p.m_tiles, p.k_iters, &p.mcast));
+  GYRE_TRY(want_pair_mode(bn, p.m_tiles, p.k_iters, &p.mcast));
+  {
+    int max_clusters = 0;
+    if (p.mcast) GYRE_TRY(gemm_max_clusters(bn, &max_clusters));
+    plan_stream_k(&p, bn, max_clusters);
+  }
   CUtensorMap tmA, tmA2, tmB, tmOut, tmRes;
   uint32_t es[2] = {1, 1};
   {
@@ -1077,8 +1088,12 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
   if (ep.rowgroup_bias != nullptr && ep.rows_per_group == Ho * Wo && best_n <= kMaxBiasGroups)
     p.rgb_rows = best_w * best_h;
   p.tma_epi = (tma_epilogue_ok(ep, Cout) && (ep.rowgroup_bias == nullptr || p.rgb_rows > 0)) ? 1 : 0;
-  plan_stream_k(&p, bn);                                   // stream-K tiles stay single-CTA
-  if (p.sk_tiles == 0) GYRE_TRY(want_pair_mode(bn, m_tiles, p.k_iters, &p.mcast));
+  GYRE_TRY(want_pair_mode(bn, m_tiles, p.k_iters, &p.mcast));
+  {
+    int max_clusters = 0;
+    if (p.mcast) GYRE_TRY(gemm_max_clusters(bn, &max_clusters));
+    plan_stream_k(&p, bn, max_clusters);
+  }
   GYRE_REQUIRE(gm.out_step == 1 || (p.tma_epi && ep.residual == nullptr),
                "conv: a strided output view needs the TMA epilogue (fp16, 16B-aligned rows, no residual)");
   CUtensorMap tmA, tmB, tmOut, tmRes;

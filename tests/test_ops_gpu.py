@@ -69,7 +69,8 @@ def test_gemm_pair_mode_bit_identical(nat, M, N, K, mode):
 
 
 @pytest.mark.parametrize("M,N,K,res", [(4096, 1280, 10240, True), (16384, 640, 5760, True), (1024, 1280, 11520, False),
-                                         (4096, 3840, 6400, False), (2000, 1280, 7680, True), (4096, 1280, 1280, True)])
+                                         (4096, 3840, 6400, False), (2000, 1280, 7680, True), (4096, 1280, 1280, True),
+                                         (2100, 1280, 7680, True)])
 def test_gemm_stream_k(nat, M, N, K, res):
     """Stream-K over the partial last wave: same result as whole-tile scheduling up to fp32 summation order
     (partials are added in a fixed slot order, so repeated runs are bit-identical)."""
