@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __grid_con
                                                                 const AttnParams p) {
   using Cfg = AttnCfg<DCH>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + Cfg::Q_BYTES;
   uint8_t* sK = sP + Cfg::P_BYTES;
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kAtt2Threads, 1) attention2_kernel(const __gri
   constexpr uint32_t kOBase = 256, kOStride = (DCH == 1 && (V & AV_PTMEM) != 0) ? 64 : 128;
   constexpr uint32_t kPBase = DCH == 1 ? 384 : 0, kPStride = DCH == 1 ? 64 : 128;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;                          // [2 tiles][DCH chunks][128 x 128 B]
   uint8_t* sP = sQ + Cfg::Q_BYTES;             // [2 groups][2 chunks][128 x 128 B] (absent with AV_PTMEM)
   uint8_t* sK = sP + Cfg::P_BYTES;
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kAtt4Threads, 1) attention4_kernel(const __gri
   using Cfg = Att4Cfg;
   constexpr int VS = V | AV_PTMEM;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + Cfg::STAGES * Cfg::KV_BYTES;
@@ -1168,7 +1168,7 @@ __global__ void __launch_bounds__(kXAttThreads, 1) xattention_kernel(const __gri
                                                                      const AttnParams p) {
   using Cfg = XAttCfg<DCH>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;                                   // [STAGES][DCH chunks]
   uint8_t* sK = sQ + Cfg::STAGES * Cfg::Q_BYTES;
   uint8_t* sV = sK + Cfg::KV_BYTES;

@@ -66,6 +66,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ mbarrier
+// 1024-byte alignment of the dynamic shared-memory base by POINTER arithmetic on the __shared__ array: rounding the
+// address up through an integer cast turns it into a generic pointer, and every access derived from it becomes a
+// generic LD / ST (slow path, long-scoreboard) instead of LDS / STS.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -34,6 +34,8 @@ struct GemmParams {
   int tma_epi;        // 1: output (and residual) tiles move through swizzled smem slices with TMA
   int rgb_rows;       // rows of a tile that share one rowgroup-bias vector (staged in smem); 0: per-thread loads
   int fast_gelu;      // GEGLU gate through gelu_fast instead of libdevice erff
+  int debug;          // measurement only (tunable DEBUG): bit 0 skips the output TMA stores, bit 1 the whole epilogue body
+                      // (main-loop time of a shape); results are wrong with either
   int stages;         // smem ring depth in use (tunable GEMM_STAGES caps it; measurement only)
   int mcast;          // CTA pairs (cluster of 2 along M) on one N tile.  1: every B tile is fetched in halves and TMA-
                       // multicast into both CTAs; 2: ONE tcgen05.mma.cta_group::2 (M = 256) per k step, each CTA holds
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                                               const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR2>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
   uint8_t* sEpi = sB + Cfg::STAGES * Cfg::B_BYTES;            // [half][out0,out1,res0,res1][kSliceBytes]
@@ -526,7 +528,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       };
 
-      if (p.tma_epi) {
+      if (p.debug & 2) {
+        // measurement only: no epilogue work at all (main-loop time of the kernel)
+        named_bar_sync(1, kEpiThreads);
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
+      } else if (p.tma_epi) {
         // ================================================= fast path: smem slices + TMA
         const bool has_res = ep.residual != nullptr;
         auto issue_res = [&](int slice, uint32_t cnt) {       // leader only
@@ -616,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           fence_proxy_async();
           named_bar_sync(2 + half, 128);
-          if (leader) {
+          if (leader && !(p.debug & 1)) {
             if (CONV)
               tma_store_4d(&tmOut, sOut + slot * kSliceBytes, col_base + sl * 32, x0, y0, n0);
             else
@@ -836,6 +843,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   GYRE_TRY(prepare<BN>(&max_clusters));
   const int sms = sm_count();
   GemmParams p = p_in;
+  p.debug = tunable(TUNE_DEBUG);
   const int cap = tunable(TUNE_GEMM_STAGES);
   p.stages = (cap >= 2 && cap < Cfg::STAGES) ? cap : Cfg::STAGES;
   if (p.mcast) {

@@ -10,7 +10,7 @@ namespace gyre {
 template <int NACC, int ATMEM>
 __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int n, int reps, long long* out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;                  // 128 x 64 halfs, 128B-swizzled K-major
   uint8_t* sB = smem + 16384;          // 256 x 64 halfs
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);

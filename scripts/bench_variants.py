@@ -169,6 +169,19 @@ if "stages" in what:
             rec("stages", f"gemm M{M} N{Nn} K{K} mcast={mc} rot=1 (L2-resident when it fits)", us, 2.0 * M * Nn * K)
         del a, o
 
+if "nostore" in what:
+    # how much of a short-K GEMM is the output TMA store (64-byte rows)?  DEBUG bit 0 skips the stores (wrong results)
+    for (M, Nn, K, res) in ((65536, 320, 320, False), (65536, 320, 320, True), (65536, 960, 320, False), (16384, 640, 640, False),
+                            (65536, 320, 1280, True), (4096, 1280, 1280, True), (4096, 1280, 5120, True)):
+        a = [torch.randn(M, K, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(Nn, K, device=dev).half() * (1 / math.sqrt(K))
+        bias = torch.randn(Nn, device=dev)
+        r = [torch.randn(M, Nn, device=dev).half() for _ in range(ROT)] if res else None
+        for dbg in (0, 1, 2):
+            us = with_tunable("DEBUG", dbg, lambda: graph_time(lambda i: N.gemm(a[i % ROT], w, bias=bias, residual=r[i % ROT] if res else None)))
+            rec("nostore", f"gemm M{M} N{Nn} K{K}{' +res' if res else ''} debug={dbg}", us, 2.0 * M * Nn * K)
+        del a, r
+
 if "streamk" in what:
     for (M, Nn, K) in ((4096, 1280, 1280), (16384, 640, 640), (16384, 640, 2560), (4096, 1280, 5120), (4096, 3840, 1280),
                        (65536, 320, 320)):
