@@ -35,7 +35,7 @@ struct GemmParams {
   int rgb_rows;       // rows of a tile that share one rowgroup-bias vector (staged in smem); 0: per-thread loads
   int fast_gelu;      // GEGLU gate through gelu_fast instead of libdevice erff
   int debug;          // measurement only (tunable DEBUG): bit 0 skips the output TMA stores, bit 1 the whole epilogue body
-                      // (main-loop time of a shape); results are wrong with either
+                      // (main-loop time of a shape) - results are wrong with either; bit 2 forces the all-variants image
   int stages;         // smem ring depth in use (tunable GEMM_STAGES caps it; measurement only)
   int mcast;          // CTA pairs (cluster of 2 along M) on one N tile.  1: every B tile is fetched in halves and TMA-
                       // multicast into both CTAs; 2: ONE tcgen05.mma.cta_group::2 (M = 256) per k step, each CTA holds
@@ -56,7 +56,7 @@ constexpr int kEpiThreads = 256;
 constexpr int kSliceBytes = kBM * 32 * 2;   // one 128-row x 32-column fp16 epilogue slice (64-byte rows)
 constexpr int kMaxBiasGroups = 2;
 
-template <int BN, bool PAIR2 = false>
+template <int BN, bool PAIR2 = false, int EPI = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;
   // B rows held per CTA and stage: the whole BN-row tile, or half of it under cta_group::2 (-> a deeper ring)
@@ -145,14 +145,21 @@ __device__ __forceinline__ void store8(const Epilogue& ep, int64_t row, int col,
 // barriers.  Each CTA drains its own 128 accumulator rows exactly as in the single-CTA kernel.
 // PAIR2 is a template parameter, not a run-time mode: a kernel image that contains cta_group::2 instructions can only be
 // launched with an even cluster size ("cluster misconfiguration" otherwise), so the single-CTA kernel must not carry them.
-template <int BN, bool CONV, bool PAIR2 = false>
+//
+// EPI selects how much epilogue code the image carries: 0 = bias / per-sample vector / residual through the TMA slices
+// only (what almost every launch of a UNet step uses), 2 = the GEGLU gate (fast GELU) through the TMA slices, 1 = every
+// variant behind run-time branches (activations, row-max, fp32 / unaligned direct stores).  With everything in one
+// image the 32-way unrolled activation blocks sit between the instructions of the plain path: the slice loop no longer
+// fits the instruction cache and the epilogue warps stall on fetches (`no_inst`), which on short-K tiles made the
+// epilogue - not the main loop - the critical path.
+template <int BN, bool CONV, bool PAIR2 = false, int EPI = 1>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmA2,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmOut,
                                                               const __grid_constant__ CUtensorMap tmRes,
                                                               const GemmParams p) {
-  using Cfg = GemmCfg<BN, PAIR2>;
+  using Cfg = GemmCfg<BN, PAIR2, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
@@ -398,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int etid = threadIdx.x - 64;      // 0..255
     const bool leader = (threadIdx.x == 64 + 128 * half);
     const Epilogue& ep = p.ep;
-    const bool geglu = ep.act == ACT_GEGLU;
+    const bool geglu = EPI == 2 || (EPI == 1 && ep.act == ACT_GEGLU);
     const int bn_out = geglu ? BN / 2 : BN;           // output columns per tile
     const int n_out = geglu ? p.N / 2 : p.N;          // output columns of the problem
     uint8_t* sOut = sEpi + half * 4 * kSliceBytes;    // 2 slots
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         named_bar_sync(1, kEpiThreads);
         mbar_wait(&tfull_bar[buf], use & 1);
         tc_fence_after();
-      } else if (p.tma_epi) {
+      } else if (EPI != 1 || p.tma_epi) {
         // ================================================= fast path: smem slices + TMA
         const bool has_res = ep.residual != nullptr;
         auto issue_res = [&](int slice, uint32_t cnt) {       // leader only
@@ -558,46 +565,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           named_bar_sync(2 + half, 128);
           float v[32];
-          if (geglu) {
-            uint32_t ra[32], rg[32];
-            tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
-            tmem_ld_32x32b_x32(lane_addr + BN / 2 + sl * 32, rg);
-            tmem_ld_wait();
-            if (sk_part) {
-              add_partials(ra, sl * 32);
-              add_partials(rg, BN / 2 + sl * 32);
-            }
-            if (p.fast_gelu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
-                const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
-                v[j] = a * gelu_fast(gg);
+          if constexpr (EPI != 0) {
+            if (geglu) {
+              uint32_t ra[32], rg[32];
+              tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
+              tmem_ld_32x32b_x32(lane_addr + BN / 2 + sl * 32, rg);
+              tmem_ld_wait();
+              if (sk_part) {
+                add_partials(ra, sl * 32);
+                add_partials(rg, BN / 2 + sl * 32);
               }
-            } else {
+              if (EPI == 2 || p.fast_gelu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
-                const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
-                v[j] = a * gelu_erf(gg);
+                for (int j = 0; j < 32; ++j) {
+                  const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+                  const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
+                  v[j] = a * gelu_fast(gg);
+                }
+              } else {
+                if constexpr (EPI == 1) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+                    const float gg = __uint_as_float(rg[j]) + sbr[BN / 2 + sl * 32 + j];
+                    v[j] = a * gelu_erf(gg);
+                  }
+                }
               }
             }
-          } else {
-            uint32_t ra[32];
-            tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
-            tmem_ld_wait();
-            if (sk_part) add_partials(ra, sl * 32);
+          }
+          if constexpr (EPI != 2) {
+            if (!geglu) {
+              uint32_t ra[32];
+              tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
+              tmem_ld_wait();
+              if (sk_part) add_partials(ra, sl * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
-            if (ep.act == ACT_SILU) {
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+              if constexpr (EPI == 1) {
+                if (ep.act == ACT_SILU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-            } else if (ep.act == ACT_QUICKGELU) {
+                  for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                } else if (ep.act == ACT_QUICKGELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = v[j] * rcp_approx(1.0f + ex2_approx(-2.4554669595930156f * v[j]));
-            } else if (ep.act == ACT_GELU) {
+                  for (int j = 0; j < 32; ++j) v[j] = v[j] * rcp_approx(1.0f + ex2_approx(-2.4554669595930156f * v[j]));
+                } else if (ep.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                  for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                }
+              }
             }
           }
           if (has_res) {
@@ -631,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tma_store_commit();
           }
         }
-      } else {
+      } else if constexpr (EPI == 1) {
         // ================================================= direct path (fp32 out, unaligned pitches, tiny N)
         const __half* rgb = (p.rgb_rows == 0 && valid && ep.rowgroup_bias)
                                 ? ep.rowgroup_bias + (out_row / ep.rows_per_group) * ep.rgb_ld
@@ -732,6 +748,33 @@ static int sm_count() {
   return n;
 }
 
+// Kernel image for a launch.  EPI 2 (GEGLU) exists at BN = 256, GEMM only; pair images at BN >= 64.
+template <int BN, bool CONV, bool PAIR2>
+static auto kernel_for(int epi) -> decltype(&gemm_tc_kernel<BN, CONV, PAIR2, 1>) {
+  if (epi == 0) return gemm_tc_kernel<BN, CONV, PAIR2, 0>;
+  if constexpr (BN == 256 && !CONV) {
+    if (epi == 2) return gemm_tc_kernel<BN, CONV, PAIR2, 2>;
+  }
+  return gemm_tc_kernel<BN, CONV, PAIR2, 1>;
+}
+// shared-memory footprint / ring depth of an image
+template <int BN, bool PAIR2>
+static void cfg_for(int epi, int* smem, int* stages) {
+  if (epi == 1) {
+    *smem = GemmCfg<BN, PAIR2, 1>::SMEM;
+    *stages = GemmCfg<BN, PAIR2, 1>::STAGES;
+  } else {
+    *smem = GemmCfg<BN, PAIR2, 0>::SMEM;
+    *stages = GemmCfg<BN, PAIR2, 0>::STAGES;
+  }
+}
+static int epi_class(const GemmParams& p) {
+  if (!p.tma_epi) return 1;
+  if (p.ep.act == ACT_NONE) return 0;
+  if (p.ep.act == ACT_GEGLU && p.fast_gelu && !p.conv) return 2;
+  return 1;
+}
+
 // One-time per tile width: opt in to the large dynamic shared memory and ask how many 2-CTA clusters of this kernel
 // the device can hold at once (GPCs with an odd SM count strand one SM).
 template <int BN>
@@ -740,15 +783,21 @@ static int prepare(int* max_clusters) {
   static bool done = false;
   static int clusters = 0;
   if (!done) {
-    GYRE_CHECK_CUDA(
-        cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    GYRE_CHECK_CUDA(
-        cudaFuncSetAttribute(gemm_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    if constexpr (BN >= 64) {
-      GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           GemmCfg<BN, true>::SMEM));
-      GYRE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           GemmCfg<BN, true>::SMEM));
+    for (int epi = 0; epi < 3; ++epi) {
+      if (epi == 2 && BN != 256) continue;          // kernel_for(2) aliases the all-variants image elsewhere
+      int smem = 0, stages = 0;
+      cfg_for<BN, false>(epi, &smem, &stages);
+      GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, false, false>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem));
+      GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, true, false>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem));
+      if constexpr (BN >= 64) {
+        cfg_for<BN, true>(epi, &smem, &stages);
+        GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, false, true>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem));
+        GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, true, true>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem));
+      }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * sm_count());
@@ -762,7 +811,7 @@ static int prepare(int* max_clusters) {
     cfg.attrs = a;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, false>, &cfg) == cudaSuccess) clusters = n;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, false, false, 1>, &cfg) == cudaSuccess) clusters = n;
     cudaGetLastError();
     done = true;
   }
@@ -844,8 +893,11 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   const int sms = sm_count();
   GemmParams p = p_in;
   p.debug = tunable(TUNE_DEBUG);
+  const int epi = (p.debug & 4) ? 1 : epi_class(p);       // DEBUG bit 2: always the all-variants image (A/B)
   const int cap = tunable(TUNE_GEMM_STAGES);
-  p.stages = (cap >= 2 && cap < Cfg::STAGES) ? cap : Cfg::STAGES;
+  int smem = 0, max_stages = 0;
+  cfg_for<BN, false>(epi, &smem, &max_stages);
+  p.stages = (cap >= 2 && cap < max_stages) ? cap : max_stages;
   if (p.mcast) {
     GYRE_REQUIRE(max_clusters > 0, "gemm: pair mode requested but clusters are unavailable");
     const long long pairs = static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles;
@@ -855,21 +907,21 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
                                              : static_cast<unsigned>(pairs < max_clusters ? pairs : max_clusters);
     if constexpr (BN >= 64) {
       if (p.mcast == 2) {
-        using Cfg2 = GemmCfg<BN, true>;
-        p.stages = (cap >= 2 && cap < Cfg2::STAGES) ? cap : Cfg2::STAGES;
+        cfg_for<BN, true>(epi, &smem, &max_stages);
+        p.stages = (cap >= 2 && cap < max_stages) ? cap : max_stages;
         if (p.conv)
-          return launch_kernel_cluster(gemm_tc_kernel<BN, true, true>, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM, st,
-                                       2, tmA, tmA2, tmB, tmOut, tmRes, p);
-        return launch_kernel_cluster(gemm_tc_kernel<BN, false, true>, dim3(2 * clusters), dim3(kThreads), Cfg2::SMEM, st,
-                                     2, tmA, tmA2, tmB, tmOut, tmRes, p);
+          return launch_kernel_cluster(kernel_for<BN, true, true>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
+                                       tmA, tmA2, tmB, tmOut, tmRes, p);
+        return launch_kernel_cluster(kernel_for<BN, false, true>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
+                                     tmA, tmA2, tmB, tmOut, tmRes, p);
       }
     }
     GYRE_REQUIRE(p.mcast == 1, "gemm: pair mode %d is not available at BN %d", p.mcast, BN);
     if (p.conv)
-      return launch_kernel_cluster(gemm_tc_kernel<BN, true>, dim3(2 * clusters), dim3(kThreads), Cfg::SMEM, st, 2, tmA,
-                                   tmA2, tmB, tmOut, tmRes, p);
-    return launch_kernel_cluster(gemm_tc_kernel<BN, false>, dim3(2 * clusters), dim3(kThreads), Cfg::SMEM, st, 2, tmA,
-                                 tmA2, tmB, tmOut, tmRes, p);
+      return launch_kernel_cluster(kernel_for<BN, true, false>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
+                                   tmA, tmA2, tmB, tmOut, tmRes, p);
+    return launch_kernel_cluster(kernel_for<BN, false, false>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
+                                 tmA, tmA2, tmB, tmOut, tmRes, p);
   }
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   GYRE_REQUIRE(tiles > 0 && tiles < (1ll << 31), "gemm: bad tile count %lld", tiles);
@@ -878,10 +930,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   // the implicit-GEMM convolution is its own instantiation (no run-time branches in the producer / epilogue, and a
   // distinct kernel name in profiles)
   if (p.conv)
-    return launch_kernel(gemm_tc_kernel<BN, true>, dim3(blocks), dim3(kThreads), Cfg::SMEM, st, tmA, tmA2, tmB, tmOut,
-                         tmRes, p);
-  return launch_kernel(gemm_tc_kernel<BN, false>, dim3(blocks), dim3(kThreads), Cfg::SMEM, st, tmA, tmA2, tmB, tmOut,
-                       tmRes, p);
+    return launch_kernel(kernel_for<BN, true, false>(epi), dim3(blocks), dim3(kThreads), smem, st, tmA, tmA2, tmB,
+                         tmOut, tmRes, p);
+  return launch_kernel(kernel_for<BN, false, false>(epi), dim3(blocks), dim3(kThreads), smem, st, tmA, tmA2, tmB,
+                       tmOut, tmRes, p);
 }
 
 // Tile width: maximise (SM wave efficiency) x (1 - N padding) x (per-tile efficiency of the shape).
