@@ -838,7 +838,7 @@ static int want_pair_mode(int bn, long long m_tiles, int k_iters, int* mcast) {
   // 0 off, 1 multicast pairs, 2 cta_group::2 pairs where they win, 3 cta_group::2 pairs everywhere (measurement)
   int mode = tunable(TUNE_MCAST);
   if (mode <= 0 || mode > 3 || m_tiles < 2 || bn < 64) return 0;
-  if (mode == 2 && k_iters < 16) return 0;   // short-K tiles: the pair's per-tile hand-offs cost more than the B half saves
+  if (mode == 2 && k_iters < 10) return 0;   // short-K tiles: the pair's per-tile hand-offs cost more than the B half saves
   if (mode == 3) mode = 2;
   int n = 0;
   GYRE_TRY(gemm_max_clusters(bn, &n));

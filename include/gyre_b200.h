@@ -53,10 +53,14 @@ int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, doubl
 
 /* Kernel-selection knobs for A/B measurement (no reference counterpart).  Names: "ATT_VARIANT" (softmax
  * variant bit flags of the d<=64 flash kernel), "PDL" (programmatic dependent launch), "GELU_FAST",
- * "GN_FUSED", "UPCONV_FOLD" (nearest-2x upsample folded into four 2x2 phase convolutions),
+ * "GN_CHUNKS", "GN_PHASE", "UPCONV_FOLD" (nearest-2x upsample folded into four 2x2 phase convolutions),
  * "CTX_KV_CACHE" (cross-attention K/V projections of an unchanged text context are reused across
- * steps), "XATTN" (short-key attention kernel).  Every knob also reads GYRE_B200_<NAME> from the
- * environment at first use.  Results stay within the documented tolerances for every setting. */
+ * steps), "XATTN" (short-key attention kernel), "ATT_D128", "MCAST" (GEMM / conv CTA pairs: 0 off,
+ * 1 TMA-multicast pairs, 2 tcgen05 cta_group::2 pairs where they win [default], 3 cta_group::2 pairs
+ * everywhere), "STREAMK", "FORCE_BN", "GEMM_STAGES" (cap of the operand ring depth), "DEBUG" (GEMM
+ * measurement bits: 1 no output stores, 2 no epilogue - both give WRONG results -, 4 all-variants image).
+ * Every knob also reads GYRE_B200_<NAME> from the environment at first use.  Results stay within the
+ * documented tolerances for every setting except the DEBUG store / epilogue bits. */
 int gyre_b200_set_tunable(const char* name, int value);
 /* Measurement only: clocks one thread needs to issue and retire `reps` tcgen05.mma (M=128, K=16, N=n) round-robin
  * over `naccs` TMEM accumulators, A from shared memory (a_tmem = 0) or TMEM; out_dev[blocks] (int64, device). */
