@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], pair2 ? 2 * kEpiThreads : kEpiThreads);
+      mbar_init(&tempty_bar[b], (pair2 ? 2 : 1) * (kEpiThreads / 32));   // one arrival per epilogue warp
     }
     for (int b = 0; b < 4; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
@@ -430,6 +430,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       return v;
     };
+    // "accumulator drained": ONE arrival per warp (256 per-thread arrivals on one mbarrier serialise in the barrier
+    // unit - and 256 remote ones per tile made the pair kernel slower than the single-CTA kernel on short-K tiles).
+    // Pairs: the leader's MMA warp waits for both CTAs, so the peer arrives on the leader's barrier.
+    auto release_accumulator = [&](uint32_t b) {
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (PAIR2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[b]), 0));
+        else mbar_arrive(&tempty_bar[b]);
+      }
+    };
     float nb0 = 0.f, nb1 = 0.f;
     Item wi, wnext;
     bool have = get_item(0, wi);
@@ -499,8 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         named_bar_sync(1, kEpiThreads);
         if (etid == 0) atomicAdd(p.sk_flags + sk_tt * npr + rank, 1);
         tc_fence_before();
-        if constexpr (PAIR2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
-        else mbar_arrive(&tempty_bar[buf]);
+        release_accumulator(buf);
         wi = wnext;
         have = have_next;
         continue;
@@ -720,8 +729,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       if (wi.kind == 2 && etid == 0) p.sk_flags[sk_tt * npr + rank] = 0;   // zero again for the next launch
       tc_fence_before();
-      if constexpr (PAIR2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader waits for both CTAs
-      else mbar_arrive(&tempty_bar[buf]);
+      release_accumulator(buf);
       wi = wnext;
       have = have_next;
     }

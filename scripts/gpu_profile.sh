@@ -11,9 +11,9 @@ echo "launch list (unet) exit $?"; wc -l gpurun_out/launches_unet.csv
 $NCU --metrics $M --csv --log-file gpurun_out/launches_vae.csv python scripts/profile_step.py --no-unet > gpurun_out/prof1b.log 2>&1
 echo "launch list (vae) exit $?"; wc -l gpurun_out/launches_vae.csv
 # conv: skip conv_in, take level-0 / level-1 convs
-$NCU --set full --import-source on --kernel-name-base demangled -k regex:"gemm_tc_kernel<.int.[0-9]+, .bool.1>" -s 1 -c 8 -o gpurun_out/prof_conv -f python scripts/profile_step.py --no-vae > gpurun_out/prof2.log 2>&1
+$NCU --set full --import-source on --kernel-name-base demangled -k regex:"gemm_tc_kernel<.int.[0-9]+, .bool.1" -s 1 -c 8 -o gpurun_out/prof_conv -f python scripts/profile_step.py --no-vae > gpurun_out/prof2.log 2>&1
 echo "conv exit $?"
-$NCU --set full --import-source on --kernel-name-base demangled -k regex:"gemm_tc_kernel<.int.[0-9]+, .bool.0>" -s 3 -c 12 -o gpurun_out/prof_gemm -f python scripts/profile_step.py --no-vae > gpurun_out/prof3.log 2>&1
+$NCU --set full --import-source on --kernel-name-base demangled -k regex:"gemm_tc_kernel<.int.[0-9]+, .bool.0" -s 3 -c 12 -o gpurun_out/prof_gemm -f python scripts/profile_step.py --no-vae > gpurun_out/prof3.log 2>&1
 echo "gemm exit $?"
 $NCU --set full --import-source on -k regex:attention -c 4 -o gpurun_out/prof_attention -f python scripts/profile_step.py --no-vae > gpurun_out/prof4.log 2>&1
 echo "attention exit $?"

@@ -74,7 +74,7 @@ def launches():
     for rows, w in ((unet, 50), (vae, 1)):
         for name, us, by in rows:
             if "gemm_tc_kernel" in name:
-                k = "conv3x3" if re.search(r"gemm_tc_kernel<\d+, 1>", name) else "gemm"
+                k = "conv3x3" if re.search(r"gemm_tc_kernel<\d+, 1[,>]", name) else "gemm"
             elif "attention" in name:
                 k = "attention"
             elif name.startswith("gn_"):
