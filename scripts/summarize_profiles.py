@@ -95,10 +95,14 @@ def launches():
 
 def ncu_reports():
     for fn in sorted(os.listdir(SRC)):
-        if not fn.endswith(".ncu-rep"):
+        if fn.endswith("_raw.csv") and fn.startswith("prof_"):      # raw page exported on the GPU box (gpu_profile.sh)
+            rows = list(csv.reader(open(os.path.join(SRC, fn))))
+            fn = fn[:-8] + ".ncu-rep"
+        elif fn.endswith(".ncu-rep"):
+            r = subprocess.run(["ncu", "-i", os.path.join(SRC, fn), "--page", "raw", "--csv"], capture_output=True, text=True)
+            rows = list(csv.reader(io.StringIO(r.stdout)))
+        else:
             continue
-        r = subprocess.run(["ncu", "-i", os.path.join(SRC, fn), "--page", "raw", "--csv"], capture_output=True, text=True)
-        rows = list(csv.reader(io.StringIO(r.stdout)))
         if len(rows) < 3:
             continue
         hdr, units = rows[0], rows[1]
