@@ -302,6 +302,19 @@ int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, i
   return static_cast<UNetModel*>(M(h))->set_context(static_cast<const __half*>(ctx), batch, ctx_len, S(stream));
 }
 
+int gyre_b200_unet_set_control_residuals(gyre_b200_handle h, const void* const* down_residuals, int n_down,
+                                         const void* mid_residual) {
+  GYRE_REQUIRE(h, "unet_set_control_residuals: null handle");
+  GYRE_REQUIRE(M(h)->is_unet(), "unet_set_control_residuals: handle is not a UNet");
+  return static_cast<UNetModel*>(M(h))->set_control_residuals(reinterpret_cast<const __half* const*>(down_residuals), n_down,
+                                                              static_cast<const __half*>(mid_residual));
+}
+
+int gyre_b200_unet_num_skips(gyre_b200_handle h) {
+  if (!h || !M(h)->is_unet()) return -1;
+  return static_cast<UNetModel*>(M(h))->num_skips();
+}
+
 int gyre_b200_unet_num_transformer_blocks(gyre_b200_handle h) {
   if (!h || !M(h)->is_unet()) return -1;
   return static_cast<UNetModel*>(M(h))->num_transformer_blocks();

@@ -47,6 +47,34 @@ int nhwc_to_nchw_f16(const __half* x, int ldx, int B, int C, int H, int W, __hal
   return 0;
 }
 
+// dst (NHWC, fp16) += src (NCHW, fp16): ControlNet residuals arrive in the reference's NCHW layout (core.py:213-239).
+// 32 x 32 (pixel, channel) tiles through shared memory: reads coalesced along pixels, writes along channels.
+__global__ void add_nchw_to_nhwc_kernel(__half* __restrict__ dst, const __half* __restrict__ src, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;           // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, p = p0 + tx;
+    tile[k][tx] = (c < C && p < HW) ? __half2float(src[(static_cast<int64_t>(b) * C + c) * HW + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int p = p0 + k, c = c0 + tx;
+    if (p < HW && c < C) {
+      __half* d = dst + (static_cast<int64_t>(b) * HW + p) * C + c;
+      *d = __float2half_rn(__half2float(*d) + tile[tx][k]);
+    }
+  }
+}
+int add_nchw_to_nhwc_f16(__half* dst_nhwc, const __half* src_nchw, int B, int C, int HW, cudaStream_t st) {
+  GYRE_REQUIRE(B > 0 && C > 0 && HW > 0 && B <= 65535, "add_nchw_to_nhwc: bad shape");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  add_nchw_to_nhwc_kernel<<<dim3((HW + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(dst_nhwc, src_nchw, C, HW);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ nearest 2x upsample, NHWC, 16B vectors
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int H, int W, int nvec, uint4* __restrict__ out,
                                   int64_t total) {

@@ -525,6 +525,26 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   return 0;
 }
 
+int UNetModel::num_skips() const {
+  const int nl = cfg_.num_levels;
+  return 1 + nl * cfg_.layers_per_block + (nl - 1);
+}
+
+int UNetModel::set_control_residuals(const __half* const* down, int n_down, const __half* mid) {
+  if (n_down == 0 && mid == nullptr) {
+    ctrl_down_.clear();
+    ctrl_mid_ = nullptr;
+    return 0;
+  }
+  GYRE_REQUIRE(n_down == 0 || n_down == num_skips(), "unet_set_control_residuals: %d down residuals given, the model has %d skips",
+               n_down, num_skips());
+  GYRE_REQUIRE(n_down == 0 || down != nullptr, "unet_set_control_residuals: null residual list");
+  ctrl_down_.assign(down, down + n_down);
+  for (const __half* p : ctrl_down_) GYRE_REQUIRE(p != nullptr, "unet_set_control_residuals: null residual tensor");
+  ctrl_mid_ = mid;
+  return 0;
+}
+
 int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B,
                        int H, int W, int L, const int32_t* tome_r, __half* out) {
   GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && L > 0, "unet_forward: empty problem");
@@ -581,9 +601,9 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   __half* hcur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
   RUN(ex, conv3x3_f16(x_nhwc, cin8, B, H, W, cin8, conv_in_.wp, ch[0], 1, 1, ep_out(hcur, ch[0], conv_in_.bias), ex.st));
 
-  struct Skip { const __half* p; int C; };
+  struct Skip { __half* p; int C; int hw; };
   std::vector<Skip> skips;
-  skips.push_back({hcur, ch[0]});
+  skips.push_back({hcur, ch[0], H * W});
   size_t ri = 0, ti = 0, di = 0, ui = 0;
   int ccur = ch[0];
   auto r_of = [&](size_t idx) { return tome_r ? tome_r[idx] : 0; };
@@ -602,7 +622,7 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
         ++ti;
         hcur = o2;
       }
-      skips.push_back({hcur, ccur});
+      skips.push_back({hcur, ccur, h_ * w_});
     }
     if (i < nl - 1) {
       ex.reset_scratch();
@@ -614,7 +634,17 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
       hcur = o;
       h_ = ho;
       w_ = wo;
-      skips.push_back({hcur, ccur});
+      skips.push_back({hcur, ccur, h_ * w_});
+    }
+  }
+  // ---- ControlNet residuals: skip_i += residual_i once the down path no longer reads the skip tensors
+  if (!ex.dry && !ctrl_down_.empty()) {
+    GYRE_REQUIRE(ctrl_down_.size() == skips.size(), "unet_forward: %zu control residuals for %zu skips", ctrl_down_.size(),
+                 skips.size());
+    for (size_t k = 0; k < skips.size(); ++k) {
+      // the last skip is also the mid block's input and diffusers adds the residual to the skip only: done after mid
+      if (k + 1 == skips.size()) continue;
+      RUN(ex, add_nchw_to_nhwc_f16(skips[k].p, ctrl_down_[k], B, skips[k].C, skips[k].hw, ex.st));
     }
   }
   // ---- mid
@@ -630,6 +660,17 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
     __half* o3 = ex.p16(static_cast<size_t>(B) * h_ * w_ * ccur);
     GYRE_TRY(resnet(ex, resnets_[ri++], o2, ccur, nullptr, 0, B, h_, w_, eps, temb_all, temb_total_, o3));
     hcur = o3;
+    if (!ex.dry && ctrl_mid_ != nullptr) RUN(ex, add_nchw_to_nhwc_f16(o3, ctrl_mid_, B, ccur, h_ * w_, ex.st));
+  }
+  if (!ex.dry && !ctrl_down_.empty()) {
+    // the deepest skip was the mid block's input: it takes its residual only now that the mid block has read it
+    const Skip& ls = skips.back();
+    RUN(ex, add_nchw_to_nhwc_f16(ls.p, ctrl_down_.back(), B, ls.C, ls.hw, ex.st));
+  }
+  // residuals are per call (core.py passes them with every UNet invocation)
+  if (!ex.dry) {
+    ctrl_down_.clear();
+    ctrl_mid_ = nullptr;
   }
   // ---- up
   for (int i = 0; i < nl; ++i) {

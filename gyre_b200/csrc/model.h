@@ -139,6 +139,12 @@ class UNetModel : public Model {
   // transformer block depend only on ctx, so they are computed here ONCE instead of once per step.
   // ctx == nullptr drops the binding.
   int set_context(const __half* ctx, int B, int L, cudaStream_t st);
+  // ControlNet residuals for the NEXT forward only (diffusers' down_block_additional_residuals /
+  // mid_block_additional_residual, passed through by gyre/pipeline/unet/core.py:213-239): NCHW fp16 tensors, one per
+  // skip connection in push order (conv_in, every resnet/attention pair, every downsampler) plus one for the mid block
+  // output.  They are added to the skip tensors AFTER the down path has run (they do not change the down path itself).
+  int set_control_residuals(const __half* const* down, int n_down, const __half* mid);
+  int num_skips() const;
   ~UNetModel() override;
 
  private:
@@ -149,6 +155,8 @@ class UNetModel : public Model {
   LinW time1_, time2_;
   LinW add1_, add2_;    // add_embedding (text_time conditioning), only when cfg_.addition_embed_dim > 0
   int n_tblocks_flat_ = 0;
+  std::vector<const __half*> ctrl_down_;   // pending ControlNet residuals (consumed by the next forward)
+  const __half* ctrl_mid_ = nullptr;
   std::vector<ResnetW> resnets_;        // in module execution order
   std::vector<TransformerW> tblocks_;   // in module execution order (== ToMe r-list order)
   std::vector<Conv3W> downs_, ups_;

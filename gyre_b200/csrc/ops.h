@@ -86,6 +86,7 @@ int softmax_rows_f32(const float* s, int rows, int n, float scale, __half* p, in
 
 // Layout / elementwise helpers
 int nchw_to_nhwc_f16(const __half* x, int B, int C, int H, int W, __half* out, int ldo, cudaStream_t st);
+int add_nchw_to_nhwc_f16(__half* dst_nhwc, const __half* src_nchw, int B, int C, int HW, cudaStream_t st);
 int nhwc_to_nchw_f16(const __half* x, int ldx, int B, int C, int H, int W, __half* out, cudaStream_t st);
 int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t st);
 int concat_channels(const __half* a, int Ca, const __half* b, int Cb, int64_t rows, __half* out, cudaStream_t st);

@@ -183,12 +183,45 @@ class B200UNet:
                                                       ws.numel(), N.stream_ptr(self.device)), "unet_forward")
         return out
 
+    def _bind_control_residuals(self, down, mid, x):
+        """ControlNet residuals (`down_block_additional_residuals` / `mid_block_additional_residual`, passed through by
+        gyre/pipeline/unet/core.py:213-239) for the next native forward.  Returns the fp16 tensors to keep alive."""
+        if down is None and mid is None:
+            return None
+        B, _, H, W = x.shape
+        cfg = self.config
+        keep, ptrs = [], None
+        if down is not None:
+            n = self._lib.gyre_b200_unet_num_skips(self._h)
+            if len(down) != n:
+                raise ValueError(f"expected {n} down_block_additional_residuals, got {len(down)}")
+            chans, sizes = [cfg.block_out_channels[0]], [(H, W)]
+            h, w = H, W
+            for i, c in enumerate(cfg.block_out_channels):
+                chans += [c] * cfg.layers_per_block
+                sizes += [(h, w)] * cfg.layers_per_block
+                if i < len(cfg.block_out_channels) - 1:
+                    h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                    chans.append(c)
+                    sizes.append((h, w))
+            for k, r in enumerate(down):
+                if tuple(r.shape) != (B, chans[k], *sizes[k]):
+                    raise ValueError(f"down residual {k}: expected {(B, chans[k], *sizes[k])}, got {tuple(r.shape)}")
+                keep.append(r.to(device=x.device, dtype=torch.float16).contiguous())
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in keep])
+        m = None
+        if mid is not None:
+            m = mid.to(device=x.device, dtype=torch.float16).contiguous()
+            keep.append(m)
+        N.check(self._lib.gyre_b200_unet_set_control_residuals(self._h, ptrs, len(down) if down is not None else 0,
+                                                               N.ptr(m)), "unet_set_control_residuals")
+        return keep
+
     def __call__(self, latents, t, *, encoder_hidden_states, down_block_additional_residuals=None,
                  mid_block_additional_residual=None, adapter_states=None, added_cond_kwargs=None, **kwargs):
-        if down_block_additional_residuals is not None or mid_block_additional_residual is not None \
-                or adapter_states is not None:
-            # ControlNet / T2I residual injection (core.py:45-64,213-239) is a "next" row
-            raise NotImplementedError("ControlNet / T2I-adapter residuals are not supported by the B200 UNet")
+        if adapter_states is not None:
+            # T2I-adapter states are added INSIDE the down path (core.py:45-64): not part of this boundary yet
+            raise NotImplementedError("T2I-adapter states are not supported by the B200 UNet")
         N.require_cuda(latents, encoder_hidden_states)
         B = latents.shape[0]
         if latents.shape[1] != self.config.in_channels:
@@ -202,5 +235,7 @@ class B200UNet:
             if not added_cond_kwargs or "text_embeds" not in added_cond_kwargs or "time_ids" not in added_cond_kwargs:
                 raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")
             add = self.added_cond_vector(added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"])
+        keep = self._bind_control_residuals(down_block_additional_residuals, mid_block_additional_residual, x)
         out = self.forward_raw(x, self._timesteps(t, B), ctx, add_cond=add)
+        del keep
         return UNetOutput(sample=out.to(latents.dtype) if latents.dtype != torch.float16 else out)

@@ -139,6 +139,15 @@ int gyre_b200_unet_forward_cond(gyre_b200_handle h, const void* sample, const in
  * transformer block) until the next call; ctx = NULL drops the binding.  The caller must re-bind
  * after changing the context tensor's contents or any attn2.to_k / to_v weight. */
 int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, int ctx_len, gyre_b200_stream stream);
+/* ControlNet residual injection (replaces the `down_block_additional_residuals=` /
+ * `mid_block_additional_residual=` keyword arguments that gyre/pipeline/unet/core.py:213-239 passes to
+ * UNet2DConditionModel.forward).  Binds, for the NEXT gyre_b200_unet_forward* call only, one NCHW fp16 device tensor
+ * per skip connection ([batch, C_i, h_i, w_i], in the order diffusers lists them: conv_in output, each down block's
+ * layer outputs, each downsampler output - gyre_b200_unet_num_skips() of them) and/or one for the mid block output.
+ * n_down = 0 and mid_residual = NULL clear the binding.  The tensors must stay valid until that forward has run. */
+int gyre_b200_unet_set_control_residuals(gyre_b200_handle h, const void* const* down_residuals, int n_down,
+                                         const void* mid_residual);
+int gyre_b200_unet_num_skips(gyre_b200_handle h);
 
 /* ------------------------------------------------------------------------------------------
  * AutoencoderKL  (replaces vae.decode(x).sample, gyre/pipeline/unified_pipeline.py:1523-1536,

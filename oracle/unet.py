@@ -300,7 +300,7 @@ def num_transformer_blocks(cfg: UNetConfig) -> int:
 
 
 def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_states, tome_r=0, taps=None,
-                 added_cond_kwargs=None):
+                 added_cond_kwargs=None, down_block_additional_residuals=None, mid_block_additional_residual=None):
     """UNet2DConditionModel.forward (call site gyre/pipeline/unet/core.py:274; encoder-half wiring
     cf. gyre/pipeline/controlnet/models.py:446-511; up path cf. nonfree/tome_unet.py:34-70).
     `tome_r`: int | (r, inflect) | list, expanded by parse_r over the transformer blocks in module
@@ -356,6 +356,14 @@ def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_stat
     h = transformer_2d(P, "mid_block.attentions.0", h, encoder_hidden_states, cfg.num_heads[-1], G, lin,
                        r_list.pop(0))
     h = resnet_block(P, "mid_block.resnets.1", h, temb, G, eps)
+    # ControlNet residual injection as the caller expects it of UNet2DConditionModel.forward
+    # (gyre/pipeline/unet/core.py:213-239 passes the summed ControlNet outputs through these two keywords):
+    # the skips - not the down path - take the residuals, the mid block output takes its own
+    if down_block_additional_residuals is not None:
+        assert len(down_block_additional_residuals) == len(res)
+        res = [r + a.to(r.dtype) for r, a in zip(res, down_block_additional_residuals)]
+    if mid_block_additional_residual is not None:
+        h = h + mid_block_additional_residual.to(h.dtype)
     tap("mid_block", h)
     rattn = list(reversed(cfg.attn_levels))
     rheads = list(reversed(cfg.num_heads))
@@ -387,7 +395,10 @@ class OracleUNet:
         self.params = params
         self.r = 0  # ToMe: set like `unet.r = int(value)` (gyre/pipeline/unified_pipeline.py:1582-1584)
 
-    def __call__(self, latents, t, *, encoder_hidden_states, added_cond_kwargs=None, **_):
+    def __call__(self, latents, t, *, encoder_hidden_states, added_cond_kwargs=None,
+                 down_block_additional_residuals=None, mid_block_additional_residual=None, **_):
         with torch.no_grad():
             return self._Out(unet_forward(self.params, self.config, latents, t, encoder_hidden_states, self.r,
-                                          added_cond_kwargs=added_cond_kwargs))
+                                          added_cond_kwargs=added_cond_kwargs,
+                                          down_block_additional_residuals=down_block_additional_residuals,
+                                          mid_block_additional_residual=mid_block_additional_residual))

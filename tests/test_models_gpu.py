@@ -85,7 +85,60 @@ def test_unet_rejects_bad_input(tiny_unet):
     with pytest.raises(NotImplementedError):
         unet(torch.zeros(1, 4, 16, 16).half().cuda(), 1,
              encoder_hidden_states=torch.zeros(1, 77, cfg.cross_attention_dim).half().cuda(),
-             mid_block_additional_residual=torch.zeros(1))
+             adapter_states=[torch.zeros(1)])
+    with pytest.raises(ValueError):      # wrong number / shape of ControlNet residuals
+        unet(torch.zeros(1, 4, 16, 16).half().cuda(), 1,
+             encoder_hidden_states=torch.zeros(1, 77, cfg.cross_attention_dim).half().cuda(),
+             down_block_additional_residuals=[torch.zeros(1, 4, 16, 16)])
+
+
+def _control_residuals(cfg, B, H, W, gen, scale=0.5):
+    """Residual tensors shaped like a ControlNet's outputs for this UNet (one per skip + mid), NCHW."""
+    shapes = [(cfg.block_out_channels[0], H, W)]
+    h, w = H, W
+    for i, c in enumerate(cfg.block_out_channels):
+        shapes += [(c, h, w)] * cfg.layers_per_block
+        if i < len(cfg.block_out_channels) - 1:
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            shapes.append((c, h, w))
+    down = [(torch.randn(B, *s, generator=gen) * scale).half() for s in shapes]
+    mid = (torch.randn(B, cfg.block_out_channels[-1], h, w, generator=gen) * scale).half()
+    return down, mid
+
+
+@pytest.mark.parametrize("which", ["both", "down", "mid"])
+def test_unet_controlnet_residuals_vs_oracle(tiny_unet, which):
+    """`down_block_additional_residuals` / `mid_block_additional_residual` (gyre/pipeline/unet/core.py:213-239): the
+    skips and the mid output take the residuals, the down path itself does not; and the binding lasts one call."""
+    from oracle.unet import unet_forward
+    cfg, P, unet = tiny_unet
+    _no_tf32()
+    gen = torch.Generator("cpu").manual_seed(77)
+    B = 2
+    x = torch.randn(B, 4, 16, 16, generator=gen).half()
+    ctx = torch.randn(B, 77, cfg.cross_attention_dim, generator=gen).half()
+    t = torch.tensor([800, 20])
+    down, mid = _control_residuals(cfg, B, 16, 16, gen)
+    kw_ref = {}
+    kw = {}
+    if which in ("both", "down"):
+        kw_ref["down_block_additional_residuals"] = [d.float() for d in down]
+        kw["down_block_additional_residuals"] = [d.cuda() for d in down]
+    if which in ("both", "mid"):
+        kw_ref["mid_block_additional_residual"] = mid.float()
+        kw["mid_block_additional_residual"] = mid.cuda()
+    with torch.no_grad():
+        ref = unet_forward(P, cfg, x.float(), t, ctx.float(), **kw_ref)
+        plain = unet_forward(P, cfg, x.float(), t, ctx.float())
+    out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda(), **kw).sample
+    err = rel_err(out.cpu(), ref)
+    moved = rel_err(ref, plain)
+    print(f"controlnet residuals ({which}): rel err {err:.3e}; the residuals move the output by {moved:.3e}")
+    assert moved > 5e-3, "test residuals too small to matter"
+    assert err < 2e-2
+    # the residuals were for that call only
+    out2 = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample
+    assert rel_err(out2.cpu(), plain) < 2e-2
 
 
 def test_unet_sd15_full_size():

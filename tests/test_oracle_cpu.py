@@ -116,3 +116,45 @@ def test_c1_fixture_present_and_sane():
     rec = torch.load(os.path.join(GOLD, "c1_sd15_ddim10.pt"))
     assert rec["latents"].shape == (1, 4, 64, 64) and rec["steps"] == 10 and rec["sampler"] == "ddim"
     assert torch.isfinite(rec["latents"]).all()
+
+
+def test_oracle_controlnet_residual_semantics():
+    """`down_block_additional_residuals` / `mid_block_additional_residual` as gyre/pipeline/unet/core.py:213-239 hands
+    them to the UNet: zero residuals change nothing, the down path does not see them, the mid output moves by exactly
+    the mid residual, and every skip residual reaches the output."""
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 4, 16, 16, generator=gen)
+    ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=gen)
+    taps0, taps1 = {}, {}
+    with torch.no_grad():
+        base = unet_forward(P, cfg, x, 300, ctx, taps=taps0)
+        shapes = [taps0["conv_in"].shape]
+        h = w = 16
+        for i, c in enumerate(cfg.block_out_channels):
+            shapes += [(1, c, h, w)] * cfg.layers_per_block
+            if i < len(cfg.block_out_channels) - 1:
+                h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                shapes.append((1, c, h, w))
+        zeros = [torch.zeros(s) for s in shapes]
+        mid0 = torch.zeros_like(taps0["mid_block"])
+        same = unet_forward(P, cfg, x, 300, ctx, down_block_additional_residuals=zeros, mid_block_additional_residual=mid0)
+        assert torch.equal(same, base)
+        down = [torch.randn(s, generator=gen) * 0.3 for s in shapes]
+        mid = torch.randn(mid0.shape, generator=gen) * 0.3
+        out = unet_forward(P, cfg, x, 300, ctx, taps=taps1, down_block_additional_residuals=down,
+                           mid_block_additional_residual=mid)
+    for k in taps0:
+        if k.startswith("down_blocks") or k == "conv_in":
+            assert torch.equal(taps0[k], taps1[k]), f"{k}: the down path must not see the residuals"
+    assert torch.allclose(taps1["mid_block"] - taps0["mid_block"], mid, atol=1e-5)
+    assert (out - base).abs().max() > 1e-3
+    # each skip residual individually reaches the output
+    for k in range(len(shapes)):
+        one = [d if j == k else z for j, (d, z) in enumerate(zip(down, zeros))]
+        with torch.no_grad():
+            o = unet_forward(P, cfg, x, 300, ctx, down_block_additional_residuals=one)
+        assert (o - base).abs().max() > 1e-5, f"skip residual {k} has no effect"
+    with pytest.raises(AssertionError):
+        unet_forward(P, cfg, x, 300, ctx, down_block_additional_residuals=zeros[:-1])
