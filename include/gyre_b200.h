@@ -58,7 +58,8 @@ int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, doubl
  * steps), "XATTN" (short-key attention kernel), "ATT_D128", "MCAST" (GEMM / conv CTA pairs: 0 off,
  * 1 TMA-multicast pairs, 2 tcgen05 cta_group::2 pairs where they win [default], 3 cta_group::2 pairs
  * everywhere), "STREAMK", "FORCE_BN", "GEMM_STAGES" (cap of the operand ring depth), "DEBUG" (GEMM
- * measurement bits: 1 no output stores, 2 no epilogue - both give WRONG results -, 4 all-variants image).
+ * measurement bits: 1 no output stores, 2 no epilogue - both give WRONG results -, 4 all-variants image),
+ * "LN_SUB" (LayerNorm: several rows per warp for C <= 320 [1, default] / <= 640 [2]).
  * Every knob also reads GYRE_B200_<NAME> from the environment at first use.  Results stay within the
  * documented tolerances for every setting except the DEBUG store / epilogue bits. */
 int gyre_b200_set_tunable(const char* name, int value);

@@ -246,11 +246,12 @@ if "gnx" in what:
         del x
 
 if "ln" in what:
-    for (rows, C) in ((65536, 320), (16384, 640), (4096, 1280)):
+    for (rows, C) in ((65536, 320), (16384, 640), (4096, 1280), (36864, 320), (1232, 768)):
         x = [torch.randn(rows, C, device=dev).half() for _ in range(ROT)]
         g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-        us = graph_time(lambda i: N.layernorm(x[i % ROT], g, b))
-        rec("ln", f"ln rows{rows} C{C}", us, 0.0, 2.0 * 2 * rows * C)
+        for sub in (0, 1):
+            us = with_tunable("LN_SUB", sub, lambda: graph_time(lambda i: N.layernorm(x[i % ROT], g, b)))
+            rec("ln", f"ln rows{rows} C{C} sub={sub}", us, 0.0, 2.0 * 2 * rows * C)
         del x
 
 if "upconv" in what:

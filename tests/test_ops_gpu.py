@@ -279,11 +279,22 @@ def test_groupnorm_batch_independent(nat):
     assert torch.equal(full[2:3], one)
 
 
-@pytest.mark.parametrize("rows,C", [(77, 64), (4096, 320), (1000, 640), (257, 1280)])
-def test_layernorm(nat, rows, C):
+@pytest.mark.parametrize("sub", [2, 1, 0])
+@pytest.mark.parametrize("rows,C", [(77, 64), (4096, 320), (1000, 640), (257, 1280), (1, 320), (4099, 320), (33, 8), (61, 768),
+                                    (130, 576)])
+def test_layernorm(nat, rows, C, sub):
+    """sub = 1 / 2: several rows per warp for C <= 320 / 640 (ragged last warp / CTA included); 0: one warp per row."""
     x = rnd(rows, C, seed=1) * 2 + 0.3
     gamma = 1 + 0.1 * rnd(C, seed=3, dtype=torch.float32)
     beta = 0.1 * rnd(C, seed=4, dtype=torch.float32)
-    out = nat.layernorm(x, gamma, beta)
+    old = nat.get_tunable("LN_SUB")
+    try:
+        nat.set_tunable("LN_SUB", sub)
+        out = nat.layernorm(x, gamma, beta)
+        # a row's result does not depend on the rows around it (batch invariance)
+        one = nat.layernorm(x[rows // 2:rows // 2 + 1].contiguous(), gamma, beta)
+    finally:
+        nat.set_tunable("LN_SUB", old)
     ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
     assert_close(out, ref, 2e-3, 2e-3, "layernorm")
+    assert torch.equal(one[0], out[rows // 2])
