@@ -360,7 +360,9 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   }
   const int nvec = C / 8;
   GYRE_REQUIRE(nvec <= 1024, "groupnorm: C=%d too large", C);
-  int rpar = 256 / nvec;
+  int gn_threads = tunable(TUNE_GN_THREADS);          // CTA size target (a function of nothing but the tunable)
+  if (gn_threads < 64 || gn_threads > 1024) gn_threads = 256;
+  int rpar = gn_threads / nvec;
   if (rpar < 1) rpar = 1;
   const int threads = nvec * rpar;
   GYRE_REQUIRE(threads >= 4 * G, "groupnorm: too few threads for %d groups", G);

@@ -245,6 +245,19 @@ if "gnx" in what:
         N.set_tunable("GN_CHUNKS", 32)
         del x
 
+if "gnt" in what:
+    # GroupNorm CTA size (threads) per pass
+    for (HW, C) in ((4096, 320), (4096, 640), (1024, 640), (1024, 1280), (256, 1280)):
+        x = [torch.randn(B2, HW, C, device=dev).half() for _ in range(ROT)]
+        g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        for thr in (256, 192, 512, 768):
+            N.set_tunable("GN_THREADS", thr)
+            for phase in (0, 1, 2):
+                us = with_tunable("GN_PHASE", phase, lambda: graph_time(lambda i: N.groupnorm(x[i % ROT], g, b, 32, 1e-5, True)))
+                rec("gnt", f"gn B{B2} HW{HW} C{C} threads={thr} phase={phase}", us, 0.0, 2.0 * B2 * HW * C * (1 if phase == 1 else 2))
+        N.set_tunable("GN_THREADS", 256)
+        del x
+
 if "ln" in what:
     for (rows, C) in ((65536, 320), (16384, 640), (4096, 1280), (36864, 320), (1232, 768)):
         x = [torch.randn(rows, C, device=dev).half() for _ in range(ROT)]
