@@ -176,8 +176,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
+    json_fd = None
     if world > 1:
-        # NCCL's own banner ("NCCL version ...") must not land on stdout: the contract is ONE JSON line there
+        # NCCL prints its banner ("NCCL version ...") with printf on the process's stdout whatever NCCL_DEBUG_FILE says,
+        # and the contract is ONE JSON line there: fd 1 is pointed at stderr for the whole run and the JSON line goes
+        # out through a duplicate of the original stdout
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -320,7 +326,11 @@ def main():
         line["cpu_baseline"] = cpu_reference(2, 1)
     if world > 1:
         dist.destroy_process_group()
-    print(json.dumps(line))
+    if json_fd is not None:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line))
     return 0
 
 
