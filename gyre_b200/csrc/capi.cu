@@ -310,6 +310,12 @@ int gyre_b200_unet_set_control_residuals(gyre_b200_handle h, const void* const* 
                                                               static_cast<const __half*>(mid_residual));
 }
 
+int gyre_b200_unet_set_adapter_states(gyre_b200_handle h, const void* const* states, int n_states) {
+  GYRE_REQUIRE(h, "unet_set_adapter_states: null handle");
+  GYRE_REQUIRE(M(h)->is_unet(), "unet_set_adapter_states: handle is not a UNet");
+  return static_cast<UNetModel*>(M(h))->set_adapter_states(reinterpret_cast<const __half* const*>(states), n_states);
+}
+
 int gyre_b200_unet_num_skips(gyre_b200_handle h) {
   if (!h || !M(h)->is_unet()) return -1;
   return static_cast<UNetModel*>(M(h))->num_skips();

@@ -545,6 +545,18 @@ int UNetModel::set_control_residuals(const __half* const* down, int n_down, cons
   return 0;
 }
 
+int UNetModel::set_adapter_states(const __half* const* states, int n) {
+  if (n == 0) {
+    adapter_.clear();
+    return 0;
+  }
+  GYRE_REQUIRE(n == cfg_.num_levels && states != nullptr, "unet_set_adapter_states: %d states given, the model has %d down blocks",
+               n, cfg_.num_levels);
+  adapter_.assign(states, states + n);
+  for (const __half* p : adapter_) GYRE_REQUIRE(p != nullptr, "unet_set_adapter_states: null state tensor");
+  return 0;
+}
+
 int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B,
                        int H, int W, int L, const int32_t* tome_r, __half* out) {
   GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && L > 0, "unet_forward: empty problem");
@@ -624,6 +636,8 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
       }
       skips.push_back({hcur, ccur, h_ * w_});
     }
+    // T2I-adapter: the block's last hidden state (== its last skip tensor) takes the level's state in place
+    if (!ex.dry && !adapter_.empty()) RUN(ex, add_nchw_to_nhwc_f16(hcur, adapter_[i], B, ccur, h_ * w_, ex.st));
     if (i < nl - 1) {
       ex.reset_scratch();
       const int ho = (h_ - 1) / 2 + 1, wo = (w_ - 1) / 2 + 1;
@@ -671,6 +685,7 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   if (!ex.dry) {
     ctrl_down_.clear();
     ctrl_mid_ = nullptr;
+    adapter_.clear();
   }
   // ---- up
   for (int i = 0; i < nl; ++i) {

@@ -145,6 +145,10 @@ class UNetModel : public Model {
   // output.  They are added to the skip tensors AFTER the down path has run (they do not change the down path itself).
   int set_control_residuals(const __half* const* down, int n_down, const __half* mid);
   int num_skips() const;
+  // T2I-adapter states for the NEXT forward only (`adapter_states=`, gyre/pipeline/t2i_adapter/unet_patcher.py:21-60,
+  // 95-110): one NCHW fp16 tensor per down block, added IN PLACE to the block's last hidden state before its
+  // downsampler - i.e. to the block's last skip tensor and to everything computed from it.
+  int set_adapter_states(const __half* const* states, int n);
   ~UNetModel() override;
 
  private:
@@ -157,6 +161,7 @@ class UNetModel : public Model {
   int n_tblocks_flat_ = 0;
   std::vector<const __half*> ctrl_down_;   // pending ControlNet residuals (consumed by the next forward)
   const __half* ctrl_mid_ = nullptr;
+  std::vector<const __half*> adapter_;     // pending T2I-adapter states (consumed by the next forward)
   std::vector<ResnetW> resnets_;        // in module execution order
   std::vector<TransformerW> tblocks_;   // in module execution order (== ToMe r-list order)
   std::vector<Conv3W> downs_, ups_;

@@ -217,11 +217,28 @@ class B200UNet:
                                                                N.ptr(m)), "unet_set_control_residuals")
         return keep
 
+    def _bind_adapter_states(self, states, x):
+        """T2I-adapter states (`adapter_states=`, gyre/pipeline/t2i_adapter/unet_patcher.py:95-110) for the next
+        native forward: one tensor per down block.  Returns the fp16 tensors to keep alive."""
+        if not states:                       # None or empty list: the reference's hook ignores both
+            return None
+        B, _, H, W = x.shape
+        ch = self.config.block_out_channels
+        if len(states) != len(ch):
+            raise ValueError(f"expected {len(ch)} adapter_states (one per down block), got {len(states)}")
+        keep = []
+        h, w = H, W
+        for i, s in enumerate(states):
+            if tuple(s.shape) != (B, ch[i], h, w):
+                raise ValueError(f"adapter state {i}: expected {(B, ch[i], h, w)}, got {tuple(s.shape)}")
+            keep.append(s.to(device=x.device, dtype=torch.float16).contiguous())
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        ptrs = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        N.check(self._lib.gyre_b200_unet_set_adapter_states(self._h, ptrs, len(keep)), "unet_set_adapter_states")
+        return keep
+
     def __call__(self, latents, t, *, encoder_hidden_states, down_block_additional_residuals=None,
                  mid_block_additional_residual=None, adapter_states=None, added_cond_kwargs=None, **kwargs):
-        if adapter_states is not None:
-            # T2I-adapter states are added INSIDE the down path (core.py:45-64): not part of this boundary yet
-            raise NotImplementedError("T2I-adapter states are not supported by the B200 UNet")
         N.require_cuda(latents, encoder_hidden_states)
         B = latents.shape[0]
         if latents.shape[1] != self.config.in_channels:
@@ -235,7 +252,8 @@ class B200UNet:
             if not added_cond_kwargs or "text_embeds" not in added_cond_kwargs or "time_ids" not in added_cond_kwargs:
                 raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")
             add = self.added_cond_vector(added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"])
-        keep = self._bind_control_residuals(down_block_additional_residuals, mid_block_additional_residual, x)
+        keep = [self._bind_control_residuals(down_block_additional_residuals, mid_block_additional_residual, x),
+                self._bind_adapter_states(adapter_states, x)]
         out = self.forward_raw(x, self._timesteps(t, B), ctx, add_cond=add)
         del keep
         return UNetOutput(sample=out.to(latents.dtype) if latents.dtype != torch.float16 else out)

@@ -149,6 +149,12 @@ int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, i
 int gyre_b200_unet_set_control_residuals(gyre_b200_handle h, const void* const* down_residuals, int n_down,
                                          const void* mid_residual);
 int gyre_b200_unet_num_skips(gyre_b200_handle h);
+/* T2I-adapter states (the `adapter_states=` keyword the reference's patched UNet takes,
+ * gyre/pipeline/t2i_adapter/unet_patcher.py:21-60,95-110; chosen per CFG half by unet/core.py:213-219): one NCHW fp16
+ * device tensor per down block ([batch, C_i, h_i, w_i] at the block's resolution), added in place to the block's last
+ * hidden state before its downsampler (so the block's last skip connection sees it too, as in the reference).
+ * Valid for the NEXT forward only; n_states = 0 clears. */
+int gyre_b200_unet_set_adapter_states(gyre_b200_handle h, const void* const* states, int n_states);
 
 /* ------------------------------------------------------------------------------------------
  * AutoencoderKL  (replaces vae.decode(x).sample, gyre/pipeline/unified_pipeline.py:1523-1536,

@@ -300,7 +300,8 @@ def num_transformer_blocks(cfg: UNetConfig) -> int:
 
 
 def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_states, tome_r=0, taps=None,
-                 added_cond_kwargs=None, down_block_additional_residuals=None, mid_block_additional_residual=None):
+                 added_cond_kwargs=None, down_block_additional_residuals=None, mid_block_additional_residual=None,
+                 adapter_states=None):
     """UNet2DConditionModel.forward (call site gyre/pipeline/unet/core.py:274; encoder-half wiring
     cf. gyre/pipeline/controlnet/models.py:446-511; up path cf. nonfree/tome_unet.py:34-70).
     `tome_r`: int | (r, inflect) | list, expanded by parse_r over the transformer blocks in module
@@ -348,6 +349,13 @@ def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_stat
                                    cfg.num_heads[i], G, lin, r_list.pop(0))
                 tap(f"down_blocks.{i}.attentions.{j}", h)
             res.append(h)
+        if adapter_states:
+            # T2I-adapter (gyre/pipeline/t2i_adapter/unet_patcher.py:21-60, 62-84): `hidden_states += adapter_state`
+            # IN PLACE just before the block's downsampler (or after the block when it has none) - the tensor is
+            # also the block's last entry of `output_states`, so that skip sees the state as well
+            assert len(adapter_states) == len(ch)
+            h = h + adapter_states[i].to(h.dtype)
+            res[-1] = h
         if i < len(ch) - 1:
             h = F.conv2d(h, P[f"down_blocks.{i}.downsamplers.0.conv.weight"],
                          P[f"down_blocks.{i}.downsamplers.0.conv.bias"], stride=2, padding=1)
@@ -396,9 +404,10 @@ class OracleUNet:
         self.r = 0  # ToMe: set like `unet.r = int(value)` (gyre/pipeline/unified_pipeline.py:1582-1584)
 
     def __call__(self, latents, t, *, encoder_hidden_states, added_cond_kwargs=None,
-                 down_block_additional_residuals=None, mid_block_additional_residual=None, **_):
+                 down_block_additional_residuals=None, mid_block_additional_residual=None, adapter_states=None, **_):
         with torch.no_grad():
             return self._Out(unet_forward(self.params, self.config, latents, t, encoder_hidden_states, self.r,
                                           added_cond_kwargs=added_cond_kwargs,
                                           down_block_additional_residuals=down_block_additional_residuals,
-                                          mid_block_additional_residual=mid_block_additional_residual))
+                                          mid_block_additional_residual=mid_block_additional_residual,
+                                          adapter_states=adapter_states))

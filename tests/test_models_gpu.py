@@ -82,7 +82,7 @@ def test_unet_rejects_bad_input(tiny_unet):
     x = torch.zeros(1, 5, 16, 16).half().cuda()
     with pytest.raises(ValueError):
         unet(x, 1, encoder_hidden_states=torch.zeros(1, 77, cfg.cross_attention_dim).half().cuda())
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):      # wrong number of T2I-adapter states
         unet(torch.zeros(1, 4, 16, 16).half().cuda(), 1,
              encoder_hidden_states=torch.zeros(1, 77, cfg.cross_attention_dim).half().cuda(),
              adapter_states=[torch.zeros(1)])
@@ -269,3 +269,29 @@ def test_unet_sdxl_topology_vs_oracle():
     e2 = (res.latents.cpu() - lat).abs().max().item() / lat.abs().max().item()
     print(f"SDXL-topology pipeline final-latent rel err {e2:.3e}")
     assert e2 < 2e-2
+
+
+def test_unet_t2i_adapter_states_vs_oracle(tiny_unet):
+    """`adapter_states` (gyre/pipeline/t2i_adapter/unet_patcher.py:21-60,95-110): one state per down block, added in
+    place before the block's downsampler - the block's last skip and the rest of the down path both see it."""
+    from oracle.unet import unet_forward
+    cfg, P, unet = tiny_unet
+    _no_tf32()
+    gen = torch.Generator("cpu").manual_seed(78)
+    B = 2
+    x = torch.randn(B, 4, 16, 16, generator=gen).half()
+    ctx = torch.randn(B, 77, cfg.cross_attention_dim, generator=gen).half()
+    t = torch.tensor([700, 40])
+    states, h = [], 16
+    for c in cfg.block_out_channels:
+        states.append((torch.randn(B, c, h, h, generator=gen) * 0.5).half())
+        h = (h - 1) // 2 + 1
+    with torch.no_grad():
+        ref = unet_forward(P, cfg, x.float(), t, ctx.float(), adapter_states=[s.float() for s in states])
+        plain = unet_forward(P, cfg, x.float(), t, ctx.float())
+    out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda(), adapter_states=[s.cuda() for s in states]).sample
+    err, moved = rel_err(out.cpu(), ref), rel_err(ref, plain)
+    print(f"t2i adapter states: rel err {err:.3e}; the states move the output by {moved:.3e}")
+    assert moved > 5e-3 and err < 2e-2
+    out2 = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda(), adapter_states=[]).sample     # one call only
+    assert rel_err(out2.cpu(), plain) < 2e-2

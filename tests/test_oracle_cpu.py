@@ -158,3 +158,30 @@ def test_oracle_controlnet_residual_semantics():
         assert (o - base).abs().max() > 1e-5, f"skip residual {k} has no effect"
     with pytest.raises(AssertionError):
         unet_forward(P, cfg, x, 300, ctx, down_block_additional_residuals=zeros[:-1])
+
+
+def test_oracle_t2i_adapter_semantics():
+    """adapter_states: in-place add before each block's downsampler (unet_patcher.py:21-60): the block's last skip and
+    the downsampler input both move by the state; earlier layers of the block do not."""
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 4, 16, 16, generator=gen)
+    ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=gen)
+    states, h = [], 16
+    for c in cfg.block_out_channels:
+        states.append(torch.randn(1, c, h, h, generator=gen) * 0.3)
+        h = (h - 1) // 2 + 1
+    t0, t1 = {}, {}
+    with torch.no_grad():
+        base = unet_forward(P, cfg, x, 300, ctx, taps=t0)
+        assert torch.equal(unet_forward(P, cfg, x, 300, ctx, adapter_states=[torch.zeros_like(s) for s in states]), base)
+        assert torch.equal(unet_forward(P, cfg, x, 300, ctx, adapter_states=[]), base)
+        out = unet_forward(P, cfg, x, 300, ctx, taps=t1, adapter_states=states)
+    # level 0 layers run before the first state is added: untouched; level 1 sees the level-0 state through the downsampler
+    for j in range(cfg.layers_per_block):
+        assert torch.equal(t0[f"down_blocks.0.resnets.{j}"], t1[f"down_blocks.0.resnets.{j}"])
+    assert not torch.equal(t0["down_blocks.1.resnets.0"], t1["down_blocks.1.resnets.0"])
+    assert (out - base).abs().max() > 1e-3
+    with pytest.raises(AssertionError):
+        unet_forward(P, cfg, x, 300, ctx, adapter_states=states[:-1])
