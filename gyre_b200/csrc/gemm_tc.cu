@@ -1,10 +1,12 @@
 // K4 / K1: tcgen05 GEMM and 3x3 implicit-GEMM convolution for sm_100a.
 //
-// One CTA (persistent, one per SM) computes 128 x BN output tiles.  Warp 0 is the TMA producer, warp 1 owns TMEM and issues
-// tcgen05.mma (one elected lane), warps 2..5 are the epilogue (one accumulator row per thread, read
-// with tcgen05.ld 32x32b).  Operands are staged by TMA into 128B-swizzled K-major shared-memory tiles
-// (64 halfs = one swizzle span per row), STAGES deep, handed over with full/empty mbarriers; the
-// accumulator (128 lanes x BN fp32 columns) lives in TMEM.
+// One persistent worker per SM - a CTA computing 128 x BN output tiles, or (PAIR2) a 2-CTA cluster computing 256 x BN
+// tiles with one tcgen05.mma.cta_group::2 per k step.  Warp 0 is the TMA producer, warp 1 owns TMEM and issues
+// tcgen05.mma (one elected lane; in a pair only the leader CTA issues), warps 2..9 are the epilogue (one accumulator
+// row per thread, read with tcgen05.ld 32x32b; two warps per TMEM lane quadrant alternate over 32-column slices).
+// Operands are staged by TMA into 128B-swizzled K-major shared-memory tiles (64 halfs = one swizzle span per row),
+// `stages` deep, handed over with full/empty mbarriers; the accumulators (128 lanes x BN fp32 columns, two buffers)
+// live in TMEM.
 //
 // Convolution: the M tile is a tile_w x tile_h x tile_n patch of output pixels; for each of the 9
 // taps and each 64-channel slice the producer issues ONE 4-D TMA box load at the shifted coordinate
