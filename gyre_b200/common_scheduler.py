@@ -15,6 +15,8 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import Literal
 
+import math
+
 import torch
 
 from . import _native as N
@@ -162,7 +164,8 @@ class KDiffusionScheduler(CommonScheduler):
     FUSED = ("sample_euler_ancestral", "sample_euler")
     GENERIC = ("sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_lms", "sample_dpmpp_2s_ancestral",
                "sample_dpmpp_sde", "sample_dpmpp_2m")
-    SAMPLERS = FUSED + GENERIC
+    SOLVER = ("sample_dpm_fast",)      # take (sigma_min, sigma_max, n), not a sigma list (common_scheduler.py:590-594)
+    SAMPLERS = FUSED + GENERIC + SOLVER
 
     def __init__(self, scheduler, *args, **kwargs):
         name = scheduler if isinstance(scheduler, str) else getattr(scheduler, "__name__", str(scheduler))
@@ -171,9 +174,10 @@ class KDiffusionScheduler(CommonScheduler):
         super().__init__(name, *args, **kwargs)
         # which keyword arguments the reference's sampler function takes (common_scheduler.py:400-408 inspects them)
         self.accepts_eta = name in ("sample_euler_ancestral", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral",
-                                    "sample_dpmpp_sde")
+                                    "sample_dpmpp_sde", "sample_dpm_fast")
         self.accepts_s_churn = name in ("sample_euler", "sample_heun", "sample_dpm_2")
-        self.accepts_sigmas = True
+        self.accepts_sigmas = name not in self.SOLVER
+        self.accepts_n = name in self.SOLVER
 
     def set_timesteps(self, num_inference_steps, start_offset=None, strength=None, prediction_type="epsilon",
                       config: SchedulerConfig = SchedulerConfig()):
@@ -254,6 +258,9 @@ class KDiffusionScheduler(CommonScheduler):
         ancestral = self.scheduler == "sample_euler_ancestral"
         eta = 1.0 if self.eta is None else self.eta
         vpred = self.prediction_type == "v_prediction"
+        if self.scheduler in self.SOLVER:
+            # the reference passes eta only when the config sets it; the solver's own default is 0 (sampling.py:482)
+            return self._loop_dpm_fast(latents, sigmas, progress_wrapper, out_dtype, 0.0 if self.eta is None else self.eta)
         if self.scheduler in self.GENERIC or (self.scheduler == "sample_euler" and self.churn):
             return self._loop_generic(latents, sigmas, progress_wrapper, out_dtype, eta)
 
@@ -370,6 +377,72 @@ class KDiffusionScheduler(CommonScheduler):
 
     def _make_engine(self, latents):
         return self._Engine(self, latents)
+
+    def _loop_dpm_fast(self, latents, sigmas, progress_wrapper, out_dtype, eta):
+        """`sample_dpm_fast` (k_diffusion/sampling.py:482-491; DPMSolver.dpm_solver_fast :392-425, the 1 / 2 / 3-stage
+        steps :356-390).  eps(x, t) = (x - denoised) / sigma(t) is never formed: every update is written as a linear
+        combination of the states and their denoised images, with the reference's scalar expressions evaluated on the
+        host in the dtype the reference evaluates them in."""
+        E = self._make_engine(latents)
+        dt = self.dtype
+        pos = sigmas[sigmas > 0]
+        # `sigma_min = sigmas[sigmas > 0].min()`, `sigma_max = sigmas.max()` on the dtype-cast schedule (:560-563);
+        # t = -log(sigma) is computed on those 0-dim tensors, i.e. in the latent dtype (sampling.py:489)
+        t_start = -(sigmas.max().to(dt).log())
+        t_end = -(pos.min().to(dt).log())
+        if eta and not t_end > t_start:
+            raise ValueError("eta must be 0 for reverse sampling")
+        nfe = self.num_inference_steps
+        m = math.floor(nfe / 3) + 1
+        ts = torch.linspace(_f(t_start), _f(t_end), m + 1)
+        orders = [3] * (m - 2) + [2, 1] if nfe % 3 == 0 else [3] * (m - 1) + [nfe % 3]
+        sig = lambda t: t.neg().exp()
+        x = latents.to(torch.float32).contiguous().clone()
+        for i in progress_wrapper(range(len(orders))):
+            E.u = self._u(i, len(orders), len(orders) + 1)
+            t, t_next = ts[i], ts[i + 1]
+            if eta:
+                sd, su = get_ancestral_step(sig(t), sig(t_next), eta)
+                t_next_ = torch.minimum(t_end.float(), -sd.log())
+                su = (sig(t_next) ** 2 - sig(t_next_) ** 2) ** 0.5
+            else:
+                t_next_, su = t_next, 0.0
+            st = sig(t)
+            den = E.denoise(x, st)
+            if self.callback and i % self.callback_steps == 0:
+                self.callback(i, self._sched.sigma_to_t(st.reshape(1))[0], den.to(self.dtype))
+            h = t_next_ - t
+            sn = sig(t_next_)
+            noise = E.noise()                       # the noise sampler is called on every step (sampling.py:423)
+            tail = [(su, noise)] if eta else []
+            order = orders[i]
+            if order == 1:
+                a = sn * h.expm1() / st                                     # x - a * (x - den)
+                x = E.lin([(1 - a, x), (a, den)] + tail)
+                continue
+            r1 = 1 / 2 if order == 2 else 1 / 3
+            s1 = t + r1 * h
+            a1 = sig(s1) * (r1 * h).expm1() / st
+            u1 = E.lin([(1 - a1, x), (a1, den)])
+            den1 = E.denoise(u1, sig(s1))
+            if order == 2:
+                A = sn * h.expm1()
+                Bc = sn / (2 * r1) * h.expm1()
+                ce, c1 = (A - Bc) / st, Bc / sig(s1)                        # x - (A - Bc) eps - Bc eps_r1
+                x = E.lin([(1 - ce, x), (ce, den), (-c1, u1), (c1, den1)] + tail)
+                continue
+            r2 = 2 / 3
+            s2 = t + r2 * h
+            A2 = sig(s2) * (r2 * h).expm1()
+            B2 = sig(s2) * (r2 / r1) * ((r2 * h).expm1() / (r2 * h) - 1)
+            ce, c1 = (A2 - B2) / st, B2 / sig(s1)
+            u2 = E.lin([(1 - ce, x), (ce, den), (-c1, u1), (c1, den1)])
+            den2 = E.denoise(u2, sig(s2))
+            A3 = sn * h.expm1()
+            B3 = sn / r2 * (h.expm1() / h - 1)
+            ce, c2 = (A3 - B3) / st, B3 / sig(s2)
+            x = E.lin([(1 - ce, x), (ce, den), (-c2, u2), (c2, den2)] + tail)
+        return x.to(out_dtype or self.dtype)
 
     def _loop_generic(self, latents, sigmas, progress_wrapper, out_dtype, eta):
         """The reference's sampler functions with every tensor expression folded into scalar coefficients of
@@ -639,6 +712,7 @@ SAMPLERS = {
     "k_dpmpp_2s_ancestral": (KDiffusionScheduler, "sample_dpmpp_2s_ancestral"),
     "k_dpmpp_sde": (KDiffusionScheduler, "sample_dpmpp_sde"),
     "k_dpmpp_2m": (KDiffusionScheduler, "sample_dpmpp_2m"),
+    "dpm_fast": (KDiffusionScheduler, "sample_dpm_fast"),
     "ddim": (DiffusersScheduler, "ddim"),
 }
 

@@ -12,6 +12,8 @@ Pinned against the vendored k-diffusion sources by scripts/make_golden.py -> tes
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 
@@ -370,6 +372,55 @@ def sample_dpmpp_2m(model, x, sigmas, warmup_lms=False, ddim_cutoff=0.0):
 
 # ----------------------------------------------------------------------------- DDIM
 
+def sample_dpm_fast(model, x, sigma_min, sigma_max, n, noise_sampler, eta=0.0, s_noise=1.0, callback=None):
+    """DPM-Solver-Fast, fixed step size (k_diffusion/sampling.py:482-491 -> DPMSolver.dpm_solver_fast :392-425 with
+    dpm_solver_{1,2,3}_step :356-390 and eps :349-354).  `sigma_min` / `sigma_max` are 0-dim tensors in the scheduler's
+    dtype, as gyre passes them (common_scheduler.py:558-559, 590-594): t = -log(sigma) inherits that dtype."""
+    t_of = lambda sigma: -sigma.log()
+    sig = lambda t: t.neg().exp()
+    t_start, t_end = t_of(torch.as_tensor(sigma_max)), t_of(torch.as_tensor(sigma_min))
+    if eta and not t_end > t_start:
+        raise ValueError("eta must be 0 for reverse sampling")
+
+    def eps_of(x_, t):
+        sigma = sig(t) * x_.new_ones([x_.shape[0]])
+        return (x_ - model(x_, sigma)) / sig(t)
+
+    m = math.floor(n / 3) + 1
+    ts = torch.linspace(t_start, t_end, m + 1, device=x.device)
+    orders = [3] * (m - 2) + [2, 1] if n % 3 == 0 else [3] * (m - 1) + [n % 3]
+    for i, order in enumerate(orders):
+        t, t_next = ts[i], ts[i + 1]
+        if eta:
+            sd, su = get_ancestral_step(sig(t), sig(t_next), eta)
+            t_next_ = torch.minimum(t_end, t_of(sd))
+            su = (sig(t_next) ** 2 - sig(t_next_) ** 2) ** 0.5
+        else:
+            t_next_, su = t_next, 0.0
+        eps = eps_of(x, t)
+        if callback is not None:
+            callback({"i": i, "sigma": sig(t), "denoised": x - sig(t) * eps})
+        h = t_next_ - t
+        if order == 1:
+            x_new = x - sig(t_next_) * h.expm1() * eps
+        elif order == 2:
+            r1 = 1 / 2
+            s1 = t + r1 * h
+            u1 = x - sig(s1) * (r1 * h).expm1() * eps
+            eps_r1 = eps_of(u1, s1)
+            x_new = x - sig(t_next_) * h.expm1() * eps - sig(t_next_) / (2 * r1) * h.expm1() * (eps_r1 - eps)
+        else:
+            r1, r2 = 1 / 3, 2 / 3
+            s1, s2 = t + r1 * h, t + r2 * h
+            u1 = x - sig(s1) * (r1 * h).expm1() * eps
+            eps_r1 = eps_of(u1, s1)
+            u2 = x - sig(s2) * (r2 * h).expm1() * eps - sig(s2) * (r2 / r1) * ((r2 * h).expm1() / (r2 * h) - 1) * (eps_r1 - eps)
+            eps_r2 = eps_of(u2, s2)
+            x_new = x - sig(t_next_) * h.expm1() * eps - sig(t_next_) / r2 * (h.expm1() / h - 1) * (eps_r2 - eps)
+        x = x_new + su * s_noise * noise_sampler(sig(t), sig(t_next))     # the sampler is called every step (:423)
+    return x
+
+
 def ddim_timesteps(n, num_train=1000, steps_offset=1):
     """scheduling_ddim.py:189-203 with the SD config (ckpt_utils.py:244-255): steps_offset=1."""
     ratio = num_train // n
@@ -469,6 +520,9 @@ def txt2img_latents(eps_unet_cfg, *, batch, in_channels, height, width, sample_s
         return sample_dpmpp_2s_ancestral(den, latents, sigmas, noise, eta=1.0 if eta is None else eta)
     if sampler == "dpmpp_sde":
         return sample_dpmpp_sde(den, latents, sigmas, noise, eta=1.0 if eta is None else eta)
+    if sampler == "dpm_fast":
+        sq = sigmas_full.to(latent_dtype)                   # sigma_min / sigma_max keep the latent dtype (:562-563)
+        return sample_dpm_fast(den, latents, sq[sq > 0].min(), sq.max(), steps, noise, eta=0.0 if eta is None else eta)
     raise ValueError(sampler)
 
 

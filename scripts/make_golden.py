@@ -110,6 +110,26 @@ def pin_samplers():
                 assert err == 0.0, f"{name}/{steps}/{dtype_name}: oracle != vendored k-diffusion ({err})"
                 out[f"{name}/{steps}/{dtype_name}"] = {"seeds": seeds, "shape": shape, "sigmas": sig_full,
                                                         "result": ref}
+    # DPM-Solver-Fast: takes (sigma_min, sigma_max, n) instead of a sigma list (common_scheduler.py:590-594)
+    for dtype_name, ldt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        for steps, eta in ((7, 0.0), (12, 0.0), (20, 0.0), (11, 0.6)):
+            shape, seeds = (2, 4, 8, 8), [420420420, 420420421]
+            ref_den = kext.DiscreteEpsDDPMDenoiser(toy_eps, acp, quantize=True)
+            sig_full = ks.append_zero(ref_den.t_to_sigma(torch.linspace(len(ref_den.sigmas) - 1, 0, steps)))
+            sig = sig_full.to(ldt)                                   # `sigmas[...].to(self.dtype)` (:560)
+            s_min, s_max = sig[sig > 0].min(), sig.max()             # 0-dim tensors in the latent dtype (:562-563)
+            gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+            x0 = (osamp.batched_randn(shape, gens, "cpu", ldt) * sig_full[0]).float()
+            ns = lambda *_: osamp.batched_randn(shape, gens, "cpu", ldt).float()
+            ref = ks.sample_dpm_fast(ref_den, x0, s_min, s_max, steps, eta=eta, noise_sampler=ns, disable=True)
+            gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+            den = osamp.EpsDenoiser(toy_eps, acp)
+            y0 = (osamp.batched_randn(shape, gens, "cpu", ldt) * sig_full[0]).float()
+            got = osamp.sample_dpm_fast(den, y0, s_min, s_max, steps,
+                                        lambda *_: osamp.batched_randn(shape, gens, "cpu", ldt).float(), eta=eta)
+            assert (got - ref).abs().max().item() == 0.0, f"dpm_fast {steps} {dtype_name}: oracle != vendored"
+            out[f"dpm_fast/{steps}/{dtype_name}" + (f"/eta{eta}" if eta else "")] = {
+                "seeds": seeds, "shape": shape, "sigmas": sig_full, "result": ref, "eta": eta, "steps": steps}
     # churn > 0 (Karras stochasticity) for the samplers that take s_churn
     for name in ("euler", "heun", "dpm_2"):
         shape, seeds, steps = (2, 4, 8, 8), [420420420, 420420421], 12
@@ -269,7 +289,7 @@ def oracle_fixtures(full: bool):
         unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1)
         cfgu = osamp.CFGParallel(unet, unc, emb, 7.5)
         for sampler, steps in (("ddim", 10), ("euler_a", 12), ("euler", 8), ("dpmpp_2m", 8), ("heun", 7), ("dpm_2", 7),
-                               ("dpm_2_a", 7), ("lms", 9), ("dpmpp_2s_a", 7), ("dpmpp_sde", 7)):
+                               ("dpm_2_a", 7), ("lms", 9), ("dpmpp_2s_a", 7), ("dpmpp_sde", 7), ("dpm_fast", 10)):
             lat = osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=128, width=128, sample_size=16,
                                         seeds=[420420420, 420420421], steps=steps, sampler=sampler)
             out[f"pipe_tiny/{sampler}"] = {"steps": steps, "latents": lat}

@@ -66,7 +66,7 @@ def test_kdiffusion_scheduler_host_state():
     sched3.set_timesteps(8, config=cs.SchedulerConfig(karras_rho=7.0))
     assert torch.equal(sched3.sigmas, osamp.get_sigmas_karras(8, den.sigma_min, den.sigma_max, 7.0))
     with pytest.raises(NotImplementedError):
-        cs.build_scheduler("k_dpm_adaptive", [torch.Generator()], "cpu", torch.float16)
+        cs.build_scheduler("dpm_adaptive", [torch.Generator()], "cpu", torch.float16)
     # the loop needs CUDA tensors: no silent CPU path
     with pytest.raises(Exception):
         sched.loop(torch.zeros(1, 4, 8, 8))
@@ -141,6 +141,30 @@ def test_churn_host_logic_vs_vendored_golden(enum_name, gold_name):
     out = sched._loop_generic(x0, sched.sigmas.float(), lambda it: it, torch.float32, 1.0)
     err = (out - gold["result"]).abs().max().item()
     assert err <= 2e-5 * max(gold["result"].abs().max().item(), 1.0), f"{enum_name} churn: {err}"
+
+
+@pytest.mark.parametrize("key,eta", [("dpm_fast/7/fp32", None), ("dpm_fast/12/fp32", None), ("dpm_fast/20/fp32", None),
+                                     ("dpm_fast/7/fp16", None), ("dpm_fast/12/fp16", None), ("dpm_fast/20/fp16", None),
+                                     ("dpm_fast/11/fp32/eta0.6", 0.6), ("dpm_fast/11/fp16/eta0.6", 0.6)])
+def test_dpm_fast_host_logic_vs_vendored_golden(key, eta):
+    """`sample_dpm_fast` (sampling.py:482-491): step orders (3...3,2,1 | 3...3,n%3), the t = -log sigma grid built from
+    the dtype-cast sigma_min / sigma_max, the three solver stages as linear maps, eta > 0 and the per-step noise draw."""
+    import os
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "samplers.pt"))[key]
+    ldt = torch.float16 if "/fp16" in key else torch.float32
+    gens = [torch.Generator("cpu").manual_seed(sd) for sd in gold["seeds"]]
+    sched = cs.build_scheduler("dpm_fast", gens, "cpu", ldt)
+    sched.set_eps_unets([_dummy_guided()])
+    sched.set_timesteps(gold["steps"], config=cs.SchedulerConfig(eta=eta))
+    assert torch.equal(sched.sigmas, gold["sigmas"])
+    x0 = sched.prepare_initial_latents(batched_randn(gold["shape"], gens, "cpu", ldt)).float()
+    sched._make_engine = lambda latents: _CpuEngine(sched, latents, _toy_eps)
+    sigmas = sched.sigmas.to(ldt).float()
+    out = sched._loop_dpm_fast(x0, sigmas, lambda it: it, torch.float32, 0.0 if eta is None else eta)
+    err = (out - gold["result"]).abs().max().item()
+    scale = gold["result"].abs().max().item()
+    print(f"{key}: host-logic max abs err {err:.3e} (scale {scale:.2f})")
+    assert err <= 5e-5 * max(scale, 1.0), f"{key}: {err}"
 
 
 def test_ddim_scheduler_host_state():

@@ -29,7 +29,8 @@ def tiny():
                                                 ("k_euler", "euler", 8), ("k_dpmpp_2m", "dpmpp_2m", 8),
                                                 ("k_heun", "heun", 7), ("k_dpm_2", "dpm_2", 7),
                                                 ("k_dpm_2_ancestral", "dpm_2_a", 7), ("k_lms", "lms", 9),
-                                                ("k_dpmpp_2s_ancestral", "dpmpp_2s_a", 7), ("k_dpmpp_sde", "dpmpp_sde", 7)])
+                                                ("k_dpmpp_2s_ancestral", "dpmpp_2s_a", 7), ("k_dpmpp_sde", "dpmpp_sde", 7),
+                                                ("dpm_fast", "dpm_fast", 10)])
 def test_pipeline_tiny_vs_golden(tiny, sampler, name, steps):
     """Golden latents were produced by the oracle with fp32 latents / schedule (scripts/make_golden.py)."""
     cfg, P, pipe, emb, unc = tiny
@@ -80,6 +81,8 @@ def test_generic_sampler_kernels_match_vendored_loops():
                                                   ("k_dpmpp_sde", "dpmpp_sde"), ("k_dpmpp_2m", "dpmpp_2m"))]
     # s_churn > 0: gamma / sigma_hat / noise injection of sample_euler, sample_heun, sample_dpm_2
     cases += [(e, f"{n}_churn/12/fp32", 12) for e, n in (("k_euler", "euler"), ("k_heun", "heun"), ("k_dpm_2", "dpm_2"))]
+    # DPM-Solver-Fast: (sigma_min, sigma_max, n) solver, three-stage steps, eta > 0
+    cases += [("dpm_fast", "dpm_fast/20/fp32", 20), ("dpm_fast", "dpm_fast/11/fp32/eta0.6", 11)]
     for enum_name, key, steps in cases:
         rec = g[key]
         gens = [torch.Generator("cpu").manual_seed(sd) for sd in rec["seeds"]]
@@ -90,11 +93,16 @@ def test_generic_sampler_kernels_match_vendored_loops():
         if "churn" in rec:
             churn, tmin, tmax = rec["churn"]
             sched.set_timesteps(steps, config=cs.SchedulerConfig(churn=churn, churn_tmin=tmin, churn_tmax=tmax))
+        elif rec.get("eta"):
+            sched.set_timesteps(steps, config=cs.SchedulerConfig(eta=rec["eta"]))
         else:
             sched.set_timesteps(steps)
         x0 = sched.prepare_initial_latents(batched_randn(rec["shape"], gens, dev, torch.float32)).float()
         sched._make_engine = lambda latents, sched=sched: Engine(sched, latents)
-        out = sched._loop_generic(x0, sched.sigmas.float(), lambda it: it, torch.float32, 1.0)
+        if enum_name == "dpm_fast":
+            out = sched._loop_dpm_fast(x0, sched.sigmas.float(), lambda it: it, torch.float32, rec.get("eta") or 0.0)
+        else:
+            out = sched._loop_generic(x0, sched.sigmas.float(), lambda it: it, torch.float32, 1.0)
         err = (out.cpu() - rec["result"]).abs().max().item()
         scale = rec["result"].abs().max().item()
         print(f"{enum_name}: max abs err {err:.3e} (scale {scale:.2f})")
