@@ -97,6 +97,8 @@ SIGNATURES = {
     "gyre_b200_cfg_combine": (_i, [_vp, _f, _i, _i64, _vp, _vp, _vp]),
     "gyre_b200_denoise": (_i, [_vp, _vp, _i, _f, _f, _f, _i, _i64, _vp, _vp]),
     "gyre_b200_lincomb": (_i, [_i, C.POINTER(_vp), C.POINTER(_f), _i, _i64, _vp, _vp, _f, _i, _vp]),
+    "gyre_b200_dpm_error_partials": (_i, [_vp, _vp, _vp, _f, _f, _i64, _vp, _vp]),
+    "gyre_b200_dpm_error_num_partials": (_i, []),
     "gyre_b200_denoise_blend": (_i, [_vp, _vp, _i, _f, _f, _f, _i, _i64, _vp, _vp, _vp, _f, _vp]),
     "gyre_b200_sched_step_blend": (_i, [C.POINTER(Step), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _f, _vp]),
     "gyre_b200_cat_channels": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _vp, _vp]),

@@ -164,7 +164,7 @@ class KDiffusionScheduler(CommonScheduler):
     FUSED = ("sample_euler_ancestral", "sample_euler")
     GENERIC = ("sample_heun", "sample_dpm_2", "sample_dpm_2_ancestral", "sample_lms", "sample_dpmpp_2s_ancestral",
                "sample_dpmpp_sde", "sample_dpmpp_2m")
-    SOLVER = ("sample_dpm_fast",)      # take (sigma_min, sigma_max, n), not a sigma list (common_scheduler.py:590-594)
+    SOLVER = ("sample_dpm_fast", "sample_dpm_adaptive")   # take (sigma_min, sigma_max[, n]), not a sigma list (:590-594)
     SAMPLERS = FUSED + GENERIC + SOLVER
 
     def __init__(self, scheduler, *args, **kwargs):
@@ -174,10 +174,10 @@ class KDiffusionScheduler(CommonScheduler):
         super().__init__(name, *args, **kwargs)
         # which keyword arguments the reference's sampler function takes (common_scheduler.py:400-408 inspects them)
         self.accepts_eta = name in ("sample_euler_ancestral", "sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral",
-                                    "sample_dpmpp_sde", "sample_dpm_fast")
+                                    "sample_dpmpp_sde", "sample_dpm_fast", "sample_dpm_adaptive")
         self.accepts_s_churn = name in ("sample_euler", "sample_heun", "sample_dpm_2")
         self.accepts_sigmas = name not in self.SOLVER
-        self.accepts_n = name in self.SOLVER
+        self.accepts_n = name == "sample_dpm_fast"
 
     def set_timesteps(self, num_inference_steps, start_offset=None, strength=None, prediction_type="epsilon",
                       config: SchedulerConfig = SchedulerConfig()):
@@ -260,7 +260,8 @@ class KDiffusionScheduler(CommonScheduler):
         vpred = self.prediction_type == "v_prediction"
         if self.scheduler in self.SOLVER:
             # the reference passes eta only when the config sets it; the solver's own default is 0 (sampling.py:482)
-            return self._loop_dpm_fast(latents, sigmas, progress_wrapper, out_dtype, 0.0 if self.eta is None else self.eta)
+            loop = self._loop_dpm_fast if self.scheduler == "sample_dpm_fast" else self._loop_dpm_adaptive
+            return loop(latents, sigmas, progress_wrapper, out_dtype, 0.0 if self.eta is None else self.eta)
         if self.scheduler in self.GENERIC or (self.scheduler == "sample_euler" and self.churn):
             return self._loop_generic(latents, sigmas, progress_wrapper, out_dtype, eta)
 
@@ -370,6 +371,22 @@ class KDiffusionScheduler(CommonScheduler):
                                                N.stream_ptr(self.dev)), "lincomb")
             return out
 
+        def err_norm(self, x_low, x_high, x_prev, atol, rtol):
+            """||(x_low - x_high) / max(atol, rtol * max(|x_low|, |x_prev|))||_2 / sqrt(numel) (sampling.py:461-462):
+            block partial sums on the device, added in index order on the host (the caller needs the value on the
+            host anyway: it decides whether the step is accepted)."""
+            n = x_low.numel()
+            if getattr(self, "_err_buf", None) is None:
+                self._err_buf = torch.empty(self.lib.gyre_b200_dpm_error_num_partials(), device=self.dev,
+                                            dtype=torch.float64)
+            N.check(self.lib.gyre_b200_dpm_error_partials(N.ptr(x_low), N.ptr(x_high), N.ptr(x_prev), float(atol),
+                                                          float(rtol), n, N.ptr(self._err_buf), N.stream_ptr(self.dev)),
+                    "dpm_error_partials")
+            total = 0.0
+            for p in self._err_buf.cpu().tolist():
+                total += p
+            return math.sqrt(total) / n ** 0.5
+
         def noise(self):
             """One `batched_randn` draw (noise sampler for "normal" noise, common_scheduler.py:596-610; also what
             TorchRandOverride.randn_like resolves to, randtools.py:67-90)."""
@@ -442,6 +459,86 @@ class KDiffusionScheduler(CommonScheduler):
             B3 = sn / r2 * (h.expm1() / h - 1)
             ce, c2 = (A3 - B3) / st, B3 / sig(s2)
             x = E.lin([(1 - ce, x), (ce, den), (-c2, u2), (c2, den2)] + tail)
+        return x.to(out_dtype or self.dtype)
+
+    def _loop_dpm_adaptive(self, latents, sigmas, progress_wrapper, out_dtype, eta, order=3, rtol=0.05, atol=0.0078,
+                           h_init=0.05, pcoeff=0.0, icoeff=1.0, dcoeff=0.0, accept_safety=0.81):
+        """`sample_dpm_adaptive` (k_diffusion/sampling.py:494-506; DPMSolver.dpm_solver_adaptive :427-479 with the PID
+        controller :304-331): an embedded 2nd / 3rd-order pair per trial step, accepted or rejected on the host from
+        the device-computed error norm.  The time variable t = -log(sigma) lives in the LATENT dtype, as it does in the
+        reference (sigma_min / sigma_max are 0-dim tensors of the dtype-cast schedule): every scalar below is evaluated
+        with the reference's expression in that dtype and only then folded into fp32 `lin` coefficients."""
+        if order != 3:
+            raise NotImplementedError("gyre never overrides `order`: only DPM-Solver-23 is built")
+        E = self._make_engine(latents)
+        dt = self.dtype
+        pos = sigmas[sigmas > 0]
+        t_start = -(sigmas.max().to(dt).log())
+        t_end = -(pos.min().to(dt).log())
+        if not t_end > t_start:
+            raise ValueError("sample_dpm_adaptive: sigma_max must exceed sigma_min")
+        sig = lambda t: t.neg().exp()
+        # PIDStepSizeController (sampling.py:304-331)
+        pid_order = 1.5 if eta else order
+        b1, b2, b3 = (pcoeff + icoeff + dcoeff) / pid_order, -(pcoeff + 2 * dcoeff) / pid_order, dcoeff / pid_order
+        pid_h, errs = abs(h_init), []
+        x = latents.to(torch.float32).contiguous().clone()
+        x_prev = x
+        s = t_start
+        r1, r2 = 1 / 3, 2 / 3
+        ticks = iter(progress_wrapper(iter(int, 1)))          # endless iterator: cancellation raises from next()
+        steps = 0
+        span = max(_f(t_end) - _f(t_start), 1e-6)
+        while s < t_end - 1e-5:
+            next(ticks)
+            E.u = min(max((_f(s) - _f(t_start)) / span, 0.0), 0.999)
+            t = torch.minimum(t_end, s + pid_h)
+            if eta:
+                sd, su = get_ancestral_step(sig(s), sig(t), eta)
+                t_ = torch.minimum(t_end, -sd.log())
+                su = (sig(t) ** 2 - sig(t_) ** 2) ** 0.5
+            else:
+                t_, su = t, 0.0
+            st = _f(sig(s))
+            den = E.denoise(x, st)
+            h = t_ - s
+            s1, s2 = s + r1 * h, s + r2 * h
+            sg1, sg2 = _f(sig(s1)), _f(sig(s2))
+            cu1 = _f(sig(s1) * (r1 * h).expm1()) / st
+            u1 = E.lin([(1 - cu1, x), (cu1, den)])
+            den1 = E.denoise(u1, sg1)
+            A = _f(sig(t_) * h.expm1())
+            Bc = _f(sig(t_) / (2 * r1) * h.expm1())
+            ce, c1 = (A - Bc) / st, Bc / sg1
+            x_low = E.lin([(1 - ce, x), (ce, den), (-c1, u1), (c1, den1)])               # dpm_solver_2_step, r1 = 1/3
+            A2 = _f(sig(s2) * (r2 * h).expm1())
+            B2 = _f(sig(s2) * (r2 / r1) * ((r2 * h).expm1() / (r2 * h) - 1))
+            ce, c1 = (A2 - B2) / st, B2 / sg1
+            u2 = E.lin([(1 - ce, x), (ce, den), (-c1, u1), (c1, den1)])
+            den2 = E.denoise(u2, sg2)
+            B3 = _f(sig(t_) / r2 * (h.expm1() / h - 1))
+            ce, c2 = (A - B3) / st, B3 / sg2
+            x_high = E.lin([(1 - ce, x), (ce, den), (-c2, u2), (c2, den2)])              # dpm_solver_3_step
+            error = E.err_norm(x_low, x_high, x_prev, atol, rtol)
+            # pid.propose_step
+            inv_error = 1 / (float(error) + 1e-8)
+            if not errs:
+                errs = [inv_error, inv_error, inv_error]
+            errs[0] = inv_error
+            factor = errs[0] ** b1 * errs[1] ** b2 * errs[2] ** b3
+            factor = 1 + math.atan(factor - 1)
+            accept = factor >= accept_safety
+            if accept:
+                errs[2], errs[1] = errs[1], errs[0]
+            pid_h *= factor
+            if accept:
+                x_prev = x_low
+                x = E.lin([(1.0, x_high), (su, E.noise())]) if eta else x_high           # noise on accepted steps only
+                s = t
+            if self.callback and steps % self.callback_steps == 0:
+                self.callback(steps, self._sched.sigma_to_t(torch.as_tensor(st).reshape(1))[0], den.to(self.dtype))
+            steps += 1
+        self.last_solver_info = {"steps": steps}
         return x.to(out_dtype or self.dtype)
 
     def _loop_generic(self, latents, sigmas, progress_wrapper, out_dtype, eta):
@@ -713,6 +810,7 @@ SAMPLERS = {
     "k_dpmpp_sde": (KDiffusionScheduler, "sample_dpmpp_sde"),
     "k_dpmpp_2m": (KDiffusionScheduler, "sample_dpmpp_2m"),
     "dpm_fast": (KDiffusionScheduler, "sample_dpm_fast"),
+    "dpm_adaptive": (KDiffusionScheduler, "sample_dpm_adaptive"),
     "ddim": (DiffusersScheduler, "ddim"),
 }
 

@@ -201,6 +201,13 @@ int gyre_b200_lincomb(int n_terms, const float* const* inputs_host, const float*
                  S(stream));
 }
 
+int gyre_b200_dpm_error_partials(const float* x_low, const float* x_high, const float* x_prev, float atol, float rtol,
+                                 int64_t n, double* partials, gyre_b200_stream stream) {
+  return dpm_error_partials(x_low, x_high, x_prev, atol, rtol, n, partials, S(stream));
+}
+
+int gyre_b200_dpm_error_num_partials(void) { return dpm_error_num_partials(); }
+
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream) {
   GYRE_REQUIRE(x && out, "scale_latents: null operand");

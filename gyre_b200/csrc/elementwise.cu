@@ -323,6 +323,40 @@ int lincomb(int n_terms, const float* const* in, const float* coef, int B, int64
   return 0;
 }
 
+// Error norm of the adaptive DPM-Solver (k_diffusion/sampling.py:461-462):
+//   delta = max(atol, rtol * max(|x_low|, |x_prev|));  partial[b] = sum over the block's elements of ((x_low - x_high) / delta)^2
+// One fp64 partial per block, a fixed number of blocks and a fixed in-block tree: the host adds the partials in order,
+// so the accept / reject decision is reproducible.
+constexpr int kErrBlocks = 256;
+__global__ void __launch_bounds__(256) dpm_error_kernel(const float* __restrict__ x_low, const float* __restrict__ x_high,
+                                                        const float* __restrict__ x_prev, float atol, float rtol,
+                                                        int64_t n, double* __restrict__ partials) {
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float lo = x_low[i];
+    const float delta = fmaxf(atol, rtol * fmaxf(fabsf(lo), fabsf(x_prev[i])));
+    const float q = (lo - x_high[i]) / delta;
+    acc += static_cast<double>(q) * static_cast<double>(q);
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+int dpm_error_partials(const float* x_low, const float* x_high, const float* x_prev, float atol, float rtol, int64_t n,
+                       double* partials, cudaStream_t st) {
+  GYRE_REQUIRE(x_low && x_high && x_prev && partials && n > 0, "dpm_error: bad arguments");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  dpm_error_kernel<<<kErrBlocks, 256, 0, st>>>(x_low, x_high, x_prev, atol, rtol, n, partials);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dpm_error_num_partials() { return kErrBlocks; }
+
 // UNet input of the inpaint / depth models (EnhancedRunwayInpaintMode.wrap_unet, unified_pipeline.py:668-690;
 // UnetWithExtraChannels, unet/core.py:21-37): out[b] = cat([x[b], extra[b % extra_batch]], dim=channel), NCHW fp16.
 // The extra channels (mask + masked-image latents) are NOT scaled by c_in (see the reference's comment there).

@@ -118,6 +118,9 @@ int cat_channels_nchw(const __half* x, int Cx, const __half* extra, int Ce, int 
 int denoise_combine(const float* x, const __half* model_out, int cfg, float guidance, float c_skip, float c_out, int B,
                     int64_t per_sample, float* den, cudaStream_t st, const float* blend_orig = nullptr,
                     const float* blend_mask = nullptr, float blend_u = 0.f);
+int dpm_error_partials(const float* x_low, const float* x_high, const float* x_prev, float atol, float rtol, int64_t n,
+                       double* partials, cudaStream_t st);
+int dpm_error_num_partials();
 int lincomb(int n_terms, const float* const* in, const float* coef, int B, int64_t per_sample, float* out,
             __half* x_in, float c_in, int dup, cudaStream_t st);
 int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_sample, __half* out16, float* out32,

@@ -255,6 +255,13 @@ int gyre_b200_denoise(const float* x, const void* model_out, int cfg, float guid
                       int batch, int64_t per_sample, float* denoised, gyre_b200_stream stream);
 int gyre_b200_lincomb(int n_terms, const float* const* inputs_host, const float* coefs_host, int batch,
                       int64_t per_sample, float* out, void* x_in_next, float c_in, int dup, gyre_b200_stream stream);
+/* Error estimate of the adaptive DPM-Solver (`sample_dpm_adaptive`, k_diffusion/sampling.py:461-462):
+ *   delta = max(atol, rtol * max(|x_low|, |x_prev|));  error = ||(x_low - x_high) / delta||_2 / sqrt(n).
+ * Writes gyre_b200_dpm_error_num_partials() fp64 block sums of ((x_low - x_high) / delta)^2 to `partials` (device);
+ * the caller adds them in index order (reproducible accept / reject decisions) and takes sqrt(sum / n). */
+int gyre_b200_dpm_error_partials(const float* x_low, const float* x_high, const float* x_prev, float atol, float rtol,
+                                 int64_t n, double* partials, gyre_b200_stream stream);
+int gyre_b200_dpm_error_num_partials(void);
 /* Legacy (4-channel UNet) inpainting: EnhancedInpaintMode.wrap_k_unet / _blend
  * (gyre/pipeline/unified_pipeline.py:620-636) replaces the predicted x0 by the original image latents
  * wherever blend_mask > u (u = progress in [0, 1), common_scheduler.py:358-389).  Same as the functions

@@ -421,6 +421,99 @@ def sample_dpm_fast(model, x, sigma_min, sigma_max, n, noise_sampler, eta=0.0, s
     return x
 
 
+class PIDStepSizeController:
+    """k_diffusion/sampling.py:304-331."""
+
+    def __init__(self, h, pcoeff, icoeff, dcoeff, order=1, accept_safety=0.81, eps=1e-8):
+        self.h = h
+        self.b1 = (pcoeff + icoeff + dcoeff) / order
+        self.b2 = -(pcoeff + 2 * dcoeff) / order
+        self.b3 = dcoeff / order
+        self.accept_safety = accept_safety
+        self.eps = eps
+        self.errs = []
+
+    def propose_step(self, error):
+        inv_error = 1 / (float(error) + self.eps)
+        if not self.errs:
+            self.errs = [inv_error, inv_error, inv_error]
+        self.errs[0] = inv_error
+        factor = self.errs[0] ** self.b1 * self.errs[1] ** self.b2 * self.errs[2] ** self.b3
+        factor = 1 + math.atan(factor - 1)
+        accept = factor >= self.accept_safety
+        if accept:
+            self.errs[2] = self.errs[1]
+            self.errs[1] = self.errs[0]
+        self.h *= factor
+        return accept
+
+
+def sample_dpm_adaptive(model, x, sigma_min, sigma_max, noise_sampler, order=3, rtol=0.05, atol=0.0078, h_init=0.05,
+                        pcoeff=0.0, icoeff=1.0, dcoeff=0.0, accept_safety=0.81, eta=0.0, s_noise=1.0, callback=None,
+                        info_out=None):
+    """DPM-Solver-12 / -23 with PID step-size control (k_diffusion/sampling.py:494-506 -> DPMSolver.dpm_solver_adaptive
+    :427-479).  Forward direction only (sigma_max -> sigma_min), which is how gyre calls it."""
+    if order not in (2, 3):
+        raise ValueError("order should be 2 or 3")
+    t_of = lambda sigma: -sigma.log()
+    sig = lambda t: t.neg().exp()
+    t_start, t_end = t_of(torch.as_tensor(sigma_max)), t_of(torch.as_tensor(sigma_min))
+
+    def eps_of(x_, t):
+        sigma = sig(t) * x_.new_ones([x_.shape[0]])
+        return (x_ - model(x_, sigma)) / sig(t)
+
+    def step2(x_, t, t_next, r1, eps):
+        h = t_next - t
+        s1 = t + r1 * h
+        u1 = x_ - sig(s1) * (r1 * h).expm1() * eps
+        eps_r1 = eps_of(u1, s1)
+        return x_ - sig(t_next) * h.expm1() * eps - sig(t_next) / (2 * r1) * h.expm1() * (eps_r1 - eps), eps_r1
+
+    atol_t, rtol_t = torch.tensor(atol), torch.tensor(rtol)
+    s, x_prev = t_start, x
+    pid = PIDStepSizeController(abs(h_init), pcoeff, icoeff, dcoeff, 1.5 if eta else order, accept_safety)
+    info = {"steps": 0, "nfe": 0, "n_accept": 0, "n_reject": 0}
+    while s < t_end - 1e-5:
+        t = torch.minimum(t_end, s + pid.h)
+        if eta:
+            sd, su = get_ancestral_step(sig(s), sig(t), eta)
+            t_ = torch.minimum(t_end, t_of(sd))
+            su = (sig(t) ** 2 - sig(t_) ** 2) ** 0.5
+        else:
+            t_, su = t, 0.0
+        eps = eps_of(x, s)
+        denoised = x - sig(s) * eps
+        h = t_ - s
+        if order == 2:
+            x_low = x - sig(t_) * h.expm1() * eps
+            x_high, _ = step2(x, s, t_, 1 / 2, eps)
+        else:
+            r1, r2 = 1 / 3, 2 / 3
+            x_low, eps_r1 = step2(x, s, t_, r1, eps)
+            s2 = s + r2 * h
+            u2 = x - sig(s2) * (r2 * h).expm1() * eps - sig(s2) * (r2 / r1) * ((r2 * h).expm1() / (r2 * h) - 1) * (eps_r1 - eps)
+            eps_r2 = eps_of(u2, s2)
+            x_high = x - sig(t_) * h.expm1() * eps - sig(t_) / r2 * (h.expm1() / h - 1) * (eps_r2 - eps)
+        delta = torch.maximum(atol_t, rtol_t * torch.maximum(x_low.abs(), x_prev.abs()))
+        error = torch.linalg.norm((x_low - x_high) / delta) / x.numel() ** 0.5
+        accept = pid.propose_step(error)
+        if accept:
+            x_prev = x_low
+            x = x_high + su * s_noise * noise_sampler(sig(s), sig(t))       # drawn on accepted steps only (:466)
+            s = t
+            info["n_accept"] += 1
+        else:
+            info["n_reject"] += 1
+        info["nfe"] += order
+        info["steps"] += 1
+        if callback is not None:
+            callback({"i": info["steps"] - 1, "sigma": sig(s), "denoised": denoised})
+    if info_out is not None:
+        info_out.update(info)
+    return x
+
+
 def ddim_timesteps(n, num_train=1000, steps_offset=1):
     """scheduling_ddim.py:189-203 with the SD config (ckpt_utils.py:244-255): steps_offset=1."""
     ratio = num_train // n
@@ -520,8 +613,10 @@ def txt2img_latents(eps_unet_cfg, *, batch, in_channels, height, width, sample_s
         return sample_dpmpp_2s_ancestral(den, latents, sigmas, noise, eta=1.0 if eta is None else eta)
     if sampler == "dpmpp_sde":
         return sample_dpmpp_sde(den, latents, sigmas, noise, eta=1.0 if eta is None else eta)
-    if sampler == "dpm_fast":
+    if sampler in ("dpm_fast", "dpm_adaptive"):
         sq = sigmas_full.to(latent_dtype)                   # sigma_min / sigma_max keep the latent dtype (:562-563)
+        if sampler == "dpm_adaptive":
+            return sample_dpm_adaptive(den, latents, sq[sq > 0].min(), sq.max(), noise, eta=0.0 if eta is None else eta)
         return sample_dpm_fast(den, latents, sq[sq > 0].min(), sq.max(), steps, noise, eta=0.0 if eta is None else eta)
     raise ValueError(sampler)
 

@@ -130,6 +130,30 @@ def pin_samplers():
             assert (got - ref).abs().max().item() == 0.0, f"dpm_fast {steps} {dtype_name}: oracle != vendored"
             out[f"dpm_fast/{steps}/{dtype_name}" + (f"/eta{eta}" if eta else "")] = {
                 "seeds": seeds, "shape": shape, "sigmas": sig_full, "result": ref, "eta": eta, "steps": steps}
+    # DPM-Solver adaptive (PID step-size control; the number of evaluations is data dependent)
+    for dtype_name, ldt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        for steps, eta in ((10, 0.0), (25, 0.0), (10, 0.5)):
+            shape, seeds = (2, 4, 8, 8), [420420420, 420420421]
+            ref_den = kext.DiscreteEpsDDPMDenoiser(toy_eps, acp, quantize=True)
+            sig_full = ks.append_zero(ref_den.t_to_sigma(torch.linspace(len(ref_den.sigmas) - 1, 0, steps)))
+            sig = sig_full.to(ldt)
+            s_min, s_max = sig[sig > 0].min(), sig.max()
+            gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+            x0 = (osamp.batched_randn(shape, gens, "cpu", ldt) * sig_full[0]).float()
+            ns = lambda *_: osamp.batched_randn(shape, gens, "cpu", ldt).float()
+            ref, info = ks.sample_dpm_adaptive(ref_den, x0, s_min, s_max, eta=eta, noise_sampler=ns, disable=True,
+                                               return_info=True)
+            gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+            den = osamp.EpsDenoiser(toy_eps, acp)
+            y0 = (osamp.batched_randn(shape, gens, "cpu", ldt) * sig_full[0]).float()
+            info2 = {}
+            got = osamp.sample_dpm_adaptive(den, y0, s_min, s_max,
+                                            lambda *_: osamp.batched_randn(shape, gens, "cpu", ldt).float(), eta=eta,
+                                            info_out=info2)
+            assert info2 == info, f"dpm_adaptive: {info2} != {info}"
+            assert (got - ref).abs().max().item() == 0.0, f"dpm_adaptive {steps} {dtype_name}: oracle != vendored"
+            out[f"dpm_adaptive/{steps}/{dtype_name}" + (f"/eta{eta}" if eta else "")] = {
+                "seeds": seeds, "shape": shape, "sigmas": sig_full, "result": ref, "eta": eta, "steps": steps, "info": info}
     # churn > 0 (Karras stochasticity) for the samplers that take s_churn
     for name in ("euler", "heun", "dpm_2"):
         shape, seeds, steps = (2, 4, 8, 8), [420420420, 420420421], 12

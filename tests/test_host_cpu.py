@@ -66,7 +66,7 @@ def test_kdiffusion_scheduler_host_state():
     sched3.set_timesteps(8, config=cs.SchedulerConfig(karras_rho=7.0))
     assert torch.equal(sched3.sigmas, osamp.get_sigmas_karras(8, den.sigma_min, den.sigma_max, 7.0))
     with pytest.raises(NotImplementedError):
-        cs.build_scheduler("dpm_adaptive", [torch.Generator()], "cpu", torch.float16)
+        cs.build_scheduler("dpm_solver_pp_2", [torch.Generator()], "cpu", torch.float16)
     # the loop needs CUDA tensors: no silent CPU path
     with pytest.raises(Exception):
         sched.loop(torch.zeros(1, 4, 8, 8))
@@ -95,6 +95,10 @@ class _CpuEngine:
 
     def noise(self):
         return batched_randn(self.shape, self.s.generators, "cpu", self.s.dtype).float()
+
+    def err_norm(self, x_low, x_high, x_prev, atol, rtol):
+        delta = torch.maximum(torch.tensor(atol), torch.tensor(rtol) * torch.maximum(x_low.abs(), x_prev.abs()))
+        return float(torch.linalg.norm((x_low - x_high) / delta) / x_low.numel() ** 0.5)
 
 
 def _toy_eps(x, t):
@@ -164,6 +168,30 @@ def test_dpm_fast_host_logic_vs_vendored_golden(key, eta):
     err = (out - gold["result"]).abs().max().item()
     scale = gold["result"].abs().max().item()
     print(f"{key}: host-logic max abs err {err:.3e} (scale {scale:.2f})")
+    assert err <= 5e-5 * max(scale, 1.0), f"{key}: {err}"
+
+
+@pytest.mark.parametrize("key,eta", [("dpm_adaptive/10/fp32", None), ("dpm_adaptive/25/fp32", None),
+                                     ("dpm_adaptive/10/fp16", None), ("dpm_adaptive/25/fp16", None),
+                                     ("dpm_adaptive/10/fp32/eta0.5", 0.5), ("dpm_adaptive/10/fp16/eta0.5", 0.5)])
+def test_dpm_adaptive_host_logic_vs_vendored_golden(key, eta):
+    """`sample_dpm_adaptive` (sampling.py:494-506): the embedded 2/3 pair, the PID controller, accept / reject, the time
+    variable kept in the latent dtype, noise on accepted steps only - same number of trial steps as the vendored run."""
+    import os
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "samplers.pt"))[key]
+    ldt = torch.float16 if "/fp16" in key else torch.float32
+    gens = [torch.Generator("cpu").manual_seed(sd) for sd in gold["seeds"]]
+    sched = cs.build_scheduler("dpm_adaptive", gens, "cpu", ldt)
+    sched.set_eps_unets([_dummy_guided()])
+    sched.set_timesteps(gold["steps"], config=cs.SchedulerConfig(eta=eta))
+    x0 = sched.prepare_initial_latents(batched_randn(gold["shape"], gens, "cpu", ldt)).float()
+    sched._make_engine = lambda latents: _CpuEngine(sched, latents, _toy_eps)
+    sigmas = sched.sigmas.to(ldt).float()
+    out = sched._loop_dpm_adaptive(x0, sigmas, lambda it: it, torch.float32, 0.0 if eta is None else eta)
+    assert sched.last_solver_info["steps"] == gold["info"]["steps"]
+    err = (out - gold["result"]).abs().max().item()
+    scale = gold["result"].abs().max().item()
+    print(f"{key}: host-logic max abs err {err:.3e} (scale {scale:.2f}), {gold['info']}")
     assert err <= 5e-5 * max(scale, 1.0), f"{key}: {err}"
 
 

@@ -298,3 +298,26 @@ def test_layernorm(nat, rows, C, sub):
     ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
     assert_close(out, ref, 2e-3, 2e-3, "layernorm")
     assert torch.equal(one[0], out[rows // 2])
+
+
+@pytest.mark.parametrize("n", [1, 1000, 2 * 4 * 64 * 64, 300001])
+def test_dpm_error_norm(nat, n):
+    """Error estimate of the adaptive DPM-Solver (k_diffusion/sampling.py:461-462) against its definition."""
+    import ctypes as C
+    g = torch.Generator().manual_seed(n)
+    lo = torch.randn(n, generator=g).cuda()
+    hi = (lo.cpu() + 0.01 * torch.randn(n, generator=g)).cuda()
+    prev = torch.randn(n, generator=g).cuda() * 3
+    atol, rtol = 0.0078, 0.05
+    lib = nat.load()
+    parts = torch.empty(lib.gyre_b200_dpm_error_num_partials(), device="cuda", dtype=torch.float64)
+    nat.check(lib.gyre_b200_dpm_error_partials(nat.ptr(lo), nat.ptr(hi), nat.ptr(prev), atol, rtol, n, nat.ptr(parts),
+                                               nat.stream_ptr()), "dpm_error_partials")
+    got = math.sqrt(sum(parts.cpu().tolist())) / n ** 0.5
+    delta = torch.maximum(torch.tensor(atol), rtol * torch.maximum(lo.cpu().abs(), prev.cpu().abs()))
+    ref = float(torch.linalg.norm(((lo.cpu() - hi.cpu()) / delta).double()) / n ** 0.5)
+    assert abs(got - ref) <= 1e-5 * max(ref, 1e-6), (got, ref)
+    parts2 = torch.empty_like(parts)
+    nat.check(lib.gyre_b200_dpm_error_partials(nat.ptr(lo), nat.ptr(hi), nat.ptr(prev), atol, rtol, n, nat.ptr(parts2),
+                                               nat.stream_ptr()), "dpm_error_partials")
+    assert torch.equal(parts, parts2), "the partial sums must be reproducible"

@@ -83,6 +83,8 @@ def test_generic_sampler_kernels_match_vendored_loops():
     cases += [(e, f"{n}_churn/12/fp32", 12) for e, n in (("k_euler", "euler"), ("k_heun", "heun"), ("k_dpm_2", "dpm_2"))]
     # DPM-Solver-Fast: (sigma_min, sigma_max, n) solver, three-stage steps, eta > 0
     cases += [("dpm_fast", "dpm_fast/20/fp32", 20), ("dpm_fast", "dpm_fast/11/fp32/eta0.6", 11)]
+    # adaptive DPM-Solver-23: device error norm -> host PID accept / reject (one rejected trial step in the eta case)
+    cases += [("dpm_adaptive", "dpm_adaptive/10/fp32", 10), ("dpm_adaptive", "dpm_adaptive/10/fp32/eta0.5", 10)]
     for enum_name, key, steps in cases:
         rec = g[key]
         gens = [torch.Generator("cpu").manual_seed(sd) for sd in rec["seeds"]]
@@ -99,7 +101,10 @@ def test_generic_sampler_kernels_match_vendored_loops():
             sched.set_timesteps(steps)
         x0 = sched.prepare_initial_latents(batched_randn(rec["shape"], gens, dev, torch.float32)).float()
         sched._make_engine = lambda latents, sched=sched: Engine(sched, latents)
-        if enum_name == "dpm_fast":
+        if enum_name == "dpm_adaptive":
+            out = sched._loop_dpm_adaptive(x0, sched.sigmas.float(), lambda it: it, torch.float32, rec.get("eta") or 0.0)
+            assert sched.last_solver_info["steps"] == rec["info"]["steps"], (sched.last_solver_info, rec["info"])
+        elif enum_name == "dpm_fast":
             out = sched._loop_dpm_fast(x0, sched.sigmas.float(), lambda it: it, torch.float32, rec.get("eta") or 0.0)
         else:
             out = sched._loop_generic(x0, sched.sigmas.float(), lambda it: it, torch.float32, 1.0)
