@@ -12,10 +12,9 @@ fp16 UNet input.  Latents stay fp32 on the device across steps.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
 from typing import Literal
-
-import math
 
 import torch
 
