@@ -69,6 +69,7 @@ SIGNATURES = {
     "gyre_b200_launch_count": (C.c_ulonglong, []),
     "gyre_b200_prof_enable": (_i, [_i]),
     "gyre_b200_prof_reset": (_i, []),
+    "gyre_b200_debug_attention_trace": (_i, [_vp, _i]),
     "gyre_b200_prof_read": (_i, [_i, C.POINTER(C.c_ulonglong), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]),
     "gyre_b200_debug_mma_bench": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
@@ -195,8 +196,12 @@ _sk_scratch = {}
 
 
 def stream_k_scratch(device):
-    """Per-device stream-K scratch for the standalone building-block calls (a model owns its own)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """Stream-K scratch (partial accumulators + flags) for the standalone building-block calls, one per
+    (device, stream): two streams running GEMMs concurrently must not share partial slots or flags (a model
+    owns its own scratch; a handle is driven by one stream at a time, like the reference's pipeline slots)."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     if key not in _sk_scratch:
         _sk_scratch[key] = (torch.empty((48 << 20,), device=device, dtype=torch.uint8),
                             torch.zeros((256,), device=device, dtype=torch.int32))

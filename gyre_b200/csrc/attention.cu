@@ -31,6 +31,8 @@ struct AttnParams {
   float scale_log2;  // scale * log2(e)
   __half* out;
   int ldo;
+  long long* trace;  // measurement only: clock64 stamps of CTA 0 (gyre_b200_debug_attention_trace)
+  int trace_cap;
 };
 
 template <int DCH>
@@ -1131,6 +1133,478 @@ __global__ void __launch_bounds__(kAtt4Threads, 1) attention4_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------ d < 64: lean softmax
+// attention5: the pipeline of attention2<AV_PTMEM | AV_SPLIT> (two 128-row query tiles per CTA, S of tile j+1
+// issued under tile j's exponentials, P kept in tensor memory, own warp feeding P V) with the per-score
+// instruction count of the softmax cut from ~5.5 to ~2.3 - 3 issue slots.  What bounds these kernels at d = 40 was
+// measured in isolation (scripts/ubench_pipes.cu, ubench_softmax.cu; profiles/r02_ubench_*.txt): a warp-wide
+// MUFU.EX2 occupies the sub-partition's XU for 8 clocks (1024 clocks per 128 x 32 score tile), FFMA2 / F2FP / LOP3
+// take 2 clocks each, and with two softmax warps per sub-partition the compiler's schedule reaches ~85 % of the MUFU
+// rate at best; every instruction that is not the exponential itself makes that worse.
+//   * no max pass.  A tile is exponentiated against the RUNNING reference max m_ref (minus a fixed head-room
+//     of 2^kA5Shift), and the packed fp16 P words are OR-ed together on the side (one LOP3 per four scores).
+//     Any p >= 2 - i.e. a score more than kA5Shift + 1 binades above the reference - shows up as bit 14 of a
+//     half (the MUFU path gives >= 2 / inf / nan there, the polynomial path saturates at exactly 2.0); only then is
+//     the tile redone the slow way (true max, rescale of O, exact recomputation from the scores still held in
+//     registers).  The first tile and ragged tiles always take the slow path.  P lives in [2^-24, 2): 5 binades
+//     of head-room above the reference, 20 below - the same bottom as fp16 P after an exact max within 2^-4.
+//   * no row-sum arithmetic (A5_ONES, needs d < 64).  A patch warp writes 1.0 into column d of every V tile after
+//     the TMA unit has zero-filled it, so the tensor core accumulates sum_k p[k] in column d of O - the sum of
+//     exactly the fp16 values it multiplied, rescaled together with O for free.  P V's N stays <= 64 (the MMA
+//     costs the same ~49 clocks for any N <= 96).
+//   * polynomial share of the exponentials (A5_POLY*): the argument is mapped onto [0, 1] with a saturating FMA
+//     (x' = sat((x + 125) / 126): the clamp at 2^-125 and the ceiling p = 2.0 - the value the overflow test looks
+//     for - cost nothing), then Cody-Waite split + degree-3 minimax + exponent insert, all on the FMA / ALU pipes.
+//   * softmax warps run with 232 registers (setmaxnreg), the four service warps with 40; mbarrier waits suspend in
+//     hardware (try_wait with a time limit) instead of re-polling every ~40 clocks.
+// Measured at B16 h8 N4096 d40 (profiles/r02_ab_attn.txt): 736 us (attention2, variant 198) -> 662 us.  What did NOT
+// help, each tried on the same box: 16 softmax warps splitting the tile by columns (819 us: the two warps of a row
+// pair must agree on the overflow bit every tile), handing P over in 64-key halves so that P V runs under the other
+// half's exponentials (720 us), hand-staging scale / ex2 / pack groups with volatile asm (1043 clocks per row in
+// isolation against 1200 compiler-ordered, but ptxas re-orders it inside the kernel: 675 us), more polynomial
+// (POLY37 / POLY50: the FMA pipe's 2-clock packed ops make a polynomial pair cost 14 clocks against 16 on the MUFU),
+// starting group 1 half a tile late (664 vs 662 us).
+constexpr int kAttDefaultLean = 2002;   // ATT_VARIANT default: attention5<A5_POLY25> (+ A5_ONES) for d < 64
+constexpr int kAtt5Threads = 384;   // warp 0 TMA, 1 S issuer, 2 P V issuer, 3 V patcher, 4..11 two softmax groups
+constexpr float kA5Shift = 4.0f;
+enum : int { A5_ONES = 1, A5_POLY25 = 2, A5_POLY50 = 4, A5_NOEXP = 8, A5_POLY12 = 16, A5_POLY37 = 64, A5_NOSTAGGER = 128, A5_TRACE = 256 };
+
+struct Att5Cfg {
+  static constexpr int STAGES = 4;
+  static constexpr int Q_BYTES = 2 * kChunkBytes;
+  static constexpr int KV_BYTES = kChunkBytes;
+  static constexpr int SMEM = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;   // S0, S1 at 0 / 128; O0, O1 at 256 / 320; P0, P1 at 384 / 448
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void set_max_regs_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void set_max_regs_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// slow path of one 32-column chunk: exact, masked (columns >= nvalid give p = 0)
+template <int V>
+__device__ __forceinline__ void a5_exp32_masked(const uint32_t (&v)[32], int col0, int nvalid, float c, float mcs,
+                                                uint32_t (&w)[16], float& lsum) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float p0 = (col0 + i < nvalid) ? ex2_approx(fmaf(__uint_as_float(v[i]), c, -mcs)) : 0.f;
+    float p1 = (col0 + i + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mcs)) : 0.f;
+    if constexpr ((V & A5_NOEXP) != 0) {
+      p0 = (col0 + i < nvalid) ? 0.03f : 0.f;
+      p1 = (col0 + i + 1 < nvalid) ? 0.03f : 0.f;
+    }
+    const __half2 hh = __floats2half2_rn(p0, p1);
+    w[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+    if constexpr ((V & A5_ONES) == 0) lsum += p0 + p1;
+  }
+}
+
+__device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], int col0, int nvalid) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (col0 + i < nvalid) m = fmaxf(m, __uint_as_float(v[i]));
+  return m;
+}
+
+template <int V>
+__device__ __forceinline__ constexpr bool a5_is_poly(int pair) {
+  return ((V & A5_POLY50) != 0 && (pair & 1) == 1) || ((V & A5_POLY25) != 0 && (pair & 3) == 3) ||
+         ((V & A5_POLY12) != 0 && (pair & 7) == 7) || ((V & A5_POLY37) != 0 && ((pair & 7) == 1 || (pair & 7) == 4 || (pair & 7) == 6));
+}
+
+// 2^y for y = 126 x' - 125, x' in [0, 1] (already saturated): n = round(y) through the 1.5 * 2^23 magic add,
+// f = y - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial, exponent inserted with an integer add.
+__device__ __forceinline__ float2 exp2_poly_sat(float2 xs) {
+  const float kM = 12582912.0f - 125.0f;
+  const float2 r = __ffma2_rn(xs, make_float2(126.0f, 126.0f), make_float2(kM, kM));          // magic + n
+  const float2 m = __fadd2_rn(r, make_float2(-kM, -kM));                                         // n + 125
+  const float2 f = __ffma2_rn(xs, make_float2(126.0f, 126.0f), make_float2(-m.x, -m.y));        // y - n  (exact: FMA)
+  float2 q = __ffma2_rn(make_float2(0.05517084f, 0.05517084f), f, make_float2(0.24260935f, 0.24260935f));
+  q = __ffma2_rn(q, f, make_float2(0.69326096f, 0.69326096f));
+  q = __ffma2_rn(q, f, make_float2(0.99992818f, 0.99992818f));
+  float2 o;
+  o.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
+  o.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
+  return o;
+}
+
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// 32 scores of one row -> 16 packed fp16x2 words of p = 2^(s*c - mcs); (cs, os) = (c, 125 - mcs) / 126 feed the
+// saturating map of the polynomial share.  ovf collects the OR of the packed words.
+template <int V>
+__device__ __forceinline__ void a5_exp32(const uint32_t (&v)[32], float c, float mcs, float cs, float os,
+                                         uint32_t (&w)[16], uint32_t& ovf, float2& lsum) {
+#pragma unroll
+  for (int pair = 0; pair < 16; ++pair) {
+    const int i = 2 * pair;
+    float2 e;
+    if constexpr ((V & A5_NOEXP) != 0) {
+      e.x = fmaf(__uint_as_float(v[i]), 1e-4f, 0.03f);
+      e.y = fmaf(__uint_as_float(v[i + 1]), 1e-4f, 0.03f);
+    } else if (a5_is_poly<V>(pair)) {
+      float2 xs;
+      xs.x = fma_sat(__uint_as_float(v[i]), cs, os);
+      xs.y = fma_sat(__uint_as_float(v[i + 1]), cs, os);
+      e = exp2_poly_sat(xs);
+    } else {
+      const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(c, c),
+                                  make_float2(-mcs, -mcs));
+      e.x = ex2_approx(x.x);
+      e.y = ex2_approx(x.y);
+    }
+    const __half2 hh = __floats2half2_rn(e.x, e.y);
+    w[pair] = *reinterpret_cast<const uint32_t*>(&hh);
+    if constexpr ((V & A5_ONES) == 0) lsum = __fadd2_rn(lsum, e);
+  }
+  uint32_t a0 = ovf, a1 = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 4) {
+    a0 |= w[k] | w[k + 1];
+    a1 |= w[k + 2] | w[k + 3];
+  }
+  ovf = a0 | a1;
+}
+
+template <int V>
+__global__ void __launch_bounds__(kAtt5Threads, 1) attention5_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                     const __grid_constant__ CUtensorMap tmK,
+                                                                     const __grid_constant__ CUtensorMap tmV,
+                                                                     const AttnParams p) {
+  using Cfg = Att5Cfg;
+  constexpr bool kOnes = (V & A5_ONES) != 0;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::STAGES * Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::STAGES * Cfg::KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + Cfg::STAGES;
+  uint64_t* v_ready = kv_empty + Cfg::STAGES;   // the ones column of V stage s is in place
+  uint64_t* s_full = v_ready + Cfg::STAGES;     // [2]
+  uint64_t* s_free = s_full + 2;                // [2] the group holds tile j's scores in registers
+  uint64_t* p_full = s_free + 2;                // [2]
+  uint64_t* pv_done = p_full + 2;               // [2]
+  uint64_t* stagger_bar = pv_done + 2;          // group 0 is half way through its first tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x % p.q_tiles;
+  const int bh = blockIdx.x / p.q_tiles;
+  const int h = bh % p.heads;
+  const int b = bh / p.heads;
+  const int q0 = q_pair * 2 * kBQ;
+  const bool two = q0 + kBQ < p.Nq;
+  const int ng = two ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&v_ready[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 128);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&pv_done[g], 1);
+    }
+    mbar_init(stagger_bar, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+  // trace slots (8 per tile per actor): actor 0 / 1 = softmax group (thread of row 0), 2 = S issuer, 3 = P V issuer
+  // (compiled in only with A5_TRACE: the stamps cost ~100 clocks each and perturb the schedule of the softmax loop)
+  const bool tr_on = (V & A5_TRACE) != 0 && p.trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int actor, int j, int k) {
+    if constexpr ((V & A5_TRACE) != 0) {
+      const int idx = (actor * p.n_kv_tiles + j) * 8 + k;
+      if (tr_on && idx < p.trace_cap) p.trace[idx] = clock64();
+    }
+  };
+
+  if (warp < 4) {
+    set_max_regs_dec<40>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, two ? Cfg::Q_BYTES : Cfg::Q_BYTES / 2);
+        tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+        if (two) tma_load_4d(sQ + kChunkBytes, &tmQ, q_full, 0, q0 + kBQ, h, b);
+        for (int j = 0; j < p.n_kv_tiles; ++j) {
+          const int s = j % Cfg::STAGES;
+          mbar_wait(&kv_empty[s], ((j / Cfg::STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+          tma_load_4d(sK + s * Cfg::KV_BYTES, &tmK, &kv_full[s], 0, j * kBKeys, h, b);
+          tma_load_4d(sV + s * Cfg::KV_BYTES, &tmV, &kv_full[s], 0, j * kBKeys, h, b);
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- S issuer
+      if (elect_one()) {
+        mbar_wait(q_full, 0);
+        for (int j = 0; j < p.n_kv_tiles; ++j) {
+          const int s = j % Cfg::STAGES;
+          const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+          const uint32_t idesc = umma_idesc_f16(kBQ, (nk_tile + 15) & ~15);
+          mbar_wait(&kv_full[s], (j / Cfg::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t ka = smem_u32(sK + s * Cfg::KV_BYTES);
+          for (int g = 0; g < ng; ++g) {
+            if (j > 0) {
+              mbar_wait(&s_free[g], (j - 1) & 1);
+              tc_fence_after();
+            }
+            const uint32_t qa = smem_u32(sQ + g * kChunkBytes);
+            stamp(2, j, g * 2);
+            for (int ks = 0; ks < p.ksteps_qk; ++ks)
+              umma_f16_ss(tmem_base + g * 128, umma_desc_kmajor_sw128(qa + ks * 32), umma_desc_kmajor_sw128(ka + ks * 32),
+                          idesc, ks != 0 ? 1u : 0u);
+            umma_commit(&s_full[g]);
+            stamp(2, j, g * 2 + 1);
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ---------------------------------------------------------------- P V issuer
+      if (elect_one()) {
+        const uint32_t idesc_pv = umma_idesc_f16(kBQ, p.npv, /*b_mn_major=*/1);
+        for (int j = 0; j < p.n_kv_tiles; ++j) {
+          const int s = j % Cfg::STAGES;
+          const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+          const int ksteps = ((nk_tile + 15) & ~15) >> 4;
+          const uint32_t va = smem_u32(sV + s * Cfg::KV_BYTES);
+          mbar_wait(kOnes ? &v_ready[s] : &kv_full[s], (j / Cfg::STAGES) & 1);
+          for (int g = 0; g < ng; ++g) {
+            mbar_wait(&p_full[g], j & 1);
+            tc_fence_after();
+            stamp(3, j, g * 2);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t db = umma_desc_mnmajor_sw128(va + ks * 2048, kChunkBytes, 1024);
+              umma_f16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + ks * 8, db, idesc_pv,
+                          (j | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&pv_done[g]);
+            stamp(3, j, g * 2 + 1);
+          }
+          umma_commit(&kv_empty[s]);
+        }
+      }
+    } else if (kOnes) {
+      // ---------------------------------------------------------------- V patcher: column d of every key row := 1.0
+      const int unit = p.d >> 3, sub = (p.d & 7) * 2;
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int s = j % Cfg::STAGES;
+        mbar_wait(&kv_full[s], (j / Cfg::STAGES) & 1);
+        uint8_t* vt = sV + s * Cfg::KV_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = lane + 32 * i;
+          *reinterpret_cast<uint16_t*>(vt + row * 128 + ((unit ^ (row & 7)) << 4) + sub) = 0x3C00;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_ready[s]);
+      }
+    }
+  } else {
+    set_max_regs_inc<232>();
+    // ------------------------------------------------------------------ softmax groups
+    const int g = (warp - 4) >> 2;
+    if (g < ng) {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t tS = tmem_base + g * 128 + lane_off;
+      const uint32_t tO = tmem_base + 256 + g * 64 + lane_off;
+      const uint32_t tP = tmem_base + 384 + g * 64 + lane_off;
+      const float c = p.scale_log2;
+      float m_ref = -INFINITY;
+      float mcs = 0.f;             // m_ref * c + kA5Shift
+      float l = 0.f;               // row sum (only without the ones column)
+      // Group 1 starts half a tile behind group 0 and stays there (the P V issuer serves g0, g1, g0, ... in turn):
+      // the two warps of a sub-partition then reach their MUFU-free phases (barrier waits, TMEM loads, the vote and
+      // the P hand-over: about a third of a tile) at different times instead of idling the MUFU together.
+      const bool stagger = (V & A5_NOSTAGGER) == 0 && two && p.n_kv_tiles >= 4;
+      if (stagger && g == 1) mbar_wait(stagger_bar, 0);
+
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        const int nk_tile = min(kBKeys, p.Nk - j * kBKeys);
+        const int n_s = (nk_tile + 15) & ~15;
+        const bool tr = (V & A5_TRACE) != 0 && r == 0;
+        if (tr) stamp(g, j, 0);
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        if (tr) stamp(g, j, 1);
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld_32x32b_x32(tS, v0);
+        tmem_ld_32x32b_x32(tS + 32, v1);
+        if (n_s > 64) {
+          tmem_ld_32x32b_x32(tS + 64, v2);
+          tmem_ld_32x32b_x32(tS + 96, v3);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);             // the S buffer may be overwritten by tile j+1
+        if (tr) stamp(g, j, 2);
+        bool slow = (j == 0) || nk_tile < kBKeys;
+        if (!slow) {
+          // ---- optimistic tile against the running reference
+          uint32_t ovf = 0;
+          float2 ls = make_float2(0.f, 0.f);
+          const float cs = c * (1.0f / 126.0f), os = (125.0f - mcs) * (1.0f / 126.0f);
+          {
+            // chunk-wise: three 32-score chunks are exponentiated before the wait on the previous tile's P V (P is
+            // single-buffered), so that MMA (~400 clocks plus its queueing behind the other group's) stays hidden
+            uint32_t w0[16], w1[16], w2[16];
+            a5_exp32<V>(v0, c, mcs, cs, os, w0, ovf, ls);
+            a5_exp32<V>(v1, c, mcs, cs, os, w1, ovf, ls);
+            a5_exp32<V>(v2, c, mcs, cs, os, w2, ovf, ls);
+            if (tr) stamp(g, j, 3);
+            mbar_wait(&pv_done[g], (j - 1) & 1);
+            tc_fence_after();
+            if (tr) stamp(g, j, 4);
+            tmem_st_32x32b_x16(tP, w0);
+            tmem_st_32x32b_x16(tP + 16, w1);
+            tmem_st_32x32b_x16(tP + 32, w2);
+            a5_exp32<V>(v3, c, mcs, cs, os, w0, ovf, ls);
+            tmem_st_32x32b_x16(tP + 48, w0);
+          }
+          // bit 14: p >= 2 (the polynomial saturates there; the MUFU path gives >= 2, inf or nan)
+          const bool bad = (ovf & 0x40004000u) != 0u;
+          if (tr) stamp(g, j, 5);
+          slow = __any_sync(0xffffffffu, bad);
+          if (!slow) l += ls.x + ls.y;
+          else tmem_st_wait();
+        }
+        if (slow) {
+          float mt = fmaxf(max32_masked(v0, 0, nk_tile), max32_masked(v1, 32, nk_tile));
+          if (n_s > 64) mt = fmaxf(mt, fmaxf(max32_masked(v2, 64, nk_tile), max32_masked(v3, 96, nk_tile)));
+          if (j == 0) {
+            m_ref = mt;
+          } else {
+            if (nk_tile < kBKeys) {            // (the optimistic path has already waited)
+              mbar_wait(&pv_done[g], (j - 1) & 1);
+              tc_fence_after();
+            }
+            const float m_new = fmaxf(m_ref, mt);
+            const float alpha = ex2_approx((m_ref - m_new) * c);
+            m_ref = m_new;
+            l *= alpha;
+            if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+              for (int c0 = 0; c0 < p.npv; c0 += 16) {
+                uint32_t o[16];
+                tmem_ld_32x32b_x16(tO + c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32b_x16(tO + c0, o);
+              }
+            }
+          }
+          mcs = fmaf(m_ref, c, kA5Shift);
+          uint32_t w[16];
+          a5_exp32_masked<V>(v0, 0, nk_tile, c, mcs, w, l);
+          tmem_st_32x32b_x16(tP, w);
+          if (n_s > 32) {
+            a5_exp32_masked<V>(v1, 32, nk_tile, c, mcs, w, l);
+            tmem_st_32x32b_x16(tP + 16, w);
+          }
+          if (stagger && g == 0 && j == 0) mbar_arrive(stagger_bar);
+          if (n_s > 64) {
+            a5_exp32_masked<V>(v2, 64, nk_tile, c, mcs, w, l);
+            tmem_st_32x32b_x16(tP + 32, w);
+          }
+          if (n_s > 96) {
+            a5_exp32_masked<V>(v3, 96, nk_tile, c, mcs, w, l);
+            tmem_st_32x32b_x16(tP + 48, w);
+          }
+        }
+        if (tr) stamp(g, j, 6);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[g]);
+        if (tr) stamp(g, j, 7);
+      }
+      // ---- epilogue
+      mbar_wait(&pv_done[g], (p.n_kv_tiles - 1) & 1);
+      tc_fence_after();
+      if constexpr (kOnes) {
+        uint32_t lbits;
+        tmem_ld_32x32b_x1(tO + p.d, lbits);
+        tmem_ld_wait();
+        l = __uint_as_float(lbits);
+      }
+      const float inv = 1.0f / l;
+      const int row = q0 + g * kBQ + r;
+      const bool valid = row < p.Nq;
+      __half* dst = p.out + (static_cast<int64_t>(b) * p.Nq + row) * p.ldo + h * p.d;
+      for (int c0 = 0; c0 < p.d; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(tO + c0, o);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int gg = 0; gg < 2; ++gg) {
+            const int col = c0 + gg * 8;
+            if (col < p.d) {
+              __align__(16) __half2 hh[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                hh[i] = __floats2half2_rn(__uint_as_float(o[gg * 8 + 2 * i]) * inv,
+                                          __uint_as_float(o[gg * 8 + 2 * i + 1]) * inv);
+              *reinterpret_cast<uint4*>(dst + col) = *reinterpret_cast<uint4*>(hh);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int V>
+static int launch_attn5_v(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, AttnParams p,
+                          unsigned blocks, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    GYRE_CHECK_CUDA(
+        cudaFuncSetAttribute(attention5_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att5Cfg::SMEM));
+    attr_done = true;
+  }
+  if ((V & A5_ONES) != 0) p.npv = (p.d + 1 + 15) & ~15;   // O carries the row sum in column d
+  return launch_kernel(attention5_kernel<V>, dim3(blocks), dim3(kAtt5Threads), Att5Cfg::SMEM, st, tq, tk, tv, p);
+}
+
 template <int V>
 static int launch_attn4_v(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                           unsigned blocks, cudaStream_t st) {
@@ -1398,7 +1872,11 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   if (p.d > 64) return launch_attn2_v<AV_PTMEM | AV_PACKED | AV_POLY25, 2>(tq, tk, tv, p, nb, st);
   // Compiled-in variants = the ones the A/B record in profiles/r01_ab_attn.txt covers (each flag alone on top of its
   // predecessor, the default, the negative results and the no-exp timing floor).
-  switch (tunable(TUNE_ATT_VARIANT)) {
+  int variant = tunable(TUNE_ATT_VARIANT);
+  // the lean-softmax kernel pays off where V has a spare column for the row sum (d < 64); at d = 64 it measures
+  // within 2 % of attention2 (317 vs 311 us at B16 h10 N2304), so the default keeps the older kernel there
+  if (variant == kAttDefaultLean && p.d >= 64) variant = AV_PTMEM | AV_SPLIT | AV_PACKED | AV_POLY25;
+  switch (variant) {
     case 0: return launch_attn2_v<0>(tq, tk, tv, p, nb, st);
     case AV_STAGGER: return launch_attn2_v<AV_STAGGER>(tq, tk, tv, p, nb, st);
     case AV_STAGGER | AV_PACKED: return launch_attn2_v<AV_STAGGER | AV_PACKED>(tq, tk, tv, p, nb, st);
@@ -1419,7 +1897,29 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
     case 1000 + (AV_PACKED | AV_POLY25): return launch_attn4_v<AV_PACKED | AV_POLY25>(tq, tk, tv, p, nb, st);
     case 1000 + (AV_PACKED | AV_NOEXP): return launch_attn4_v<AV_PACKED | AV_NOEXP>(tq, tk, tv, p, nb, st);
   }
-  set_last_error("attention: variant %d is not compiled in", tunable(TUNE_ATT_VARIANT));
+  // 2000+: the lean-softmax kernel (attention5); low bits = A5_* flags.  The ones column needs a spare column in
+  // the 64-wide V chunk, so d = 64 runs the same kernel with the packed row sum instead.
+  const int v5 = variant - 2000;
+  if (v5 >= 0 && v5 < 512) {
+    const bool ones = p.d < 64;
+#define GYRE_A5_CASE(F)                                                                              \
+  case F:                                                                                            \
+    return ones ? launch_attn5_v<(F) | A5_ONES>(tq, tk, tv, p, nb, st) : launch_attn5_v<(F)>(tq, tk, tv, p, nb, st);
+    switch (v5 & ~A5_ONES) {
+      GYRE_A5_CASE(0)
+      GYRE_A5_CASE(A5_POLY12)
+      GYRE_A5_CASE(A5_POLY25)
+      GYRE_A5_CASE(A5_POLY37)
+      GYRE_A5_CASE(A5_POLY50)
+      GYRE_A5_CASE(A5_NOEXP)
+      GYRE_A5_CASE(A5_NOSTAGGER)
+      GYRE_A5_CASE(A5_NOSTAGGER | A5_POLY25)
+      GYRE_A5_CASE(A5_TRACE | A5_POLY25)
+      GYRE_A5_CASE(A5_TRACE | A5_NOSTAGGER | A5_POLY25)
+    }
+#undef GYRE_A5_CASE
+  }
+  set_last_error("attention: variant %d is not compiled in", variant);
   return -2;
 }
 
@@ -1447,6 +1947,13 @@ static int make_head_map(CUtensorMap* m, const __half* base, int ld, int N, int 
   return encode_tmap_f16(m, base, 4, dims, strides, box, es, true);
 }
 
+static long long* g_attn_trace = nullptr;
+static int g_attn_trace_cap = 0;
+void attention_set_trace(long long* dev_buf, int capacity) {
+  g_attn_trace = dev_buf;
+  g_attn_trace_cap = capacity;
+}
+
 int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, int B, int heads,
                   int Nq, int Nk, int d, float scale, __half* out, int ldo, cudaStream_t st) {
   GYRE_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: empty problem");
@@ -1469,6 +1976,8 @@ int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __ha
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out;
   p.ldo = ldo;
+  p.trace = g_attn_trace;
+  p.trace_cap = g_attn_trace_cap;
   CUtensorMap tq, tk, tv;
   GYRE_TRY(make_head_map(&tq, q, ldq, Nq, heads, d, B, kBQ));
   GYRE_TRY(make_head_map(&tk, k, ldk, Nk, heads, d, B, kBKeys));

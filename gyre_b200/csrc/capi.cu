@@ -68,6 +68,11 @@ int gyre_b200_debug_mma_bench(int n, int naccs, int a_tmem, int reps, int blocks
   return mma_bench(n, naccs, a_tmem, reps, blocks, out_dev, S(stream));
 }
 
+int gyre_b200_debug_attention_trace(long long* dev_buf, int capacity) {
+  attention_set_trace(dev_buf, capacity);
+  return 0;
+}
+
 int gyre_b200_set_tunable(const char* name, int value) { return set_tunable_by_name(name, value); }
 int gyre_b200_get_tunable(const char* name, int* value) { return get_tunable_by_name(name, value); }
 

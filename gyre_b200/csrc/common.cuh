@@ -88,24 +88,30 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or a time limit passes; the explicit limit
+// (20 us) keeps a waiting warp from re-issuing the poll every ~40 clocks - measured on the attention kernels, the
+// polling loops of the service warps were a quarter of all issued instructions.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU box.
+// Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU box.  No printf on the way out
+// unless GYRE_DEBUG_BARRIERS is defined: the call forces every value that is live across a wait through the stack.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 22)) {
+#ifdef GYRE_DEBUG_BARRIERS
       printf("gyre_b200: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x);
+#endif
       __trap();
     }
   }
@@ -405,36 +411,59 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int b_mn_maj
 int tunable(int id);
 #ifdef __CUDACC__
 // Launch with the programmatic-stream-serialization attribute (tunable PDL, id 1): the kernel MUST call pdl_wait().
+// cooperative = true: the grid is launched all-or-nothing co-resident (kernels whose CTAs wait on each other through
+// global flags - stream-K - must not be launched any other way: a CTA that is not yet resident never raises its flag).
+// 0 = PDL + cooperative not probed yet, 1 = accepted together, 2 = the driver refuses the pair (cooperative alone)
+int& coop_pdl_state();
 template <typename... KArgs, typename... Args>
 inline int launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                 int cluster_x, Args&&... args) {
+                                 int cluster_x, bool cooperative, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  if (tunable(1) != 0) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    cudaLaunchAttribute attr[3];
+    int na = 0;
+    const bool pdl = tunable(1) != 0 && !(cooperative && (coop_pdl_state() == 2 || attempt == 1));
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (cluster_x > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (cooperative) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e == cudaSuccess) {
+      if (cooperative && pdl) coop_pdl_state() = 1;
+      return 0;
+    }
+    if (cooperative && pdl && coop_pdl_state() == 0 && (e == cudaErrorInvalidValue || e == cudaErrorNotSupported)) {
+      (void)cudaGetLastError();   // not sticky: retry once without the PDL attribute and remember the answer
+      coop_pdl_state() = 2;
+      continue;
+    }
+    gyre::set_last_error("%s:%d cudaLaunchKernelEx -> %s", __FILE__, __LINE__, cudaGetErrorString(e));
+    return -1;
   }
-  if (cluster_x > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = static_cast<unsigned>(cluster_x);
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = na;
-  GYRE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
-  return 0;
+  return -1;
 }
 template <typename... KArgs, typename... Args>
 inline int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  return launch_kernel_cluster(kernel, grid, block, smem, st, 1, static_cast<Args&&>(args)...);
+  return launch_kernel_cluster(kernel, grid, block, smem, st, 1, false, static_cast<Args&&>(args)...);
 }
 #endif
 

@@ -908,6 +908,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   int smem = 0, max_stages = 0;
   cfg_for<BN, false>(epi, &smem, &max_stages);
   p.stages = (cap >= 2 && cap < max_stages) ? cap : max_stages;
+  // stream-K owners spin on flags that other CTAs of the same grid raise: the grid must be co-resident as a whole, which
+  // only a cooperative launch guarantees when the device is shared with other streams / processes
+  const bool coop = p.sk_tiles > 0;
   if (p.mcast) {
     GYRE_REQUIRE(max_clusters > 0, "gemm: pair mode requested but clusters are unavailable");
     const long long pairs = static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles;
@@ -921,17 +924,17 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
         p.stages = (cap >= 2 && cap < max_stages) ? cap : max_stages;
         if (p.conv)
           return launch_kernel_cluster(kernel_for<BN, true, true>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
-                                       tmA, tmA2, tmB, tmOut, tmRes, p);
+                                       coop, tmA, tmA2, tmB, tmOut, tmRes, p);
         return launch_kernel_cluster(kernel_for<BN, false, true>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
-                                     tmA, tmA2, tmB, tmOut, tmRes, p);
+                                     coop, tmA, tmA2, tmB, tmOut, tmRes, p);
       }
     }
     GYRE_REQUIRE(p.mcast == 1, "gemm: pair mode %d is not available at BN %d", p.mcast, BN);
     if (p.conv)
       return launch_kernel_cluster(kernel_for<BN, true, false>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
-                                   tmA, tmA2, tmB, tmOut, tmRes, p);
+                                   coop, tmA, tmA2, tmB, tmOut, tmRes, p);
     return launch_kernel_cluster(kernel_for<BN, false, false>(epi), dim3(2 * clusters), dim3(kThreads), smem, st, 2,
-                                 tmA, tmA2, tmB, tmOut, tmRes, p);
+                                 coop, tmA, tmA2, tmB, tmOut, tmRes, p);
   }
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   GYRE_REQUIRE(tiles > 0 && tiles < (1ll << 31), "gemm: bad tile count %lld", tiles);
@@ -940,10 +943,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   // the implicit-GEMM convolution is its own instantiation (no run-time branches in the producer / epilogue, and a
   // distinct kernel name in profiles)
   if (p.conv)
-    return launch_kernel(kernel_for<BN, true, false>(epi), dim3(blocks), dim3(kThreads), smem, st, tmA, tmA2, tmB,
-                         tmOut, tmRes, p);
-  return launch_kernel(kernel_for<BN, false, false>(epi), dim3(blocks), dim3(kThreads), smem, st, tmA, tmA2, tmB,
-                       tmOut, tmRes, p);
+    return launch_kernel_cluster(kernel_for<BN, true, false>(epi), dim3(blocks), dim3(kThreads), smem, st, 1, coop, tmA,
+                                 tmA2, tmB, tmOut, tmRes, p);
+  return launch_kernel_cluster(kernel_for<BN, false, false>(epi), dim3(blocks), dim3(kThreads), smem, st, 1, coop, tmA,
+                               tmA2, tmB, tmOut, tmRes, p);
 }
 
 // Tile width: maximise (SM wave efficiency) x (1 - N padding) x (per-tile efficiency of the shape).

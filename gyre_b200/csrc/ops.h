@@ -72,6 +72,7 @@ int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gam
 
 // Flash attention reading Q/K/V in place from token-major projections: q [B, Nq, ldq] (head h at columns
 // h*d), k/v [B, Nk, ldk/ldv]; writes out [B, Nq, ldo] (head h at columns h*d).  d % 8 == 0, d <= 192.
+void attention_set_trace(long long* dev_buf, int capacity);
 int attention_f16(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, int B, int heads,
                   int Nq, int Nk, int d, float scale, __half* out, int ldo, cudaStream_t st);
 

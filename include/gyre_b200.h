@@ -50,6 +50,10 @@ unsigned long long gyre_b200_launch_count(void);
 int gyre_b200_prof_enable(int on);
 int gyre_b200_prof_reset(void);
 int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, double* flops, double* bytes);
+/* Measurement hook: while a device buffer is registered, CTA 0 of the lean-softmax attention kernel writes clock64
+ * time stamps of its pipeline events into it (layout: scripts/attn_trace.py); NULL switches it off.  Not part of
+ * the product path. */
+int gyre_b200_debug_attention_trace(long long* dev_buf, int capacity);
 
 /* Kernel-selection knobs for A/B measurement (no reference counterpart).  Names: "ATT_VARIANT" (softmax
  * variant bit flags of the d<=64 flash kernel), "PDL" (programmatic dependent launch), "GELU_FAST",

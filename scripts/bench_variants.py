@@ -70,7 +70,7 @@ if "attn" in what:
         C = heads * d
         qkv = [torch.randn(B2, Nq, 3 * C, device=dev).half() for _ in range(ROT)]
         fl = 4.0 * B2 * heads * Nq * Nq * d
-        for v in (0, 1, 3, 7, 64, 70, 192, 198, 202, 224, 454, 710, 1006, 1034):
+        for v in (198, 224, 2000, 2016, 2002, 2064, 2004, 2008, 2130):
             us = with_tunable("ATT_VARIANT", v, lambda: graph_time(
                 lambda i: N.attention(qkv[i % ROT][:, :, :C], qkv[i % ROT][:, :, C:2 * C], qkv[i % ROT][:, :, 2 * C:], heads)))
             rec("attn", f"self B{B2} h{heads} N{Nq} d{d} variant {v}", us, fl)

@@ -140,3 +140,62 @@ def test_attention_short_key_kernel_matches_flash(nat):
     finally:
         nat.set_tunable("XATTN", old)
     assert (a.float() - b.float()).abs().max().item() < 2e-3
+
+
+# ---- lean-softmax kernel (attention5, ATT_VARIANT 2000 + flags): optimistic exponentials against the running
+# reference max with overflow detection on the packed fp16 P words, row sum from a ones column of V
+A5_CASES = [(2, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (1, 8, 1024, 768, 40), (2, 5, 300, 300, 64),
+            (2, 4, 256, 256, 16), (1, 2, 100, 13, 32), (1, 3, 700, 333, 40), (1, 10, 2304, 2304, 64),
+            (1, 4, 512, 640, 56), (1, 8, 256, 77, 40)]
+
+
+@pytest.mark.parametrize("variant", [2000, 2002, 2004, 2016, 2064, 2130])
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", A5_CASES)
+def test_attention5(nat, B, heads, Nq, Nk, d, variant):
+    C = heads * d
+    q, k, v = rnd(B, Nq, C, seed=1), rnd(B, Nk, C, seed=2), rnd(B, Nk, C, seed=3)
+    old = nat.get_tunable("ATT_VARIANT")
+    nat.set_tunable("ATT_VARIANT", variant)
+    try:
+        out = nat.attention(q, k, v, heads)
+    finally:
+        nat.set_tunable("ATT_VARIANT", old)
+    err = (out.float() - ref_attention(q, k, v, heads)).abs().max().item()
+    assert err < 4e-3, f"attention5 v{variant} B{B} h{heads} Nq{Nq} Nk{Nk} d{d}: max abs err {err}"
+
+
+@pytest.mark.parametrize("variant", [2000, 2002, 2004, 2016, 2064, 2130])
+@pytest.mark.parametrize("kind", ["ramp", "spike", "huge", "late_spike_poly_slot"])
+def test_attention5_running_max_growth(nat, variant, kind):
+    """Keys whose scores keep growing along the sequence (every tile raises the row max by more than the
+    optimistic head-room), single outlier keys, and jumps large enough to overflow fp16 / the polynomial's
+    exponent insert: the redo path must give the exact softmax."""
+    B, heads, N, d = 1, 2, 1024, 40
+    C = heads * d
+    g = torch.Generator("cpu").manual_seed(7)
+    q = torch.randn(B, N, C, generator=g)
+    k = torch.randn(B, N, C, generator=g)
+    v = torch.randn(B, N, C, generator=g)
+    if kind == "ramp":
+        k = k * torch.linspace(0.2, 6.0, N).view(1, N, 1)
+    elif kind == "spike":
+        k[:, 700] = q[:, 5] * 3.0
+        k[:, 130] = q[:, 300] * 2.0
+    elif kind == "huge":
+        q = q * 6.0
+        k = k * 6.0
+        k[:, 900] *= 8.0
+    else:
+        # outlier keys sitting on columns the polynomial path handles (pairs 3, 7, 11, 15 of each 32-column chunk)
+        for col in (256 + 6, 256 + 7, 512 + 14, 640 + 30, 896 + 31):
+            k[:, col] = q[:, 11] * 40.0
+    q, k, v = q.half().cuda(), k.half().cuda(), v.half().cuda()
+    old = nat.get_tunable("ATT_VARIANT")
+    nat.set_tunable("ATT_VARIANT", variant)
+    try:
+        out = nat.attention(q, k, v, heads)
+    finally:
+        nat.set_tunable("ATT_VARIANT", old)
+    assert torch.isfinite(out).all()
+    err = (out.float() - ref_attention(q, k, v, heads)).abs().max().item()
+    assert err < 6e-3, f"attention5 v{variant} {kind}: max abs err {err}"
