@@ -55,16 +55,83 @@ class UNetConfig:
 
     @classmethod
     def from_any(cls, cfg):
-        """Accepts this class, a dict, or any object with the same attribute names (e.g. the oracle's or a
-        diffusers config)."""
+        """Accepts this class, a dict / object with this class's field names (the oracle's config), or a diffusers
+        `UNet2DConditionModel.config` (a dict-like with the diffusers names).  The diffusers names that differ from
+        ours are mapped explicitly (reference construction sites: gyre/pipeline/ckpt_utils.py:280-304,
+        gyre/pipeline/controlnet/models.py:100-131):
+
+        * `attention_head_dim` (int or per-level list) is the NUMBER of heads in diffusers 0.16 -> `num_heads`
+          (`num_attention_heads`, when a newer config carries it, wins);
+        * `down_block_types` -> `attn_levels` ("CrossAttnDownBlock2D" levels have transformers);
+        * `only_cross_attention`, `dual_cross_attention`, `class_embed_type`, `num_class_embeds`, a non-default
+          `act_fn` / `time_embedding_type` / `resnet_time_scale_shift` are not built: they raise.
+        A config from which the head count or the attention levels cannot be resolved raises instead of silently
+        running every attention layer with the wrong head split."""
         if isinstance(cfg, cls):
             return cfg
-        get = (lambda k, d=None: cfg.get(k, d)) if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+        if isinstance(cfg, dict):
+            has = lambda k: k in cfg and cfg[k] is not None          # noqa: E731
+            get = lambda k, d=None: cfg[k] if has(k) else d          # noqa: E731
+        else:
+            has = lambda k: getattr(cfg, k, None) is not None        # noqa: E731
+            get = lambda k, d=None: getattr(cfg, k, d) if has(k) else d   # noqa: E731
         out = cls()
         for f in cls.__dataclass_fields__:
             v = get(f)
             if v is not None:
                 setattr(out, f, tuple(v) if isinstance(v, (list, tuple)) else v)
+        n_levels = len(out.block_out_channels)
+
+        def per_level(v, name):
+            if isinstance(v, (list, tuple)):
+                if len(v) != n_levels:
+                    raise ValueError(f"UNet config: {name} has {len(v)} entries for {n_levels} levels")
+                return tuple(int(x) for x in v)
+            return (int(v),) * n_levels
+
+        diffusers_style = has("attention_head_dim") or has("down_block_types") or has("num_attention_heads")
+        if has("num_attention_heads"):
+            out.num_heads = per_level(get("num_attention_heads"), "num_attention_heads")
+        elif has("attention_head_dim") and not has("num_heads"):
+            out.num_heads = per_level(get("attention_head_dim"), "attention_head_dim")
+        elif diffusers_style and not has("num_heads"):
+            raise ValueError("UNet config: cannot resolve the number of attention heads "
+                             "(no attention_head_dim / num_attention_heads / num_heads)")
+        if has("down_block_types") and not has("attn_levels"):
+            types = list(get("down_block_types"))
+            if len(types) != n_levels:
+                raise ValueError(f"UNet config: {len(types)} down_block_types for {n_levels} levels")
+            known = {"CrossAttnDownBlock2D": True, "DownBlock2D": False}
+            for t in types:
+                if t not in known:
+                    raise NotImplementedError(f"UNet config: down block type {t!r} is not built")
+            out.attn_levels = tuple(known[t] for t in types)
+            if has("up_block_types"):
+                ups = list(get("up_block_types"))
+                want = ["CrossAttnUpBlock2D" if a else "UpBlock2D" for a in reversed(out.attn_levels)]
+                if ups != want:
+                    raise NotImplementedError(f"UNet config: up_block_types {ups} do not mirror the down blocks")
+        elif diffusers_style and not has("attn_levels"):
+            raise ValueError("UNet config: cannot resolve which levels carry attention (no down_block_types / attn_levels)")
+        if has("transformer_layers_per_block"):
+            out.transformer_layers_per_block = per_level(get("transformer_layers_per_block"), "transformer_layers_per_block")
+        if len(out.num_heads) != n_levels or len(out.attn_levels) != n_levels:
+            raise ValueError("UNet config: num_heads / attn_levels must have one entry per level")
+        for c, h_, a_ in zip(out.block_out_channels, out.num_heads, out.attn_levels):
+            if a_ and (h_ <= 0 or c % h_ != 0):
+                raise ValueError(f"UNet config: {c} channels do not split into {h_} heads")
+        oca = get("only_cross_attention", False)
+        if (any(oca) if isinstance(oca, (list, tuple)) else bool(oca)) or get("dual_cross_attention", False):
+            raise NotImplementedError("UNet config: only_cross_attention / dual_cross_attention are not built")
+        if get("class_embed_type") is not None or get("num_class_embeds") is not None:
+            raise NotImplementedError("UNet config: class embeddings are not built")
+        if get("act_fn", "silu") not in ("silu", "swish"):
+            raise NotImplementedError(f"UNet config: act_fn {get('act_fn')!r} is not built")
+        if get("resnet_time_scale_shift", "default") != "default" or get("time_embedding_type", "positional") != "positional":
+            raise NotImplementedError("UNet config: only default resnet_time_scale_shift / positional time embedding are built")
+        aet = get("addition_embed_type")
+        if aet not in (None, "text_time"):
+            raise NotImplementedError(f"UNet config: addition_embed_type {aet!r} is not built")
         return out
 
 

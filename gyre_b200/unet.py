@@ -80,7 +80,7 @@ class B200UNet:
             self._h = None
 
     # -- parameters ---------------------------------------------------------------------------------
-    def load_weight(self, key: str, tensor: torch.Tensor):
+    def load_weight(self, key: str, tensor: torch.Tensor, _keep=None):
         t = tensor.detach()
         if t.dtype not in (torch.float16, torch.float32):
             t = t.float()
@@ -89,13 +89,22 @@ class B200UNet:
         with torch.cuda.device(self.device):
             N.check(self._lib.gyre_b200_load_weight(self._h, key.encode(), N.ptr(t), N.dtype_code(t), shape, t.ndim,
                                                     N.stream_ptr(self.device)), f"load_weight({key})")
-            # the packing kernels read `t` asynchronously; keep it alive until they are done
-            torch.cuda.current_stream(self.device).synchronize()
+            # the packing kernels read `t` asynchronously: the caller either keeps it alive until it synchronises
+            # (load_state_dict: ONE synchronize for the whole state dict) or we wait here
+            if _keep is not None:
+                _keep.append(t)
+            else:
+                torch.cuda.current_stream(self.device).synchronize()
 
     def load_state_dict(self, state_dict, strict: bool = True):
         self.set_context(None)          # cached K/V projections depend on the attn2 weights
-        for k, v in state_dict.items():
-            self.load_weight(k, v)
+        keep = []
+        try:
+            for k, v in state_dict.items():
+                self.load_weight(k, v, _keep=keep)
+        finally:
+            torch.cuda.current_stream(self.device).synchronize()
+            keep.clear()
         if strict:
             N.check(self._lib.gyre_b200_finalize(self._h), "finalize")
         self._loaded = True
@@ -187,6 +196,8 @@ class B200UNet:
         """ControlNet residuals (`down_block_additional_residuals` / `mid_block_additional_residual`, passed through by
         gyre/pipeline/unet/core.py:213-239) for the next native forward.  Returns the fp16 tensors to keep alive."""
         if down is None and mid is None:
+            # nothing to bind: make sure no pointer of an earlier (possibly failed) forward is still set
+            N.check(self._lib.gyre_b200_unet_set_control_residuals(self._h, None, 0, None), "unet_set_control_residuals")
             return None
         B, _, H, W = x.shape
         cfg = self.config
@@ -221,6 +232,7 @@ class B200UNet:
         """T2I-adapter states (`adapter_states=`, gyre/pipeline/t2i_adapter/unet_patcher.py:95-110) for the next
         native forward: one tensor per down block.  Returns the fp16 tensors to keep alive."""
         if not states:                       # None or empty list: the reference's hook ignores both
+            N.check(self._lib.gyre_b200_unet_set_adapter_states(self._h, None, 0), "unet_set_adapter_states")
             return None
         B, _, H, W = x.shape
         ch = self.config.block_out_channels
@@ -252,8 +264,15 @@ class B200UNet:
             if not added_cond_kwargs or "text_embeds" not in added_cond_kwargs or "time_ids" not in added_cond_kwargs:
                 raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")
             add = self.added_cond_vector(added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"])
-        keep = [self._bind_control_residuals(down_block_additional_residuals, mid_block_additional_residual, x),
-                self._bind_adapter_states(adapter_states, x)]
-        out = self.forward_raw(x, self._timesteps(t, B), ctx, add_cond=add)
-        del keep
+        keep = None
+        try:
+            keep = [self._bind_control_residuals(down_block_additional_residuals, mid_block_additional_residual, x),
+                    self._bind_adapter_states(adapter_states, x)]
+            out = self.forward_raw(x, self._timesteps(t, B), ctx, add_cond=add)
+        finally:
+            # the residual / state pointers are valid for ONE forward, like the keyword arguments: whatever happened
+            # above (a failed bind, a failed forward), nothing may stay bound once `keep` is released
+            self._lib.gyre_b200_unet_set_control_residuals(self._h, None, 0, None)
+            self._lib.gyre_b200_unet_set_adapter_states(self._h, None, 0)
+            del keep
         return UNetOutput(sample=out.to(latents.dtype) if latents.dtype != torch.float16 else out)

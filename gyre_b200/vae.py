@@ -72,7 +72,7 @@ class B200VAE:
                 pass
             self._h = None
 
-    def load_weight(self, key, tensor):
+    def load_weight(self, key, tensor, _keep=None):
         t = tensor.detach()
         if t.dtype not in (torch.float16, torch.float32):
             t = t.float()
@@ -81,11 +81,20 @@ class B200VAE:
         with torch.cuda.device(self.device):
             N.check(self._lib.gyre_b200_load_weight(self._h, key.encode(), N.ptr(t), N.dtype_code(t), shape, t.ndim,
                                                     N.stream_ptr(self.device)), f"load_weight({key})")
-            torch.cuda.current_stream(self.device).synchronize()
+            # the packing kernels read `t` asynchronously (see B200UNet.load_weight)
+            if _keep is not None:
+                _keep.append(t)
+            else:
+                torch.cuda.current_stream(self.device).synchronize()
 
     def load_state_dict(self, state_dict, strict: bool = True):
-        for k, v in state_dict.items():
-            self.load_weight(k, v)
+        keep = []
+        try:
+            for k, v in state_dict.items():
+                self.load_weight(k, v, _keep=keep)
+        finally:
+            torch.cuda.current_stream(self.device).synchronize()
+            keep.clear()
         if strict:
             N.check(self._lib.gyre_b200_finalize(self._h), "finalize")
         self._loaded = True

@@ -301,3 +301,54 @@ def test_no_cpu_fallback():
         B200VAE(VAEConfig.tiny())
     with pytest.raises(N.NativeError):
         N.gemm(torch.zeros(8, 8).half(), torch.zeros(8, 8).half())
+
+
+def _diffusers_unet_config(**kw):
+    """What `UNet2DConditionModel.config` looks like in diffusers 0.16 (the names gyre's ckpt_utils.py:280-304 writes)."""
+    d = dict(act_fn="silu", attention_head_dim=8, block_out_channels=[320, 640, 1280, 1280], center_input_sample=False,
+             cross_attention_dim=768, down_block_types=["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"],
+             up_block_types=["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3, downsample_padding=1, flip_sin_to_cos=True,
+             freq_shift=0, in_channels=4, layers_per_block=2, mid_block_scale_factor=1, norm_eps=1e-5,
+             norm_num_groups=32, out_channels=4, sample_size=64, only_cross_attention=False, dual_cross_attention=False,
+             class_embed_type=None, num_class_embeds=None, use_linear_projection=False, upcast_attention=False)
+    d.update(kw)
+    return d
+
+
+def test_unet_config_from_diffusers_names():
+    """a diffusers config must map attention_head_dim -> heads and down_block_types -> attention levels
+    (an SD2.x config used to get 8 heads per level silently)."""
+    sd15 = UNetConfig.from_any(_diffusers_unet_config())
+    assert sd15.num_heads == (8, 8, 8, 8) and sd15.attn_levels == (True, True, True, False)
+    sd21 = UNetConfig.from_any(_diffusers_unet_config(attention_head_dim=[5, 10, 20, 20], cross_attention_dim=1024,
+                                                      use_linear_projection=True, upcast_attention=True,
+                                                      sample_size=96, prediction_type="v_prediction"))
+    assert sd21.num_heads == (5, 10, 20, 20) and sd21.use_linear_projection and sd21.upcast_attention
+    assert sd21 == UNetConfig.sd21_v()
+    sdxl = UNetConfig.from_any(dict(block_out_channels=[320, 640, 1280], attention_head_dim=[5, 10, 20],
+                                    down_block_types=["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"],
+                                    up_block_types=["CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"],
+                                    transformer_layers_per_block=[1, 2, 10], cross_attention_dim=2048,
+                                    use_linear_projection=True, sample_size=128, addition_embed_type="text_time",
+                                    addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816))
+    assert sdxl == UNetConfig.sdxl()
+
+    class Obj:      # attribute-style config (diffusers FrozenDict also allows attribute access)
+        pass
+    o = Obj()
+    for k, v in _diffusers_unet_config(attention_head_dim=[5, 10, 20, 20]).items():
+        setattr(o, k, v)
+    assert UNetConfig.from_any(o).num_heads == (5, 10, 20, 20)
+    # the oracle's config (our own field names) still round-trips
+    assert UNetConfig.from_any(ounet.UNetConfig.tiny()).num_heads == UNetConfig.tiny().num_heads
+    with pytest.raises(ValueError):          # heads unresolvable
+        UNetConfig.from_any(dict(block_out_channels=[320, 640, 1280, 1280],
+                                 down_block_types=["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"]))
+    with pytest.raises(ValueError):          # attention levels unresolvable
+        UNetConfig.from_any(dict(block_out_channels=[320, 640, 1280, 1280], attention_head_dim=8))
+    with pytest.raises(ValueError):          # 320 channels do not split into 7 heads
+        UNetConfig.from_any(_diffusers_unet_config(attention_head_dim=7))
+    with pytest.raises(NotImplementedError):
+        UNetConfig.from_any(_diffusers_unet_config(only_cross_attention=True))
+    with pytest.raises(NotImplementedError):
+        UNetConfig.from_any(_diffusers_unet_config(down_block_types=["AttnDownBlock2D"] * 4))
