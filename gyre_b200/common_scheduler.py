@@ -237,7 +237,13 @@ class KDiffusionScheduler(CommonScheduler):
         return latents * c_in.to(latents.dtype).to(latents.device)
 
     def add_noise(self, latents, noise, t):
-        sigma = self._sched.t_to_sigma(torch.as_tensor(t).cpu())
+        """`latents + noise * match_shape(t_to_sigma(t), noise)` (reference :550-553).  `match_shape` gives sigma a
+        shape of [1, 1, 1, 1] in fp32, so type promotion makes the product AND the sum fp32: the caller's
+        `.to(latents.dtype)` (`_addInitialNoise`, unified_pipeline.py:323-332) rounds ONCE.  (A 0-dim sigma would
+        keep both operations in fp16 and round twice.)"""
+        sigma = self._sched.t_to_sigma(torch.as_tensor(t).cpu()).float().flatten()
+        while sigma.ndim < noise.ndim:
+            sigma = sigma[..., None]
         return latents + noise * sigma.to(noise.device)
 
     @torch.no_grad()
@@ -329,6 +335,10 @@ class KDiffusionScheduler(CommonScheduler):
             self.eps2 = torch.empty_like(self.x_in)
             self.lib = N.load()
             self.u = 0.0            # progress of the current step (legacy inpaint blend)
+            # dpm_fast / dpm_adaptive never enter `trange`, so the reference's KDiffusionPositionTracker.get_u falls back
+            # to counting the schedule sigmas >= the sigma being evaluated, on EVERY model call, intermediate stages
+            # included (common_scheduler.py:369-381): (u_off, dtype-cast sigmas[start:]) when that rule applies
+            self.u_from_sigma = None
 
         def new(self):
             return torch.empty(self.shape, device=self.dev, dtype=torch.float32)
@@ -337,6 +347,11 @@ class KDiffusionScheduler(CommonScheduler):
             """KDiffusionUNetWrapper + Discrete{Eps,V}DDPMDenoiser.forward (common_scheduler.py:342-355,
             external.py:96-113,149-167): x0 = x * c_skip + unet(x * c_in, t(sigma)) * c_out, with CFG inside."""
             sg = torch.as_tensor(sigma, dtype=torch.float32)
+            if self.u_from_sigma is not None:
+                u_off, sched_sigmas = self.u_from_sigma
+                cmp = torch.as_tensor(sigma).to(sched_sigmas.dtype).reshape(-1)[0]
+                i = int((sched_sigmas >= cmp).sum())
+                self.u = max(min(u_off + (1 - u_off) * i / (len(sched_sigmas) - 1), 0.999), 0)
             c_in = 1 / (sg ** 2 + 1.0) ** 0.5
             if self.vpred:
                 c_skip, c_out = 1.0 / (sg ** 2 + 1.0), -sg / (sg ** 2 + 1.0) ** 0.5
@@ -414,8 +429,8 @@ class KDiffusionScheduler(CommonScheduler):
         orders = [3] * (m - 2) + [2, 1] if nfe % 3 == 0 else [3] * (m - 1) + [nfe % 3]
         sig = lambda t: t.neg().exp()
         x = latents.to(torch.float32).contiguous().clone()
+        E.u_from_sigma = (self.start_offset / len(self.sigmas), sigmas.to(dt).cpu())
         for i in progress_wrapper(range(len(orders))):
-            E.u = self._u(i, len(orders), len(orders) + 1)
             t, t_next = ts[i], ts[i + 1]
             if eta:
                 sd, su = get_ancestral_step(sig(t), sig(t_next), eta)
@@ -487,10 +502,9 @@ class KDiffusionScheduler(CommonScheduler):
         r1, r2 = 1 / 3, 2 / 3
         ticks = iter(progress_wrapper(iter(int, 1)))          # endless iterator: cancellation raises from next()
         steps = 0
-        span = max(_f(t_end) - _f(t_start), 1e-6)
+        E.u_from_sigma = (self.start_offset / len(self.sigmas), sigmas.to(dt).cpu())
         while s < t_end - 1e-5:
             next(ticks)
-            E.u = min(max((_f(s) - _f(t_start)) / span, 0.0), 0.999)
             t = torch.minimum(t_end, s + pid_h)
             if eta:
                 sd, su = get_ancestral_step(sig(s), sig(t), eta)
@@ -535,7 +549,9 @@ class KDiffusionScheduler(CommonScheduler):
                 x = E.lin([(1.0, x_high), (su, E.noise())]) if eta else x_high           # noise on accepted steps only
                 s = t
             if self.callback and steps % self.callback_steps == 0:
-                self.callback(steps, self._sched.sigma_to_t(torch.as_tensor(st).reshape(1))[0], den.to(self.dtype))
+                # info_callback fires AFTER the accept update: sigma = sigma(info['t']) with t = the new s
+                # (sampling.py:476-479, 503-505)
+                self.callback(steps, self._sched.sigma_to_t(torch.as_tensor(_f(sig(s))).reshape(1))[0], den.to(self.dtype))
             steps += 1
         self.last_solver_info = {"steps": steps}
         return x.to(out_dtype or self.dtype)

@@ -695,7 +695,10 @@ def image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image
         init = init * latent_mask + torch.cat(batch_noise, dim=0) * (1 - latent_mask)
     image_noise = batched_randn(init.shape, generators, "cpu", latent_dtype)
     sigma_start = den_probe.t_to_sigma(start_t)
-    latents = (init + image_noise * sigma_start).to(latent_dtype)
+    # KDiffusionScheduler.add_noise (common_scheduler.py:550-553): match_shape turns sigma into a [1, 1, 1, 1] fp32
+    # tensor, so `latents + noise * sigmas` is evaluated in fp32 and `_addInitialNoise` rounds once
+    sig4 = torch.as_tensor(sigma_start, dtype=torch.float32).flatten()[:, None, None, None]
+    latents = (init + image_noise * sig4).to(latent_dtype)
 
     # eps model with CFG (+ the Runway extra channels)
     emb = torch.cat([uncond_emb, cond_emb])

@@ -99,3 +99,20 @@ def gyre_ddim():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def gyre_pipeline_pure():
+    """The pure-torch pieces of gyre/pipeline that the hot path is wrapped in, loaded file by file under synthetic
+    `gyre`, `gyre.pipeline`, `gyre.pipeline.unet` packages (the real package __init__ files pull in diffusers, which is
+    absent): randtools.py, unet/types.py, unet/cfg.py, unet/core.py.  Returns (randtools, types, cfg, core)."""
+    for name, rel in (("gyre", "gyre"), ("gyre.pipeline", "gyre/pipeline"), ("gyre.pipeline.unet", "gyre/pipeline/unet")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF, rel)]
+            sys.modules[name] = m
+    rt = _load("gyre.pipeline", os.path.join(REF, "gyre/pipeline"), "randtools")
+    base = os.path.join(REF, "gyre/pipeline/unet")
+    ty = _load("gyre.pipeline.unet", base, "types")
+    cfg = _load("gyre.pipeline.unet", base, "cfg")
+    core = _load("gyre.pipeline.unet", base, "core")
+    return rt, ty, cfg, core

@@ -290,6 +290,96 @@ def pin_clip():
     print("clip pinned against transformers", __import__("transformers").__version__)
 
 
+
+class FakeDiffusersUNet:
+    """A deterministic stand-in for `UNet2DConditionModel` with the `DiffusersUNet` call signature
+    (gyre/pipeline/unet/types.py:30-39): its output depends on the latents, the timestep, the ORDER of the text
+    embeddings in the batch and on every extra input channel, so any mistake in CFG ordering, latent duplication,
+    timestep duplication or extra-channel concatenation changes the result."""
+
+    class _Out:
+        def __init__(self, sample):
+            self.sample = sample
+
+    def __call__(self, latents, t, *, encoder_hidden_states, **kwargs):
+        x = latents[:, :4].float()
+        tt = torch.as_tensor(t).float().reshape(-1)
+        tt = tt.expand(latents.shape[0]) if tt.numel() == 1 else tt
+        e = encoder_hidden_states.float().mean(dim=(1, 2))
+        out = 0.7 * torch.tanh(x) + 0.001 * tt[:, None, None, None] * x.roll(1, -1) + 0.1 * e[:, None, None, None]
+        if latents.shape[1] > 4:
+            w = torch.arange(1, latents.shape[1] - 3, dtype=torch.float32)[None, :, None, None]
+            out = out + 0.05 * (latents[:, 4:].float() * w).sum(dim=1, keepdim=True)
+        return self._Out(out.to(latents.dtype))
+
+
+def pin_wrappers():
+    """PINS the RNG contract and the CFG / embedding / extra-channel wrapper stack against the reference's own code
+    (gyre/pipeline/randtools.py, unet/cfg.py, unet/core.py - pure torch, imported file by file) on a fake UNet, the
+    way UnifiedPipeline composes them (unified_pipeline.py:2238, 2326-2337, 2412, 139-146)."""
+    rt, _, rcfg, rcore = _vendored.gyre_pipeline_pure()
+    from gyre_b200 import randtools as ours_rt
+    out = {}
+    # ---- batched_randn: one draw of (1, *shape[1:]) per generator per call, generators advance in lock-step
+    for dt_name, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        seeds = [420420420, 420420421, 7]
+        shape = (3, 4, 8, 8)
+        gr = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+        go = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+        gb = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+        for call in range(3):
+            ref = rt.batched_randn(shape, gr, torch.device("cpu"), dt)
+            assert torch.equal(ref, osamp.batched_randn(shape, go, "cpu", dt)), "oracle batched_randn"
+            assert torch.equal(ref, ours_rt.batched_randn(shape, gb, torch.device("cpu"), dt)), "gyre_b200 batched_randn"
+            out[f"randn_{dt_name}_{call}"] = ref
+        # shape[0] a multiple of len(generators): the generator list is cycled (randtools.py:57)
+        g2r = [torch.Generator("cpu").manual_seed(5), torch.Generator("cpu").manual_seed(6)]
+        g2o = [torch.Generator("cpu").manual_seed(5), torch.Generator("cpu").manual_seed(6)]
+        g2b = [torch.Generator("cpu").manual_seed(5), torch.Generator("cpu").manual_seed(6)]
+        ref = rt.batched_randn((4, 4, 4, 4), g2r, torch.device("cpu"), dt)
+        assert torch.equal(ref, osamp.batched_randn((4, 4, 4, 4), g2o, "cpu", dt))
+        assert torch.equal(ref, ours_rt.batched_randn((4, 4, 4, 4), g2b, torch.device("cpu"), dt))
+        out[f"randn_cycled_{dt_name}"] = ref
+    # ---- wrapper stack
+    g = torch.Generator("cpu").manual_seed(99)
+    B = 3
+    lat = torch.randn(B, 4, 8, 8, generator=g)
+    cond = torch.randn(B, 77, 16, generator=g)
+    unc = torch.randn(B, 77, 16, generator=g)
+    extra = torch.randn(B, 5, 8, 8, generator=g)
+    t_vec = torch.tensor([801, 801, 801])
+    base = FakeDiffusersUNet()
+    for dt_name, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        for with_extra in (False, True):
+            for t_name, t in (("tvec", t_vec), ("tint", 401)):
+                unet = rcore.CFGUNetFromDiffusersUNet(base)
+                kids = rcfg.CFGChildUnets(g=rcore.UNetWithEmbeddings(unet, cond.to(dt), "g"),
+                                          u=rcore.UNetWithEmbeddings(unet, unc.to(dt), "u"),
+                                          f=rcore.UNetWithEmbeddings(unet, torch.cat([unc, cond]).to(dt), "f"))
+                if with_extra:       # EnhancedRunwayInpaintMode.wrap_unet (unified_pipeline.py:668-690)
+                    kids = kids.wrap_all(rcore.UnetWithExtraChannels, extra.to(dt))
+                par = rcfg.CFGUNet_Parallel(kids, 7.5, B)(lat.to(dt), t)
+                seq = rcfg.CFGUNet_Sequential(kids, 7.5, B)(lat.to(dt), t)
+                # oracle restatement
+                x_in = lat.to(dt)
+                ocfg = osamp.CFGParallel(base, unc.to(dt), cond.to(dt), 7.5)
+                if with_extra:
+                    class _X:            # the oracle's image modes concatenate inside eps_cfg (oracle/sampling.py)
+                        def __call__(self, latents, tt, *, encoder_hidden_states, **kw):
+                            e2 = torch.cat([extra.to(dt)] * (latents.shape[0] // B))
+                            return base(torch.cat([latents, e2], dim=1), tt, encoder_hidden_states=encoder_hidden_states)
+                    ocfg = osamp.CFGParallel(_X(), unc.to(dt), cond.to(dt), 7.5)
+                mine = ocfg(x_in, t)
+                assert torch.equal(par, mine), f"oracle CFGParallel vs reference ({dt_name}, extra={with_extra}, {t_name})"
+                key = f"cfg_{dt_name}_{'extra' if with_extra else 'plain'}_{t_name}"
+                out[key + "_parallel"] = par
+                out[key + "_sequential"] = seq
+    out["inputs"] = {"lat": lat, "cond": cond, "unc": unc, "extra": extra, "t_vec": t_vec, "t_int": 401, "scale": 7.5}
+    torch.save(out, os.path.join(GOLD, "wrappers.pt"))
+    print(f"wrappers: {len(out) - 1} reference vectors pinned (batched_randn bit-exact for the oracle and gyre_b200.randtools; "
+          "CFGUNet_Parallel / Sequential + UNetWithEmbeddings + UnetWithExtraChannels bit-exact for the oracle)")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -346,4 +436,5 @@ if __name__ == "__main__":
     pin_ddim()
     pin_tome()
     pin_clip()
+    pin_wrappers()
     oracle_fixtures(a.full)

@@ -185,3 +185,45 @@ def test_oracle_t2i_adapter_semantics():
     assert (out - base).abs().max() > 1e-3
     with pytest.raises(AssertionError):
         unet_forward(P, cfg, x, 300, ctx, adapter_states=states[:-1])
+
+
+# ---- RNG contract + CFG / embedding / extra-channel wrappers vs the reference's own classes (wrappers.pt)
+def _wrappers():
+    return torch.load(os.path.join(GOLD, "wrappers.pt"))
+
+
+@pytest.mark.parametrize("dt_name,dt", [("fp32", torch.float32), ("fp16", torch.float16)])
+def test_batched_randn_matches_reference_randtools(dt_name, dt):
+    """gyre/pipeline/randtools.py:39-64 imported by scripts/make_golden.py: oracle AND product host code, bit-exact."""
+    from gyre_b200 import randtools as ours
+    W = _wrappers()
+    seeds = [420420420, 420420421, 7]
+    go = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    gb = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    for call in range(3):
+        ref = W[f"randn_{dt_name}_{call}"]
+        assert torch.equal(osamp.batched_randn((3, 4, 8, 8), go, "cpu", dt), ref)
+        assert torch.equal(ours.batched_randn((3, 4, 8, 8), gb, torch.device("cpu"), dt), ref)
+    g2o = [torch.Generator("cpu").manual_seed(5), torch.Generator("cpu").manual_seed(6)]
+    g2b = [torch.Generator("cpu").manual_seed(5), torch.Generator("cpu").manual_seed(6)]
+    assert torch.equal(osamp.batched_randn((4, 4, 4, 4), g2o, "cpu", dt), W[f"randn_cycled_{dt_name}"])
+    assert torch.equal(ours.batched_randn((4, 4, 4, 4), g2b, torch.device("cpu"), dt), W[f"randn_cycled_{dt_name}"])
+    with pytest.raises(ValueError):
+        ours.batched_randn((3, 4, 4, 4), g2b, torch.device("cpu"), dt)
+
+
+@pytest.mark.parametrize("dt_name,dt", [("fp32", torch.float32), ("fp16", torch.float16)])
+@pytest.mark.parametrize("t_name", ["tvec", "tint"])
+def test_cfg_wrapper_stack_matches_reference(dt_name, dt, t_name):
+    """CFGUNet_Parallel / CFGUNet_Sequential over UNetWithEmbeddings over CFGUNetFromDiffusersUNet
+    (gyre/pipeline/unet/cfg.py:26-57, core.py:242-274), as composed at unified_pipeline.py:2238,2326-2337."""
+    from fakes import FakeDiffusersUNet
+    W = _wrappers()
+    I = W["inputs"]
+    t = I["t_vec"] if t_name == "tvec" else I["t_int"]
+    ocfg = osamp.CFGParallel(FakeDiffusersUNet(), I["unc"].to(dt), I["cond"].to(dt), I["scale"])
+    got = ocfg(I["lat"].to(dt), t)
+    assert torch.equal(got, W[f"cfg_{dt_name}_plain_{t_name}_parallel"])
+    # the sequential execution mode is the same function up to the rounding of two separate UNet calls
+    seq = W[f"cfg_{dt_name}_plain_{t_name}_sequential"]
+    assert torch.allclose(got.float(), seq.float(), atol=2e-2 if dt == torch.float16 else 1e-5)
