@@ -105,6 +105,7 @@ SIGNATURES = {
     "gyre_b200_cat_channels": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _vp, _vp]),
     "gyre_b200_scale_latents": (_i, [_vp, _f, _i, _i, _i64, _vp, _vp]),
     "gyre_b200_tome_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "gyre_b200_tome_plan_offsets": (_i, [_i, _i, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "gyre_b200_tome_merge_kv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "gyre_b200_gemm": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, C.POINTER(Epilogue), _vp]),
     "gyre_b200_pack_geglu": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
@@ -345,8 +346,10 @@ def attention(q, k, v, heads, scale=None):
     return out
 
 
-def tome_merge_kv(k, v, r):
-    """k, v [B, N, C] fp16 (dense) -> merged [B, N - r, C] pair (reference: bipartite_soft_matching + merge_wavg)."""
+def tome_merge_kv(k, v, r, return_plan=False):
+    """k, v [B, N, C] fp16 (dense) -> merged [B, N - r, C] pair (reference: bipartite_soft_matching + merge_wavg).
+    return_plan: also (node_idx [B, Na], unm_idx [B, Na - r], src_idx [B, r]) as int64 tensors - the plan the kernels
+    built (include/gyre_b200.h: gyre_b200_tome_plan_offsets)."""
     require_cuda(k, v)
     B, Nt, Cc = k.shape
     r = min(r, Nt // 2)
@@ -358,7 +361,13 @@ def tome_merge_kv(k, v, r):
     k, v = k.contiguous(), v.contiguous()
     check(load().gyre_b200_tome_merge_kv(ptr(k), ptr(v), B, Nt, Cc, r, ptr(ko), ptr(vo), ptr(ws), ws.numel(),
                                          stream_ptr(k.device)), "tome_merge_kv")
-    return ko, vo
+    if not return_plan:
+        return ko, vo
+    o = [C.c_size_t(), C.c_size_t(), C.c_size_t()]
+    check(load().gyre_b200_tome_plan_offsets(B, Nt, Cc, C.byref(o[0]), C.byref(o[1]), C.byref(o[2])), "tome_plan_offsets")
+    Na = (Nt + 1) // 2
+    arr = [ws[x.value:x.value + B * Na * 4].view(torch.int32).view(B, Na).long() for x in o]
+    return ko, vo, (arr[0], arr[1][:, :Na - r], arr[2][:, :r])
 
 
 FAMILIES = ("gemm", "conv3x3", "attention", "groupnorm", "layernorm", "softmax", "elementwise", "tome")

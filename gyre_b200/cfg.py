@@ -17,6 +17,11 @@ class B200GuidedUNet:
         if uncond_embeddings.shape != text_embeddings.shape:
             raise ValueError("uncond and text embeddings must have the same shape")
         self.unet = unet
+        # the wrappers are built per request, after LoRA hooks were applied / removed (unified_pipeline.py:2193-2238):
+        # fold them into the packed weights once here, not on every step
+        sync = getattr(unet, "_sync_lora", None)
+        if sync is not None:
+            sync()
         self.guidance_scale = float(guidance_scale)
         self.batch = text_embeddings.shape[0]
         # CFGUNet_Parallel (one UNet call on the doubled batch, cfg.py:41-57) or CFGUNet_Sequential (two calls of the

@@ -108,6 +108,7 @@ class CommonScheduler:
         self.eps_unets = []
         self.unet = None
         self._blend = None          # (orig fp32, mask fp32): legacy inpaint x0 blend (set_x0_blend)
+        self.use_cuda_graph = False  # whole-loop CUDA graph for the fused Euler / Euler-ancestral path (_loop_graphed)
 
     def set_callback(self, callback, callback_steps: int = 1):
         self.callback = callback
@@ -296,6 +297,9 @@ class KDiffusionScheduler(CommonScheduler):
         noise = predraw_noise(n_draws, shape, self.generators, self.device, self.dtype) if n_draws else None
         noise32 = noise.float() if (noise is not None and ancestral) else None
 
+        if self.use_cuda_graph and self._graphable(guided):
+            return self._loop_graphed(guided, latents, steps, t_dev, noise32, sigmas, progress_wrapper, out_dtype)
+
         x = latents.to(torch.float32).contiguous().clone()
         x_next = torch.empty_like(x)
         x_in = torch.empty((2 * B, *shape[1:]), device=self.device, dtype=torch.float16)
@@ -318,6 +322,82 @@ class KDiffusionScheduler(CommonScheduler):
                 self.callback(i, t_all[i], den.to(self.dtype))
         return x.to(out_dtype or self.dtype)
 
+    # -- whole-loop CUDA graph -----------------------------------------------------------------------
+    def _graphable(self, guided):
+        """One graph holds ALL steps of a run (UNet forwards + fused scheduler steps): possible when nothing has to
+        happen on the host between steps - no per-step callback, no legacy-inpaint blend, no per-run extra channels -
+        at the price of cancellation granularity (the progress iterator is ticked after the replay, not between steps)."""
+        return (self.callback is None and self._blend is None and guided.extra is None and guided.parallel and
+                N.get_tunable("CTX_KV_CACHE") != 0)
+
+    def _loop_graphed(self, guided, latents, steps, t_dev, noise32, sigmas, progress_wrapper, out_dtype):
+        """SURVEY section 7 step 4.  At CFG batch 16 the ~390 launches of a step are hidden behind 19 ms of GPU work; at one
+        or two images per GPU (strong scaling, B / R <= 2) a step is a few ms and the host-side launch path is what the
+        GPU waits for.  The graph is cached on the UNet per (shape, schedule, guidance, ToMe) key; its inputs - start
+        latents, pre-drawn noise, the bound text context, the additional conditioning - live in fixed buffers that are
+        refreshed before every replay.  The first run with a new key executes eagerly (and warms every lazy
+        initialisation), then the same loop is captured for the following runs."""
+        unet = guided.unet
+        n = len(steps)
+        B = latents.shape[0]
+        shape = tuple(latents.shape)
+        per_sample = latents[0].numel()
+        key = ("euler", shape, n, tuple((s.sigma, s.dt, s.sigma_up, s.c_in_next, s.v_pred, s.guidance) for s in steps),
+               tuple(unet.tome_r_list() or ()), None if guided.add_cond is None else tuple(guided.add_cond.shape),
+               guided.embeddings.shape)
+        cache = unet.__dict__.setdefault("_loop_graphs", {})
+        ent = cache.get(key)
+        # the context of THIS run: projected into the model-owned K/V cache outside the graph
+        unet.set_context(guided.embeddings, owner=guided)
+        if ent is None:
+            ent = {"x0": torch.empty(shape, device=self.device, dtype=torch.float32),
+                   "xa": torch.empty(shape, device=self.device, dtype=torch.float32),
+                   "xb": torch.empty(shape, device=self.device, dtype=torch.float32),
+                   "x_in": torch.empty((2 * B, *shape[1:]), device=self.device, dtype=torch.float16),
+                   "eps2": torch.empty((2 * B, *shape[1:]), device=self.device, dtype=torch.float16),
+                   "noise": None if noise32 is None else torch.empty_like(noise32),
+                   "t": t_dev.clone(), "add": None if guided.add_cond is None else guided.add_cond.clone(),
+                   "graph": None, "steps": steps}
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            cache[key] = ent
+
+        def body():
+            # x0 -> xa / xb ping-pong; every pointer below is fixed for the life of the cache entry
+            self._first_input(ent["x0"], _f(1 / (sigmas[0] ** 2 + 1.0) ** 0.5), True, B, per_sample, ent["x_in"])
+            x, x_next = ent["x0"], ent["xa"]
+            k = 0
+            for i in range(n):
+                unet.forward_raw(ent["x_in"], ent["t"][i], None, out=ent["eps2"], add_cond=ent["add"])
+                st = ent["steps"][i]
+                nz = None
+                if st.sigma_up != 0.0:
+                    nz = ent["noise"][k]
+                    k += 1
+                self._step(st, x, ent["eps2"], nz, x_next, None, ent["x_in"] if st.c_in_next != 0.0 else None, B, per_sample)
+                x, x_next = x_next, (ent["xb"] if x_next is ent["xa"] else ent["xa"])
+            return x
+
+        ent["x0"].copy_(latents)
+        if noise32 is not None:
+            ent["noise"].copy_(noise32)
+        if ent["add"] is not None:
+            ent["add"].copy_(guided.add_cond)
+        if ent["graph"] is None:
+            out = body()                                   # eager: run 1 with this key (also the warm-up for capture)
+            result = out.to(out_dtype or self.dtype)
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent["out"] = body()
+            ent["graph"] = g
+            # replaying would redo run 1 from the same inputs; keep the eager result
+        else:
+            ent["graph"].replay()
+            result = ent["out"].to(out_dtype or self.dtype)
+        for _ in progress_wrapper(range(n)):               # cancellation point: after the loop
+            pass
+        return result
 
     # -- generic samplers -------------------------------------------------------------------------
     class _Engine:

@@ -433,6 +433,10 @@ int gyre_b200_destroy(gyre_b200_handle h) {
   return 0;
 }
 
+int gyre_b200_tome_plan_offsets(int batch, int tokens, int channels, size_t* node_idx, size_t* unm_idx, size_t* src_idx) {
+  GYRE_REQUIRE(node_idx && unm_idx && src_idx, "tome_plan_offsets: null argument");
+  return tome_plan_offsets(batch, tokens, channels, node_idx, unm_idx, src_idx);
+}
 int gyre_b200_tome_workspace_bytes(int batch, int tokens, int channels, size_t* bytes) {
   GYRE_REQUIRE(bytes, "tome_workspace_bytes: null argument");
   return tome_workspace_bytes(batch, tokens, channels, bytes);

@@ -148,6 +148,7 @@ int pack_geglu(const void* w, int dtype, int F, int K, const void* bias, int bia
 const char* last_error();
 // ---- ToMe K/V merge (tome.cu): k, v [B, N, C] with row pitch ld -> k_out, v_out [B, N-r, C] dense
 int tome_workspace_bytes(int B, int N, int C, size_t* bytes);
+int tome_plan_offsets(int B, int N, int C, size_t* node_idx, size_t* unm_idx, size_t* src_idx);
 int tome_merge_kv(const __half* k, const __half* v, int ld, int B, int N, int C, int r, __half* k_out, __half* v_out,
                   void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace gyre

@@ -40,6 +40,15 @@ static TomeLayout tome_layout(int B, int N, int C) {
   return L;
 }
 
+int tome_plan_offsets(int B, int N, int C, size_t* node_idx, size_t* unm_idx, size_t* src_idx) {
+  GYRE_REQUIRE(B > 0 && N > 1 && C > 0, "tome: empty problem");
+  const TomeLayout L = tome_layout(B, N, C);
+  *node_idx = L.off_nidx;
+  *unm_idx = L.off_unm;
+  *src_idx = L.off_src;
+  return 0;
+}
+
 int tome_workspace_bytes(int B, int N, int C, size_t* bytes) {
   GYRE_REQUIRE(B > 0 && N > 1 && C > 0, "tome: empty problem");
   *bytes = tome_layout(B, N, C).total;

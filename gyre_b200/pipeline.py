@@ -126,6 +126,7 @@ class B200Pipeline:
             guided.set_added_cond(negative_added_cond_kwargs or added_cond_kwargs, added_cond_kwargs)
         sched = build_scheduler(sampler, generators, self.device, latents_dtype, callback, callback_steps)
         sched.set_eps_unets([guided])
+        sched.use_cuda_graph = bool(getattr(self, "use_cuda_graph", False))
         ts_args = {"strength": min(strength, 1.0)} if image is not None else {}
         sched.set_timesteps(num_inference_steps, prediction_type=cfg.prediction_type,
                             config=scheduler_config or SchedulerConfig(), **ts_args)

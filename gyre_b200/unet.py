@@ -9,6 +9,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _native as N
+from . import module_tree as MT
 from .config import UNetConfig
 
 
@@ -34,21 +35,33 @@ def parse_r(num_layers: int, r):
     return [int(min_val + step * i) for i in range(num_layers)]
 
 
-class B200UNet:
-    """UNet2DConditionModel replacement.  `unet(latents, t, encoder_hidden_states=ctx).sample`."""
+class B200UNet(torch.nn.Module):
+    """UNet2DConditionModel replacement.  `unet(latents, t, encoder_hidden_states=ctx).sample`.
 
-    def __init__(self, config, device=None):
+    An `nn.Module` with the surface the reference pipeline reads off its UNet: `.config.in_channels` /
+    `.config.sample_size`, `.modules()` / `.named_modules()` / `.parameters()` under the diffusers names, `.dtype` /
+    `.device`, `set_attention_slice`, `set_use_memory_efficient_attention_xformers`, ToMe's `.r`.  It HOLDS the original
+    parameters next to the packed native copy (`from_module`: the caller's own module tree; `load_state_dict`: a tree
+    rebuilt from the state dict), so gyre's LoRA hooks (gyre/pipeline/lora.py:99-166) attach to it like to the original
+    - and are folded into the packed weights before the next forward (`_sync_lora`)."""
+
+    def __init__(self, config, device=None, hold_parameters: bool = True):
+        super().__init__()
         self.config = UNetConfig.from_any(config)
         if not torch.cuda.is_available():
             raise N.NativeError("B200UNet needs a CUDA device: there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dtype = torch.float16
         self.r = 0                      # ToMe: `unet.r = int(value)` (unified_pipeline.py:1582-1584)
+        self.hold_parameters = hold_parameters
         self._lib = N.load()
         self._h = C.c_void_p()
         self._ws = {}
         self._loaded = False
         self._ctx_bound = None          # (owner, B, L) of the context bound with set_context
+        self._lora_sig = ()             # LoRA hooks folded into the packed weights right now
+        self._attention_slice = None    # recorded only: the native attention is a flash kernel, nothing to slice
+        self._xformers = True
         cfg = self.config
         c = N.UNetConfigC()
         c.in_channels, c.out_channels = cfg.in_channels, cfg.out_channels
@@ -69,6 +82,37 @@ class B200UNet:
         with torch.cuda.device(self.device):
             N.check(self._lib.gyre_b200_unet_create(C.byref(c), C.byref(self._h)), "unet_create")
         self.num_transformer_blocks = self._lib.gyre_b200_unet_num_transformer_blocks(self._h)
+
+    @classmethod
+    def from_module(cls, module: torch.nn.Module, config=None, device=None):
+        """Wraps the caller's original UNet (`diffusers.UNet2DConditionModel` layout): config from `module.config`, weights
+        packed from `module.state_dict()`, and the module tree itself adopted - the parameters stay the caller's."""
+        self = cls(config if config is not None else module.config, device=device, hold_parameters=False)
+        MT.adopt_module(self, module)
+        self._load_packed(module.state_dict(), strict=True)
+        return self
+
+    # -- the diffusers / gyre switches the pipeline flips on its UNet (unified_pipeline.py:1430-1450) -------------------
+    def set_attention_slice(self, slice_size):
+        self._attention_slice = slice_size
+
+    def set_use_memory_efficient_attention_xformers(self, valid: bool, *args, **kwargs):
+        self._xformers = bool(valid)
+
+    def enable_xformers_memory_efficient_attention(self, *args, **kwargs):
+        self._xformers = True
+
+    def disable_xformers_memory_efficient_attention(self):
+        self._xformers = False
+
+    def to(self, *args, **kwargs):
+        """The native weights are bound to `self.device`; `.to()` may only name that device (or a dtype for the held
+        parameters, which does not affect the fp16 compute path)."""
+        dev = kwargs.get("device", next((a for a in args if isinstance(a, (str, torch.device, int))), None))
+        if dev is not None and torch.device(dev if not isinstance(dev, int) else f"cuda:{dev}").type == "cuda" and \
+                torch.device(dev if not isinstance(dev, int) else f"cuda:{dev}").index not in (None, self.device.index):
+            raise N.NativeError(f"B200UNet is bound to {self.device}; create a new one on {dev}")
+        return self
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -96,7 +140,7 @@ class B200UNet:
             else:
                 torch.cuda.current_stream(self.device).synchronize()
 
-    def load_state_dict(self, state_dict, strict: bool = True):
+    def _load_packed(self, state_dict, strict=True):
         self.set_context(None)          # cached K/V projections depend on the attn2 weights
         keep = []
         try:
@@ -108,7 +152,31 @@ class B200UNet:
         if strict:
             N.check(self._lib.gyre_b200_finalize(self._h), "finalize")
         self._loaded = True
+        self._lora_sig = ()
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._load_packed(state_dict, strict)
+        if self.hold_parameters:
+            MT.build_param_tree(self, state_dict)
         return self
+
+    def _sync_lora(self):
+        """Folds the LoRA hooks currently attached to the held modules into the packed weights (and un-folds the ones that
+        were removed): `W + scale * alpha / r * up . down` per hooked layer (gyre/pipeline/lora.py:150-160 applies the
+        same product to the layer's input at run time).  Only layers whose hooks changed are re-packed."""
+        sig = MT.lora_signature(self)
+        if sig == self._lora_sig:
+            return
+        touched = {e[0] for e in sig} | {e[0] for e in self._lora_sig}
+        keep = []
+        try:
+            for key, w in MT.lora_folded_weights(self, sorted(touched)).items():
+                self.load_weight(key, w, _keep=keep)
+        finally:
+            torch.cuda.current_stream(self.device).synchronize()
+            keep.clear()
+        self.set_context(None)
+        self._lora_sig = sig
 
     # -- forward ------------------------------------------------------------------------------------
     def _workspace(self, B, H, W, L):
@@ -249,9 +317,10 @@ class B200UNet:
         N.check(self._lib.gyre_b200_unet_set_adapter_states(self._h, ptrs, len(keep)), "unet_set_adapter_states")
         return keep
 
-    def __call__(self, latents, t, *, encoder_hidden_states, down_block_additional_residuals=None,
+    def forward(self, latents, t, *, encoder_hidden_states, down_block_additional_residuals=None,
                  mid_block_additional_residual=None, adapter_states=None, added_cond_kwargs=None, **kwargs):
         N.require_cuda(latents, encoder_hidden_states)
+        self._sync_lora()
         B = latents.shape[0]
         if latents.shape[1] != self.config.in_channels:
             raise ValueError(f"expected {self.config.in_channels} input channels, got {latents.shape[1]}")

@@ -9,6 +9,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _native as N
+from . import module_tree as MT
 from .config import VAEConfig
 
 
@@ -41,13 +42,30 @@ class EncoderOutput:
     latent_dist: DiagonalGaussianDistribution
 
 
-class B200VAE:
-    def __init__(self, config, device=None):
+class B200VAE(torch.nn.Module):
+    """AutoencoderKL replacement: an `nn.Module` holding the original parameters under the diffusers names next to the
+    packed native copy (see B200UNet), with the switches the reference flips on its VAE: `enable_slicing` /
+    `disable_slicing` (decode one image per call - same results, the reference's low-memory mode,
+    pipeline_wrapper.py:171-186), `enable_tiling` / `disable_tiling` (accepted and recorded; the native decoder never
+    needs it - a 1024x1024 decode takes ~3.5 GB of workspace - and tiled decoding would CHANGE the image through its
+    seam blending, so full-frame decoding is kept), `.dtype` (`vae_dtype`, unified_pipeline.py:1526-1536).
+
+    `dtype=torch.float32` gives the fp32 INTERFACE the reference uses for VAEs that overflow in fp16 (inputs and outputs
+    are fp32 tensors); the arithmetic stays fp16 tensor-core MMA with fp32 accumulation and fp32 GroupNorm statistics -
+    a true fp32 convolution path is not built."""
+
+    def __init__(self, config, device=None, dtype=torch.float16, hold_parameters: bool = True):
+        super().__init__()
         self.config = VAEConfig.from_any(config)
         if not torch.cuda.is_available():
             raise N.NativeError("B200VAE needs a CUDA device: there is no CPU path")
+        if dtype not in (torch.float16, torch.float32):
+            raise ValueError("B200VAE dtype must be float16 or float32")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.dtype = torch.float16
+        self.dtype = dtype
+        self.hold_parameters = hold_parameters
+        self.use_slicing = False
+        self.use_tiling = False
         self._lib = N.load()
         self._h = C.c_void_p()
         self._ws = {}
@@ -62,6 +80,27 @@ class B200VAE:
         c.norm_num_groups = cfg.norm_num_groups
         with torch.cuda.device(self.device):
             N.check(self._lib.gyre_b200_vae_create(C.byref(c), C.byref(self._h)), "vae_create")
+
+    @classmethod
+    def from_module(cls, module: torch.nn.Module, config=None, device=None, dtype=None):
+        p = next(module.parameters(), None)
+        dt = dtype or (torch.float32 if p is not None and p.dtype == torch.float32 else torch.float16)
+        self = cls(config if config is not None else module.config, device=device, dtype=dt, hold_parameters=False)
+        MT.adopt_module(self, module)
+        self._load_packed(module.state_dict(), strict=True)
+        return self
+
+    def enable_slicing(self):
+        self.use_slicing = True
+
+    def disable_slicing(self):
+        self.use_slicing = False
+
+    def enable_tiling(self, *args, **kwargs):
+        self.use_tiling = True
+
+    def disable_tiling(self):
+        self.use_tiling = False
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -88,6 +127,12 @@ class B200VAE:
                 torch.cuda.current_stream(self.device).synchronize()
 
     def load_state_dict(self, state_dict, strict: bool = True):
+        self._load_packed(state_dict, strict)
+        if self.hold_parameters:
+            MT.build_param_tree(self, state_dict)
+        return self
+
+    def _load_packed(self, state_dict, strict=True):
         keep = []
         try:
             for k, v in state_dict.items():
@@ -98,7 +143,6 @@ class B200VAE:
         if strict:
             N.check(self._lib.gyre_b200_finalize(self._h), "finalize")
         self._loaded = True
-        return self
 
     def _workspace(self, B, h, w):
         key = (B, h, w)
@@ -125,8 +169,13 @@ class B200VAE:
 
     def decode(self, z):
         N.require_cuda(z)
-        img, _ = self.decode_raw(z.to(torch.float16).contiguous())
-        return DecoderOutput(sample=img if z.dtype == torch.float16 else img.to(z.dtype))
+        z16 = z.to(torch.float16).contiguous()
+        if self.use_slicing and z16.shape[0] > 1:
+            img = torch.cat([self.decode_raw(z16[i:i + 1])[0] for i in range(z16.shape[0])])
+        else:
+            img, _ = self.decode_raw(z16)
+        out_dtype = z.dtype if z.dtype in (torch.float16, torch.float32) else self.dtype
+        return DecoderOutput(sample=img if out_dtype == torch.float16 else img.to(out_dtype))
 
     def encode(self, image):
         if not self._loaded:

@@ -293,6 +293,14 @@ int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int6
  * ([unmerged even tokens in descending-score order ..., odd tokens ...]).
  * ------------------------------------------------------------------------------------------ */
 int gyre_b200_tome_workspace_bytes(int batch, int tokens, int channels, size_t* bytes);
+/* The merge plan (merge.py:41-64) stays in the workspace after gyre_b200_tome_merge_kv; byte offsets of its int32 arrays,
+ * Na = ceil(tokens / 2) entries per sample each:
+ *   node_idx [batch, Na]  every even ("a") token's best odd ("b") partner  (merge.py: node_idx)
+ *   unm_idx  [batch, Na]  first Na - r entries: the a-tokens that stay, in descending-score order (merge.py: unm_idx)
+ *   src_idx  [batch, Na]  first r entries: the merged a-tokens, ordered by (destination, token) - the summation order;
+ *                         as a set they are merge.py's src_idx, their destinations are node_idx[src]
+ * Tie rule: equal best scores are ordered by ascending token index; equal scores of one a-token pick the lowest b. */
+int gyre_b200_tome_plan_offsets(int batch, int tokens, int channels, size_t* node_idx, size_t* unm_idx, size_t* src_idx);
 int gyre_b200_tome_merge_kv(const void* k, const void* v, int batch, int tokens, int channels, int r, void* k_out,
                             void* v_out, void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
 

@@ -39,7 +39,7 @@ def test_unet_tiny_vs_golden(tiny_unet):
     out = unet(g["x"].cuda().half(), g["t"].cuda(), encoder_hidden_states=g["ctx"].cuda().half()).sample
     err = rel_err(out.cpu(), g["eps"])
     print("tiny unet rel err vs fp32 golden:", err)
-    assert err < 2e-2
+    assert err < 4.5e-3        # measured 1.45e-3 on B200
 
 
 def test_unet_tiny_taps(tiny_unet):
@@ -56,12 +56,12 @@ def test_unet_tiny_taps(tiny_unet):
     out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample
     err = rel_err(out.cpu(), ref)
     print("tiny unet B=3 rel err:", err)
-    assert err < 2e-2
+    assert err < 5e-3          # measured 1.65e-3
     # scalar / 0-dim timesteps broadcast like the reference (`t.expand(B)`)
     out2 = unet(x.cuda(), 500, encoder_hidden_states=ctx.cuda()).sample
     with torch.no_grad():
         ref2 = unet_forward(P, cfg, x.float(), 500, ctx.float())
-    assert rel_err(out2.cpu(), ref2) < 2e-2
+    assert rel_err(out2.cpu(), ref2) < 5e-3
 
 
 def test_unet_batch_independence(tiny_unet):
@@ -135,10 +135,10 @@ def test_unet_controlnet_residuals_vs_oracle(tiny_unet, which):
     moved = rel_err(ref, plain)
     print(f"controlnet residuals ({which}): rel err {err:.3e}; the residuals move the output by {moved:.3e}")
     assert moved > 5e-3, "test residuals too small to matter"
-    assert err < 2e-2
+    assert err < 4.5e-3        # measured 1.2 - 1.4e-3
     # the residuals were for that call only
     out2 = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample
-    assert rel_err(out2.cpu(), plain) < 2e-2
+    assert rel_err(out2.cpu(), plain) < 5e-3
 
 
 def test_unet_sd15_full_size():
@@ -164,8 +164,8 @@ def test_unet_sd15_full_size():
     print(f"SD1.5 64x64 forward: gyre_b200 rel err {err:.3e}; torch-fp16 oracle rel err (noise floor) {floor:.3e}; "
           f"|eps|max {ref.abs().max().item():.3f}")
     assert torch.isfinite(out).all()
-    assert err < 2e-2
-    assert err < 4 * floor + 2e-3
+    assert err < 4e-3          # measured 1.28e-3 (the fp16 evaluation of the oracle itself: 1.81e-3)
+    assert err < 1.5 * floor
 
 
 @pytest.fixture(scope="module")
@@ -184,7 +184,7 @@ def test_vae_tiny_decode_vs_golden(tiny_vae):
     img = vae.decode(g["z"].cuda().half()).sample
     err = rel_err(img.cpu(), g["img"])
     print("tiny vae decode rel err:", err)
-    assert err < 2e-2
+    assert err < 5e-3          # measured 1.68e-3
 
 
 def test_vae_tiny_encode_vs_golden(tiny_vae):
@@ -193,7 +193,7 @@ def test_vae_tiny_encode_vs_golden(tiny_vae):
     dist = vae.encode(g["img"].cuda().half()).latent_dist
     err = rel_err(dist.parameters.cpu(), g["moments"])
     print("tiny vae encode rel err:", err)
-    assert err < 2e-2
+    assert err < 4e-3          # measured 1.23e-3
     # sampling draws on the generator's device like the reference (unified_pipeline.py:309-313)
     g1 = torch.Generator("cpu").manual_seed(3)
     s1 = dist.sample(generator=g1)
@@ -220,7 +220,7 @@ def test_vae_sd_decode_full_size():
     err = rel_err(img, ref)
     print(f"SD VAE decode 512x512 rel err {err:.3e}, |img|max {ref.abs().max().item():.3f}")
     assert torch.isfinite(img).all()
-    assert err < 2e-2
+    assert err < 4.5e-3        # measured 1.48e-3
     # pipeline tail (unified_pipeline.py:2491) fused into the last kernel
     post, u8 = vae.decode_raw(z.cuda(), postprocess=True, want_u8=True)
     ref_post = (ref / 2 + 0.5).clamp(0, 1)
@@ -248,7 +248,7 @@ def test_unet_sdxl_topology_vs_oracle():
                added_cond_kwargs={k: v.cuda() for k, v in added.items()}).sample
     err = (out.float().cpu() - ref).abs().max().item() / ref.abs().max().item()
     print(f"SDXL-topology UNet forward rel err {err:.3e}")
-    assert err < 2e-2
+    assert err < 3e-3          # measured 1.01e-3
     with pytest.raises(ValueError):
         unet(x.cuda().half(), t.cuda(), encoder_hidden_states=ctx.cuda().half())
     # pipeline: 8 Euler-a steps with CFG (uncond half gets its own pooled embedding)
@@ -268,7 +268,7 @@ def test_unet_sdxl_topology_vs_oracle():
                                 height=128, width=128, sample_size=16, seeds=seeds, steps=8, sampler="euler_a")
     e2 = (res.latents.cpu() - lat).abs().max().item() / lat.abs().max().item()
     print(f"SDXL-topology pipeline final-latent rel err {e2:.3e}")
-    assert e2 < 2e-2
+    assert e2 < 8e-3           # measured 2.61e-3
 
 
 def test_unet_t2i_adapter_states_vs_oracle(tiny_unet):
@@ -292,6 +292,217 @@ def test_unet_t2i_adapter_states_vs_oracle(tiny_unet):
     out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda(), adapter_states=[s.cuda() for s in states]).sample
     err, moved = rel_err(out.cpu(), ref), rel_err(ref, plain)
     print(f"t2i adapter states: rel err {err:.3e}; the states move the output by {moved:.3e}")
-    assert moved > 5e-3 and err < 2e-2
+    assert moved > 5e-3 and err < 4e-3          # measured 1.27e-3
     out2 = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda(), adapter_states=[]).sample     # one call only
     assert rel_err(out2.cpu(), plain) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Full-size parity of the other BASELINE.json configurations (C3: SD1.5-inpaint 768x768, C4: SD2.1-768-v with ToMe,
+# C5: SDXL-base topology 1024x1024, VAE decode at the bench batch): native forward vs the fp32 oracle evaluated with
+# TF32 off on the same GPU (a checker, not a product path), with the fp16 evaluation of the same oracle as the noise
+# floor.  Bounds are <= 3x the values measured on B200 (printed; profiles/r02_parity.txt).
+def _full_size_unet(cfg, shape_hw, seed, in_ch=4, tome_r=0, added=None, batch=2):
+    from oracle.unet import synth_params, unet_forward, unet_param_shapes
+    from gyre_b200.tome_patcher import apply_tome
+    from gyre_b200.unet import B200UNet
+    _no_tf32()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    unet = B200UNet(cfg).load_state_dict(P)
+    gen = torch.Generator("cpu").manual_seed(seed)
+    x = torch.randn(batch, in_ch, *shape_hw, generator=gen).half()
+    ctx = torch.randn(batch, 77, cfg.cross_attention_dim, generator=gen).half()
+    t = torch.tensor([981] * batch)
+    Pc = {k: v.cuda() for k, v in P.items()}
+    kw = {}
+    if added is not None:
+        kw["added_cond_kwargs"] = {k: v.cuda() for k, v in added.items()}
+    with torch.no_grad():
+        ref = unet_forward(Pc, cfg, x.cuda().float(), t.cuda(), ctx.cuda().float(), tome_r=tome_r, **kw)
+        Ph = {k: v.half() for k, v in Pc.items()}
+        ref16 = unet_forward(Ph, cfg, x.cuda(), t.cuda(), ctx.cuda(), tome_r=tome_r,
+                             **({"added_cond_kwargs": {k: v.cuda().half() for k, v in added.items()}} if added else {}))
+        del Ph
+    if tome_r:
+        apply_tome(unet)
+        unet.r = tome_r
+    out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda(), **kw).sample
+    assert torch.isfinite(out).all()
+    return rel_err(out, ref), rel_err(ref16, ref), ref.abs().max().item()
+
+
+def test_unet_c3_sd15_inpaint_full_size():
+    """BASELINE configs[2]: SD1.5-inpaint architecture (9 input channels) at 96x96 latents (768x768)."""
+    from oracle.unet import UNetConfig
+    err, floor, scale = _full_size_unet(UNetConfig.sd15_inpaint(), (96, 96), seed=31, in_ch=9)
+    print(f"C3 SD1.5-inpaint 96x96 forward: gyre_b200 rel err {err:.3e}; torch-fp16 oracle rel err (noise floor) {floor:.3e}; "
+          f"|eps|max {scale:.3f}")
+    assert err < 3.6e-3        # measured 1.21e-3 (fp16 floor 1.68e-3)
+    assert err < 1.5 * floor
+
+
+def test_unet_c4_sd21_v_tome_full_size():
+    """BASELINE configs[3]: SD2.1-768-v architecture (head dim 64, linear projections, upcast attention) at 96x96
+    latents with ToMe r = N/2 in every block (50 % of K/V merged).  The merge plan is a discontinuous function of the
+    scores, so a near-tie resolved differently moves single tokens: the bound is wider than the un-merged one and the
+    fp16 evaluation of the oracle (which flips merges of its own) is printed next to it."""
+    from oracle.unet import UNetConfig
+    cfg = UNetConfig.sd21_v()
+    err0, floor0, _ = _full_size_unet(cfg, (96, 96), seed=41)
+    print(f"C4 SD2.1-v 96x96 forward (no ToMe): gyre_b200 rel err {err0:.3e}; fp16 floor {floor0:.3e}")
+    assert err0 < 3.7e-3       # measured 1.23e-3
+    err, floor, scale = _full_size_unet(cfg, (96, 96), seed=41, tome_r=96 * 96 // 2)
+    print(f"C4 SD2.1-v 96x96 forward, ToMe r=N/2: gyre_b200 rel err {err:.3e}; torch-fp16 oracle rel err {floor:.3e}; "
+          f"|v|max {scale:.3f}")
+    assert err < 4e-3          # measured 1.33e-3: no merge flipped against the fp32 plan at this size
+    assert err < 1.5 * floor
+
+
+def test_unet_c5_sdxl_full_size():
+    """BASELINE configs[4]: SDXL-base topology (3 levels, transformer depth 1 / 2 / 10, ctx 2048, text_time
+    conditioning) at 128x128 latents (1024x1024).  No reference path exists for it: parity vs the oracle."""
+    from oracle.unet import UNetConfig
+    gen = torch.Generator("cpu").manual_seed(5)
+    added = {"text_embeds": torch.randn(2, 1280, generator=gen),
+             "time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * 2)}
+    err, floor, scale = _full_size_unet(UNetConfig.sdxl(), (128, 128), seed=51, added=added)
+    print(f"C5 SDXL 128x128 forward: gyre_b200 rel err {err:.3e}; torch-fp16 oracle rel err (noise floor) {floor:.3e}; "
+          f"|eps|max {scale:.3f}")
+    assert err < 4.3e-3        # measured 1.45e-3 (fp16 floor 1.70e-3)
+    assert err < 1.5 * floor
+
+
+def test_vae_sd_decode_batch8_full_size():
+    """The bench's decode: 8 latents of 64x64 -> 8 images of 512x512, vs the fp32 oracle, plus batch independence."""
+    from oracle.unet import synth_params
+    from oracle.vae import VAEConfig, vae_decode, vae_param_shapes
+    from gyre_b200.vae import B200VAE
+    _no_tf32()
+    cfg = VAEConfig.sd()
+    P = synth_params(vae_param_shapes(cfg, encoder=True, decoder=True), seed=4321)
+    vae = B200VAE(cfg).load_state_dict(P)
+    z = torch.randn(8, 4, 64, 64, generator=torch.Generator("cpu").manual_seed(2)).half()
+    Pc = {k: v.cuda() for k, v in P.items()}
+    img = vae.decode(z.cuda()).sample
+    errs = []
+    with torch.no_grad():
+        for i in range(0, 8, 2):       # the fp32 oracle two images at a time (activation memory)
+            ref = vae_decode(Pc, cfg, z[i:i + 2].cuda().float())
+            errs.append(rel_err(img[i:i + 2], ref))
+    print(f"SD VAE decode 512x512 batch 8: rel err per pair {['%.3e' % e for e in errs]}")
+    assert torch.isfinite(img).all()
+    assert max(errs) < 5e-3    # measured 1.34 - 1.67e-3
+    # Batch independence.  With stream-K on (default) the K split of a conv tile depends on the tile count, i.e. on the
+    # batch: results agree to the last fp16 bit or two, not bitwise (DESIGN.md, numerical note).  STREAMK=0 is bitwise.
+    one = vae.decode(z[3:4].cuda()).sample
+    d = (one[0].float() - img[3].float()).abs().max().item()
+    print(f"batch 1 vs batch 8, stream-K on: max abs diff {d:.3e} (|img| max {img[3].abs().max().item():.2f})")
+    assert d < 1.6e-2
+    from gyre_b200 import _native
+    old = _native.get_tunable("STREAMK")
+    _native.set_tunable("STREAMK", 0)
+    try:
+        a = vae.decode(z.cuda()).sample
+        b = vae.decode(z[3:4].cuda()).sample
+    finally:
+        _native.set_tunable("STREAMK", old)
+    assert torch.equal(b[0], a[3]), "image 3 differs between batch 1 and batch 8 with stream-K off"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Boundary surface (SURVEY 8b, "attributes the pipeline reads off the UNet object")
+class LoraHook:
+    """What gyre/pipeline/lora.py:99-112 stores on a hooked module (accelerate is not installed here)."""
+
+    def __init__(self, id, up_weight, down_weight, r=4, alpha=None, scale=1.0):
+        self.id, self._up_weight, self._down_weight, self._r = id, up_weight, down_weight, r
+        self._iscale = alpha / r if alpha else 1.0
+        self._scale = scale
+
+
+def test_unet_is_an_nn_module_and_folds_lora_hooks():
+    from oracle.unet import UNetConfig, synth_params, unet_forward, unet_param_shapes
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    unet = B200UNet(cfg).load_state_dict(P)
+    assert isinstance(unet, torch.nn.Module)
+    assert unet.config.in_channels == 4 and unet.config.sample_size == 16
+    assert unet.dtype == torch.float16 and unet.device.type == "cuda"
+    assert set(dict(unet.named_parameters())) == set(P)
+    assert sum(p.numel() for p in unet.parameters()) == sum(v.numel() for v in P.values())
+    unet.set_attention_slice("auto")
+    unet.set_use_memory_efficient_attention_xformers(True)
+    mods = dict(unet.named_modules())
+    g = torch.load(os.path.join(GOLD, "oracle_tiny.pt"))["unet_tiny"]
+    x, t, ctx = g["x"].cuda().half(), g["t"].cuda(), g["ctx"].cuda().half()
+    base = unet(x, t, encoder_hidden_states=ctx).sample.float().cpu()
+    # one LoRA on a self-attention projection, a cross-attention K projection and a 3x3 conv
+    gen = torch.Generator().manual_seed(4)
+    r = 4
+    targets = ["down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q",
+               "up_blocks.2.attentions.1.transformer_blocks.0.attn2.to_k", "mid_block.resnets.0.conv1"]
+    hooks = {}
+    for name in targets:
+        w = mods[name].weight
+        if w.ndim == 2:
+            up, down = torch.randn(w.shape[0], r, generator=gen) * 0.3, torch.randn(r, w.shape[1], generator=gen) * 0.3
+        else:
+            up = torch.randn(w.shape[0], r, 1, 1, generator=gen) * 0.1
+            down = torch.randn(r, w.shape[1], 3, 3, generator=gen) * 0.1
+        hooks[name] = LoraHook(0, up, down, r=r, alpha=2.0, scale=0.8)
+        mods[name]._hf_hook = hooks[name]
+
+    def folded_params(scale):
+        Q = dict(P)
+        for name, h in hooks.items():
+            w = P[name + ".weight"].float()
+            if w.ndim == 2:
+                d = h._up_weight @ h._down_weight
+            else:
+                d = torch.einsum("or,rikl->oikl", h._up_weight[:, :, 0, 0], h._down_weight)
+            Q[name + ".weight"] = w + d * h._iscale * scale
+        return Q
+
+    out = unet(x, t, encoder_hidden_states=ctx).sample.float().cpu()
+    ref = unet_forward(folded_params(0.8), cfg, g["x"], g["t"], g["ctx"])
+    err, moved = rel_err(out, ref), rel_err(ref, g["eps"])
+    print(f"LoRA folded into the native UNet: rel err vs oracle with the folded weights {err:.3e}; the LoRA moves the output "
+          f"by {moved:.3e}")
+    assert moved > 1e-2 and err < 5e-3
+    for h in hooks.values():                 # set_lora_scale (lora.py:183-187)
+        h._scale = -0.5
+    out2 = unet(x, t, encoder_hidden_states=ctx).sample.float().cpu()
+    assert rel_err(out2, unet_forward(folded_params(-0.5), cfg, g["x"], g["t"], g["ctx"])) < 5e-3
+    for name in targets:                     # remove_lora_from_model (lora.py:175-180)
+        del mods[name]._hf_hook
+    out3 = unet(x, t, encoder_hidden_states=ctx).sample.float().cpu()
+    assert torch.equal(out3, base), "removing the hooks must restore the packed weights exactly"
+
+    class ForwardPatch:
+        pass
+    mods[targets[0]]._hf_hook = ForwardPatch()
+    with pytest.raises(NotImplementedError):
+        unet(x, t, encoder_hidden_states=ctx)
+    del mods[targets[0]]._hf_hook
+
+
+def test_vae_module_surface_slicing_and_fp32_interface(tiny_vae):
+    from gyre_b200.vae import B200VAE
+    cfg, P, vae = tiny_vae
+    assert isinstance(vae, torch.nn.Module) and set(dict(vae.named_parameters())) == set(P)
+    assert vae.config.block_out_channels == tuple(cfg.block_out_channels) and vae.dtype == torch.float16
+    z = torch.randn(3, 4, 8, 8, generator=torch.Generator().manual_seed(1)).half().cuda()
+    full = vae.decode(z).sample
+    vae.enable_slicing()
+    vae.enable_tiling()
+    sliced = vae.decode(z).sample
+    vae.disable_slicing()
+    vae.disable_tiling()
+    assert torch.equal(full, sliced)
+    v32 = B200VAE(cfg, dtype=torch.float32).load_state_dict(P)
+    assert v32.dtype == torch.float32
+    img32 = v32.decode(z.float()).sample
+    assert img32.dtype == torch.float32 and torch.equal(img32, full.float())
+    mom = v32.encode(img32.clamp(-1, 1)).latent_dist.parameters
+    assert mom.dtype == torch.float32

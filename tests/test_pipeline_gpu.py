@@ -43,7 +43,7 @@ def test_pipeline_tiny_vs_golden(tiny, sampler, name, steps):
     err = (out.latents.cpu() - ref).abs().max().item()
     scale = ref.abs().max().item()
     print(f"pipeline tiny {sampler}: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
-    assert err < 2e-2 * scale
+    assert err < 1.4e-2 * scale      # measured <= 4.7e-3 of the latent scale over the 11 samplers
 
 
 def test_generic_sampler_kernels_match_vendored_loops():
@@ -112,7 +112,7 @@ def test_generic_sampler_kernels_match_vendored_loops():
         scale = rec["result"].abs().max().item()
         print(f"{enum_name}: max abs err {err:.3e} (scale {scale:.2f})")
         # eps passes through fp16 ([uncond ; cond] layout of the model output): 2^-11 relative per evaluation
-        assert err < 5e-3 * max(scale, 1.0), f"{enum_name}: {err}"
+        assert err < 3e-3 * max(scale, 1.0), f"{enum_name}: {err}"      # measured <= 9.7e-4
 
 
 def test_scheduler_step_kernel_matches_vendored_loop():
@@ -241,7 +241,7 @@ def test_c1_sd15_ddim10_final_latents_vs_golden():
     err = (out.latents.cpu() - ref).abs().max().item()
     print(f"C1 SD1.5 512x512 10-step DDIM: final-latent max abs err {err:.4e} (latent max {ref.abs().max().item():.3f}, "
           f"rel {err / ref.abs().max().item():.3e})")
-    assert err < 2e-2 * ref.abs().max().item()
+    assert err < 9e-3 * ref.abs().max().item()      # measured 2.9e-3
 
 
 def test_c2_sd15_euler_a_50_final_latents_vs_oracle():
@@ -283,7 +283,8 @@ def test_c2_sd15_euler_a_50_final_latents_vs_oracle():
     print(f"C2 SD1.5 512x512 50-step Euler-a (2 samples): final-latent max abs err {err:.4e}; torch-fp16 evaluation "
           f"of the oracle differs by {floor:.4e} (noise floor); latent max {scale:.3f}")
     assert torch.isfinite(out.latents).all()
-    assert err < max(4 * floor, 5e-2 * scale)
+    assert err < 6e-3 * scale        # measured 1.6e-3 of the latent scale (0.20 on |x| <= 125)
+    assert err < 2 * floor           # and below what PyTorch's own fp16 evaluation of the oracle moves (0.25)
 
 
 @pytest.mark.parametrize("kind", ["img2img", "runway_inpaint", "runway_inpaint_strength1", "legacy_inpaint"])
@@ -324,7 +325,7 @@ def test_image_modes_vs_oracle(kind):
     err = (out.latents.cpu() - ref).abs().max().item()
     scale = ref.abs().max().item()
     print(f"{kind}: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
-    assert err < 2e-2 * scale
+    assert err < 1.2e-2 * scale      # measured 3.7 - 4.1e-3 of the latent scale
 
 
 def test_c4_shape_vprediction_linear_proj_tome():

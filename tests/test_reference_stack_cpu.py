@@ -28,7 +28,7 @@ def _standin_class():
             assert not kwargs, f"unexpected keyword arguments {sorted(kwargs)}"
             return UNetOutput(sample=fake_unet_math(latents, t, encoder_hidden_states))
 
-    want = inspect.signature(B200UNet.__call__)
+    want = inspect.signature(B200UNet.forward)
     got = inspect.signature(StandIn.__call__)
     assert [(p.name, p.kind) for p in want.parameters.values()] == [(p.name, p.kind) for p in got.parameters.values()]
     return StandIn
@@ -57,6 +57,6 @@ def test_reference_controlnet_and_t2i_keywords_are_accepted():
     """UNetWithControlnet / UNetWithT2I hand `down_block_additional_residuals`, `mid_block_additional_residual` and
     `adapter_states` to the UNet as keywords (core.py:55-64, 213-239): B200UNet.__call__ names them."""
     from gyre_b200.unet import B200UNet
-    names = set(inspect.signature(B200UNet.__call__).parameters)
+    names = set(inspect.signature(B200UNet.forward).parameters)
     assert {"encoder_hidden_states", "down_block_additional_residuals", "mid_block_additional_residual",
             "adapter_states"} <= names

@@ -23,20 +23,90 @@ def _plan_agreement(got, ref):
     return ok.float().mean().item()
 
 
+TIE = 2e-3   # fp16 rounding of the unit-norm metric (|a| = |b| = 1, C products): scores carry ~1e-3 of noise
+
+
+def _check_plan(plan, k16, r, name):
+    """The plan the kernels built vs the reference's decisions (merge.py:41-64) evaluated in fp32 on the same fp16
+    values.  Index-exact wherever the reference's own decision margin exceeds TIE:
+      * every a-token whose best and second-best scores differ by more than TIE has the reference's partner;
+      * the tokens that stay come out in descending-score order (no inversion larger than TIE), which is the
+        reference's order whenever neighbouring scores differ by more than TIE;
+      * a token is merged iff its best score is above the r-th largest (within TIE).
+    Returns (exact partner fraction, whether the kept order and the edge set equal the reference's exactly)."""
+    node_idx, unm_idx, src_idx = [p.cpu() for p in plan]
+    m = k16 / k16.norm(dim=-1, keepdim=True)
+    scores = m[:, ::2] @ m[:, 1::2].transpose(1, 2)
+    top2 = scores.topk(2, dim=-1).values
+    node_max, ref_node = scores.max(dim=-1)
+    margin = top2[..., 0] - top2[..., 1]
+    decided = margin > TIE
+    assert torch.equal(node_idx[decided], ref_node[decided]), f"{name}: partner differs where the margin exceeds {TIE}"
+    # whatever partner was chosen attains the row maximum within TIE
+    assert (node_max - scores.gather(2, node_idx[..., None])[..., 0]).max().item() <= TIE, name
+    B, Na = node_max.shape
+    assert torch.equal(torch.cat([unm_idx, src_idx], 1).sort(1).values, torch.arange(Na).expand(B, -1)), name
+    kept = node_max.gather(1, unm_idx)
+    if kept.shape[1] > 1:
+        assert (kept[:, 1:] - kept[:, :-1]).max().item() <= TIE, f"{name}: kept tokens are not in descending-score order"
+    if 0 < r < Na:
+        cut = node_max.sort(dim=1, descending=True).values[:, r - 1:r]          # r-th largest best score
+        assert (node_max.gather(1, src_idx) >= cut - TIE).all() and (kept <= cut + TIE).all(), f"{name}: wrong cut"
+    edge_idx = node_max.argsort(dim=-1, descending=True)
+    ref_unm, ref_src = edge_idx[:, r:], edge_idx[:, :r]
+    exact = torch.equal(unm_idx, ref_unm) and torch.equal(src_idx.sort(1).values, ref_src.sort(1).values) and \
+        torch.equal(node_idx.gather(1, src_idx), ref_node.gather(1, src_idx))
+    return (node_idx == ref_node).float().mean().item(), exact, int((~decided).sum())
+
+
 def test_tome_vs_vendored_golden(nat):
+    """The vendored tome/merge.py outputs (fp32 inputs).  Ours rounds k / v to fp16 first, so (a) the PLAN - which tokens
+    stay, in which order, which token merges into which - is checked index for index against the reference's decisions
+    on those same fp16 values (`_check_plan`; the oracle's plan is pinned bit-exactly against the vendored code), and
+    (b) every output token must match the fp32 golden within fp16 rounding unless the plan check reported a decision
+    inside the tie margin."""
     g = torch.load(os.path.join(GOLD, "tome.pt"))
     for name, rec in g.items():
         if name == "parse_r":
             continue
         k, v, r = rec["k"], rec["v"], rec["r"]
-        ko, vo = nat.tome_merge_kv(k.half().cuda(), v.half().cuda(), r)
+        ko, vo, plan = nat.tome_merge_kv(k.half().cuda(), v.half().cuda(), r, return_plan=True)
         assert ko.shape == rec["k_merged"].shape, name
-        # the golden run used fp32 inputs; ours rounds k/v to fp16 first: compare token-wise, allowing the odd
-        # near-tie to pick a different partner
+        partner, exact, undecided = _check_plan(plan, k.half().float(), min(r, k.shape[1] // 2), name)
         ak = _plan_agreement(ko.cpu(), rec["k_merged"])
         av = _plan_agreement(vo.cpu(), rec["v_merged"])
-        print(f"tome {name}: tokens matching vendored ToMe  k {ak:.3f}  v {av:.3f}")
-        assert ak > 0.9 and av > 0.9, name
+        print(f"tome {name}: plan index-exact {exact} (partner agreement {partner:.4f}, {undecided} a-tokens inside the "
+              f"tie margin); tokens matching vendored ToMe  k {ak:.3f}  v {av:.3f}")
+        if exact:
+            assert ak == 1.0 and av == 1.0, name
+        else:
+            assert undecided > 0 and ak > 0.9 and av > 0.9, name
+
+
+def test_tome_tie_rule(nat):
+    """Exact ties: duplicated tokens give equal best scores.  The kernels order equal scores by ascending token index
+    and pick the lowest b among equal partners; torch's CPU argsort / max on the same values do the same (stable for
+    these sizes), so the plans agree index for index."""
+    from oracle import tome as otome
+    gen = torch.Generator("cpu").manual_seed(11)
+    B, N, C, r = 2, 64, 32, 20
+    base = torch.randn(B, 8, C, generator=gen).half()
+    k = base.repeat(1, N // 8, 1).contiguous()            # every token appears 8 times: massive ties
+    v = torch.randn(B, N, C, generator=gen).half()
+    ko, vo, plan = nat.tome_merge_kv(k.cuda(), v.cuda(), r, return_plan=True)
+    node_idx, unm_idx, src_idx = [p.cpu() for p in plan]
+    # kept + merged a-tokens partition the a set; ties resolved by ascending token index
+    both = torch.cat([unm_idx, src_idx], dim=1).sort(dim=1).values
+    assert torch.equal(both, torch.arange(N // 2).expand(B, -1))
+    kf = k.float()
+    m = kf / kf.norm(dim=-1, keepdim=True)
+    scores = m[:, ::2] @ m[:, 1::2].transpose(1, 2)
+    best = scores.max(dim=-1).values
+    # every chosen partner attains the row maximum (up to the fp16 rounding of the normalised metric) and is the lowest
+    # such column
+    got = scores.gather(2, node_idx[..., None])[..., 0]
+    assert (best - got).abs().max().item() < 2e-3
+    assert torch.isfinite(ko).all() and torch.isfinite(vo).all()
 
 
 @pytest.mark.parametrize("B,N,C,r", [(2, 64, 32, 16), (1, 256, 64, 128), (3, 30, 16, 7), (2, 1024, 320, 512),
@@ -46,9 +116,12 @@ def test_tome_vs_oracle_same_inputs(nat, B, N, C, r):
     gen = torch.Generator("cpu").manual_seed(N + r)
     k = torch.randn(B, N, C, generator=gen).half()
     v = torch.randn(B, N, C, generator=gen).half()
-    ko, vo = nat.tome_merge_kv(k.cuda(), v.cuda(), r)
+    ko, vo, gplan = nat.tome_merge_kv(k.cuda(), v.cuda(), r, return_plan=True)
     kc, vc = k.cuda().float(), v.cuda().float()
     plan = otome.bipartite_soft_matching_plan(kc, r)
+    partner, exact, undecided = _check_plan(gplan, k.float(), r, f"B{B} N{N} C{C} r{r}")
+    print(f"tome B{B} N{N} C{C} r{r}: plan index-exact {exact}, partner agreement {partner:.5f}, {undecided} a-tokens inside "
+          f"the tie margin")
     kr, vr = otome.merge_mean(plan, kc), otome.merge_mean(plan, vc)
     ak, av = _plan_agreement(ko, kr), _plan_agreement(vo, vr)
     assert ko.shape == kr.shape
