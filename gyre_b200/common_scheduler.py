@@ -385,7 +385,8 @@ class KDiffusionScheduler(CommonScheduler):
             ent["add"].copy_(guided.add_cond)
         if ent["graph"] is None:
             out = body()                                   # eager: run 1 with this key (also the warm-up for capture)
-            result = out.to(out_dtype or self.dtype)
+            # copy=True: the result must not alias the cache entry's buffers, the next replay overwrites them
+            result = out.to(out_dtype or self.dtype, copy=True)
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -394,7 +395,7 @@ class KDiffusionScheduler(CommonScheduler):
             # replaying would redo run 1 from the same inputs; keep the eager result
         else:
             ent["graph"].replay()
-            result = ent["out"].to(out_dtype or self.dtype)
+            result = ent["out"].to(out_dtype or self.dtype, copy=True)
         for _ in progress_wrapper(range(n)):               # cancellation point: after the loop
             pass
         return result

@@ -1,0 +1,284 @@
+"""TEST INFRASTRUCTURE ONLY (oracle): CPU restatement of the reference's hires-fix and graft scheduler-UNet wrappers.
+
+Follows gyre/pipeline/unet/hires_fix.py:22-235 (`pad_like`, `scale_into`, `down_scale_factor`, `up_scale_factor`,
+`scale_strategy`, `HiresUnetWrapper`), gyre/pipeline/unet/graft.py:16-56 (`GraftUnets`), gyre/pipeline/easing.py:22-49
+(`Easing`) and the vendored ResizeRight (gyre/src/ResizeRight/resize_right.py:30-127, 203-252 - separable resampling
+with a 4-tap lanczos2 window, interp_methods.py:47-51) for the one call shape gyre uses: a scalar scale factor on the
+last two dims, `antialiasing=False`, `pad_mode="replicate"`, `by_convs=False`.
+
+The easing curves themselves live in a third-party dependency that is absent here - `easing-functions ~= 1.0.4`
+(pyproject.toml:24): `EasingBase.ease(alpha)` = end * f(t) + start * (1 - f(t)), t = alpha / duration, with the
+published Penner in-out curves restated below.  Everything else is PINNED: scripts/make_golden.py runs the reference's
+own hires_fix.py / graft.py / easing.py / resize_right.py (with these curves standing in for the absent package) and
+asserts this restatement reproduces them bit for bit (tests/golden/hires.pt).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may import this module.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+Hi, Wi = -2, -1
+
+
+# --------------------------------------------------------------------------------------------- easing-functions 1.0.4
+class EasingBase:
+    limit = (0, 1)
+
+    def __init__(self, start=0, end=1, duration=1):
+        self.start, self.end, self.duration = start, end, duration
+
+    def func(self, t):
+        raise NotImplementedError
+
+    def ease(self, alpha):
+        t = self.limit[0] * (1 - alpha) + self.limit[1] * alpha
+        t /= self.duration
+        a = self.func(t)
+        return self.end * a + self.start * (1 - a)
+
+    def __call__(self, alpha):
+        return self.ease(alpha)
+
+
+class LinearInOut(EasingBase):
+    def func(self, t):
+        return t
+
+
+class QuadEaseInOut(EasingBase):
+    def func(self, t):
+        if t < 0.5:
+            return 2 * t * t
+        return (-2 * t * t) + (4 * t) - 1
+
+
+class CubicEaseInOut(EasingBase):
+    def func(self, t):
+        if t < 0.5:
+            return 4 * t * t * t
+        p = 2 * t - 2
+        return 0.5 * p * p * p + 1
+
+
+class QuarticEaseInOut(EasingBase):
+    def func(self, t):
+        if t < 0.5:
+            return 8 * t * t * t * t
+        p = t - 1
+        return -8 * p * p * p * p + 1
+
+
+class QuinticEaseInOut(EasingBase):
+    def func(self, t):
+        if t < 0.5:
+            return 16 * t * t * t * t * t
+        p = (2 * t) - 2
+        return 0.5 * p * p * p * p * p + 1
+
+
+class SineEaseInOut(EasingBase):
+    def func(self, t):
+        return 0.5 * (1 - math.cos(t * math.pi))
+
+
+class CircularEaseInOut(EasingBase):
+    def func(self, t):
+        if t < 0.5:
+            return 0.5 * (1 - math.sqrt(1 - 4 * (t * t)))
+        return 0.5 * (math.sqrt(-((2 * t) - 3) * ((2 * t) - 1)) + 1)
+
+
+class ExponentialEaseInOut(EasingBase):
+    def func(self, t):
+        if t == 0 or t == 1:
+            return t
+        if t < 0.5:
+            return 0.5 * math.pow(2, (20 * t) - 10)
+        return -0.5 * math.pow(2, (-20 * t) + 10) + 1
+
+
+EASINGS = {"linear": LinearInOut, "quad": QuadEaseInOut, "cubic": CubicEaseInOut, "quartic": QuarticEaseInOut,
+           "quintic": QuinticEaseInOut, "sine": SineEaseInOut, "circular": CircularEaseInOut, "expo": ExponentialEaseInOut}
+
+
+class Easing:
+    """gyre/pipeline/easing.py:22-49."""
+
+    def __init__(self, floor, start, end, easing):
+        self.floor, self.start, self.end = floor, start, end
+        if isinstance(easing, str):
+            easing = EASINGS[easing]
+        self.easing = easing(end=1 - floor, duration=(end - start))
+
+    def interp(self, u):
+        if u < self.start:
+            return self.floor
+        if u > self.end:
+            return 1
+        return self.floor + self.easing(u - self.start)
+
+
+# --------------------------------------------------------------------------------------------- ResizeRight, lanczos2
+def lanczos2(x):
+    """interp_methods.py:47-51 (fp32 in, fp32 out)."""
+    eps = torch.finfo(torch.float32).eps
+    return ((torch.sin(math.pi * x) * torch.sin(math.pi * x / 2) + eps) / ((math.pi ** 2 * x ** 2 / 2) + eps)) * (abs(x) < 2).to(x.dtype)
+
+
+def resample_taps(in_sz: int, scale: float):
+    """The 1-D plan of resize_right.py:70-118 for one dim: out_sz = ceil(scale * in_sz); per output position the 4
+    source indices (replicate padding == clamped indices) and normalised lanczos2 weights (fp32)."""
+    eps = torch.finfo(torch.float32).eps
+    out_sz = math.ceil(scale * in_sz)
+    out_coords = torch.arange(out_sz)
+    grid = out_coords / float(scale) + (in_sz - 1) / 2 - (out_sz - 1) / (2 * float(scale))      # get_projected_grid :128-141
+    left = (grid - 4 / 2 - eps).ceil().long()                                                     # get_field_of_view :144-154
+    fov = left[:, None] + torch.arange(math.ceil(4 - eps))
+    # calc_pad_sz :157-172: the (generalised, possibly negative) left pad shifts BOTH the field of view and the fp32
+    # grid before the weights are formed - the shift is part of the weights' rounding
+    pad0 = -fov[0, 0].item()
+    w = lanczos2((grid + pad0)[:, None] - (fov + pad0))                                           # get_weights :203-213
+    s = w.sum(1, keepdim=True)
+    s[s == 0] = 1
+    w = w / s
+    return fov.clamp(0, in_sz - 1), w, out_sz
+
+
+def resize_lanczos2(x, scale: float):
+    """resize_right.resize(x, scale_factors=scale, interp_method=lanczos2, pad_mode="replicate", antialiasing=False)
+    followed by gyre's cast back to the input dtype (gyre/resize_right.py:41-42).  Dims are processed in ascending
+    scale order (:55-59) - equal scales keep H before W - and a scale of exactly 1 is skipped."""
+    if float(scale) == 1.0:
+        return x
+    out = x
+    for dim in (-2, -1):
+        idx, w, _ = resample_taps(out.shape[dim], scale)
+        t = out.transpose(dim, 0)                       # apply_weights :216-250
+        nb = t[idx]                                     # [out, 4, ...]
+        ww = w.reshape(*w.shape, *([1] * (t.ndim - 1)))
+        out = (nb * ww).sum(1).transpose(0, dim)
+    return out.to(x.dtype)
+
+
+def scale_into(latents, scale, target=None, target_shape=None):
+    """hires_fix.py:45-92 (mode "lanczos")."""
+    latents = resize_lanczos2(latents, scale)
+    if (target is None) == (target_shape is None):
+        raise ValueError("exactly one of target or target_shape")
+    if target_shape is None:
+        target_shape = target.shape
+    offh = (target_shape[Hi] - latents.shape[Hi]) // 2
+    offw = (target_shape[Wi] - latents.shape[Wi]) // 2
+    if offh < 0:
+        latents = latents[:, :, -offh:-offh + target_shape[Hi], :]
+        offh = 0
+    if offw < 0:
+        latents = latents[:, :, :, -offw:-offw + target_shape[Wi]]
+        offw = 0
+    if target is not None:
+        target[:, :, offh:offh + latents.shape[Hi], offw:offw + latents.shape[Wi]] = latents
+        return target
+    pad_w = [offw, (target_shape[Wi] - latents.shape[Wi]) - offw]
+    pad_h = [offh, (target_shape[Hi] - latents.shape[Hi]) - offh]
+    return torch.nn.functional.pad(latents, pad_w + pad_h, mode="replicate")
+
+
+def down_scale_factor(latents_shape, target_shape, oos_fraction):
+    """hires_fix.py:95-99."""
+    scales = target_shape[Hi] / latents_shape[Hi], target_shape[Wi] / latents_shape[Wi]
+    scale_min, scale_max = min(*scales), max(*scales)
+    return scale_min * oos_fraction + scale_max * (1 - oos_fraction)
+
+
+def up_scale_factor(latents_shape, target_shape, oos_fraction):
+    return 1 / down_scale_factor(target_shape, latents_shape, oos_fraction)
+
+
+def batched_rand(shape, generators, device, dtype):
+    """gyre/pipeline/randtools.py:11-36."""
+    if shape[0] % len(generators) != 0:
+        raise ValueError("shape[0] needs to be a multiple of len(generators)")
+    return torch.cat([torch.rand((1, *shape[1:]), generator=g, device=g.device, dtype=dtype)
+                      for g in list(generators) * (shape[0] // len(generators))], dim=0).to(device)
+
+
+class HiresUnetWrapper:
+    """hires_fix.py:123-235: `latents` holds [lo (natural size, zero-padded into the full frame) ; hi]."""
+
+    def __init__(self, unet_natural, unet_hires, generators, natural_size, oos_fraction, latent_debugger=None):
+        self.unet_natural, self.unet_hires = unet_natural, unet_hires
+        self.generators, self.natural_size, self.oos_fraction = generators, natural_size, oos_fraction
+        self.easing = Easing(floor=0, start=0, end=0.667, easing="cubic")
+
+    def __call__(self, latents, step, u):
+        p = self.easing.interp(u)
+        lo_in, hi_in = latents.chunk(2)
+        if isinstance(step, torch.Tensor) and step.shape:
+            lo_t, hi_t = step.chunk(2)
+        else:
+            lo_t = hi_t = step
+        hi = self.unet_hires(hi_in, hi_t, u=u)
+        if p >= 0.999:
+            return torch.concat([lo_in, hi])
+        *_, h, w = latents.shape
+        th, tw = self.natural_size
+        offseth, offsetw = (h - th) // 2, (w - tw) // 2
+        lo_in = lo_in[:, :, offseth:offseth + th, offsetw:offsetw + tw]
+        lo = self.unet_natural(lo_in, lo_t, u=u)
+        hi_down = scale_into(hi, down_scale_factor(hi.shape, lo.shape, self.oos_fraction), target_shape=lo.shape)   # "pad"
+        randmap = batched_rand(lo.shape, self.generators, lo.device, lo.dtype)
+        lo_merged = torch.where(randmap >= p, lo, hi_down)
+        lo_up = scale_into(lo, up_scale_factor(lo.shape, hi.shape, self.oos_fraction), target=hi.clone())           # "clone"
+        randmap = batched_rand(hi.shape, self.generators, hi.device, hi.dtype)
+        hi_merged = torch.where(randmap >= p, lo_up, hi)
+        lo_expanded = torch.zeros_like(hi_merged)
+        lo_expanded[:, :, offseth:offseth + th, offsetw:offsetw + tw] = lo_merged
+        return torch.concat([lo_expanded, hi_merged])
+
+    @classmethod
+    def image_to_natural(cls, natural_size, image, oos_fraction):
+        target_shape = [natural_size, natural_size]
+        return scale_into(image, down_scale_factor(image.shape, target_shape, oos_fraction), target_shape=target_shape)
+
+    @classmethod
+    def merge_initial_latents(cls, left, right):
+        left_resized = torch.zeros_like(right)
+        *_, th, tw = left.shape
+        *_, h, w = right.shape
+        offseth, offsetw = (h - th) // 2, (w - tw) // 2
+        left_resized[:, :, offseth:offseth + th, offsetw:offsetw + tw] = left
+        return torch.concat([left_resized, right])
+
+    @classmethod
+    def split_result(cls, left, right):
+        return right.chunk(2)[1]
+
+
+class GraftUnets:
+    """graft.py:16-56."""
+
+    def __init__(self, unet_root, unet_top, generators, blend={}):
+        self.unet_root, self.unet_top, self.generators = unet_root, unet_top, generators
+        self.easing = Easing(**{"floor": 0, "start": 0.1, "end": 0.3, "easing": "sine", **blend})
+
+    def __call__(self, latents, step, u):
+        p = self.easing.interp(u)
+        if p <= 0:
+            return self.unet_root(latents, step, u=u)
+        if p >= 1:
+            return self.unet_top(latents, step, u=u)
+        root = self.unet_root(latents, step, u=u)
+        top = self.unet_top(latents, step, u=u)
+        randmap = batched_rand(top.shape, self.generators, top.device, top.dtype)
+        return torch.where(randmap >= p, root, top)
+
+    @classmethod
+    def merge_initial_latents(cls, left, right):
+        return left
+
+    @classmethod
+    def split_result(cls, left, right):
+        return right

@@ -235,6 +235,9 @@ def resnet_block(P, p, x, temb, groups, eps):
     return x + h
 
 
+ATTENTION_IMPL = "explicit"
+
+
 def attention(P, p, x, ctx, heads, tome_r=0, upcast=False):
     """to_q/k/v -> [B*h,N,d] -> softmax(QK^T d^-1/2) V -> to_out
     (gyre/pipeline/models/memory_efficient_cross_attention.py:32-60).  With tome_r>0 this is
@@ -256,8 +259,11 @@ def attention(P, p, x, ctx, heads, tome_r=0, upcast=False):
         return t.reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3)
 
     q, k, v = split(q), split(k), split(v)
-    s = (q @ k.transpose(-1, -2)) * (d ** -0.5)
-    o = torch.softmax(s, dim=-1) @ v
+    if ATTENTION_IMPL == "sdpa":      # bench.py --impl torchlib only: PyTorch's fused attention (same maths, library kernel)
+        o = F.scaled_dot_product_attention(q, k, v)
+    else:
+        s = (q @ k.transpose(-1, -2)) * (d ** -0.5)
+        o = torch.softmax(s, dim=-1) @ v
     o = o.permute(0, 2, 1, 3).reshape(B, N, C)
     return F.linear(o, P[f"{p}.to_out.0.weight"], P[f"{p}.to_out.0.bias"])
 

@@ -116,3 +116,35 @@ def gyre_pipeline_pure():
     cfg = _load("gyre.pipeline.unet", base, "cfg")
     core = _load("gyre.pipeline.unet", base, "core")
     return rt, ty, cfg, core
+
+
+def gyre_hires():
+    """gyre/pipeline/unet/hires_fix.py, unet/graft.py and easing.py with the REAL vendored ResizeRight
+    (gyre/src/ResizeRight, through gyre/resize_right.py).  The absent third-party `easing_functions` package
+    (easing-functions ~= 1.0.4) is stood in for by the oracle's restated curves (oracle/hires.py), so `Easing.interp`
+    itself is the reference's.  Returns (hires_fix, graft, easing)."""
+    from oracle import hires as ohires
+    gyre_pipeline_pure()
+    if "easing_functions" not in sys.modules:
+        ef = types.ModuleType("easing_functions")
+        efe = types.ModuleType("easing_functions.easing")
+        for n in ("EasingBase", "LinearInOut", "QuadEaseInOut", "CubicEaseInOut", "QuarticEaseInOut", "QuinticEaseInOut",
+                  "SineEaseInOut", "CircularEaseInOut", "ExponentialEaseInOut"):
+            setattr(efe, n, getattr(ohires, n))
+        ef.easing = efe
+        sys.modules["easing_functions"], sys.modules["easing_functions.easing"] = ef, efe
+    for name, rel in (("gyre.src", "gyre/src"), ("gyre.src.ResizeRight", "gyre/src/ResizeRight")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF, rel)]
+            sys.modules[name] = m
+    rr_base = os.path.join(REF, "gyre/src/ResizeRight")
+    im = _load("gyre.src.ResizeRight", rr_base, "interp_methods")
+    sys.modules["interp_methods"] = im
+    _load("gyre.src.ResizeRight", rr_base, "resize_right")
+    _load("gyre", os.path.join(REF, "gyre"), "resize_right")
+    easing = _load("gyre.pipeline", os.path.join(REF, "gyre/pipeline"), "easing")
+    base = os.path.join(REF, "gyre/pipeline/unet")
+    hf = _load("gyre.pipeline.unet", base, "hires_fix")
+    gr = _load("gyre.pipeline.unet", base, "graft")
+    return hf, gr, easing

@@ -380,6 +380,109 @@ def pin_wrappers():
           "CFGUNet_Parallel / Sequential + UNetWithEmbeddings + UnetWithExtraChannels bit-exact for the oracle)")
 
 
+def toy_kunet(kind):
+    """A deterministic stand-in for a `KDiffusionSchedulerUNet(latents, sigma, u) -> x0` leaf (types.py:63-67): depends on
+    the pixel neighbourhood, on sigma and on u, and differs between the natural / hires (root / top) leaves."""
+    a, b = (0.8, 0.05) if kind == "a" else (0.6, -0.08)
+
+    def f(latents, sigma, u):
+        s = torch.as_tensor(sigma).float().reshape(-1)
+        s = s[:, None, None, None] if s.numel() > 1 else s
+        x = latents.float()
+        return (a * torch.tanh(x) + b * x.roll(1, -1) / (1 + s) + 0.1 * u * x.roll(1, -2)).to(latents.dtype)
+    return f
+
+
+def pin_hires():
+    """PINS the hires-fix and graft wrappers (gyre/pipeline/unet/hires_fix.py, unet/graft.py, easing.py and the vendored
+    ResizeRight) against the oracle restatement: lanczos2 resizes, scale_into placement, Easing, and whole wrapper
+    calls over toy leaves with per-sample generators."""
+    hf, gr, ea = _vendored.gyre_hires()
+    from gyre import resize_right as rr
+    from oracle import hires as oh
+    out = {}
+    g = torch.Generator("cpu").manual_seed(31)
+    # ---- Easing.interp for both wrappers' curves (and the other published curves)
+    for name in ("linear", "quad", "cubic", "quartic", "quintic", "sine", "circular", "expo"):
+        for floor, start, end in ((0, 0, 0.667), (0, 0.1, 0.3), (0.2, 0.05, 0.9)):
+            us = [i / 40 for i in range(41)]
+            ref = [ea.Easing(floor=floor, start=start, end=end, easing=name).interp(u) for u in us]
+            mine = [oh.Easing(floor=floor, start=start, end=end, easing=name).interp(u) for u in us]
+            assert ref == mine, f"Easing {name}"
+            out[f"easing/{name}/{floor}_{start}_{end}"] = {"u": us, "p": ref}
+    # ---- resize + scale_into
+    for dt_name, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        for shape, scale in (((2, 4, 24, 24), 16 / 24), ((2, 4, 16, 16), 1.5), ((1, 4, 24, 16), 0.8), ((1, 4, 16, 16), 1.3),
+                             ((1, 3, 48, 40), 0.7333), ((1, 4, 12, 16), 1.0)):
+            x = torch.randn(shape, generator=g).to(dt)
+            ref = rr.resize(x, scale_factors=scale, interp_method=rr.interp_methods.lanczos2, pad_mode="replicate",
+                            antialiasing=False)
+            assert torch.equal(ref, oh.resize_lanczos2(x, scale)), f"resize {shape} {scale}"
+            out[f"resize/{dt_name}/{'x'.join(map(str, shape))}/{scale:.4f}"] = {"x": x, "scale": scale, "out": ref}
+            for tshape in ((shape[0], shape[1], 16, 16), (shape[0], shape[1], 20, 12), (shape[0], shape[1], 40, 44)):
+                if dt is torch.float16 and tshape[2] != 20:
+                    continue            # keeps the fixture small: fp16 adds no placement logic
+                ref_p = hf.scale_into(x, scale, target_shape=torch.Size(tshape))
+                assert torch.equal(ref_p, oh.scale_into(x, scale, target_shape=tshape)), f"scale_into pad {shape} {tshape}"
+                bg = torch.randn(tshape, generator=g).to(dt)
+                ref_c = hf.scale_into(x, scale, target=bg.clone())
+                assert torch.equal(ref_c, oh.scale_into(x, scale, target=bg.clone())), f"scale_into clone {shape} {tshape}"
+                out[f"scale_into/{dt_name}/{'x'.join(map(str, shape))}/{scale:.4f}/{tshape[2]}x{tshape[3]}"] = {
+                    "x": x, "scale": scale, "bg": bg, "pad": ref_p, "clone": ref_c}
+    # ---- HiresUnetWrapper over toy leaves
+    seeds = [420420420, 420420421]
+    for dt_name, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        for (h, w), nat, oos in (((24, 24), 16, 0.6), ((24, 16), 16, 0.6), ((16, 24), 16, 1.0), ((32, 24), 16, 0.3)):
+            B = 2
+            lat = torch.randn(2 * B, 4, h, w, generator=g).to(dt)
+            sig = torch.tensor(3.7)
+            gens_r = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+            gens_o = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+
+            class _Dbg:
+                def log(self, *a, **k):
+                    pass
+            ref_w = hf.HiresUnetWrapper(toy_kunet("a"), toy_kunet("b"), gens_r, [nat, nat], oos, _Dbg())
+            my_w = oh.HiresUnetWrapper(toy_kunet("a"), toy_kunet("b"), gens_o, [nat, nat], oos)
+            calls = []
+            for u in (0.0, 0.2, 0.45, 0.66, 0.8):        # consecutive calls: the generators advance between them
+                ref = ref_w(lat, sig, u)
+                mine = my_w(lat, sig, u)
+                assert torch.equal(ref, mine), f"HiresUnetWrapper {dt_name} {h}x{w} u={u}"
+                calls.append({"u": u, "out": ref})
+            left = torch.randn(B, 4, nat, nat, generator=g).to(dt)
+            right = torch.randn(B, 4, h, w, generator=g).to(dt)
+            merged = hf.HiresUnetWrapper.merge_initial_latents(left, right)
+            assert torch.equal(merged, oh.HiresUnetWrapper.merge_initial_latents(left, right))
+            assert torch.equal(hf.HiresUnetWrapper.split_result(None, merged), oh.HiresUnetWrapper.split_result(None, merged))
+            out[f"hires/{dt_name}/{h}x{w}/nat{nat}/oos{oos}"] = {"latents": lat, "sigma": sig, "seeds": seeds, "natural": nat,
+                                                              "oos": oos, "calls": calls, "left": left, "right": right,
+                                                              "merged": merged}
+        # image_to_natural (pixels)
+        img = torch.rand(1, 3, 96, 72, generator=g).to(dt)
+        for oos in (0.6, 1.0):
+            ref = hf.HiresUnetWrapper.image_to_natural(64, img, oos)
+            assert torch.equal(ref, oh.HiresUnetWrapper.image_to_natural(64, img, oos))
+            out[f"image_to_natural/{dt_name}/oos{oos}"] = {"image": img, "out": ref}
+        # ---- GraftUnets
+        lat = torch.randn(2, 4, 16, 16, generator=g).to(dt)
+        for blend in ({}, {"start": 0.0, "end": 0.8, "easing": "linear"}):
+            gens_r = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+            gens_o = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+            ref_w = gr.GraftUnets(toy_kunet("a"), toy_kunet("b"), gens_r, blend=blend)
+            my_w = oh.GraftUnets(toy_kunet("a"), toy_kunet("b"), gens_o, blend=blend)
+            calls = []
+            for u in (0.0, 0.05, 0.15, 0.2, 0.28, 0.5, 0.9):
+                ref = ref_w(lat, torch.tensor(2.5), u)
+                assert torch.equal(ref, my_w(lat, torch.tensor(2.5), u)), f"GraftUnets {dt_name} u={u}"
+                calls.append({"u": u, "out": ref})
+            out[f"graft/{dt_name}/{'default' if not blend else 'linear'}"] = {"latents": lat, "sigma": torch.tensor(2.5),
+                                                                              "seeds": seeds, "blend": blend, "calls": calls}
+    torch.save(out, os.path.join(GOLD, "hires.pt"))
+    print(f"hires: {len(out)} reference vectors pinned (Easing, lanczos2 resize, scale_into, HiresUnetWrapper, GraftUnets: "
+          "oracle bit-exact against gyre/pipeline/unet/hires_fix.py, graft.py, easing.py and the vendored ResizeRight)")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -429,12 +532,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
-    pin_samplers()
-    pin_ddim()
-    pin_tome()
-    pin_clip()
-    pin_wrappers()
-    oracle_fixtures(a.full)
+    parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
+             "hires": pin_hires, "oracle": lambda: oracle_fixtures(a.full)}
+    for name, fn in parts.items():
+        if not a.only or name in a.only.split(","):
+            fn()

@@ -380,3 +380,45 @@ def test_full_size_run_to_run_determinism():
                          sampler="k_euler_ancestral", output_type="latent", return_fp32_latents=True).latents)
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("sampler", ["k_euler_ancestral", "k_euler"])
+def test_whole_loop_cuda_graph_is_bitwise_the_eager_loop(tiny, sampler):
+    """`pipe.use_cuda_graph`: the first run with a new (shape, schedule) key executes eagerly and captures, later runs
+    replay - with other seeds, other text embeddings and another guidance-independent input, bit for bit what the eager
+    loop gives; a different step count gets its own graph."""
+    cfg, P, pipe, emb, unc = tiny
+
+    def run(seed0, e, u, steps, graph):
+        pipe.use_cuda_graph = graph
+        try:
+            gens = [torch.Generator("cpu").manual_seed(seed0 + i) for i in range(2)]
+            return pipe(e.cuda(), u.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
+                        generator=gens, sampler=sampler, output_type="latent", return_fp32_latents=True).latents
+        finally:
+            pipe.use_cuda_graph = False
+
+    emb2 = torch.randn(2, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(21))
+    eager = [run(100, emb, unc, 9, False), run(200, emb2, unc, 9, False), run(300, emb, unc, 6, False)]
+    graphed = [run(100, emb, unc, 9, True),       # eager + capture
+               run(200, emb2, unc, 9, True),      # replay with new seeds and a new context
+               run(300, emb, unc, 6, True)]       # new key: its own graph
+    again = run(100, emb, unc, 9, True)           # replay of the first key after another key was used
+    names = ["first run (eager body + capture)", "replay with new seeds / context", "second key"]
+    for nm, a_, b_ in zip(names, eager, graphed):
+        d = (a_ - b_).abs().max().item()
+        assert torch.equal(a_, b_), f"{nm}: max abs diff {d}"
+    assert torch.equal(again, eager[0]), "replay of the first key"
+
+    assert len(pipe.unet._loop_graphs) >= 2
+    # a per-step callback needs the host between steps: the loop falls back to eager launches
+    seen = []
+    pipe.use_cuda_graph = True
+    try:
+        gens = [torch.Generator("cpu").manual_seed(100 + i) for i in range(2)]
+        out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=9, guidance_scale=7.5, generator=gens,
+                   sampler=sampler, output_type="latent", return_fp32_latents=True,
+                   callback=lambda i, t, x: seen.append(i)).latents
+    finally:
+        pipe.use_cuda_graph = False
+    assert seen == list(range(9)) and torch.equal(out, eager[0])
