@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--batch", type=int, default=None, help="weak: images per GPU per step; strong: global batch")
     ap.add_argument("--cuda-graph", action="store_true")
+    ap.add_argument("--hires-fix", action="store_true",
+                    help="c3 as the reference runs it by default: natural-size twin + cross-blend while u < 0.667")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     a = ap.parse_args()
@@ -264,7 +266,7 @@ def main():
     config = {"workload": cfgd["workload"] + f", batch {B} per GPU", "config": a.config,
               "per_gpu_batch": B, "global_batch": global_batch, "steps_per_image": STEPS_PER_IMAGE,
               "parallelism": f"dp{world} (independent images sharded across GPUs; weights broadcast once; images gathered)",
-              "cuda_graph": bool(a.cuda_graph),
+              "cuda_graph": bool(a.cuda_graph), "hires_fix": bool(a.hires_fix),
               "l2": "no flush: per-step working set (GBs of weights + activations) exceeds the 126 MB L2"}
 
     if a.impl == "reference":
@@ -356,6 +358,7 @@ def main():
                                             "time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B).pin_memory()}}
         extra_dev = {"added_cond_kwargs": {k: v.to(dev) for k, v in extra_host["added_cond_kwargs"].items()}}
     fixed = {"strength": 1.0} if cfgd.get("inpaint") else {}
+    fixed["hires_fix"] = bool(a.hires_fix)      # BASELINE configs state hires_fix=False; only c3 is above native size
     h2d_extra = sum(v.numel() * v.element_size() for v in
                     (extra_host.get("added_cond_kwargs", {}).values() if cfgd.get("sdxl") else extra_host.values()))
 

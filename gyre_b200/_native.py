@@ -104,6 +104,9 @@ SIGNATURES = {
     "gyre_b200_sched_step_blend": (_i, [C.POINTER(Step), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _f, _vp]),
     "gyre_b200_cat_channels": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _vp, _vp]),
     "gyre_b200_scale_latents": (_i, [_vp, _f, _i, _i, _i64, _vp, _vp]),
+    "gyre_b200_resample_select": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i,
+                                       _vp, _i, _i, _i, _i, _vp]),
+    "gyre_b200_rand_select": (_i, [_vp, _vp, _vp, _f, _i64, _vp, _vp]),
     "gyre_b200_tome_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_tome_plan_offsets": (_i, [_i, _i, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "gyre_b200_tome_merge_kv": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -30,6 +30,9 @@ class B200GuidedUNet:
         # CFG order is [uncond, cond] (unified_pipeline.py:2335, cfg.py:54)
         self.embeddings = torch.cat([uncond_embeddings, text_embeddings]).to(device=unet.device,
                                                                               dtype=torch.float16).contiguous()
+        # who "owns" the K/V projections cached in the UNet: leaves of one request that share the embeddings (hires-fix:
+        # natural + full size) point this at the same object so that alternating between them does not re-project
+        self.ctx_owner = self
         self.extra = None           # [B, Ce, h, w] fp16: mask + masked-image latents of the inpaint UNets
         self._xcat = None
         self.add_cond = None        # [2B, proj_in] fp16: text_time conditioning of SDXL-style UNets ([uncond ; cond])
@@ -74,8 +77,8 @@ class B200GuidedUNet:
         # the UNet projects them to cross-attention K/V once instead of at every step (tunable CTX_KV_CACHE).
         if N.get_tunable("CTX_KV_CACHE"):
             bound = self.unet._ctx_bound
-            if bound is None or bound[0] is not self:
-                self.unet.set_context(self.embeddings, owner=self)
+            if bound is None or bound[0] is not self.ctx_owner:
+                self.unet.set_context(self.embeddings, owner=self.ctx_owner)
             return self.unet.forward_raw(x2_f16, t2_i64, None, out=out, add_cond=self.add_cond)
         return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out, add_cond=self.add_cond)
 

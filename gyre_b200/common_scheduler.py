@@ -94,6 +94,56 @@ def _f(v) -> float:
     return float(v.item()) if torch.is_tensor(v) else float(v)
 
 
+class B200KUNet:
+    """`KDiffusionSchedulerUNet(latents, sigma, u) -> x0` (gyre/pipeline/unet/types.py:63-67): what the reference builds
+    per leaf as KDiffusionUNetWrapper around Discrete{Eps,V}DDPMDenoiser (common_scheduler.py:342-355, 400-428;
+    external.py:96-113, 149-167) and then wraps with the mode's `wrap_k_unet` (legacy-inpaint x0 blend,
+    unified_pipeline.py:627-636): x0 = x * c_skip + cfg(unet(x * c_in, t(sigma))) * c_out, fp32 latents in and out.
+    The hires-fix / graft wrappers (gyre_b200.hires_fix, gyre_b200.graft) compose these leaves."""
+
+    def __init__(self, sched, guided, blend=None):
+        self.sched = sched
+        self.guided = guided
+        self.blend = blend          # (orig fp32, mask fp32) of THIS leaf, or None: the scheduler's set_x0_blend pair
+        self._buf = {}
+
+    def _buffers(self, shape):
+        b = self._buf.get(shape)
+        if b is None:
+            dev = self.sched.device
+            x_in = torch.empty((2 * shape[0], *shape[1:]), device=dev, dtype=torch.float16)
+            b = self._buf[shape] = (x_in, torch.empty_like(x_in))
+        return b
+
+    def __call__(self, x, sigma, u=0.0):
+        s = self.sched
+        lib = N.load()
+        B, per_sample = x.shape[0], x[0].numel()
+        x = x.contiguous()
+        x_in, eps2 = self._buffers(tuple(x.shape))
+        sg = torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[0].cpu()
+        c_in = 1 / (sg ** 2 + 1.0) ** 0.5
+        if s.prediction_type == "v_prediction":
+            c_skip, c_out = 1.0 / (sg ** 2 + 1.0), -sg / (sg ** 2 + 1.0) ** 0.5
+        else:
+            c_skip, c_out = torch.tensor(1.0), -sg
+        t = s._sched.sigma_to_t(sg.reshape(1))
+        t2 = t.to(s.device).expand(2 * B).contiguous()
+        st = N.stream_ptr(s.device)
+        N.check(lib.gyre_b200_scale_latents(N.ptr(x), _f(c_in), 1, B, per_sample, N.ptr(x_in), st), "scale_latents")
+        self.guided.raw(x_in, t2, out=eps2)
+        den = torch.empty(x.shape, device=s.device, dtype=torch.float32)
+        blend = self.blend if self.blend is not None else s._blend
+        if blend is not None:
+            N.check(lib.gyre_b200_denoise_blend(N.ptr(x), N.ptr(eps2), 1, self.guided.guidance_scale, _f(c_skip),
+                                                _f(c_out), B, per_sample, N.ptr(den), N.ptr(blend[0]), N.ptr(blend[1]),
+                                                float(u), st), "denoise_blend")
+        else:
+            N.check(lib.gyre_b200_denoise(N.ptr(x), N.ptr(eps2), 1, self.guided.guidance_scale, _f(c_skip), _f(c_out), B,
+                                          per_sample, N.ptr(den), st), "denoise")
+        return den
+
+
 class CommonScheduler:
     """Interface of gyre/pipeline/common_scheduler.py:97-177."""
 
@@ -225,7 +275,9 @@ class KDiffusionScheduler(CommonScheduler):
         else:
             self.start_offset = 0
         self.start_timestep = sch.sigma_to_t(self.sigmas[self.start_offset])
-        self.unets = list(self.eps_unets)
+        # one k-unet per eps unet, in order (`cscheduler.unets[i]`, unified_pipeline.py:2461-2468); the pipeline may replace
+        # `self.unet` by a composition of them (`cscheduler.unet = mode_tree.collapse()`, :2471)
+        self.unets = [B200KUNet(self, g) for g in self.eps_unets]
         self.unet = self.unets[0]
         self._timesteps_set = True
 
@@ -268,7 +320,12 @@ class KDiffusionScheduler(CommonScheduler):
             # the reference passes eta only when the config sets it; the solver's own default is 0 (sampling.py:482)
             loop = self._loop_dpm_fast if self.scheduler == "sample_dpm_fast" else self._loop_dpm_adaptive
             return loop(latents, sigmas, progress_wrapper, out_dtype, 0.0 if self.eta is None else self.eta)
-        if self.scheduler in self.GENERIC or (self.scheduler == "sample_euler" and self.churn):
+        if not callable(self.unet):
+            raise TypeError("scheduler.unet must be a KDiffusionSchedulerUNet: (latents, sigma, u) -> x0")
+        # the fused one-kernel-per-step path needs a plain leaf: a hires-fix / graft composition (or a leaf with its own
+        # x0 blend) evaluates several UNets per step and goes through the generic denoise / lincomb kernels
+        plain = isinstance(self.unet, B200KUNet) and self.unet.guided is guided and self.unet.blend is None
+        if self.scheduler in self.GENERIC or (self.scheduler == "sample_euler" and self.churn) or not plain:
             return self._loop_generic(latents, sigmas, progress_wrapper, out_dtype, eta)
 
         # ---- host-side scalars for every step, with the reference's fp32 expressions
@@ -348,7 +405,7 @@ class KDiffusionScheduler(CommonScheduler):
         cache = unet.__dict__.setdefault("_loop_graphs", {})
         ent = cache.get(key)
         # the context of THIS run: projected into the model-owned K/V cache outside the graph
-        unet.set_context(guided.embeddings, owner=guided)
+        unet.set_context(guided.embeddings, owner=guided.ctx_owner)
         if ent is None:
             ent = {"x0": torch.empty(shape, device=self.device, dtype=torch.float32),
                    "xa": torch.empty(shape, device=self.device, dtype=torch.float32),
@@ -406,14 +463,10 @@ class KDiffusionScheduler(CommonScheduler):
 
         def __init__(self, sched, latents):
             self.s = sched
-            self.guided = sched._guided()
             self.dev = sched.device
             self.B = latents.shape[0]
             self.shape = tuple(latents.shape)
             self.per_sample = latents[0].numel()
-            self.vpred = sched.prediction_type == "v_prediction"
-            self.x_in = torch.empty((2 * self.B, *self.shape[1:]), device=self.dev, dtype=torch.float16)
-            self.eps2 = torch.empty_like(self.x_in)
             self.lib = N.load()
             self.u = 0.0            # progress of the current step (legacy inpaint blend)
             # dpm_fast / dpm_adaptive never enter `trange`, so the reference's KDiffusionPositionTracker.get_u falls back
@@ -425,35 +478,14 @@ class KDiffusionScheduler(CommonScheduler):
             return torch.empty(self.shape, device=self.dev, dtype=torch.float32)
 
         def denoise(self, x, sigma):
-            """KDiffusionUNetWrapper + Discrete{Eps,V}DDPMDenoiser.forward (common_scheduler.py:342-355,
-            external.py:96-113,149-167): x0 = x * c_skip + unet(x * c_in, t(sigma)) * c_out, with CFG inside."""
-            sg = torch.as_tensor(sigma, dtype=torch.float32)
+            """`model(x, sigma)` of the sampler functions: the scheduler's top-level k-unet (a B200KUNet leaf, or a
+            hires-fix / graft composition of leaves) called with the progress u of the evaluation."""
             if self.u_from_sigma is not None:
                 u_off, sched_sigmas = self.u_from_sigma
                 cmp = torch.as_tensor(sigma).to(sched_sigmas.dtype).reshape(-1)[0]
                 i = int((sched_sigmas >= cmp).sum())
                 self.u = max(min(u_off + (1 - u_off) * i / (len(sched_sigmas) - 1), 0.999), 0)
-            c_in = 1 / (sg ** 2 + 1.0) ** 0.5
-            if self.vpred:
-                c_skip, c_out = 1.0 / (sg ** 2 + 1.0), -sg / (sg ** 2 + 1.0) ** 0.5
-            else:
-                c_skip, c_out = torch.tensor(1.0), -sg
-            t = self.s._sched.sigma_to_t(sg.reshape(1))
-            t2 = t.to(self.dev).expand(2 * self.B).contiguous()
-            st = N.stream_ptr(self.dev)
-            N.check(self.lib.gyre_b200_scale_latents(N.ptr(x), _f(c_in), 1, self.B, self.per_sample, N.ptr(self.x_in), st),
-                    "scale_latents")
-            self.guided.raw(self.x_in, t2, out=self.eps2)
-            den = self.new()
-            if self.s._blend is not None:
-                N.check(self.lib.gyre_b200_denoise_blend(N.ptr(x), N.ptr(self.eps2), 1, self.guided.guidance_scale,
-                                                         _f(c_skip), _f(c_out), self.B, self.per_sample, N.ptr(den),
-                                                         N.ptr(self.s._blend[0]), N.ptr(self.s._blend[1]), float(self.u),
-                                                         st), "denoise_blend")
-            else:
-                N.check(self.lib.gyre_b200_denoise(N.ptr(x), N.ptr(self.eps2), 1, self.guided.guidance_scale, _f(c_skip),
-                                                   _f(c_out), self.B, self.per_sample, N.ptr(den), st), "denoise")
-            return den
+            return self.s.unet(x, sigma, u=self.u)
 
         def lin(self, terms, out=None):
             """out = sum(coef * tensor): every sampler update is one of these."""
@@ -688,6 +720,16 @@ class KDiffusionScheduler(CommonScheduler):
                     x_2 = E.lin([(1 + dt_1 / s, x), (-dt_1 / s, den)])
                     den_2 = E.denoise(x_2, s_mid)
                     x = E.lin([(1.0, x), (dt_2 / s_mid, x_2), (-dt_2 / s_mid, den_2)])
+            elif name == "sample_euler_ancestral":
+                # sampling.py:139-155 on the generic kernels (the composed-UNet path; a plain leaf takes the fused kernel)
+                den = E.denoise(x, s)
+                cb(i, den)
+                s_down, s_up = get_ancestral_step(s, s_next, eta=eta)
+                dt = s_down - s
+                terms = [(1 + dt / s, x), (-dt / s, den)]
+                if s_next > 0:
+                    terms.append((s_up, E.noise()))
+                x = E.lin(terms)
             elif name == "sample_dpm_2_ancestral":
                 den = E.denoise(x, s)
                 cb(i, den)

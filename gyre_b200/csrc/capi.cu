@@ -219,6 +219,22 @@ int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int6
   return scale_dup_latents(x, c_in, dup, batch, per_sample, static_cast<__half*>(out), S(stream));
 }
 
+int gyre_b200_resample_select(const float* src, int planes, int src_h, int src_w, const int32_t* taps_y_idx,
+                              const float* taps_y_w, int resized_h, const int32_t* taps_x_idx, const float* taps_x_w,
+                              int resized_w, int target_h, int target_w, int off_y, int off_x, int mode,
+                              const float* background, const float* other, const float* rand_map, float p,
+                              int resampled_if_ge, float* out, int frame_h, int frame_w, int frame_y, int frame_x,
+                              gyre_b200_stream stream) {
+  return resample_select(src, planes, src_h, src_w, taps_y_idx, taps_y_w, resized_h, taps_x_idx, taps_x_w, resized_w,
+                         target_h, target_w, off_y, off_x, mode, background, other, rand_map, p, resampled_if_ge, out,
+                         frame_h, frame_w, frame_y, frame_x, S(stream));
+}
+
+int gyre_b200_rand_select(const float* a, const float* b, const float* rand_map, float p, int64_t n, float* out,
+                          gyre_b200_stream stream) {
+  return rand_select(a, b, rand_map, p, n, out, S(stream));
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------ models

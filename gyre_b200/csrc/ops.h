@@ -126,6 +126,12 @@ int lincomb(int n_terms, const float* const* in, const float* coef, int B, int64
             __half* x_in, float c_in, int dup, cudaStream_t st);
 int cfg_combine(const __half* model_out, float guidance, int B, int64_t per_sample, __half* out16, float* out32,
                 cudaStream_t st);
+// hires-fix / graft blending (blend.cu): separable lanczos resample + placement + where(rand >= p, ..) in one launch
+int resample_select(const float* src, int BC, int SH, int SW, const int* ty_idx, const float* ty_w, int RH,
+                    const int* tx_idx, const float* tx_w, int RW, int TH, int TW, int offy, int offx, int mode,
+                    const float* bg, const float* other, const float* rnd, float p, int resampled_if_ge, float* out,
+                    int FH, int FW, int oy, int ox, cudaStream_t st);
+int rand_select(const float* a, const float* b, const float* rnd, float p, int64_t n, float* out, cudaStream_t st);
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)
 int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sample, __half* out, cudaStream_t st);
 // VAE tail: img = clamp(x/2+0.5, 0, 1): NHWC fp16 [B,H,W,ldx>=3] -> NCHW fp16 [B,3,H,W] (+ optional uint8 copy)

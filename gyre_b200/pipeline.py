@@ -4,17 +4,21 @@
 the image tail), driven through the same objects the reference composes: a guided eps-UNet, a
 CommonScheduler and a VAE - all backed by libgyre_b200.
 
-Text encoding is out of scope for this round: the pipeline takes the `[B, 77, C]` text /
-uncond embeddings the reference's LPW encoder would produce.
+The mode tree (ModeTreeRoot / Node / Leaf, unified_pipeline.py:1065-1217) is kept: a request is one leaf, or a
+GraftUnets / HiresUnetWrapper composition of leaves, each leaf with its own guided UNet, mode and k-unet.
+
+The pipeline takes the `[B, 77, C]` text / uncond embeddings (the LPW encoder of SURVEY.md 8f1 produces them, see
+gyre_b200.text_encoder).
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 
 import torch
 
 from .cfg import B200GuidedUNet
-from .common_scheduler import KDiffusionScheduler, SchedulerConfig, build_scheduler
+from .common_scheduler import SAMPLERS, KDiffusionScheduler, SchedulerConfig, build_scheduler
 from .modes import EnhancedInpaintMode, EnhancedRunwayInpaintMode, Img2imgMode
 from .randtools import batched_randn
 
@@ -45,21 +49,98 @@ def generate_latents(generators, batch, in_channels, height, width, sample_size,
     return latents
 
 
+class _Txt2imgLeafMode:
+    """Txt2imgMode (unified_pipeline.py:161-237) as the object a mode-tree leaf holds."""
+
+    def __init__(self, pipeline, scheduler, generators, unet, height, width, latents_dtype, batch_total):
+        self.args = (generators, batch_total, 4, height, width, pipeline.get_unet_sample_size(unet), pipeline.device,
+                     latents_dtype)
+        self.scheduler = scheduler
+
+    def generate_latents(self):
+        return self.scheduler.prepare_initial_latents(generate_latents(*self.args))
+
+    def unet_extra_channels(self):
+        return None
+
+    def x0_blend(self):
+        return None
+
+
+class _Leaf:
+    """ModeTreeLeaf (unified_pipeline.py:1183-1217): the options of one UNet evaluation path."""
+
+    def __init__(self, **opts):
+        self.opts = opts
+        self.mode = None
+        self.guided = None
+        self.k_unet = None
+
+    def clone(self, **overrides):
+        return _Leaf(**{**self.opts, **overrides})
+
+    @property
+    def leaves(self):
+        return [self]
+
+    def collapse(self):
+        return self.k_unet
+
+    def initial_latents(self):
+        return self.mode.generate_latents()
+
+    def split_result(self, result):
+        return result
+
+
+class _Node:
+    """ModeTreeNode (unified_pipeline.py:1140-1180): two sub-trees merged by HiresUnetWrapper / GraftUnets."""
+
+    def __init__(self, left, right, merger, **kwargs):
+        self.left, self.right, self.merger, self.kwargs = left, right, merger, kwargs
+
+    def clone(self, **overrides):
+        return _Node(self.left.clone(**overrides), self.right.clone(**overrides), self.merger, **self.kwargs)
+
+    @property
+    def leaves(self):
+        return self.left.leaves + self.right.leaves
+
+    def collapse(self):
+        return self.merger(self.left.collapse(), self.right.collapse(), **self.kwargs)
+
+    def initial_latents(self):
+        return self.merger.merge_initial_latents(self.left.initial_latents(), self.right.initial_latents())
+
+    def split_result(self, result):
+        return self.merger.split_result(self.left.split_result(result), self.right.split_result(result))
+
+
 class B200Pipeline:
-    def __init__(self, unet, vae=None, text_encoder=None):
+    def __init__(self, unet, vae=None, text_encoder=None, inpaint_unet=None):
         self.unet = unet
+        self.inpaint_unet = inpaint_unet   # 9-channel UNet of the same family (unified_pipeline.py:2059-2062), or None
         self.vae = vae
         self.text_encoder = text_encoder   # B200CLIPTextModel (SURVEY 8f1) or None: embeddings are passed in
         self.device = unet.device
         self.vae_scale_factor = 8
         self._options = {}
         self.unet_sample_size_override = None   # tests with sub-64 toy UNets
+        # engine defaults of the reference (unified_pipeline.py:1362-1373)
+        self._grafted_inpaint = False
+        self._hires_fix = True
+        self._hires_threshold_fraction = 0.0333
+        self._hires_oos_fraction = 0.6
+        self._hires_image_oos_fraction = 1.0
 
     def get_unet_sample_size(self, unet):
         """unified_pipeline.py:1317-1320: forced minimum of 64."""
         if self.unet_sample_size_override is not None:
             return self.unet_sample_size_override
         return max(64, getattr(unet.config, "sample_size", 64))
+
+    def get_unet_pixel_size(self, unet):
+        return self.get_unet_sample_size(unet) * self.vae_scale_factor
 
     def encode_prompt(self, input_ids, clip_layer="final"):
         """Token ids [B, 77] -> text embeddings [B, 77, C] on the native text encoder, with TextEncoderAltLayer's
@@ -76,9 +157,25 @@ class B200Pipeline:
                 from .tome_patcher import apply_tome
                 apply_tome(self.unet)
                 self.unet.r = int(value) if not isinstance(value, (tuple, list)) else value
-            elif key in ("hires_fix", "grafted_inpaint", "grafted_depth"):
+            elif key == "hires_fix":
+                self._hires_fix = bool(value)
+            elif key == "hires":
+                for subkey, subval in value.items():
+                    if subkey == "enable":
+                        self._hires_fix = bool(subval)
+                    elif subkey == "threshold_fraction":
+                        self._hires_threshold_fraction = float(subval)
+                    elif subkey == "oos_fraction":
+                        self._hires_oos_fraction = float(subval)
+                    elif subkey == "image_oos_fraction":
+                        self._hires_image_oos_fraction = float(subval)
+                    else:
+                        raise ValueError(f"Unknown option {subkey}: {subval} passed as part of hires settings")
+            elif key == "grafted_inpaint":
+                self._grafted_inpaint = value if isinstance(value, dict) else bool(value)
+            elif key == "grafted_depth":
                 if value:
-                    raise NotImplementedError(f"option {key!r} composes around the boundary and is out of scope")
+                    raise NotImplementedError("grafted_depth needs a depth UNet and a depth estimator (out of scope)")
             else:
                 raise ValueError(f"Unknown option {key!r}")
             self._options[key] = value
@@ -90,11 +187,14 @@ class B200Pipeline:
                  output_type: str = "pt", callback=None, callback_steps: int = 1, progress_wrapper=None,
                  latents_dtype=torch.float16, return_fp32_latents: bool = False, image=None, mask_image=None,
                  strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None,
-                 cfg_execution: str = "parallel") -> PipelineOutput:
+                 cfg_execution: str = "parallel", hires_fix: bool | None = None,
+                 hires_oos_fraction: float | None = None) -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
-        unified_pipeline.py:2100-2181.  `image` / `mask_image` are [1, C, H, W] tensors in [0, 1]; the mask is white =
-        repaint (the reference's default input convention, preprocess_mask_tensor(inputIs0K1D=True))."""
+        unified_pipeline.py:2055-2066 - optionally grafted (inpaint UNet early, main UNet late, :2069-2098) and, for
+        requests above the UNet's native size, doubled by the hires fix (:2100-2181).  `image` / `mask_image` are
+        [1, C, H, W] tensors in [0, 1]; the mask is white = repaint (the reference's default input convention,
+        preprocess_mask_tensor(inputIs0K1D=True))."""
         if height % 8 != 0 or width % 8 != 0:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
         if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
@@ -105,54 +205,112 @@ class B200Pipeline:
         generators = list(generator) if isinstance(generator, (list, tuple)) else [generator]
         if B % len(generators) != 0:
             raise ValueError(f"batch {B} is not a multiple of the {len(generators)} generators")
-        cfg = self.unet.config
         if image is None and mask_image is not None:
             raise ValueError("Can't pass a mask without an image")
-        runway = cfg.in_channels == 9
-        if cfg.in_channels not in (4, 9):
-            raise NotImplementedError(f"in_channels={cfg.in_channels}: only the 4- and 9-channel UNets are wired up")
-        if runway and mask_image is None:
-            raise ValueError("an inpainting UNet (in_channels=9) needs image + mask_image")
         if image is not None and self.vae is None:
             raise ValueError("img2img / inpaint need the VAE (encode)")
-
+        if image is not None and tuple(image.shape[-2:]) != (height, width):
+            raise ValueError(f"image is {tuple(image.shape[-2:])}, expected ({height}, {width})")
         if cfg_execution not in ("parallel", "sequential"):
             raise ValueError(f"cfg_execution must be 'parallel' or 'sequential', got {cfg_execution!r}")
-        guided = B200GuidedUNet(self.unet, negative_prompt_embeds, prompt_embeds, guidance_scale,
-                                parallel=cfg_execution == "parallel")
-        if cfg.addition_time_embed_dim:
-            if added_cond_kwargs is None:
-                raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")
-            guided.set_added_cond(negative_added_cond_kwargs or added_cond_kwargs, added_cond_kwargs)
+        if hires_fix is None:
+            hires_fix = self._hires_fix
+        if hires_oos_fraction is None:
+            hires_oos_fraction = self._hires_image_oos_fraction if image is not None else self._hires_oos_fraction
+
+        # ---- the main mode leaf (unified_pipeline.py:2055-2066)
+        main_unet = self.unet
+        if mask_image is not None and self.inpaint_unet is not None:
+            main_unet = self.inpaint_unet
+        cfg = main_unet.config
+        if cfg.in_channels not in (4, 9):
+            raise NotImplementedError(f"in_channels={cfg.in_channels}: only the 4- and 9-channel UNets are wired up")
+        if cfg.in_channels == 9 and mask_image is None:
+            raise ValueError("an inpainting UNet (in_channels=9) needs image + mask_image")
+        if mask_image is not None:
+            kind = "runway" if cfg.in_channels == 9 else "inpaint"
+        else:
+            kind = "img2img" if image is not None else "txt2img"
+        tree = _Leaf(kind=kind, unet=main_unet, height=height, width=width, image=image, mask_image=mask_image)
+
+        # ---- graft: inpaint UNet for the early steps, the main UNet with the legacy x0 blend for the late ones (:2069-2098)
+        if kind == "runway" and self._grafted_inpaint and main_unet is self.inpaint_unet and self.unet is not main_unet:
+            from .graft import GraftUnets
+            blend = self._grafted_inpaint if isinstance(self._grafted_inpaint, dict) else {}
+            tree = _Node(tree.clone(), tree.clone(kind="inpaint", unet=self.unet), GraftUnets, generators=generators,
+                         blend=blend, rand_dtype=latents_dtype)
+
+        # ---- hires fix: a natural-size twin of every leaf, cross-blended with the full-size one (:2100-2181)
+        if hires_fix:
+            unet_pixel_size = self.get_unet_pixel_size(self.unet)
+            sample_size = self.get_unet_sample_size(self.unet)
+            threshold = math.floor(unet_pixel_size * (1 + self._hires_threshold_fraction))
+            too_small = width < unet_pixel_size or height < unet_pixel_size
+            if not too_small and not (width <= threshold and height <= threshold):
+                if sampler not in SAMPLERS or SAMPLERS[sampler][0] is not KDiffusionScheduler:
+                    raise ValueError("Can't use Diffuser schedulers with Hires fix. "
+                                     "Either use a K-Diffusion scheduler or disable Hires fix.")
+                from .hires_fix import HiresUnetWrapper
+
+                def to_natural(t):
+                    return None if t is None else HiresUnetWrapper.image_to_natural(
+                        unet_pixel_size, t.to(self.device), oos_fraction=hires_oos_fraction)
+                natural = tree.clone(width=unet_pixel_size, height=unet_pixel_size, image=to_natural(image),
+                                     mask_image=to_natural(mask_image))
+                tree = _Node(natural, tree, HiresUnetWrapper, generators=generators,
+                             natural_size=[sample_size, sample_size], oos_fraction=hires_oos_fraction,
+                             latent_debugger=None, rand_dtype=latents_dtype)
+        leaves = tree.leaves
+
+        # ---- one guided eps-UNet per leaf (CFG + embeddings, :2326-2337); leaves of one UNet share its K/V context
+        first_of = {}
+        for leaf in leaves:
+            u = leaf.opts["unet"]
+            g = B200GuidedUNet(u, negative_prompt_embeds, prompt_embeds, guidance_scale, parallel=cfg_execution == "parallel")
+            if u.config.addition_time_embed_dim:
+                if added_cond_kwargs is None:
+                    raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")
+                g.set_added_cond(negative_added_cond_kwargs or added_cond_kwargs, added_cond_kwargs)
+            g.ctx_owner = first_of.setdefault(id(u), g)
+            leaf.guided = g
         sched = build_scheduler(sampler, generators, self.device, latents_dtype, callback, callback_steps)
-        sched.set_eps_unets([guided])
+        sched.set_eps_unets([leaf.guided for leaf in leaves])
         sched.use_cuda_graph = bool(getattr(self, "use_cuda_graph", False))
         ts_args = {"strength": min(strength, 1.0)} if image is not None else {}
         sched.set_timesteps(num_inference_steps, prediction_type=cfg.prediction_type,
                             config=scheduler_config or SchedulerConfig(), **ts_args)
-        if image is None:
-            latents = generate_latents(generators, B, 4, height, width, self.get_unet_sample_size(self.unet),
-                                       self.device, latents_dtype)
-            latents = sched.prepare_initial_latents(latents)
-        else:
-            if tuple(image.shape[-2:]) != (height, width):
-                raise ValueError(f"image is {tuple(image.shape[-2:])}, expected ({height}, {width})")
-            common = dict(pipeline=self, scheduler=sched, generators=generators, image=image,
-                          latents_dtype=latents_dtype, batch_total=B)
-            if mask_image is None:
-                mode = Img2imgMode(strength=strength, **common)
-            elif runway:
-                mode = EnhancedRunwayInpaintMode(mask_image=mask_image, strength=strength, **common)
+
+        # ---- modes, in leaf order (construction already consumes generator draws: posterior samples of the encodes)
+        for leaf in leaves:
+            o = leaf.opts
+            common = dict(pipeline=self, scheduler=sched, generators=generators, latents_dtype=latents_dtype, batch_total=B)
+            if o["kind"] == "txt2img":
+                leaf.mode = _Txt2imgLeafMode(unet=o["unet"], height=o["height"], width=o["width"], **common)
+            elif o["kind"] == "img2img":
+                leaf.mode = Img2imgMode(image=o["image"], strength=strength, **common)
+            elif o["kind"] == "runway":
+                leaf.mode = EnhancedRunwayInpaintMode(image=o["image"], mask_image=o["mask_image"], strength=strength, **common)
             else:
                 if not isinstance(sched, KDiffusionScheduler):
                     raise NotImplementedError("legacy (4-channel) inpainting is wired for the k-diffusion samplers")
-                mode = EnhancedInpaintMode(mask_image=mask_image, strength=strength, **common)
-            latents = mode.generate_latents()
-            guided.set_extra_channels(mode.unet_extra_channels())
-            blend = mode.x0_blend()
+                leaf.mode = EnhancedInpaintMode(image=o["image"], mask_image=o["mask_image"], strength=strength, **common)
+            leaf.guided.set_extra_channels(leaf.mode.unet_extra_channels())
+        if len(leaves) == 1:
+            blend = leaves[0].mode.x0_blend()
             if blend is not None:
                 sched.set_x0_blend(*blend)
+        else:
+            # `leaf.k_unet = leaf.mode.wrap_k_unet(cscheduler.unets[i])`, then `cscheduler.unet = mode_tree.collapse()`
+            # (:2461-2471)
+            for i, leaf in enumerate(leaves):
+                leaf.k_unet = sched.unets[i]
+                blend = leaf.mode.x0_blend()
+                if blend is not None:
+                    leaf.k_unet.blend = (blend[0].float().contiguous(), blend[1].float().contiguous())
+            sched.unet = tree.collapse()
+        latents = tree.initial_latents()
         latents = sched.loop(latents, progress_wrapper, out_dtype=torch.float32 if return_fp32_latents else None)
+        latents = tree.split_result(latents)
         if output_type == "latent" or self.vae is None:
             return PipelineOutput(images=None, latents=latents)
         z = (1 / self.vae.config.scaling_factor * latents.float()).to(torch.float16)

@@ -185,7 +185,9 @@ class B200UNet(torch.nn.Module):
         if ws is None:
             n = C.c_size_t()
             N.check(self._lib.gyre_b200_unet_workspace_bytes(self._h, B, H, W, L, C.byref(n)), "unet_workspace_bytes")
-            self._ws.clear()            # one live shape at a time is the pipeline's usage pattern
+            # one live shape is the usual pattern; a hires-fix run alternates between two (natural / full size)
+            while len(self._ws) >= 2:
+                self._ws.pop(next(iter(self._ws)))
             ws = torch.empty((n.value,), device=self.device, dtype=torch.uint8)
             self._ws[key] = ws
         return ws

@@ -286,6 +286,25 @@ int gyre_b200_cat_channels(const void* x, int channels, const void* extra, int e
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream);
 
+/* Hires-fix / graft blending of the scheduler-UNet wrappers (replaces the ~20 torch ops per step of
+ * gyre/pipeline/unet/hires_fix.py:142-205 HiresUnetWrapper.__call__ and gyre/pipeline/unet/graft.py:31-48):
+ *   resample_select: `scale_into` (hires_fix.py:45-92) - a separable 4-tap lanczos2 resample of src [planes, src_h, src_w]
+ *   fp32 (tap tables [resized, 4] built on the host with ResizeRight's expressions, resize_right.py:70-118,203-213; NULL
+ *   tables = that dimension is not resampled), placed at (off_y, off_x) in a [target_h, target_w] frame (negative
+ *   offsets crop the centre), outside it replicate padding (mode 0, strategy "pad") or `background` (mode 1, strategy
+ *   "clone") - then, when `other` is given, where(rand_map >= p, A, B) with (A, B) = (resampled, other) if
+ *   resampled_if_ge else (other, resampled) - written at (frame_y, frame_x) into out [planes, frame_h, frame_w], zero
+ *   elsewhere (`lo_expanded`, hires_fix.py:196-198).
+ *   rand_select: out = where(rand_map >= p, a, b)  (graft.py:44-46). */
+int gyre_b200_resample_select(const float* src, int planes, int src_h, int src_w, const int32_t* taps_y_idx,
+                              const float* taps_y_w, int resized_h, const int32_t* taps_x_idx, const float* taps_x_w,
+                              int resized_w, int target_h, int target_w, int off_y, int off_x, int mode,
+                              const float* background, const float* other, const float* rand_map, float p,
+                              int resampled_if_ge, float* out, int frame_h, int frame_w, int frame_y, int frame_x,
+                              gyre_b200_stream stream);
+int gyre_b200_rand_select(const float* a, const float* b, const float* rand_map, float p, int64_t n, float* out,
+                          gyre_b200_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Attention patcher  (replaces ToMeMemoryEfficientCrossAttention.forward's merge,
  *   nonfree/tome_memory_efficient_cross_attention.py:28-50, i.e. tome/merge.py:18-97,210-224)

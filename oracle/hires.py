@@ -282,3 +282,103 @@ class GraftUnets:
     @classmethod
     def split_result(cls, left, right):
         return right
+
+
+# --------------------------------------------------------------------------------------------- pipeline composition
+def hires_txt2img_latents(eps_unet_cfg, *, batch, height, width, sample_size, seeds, steps, oos_fraction=0.6,
+                          latent_dtype=torch.float32, eta=1.0, prediction_type="epsilon", graft_top_cfg=None,
+                          graft_blend=None):
+    """txt2img with the hires fix engaged, the way UnifiedPipeline composes it (unified_pipeline.py:2100-2181 mode tree,
+    :2461-2486 collapse / initial latents / loop / split_result) with the Euler-ancestral sampler: leaves share the CFG'd
+    eps UNet, the natural leaf runs at sample_size^2, u = i / n per step (KDiffusionPositionTracker inside trange,
+    common_scheduler.py:358-389).  With `graft_top_cfg` every leaf is a GraftUnets(root = eps_unet_cfg, top = graft_top_cfg)
+    pair instead (graft + hires nesting)."""
+    from . import sampling as S
+    gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+
+    def gen_latents(h, w):
+        shape = (batch, 4, h, w)
+        mid = S.batched_randn([batch, 4, sample_size, sample_size], gens, "cpu", latent_dtype)
+        off2, off3 = (sample_size - h) // 2, (sample_size - w) // 2
+        if off2 > 0:
+            mid = mid[:, :, off2:off2 + h, :]
+        if off3 > 0:
+            mid = mid[:, :, :, off3:off3 + w]
+        if off2 >= 0 and off3 >= 0:
+            return mid
+        lat = S.batched_randn(shape, gens, "cpu", latent_dtype)
+        o2, o3 = (lat.shape[2] - mid.shape[2]) // 2, (lat.shape[3] - mid.shape[3]) // 2
+        lat[:, :, o2:o2 + mid.shape[2], o3:o3 + mid.shape[3]] = mid
+        return lat
+
+    acp = S.sd_alphas_cumprod("cpu")
+    Den = S.VDenoiser if prediction_type == "v_prediction" else S.EpsDenoiser
+    den = Den(eps_unet_cfg, acp)
+    sig_full = S.k_sigmas(den, steps)
+    left = gen_latents(sample_size, sample_size) * sig_full[0]
+    right = gen_latents(height // 8, width // 8) * sig_full[0]
+    latents = HiresUnetWrapper.merge_initial_latents(left, right).float()
+    sigmas = sig_full.to(latent_dtype).float()
+
+    def leaf_of(d):
+        return lambda x, sigma, u: d(x, sigma)
+    if graft_top_cfg is None:
+        nat = hi = leaf_of(den)
+    else:
+        top = Den(graft_top_cfg, acp)
+        nat = GraftUnets(leaf_of(den), leaf_of(top), gens, blend=graft_blend or {})
+        hi = GraftUnets(leaf_of(den), leaf_of(top), gens, blend=graft_blend or {})
+    wrapper = HiresUnetWrapper(nat, hi, gens, [sample_size, sample_size], oos_fraction)
+    n = len(sigmas) - 1
+    calls = {"i": 0}
+
+    def model(x, sigma):
+        u = max(min(calls["i"] / n, 0.999), 0)
+        calls["i"] += 1
+        return wrapper(x, sigma, u)
+    noise = lambda *_: S.batched_randn(latents.shape, gens, "cpu", latent_dtype).float()
+    out = S.sample_euler_ancestral(model, latents, sigmas, noise, eta=eta)
+    return HiresUnetWrapper.split_result(None, out)
+
+
+def grafted_inpaint_latents(inpaint_unet, main_unet, vae, uncond_emb, cond_emb, guidance_scale, *, image, mask_image, seeds,
+                            steps, strength, blend=None, latent_dtype=torch.float32):
+    """Grafted inpaint as UnifiedPipeline composes it (unified_pipeline.py:2069-2098): GraftUnets(root = the inpaint UNet
+    in EnhancedRunwayInpaintMode, top = the main UNet in EnhancedInpaintMode), both modes constructed and then both
+    `generateLatents` run on the shared generators; the root's latents start the loop (graft.py:50-52)."""
+    from . import sampling as S
+    gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    kw = dict(image=image, mask_image=mask_image, generators=gens, steps=steps, strength=strength, latent_dtype=latent_dtype)
+    ph_root = S.image_mode_phases(inpaint_unet, vae, uncond_emb, cond_emb, guidance_scale, **kw)
+    ph_top = S.image_mode_phases(main_unet, vae, uncond_emb, cond_emb, guidance_scale, **kw)
+    next(ph_root)
+    next(ph_top)
+    root = next(ph_root)
+    top = next(ph_top)
+    graft = GraftUnets(lambda x, s, u: root["k_unet"](x, s, u), lambda x, s, u: top["k_unet"](x, s, u), gens, blend=blend or {})
+    return S.euler_ancestral_with_u(lambda x, s, u: graft(x, s, u), root["latents"], root["sigmas"], root["u_off"], gens,
+                                    latent_dtype)
+
+
+def hires_image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image, mask_image=None, seeds, steps,
+                             strength, sample_size, oos_fraction=1.0, latent_dtype=torch.float32):
+    """img2img / inpaint with the hires fix engaged (unified_pipeline.py:2100-2181): the natural leaf works on the image
+    (and mask) shrunk by `image_to_natural` (oos_fraction defaults to `_hires_image_oos_fraction` = 1.0 when an image is
+    given, :1840-1843); both leaves' modes are constructed, then both generate their latents, on shared generators."""
+    from . import sampling as S
+    gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    px = sample_size * 8
+    nat_image = HiresUnetWrapper.image_to_natural(px, image, oos_fraction)
+    nat_mask = None if mask_image is None else HiresUnetWrapper.image_to_natural(px, mask_image, oos_fraction)
+    kw = dict(generators=gens, steps=steps, strength=strength, latent_dtype=latent_dtype)
+    ph_n = S.image_mode_phases(unet, vae, uncond_emb, cond_emb, guidance_scale, image=nat_image, mask_image=nat_mask, **kw)
+    ph_h = S.image_mode_phases(unet, vae, uncond_emb, cond_emb, guidance_scale, image=image, mask_image=mask_image, **kw)
+    next(ph_n)
+    next(ph_h)
+    nat = next(ph_n)
+    hi = next(ph_h)
+    latents = HiresUnetWrapper.merge_initial_latents(nat["latents"], hi["latents"])
+    w = HiresUnetWrapper(lambda x, s, u: nat["k_unet"](x, s, u), lambda x, s, u: hi["k_unet"](x, s, u), gens,
+                         [sample_size, sample_size], oos_fraction)
+    out = S.euler_ancestral_with_u(lambda x, s, u: w(x, s, u), latents, hi["sigmas"], hi["u_off"], gens, latent_dtype)
+    return HiresUnetWrapper.split_result(None, out)

@@ -644,9 +644,44 @@ def image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image
     (unified_pipeline.py:240-337, 400-696; common_scheduler.py:430-623), k-diffusion samplers only.
     `unet.cfg.in_channels == 9` selects the Runway path (mask + masked-image latents appended to the UNet input,
     un-scaled); a mask with a 4-channel UNet selects the legacy x0 blend."""
-    import numpy as np
     generators = [torch.Generator(device="cpu").manual_seed(s) for s in seeds]
-    B = len(seeds)
+    ph = image_mode_phases(unet, vae, uncond_emb, cond_emb, guidance_scale, image=image, mask_image=mask_image,
+                           generators=generators, steps=steps, strength=strength, latent_dtype=latent_dtype,
+                           prediction_type=prediction_type)
+    next(ph)                                                   # mode construction
+    leaf = next(ph)                                            # generateLatents
+    if sampler != "euler_a":
+        raise ValueError("image_mode_latents restates the Euler-ancestral loop only")
+    return euler_ancestral_with_u(leaf["k_unet"], leaf["latents"], leaf["sigmas"], leaf["u_off"], generators, latent_dtype,
+                                  1.0 if eta is None else eta)
+
+
+def euler_ancestral_with_u(k_unet, latents, sigmas, u_off, generators, latent_dtype, eta=1.0):
+    """sample_euler_ancestral (sampling.py:139-155) around a `KDiffusionSchedulerUNet(latents, sigma, u)`, with the
+    progress u of KDiffusionPositionTracker.get_u inside trange (common_scheduler.py:358-389)."""
+    x = latents.float()
+    shape = tuple(x.shape)
+    n = len(sigmas) - 1
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(n):
+        u = max(min(u_off + (1 - u_off) * i / n, 0.999), 0)
+        denoised = k_unet(x, sigmas[i] * s_in, u)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        d = to_d(x, sigmas[i], denoised)
+        x = x + d * (sigma_down - sigmas[i])
+        if sigmas[i + 1] > 0:
+            x = x + batched_randn(shape, generators, "cpu", latent_dtype).float() * sigma_up
+    return x
+
+
+def image_mode_phases(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image, mask_image=None, generators, steps,
+                      strength, latent_dtype=torch.float32, prediction_type="epsilon"):
+    """One mode-tree leaf of an image mode as a two-phase generator, because the reference interleaves the phases of
+    several leaves on the SAME generators: first every leaf's mode is constructed (the masked-image encode draws its
+    posterior sample there, unified_pipeline.py:400-440), then every leaf's `generateLatents` runs (:2474).  The first
+    `next()` runs the construction, the second returns {"latents", "k_unet"(x, sigma, u), "sigmas", "u_off"}."""
+    import numpy as np
+    B = len(generators)
     acp = sd_alphas_cumprod()
     img = image if image.ndim == 4 else image[None]
     img = 2.0 * img[:, [0, 1, 2]] - 1.0
@@ -676,6 +711,7 @@ def image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image
     init_timestep = min(int(steps * strength), steps)
     start_offset = max(steps - init_timestep, 0)
     start_t = den_probe.sigma_to_t(sigmas_full[start_offset])
+    yield None                                                 # ---- end of mode construction
 
     init = to_latents(img)
     if mask_image is not None and fill:
@@ -716,34 +752,16 @@ def image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image
 
     den = (VDenoiser if prediction_type == "v_prediction" else EpsDenoiser)(eps_cfg, acp)
     sigmas = sigmas_full[start_offset:].to(latent_dtype).float()
-    n = len(sigmas) - 1
-    state = {"i": 0}
-    model = den
+    u_off = start_offset / len(sigmas_full)
     if mask_image is not None and not runway:
-        u_off = start_offset / len(sigmas_full)
-
-        def model(x, sigma):                                   # wrap_k_unet + KDiffusionPositionTracker.get_u
-            u = max(min(u_off + (1 - u_off) * state["i"] / n, 0.999), 0)
+        def k_unet(x, sigma, u):                               # wrap_k_unet (unified_pipeline.py:627-636)
             px0 = den(x, sigma)
             keep_orig = latent_mask.gt(u).to(px0.dtype)
             return init_orig.to(px0.dtype) * keep_orig + px0 * (1 - keep_orig)
-    latents = latents.float()
-    shape = tuple(latents.shape)
-    noise = lambda *_: batched_randn(shape, generators, "cpu", latent_dtype).float()
-    if sampler != "euler_a":
-        raise ValueError("image_mode_latents restates the Euler-ancestral loop only")
-    x = latents
-    s_in = x.new_ones([x.shape[0]])
-    e = 1.0 if eta is None else eta
-    for i in range(n):                                         # sample_euler_ancestral with the step index exposed
-        state["i"] = i
-        denoised = model(x, sigmas[i] * s_in)
-        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=e)
-        d = to_d(x, sigmas[i], denoised)
-        x = x + d * (sigma_down - sigmas[i])
-        if sigmas[i + 1] > 0:
-            x = x + noise() * sigma_up
-    return x
+    else:
+        def k_unet(x, sigma, u):
+            return den(x, sigma)
+    yield {"latents": latents.float(), "k_unet": k_unet, "sigmas": sigmas, "u_off": u_off}
 
 
 def decode_image(vae, latents, scaling=0.18215):

@@ -1,0 +1,235 @@
+"""Hires-fix / graft wrappers on the native kernels against the REFERENCE vectors of tests/golden/hires.pt (produced by
+scripts/make_golden.py from gyre/pipeline/unet/hires_fix.py, unet/graft.py, easing.py and the vendored ResizeRight) and,
+at pipeline level, against the oracle's composition of the same wrappers."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(GOLD, "hires.pt"))
+
+
+def toy_kunet(kind):
+    """scripts/make_golden.py:toy_kunet, evaluated on whatever device the latents live on."""
+    a, b = (0.8, 0.05) if kind == "a" else (0.6, -0.08)
+
+    def f(latents, sigma, u):
+        s = torch.as_tensor(sigma).float().reshape(-1).to(latents.device)
+        s = s[:, None, None, None] if s.numel() > 1 else s
+        x = latents.float()
+        return (a * torch.tanh(x) + b * x.roll(1, -1) / (1 + s) + 0.1 * u * x.roll(1, -2)).to(latents.dtype)
+    return f
+
+
+def test_scale_into_kernel_vs_reference(gold):
+    """resample + placement in one launch == ResizeRight lanczos2 + hires_fix.scale_into ("pad" and "clone")."""
+    from gyre_b200.hires_fix import scale_into
+    n = 0
+    for key, v in gold.items():
+        if not key.startswith("scale_into/fp32/"):
+            continue
+        x = v["x"].cuda()
+        pad = scale_into(x, v["scale"], target_shape=tuple(v["pad"].shape))
+        clone = scale_into(x, v["scale"], target=v["bg"].cuda().contiguous())
+        for name, mine, ref in (("pad", pad, v["pad"]), ("clone", clone, v["clone"])):
+            err = (mine.cpu() - ref).abs().max().item()
+            # tanh-free arithmetic: 16 products and 15 adds in the reference's order; only fused-multiply-add
+            # contraction could differ, and the kernel forbids it
+            assert err <= 1e-6, f"{key} {name}: {err}"
+        n += 1
+    assert n >= 12
+    # plain resize (identity placement), including the scale == 1 short cut
+    for key, v in gold.items():
+        if key.startswith("resize/fp32/"):
+            mine = scale_into(v["x"].cuda(), v["scale"], target_shape=tuple(v["out"].shape))
+            assert (mine.cpu() - v["out"]).abs().max().item() <= 1e-6, key
+
+
+@pytest.mark.parametrize("dt_name", ["fp32", "fp16"])
+def test_hires_wrapper_vs_reference(gold, dt_name):
+    from gyre_b200.hires_fix import HiresUnetWrapper
+    dt = torch.float32 if dt_name == "fp32" else torch.float16
+    n = 0
+    for key, v in gold.items():
+        if not key.startswith(f"hires/{dt_name}/"):
+            continue
+        gens = [torch.Generator("cpu").manual_seed(s) for s in v["seeds"]]
+        w = HiresUnetWrapper(toy_kunet("a"), toy_kunet("b"), gens, [v["natural"]] * 2, v["oos"], None, rand_dtype=dt)
+        lat = v["latents"].float().cuda()
+        for call in v["calls"]:
+            out = w(lat, v["sigma"], call["u"])
+            err = (out.cpu() - call["out"].float()).abs().max().item()
+            scale = call["out"].float().abs().max().item()
+            # fp32 vectors: same selections, same arithmetic up to tanh's device implementation; fp16 vectors carry the
+            # reference's fp16 rounding of every intermediate (the B200 path keeps fp32)
+            tol = 2e-6 if dt_name == "fp32" else 3e-3
+            assert err <= tol * max(scale, 1.0), f"{key} u={call['u']}: {err}"
+        merged = HiresUnetWrapper.merge_initial_latents(v["left"].cuda(), v["right"].cuda())
+        assert torch.equal(merged.cpu(), v["merged"])
+        assert torch.equal(HiresUnetWrapper.split_result(None, merged).cpu(), v["merged"].chunk(2)[1])
+        n += 1
+    assert n == 4
+    for oos in (0.6, 1.0):
+        v = gold[f"image_to_natural/{dt_name}/oos{oos}"]
+        out = HiresUnetWrapper.image_to_natural(64, v["image"].cuda(), oos)
+        assert out.dtype == v["image"].dtype
+        assert (out.float().cpu() - v["out"].float()).abs().max().item() <= (1e-6 if dt_name == "fp32" else 1e-3)
+
+
+@pytest.mark.parametrize("dt_name", ["fp32", "fp16"])
+def test_graft_vs_reference(gold, dt_name):
+    from gyre_b200.graft import GraftUnets
+    dt = torch.float32 if dt_name == "fp32" else torch.float16
+    for variant in ("default", "linear"):
+        v = gold[f"graft/{dt_name}/{variant}"]
+        gens = [torch.Generator("cpu").manual_seed(s) for s in v["seeds"]]
+        w = GraftUnets(toy_kunet("a"), toy_kunet("b"), gens, blend=v["blend"], rand_dtype=dt)
+        lat = v["latents"].float().cuda()
+        for call in v["calls"]:
+            out = w(lat, v["sigma"], call["u"])
+            err = (out.cpu() - call["out"].float()).abs().max().item()
+            assert err <= (2e-6 if dt_name == "fp32" else 2e-3), f"graft {variant} u={call['u']}: {err}"
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from oracle.unet import UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    pipe = B200Pipeline(B200UNet(cfg).load_state_dict(P), None)
+    pipe.unet_sample_size_override = 16
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(11))
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1).contiguous()
+    return cfg, P, pipe, emb, unc
+
+
+@pytest.mark.parametrize("hw", [(192, 192), (256, 192)])
+def test_pipeline_hires_txt2img_vs_oracle(tiny, hw):
+    """The reference's default for a request above the UNet's native size: [natural ; full] latents, both leaves every
+    step, cross-blend while p < 1 - through B200Pipeline with the option left at its default (on)."""
+    from oracle import hires as ohires
+    from oracle import sampling as osamp
+    from oracle.unet import OracleUNet
+    cfg, P, pipe, emb, unc = tiny
+    H, W = hw
+    seeds, steps = [420420420, 420420421], 9
+    gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    out = pipe(emb.cuda(), unc.cuda(), height=H, width=W, num_inference_steps=steps, guidance_scale=7.5, generator=gens,
+               sampler="k_euler_ancestral", output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True)
+    assert tuple(out.latents.shape) == (2, 4, H // 8, W // 8)
+    with torch.no_grad():
+        ref = ohires.hires_txt2img_latents(osamp.CFGParallel(OracleUNet(cfg, P), unc, emb, 7.5), batch=2, height=H, width=W,
+                                           sample_size=16, seeds=seeds, steps=steps, oos_fraction=0.6)
+    err = (out.latents.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"hires txt2img {H}x{W}: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
+    assert err < 1.4e-2 * scale
+    # the option off gives the plain single-leaf run (and a different result)
+    gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    off = pipe(emb.cuda(), unc.cuda(), height=H, width=W, num_inference_steps=steps, guidance_scale=7.5, generator=gens,
+               sampler="k_euler_ancestral", output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True,
+               hires_fix=False)
+    with torch.no_grad():
+        ref_off = osamp.txt2img_latents(osamp.CFGParallel(OracleUNet(cfg, P), unc, emb, 7.5), batch=2, in_channels=4,
+                                        height=H, width=W, sample_size=16, seeds=seeds, steps=steps, sampler="euler_a")
+    assert (off.latents.cpu() - ref_off).abs().max().item() < 1.4e-2 * ref_off.abs().max().item()
+    assert (off.latents - out.latents).abs().max().item() > 0.05 * scale
+
+
+def test_pipeline_hires_rejects_diffusers_schedulers(tiny):
+    cfg, P, pipe, emb, unc = tiny
+    gens = [torch.Generator("cpu").manual_seed(s) for s in (1, 2)]
+    with pytest.raises(ValueError, match="Hires fix"):
+        pipe(emb.cuda(), unc.cuda(), height=192, width=192, num_inference_steps=4, generator=gens, sampler="ddim",
+             output_type="latent")
+    # at or below the threshold (3.33 % above native) nothing engages
+    gens = [torch.Generator("cpu").manual_seed(s) for s in (1, 2)]
+    pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=3, generator=gens, sampler="ddim",
+         output_type="latent")
+
+
+def test_pipeline_grafted_inpaint_vs_oracle():
+    """grafted_inpaint: the 9-channel inpaint UNet predicts the early steps, the main UNet (legacy x0 blend) the late
+    ones, a uniform map picks per pixel inside the eased window - both UNets native, one rand_select launch per step."""
+    from oracle import hires as ohires
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_param_shapes
+    from oracle.vae import OracleVAE, VAEConfig, vae_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    from gyre_b200.vae import B200VAE
+    cfg_i, cfg_m = UNetConfig.tiny(in_channels=9), UNetConfig.tiny()
+    P_i = synth_params(unet_param_shapes(cfg_i), seed=1234)
+    P_m = synth_params(unet_param_shapes(cfg_m), seed=99)
+    vcfg = VAEConfig.tiny()
+    VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+    pipe = B200Pipeline(B200UNet(cfg_m).load_state_dict(P_m), B200VAE(vcfg).load_state_dict(VP),
+                        inpaint_unet=B200UNet(cfg_i).load_state_dict(P_i))
+    pipe.unet_sample_size_override = 16
+    blend = {"start": 0.15, "end": 0.75, "easing": "sine"}
+    pipe.set_options({"grafted_inpaint": blend})
+    g = torch.Generator().manual_seed(21)
+    emb = torch.randn(2, 77, cfg_m.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg_m.cross_attention_dim, generator=g).expand(2, -1, -1).contiguous()
+    image = torch.rand(1, 3, 128, 128, generator=g)
+    mask = torch.zeros(1, 1, 128, 128)
+    mask[:, :, 32:96, 40:104] = 1.0
+    seeds, steps, strength = [420420420, 420420421], 10, 0.8
+    out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
+               output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True, image=image.cuda(),
+               mask_image=mask.cuda(), strength=strength)
+    with torch.no_grad():
+        ref = ohires.grafted_inpaint_latents(OracleUNet(cfg_i, P_i), OracleUNet(cfg_m, P_m),
+                                             OracleVAE(vcfg, VP, sample_dtype=torch.float16), unc, emb, 7.5, image=image,
+                                             mask_image=mask, seeds=seeds, steps=steps, strength=strength, blend=blend)
+    err = (out.latents.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"grafted inpaint: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
+    assert err < 1.4e-2 * scale
+
+
+@pytest.mark.parametrize("kind", ["img2img", "runway_inpaint"])
+def test_pipeline_hires_image_modes_vs_oracle(kind):
+    """Config 3 as gyre runs it by default: an image mode above the native size -> natural-size twin working on the
+    lanczos-shrunk image / mask, cross-blended with the full-size leaf."""
+    from oracle import hires as ohires
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_param_shapes
+    from oracle.vae import OracleVAE, VAEConfig, vae_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    from gyre_b200.vae import B200VAE
+    cfg = UNetConfig.tiny(in_channels=9) if kind == "runway_inpaint" else UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    vcfg = VAEConfig.tiny()
+    VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+    pipe = B200Pipeline(B200UNet(cfg).load_state_dict(P), B200VAE(vcfg).load_state_dict(VP))
+    pipe.unet_sample_size_override = 16
+    g = torch.Generator().manual_seed(21)
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).expand(2, -1, -1).contiguous()
+    H = W = 192
+    image = torch.rand(1, 3, H, W, generator=g)
+    mask = torch.zeros(1, 1, H, W)
+    mask[:, :, 48:144, 64:160] = 1.0
+    seeds, steps, strength = [420420420, 420420421], 9, 0.8
+    kw = {} if kind == "img2img" else {"mask_image": mask.cuda()}
+    out = pipe(emb.cuda(), unc.cuda(), height=H, width=W, num_inference_steps=steps, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
+               output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True, image=image.cuda(),
+               strength=strength, **kw)
+    with torch.no_grad():
+        ref = ohires.hires_image_mode_latents(OracleUNet(cfg, P), OracleVAE(vcfg, VP, sample_dtype=torch.float16), unc, emb,
+                                              7.5, image=image, mask_image=None if kind == "img2img" else mask, seeds=seeds,
+                                              steps=steps, strength=strength, sample_size=16, oos_fraction=1.0)
+    err = (out.latents.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"hires {kind}: final-latent max abs err {err:.4e} (latent max {scale:.3f})")
+    assert err < 1.4e-2 * scale
