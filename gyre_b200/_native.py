@@ -22,6 +22,8 @@ class Epilogue(C.Structure):
         ("residual", C.c_void_p), ("ldr", C.c_int32), ("act", C.c_int32), ("out_f32", C.c_int32),
         ("out", C.c_void_p), ("ldo", C.c_int32),
         ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t), ("sk_flags", C.c_void_p), ("sk_flags_count", C.c_int32),
+        ("rowstat_out", C.c_void_p), ("ln_rowstat", C.c_void_p), ("ln_colsum", C.c_void_p),
+        ("ln_parts", C.c_int32), ("ln_inv_c", C.c_float), ("ln_eps", C.c_float),
     ]
 
 
@@ -104,6 +106,9 @@ SIGNATURES = {
     "gyre_b200_sched_step_blend": (_i, [C.POINTER(Step), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _f, _vp]),
     "gyre_b200_cat_channels": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _vp, _vp]),
     "gyre_b200_scale_latents": (_i, [_vp, _f, _i, _i, _i64, _vp, _vp]),
+    "gyre_b200_gemm_rowstat_parts": (_i, [_i, _i]),
+    "gyre_b200_ln_finalize_rows": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
+    "gyre_b200_ln_fold_linear": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gyre_b200_resample_select": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i,
                                        _vp, _i, _i, _i, _i, _vp]),
     "gyre_b200_rand_select": (_i, [_vp, _vp, _vp, _f, _i64, _vp, _vp]),
@@ -150,7 +155,7 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)     # AttributeError here == header/library drift: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.gyre_b200_abi_version() != 1:
+        if lib.gyre_b200_abi_version() != 2:
             raise NativeError("libgyre_b200 ABI version mismatch")
         _lib = lib
         return lib
@@ -230,8 +235,9 @@ def _epilogue(out, bias=None, residual=None, act=0, rowgroup_bias=None, rows_per
 
 
 def gemm(a, w, bias=None, residual=None, act=0, a2=None, out_dtype=torch.float16, rowgroup_bias=None,
-         rows_per_group=1, out=None):
-    """out = epilogue([a | a2] @ w.T); a [M, K1] fp16, w [N, K1+K2] fp16 (GEGLU: pre-packed), bias fp32."""
+         rows_per_group=1, out=None, rowstat_out=None, ln_rowstat=None, ln_colsum=None, ln_raw_parts=False, ln_eps=1e-5):
+    """out = epilogue([a | a2] @ w.T); a [M, K1] fp16, w [N, K1+K2] fp16 (GEGLU: pre-packed), bias fp32.
+    rowstat_out / ln_rowstat / ln_colsum: the folded-LayerNorm epilogues (include/gyre_b200.h)."""
     require_cuda(a, w)
     M, K1 = a.shape
     K2 = a2.shape[1] if a2 is not None else 0
@@ -240,9 +246,40 @@ def gemm(a, w, bias=None, residual=None, act=0, a2=None, out_dtype=torch.float16
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
     e = _epilogue(out, bias, residual, act, rowgroup_bias, rows_per_group)
+    e.rowstat_out, e.ln_rowstat, e.ln_colsum = ptr(rowstat_out), ptr(ln_rowstat), ptr(ln_colsum)
+    if ln_raw_parts:       # ln_rowstat = the producer's partials [parts <= 4, M, 2]: folded by the consumer itself
+        e.ln_parts, e.ln_inv_c, e.ln_eps = ln_rowstat.shape[0], 1.0 / K1, float(ln_eps)
     check(load().gyre_b200_gemm(ptr(a), a.stride(0), K1, ptr(a2), a2.stride(0) if a2 is not None else 0, K2, ptr(w),
                                 w.stride(0), M, N, C.byref(e), stream_ptr(a.device)), "gemm")
     return out
+
+
+def gemm_rowstat_buffer(M, N, device):
+    """float2 [parts][M] scratch for `gemm(..., rowstat_out=)` with N output columns."""
+    parts = load().gyre_b200_gemm_rowstat_parts(M, N)
+    return torch.zeros((parts, M, 2), device=device, dtype=torch.float32)
+
+
+def ln_finalize_rows(parts, C_cols, eps=1e-5):
+    """(mean, rstd) [M, 2] fp32 from the row-segment partials a GEMM left."""
+    nparts, M, _ = parts.shape
+    out = torch.empty((M, 2), device=parts.device, dtype=torch.float32)
+    check(load().gyre_b200_ln_finalize_rows(ptr(parts), nparts, M, C_cols, float(eps), ptr(out), stream_ptr(parts.device)),
+          "ln_finalize_rows")
+    return out
+
+
+def ln_fold_linear(w, gamma, beta, bias=None):
+    """(W' fp16 [N, K], colsum fp32 [N], lnbias fp32 [N]) for LayerNorm(gamma, beta) followed by Linear(w, bias)."""
+    require_cuda(w, gamma, beta)
+    w = w.contiguous()
+    Nn, K = w.shape
+    wo = torch.empty_like(w)
+    cs = torch.empty((Nn,), device=w.device, dtype=torch.float32)
+    lb = torch.empty((Nn,), device=w.device, dtype=torch.float32)
+    check(load().gyre_b200_ln_fold_linear(ptr(w), Nn, K, ptr(gamma.float().contiguous()), ptr(beta.float().contiguous()),
+                                          ptr(bias), ptr(wo), ptr(cs), ptr(lb), stream_ptr(w.device)), "ln_fold_linear")
+    return wo, cs, lb
 
 
 def pack_geglu(w, bias):

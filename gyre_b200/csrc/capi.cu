@@ -29,6 +29,12 @@ int to_epilogue(const gyre_b200_epilogue* e, Epilogue* out) {
   out->sk_ws_bytes = e->sk_ws_bytes;
   out->sk_flags = e->sk_flags;
   out->sk_flags_count = e->sk_flags_count;
+  out->rowstat_out = static_cast<float2*>(e->rowstat_out);
+  out->ln_rowstat = static_cast<const float2*>(e->ln_rowstat);
+  out->ln_colsum = e->ln_colsum;
+  out->ln_parts = e->ln_parts;
+  out->ln_inv_c = e->ln_inv_c;
+  out->ln_eps = e->ln_eps;
   return 0;
 }
 }  // namespace
@@ -217,6 +223,19 @@ int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int6
                             gyre_b200_stream stream) {
   GYRE_REQUIRE(x && out, "scale_latents: null operand");
   return scale_dup_latents(x, c_in, dup, batch, per_sample, static_cast<__half*>(out), S(stream));
+}
+
+int gyre_b200_gemm_rowstat_parts(int M, int N) { return gemm_rowstat_parts(M, N); }
+
+int gyre_b200_ln_finalize_rows(const void* parts, int nparts, int M, int C, float eps, void* mean_rstd,
+                               gyre_b200_stream stream) {
+  return ln_finalize_rows(static_cast<const float2*>(parts), nparts, M, C, eps, static_cast<float2*>(mean_rstd), S(stream));
+}
+
+int gyre_b200_ln_fold_linear(const void* W, int N, int K, const float* gamma, const float* beta, const float* bias,
+                             void* W_out, float* colsum, float* lnbias, gyre_b200_stream stream) {
+  return ln_fold_linear(static_cast<const __half*>(W), N, K, gamma, beta, bias, static_cast<__half*>(W_out), colsum,
+                        lnbias, S(stream));
 }
 
 int gyre_b200_resample_select(const float* src, int planes, int src_h, int src_w, const int32_t* taps_y_idx,

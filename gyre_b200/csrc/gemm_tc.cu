@@ -407,7 +407,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int etid = threadIdx.x - 64;      // 0..255
     const bool leader = (threadIdx.x == 64 + 128 * half);
     const Epilogue& ep = p.ep;
-    const bool geglu = EPI == 2 || (EPI == 1 && ep.act == ACT_GEGLU);
+    // EPI 3: the lean image + per-row (sum, sum of squares) of the produced row segments (LayerNorm statistics for the
+    // next GEMM); EPI 4 / 5: the lean / GEGLU image consuming such statistics (LayerNorm folded into this GEMM)
+    constexpr bool kGegluCode = (EPI == 1 || EPI == 2 || EPI == 5);
+    constexpr bool kPlainCode = (EPI != 2 && EPI != 5);
+    constexpr bool kRowStat = (EPI == 3);
+    constexpr bool kLnConsume = (EPI == 4 || EPI == 5);
+    const bool geglu = EPI == 2 || EPI == 5 || (EPI == 1 && ep.act == ACT_GEGLU);
     const int bn_out = geglu ? BN / 2 : BN;           // output columns per tile
     const int n_out = geglu ? p.N / 2 : p.N;          // output columns of the problem
     uint8_t* sOut = sEpi + half * 4 * kSliceBytes;    // 2 slots
@@ -418,12 +424,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint32_t slice_cnt = 0;                           // slices processed by this half (slot = cnt & 1)
     uint32_t lt = 0;
     // bias (+ per-sample vector) entry i of tile tt: i = group * BN + column
-    const int nbias = (p.rgb_rows > 0 ? (kBM / p.rgb_rows) : 1) * BN;
+    const int nbias = (kLnConsume ? 2 : (p.rgb_rows > 0 ? (kBM / p.rgb_rows) : 1)) * BN;
     auto bias_of = [&](int tt, int i) -> float {
       if (i >= nbias) return 0.f;
       const int gi = i / BN;
       const int col = (tt % p.n_tiles) * BN + (i - gi * BN);        // accumulator column == bias index
       if (col >= p.N) return 0.f;
+      if constexpr (kLnConsume) {
+        if (gi == 1) return __ldg(ep.ln_colsum + col);              // second group: column sums of gamma (.) W
+      }
       float v = ep.bias ? __ldg(ep.bias + col) : 0.f;
       if (p.rgb_rows > 0) {
         const int mt = p.mcast ? 2 * (tt / p.n_tiles) + rank : tt / p.n_tiles;
@@ -443,11 +452,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     };
     float nb0 = 0.f, nb1 = 0.f;
+    // LayerNorm consumer: (mean, rstd) of this thread's row, requested one tile ahead like the bias
+    // (ln_parts == 0: finished (mean, rstd); 1..4: the producer's raw partials, folded when the tile starts - the loads
+    // are issued a tile ahead and consumed a tile later, so their latency never sits in an epilogue)
+    struct RowStatRaw { float2 v[4]; };
+    auto rowstat_of = [&](int tt) -> RowStatRaw {
+      RowStatRaw o;
+      const int mt = p.mcast ? 2 * (tt / p.n_tiles) + rank : tt / p.n_tiles;
+      const int64_t row = static_cast<int64_t>(mt) * kBM + r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        o.v[i] = (row < p.M && i < (ep.ln_parts == 0 ? 1 : ep.ln_parts))
+                     ? __ldg(ep.ln_rowstat + static_cast<int64_t>(i) * p.M + row)
+                     : make_float2(0.f, 0.f);
+      return o;
+    };
+    auto rowstat_fold = [&](const RowStatRaw& o) -> float2 {
+      if (ep.ln_parts == 0) return o.v[0];
+      const float s = (o.v[0].x + o.v[1].x) + (o.v[2].x + o.v[3].x);
+      const float q2 = (o.v[0].y + o.v[1].y) + (o.v[2].y + o.v[3].y);
+      const float mean = s * ep.ln_inv_c;
+      const float var = fmaxf(fmaf(-mean, mean, q2 * ep.ln_inv_c), 0.f);
+      return make_float2(mean, rsqrtf(var + ep.ln_eps));
+    };
+    RowStatRaw ln_next;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ln_next.v[i] = make_float2(0.f, 0.f);
     Item wi, wnext;
     bool have = get_item(0, wi);
     if (have) {
       nb0 = bias_of(wi.t, etid);
       nb1 = bias_of(wi.t, etid + kEpiThreads);
+      if constexpr (kLnConsume) ln_next = rowstat_of(wi.t);
     }
     for (int idx = 0; have; ++idx, ++lt) {
       const bool have_next = get_item(idx + 1, wnext);
@@ -482,11 +518,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       float* sb = sbias + buf * (kMaxBiasGroups * BN);
       if (etid < nbias) sb[etid] = nb0;
       if (etid + kEpiThreads < nbias) sb[etid + kEpiThreads] = nb1;
+      float ln_mean = 0.f, ln_rstd = 0.f;
+      if constexpr (kLnConsume) {
+        const float2 ms = rowstat_fold(ln_next);
+        ln_mean = ms.x;
+        ln_rstd = ms.y;
+      }
       if (have_next) {
         nb0 = bias_of(wnext.t, etid);
         nb1 = bias_of(wnext.t, etid + kEpiThreads);
+        if constexpr (kLnConsume) ln_next = rowstat_of(wnext.t);
       }
       const float* sbr = sb + (p.rgb_rows > 0 ? (r / p.rgb_rows) * BN : 0);
+      const float* scs = sb + BN;       // LayerNorm consumer: column sums of the gamma-scaled weights
+      float rs = 0.f, rq = 0.f;         // row-statistics producer: this thread's share of its row
+      (void)ln_mean; (void)ln_rstd; (void)scs;
       const uint32_t lane_addr = tmem_base + buf * Cfg::BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
 
       // ---- stream-K bookkeeping of this item
@@ -576,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           named_bar_sync(2 + half, 128);
           float v[32];
-          if constexpr (EPI != 0) {
+          if constexpr (kGegluCode) {
             if (geglu) {
               uint32_t ra[32], rg[32];
               tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
@@ -586,7 +632,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 add_partials(ra, sl * 32);
                 add_partials(rg, BN / 2 + sl * 32);
               }
-              if (EPI == 2 || p.fast_gelu) {
+              if constexpr (EPI == 5) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float a = fmaf(ln_rstd, fmaf(-ln_mean, scs[sl * 32 + j], __uint_as_float(ra[j])), sbr[sl * 32 + j]);
+                  const float gg = fmaf(ln_rstd, fmaf(-ln_mean, scs[BN / 2 + sl * 32 + j], __uint_as_float(rg[j])),
+                                        sbr[BN / 2 + sl * 32 + j]);
+                  v[j] = a * gelu_fast(gg);
+                }
+              } else if (EPI == 2 || p.fast_gelu) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   const float a = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
@@ -605,14 +659,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               }
             }
           }
-          if constexpr (EPI != 2) {
+          if constexpr (kPlainCode) {
             if (!geglu) {
               uint32_t ra[32];
               tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
               tmem_ld_wait();
               if (sk_part) add_partials(ra, sl * 32);
+              if constexpr (kLnConsume) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+                for (int j = 0; j < 32; ++j)
+                  v[j] = fmaf(ln_rstd, fmaf(-ln_mean, scs[sl * 32 + j], __uint_as_float(ra[j])), sbr[sl * 32 + j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+              }
               if constexpr (EPI == 1) {
                 if (ep.act == ACT_SILU) {
 #pragma unroll
@@ -641,6 +701,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               }
             }
           }
+          if constexpr (kRowStat) {
+            // columns past N hold exact zeros (zero-filled B rows, no bias, zero-filled residual): they add nothing
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              rs += v[j];
+              rq = fmaf(v[j], v[j], rq);
+            }
+          }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             __align__(16) __half2 h[4];
@@ -657,6 +725,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               tma_store_2d(&tmOut, sOut + slot * kSliceBytes, col_base + sl * 32, m_tile * kBM);
             tma_store_commit();
           }
+        }
+        if constexpr (kRowStat) {
+          if (valid)
+            ep.rowstat_out[(static_cast<int64_t>(n_tile) * 2 + half) * p.M + out_row] = make_float2(rs, rq);
         }
       } else if constexpr (EPI == 1) {
         // ================================================= direct path (fp32 out, unaligned pitches, tiny N)
@@ -764,6 +836,11 @@ static auto kernel_for(int epi) -> decltype(&gemm_tc_kernel<BN, CONV, PAIR2, 1>)
   if (epi == 0) return gemm_tc_kernel<BN, CONV, PAIR2, 0>;
   if constexpr (BN == 256 && !CONV) {
     if (epi == 2) return gemm_tc_kernel<BN, CONV, PAIR2, 2>;
+    if (epi == 5) return gemm_tc_kernel<BN, CONV, PAIR2, 5>;
+  }
+  if constexpr (BN >= 64 && !CONV) {      // LayerNorm-fusion images (row statistics out / in): GEMM only
+    if (epi == 3) return gemm_tc_kernel<BN, CONV, PAIR2, 3>;
+    if (epi == 4) return gemm_tc_kernel<BN, CONV, PAIR2, 4>;
   }
   return gemm_tc_kernel<BN, CONV, PAIR2, 1>;
 }
@@ -780,6 +857,8 @@ static void cfg_for(int epi, int* smem, int* stages) {
 }
 static int epi_class(const GemmParams& p) {
   if (!p.tma_epi) return 1;
+  if (p.ep.ln_rowstat != nullptr) return p.ep.act == ACT_GEGLU ? 5 : 4;   // validated in gemm2_f16
+  if (p.ep.rowstat_out != nullptr) return 3;
   if (p.ep.act == ACT_NONE) return 0;
   if (p.ep.act == ACT_GEGLU && p.fast_gelu && !p.conv) return 2;
   return 1;
@@ -793,8 +872,9 @@ static int prepare(int* max_clusters) {
   static bool done = false;
   static int clusters = 0;
   if (!done) {
-    for (int epi = 0; epi < 3; ++epi) {
-      if (epi == 2 && BN != 256) continue;          // kernel_for(2) aliases the all-variants image elsewhere
+    for (int epi = 0; epi < 6; ++epi) {
+      if ((epi == 2 || epi == 5) && BN != 256) continue;   // kernel_for aliases the all-variants image elsewhere
+      if ((epi == 3 || epi == 4) && BN < 64) continue;
       int smem = 0, stages = 0;
       cfg_for<BN, false>(epi, &smem, &stages);
       GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, false, false>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1006,6 +1086,11 @@ int gemm_rowmax_partials(int M, int N) {
   return 2 * ((N + bn - 1) / bn);
 }
 
+int gemm_rowstat_parts(int M, int N) {
+  const int bn = pick_bn((M + kBM - 1) / kBM, N, ACT_NONE);
+  return 2 * ((N + bn - 1) / bn);
+}
+
 int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const Epilogue& ep,
              cudaStream_t st) {
   return gemm2_f16(A, lda, K, nullptr, 0, 0, W, ldw, M, N, ep, st);
@@ -1039,6 +1124,14 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
   p.ep = ep;
   p.rgb_rows = 0;
   p.tma_epi = (tma_epilogue_ok(ep, n_out) && ep.rowgroup_bias == nullptr) ? 1 : 0;
+  if (ep.rowstat_out != nullptr)
+    GYRE_REQUIRE(p.tma_epi && ep.act == ACT_NONE && bn >= 64 && ep.ln_rowstat == nullptr,
+                 "gemm: row statistics need the fp16 TMA epilogue without activation (N=%d, ldo=%d)", N, ep.ldo);
+  if (ep.ln_rowstat != nullptr)
+    GYRE_REQUIRE(p.tma_epi && ep.ln_colsum != nullptr && bn >= 64 && ep.ln_parts >= 0 && ep.ln_parts <= 4 &&
+                     (ep.ln_parts == 0 || ep.ln_inv_c > 0.f) &&
+                     (ep.act == ACT_NONE || (ep.act == ACT_GEGLU && p.fast_gelu)),
+                 "gemm: the folded LayerNorm needs the fp16 TMA epilogue, column sums and no activation but the fast GEGLU");
   GYRE_TRY(want_pair_mode(bn, p.m_tiles, p.k_iters, &p.mcast));
   {
     int max_clusters = 0;

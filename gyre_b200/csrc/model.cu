@@ -210,6 +210,7 @@ int Model::load(const char* key, const void* data, int dtype, const int64_t* sha
       GYRE_REQUIRE(false, "load_weight(%s): bad slot", key);
   }
   s.loaded = true;
+  on_load(key);
   return 0;
 }
 
@@ -287,6 +288,7 @@ int Model::resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __
 
 // ------------------------------------------------------------------------------------------ UNet
 UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
+  ln_fuse_ = tunable(TUNE_LN_FUSE) != 0;
   groups_ = cfg.norm_num_groups;
   const int L = cfg.num_levels;
   const int* ch = cfg.block_out_channels;
@@ -341,6 +343,16 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
       reg(b + ".ff.net.0.proj.weight", P_GEGLU_W, k->geglu.w, {8 * C, C});
       reg(b + ".ff.net.0.proj.bias", P_GEGLU_B, k->geglu.bias, {8 * C});
       reg_linear(b + ".ff.net.2", C, 4 * C, true, &k->ff2);
+      if (ln_fuse_) {
+        auto derived = [&](LnFoldW* f, int N) {
+          f->w = static_cast<__half*>(dalloc(sizeof(__half) * N * C));
+          f->colsum = static_cast<float*>(dalloc(sizeof(float) * N));
+          f->bias = static_cast<float*>(dalloc(sizeof(float) * N));
+        };
+        derived(&k->qkv_ln, 3 * C);
+        derived(&k->q2_ln, C);
+        derived(&k->geglu_ln, 8 * C);
+      }
     }
   };
   auto depth_of = [&](int lvl) { return cfg.transformer_depth[lvl] > 0 ? cfg.transformer_depth[lvl] : 1; };
@@ -424,6 +436,27 @@ UNetModel::~UNetModel() {
     if (p) cudaFree(p);
 }
 
+void UNetModel::on_load(const std::string& key) {
+  if (key.find(".transformer_blocks.") != std::string::npos) ln_dirty_ = true;
+}
+
+// Derives, for every Linear that follows a LayerNorm (attn1 q|k|v, attn2 to_q, the GEGLU projection), the gamma-scaled
+// weight copy, its column sums and the beta-folded bias.  Runs once after a (re)load, before the next forward.
+int UNetModel::refold_layernorms(cudaStream_t st) {
+  for (TransformerW& t : tblocks_)
+    for (TBlockW& k : t.blocks) {
+      const int C = t.C;
+      GYRE_TRY(ln_fold_linear(k.qkv.w, 3 * C, C, k.ln1.g, k.ln1.b, nullptr, k.qkv_ln.w, k.qkv_ln.colsum, k.qkv_ln.bias, st));
+      GYRE_TRY(ln_fold_linear(k.q2.w, C, C, k.ln2.g, k.ln2.b, nullptr, k.q2_ln.w, k.q2_ln.colsum, k.q2_ln.bias, st));
+      // the GEGLU weight is packed (value / gate rows interleaved per tile) and so is its bias: row n of one is row n
+      // of the other, which is all the fold needs
+      GYRE_TRY(ln_fold_linear(k.geglu.w, 8 * C, C, k.ln3.g, k.ln3.b, k.geglu.bias, k.geglu_ln.w, k.geglu_ln.colsum,
+                              k.geglu_ln.bias, st));
+    }
+  ln_dirty_ = false;
+  return 0;
+}
+
 int UNetModel::set_context(const __half* ctx, int B, int L, cudaStream_t st) {
   GYRE_TRY(ensure_device());
   if (ctx == nullptr) {
@@ -465,7 +498,40 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   __half* tn = ex.s16(n);
   RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, B, HW, groups_, 1e-6f, t.gn.g, t.gn.b, false, tn, gn_scratch, ex.st));
   __half* h = ex.s16(n);
-  RUN(ex, gemm_f16(tn, C, t.proj_in.w, C, M, C, C, ep_out(h, C, t.proj_in.bias), ex.st));
+  // LayerNorm folded into the GEMMs around it: the GEMM that PRODUCES a residual-stream tensor also emits
+  // per-row (sum, sum of squares) partials; a tiny kernel turns them into (mean, rstd); the GEMM that CONSUMES the
+  // normalised tensor reads the RAW rows against gamma-scaled weights and applies rstd * (acc - mean * colsum) + bias'
+  // in its epilogue.  The standalone LayerNorm pass (one read + one write of the tensor, three times per block) is gone.
+  // The scratch is reserved whenever the model was built with the folded weights, so the workspace size does not
+  // depend on the run-time tunable.
+  const bool fuse = ln_fuse_ && tunable(TUNE_LN_FUSE) != 0 && C > 32;
+  const int ln_parts = ln_fuse_ ? gemm_rowstat_parts(M, C) : 0;
+  float2* ln_part = ln_fuse_ ? reinterpret_cast<float2*>(ex.s32(static_cast<size_t>(2) * ln_parts * M)) : nullptr;
+  float2* ln_stat = ln_fuse_ ? reinterpret_cast<float2*>(ex.s32(static_cast<size_t>(2) * M)) : nullptr;
+  // producer epilogue: also leave the row statistics of what it writes
+  auto with_stats = [&](Epilogue e) {
+    if (fuse) e.rowstat_out = ln_part;
+    return e;
+  };
+  // up to 4 partials per row (C = 320: two 160-column tiles x two column halves) the consumer folds them itself;
+  // wider rows go through the finalize kernel
+  const bool direct = ln_parts <= 4;
+  auto finalize_stats = [&]() -> int {
+    if (fuse && !direct) RUN(ex, ln_finalize_rows(ln_part, ln_parts, M, C, 1e-5f, ln_stat, ex.st));
+    return 0;
+  };
+  // consumer epilogue: LayerNorm(x) @ W^T from the raw rows
+  auto ln_ep = [&](Epilogue e, const LnFoldW& f) {
+    e.bias = f.bias;
+    e.ln_colsum = f.colsum;
+    e.ln_rowstat = direct ? ln_part : ln_stat;
+    e.ln_parts = direct ? ln_parts : 0;
+    e.ln_inv_c = 1.0f / static_cast<float>(C);
+    e.ln_eps = 1e-5f;
+    return e;
+  };
+  RUN(ex, gemm_f16(tn, C, t.proj_in.w, C, M, C, C, with_stats(ep_out(h, C, t.proj_in.bias)), ex.st));
+  GYRE_TRY(finalize_stats());
   __half* nrm = tn;   // the GroupNorm output is dead after proj_in: reuse it for the LayerNorm outputs
   __half* qkv = ex.s16(n * 3);
   __half* o = ex.s16(n);
@@ -490,8 +556,12 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   for (size_t bi = 0; bi < t.blocks.size(); ++bi) {
     const TBlockW& k = t.blocks[bi];
     // ---- self-attention
-    RUN(ex, layernorm_rows(h, M, C, 1e-5f, k.ln1.g, k.ln1.b, nrm, ex.st));
-    RUN(ex, gemm_f16(nrm, C, k.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C), ex.st));
+    if (fuse) {
+      RUN(ex, gemm_f16(h, C, k.qkv_ln.w, C, M, 3 * C, C, ln_ep(ep_out(qkv, 3 * C), k.qkv_ln), ex.st));
+    } else {
+      RUN(ex, layernorm_rows(h, M, C, 1e-5f, k.ln1.g, k.ln1.b, nrm, ex.st));
+      RUN(ex, gemm_f16(nrm, C, k.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C), ex.st));
+    }
     if (rr > 0) {
       // ToMe (nonfree/tome_memory_efficient_cross_attention.py:28-50): merge K and V with one plan built from K
       const int nk = HW - rr;
@@ -500,11 +570,16 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
     } else {
       RUN(ex, attention_f16(qkv, 3 * C, off(qkv, C), 3 * C, off(qkv, 2 * C), 3 * C, B, t.heads, HW, HW, d, scale, o, C, ex.st));
     }
-    RUN(ex, gemm_f16(o, C, k.o1.w, C, M, C, C, ep_out(h2, C, k.o1.bias, h, C), ex.st));
+    RUN(ex, gemm_f16(o, C, k.o1.w, C, M, C, C, with_stats(ep_out(h2, C, k.o1.bias, h, C)), ex.st));
+    GYRE_TRY(finalize_stats());
     // ---- cross-attention
-    RUN(ex, layernorm_rows(h2, M, C, 1e-5f, k.ln2.g, k.ln2.b, nrm, ex.st));
     __half* q = qkv;   // dead after self-attention
-    RUN(ex, gemm_f16(nrm, C, k.q2.w, C, M, C, C, ep_out(q, C), ex.st));
+    if (fuse) {
+      RUN(ex, gemm_f16(h2, C, k.q2_ln.w, C, M, C, C, ln_ep(ep_out(q, C), k.q2_ln), ex.st));
+    } else {
+      RUN(ex, layernorm_rows(h2, M, C, 1e-5f, k.ln2.g, k.ln2.b, nrm, ex.st));
+      RUN(ex, gemm_f16(nrm, C, k.q2.w, C, M, C, C, ep_out(q, C), ex.st));
+    }
     const __half* kv;
     if (ctx != nullptr || ex.dry) {
       RUN(ex, gemm_f16(ctx, k.kv2.K, k.kv2.w, k.kv2.K, B * L, 2 * C, k.kv2.K, ep_out(kv_new, 2 * C), ex.st));
@@ -513,11 +588,22 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
       kv = kv_cache_[static_cast<size_t>(k.flat)];
     }
     RUN(ex, attention_f16(q, C, kv, 2 * C, off(kv, C), 2 * C, B, t.heads, HW, L, d, scale, o, C, ex.st));
-    RUN(ex, gemm_f16(o, C, k.o2.w, C, M, C, C, ep_out(h, C, k.o2.bias, h2, C), ex.st));   // h <- h2 + attn2
+    RUN(ex, gemm_f16(o, C, k.o2.w, C, M, C, C, with_stats(ep_out(h, C, k.o2.bias, h2, C)), ex.st));   // h <- h2 + attn2
+    GYRE_TRY(finalize_stats());
     // ---- GEGLU feed-forward
-    RUN(ex, layernorm_rows(h, M, C, 1e-5f, k.ln3.g, k.ln3.b, nrm, ex.st));
-    RUN(ex, gemm_f16(nrm, C, k.geglu.w, C, M, 8 * C, C, ep_out(g, 4 * C, k.geglu.bias, nullptr, 0, ACT_GEGLU), ex.st));
-    RUN(ex, gemm_f16(g, 4 * C, k.ff2.w, 4 * C, M, C, 4 * C, ep_out(h2, C, k.ff2.bias, h, C), ex.st));   // h2 <- h + ff
+    const bool fuse_ff = fuse && tunable(TUNE_GELU_FAST) != 0;     // the folded GEGLU image carries the fast GELU only
+    if (fuse_ff) {
+      RUN(ex, gemm_f16(h, C, k.geglu_ln.w, C, M, 8 * C, C,
+                       ln_ep(ep_out(g, 4 * C, nullptr, nullptr, 0, ACT_GEGLU), k.geglu_ln), ex.st));
+    } else {
+      RUN(ex, layernorm_rows(h, M, C, 1e-5f, k.ln3.g, k.ln3.b, nrm, ex.st));
+      RUN(ex, gemm_f16(nrm, C, k.geglu.w, C, M, 8 * C, C, ep_out(g, 4 * C, k.geglu.bias, nullptr, 0, ACT_GEGLU), ex.st));
+    }
+    // h2 <- h + ff; with another block behind it, its norm1 needs the statistics of what this GEMM writes
+    const bool more = bi + 1 < t.blocks.size();
+    Epilogue e_ff2 = ep_out(h2, C, k.ff2.bias, h, C);
+    RUN(ex, gemm_f16(g, 4 * C, k.ff2.w, 4 * C, M, C, 4 * C, more ? with_stats(e_ff2) : e_ff2, ex.st));
+    if (more) GYRE_TRY(finalize_stats());
     std::swap(h, h2);   // the block's output becomes the next block's residual stream
   }
   h2 = h;
@@ -573,6 +659,7 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   const int* ch = cfg_.block_out_channels;
   const float eps = cfg_.norm_eps;
   if (!ex.dry) GYRE_TRY(ensure_device());
+  if (!ex.dry && ln_fuse_ && ln_dirty_) GYRE_TRY(refold_layernorms(ex.st));
 
   // ---- time embedding: sinusoid -> Linear -> SiLU -> Linear ; every consumer applies SiLU first, so the
   // second Linear's epilogue applies it once; then ONE fused GEMM produces all 22 resnet projections.

@@ -53,9 +53,14 @@ struct ResnetW {
   int temb_off = -1;    // column offset into the fused time_emb_proj output (-1: no temb)
 };
 
+// A Linear that directly follows a LayerNorm, prepared for the folded form (ops.h, Epilogue::ln_rowstat): gamma-scaled
+// copy of the packed weight, its column sums and bias + beta @ W^T.  Derived data: rebuilt after any (re)load.
+struct LnFoldW { __half* w = nullptr; float* colsum = nullptr; float* bias = nullptr; };
+
 struct TBlockW {          // one BasicTransformerBlock
   NormW ln1, ln2, ln3;
   LinW qkv, o1, q2, kv2, o2, geglu, ff2;
+  LnFoldW qkv_ln, q2_ln, geglu_ln;
   int flat = 0;           // index among all BasicTransformerBlocks of the model (bound-context cache slot)
 };
 
@@ -107,6 +112,7 @@ class Model {
   int resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __half* x2, int C2, int B, int H, int W,
              float eps, const __half* temb_all, int temb_ld, __half* out);
   int ensure_device();
+  virtual void on_load(const std::string& key) { (void)key; }   // a parameter was (re)loaded
   // epilogue descriptor carrying this model's stream-K scratch
   Epilogue ep_out(__half* out, int ldo, const float* bias = nullptr, const __half* residual = nullptr, int ldr = 0,
                   int act = 0) const;
@@ -154,6 +160,10 @@ class UNetModel : public Model {
  private:
   int transformer(Exec& ex, const TransformerW& t, const __half* x, int B, int HW, const __half* ctx, int L, int r,
                   __half* out);
+  void on_load(const std::string& key) override;
+  int refold_layernorms(cudaStream_t st);
+  bool ln_fuse_ = false;    // LayerNorm folded into the GEMMs around it (tunable LN_FUSE at creation)
+  bool ln_dirty_ = true;    // a transformer-block parameter changed since the folded weights were derived
   gyre_b200_unet_config cfg_;
   Conv3W conv_in_;      // Cin = in_channels (4/5/9): the input is staged NHWC with the channel pitch padded to 8
   LinW time1_, time2_;

@@ -590,6 +590,67 @@ int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gam
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ LayerNorm folded into GEMMs
+// (mean, rstd) per row from the per-(n-tile, column-half) partial sums the producing GEMM's epilogue left
+// (Epilogue::rowstat_out).  Fixed summation order; the final E[x^2] - mean^2 in fp64.
+__global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restrict__ parts, int nparts, int M, float inv_c,
+                                                          float eps, float2* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  if (row >= M) return;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    const float2 v = parts[static_cast<int64_t>(p) * M + row];
+    s += static_cast<double>(v.x);
+    q += static_cast<double>(v.y);
+  }
+  const double mean = s * static_cast<double>(inv_c);
+  double var = q * static_cast<double>(inv_c) - mean * mean;
+  if (var < 0.0) var = 0.0;
+  out[row] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+
+int ln_finalize_rows(const float2* parts, int nparts, int M, int C, float eps, float2* out, cudaStream_t st) {
+  GYRE_REQUIRE(parts && out && nparts > 0 && M > 0 && C > 0, "ln_finalize: bad arguments");
+  prof::Scope ps(prof::F_LAYERNORM, 0.0, 8.0 * M * (nparts + 1), st);
+  GYRE_TRY(launch_kernel(ln_finalize_kernel, dim3((M + 255) / 256), dim3(256), 0, st, parts, nparts, M, 1.0f / C, eps, out));
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Weight preparation (once per load): one warp per output row n of W [N, K].
+__global__ void __launch_bounds__(256) ln_fold_kernel(const __half* __restrict__ w, int N, int K,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ bias, __half* __restrict__ w_out,
+                                                      float* __restrict__ colsum, float* __restrict__ lnbias) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bw = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __half2float(w[static_cast<int64_t>(n) * K + k]);
+    const __half ws = __float2half_rn(wv * gamma[k]);
+    w_out[static_cast<int64_t>(n) * K + k] = ws;
+    cs += __half2float(ws);             // the column sum of what the tensor core will actually multiply by
+    bw = fmaf(beta[k], wv, bw);
+  }
+  cs = warp_sum(cs);
+  bw = warp_sum(bw);
+  if (lane == 0) {
+    colsum[n] = cs;
+    lnbias[n] = (bias ? bias[n] : 0.f) + bw;
+  }
+}
+
+int ln_fold_linear(const __half* w, int N, int K, const float* gamma, const float* beta, const float* bias, __half* w_out,
+                   float* colsum, float* lnbias, cudaStream_t st) {
+  GYRE_REQUIRE(w && gamma && beta && w_out && colsum && lnbias && N > 0 && K > 0, "ln_fold: bad arguments");
+  ln_fold_kernel<<<(N + 7) / 8, 256, 0, st>>>(w, N, K, gamma, beta, bias, w_out, colsum, lnbias);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ row softmax (fp32 -> fp16)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int n, float scale,
                                                            __half* __restrict__ p, int ldp) {

@@ -28,6 +28,21 @@ struct Epilogue {
   float* rowmax_val = nullptr;
   int* rowmax_idx = nullptr;
   int rowmax_ld = 0;
+  // LayerNorm folded into the GEMMs around it (GEMM only, TMA epilogue):
+  //   producer side - rowstat_out [2 * n_tiles][M] float2: per output row the (sum, sum of squares) of the row segment
+  //   each (n-tile, column-half) of this launch produced (after bias / residual); ln_finalize_rows folds them into
+  //   (mean, rstd) per row.
+  //   consumer side - A holds the RAW rows x, W the gamma-scaled weights W' = gamma (.) W; with ln_rowstat [M] float2
+  //   (mean, rstd) and ln_colsum [N] = sum_k W'[n, k] the epilogue turns the accumulator into LayerNorm(x) @ W^T:
+  //   rstd * (acc - mean * colsum[n]) + bias[n], bias already holding beta @ W^T.
+  //   With ln_parts in 1..4 the consumer folds the producer's partials itself (ln_rowstat = [ln_parts][M] raw partials,
+  //   ln_inv_c = 1 / C, ln_eps) and no finalize launch is needed.
+  float2* rowstat_out = nullptr;
+  const float2* ln_rowstat = nullptr;
+  const float* ln_colsum = nullptr;
+  int ln_parts = 0;
+  float ln_inv_c = 0.f;
+  float ln_eps = 1e-5f;
   // optional stream-K scratch (owned by the caller, reused by every launch on one stream): fp32 partial
   // accumulators + one int flag per tile of the partial wave (flags must be zero; the kernel leaves them zero)
   void* sk_ws = nullptr;
@@ -46,6 +61,14 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
               int N, const Epilogue& ep, cudaStream_t st);
 // number of (max, argmax) partials per row an ACT_ROWMAX GEMM of this shape writes
 int gemm_rowmax_partials(int M, int N);
+// number of float2 partials per row a GEMM of this shape writes to Epilogue::rowstat_out
+int gemm_rowstat_parts(int M, int N);
+// (mean, rstd) per row from the row-segment partials of a producing GEMM: parts [nparts][M] -> out [M]
+int ln_finalize_rows(const float2* parts, int nparts, int M, int C, float eps, float2* out, cudaStream_t st);
+// LayerNorm affine folded into the following Linear: w_out[n, k] = fp16(w[n, k] * gamma[k]), colsum[n] = sum_k w_out[n, k],
+// lnbias[n] = bias[n] (0 if null) + sum_k beta[k] * w[n, k].  w / w_out: [N, K] fp16 row pitch K (any row order).
+int ln_fold_linear(const __half* w, int N, int K, const float* gamma, const float* beta, const float* bias, __half* w_out,
+                   float* colsum, float* lnbias, cudaStream_t st);
 
 // 3x3 convolution as implicit GEMM.  X: [B, H, W, Cin] fp16 NHWC with channel pitch ldx; Wp: packed
 // [Cout, 9*cin_pad] (tap-major, cin_pad = round_up(Cin, 64)); output rows are pixels of [B, Ho, Wo].
@@ -165,7 +188,7 @@ int mma_bench(int n, int naccs, int a_tmem, int reps, int blocks, long long* out
 // ---- tunables: small integer knobs read on the host at launch time.  Each starts from the environment
 // variable GYRE_B200_<NAME> (if set) and can be changed through gyre_b200_set_tunable (A/B measurements).
 enum Tunable { TUNE_ATT_VARIANT = 0, TUNE_PDL = 1, TUNE_GELU_FAST = 2, TUNE_GN_CHUNKS = 3, TUNE_UPCONV_FOLD = 4,
-               TUNE_CTX_KV_CACHE = 5, TUNE_XATTN = 6, TUNE_GN_PHASE = 7, TUNE_MCAST = 8, TUNE_ATT_D128 = 9, TUNE_STREAMK = 10, TUNE_FORCE_BN = 11, TUNE_GEMM_STAGES = 12, TUNE_DEBUG = 13, TUNE_LN_SUB = 14, TUNE_GN_THREADS = 15, TUNE_COUNT = 16 };
+               TUNE_CTX_KV_CACHE = 5, TUNE_XATTN = 6, TUNE_GN_PHASE = 7, TUNE_MCAST = 8, TUNE_ATT_D128 = 9, TUNE_STREAMK = 10, TUNE_FORCE_BN = 11, TUNE_GEMM_STAGES = 12, TUNE_DEBUG = 13, TUNE_LN_SUB = 14, TUNE_GN_THREADS = 15, TUNE_LN_FUSE = 16, TUNE_COUNT = 17 };
 int tunable(int id);
 int set_tunable_by_name(const char* name, int value);
 int get_tunable_by_name(const char* name, int* value);

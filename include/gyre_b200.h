@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GYRE_B200_ABI_VERSION 1
+#define GYRE_B200_ABI_VERSION 2
 
 typedef void* gyre_b200_stream;  /* cudaStream_t */
 typedef struct gyre_b200_model* gyre_b200_handle;
@@ -347,12 +347,33 @@ typedef struct gyre_b200_epilogue {
   size_t sk_ws_bytes;
   int32_t* sk_flags;
   int32_t sk_flags_count;
+  /* LayerNorm folded into the GEMMs around it (gyre_b200_gemm only; all NULL: off).  Replaces the F.layer_norm between
+   * two Linears of a BasicTransformerBlock (diffusers attention.py; structure restated in nonfree/tome_unet.py:114-136):
+   *   rowstat_out [gyre_b200_gemm_rowstat_parts(M, N)][M] float2 - the producing GEMM also leaves, per output row, the
+   *     (sum, sum of squares) of every row segment it writes; gyre_b200_ln_finalize_rows folds them to (mean, rstd);
+   *   ln_rowstat [M] float2 (mean, rstd) + ln_colsum [N] - the consuming GEMM takes the RAW rows as A and weights
+   *     prepared by gyre_b200_ln_fold_linear (W' = gamma (.) W, colsum, bias' = bias + beta @ W^T) and stores
+   *     rstd * (acc - mean * colsum[n]) + bias'[n]  ==  LayerNorm(x) @ W^T + bias  (act: none or GEGLU). */
+  void* rowstat_out;
+  const void* ln_rowstat;
+  const float* ln_colsum;
+  /* ln_parts in 1..4: ln_rowstat holds the producer's raw partials [ln_parts][M] and the consumer folds them itself
+   * with ln_inv_c = 1 / C and ln_eps (no finalize launch); 0: ln_rowstat holds finished (mean, rstd) pairs. */
+  int32_t ln_parts;
+  float ln_inv_c;
+  float ln_eps;
 } gyre_b200_epilogue;
 
 /* out = epilogue([A | A2] @ W^T): A [M, K1] pitch lda, A2 [M, K2] pitch lda2 (may be NULL/0),
  * W [N, K1+K2] pitch ldw; fp16, fp32 accumulate (replaces F.linear / 1x1 conv: cuBLAS HGEMM). */
 int gyre_b200_gemm(const void* A, int lda, int K1, const void* A2, int lda2, int K2, const void* W, int ldw, int M,
                    int N, const gyre_b200_epilogue* ep, gyre_b200_stream stream);
+int gyre_b200_gemm_rowstat_parts(int M, int N);
+int gyre_b200_ln_finalize_rows(const void* parts, int nparts, int M, int C, float eps, void* mean_rstd,
+                               gyre_b200_stream stream);
+/* W [N, K] fp16 (any row order, e.g. GEGLU-packed) -> W' [N, K] fp16, colsum [N], lnbias [N] (bias may be NULL) */
+int gyre_b200_ln_fold_linear(const void* W, int N, int K, const float* gamma, const float* beta, const float* bias,
+                             void* W_out, float* colsum, float* lnbias, gyre_b200_stream stream);
 /* GEGLU weights must be re-ordered so that each 256-row tile holds 128 value rows then their 128
  * gate rows: packs W [2*F, K] (diffusers ff.net.0.proj layout) into Wp [2*F, K]. F % 128 == 0. */
 int gyre_b200_pack_geglu(const void* W, int dtype, int F, int K, const void* bias, int bias_dtype, void* Wp,

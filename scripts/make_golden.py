@@ -506,9 +506,10 @@ def oracle_fixtures(full: bool):
         unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1)
         cfgu = osamp.CFGParallel(unet, unc, emb, 7.5)
         for sampler, steps in (("ddim", 10), ("euler_a", 12), ("euler", 8), ("dpmpp_2m", 8), ("heun", 7), ("dpm_2", 7),
-                               ("dpm_2_a", 7), ("lms", 9), ("dpmpp_2s_a", 7), ("dpmpp_sde", 7), ("dpm_fast", 10)):
+                               ("dpm_2_a", 7), ("lms", 9), ("dpmpp_2s_a", 7), ("dpmpp_sde", 7), ("dpm_fast", 10), ("plms", 9),
+                               ("dpmsolverpp_1", 9), ("dpmsolverpp_2", 9), ("dpmsolverpp_3", 11), ("dpmsolverpp_3b", 20)):
             lat = osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=128, width=128, sample_size=16,
-                                        seeds=[420420420, 420420421], steps=steps, sampler=sampler)
+                                        seeds=[420420420, 420420421], steps=steps, sampler=sampler.rstrip("b"))
             out[f"pipe_tiny/{sampler}"] = {"steps": steps, "latents": lat}
     torch.save(out, os.path.join(GOLD, "oracle_tiny.pt"))
     print("oracle tiny fixtures:", list(out))

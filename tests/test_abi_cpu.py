@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert not not_bound, f"declared in gyre_b200.h but missing from the ctypes table: {not_bound}"
     extra = [n for n in _native.SIGNATURES if n not in names]
     assert not extra, f"bound in _native.py but not declared in the header: {extra}"
-    assert _native.load(build_if_missing=False).gyre_b200_abi_version() == 1
+    assert _native.load(build_if_missing=False).gyre_b200_abi_version() == 2
 
 
 def test_error_channel_without_gpu():

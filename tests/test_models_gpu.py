@@ -506,3 +506,31 @@ def test_vae_module_surface_slicing_and_fp32_interface(tiny_vae):
     assert img32.dtype == torch.float32 and torch.equal(img32, full.float())
     mom = v32.encode(img32.clamp(-1, 1)).latent_dist.parameters
     assert mom.dtype == torch.float32
+
+
+def test_unet_layernorm_fold_ab(tiny_unet):
+    """LN_FUSE (default on): the three LayerNorms of every transformer block are folded into the GEMMs around them.  Off,
+    the standalone LayerNorm kernel runs.  Both evaluate the same function; the folded form skips one fp16 rounding (the
+    normalised tensor is never materialised), so it may only be closer to the fp32 oracle, not farther."""
+    from gyre_b200 import _native as N
+    from oracle.unet import unet_forward
+    cfg, P, unet = tiny_unet
+    _no_tf32()
+    gen = torch.Generator("cpu").manual_seed(19)
+    x = torch.randn(2, 4, 16, 16, generator=gen).half()
+    ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=gen).half()
+    t = torch.tensor([900, 40])
+    with torch.no_grad():
+        ref = unet_forward(P, cfg, x.float(), t, ctx.float())
+    assert N.get_tunable("LN_FUSE") == 1
+    fused = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample.clone()
+    try:
+        N.set_tunable("LN_FUSE", 0)
+        plain = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample.clone()
+    finally:
+        N.set_tunable("LN_FUSE", 1)
+    e_f, e_p = rel_err(fused.cpu(), ref), rel_err(plain.cpu(), ref)
+    print(f"tiny unet rel err vs oracle: LayerNorm folded {e_f:.3e}, standalone LayerNorm kernels {e_p:.3e}")
+    assert e_f < 5e-3 and e_p < 5e-3
+    assert rel_err(fused, plain) < 5e-3
+    assert not torch.equal(fused, plain)          # the two paths really are different kernels

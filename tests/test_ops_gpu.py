@@ -321,3 +321,67 @@ def test_dpm_error_norm(nat, n):
     nat.check(lib.gyre_b200_dpm_error_partials(nat.ptr(lo), nat.ptr(hi), nat.ptr(prev), atol, rtol, n, nat.ptr(parts2),
                                                nat.stream_ptr()), "dpm_error_partials")
     assert torch.equal(parts, parts2), "the partial sums must be reproducible"
+
+
+@pytest.mark.parametrize("M,C,N2", [(4096, 320, 960), (65536, 320, 320), (16384, 640, 1920), (4096, 1280, 1280), (1000, 320, 320),
+                                    (300, 64, 192)])
+def test_layernorm_folded_into_gemms(nat, M, C, N2):
+    """The producing GEMM leaves per-row (sum, sum of squares) partials of what it writes; the consuming GEMM reads the RAW
+    rows against gamma-scaled weights and applies rstd * (acc - mean * colsum) + bias' in its epilogue.  Reference:
+    F.layer_norm of the produced fp16 tensor followed by F.linear, in fp32."""
+    a = rnd(M, C, seed=1)
+    w1 = rnd(C, C, seed=2, scale=1 / math.sqrt(C))
+    b1 = rnd(C, seed=3, dtype=torch.float32)
+    res = rnd(M, C, seed=4, scale=2.0) + 0.5          # a residual stream with a non-zero row mean
+    gamma = (1.0 + 0.3 * rnd(C, seed=5, dtype=torch.float32)).contiguous()
+    beta = 0.2 * rnd(C, seed=6, dtype=torch.float32)
+    w2 = rnd(N2, C, seed=7, scale=1 / math.sqrt(C))
+    b2 = rnd(N2, seed=8, dtype=torch.float32)
+    parts = nat.gemm_rowstat_buffer(M, C, a.device)
+    h = nat.gemm(a, w1, bias=b1, residual=res, rowstat_out=parts)
+    href = a.float() @ w1.float().t() + b1 + res.float()
+    assert_close(h, href, 4e-3, 2e-3, "producer output")
+    # the statistics are those of the rounded tensor up to the rounding itself
+    stat = nat.ln_finalize_rows(parts, C)
+    hf = h.float()
+    mean_ref = hf.mean(dim=1)
+    rstd_ref = 1.0 / torch.sqrt(hf.var(dim=1, unbiased=False) + 1e-5)
+    assert (stat[:, 0] - mean_ref).abs().max().item() < 2e-3
+    assert ((stat[:, 1] - rstd_ref).abs() / rstd_ref).max().item() < 2e-3
+    wf, cs, lb = nat.ln_fold_linear(w2, gamma, beta, b2)
+    out = nat.gemm(h, wf, bias=lb, ln_rowstat=stat, ln_colsum=cs)
+    ref = F.linear(F.layer_norm(hf, (C,), gamma, beta, 1e-5), w2.float(), b2)
+    assert_close(out, ref, 6e-3, 4e-3, f"folded LayerNorm -> Linear {M}x{C}->{N2}")
+    # the unfused pair of kernels is no closer to the fp32 reference than the folded form
+    ln = nat.layernorm(h, gamma, beta)
+    unfused = nat.gemm(ln, w2, bias=b2)
+    if parts.shape[0] <= 4:
+        # narrow rows: the consumer folds the raw partials itself, no finalize launch
+        out_direct = nat.gemm(h, wf, bias=lb, ln_rowstat=parts, ln_colsum=cs, ln_raw_parts=True)
+        assert_close(out_direct, ref, 6e-3, 4e-3, f"folded LayerNorm (raw partials) -> Linear {M}x{C}->{N2}")
+        assert (out_direct.float() - out.float()).abs().max().item() < 4e-3
+    e_f = (out.float() - ref).abs().max().item()
+    e_u = (unfused.float() - ref).abs().max().item()
+    print(f"folded LN {M}x{C}->{N2}: max abs err folded {e_f:.3e}, LayerNorm kernel + GEMM {e_u:.3e}")
+    assert e_f <= 1.5 * e_u + 1e-3
+
+
+@pytest.mark.parametrize("M,C", [(4096, 320), (16384, 640), (1024, 1280)])
+def test_layernorm_folded_into_geglu(nat, M, C):
+    a = rnd(M, C, seed=1)
+    w1 = rnd(C, C, seed=2, scale=1 / math.sqrt(C))
+    res = rnd(M, C, seed=4) - 0.3
+    gamma = (1.0 + 0.3 * rnd(C, seed=5, dtype=torch.float32)).contiguous()
+    beta = 0.2 * rnd(C, seed=6, dtype=torch.float32)
+    Fdim = 4 * C
+    w2 = rnd(2 * Fdim, C, seed=7, scale=1 / math.sqrt(C))
+    b2 = rnd(2 * Fdim, seed=8, dtype=torch.float32)
+    parts = nat.gemm_rowstat_buffer(M, C, a.device)
+    h = nat.gemm(a, w1, residual=res, rowstat_out=parts)
+    stat = nat.ln_finalize_rows(parts, C)
+    wp, bp = nat.pack_geglu(w2, b2)
+    wf, cs, lb = nat.ln_fold_linear(wp, gamma, beta, bp)
+    out = nat.gemm(h, wf, bias=lb, act=1, ln_rowstat=stat, ln_colsum=cs)
+    y = F.linear(F.layer_norm(h.float(), (C,), gamma, beta, 1e-5), w2.float(), b2)
+    ref = y[:, :Fdim] * F.gelu(y[:, Fdim:])
+    assert_close(out, ref, 8e-3, 6e-3, f"folded LayerNorm -> GEGLU {M}x{C}")

@@ -30,7 +30,11 @@ def tiny():
                                                 ("k_heun", "heun", 7), ("k_dpm_2", "dpm_2", 7),
                                                 ("k_dpm_2_ancestral", "dpm_2_a", 7), ("k_lms", "lms", 9),
                                                 ("k_dpmpp_2s_ancestral", "dpmpp_2s_a", 7), ("k_dpmpp_sde", "dpmpp_sde", 7),
-                                                ("dpm_fast", "dpm_fast", 10)])
+                                                ("dpm_fast", "dpm_fast", 10), ("plms", "plms", 9),
+                                                ("dpmsolverpp_1order", "dpmsolverpp_1", 9),
+                                                ("dpmsolverpp_2order", "dpmsolverpp_2", 9),
+                                                ("dpmsolverpp_3order", "dpmsolverpp_3", 11),
+                                                ("dpmsolverpp_3order", "dpmsolverpp_3b", 20)])
 def test_pipeline_tiny_vs_golden(tiny, sampler, name, steps):
     """Golden latents were produced by the oracle with fp32 latents / schedule (scripts/make_golden.py)."""
     cfg, P, pipe, emb, unc = tiny
