@@ -106,6 +106,7 @@ SIGNATURES = {
     "gyre_b200_sched_step_blend": (_i, [C.POINTER(Step), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _f, _vp]),
     "gyre_b200_cat_channels": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _vp, _vp]),
     "gyre_b200_scale_latents": (_i, [_vp, _f, _i, _i, _i64, _vp, _vp]),
+    "gyre_b200_lpw_weight": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "gyre_b200_gemm_rowstat_parts": (_i, [_i, _i]),
     "gyre_b200_ln_finalize_rows": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "gyre_b200_ln_fold_linear": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

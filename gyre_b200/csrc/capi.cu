@@ -225,6 +225,11 @@ int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int6
   return scale_dup_latents(x, c_in, dup, batch, per_sample, static_cast<__half*>(out), S(stream));
 }
 
+int gyre_b200_lpw_weight(const void* emb, const float* weights, int batch, int tokens, int channels, void* out,
+                         gyre_b200_stream stream) {
+  return lpw_weight(static_cast<const __half*>(emb), weights, batch, tokens, channels, static_cast<__half*>(out), S(stream));
+}
+
 int gyre_b200_gemm_rowstat_parts(int M, int N) { return gemm_rowstat_parts(M, N); }
 
 int gyre_b200_ln_finalize_rows(const void* parts, int nparts, int M, int C, float eps, void* mean_rstd,

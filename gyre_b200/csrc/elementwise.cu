@@ -357,6 +357,44 @@ int dpm_error_partials(const float* x_low, const float* x_high, const float* x_p
 }
 int dpm_error_num_partials() { return kErrBlocks; }
 
+// Prompt weighting of the LPW text embedding (gyre/pipeline/text_embedding/lpw_text_embedding.py:352-371):
+//   previous_mean = emb.mean([-2, -1]); emb *= weights[..., None]; emb *= previous_mean / emb.mean([-2, -1])
+// One CTA per prompt, two passes over its [L, C] block (the second one from L2): fixed-order fp32 sums, one rounding.
+__global__ void __launch_bounds__(256) lpw_weight_kernel(const __half* __restrict__ emb, const float* __restrict__ w, int L,
+                                                         int C, __half* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int64_t n = static_cast<int64_t>(L) * C;
+  const __half* e = emb + b * n;
+  const float* wb = w + static_cast<int64_t>(b) * L;
+  float s0 = 0.f, s1 = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const float v = __half2float(e[i]);
+    s0 += v;
+    s1 = fmaf(v, wb[i / C], s1);
+  }
+  __shared__ float r0[256], r1[256];
+  r0[threadIdx.x] = s0;
+  r1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) {
+      r0[threadIdx.x] += r0[threadIdx.x + o];
+      r1[threadIdx.x] += r1[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const float scale = r0[0] / r1[0];     // ratio of the means == ratio of the sums
+  __half* o_ = out + b * n;
+  for (int64_t i = threadIdx.x; i < n; i += 256) o_[i] = __float2half_rn(__half2float(e[i]) * wb[i / C] * scale);
+}
+int lpw_weight(const __half* emb, const float* weights, int B, int L, int C, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(emb && weights && out && B > 0 && L > 0 && C > 0, "lpw_weight: bad arguments");
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  lpw_weight_kernel<<<B, 256, 0, st>>>(emb, weights, L, C, out);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // UNet input of the inpaint / depth models (EnhancedRunwayInpaintMode.wrap_unet, unified_pipeline.py:668-690;
 // UnetWithExtraChannels, unet/core.py:21-37): out[b] = cat([x[b], extra[b % extra_batch]], dim=channel), NCHW fp16.
 // The extra channels (mask + masked-image latents) are NOT scaled by c_in (see the reference's comment there).

@@ -155,6 +155,8 @@ int resample_select(const float* src, int BC, int SH, int SW, const int* ty_idx,
                     const float* bg, const float* other, const float* rnd, float p, int resampled_if_ge, float* out,
                     int FH, int FW, int oy, int ox, cudaStream_t st);
 int rand_select(const float* a, const float* b, const float* rnd, float p, int64_t n, float* out, cudaStream_t st);
+// LPW prompt weighting: out = emb * w[b, l] * (mean(emb[b]) / mean(emb[b] * w[b]))
+int lpw_weight(const __half* emb, const float* weights, int B, int L, int C, __half* out, cudaStream_t st);
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)
 int scale_dup_latents(const float* x, float c_in, int dup, int B, int64_t per_sample, __half* out, cudaStream_t st);
 // VAE tail: img = clamp(x/2+0.5, 0, 1): NHWC fp16 [B,H,W,ldx>=3] -> NCHW fp16 [B,3,H,W] (+ optional uint8 copy)

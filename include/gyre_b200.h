@@ -286,6 +286,12 @@ int gyre_b200_cat_channels(const void* x, int channels, const void* extra, int e
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream);
 
+/* Prompt weighting of the LPW text embedding (gyre/pipeline/text_embedding/lpw_text_embedding.py:352-371):
+ * emb [batch, tokens, channels] fp16, weights [batch, tokens] fp32 ->
+ * out = emb * w * (mean(emb) / mean(emb * w)) per prompt (the weighted embedding keeps its mean). */
+int gyre_b200_lpw_weight(const void* emb, const float* weights, int batch, int tokens, int channels, void* out,
+                         gyre_b200_stream stream);
+
 /* Hires-fix / graft blending of the scheduler-UNet wrappers (replaces the ~20 torch ops per step of
  * gyre/pipeline/unet/hires_fix.py:142-205 HiresUnetWrapper.__call__ and gyre/pipeline/unet/graft.py:31-48):
  *   resample_select: `scale_into` (hires_fix.py:45-92) - a separable 4-tap lanczos2 resample of src [planes, src_h, src_w]

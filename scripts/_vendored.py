@@ -148,3 +148,17 @@ def gyre_hires():
     hf = _load("gyre.pipeline.unet", base, "hires_fix")
     gr = _load("gyre.pipeline.unet", base, "graft")
     return hf, gr, easing
+
+
+def gyre_lpw():
+    """gyre/pipeline/text_embedding/lpw_text_embedding.py (imports the INSTALLED transformers CLIP classes for type
+    annotations only) under a synthetic `gyre.pipeline.text_embedding` package."""
+    gyre_pipeline_pure()
+    name = "gyre.pipeline.text_embedding"
+    base = os.path.join(REF, "gyre/pipeline/text_embedding")
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.__path__ = [base]
+        sys.modules[name] = m
+    _load(name, base, "text_embedding")
+    return _load(name, base, "lpw_text_embedding")

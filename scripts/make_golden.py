@@ -483,6 +483,110 @@ def pin_hires():
           "oracle bit-exact against gyre/pipeline/unet/hires_fix.py, graft.py, easing.py and the vendored ResizeRight)")
 
 
+class ToyTokenizer:
+    """Deterministic stand-in for CLIPTokenizer (no vocabulary files on the box): lower-cased words and punctuation marks
+    map to ids by a stable hash; `__call__(text).input_ids` = [bos] + ids + [eos] like the real tokenizer."""
+    model_max_length = 77
+    bos_token_id = 998
+    eos_token_id = 999
+
+    class _Out:
+        def __init__(self, ids):
+            self.input_ids = ids
+
+    @staticmethod
+    def _ids(text):
+        import re
+        import zlib
+        return [1 + zlib.crc32(w.encode()) % 990 for w in re.findall(r"[a-z0-9]+|[^\sa-z0-9]", text.lower())]
+
+    def __call__(self, text, max_length=None, truncation=False, **_):
+        if isinstance(text, (list, tuple)):
+            return self._Out([self(t, max_length, truncation).input_ids for t in text])
+        ids = [self.bos_token_id] + self._ids(text) + [self.eos_token_id]
+        if truncation and max_length is not None and len(ids) > max_length:
+            ids = ids[:max_length - 1] + [self.eos_token_id]
+        return self._Out(ids)
+
+
+LPW_PROMPTS = [
+    "a (very beautiful:1.3) masterpiece, [dull] colours, ((sharp)) focus",
+    "an \\(escaped\\) bracket and a lone : colon (unbalanced",
+    "plain prompt without any weighting at all",
+    " ".join(f"(word{i}:{1 + (i % 7) / 10:.1f}) filler{i}," for i in range(60)),          # > 150 tokens: three chunks
+    "",
+]
+LPW_NEGATIVE = ["blurry, (low quality:1.4), [[watermark]]", "", "text", "(bad:1.2) " * 50, "ugly"]
+
+
+def pin_lpw():
+    """PINS the LPW prompt-weighting front end against the reference's own lpw_text_embedding.py: the bracket grammar,
+    token / weight lists, padding, chunked encoding and the mean-preserving weighting, with the installed transformers
+    CLIPTextModel (random init) as the text encoder and a toy tokenizer."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from gyre_b200 import lpw_text_embedding as mine
+    ref = _vendored.gyre_lpw()
+    out = {}
+    # ---- the grammar, on the reference's own doctest strings and more
+    cases = ["normal text", "an (important) word", "(unbalanced", "\\(literal\\]", "(unnecessary)(parens)",
+             "a (((house:1.3)) [on] a (hill:0.5), sun, (((sky))).", "a:b (c:d) e:1.2) [f:2.0] (g:-0.5) (h:+.5)", "\\", "a\\b",
+             "((a:1.2):0.5) [b (c] d)", ":", "(:1.1)", "x (y:1.) z", "]) stray closers [("] + LPW_PROMPTS + LPW_NEGATIVE
+    parsed = []
+    for c in cases:
+        r = ref.parse_prompt_attention(c)
+        assert mine.parse_prompt_attention(c) == r, f"parse_prompt_attention({c!r}): {mine.parse_prompt_attention(c)} vs {r}"
+        parsed.append(r)
+    out["parse"] = {"cases": cases, "parsed": parsed}
+    tok = ToyTokenizer()
+    cfg = CLIPTextConfig(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=3,
+                         num_attention_heads=4, max_position_embeddings=77, hidden_act="quick_gelu")
+    torch.manual_seed(11)
+    model = CLIPTextModel(cfg).eval()
+    g = torch.Generator().manual_seed(5)
+    sd = {}
+    for k, v in model.state_dict().items():
+        if k.endswith("position_ids"):
+            continue
+        if "layer_norm" in k:      # non-trivial affine parameters
+            v = v + 0.2 * torch.randn(v.shape, generator=g)
+        sd[k] = v.half().float()
+    model.load_state_dict(sd, strict=False)
+    out["clip_config"] = dict(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=3,
+                              num_attention_heads=4, max_position_embeddings=77, hidden_act="quick_gelu")
+    out["clip_state_dict"] = {k: v.half() for k, v in sd.items()}
+    with torch.no_grad():
+        for mult in (1, 3):
+            for bos_mid in (False, True):
+                max_len = (tok.model_max_length - 2) * mult + 2
+                t_ref, w_ref = ref.get_prompts_with_weights(tok, LPW_PROMPTS, max_len - 2)
+                t_mine, w_mine = mine.get_prompts_with_weights(tok, LPW_PROMPTS, max_len - 2)
+                assert t_ref == t_mine and w_ref == w_mine, "get_prompts_with_weights"
+                emb, unc = ref.get_weighted_text_embeddings(tok, model, model, torch.device("cpu"), list(LPW_PROMPTS),
+                                                            list(LPW_NEGATIVE), max_embeddings_multiples=mult,
+                                                            no_boseos_middle=bos_mid)
+                raw, _ = ref.get_weighted_text_embeddings(tok, model, model, torch.device("cpu"), list(LPW_PROMPTS), None,
+                                                          max_embeddings_multiples=mult, no_boseos_middle=bos_mid,
+                                                          skip_weighting=True)
+                # padded tokens / weights as the reference builds them (re-derived here for the host-logic test)
+                longest = max(max(len(t) for t in t_ref), max(len(t) for t in ref.get_prompts_with_weights(
+                    tok, LPW_NEGATIVE, max_len - 2)[0]))
+                m2 = max(1, min(mult, (longest - 1) // 75 + 1))
+                ml = 75 * m2 + 2
+                pt, pw = ref.pad_tokens_and_weights([list(t) for t in t_ref], [list(w) for w in w_ref], ml, tok.bos_token_id,
+                                                    tok.eos_token_id, no_boseos_middle=bos_mid, chunk_length=77)
+                pt2, pw2 = mine.pad_tokens_and_weights([list(t) for t in t_ref], [list(w) for w in w_ref], ml,
+                                                       tok.bos_token_id, tok.eos_token_id, no_boseos_middle=bos_mid,
+                                                       chunk_length=77)
+                assert pt == pt2 and pw == pw2, "pad_tokens_and_weights"
+                out[f"lpw/mult{mult}/{'nomid' if bos_mid else 'mid'}"] = {
+                    "tokens": torch.tensor(pt), "weights": torch.tensor(pw), "text": emb, "uncond": unc}
+                if mult == 3 and not bos_mid:
+                    out[f"lpw/mult{mult}/mid"]["unweighted"] = raw
+    torch.save(out, os.path.join(GOLD, "lpw.pt"))
+    print(f"lpw: grammar ({len(cases)} strings), token / weight lists and padding identical to the reference's; "
+          f"{sum(k.startswith('lpw/') for k in out)} weighted-embedding vectors stored")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -533,12 +637,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,oracle")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
-             "hires": pin_hires, "oracle": lambda: oracle_fixtures(a.full)}
+             "hires": pin_hires, "lpw": pin_lpw, "oracle": lambda: oracle_fixtures(a.full)}
     for name, fn in parts.items():
         if not a.only or name in a.only.split(","):
             fn()

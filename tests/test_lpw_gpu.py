@@ -1,0 +1,64 @@
+"""LPW text embedding end to end on the GPU - chunked native CLIP forward + the weighting kernel - against the vectors
+the reference's get_weighted_text_embeddings produced with transformers' CLIPTextModel in fp32 (tests/golden/lpw.pt)."""
+import os
+
+import pytest
+import torch
+
+from test_lpw_cpu import NEGATIVE, PROMPTS, ToyTokenizer
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "lpw.pt")
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from gyre_b200.text_encoder import B200CLIPTextModel, ClipTextConfig
+    g = torch.load(GOLD)
+    enc = B200CLIPTextModel(ClipTextConfig.from_any(g["clip_config"])).load_state_dict(g["clip_state_dict"])
+    return g, enc
+
+
+@pytest.mark.parametrize("mult", [1, 3])
+@pytest.mark.parametrize("nomid", [False, True])
+def test_weighted_embeddings_vs_reference(setup, mult, nomid):
+    from gyre_b200 import lpw_text_embedding as lpw
+    g, enc = setup
+    v = g[f"lpw/mult{mult}/{'nomid' if nomid else 'mid'}"]
+    text, unc = lpw.get_weighted_text_embeddings(ToyTokenizer(), enc, enc, enc.device, list(PROMPTS), list(NEGATIVE),
+                                                 max_embeddings_multiples=mult, no_boseos_middle=nomid)
+    assert tuple(text.shape) == tuple(v["text"].shape) and tuple(unc.shape) == tuple(v["uncond"].shape)
+    for name, mine, ref in (("text", text, v["text"]), ("uncond", unc, v["uncond"])):
+        err = (mine.float().cpu() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        print(f"LPW mult {mult} nomid {nomid} {name}: max abs err {err:.3e} (|emb| max {scale:.3f})")
+        # fp16 encoder (measured ~1.5e-3 of the scale on the CLIP tests) + one fp16 rounding of the weighted value
+        assert err < 6e-3 * scale
+    if "unweighted" in v:
+        raw, _ = lpw.get_weighted_text_embeddings(ToyTokenizer(), enc, enc, enc.device, list(PROMPTS), None,
+                                                  max_embeddings_multiples=mult, no_boseos_middle=nomid, skip_weighting=True)
+        assert (raw.float().cpu() - v["unweighted"]).abs().max().item() < 6e-3 * v["unweighted"].abs().max().item()
+
+
+def test_lpw_weight_kernel_vs_torch(setup):
+    """The weighting launch alone against the reference's three in-place tensor statements, in fp32."""
+    from gyre_b200 import lpw_text_embedding as lpw
+    gen = torch.Generator().manual_seed(3)
+    emb = (torch.randn(3, 231, 64, generator=gen) + 0.05).half()
+    w = 0.5 + torch.rand(3, 231, generator=gen)
+    out = lpw.apply_weights(emb.cuda(), w)
+    ref = emb.float()
+    prev = ref.mean(dim=[-2, -1])
+    ref = ref * w[..., None]
+    ref = ref * (prev / ref.mean(dim=[-2, -1]))[:, None, None]
+    assert (out.float().cpu() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_lpw_class_surface(setup):
+    from gyre_b200.lpw_text_embedding import LPWTextEmbedding
+    g, enc = setup
+    calc = LPWTextEmbedding(3, tokenizer=ToyTokenizer(), text_encoder=enc, uncond_encoder=enc, device=enc.device)
+    text, unc = calc.get_embeddings(PROMPTS[:2], NEGATIVE[:2])
+    assert text.shape == unc.shape and text.shape[0] == 2 and text.shape[1] == 77
+    rep = calc.repeat(text, 3)
+    assert rep.shape[0] == 6 and torch.equal(rep[0], text[0]) and torch.equal(rep[3], text[1])
