@@ -43,6 +43,7 @@ class UNetConfigC(C.Structure):
         ("layers_per_block", C.c_int32), ("cross_attention_dim", C.c_int32), ("norm_num_groups", C.c_int32),
         ("norm_eps", C.c_float), ("use_linear_projection", C.c_int32), ("upcast_attention", C.c_int32),
         ("transformer_depth", C.c_int32 * 4), ("addition_embed_dim", C.c_int32),
+        ("controlnet", C.c_int32), ("conditioning_channels", C.c_int32),
     ]
 
 
@@ -88,6 +89,7 @@ SIGNATURES = {
     "gyre_b200_unet_num_skips": (_i, [_vp]),
     "gyre_b200_unet_set_adapter_states": (_i, [_vp, C.POINTER(C.c_void_p), _i]),
     "gyre_b200_unet_forward_cond": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
+    "gyre_b200_controlnet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _i, _vp, _vp, _sz, _vp]),
     "gyre_b200_vae_create": (_i, [C.POINTER(VAEConfigC), C.POINTER(_vp)]),
     "gyre_b200_vae_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -106,6 +108,8 @@ SIGNATURES = {
     "gyre_b200_sched_step_blend": (_i, [C.POINTER(Step), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _f, _vp]),
     "gyre_b200_cat_channels": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _vp, _vp]),
     "gyre_b200_scale_latents": (_i, [_vp, _f, _i, _i, _i64, _vp, _vp]),
+    "gyre_b200_outpaint_scratch_bytes": (_sz, []),
+    "gyre_b200_outpaint_match_histograms": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
     "gyre_b200_lpw_weight": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "gyre_b200_gemm_rowstat_parts": (_i, [_i, _i]),
     "gyre_b200_ln_finalize_rows": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),

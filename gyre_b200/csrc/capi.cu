@@ -225,6 +225,15 @@ int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int6
   return scale_dup_latents(x, c_in, dup, batch, per_sample, static_cast<__half*>(out), S(stream));
 }
 
+size_t gyre_b200_outpaint_scratch_bytes(void) { return outpaint_scratch_bytes(); }
+
+int gyre_b200_outpaint_match_histograms(const void* result, const void* source, const void* outmask, int batch, int64_t hw,
+                                        void* out, void* scratch, gyre_b200_stream stream) {
+  return outpaint_match_histograms(static_cast<const __half*>(result), static_cast<const __half*>(source),
+                                   static_cast<const __half*>(outmask), batch, hw, static_cast<__half*>(out), scratch,
+                                   S(stream));
+}
+
 int gyre_b200_lpw_weight(const void* emb, const float* weights, int batch, int tokens, int channels, void* out,
                          gyre_b200_stream stream) {
   return lpw_weight(static_cast<const __half*>(emb), weights, batch, tokens, channels, static_cast<__half*>(out), S(stream));
@@ -339,6 +348,25 @@ int gyre_b200_unet_forward_cond(gyre_b200_handle h, const void* sample, const in
   return static_cast<UNetModel*>(M(h))->forward(ex, static_cast<const __half*>(sample), timestep,
                                                 static_cast<const __half*>(ctx), static_cast<const __half*>(add_cond),
                                                 batch, height, width, ctx_len, tome_r_host, static_cast<__half*>(out));
+}
+
+int gyre_b200_controlnet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx,
+                                 const void* cond, int batch, int height, int width, int ctx_len, void* const* down_out,
+                                 int n_down, void* mid_out, void* workspace, size_t workspace_bytes,
+                                 gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && sample && timestep && ctx && cond && down_out && mid_out, "controlnet_forward: null argument");
+  GYRE_REQUIRE(M(h)->is_unet() && static_cast<UNetModel*>(M(h))->is_controlnet(),
+               "controlnet_forward: handle is not a ControlNet (create it with cfg.controlnet = 1)");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  ControlNetIO io;
+  io.cond = static_cast<const __half*>(cond);
+  io.down_out = reinterpret_cast<__half* const*>(down_out);
+  io.n_down = n_down;
+  io.mid_out = static_cast<__half*>(mid_out);
+  return static_cast<UNetModel*>(M(h))->forward(ex, static_cast<const __half*>(sample), timestep,
+                                                static_cast<const __half*>(ctx), nullptr, batch, height, width, ctx_len,
+                                                nullptr, nullptr, &io);
 }
 
 int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx, int batch,

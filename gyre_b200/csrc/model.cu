@@ -386,7 +386,23 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
   add_resnet("mid_block.resnets.0", cin, cin);
   add_transformer("mid_block.attentions.0", cin, cfg.num_heads[L - 1], depth_of(L - 1));
   add_resnet("mid_block.resnets.1", cin, cin);
-  for (int i = 0; i < L; ++i) {
+  if (cfg.controlnet) {
+    // controlnet/models.py:41-94 (conditioning embedding) and :216-262 (one zero-initialised 1x1 conv per skip + mid)
+    const int ec[4] = {16, 32, 96, 256};
+    const int cc = cfg.conditioning_channels > 0 ? cfg.conditioning_channels : 3;
+    cn_embed_.resize(8);
+    reg_conv3("controlnet_cond_embedding.conv_in", cc, ec[0], &cn_embed_[0]);
+    for (int i = 0; i < 3; ++i) {
+      reg_conv3("controlnet_cond_embedding.blocks." + std::to_string(2 * i), ec[i], ec[i], &cn_embed_[1 + 2 * i]);
+      reg_conv3("controlnet_cond_embedding.blocks." + std::to_string(2 * i + 1), ec[i], ec[i + 1], &cn_embed_[2 + 2 * i]);
+    }
+    reg_conv3("controlnet_cond_embedding.conv_out", ec[3], ch[0], &cn_embed_[7]);
+    cn_down_.resize(skips.size());
+    for (size_t k = 0; k < skips.size(); ++k)
+      reg_linear("controlnet_down_blocks." + std::to_string(k), skips[k], skips[k], true, &cn_down_[k]);
+    reg_linear("controlnet_mid_block", cin, cin, true, &cn_mid_);
+  }
+  for (int i = 0; i < (cfg.controlnet ? 0 : L); ++i) {
     const int lvl = L - 1 - i;
     const int c = ch[lvl];
     for (int j = 0; j < cfg.layers_per_block + 1; ++j) {
@@ -402,8 +418,10 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
       reg_conv3("up_blocks." + std::to_string(i) + ".upsamplers.0.conv", c, c, &ups_.back(), true);
     }
   }
-  reg_norm("conv_norm_out", ch[0], &norm_out_);
-  reg_conv3("conv_out", ch[0], cfg.out_channels, &conv_out_);
+  if (!cfg.controlnet) {
+    reg_norm("conv_norm_out", ch[0], &norm_out_);
+    reg_conv3("conv_out", ch[0], cfg.out_channels, &conv_out_);
+  }
 
   // fused time_emb_proj: one [sum(cout), temb_dim] GEMM per forward instead of 22 M=batch GEMMs
   temb_proj_.N = temb_total_;
@@ -425,7 +443,7 @@ UNetModel::UNetModel(const gyre_b200_unet_config& cfg) : cfg_(cfg) {
         reg_temb("down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
     reg_temb("mid_block.resnets.0");
     reg_temb("mid_block.resnets.1");
-    for (int i = 0; i < L; ++i)
+    for (int i = 0; i < (cfg.controlnet ? 0 : L); ++i)
       for (int j = 0; j < cfg.layers_per_block + 1; ++j)
         reg_temb("up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
   }
@@ -644,8 +662,10 @@ int UNetModel::set_adapter_states(const __half* const* states, int n) {
 }
 
 int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B,
-                       int H, int W, int L, const int32_t* tome_r, __half* out) {
+                       int H, int W, int L, const int32_t* tome_r, __half* out, const ControlNetIO* cn) {
   GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && L > 0, "unet_forward: empty problem");
+  GYRE_REQUIRE(ex.dry || (cfg_.controlnet != 0) == (cn != nullptr),
+               "unet_forward: a ControlNet handle runs through gyre_b200_controlnet_forward (and only it)");
   if (!ex.dry)
     GYRE_REQUIRE((cfg_.addition_embed_dim > 0) == (add_cond != nullptr),
                  "unet_forward: this model %s an additional conditioning vector (addition_embed_dim = %d)",
@@ -698,7 +718,35 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   __half* x_nhwc = ex.p16(static_cast<size_t>(B) * H * W * cin8);
   RUN(ex, nchw_to_nhwc_f16(sample, B, cfg_.in_channels, H, W, x_nhwc, cin8, ex.st));
   __half* hcur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
-  RUN(ex, conv3x3_f16(x_nhwc, cin8, B, H, W, cin8, conv_in_.wp, ch[0], 1, 1, ep_out(hcur, ch[0], conv_in_.bias), ex.st));
+  const __half* cond_emb = nullptr;
+  if (cfg_.controlnet) {
+    // ControlNetConditioningEmbedding.forward (controlnet/models.py:84-94) on the tensor-core conv kernel: the image is
+    // staged NHWC with its channel pitch padded to 8, every conv but the last applies SiLU in its epilogue, every second
+    // block conv has stride 2 (8H -> H); the result is added to conv_in's output through that conv's residual input
+    const int cc = cfg_.conditioning_channels > 0 ? cfg_.conditioning_channels : 3;
+    const int cc8 = (cc + 7) & ~7;
+    int eh = 8 * H, ew = 8 * W;
+    __half* e0 = ex.p16(static_cast<size_t>(B) * eh * ew * cc8);
+    RUN(ex, nchw_to_nhwc_f16(cn ? cn->cond : nullptr, B, cc, eh, ew, e0, cc8, ex.st));
+    const __half* ecur = e0;
+    int ecin = cc8;
+    for (int i = 0; i < 8; ++i) {
+      const Conv3W& c = cn_embed_[i];
+      const int stride = (i >= 1 && i <= 6 && (i % 2 == 0)) ? 2 : 1;       // blocks.1 / .3 / .5
+      const int oh = stride == 2 ? (eh - 1) / 2 + 1 : eh, ow = stride == 2 ? (ew - 1) / 2 + 1 : ew;
+      __half* eo = ex.p16(static_cast<size_t>(B) * oh * ow * c.Cout);
+      RUN(ex, conv3x3_f16(ecur, ecin, B, eh, ew, ecin, c.wp, c.Cout, stride, 1,
+                          ep_out(eo, c.Cout, c.bias, nullptr, 0, i < 7 ? ACT_SILU : ACT_NONE), ex.st));
+      ecur = eo;
+      ecin = c.Cout;
+      eh = oh;
+      ew = ow;
+    }
+    GYRE_REQUIRE(eh == H && ew == W, "controlnet: the conditioning image must be 8x the latent size");
+    cond_emb = ecur;
+  }
+  RUN(ex, conv3x3_f16(x_nhwc, cin8, B, H, W, cin8, conv_in_.wp, ch[0], 1, 1,
+                      ep_out(hcur, ch[0], conv_in_.bias, cond_emb, cond_emb ? ch[0] : 0), ex.st));
 
   struct Skip { __half* p; int C; int hw; };
   std::vector<Skip> skips;
@@ -773,6 +821,25 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
     ctrl_down_.clear();
     ctrl_mid_ = nullptr;
     adapter_.clear();
+  }
+  if (cfg_.controlnet) {
+    // ---- zero convolutions (controlnet/models.py:519-535): one 1x1 conv per skip tensor and one for the mid output,
+    // written back in the NCHW layout gyre_b200_unet_set_control_residuals takes
+    GYRE_REQUIRE(ex.dry || (cn->n_down == static_cast<int>(skips.size()) && cn->down_out && cn->mid_out),
+                 "controlnet_forward: %d output tensors given, the model has %zu skips", cn ? cn->n_down : 0, skips.size());
+    for (size_t k = 0; k <= skips.size(); ++k) {
+      const bool mid = k == skips.size();
+      const __half* src = mid ? hcur : skips[k].p;
+      const int C = mid ? ccur : skips[k].C;
+      const int hw = mid ? h_ * w_ : skips[k].hw;
+      const LinW& z = mid ? cn_mid_ : cn_down_[k];
+      ex.reset_scratch();
+      __half* tmp = ex.s16(static_cast<size_t>(B) * hw * C);
+      RUN(ex, gemm_f16(src, C, z.w, C, B * hw, C, C, ep_out(tmp, C, z.bias), ex.st));
+      // [B, hw, C] -> [B, C, hw]: the spatial extent only matters as a product here
+      RUN(ex, nhwc_to_nchw_f16(tmp, C, B, C, hw, 1, mid ? cn->mid_out : cn->down_out[k], ex.st));
+    }
+    return 0;
   }
   // ---- up
   for (int i = 0; i < nl; ++i) {

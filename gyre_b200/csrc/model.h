@@ -132,6 +132,14 @@ class Model {
   int* sk_flags_ = nullptr;
 };
 
+// ControlNet mode of UNetModel::forward: the conditioning image in, one residual per skip + the mid residual out (NCHW)
+struct ControlNetIO {
+  const __half* cond = nullptr;        // [B, conditioning_channels, 8H, 8W] NCHW fp16
+  __half* const* down_out = nullptr;   // host array of num_skips() device pointers
+  int n_down = 0;
+  __half* mid_out = nullptr;
+};
+
 class UNetModel : public Model {
  public:
   explicit UNetModel(const gyre_b200_unet_config& cfg);
@@ -139,7 +147,8 @@ class UNetModel : public Model {
   int num_transformer_blocks() const { return static_cast<int>(tblocks_.size()); }
   // dry == true sizes the workspace (ex.peak) without launching anything
   int forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B, int H,
-              int W, int L, const int32_t* tome_r, __half* out);
+              int W, int L, const int32_t* tome_r, __half* out, const ControlNetIO* cn = nullptr);
+  bool is_controlnet() const { return cfg_.controlnet != 0; }
   // Binds a text context for the following forwards (the reference binds the embeddings once per request:
   // UNetWithEmbeddings, gyre/pipeline/unet/core.py:253-259): the cross-attention K/V projections of every
   // transformer block depend only on ctx, so they are computed here ONCE instead of once per step.
@@ -177,6 +186,10 @@ class UNetModel : public Model {
   std::vector<Conv3W> downs_, ups_;
   NormW norm_out_;
   Conv3W conv_out_;
+  // ControlNet only: conditioning embedding (conv_in, 6 blocks, conv_out) and the zero convolutions
+  std::vector<Conv3W> cn_embed_;
+  std::vector<LinW> cn_down_;
+  LinW cn_mid_;
   // bound-context cache: per transformer block [ctx_B_ * ctx_L_, 2C] fp16 (k | v)
   std::vector<__half*> kv_cache_;
   std::vector<size_t> kv_cache_elems_;

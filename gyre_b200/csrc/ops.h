@@ -155,6 +155,11 @@ int resample_select(const float* src, int BC, int SH, int SW, const int* ty_idx,
                     const float* bg, const float* other, const float* rnd, float p, int resampled_if_ge, float* out,
                     int FH, int FW, int oy, int ox, cudaStream_t st);
 int rand_select(const float* a, const float* b, const float* rnd, float p, int64_t n, float* out, cudaStream_t st);
+// Outpaint tail: histogram-match `result` to (source outside the mask + result inside it) over the whole batch, then mix the
+// source back over it (postprocess.cu).  result / source / mask / out: [B, 3, HW] fp16 in [0, 1].
+size_t outpaint_scratch_bytes();
+int outpaint_match_histograms(const __half* result, const __half* source, const __half* mask, int B, int64_t hw, __half* out,
+                              void* scratch, cudaStream_t st);
 // LPW prompt weighting: out = emb * w[b, l] * (mean(emb[b]) / mean(emb[b] * w[b]))
 int lpw_weight(const __half* emb, const float* weights, int B, int L, int C, __half* out, cudaStream_t st);
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)

@@ -96,9 +96,23 @@ typedef struct gyre_b200_unet_config {
                                       uses the last level's value                                            */
   int32_t addition_embed_dim;      /* 0: none.  > 0: input width of `add_embedding.linear_1` (text_time
                                       conditioning: pooled text embedding ++ sinusoids of the 6 time ids)    */
+  /* ControlNet encoder (gyre/pipeline/controlnet/models.py:97-544): the UNet's conv_in / down blocks / mid block plus
+   * `controlnet_cond_embedding` (conv stack 3 -> 16/32/96/256 -> C0 on the 8x larger conditioning image), one 1x1
+   * `controlnet_down_blocks.k` per skip tensor and `controlnet_mid_block`; no up path.  0: plain UNet. */
+  int32_t controlnet;
+  int32_t conditioning_channels;   /* 3 */
 } gyre_b200_unet_config;
 
 int gyre_b200_unet_create(const gyre_b200_unet_config* cfg, gyre_b200_handle* out);
+/* ControlNetModel.forward (controlnet/models.py:420-544) of a handle created with cfg.controlnet = 1:
+ * sample [B, Cin, H, W], cond [B, conditioning_channels, 8H, 8W], ctx [B, L, Cc] fp16 -> the gyre_b200_unet_num_skips(h)
+ * residual tensors (NCHW fp16, shapes of the UNet's skips, device pointers in the HOST array down_out) and the mid
+ * residual [B, C_last, H/8, W/8] - ready for gyre_b200_unet_set_control_residuals of the UNet they condition.
+ * Workspace: gyre_b200_unet_workspace_bytes on the same handle. */
+int gyre_b200_controlnet_forward(gyre_b200_handle h, const void* sample, const int64_t* timestep, const void* ctx,
+                                 const void* cond, int batch, int height, int width, int ctx_len, void* const* down_out,
+                                 int n_down, void* mid_out, void* workspace, size_t workspace_bytes,
+                                 gyre_b200_stream stream);
 /* Number of transformer blocks == length of the ToMe r-list (nonfree/tome_unet.py:243). */
 int gyre_b200_unet_num_transformer_blocks(gyre_b200_handle h);
 
@@ -285,6 +299,15 @@ int gyre_b200_cat_channels(const void* x, int channels, const void* extra, int e
 /* out_f16[(dup?2:1) * B, ...] = x * c_in  (first unet input of a run) */
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream);
+
+/* Image-space tail of an outpaint request (gyre/pipeline/unified_pipeline.py:2493-2510 with gyre/images.py:667-672 and
+ * gyre/match_histograms.py:12-37 - done on the host with numpy in the reference): result / source / outmask / out are
+ * [batch, 3, hw] fp16 images in [0, 1]; out = source * (1 - outmask) + match_histograms(result, source * (1 - outmask) +
+ * result * outmask) * outmask, the match being the per-channel uint8 CDF match over the whole batch.  Bit-identical to
+ * the reference's fp16 evaluation.  scratch: gyre_b200_outpaint_scratch_bytes() bytes. */
+size_t gyre_b200_outpaint_scratch_bytes(void);
+int gyre_b200_outpaint_match_histograms(const void* result, const void* source, const void* outmask, int batch, int64_t hw,
+                                        void* out, void* scratch, gyre_b200_stream stream);
 
 /* Prompt weighting of the LPW text embedding (gyre/pipeline/text_embedding/lpw_text_embedding.py:352-371):
  * emb [batch, tokens, channels] fp16, weights [batch, tokens] fp32 ->
