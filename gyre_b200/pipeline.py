@@ -188,7 +188,7 @@ class B200Pipeline:
                  latents_dtype=torch.float16, return_fp32_latents: bool = False, image=None, mask_image=None,
                  strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None,
                  cfg_execution: str = "parallel", hires_fix: bool | None = None,
-                 hires_oos_fraction: float | None = None) -> PipelineOutput:
+                 hires_oos_fraction: float | None = None, outmask_image=None) -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
         unified_pipeline.py:2055-2066 - optionally grafted (inpaint UNet early, main UNet late, :2069-2098) and, for
@@ -314,5 +314,11 @@ class B200Pipeline:
         if output_type == "latent" or self.vae is None:
             return PipelineOutput(images=None, latents=latents)
         z = (1 / self.vae.config.scaling_factor * latents.float()).to(torch.float16)
-        img, u8 = self.vae.decode_raw(z.contiguous(), postprocess=True, want_u8=(output_type == "uint8"))
+        outpaint = image is not None and outmask_image is not None
+        img, u8 = self.vae.decode_raw(z.contiguous(), postprocess=True, want_u8=(output_type == "uint8" and not outpaint))
+        if outpaint:
+            # unified_pipeline.py:2493-2510: histogram-match the result to the source around it, mix the source back in
+            from .images import match_histograms_outpaint, to_uint8_nhwc
+            img = match_histograms_outpaint(img, image, outmask_image)
+            u8 = to_uint8_nhwc(img) if output_type == "uint8" else None
         return PipelineOutput(images=u8 if output_type == "uint8" else img, latents=latents)

@@ -162,3 +162,17 @@ def gyre_lpw():
         sys.modules[name] = m
     _load(name, base, "text_embedding")
     return _load(name, base, "lpw_text_embedding")
+
+
+def gyre_t2i_adapter():
+    """gyre/pipeline/t2i_adapter/adapter.py (pure torch; its package __init__ and models.py import diffusers, so the file
+    and its utils.py are loaded under a synthetic package)."""
+    gyre_pipeline_pure()
+    name = "gyre.pipeline.t2i_adapter"
+    base = os.path.join(REF, "gyre/pipeline/t2i_adapter")
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.__path__ = [base]
+        sys.modules[name] = m
+    _load(name, base, "utils")
+    return _load(name, base, "adapter")

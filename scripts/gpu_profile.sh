@@ -4,6 +4,9 @@
 #                                          compare SHARES with the live numbers, not absolutes)
 #   prof_*.ncu-rep                         --set full captures of the top kernels
 mkdir -p gpurun_out
+# ncu cannot replay the cooperative cluster launches of the stream-K convs (launch list stops with exit 9 at the first
+# one): the profiling passes run with stream-K off (whole-tile scheduling of the 8x8-level convs; everything else unchanged)
+export GYRE_B200_STREAMK=0
 NCU="ncu --clock-control none --profile-from-start off"
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
 $NCU --metrics $M --csv --log-file gpurun_out/launches_unet.csv python scripts/profile_step.py --no-vae > gpurun_out/prof1.log 2>&1

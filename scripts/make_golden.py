@@ -587,6 +587,75 @@ def pin_lpw():
           f"{sum(k.startswith('lpw/') for k in out)} weighted-embedding vectors stored")
 
 
+def pin_images():
+    """PINS the outpaint image tail against the reference's own numpy histogram matching (gyre/match_histograms.py, pure
+    numpy, imported as is) wrapped in the tensor statements of unified_pipeline.py:2493-2510 and the uint8 conversions of
+    gyre/images.py:64-83, 667-672 (images.py itself imports cv2 / PIL at module level: its four conversion lines are
+    restated here, cited)."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("_gyre_match_histograms", os.path.join(_vendored.REF, "gyre/match_histograms.py"))
+    mh = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mh)
+
+    def to_cv(t):        # images.py:69-83 (the BGR flip permutes channels consistently on both sides: omitted)
+        return (t.permute(0, 2, 3, 1).to(torch.float32) * 255).round().to(torch.uint8).cpu().numpy()
+
+    def from_cv(a):      # images.py:50-66
+        return (torch.from_numpy(a).to(torch.float32) / 255.0).permute(0, 3, 1, 2)
+
+    out = {}
+    g = torch.Generator().manual_seed(41)
+    for name, (B, H, W) in (("small", (2, 24, 40)), ("batch3", (3, 64, 64))):
+        for dt_name, dt in (("fp16", torch.float16),):
+            result = torch.rand(B, 3, H, W, generator=g).pow(1.7).to(dt)                 # skewed histogram
+            source = (torch.rand(1, 3, H, W, generator=g) * 0.8 + 0.1).to(dt).expand(B, -1, -1, -1).contiguous()
+            mask = torch.zeros(1, 3, H, W)
+            mask[:, :, H // 4:, W // 3:] = 1.0
+            mask[:, :, H // 4:H // 2, W // 3:W // 2] = 0.5                               # a soft edge
+            mask = mask.to(dt).expand(B, -1, -1, -1).contiguous()
+            reference = source * (1 - mask) + result * mask
+            matched = mh.match_histograms(to_cv(result), to_cv(reference), channel_axis=3)
+            assert matched.dtype == np.uint8
+            res = from_cv(matched).to(result)
+            final = source * (1 - mask) + res * mask
+            out[f"{name}/{dt_name}"] = {"result": result, "source": source, "outmask": mask, "final": final,
+                                        "matched_u8": torch.from_numpy(matched)}
+    torch.save(out, os.path.join(GOLD, "images.pt"))
+    print(f"images: {len(out)} outpaint histogram-match vectors from gyre/match_histograms.py stored")
+
+
+def pin_t2i_adapter():
+    """PINS the T2I-adapter encoder oracle against the reference's own gyre/pipeline/t2i_adapter/adapter.py (`Adapter`)."""
+    from oracle import t2i_adapter as oad
+    ad = _vendored.gyre_t2i_adapter()
+    out = {}
+    for name, kw in (("main_tiny", dict(channels=[32, 64, 96, 96], nums_rb=2, cin=192, ksize=1, sk=True, use_conv=False)),
+                     ("conv_tiny", dict(channels=[32, 32, 32], nums_rb=2, cin=64, ksize=3, sk=False, use_conv=True))):
+        torch.manual_seed(17)
+        m = ad.Adapter(**kw).eval()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        shapes = oad.adapter_param_shapes(**kw)
+        assert {k: tuple(v.shape) for k, v in sd.items()} == shapes, f"adapter parameter inventory ({name})"
+        g = torch.Generator().manual_seed(3)
+        cin_img = kw["cin"] // 64
+        x = torch.rand(2, cin_img, 128, 96, generator=g)
+        with torch.no_grad():
+            ref = m(x)
+            mine = oad.adapter_forward(sd, x, **{k: v for k, v in kw.items() if k != "cin"})
+        for a_, b_ in zip(ref, mine):
+            assert torch.equal(a_, b_), f"Adapter.forward ({name})"
+        # (sk=False only works upstream when consecutive levels have equal widths: `skep` is declared on in_c channels but
+        # applied after in_conv, adapter.py:76-78, 91-97 - hence the constant widths of the second configuration)
+        out[name] = {"config": kw, "state_dict": {k: v.half() for k, v in sd.items()}, "x": x.half()}
+        # features of the fp16-rounded weights / input, evaluated in fp32 (what the native fp16 path is compared with)
+        sd16 = {k: v.half().float() for k, v in sd.items()}
+        with torch.no_grad():
+            out[name]["features"] = oad.adapter_forward(sd16, x.half().float(), **{k: v for k, v in kw.items() if k != "cin"})
+    torch.save(out, os.path.join(GOLD, "t2i_adapter.pt"))
+    print(f"t2i_adapter: {len(out)} configurations, oracle bit-exact against gyre/pipeline/t2i_adapter/adapter.py")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -637,12 +706,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,oracle")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
-             "hires": pin_hires, "lpw": pin_lpw, "oracle": lambda: oracle_fixtures(a.full)}
+             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "oracle": lambda: oracle_fixtures(a.full)}
     for name, fn in parts.items():
         if not a.only or name in a.only.split(","):
             fn()
