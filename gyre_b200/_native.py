@@ -47,6 +47,13 @@ class UNetConfigC(C.Structure):
     ]
 
 
+class AdapterConfigC(C.Structure):
+    _fields_ = [
+        ("cin", C.c_int32), ("num_levels", C.c_int32), ("channels", C.c_int32 * 4), ("nums_rb", C.c_int32),
+        ("ksize", C.c_int32), ("sk", C.c_int32), ("use_conv", C.c_int32),
+    ]
+
+
 class ClipConfigC(C.Structure):
     _fields_ = [
         ("vocab_size", C.c_int32), ("hidden_size", C.c_int32), ("intermediate_size", C.c_int32),
@@ -90,6 +97,9 @@ SIGNATURES = {
     "gyre_b200_unet_set_adapter_states": (_i, [_vp, C.POINTER(C.c_void_p), _i]),
     "gyre_b200_unet_forward_cond": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
     "gyre_b200_controlnet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _i, _vp, _vp, _sz, _vp]),
+    "gyre_b200_adapter_create": (_i, [C.POINTER(AdapterConfigC), C.POINTER(_vp)]),
+    "gyre_b200_adapter_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
+    "gyre_b200_adapter_forward": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_void_p), _i, _vp, _sz, _vp]),
     "gyre_b200_vae_create": (_i, [C.POINTER(VAEConfigC), C.POINTER(_vp)]),
     "gyre_b200_vae_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -459,6 +459,44 @@ int gyre_b200_vae_encode(gyre_b200_handle h, const void* img, int batch, int hei
                                               static_cast<__half*>(moments));
 }
 
+int gyre_b200_adapter_create(const gyre_b200_adapter_config* cfg, gyre_b200_handle* out) {
+  GYRE_REQUIRE(cfg && out, "adapter_create: null argument");
+  GYRE_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= 4 && cfg->nums_rb >= 1 && cfg->nums_rb <= 8, "adapter_create: bad sizes");
+  GYRE_REQUIRE(cfg->cin > 0 && cfg->cin % 64 == 0, "adapter_create: cin = %d must be 64 x image channels", cfg->cin);
+  GYRE_REQUIRE(cfg->ksize == 1 || cfg->ksize == 3, "adapter_create: ksize must be 1 or 3");
+  for (int i = 0; i < cfg->num_levels; ++i)
+    GYRE_REQUIRE(cfg->channels[i] > 0 && cfg->channels[i] % 8 == 0, "adapter_create: channels[%d] = %d must be a multiple of 8",
+                 i, cfg->channels[i]);
+  AdapterModel* m = new (std::nothrow) AdapterModel(*cfg);
+  GYRE_REQUIRE(m != nullptr, "adapter_create: out of host memory");
+  *out = reinterpret_cast<gyre_b200_handle>(static_cast<Model*>(m));
+  return 0;
+}
+
+int gyre_b200_adapter_workspace_bytes(gyre_b200_handle h, int batch, int height, int width, size_t* bytes) {
+  GYRE_REQUIRE(h && bytes, "adapter_workspace_bytes: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 3, "adapter_workspace_bytes: handle is not a T2I adapter");
+  Exec ex;
+  ex.dry = true;
+  ex.cap = static_cast<size_t>(1) << 60;
+  GYRE_TRY(static_cast<AdapterModel*>(M(h))->forward(ex, nullptr, batch, height, width, nullptr));
+  *bytes = ex.peak + 4096;
+  return 0;
+}
+
+int gyre_b200_adapter_forward(gyre_b200_handle h, const void* image, int batch, int height, int width, void* const* features,
+                              int n_features, void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && image && features, "adapter_forward: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 3, "adapter_forward: handle is not a T2I adapter");
+  AdapterModel* m = static_cast<AdapterModel*>(M(h));
+  GYRE_REQUIRE(n_features == m->num_levels(), "adapter_forward: %d feature buffers given, the model has %d levels", n_features,
+               m->num_levels());
+  for (int i = 0; i < n_features; ++i) GYRE_REQUIRE(features[i] != nullptr, "adapter_forward: null feature buffer %d", i);
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return m->forward(ex, static_cast<const __half*>(image), batch, height, width, reinterpret_cast<__half* const*>(features));
+}
+
 int gyre_b200_clip_create(const gyre_b200_clip_config* cfg, gyre_b200_handle* out) {
   GYRE_REQUIRE(cfg && out, "clip_create: null argument");
   GYRE_REQUIRE(cfg->vocab_size > 0 && cfg->num_layers > 0 && cfg->num_heads > 0 && cfg->max_positions > 0 &&

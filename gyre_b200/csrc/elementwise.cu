@@ -357,6 +357,70 @@ int dpm_error_partials(const float* x_low, const float* x_high, const float* x_p
 }
 int dpm_error_num_partials() { return kErrBlocks; }
 
+// T2I-adapter front end (gyre/pipeline/t2i_adapter/adapter.py:104, 119-122): nn.PixelUnshuffle(8) fused with the
+// NCHW -> NHWC transpose: out[b, y, x, c * 64 + dy * 8 + dx] = in[b, c, 8y + dy, 8x + dx].
+__global__ void pixel_unshuffle8_kernel(const __half* __restrict__ x, int C, int H, int W, __half* __restrict__ out,
+                                        int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over the output
+  if (i >= total) return;
+  const int Co = C * 64, Ho = H / 8, Wo = W / 8;
+  const int co = static_cast<int>(i % Co);
+  const int64_t p = i / Co;
+  const int xo = static_cast<int>(p % Wo);
+  const int yo = static_cast<int>((p / Wo) % Ho);
+  const int64_t b = p / (static_cast<int64_t>(Wo) * Ho);
+  const int c = co >> 6, dy = (co >> 3) & 7, dx = co & 7;
+  out[i] = x[((b * C + c) * H + (8 * yo + dy)) * W + (8 * xo + dx)];
+}
+int pixel_unshuffle8_nchw_to_nhwc(const __half* x, int B, int C, int H, int W, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(x && out && B > 0 && C > 0 && H % 8 == 0 && W % 8 == 0 && H > 0 && W > 0, "pixel_unshuffle: bad shape");
+  const int64_t total = static_cast<int64_t>(B) * C * H * W;
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  pixel_unshuffle8_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, C, H, W, out, total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// nn.AvgPool2d(kernel_size=2, stride=2) (adapter.py Downsample without conv, :56-58) on NHWC, 8 channels per thread
+__global__ void avg_pool2x2_kernel(const __half* __restrict__ x, int H, int W, int C, __half* __restrict__ out, int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // over output vectors of 8 channels
+  if (i >= total) return;
+  const int nv = C >> 3, Ho = H / 2, Wo = W / 2;
+  const int v = static_cast<int>(i % nv);
+  const int64_t p = i / nv;
+  const int xo = static_cast<int>(p % Wo);
+  const int yo = static_cast<int>((p / Wo) % Ho);
+  const int64_t b = p / (static_cast<int64_t>(Wo) * Ho);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (((b * H + 2 * yo + dy) * W + 2 * xo + dx) * C + v * 8));
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        acc[2 * k] += f.x;
+        acc[2 * k + 1] += f.y;
+      }
+    }
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = __floats2half2_rn(acc[2 * k] * 0.25f, acc[2 * k + 1] * 0.25f);
+  *reinterpret_cast<uint4*>(out + (((b * Ho + yo) * Wo + xo) * C + v * 8)) = *reinterpret_cast<uint4*>(o);
+}
+int avg_pool2x2_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t st) {
+  GYRE_REQUIRE(x && out && B > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0, "avg_pool2x2: bad shape");
+  const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2) * (C / 8);
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  avg_pool2x2_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, H, W, C, out, total);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Prompt weighting of the LPW text embedding (gyre/pipeline/text_embedding/lpw_text_embedding.py:352-371):
 //   previous_mean = emb.mean([-2, -1]); emb *= weights[..., None]; emb *= previous_mean / emb.mean([-2, -1])
 // One CTA per prompt, two passes over its [L, C] block (the second one from L2): fixed-order fp32 sums, one rounding.

@@ -683,6 +683,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 } else if (ep.act == ACT_GELU) {
 #pragma unroll
                   for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
               }
             }
@@ -785,6 +788,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             } else if (ep.act == ACT_GELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            } else if (ep.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (res) {
               for (int j = 0; j < 32; ++j)

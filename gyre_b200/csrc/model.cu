@@ -1220,4 +1220,103 @@ int ClipTextModel::forward(Exec& ex, const int64_t* ids, int B, int L, int skip_
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ T2I-adapter encoder
+// gyre/pipeline/t2i_adapter/adapter.py: PixelUnshuffle(8) -> conv_in -> per level `nums_rb` ResnetBlocks
+// ([Downsample] -> [in_conv] -> block1 3x3 -> ReLU -> block2 -> + skip) -> one feature map per level.
+AdapterModel::AdapterModel(const gyre_b200_adapter_config& cfg) : cfg_(cfg) {
+  const int* ch = cfg.channels;
+  reg_conv3("conv_in", cfg.cin, ch[0], &conv_in_);
+  body_.resize(static_cast<size_t>(cfg.num_levels) * cfg.nums_rb);
+  for (int i = 0; i < cfg.num_levels; ++i)
+    for (int j = 0; j < cfg.nums_rb; ++j) {
+      AdapterBlockW* b = &body_[static_cast<size_t>(i) * cfg.nums_rb + j];
+      const std::string p = "body." + std::to_string(i * cfg.nums_rb + j);
+      b->down = i != 0 && j == 0;
+      b->in_c = b->down ? ch[i - 1] : ch[i];
+      b->out_c = ch[i];
+      b->has_in = b->in_c != b->out_c || !cfg.sk;
+      b->has_skep = !cfg.sk;
+      if (b->down && cfg.use_conv) reg_conv3(p + ".down_opt.op", b->in_c, b->in_c, &b->down3);
+      if (b->has_in) {
+        if (cfg.ksize == 3) reg_conv3(p + ".in_conv", b->in_c, b->out_c, &b->in3);
+        else reg_linear(p + ".in_conv", b->out_c, b->in_c, true, &b->in1);
+      }
+      reg_conv3(p + ".block1", b->out_c, b->out_c, &b->b1);
+      if (cfg.ksize == 3) reg_conv3(p + ".block2", b->out_c, b->out_c, &b->b2_3);
+      else reg_linear(p + ".block2", b->out_c, b->out_c, true, &b->b2_1);
+      if (b->has_skep) {
+        // upstream declares skep on in_c channels but applies it after in_conv (adapter.py:76-78, 91-97): the widths
+        // must agree, as they do in every configuration upstream can run
+        if (cfg.ksize == 3) reg_conv3(p + ".skep", b->in_c, b->out_c, &b->sk3);
+        else reg_linear(p + ".skep", b->out_c, b->in_c, true, &b->sk1);
+      }
+    }
+}
+
+int AdapterModel::forward(Exec& ex, const __half* image, int B, int H, int W, __half* const* features) {
+  GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, "adapter_forward: image %dx%d must be a multiple of 8", H, W);
+  if (!ex.dry) GYRE_TRY(ensure_device());
+  const int* ch = cfg_.channels;
+  const int cimg = cfg_.cin / 64;
+  int h = H / 8, w = W / 8;
+  __half* x0 = ex.p16(static_cast<size_t>(B) * h * w * cfg_.cin);
+  RUN(ex, pixel_unshuffle8_nchw_to_nhwc(image, B, cimg, H, W, x0, ex.st));
+  __half* x = ex.p16(static_cast<size_t>(B) * h * w * ch[0]);
+  RUN(ex, conv3x3_f16(x0, cfg_.cin, B, h, w, cfg_.cin, conv_in_.wp, ch[0], 1, 1, ep_out(x, ch[0], conv_in_.bias), ex.st));
+  // one op of the ksize-1 / ksize-3 pair: 1x1 conv == GEMM over the pixels
+  auto conv_k = [&](const Conv3W& c3, const LinW& c1, const __half* src, int cin, int cout, __half* dst,
+                    const __half* residual) -> int {
+    if (cfg_.ksize == 3)
+      RUN(ex, conv3x3_f16(src, cin, B, h, w, cin, c3.wp, cout, 1, 1, ep_out(dst, cout, c3.bias, residual, residual ? cout : 0),
+                          ex.st));
+    else
+      RUN(ex, gemm_f16(src, cin, c1.w, cin, B * h * w, cout, cin, ep_out(dst, cout, c1.bias, residual, residual ? cout : 0),
+                       ex.st));
+    return 0;
+  };
+  for (int i = 0; i < cfg_.num_levels; ++i) {
+    for (int j = 0; j < cfg_.nums_rb; ++j) {
+      const AdapterBlockW& b = body_[static_cast<size_t>(i) * cfg_.nums_rb + j];
+      if (b.down) {
+        GYRE_REQUIRE(b.has_skep == false || b.in_c == b.out_c, "adapter: sk = 0 needs equal widths on consecutive levels");
+        if (cfg_.use_conv) {
+          const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+          __half* d = ex.p16(static_cast<size_t>(B) * ho * wo * b.in_c);
+          RUN(ex, conv3x3_f16(x, b.in_c, B, h, w, b.in_c, b.down3.wp, b.in_c, 2, 1, ep_out(d, b.in_c, b.down3.bias), ex.st));
+          x = d;
+          h = ho;
+          w = wo;
+        } else {
+          GYRE_REQUIRE(h >= 2 && w >= 2, "adapter: feature map %dx%d too small to pool", h, w);
+          __half* d = ex.p16(static_cast<size_t>(B) * (h / 2) * (w / 2) * b.in_c);
+          RUN(ex, avg_pool2x2_nhwc(x, B, h, w, b.in_c, d, ex.st));
+          x = d;
+          h /= 2;
+          w /= 2;
+        }
+      }
+      const size_t n = static_cast<size_t>(B) * h * w * b.out_c;
+      if (b.has_in) {
+        __half* t = ex.p16(n);
+        GYRE_TRY(conv_k(b.in3, b.in1, x, b.in_c, b.out_c, t, nullptr));
+        x = t;
+      }
+      __half* h1 = ex.p16(n);
+      RUN(ex, conv3x3_f16(x, b.out_c, B, h, w, b.out_c, b.b1.wp, b.out_c, 1, 1,
+                          ep_out(h1, b.out_c, b.b1.bias, nullptr, 0, ACT_RELU), ex.st));
+      const __half* skip = x;
+      if (b.has_skep) {
+        __half* sk = ex.p16(n);
+        GYRE_TRY(conv_k(b.sk3, b.sk1, x, b.out_c, b.out_c, sk, nullptr));
+        skip = sk;
+      }
+      __half* o = ex.p16(n);
+      GYRE_TRY(conv_k(b.b2_3, b.b2_1, h1, b.out_c, b.out_c, o, skip));
+      x = o;
+    }
+    RUN(ex, nhwc_to_nchw_f16(x, ch[i], B, ch[i], h, w, features[i], ex.st));
+  }
+  return 0;
+}
+
 }  // namespace gyre

@@ -246,4 +246,29 @@ class ClipTextModel : public Model {
   NormW final_ln_;
 };
 
+// T2I-adapter encoder (gyre/pipeline/t2i_adapter/adapter.py:65-132)
+struct AdapterBlockW {
+  Conv3W down3;            // Downsample with conv (use_conv)
+  Conv3W in3, b2_3, sk3;   // ksize 3 variants
+  LinW in1, b2_1, sk1;     // ksize 1 variants
+  Conv3W b1;               // block1 is always 3x3
+  bool down = false, has_in = false, has_skep = false;
+  int in_c = 0, out_c = 0;
+};
+
+class AdapterModel : public Model {
+ public:
+  explicit AdapterModel(const gyre_b200_adapter_config& cfg);
+  bool is_unet() const override { return false; }
+  int kind() const override { return 3; }
+  int num_levels() const { return cfg_.num_levels; }
+  // image [B, cin / 64, H, W] NCHW fp16 (H, W multiples of 8) -> one NCHW fp16 feature map per level (host pointer array)
+  int forward(Exec& ex, const __half* image, int B, int H, int W, __half* const* features);
+
+ private:
+  gyre_b200_adapter_config cfg_;
+  Conv3W conv_in_;
+  std::vector<AdapterBlockW> body_;
+};
+
 }  // namespace gyre

@@ -9,7 +9,7 @@
 namespace gyre {
 
 enum OutMode { OUT_F16 = 0, OUT_F32 = 1 };
-enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2, ACT_ROWMAX = 3, ACT_QUICKGELU = 4, ACT_GELU = 5 };
+enum Act { ACT_NONE = 0, ACT_GEGLU = 1, ACT_SILU = 2, ACT_ROWMAX = 3, ACT_QUICKGELU = 4, ACT_GELU = 5, ACT_RELU = 6 };
 
 // Epilogue description shared by the GEMM and the implicit-GEMM conv.
 struct Epilogue {
@@ -160,6 +160,10 @@ int rand_select(const float* a, const float* b, const float* rnd, float p, int64
 size_t outpaint_scratch_bytes();
 int outpaint_match_histograms(const __half* result, const __half* source, const __half* mask, int B, int64_t hw, __half* out,
                               void* scratch, cudaStream_t st);
+// T2I-adapter front end: PixelUnshuffle(8) of an NCHW image into token-major NHWC [B, H/8 * W/8, C * 64] (channel
+// c * 64 + dy * 8 + dx), and 2x2 average pooling of NHWC [B, H, W, C] (floor sizes, fp32 accumulation)
+int pixel_unshuffle8_nchw_to_nhwc(const __half* x, int B, int C, int H, int W, __half* out, cudaStream_t st);
+int avg_pool2x2_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t st);
 // LPW prompt weighting: out = emb * w[b, l] * (mean(emb[b]) / mean(emb[b] * w[b]))
 int lpw_weight(const __half* emb, const float* weights, int B, int L, int C, __half* out, cudaStream_t st);
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)

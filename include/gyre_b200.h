@@ -300,6 +300,28 @@ int gyre_b200_cat_channels(const void* x, int channels, const void* extra, int e
 int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int64_t per_sample, void* out,
                             gyre_b200_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * T2I-adapter encoder  (replaces `Adapter.forward`, gyre/pipeline/t2i_adapter/adapter.py:102-132; defaults of
+ * T2iAdapter_main, t2i_adapter/models.py:80-88).  Parameter keys are the nn.Module state-dict names
+ * ("conv_in.weight", "body.3.block1.bias", "body.2.down_opt.op.weight", ...).
+ * image [B, cin / 64, H, W] NCHW fp16 (H, W multiples of 8) -> num_levels feature maps, NCHW fp16
+ * [B, channels[i], H / 8 / 2^i, W / 8 / 2^i] (device pointers in the HOST array `features`) - the `adapter_states` of
+ * gyre_b200_unet_set_adapter_states.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gyre_b200_adapter_config {
+  int32_t cin;            /* channels after PixelUnshuffle(8): 64 x image channels (192 for RGB hints) */
+  int32_t num_levels;     /* <= 4 */
+  int32_t channels[4];    /* (320, 640, 1280, 1280) */
+  int32_t nums_rb;        /* ResnetBlocks per level (2) */
+  int32_t ksize;          /* 1 | 3: kernel of in_conv / block2 / skep (1) */
+  int32_t sk;             /* 1: identity skip, in_conv only where the width changes (1) */
+  int32_t use_conv;       /* 0: AvgPool2d(2) downsample, 1: stride-2 conv3x3 (0) */
+} gyre_b200_adapter_config;
+int gyre_b200_adapter_create(const gyre_b200_adapter_config* cfg, gyre_b200_handle* out);
+int gyre_b200_adapter_workspace_bytes(gyre_b200_handle h, int batch, int height, int width, size_t* bytes);
+int gyre_b200_adapter_forward(gyre_b200_handle h, const void* image, int batch, int height, int width, void* const* features,
+                              int n_features, void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+
 /* Image-space tail of an outpaint request (gyre/pipeline/unified_pipeline.py:2493-2510 with gyre/images.py:667-672 and
  * gyre/match_histograms.py:12-37 - done on the host with numpy in the reference): result / source / outmask / out are
  * [batch, 3, hw] fp16 images in [0, 1]; out = source * (1 - outmask) + match_histograms(result, source * (1 - outmask) +

@@ -1,0 +1,76 @@
+"""T2I-adapter encoder on the native kernels against vectors of the oracle that scripts/make_golden.py pinned bit for bit
+to the reference's own gyre/pipeline/t2i_adapter/adapter.py (tests/golden/t2i_adapter.pt), and chained into the native UNet."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "t2i_adapter.pt")
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.mark.parametrize("name", ["main_tiny", "conv_tiny"])
+def test_adapter_vs_reference_vectors(name):
+    from gyre_b200.t2i_adapter import B200T2iAdapter, adapter_param_shapes
+    v = torch.load(GOLD)[name]
+    kw = v["config"]
+    assert adapter_param_shapes(**kw) == {k: tuple(t.shape) for k, t in v["state_dict"].items()}
+    ad = B200T2iAdapter(**kw).load_state_dict(v["state_dict"])
+    feats = ad(v["x"].cuda())
+    assert len(feats) == len(v["features"])
+    errs = []
+    for mine, ref in zip(feats, v["features"]):
+        assert tuple(mine.shape) == tuple(ref.shape)
+        errs.append(rel_err(mine.cpu(), ref))
+    print(f"t2i adapter {name}: rel err per level {['%.2e' % e for e in errs]}")
+    assert max(errs) < 4e-3          # fp16 activations between ~20 convolutions, fp32 accumulation
+
+
+def test_adapter_into_unet_vs_oracle():
+    """Native adapter -> native UNet (`adapter_states=`) == oracle adapter -> oracle UNet, SD-shaped widths in miniature."""
+    from oracle import t2i_adapter as oad
+    from oracle.unet import UNetConfig, synth_params, unet_forward, unet_param_shapes
+    from gyre_b200.t2i_adapter import B200T2iAdapter
+    from gyre_b200.unet import B200UNet
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = UNetConfig.tiny()
+    PU = synth_params(unet_param_shapes(cfg), seed=1234)
+    kw = dict(channels=list(cfg.block_out_channels), nums_rb=2, cin=192, ksize=1, sk=True, use_conv=False)
+    PA = synth_params(oad.adapter_param_shapes(**kw), seed=55)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 4, 16, 16, generator=g).half()
+    ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=g).half()
+    hint = torch.rand(2, 3, 128, 128, generator=g).half()
+    t = torch.tensor([700, 300])
+    with torch.no_grad():
+        states = oad.adapter_forward(PA, hint.float(), **{k: v for k, v in kw.items() if k != "cin"})
+        ref = unet_forward(PU, cfg, x.float(), t, ctx.float(), adapter_states=states)
+        plain = unet_forward(PU, cfg, x.float(), t, ctx.float())
+    ad = B200T2iAdapter(**kw).load_state_dict(PA)
+    unet = B200UNet(cfg).load_state_dict(PU)
+    out = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda(), adapter_states=ad(hint.cuda())).sample
+    err, moved = rel_err(out.cpu(), ref), rel_err(ref, plain)
+    print(f"t2i adapter -> unet: rel err {err:.3e}; the adapter moves the output by {moved:.3e}")
+    assert err < 5e-3 and moved > 5e-2
+
+
+def test_adapter_autoinvert_and_errors():
+    from gyre_b200.t2i_adapter import B200T2iAdapter
+    v = torch.load(GOLD)["main_tiny"]
+    kw = v["config"]
+    plain = B200T2iAdapter(**kw).load_state_dict(v["state_dict"])
+    inv = B200T2iAdapter(autoinvert=True, **kw).load_state_dict(v["state_dict"])
+    white = (0.9 + 0.1 * v["x"]).cuda()                 # mostly white: inverted before the encoder
+    a, b = inv(white), plain(1 - white)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+    dark = (0.3 * v["x"]).cuda()
+    assert all(torch.equal(p, q) for p, q in zip(inv(dark), plain(dark)))
+    with pytest.raises(ValueError):
+        plain(torch.zeros(1, 1, 64, 64).half().cuda())
+    with pytest.raises(ValueError):
+        plain(torch.zeros(1, 3, 60, 64).half().cuda())
