@@ -262,7 +262,7 @@ def gemm(a, w, bias=None, residual=None, act=0, a2=None, out_dtype=torch.float16
         out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
     e = _epilogue(out, bias, residual, act, rowgroup_bias, rows_per_group)
     e.rowstat_out, e.ln_rowstat, e.ln_colsum = ptr(rowstat_out), ptr(ln_rowstat), ptr(ln_colsum)
-    if ln_raw_parts:       # ln_rowstat = the producer's partials [parts <= 4, M, 2]: folded by the consumer itself
+    if ln_raw_parts:       # ln_rowstat = the producer's partials [parts <= 8, M, 2]: folded by the consumer itself
         e.ln_parts, e.ln_inv_c, e.ln_eps = ln_rowstat.shape[0], 1.0 / K1, float(ln_eps)
     check(load().gyre_b200_gemm(ptr(a), a.stride(0), K1, ptr(a2), a2.stride(0) if a2 is not None else 0, K2, ptr(w),
                                 w.stride(0), M, N, C.byref(e), stream_ptr(a.device)), "gemm")

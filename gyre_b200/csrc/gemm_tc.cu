@@ -453,15 +453,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     };
     float nb0 = 0.f, nb1 = 0.f;
     // LayerNorm consumer: (mean, rstd) of this thread's row, requested one tile ahead like the bias
-    // (ln_parts == 0: finished (mean, rstd); 1..4: the producer's raw partials, folded when the tile starts - the loads
+    // (ln_parts == 0: finished (mean, rstd); 1..8: the producer's raw partials, folded when the tile starts - the loads
     // are issued a tile ahead and consumed a tile later, so their latency never sits in an epilogue)
-    struct RowStatRaw { float2 v[4]; };
+    struct RowStatRaw { float2 v[8]; };
     auto rowstat_of = [&](int tt) -> RowStatRaw {
       RowStatRaw o;
       const int mt = p.mcast ? 2 * (tt / p.n_tiles) + rank : tt / p.n_tiles;
       const int64_t row = static_cast<int64_t>(mt) * kBM + r;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
         o.v[i] = (row < p.M && i < (ep.ln_parts == 0 ? 1 : ep.ln_parts))
                      ? __ldg(ep.ln_rowstat + static_cast<int64_t>(i) * p.M + row)
                      : make_float2(0.f, 0.f);
@@ -469,15 +469,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     };
     auto rowstat_fold = [&](const RowStatRaw& o) -> float2 {
       if (ep.ln_parts == 0) return o.v[0];
-      const float s = (o.v[0].x + o.v[1].x) + (o.v[2].x + o.v[3].x);
-      const float q2 = (o.v[0].y + o.v[1].y) + (o.v[2].y + o.v[3].y);
+      const float s = ((o.v[0].x + o.v[1].x) + (o.v[2].x + o.v[3].x)) + ((o.v[4].x + o.v[5].x) + (o.v[6].x + o.v[7].x));
+      const float q2 = ((o.v[0].y + o.v[1].y) + (o.v[2].y + o.v[3].y)) + ((o.v[4].y + o.v[5].y) + (o.v[6].y + o.v[7].y));
       const float mean = s * ep.ln_inv_c;
       const float var = fmaxf(fmaf(-mean, mean, q2 * ep.ln_inv_c), 0.f);
       return make_float2(mean, rsqrtf(var + ep.ln_eps));
     };
     RowStatRaw ln_next;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ln_next.v[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < 8; ++i) ln_next.v[i] = make_float2(0.f, 0.f);
     Item wi, wnext;
     bool have = get_item(0, wi);
     if (have) {
@@ -1134,7 +1134,7 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
     GYRE_REQUIRE(p.tma_epi && ep.act == ACT_NONE && bn >= 64 && ep.ln_rowstat == nullptr,
                  "gemm: row statistics need the fp16 TMA epilogue without activation (N=%d, ldo=%d)", N, ep.ldo);
   if (ep.ln_rowstat != nullptr)
-    GYRE_REQUIRE(p.tma_epi && ep.ln_colsum != nullptr && bn >= 64 && ep.ln_parts >= 0 && ep.ln_parts <= 4 &&
+    GYRE_REQUIRE(p.tma_epi && ep.ln_colsum != nullptr && bn >= 64 && ep.ln_parts >= 0 && ep.ln_parts <= 8 &&
                      (ep.ln_parts == 0 || ep.ln_inv_c > 0.f) &&
                      (ep.act == ACT_NONE || (ep.act == ACT_GEGLU && p.fast_gelu)),
                  "gemm: the folded LayerNorm needs the fp16 TMA epilogue, column sums and no activation but the fast GEGLU");

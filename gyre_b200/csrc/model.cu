@@ -531,9 +531,9 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
     if (fuse) e.rowstat_out = ln_part;
     return e;
   };
-  // up to 4 partials per row (C = 320: two 160-column tiles x two column halves) the consumer folds them itself;
+  // up to 8 partials per row (C = 320 / 640: two / four 160-column tiles x two column halves) the consumer folds them itself;
   // wider rows go through the finalize kernel
-  const bool direct = ln_parts <= 4;
+  const bool direct = ln_parts <= 8;
   auto finalize_stats = [&]() -> int {
     if (fuse && !direct) RUN(ex, ln_finalize_rows(ln_part, ln_parts, M, C, 1e-5f, ln_stat, ex.st));
     return 0;

@@ -35,7 +35,7 @@ struct Epilogue {
   //   consumer side - A holds the RAW rows x, W the gamma-scaled weights W' = gamma (.) W; with ln_rowstat [M] float2
   //   (mean, rstd) and ln_colsum [N] = sum_k W'[n, k] the epilogue turns the accumulator into LayerNorm(x) @ W^T:
   //   rstd * (acc - mean * colsum[n]) + bias[n], bias already holding beta @ W^T.
-  //   With ln_parts in 1..4 the consumer folds the producer's partials itself (ln_rowstat = [ln_parts][M] raw partials,
+  //   With ln_parts in 1..8 the consumer folds the producer's partials itself (ln_rowstat = [ln_parts][M] raw partials,
   //   ln_inv_c = 1 / C, ln_eps) and no finalize launch is needed.
   float2* rowstat_out = nullptr;
   const float2* ln_rowstat = nullptr;

@@ -408,7 +408,7 @@ typedef struct gyre_b200_epilogue {
   void* rowstat_out;
   const void* ln_rowstat;
   const float* ln_colsum;
-  /* ln_parts in 1..4: ln_rowstat holds the producer's raw partials [ln_parts][M] and the consumer folds them itself
+  /* ln_parts in 1..8: ln_rowstat holds the producer's raw partials [ln_parts][M] and the consumer folds them itself
    * with ln_inv_c = 1 / C and ln_eps (no finalize launch); 0: ln_rowstat holds finished (mean, rstd) pairs. */
   int32_t ln_parts;
   float ln_inv_c;

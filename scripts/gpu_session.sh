@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 for what in "$@"; do
   case "$what" in
     tests)
-      for f in tests/test_ops_gpu.py tests/test_attention_gpu.py tests/test_tome_gpu.py tests/test_models_gpu.py tests/test_clip_gpu.py tests/test_pipeline_gpu.py; do
+      for f in tests/test_*_gpu.py; do
         name=$(basename "$f" .py)
         timeout 900 python -m pytest "$f" -m gpu -q -x --tb=short > "gpurun_out/$name.log" 2>&1
         echo "== $f -> exit $?"; tail -n 3 "gpurun_out/$name.log"

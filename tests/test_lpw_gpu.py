@@ -32,12 +32,12 @@ def test_weighted_embeddings_vs_reference(setup, mult, nomid):
         err = (mine.float().cpu() - ref).abs().max().item()
         scale = ref.abs().max().item()
         print(f"LPW mult {mult} nomid {nomid} {name}: max abs err {err:.3e} (|emb| max {scale:.3f})")
-        # fp16 encoder (measured ~1.5e-3 of the scale on the CLIP tests) + one fp16 rounding of the weighted value
-        assert err < 6e-3 * scale
+        # fp16 encoder + one fp16 rounding of the weighted value: measured 0.9 - 0.95e-3 of the scale on B200
+        assert err < 3e-3 * scale
     if "unweighted" in v:
         raw, _ = lpw.get_weighted_text_embeddings(ToyTokenizer(), enc, enc, enc.device, list(PROMPTS), None,
                                                   max_embeddings_multiples=mult, no_boseos_middle=nomid, skip_weighting=True)
-        assert (raw.float().cpu() - v["unweighted"]).abs().max().item() < 6e-3 * v["unweighted"].abs().max().item()
+        assert (raw.float().cpu() - v["unweighted"]).abs().max().item() < 3e-3 * v["unweighted"].abs().max().item()
 
 
 def test_lpw_weight_kernel_vs_torch(setup):

@@ -355,7 +355,7 @@ def test_layernorm_folded_into_gemms(nat, M, C, N2):
     # the unfused pair of kernels is no closer to the fp32 reference than the folded form
     ln = nat.layernorm(h, gamma, beta)
     unfused = nat.gemm(ln, w2, bias=b2)
-    if parts.shape[0] <= 4:
+    if parts.shape[0] <= 8:
         # narrow rows: the consumer folds the raw partials itself, no finalize launch
         out_direct = nat.gemm(h, wf, bias=lb, ln_rowstat=parts, ln_colsum=cs, ln_raw_parts=True)
         assert_close(out_direct, ref, 6e-3, 4e-3, f"folded LayerNorm (raw partials) -> Linear {M}x{C}->{N2}")
