@@ -117,8 +117,9 @@ class _Node:
 
 
 class B200Pipeline:
-    def __init__(self, unet, vae=None, text_encoder=None, inpaint_unet=None):
+    def __init__(self, unet, vae=None, text_encoder=None, inpaint_unet=None, tokenizer=None):
         self.unet = unet
+        self.tokenizer = tokenizer         # the caller's CLIPTokenizer (or any object with its call surface) for `prompt=`
         self.inpaint_unet = inpaint_unet   # 9-channel UNet of the same family (unified_pipeline.py:2059-2062), or None
         self.vae = vae
         self.text_encoder = text_encoder   # B200CLIPTextModel or None: embeddings are passed in
@@ -180,15 +181,32 @@ class B200Pipeline:
                 raise ValueError(f"Unknown option {key!r}")
             self._options[key] = value
 
+    def embed_prompts(self, prompt, negative_prompt=None, max_embeddings_multiples: int = 3, clip_layer="final"):
+        """`LPWTextEmbedding(...).get_embeddings(prompt, uncond_prompt)` (unified_pipeline.py:2269-2304): weighted text and
+        uncond embeddings [B, 77 * k, C] from prompt strings (or pre-parsed (text, weight) lists) on the native CLIP."""
+        if self.text_encoder is None or self.tokenizer is None:
+            raise ValueError("text prompts need a text encoder and a tokenizer attached to the pipeline")
+        from .lpw_text_embedding import LPWTextEmbedding
+        prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        if negative_prompt is None:
+            negative_prompt = [""] * len(prompts)
+        negs = [negative_prompt] * len(prompts) if isinstance(negative_prompt, str) else list(negative_prompt)
+        if len(negs) != len(prompts):
+            raise ValueError(f"`negative_prompt` has batch size {len(negs)}, `prompt` has {len(prompts)}")
+        calc = LPWTextEmbedding(max_embeddings_multiples, tokenizer=self.tokenizer, text_encoder=self.text_encoder,
+                                uncond_encoder=self.text_encoder, device=self.device, clip_layer=clip_layer)
+        return calc.get_embeddings(prompts, negs)
+
     @torch.no_grad()
-    def __call__(self, prompt_embeds, negative_prompt_embeds, height: int = 512, width: int = 512,
+    def __call__(self, prompt_embeds=None, negative_prompt_embeds=None, height: int = 512, width: int = 512,
                  num_inference_steps: int = 50, guidance_scale: float = 7.5, generator=None,
                  sampler: str = "k_euler_ancestral", scheduler_config: SchedulerConfig | None = None,
                  output_type: str = "pt", callback=None, callback_steps: int = 1, progress_wrapper=None,
                  latents_dtype=torch.float16, return_fp32_latents: bool = False, image=None, mask_image=None,
                  strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None,
                  cfg_execution: str = "parallel", hires_fix: bool | None = None,
-                 hires_oos_fraction: float | None = None, outmask_image=None) -> PipelineOutput:
+                 hires_oos_fraction: float | None = None, outmask_image=None, prompt=None, negative_prompt=None,
+                 max_embeddings_multiples: int = 3, clip_layer="final") -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
         unified_pipeline.py:2055-2066 - optionally grafted (inpaint UNet early, main UNet late, :2069-2098) and, for
@@ -197,6 +215,13 @@ class B200Pipeline:
         preprocess_mask_tensor(inputIs0K1D=True))."""
         if height % 8 != 0 or width % 8 != 0:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if prompt_embeds is None:
+            if prompt is None:
+                raise ValueError("pass `prompt` (text, needs the text encoder + tokenizer) or `prompt_embeds`")
+            prompt_embeds, negative_prompt_embeds = self.embed_prompts(prompt, negative_prompt, max_embeddings_multiples,
+                                                                       clip_layer)
+        elif prompt is not None:
+            raise ValueError("pass either `prompt` or `prompt_embeds`, not both")
         if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
             raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps}")
         B = prompt_embeds.shape[0]

@@ -36,7 +36,10 @@ CASES = [(1, 1, 128, 128, 64), (2, 4, 256, 256, 16), (2, 8, 1024, 1024, 40), (1,
          (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 10, 2304, 77, 64), (1, 5, 9216, 77, 64),
          (1, 3, 700, 77, 40), (2, 4, 512, 128, 64), (1, 2, 640, 16, 128), (1, 8, 1000, 100, 72),
          # ping-pong kernel at 64 < d <= 128 (P aliased onto S in TMEM): SD1.5 level 1, ragged keys, d = 128
-         (2, 8, 1024, 1024, 80), (1, 5, 640, 640, 128), (1, 4, 384, 300, 96), (1, 2, 2048, 1500, 104), (1, 8, 300, 290, 80)]
+         (2, 8, 1024, 1024, 80), (1, 5, 640, 640, 128), (1, 4, 384, 300, 96), (1, 2, 2048, 1500, 104), (1, 8, 300, 290, 80),
+         # cross-attention against LPW multi-chunk prompts (2 / 3 chunks of 77 tokens) at the SD1.5 / SD2.1 levels
+         (2, 8, 4096, 154, 40), (2, 8, 4096, 231, 40), (1, 8, 1024, 231, 80), (2, 8, 256, 231, 160), (1, 8, 64, 231, 160),
+         (1, 10, 2304, 231, 64)]
 
 
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", CASES)

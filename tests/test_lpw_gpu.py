@@ -62,3 +62,33 @@ def test_lpw_class_surface(setup):
     assert text.shape == unc.shape and text.shape[0] == 2 and text.shape[1] == 77
     rep = calc.repeat(text, 3)
     assert rep.shape[0] == 6 and torch.equal(rep[0], text[0]) and torch.equal(rep[3], text[1])
+
+
+def test_pipeline_from_text_prompts_vs_oracle(setup):
+    """`B200Pipeline(prompt=, negative_prompt=)`: LPW (three chunks, [B, 231, C] embeddings) -> CFG -> sampler, against the
+    oracle UNet fed the REFERENCE's weighted embeddings for the same prompts."""
+    from oracle import sampling as osamp
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    g, enc = setup
+    cfg = UNetConfig.tiny()          # cross_attention_dim 64 == the tiny CLIP's hidden size
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    pipe = B200Pipeline(B200UNet(cfg).load_state_dict(P), None, text_encoder=enc, tokenizer=ToyTokenizer())
+    pipe.unet_sample_size_override = 16
+    v = g["lpw/mult3/mid"]
+    seeds, steps = [420420420 + i for i in range(len(PROMPTS))], 6
+    out = pipe(prompt=list(PROMPTS), negative_prompt=list(NEGATIVE), height=128, width=128, num_inference_steps=steps,
+               guidance_scale=7.5, generator=[torch.Generator("cpu").manual_seed(s) for s in seeds],
+               sampler="k_euler_ancestral", output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True)
+    with torch.no_grad():
+        ref = osamp.txt2img_latents(osamp.CFGParallel(OracleUNet(cfg, P), v["uncond"], v["text"], 7.5), batch=len(PROMPTS),
+                                    in_channels=4, height=128, width=128, sample_size=16, seeds=seeds, steps=steps,
+                                    sampler="euler_a")
+    err = (out.latents.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"pipeline from text (3 LPW chunks): final-latent max abs err {err:.4e} (latent max {scale:.3f})")
+    assert err < 1.4e-2 * scale
+    with pytest.raises(ValueError):
+        pipe(prompt="a", prompt_embeds=v["text"][:1].cuda(), negative_prompt_embeds=v["uncond"][:1].cuda(),
+             generator=[torch.Generator("cpu")], output_type="latent")
