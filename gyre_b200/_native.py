@@ -92,6 +92,7 @@ SIGNATURES = {
     "gyre_b200_unet_workspace_bytes": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
     "gyre_b200_unet_set_context": (_i, [_vp, _vp, _i, _i, _vp]),
+    "gyre_b200_unet_set_cfg_duplicate": (_i, [_vp, _i]),
     "gyre_b200_unet_set_control_residuals": (_i, [_vp, C.POINTER(C.c_void_p), _i, _vp]),
     "gyre_b200_unet_num_skips": (_i, [_vp]),
     "gyre_b200_unet_set_adapter_states": (_i, [_vp, C.POINTER(C.c_void_p), _i]),

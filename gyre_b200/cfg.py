@@ -33,6 +33,10 @@ class B200GuidedUNet:
         # who "owns" the K/V projections cached in the UNet: leaves of one request that share the embeddings (hires-fix:
         # natural + full size) point this at the same object so that alternating between them does not re-project
         self.ctx_owner = self
+        # `raw` is fed `torch.cat([latents] * 2)` with one timestep (CFGUNet_Parallel, cfg.py:47-57; the schedulers build
+        # the same layout on the device): the native UNet computes what both halves share once.  Callers that hand `raw`
+        # two DIFFERENT halves must clear this.
+        self.duplicated_halves = True
         self.extra = None           # [B, Ce, h, w] fp16: mask + masked-image latents of the inpaint UNets
         self._xcat = None
         self.add_cond = None        # [2B, proj_in] fp16: text_time conditioning of SDXL-style UNets ([uncond ; cond])
@@ -79,8 +83,10 @@ class B200GuidedUNet:
             bound = self.unet._ctx_bound
             if bound is None or bound[0] is not self.ctx_owner:
                 self.unet.set_context(self.embeddings, owner=self.ctx_owner)
-            return self.unet.forward_raw(x2_f16, t2_i64, None, out=out, add_cond=self.add_cond)
-        return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out, add_cond=self.add_cond)
+            return self.unet.forward_raw(x2_f16, t2_i64, None, out=out, add_cond=self.add_cond,
+                                         cfg_duplicate=self.duplicated_halves)
+        return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out, add_cond=self.add_cond,
+                                     cfg_duplicate=self.duplicated_halves)
 
     def _raw_sequential(self, x2_f16, t2_i64, out):
         """[uncond ; cond] evaluated as two UNet calls of batch B (CFGUNet_Sequential)."""

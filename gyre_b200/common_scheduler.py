@@ -425,7 +425,8 @@ class KDiffusionScheduler(CommonScheduler):
             x, x_next = ent["x0"], ent["xa"]
             k = 0
             for i in range(n):
-                unet.forward_raw(ent["x_in"], ent["t"][i], None, out=ent["eps2"], add_cond=ent["add"])
+                unet.forward_raw(ent["x_in"], ent["t"][i], None, out=ent["eps2"], add_cond=ent["add"],
+                                 cfg_duplicate=guided.duplicated_halves)
                 st = ent["steps"][i]
                 nz = None
                 if st.sigma_up != 0.0:

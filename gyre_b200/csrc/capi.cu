@@ -376,6 +376,13 @@ int gyre_b200_unet_forward(gyre_b200_handle h, const void* sample, const int64_t
                                      workspace, workspace_bytes, stream);
 }
 
+int gyre_b200_unet_set_cfg_duplicate(gyre_b200_handle h, int on) {
+  GYRE_REQUIRE(h, "unet_set_cfg_duplicate: null handle");
+  GYRE_REQUIRE(M(h)->is_unet(), "unet_set_cfg_duplicate: handle is not a UNet");
+  static_cast<UNetModel*>(M(h))->set_cfg_duplicate(on != 0);
+  return 0;
+}
+
 int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, int ctx_len, gyre_b200_stream stream) {
   GYRE_REQUIRE(h, "unet_set_context: null handle");
   GYRE_REQUIRE(M(h)->is_unet(), "unet_set_context: handle is not a UNet");

@@ -731,7 +731,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         if constexpr (kRowStat) {
           if (valid)
-            ep.rowstat_out[(static_cast<int64_t>(n_tile) * 2 + half) * p.M + out_row] = make_float2(rs, rq);
+            ep.rowstat_out[(static_cast<int64_t>(n_tile) * 2 + half) * (ep.rowstat_ld > 0 ? ep.rowstat_ld : p.M) + out_row] =
+                make_float2(rs, rq);
         }
       } else if constexpr (EPI == 1) {
         // ================================================= direct path (fp32 out, unaligned pitches, tiny N)

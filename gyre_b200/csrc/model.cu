@@ -506,15 +506,21 @@ int UNetModel::set_context(const __half* ctx, int B, int L, cudaStream_t st) {
 
 // Transformer2DModel + BasicTransformerBlock (nonfree/tome_unet.py:114-136)
 int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int B, int HW, const __half* ctx, int L,
-                           int r, __half* out) {
+                           int r, __half* out, bool share) {
+  // `share` (CFG-parallel input, UNetModel::forward): the two halves of the batch are the SAME samples with different
+  // text contexts, so everything up to the first cross-attention - GroupNorm, proj_in, the whole self-attention, attn2's
+  // query projection - is computed once on `x` = [B / 2] samples; the halves part ways at the cross-attention's K / V.
   const int C = t.C;
-  const int M = B * HW;
+  const int Bs = share ? B / 2 : B;             // samples of the shared prefix
+  const int M = B * HW, Ms = Bs * HW;
+  const int nh = share ? 2 : 1;                 // launches that fan the shared rows out to both halves
   const size_t n = static_cast<size_t>(M) * C;
+  const size_t ns = static_cast<size_t>(Ms) * C;
   const int d = C / t.heads;
   const float scale = 1.0f / sqrtf(static_cast<float>(d));
   float* gn_scratch = ex.s32(gn_partials_floats(B, HW, groups_));
   __half* tn = ex.s16(n);
-  RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, B, HW, groups_, 1e-6f, t.gn.g, t.gn.b, false, tn, gn_scratch, ex.st));
+  RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, Bs, HW, groups_, 1e-6f, t.gn.g, t.gn.b, false, tn, gn_scratch, ex.st));
   __half* h = ex.s16(n);
   // LayerNorm folded into the GEMMs around it: the GEMM that PRODUCES a residual-stream tensor also emits
   // per-row (sum, sum of squares) partials; a tiny kernel turns them into (mean, rstd); the GEMM that CONSUMES the
@@ -523,32 +529,42 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   // The scratch is reserved whenever the model was built with the folded weights, so the workspace size does not
   // depend on the run-time tunable.
   const bool fuse = ln_fuse_ && tunable(TUNE_LN_FUSE) != 0 && C > 32;
-  const int ln_parts = ln_fuse_ ? gemm_rowstat_parts(M, C) : 0;
-  float2* ln_part = ln_fuse_ ? reinterpret_cast<float2*>(ex.s32(static_cast<size_t>(2) * ln_parts * M)) : nullptr;
+  const int parts_full = ln_fuse_ ? gemm_rowstat_parts(M, C) : 0;
+  const int parts_s = ln_fuse_ ? gemm_rowstat_parts(Ms, C) : 0;       // what a producer launched on Ms rows writes
+  const int parts_max = parts_full > parts_s ? parts_full : parts_s;
+  float2* ln_part = ln_fuse_ ? reinterpret_cast<float2*>(ex.s32(static_cast<size_t>(2) * parts_max * M)) : nullptr;
   float2* ln_stat = ln_fuse_ ? reinterpret_cast<float2*>(ex.s32(static_cast<size_t>(2) * M)) : nullptr;
-  // producer epilogue: also leave the row statistics of what it writes
-  auto with_stats = [&](Epilogue e) {
-    if (fuse) e.rowstat_out = ln_part;
+  // State of the statistics the last producer(s) left: `cur_parts` partials per row, laid out [cur_parts][cur_rows].
+  int cur_parts = 0, cur_rows = 0;
+  // producer epilogue: also leave the row statistics of what it writes (rows [row0, row0 + launch rows) of `rows` in all)
+  auto with_stats = [&](Epilogue e, int launch_rows, int rows, int row0) {
+    if (fuse) {
+      e.rowstat_out = ln_part + row0;
+      e.rowstat_ld = rows;
+      cur_parts = gemm_rowstat_parts(launch_rows, C);
+      cur_rows = rows;
+    }
     return e;
   };
-  // up to 8 partials per row (C = 320 / 640: two / four 160-column tiles x two column halves) the consumer folds them itself;
-  // wider rows go through the finalize kernel
-  const bool direct = ln_parts <= 8;
+  // up to 8 partials per row (C = 320 / 640: two / four 160-column tiles x two column halves) the consumer folds them
+  // itself; wider rows go through the finalize kernel
   auto finalize_stats = [&]() -> int {
-    if (fuse && !direct) RUN(ex, ln_finalize_rows(ln_part, ln_parts, M, C, 1e-5f, ln_stat, ex.st));
+    if (fuse && cur_parts > 8) RUN(ex, ln_finalize_rows(ln_part, cur_parts, cur_rows, C, 1e-5f, ln_stat, ex.st));
     return 0;
   };
   // consumer epilogue: LayerNorm(x) @ W^T from the raw rows
   auto ln_ep = [&](Epilogue e, const LnFoldW& f) {
+    const bool direct = cur_parts <= 8;
     e.bias = f.bias;
     e.ln_colsum = f.colsum;
     e.ln_rowstat = direct ? ln_part : ln_stat;
-    e.ln_parts = direct ? ln_parts : 0;
+    e.ln_parts = direct ? cur_parts : 0;
     e.ln_inv_c = 1.0f / static_cast<float>(C);
     e.ln_eps = 1e-5f;
     return e;
   };
-  RUN(ex, gemm_f16(tn, C, t.proj_in.w, C, M, C, C, with_stats(ep_out(h, C, t.proj_in.bias)), ex.st));
+  (void)parts_s;
+  RUN(ex, gemm_f16(tn, C, t.proj_in.w, C, Ms, C, C, with_stats(ep_out(h, C, t.proj_in.bias), Ms, Ms, 0), ex.st));
   GYRE_TRY(finalize_stats());
   __half* nrm = tn;   // the GroupNorm output is dead after proj_in: reuse it for the LayerNorm outputs
   __half* qkv = ex.s16(n * 3);
@@ -573,30 +589,33 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   // h holds the residual stream on entry to every block and again on exit (h -> h2 -> h -> h2 -> copy-free swap)
   for (size_t bi = 0; bi < t.blocks.size(); ++bi) {
     const TBlockW& k = t.blocks[bi];
+    // rows / samples of this block's self-attention part: the shared prefix exists in the first block only
+    const bool sh = share && bi == 0;
+    const int Bp = sh ? Bs : B, Mp = sh ? Ms : M;
     // ---- self-attention
     if (fuse) {
-      RUN(ex, gemm_f16(h, C, k.qkv_ln.w, C, M, 3 * C, C, ln_ep(ep_out(qkv, 3 * C), k.qkv_ln), ex.st));
+      RUN(ex, gemm_f16(h, C, k.qkv_ln.w, C, Mp, 3 * C, C, ln_ep(ep_out(qkv, 3 * C), k.qkv_ln), ex.st));
     } else {
-      RUN(ex, layernorm_rows(h, M, C, 1e-5f, k.ln1.g, k.ln1.b, nrm, ex.st));
-      RUN(ex, gemm_f16(nrm, C, k.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C), ex.st));
+      RUN(ex, layernorm_rows(h, Mp, C, 1e-5f, k.ln1.g, k.ln1.b, nrm, ex.st));
+      RUN(ex, gemm_f16(nrm, C, k.qkv.w, C, Mp, 3 * C, C, ep_out(qkv, 3 * C), ex.st));
     }
     if (rr > 0) {
       // ToMe (nonfree/tome_memory_efficient_cross_attention.py:28-50): merge K and V with one plan built from K
       const int nk = HW - rr;
-      RUN(ex, tome_merge_kv(off(qkv, C), off(qkv, 2 * C), 3 * C, B, HW, C, rr, km, vm, tws, tome_bytes, ex.st));
-      RUN(ex, attention_f16(qkv, 3 * C, km, C, vm, C, B, t.heads, HW, nk, d, scale, o, C, ex.st));
+      RUN(ex, tome_merge_kv(off(qkv, C), off(qkv, 2 * C), 3 * C, Bp, HW, C, rr, km, vm, tws, tome_bytes, ex.st));
+      RUN(ex, attention_f16(qkv, 3 * C, km, C, vm, C, Bp, t.heads, HW, nk, d, scale, o, C, ex.st));
     } else {
-      RUN(ex, attention_f16(qkv, 3 * C, off(qkv, C), 3 * C, off(qkv, 2 * C), 3 * C, B, t.heads, HW, HW, d, scale, o, C, ex.st));
+      RUN(ex, attention_f16(qkv, 3 * C, off(qkv, C), 3 * C, off(qkv, 2 * C), 3 * C, Bp, t.heads, HW, HW, d, scale, o, C, ex.st));
     }
-    RUN(ex, gemm_f16(o, C, k.o1.w, C, M, C, C, with_stats(ep_out(h2, C, k.o1.bias, h, C)), ex.st));
+    RUN(ex, gemm_f16(o, C, k.o1.w, C, Mp, C, C, with_stats(ep_out(h2, C, k.o1.bias, h, C), Mp, Mp, 0), ex.st));
     GYRE_TRY(finalize_stats());
-    // ---- cross-attention
+    // ---- cross-attention: the query projection still belongs to the shared prefix
     __half* q = qkv;   // dead after self-attention
     if (fuse) {
-      RUN(ex, gemm_f16(h2, C, k.q2_ln.w, C, M, C, C, ln_ep(ep_out(q, C), k.q2_ln), ex.st));
+      RUN(ex, gemm_f16(h2, C, k.q2_ln.w, C, Mp, C, C, ln_ep(ep_out(q, C), k.q2_ln), ex.st));
     } else {
-      RUN(ex, layernorm_rows(h2, M, C, 1e-5f, k.ln2.g, k.ln2.b, nrm, ex.st));
-      RUN(ex, gemm_f16(nrm, C, k.q2.w, C, M, C, C, ep_out(q, C), ex.st));
+      RUN(ex, layernorm_rows(h2, Mp, C, 1e-5f, k.ln2.g, k.ln2.b, nrm, ex.st));
+      RUN(ex, gemm_f16(nrm, C, k.q2.w, C, Mp, C, C, ep_out(q, C), ex.st));
     }
     const __half* kv;
     if (ctx != nullptr || ex.dry) {
@@ -605,8 +624,19 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
     } else {
       kv = kv_cache_[static_cast<size_t>(k.flat)];
     }
-    RUN(ex, attention_f16(q, C, kv, 2 * C, off(kv, C), 2 * C, B, t.heads, HW, L, d, scale, o, C, ex.st));
-    RUN(ex, gemm_f16(o, C, k.o2.w, C, M, C, C, with_stats(ep_out(h, C, k.o2.bias, h2, C)), ex.st));   // h <- h2 + attn2
+    // shared prefix: the same queries against each half's keys / values, then attn2's output projection with the same
+    // residual rows - from here on the two halves are different tensors
+    const int fan = sh ? nh : 1;
+    for (int hf = 0; hf < fan; ++hf) {
+      const size_t kvo = static_cast<size_t>(hf) * Bp * L * 2 * C, oo = static_cast<size_t>(hf) * Mp * C;
+      RUN(ex, attention_f16(q, C, off(kv, kvo), 2 * C, off(kv, kvo + C), 2 * C, Bp, t.heads, HW, L, d, scale, off(o, oo), C,
+                            ex.st));
+    }
+    for (int hf = 0; hf < fan; ++hf) {
+      const size_t oo = static_cast<size_t>(hf) * Mp * C;
+      RUN(ex, gemm_f16(off(o, oo), C, k.o2.w, C, Mp, C, C,
+                       with_stats(ep_out(off(h, oo), C, k.o2.bias, h2, C), Mp, fan * Mp, hf * Mp), ex.st));   // h <- h2 + attn2
+    }
     GYRE_TRY(finalize_stats());
     // ---- GEGLU feed-forward
     const bool fuse_ff = fuse && tunable(TUNE_GELU_FAST) != 0;     // the folded GEGLU image carries the fast GELU only
@@ -620,12 +650,17 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
     // h2 <- h + ff; with another block behind it, its norm1 needs the statistics of what this GEMM writes
     const bool more = bi + 1 < t.blocks.size();
     Epilogue e_ff2 = ep_out(h2, C, k.ff2.bias, h, C);
-    RUN(ex, gemm_f16(g, 4 * C, k.ff2.w, 4 * C, M, C, 4 * C, more ? with_stats(e_ff2) : e_ff2, ex.st));
+    RUN(ex, gemm_f16(g, 4 * C, k.ff2.w, 4 * C, M, C, 4 * C, more ? with_stats(e_ff2, M, M, 0) : e_ff2, ex.st));
     if (more) GYRE_TRY(finalize_stats());
     std::swap(h, h2);   // the block's output becomes the next block's residual stream
   }
   h2 = h;
-  RUN(ex, gemm_f16(h2, C, t.proj_out.w, C, M, C, C, ep_out(out, C, t.proj_out.bias, x, C), ex.st));
+  // proj_out + the transformer's input as residual (shared prefix: the same input rows for both halves)
+  for (int hf = 0; hf < nh; ++hf) {
+    const size_t oo = static_cast<size_t>(hf) * Ms * C;
+    RUN(ex, gemm_f16(off(h2, oo), C, t.proj_out.w, C, Ms, C, C, ep_out(off(out, oo), C, t.proj_out.bias, x, C), ex.st));
+  }
+  (void)ns;
   return 0;
 }
 
@@ -715,8 +750,15 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   // conv_in on the tensor cores too: the 4/9-channel latent is staged NHWC with a zero-padded channel pitch of
   // 8/16 (TMA needs 16-byte pixel rows); the padded K slice costs nothing measurable
   const int cin8 = (cfg_.in_channels + 7) & ~7;
+  // CFG-parallel batches ([x ; x], same timesteps: set_cfg_duplicate): conv_in, the first resnet and the first
+  // transformer up to its cross-attention see identical rows in both halves - they run ONCE, on the first half.  The
+  // text_time conditioning of SDXL-style models differs between the halves (it enters through the time embedding), a
+  // ControlNet's conditioning image may too: no sharing there.  The buffers keep their full-batch size either way.
+  const bool share = cfg_dup_ && tunable(TUNE_CFG_SHARE) != 0 && B % 2 == 0 && cfg_.addition_embed_dim == 0 &&
+                     !cfg_.controlnet && cfg_.attn_levels[0] && cfg_.layers_per_block >= 1;
+  const int Bs = share ? B / 2 : B;
   __half* x_nhwc = ex.p16(static_cast<size_t>(B) * H * W * cin8);
-  RUN(ex, nchw_to_nhwc_f16(sample, B, cfg_.in_channels, H, W, x_nhwc, cin8, ex.st));
+  RUN(ex, nchw_to_nhwc_f16(sample, Bs, cfg_.in_channels, H, W, x_nhwc, cin8, ex.st));
   __half* hcur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
   const __half* cond_emb = nullptr;
   if (cfg_.controlnet) {
@@ -745,8 +787,13 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
     GYRE_REQUIRE(eh == H && ew == W, "controlnet: the conditioning image must be 8x the latent size");
     cond_emb = ecur;
   }
-  RUN(ex, conv3x3_f16(x_nhwc, cin8, B, H, W, cin8, conv_in_.wp, ch[0], 1, 1,
+  RUN(ex, conv3x3_f16(x_nhwc, cin8, Bs, H, W, cin8, conv_in_.wp, ch[0], 1, 1,
                       ep_out(hcur, ch[0], conv_in_.bias, cond_emb, cond_emb ? ch[0] : 0), ex.st));
+  if (share && !ex.dry) {
+    // conv_in's output is also the first skip tensor, which the up path reads at the full batch: duplicate it
+    const size_t half = static_cast<size_t>(Bs) * H * W * ch[0];
+    GYRE_CHECK_CUDA(cudaMemcpyAsync(hcur + half, hcur, half * sizeof(__half), cudaMemcpyDeviceToDevice, ex.st));
+  }
 
   struct Skip { __half* p; int C; int hw; };
   std::vector<Skip> skips;
@@ -758,14 +805,17 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   for (int i = 0; i < nl; ++i) {
     for (int j = 0; j < cfg_.layers_per_block; ++j) {
       ex.reset_scratch();
+      // the very first resnet + transformer of a shared CFG batch work on the first half (the time-embedding rows of the
+      // two halves are equal too); the transformer fans out to the full batch at its cross-attention
+      const bool sh = share && i == 0 && j == 0;
       __half* o = ex.p16(static_cast<size_t>(B) * h_ * w_ * ch[i]);
-      GYRE_TRY(resnet(ex, resnets_[ri++], hcur, ccur, nullptr, 0, B, h_, w_, eps, temb_all, temb_total_, o));
+      GYRE_TRY(resnet(ex, resnets_[ri++], hcur, ccur, nullptr, 0, sh ? Bs : B, h_, w_, eps, temb_all, temb_total_, o));
       hcur = o;
       ccur = ch[i];
       if (cfg_.attn_levels[i]) {
         ex.reset_scratch();
         __half* o2 = ex.p16(static_cast<size_t>(B) * h_ * w_ * ccur);
-        GYRE_TRY(transformer(ex, tblocks_[ti], hcur, B, h_ * w_, ctx, L, r_of(ti), o2));
+        GYRE_TRY(transformer(ex, tblocks_[ti], hcur, B, h_ * w_, ctx, L, r_of(ti), o2, sh));
         ++ti;
         hcur = o2;
       }

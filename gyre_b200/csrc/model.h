@@ -149,6 +149,10 @@ class UNetModel : public Model {
   int forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B, int H,
               int W, int L, const int32_t* tome_r, __half* out, const ControlNetIO* cn = nullptr);
   bool is_controlnet() const { return cfg_.controlnet != 0; }
+  // The caller promises that the next forwards' batches are [x ; x] with equal timesteps in both halves (what
+  // CFGUNet_Parallel feeds the UNet, gyre/pipeline/unet/cfg.py:47-57): everything before the first cross-attention is
+  // then computed once for both halves.
+  void set_cfg_duplicate(bool on) { cfg_dup_ = on; }
   // Binds a text context for the following forwards (the reference binds the embeddings once per request:
   // UNetWithEmbeddings, gyre/pipeline/unet/core.py:253-259): the cross-attention K/V projections of every
   // transformer block depend only on ctx, so they are computed here ONCE instead of once per step.
@@ -168,9 +172,10 @@ class UNetModel : public Model {
 
  private:
   int transformer(Exec& ex, const TransformerW& t, const __half* x, int B, int HW, const __half* ctx, int L, int r,
-                  __half* out);
+                  __half* out, bool share = false);
   void on_load(const std::string& key) override;
   int refold_layernorms(cudaStream_t st);
+  bool cfg_dup_ = false;    // set_cfg_duplicate
   bool ln_fuse_ = false;    // LayerNorm folded into the GEMMs around it (tunable LN_FUSE at creation)
   bool ln_dirty_ = true;    // a transformer-block parameter changed since the folded weights were derived
   gyre_b200_unet_config cfg_;

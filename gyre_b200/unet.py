@@ -240,11 +240,16 @@ class B200UNet(torch.nn.Module):
         emb = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).reshape(time_ids.shape[0], -1)
         return torch.cat([text_embeds.to(self.device).float(), emb], dim=-1).to(torch.float16).contiguous()
 
-    def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None, add_cond=None):
+    def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None, add_cond=None, cfg_duplicate: bool = False):
         """No conversions: fp16 NCHW sample, int64 [B] timesteps, fp16 [B, L, Cc] context (or None: the context
-        bound with `set_context`), all on device."""
+        bound with `set_context`), all on device.  `cfg_duplicate`: the caller's promise that the batch is [x ; x] with
+        equal timesteps in both halves (CFGUNet_Parallel): the part of the network in front of the first cross-attention
+        then runs once for both halves (gyre_b200_unet_set_cfg_duplicate)."""
         if not self._loaded:
             raise N.NativeError("B200UNet: weights not loaded")
+        if bool(cfg_duplicate) != getattr(self, "_cfg_dup", False):
+            N.check(self._lib.gyre_b200_unet_set_cfg_duplicate(self._h, 1 if cfg_duplicate else 0), "unet_set_cfg_duplicate")
+            self._cfg_dup = bool(cfg_duplicate)
         B, Cin, H, W = sample_f16.shape
         if ctx_f16 is None:
             if self._ctx_bound is None or self._ctx_bound[1] != B:

@@ -158,6 +158,14 @@ int gyre_b200_unet_forward_cond(gyre_b200_handle h, const void* sample, const in
  * transformer block) until the next call; ctx = NULL drops the binding.  The caller must re-bind
  * after changing the context tensor's contents or any attn2.to_k / to_v weight. */
 int gyre_b200_unet_set_context(gyre_b200_handle h, const void* ctx, int batch, int ctx_len, gyre_b200_stream stream);
+/* Classifier-free guidance as the reference runs it (CFGUNet_Parallel, gyre/pipeline/unet/cfg.py:47-57) feeds the UNet
+ * `torch.cat([latents] * 2)` with the [uncond ; cond] text contexts: the two halves of the batch are the SAME samples
+ * and timesteps until the first cross-attention reads the context.  on = 1 is the caller's promise that the following
+ * forwards have that form (sample[b] == sample[b + batch / 2], timestep likewise): conv_in, the first resnet and the first
+ * transformer's self-attention half are then computed once for both halves - the outputs are what the full computation
+ * gives (bit for bit when the kernels involved are batch-invariant, i.e. with stream-K off; to the last fp16 bit
+ * otherwise).  Sticky until changed; 0 (default) makes no assumption.  Tunable CFG_SHARE = 0 disables it globally. */
+int gyre_b200_unet_set_cfg_duplicate(gyre_b200_handle h, int on);
 /* ControlNet residual injection (replaces the `down_block_additional_residuals=` /
  * `mid_block_additional_residual=` keyword arguments that gyre/pipeline/unet/core.py:213-239 passes to
  * UNet2DConditionModel.forward).  Binds, for the NEXT gyre_b200_unet_forward* call only, one NCHW fp16 device tensor

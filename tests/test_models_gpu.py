@@ -534,3 +534,44 @@ def test_unet_layernorm_fold_ab(tiny_unet):
     assert e_f < 5e-3 and e_p < 5e-3
     assert rel_err(fused, plain) < 5e-3
     assert not torch.equal(fused, plain)          # the two paths really are different kernels
+
+
+@pytest.mark.parametrize("variant", ["plain", "tome", "ln_kernels", "inpaint9"])
+def test_cfg_shared_prefix_is_the_full_computation(variant):
+    """CFG-parallel batches are [x ; x] with [uncond ; cond] contexts: with `cfg_duplicate` the native UNet computes conv_in,
+    the first resnet and the first transformer's self-attention half once for both halves.  The result must be what the
+    full-batch computation gives - bit for bit (every kernel on that prefix is batch-invariant once stream-K is off)."""
+    from gyre_b200 import _native as N
+    from oracle.unet import UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny(in_channels=9) if variant == "inpaint9" else UNetConfig.tiny()
+    unet = B200UNet(cfg).load_state_dict(synth_params(unet_param_shapes(cfg), seed=1234))
+    gen = torch.Generator("cpu").manual_seed(23)
+    B = 3
+    x = torch.randn(B, cfg.in_channels, 16, 16, generator=gen).half().cuda()
+    x2 = torch.cat([x, x]).contiguous()
+    t = torch.tensor([900, 500, 30]).cuda()
+    t2 = torch.cat([t, t]).contiguous()
+    ctx = torch.randn(2 * B, 77, cfg.cross_attention_dim, generator=gen).half().cuda()
+    saved = {k: N.get_tunable(k) for k in ("STREAMK", "LN_FUSE")}
+    try:
+        N.set_tunable("STREAMK", 0)
+        if variant == "ln_kernels":
+            N.set_tunable("LN_FUSE", 0)
+        if variant == "tome":
+            unet.r = 48
+        full = unet.forward_raw(x2, t2, ctx).clone()
+        shared = unet.forward_raw(x2, t2, ctx, cfg_duplicate=True).clone()
+        assert torch.equal(full, shared), f"{variant}: max abs diff {(full.float() - shared.float()).abs().max().item()}"
+        # the two halves really differ (the contexts do), and the promise is not assumed when it is not given
+        assert not torch.equal(full[:B], full[B:])
+        other = torch.cat([x, x.flip(0)]).contiguous()
+        a = unet.forward_raw(other, t2, ctx).clone()
+        N.set_tunable("CFG_SHARE", 0)
+        b = unet.forward_raw(other, t2, ctx, cfg_duplicate=True).clone()     # tunable off: no sharing even when promised
+        assert torch.equal(a, b)
+    finally:
+        N.set_tunable("CFG_SHARE", 1)
+        for k, v in saved.items():
+            N.set_tunable(k, v)
+        unet.r = 0
