@@ -10,6 +10,7 @@ for b in 1 2 4; do
 done
 run --config c2 --steps 3 --warmup 3 --cuda-graph --no-profile
 run --config c3 --steps 2 --warmup 2
+run --config c3 --steps 2 --warmup 2 --hires-fix --no-profile          # config 3 with the reference's default option
 run --config c4 --steps 2 --warmup 2
 run --config c5 --steps 2 --warmup 2
 run --config c2 --impl torchlib --steps 2 --warmup 2

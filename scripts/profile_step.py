@@ -24,10 +24,11 @@ B = a.batch
 if not a.no_unet:
     ucfg = UNetConfig.sd15()
     unet = B200UNet(ucfg, dev).load_state_dict(synth_state_dict(unet_param_shapes(ucfg), 1234, torch.float16, device=dev))
-    x = torch.randn(2 * B, 4, 64, 64, device=dev).half()
+    x = torch.randn(B, 4, 64, 64, device=dev).half()
+    x = torch.cat([x, x]).contiguous()          # CFG-parallel layout: [x ; x], what the sampling loop feeds the UNet
     t = torch.full((2 * B,), 500, device=dev, dtype=torch.int64)
     ctx = torch.randn(2 * B, 77, 768, device=dev).half()
-    unet.forward_raw(x, t, ctx)
+    unet.forward_raw(x, t, ctx, cfg_duplicate=True)
 if not a.no_vae:
     vcfg = VAEConfig.sd()
     vae = B200VAE(vcfg, dev).load_state_dict(synth_state_dict(vae_param_shapes(vcfg), 4321, torch.float16, device=dev))
@@ -36,7 +37,7 @@ if not a.no_vae:
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 if not a.no_unet:
-    unet.forward_raw(x, t, ctx)
+    unet.forward_raw(x, t, ctx, cfg_duplicate=True)
 if not a.no_vae:
     vae.decode_raw(z, postprocess=True, want_u8=True)
 torch.cuda.synchronize()

@@ -31,7 +31,10 @@ class FakeNativeUNet:
         t = torch.as_tensor(t, device=self.device)
         return t.reshape(-1).to(torch.int64).expand(B).contiguous()
 
-    def forward_raw(self, x, t, ctx, out=None, add_cond=None):
+    def forward_raw(self, x, t, ctx, out=None, add_cond=None, cfg_duplicate=False):
+        # cfg_duplicate: the guided wrapper's promise that x is [x ; x] - checked here, it is what lets the native UNet share work
+        if cfg_duplicate:
+            assert torch.equal(x[:x.shape[0] // 2], x[x.shape[0] // 2:]) and torch.equal(t[:t.shape[0] // 2], t[t.shape[0] // 2:])
         ctx = self._ctx if ctx is None else ctx
         res = fake_unet_math(x, t, ctx)
         if out is not None:
