@@ -426,11 +426,11 @@ def main():
         N.prof_reset()
         N.prof_enable(True)
         step_resident(300)
-        families = N.prof_read()
+        peaks = measured_peaks()
+        families = N.prof_read(peaks["tflops_sustained"], peaks["hbm_gbs"])
         N.prof_enable(False)
         N.prof_reset()
         pipe.use_cuda_graph = was_graph
-        peaks = measured_peaks()
         tc = {k: v for k, v in families.items() if v["flops"] > 0 and v["ms"] > 0}
         dom = max(tc, key=lambda k: tc[k]["ms"])
         ach = tc[dom]["flops"] / (tc[dom]["ms"] * 1e-3) / 1e12
@@ -452,11 +452,16 @@ def main():
                     ", sustained figure (kernel timed inside a long step)",
                     "launches": tc[dom]["count"], "avg_launch_ms": tc[dom]["ms"] / tc[dom]["count"],
                     "algorithmic_gflop_per_launch": tc[dom]["flops"] / tc[dom]["count"] / 1e9,
-                    "share_of_step_device_time": tc[dom]["ms"] / sum(v["ms"] for v in families.values())}
+                    "share_of_step_device_time": tc[dom]["ms"] / sum(v["ms"] for v in families.values()),
+                    # the family mixes tensor-bound and HBM-bound shapes (K = 320 GEMMs are HBM-bound): the sum over its
+                    # launches of max(flops / tensor peak, algorithmic bytes / HBM peak) against the measured time
+                    "frac_vs_binding_roof_per_launch": tc[dom]["roofline_ms"] / tc[dom]["ms"],
+                    "hbm_peak": peaks["hbm_gbs"]}
         for k, v in families.items():
             if v["ms"] > 0:
                 v["tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
                 v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+                v["frac_vs_binding_roof"] = v["roofline_ms"] / v["ms"]
 
     if rank != 0:
         if world > 1:

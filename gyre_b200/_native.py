@@ -82,6 +82,7 @@ SIGNATURES = {
     "gyre_b200_debug_attention_trace": (_i, [_vp, _i]),
     "gyre_b200_prof_read": (_i, [_i, C.POINTER(C.c_ulonglong), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]),
+    "gyre_b200_prof_read_roofline": (_i, [_i, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "gyre_b200_debug_mma_bench": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
     "gyre_b200_set_tunable": (_i, [C.c_char_p, _i]),
     "gyre_b200_get_tunable": (_i, [C.c_char_p, C.POINTER(_i)]),
@@ -451,11 +452,17 @@ def prof_reset():
     load().gyre_b200_prof_reset()
 
 
-def prof_read() -> dict:
-    """{family: {count, ms, flops, bytes}} since the last reset (synchronises the device)."""
+def prof_read(peak_tflops=None, peak_gbs=None) -> dict:
+    """{family: {count, ms, flops, bytes[, roofline_ms]}} since the last reset (synchronises the device).  With the two
+    peaks, `roofline_ms` = sum over the launches of max(flops / peak_tflops, bytes / peak_gbs)."""
     out = {}
     for i, name in enumerate(FAMILIES):
         c, ms, fl, by = C.c_ulonglong(), C.c_double(), C.c_double(), C.c_double()
         check(load().gyre_b200_prof_read(i, C.byref(c), C.byref(ms), C.byref(fl), C.byref(by)), "prof_read")
         out[name] = {"count": c.value, "ms": ms.value, "flops": fl.value, "bytes": by.value}
+        if peak_tflops and peak_gbs:
+            ideal = C.c_double()
+            check(load().gyre_b200_prof_read_roofline(i, float(peak_tflops), float(peak_gbs), C.byref(ideal)),
+                  "prof_read_roofline")
+            out[name]["roofline_ms"] = ideal.value
     return out

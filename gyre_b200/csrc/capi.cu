@@ -68,6 +68,11 @@ int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, doubl
   return prof::read(family, count, ms, flops, bytes);
 }
 
+int gyre_b200_prof_read_roofline(int family, double peak_tflops, double peak_gbs, double* ideal_ms) {
+  GYRE_REQUIRE(family >= 0 && family < prof::F_COUNT, "prof_read_roofline: family %d", family);
+  return prof::read_roofline_ms(family, peak_tflops, peak_gbs, ideal_ms);
+}
+
 int gyre_b200_debug_mma_bench(int n, int naccs, int a_tmem, int reps, int blocks, long long* out_dev,
                               gyre_b200_stream stream) {
   GYRE_REQUIRE(out_dev, "mma_bench: null output");

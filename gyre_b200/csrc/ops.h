@@ -214,6 +214,7 @@ void enable(int on);
 bool enabled();
 void reset();
 int read(int family, unsigned long long* count, double* ms, double* flops, double* bytes);
+int read_roofline_ms(int family, double peak_tflops, double peak_gbs, double* ideal_ms);
 // RAII: counts `kernels` launches; when profiling is enabled brackets them with events on `st`.
 class Scope {
  public:

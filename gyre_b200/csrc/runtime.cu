@@ -187,6 +187,21 @@ Scope::~Scope() {
   }
 }
 
+// Sum over the family's launches of max(flops / peak_flops, bytes / peak_bw): the time the launches would take if each
+// ran exactly on whichever of the two roofs binds it (a family mixes tensor-bound and HBM-bound shapes).
+int read_roofline_ms(int family, double peak_tflops, double peak_gbs, double* ideal_ms) {
+  GYRE_REQUIRE(peak_tflops > 0 && peak_gbs > 0 && ideal_ms, "prof_read_roofline: bad arguments");
+  std::lock_guard<std::mutex> lk(g_mu);
+  double t = 0;
+  for (auto& r : g_recs) {
+    if (r.family != family) continue;
+    const double tf = r.flops / (peak_tflops * 1e12), tb = r.bytes / (peak_gbs * 1e9);
+    t += (tf > tb ? tf : tb) * 1e3;
+  }
+  *ideal_ms = t;
+  return 0;
+}
+
 int read(int family, unsigned long long* count, double* ms, double* flops, double* bytes) {
   GYRE_CHECK_CUDA(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> lk(g_mu);

@@ -50,6 +50,9 @@ unsigned long long gyre_b200_launch_count(void);
 int gyre_b200_prof_enable(int on);
 int gyre_b200_prof_reset(void);
 int gyre_b200_prof_read(int family, unsigned long long* count, double* ms, double* flops, double* bytes);
+/* Sum over the family's recorded launches of max(flops / peak_tflops, bytes / peak_gbs) in ms: what they would take if
+ * every launch ran on whichever roof binds it (a family mixes tensor-bound and HBM-bound shapes). */
+int gyre_b200_prof_read_roofline(int family, double peak_tflops, double peak_gbs, double* ideal_ms);
 /* Measurement hook: while a device buffer is registered, CTA 0 of the lean-softmax attention kernel writes clock64
  * time stamps of its pipeline events into it (layout: scripts/attn_trace.py); NULL switches it off.  Not part of
  * the product path. */
