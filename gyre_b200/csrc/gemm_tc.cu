@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       const float* sbr = sb + (p.rgb_rows > 0 ? (r / p.rgb_rows) * BN : 0);
       const float* scs = sb + BN;       // LayerNorm consumer: column sums of the gamma-scaled weights
-      float rs = 0.f, rq = 0.f;         // row-statistics producer: this thread's share of its row
+      float2 rs2 = make_float2(0.f, 0.f), rq2 = make_float2(0.f, 0.f);   // row-statistics producer: this thread's share of its row (two lanes)
       (void)ln_mean; (void)ln_rstd; (void)scs;
       const uint32_t lane_addr = tmem_base + buf * Cfg::BUF_COLS + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -665,13 +665,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               tmem_ld_32x32b_x32(lane_addr + sl * 32, ra);
               tmem_ld_wait();
               if (sk_part) add_partials(ra, sl * 32);
+              // packed fp32x2 arithmetic (FADD2 / FFMA2): half the issue slots of the slice loop, same roundings
               if constexpr (kLnConsume) {
+                const float2 nm = make_float2(-ln_mean, -ln_mean), rs2v = make_float2(ln_rstd, ln_rstd);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  v[j] = fmaf(ln_rstd, fmaf(-ln_mean, scs[sl * 32 + j], __uint_as_float(ra[j])), sbr[sl * 32 + j]);
+                for (int j = 0; j < 32; j += 2) {
+                  const float2 acc2 = make_float2(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
+                  const float2 cs2 = *reinterpret_cast<const float2*>(scs + sl * 32 + j);
+                  const float2 b2 = *reinterpret_cast<const float2*>(sbr + sl * 32 + j);
+                  const float2 r2 = __ffma2_rn(rs2v, __ffma2_rn(nm, cs2, acc2), b2);
+                  v[j] = r2.x;
+                  v[j + 1] = r2.y;
+                }
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sbr[sl * 32 + j];
+                for (int j = 0; j < 32; j += 2) {
+                  const float2 r2 = __fadd2_rn(make_float2(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1])),
+                                               *reinterpret_cast<const float2*>(sbr + sl * 32 + j));
+                  v[j] = r2.x;
+                  v[j + 1] = r2.y;
+                }
               }
               if constexpr (EPI == 1) {
                 if (ep.act == ACT_SILU) {
@@ -698,18 +711,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(rh[i]);
-                v[u * 8 + 2 * i] += f.x;
-                v[u * 8 + 2 * i + 1] += f.y;
+                const float2 r2 = __fadd2_rn(make_float2(v[u * 8 + 2 * i], v[u * 8 + 2 * i + 1]), __half22float2(rh[i]));
+                v[u * 8 + 2 * i] = r2.x;
+                v[u * 8 + 2 * i + 1] = r2.y;
               }
             }
           }
           if constexpr (kRowStat) {
             // columns past N hold exact zeros (zero-filled B rows, no bias, zero-filled residual): they add nothing
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              rs += v[j];
-              rq = fmaf(v[j], v[j], rq);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 v2 = make_float2(v[j], v[j + 1]);
+              rs2 = __fadd2_rn(rs2, v2);
+              rq2 = __ffma2_rn(v2, v2, rq2);
             }
           }
 #pragma unroll
@@ -732,7 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if constexpr (kRowStat) {
           if (valid)
             ep.rowstat_out[(static_cast<int64_t>(n_tile) * 2 + half) * (ep.rowstat_ld > 0 ? ep.rowstat_ld : p.M) + out_row] =
-                make_float2(rs, rq);
+                make_float2(rs2.x + rs2.y, rq2.x + rq2.y);
         }
       } else if constexpr (EPI == 1) {
         // ================================================= direct path (fp32 out, unaligned pitches, tiny N)
