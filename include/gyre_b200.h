@@ -66,7 +66,9 @@ int gyre_b200_debug_attention_trace(long long* dev_buf, int capacity);
  * 1 TMA-multicast pairs, 2 tcgen05 cta_group::2 pairs where they win [default], 3 cta_group::2 pairs
  * everywhere), "STREAMK", "FORCE_BN", "GEMM_STAGES" (cap of the operand ring depth), "DEBUG" (GEMM
  * measurement bits: 1 no output stores, 2 no epilogue - both give WRONG results -, 4 all-variants image),
- * "LN_SUB" (LayerNorm: several rows per warp for C <= 320 [1, default] / <= 640 [2]).
+ * "LN_SUB" (LayerNorm: several rows per warp for C <= 320 [1, default] / <= 640 [2]), "GN_THREADS", "LN_FUSE"
+ * (LayerNorm folded into the GEMMs around it; read when a UNet is created [derived weights] and at every forward),
+ * "CFG_SHARE" (0: ignore gyre_b200_unet_set_cfg_duplicate).
  * Every knob also reads GYRE_B200_<NAME> from the environment at first use.  Results stay within the
  * documented tolerances for every setting except the DEBUG store / epilogue bits. */
 int gyre_b200_set_tunable(const char* name, int value);
