@@ -83,7 +83,6 @@ def test_controlnet_into_unet_vs_oracle(setup):
 
 
 def test_controlnet_rejects_wrong_use(setup):
-    from gyre_b200 import _native as N
     cfg, PC, PU, cn, unet = setup
     x = torch.zeros(1, 4, 16, 16).half().cuda()
     ctx = torch.zeros(1, 77, cfg.cross_attention_dim).half().cuda()

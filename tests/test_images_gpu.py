@@ -34,7 +34,6 @@ def test_pipeline_outpaint_tail():
     """`B200Pipeline(..., image=, mask_image=, outmask_image=)`: the decoded image goes through the device histogram match +
     source composite (unified_pipeline.py:2493-2510) - equal to applying the reference's numpy statements to the image the
     same request gives without `outmask_image`, in "pt" and in "uint8" output."""
-    import importlib.util
     import numpy as np
     from oracle.unet import UNetConfig, synth_params, unet_param_shapes
     from oracle.vae import VAEConfig, vae_param_shapes
