@@ -117,8 +117,9 @@ class _Node:
 
 
 class B200Pipeline:
-    def __init__(self, unet, vae=None, text_encoder=None, inpaint_unet=None, tokenizer=None):
+    def __init__(self, unet, vae=None, text_encoder=None, inpaint_unet=None, tokenizer=None, depth_unet=None):
         self.unet = unet
+        self.depth_unet = depth_unet       # 5-channel depth2img UNet (unified_pipeline.py:1334, 1974-2013), or None
         self.tokenizer = tokenizer         # the caller's CLIPTokenizer (or any object with its call surface) for `prompt=`
         self.inpaint_unet = inpaint_unet   # 9-channel UNet of the same family (unified_pipeline.py:2059-2062), or None
         self.vae = vae
@@ -129,6 +130,7 @@ class B200Pipeline:
         self.unet_sample_size_override = None   # tests with sub-64 toy UNets
         # engine defaults of the reference (unified_pipeline.py:1362-1373)
         self._grafted_inpaint = False
+        self._grafted_depth = False
         self._hires_fix = True
         self._hires_threshold_fraction = 0.0333
         self._hires_oos_fraction = 0.6
@@ -175,8 +177,7 @@ class B200Pipeline:
             elif key == "grafted_inpaint":
                 self._grafted_inpaint = value if isinstance(value, dict) else bool(value)
             elif key == "grafted_depth":
-                if value:
-                    raise NotImplementedError("grafted_depth needs a depth UNet and a depth estimator (out of scope)")
+                self._grafted_depth = value if isinstance(value, dict) else bool(value)
             else:
                 raise ValueError(f"Unknown option {key!r}")
             self._options[key] = value
@@ -206,7 +207,7 @@ class B200Pipeline:
                  strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None,
                  cfg_execution: str = "parallel", hires_fix: bool | None = None,
                  hires_oos_fraction: float | None = None, outmask_image=None, prompt=None, negative_prompt=None,
-                 max_embeddings_multiples: int = 3, clip_layer="final") -> PipelineOutput:
+                 max_embeddings_multiples: int = 3, clip_layer="final", depth_map=None) -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
         unified_pipeline.py:2055-2066 - optionally grafted (inpaint UNet early, main UNet late, :2069-2098) and, for
@@ -247,22 +248,41 @@ class B200Pipeline:
         main_unet = self.unet
         if mask_image is not None and self.inpaint_unet is not None:
             main_unet = self.inpaint_unet
+        # a depth hint goes to the depth UNet when the engine has one and no mask is given (:1974-2013); `depth_map` is the
+        # hint already normalised to [-1, 1] at latent resolution ([1 | B, 1, H / 8, W / 8]) - estimating and resizing it is
+        # the hinter's job upstream
+        if depth_map is not None:
+            if self.depth_unet is None or mask_image is not None:
+                raise EnvironmentError("a depth map needs a depth UNet and cannot be combined with a mask")
+            if tuple(depth_map.shape[-2:]) != (height // 8, width // 8) or depth_map.shape[1] != 1:
+                raise ValueError(f"depth_map is {tuple(depth_map.shape)}, expected [1 | B, 1, {height // 8}, {width // 8}]")
+            main_unet = self.depth_unet
         cfg = main_unet.config
-        if cfg.in_channels not in (4, 9):
-            raise NotImplementedError(f"in_channels={cfg.in_channels}: only the 4- and 9-channel UNets are wired up")
+        if cfg.in_channels not in (4, 5, 9):
+            raise NotImplementedError(f"in_channels={cfg.in_channels}: only the 4-, 5- and 9-channel UNets are wired up")
         if cfg.in_channels == 9 and mask_image is None:
             raise ValueError("an inpainting UNet (in_channels=9) needs image + mask_image")
+        if (cfg.in_channels == 5) != (depth_map is not None):
+            raise ValueError("a depth UNet (in_channels=5) needs depth_map, and only it takes one")
         if mask_image is not None:
             kind = "runway" if cfg.in_channels == 9 else "inpaint"
         else:
             kind = "img2img" if image is not None else "txt2img"
-        tree = _Leaf(kind=kind, unet=main_unet, height=height, width=width, image=image, mask_image=mask_image)
+        tree = _Leaf(kind=kind, unet=main_unet, height=height, width=width, image=image, mask_image=mask_image,
+                     depth_map=depth_map)
 
         # ---- graft: inpaint UNet for the early steps, the main UNet with the legacy x0 blend for the late ones (:2069-2098)
         if kind == "runway" and self._grafted_inpaint and main_unet is self.inpaint_unet and self.unet is not main_unet:
             from .graft import GraftUnets
             blend = self._grafted_inpaint if isinstance(self._grafted_inpaint, dict) else {}
             tree = _Node(tree.clone(), tree.clone(kind="inpaint", unet=self.unet), GraftUnets, generators=generators,
+                         blend=blend, rand_dtype=latents_dtype)
+
+        # ---- grafted depth: the depth UNet for the early steps, the main UNet (no depth input) for the late ones
+        if depth_map is not None and self._grafted_depth and self.unet is not main_unet:
+            from .graft import GraftUnets
+            blend = self._grafted_depth if isinstance(self._grafted_depth, dict) else {}
+            tree = _Node(tree.clone(), tree.clone(unet=self.unet, depth_map=None), GraftUnets, generators=generators,
                          blend=blend, rand_dtype=latents_dtype)
 
         # ---- hires fix: a natural-size twin of every leaf, cross-blended with the full-size one (:2100-2181)
@@ -280,8 +300,15 @@ class B200Pipeline:
                 def to_natural(t):
                     return None if t is None else HiresUnetWrapper.image_to_natural(
                         unet_pixel_size, t.to(self.device), oos_fraction=hires_oos_fraction)
+
+                def depth_to_natural(leaf_opts):
+                    d = leaf_opts.get("depth_map")
+                    return None if d is None else HiresUnetWrapper.image_to_natural(sample_size, d.to(self.device),
+                                                                                    oos_fraction=hires_oos_fraction)
                 natural = tree.clone(width=unet_pixel_size, height=unet_pixel_size, image=to_natural(image),
                                      mask_image=to_natural(mask_image))
+                for leaf in natural.leaves:          # per leaf: a grafted twin has no depth map
+                    leaf.opts["depth_map"] = depth_to_natural(leaf.opts)
                 tree = _Node(natural, tree, HiresUnetWrapper, generators=generators,
                              natural_size=[sample_size, sample_size], oos_fraction=hires_oos_fraction,
                              latent_debugger=None, rand_dtype=latents_dtype)
@@ -319,7 +346,11 @@ class B200Pipeline:
                 if not isinstance(sched, KDiffusionScheduler):
                     raise NotImplementedError("legacy (4-channel) inpainting is wired for the k-diffusion samplers")
                 leaf.mode = EnhancedInpaintMode(image=o["image"], mask_image=o["mask_image"], strength=strength, **common)
-            leaf.guided.set_extra_channels(leaf.mode.unet_extra_channels())
+            extra = leaf.mode.unet_extra_channels()
+            if o.get("depth_map") is not None:
+                # UnetWithExtraChannels(unet, depth_map) (unified_pipeline.py:2306-2310, unet/core.py:21-37): un-scaled
+                extra = o["depth_map"].to(self.device, torch.float16).expand(B, -1, -1, -1).contiguous()
+            leaf.guided.set_extra_channels(extra)
         if len(leaves) == 1:
             blend = leaves[0].mode.x0_blend()
             if blend is not None:
