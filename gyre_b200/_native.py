@@ -47,6 +47,14 @@ class UNetConfigC(C.Structure):
     ]
 
 
+class ClipVisionConfigC(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int32), ("patch_size", C.c_int32), ("hidden_size", C.c_int32), ("intermediate_size", C.c_int32),
+        ("num_layers", C.c_int32), ("num_heads", C.c_int32), ("hidden_act", C.c_int32), ("layer_norm_eps", C.c_float),
+        ("projection_dim", C.c_int32), ("num_concepts", C.c_int32), ("num_special", C.c_int32),
+    ]
+
+
 class AdapterConfigC(C.Structure):
     _fields_ = [
         ("cin", C.c_int32), ("num_levels", C.c_int32), ("channels", C.c_int32 * 4), ("nums_rb", C.c_int32),
@@ -99,6 +107,11 @@ SIGNATURES = {
     "gyre_b200_unet_set_adapter_states": (_i, [_vp, C.POINTER(C.c_void_p), _i]),
     "gyre_b200_unet_forward_cond": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
     "gyre_b200_controlnet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _i, _vp, _vp, _sz, _vp]),
+    "gyre_b200_clip_vision_create": (_i, [C.POINTER(ClipVisionConfigC), C.POINTER(_vp)]),
+    "gyre_b200_clip_vision_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
+    "gyre_b200_safety_scores": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "gyre_b200_resample_u8": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "gyre_b200_clip_normalize": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "gyre_b200_adapter_create": (_i, [C.POINTER(AdapterConfigC), C.POINTER(_vp)]),
     "gyre_b200_adapter_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "gyre_b200_adapter_forward": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_void_p), _i, _vp, _sz, _vp]),

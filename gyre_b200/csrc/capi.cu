@@ -471,6 +471,56 @@ int gyre_b200_vae_encode(gyre_b200_handle h, const void* img, int batch, int hei
                                               static_cast<__half*>(moments));
 }
 
+int gyre_b200_clip_vision_create(const gyre_b200_clip_vision_config* cfg, gyre_b200_handle* out) {
+  GYRE_REQUIRE(cfg && out, "clip_vision_create: null argument");
+  GYRE_REQUIRE(cfg->image_size > 0 && cfg->patch_size > 0 && cfg->image_size % cfg->patch_size == 0 && cfg->num_layers > 0,
+               "clip_vision_create: bad sizes");
+  GYRE_REQUIRE(cfg->hidden_size % 8 == 0 && cfg->intermediate_size % 8 == 0 && cfg->projection_dim % 8 == 0 &&
+                   cfg->num_heads > 0 && cfg->hidden_size % cfg->num_heads == 0 && (cfg->hidden_size / cfg->num_heads) % 8 == 0 &&
+                   (cfg->hidden_size / cfg->num_heads) <= 192,
+               "clip_vision_create: hidden %d / heads %d / projection %d unsupported", cfg->hidden_size, cfg->num_heads,
+               cfg->projection_dim);
+  GYRE_REQUIRE(cfg->hidden_act == 0 || cfg->hidden_act == 1, "clip_vision_create: hidden_act must be quick_gelu (0) or gelu (1)");
+  GYRE_REQUIRE(cfg->num_concepts > 0 && cfg->num_special >= 0, "clip_vision_create: bad concept counts");
+  ClipVisionModel* m = new (std::nothrow) ClipVisionModel(*cfg);
+  GYRE_REQUIRE(m != nullptr, "clip_vision_create: out of host memory");
+  *out = reinterpret_cast<gyre_b200_handle>(static_cast<Model*>(m));
+  return 0;
+}
+
+int gyre_b200_clip_vision_workspace_bytes(gyre_b200_handle h, int batch, size_t* bytes) {
+  GYRE_REQUIRE(h && bytes, "clip_vision_workspace_bytes: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 4, "clip_vision_workspace_bytes: handle is not a CLIP vision model");
+  Exec ex;
+  ex.dry = true;
+  ex.cap = static_cast<size_t>(1) << 60;
+  GYRE_TRY(static_cast<ClipVisionModel*>(M(h))->forward(ex, nullptr, batch, nullptr, nullptr));
+  *bytes = ex.peak + 4096;
+  return 0;
+}
+
+int gyre_b200_safety_scores(gyre_b200_handle h, const void* pixel_values, int batch, void* image_embeds, float* scores,
+                            void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && pixel_values && scores, "safety_scores: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 4, "safety_scores: handle is not a CLIP vision model");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return static_cast<ClipVisionModel*>(M(h))->forward(ex, static_cast<const __half*>(pixel_values), batch,
+                                                      static_cast<__half*>(image_embeds), scores);
+}
+
+int gyre_b200_resample_u8(const void* src, int64_t n_outer, int in_size, int inner, const int32_t* bounds,
+                          const int32_t* coeffs, int ksize, int out_size, void* dst, gyre_b200_stream stream) {
+  return resample_u8(static_cast<const uint8_t*>(src), n_outer, in_size, inner, bounds, coeffs, ksize, out_size,
+                     static_cast<uint8_t*>(dst), S(stream));
+}
+
+int gyre_b200_clip_normalize(const void* src_u8_nhwc, int batch, int height, int width, int crop, const float* mean3,
+                             const float* std3, void* out, gyre_b200_stream stream) {
+  return clip_normalize(static_cast<const uint8_t*>(src_u8_nhwc), batch, height, width, crop, mean3, std3,
+                        static_cast<__half*>(out), S(stream));
+}
+
 int gyre_b200_adapter_create(const gyre_b200_adapter_config* cfg, gyre_b200_handle* out) {
   GYRE_REQUIRE(cfg && out, "adapter_create: null argument");
   GYRE_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= 4 && cfg->nums_rb >= 1 && cfg->nums_rb <= 8, "adapter_create: bad sizes");

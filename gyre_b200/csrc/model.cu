@@ -175,7 +175,8 @@ int Model::load(const char* key, const void* data, int dtype, const int64_t* sha
     ok = true;
     for (int i = 0; i < ndim; ++i) ok = ok && shape[i] == s.shape[i];
   } else if ((s.kind == P_LINEAR || s.kind == P_F32MAT) && s.ndim == 2 && ndim == 4) {
-    ok = shape[0] == s.shape[0] && shape[1] == s.shape[1] && shape[2] == 1 && shape[3] == 1;
+    // [N, K, 1, 1] (1x1 conv) or, generally, a conv weight whose trailing dims flatten to K (ViT patch embedding)
+    ok = shape[0] == s.shape[0] && shape[1] * shape[2] * shape[3] == s.shape[1];
   }
   GYRE_REQUIRE(ok, "load_weight(%s): shape mismatch (got ndim %d [%lld,%lld,..], want ndim %d [%lld,%lld,..])", key,
                ndim, (long long)shape[0], (long long)(ndim > 1 ? shape[1] : 0), s.ndim, (long long)s.shape[0],
@@ -1266,6 +1267,105 @@ int ClipTextModel::forward(Exec& ex, const int64_t* ids, int B, int L, int skip_
   } else if (!ex.dry) {
     GYRE_CHECK_CUDA(cudaMemcpyAsync(out, h, n * sizeof(__half), cudaMemcpyDeviceToDevice, ex.st));
   }
+  EX_CHECK(ex);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ CLIP vision tower
+// transformers CLIPVisionModel (CLIPVisionTransformer): patch embedding (Conv2d(3, C, P, stride P) == a GEMM over
+// flattened patches) + class token + position embedding -> pre-LayerNorm -> num_layers x [LN1 -> full self-attention ->
+// +res ; LN2 -> fc1 -> quick_gelu -> fc2 -> +res] -> post-LayerNorm of the class token (pooled output) -> visual
+// projection -> cosine similarity against the checker's concept embeddings (safety_checkers.py:32-37).
+ClipVisionModel::ClipVisionModel(const gyre_b200_clip_vision_config& cfg) : cfg_(cfg) {
+  const int C = cfg.hidden_size, F = cfg.intermediate_size, P = cfg.patch_size;
+  const int ntok = (cfg.image_size / P) * (cfg.image_size / P) + 1;
+  const int K = 3 * P * P;
+  Kp_ = (K + 7) & ~7;
+  patch_.N = C;
+  patch_.K = Kp_;
+  patch_.w = static_cast<__half*>(dalloc(sizeof(__half) * static_cast<size_t>(C) * Kp_));     // zero-filled: the pad stays 0
+  reg("vision_model.embeddings.patch_embedding.weight", P_LINEAR, patch_.w, {C, K}, Kp_);
+  class_emb_ = static_cast<float*>(dalloc(sizeof(float) * C));
+  reg("vision_model.embeddings.class_embedding", P_F32, class_emb_, {C});
+  pos_emb_ = static_cast<__half*>(dalloc(sizeof(__half) * static_cast<size_t>(ntok) * C));
+  reg("vision_model.embeddings.position_embedding.weight", P_LINEAR, pos_emb_, {ntok, C}, C);
+  reg_norm("vision_model.pre_layrnorm", C, &pre_ln_);          // the checkpoint key really is spelled like this
+  reg_norm("vision_model.post_layernorm", C, &post_ln_);
+  layers_.resize(cfg.num_layers);
+  for (int i = 0; i < cfg.num_layers; ++i) {
+    ClipLayerW* l = &layers_[i];
+    const std::string p = "vision_model.encoder.layers." + std::to_string(i);
+    reg_norm(p + ".layer_norm1", C, &l->ln1);
+    reg_norm(p + ".layer_norm2", C, &l->ln2);
+    l->qkv.N = 3 * C;
+    l->qkv.K = C;
+    l->qkv.w = static_cast<__half*>(dalloc(sizeof(__half) * 3 * C * C));
+    l->qkv.bias = static_cast<float*>(dalloc(sizeof(float) * 3 * C));
+    const char* names[3] = {"q_proj", "k_proj", "v_proj"};
+    for (int j = 0; j < 3; ++j) {
+      reg(p + ".self_attn." + names[j] + ".weight", P_LINEAR, l->qkv.w ? l->qkv.w + static_cast<size_t>(j) * C * C : nullptr,
+          {C, C}, C);
+      reg(p + ".self_attn." + names[j] + ".bias", P_F32, l->qkv.bias ? l->qkv.bias + j * C : nullptr, {C});
+    }
+    reg_linear(p + ".self_attn.out_proj", C, C, true, &l->out);
+    reg_linear(p + ".mlp.fc1", F, C, true, &l->fc1);
+    reg_linear(p + ".mlp.fc2", C, F, true, &l->fc2);
+  }
+  reg_linear("visual_projection", cfg.projection_dim, C, false, &proj_);
+  const int ne = cfg.num_special + cfg.num_concepts, D = cfg.projection_dim;
+  embeds_ = static_cast<float*>(dalloc(sizeof(float) * static_cast<size_t>(ne) * D));
+  thresholds_ = static_cast<float*>(dalloc(sizeof(float) * ne));
+  reg("special_care_embeds", P_F32MAT, embeds_, {cfg.num_special, D});
+  reg("concept_embeds", P_F32MAT, embeds_ ? embeds_ + static_cast<size_t>(cfg.num_special) * D : nullptr, {cfg.num_concepts, D});
+  reg("special_care_embeds_weights", P_F32, thresholds_, {cfg.num_special});
+  reg("concept_embeds_weights", P_F32, thresholds_ ? thresholds_ + cfg.num_special : nullptr, {cfg.num_concepts});
+}
+
+int ClipVisionModel::forward(Exec& ex, const __half* pixel_values, int B, __half* image_embeds, float* scores) {
+  GYRE_REQUIRE(B > 0, "safety_scores: empty batch");
+  if (!ex.dry) GYRE_TRY(ensure_device());
+  const int C = cfg_.hidden_size, F = cfg_.intermediate_size, H = cfg_.num_heads, P = cfg_.patch_size, S = cfg_.image_size;
+  const int np = (S / P) * (S / P), N = np + 1;
+  const int d = C / H;
+  const int M = B * N;
+  const size_t n = static_cast<size_t>(M) * C;
+  const float eps = cfg_.layer_norm_eps;
+  const float scale = 1.0f / sqrtf(static_cast<float>(d));
+  __half* patches_in = ex.p16(static_cast<size_t>(B) * np * Kp_);
+  __half* patches = ex.p16(static_cast<size_t>(B) * np * C);
+  __half* h = ex.p16(n);
+  __half* h2 = ex.p16(n);
+  __half* nrm = ex.p16(n);
+  __half* qkv = ex.p16(n * 3);
+  __half* att = ex.p16(n);
+  __half* mid = ex.p16(static_cast<size_t>(M) * F);
+  __half* cls = ex.p16(static_cast<size_t>(B) * C);
+  __half* pooled = ex.p16(static_cast<size_t>(B) * C);
+  __half* emb_local = ex.p16(static_cast<size_t>(B) * cfg_.projection_dim);
+  RUN(ex, patchify(pixel_values, B, S, P, Kp_, patches_in, ex.st));
+  RUN(ex, gemm_f16(patches_in, Kp_, patch_.w, Kp_, B * np, C, Kp_, ep_out(patches, C), ex.st));
+  RUN(ex, vision_embed(patches, class_emb_, pos_emb_, B, N, C, h2, ex.st));
+  RUN(ex, layernorm_rows(h2, M, C, eps, pre_ln_.g, pre_ln_.b, h, ex.st));
+  const int act = cfg_.hidden_act == 0 ? ACT_QUICKGELU : ACT_GELU;
+  for (int i = 0; i < cfg_.num_layers; ++i) {
+    const ClipLayerW& l = layers_[i];
+    RUN(ex, layernorm_rows(h, M, C, eps, l.ln1.g, l.ln1.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, C, l.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C, l.qkv.bias), ex.st));
+    RUN(ex, attention_f16(qkv, 3 * C, off(qkv, C), 3 * C, off(qkv, 2 * C), 3 * C, B, H, N, N, d, scale, att, C, ex.st));
+    RUN(ex, gemm_f16(att, C, l.out.w, C, M, C, C, ep_out(h2, C, l.out.bias, h, C), ex.st));          // h2 = h + attn
+    RUN(ex, layernorm_rows(h2, M, C, eps, l.ln2.g, l.ln2.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, C, l.fc1.w, C, M, F, C, ep_out(mid, F, l.fc1.bias, nullptr, 0, act), ex.st));
+    RUN(ex, gemm_f16(mid, F, l.fc2.w, F, M, C, F, ep_out(h, C, l.fc2.bias, h2, C), ex.st));           // h = h2 + mlp
+  }
+  // pooled_output = post_layernorm(last_hidden_state[:, 0]): gather the class-token rows, normalise, project
+  if (!ex.dry)
+    GYRE_CHECK_CUDA(cudaMemcpy2DAsync(cls, static_cast<size_t>(C) * sizeof(__half), h, static_cast<size_t>(N) * C * sizeof(__half),
+                                      static_cast<size_t>(C) * sizeof(__half), B, cudaMemcpyDeviceToDevice, ex.st));
+  RUN(ex, layernorm_rows(cls, B, C, eps, post_ln_.g, post_ln_.b, pooled, ex.st));
+  __half* emb_out = image_embeds ? image_embeds : emb_local;
+  RUN(ex, gemm_f16(pooled, C, proj_.w, C, B, cfg_.projection_dim, C, ep_out(emb_out, cfg_.projection_dim), ex.st));
+  if (scores || ex.dry)
+    RUN(ex, cosine_scores(emb_out, B, cfg_.projection_dim, embeds_, cfg_.num_special + cfg_.num_concepts, scores, ex.st));
   EX_CHECK(ex);
   return 0;
 }

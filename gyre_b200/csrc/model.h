@@ -251,6 +251,27 @@ class ClipTextModel : public Model {
   NormW final_ln_;
 };
 
+// CLIP vision tower + concept embeddings of the safety checker (gyre/pipeline/safety_checkers.py:13-66)
+class ClipVisionModel : public Model {
+ public:
+  explicit ClipVisionModel(const gyre_b200_clip_vision_config& cfg);
+  bool is_unet() const override { return false; }
+  int kind() const override { return 4; }
+  int forward(Exec& ex, const __half* pixel_values, int B, __half* image_embeds, float* scores);
+
+ private:
+  gyre_b200_clip_vision_config cfg_;
+  int Kp_ = 0;                    // patch-embedding K (3 * P * P) padded to a multiple of 8
+  LinW patch_;                    // [C, Kp]
+  float* class_emb_ = nullptr;    // [C]
+  __half* pos_emb_ = nullptr;     // [tokens, C]
+  NormW pre_ln_, post_ln_;
+  std::vector<ClipLayerW> layers_;
+  LinW proj_;                     // visual_projection [projection_dim, C]
+  float* embeds_ = nullptr;       // [num_special + num_concepts, projection_dim]: special-care rows first
+  float* thresholds_ = nullptr;   // [num_special + num_concepts] (kept for completeness; the host applies them)
+};
+
 // T2I-adapter encoder (gyre/pipeline/t2i_adapter/adapter.py:65-132)
 struct AdapterBlockW {
   Conv3W down3;            // Downsample with conv (use_conv)

@@ -165,6 +165,14 @@ int outpaint_match_histograms(const __half* result, const __half* source, const 
 // c * 64 + dy * 8 + dx), and 2x2 average pooling of NHWC [B, H, W, C] (floor sizes, fp32 accumulation)
 int pixel_unshuffle8_nchw_to_nhwc(const __half* x, int B, int C, int H, int W, __half* out, cudaStream_t st);
 int avg_pool2x2_nhwc(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t st);
+// Safety-checker front end and CLIP vision tower helpers (postprocess.cu)
+int resample_u8(const uint8_t* src, int64_t n_outer, int in_sz, int inner, const int* bounds, const int* kk, int ksize,
+                int out_sz, uint8_t* dst, cudaStream_t st);
+int clip_normalize(const uint8_t* src, int B, int H, int W, int S, const float* mean3, const float* std3, __half* out,
+                   cudaStream_t st);
+int patchify(const __half* x, int B, int S, int P, int Kp, __half* out, cudaStream_t st);
+int vision_embed(const __half* patches, const float* cls, const __half* pos, int B, int Ntok, int C, __half* out, cudaStream_t st);
+int cosine_scores(const __half* img, int B, int D, const float* emb, int n_emb, float* scores, cudaStream_t st);
 // LPW prompt weighting: out = emb * w[b, l] * (mean(emb[b]) / mean(emb[b] * w[b]))
 int lpw_weight(const __half* emb, const float* weights, int B, int L, int C, __half* out, cudaStream_t st);
 // unet input prep: out_f16[2B or B] = x * c_in (duplicated for CFG)

@@ -27,6 +27,7 @@ from .randtools import batched_randn
 class PipelineOutput:
     images: torch.Tensor | None      # [B, 3, H, W] in [0, 1] (output_type "pt"), uint8 NHWC ("uint8"), None ("latent")
     latents: torch.Tensor            # final latents (before the 1/0.18215 scaling)
+    nsfw_content_detected: list | None = None   # per image, from the safety checker (unified_pipeline.py:2514-2524)
 
 
 def generate_latents(generators, batch, in_channels, height, width, sample_size, device, dtype):
@@ -117,8 +118,15 @@ class _Node:
 
 
 class B200Pipeline:
-    def __init__(self, unet, vae=None, text_encoder=None, inpaint_unet=None, tokenizer=None, depth_unet=None):
+    def __init__(self, unet, vae=None, text_encoder=None, inpaint_unet=None, tokenizer=None, depth_unet=None,
+                 safety_checker=None, feature_extractor=None):
         self.unet = unet
+        # B200SafetyChecker + B200FeatureExtractor, or None: no check, every image reported clean
+        self.safety_checker = safety_checker
+        self.feature_extractor = feature_extractor
+        if safety_checker is not None and feature_extractor is None:
+            from .safety_checker import B200FeatureExtractor
+            self.feature_extractor = B200FeatureExtractor(size=safety_checker.config.image_size, device=unet.device)
         self.depth_unet = depth_unet       # 5-channel depth2img UNet (unified_pipeline.py:1334, 1974-2013), or None
         self.tokenizer = tokenizer         # the caller's CLIPTokenizer (or any object with its call surface) for `prompt=`
         self.inpaint_unet = inpaint_unet   # 9-channel UNet of the same family (unified_pipeline.py:2059-2062), or None
@@ -207,7 +215,8 @@ class B200Pipeline:
                  strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None,
                  cfg_execution: str = "parallel", hires_fix: bool | None = None,
                  hires_oos_fraction: float | None = None, outmask_image=None, prompt=None, negative_prompt=None,
-                 max_embeddings_multiples: int = 3, clip_layer="final", depth_map=None) -> PipelineOutput:
+                 max_embeddings_multiples: int = 3, clip_layer="final", depth_map=None,
+                 run_safety_checker: bool = True) -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
         unified_pipeline.py:2055-2066 - optionally grafted (inpaint UNet early, main UNet late, :2069-2098) and, for
@@ -377,4 +386,11 @@ class B200Pipeline:
             from .images import match_histograms_outpaint, to_uint8_nhwc
             img = match_histograms_outpaint(img, image, outmask_image)
             u8 = to_uint8_nhwc(img) if output_type == "uint8" else None
-        return PipelineOutput(images=u8 if output_type == "uint8" else img, latents=latents)
+        if run_safety_checker and self.safety_checker is not None:
+            # unified_pipeline.py:2514-2522: the checker looks at the 8-bit image (numpy_to_pil's quantisation) through the
+            # CLIP feature extractor; here both stay on the device and only the 20 scores per image come back
+            clip_input = self.feature_extractor(u8 if u8 is not None else img, return_tensors="pt").pixel_values
+            _, has_nsfw = self.safety_checker(images=img, clip_input=clip_input.to(latents_dtype))
+        else:
+            has_nsfw = [False] * img.shape[0]
+        return PipelineOutput(images=u8 if output_type == "uint8" else img, latents=latents, nsfw_content_detected=has_nsfw)

@@ -244,6 +244,45 @@ int gyre_b200_clip_forward(gyre_b200_handle h, const int64_t* input_ids, int bat
                            int apply_final_ln, void* out, void* workspace, size_t workspace_bytes,
                            gyre_b200_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Safety checker  (replaces gyre/pipeline/safety_checkers.py:13-66 FlagOnlySafetyChecker.forward - and the vision half
+ *   of diffusers' StableDiffusionSafetyChecker it is derived from - plus the CLIPFeatureExtractor call in front of it,
+ *   gyre/pipeline/unified_pipeline.py:2512-2522)
+ * Parameter keys are the checker's state-dict names: "vision_model.embeddings.class_embedding",
+ * "vision_model.embeddings.patch_embedding.weight", "vision_model.embeddings.position_embedding.weight",
+ * "vision_model.pre_layrnorm.*" (sic), "vision_model.encoder.layers.N.*", "vision_model.post_layernorm.*",
+ * "visual_projection.weight", "concept_embeds", "special_care_embeds", "concept_embeds_weights",
+ * "special_care_embeds_weights".
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gyre_b200_clip_vision_config {
+  int32_t image_size;              /* 224                            */
+  int32_t patch_size;              /* 14                             */
+  int32_t hidden_size;             /* 1024 (ViT-L/14)                */
+  int32_t intermediate_size;       /* 4096                           */
+  int32_t num_layers;              /* 24                             */
+  int32_t num_heads;               /* 16                             */
+  int32_t hidden_act;              /* 0 quick_gelu, 1 gelu (erf)     */
+  float layer_norm_eps;            /* 1e-5                           */
+  int32_t projection_dim;          /* 768                            */
+  int32_t num_concepts;            /* 17                             */
+  int32_t num_special;             /* 3                              */
+} gyre_b200_clip_vision_config;
+int gyre_b200_clip_vision_create(const gyre_b200_clip_vision_config* cfg, gyre_b200_handle* out);
+int gyre_b200_clip_vision_workspace_bytes(gyre_b200_handle h, int batch, size_t* bytes);
+/* pixel_values [batch, 3, S, S] fp16 -> image_embeds [batch, projection_dim] fp16 (nullable) and
+ * scores [batch, num_special + num_concepts] fp32 = cosine similarity against the special-care embeddings, then the
+ * concept embeddings (the thresholding is a handful of host scalars per image: gyre_b200.safety_checker). */
+int gyre_b200_safety_scores(gyre_b200_handle h, const void* pixel_values, int batch, void* image_embeds, float* scores,
+                            void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+/* CLIPFeatureExtractor on the device.  One pass of PIL's 8-bit resample along the middle dimension of
+ * src [n_outer, in_size, inner] -> dst [n_outer, out_size, inner] (bounds [out_size, 2] = first source index and tap
+ * count, coeffs [out_size, ksize] 22-bit fixed point: built on the host with PIL's expressions), and the centre crop +
+ * x 1/255 + (x - mean) / std of u8 NHWC [batch, H, W, 3] -> fp16 NCHW [batch, 3, S, S]. */
+int gyre_b200_resample_u8(const void* src, int64_t n_outer, int in_size, int inner, const int32_t* bounds,
+                          const int32_t* coeffs, int ksize, int out_size, void* dst, gyre_b200_stream stream);
+int gyre_b200_clip_normalize(const void* src_u8_nhwc, int batch, int height, int width, int crop, const float* mean3,
+                             const float* std3, void* out, gyre_b200_stream stream);
+
 int gyre_b200_destroy(gyre_b200_handle h);
 
 /* ------------------------------------------------------------------------------------------

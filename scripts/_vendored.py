@@ -176,3 +176,16 @@ def gyre_t2i_adapter():
         sys.modules[name] = m
     _load(name, base, "utils")
     return _load(name, base, "adapter")
+
+
+def gyre_safety_checkers():
+    """gyre/pipeline/safety_checkers.py: imports only torch / numpy / transformers (installed), loaded as a lone file."""
+    p = os.path.join(REF, "gyre/pipeline/safety_checkers.py")
+    name = "_gyre_safety_checkers"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, p)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod

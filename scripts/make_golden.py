@@ -656,6 +656,117 @@ def pin_t2i_adapter():
     print(f"t2i_adapter: {len(out)} configurations, oracle bit-exact against gyre/pipeline/t2i_adapter/adapter.py")
 
 
+def pin_safety():
+    """PINS the safety-checker oracle: the resize against Pillow's own `Image.resize(BICUBIC)` (bit-exact), the vision
+    tower / projection / cosine scores / flag loop against the reference's FlagOnlySafetyChecker
+    (gyre/pipeline/safety_checkers.py) built on the installed transformers.  (CLIPFeatureExtractor 4.28's rescale /
+    normalise lines are restated - transformers 5.5's processor resizes with torch and lands one LSB away from Pillow,
+    so it is not the pin target.)"""
+    import numpy as np
+    from PIL import Image
+    from transformers import CLIPConfig
+    from oracle import safety as osf
+    sc = _vendored.gyre_safety_checkers()
+    out = {"resize": [], "models": {}}
+    for (h, w) in [(512, 512), (64, 96), (300, 224), (160, 96), (100, 37), (224, 224)]:
+        img = osf.synthetic_image(h, w)
+        nh, nw = osf.resize_output_size(h, w, 224)
+        ref = np.asarray(Image.fromarray(img).resize((nw, nh), resample=Image.BICUBIC))
+        got = osf.pil_resize_bicubic(img, nw, nh)
+        assert np.array_equal(ref, got), f"PIL resize {(h, w)} -> {(nh, nw)}"
+        pv = osf.clip_preprocess(img[None])
+        # the crop / rescale / normalise lines on Pillow's own resize output
+        top, left = (nh - 224) // 2, (nw - 224) // 2
+        x = (ref[top:top + 224, left:left + 224] * (1 / 255)).astype(np.float32)
+        x = ((x - np.array(osf.CLIP_MEAN, np.float32)) / np.array(osf.CLIP_STD, np.float32)).transpose(2, 0, 1)
+        assert np.array_equal(pv[0], x)
+        keep_resized = (h, w) in ((64, 96), (160, 96))
+        out["resize"].append({"image_hw": (h, w), "size": (nh, nw),
+                              "resized": torch.from_numpy(ref.copy()) if keep_resized else None,
+                              "resized_sum": int(ref.astype(np.int64).sum()),
+                              "resized_crc": int(np.bitwise_xor.reduce((ref.astype(np.int64).ravel() * (np.arange(ref.size) % 65521 + 1)) % (1 << 31))),
+                              "pixel_values_f16": torch.from_numpy(pv[0]).half()})
+    for name, vis, proj in (("tiny", dict(image_size=56, patch_size=14, hidden_size=64, intermediate_size=256, num_hidden_layers=2,
+                                         num_attention_heads=4, hidden_act="quick_gelu"), 32),
+                            ("vit224", dict(image_size=224, patch_size=14, hidden_size=128, intermediate_size=512,
+                                            num_hidden_layers=2, num_attention_heads=2, hidden_act="quick_gelu"), 64),
+                            ("gelu", dict(image_size=64, patch_size=16, hidden_size=64, intermediate_size=128, num_hidden_layers=1,
+                                          num_attention_heads=1, hidden_act="gelu"), 40)):
+        cfg = CLIPConfig(vision_config=vis, projection_dim=proj)
+        torch.manual_seed(23)
+        m = sc.FlagOnlySafetyChecker(cfg).eval()
+        g = torch.Generator().manual_seed(9)
+        sd = {k: v.clone() for k, v in m.state_dict().items() if not k.endswith("position_ids")}
+        for k in sd:
+            if k.endswith("bias") or "norm" in k:
+                sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
+        sd["vision_model.vision_model.embeddings.class_embedding"] = torch.randn(vis["hidden_size"], generator=g) * 0.5
+        # random-init CLIP barely looks at its input (patch weights ~0.02 against unit position embeddings): make it look
+        pe = "vision_model.vision_model.embeddings.patch_embedding.weight"
+        sd[pe] = sd[pe] * (1.0 / sd[pe].std()) * 0.08
+        for k in sd:
+            if k.endswith(("v_proj.weight", "out_proj.weight", "fc2.weight")):
+                sd[k] = sd[k] * 3.0
+        sd["concept_embeds"] = torch.randn(17, proj, generator=g)
+        sd["special_care_embeds"] = torch.randn(3, proj, generator=g)
+        B = 4 if name == "vit224" else 6
+        S = vis["image_size"]
+        x = (torch.randn(B, 3, S, S, generator=g) * torch.linspace(0.5, 2.5, B)[:, None, None, None]
+             + torch.randn(B, 3, 1, 1, generator=g)).half().float()
+        # everything the native path rounds to fp16 on load is rounded here too, then evaluated in fp32
+        sd = {k: (v if k.endswith("embeds") or k.endswith("embeds_weights") or "norm" in k or k.endswith("bias")
+                  or k.endswith("class_embedding") else v.half().float()) for k, v in sd.items()}
+        m.load_state_dict(sd, strict=False)
+        P = {k[len("vision_model."):] if k.startswith("vision_model.vision_model.") else k: v for k, v in sd.items()}
+        with torch.no_grad():
+            pooled_ref = m.vision_model(x)[1]
+            emb_ref = m.visual_projection(pooled_ref)
+            pooled, emb = osf.clip_vision_forward(P, x, num_layers=vis["num_hidden_layers"], num_heads=vis["num_attention_heads"],
+                                                  patch_size=vis["patch_size"], hidden_act=vis["hidden_act"])
+            assert (pooled - pooled_ref).abs().max().item() < 2e-5 and (emb - emb_ref).abs().max().item() < 2e-5, name
+            scores = osf.cosine_scores(emb_ref, P)
+        print(f"  {name}: score spread across the batch (std per column, mean) {scores.std(0).mean().item():.3f}")
+        # thresholds in the middle of the score distribution so the flags are mixed, special-care hits included, and no
+        # margin closer to zero than the fp16 tower's error
+        def gap_threshold(col, high):
+            v = col.sort().values
+            gaps = v[1:] - v[:-1]
+            ok = [i for i in range(len(gaps)) if gaps[i] > 0.05 and (i >= len(gaps) // 2 if high else True)] or [int(gaps.argmax())]
+            i = ok[int(torch.randint(len(ok), (1,), generator=g))]
+            return (v[i] + v[i + 1]) / 2
+
+        for attempt in range(200):
+            # most concepts never fire (threshold above every score); a few columns split the batch at a gap
+            thr_s = scores[:, :3].max(0).values + 0.05
+            thr_c = scores[:, 3:].max(0).values + 0.05
+            i = int(torch.randint(3, (1,), generator=g))
+            thr_s[i] = gap_threshold(scores[:, i], True)
+            for j in torch.randperm(17, generator=g)[:3].tolist():
+                thr_c[j] = gap_threshold(scores[:, 3 + j], True)
+            res, flags = osf.flag_only(scores.numpy(), thr_s, thr_c)
+            margins = [abs(v) for r in res for v in list(r["special_scores"].values()) + list(r["concept_scores"].values())]
+            n_special = sum(len(r["special_care"]) > 0 for r in res)
+            if min(margins) > 0.008 and 0 < sum(flags) < B and 0 < n_special < B:
+                break
+        else:
+            raise AssertionError(f"no robust thresholds found ({name}): min margin {min(margins)}, flags {flags}, special {n_special}\n{scores}")
+        sd["special_care_embeds_weights"], sd["concept_embeds_weights"] = thr_s.clone(), thr_c.clone()
+        m.load_state_dict(sd, strict=False)
+        imgs = np.zeros((B, 8, 8, 3), np.float32)
+        with torch.no_grad():
+            imgs_out, flags_ref = m(clip_input=x, images=imgs)
+        assert imgs_out is imgs and list(flags_ref) == list(flags), f"FlagOnlySafetyChecker.forward ({name}): {flags_ref} vs {flags}"
+        sd = {k: (v.half() if torch.equal(v.half().float(), v) else v) for k, v in sd.items()}
+        out["models"][name] = {"vision_config": vis, "projection_dim": proj, "state_dict": sd, "clip_input": x.half(),
+                               "image_embeds": emb_ref, "scores": scores, "flags": [bool(f) for f in flags],
+                               "result": [{"special_scores": [float(v) for v in r["special_scores"].values()],
+                                           "concept_scores": [float(v) for v in r["concept_scores"].values()],
+                                           "bad_concepts": [int(v) for v in r["bad_concepts"]]} for r in res]}
+    torch.save(out, os.path.join(GOLD, "safety.pt"))
+    print(f"safety: {len(out['resize'])} resizes bit-exact against Pillow {__import__('PIL').__version__}; "
+          f"{len(out['models'])} checkers against gyre/pipeline/safety_checkers.py on transformers {__import__('transformers').__version__}")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -706,12 +817,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,oracle")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
-             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "oracle": lambda: oracle_fixtures(a.full)}
+             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "oracle": lambda: oracle_fixtures(a.full)}
     for name, fn in parts.items():
         if not a.only or name in a.only.split(","):
             fn()
