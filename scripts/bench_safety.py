@@ -72,6 +72,14 @@ def main():
         out["resize_bit_exact_vs_pillow"] = bool(np.array_equal(arr, dev))
     except ImportError:
         pass
+    gold = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "safety.pt")
+    if os.path.exists(gold):
+        errs = {}
+        for name, m in torch.load(gold)["models"].items():
+            c = B200SafetyChecker({"vision_config": m["vision_config"], "projection_dim": m["projection_dim"]})
+            c.load_state_dict(m["state_dict"])
+            errs[name] = round((c.scores(m["clip_input"].cuda()).cpu() - m["scores"]).abs().max().item(), 6)
+        out["fixture_score_max_abs_err"] = errs
     print(json.dumps(out))
 
 

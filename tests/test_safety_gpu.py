@@ -64,14 +64,14 @@ def test_safety_checker_matches_reference_fixture(gold, name):
     rel = (embeds.float().cpu() - ref_e).norm() / ref_e.norm()
     assert rel < 5e-3, f"image_embeds rel err {rel}"
     err = (scores.cpu() - m["scores"]).abs().max().item()
-    assert err < 3e-3, f"cosine scores: max abs err {err}"                   # fp16 tower vs the fp32 reference; margins >= 8e-3
+    assert err < 1e-3, f"cosine scores: max abs err {err}"    # fp16 tower vs the fp32 reference (measured 1.9 - 3.3e-4); margins >= 8e-3
     images = np.zeros((scores.shape[0], 8, 8, 3), np.float32)
     out, flags = sc(clip_input=m["clip_input"].cuda(), images=images)
     assert out is images and flags == m["flags"]
     for r, g in zip(sc.last_result, m["result"]):
         assert r["bad_concepts"] == g["bad_concepts"]
-        assert np.abs(np.array(list(r["concept_scores"].values())) - np.array(g["concept_scores"])).max() < 4e-3
-        assert np.abs(np.array(list(r["special_scores"].values())) - np.array(g["special_scores"])).max() < 4e-3
+        assert np.abs(np.array(list(r["concept_scores"].values())) - np.array(g["concept_scores"])).max() < 2e-3
+        assert np.abs(np.array(list(r["special_scores"].values())) - np.array(g["special_scores"])).max() < 2e-3
 
 
 def test_safety_checker_errors(gold):
