@@ -283,6 +283,20 @@ int gyre_b200_resample_u8(const void* src, int64_t n_outer, int in_size, int inn
 int gyre_b200_clip_normalize(const void* src_u8_nhwc, int batch, int height, int width, int crop, const float* mean3,
                              const float* std3, void* out, gyre_b200_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * PNG encoding  (replaces gyre/images.py:93-111 toPngBytes -> torchvision.io.encode_png per image on the host, called by
+ *   gyre/services/generate.py:79 image_to_artifact)
+ * images u8 NHWC [batch, height, width, channels] on the device (channels 1 grey, 2 grey + alpha, 3 RGB, 4 RGBA; 8 bits) ->
+ * out [batch][out_stride] bytes, one complete PNG file per image, its length in out_lengths[i].  gyre_b200_png_sizes gives
+ * the workspace size and the smallest out_stride (worst case: incompressible input).  Lossless: any PNG decoder returns
+ * the input pixels; the byte stream is this library's own (chunk-parallel filters + Huffman coding), not libpng's.
+ * Scanlines longer than 32768 bytes are refused.
+ * ------------------------------------------------------------------------------------------ */
+int gyre_b200_png_sizes(int batch, int height, int width, int channels, size_t* workspace_bytes, size_t* out_stride);
+int gyre_b200_png_encode(const void* images_u8_nhwc, int batch, int height, int width, int channels, void* out,
+                         size_t out_stride, int64_t* out_lengths, void* workspace, size_t workspace_bytes,
+                         gyre_b200_stream stream);
+
 int gyre_b200_destroy(gyre_b200_handle h);
 
 /* ------------------------------------------------------------------------------------------
