@@ -40,6 +40,8 @@ class B200GuidedUNet:
         self.extra = None           # [B, Ce, h, w] fp16: mask + masked-image latents of the inpaint UNets
         self._xcat = None
         self.add_cond = None        # [2B, proj_in] fp16: text_time conditioning of SDXL-style UNets ([uncond ; cond])
+        self.controlnets = []       # B200ControlnetHint objects (gyre_b200.hints): evaluated at every UNet call
+        self.t2i = None             # UNetWithT2I-style provider of the per-request adapter states
 
     def set_added_cond(self, uncond_kwargs, cond_kwargs):
         """`added_cond_kwargs` of text_time models ({text_embeds [B, P], time_ids [B, 6]}), for the uncond and the
@@ -49,6 +51,33 @@ class B200GuidedUNet:
         if te.shape[0] != 2 * self.batch:
             raise ValueError("added_cond_kwargs batch does not match the embeddings")
         self.add_cond = self.unet.added_cond_vector(te, ti)
+
+    def set_hints(self, hints):
+        """`hints` of a mode-tree leaf (unified_pipeline.py:2312-2323): grouped by kind like the reference groups them by
+        class - the ControlNets run at every UNet call on the latents it is about to see, the T2I-adapter states are
+        computed once here."""
+        from .hints import B200ControlnetHint, B200T2iHint, UNetWithT2I
+        hints = list(hints or [])
+        unknown = [h for h in hints if not isinstance(h, (B200ControlnetHint, B200T2iHint))]
+        if unknown:
+            raise ValueError(f"unknown hint objects: {unknown}")
+        self.controlnets = [h for h in hints if isinstance(h, B200ControlnetHint)]
+        t2i = [h for h in hints if isinstance(h, B200T2iHint)]
+        self.t2i = UNetWithT2I(None, t2i) if t2i else None
+
+    def _hint_kwargs(self, x_in, t_i64, embeddings, cfg_meta):
+        """UNetWithControlnet / UNetWithT2I (unet/core.py:38-64, 212-239) for one native UNet call."""
+        if not self.controlnets and self.t2i is None:
+            return {}
+        from .hints import controlnet_residual_kwargs
+        kw = {}
+        if self.controlnets:
+            kw.update(controlnet_residual_kwargs(self.controlnets, x_in, t_i64, embeddings, cfg_meta))
+            if not torch.is_tensor(kw["mid_block_additional_residual"]):        # every ControlNet was cfg_only on the "u" side
+                kw = {}
+        if self.t2i is not None:
+            kw["adapter_states"] = self.t2i.states_for(cfg_meta, x_in.shape[0])
+        return kw
 
     def set_extra_channels(self, extra):
         """EnhancedRunwayInpaintMode.wrap_unet (unified_pipeline.py:668-690) / UnetWithExtraChannels (unet/core.py:21-37):
@@ -84,9 +113,11 @@ class B200GuidedUNet:
             if bound is None or bound[0] is not self.ctx_owner:
                 self.unet.set_context(self.embeddings, owner=self.ctx_owner)
             return self.unet.forward_raw(x2_f16, t2_i64, None, out=out, add_cond=self.add_cond,
-                                         cfg_duplicate=self.duplicated_halves)
+                                         cfg_duplicate=self.duplicated_halves,
+                                         **self._hint_kwargs(x2_f16, t2_i64, self.embeddings, "f"))
         return self.unet.forward_raw(x2_f16, t2_i64, self.embeddings, out=out, add_cond=self.add_cond,
-                                     cfg_duplicate=self.duplicated_halves)
+                                     cfg_duplicate=self.duplicated_halves,
+                                     **self._hint_kwargs(x2_f16, t2_i64, self.embeddings, "f"))
 
     def _raw_sequential(self, x2_f16, t2_i64, out):
         """[uncond ; cond] evaluated as two UNet calls of batch B (CFGUNet_Sequential)."""
@@ -98,8 +129,8 @@ class B200GuidedUNet:
         for half in (0, 1):
             sl = slice(half * B, (half + 1) * B)
             add = self.add_cond[sl].contiguous() if self.add_cond is not None else None
-            self.unet.forward_raw(xe[sl].contiguous(), t2_i64[sl].contiguous(), self.embeddings[sl].contiguous(),
-                                  out=out[sl], add_cond=add)
+            xh, th, eh = xe[sl].contiguous(), t2_i64[sl].contiguous(), self.embeddings[sl].contiguous()
+            self.unet.forward_raw(xh, th, eh, out=out[sl], add_cond=add, **self._hint_kwargs(xh, th, eh, "ug"[half]))
         return out
 
     def __call__(self, latents, t):

@@ -158,7 +158,9 @@ class B200ControlNet:
 
     @torch.no_grad()
     def __call__(self, sample, timestep, encoder_hidden_states, controlnet_cond, conditioning_scale: float = 1.0,
-                 return_dict: bool = True, **kwargs):
+                 return_dict: bool = True, out=None, **kwargs):
+        """`out`: optional preallocated fp16 tensors (the skip residuals, then the mid residual) to write into - e.g. the
+        guided half of zero-filled full-batch tensors (gyre_b200.hints, cfg_only)."""
         if not self._loaded:
             raise N.NativeError("B200ControlNet: weights not loaded")
         unsupported = [k for k, v in kwargs.items() if v is not None]
@@ -181,8 +183,16 @@ class B200ControlNet:
         t = t.to(device=self.device, dtype=torch.int64).expand(B).contiguous()
         L = ctx.shape[1]
         shapes, mid_shape = self._skip_shapes(B, H, W)
-        down = [torch.empty(s, device=self.device, dtype=torch.float16) for s in shapes]
-        mid = torch.empty(mid_shape, device=self.device, dtype=torch.float16)
+        if out is not None:
+            if len(out) != len(shapes) + 1:
+                raise ValueError(f"out: expected {len(shapes) + 1} tensors, got {len(out)}")
+            for o, shp in zip(out, shapes + [mid_shape]):
+                if tuple(o.shape) != tuple(shp) or o.dtype != torch.float16 or not o.is_contiguous():
+                    raise ValueError(f"out: expected contiguous fp16 {tuple(shp)}, got {o.dtype} {tuple(o.shape)}")
+            down, mid = list(out[:-1]), out[-1]
+        else:
+            down = [torch.empty(s, device=self.device, dtype=torch.float16) for s in shapes]
+            mid = torch.empty(mid_shape, device=self.device, dtype=torch.float16)
         ptrs = (C.c_void_p * len(down))(*[d.data_ptr() for d in down])
         ws = self._workspace(B, H, W, L)
         with torch.cuda.device(self.device):
@@ -190,8 +200,9 @@ class B200ControlNet:
                                                            ptrs, len(down), N.ptr(mid), N.ptr(ws), ws.numel(),
                                                            N.stream_ptr(self.device)), "controlnet_forward")
         if conditioning_scale != 1.0:
-            down = [d * conditioning_scale for d in down]
-            mid = mid * conditioning_scale
+            for d in down:
+                d.mul_(conditioning_scale)
+            mid.mul_(conditioning_scale)
         if not return_dict:
             return tuple(down), mid
         return ControlNetOutput(down_block_res_samples=tuple(down), mid_block_res_sample=mid)

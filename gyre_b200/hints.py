@@ -1,0 +1,225 @@
+"""Hint images (ControlNet / T2I-adapter) between the CFG wrapper and the native UNet (the callers' side).
+
+Mirrors, with the reference's names and argument meaning:
+  * `UnifiedPipelineHint_Controlnet.__call__`  (gyre/pipeline/unified_pipeline.py:957-1058): which half of a CFG batch the
+    ControlNet sees (`cfg_only`), per-layer `soft_injection` weights `logspace(-1, 0, 13)`, `weight`;
+  * `UnifiedPipelineHint_T2i.standard_call`    (:925-939): `state * weight * layer_weight`, `logspace(-0.25, 0, 4)` with the
+    first entry 0.25 for cfg_only;
+  * `UNetWithControlnet`, `AdapterStateList`, `UNetWithT2I` (gyre/pipeline/unet/core.py:38-64, 67-94, 97-239): the sums over
+    several ControlNets / adapters and the u / g / f (unconditional / guided / fused) selection.
+The models are `B200ControlNet` / `B200T2iAdapter`; their outputs go to the native UNet through
+`gyre_b200_unet_set_control_residuals` / `_set_adapter_states` (B200UNet.forward_raw keywords).
+
+Not built (raise): hint masks and ControlNets under the 9-channel inpaint UNets (both need `images.resize`, the lanczos3
+ResizeRight call of gyre/images.py:324-340, every step), style adapters, co-adapters + fuser."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+CONTROLNET_LAYERS = 13
+
+
+class B200ControlnetHint:
+    """UnifiedPipelineHint_Controlnet (unified_pipeline.py:957-1058)."""
+
+    def __init__(self, model, image, mask=None, weight=1.0, soft_injection=False, cfg_only=False):
+        if mask is not None:
+            raise NotImplementedError("hint masks need the per-step lanczos3 mask resize (images.resize): not built")
+        if image.ndim != 4 or image.shape[1] < 3:
+            raise ValueError(f"hint image must be [B, 3, H, W], got {tuple(image.shape)}")
+        self.model = model
+        self.image = image[:, :3].to(device=model.device, dtype=torch.float16).contiguous()
+        self.mask = None
+        self.weight = float(weight)
+        self.soft_injection = bool(soft_injection)
+        self.cfg_only = bool(cfg_only)
+        self._cond = None
+        # soft injection: later layers count more (the reference's experimentally chosen guess-mode weights)
+        lw = torch.logspace(-1, 0, CONTROLNET_LAYERS).tolist() if self.soft_injection else [1.0] * CONTROLNET_LAYERS
+        self.layer_weights = lw
+
+    def to(self, device=None, dtype=None):
+        return self
+
+    def _condition(self, B):
+        if self._cond is None or self._cond.shape[0] != B:
+            if self.image.shape[0] not in (1, B):
+                raise ValueError(f"hint image batch {self.image.shape[0]} does not match the UNet batch {B}")
+            self._cond = self.image.expand(B, -1, -1, -1).contiguous()
+        return self._cond
+
+    def __call__(self, latents, t, encoder_hidden_states, cfg_meta=None):
+        if latents.shape[1] == 9:
+            raise NotImplementedError("ControlNet under a 9-channel inpaint UNet needs the per-step mask resize: not built")
+        cnlatents = latents[:, 0:4]
+        B_full = latents.shape[0]
+        fused_cfg_only = self.cfg_only and cfg_meta == "f"
+        if self.cfg_only:
+            if cfg_meta == "f":
+                # only the guided half goes through the ControlNet; the unconditional half gets zeros
+                cnlatents = cnlatents.chunk(2)[-1]
+                t = t.chunk(2)[-1] if isinstance(t, torch.Tensor) and t.ndim > 0 else t
+                encoder_hidden_states = encoder_hidden_states.chunk(2)[-1]
+            elif cfg_meta == "u":
+                return SimpleNamespace(down_block_res_samples=[0] * CONTROLNET_LAYERS, mid_block_res_sample=0)
+        B = cnlatents.shape[0]
+        out = None
+        if fused_cfg_only:
+            # [zeros ; residual] without a concatenation per tensor per step: the ControlNet writes the second half
+            shapes, mid_shape = self.model._skip_shapes(B_full, *latents.shape[2:])
+            full = [torch.zeros(s, device=latents.device, dtype=torch.float16) for s in shapes + [mid_shape]]
+            out = [f[B_full // 2:] for f in full]
+        res = self.model(cnlatents.contiguous(), t, encoder_hidden_states=encoder_hidden_states.contiguous(),
+                         controlnet_cond=self._condition(B), out=out)
+        down = list(full[:-1]) if fused_cfg_only else list(res.down_block_res_samples)
+        mid = full[-1] if fused_cfg_only else res.mid_block_res_sample
+        n = len(down)
+        lw = self.layer_weights if n == CONTROLNET_LAYERS - 1 else [1.0] * (n + 1)   # 12 skips + mid = the 13 layers
+        for k in range(n):
+            s = self.weight * lw[k]
+            if s != 1.0:
+                down[k].mul_(s)
+        s = self.weight * lw[-1]
+        if s != 1.0:
+            mid.mul_(s)
+        return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid)
+
+
+class B200T2iHint:
+    """UnifiedPipelineHint_T2i, standard (non-style) adapters (unified_pipeline.py:836-955)."""
+
+    def __init__(self, model, image, mask=None, weight=1.0, soft_injection=False, cfg_only=False):
+        if mask is not None:
+            raise NotImplementedError("hint masks need the lanczos3 mask resize (images.resize): not built")
+        self.model = model
+        channels = model.cin // 64
+        img = image
+        if img.shape[1] != channels:
+            if channels == 1:
+                img = img[:, :3].mean(dim=1, keepdim=True) if img.shape[1] >= 3 else img[:, :1]
+            elif img.shape[1] == 1:
+                img = img.expand(-1, channels, -1, -1)
+            else:
+                img = img[:, :channels]
+        self.image = img.to(device=model.device, dtype=torch.float16).contiguous()
+        self.weight = float(weight)
+        self.soft_injection = bool(soft_injection)
+        self.cfg_only = bool(cfg_only)
+        self.fuser = None
+
+    def to(self, device=None, dtype=None):
+        return self
+
+    def coadapter_type(self):
+        return False
+
+    def __call__(self):
+        layer_weights = [1.0, 1.0, 1.0, 1.0]
+        if self.soft_injection:
+            layer_weights = torch.logspace(-0.25, 0, 4).tolist()
+            if self.cfg_only:
+                layer_weights[0] = 0.25
+        states = self.model(self.image)
+        if len(states) != 4:
+            layer_weights = [1.0] * len(states)
+        out = []
+        for state, lw in zip(states, layer_weights):
+            s = self.weight * lw
+            out.append(state if s == 1.0 else state * s)
+        return out
+
+
+class AdapterStateList:
+    """core.py:67-94: adapter states with their cfg_only flag; `all` feeds the guided side, `either` the unconditional one
+    (cfg_only states become zeros there)."""
+
+    def __init__(self):
+        self.items = []
+
+    def append(self, item, cfg_only: bool):
+        self.items.append((item, cfg_only))
+
+    @staticmethod
+    def _zeros_like(item):
+        return torch.zeros_like(item) if isinstance(item, torch.Tensor) else [AdapterStateList._zeros_like(s) for s in item]
+
+    @property
+    def all(self):
+        return (item for item, _ in self.items)
+
+    @property
+    def cfg_only(self):
+        return (item if cfg_only else self._zeros_like(item) for item, cfg_only in self.items)
+
+    @property
+    def either(self):
+        return (item if not cfg_only else self._zeros_like(item) for item, cfg_only in self.items)
+
+
+def _sum_lists(lists):
+    return [sum(parts) for parts in zip(*lists)]
+
+
+def controlnet_residual_kwargs(controlnets, latents, t, encoder_hidden_states, cfg_meta):
+    """UNetWithControlnet.__call__ (core.py:44-64): every ControlNet sees the same latents / timestep / embeddings, their
+    residuals are summed layer by layer."""
+    res = [cn(latents, t, encoder_hidden_states=encoder_hidden_states, cfg_meta=cfg_meta) for cn in controlnets]
+    return {"down_block_additional_residuals": _sum_lists([r.down_block_res_samples for r in res]),
+            "mid_block_additional_residual": sum(r.mid_block_res_sample for r in res)}
+
+
+class UNetWithControlnet:
+    def __init__(self, unet, controlnets):
+        self.unet = unet
+        self.controlnets = controlnets
+
+    def __call__(self, latents, t, **kwargs):
+        resargs = controlnet_residual_kwargs(self.controlnets, latents, t, kwargs.get("encoder_hidden_states"),
+                                             kwargs.get("cfg_meta"))
+        return self.unet(latents, t, **kwargs, **resargs)
+
+
+class UNetWithT2I:
+    """core.py:97-239 for standard adapters: the states are computed ONCE (they depend on the hint image only), summed over
+    adapters, and selected per call by `cfg_meta` ("u" / "g" / "f" = [u ; g])."""
+
+    def __init__(self, unet, t2i_adapters):
+        self.unet = unet
+        self.standard_states = None
+        self.style_states = None
+        standard = AdapterStateList()
+        for adapter in t2i_adapters:
+            if adapter.coadapter_type():
+                raise NotImplementedError("co-adapters need the fuser model: not built")
+            state = adapter()
+            if not isinstance(state, list):
+                raise NotImplementedError("style adapters (token states) are not built")
+            standard.append(state, adapter.cfg_only)
+        g, u = list(standard.all), list(standard.either)
+        if g:
+            self.standard_states = {"u": _sum_lists(u), "g": _sum_lists(g)}
+            self.standard_dim0 = self.standard_states["g"][0].shape[0]
+            self.standard_states["f"] = [torch.cat([a, b], dim=0) for a, b in zip(self.standard_states["u"], self.standard_states["g"])]
+
+    def states_for(self, cfg_meta, batch):
+        """The states for a UNet batch of `batch` rows: one hint image serves every sample of the request."""
+        if self.standard_states is None:
+            return None
+        states = self.standard_states[cfg_meta]
+        rows = batch // 2 if cfg_meta == "f" else batch
+        if states[0].shape[0] == (2 if cfg_meta == "f" else 1) and rows > 1:
+            if cfg_meta == "f":
+                states = [torch.cat([s[:1].expand(rows, -1, -1, -1), s[1:].expand(rows, -1, -1, -1)]).contiguous() for s in states]
+            else:
+                states = [s.expand(rows, -1, -1, -1).contiguous() for s in states]
+            self.standard_states = dict(self.standard_states, **{cfg_meta: states})      # expanded once per request
+        return states
+
+    def __call__(self, latents, t, **kwargs):
+        is_f = kwargs["encoder_hidden_states"].shape[0] == self.standard_dim0 * 2
+        cfg_meta = kwargs.get("cfg_meta", "f" if is_f else "g")
+        if self.standard_states is not None:
+            kwargs["adapter_states"] = self.standard_states[cfg_meta]
+        return self.unet(latents, t, **kwargs)

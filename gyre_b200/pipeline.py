@@ -25,7 +25,8 @@ from .randtools import batched_randn
 
 @dataclass
 class PipelineOutput:
-    images: torch.Tensor | None      # [B, 3, H, W] in [0, 1] (output_type "pt"), uint8 NHWC ("uint8"), None ("latent")
+    images: object                   # [B, 3, H, W] in [0, 1] (output_type "pt"), uint8 NHWC ("uint8"), list of PNG files as
+                                     # bytes ("png": images.toPngBytes of the reference, encoded on the device), None ("latent")
     latents: torch.Tensor            # final latents (before the 1/0.18215 scaling)
     nsfw_content_detected: list | None = None   # per image, from the safety checker (unified_pipeline.py:2514-2524)
 
@@ -216,7 +217,7 @@ class B200Pipeline:
                  cfg_execution: str = "parallel", hires_fix: bool | None = None,
                  hires_oos_fraction: float | None = None, outmask_image=None, prompt=None, negative_prompt=None,
                  max_embeddings_multiples: int = 3, clip_layer="final", depth_map=None,
-                 run_safety_checker: bool = True) -> PipelineOutput:
+                 run_safety_checker: bool = True, hints=None) -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
         unified_pipeline.py:2055-2066 - optionally grafted (inpaint UNet early, main UNet late, :2069-2098) and, for
@@ -277,8 +278,10 @@ class B200Pipeline:
             kind = "runway" if cfg.in_channels == 9 else "inpaint"
         else:
             kind = "img2img" if image is not None else "txt2img"
+        # `hints`: B200ControlnetHint / B200T2iHint objects (gyre_b200.hints; UnifiedPipelineHint.for_model upstream,
+        # unified_pipeline.py:2018-2034): ControlNets run at every UNet call, adapter states once per request
         tree = _Leaf(kind=kind, unet=main_unet, height=height, width=width, image=image, mask_image=mask_image,
-                     depth_map=depth_map)
+                     depth_map=depth_map, hints=list(hints or []))
 
         # ---- graft: inpaint UNet for the early steps, the main UNet with the legacy x0 blend for the late ones (:2069-2098)
         if kind == "runway" and self._grafted_inpaint and main_unet is self.inpaint_unet and self.unet is not main_unet:
@@ -318,6 +321,9 @@ class B200Pipeline:
                                      mask_image=to_natural(mask_image))
                 for leaf in natural.leaves:          # per leaf: a grafted twin has no depth map
                     leaf.opts["depth_map"] = depth_to_natural(leaf.opts)
+                    # the natural-size twin sees the hint image scaled like the init image (:2148-2158)
+                    leaf.opts["hints"] = [type(h)(h.model, to_natural(h.image.float()), None, h.weight, h.soft_injection, h.cfg_only)
+                                          for h in leaf.opts.get("hints") or []]
                 tree = _Node(natural, tree, HiresUnetWrapper, generators=generators,
                              natural_size=[sample_size, sample_size], oos_fraction=hires_oos_fraction,
                              latent_debugger=None, rand_dtype=latents_dtype)
@@ -333,10 +339,12 @@ class B200Pipeline:
                     raise ValueError("this UNet needs added_cond_kwargs = {text_embeds, time_ids} (text_time conditioning)")
                 g.set_added_cond(negative_added_cond_kwargs or added_cond_kwargs, added_cond_kwargs)
             g.ctx_owner = first_of.setdefault(id(u), g)
+            g.set_hints(leaf.opts.get("hints"))
             leaf.guided = g
         sched = build_scheduler(sampler, generators, self.device, latents_dtype, callback, callback_steps)
         sched.set_eps_unets([leaf.guided for leaf in leaves])
-        sched.use_cuda_graph = bool(getattr(self, "use_cuda_graph", False))
+        # (hints allocate per call: the whole-loop graph is for the plain path)
+        sched.use_cuda_graph = bool(getattr(self, "use_cuda_graph", False)) and not hints
         ts_args = {"strength": min(strength, 1.0)} if image is not None else {}
         sched.set_timesteps(num_inference_steps, prediction_type=cfg.prediction_type,
                             config=scheduler_config or SchedulerConfig(), **ts_args)
@@ -380,12 +388,12 @@ class B200Pipeline:
             return PipelineOutput(images=None, latents=latents)
         z = (1 / self.vae.config.scaling_factor * latents.float()).to(torch.float16)
         outpaint = image is not None and outmask_image is not None
-        img, u8 = self.vae.decode_raw(z.contiguous(), postprocess=True, want_u8=(output_type == "uint8" and not outpaint))
+        img, u8 = self.vae.decode_raw(z.contiguous(), postprocess=True, want_u8=(output_type in ("uint8", "png") and not outpaint))
         if outpaint:
             # unified_pipeline.py:2493-2510: histogram-match the result to the source around it, mix the source back in
             from .images import match_histograms_outpaint, to_uint8_nhwc
             img = match_histograms_outpaint(img, image, outmask_image)
-            u8 = to_uint8_nhwc(img) if output_type == "uint8" else None
+            u8 = to_uint8_nhwc(img) if output_type in ("uint8", "png") else None
         if run_safety_checker and self.safety_checker is not None:
             # unified_pipeline.py:2514-2522: the checker looks at the 8-bit image (numpy_to_pil's quantisation) through the
             # CLIP feature extractor; here both stay on the device and only the 20 scores per image come back
@@ -393,4 +401,7 @@ class B200Pipeline:
             _, has_nsfw = self.safety_checker(images=img, clip_input=clip_input.to(latents_dtype))
         else:
             has_nsfw = [False] * img.shape[0]
+        if output_type == "png":
+            from .images import to_png_bytes
+            return PipelineOutput(images=to_png_bytes(u8), latents=latents, nsfw_content_detected=has_nsfw)
         return PipelineOutput(images=u8 if output_type == "uint8" else img, latents=latents, nsfw_content_detected=has_nsfw)

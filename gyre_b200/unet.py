@@ -240,7 +240,22 @@ class B200UNet(torch.nn.Module):
         emb = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).reshape(time_ids.shape[0], -1)
         return torch.cat([text_embeds.to(self.device).float(), emb], dim=-1).to(torch.float16).contiguous()
 
-    def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None, add_cond=None, cfg_duplicate: bool = False):
+    def forward_raw(self, sample_f16, t_i64, ctx_f16, out=None, add_cond=None, cfg_duplicate: bool = False,
+                    down_block_additional_residuals=None, mid_block_additional_residual=None, adapter_states=None):
+        if down_block_additional_residuals is None and mid_block_additional_residual is None and not adapter_states:
+            return self._forward_raw(sample_f16, t_i64, ctx_f16, out, add_cond, cfg_duplicate)
+        keep = None
+        try:
+            keep = [self._bind_control_residuals(down_block_additional_residuals, mid_block_additional_residual, sample_f16),
+                    self._bind_adapter_states(adapter_states, sample_f16)]
+            return self._forward_raw(sample_f16, t_i64, ctx_f16, out, add_cond, cfg_duplicate)
+        finally:
+            # valid for ONE forward, like the keyword arguments (see forward)
+            self._lib.gyre_b200_unet_set_control_residuals(self._h, None, 0, None)
+            self._lib.gyre_b200_unet_set_adapter_states(self._h, None, 0)
+            del keep
+
+    def _forward_raw(self, sample_f16, t_i64, ctx_f16, out=None, add_cond=None, cfg_duplicate: bool = False):
         """No conversions: fp16 NCHW sample, int64 [B] timesteps, fp16 [B, L, Cc] context (or None: the context
         bound with `set_context`), all on device.  `cfg_duplicate`: the caller's promise that the batch is [x ; x] with
         equal timesteps in both halves (CFGUNet_Parallel): the part of the network in front of the first cross-attention

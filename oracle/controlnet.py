@@ -3,7 +3,10 @@
 ControlNetModel.forward :420-544).  The file itself imports diffusers (absent), but everything it wires is stated in it:
 conv_in, `sample += controlnet_cond_embedding(cond)`, the UNet's down blocks and mid block (the blocks themselves are the
 ones oracle/unet.py restates), then one zero-initialised 1x1 convolution per skip tensor and one for the mid output.
-PARITY UNPINNED below the block level (diffusers blocks), like oracle/unet.py.
+PINNED at what the file states: scripts/make_golden.py:pin_controlnet runs the reference's ControlNetModel (loaded by
+scripts/_vendored.py:gyre_controlnet with the absent diffusers building blocks replaced by stand-ins that evaluate
+oracle/unet.py's blocks) and asserts bit-equality of all 13 outputs, the conditioning embedding and the parameter inventory
+(tests/golden/controlnet.pt).  PARITY UNPINNED below the block level (diffusers blocks), like oracle/unet.py.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may import this module."""
 from __future__ import annotations

@@ -1,0 +1,166 @@
+"""Oracle: ControlNet / T2I-adapter hints between the CFG wrapper and the UNet, restated on the CPU (TEST ONLY).
+
+  * `UNetWithControlnet`, `AdapterStateList`, `UNetWithT2I` follow gyre/pipeline/unet/core.py:38-64, 67-94, 97-239 (standard
+    adapter states only; no co-adapters / style states).  core.py is pure torch and importable: PINNED by
+    scripts/make_golden.py:pin_hints against the reference's own classes over fake models (tests/golden/hints.pt).
+  * `ControlnetHint.__call__`, `T2iHint.__call__` follow gyre/pipeline/unified_pipeline.py:957-1058 and :925-939
+    (UnifiedPipelineHint_Controlnet / _T2i.standard_call).  unified_pipeline.py imports diffusers at module level and cannot
+    be loaded here: these two are PARITY UNPINNED restatements (mask-less hints, 4-channel latents)."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+
+class ControlnetHint:
+    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False):
+        """model(cnlatents, t, encoder_hidden_states=, controlnet_cond=) -> object with down_block_res_samples, mid_block_res_sample."""
+        self.model, self.image = model, image
+        self.weight, self.soft_injection, self.cfg_only = weight, soft_injection, cfg_only
+
+    def __call__(self, latents, t, encoder_hidden_states, cfg_meta=None):
+        cnlatents = latents[:, 0:4]
+        if self.cfg_only:
+            if cfg_meta == "f":
+                cnlatents = cnlatents.chunk(2)[-1]
+                t = t.chunk(2)[-1] if isinstance(t, torch.Tensor) else t
+                encoder_hidden_states = encoder_hidden_states.chunk(2)[-1]
+            elif cfg_meta == "u":
+                return SimpleNamespace(down_block_res_samples=[torch.tensor(0)] * 13, mid_block_res_sample=torch.tensor(0))
+        res = self.model(cnlatents, t, encoder_hidden_states=encoder_hidden_states, controlnet_cond=self.image)
+
+        def basic(r, lw):
+            return r * self.weight * lw
+
+        process = basic
+        if self.cfg_only and cfg_meta == "f":
+            process = lambda r, lw: torch.cat([torch.zeros_like(r), basic(r, lw)], dim=0)
+        layer_weights = torch.logspace(-1, 0, 13) if self.soft_injection else [1] * 13
+        down = [process(r, lw) for r, lw in zip(res.down_block_res_samples, layer_weights)]
+        mid = process(res.mid_block_res_sample, layer_weights[-1])
+        return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid)
+
+
+class T2iHint:
+    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False):
+        self.model, self.image = model, image
+        self.weight, self.soft_injection, self.cfg_only = weight, soft_injection, cfg_only
+        self.fuser = None
+
+    def coadapter_type(self):
+        return False
+
+    def __call__(self):
+        layer_weights = (1.0, 1.0, 1.0, 1.0)
+        if self.soft_injection:
+            layer_weights = torch.logspace(-0.25, 0, 4)
+            if self.cfg_only:
+                layer_weights[0] = 0.25
+        return [state * self.weight * lw for state, lw in zip(self.model(self.image), layer_weights)]
+
+
+class UNetWithControlnet:
+    def __init__(self, unet, controlnets):
+        self.unet, self.controlnets = unet, controlnets
+
+    def __call__(self, latents, t, **kwargs):
+        cnargs = {"encoder_hidden_states": kwargs.get("encoder_hidden_states"), "cfg_meta": kwargs.get("cfg_meta")}
+        residuals = [cn(latents, t, **cnargs) for cn in self.controlnets]
+        resargs = {"down_block_additional_residuals": [sum(i) for i in zip(*[r.down_block_res_samples for r in residuals])],
+                   "mid_block_additional_residual": sum([r.mid_block_res_sample for r in residuals])}
+        return self.unet(latents, t, **kwargs, **resargs)
+
+
+class AdapterStateList:
+    def __init__(self):
+        self.items = []
+
+    def append(self, item, cfg_only):
+        self.items.append((item, cfg_only))
+
+    def _zeros_like(self, item):
+        return torch.zeros_like(item) if isinstance(item, torch.Tensor) else [self._zeros_like(s) for s in item]
+
+    @property
+    def all(self):
+        for item, _ in self.items:
+            yield item
+
+    @property
+    def cfg_only(self):
+        for item, cfg_only in self.items:
+            yield item if cfg_only else self._zeros_like(item)
+
+    @property
+    def either(self):
+        for item, cfg_only in self.items:
+            yield item if not cfg_only else self._zeros_like(item)
+
+
+class UNetWithT2I:
+    def __init__(self, unet, t2i_adapters):
+        self.unet = unet
+        self.standard_states = None
+        standard = AdapterStateList()
+        for adapter in t2i_adapters:
+            assert not adapter.coadapter_type()
+            standard.append(adapter(), adapter.cfg_only)
+        g, u = list(standard.all), list(standard.either)
+        if g:
+            self.standard_states = {"u": [sum(i) for i in zip(*u)], "g": [sum(i) for i in zip(*g)]}
+            self.standard_dim0 = self.standard_states["g"][0].shape[0]
+            self.standard_states["f"] = [torch.cat([a, b], dim=0) for a, b in zip(self.standard_states["u"], self.standard_states["g"])]
+
+    def __call__(self, latents, t, **kwargs):
+        is_f = kwargs["encoder_hidden_states"].shape[0] == self.standard_dim0 * 2
+        cfg_meta = kwargs.get("cfg_meta", "f" if is_f else "g")
+        if self.standard_states is not None:
+            kwargs["adapter_states"] = self.standard_states[cfg_meta]
+        return self.unet(latents, t, **kwargs)
+
+
+class FromDiffusersUNet:
+    """CFGUNetFromDiffusersUNet (core.py:262-274): drops cfg_meta, unwraps .sample."""
+
+    def __init__(self, unet):
+        self.unet = unet
+
+    def __call__(self, latents, t, **kwargs):
+        kwargs.pop("cfg_meta", None)
+        return self.unet(latents, t, **kwargs).sample
+
+
+class UNetWithEmbeddings:
+    """core.py:242-259."""
+
+    def __init__(self, unet, text_embeddings, cfg_meta):
+        self.unet, self.text_embeddings, self.cfg_meta = unet, text_embeddings, cfg_meta
+
+    def __call__(self, latents, t):
+        return self.unet(latents, t, encoder_hidden_states=self.text_embeddings, cfg_meta=self.cfg_meta)
+
+
+def guided_eps_unet(diffusers_unet, uncond, cond, guidance_scale, hints, parallel=True):
+    """The wrapper stack of unified_pipeline.py:2284-2337 for one leaf: hints grouped by class (T2I / ControlNet wrap in the
+    order they were first seen), embeddings bound, CFG parallel ("f") or sequential ("u", "g")."""
+    unet = FromDiffusersUNet(diffusers_unet)
+    grouped = {}
+    for h in hints:
+        grouped.setdefault(type(h), []).append(h)
+    for cls, hs in grouped.items():
+        unet = (UNetWithControlnet if cls is ControlnetHint else UNetWithT2I)(unet, hs)
+    if parallel:
+        f = UNetWithEmbeddings(unet, torch.cat([uncond, cond]), "f")
+
+        def eps(latents, t):
+            t2 = torch.cat([t, t]) if isinstance(t, torch.Tensor) and t.shape else t
+            u, g = f(torch.cat([latents, latents]), t2).chunk(2)
+            return u + guidance_scale * (g - u)
+        return eps
+    uu, gg = UNetWithEmbeddings(unet, uncond, "u"), UNetWithEmbeddings(unet, cond, "g")
+
+    def eps(latents, t):
+        u, g = uu(latents, t), gg(latents, t)
+        return u + guidance_scale * (g - u)
+    return eps

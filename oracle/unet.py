@@ -374,7 +374,9 @@ def unet_forward(P: dict, cfg: UNetConfig, sample, timestep, encoder_hidden_stat
     # (gyre/pipeline/unet/core.py:213-239 passes the summed ControlNet outputs through these two keywords):
     # the skips - not the down path - take the residuals, the mid block output takes its own
     if down_block_additional_residuals is not None:
-        assert len(down_block_additional_residuals) == len(res)
+        # (diffusers zips the two lists: a longer list of residuals - the 13 scalar zeros a cfg_only ControlNet hint returns
+        # for the unconditional side, unified_pipeline.py:1001-1006 - is cut to the number of skips)
+        assert len(down_block_additional_residuals) >= len(res)
         res = [r + a.to(r.dtype) for r, a in zip(res, down_block_additional_residuals)]
     if mid_block_additional_residual is not None:
         h = h + mid_block_additional_residual.to(h.dtype)

@@ -189,3 +189,162 @@ def gyre_safety_checkers():
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def gyre_controlnet():
+    """gyre/pipeline/controlnet/models.py (the in-tree ControlNetModel: ControlNetConditioningEmbedding, zero convolutions,
+    construction and forward wiring) with the absent `diffusers` building blocks stood in for by nn.Modules that hold their
+    parameters under the diffusers names and evaluate the oracle's restated blocks (oracle/unet.py: resnet_block,
+    transformer_2d, timestep_embedding).  What this makes checkable is everything the FILE states - not the blocks."""
+    import torch
+    from torch import nn
+    from oracle import unet as ou
+    gyre_ddim()                                    # installs the diffusers.configuration_utils / utils stubs
+    d = sys.modules["diffusers"]
+    ut = sys.modules["diffusers.utils"]
+    if not hasattr(ut, "logging"):
+        lg = types.ModuleType("diffusers.utils.logging")
+        import logging as _pylog
+        lg.get_logger = _pylog.getLogger
+        ut.logging = lg
+        sys.modules["diffusers.utils.logging"] = lg
+    if "diffusers.models.unet_2d_blocks" not in sys.modules:
+        models = types.ModuleType("diffusers.models")
+        ca = types.ModuleType("diffusers.models.cross_attention")
+        emb = types.ModuleType("diffusers.models.embeddings")
+        mu = types.ModuleType("diffusers.models.modeling_utils")
+        blk = types.ModuleType("diffusers.models.unet_2d_blocks")
+
+        class AttnProcessor:
+            pass
+
+        class ModelMixin(nn.Module):
+            @property
+            def dtype(self):
+                return next(self.parameters()).dtype
+
+        class Timesteps(nn.Module):
+            def __init__(self, num_channels, flip_sin_to_cos, downscale_freq_shift):
+                super().__init__()
+                assert flip_sin_to_cos and downscale_freq_shift == 0          # what the oracle restates (SD configs)
+                self.num_channels = num_channels
+
+            def forward(self, t):
+                return ou.timestep_embedding(t, self.num_channels)
+
+        class TimestepEmbedding(nn.Module):
+            def __init__(self, in_channels, time_embed_dim, act_fn="silu"):
+                super().__init__()
+                assert act_fn == "silu"
+                self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+                self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+
+            def forward(self, sample, condition=None):
+                assert condition is None
+                return self.linear_2(torch.nn.functional.silu(self.linear_1(sample)))
+
+        def _register(mod, shapes, prefix):
+            """Parameters of an oracle block as (nested) module attributes so that state_dict() has the diffusers names."""
+            for k, shp in shapes.items():
+                assert k.startswith(prefix + ".")
+                parts = k[len(prefix) + 1:].split(".")
+                cur = mod
+                for p_ in parts[:-1]:
+                    if not hasattr(cur, p_):
+                        setattr(cur, p_, nn.Module())
+                    cur = getattr(cur, p_)
+                setattr(cur, parts[-1], nn.Parameter(torch.randn(shp) / max(1, int(torch.tensor(shp[1:]).prod())) ** 0.5))
+
+        class _Block(nn.Module):
+            def params(self, prefix):
+                return {f"{prefix}.{k}": v for k, v in self.state_dict().items()}
+
+        class DownBlock2D(_Block):
+            has_cross_attention = False
+
+            def __init__(self, num_layers, in_channels, out_channels, temb_channels, add_downsample, resnet_eps, resnet_groups,
+                         cross_attention_dim=None, heads=None, linear=False, **_):
+                super().__init__()
+                self.n, self.eps, self.groups, self.heads, self.linear = num_layers, resnet_eps, resnet_groups, heads, linear
+                self.add_downsample = add_downsample
+                shapes = {}
+                cin = in_channels
+                for j in range(num_layers):
+                    shapes.update(ou._resnet_keys(f"b.resnets.{j}", cin, out_channels, temb_channels))
+                    cin = out_channels
+                    if self.has_cross_attention:
+                        shapes.update(ou._transformer_keys(f"b.attentions.{j}", out_channels, cross_attention_dim, linear, 1))
+                if add_downsample:
+                    shapes["b.downsamplers.0.conv.weight"] = (out_channels, out_channels, 3, 3)
+                    shapes["b.downsamplers.0.conv.bias"] = (out_channels,)
+                _register(self, shapes, "b")
+
+            def forward(self, hidden_states, temb=None, encoder_hidden_states=None, attention_mask=None,
+                        cross_attention_kwargs=None):
+                assert attention_mask is None and cross_attention_kwargs is None
+                P = self.params("b")
+                out = ()
+                h = hidden_states
+                for j in range(self.n):
+                    h = ou.resnet_block(P, f"b.resnets.{j}", h, temb, self.groups, self.eps)
+                    if self.has_cross_attention:
+                        h = ou.transformer_2d(P, f"b.attentions.{j}", h, encoder_hidden_states, self.heads, self.groups,
+                                              self.linear, 0)
+                    out += (h,)
+                if self.add_downsample:
+                    h = torch.nn.functional.conv2d(h, P["b.downsamplers.0.conv.weight"], P["b.downsamplers.0.conv.bias"],
+                                                   stride=2, padding=1)
+                    out += (h,)
+                return h, out
+
+        class CrossAttnDownBlock2D(DownBlock2D):
+            has_cross_attention = True
+
+        def get_down_block(down_block_type, num_layers, in_channels, out_channels, temb_channels, add_downsample, resnet_eps,
+                           resnet_act_fn, resnet_groups, cross_attention_dim, attn_num_head_channels, downsample_padding,
+                           use_linear_projection, only_cross_attention, upcast_attention, resnet_time_scale_shift):
+            assert resnet_act_fn == "silu" and downsample_padding == 1 and not only_cross_attention and not upcast_attention
+            assert resnet_time_scale_shift == "default"
+            cls = {"CrossAttnDownBlock2D": CrossAttnDownBlock2D, "DownBlock2D": DownBlock2D}[down_block_type]
+            return cls(num_layers, in_channels, out_channels, temb_channels, add_downsample, resnet_eps, resnet_groups,
+                       cross_attention_dim=cross_attention_dim, heads=attn_num_head_channels, linear=use_linear_projection)
+
+        class UNetMidBlock2DCrossAttn(_Block):
+            def __init__(self, in_channels, temb_channels, resnet_eps, resnet_act_fn, output_scale_factor,
+                         resnet_time_scale_shift, cross_attention_dim, attn_num_head_channels, resnet_groups,
+                         use_linear_projection, upcast_attention):
+                super().__init__()
+                assert output_scale_factor == 1 and resnet_act_fn == "silu" and not upcast_attention
+                self.eps, self.groups, self.heads, self.linear = resnet_eps, resnet_groups, attn_num_head_channels, use_linear_projection
+                shapes = {}
+                shapes.update(ou._resnet_keys("b.resnets.0", in_channels, in_channels, temb_channels))
+                shapes.update(ou._transformer_keys("b.attentions.0", in_channels, cross_attention_dim, use_linear_projection, 1))
+                shapes.update(ou._resnet_keys("b.resnets.1", in_channels, in_channels, temb_channels))
+                _register(self, shapes, "b")
+
+            def forward(self, hidden_states, temb=None, encoder_hidden_states=None, attention_mask=None,
+                        cross_attention_kwargs=None):
+                assert attention_mask is None and cross_attention_kwargs is None
+                P = self.params("b")
+                h = ou.resnet_block(P, "b.resnets.0", hidden_states, temb, self.groups, self.eps)
+                h = ou.transformer_2d(P, "b.attentions.0", h, encoder_hidden_states, self.heads, self.groups, self.linear, 0)
+                return ou.resnet_block(P, "b.resnets.1", h, temb, self.groups, self.eps)
+
+        ca.AttnProcessor = AttnProcessor
+        emb.Timesteps, emb.TimestepEmbedding = Timesteps, TimestepEmbedding
+        mu.ModelMixin = ModelMixin
+        blk.CrossAttnDownBlock2D, blk.DownBlock2D = CrossAttnDownBlock2D, DownBlock2D
+        blk.UNetMidBlock2DCrossAttn, blk.get_down_block = UNetMidBlock2DCrossAttn, get_down_block
+        d.models = models
+        for n, m in (("diffusers.models", models), ("diffusers.models.cross_attention", ca), ("diffusers.models.embeddings", emb),
+                     ("diffusers.models.modeling_utils", mu), ("diffusers.models.unet_2d_blocks", blk)):
+            sys.modules[n] = m
+    p = os.path.join(REF, "gyre/pipeline/controlnet/models.py")
+    name = "_gyre_controlnet_models"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, p)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod

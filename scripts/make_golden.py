@@ -18,6 +18,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import _vendored  # noqa: E402
 from oracle import sampling as osamp  # noqa: E402
@@ -767,6 +768,106 @@ def pin_safety():
           f"{len(out['models'])} checkers against gyre/pipeline/safety_checkers.py on transformers {__import__('transformers').__version__}")
 
 
+def pin_controlnet():
+    """PINS what gyre/pipeline/controlnet/models.py itself states - ControlNetConditioningEmbedding, the zero-convolution
+    list, the parameter inventory of those parts, timestep handling, channel-order flip and the forward wiring - against
+    oracle/controlnet.py, by running the reference's ControlNetModel with the absent diffusers blocks replaced by stand-ins
+    that evaluate the oracle's own blocks (scripts/_vendored.py:gyre_controlnet).  The blocks themselves stay unpinned."""
+    from oracle import controlnet as ocn
+    cn = _vendored.gyre_controlnet()
+    cfg = UNetConfig.tiny()
+    out = {}
+    for name, order in (("rgb", "rgb"), ("bgr", "bgr")):
+        torch.manual_seed(29)
+        m = cn.ControlNetModel(in_channels=cfg.in_channels, block_out_channels=cfg.block_out_channels,
+                               layers_per_block=cfg.layers_per_block, cross_attention_dim=cfg.cross_attention_dim,
+                               attention_head_dim=cfg.num_heads[0], norm_num_groups=cfg.norm_num_groups, norm_eps=cfg.norm_eps,
+                               use_linear_projection=cfg.use_linear_projection,
+                               controlnet_conditioning_channel_order=order).eval()
+        g = torch.Generator().manual_seed(13)
+        # (the reference zero-initialises the 14 output convolutions and the embedding's conv_out: seeded values everywhere)
+        sd = synth_params(ocn.controlnet_param_shapes(cfg), seed=77)
+        assert set(sd) == set(m.state_dict())
+        m.load_state_dict(sd)
+        shapes = ocn.controlnet_param_shapes(cfg)
+        assert {k: tuple(v.shape) for k, v in sd.items()} == shapes, "ControlNet parameter inventory"
+        x = torch.randn(2, cfg.in_channels, 16, 16, generator=g)
+        ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+        cond = torch.rand(2, 3, 128, 128, generator=g).half().float()
+        cases = {"tvec": torch.tensor([981, 21]), "tscalar": torch.tensor(500), "tint": 37}
+        res = {}
+        for tn, t in cases.items():
+            with torch.no_grad():
+                ref = m(x.clone(), t, ctx, cond, return_dict=False)
+                cond_o = torch.flip(cond, dims=[1]) if order == "bgr" else cond
+                mine = ocn.controlnet_forward(sd, cfg, x, t, ctx, cond_o)
+            assert len(ref[0]) == len(mine[0]) == 12
+            for a_, b_ in zip(ref[0] + (ref[1],), mine[0] + (mine[1],)):
+                assert torch.equal(a_, b_), f"ControlNetModel.forward ({name}, {tn})"
+            res[tn] = {"down": [t_.clone() for t_ in ref[0]], "mid": ref[1].clone()}
+        with torch.no_grad():
+            e_ref = m.controlnet_cond_embedding(cond)
+            assert torch.equal(e_ref, ocn.cond_embedding(sd, cond))
+        out[name] = {"weights_seed": 77, "x": x, "ctx": ctx, "cond": cond.half(), "t": {k: v for k, v in cases.items()},
+                     # per-tensor sums: the full tensors are regenerated by the oracle in the tests, these pin them
+                     "sums": {tn: [float(t_.double().sum()) for t_ in r["down"]] + [float(r["mid"].double().sum())]
+                              for tn, r in res.items()}}
+    torch.save(out, os.path.join(GOLD, "controlnet.pt"))
+    print("controlnet: ControlNetModel.forward (rgb / bgr, 3 timestep forms), conditioning embedding and parameter inventory "
+          "bit-exact against gyre/pipeline/controlnet/models.py (diffusers blocks stood in for by the oracle's)")
+
+
+def pin_hints():
+    """PINS the hint wrappers (oracle/hints.py UNetWithControlnet / AdapterStateList / UNetWithT2I, and the product's copies in
+    gyre_b200/hints.py, which are plain torch) against the reference's own gyre/pipeline/unet/core.py classes over fake
+    ControlNets / adapters / UNet whose outputs depend on every argument they are handed."""
+    from types import SimpleNamespace as SN
+    from oracle import hints as oh
+    _, _, _, core = _vendored.gyre_pipeline_pure()
+    g = torch.Generator().manual_seed(41)
+
+    from fakes import FakeHintAdapter as FakeAdapter, FakeHintControlnet as FakeControlnet, FakeHintUNet as FakeUNet
+    lat = torch.randn(2, 4, 8, 8, generator=g)
+    t = torch.tensor([500, 500])
+    ehs = torch.randn(2, 5, 6, generator=g)
+    out = {"inputs": {"lat": lat, "t": t, "ehs": ehs}, "controlnet": {}, "t2i": {}}
+    for meta in ("f", "g", "u"):
+        for combo in ((False,), (True,), (False, True)):
+            cns = [FakeControlnet(100 * (i + 1), c) for i, c in enumerate(combo)]
+            if meta == "u" and all(combo):
+                continue          # the reference hands sum(ints) to the UNet there; nothing to compare
+            ref = core.UNetWithControlnet(FakeUNet(), cns)(lat, t, encoder_hidden_states=ehs, cfg_meta=meta)
+            mine = oh.UNetWithControlnet(FakeUNet(), cns)(lat, t, encoder_hidden_states=ehs, cfg_meta=meta)
+            assert torch.equal(ref, mine), ("UNetWithControlnet", meta, combo)
+            out["controlnet"][f"{meta}/{''.join('c' if c else 'b' for c in combo)}"] = ref
+        for combo in ((False,), (True,), (False, True), (True, True)):
+            ads = [FakeAdapter(1000 * (i + 1), c) for i, c in enumerate(combo)]
+            e = torch.cat([ehs[:1], ehs[:1]]) if meta == "f" else ehs[:1]
+            l = torch.cat([lat[:1], lat[:1]]) if meta == "f" else lat[:1]
+            tt = t[:2] if meta == "f" else t[:1]
+            ref_w = core.UNetWithT2I(FakeUNet(), ads)
+            mine_w = oh.UNetWithT2I(FakeUNet(), ads)
+            ref = ref_w(l, tt, encoder_hidden_states=e, cfg_meta=meta)
+            assert torch.equal(ref, mine_w(l, tt, encoder_hidden_states=e, cfg_meta=meta)), ("UNetWithT2I", meta, combo)
+            # cfg_meta inferred from the embedding batch when absent (core.py:213-214)
+            assert torch.equal(ref_w(l, tt, encoder_hidden_states=e), mine_w(l, tt, encoder_hidden_states=e))
+            for k in ("u", "g", "f"):
+                for a_, b_ in zip(ref_w.standard_states[k], mine_w.standard_states[k]):
+                    assert torch.equal(a_, b_)
+            out["t2i"][f"{meta}/{''.join('c' if c else 'b' for c in combo)}"] = ref
+    rl, ml = core.AdapterStateList(), oh.AdapterStateList()
+    for i, c in enumerate((False, True, False)):
+        st = FakeAdapter(7 + i, c).state
+        rl.append(st, c)
+        ml.append(st, c)
+    for prop in ("all", "cfg_only", "either"):
+        for a_, b_ in zip(getattr(rl, prop), getattr(ml, prop)):
+            assert all(torch.equal(x_, y_) for x_, y_ in zip(a_, b_)), prop
+    torch.save(out, os.path.join(GOLD, "hints.pt"))
+    print(f"hints: UNetWithControlnet ({len(out['controlnet'])} cases), UNetWithT2I ({len(out['t2i'])} cases), AdapterStateList "
+          "bit-exact against gyre/pipeline/unet/core.py")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -817,12 +918,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,oracle")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,controlnet,hints,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
-             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "oracle": lambda: oracle_fixtures(a.full)}
+             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "controlnet": pin_controlnet, "hints": pin_hints, "oracle": lambda: oracle_fixtures(a.full)}
     for name, fn in parts.items():
         if not a.only or name in a.only.split(","):
             fn()

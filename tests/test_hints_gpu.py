@@ -1,0 +1,110 @@
+"""ControlNet / T2I-adapter hints end to end: B200Pipeline(hints=[...]) - the native ControlNet at every UNet call, adapter
+states once per request, both injected into the native UNet - against the oracle's composition of the wrapper stack
+(oracle/hints.py, pinned to gyre/pipeline/unet/core.py) over the oracle ControlNet / adapter / UNet on the CPU."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from oracle import controlnet as ocn
+    from oracle import t2i_adapter as oad
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.controlnet import B200ControlNet
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.t2i_adapter import B200T2iAdapter
+    from gyre_b200.unet import B200UNet
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    Pcn = synth_params(ocn.controlnet_param_shapes(cfg), seed=77)
+    akw = dict(channels=list(cfg.block_out_channels), nums_rb=2, cin=192, ksize=1, sk=True, use_conv=False)
+    Pad = synth_params(oad.adapter_param_shapes(**akw), seed=91)
+    pipe = B200Pipeline(B200UNet(cfg).load_state_dict(P), None)
+    pipe.unet_sample_size_override = 16
+    cn = B200ControlNet(cfg).load_state_dict(Pcn)
+    ad = B200T2iAdapter(**akw).load_state_dict(Pad)
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).expand(2, -1, -1).contiguous()
+    hint_img = torch.rand(1, 3, 128, 128, generator=g).half().float()
+
+    def o_cn(cnlatents, t, encoder_hidden_states, controlnet_cond):
+        with torch.no_grad():
+            down, mid = ocn.controlnet_forward(Pcn, cfg, cnlatents, t, encoder_hidden_states, controlnet_cond)
+        return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid)
+
+    def o_ad(x):
+        with torch.no_grad():
+            return oad.adapter_forward(Pad, x, **{k: v for k, v in akw.items() if k != "cin"})
+    return SimpleNamespace(cfg=cfg, pipe=pipe, cn=cn, ad=ad, o_cn=o_cn, o_ad=o_ad, o_unet=OracleUNet(cfg, P), emb=emb, unc=unc,
+                           img=hint_img)
+
+
+CASES = [("controlnet", dict(weight=1.0, soft_injection=False, cfg_only=False), None, "parallel"),
+         ("controlnet soft 0.7", dict(weight=0.7, soft_injection=True, cfg_only=False), None, "parallel"),
+         ("controlnet cfg_only", dict(weight=0.8, soft_injection=True, cfg_only=True), None, "parallel"),
+         ("controlnet cfg_only sequential", dict(weight=0.8, soft_injection=False, cfg_only=True), None, "sequential"),
+         ("t2i", None, dict(weight=1.0, soft_injection=False, cfg_only=False), "parallel"),
+         ("t2i soft cfg_only + controlnet", dict(weight=0.5, soft_injection=False, cfg_only=False),
+          dict(weight=0.9, soft_injection=True, cfg_only=True), "parallel"),
+         ("t2i cfg_only sequential", None, dict(weight=1.0, soft_injection=False, cfg_only=True), "sequential")]
+
+
+@pytest.mark.parametrize("name,cn_kw,ad_kw,execution", CASES, ids=[c[0] for c in CASES])
+def test_pipeline_with_hints_vs_oracle(setup, name, cn_kw, ad_kw, execution):
+    from oracle import hints as oh
+    from oracle import sampling as osamp
+    from gyre_b200.hints import B200ControlnetHint, B200T2iHint
+    s = setup
+    hints, ohints = [], []
+    if cn_kw is not None:
+        hints.append(B200ControlnetHint(s.cn, s.img.cuda(), **cn_kw))
+        ohints.append(oh.ControlnetHint(s.o_cn, s.img, **cn_kw))
+    if ad_kw is not None:
+        hints.append(B200T2iHint(s.ad, s.img.cuda(), **ad_kw))
+        ohints.append(oh.T2iHint(s.o_ad, s.img, **ad_kw))
+    seeds, steps = [420420420, 420420421], 8
+    out = s.pipe(s.emb.cuda(), s.unc.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
+                 generator=[torch.Generator("cpu").manual_seed(x) for x in seeds], sampler="k_euler_ancestral",
+                 output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True, hints=hints,
+                 cfg_execution=execution)
+    eps = oh.guided_eps_unet(s.o_unet, s.unc, s.emb, 7.5, ohints, parallel=execution == "parallel")
+    with torch.no_grad():
+        ref = osamp.txt2img_latents(eps, batch=2, in_channels=4, height=128, width=128, sample_size=16, seeds=seeds,
+                                    steps=steps, sampler="euler_a")
+        plain = osamp.txt2img_latents(oh.guided_eps_unet(s.o_unet, s.unc, s.emb, 7.5, []), batch=2, in_channels=4, height=128,
+                                      width=128, sample_size=16, seeds=seeds, steps=steps, sampler="euler_a")
+    got = out.latents.float().cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item() / scale
+    moved = (plain - ref).abs().max().item() / scale
+    assert moved > 0.05, f"the hint did not change the result ({moved}): the test would prove nothing"
+    assert err < 1.4e-2, f"{name}: rel err {err} (hint moves the latents by {moved})"
+
+
+def test_hints_leave_no_residuals_bound(setup):
+    """A hinted run followed by a plain one equals a plain run (the residual / state pointers are per call)."""
+    from gyre_b200.hints import B200ControlnetHint
+    s = setup
+    kw = dict(height=128, width=128, num_inference_steps=4, guidance_scale=7.5, sampler="k_euler", output_type="latent")
+    gen = lambda: [torch.Generator("cpu").manual_seed(x) for x in (1, 2)]
+    a = s.pipe(s.emb.cuda(), s.unc.cuda(), generator=gen(), **kw).latents
+    s.pipe(s.emb.cuda(), s.unc.cuda(), generator=gen(), hints=[B200ControlnetHint(s.cn, s.img.cuda())], **kw)
+    b = s.pipe(s.emb.cuda(), s.unc.cuda(), generator=gen(), **kw).latents
+    assert torch.equal(a, b)
+
+
+def test_hints_with_hires_fix_run(setup):
+    """Above the native size the natural-size twin gets the hint image scaled like the init image (unified_pipeline.py:2148-2158)."""
+    from gyre_b200.hints import B200ControlnetHint, B200T2iHint
+    s = setup
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(1, 3, 192, 192, generator=g)
+    out = s.pipe(s.emb.cuda(), s.unc.cuda(), height=192, width=192, num_inference_steps=4, guidance_scale=7.5,
+                 generator=[torch.Generator("cpu").manual_seed(x) for x in (1, 2)], sampler="k_euler", output_type="latent",
+                 hints=[B200ControlnetHint(s.cn, img.cuda(), weight=0.5), B200T2iHint(s.ad, img.cuda())], hires_fix=True)
+    assert tuple(out.latents.shape) == (2, 4, 24, 24) and torch.isfinite(out.latents.float()).all()

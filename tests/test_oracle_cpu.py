@@ -227,3 +227,25 @@ def test_cfg_wrapper_stack_matches_reference(dt_name, dt, t_name):
     # the sequential execution mode is the same function up to the rounding of two separate UNet calls
     seq = W[f"cfg_{dt_name}_plain_{t_name}_sequential"]
     assert torch.allclose(got.float(), seq.float(), atol=2e-2 if dt == torch.float16 else 1e-5)
+
+
+def test_controlnet_oracle_matches_reference_fixture():
+    """tests/golden/controlnet.pt: per-tensor sums of what the reference's in-tree ControlNetModel.forward returned (diffusers
+    blocks stood in for by the oracle's; scripts/make_golden.py:pin_controlnet asserted bit-equality tensor by tensor)."""
+    import os
+    import torch
+    from oracle import controlnet as ocn
+    from oracle.unet import UNetConfig, synth_params
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "controlnet.pt"))
+    cfg = UNetConfig.tiny()
+    for order in ("rgb", "bgr"):
+        g = G[order]
+        P = synth_params(ocn.controlnet_param_shapes(cfg), seed=g["weights_seed"])
+        cond = g["cond"].float()
+        cond = torch.flip(cond, dims=[1]) if order == "bgr" else cond
+        for tn, t in g["t"].items():
+            with torch.no_grad():
+                down, mid = ocn.controlnet_forward(P, cfg, g["x"], t, g["ctx"], cond)
+            sums = [float(d.double().sum()) for d in down] + [float(mid.double().sum())]
+            for a, b in zip(sums, g["sums"][tn]):
+                assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (order, tn)

@@ -98,3 +98,24 @@ def test_png_refuses_overlong_scanlines():
         encode_png_u8(torch.zeros(1, 2, 11000, 3, dtype=torch.uint8).cuda())
     with pytest.raises(ValueError):
         encode_png_u8(torch.zeros(1, 3, 8, 8).cuda())
+
+
+def test_pipeline_png_output_decodes_to_uint8_output():
+    from oracle.unet import UNetConfig, synth_params, unet_param_shapes
+    from oracle.vae import VAEConfig, vae_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    from gyre_b200.vae import B200VAE
+    ucfg, vcfg = UNetConfig.tiny(), VAEConfig.tiny()
+    pipe = B200Pipeline(B200UNet(ucfg).load_state_dict(synth_params(unet_param_shapes(ucfg), seed=1234)),
+                        B200VAE(vcfg).load_state_dict(synth_params(vae_param_shapes(vcfg), seed=4321)))
+    pipe.unet_sample_size_override = 16
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 77, ucfg.cross_attention_dim, generator=g).half().cuda()
+    unc = torch.randn(2, 77, ucfg.cross_attention_dim, generator=g).half().cuda()
+    kw = dict(height=128, width=128, num_inference_steps=3, sampler="k_euler")
+    u8 = pipe(emb, unc, generator=[torch.Generator("cpu").manual_seed(s) for s in (5, 6)], output_type="uint8", **kw).images
+    png = pipe(emb, unc, generator=[torch.Generator("cpu").manual_seed(s) for s in (5, 6)], output_type="png", **kw).images
+    assert isinstance(png, list) and len(png) == 2 and all(isinstance(p, bytes) for p in png)
+    for f, ref in zip(png, u8.cpu().numpy()):
+        assert np.array_equal(_decode_pil(f, ref.shape), ref)
