@@ -348,3 +348,60 @@ def gyre_controlnet():
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def gyre_attention_modules():
+    """gyre/pipeline/models/memory_efficient_cross_attention.py (a pure nn.Module) and
+    nonfree/tome_memory_efficient_cross_attention.py (its ToMe variant, a subclass of diffusers' CrossAttention) with
+      * `xformers.ops.memory_efficient_attention(q, k, v, attn_bias=None, op=...)` stood in for by its published definition,
+        softmax(q k^T / sqrt(d)) v over [B * heads, N, d] (xformers is absent);
+      * `diffusers.models.attention.CrossAttention` stood in for by an nn.Module with the attributes the subclass reads
+        (to_q / to_k / to_v without bias, to_out = [Linear, Dropout], heads, dim_head);
+      * the REAL vendored ToMe merge (nonfree/ToMe/tome/merge.py) and tome/utils.parse_r.
+    Returns (memory_efficient_cross_attention module, tome_memory_efficient_cross_attention module)."""
+    import torch
+    from torch import nn
+    if "xformers" not in sys.modules or not hasattr(sys.modules["xformers"], "ops"):
+        xf = types.ModuleType("xformers")
+        ops = types.ModuleType("xformers.ops")
+
+        def memory_efficient_attention(q, k, v, attn_bias=None, op=None):
+            assert attn_bias is None
+            s = (q @ k.transpose(-1, -2)) * (q.shape[-1] ** -0.5)
+            return torch.softmax(s, dim=-1) @ v
+        ops.memory_efficient_attention = memory_efficient_attention
+        xf.ops = ops
+        sys.modules["xformers"], sys.modules["xformers.ops"] = xf, ops
+    gyre_ddim()
+    if "diffusers.models" not in sys.modules:
+        sys.modules["diffusers.models"] = types.ModuleType("diffusers.models")
+        sys.modules["diffusers"].models = sys.modules["diffusers.models"]
+    if "diffusers.models.attention" not in sys.modules:
+        att = types.ModuleType("diffusers.models.attention")
+
+        class CrossAttention(nn.Module):
+            def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, dropout=0.0):
+                super().__init__()
+                inner = dim_head * heads
+                cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+                self.heads, self.dim_head = heads, dim_head
+                self.to_q = nn.Linear(query_dim, inner, bias=False)
+                self.to_k = nn.Linear(cross_attention_dim, inner, bias=False)
+                self.to_v = nn.Linear(cross_attention_dim, inner, bias=False)
+                # the subclass calls `self.to_out(out)`: the CrossAttention it was written against held an nn.Sequential
+                self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(dropout))
+        att.CrossAttention = CrossAttention
+        sys.modules["diffusers.models.attention"] = att
+        sys.modules["diffusers.models"].attention = att
+    tome_merge()
+    _load("tome", os.path.join(REF, "nonfree/ToMe/tome"), "utils")
+    out = []
+    for name, rel in (("_gyre_mem_eff_attn", "gyre/pipeline/models/memory_efficient_cross_attention.py"),
+                      ("_gyre_tome_mem_eff_attn", "nonfree/tome_memory_efficient_cross_attention.py")):
+        if name not in sys.modules:
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+        out.append(sys.modules[name])
+    return tuple(out)

@@ -868,6 +868,45 @@ def pin_hints():
           "bit-exact against gyre/pipeline/unet/core.py")
 
 
+def pin_attention():
+    """PINS the oracle's attention module (oracle/unet.py:attention - projections, head split, softmax(QK^T/sqrt d)V, output
+    projection, and the ToMe K/V merge inside it) against the reference's own modules: MemoryEfficientCrossAttention
+    (gyre/pipeline/models/memory_efficient_cross_attention.py) and ToMeMemoryEfficientCrossAttention
+    (nonfree/tome_memory_efficient_cross_attention.py, with the REAL vendored tome.merge).  Stand-ins: xformers'
+    memory_efficient_attention by its definition, diffusers' CrossAttention base class by its attribute set."""
+    from oracle.unet import attention as oattn
+    mea, tmea = _vendored.gyre_attention_modules()
+    out = {}
+    g = torch.Generator().manual_seed(19)
+    for name, (C_, heads, N_, ctx_dim, L, r) in {"self": (64, 4, 64, None, 0, 0), "cross": (64, 4, 64, 48, 77, 0),
+                                                  "self_d40": (80, 2, 96, None, 0, 0),
+                                                  "tome_r16": (64, 4, 64, None, 0, 16), "tome_half": (64, 4, 64, None, 0, 32),
+                                                  "tome_odd": (64, 2, 51, None, 0, 20)}.items():
+        torch.manual_seed(3)
+        d = C_ // heads
+        if r:
+            m = tmea.ToMeMemoryEfficientCrossAttention(C_, ctx_dim, heads=heads, dim_head=d).eval()
+            m._tome_info = {"r": [r], "class_token": False, "distill_token": False, "trace_source": False, "size": None,
+                            "source": None}
+        else:
+            m = mea.MemoryEfficientCrossAttention(C_, ctx_dim, heads=heads, dim_head=d).eval()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        sd["to_out.0.bias"] = 0.1 * torch.randn(C_, generator=g)
+        m.load_state_dict(sd)
+        x = torch.randn(2, N_, C_, generator=g)
+        ctx = torch.randn(2, L, ctx_dim, generator=g) if ctx_dim else None
+        with torch.no_grad():
+            ref = m(x, context=ctx)
+            P = {f"a.{k}": v for k, v in sd.items()}
+            mine = oattn(P, "a", x, ctx, heads, tome_r=r)
+        err = (ref - mine).abs().max().item()
+        assert err <= 2e-6, f"attention module ({name}): {err}"
+        out[name] = {"config": (C_, heads, N_, ctx_dim, L, r), "state_dict": sd, "x": x, "ctx": ctx, "out": ref}
+        print(f"  attention {name}: max abs diff {err:.2e}")
+    torch.save(out, os.path.join(GOLD, "attention.pt"))
+    print("attention: oracle module == MemoryEfficientCrossAttention / ToMeMemoryEfficientCrossAttention")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -918,12 +957,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,controlnet,hints,oracle")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,controlnet,hints,attention,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
-             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "controlnet": pin_controlnet, "hints": pin_hints, "oracle": lambda: oracle_fixtures(a.full)}
+             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "controlnet": pin_controlnet, "hints": pin_hints, "attention": pin_attention, "oracle": lambda: oracle_fixtures(a.full)}
     for name, fn in parts.items():
         if not a.only or name in a.only.split(","):
             fn()

@@ -249,3 +249,19 @@ def test_controlnet_oracle_matches_reference_fixture():
             sums = [float(d.double().sum()) for d in down] + [float(mid.double().sum())]
             for a, b in zip(sums, g["sums"][tn]):
                 assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (order, tn)
+
+
+def test_attention_module_oracle_matches_reference_fixture():
+    """tests/golden/attention.pt: outputs of the REFERENCE's MemoryEfficientCrossAttention / ToMeMemoryEfficientCrossAttention
+    modules (scripts/make_golden.py:pin_attention; real vendored tome.merge inside the ToMe variant)."""
+    import os
+    import torch
+    from oracle.unet import attention
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "attention.pt"))
+    assert set(G) == {"self", "cross", "self_d40", "tome_r16", "tome_half", "tome_odd"}
+    for name, g in G.items():
+        C_, heads, N_, ctx_dim, L, r = g["config"]
+        P = {f"a.{k}": v for k, v in g["state_dict"].items()}
+        with torch.no_grad():
+            out = attention(P, "a", g["x"], g["ctx"], heads, tome_r=r)
+        assert (out - g["out"]).abs().max().item() <= 2e-6, name
