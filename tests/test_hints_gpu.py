@@ -66,7 +66,9 @@ def test_pipeline_with_hints_vs_oracle(setup, name, cn_kw, ad_kw, execution):
         ohints.append(oh.ControlnetHint(s.o_cn, s.img, **cn_kw))
     if ad_kw is not None:
         hints.append(B200T2iHint(s.ad, s.img.cuda(), **ad_kw))
-        ohints.append(oh.T2iHint(s.o_ad, s.img, **ad_kw))
+        # (the reference adds the states to the UNet's hidden states as they are: its hint batch has to equal the sample
+        # batch; the product expands a single hint image to the batch itself)
+        ohints.append(oh.T2iHint(s.o_ad, s.img.expand(2, -1, -1, -1), **ad_kw))
     seeds, steps = [420420420, 420420421], 8
     out = s.pipe(s.emb.cuda(), s.unc.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
                  generator=[torch.Generator("cpu").manual_seed(x) for x in seeds], sampler="k_euler_ancestral",

@@ -79,7 +79,7 @@ def test_to_png_bytes_mirrors_reference_signature():
     u8 = (x * 255).round().to(torch.uint8).permute(0, 2, 3, 1).numpy()
     for f, ref in zip(files, u8):
         assert np.array_equal(_decode_pil(f, ref.shape), ref)
-    one = to_png_bytes(x[0].half().cuda())
+    one = to_png_bytes(x[0].cuda())                      # [C, H, W] like the reference's ndim == 3 branch
     assert len(one) == 1 and one[0] == files[0]
     rgba = torch.rand(1, 4, 8, 8, generator=g)
     dec = _decode_pil(to_png_bytes(rgba.cuda())[0], (8, 8, 4))
