@@ -5,7 +5,10 @@
     scripts/make_golden.py:pin_hints against the reference's own classes over fake models (tests/golden/hints.pt).
   * `ControlnetHint.__call__`, `T2iHint.__call__` follow gyre/pipeline/unified_pipeline.py:957-1058 and :925-939
     (UnifiedPipelineHint_Controlnet / _T2i.standard_call).  unified_pipeline.py imports diffusers at module level and cannot
-    be loaded here: these two are PARITY UNPINNED restatements (mask-less hints, 4-channel latents)."""
+    be loaded plainly; scripts/_vendored.py:gyre_unified_pipeline loads it with the absent third-party packages stood in for
+    by empty classes, and scripts/make_golden.py:pin_hint_classes runs the reference's two classes inside the reference's own
+    wrapper stack / scheduler / Txt2imgMode: PINNED, 7 runs bit-identical (tests/golden/hint_classes.pt; mask-less hints,
+    4-channel latents)."""
 from __future__ import annotations
 
 from types import SimpleNamespace

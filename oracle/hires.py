@@ -10,7 +10,10 @@ The easing curves themselves live in a third-party dependency that is absent her
 (pyproject.toml:24): `EasingBase.ease(alpha)` = end * f(t) + start * (1 - f(t)), t = alpha / duration, with the
 published Penner in-out curves restated below.  Everything else is PINNED: scripts/make_golden.py runs the reference's
 own hires_fix.py / graft.py / easing.py / resize_right.py (with these curves standing in for the absent package) and
-asserts this restatement reproduces them bit for bit (tests/golden/hires.pt).
+asserts this restatement reproduces them bit for bit (tests/golden/hires.pt); the request-level compositions
+(hires_txt2img_latents, hires_image_mode_latents, grafted_inpaint_latents) are pinned against UnifiedPipeline.__call__
+itself - the reference's mode tree deciding about the hires fix and the graft (scripts/make_golden.py:pin_call,
+tests/golden/call.pt).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may import this module.
 """

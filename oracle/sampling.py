@@ -8,7 +8,10 @@ Follows (all under /root/reference):
   gyre/pipeline/common_scheduler.py:410-428,430-541,555-623     KDiffusionScheduler
   gyre/pipeline/unet/cfg.py:41-57                               CFGUNet_Parallel
   gyre/pipeline/randtools.py:39-64                              batched_randn
-Pinned against the vendored k-diffusion sources by scripts/make_golden.py -> tests/golden.
+Pinned against the vendored k-diffusion sources by scripts/make_golden.py -> tests/golden, and - the request-level
+functions txt2img_latents / image_mode_latents / image_mode_phases with the CFG wrappers - against the reference's OWN mode
+classes, KDiffusionScheduler / DiffusersScheduler and UnifiedPipeline.__call__ (pin_segment / pin_call: 26 runs, bit-identical
+final latents; tests/golden/segment.pt, call.pt; re-checked without /root/reference by tests/test_reference_segment_cpu.py).
 """
 from __future__ import annotations
 
@@ -137,6 +140,18 @@ class CFGParallel:
         kw = {"added_cond_kwargs": self.added} if self.added is not None else {}
         noise_pred = self.unet(latents, t, encoder_hidden_states=self.emb, **kw).sample
         u, g = noise_pred.chunk(2)
+        return u + self.guidance_scale * (g - u)
+
+
+class CFGSequential:
+    """cfg.py:27-38: two UNet calls of batch B (guided first), same combination."""
+
+    def __init__(self, unet, uncond_emb, cond_emb, guidance_scale):
+        self.unet, self.unc, self.cond, self.guidance_scale = unet, uncond_emb, cond_emb, guidance_scale
+
+    def __call__(self, latents, t):
+        g = self.unet(latents, t, encoder_hidden_states=self.cond).sample
+        u = self.unet(latents, t, encoder_hidden_states=self.unc).sample
         return u + self.guidance_scale * (g - u)
 
 

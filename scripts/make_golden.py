@@ -907,6 +907,360 @@ def pin_attention():
     print("attention: oracle module == MemoryEfficientCrossAttention / ToMeMemoryEfficientCrossAttention")
 
 
+def _reference_segment(up, unet_like, vae_like, unc, emb, *, kind, sampler_fn, steps, seeds, height, width, sample_size,
+                       image=None, mask_image=None, strength=0.8, guidance_scale=7.5, cfg_execution="parallel",
+                       latents_dtype=torch.float32, prediction_type="epsilon", eta=None, karras_rho=None, hints=()):
+    """The hot segment of UnifiedPipeline.__call__ (unified_pipeline.py:2284-2483) driven with the REFERENCE's own classes -
+    CFGUNetFromDiffusersUNet / UNetWithEmbeddings / CFGChildUnets / CFGUNet_* (unet/core.py, unet/cfg.py), the mode classes
+    (unified_pipeline.py:126-696), KDiffusionScheduler (common_scheduler.py) over the vendored k-diffusion - around a
+    DiffusersUNet-protocol object and a VAE-protocol object.  The glue below is the call sequence of `__call__`."""
+    from types import SimpleNamespace as SN
+    cs = sys.modules["gyre.pipeline.common_scheduler"]
+    core = sys.modules["gyre.pipeline.unet.core"]
+    cfgm = sys.modules["gyre.pipeline.unet.cfg"]
+    dev = torch.device("cpu")
+    B = len(seeds)
+    generators = [torch.Generator(device="cpu").manual_seed(s_) for s_ in seeds]
+    pipeline = SN(vae_scale_factor=8, execution_device=dev, unet=unet_like, vae=vae_like, vae_dtype=torch.float32,
+                  get_unet_sample_size=lambda u: sample_size)
+    cscheduler = cs.KDiffusionScheduler(sampler_fn, generators, dev, latents_dtype)
+    unet = core.CFGUNetFromDiffusersUNet(unet_like)
+    grouped = {}
+    for h in hints:
+        grouped.setdefault(type(h), []).append(h)
+    for cls, hs in grouped.items():
+        unet = cls.wrap_unet(unet, list(hs))
+    unet_cfg = cfgm.CFGChildUnets(g=core.UNetWithEmbeddings(unet, emb, "g"), u=core.UNetWithEmbeddings(unet, unc, "u"),
+                                  f=core.UNetWithEmbeddings(unet, torch.cat([unc, emb]), "f"))
+    common = dict(pipeline=pipeline, scheduler=cscheduler, generators=generators, width=width, height=height, image=image,
+                  mask_image=mask_image, latents_dtype=latents_dtype, batch_total=B, num_inference_steps=steps,
+                  strength=strength, do_classifier_free_guidance=True, cfg_execution=cfg_execution,
+                  latent_debugger=SN(log=lambda *a, **k: None))
+    mode = {"txt2img": up.Txt2imgMode, "img2img": up.Img2imgMode, "inpaint": up.EnhancedInpaintMode,
+            "runway": up.EnhancedRunwayInpaintMode}[kind](**common)
+    unet_cfg = unet_cfg.wrap_all(mode.wrap_unet)
+    eps_unet = mode.wrap_guidance_unet(unet_cfg, guidance_scale, B)
+    cscheduler.set_eps_unets([eps_unet])
+    targs = {"strength": strength} if image is not None else {}
+    cscheduler.set_timesteps(steps, config=cs.SchedulerConfig(eta=eta, karras_rho=karras_rho), prediction_type=prediction_type,
+                             **targs)
+    cscheduler.unet = mode.wrap_k_unet(cscheduler.unets[0])
+    latents = mode.generateLatents()
+    smod = __import__("inspect").getmodule(getattr(sampler_fn, "func", sampler_fn))
+    keep = {k_: getattr(smod, k_) for k_ in ("torch", "trange", "tqdm") if hasattr(smod, k_)}
+    try:
+        with torch.no_grad():
+            return cscheduler.loop(latents, lambda it: it)
+    finally:
+        for k_, v_ in keep.items():
+            setattr(smod, k_, v_)
+
+
+def pin_segment():
+    """PINS the oracle's restatement of the host-side hot segment (oracle/sampling.py: txt2img_latents, image_mode_latents -
+    generateLatents, the image modes, KDiffusionScheduler.set_timesteps / loop, the CFG wrapper stack) against the reference's
+    own classes run here (scripts/_vendored.py:gyre_unified_pipeline loads gyre/pipeline/unified_pipeline.py and
+    common_scheduler.py with absent third-party packages stood in for by empty classes).  Only the UNet and the VAE under the
+    segment are the oracle's (diffusers is absent)."""
+    up = _vendored.gyre_unified_pipeline()
+    _, ksamp, _ = _vendored.k_diffusion()
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    unet = OracleUNet(cfg, P)
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1)
+    seeds = [420420420, 420420421]
+    out = {}
+    fns = {"euler_a": ksamp.sample_euler_ancestral, "euler": ksamp.sample_euler, "heun": ksamp.sample_heun,
+           "dpm_2": ksamp.sample_dpm_2, "dpm_2_a": ksamp.sample_dpm_2_ancestral, "lms": ksamp.sample_lms,
+           "dpmpp_2s_a": ksamp.sample_dpmpp_2s_ancestral, # samplers.py:58-60 registers gyre's DPM++ 2M with these two arguments bound
+           "dpmpp_2m": __import__("functools").partial(_vendored.gyre_dpmpp_2m().sample_dpmpp_2m, warmup_lms=True, ddim_cutoff=0.1)}
+    for (name, steps, hw, execution, ldt) in (("euler_a", 6, (128, 128), "parallel", torch.float32),
+                                              ("euler_a", 5, (128, 128), "sequential", torch.float32),
+                                              ("euler_a", 5, (128, 128), "parallel", torch.float16),
+                                              ("euler", 5, (192, 128), "parallel", torch.float32),
+                                              ("euler_a", 4, (64, 128), "parallel", torch.float32),
+                                              ("heun", 4, (128, 128), "parallel", torch.float32),
+                                              ("dpm_2", 4, (128, 128), "parallel", torch.float32),
+                                              ("dpm_2_a", 4, (128, 128), "parallel", torch.float32),
+                                              ("lms", 5, (128, 128), "parallel", torch.float32),
+                                              ("dpmpp_2s_a", 4, (128, 128), "parallel", torch.float32),
+                                              ("dpmpp_2m", 5, (128, 128), "parallel", torch.float32)):
+        u_ = unet
+        if ldt != torch.float32:
+            class _Cast:                      # an fp32 UNet under fp16 latents (the CPU has no fp16 kernels for the blocks)
+                config = unet.config
+
+                def __call__(self, latents, t, **kw):
+                    return OracleUNet._Out(unet(latents.float(), t, **{k: (v.float() if torch.is_tensor(v) else v)
+                                                                       for k, v in kw.items()}).sample.to(latents.dtype))
+            u_ = _Cast()
+        ref = _reference_segment(up, u_, None, unc, emb, kind="txt2img", sampler_fn=fns[name], steps=steps, seeds=seeds,
+                                 height=hw[0], width=hw[1], sample_size=16, cfg_execution=execution, latents_dtype=ldt)
+        cfgu = (osamp.CFGParallel if execution == "parallel" else osamp.CFGSequential)(u_, unc, emb, 7.5)
+        mine = osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=hw[0], width=hw[1], sample_size=16, seeds=seeds,
+                                     steps=steps, sampler=name, latent_dtype=ldt)
+        err = (ref.float() - mine.float()).abs().max().item() / ref.float().abs().max().item()
+        key = f"txt2img/{name}/{steps}/{hw[0]}x{hw[1]}/{execution}/{str(ldt).split('.')[-1]}"
+        print(f"  {key}: rel diff {err:.2e}")
+        # (fp16 latents: the reference rounds every update to fp16, the oracle keeps the state in fp32 and reproduces the casts
+        # that change the RESULT'S MEANING - sigma, noise draws - so this case agrees to fp16 rounding only)
+        assert err < (2e-5 if ldt == torch.float32 else 4e-3), key
+        out[key] = ref
+    vcfg = VAEConfig.tiny()
+    VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+    gi = torch.Generator().manual_seed(21)
+    emb_i = torch.randn(2, 77, cfg.cross_attention_dim, generator=gi)
+    unc_i = torch.randn(1, 77, cfg.cross_attention_dim, generator=gi).expand(2, -1, -1).contiguous()
+    image = torch.rand(1, 3, 128, 128, generator=gi)
+    mask = torch.zeros(1, 1, 128, 128)
+    mask[:, :, 32:96, 40:104] = 1.0
+    cfg9 = UNetConfig.tiny(in_channels=9)
+    unet9 = OracleUNet(cfg9, synth_params(unet_param_shapes(cfg9), seed=1234))
+    for kind, strength, u_ in (("img2img", 0.6, unet), ("runway", 0.75, unet9), ("runway", 1.0, unet9), ("inpaint", 0.8, unet)):
+        vae = OracleVAE(vcfg, VP)
+        kw = {} if kind == "img2img" else {"mask_image": mask}
+        ref = _reference_segment(up, u_, vae, unc_i, emb_i, kind=kind, sampler_fn=ksamp.sample_euler_ancestral, steps=10,
+                                 seeds=seeds, height=128, width=128, sample_size=16, image=image, strength=strength, **kw)
+        mine = osamp.image_mode_latents(u_, OracleVAE(vcfg, VP), unc_i, emb_i, 7.5, image=image, seeds=seeds, steps=10,
+                                        strength=strength, **kw)
+        err = (ref.float() - mine.float()).abs().max().item() / ref.float().abs().max().item()
+        key = f"{kind}/{strength}"
+        print(f"  {key}: rel diff {err:.2e}")
+        assert err < 2e-5, key
+        out[key] = ref
+    torch.save(out, os.path.join(GOLD, "segment.pt"))
+    print(f"segment: {len(out)} runs of the reference's own mode / scheduler / CFG classes == oracle/sampling.py")
+
+
+def pin_hint_classes():
+    """PINS oracle/hints.py ControlnetHint / T2iHint (and with them the hint path of gyre_b200/hints.py, tested against the
+    oracle on the GPU) against the reference's UnifiedPipelineHint_Controlnet / UnifiedPipelineHint_T2i run inside the
+    reference's own wrapper stack, scheduler and Txt2imgMode (see pin_segment); the ControlNet / adapter / UNet under them are
+    the oracle's."""
+    from types import SimpleNamespace as SN
+    from oracle import controlnet as ocn
+    from oracle import hints as oh
+    from oracle import t2i_adapter as oad
+    up = _vendored.gyre_unified_pipeline()
+    _, ksamp, _ = _vendored.k_diffusion()
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    Pcn = synth_params(ocn.controlnet_param_shapes(cfg), seed=77)
+    akw = dict(channels=list(cfg.block_out_channels), nums_rb=2, cin=192, ksize=1, sk=True, use_conv=False)
+    Pad = synth_params(oad.adapter_param_shapes(**akw), seed=91)
+    unet = OracleUNet(cfg, P)
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).expand(2, -1, -1).contiguous()
+    img = torch.rand(1, 3, 128, 128, generator=g).half().float()
+
+    class CN:
+        config = {}
+
+        def __call__(self, cnlatents, t, encoder_hidden_states, controlnet_cond):
+            with torch.no_grad():
+                down, mid = ocn.controlnet_forward(Pcn, cfg, cnlatents, t, encoder_hidden_states, controlnet_cond)
+            return SN(down_block_res_samples=down, mid_block_res_sample=mid)
+
+    class _Cfg(dict):
+        __getattr__ = dict.__getitem__
+
+    class AD:
+        config = _Cfg(cin=192)
+
+        def __call__(self, x):
+            with torch.no_grad():
+                return oad.adapter_forward(Pad, x, **{k: v for k, v in akw.items() if k != "cin"})
+
+        def parameters(self):
+            return iter([torch.zeros(1)])
+
+    seeds, steps = [420420420, 420420421], 5
+    cases = [("controlnet", dict(weight=1.0, soft_injection=False, cfg_only=False), None, "parallel"),
+             ("controlnet soft 0.7", dict(weight=0.7, soft_injection=True, cfg_only=False), None, "parallel"),
+             ("controlnet cfg_only", dict(weight=0.8, soft_injection=True, cfg_only=True), None, "parallel"),
+             ("controlnet cfg_only sequential", dict(weight=0.8, soft_injection=False, cfg_only=True), None, "sequential"),
+             ("t2i", None, dict(weight=1.0, soft_injection=False, cfg_only=False), "parallel"),
+             ("t2i soft cfg_only + controlnet", dict(weight=0.5, soft_injection=False, cfg_only=False),
+              dict(weight=0.9, soft_injection=True, cfg_only=True), "parallel"),
+             ("t2i cfg_only sequential", None, dict(weight=1.0, soft_injection=False, cfg_only=True), "sequential")]
+    out = {}
+    for name, cn_kw, ad_kw, execution in cases:
+        rh, ohints = [], []
+        if cn_kw is not None:
+            rh.append(up.UnifiedPipelineHint_Controlnet(CN(), img, None, cn_kw["weight"], cn_kw["soft_injection"],
+                                                        cn_kw["cfg_only"], batch_total=2))
+            ohints.append(oh.ControlnetHint(CN(), img, **cn_kw))
+        if ad_kw is not None:
+            # (the reference adds adapter states to the hidden states as they are: hint batch = sample batch)
+            rh.append(up.UnifiedPipelineHint_T2i(AD(), img.expand(2, -1, -1, -1), None, None, None, None, ad_kw["weight"],
+                                                 ad_kw["soft_injection"], ad_kw["cfg_only"], None))
+            ohints.append(oh.T2iHint(AD(), img.expand(2, -1, -1, -1), **ad_kw))
+        for h in rh:
+            h.to(torch.device("cpu"), torch.float32)
+        ref = _reference_segment(up, unet, None, unc, emb, kind="txt2img", sampler_fn=ksamp.sample_euler_ancestral, steps=steps,
+                                 seeds=seeds, height=128, width=128, sample_size=16, cfg_execution=execution, hints=rh)
+        eps = oh.guided_eps_unet(unet, unc, emb, 7.5, ohints, parallel=execution == "parallel")
+        with torch.no_grad():
+            mine = osamp.txt2img_latents(eps, batch=2, in_channels=4, height=128, width=128, sample_size=16, seeds=seeds,
+                                         steps=steps, sampler="euler_a")
+        err = (ref - mine).abs().max().item() / ref.abs().max().item()
+        print(f"  hints/{name}: rel diff {err:.2e}")
+        assert err < 2e-5, name
+        out[name] = ref
+    torch.save(out, os.path.join(GOLD, "hint_classes.pt"))
+    print(f"hint classes: {len(out)} runs of UnifiedPipelineHint_Controlnet / _T2i inside the reference's stack == oracle/hints.py")
+
+
+def _reference_call(up, *, unet, vae, unc, emb, sampler_fn, seeds, inpaint_unet=None, depth_unet=None, options=None,
+                    sample_size=16, **call_kwargs):
+    """UnifiedPipeline.__call__ ITSELF (unified_pipeline.py:1722-2531) on an instance assembled without `__init__` (which
+    registers diffusers modules): mode-tree construction with its hires-fix / graft decisions, the per-leaf wrapper stacks,
+    scheduler, loop, split.  Stand-ins: the text-embedding calculator returns the given embeddings (LPW is pinned on its own),
+    `vae_decode` captures what it is handed (= final latents / 0.18215) and returns a blank image."""
+    from types import SimpleNamespace as SN
+    up.DiffusionPipeline.device = torch.device("cpu")
+    pipe = object.__new__(up.UnifiedPipeline)
+    pipe.unet, pipe.vae, pipe.inpaint_unet, pipe.depth_unet = unet, vae, inpaint_unet, depth_unet
+    pipe.text_encoder = pipe.inpaint_text_encoder = pipe.depth_text_encoder = None
+    pipe.tokenizer = pipe.clip_tokenizer = SN(model_max_length=77)
+    pipe.clip_model = pipe.safety_checker = pipe.feature_extractor = pipe.hintset_manager = None
+    pipe.scheduler = sampler_fn
+    pipe.vae_scale_factor, pipe.vae_dtype = 8, torch.float32
+    pipe._grafted_depth = pipe._grafted_inpaint = False
+    pipe._hires_fix, pipe._hires_threshold_fraction, pipe._hires_oos_fraction, pipe._hires_image_oos_fraction = True, 0.0333, 0.6, 1.0
+    pipe._structured_diffusion, pipe._text_embedding_layer = False, "final"
+    pipe.clip_default_config = SN(guidance_scale=0, guidance_base="guided", gradient_length=15, gradient_threshold=0.01,
+                                  gradient_maxloss=1.0, vae_cutouts=2, approx_cutouts=2, no_cutouts=False)
+    for k_, v_ in (options or {}).items():
+        setattr(pipe, k_, v_)
+    pipe.set_tiling_mode = lambda tiling: None
+    pipe.progress_bar = lambda it: it
+    pipe.get_unet_sample_size = lambda u: sample_size          # (the reference forces >= 64; the tiny UNets are 16)
+    captured = {}
+
+    def vae_decode(latents):
+        captured["z"] = latents.clone()
+        return torch.zeros(latents.shape[0], 3, latents.shape[2] * 8, latents.shape[3] * 8)
+    pipe.vae_decode = vae_decode
+
+    class Emb:                                                 # LPWTextEmbedding's surface as __call__ uses it (:2269-2304)
+        def __init__(self, **kw):
+            pass
+
+        def get_embeddings(self, prompt, uncond_prompt=None):
+            return emb, (unc if uncond_prompt is not None else None)
+
+        def repeat(self, x, n):
+            return x
+    saved = up.LPWTextEmbedding
+    up.LPWTextEmbedding = Emb
+    # __call__ patches `torch` / `trange` / `tqdm` inside the sampler's module (gyre/patching.py): put them back afterwards
+    smod = __import__("inspect").getmodule(getattr(sampler_fn, "func", sampler_fn))
+    keep = {k_: getattr(smod, k_) for k_ in ("torch", "trange", "tqdm") if hasattr(smod, k_)}
+    try:
+        pipe(prompt=["a"] * len(seeds), generator=[torch.Generator("cpu").manual_seed(s_) for s_ in seeds],
+             scheduler=sampler_fn, output_type="tensor", return_dict=False, run_safety_checker=False, **call_kwargs)
+    finally:
+        up.LPWTextEmbedding = saved
+        for k_, v_ in keep.items():
+            setattr(smod, k_, v_)
+    return captured["z"]
+
+
+def pin_call():
+    """PINS the oracle's compositions of a whole request (oracle/hires.py hires_txt2img_latents / hires_image_mode_latents /
+    grafted_inpaint_latents, oracle/sampling.py txt2img_latents / image_mode_latents) against UnifiedPipeline.__call__ itself,
+    run here from /root/reference (see _reference_call) over the oracle UNets / VAE."""
+    from oracle import hires as ohires
+    up = _vendored.gyre_unified_pipeline()
+    _, ksamp, _ = _vendored.k_diffusion()
+    cfg = UNetConfig.tiny()
+    P = synth_params(unet_param_shapes(cfg), seed=1234)
+    unet = OracleUNet(cfg, P)
+    cfg9 = UNetConfig.tiny(in_channels=9)
+    unet9 = OracleUNet(cfg9, synth_params(unet_param_shapes(cfg9), seed=1234))
+    vcfg = VAEConfig.tiny()
+    VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1).contiguous()
+    seeds = [420420420, 420420421]
+    out = {}
+
+    def check(key, ref_z, mine):
+        ref = 0.18215 * ref_z
+        err = (ref - mine).abs().max().item() / mine.abs().max().item()
+        print(f"  call/{key}: rel diff {err:.2e}")
+        assert err < 2e-6, key
+        out[key] = ref
+
+    # txt2img at the native size (no hires fix: below the threshold)
+    z = _reference_call(up, unet=unet, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ksamp.sample_euler_ancestral,
+                        seeds=seeds, height=128, width=128, num_inference_steps=6)
+    mine = osamp.txt2img_latents(osamp.CFGParallel(unet, unc, emb, 7.5), batch=2, in_channels=4, height=128, width=128,
+                                 sample_size=16, seeds=seeds, steps=6, sampler="euler_a")
+    check("txt2img 128", z, mine)
+
+    # above the native size: the hires fix engages by default (natural-size twin, HiresUnetWrapper)
+    for (H, W) in ((192, 192), (256, 192)):
+        z = _reference_call(up, unet=unet, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ksamp.sample_euler_ancestral,
+                            seeds=seeds, height=H, width=W, num_inference_steps=5)
+        mine = ohires.hires_txt2img_latents(osamp.CFGParallel(unet, unc, emb, 7.5), batch=2, height=H, width=W, sample_size=16,
+                                            seeds=seeds, steps=5, oos_fraction=0.6)
+        check(f"hires txt2img {H}x{W}", z, mine)
+    # ... and hires_fix=False gives the plain single-leaf run
+    z = _reference_call(up, unet=unet, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ksamp.sample_euler_ancestral,
+                        seeds=seeds, height=192, width=192, num_inference_steps=5, hires_fix=False)
+    mine = osamp.txt2img_latents(osamp.CFGParallel(unet, unc, emb, 7.5), batch=2, in_channels=4, height=192, width=192,
+                                 sample_size=16, seeds=seeds, steps=5, sampler="euler_a")
+    check("txt2img 192 hires off", z, mine)
+
+    gi = torch.Generator().manual_seed(21)
+    image = torch.rand(1, 3, 128, 128, generator=gi)
+    mask = torch.zeros(1, 1, 128, 128)
+    mask[:, :, 32:96, 40:104] = 1.0
+    big_image = torch.rand(1, 3, 192, 192, generator=gi)
+    big_mask = torch.zeros(1, 1, 192, 192)
+    big_mask[:, :, 48:144, 60:156] = 1.0
+    # image modes through __call__ (mode selection :2055-2066): img2img, Runway inpaint (9-channel UNet), legacy inpaint
+    for key, u_, kw in (("img2img", unet, dict(image=image, strength=0.6)),
+                        ("runway inpaint", unet9, dict(image=image, mask_image=mask, strength=0.75)),
+                        ("legacy inpaint", unet, dict(image=image, mask_image=mask, strength=0.8))):
+        z = _reference_call(up, unet=u_, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ksamp.sample_euler_ancestral,
+                            seeds=seeds, inpaint_unet=u_ if u_ is unet9 else None, height=128, width=128, num_inference_steps=8, **kw)
+        mine = osamp.image_mode_latents(u_, OracleVAE(vcfg, VP), unc, emb, 7.5, seeds=seeds, steps=8,
+                                        **{("mask_image" if k == "mask_image" else k): v for k, v in kw.items()})
+        check(key, z, mine)
+    # grafted inpaint (:2069-2098): inpaint UNet early, main UNet with the legacy blend late
+    z = _reference_call(up, unet=unet, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ksamp.sample_euler_ancestral,
+                        seeds=seeds, inpaint_unet=unet9, options={"_grafted_inpaint": True}, height=128, width=128,
+                        num_inference_steps=8, image=image, mask_image=mask, strength=0.75)
+    mine = ohires.grafted_inpaint_latents(unet9, unet, OracleVAE(vcfg, VP), unc, emb, 7.5, image=image, mask_image=mask,
+                                          seeds=seeds, steps=8, strength=0.75)
+    check("grafted inpaint", z, mine)
+    # hires fix over the image modes (oos fraction 1.0 when an image is given, :1840-1843)
+    for key, u_, kw in (("hires img2img", unet, dict(image=big_image, strength=0.6)),
+                        ("hires runway inpaint", unet9, dict(image=big_image, mask_image=big_mask, strength=0.75))):
+        z = _reference_call(up, unet=u_, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ksamp.sample_euler_ancestral,
+                            seeds=seeds, inpaint_unet=u_ if u_ is unet9 else None, height=192, width=192, num_inference_steps=6, **kw)
+        mine = ohires.hires_image_mode_latents(u_, OracleVAE(vcfg, VP), unc, emb, 7.5, seeds=seeds, steps=6, sample_size=16,
+                                               oos_fraction=1.0, **kw)
+        check(key, z, mine)
+    # a diffusers-protocol scheduler (DiffusersScheduler wrapper, common_scheduler.py:179-331) around the in-tree DDIM copy
+    ddim = _vendored.gyre_ddim().DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                              clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    z = _reference_call(up, unet=unet, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ddim, seeds=seeds, height=128,
+                        width=128, num_inference_steps=8)
+    mine = osamp.txt2img_latents(osamp.CFGParallel(unet, unc, emb, 7.5), batch=2, in_channels=4, height=128, width=128,
+                                 sample_size=16, seeds=seeds, steps=8, sampler="ddim")
+    check("ddim", z, mine)
+    torch.save(out, os.path.join(GOLD, "call.pt"))
+    print(f"call: {len(out)} runs of UnifiedPipeline.__call__ == the oracle's compositions")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -957,12 +1311,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,controlnet,hints,attention,oracle")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,controlnet,hints,attention,segment,hint_classes,call,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
-             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "controlnet": pin_controlnet, "hints": pin_hints, "attention": pin_attention, "oracle": lambda: oracle_fixtures(a.full)}
+             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "controlnet": pin_controlnet, "hints": pin_hints, "attention": pin_attention, "segment": pin_segment, "hint_classes": pin_hint_classes, "call": pin_call, "oracle": lambda: oracle_fixtures(a.full)}
     for name, fn in parts.items():
         if not a.only or name in a.only.split(","):
             fn()
