@@ -385,3 +385,41 @@ def hires_image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *,
                          [sample_size, sample_size], oos_fraction)
     out = S.euler_ancestral_with_u(lambda x, s, u: w(x, s, u), latents, hi["sigmas"], hi["u_off"], gens, latent_dtype)
     return HiresUnetWrapper.split_result(None, out)
+
+
+class WithExtraChannels:
+    """UnetWithExtraChannels (gyre/pipeline/unet/core.py:21-37) around a DiffusersUNet-protocol object: the same un-scaled
+    extra channels (a depth map) appended to the latents at every call."""
+
+    def __init__(self, unet, extra):
+        self.unet, self.extra, self.config = unet, extra, unet.config
+
+    def __call__(self, latents, t, *, encoder_hidden_states, **kw):
+        e = torch.cat([self.extra] * (latents.shape[0] // self.extra.shape[0]))
+        return self.unet(torch.cat([latents, e.to(latents.dtype)], dim=1), t, encoder_hidden_states=encoder_hidden_states)
+
+
+def depth_txt2img_latents(depth_unet, main_unet, uncond_emb, cond_emb, guidance_scale, *, depth_map, seeds, steps, sample_size,
+                          height, width, graft_blend=None, latent_dtype=torch.float32):
+    """A depth hint as UnifiedPipeline composes it (unified_pipeline.py:2004-2013, 2069-2098, 2305-2309): the request goes to
+    the 5-channel depth UNet with the depth map (already 2 * d - 1 at latent resolution) as its fifth input channel; with
+    `graft_blend` (engine option grafted_depth) GraftUnets(root = depth leaf, top = main UNet without the depth input) - both
+    leaves draw their initial latents on the shared generators, the root's start the loop.  PINNED against
+    UnifiedPipeline.__call__ (scripts/make_golden.py:pin_call)."""
+    from . import sampling as S
+    B = len(seeds)
+    depth_cfg = S.CFGParallel(WithExtraChannels(depth_unet, depth_map.expand(B, -1, -1, -1).contiguous()), uncond_emb, cond_emb,
+                              guidance_scale)
+    if graft_blend is None:
+        return S.txt2img_latents(depth_cfg, batch=B, in_channels=4, height=height, width=width, sample_size=sample_size,
+                                 seeds=seeds, steps=steps, sampler="euler_a", latent_dtype=latent_dtype)
+    gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
+    acp = S.sd_alphas_cumprod()
+    den_root = S.EpsDenoiser(depth_cfg, acp)
+    den_top = S.EpsDenoiser(S.CFGParallel(main_unet, uncond_emb, cond_emb, guidance_scale), acp)
+    sig = S.k_sigmas(den_root, steps)
+    h, w = height // 8, width // 8
+    lat_root = S.batched_randn([B, 4, h, w], gens, "cpu", latent_dtype) * sig[0]
+    S.batched_randn([B, 4, h, w], gens, "cpu", latent_dtype)                  # the top leaf's (discarded) draw
+    graft = GraftUnets(lambda x, s, u: den_root(x, s), lambda x, s, u: den_top(x, s), gens, blend=graft_blend)
+    return S.euler_ancestral_with_u(lambda x, s, u: graft(x, s, u), lat_root, sig.float(), 0.0, gens, latent_dtype)

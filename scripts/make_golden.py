@@ -1249,6 +1249,24 @@ def pin_call():
         mine = ohires.hires_image_mode_latents(u_, OracleVAE(vcfg, VP), unc, emb, 7.5, seeds=seeds, steps=6, sample_size=16,
                                                oos_fraction=1.0, **kw)
         check(key, z, mine)
+    # a depth hint: the request goes to the 5-channel depth UNet (:2004-2013), optionally grafted onto the main UNet
+    gim = sys.modules["gyre.images"]
+    pt = sys.modules["gyre.pipeline.prompt_types"]
+    cfg5 = UNetConfig.tiny(in_channels=5)
+    unet5 = OracleUNet(cfg5, synth_params(unet_param_shapes(cfg5), seed=321))
+    # (UnetWithExtraChannels takes the channels as they are: the hint batch has to equal the sample batch, core.py:22-25)
+    depth_img = torch.rand(1, 1, 128, 128, generator=torch.Generator().manual_seed(31)).expand(2, -1, -1, -1).contiguous()
+    depth_map = 2.0 * gim.resize(gim.normalise_tensor(depth_img, 1), (1 / 8, 1 / 8), sharpness=2) - 1.0     # the reference's lines
+    out["depth_map"] = depth_map
+    out["depth_image"] = depth_img
+    blend = {"start": 0.15, "end": 0.75, "easing": "sine"}
+    for key, opts, gb in (("depth", {}, None), ("grafted depth", {"_grafted_depth": blend}, blend)):
+        z = _reference_call(up, unet=unet, vae=OracleVAE(vcfg, VP), unc=unc, emb=emb, sampler_fn=ksamp.sample_euler_ancestral,
+                            seeds=seeds, depth_unet=unet5, options=opts, height=128, width=128, num_inference_steps=7,
+                            hint_images=[pt.HintImage(image=depth_img, hint_type="depth")])
+        mine = ohires.depth_txt2img_latents(unet5, unet, unc, emb, 7.5, depth_map=depth_map, seeds=seeds, steps=7,
+                                            sample_size=16, height=128, width=128, graft_blend=gb)
+        check(key, z, mine)
     # a diffusers-protocol scheduler (DiffusersScheduler wrapper, common_scheduler.py:179-331) around the in-tree DDIM copy
     ddim = _vendored.gyre_ddim().DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
                                               clip_sample=False, set_alpha_to_one=False, steps_offset=1)
@@ -1258,7 +1276,7 @@ def pin_call():
                                  sample_size=16, seeds=seeds, steps=8, sampler="ddim")
     check("ddim", z, mine)
     torch.save(out, os.path.join(GOLD, "call.pt"))
-    print(f"call: {len(out)} runs of UnifiedPipeline.__call__ == the oracle's compositions")
+    print(f"call: {len(out) - 2} runs of UnifiedPipeline.__call__ == the oracle's compositions")
 
 
 def oracle_fixtures(full: bool):

@@ -235,17 +235,6 @@ def test_pipeline_hires_image_modes_vs_oracle(kind):
     assert err < 1.4e-2 * scale
 
 
-class _WithExtraChannels:
-    """Oracle-side UnetWithExtraChannels (gyre/pipeline/unet/core.py:21-37) around an OracleUNet."""
-
-    def __init__(self, unet, extra):
-        self.unet, self.extra, self.config = unet, extra, unet.config
-
-    def __call__(self, latents, t, *, encoder_hidden_states, **kw):
-        e = torch.cat([self.extra] * (latents.shape[0] // self.extra.shape[0]))
-        return self.unet(torch.cat([latents, e.to(latents.dtype)], dim=1), t, encoder_hidden_states=encoder_hidden_states)
-
-
 @pytest.mark.parametrize("grafted", [False, True])
 def test_pipeline_depth_unet_vs_oracle(grafted):
     """A depth hint routes the request to the 5-channel depth UNet (the depth map rides along un-scaled as the fifth
@@ -271,24 +260,11 @@ def test_pipeline_depth_unet_vs_oracle(grafted):
     out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
                generator=[torch.Generator("cpu").manual_seed(s) for s in seeds], sampler="k_euler_ancestral",
                output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True, depth_map=depth.cuda()).latents
-    depth_cfg = osamp.CFGParallel(_WithExtraChannels(OracleUNet(cfg_d, P_d), depth.expand(2, -1, -1, -1)), unc, emb, 7.5)
     with torch.no_grad():
-        if not grafted:
-            ref = osamp.txt2img_latents(depth_cfg, batch=2, in_channels=4, height=128, width=128, sample_size=16, seeds=seeds,
-                                        steps=steps, sampler="euler_a")
-        else:
-            # GraftUnets(root = depth leaf, top = main leaf): both leaves generate their latents (the root's start the
-            # loop), the wrapper picks per pixel inside the window (unified_pipeline.py:2069-2098, graft.py:31-52)
-            gens = [torch.Generator("cpu").manual_seed(s) for s in seeds]
-            acp = osamp.sd_alphas_cumprod()
-            den_root = osamp.EpsDenoiser(depth_cfg, acp)
-            den_top = osamp.EpsDenoiser(osamp.CFGParallel(OracleUNet(cfg_m, P_m), unc, emb, 7.5), acp)
-            sig_full = osamp.k_sigmas(den_root, steps)
-            lat_root = osamp.batched_randn([2, 4, 16, 16], gens, "cpu", torch.float32) * sig_full[0]
-            osamp.batched_randn([2, 4, 16, 16], gens, "cpu", torch.float32)          # the top leaf's (discarded) draw
-            graft = ohires.GraftUnets(lambda x, s, u: den_root(x, s), lambda x, s, u: den_top(x, s), gens, blend=blend)
-            ref = osamp.euler_ancestral_with_u(lambda x, s, u: graft(x, s, u), lat_root, sig_full.float(), 0.0, gens,
-                                               torch.float32)
+        # (the composition is pinned against UnifiedPipeline.__call__ with a depth hint, tests/golden/call.pt)
+        ref = ohires.depth_txt2img_latents(OracleUNet(cfg_d, P_d), OracleUNet(cfg_m, P_m), unc, emb, 7.5, depth_map=depth,
+                                           seeds=seeds, steps=steps, sample_size=16, height=128, width=128,
+                                           graft_blend=blend if grafted else None)
     err = (out.cpu() - ref).abs().max().item()
     scale = ref.abs().max().item()
     print(f"depth UNet (grafted={grafted}): final-latent max abs err {err:.4e} (latent max {scale:.3f})")

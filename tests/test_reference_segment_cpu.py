@@ -100,7 +100,16 @@ def test_whole_call_compositions_match_reference_call(models):
             "ddim": lambda: osamp.txt2img_latents(cfgu, batch=2, in_channels=4, height=128, width=128, sample_size=16,
                                                   seeds=SEEDS, steps=8, sampler="ddim"),
         }
-        assert set(runs) <= set(G) and len(G) == 11
+        cfg5 = UNetConfig.tiny(in_channels=5)
+        unet5 = OracleUNet(cfg5, synth_params(unet_param_shapes(cfg5), seed=321))
+        blend = {"start": 0.15, "end": 0.75, "easing": "sine"}
+        # the depth map is what the reference's own lines made of the hint image (2 * images.resize(.., 1/8, sharpness=2) - 1)
+        runs["grafted depth"] = lambda: ohires.depth_txt2img_latents(unet5, m["unet"], m["unc"], m["emb"], 7.5,
+                                                                     depth_map=G["depth_map"], seeds=SEEDS, steps=7, sample_size=16,
+                                                                     height=128, width=128, graft_blend=blend)
+        runs["depth"] = lambda: ohires.depth_txt2img_latents(unet5, m["unet"], m["unc"], m["emb"], 7.5, depth_map=G["depth_map"],
+                                                             seeds=SEEDS, steps=7, sample_size=16, height=128, width=128)
+        assert set(runs) <= set(G) and len(G) == 13 + 2
         for key, fn in runs.items():
             assert _rel(fn(), G[key]) < 2e-6, key
 
