@@ -894,6 +894,33 @@ def pin_attention():
         sd["to_out.0.bias"] = 0.1 * torch.randn(C_, generator=g)
         m.load_state_dict(sd)
         x = torch.randn(2, N_, C_, generator=g)
+        if r:
+            # ToMe: tokens whose merge plan survives fp16 arithmetic (the GPU test runs the same module in fp16) - every even
+            # token is a noisy copy of one odd token, the noise levels spread so that the scores that rank the merges differ
+            # by more than fp16 resolves; the plan is checked below to have no near-ties on the projected keys
+            for attempt in range(200):
+                nb = N_ // 2
+                base = torch.randn(2, nb, C_, generator=g)
+                na = N_ - nb
+                cos = torch.linspace(0.97, 0.55, na)
+                noise = torch.randn(2, na, C_, generator=g)
+                src = base[:, torch.randperm(nb, generator=g)[torch.arange(na) % nb]]
+                a_tok = src + noise * (1 / cos ** 2 - 1).sqrt()[None, :, None]
+                x = torch.empty(2, N_, C_)
+                x[:, 0::2], x[:, 1::2] = a_tok, base
+                k_ = torch.nn.functional.linear(x, sd["to_k.weight"])
+                k_ = k_ / k_.norm(dim=-1, keepdim=True)
+                sc = k_[:, 0::2] @ k_[:, 1::2].transpose(-1, -2)
+                top2 = sc.topk(2, dim=-1).values
+                # what has to be unambiguous: each token's best partner, and WHICH r tokens are merged (the order inside the two
+                # sets does not matter - attention is invariant to the order of its keys)
+                best = top2[..., 0].sort(dim=-1, descending=True).values
+                r_eff = min(r, na)
+                edge = (best[:, r_eff - 1] - best[:, r_eff]).min().item() if r_eff < na else 1.0
+                if (top2[..., 0] - top2[..., 1]).min() > 0.02 and edge > 5e-3:
+                    break
+            else:
+                raise AssertionError("no tie-free ToMe fixture found")
         ctx = torch.randn(2, L, ctx_dim, generator=g) if ctx_dim else None
         with torch.no_grad():
             ref = m(x, context=ctx)

@@ -226,6 +226,6 @@ def test_attention_module_vs_reference_fixture(name):
     out = N.gemm(o.reshape(-1, C_), sd["to_out.0.weight"].half(), bias=sd["to_out.0.bias"].float()).reshape(B, N_, C_)
     ref = g["out"]
     err = (out.float().cpu() - ref).abs().max().item()
-    # fp16 operands against the fp32 reference module; a merge flipped by fp16 scores (ToMe cases) moves single K / V rows
-    bound = 6e-3 if not r else 2e-2
+    # fp16 operands against the fp32 reference module (the ToMe fixtures are built free of near-ties: the same plan in fp16)
+    bound = 6e-3 if not r else 1e-2
     assert err < bound * max(1.0, ref.abs().max().item()), f"{name}: max abs err {err} (|ref| <= {ref.abs().max().item():.2f})"
