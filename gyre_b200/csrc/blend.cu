@@ -149,4 +149,37 @@ int rand_select(const float* a, const float* b, const float* rnd, float p, int64
   return 0;
 }
 
+// One pass of a separable resample with host-built tap tables (gyre/images.py:324-340 `resize` = ResizeRight with lanczos3,
+// reflect padding folded into the indices, antialiasing = a window stretched by 1 / scale: up to a few hundred taps):
+// src [n_outer, in_size, inner] -> dst [n_outer, out_size, inner] along the middle dimension, products rounded before they
+// are added like `(neighbors * weights).sum(1)`, optional clamp to [0, 1].
+__global__ void resample_f32_kernel(const float* __restrict__ src, int64_t n_outer, int in_sz, int inner,
+                                    const int* __restrict__ idx, const float* __restrict__ w, int ksize, int out_sz, int clamp01,
+                                    float* __restrict__ dst) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t total = n_outer * out_sz * inner;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % inner);
+  const int o = static_cast<int>((i / inner) % out_sz);
+  const int64_t b = i / (static_cast<int64_t>(inner) * out_sz);
+  const float* s0 = src + b * in_sz * inner + c;
+  const int* ii = idx + static_cast<int64_t>(o) * ksize;
+  const float* ww = w + static_cast<int64_t>(o) * ksize;
+  float acc = 0.f;
+  for (int k = 0; k < ksize; ++k) acc = __fadd_rn(acc, __fmul_rn(s0[static_cast<int64_t>(ii[k]) * inner], ww[k]));
+  if (clamp01) acc = fminf(fmaxf(acc, 0.f), 1.f);
+  dst[i] = acc;
+}
+
+int resample_f32(const float* src, int64_t n_outer, int in_sz, int inner, const int* idx, const float* w, int ksize, int out_sz,
+                 int clamp01, float* dst, cudaStream_t st) {
+  GYRE_REQUIRE(src && dst && idx && w && n_outer > 0 && in_sz > 0 && inner > 0 && out_sz > 0 && ksize > 0,
+               "resample_f32: bad arguments");
+  const int64_t total = n_outer * out_sz * inner;
+  prof::Scope ps(prof::F_ELEMENTWISE, 0.0, 0.0, st);
+  resample_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(src, n_outer, in_sz, inner, idx, w, ksize, out_sz, clamp01, dst);
+  GYRE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace gyre

@@ -230,6 +230,11 @@ int gyre_b200_scale_latents(const float* x, float c_in, int dup, int batch, int6
   return scale_dup_latents(x, c_in, dup, batch, per_sample, static_cast<__half*>(out), S(stream));
 }
 
+int gyre_b200_resample_f32(const float* src, int64_t n_outer, int in_size, int inner, const int32_t* idx, const float* weights,
+                           int ksize, int out_size, int clamp01, float* dst, gyre_b200_stream stream) {
+  return resample_f32(src, n_outer, in_size, inner, idx, weights, ksize, out_size, clamp01, dst, S(stream));
+}
+
 int gyre_b200_png_sizes(int batch, int height, int width, int channels, size_t* workspace_bytes, size_t* out_stride) {
   return png_sizes(batch, height, width, channels, workspace_bytes, out_stride);
 }

@@ -158,6 +158,8 @@ int resample_select(const float* src, int BC, int SH, int SW, const int* ty_idx,
 int rand_select(const float* a, const float* b, const float* rnd, float p, int64_t n, float* out, cudaStream_t st);
 // Outpaint tail: histogram-match `result` to (source outside the mask + result inside it) over the whole batch, then mix the
 // source back over it (postprocess.cu).  result / source / mask / out: [B, 3, HW] fp16 in [0, 1].
+int resample_f32(const float* src, int64_t n_outer, int in_sz, int inner, const int* idx, const float* w, int ksize, int out_sz,
+                 int clamp01, float* dst, cudaStream_t st);
 // PNG encoder (png.cu): u8 NHWC [B, H, W, C] (C = 1 grey, 2 grey + alpha, 3 RGB, 4 RGBA) -> one PNG file per image
 int png_sizes(int B, int H, int W, int C, size_t* workspace_bytes, size_t* out_stride);
 int png_encode(const uint8_t* images, int B, int H, int W, int C, uint8_t* out, size_t out_stride, int64_t* out_len,

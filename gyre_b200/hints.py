@@ -10,8 +10,9 @@ Mirrors, with the reference's names and argument meaning:
 The models are `B200ControlNet` / `B200T2iAdapter`; their outputs go to the native UNet through
 `gyre_b200_unet_set_control_residuals` / `_set_adapter_states` (B200UNet.forward_raw keywords).
 
-Not built (raise): hint masks and ControlNets under the 9-channel inpaint UNets (both need `images.resize`, the lanczos3
-ResizeRight call of gyre/images.py:324-340, every step), style adapters, co-adapters + fuser."""
+Hint masks (the alpha channel of an RGBA hint, or `mask=`) and ControlNets under the 9-channel inpaint UNets go through
+`gyre_b200.images.resize` (the lanczos3 ResizeRight call of gyre/images.py:324-340 on the device); the resized masks are
+cached per request - they do not change between steps.  Not built (raise): style adapters, co-adapters + fuser."""
 from __future__ import annotations
 
 from types import SimpleNamespace
@@ -21,17 +22,58 @@ import torch
 CONTROLNET_LAYERS = 13
 
 
+def _split_hint(image, mask, channels=3):
+    """UnifiedPipelineHint.__init__ (unified_pipeline.py:748-775): an RGBA hint carries its mask in the alpha channel; a mask
+    of pure ones is dropped; image -> `channels` channels, mask -> 1."""
+    if image.ndim == 3:
+        image = image[None]
+    if mask is None and image.shape[1] == 4:
+        mask = image[:, [3]]
+    if channels == 1:
+        image = image[:, [0]]
+    else:
+        image = image[:, [0, 1, 2]] if image.shape[1] >= 3 else image[:, [0, 0, 0]]
+    if mask is not None:
+        mask = mask[None] if mask.ndim == 3 else mask
+        mask = mask[:, [0]]
+        if float(mask.float().mean()) == 1.0 and float(mask.float().std()) == 0.0:
+            mask = None
+    return image, mask
+
+
+class _MaskResizer:
+    """`resized_mask` (unified_pipeline.py:790-808): the mask scaled to a state's resolution with images.resize; the two sizes
+    must be integer multiples of each other.  Cached per (mask, target size)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def __call__(self, state, mask):
+        from .images import resize
+        key = (mask.data_ptr(), tuple(mask.shape), tuple(state.shape[-2:]))
+        hit = self._cache.get(key)
+        if hit is None:
+            hd, wd = (mask.shape[-2], state.shape[-2]), (mask.shape[-1], state.shape[-1])
+            if max(hd) % min(hd) or max(wd) % min(wd):
+                raise ValueError(f"hint mask {tuple(mask.shape[-2:])} is not an integer multiple of the state {tuple(state.shape[-2:])}")
+            scale = (state.shape[-2] / mask.shape[-2], state.shape[-1] / mask.shape[-1])
+            hit = (mask, resize(mask.float(), scale).to(state.dtype))          # (keeps `mask` alive: the key is its address)
+            if len(self._cache) > 64:
+                self._cache.clear()
+            self._cache[key] = hit
+        return hit[1]
+
+
 class B200ControlnetHint:
     """UnifiedPipelineHint_Controlnet (unified_pipeline.py:957-1058)."""
 
     def __init__(self, model, image, mask=None, weight=1.0, soft_injection=False, cfg_only=False):
-        if mask is not None:
-            raise NotImplementedError("hint masks need the per-step lanczos3 mask resize (images.resize): not built")
-        if image.ndim != 4 or image.shape[1] < 3:
-            raise ValueError(f"hint image must be [B, 3, H, W], got {tuple(image.shape)}")
+        image, mask = _split_hint(image, mask)
         self.model = model
-        self.image = image[:, :3].to(device=model.device, dtype=torch.float16).contiguous()
-        self.mask = None
+        self.image = image.to(device=model.device, dtype=torch.float16).contiguous()
+        self.mask = None if mask is None else mask.to(device=model.device, dtype=torch.float16).contiguous()
+        self._resized = _MaskResizer()
+        self._masked_cond = {}
         self.weight = float(weight)
         self.soft_injection = bool(soft_injection)
         self.cfg_only = bool(cfg_only)
@@ -51,10 +93,9 @@ class B200ControlnetHint:
         return self._cond
 
     def __call__(self, latents, t, encoder_hidden_states, cfg_meta=None):
-        if latents.shape[1] == 9:
-            raise NotImplementedError("ControlNet under a 9-channel inpaint UNet needs the per-step mask resize: not built")
         cnlatents = latents[:, 0:4]
         B_full = latents.shape[0]
+        mask = self.mask
         fused_cfg_only = self.cfg_only and cfg_meta == "f"
         if self.cfg_only:
             if cfg_meta == "f":
@@ -65,6 +106,24 @@ class B200ControlnetHint:
             elif cfg_meta == "u":
                 return SimpleNamespace(down_block_res_samples=[0] * CONTROLNET_LAYERS, mid_block_res_sample=0)
         B = cnlatents.shape[0]
+        condition = self._condition(B)
+        if latents.shape[1] == 9:
+            # under an inpaint UNet (:1008-1018) the ControlNet sees the latents and its conditioning image through the inpaint
+            # mask (channel 4 of the UNet input, the same at every step), scaled up to the image with images.resize
+            if self.cfg_only and cfg_meta == "f":
+                raise NotImplementedError("cfg_only ControlNet hints under a 9-channel UNet in one fused CFG batch "
+                                          "(the reference's own shapes do not line up there)")
+            lmask = latents[:, [4]]
+            cnlatents = cnlatents * lmask
+            key = (lmask.data_ptr(), tuple(lmask.shape))
+            hit = self._masked_cond.get(key)
+            if hit is None:
+                m = self._resized(condition, lmask.contiguous())
+                if self.mask is not None:
+                    m = m * self.mask
+                hit = (m, (condition * m).contiguous())
+                self._masked_cond = {key: hit}
+            mask, condition = hit
         out = None
         if fused_cfg_only:
             # [zeros ; residual] without a concatenation per tensor per step: the ControlNet writes the second half
@@ -72,7 +131,7 @@ class B200ControlnetHint:
             full = [torch.zeros(s, device=latents.device, dtype=torch.float16) for s in shapes + [mid_shape]]
             out = [f[B_full // 2:] for f in full]
         res = self.model(cnlatents.contiguous(), t, encoder_hidden_states=encoder_hidden_states.contiguous(),
-                         controlnet_cond=self._condition(B), out=out)
+                         controlnet_cond=condition, out=out)
         down = list(full[:-1]) if fused_cfg_only else list(res.down_block_res_samples)
         mid = full[-1] if fused_cfg_only else res.mid_block_res_sample
         n = len(down)
@@ -81,9 +140,13 @@ class B200ControlnetHint:
             s = self.weight * lw[k]
             if s != 1.0:
                 down[k].mul_(s)
+            if mask is not None:
+                down[k].mul_(self._resized(down[k], mask))
         s = self.weight * lw[-1]
         if s != 1.0:
             mid.mul_(s)
+        if mask is not None:
+            mid.mul_(self._resized(mid, mask))
         return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid)
 
 
@@ -91,19 +154,12 @@ class B200T2iHint:
     """UnifiedPipelineHint_T2i, standard (non-style) adapters (unified_pipeline.py:836-955)."""
 
     def __init__(self, model, image, mask=None, weight=1.0, soft_injection=False, cfg_only=False):
-        if mask is not None:
-            raise NotImplementedError("hint masks need the lanczos3 mask resize (images.resize): not built")
         self.model = model
-        channels = model.cin // 64
-        img = image
-        if img.shape[1] != channels:
-            if channels == 1:
-                img = img[:, :3].mean(dim=1, keepdim=True) if img.shape[1] >= 3 else img[:, :1]
-            elif img.shape[1] == 1:
-                img = img.expand(-1, channels, -1, -1)
-            else:
-                img = img[:, :channels]
+        channels = model.cin // 64               # (`model.config.cin // 64`, unified_pipeline.py:869)
+        img, mask = _split_hint(image, mask, channels=1 if channels == 1 else 3)
         self.image = img.to(device=model.device, dtype=torch.float16).contiguous()
+        self.mask = None if mask is None else mask.to(device=model.device, dtype=torch.float16).contiguous()
+        self._resized = _MaskResizer()
         self.weight = float(weight)
         self.soft_injection = bool(soft_injection)
         self.cfg_only = bool(cfg_only)
@@ -127,7 +183,10 @@ class B200T2iHint:
         out = []
         for state, lw in zip(states, layer_weights):
             s = self.weight * lw
-            out.append(state if s == 1.0 else state * s)
+            state = state if s == 1.0 else state * s
+            if self.mask is not None:
+                state = state * self._resized(state, self.mask)
+            out.append(state)
         return out
 
 

@@ -90,3 +90,84 @@ def add_text_chunk_to_png_bytes(binary: bytes, key: str, text: str) -> bytes:
     at = binary.rindex(b"IEND") - 4
     chunk = struct.pack(">I", len(body)) + b"tEXt" + body + struct.pack(">I", zlib.crc32(b"tEXt" + body))
     return binary[:at] + chunk + binary[at:]
+
+
+_RESIZE_TAPS = {}
+
+
+def _lanczos3_taps(in_sz: int, scale: float, antialiasing: bool, device):
+    """ResizeRight's 1-D plan (gyre/src/ResizeRight/resize_right.py:70-118, 128-213) for interp_methods.lanczos3 (support 6)
+    with reflect padding folded into the source indices; antialiasing stretches the window by 1 / scale when downscaling.
+    fp32 throughout, in ResizeRight's order of operations.  Returns (idx int32 [out, K], w fp32 [out, K], out_sz)."""
+    import math
+    key = (in_sz, float(scale), bool(antialiasing), str(device))
+    hit = _RESIZE_TAPS.get(key)
+    if hit is not None:
+        return hit
+    eps = torch.finfo(torch.float32).eps
+    scale = float(scale)
+    out_sz = math.ceil(scale * in_sz)
+
+    def lanczos3(x):
+        return ((torch.sin(math.pi * x) * torch.sin(math.pi * x / 3) + eps) / ((math.pi ** 2 * x ** 2 / 3) + eps)) * (abs(x) < 3).to(x.dtype)
+    grid = torch.arange(out_sz) / scale + (in_sz - 1) / 2 - (out_sz - 1) / (2 * scale)
+    support = 6.0
+    if antialiasing and scale < 1.0:
+        interp, support = (lambda arg: scale * lanczos3(scale * arg)), support / scale
+    else:
+        interp = lanczos3
+    left = (grid - support / 2 - eps).ceil().long()
+    fov = left[:, None] + torch.arange(math.ceil(support - eps))
+    pad0 = -fov[0, 0].item()
+    w = interp((grid + pad0)[:, None] - (fov + pad0))
+    tot = w.sum(1, keepdim=True)
+    tot[tot == 0] = 1
+    w = (w / tot).to(torch.float32)
+    idx = torch.where(fov < 0, -fov, fov)
+    idx = torch.where(idx > in_sz - 1, 2 * (in_sz - 1) - idx, idx)
+    if idx.min() < 0 or idx.max() > in_sz - 1:
+        raise ValueError(f"resize: the filter window ({w.shape[1]} taps) needs more reflect padding than a dimension of {in_sz} "
+                         f"allows (the reference fails here too)")
+    hit = (idx.to(torch.int32).contiguous().to(device), w.contiguous().to(device), out_sz)
+    if len(_RESIZE_TAPS) > 128:
+        _RESIZE_TAPS.clear()
+    _RESIZE_TAPS[key] = hit
+    return hit
+
+
+def resize(tensor, factors, sharpness=1):
+    """gyre/images.py:324-340 `resize`: [B, C, H, W] scaled by `factors` (a number or (fy, fx)) with lanczos3 through ResizeRight,
+    reflect padding, antialiasing for sharpness 1 (none for 2), clamped to [0, 1], cast back to the input dtype.  One launch per
+    resized dimension (gyre_b200_resample_f32), dimensions in ascending scale order like ResizeRight.  sharpness 0 (area
+    downscale) is not built."""
+    import ctypes as C  # noqa: F401
+    if sharpness not in (1, 2):
+        raise NotImplementedError("images.resize: sharpness 0 (area downscale) is not built")
+    N.require_cuda(tensor)
+    if not isinstance(factors, (tuple, list)):
+        factors = (factors, factors)
+    elif len(factors) == 1:
+        factors = (factors[0], factors[0])
+    if tensor.ndim != 4:
+        raise ValueError(f"images.resize: want [B, C, H, W], got {tuple(tensor.shape)}")
+    lib = N.load()
+    cur = tensor.to(torch.float32).contiguous()
+    st = N.stream_ptr(cur.device)
+    for d in sorted((2, 3), key=lambda a: float(factors[a - 2])):
+        f = float(factors[d - 2])
+        if f == 1.0:
+            continue
+        B, Cc, H, W = cur.shape
+        idx, w, out_sz = _lanczos3_taps(cur.shape[d], f, sharpness == 1, cur.device)
+        if d == 2:
+            dst = torch.empty((B, Cc, out_sz, W), device=cur.device, dtype=torch.float32)
+            n_outer, in_sz, inner = B * Cc, H, W
+        else:
+            dst = torch.empty((B, Cc, H, out_sz), device=cur.device, dtype=torch.float32)
+            n_outer, in_sz, inner = B * Cc * H, W, 1
+        with torch.cuda.device(cur.device):
+            N.check(lib.gyre_b200_resample_f32(N.ptr(cur), n_outer, in_sz, inner, N.ptr(idx), N.ptr(w), w.shape[1], out_sz, 0,
+                                               N.ptr(dst), st), "resample_f32")
+        cur = dst
+    # (the reference casts back to the input dtype first and clamps after: an fp16 input is clamped in fp16)
+    return cur.to(tensor.dtype).clamp(0, 1)

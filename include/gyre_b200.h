@@ -419,6 +419,12 @@ int gyre_b200_resample_select(const float* src, int planes, int src_h, int src_w
                               const float* background, const float* other, const float* rand_map, float p,
                               int resampled_if_ge, float* out, int frame_h, int frame_w, int frame_y, int frame_x,
                               gyre_b200_stream stream);
+/* One pass of `images.resize` (gyre/images.py:324-340: ResizeRight, lanczos3, reflect padding, antialiasing for sharpness 1;
+ * used for hint masks, unified_pipeline.py:790-808, and the depth hint, :2007-2008): src [n_outer, in_size, inner] fp32 ->
+ * dst [n_outer, out_size, inner] along the middle dimension with host-built tables idx / weights [out_size, ksize] (the
+ * reflect padding is folded into idx; gyre_b200.images.resize builds them with ResizeRight's expressions). */
+int gyre_b200_resample_f32(const float* src, int64_t n_outer, int in_size, int inner, const int32_t* idx, const float* weights,
+                           int ksize, int out_size, int clamp01, float* dst, gyre_b200_stream stream);
 int gyre_b200_rand_select(const float* a, const float* b, const float* rand_map, float p, int64_t n, float* out,
                           gyre_b200_stream stream);
 

@@ -16,10 +16,33 @@ from types import SimpleNamespace
 import torch
 
 
+def split_hint(image, mask, channels=3):
+    """UnifiedPipelineHint.__init__ (unified_pipeline.py:748-775)."""
+    if mask is None and image.shape[1] == 4:
+        mask = image[:, [3]]
+    image = image[:, [0]] if channels == 1 else (image[:, [0, 1, 2]] if image.shape[1] >= 3 else image[:, [0, 0, 0]])
+    if mask is not None:
+        mask = mask[:, [0]]
+        if mask.mean() == 1.0 and mask.std() == 0.0:
+            mask = None
+    return image, mask
+
+
+def resized_mask(state, mask):
+    """unified_pipeline.py:790-808."""
+    from .hires import images_resize
+    if mask is None:
+        return torch.ones_like(state)
+    hd, wd = (mask.shape[-2], state.shape[-2]), (mask.shape[-1], state.shape[-1])
+    assert max(hd) % min(hd) == 0 and max(wd) % min(wd) == 0
+    return images_resize(mask, (state.shape[-2] / mask.shape[-2], state.shape[-1] / mask.shape[-1])).to(state.dtype)
+
+
 class ControlnetHint:
-    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False):
+    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False, mask=None):
         """model(cnlatents, t, encoder_hidden_states=, controlnet_cond=) -> object with down_block_res_samples, mid_block_res_sample."""
-        self.model, self.image = model, image
+        self.model = model
+        self.image, self.mask = split_hint(image, mask)
         self.weight, self.soft_injection, self.cfg_only = weight, soft_injection, cfg_only
 
     def __call__(self, latents, t, encoder_hidden_states, cfg_meta=None):
@@ -31,10 +54,18 @@ class ControlnetHint:
                 encoder_hidden_states = encoder_hidden_states.chunk(2)[-1]
             elif cfg_meta == "u":
                 return SimpleNamespace(down_block_res_samples=[torch.tensor(0)] * 13, mid_block_res_sample=torch.tensor(0))
-        res = self.model(cnlatents, t, encoder_hidden_states=encoder_hidden_states, controlnet_cond=self.image)
+        condition, mask = self.image, self.mask
+        if latents.shape[1] == 9:
+            mask = latents[:, [4]]
+            cnlatents = cnlatents * mask
+            mask = resized_mask(condition, mask)
+            if self.mask is not None:
+                mask = mask * self.mask
+            condition = condition * mask
+        res = self.model(cnlatents, t, encoder_hidden_states=encoder_hidden_states, controlnet_cond=condition)
 
         def basic(r, lw):
-            return r * self.weight * lw
+            return r * self.weight * lw * resized_mask(r, mask)
 
         process = basic
         if self.cfg_only and cfg_meta == "f":
@@ -46,8 +77,9 @@ class ControlnetHint:
 
 
 class T2iHint:
-    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False):
-        self.model, self.image = model, image
+    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False, mask=None, channels=3):
+        self.model = model
+        self.image, self.mask = split_hint(image, mask, channels)
         self.weight, self.soft_injection, self.cfg_only = weight, soft_injection, cfg_only
         self.fuser = None
 
@@ -60,7 +92,7 @@ class T2iHint:
             layer_weights = torch.logspace(-0.25, 0, 4)
             if self.cfg_only:
                 layer_weights[0] = 0.25
-        return [state * self.weight * lw for state, lw in zip(self.model(self.image), layer_weights)]
+        return [state * self.weight * lw * resized_mask(state, self.mask) for state, lw in zip(self.model(self.image), layer_weights)]
 
 
 class UNetWithControlnet:

@@ -423,3 +423,59 @@ def depth_txt2img_latents(depth_unet, main_unet, uncond_emb, cond_emb, guidance_
     S.batched_randn([B, 4, h, w], gens, "cpu", latent_dtype)                  # the top leaf's (discarded) draw
     graft = GraftUnets(lambda x, s, u: den_root(x, s), lambda x, s, u: den_top(x, s), gens, blend=graft_blend)
     return S.euler_ancestral_with_u(lambda x, s, u: graft(x, s, u), lat_root, sig.float(), 0.0, gens, latent_dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# gyre/images.py:324-340 `resize(tensor, factors, sharpness)` for sharpness 1 / 2: ResizeRight with lanczos3, reflect padding,
+# antialiasing iff sharpness == 1, clamped to [0, 1] - what hint masks (unified_pipeline.py:790-808 resized_mask) and the depth
+# hint (:2007-2008) go through.  PINNED against the reference's own gyre/images.py + vendored ResizeRight
+# (scripts/make_golden.py:pin_resize, tests/golden/resize.pt).
+def lanczos3(x):
+    """interp_methods.py:54-57."""
+    eps = torch.finfo(torch.float32).eps
+    return ((torch.sin(math.pi * x) * torch.sin(math.pi * x / 3) + eps) / ((math.pi ** 2 * x ** 2 / 3) + eps)) * (abs(x) < 3).to(x.dtype)
+
+
+def resize_taps_general(in_sz: int, scale: float, support: float = 6.0, antialiasing: bool = True, method=lanczos3):
+    """resize_right.py:70-118 for one dim: (source indices [out, K] with reflect padding folded in, weights [out, K], out_sz).
+    Antialiasing (apply_antialiasing_if_needed :175-200) stretches the window by 1 / scale when downscaling."""
+    eps = torch.finfo(torch.float32).eps
+    scale = float(scale)
+    out_sz = math.ceil(scale * in_sz)
+    grid = torch.arange(out_sz) / scale + (in_sz - 1) / 2 - (out_sz - 1) / (2 * scale)
+    if antialiasing and scale < 1.0:
+        interp = lambda arg: scale * method(scale * arg)
+        cur_support = support / scale
+    else:
+        interp, cur_support = method, support
+    left = (grid - cur_support / 2 - eps).ceil().long()
+    fov = left[:, None] + torch.arange(math.ceil(cur_support - eps))
+    pad0 = -fov[0, 0].item()
+    w = interp((grid + pad0)[:, None] - (fov + pad0))
+    s = w.sum(1, keepdim=True)
+    s[s == 0] = 1
+    w = w / s
+    idx = torch.where(fov < 0, -fov, fov)
+    idx = torch.where(idx > in_sz - 1, 2 * (in_sz - 1) - idx, idx)
+    assert idx.min() >= 0 and idx.max() <= in_sz - 1, "reflect padding wider than the image"
+    return idx, w, out_sz
+
+
+def images_resize(tensor, factors, sharpness=1):
+    """gyre/images.py:324-340 (sharpness 1: antialiased, 2: not; 0 - the area-downscale variant - is not restated)."""
+    if sharpness not in (1, 2):
+        raise NotImplementedError("sharpness 0 (area downscale) is not restated")
+    if not isinstance(factors, (tuple, list)):
+        factors = (factors, factors)
+    elif len(factors) == 1:
+        factors = (factors[0], factors[0])
+    out = tensor
+    dims = sorted((-2, -1), key=lambda d: float(factors[d]))            # ascending scale, H before W on ties
+    for d in dims:
+        if float(factors[d]) == 1.0:
+            continue
+        idx, w, _ = resize_taps_general(out.shape[d], factors[d], antialiasing=sharpness == 1)
+        t = out.transpose(d, 0)
+        ww = w.reshape(*w.shape, *([1] * (t.ndim - 1)))
+        out = (t[idx] * ww).sum(1).transpose(0, d)
+    return out.to(tensor.dtype).clamp(0, 1)

@@ -780,7 +780,7 @@ def _round_mask(mask, threshold):
 
 
 def image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image, mask_image=None, seeds, steps,
-                       strength, sampler="euler_a", latent_dtype=torch.float32, prediction_type="epsilon", eta=None):
+                       strength, sampler="euler_a", latent_dtype=torch.float32, prediction_type="epsilon", eta=None, hints=()):
     """Img2imgMode / EnhancedInpaintMode / EnhancedRunwayInpaintMode + KDiffusionScheduler on the CPU
     (unified_pipeline.py:240-337, 400-696; common_scheduler.py:430-623), k-diffusion samplers only.
     `unet.cfg.in_channels == 9` selects the Runway path (mask + masked-image latents appended to the UNet input,
@@ -788,7 +788,7 @@ def image_mode_latents(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image
     generators = [torch.Generator(device="cpu").manual_seed(s) for s in seeds]
     ph = image_mode_phases(unet, vae, uncond_emb, cond_emb, guidance_scale, image=image, mask_image=mask_image,
                            generators=generators, steps=steps, strength=strength, latent_dtype=latent_dtype,
-                           prediction_type=prediction_type)
+                           prediction_type=prediction_type, hints=hints)
     next(ph)                                                   # mode construction
     leaf = next(ph)                                            # generateLatents
     if sampler != "euler_a":
@@ -816,7 +816,7 @@ def euler_ancestral_with_u(k_unet, latents, sigmas, u_off, generators, latent_dt
 
 
 def image_mode_phases(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image, mask_image=None, generators, steps,
-                      strength, latent_dtype=torch.float32, prediction_type="epsilon"):
+                      strength, latent_dtype=torch.float32, prediction_type="epsilon", hints=()):
     """One mode-tree leaf of an image mode as a two-phase generator, because the reference interleaves the phases of
     several leaves on the SAME generators: first every leaf's mode is constructed (the masked-image encode draws its
     posterior sample there, unified_pipeline.py:400-440), then every leaf's `generateLatents` runs (:2474).  The first
@@ -882,12 +882,27 @@ def image_mode_phases(unet, vae, uncond_emb, cond_emb, guidance_scale, *, image,
     if runway:
         extra = torch.cat([1 - high[:, [0]], init_orig], dim=1)
 
+    chain = None
+    if hints:
+        # hints wrap the UNet under the embeddings and the mode's extra channels (unified_pipeline.py:2312-2337): the
+        # ControlNet sees the 9-channel input of an inpaint UNet
+        from . import hints as H
+        chain = H.FromDiffusersUNet(unet)
+        grouped = {}
+        for h in hints:
+            grouped.setdefault(type(h), []).append(h)
+        for cls, hs in grouped.items():
+            chain = (H.UNetWithControlnet if cls is H.ControlnetHint else H.UNetWithT2I)(chain, hs)
+
     def eps_cfg(x, t):
         x2 = torch.cat([x, x])
         if runway:
             x2 = torch.cat([x2, torch.cat([extra, extra]).to(x2.dtype)], dim=1)
         t2 = torch.cat([t, t]) if (torch.is_tensor(t) and t.shape) else t
-        out = unet(x2, t2, encoder_hidden_states=emb).sample
+        if chain is not None:
+            out = chain(x2, t2, encoder_hidden_states=emb, cfg_meta="f")
+        else:
+            out = unet(x2, t2, encoder_hidden_states=emb).sample
         u, g = out.chunk(2)
         return u + guidance_scale * (g - u)
 

@@ -1104,6 +1104,50 @@ def pin_hint_classes():
         def parameters(self):
             return iter([torch.zeros(1)])
 
+    # hint masks: an RGBA hint (mask = alpha) at 256 x 256 - the 1 / 64 antialiased downscale for the deepest residual needs
+    # 192 pixels of reflect padding, more than a 128-pixel mask has (the reference fails there) - and a ControlNet under the
+    # 9-channel inpaint UNet, whose mask comes from the UNet input
+    big = torch.rand(1, 3, 256, 256, generator=g).half().float()
+    alpha = torch.zeros(1, 1, 256, 256)
+    alpha[:, :, 64:224, 32:160] = 1.0
+    rgba = torch.cat([big, alpha], dim=1)
+    cfg9 = UNetConfig.tiny(in_channels=9)
+    unet9 = OracleUNet(cfg9, synth_params(unet_param_shapes(cfg9), seed=1234))
+    vcfg = VAEConfig.tiny()
+    VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+    out = {"rgba": rgba.half()}
+    for name, kind in (("masked controlnet + t2i", "txt2img"), ("controlnet under runway inpaint", "runway")):
+        if kind == "txt2img":
+            rh = [up.UnifiedPipelineHint_Controlnet(CN(), rgba.clone(), None, 0.9, True, False, batch_total=2),
+                  up.UnifiedPipelineHint_T2i(AD(), rgba.expand(2, -1, -1, -1).clone(), None, None, None, None, 0.8, False, False, None)]
+            ohints = [oh.ControlnetHint(CN(), rgba, weight=0.9, soft_injection=True, cfg_only=False),
+                      oh.T2iHint(AD(), rgba.expand(2, -1, -1, -1), weight=0.8, soft_injection=False, cfg_only=False)]
+            kw, u_ = {}, unet
+        else:
+            rh = [up.UnifiedPipelineHint_Controlnet(CN(), rgba.clone(), None, 1.0, False, False, batch_total=2)]
+            ohints = [oh.ControlnetHint(CN(), rgba, weight=1.0, soft_injection=False, cfg_only=False)]
+            img_in = torch.rand(1, 3, 256, 256, generator=g).half().float()
+            msk_in = torch.zeros(1, 1, 256, 256)
+            msk_in[:, :, 96:192, 64:200] = 1.0
+            kw, u_ = dict(image=img_in, mask_image=msk_in, strength=0.8), unet9
+            out["runway_image"], out["runway_mask"] = img_in.half(), msk_in.half()
+        for h in rh:
+            h.to(torch.device("cpu"), torch.float32)
+        ref = _reference_segment(up, u_, OracleVAE(vcfg, VP), unc, emb, kind=kind, sampler_fn=ksamp.sample_euler_ancestral, steps=4,
+                                 seeds=[420420420, 420420421], height=256, width=256, sample_size=16, hints=rh, **kw)
+        if kind == "txt2img":
+            eps = oh.guided_eps_unet(u_, unc, emb, 7.5, ohints)
+            with torch.no_grad():
+                mine = osamp.txt2img_latents(eps, batch=2, in_channels=4, height=256, width=256, sample_size=16,
+                                             seeds=[420420420, 420420421], steps=4, sampler="euler_a")
+        else:
+            with torch.no_grad():
+                mine = osamp.image_mode_latents(u_, OracleVAE(vcfg, VP), unc, emb, 7.5, seeds=[420420420, 420420421], steps=4,
+                                                hints=ohints, **kw)
+        err = (ref - mine).abs().max().item() / ref.abs().max().item()
+        print(f"  hints/{name}: rel diff {err:.2e}")
+        assert err < 2e-5, name
+        out[name] = ref
     seeds, steps = [420420420, 420420421], 5
     cases = [("controlnet", dict(weight=1.0, soft_injection=False, cfg_only=False), None, "parallel"),
              ("controlnet soft 0.7", dict(weight=0.7, soft_injection=True, cfg_only=False), None, "parallel"),
@@ -1113,7 +1157,6 @@ def pin_hint_classes():
              ("t2i soft cfg_only + controlnet", dict(weight=0.5, soft_injection=False, cfg_only=False),
               dict(weight=0.9, soft_injection=True, cfg_only=True), "parallel"),
              ("t2i cfg_only sequential", None, dict(weight=1.0, soft_injection=False, cfg_only=True), "sequential")]
-    out = {}
     for name, cn_kw, ad_kw, execution in cases:
         rh, ohints = [], []
         if cn_kw is not None:
@@ -1138,7 +1181,7 @@ def pin_hint_classes():
         assert err < 2e-5, name
         out[name] = ref
     torch.save(out, os.path.join(GOLD, "hint_classes.pt"))
-    print(f"hint classes: {len(out)} runs of UnifiedPipelineHint_Controlnet / _T2i inside the reference's stack == oracle/hints.py")
+    print(f"hint classes: {len([k for k in out if not k.startswith('r')])} runs of UnifiedPipelineHint_Controlnet / _T2i inside the reference's stack == oracle/hints.py")
 
 
 def _reference_call(up, *, unet, vae, unc, emb, sampler_fn, seeds, inpaint_unet=None, depth_unet=None, options=None,
@@ -1306,6 +1349,29 @@ def pin_call():
     print(f"call: {len(out) - 2} runs of UnifiedPipeline.__call__ == the oracle's compositions")
 
 
+def pin_resize():
+    """PINS oracle/hires.py:images_resize (and through tests/test_images_gpu.py the native gyre_b200.images.resize) against the
+    reference's gyre/images.py:resize over the vendored ResizeRight."""
+    from oracle import hires as ohires
+    _vendored.gyre_unified_pipeline()
+    gim = sys.modules["gyre.images"]
+    g = torch.Generator().manual_seed(0)
+    out = []
+    for shape, f, sh in [((1, 1, 128, 128), (1 / 8, 1 / 8), 1), ((1, 1, 128, 128), (1 / 8, 1 / 8), 2), ((2, 1, 16, 16), (8, 8), 1),
+                         ((1, 1, 96, 128), (0.25, 0.125), 1), ((1, 3, 40, 24), (2.0, 1.0), 1), ((1, 1, 256, 256), (1 / 32, 1 / 32), 1),
+                         ((1, 1, 64, 64), (0.5, 0.5), 2), ((1, 1, 128, 128), (1 / 16, 1 / 16), 1), ((2, 1, 16, 24), (8, 8), 2)]:
+        x = torch.rand(shape, generator=g)
+        if shape[-1] == 16:
+            x = (x > 0.5).float()                       # a hard mask: the lanczos overshoot meets the clamp
+        ref = gim.resize(x, f, sharpness=sh)
+        mine = ohires.images_resize(x, f, sharpness=sh)
+        err = (ref - mine).abs().max().item()
+        assert ref.shape == mine.shape and err <= 5e-7, (shape, f, sh, err)
+        out.append({"x": x, "factors": f, "sharpness": sh, "out": ref})
+    torch.save(out, os.path.join(GOLD, "resize.pt"))
+    print(f"resize: {len(out)} cases of gyre.images.resize == oracle (<= 5e-7: torch.sum's summation order)")
+
+
 def oracle_fixtures(full: bool):
     """Oracle self-fixtures (unpinned at the diffusers boundary)."""
     out = {}
@@ -1356,12 +1422,12 @@ def oracle_fixtures(full: bool):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,controlnet,hints,attention,segment,hint_classes,call,oracle")
+    ap.add_argument("--only", default="", help="comma-separated subset: samplers,ddim,tome,clip,wrappers,hires,lpw,images,t2i_adapter,safety,controlnet,hints,attention,segment,hint_classes,call,resize,oracle")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     parts = {"samplers": pin_samplers, "ddim": pin_ddim, "tome": pin_tome, "clip": pin_clip, "wrappers": pin_wrappers,
-             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "controlnet": pin_controlnet, "hints": pin_hints, "attention": pin_attention, "segment": pin_segment, "hint_classes": pin_hint_classes, "call": pin_call, "oracle": lambda: oracle_fixtures(a.full)}
+             "hires": pin_hires, "lpw": pin_lpw, "images": pin_images, "t2i_adapter": pin_t2i_adapter, "safety": pin_safety, "controlnet": pin_controlnet, "hints": pin_hints, "attention": pin_attention, "segment": pin_segment, "hint_classes": pin_hint_classes, "call": pin_call, "resize": pin_resize, "oracle": lambda: oracle_fixtures(a.full)}
     for name, fn in parts.items():
         if not a.only or name in a.only.split(","):
             fn()

@@ -60,18 +60,16 @@ def test_t2i_states_expand_to_the_unet_batch():
 
 
 def test_unbuilt_hint_features_raise():
-    from gyre_b200.hints import B200ControlnetHint, B200T2iHint, UNetWithT2I
-
-    class M:
-        device = "cpu"
-        cin = 192
-    with pytest.raises(NotImplementedError):
-        B200ControlnetHint(M(), torch.zeros(1, 3, 8, 8), mask=torch.ones(1, 1, 8, 8))
-    with pytest.raises(NotImplementedError):
-        B200T2iHint(M(), torch.zeros(1, 3, 8, 8), mask=torch.ones(1, 1, 8, 8))
+    from gyre_b200.hints import UNetWithT2I, _split_hint
 
     class Style(FakeHintAdapter):
         def __call__(self):
             return torch.zeros(1, 8, 16)
     with pytest.raises(NotImplementedError):
         UNetWithT2I(None, [Style(1, False)])
+    # an RGBA hint carries its mask in the alpha channel; a mask of ones is dropped (unified_pipeline.py:758-771)
+    rgba = torch.rand(1, 4, 8, 8)
+    img, mask = _split_hint(rgba, None)
+    assert torch.equal(img, rgba[:, :3]) and torch.equal(mask, rgba[:, 3:])
+    assert _split_hint(torch.cat([rgba[:, :3], torch.ones(1, 1, 8, 8)], 1), None)[1] is None
+    assert _split_hint(rgba[:, :1], None)[0].shape[1] == 3

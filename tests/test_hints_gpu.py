@@ -110,3 +110,75 @@ def test_hints_with_hires_fix_run(setup):
                  generator=[torch.Generator("cpu").manual_seed(x) for x in (1, 2)], sampler="k_euler", output_type="latent",
                  hints=[B200ControlnetHint(s.cn, img.cuda(), weight=0.5), B200T2iHint(s.ad, img.cuda())], hires_fix=True)
     assert tuple(out.latents.shape) == (2, 4, 24, 24) and torch.isfinite(out.latents.float()).all()
+
+
+def test_masked_hints_vs_oracle(setup):
+    """RGBA hints: the alpha channel masks every ControlNet residual / adapter state at its own resolution (images.resize,
+    antialiased lanczos3, cached per request).  Oracle pinned against the reference's hint classes (hint_classes.pt)."""
+    from oracle import hints as oh
+    from oracle import sampling as osamp
+    from gyre_b200.hints import B200ControlnetHint, B200T2iHint
+    s = setup
+    g = torch.Generator().manual_seed(3)
+    big = torch.rand(1, 3, 256, 256, generator=g).half().float()
+    alpha = torch.zeros(1, 1, 256, 256)
+    alpha[:, :, 64:224, 32:160] = 1.0
+    rgba = torch.cat([big, alpha], dim=1)
+    seeds, steps = [420420420, 420420421], 4
+    hints = [B200ControlnetHint(s.cn, rgba.cuda(), weight=0.9, soft_injection=True), B200T2iHint(s.ad, rgba.cuda(), weight=0.8)]
+    assert hints[0].mask is not None and hints[1].mask is not None
+    out = s.pipe(s.emb.cuda(), s.unc.cuda(), height=256, width=256, num_inference_steps=steps, guidance_scale=7.5,
+                 generator=[torch.Generator("cpu").manual_seed(x) for x in seeds], sampler="k_euler_ancestral", output_type="latent",
+                 latents_dtype=torch.float32, return_fp32_latents=True, hints=hints, hires_fix=False).latents
+    ohints = [oh.ControlnetHint(s.o_cn, rgba, weight=0.9, soft_injection=True, cfg_only=False),
+              oh.T2iHint(s.o_ad, rgba.expand(2, -1, -1, -1), weight=0.8, soft_injection=False, cfg_only=False)]
+    with torch.no_grad():
+        ref = osamp.txt2img_latents(oh.guided_eps_unet(s.o_unet, s.unc, s.emb, 7.5, ohints), batch=2, in_channels=4, height=256,
+                                    width=256, sample_size=16, seeds=seeds, steps=steps, sampler="euler_a")
+        unmasked = osamp.txt2img_latents(oh.guided_eps_unet(s.o_unet, s.unc, s.emb, 7.5, [
+            oh.ControlnetHint(s.o_cn, big, weight=0.9, soft_injection=True, cfg_only=False),
+            oh.T2iHint(s.o_ad, big.expand(2, -1, -1, -1), weight=0.8)]), batch=2, in_channels=4, height=256, width=256,
+            sample_size=16, seeds=seeds, steps=steps, sampler="euler_a")
+    scale = ref.abs().max().item()
+    err = (out.float().cpu() - ref).abs().max().item() / scale
+    assert (unmasked - ref).abs().max().item() / scale > 0.02, "the mask did not change the result"
+    assert err < 1.4e-2, f"masked hints: rel err {err}"
+
+
+def test_controlnet_under_inpaint_unet_vs_oracle(setup):
+    """A ControlNet hint with the 9-channel (Runway) inpaint UNet: latents and conditioning image go through the inpaint mask
+    (channel 4 of the UNet input, scaled up 8x with images.resize), residuals through its scaled-down copies."""
+    from oracle import hints as oh
+    from oracle import sampling as osamp
+    from oracle.unet import OracleUNet, UNetConfig, synth_params, unet_param_shapes
+    from oracle.vae import OracleVAE, VAEConfig, vae_param_shapes
+    from gyre_b200.hints import B200ControlnetHint
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    from gyre_b200.vae import B200VAE
+    s = setup
+    cfg9 = UNetConfig.tiny(in_channels=9)
+    P9 = synth_params(unet_param_shapes(cfg9), seed=1234)
+    vcfg = VAEConfig.tiny()
+    VP = synth_params(vae_param_shapes(vcfg), seed=4321)
+    pipe = B200Pipeline(B200UNet(cfg9).load_state_dict(P9), B200VAE(vcfg).load_state_dict(VP))
+    pipe.unet_sample_size_override = 16
+    g = torch.Generator().manual_seed(9)
+    hint = torch.rand(1, 3, 256, 256, generator=g).half().float()
+    image = torch.rand(1, 3, 256, 256, generator=g).half().float()
+    mask = torch.zeros(1, 1, 256, 256)
+    mask[:, :, 96:192, 64:200] = 1.0
+    seeds, steps = [420420420, 420420421], 4
+    out = pipe(s.emb.cuda(), s.unc.cuda(), height=256, width=256, num_inference_steps=steps, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(x) for x in seeds], sampler="k_euler_ancestral", output_type="latent",
+               latents_dtype=torch.float32, return_fp32_latents=True, image=image.cuda(), mask_image=mask.cuda(), strength=0.8,
+               hints=[B200ControlnetHint(s.cn, hint.cuda())], hires_fix=False).latents
+    with torch.no_grad():
+        kw = dict(image=image, mask_image=mask, seeds=seeds, steps=steps, strength=0.8)
+        ref = osamp.image_mode_latents(OracleUNet(cfg9, P9), OracleVAE(vcfg, VP, sample_dtype=torch.float16), s.unc, s.emb, 7.5,
+                                       hints=[oh.ControlnetHint(s.o_cn, hint)], **kw)
+        plain = osamp.image_mode_latents(OracleUNet(cfg9, P9), OracleVAE(vcfg, VP, sample_dtype=torch.float16), s.unc, s.emb, 7.5, **kw)
+    scale = ref.abs().max().item()
+    err = (out.float().cpu() - ref).abs().max().item() / scale
+    assert (plain - ref).abs().max().item() / scale > 0.02
+    assert err < 1.4e-2, f"ControlNet under the inpaint UNet: rel err {err}"

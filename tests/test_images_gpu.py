@@ -82,3 +82,24 @@ def test_pipeline_outpaint_tail():
     assert torch.equal(out.cpu(), final)
     assert torch.equal(out_u8.cpu(), (final.permute(0, 2, 3, 1).to(torch.float32) * 255).round().to(torch.uint8))
     assert not torch.equal(out, plain)
+
+
+def test_images_resize_matches_reference_fixture():
+    """gyre_b200.images.resize (lanczos3 ResizeRight on the device) against outputs of the reference's gyre/images.py:resize
+    (tests/golden/resize.pt, scripts/make_golden.py:pin_resize): down / up / anisotropic scales, both sharpness modes, hard masks."""
+    import os
+    from gyre_b200.images import resize
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "resize.pt"))
+    assert len(G) == 9
+    for c in G:
+        got = resize(c["x"].cuda(), c["factors"], sharpness=c["sharpness"])
+        assert got.shape == c["out"].shape and got.dtype == c["x"].dtype
+        err = (got.cpu() - c["out"]).abs().max().item()
+        assert err < 2e-6, (tuple(c["x"].shape), c["factors"], c["sharpness"], err)
+    x16 = G[0]["x"].half().cuda()
+    out16 = resize(x16, G[0]["factors"])
+    assert out16.dtype == torch.float16 and (out16.float().cpu() - G[0]["out"]).abs().max().item() < 2e-3
+    with pytest.raises(NotImplementedError):
+        resize(x16, 0.5, sharpness=0)
+    with pytest.raises(ValueError):
+        resize(torch.rand(1, 1, 64, 64).cuda(), 1 / 64)              # window wider than the image: the reference fails too
