@@ -217,7 +217,7 @@ class B200Pipeline:
                  cfg_execution: str = "parallel", hires_fix: bool | None = None,
                  hires_oos_fraction: float | None = None, outmask_image=None, prompt=None, negative_prompt=None,
                  max_embeddings_multiples: int = 3, clip_layer="final", depth_map=None,
-                 run_safety_checker: bool = True, hints=None) -> PipelineOutput:
+                 run_safety_checker: bool = True, hints=None, depth_image=None) -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
         unified_pipeline.py:2055-2066 - optionally grafted (inpaint UNet early, main UNet late, :2069-2098) and, for
@@ -261,6 +261,14 @@ class B200Pipeline:
         # a depth hint goes to the depth UNet when the engine has one and no mask is given (:1974-2013); `depth_map` is the
         # hint already normalised to [-1, 1] at latent resolution ([1 | B, 1, H / 8, W / 8]) - estimating and resizing it is
         # the hinter's job upstream
+        if depth_image is not None:
+            # a depth hint at image resolution (unified_pipeline.py:2004-2013): first channel, scaled to the latent grid with
+            # images.resize(.., 1 / 8, sharpness=2) - lanczos3 without antialiasing - and mapped to [-1, 1]
+            if depth_map is not None:
+                raise ValueError("pass either depth_map (latent resolution, [-1, 1]) or depth_image ([0, 1]), not both")
+            from .images import resize
+            d = depth_image if depth_image.ndim == 4 else depth_image[None]
+            depth_map = 2.0 * resize(d[:, [0]].to(self.device), (1 / 8, 1 / 8), sharpness=2) - 1.0
         if depth_map is not None:
             if self.depth_unet is None or mask_image is not None:
                 raise EnvironmentError("a depth map needs a depth UNet and cannot be combined with a mask")

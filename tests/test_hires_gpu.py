@@ -272,3 +272,30 @@ def test_pipeline_depth_unet_vs_oracle(grafted):
     with pytest.raises(ValueError):
         pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=2, generator=[torch.Generator("cpu")] * 2,
              output_type="latent", depth_map=torch.zeros(1, 1, 8, 8).cuda())
+
+
+def test_depth_image_hint_matches_reference_call():
+    """`depth_image=` (a depth hint at image resolution): the latent-resolution map the pipeline derives equals the one the
+    reference's own lines produced, and the run equals what UnifiedPipeline.__call__ returned for that hint
+    (tests/golden/call.pt "depth", scripts/make_golden.py:pin_call) up to the fp16 UNet."""
+    import os
+    from oracle.unet import UNetConfig, synth_params, unet_param_shapes
+    from gyre_b200.images import resize
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "call.pt"))
+    dm = 2.0 * resize(G["depth_image"].cuda(), (1 / 8, 1 / 8), sharpness=2) - 1.0
+    assert (dm.cpu() - G["depth_map"]).abs().max().item() < 2e-6
+    cfg_d, cfg_m = UNetConfig.tiny(in_channels=5), UNetConfig.tiny()
+    pipe = B200Pipeline(B200UNet(cfg_m).load_state_dict(synth_params(unet_param_shapes(cfg_m), seed=1234)), None,
+                        depth_unet=B200UNet(cfg_d).load_state_dict(synth_params(unet_param_shapes(cfg_d), seed=321)))
+    pipe.unet_sample_size_override = 16
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 77, cfg_m.cross_attention_dim, generator=g)
+    unc = torch.randn(1, 77, cfg_m.cross_attention_dim, generator=torch.Generator().manual_seed(12)).expand(2, -1, -1).contiguous()
+    out = pipe(emb.cuda(), unc.cuda(), height=128, width=128, num_inference_steps=7, guidance_scale=7.5,
+               generator=[torch.Generator("cpu").manual_seed(s) for s in (420420420, 420420421)], sampler="k_euler_ancestral",
+               output_type="latent", latents_dtype=torch.float32, return_fp32_latents=True, depth_image=G["depth_image"].cuda()).latents
+    ref = G["depth"]
+    err = (out.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1.4e-2, f"depth hint vs the reference's own __call__: rel err {err}"
