@@ -58,7 +58,7 @@ class ClipVisionConfigC(C.Structure):
 class AdapterConfigC(C.Structure):
     _fields_ = [
         ("cin", C.c_int32), ("num_levels", C.c_int32), ("channels", C.c_int32 * 4), ("nums_rb", C.c_int32),
-        ("ksize", C.c_int32), ("sk", C.c_int32), ("use_conv", C.c_int32),
+        ("ksize", C.c_int32), ("sk", C.c_int32), ("use_conv", C.c_int32), ("light", C.c_int32),
     ]
 
 

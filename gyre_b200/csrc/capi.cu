@@ -541,7 +541,11 @@ int gyre_b200_adapter_create(const gyre_b200_adapter_config* cfg, gyre_b200_hand
   GYRE_REQUIRE(cfg && out, "adapter_create: null argument");
   GYRE_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= 4 && cfg->nums_rb >= 1 && cfg->nums_rb <= 8, "adapter_create: bad sizes");
   GYRE_REQUIRE(cfg->cin > 0 && cfg->cin % 64 == 0, "adapter_create: cin = %d must be 64 x image channels", cfg->cin);
-  GYRE_REQUIRE(cfg->ksize == 1 || cfg->ksize == 3, "adapter_create: ksize must be 1 or 3");
+  GYRE_REQUIRE(cfg->light || cfg->ksize == 1 || cfg->ksize == 3, "adapter_create: ksize must be 1 or 3");
+  if (cfg->light)
+    for (int i = 0; i < cfg->num_levels; ++i)
+      GYRE_REQUIRE(cfg->channels[i] % 32 == 0, "adapter_create: light adapters work at channels / 4 (channels[%d] = %d)", i,
+                   cfg->channels[i]);
   for (int i = 0; i < cfg->num_levels; ++i)
     GYRE_REQUIRE(cfg->channels[i] > 0 && cfg->channels[i] % 8 == 0, "adapter_create: channels[%d] = %d must be a multiple of 8",
                  i, cfg->channels[i]);

@@ -1375,6 +1375,26 @@ int ClipVisionModel::forward(Exec& ex, const __half* pixel_values, int B, __half
 // ([Downsample] -> [in_conv] -> block1 3x3 -> ReLU -> block2 -> + skip) -> one feature map per level.
 AdapterModel::AdapterModel(const gyre_b200_adapter_config& cfg) : cfg_(cfg) {
   const int* ch = cfg.channels;
+  if (cfg.light) {
+    // Adapter_light (adapter.py:202-263): state-dict names body.{level}.in_conv / .body.{j}.block1 / .block2 / .out_conv
+    light_.resize(cfg.num_levels);
+    for (int i = 0; i < cfg.num_levels; ++i) {
+      AdapterLightW* e = &light_[i];
+      const std::string p = "body." + std::to_string(i);
+      e->in_c = i == 0 ? cfg.cin : ch[i - 1];
+      e->inter_c = ch[i] / 4;
+      e->out_c = ch[i];
+      reg_linear(p + ".in_conv", e->inter_c, e->in_c, true, &e->in1);
+      e->b1.resize(cfg.nums_rb);
+      e->b2.resize(cfg.nums_rb);
+      for (int j = 0; j < cfg.nums_rb; ++j) {
+        reg_conv3(p + ".body." + std::to_string(j) + ".block1", e->inter_c, e->inter_c, &e->b1[j]);
+        reg_conv3(p + ".body." + std::to_string(j) + ".block2", e->inter_c, e->inter_c, &e->b2[j]);
+      }
+      reg_linear(p + ".out_conv", e->out_c, e->inter_c, true, &e->out1);
+    }
+    return;
+  }
   reg_conv3("conv_in", cfg.cin, ch[0], &conv_in_);
   body_.resize(static_cast<size_t>(cfg.num_levels) * cfg.nums_rb);
   for (int i = 0; i < cfg.num_levels; ++i)
@@ -1403,9 +1423,45 @@ AdapterModel::AdapterModel(const gyre_b200_adapter_config& cfg) : cfg_(cfg) {
     }
 }
 
+int AdapterModel::forward_light(Exec& ex, const __half* image, int B, int H, int W, __half* const* features) {
+  const int cimg = cfg_.cin / 64;
+  int h = H / 8, w = W / 8;
+  __half* x = ex.p16(static_cast<size_t>(B) * h * w * cfg_.cin);
+  RUN(ex, pixel_unshuffle8_nchw_to_nhwc(image, B, cimg, H, W, x, ex.st));
+  for (int i = 0; i < cfg_.num_levels; ++i) {
+    const AdapterLightW& e = light_[i];
+    if (i > 0) {
+      GYRE_REQUIRE(h >= 2 && w >= 2, "adapter: feature map %dx%d too small to pool", h, w);
+      __half* d = ex.p16(static_cast<size_t>(B) * (h / 2) * (w / 2) * e.in_c);
+      RUN(ex, avg_pool2x2_nhwc(x, B, h, w, e.in_c, d, ex.st));
+      x = d;
+      h /= 2;
+      w /= 2;
+    }
+    const size_t n = static_cast<size_t>(B) * h * w * e.inter_c;
+    __half* t = ex.p16(n);
+    RUN(ex, gemm_f16(x, e.in_c, e.in1.w, e.in_c, B * h * w, e.inter_c, e.in_c, ep_out(t, e.inter_c, e.in1.bias), ex.st));
+    for (int j = 0; j < cfg_.nums_rb; ++j) {
+      __half* h1 = ex.p16(n);
+      RUN(ex, conv3x3_f16(t, e.inter_c, B, h, w, e.inter_c, e.b1[j].wp, e.inter_c, 1, 1,
+                          ep_out(h1, e.inter_c, e.b1[j].bias, nullptr, 0, ACT_RELU), ex.st));
+      __half* o = ex.p16(n);
+      RUN(ex, conv3x3_f16(h1, e.inter_c, B, h, w, e.inter_c, e.b2[j].wp, e.inter_c, 1, 1,
+                          ep_out(o, e.inter_c, e.b2[j].bias, t, e.inter_c), ex.st));
+      t = o;
+    }
+    __half* f = ex.p16(static_cast<size_t>(B) * h * w * e.out_c);
+    RUN(ex, gemm_f16(t, e.inter_c, e.out1.w, e.inter_c, B * h * w, e.out_c, e.inter_c, ep_out(f, e.out_c, e.out1.bias), ex.st));
+    RUN(ex, nhwc_to_nchw_f16(f, e.out_c, B, e.out_c, h, w, features[i], ex.st));
+    x = f;
+  }
+  return 0;
+}
+
 int AdapterModel::forward(Exec& ex, const __half* image, int B, int H, int W, __half* const* features) {
   GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, "adapter_forward: image %dx%d must be a multiple of 8", H, W);
   if (!ex.dry) GYRE_TRY(ensure_device());
+  if (cfg_.light) return forward_light(ex, image, B, H, W, features);
   const int* ch = cfg_.channels;
   const int cimg = cfg_.cin / 64;
   int h = H / 8, w = W / 8;

@@ -273,6 +273,12 @@ class ClipVisionModel : public Model {
 };
 
 // T2I-adapter encoder (gyre/pipeline/t2i_adapter/adapter.py:65-132)
+struct AdapterLightW {     // one `extractor` of Adapter_light
+  LinW in1, out1;
+  std::vector<Conv3W> b1, b2;
+  int in_c = 0, inter_c = 0, out_c = 0;
+};
+
 struct AdapterBlockW {
   Conv3W down3;            // Downsample with conv (use_conv)
   Conv3W in3, b2_3, sk3;   // ksize 3 variants
@@ -295,6 +301,8 @@ class AdapterModel : public Model {
   gyre_b200_adapter_config cfg_;
   Conv3W conv_in_;
   std::vector<AdapterBlockW> body_;
+  std::vector<AdapterLightW> light_;
+  int forward_light(Exec& ex, const __half* image, int B, int H, int W, __half* const* features);
 };
 
 }  // namespace gyre

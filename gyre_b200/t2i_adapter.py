@@ -42,24 +42,31 @@ class B200T2iAdapter:
     [B, cin / 64, H, W] in [0, 1], returns the list of per-level feature maps."""
 
     def __init__(self, channels=(320, 640, 1280, 1280), nums_rb=3, cin=64, ksize=3, sk=False, use_conv=True,
-                 autoinvert=False, device=None):
+                 autoinvert=False, device=None, light=False):
         if not torch.cuda.is_available():
             raise N.NativeError("B200T2iAdapter needs a CUDA device: there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dtype = torch.float16
         self.channels, self.nums_rb, self.cin = tuple(channels), nums_rb, cin
         self.ksize, self.sk, self.use_conv, self.autoinvert = ksize, bool(sk), bool(use_conv), bool(autoinvert)
+        self.is_light = bool(light)          # Adapter_light (adapter.py:240-263; `type: light`, models.py:186-195)
         self._lib = N.load()
         self._h = C.c_void_p()
         self._ws = {}
         self._loaded = False
         c = N.AdapterConfigC()
         c.cin, c.num_levels, c.nums_rb, c.ksize = cin, len(self.channels), nums_rb, ksize
-        c.sk, c.use_conv = int(self.sk), int(self.use_conv)
+        c.sk, c.use_conv, c.light = int(self.sk), int(self.use_conv), int(self.is_light)
         for i, v in enumerate(self.channels):
             c.channels[i] = v
         with torch.cuda.device(self.device):
             N.check(self._lib.gyre_b200_adapter_create(C.byref(c), C.byref(self._h)), "adapter_create")
+
+    @classmethod
+    def light(cls, **config):
+        """`type: light` adapters (T2iAdapter_light, models.py:186-195: cin 192, nums_rb 4): every level works at a quarter of
+        the UNet's width - 1x1 in / out convolutions around plain conv-ReLU-conv residual blocks."""
+        return cls(**{**dict(cin=192, channels=(320, 640, 1280, 1280), nums_rb=4), **config, "light": True})
 
     @classmethod
     def main(cls, **config):
@@ -123,7 +130,8 @@ class B200T2iAdapter:
         feats, h, w = [], H // 8, W // 8
         for i, c in enumerate(self.channels):
             if i:
-                h, w = ((h - 1) // 2 + 1, (w - 1) // 2 + 1) if self.use_conv else (h // 2, w // 2)
+                # (light adapters always pool: floor halving, like use_conv=False)
+                h, w = ((h - 1) // 2 + 1, (w - 1) // 2 + 1) if (self.use_conv and not self.is_light) else (h // 2, w // 2)
             feats.append(torch.empty((B, c, h, w), device=self.device, dtype=torch.float16))
         ptrs = (C.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
         ws = self._workspace(B, H, W)

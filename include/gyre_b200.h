@@ -382,6 +382,8 @@ typedef struct gyre_b200_adapter_config {
   int32_t ksize;          /* 1 | 3: kernel of in_conv / block2 / skep (1) */
   int32_t sk;             /* 1: identity skip, in_conv only where the width changes (1) */
   int32_t use_conv;       /* 0: AvgPool2d(2) downsample, 1: stride-2 conv3x3 (0) */
+  int32_t light;          /* 1: Adapter_light (adapter.py:240-263): per level [AvgPool2d(2)] -> 1x1 in_conv to channels / 4 ->
+                             nums_rb x (conv3x3, ReLU, conv3x3, + x) -> 1x1 out_conv; no conv_in; ksize / sk / use_conv unused */
 } gyre_b200_adapter_config;
 int gyre_b200_adapter_create(const gyre_b200_adapter_config* cfg, gyre_b200_handle* out);
 int gyre_b200_adapter_workspace_bytes(gyre_b200_handle h, int batch, int height, int width, size_t* bytes);

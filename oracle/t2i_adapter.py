@@ -61,3 +61,35 @@ def adapter_forward(P, x, channels=(320, 640, 1280, 1280), nums_rb=2, ksize=1, s
                 x = h + x
         feats.append(x)
     return feats
+
+
+def adapter_light_param_shapes(channels=(320, 640, 1280, 1280), nums_rb=4, cin=192) -> dict:
+    """nn.Module state-dict names of `Adapter_light` (adapter.py:240-263) -> shapes."""
+    ks = {}
+    for i, c in enumerate(channels):
+        in_c, inter = (cin if i == 0 else channels[i - 1]), c // 4
+        ks[f"body.{i}.in_conv.weight"], ks[f"body.{i}.in_conv.bias"] = (inter, in_c, 1, 1), (inter,)
+        for j in range(nums_rb):
+            for b in ("block1", "block2"):
+                ks[f"body.{i}.body.{j}.{b}.weight"], ks[f"body.{i}.body.{j}.{b}.bias"] = (inter, inter, 3, 3), (inter,)
+        ks[f"body.{i}.out_conv.weight"], ks[f"body.{i}.out_conv.bias"] = (c, inter, 1, 1), (c,)
+    return ks
+
+
+def adapter_light_forward(P, x, channels=(320, 640, 1280, 1280), nums_rb=4):
+    """Adapter_light.forward (adapter.py:254-263) over `extractor` (:217-237) and ResnetBlock_light (:202-214): PixelUnshuffle(8);
+    per level [AvgPool2d(2)] -> 1x1 in_conv -> nums_rb x (conv3x3, ReLU, conv3x3, + x) -> 1x1 out_conv, which is both the
+    level's feature map and the next level's input.  PINNED against the reference class (scripts/make_golden.py:pin_t2i_adapter)."""
+    x = F.pixel_unshuffle(x, 8)
+    feats = []
+    for i in range(len(channels)):
+        p = f"body.{i}"
+        if i > 0:
+            x = F.avg_pool2d(x, kernel_size=2, stride=2)
+        x = F.conv2d(x, P[f"{p}.in_conv.weight"], P[f"{p}.in_conv.bias"])
+        for j in range(nums_rb):
+            h = F.relu(F.conv2d(x, P[f"{p}.body.{j}.block1.weight"], P[f"{p}.body.{j}.block1.bias"], padding=1))
+            x = F.conv2d(h, P[f"{p}.body.{j}.block2.weight"], P[f"{p}.body.{j}.block2.bias"], padding=1) + x
+        x = F.conv2d(x, P[f"{p}.out_conv.weight"], P[f"{p}.out_conv.bias"])
+        feats.append(x)
+    return feats

@@ -653,6 +653,22 @@ def pin_t2i_adapter():
         sd16 = {k: v.half().float() for k, v in sd.items()}
         with torch.no_grad():
             out[name]["features"] = oad.adapter_forward(sd16, x.half().float(), **{k: v for k, v in kw.items() if k != "cin"})
+    # Adapter_light (`type: light`)
+    lkw = dict(channels=[32, 64, 96, 96], nums_rb=2, cin=192)
+    torch.manual_seed(19)
+    m = ad.Adapter_light(**lkw).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == oad.adapter_light_param_shapes(**lkw), "light adapter parameter inventory"
+    x = torch.rand(2, 3, 128, 96, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = m(x)
+        mine = oad.adapter_light_forward(sd, x, channels=lkw["channels"], nums_rb=lkw["nums_rb"])
+        for a_, b_ in zip(ref, mine):
+            assert torch.equal(a_, b_), "Adapter_light.forward"
+        sd16 = {k: v.half().float() for k, v in sd.items()}
+        out["light_tiny"] = {"config": lkw, "state_dict": {k: v.half() for k, v in sd.items()}, "x": x.half(),
+                             "features": oad.adapter_light_forward(sd16, x.half().float(), channels=lkw["channels"],
+                                                                   nums_rb=lkw["nums_rb"])}
     torch.save(out, os.path.join(GOLD, "t2i_adapter.pt"))
     print(f"t2i_adapter: {len(out)} configurations, oracle bit-exact against gyre/pipeline/t2i_adapter/adapter.py")
 

@@ -30,6 +30,20 @@ def test_adapter_vs_reference_vectors(name):
     assert max(errs) < 4e-3          # fp16 activations between ~20 convolutions, fp32 accumulation
 
 
+def test_light_adapter_vs_reference_vectors():
+    """`type: light` (Adapter_light): vectors of the oracle pinned bit for bit to the reference class."""
+    from gyre_b200.t2i_adapter import B200T2iAdapter
+    v = torch.load(GOLD)["light_tiny"]
+    ad = B200T2iAdapter.light(**v["config"]).load_state_dict(v["state_dict"])
+    feats = ad(v["x"].cuda())
+    assert [tuple(f.shape) for f in feats] == [tuple(r.shape) for r in v["features"]]
+    errs = [rel_err(mine.cpu(), ref) for mine, ref in zip(feats, v["features"])]
+    print(f"light t2i adapter: rel err per level {['%.2e' % e for e in errs]}")
+    assert max(errs) < 4e-3
+    with pytest.raises(Exception):
+        B200T2iAdapter.light(channels=(40, 80, 120, 120))          # channels / 4 must stay a multiple of 8
+
+
 def test_adapter_into_unet_vs_oracle():
     """Native adapter -> native UNet (`adapter_states=`) == oracle adapter -> oracle UNet, SD-shaped widths in miniature."""
     from oracle import t2i_adapter as oad
