@@ -144,6 +144,7 @@ class B200Pipeline:
         self._hires_threshold_fraction = 0.0333
         self._hires_oos_fraction = 0.6
         self._hires_image_oos_fraction = 1.0
+        self._text_embedding_layer = "final"
 
     def get_unet_sample_size(self, unet):
         """unified_pipeline.py:1317-1320: forced minimum of 64."""
@@ -187,8 +188,22 @@ class B200Pipeline:
                 self._grafted_inpaint = value if isinstance(value, dict) else bool(value)
             elif key == "grafted_depth":
                 self._grafted_depth = value if isinstance(value, dict) else bool(value)
+            elif key == "text_embedding_layer":
+                # the CLIP layer prompts are embedded at unless the request says otherwise (:1624-1625, 2228-2243)
+                self._text_embedding_layer = value
+            elif key == "xformers":
+                pass        # attention always runs on the native flash kernel: nothing to switch (:1567-1579)
+            elif key == "graft_factor":
+                print("Graft Factor is no longer used. Please remove it from your engines.yaml.")       # (:1562-1566)
+            elif key == "structured_diffusion":
+                if value:
+                    print("structured diffusion is deprecated")                                       # (:1589-1590)
+            elif key in ("clip", "clip_vae_grad"):
+                # CLIP guidance differentiates a CLIP loss through the UNet and the VAE (unet/clipguided.py:301-338):
+                # inference-only kernels cannot serve it
+                raise NotImplementedError("CLIP guidance options: not available on the native path (needs autograd through the UNet / VAE)")
             else:
-                raise ValueError(f"Unknown option {key!r}")
+                raise ValueError(f"Unknown option {key}: {value} passed to UnifiedPipeline")
             self._options[key] = value
 
     def embed_prompts(self, prompt, negative_prompt=None, max_embeddings_multiples: int = 3, clip_layer="final"):
@@ -216,7 +231,7 @@ class B200Pipeline:
                  strength: float = 0.8, added_cond_kwargs=None, negative_added_cond_kwargs=None,
                  cfg_execution: str = "parallel", hires_fix: bool | None = None,
                  hires_oos_fraction: float | None = None, outmask_image=None, prompt=None, negative_prompt=None,
-                 max_embeddings_multiples: int = 3, clip_layer="final", depth_map=None,
+                 max_embeddings_multiples: int = 3, clip_layer=None, depth_map=None,
                  run_safety_checker: bool = True, hints=None, depth_image=None) -> PipelineOutput:
         """txt2img (image is None), img2img (image), inpaint (image + mask_image: the 9-channel UNets take the
         EnhancedRunwayInpaintMode path, 4-channel UNets the legacy x0-blend path) - the mode choice of
@@ -229,8 +244,8 @@ class B200Pipeline:
         if prompt_embeds is None:
             if prompt is None:
                 raise ValueError("pass `prompt` (text, needs the text encoder + tokenizer) or `prompt_embeds`")
-            prompt_embeds, negative_prompt_embeds = self.embed_prompts(prompt, negative_prompt, max_embeddings_multiples,
-                                                                       clip_layer)
+            prompt_embeds, negative_prompt_embeds = self.embed_prompts(
+                prompt, negative_prompt, max_embeddings_multiples, self._text_embedding_layer if clip_layer is None else clip_layer)
         elif prompt is not None:
             raise ValueError("pass either `prompt` or `prompt_embeds`, not both")
         if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
