@@ -55,6 +55,11 @@ class ClipVisionConfigC(C.Structure):
     ]
 
 
+class StyleAdapterConfigC(C.Structure):
+    _fields_ = [("width", C.c_int32), ("context_dim", C.c_int32), ("num_head", C.c_int32), ("n_layers", C.c_int32),
+                ("num_token", C.c_int32)]
+
+
 class AdapterConfigC(C.Structure):
     _fields_ = [
         ("cin", C.c_int32), ("num_levels", C.c_int32), ("channels", C.c_int32 * 4), ("nums_rb", C.c_int32),
@@ -113,6 +118,10 @@ SIGNATURES = {
     "gyre_b200_clip_vision_create": (_i, [C.POINTER(ClipVisionConfigC), C.POINTER(_vp)]),
     "gyre_b200_clip_vision_workspace_bytes": (_i, [_vp, _i, C.POINTER(_sz)]),
     "gyre_b200_safety_scores": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "gyre_b200_clip_vision_hidden": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "gyre_b200_style_adapter_create": (_i, [C.POINTER(StyleAdapterConfigC), C.POINTER(_vp)]),
+    "gyre_b200_style_adapter_workspace_bytes": (_i, [_vp, _i, _i, C.POINTER(_sz)]),
+    "gyre_b200_style_adapter_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "gyre_b200_resample_u8": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "gyre_b200_clip_normalize": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "gyre_b200_adapter_create": (_i, [C.POINTER(AdapterConfigC), C.POINTER(_vp)]),

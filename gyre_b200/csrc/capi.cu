@@ -497,7 +497,7 @@ int gyre_b200_clip_vision_create(const gyre_b200_clip_vision_config* cfg, gyre_b
                "clip_vision_create: hidden %d / heads %d / projection %d unsupported", cfg->hidden_size, cfg->num_heads,
                cfg->projection_dim);
   GYRE_REQUIRE(cfg->hidden_act == 0 || cfg->hidden_act == 1, "clip_vision_create: hidden_act must be quick_gelu (0) or gelu (1)");
-  GYRE_REQUIRE(cfg->num_concepts > 0 && cfg->num_special >= 0, "clip_vision_create: bad concept counts");
+  GYRE_REQUIRE(cfg->num_concepts >= 0 && cfg->num_special >= 0 && cfg->projection_dim >= 0, "clip_vision_create: bad concept counts");
   ClipVisionModel* m = new (std::nothrow) ClipVisionModel(*cfg);
   GYRE_REQUIRE(m != nullptr, "clip_vision_create: out of host memory");
   *out = reinterpret_cast<gyre_b200_handle>(static_cast<Model*>(m));
@@ -510,9 +510,51 @@ int gyre_b200_clip_vision_workspace_bytes(gyre_b200_handle h, int batch, size_t*
   Exec ex;
   ex.dry = true;
   ex.cap = static_cast<size_t>(1) << 60;
-  GYRE_TRY(static_cast<ClipVisionModel*>(M(h))->forward(ex, nullptr, batch, nullptr, nullptr));
+  GYRE_TRY(static_cast<ClipVisionModel*>(M(h))->forward(ex, nullptr, batch, nullptr, nullptr, nullptr, 0, true));
+  *bytes = ex.peak + 65536;     // (the scores path adds a few class-token rows on top of the tower's buffers)
+  return 0;
+}
+
+int gyre_b200_clip_vision_hidden(gyre_b200_handle h, const void* pixel_values, int batch, int skip_last, void* hidden,
+                                 void* workspace, size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && pixel_values && hidden, "clip_vision_hidden: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 4, "clip_vision_hidden: handle is not a CLIP vision model");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return static_cast<ClipVisionModel*>(M(h))->forward(ex, static_cast<const __half*>(pixel_values), batch, nullptr, nullptr,
+                                                      static_cast<__half*>(hidden), skip_last, true);
+}
+
+int gyre_b200_style_adapter_create(const gyre_b200_style_adapter_config* cfg, gyre_b200_handle* out) {
+  GYRE_REQUIRE(cfg && out, "style_adapter_create: null argument");
+  GYRE_REQUIRE(cfg->width > 0 && cfg->width % 8 == 0 && cfg->context_dim > 0 && cfg->context_dim % 8 == 0 && cfg->num_head > 0 &&
+                   cfg->width % cfg->num_head == 0 && (cfg->width / cfg->num_head) % 8 == 0 && cfg->width / cfg->num_head <= 192,
+               "style_adapter_create: width %d / heads %d / context %d unsupported", cfg->width, cfg->num_head, cfg->context_dim);
+  GYRE_REQUIRE(cfg->n_layers > 0 && cfg->num_token > 0, "style_adapter_create: bad sizes");
+  StyleAdapterModel* m = new (std::nothrow) StyleAdapterModel(*cfg);
+  GYRE_REQUIRE(m != nullptr, "style_adapter_create: out of host memory");
+  *out = reinterpret_cast<gyre_b200_handle>(static_cast<Model*>(m));
+  return 0;
+}
+
+int gyre_b200_style_adapter_workspace_bytes(gyre_b200_handle h, int batch, int tokens, size_t* bytes) {
+  GYRE_REQUIRE(h && bytes, "style_adapter_workspace_bytes: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 5, "style_adapter_workspace_bytes: handle is not a style adapter");
+  Exec ex;
+  ex.dry = true;
+  ex.cap = static_cast<size_t>(1) << 60;
+  GYRE_TRY(static_cast<StyleAdapterModel*>(M(h))->forward(ex, nullptr, batch, tokens, nullptr));
   *bytes = ex.peak + 4096;
   return 0;
+}
+
+int gyre_b200_style_adapter_forward(gyre_b200_handle h, const void* x, int batch, int tokens, void* out, void* workspace,
+                                    size_t workspace_bytes, gyre_b200_stream stream) {
+  GYRE_REQUIRE(h && x && out, "style_adapter_forward: null argument");
+  GYRE_REQUIRE(M(h)->kind() == 5, "style_adapter_forward: handle is not a style adapter");
+  Exec ex;
+  GYRE_TRY(make_exec(&ex, workspace, workspace_bytes, stream));
+  return static_cast<StyleAdapterModel*>(M(h))->forward(ex, static_cast<const __half*>(x), batch, tokens, static_cast<__half*>(out));
 }
 
 int gyre_b200_safety_scores(gyre_b200_handle h, const void* pixel_values, int batch, void* image_embeds, float* scores,

@@ -1311,7 +1311,8 @@ ClipVisionModel::ClipVisionModel(const gyre_b200_clip_vision_config& cfg) : cfg_
     reg_linear(p + ".mlp.fc1", F, C, true, &l->fc1);
     reg_linear(p + ".mlp.fc2", C, F, true, &l->fc2);
   }
-  reg_linear("visual_projection", cfg.projection_dim, C, false, &proj_);
+  if (cfg.projection_dim > 0) reg_linear("visual_projection", cfg.projection_dim, C, false, &proj_);
+  if (cfg.num_concepts <= 0 || cfg.projection_dim <= 0) return;       // tower only (style adapter's CLIP vision model)
   const int ne = cfg.num_special + cfg.num_concepts, D = cfg.projection_dim;
   embeds_ = static_cast<float*>(dalloc(sizeof(float) * static_cast<size_t>(ne) * D));
   thresholds_ = static_cast<float*>(dalloc(sizeof(float) * ne));
@@ -1321,8 +1322,12 @@ ClipVisionModel::ClipVisionModel(const gyre_b200_clip_vision_config& cfg) : cfg_
   reg("concept_embeds_weights", P_F32, thresholds_ ? thresholds_ + cfg.num_special : nullptr, {cfg.num_concepts});
 }
 
-int ClipVisionModel::forward(Exec& ex, const __half* pixel_values, int B, __half* image_embeds, float* scores) {
-  GYRE_REQUIRE(B > 0, "safety_scores: empty batch");
+int ClipVisionModel::forward(Exec& ex, const __half* pixel_values, int B, __half* image_embeds, float* scores, __half* hidden,
+                             int skip_last, bool hidden_only) {
+  GYRE_REQUIRE(B > 0, "clip vision: empty batch");
+  GYRE_REQUIRE(skip_last >= 0 && skip_last <= cfg_.num_layers, "clip vision: skip_last %d", skip_last);
+  GYRE_REQUIRE(hidden_only || (cfg_.num_concepts > 0 && cfg_.projection_dim > 0),
+               "safety_scores: this handle holds the vision tower only (no projection / concept embeddings)");
   if (!ex.dry) GYRE_TRY(ensure_device());
   const int C = cfg_.hidden_size, F = cfg_.intermediate_size, H = cfg_.num_heads, P = cfg_.patch_size, S = cfg_.image_size;
   const int np = (S / P) * (S / P), N = np + 1;
@@ -1347,7 +1352,7 @@ int ClipVisionModel::forward(Exec& ex, const __half* pixel_values, int B, __half
   RUN(ex, vision_embed(patches, class_emb_, pos_emb_, B, N, C, h2, ex.st));
   RUN(ex, layernorm_rows(h2, M, C, eps, pre_ln_.g, pre_ln_.b, h, ex.st));
   const int act = cfg_.hidden_act == 0 ? ACT_QUICKGELU : ACT_GELU;
-  for (int i = 0; i < cfg_.num_layers; ++i) {
+  for (int i = 0; i < cfg_.num_layers - (hidden_only ? skip_last : 0); ++i) {
     const ClipLayerW& l = layers_[i];
     RUN(ex, layernorm_rows(h, M, C, eps, l.ln1.g, l.ln1.b, nrm, ex.st));
     RUN(ex, gemm_f16(nrm, C, l.qkv.w, C, M, 3 * C, C, ep_out(qkv, 3 * C, l.qkv.bias), ex.st));
@@ -1356,6 +1361,11 @@ int ClipVisionModel::forward(Exec& ex, const __half* pixel_values, int B, __half
     RUN(ex, layernorm_rows(h2, M, C, eps, l.ln2.g, l.ln2.b, nrm, ex.st));
     RUN(ex, gemm_f16(nrm, C, l.fc1.w, C, M, F, C, ep_out(mid, F, l.fc1.bias, nullptr, 0, act), ex.st));
     RUN(ex, gemm_f16(mid, F, l.fc2.w, F, M, C, F, ep_out(h, C, l.fc2.bias, h2, C), ex.st));           // h = h2 + mlp
+  }
+  if (hidden_only) {
+    if (!ex.dry) GYRE_CHECK_CUDA(cudaMemcpyAsync(hidden, h, n * sizeof(__half), cudaMemcpyDeviceToDevice, ex.st));
+    EX_CHECK(ex);
+    return 0;
   }
   // pooled_output = post_layernorm(last_hidden_state[:, 0]): gather the class-token rows, normalise, project
   if (!ex.dry)
@@ -1366,6 +1376,84 @@ int ClipVisionModel::forward(Exec& ex, const __half* pixel_values, int B, __half
   RUN(ex, gemm_f16(pooled, C, proj_.w, C, B, cfg_.projection_dim, C, ep_out(emb_out, cfg_.projection_dim), ex.st));
   if (scores || ex.dry)
     RUN(ex, cosine_scores(emb_out, B, cfg_.projection_dim, embeds_, cfg_.num_special + cfg_.num_concepts, scores, ex.st));
+  EX_CHECK(ex);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ style T2I-adapter
+// StyleAdapter.forward (adapter.py:186-199): [x ; style_embedding] -> ln_pre -> n_layers x ResidualAttentionBlock
+// (x + MHA(ln_1 x); x + c_proj(quick_gelu(c_fc(ln_2 x))), nn.MultiheadAttention = packed q|k|v in_proj + out_proj, attention
+// across the tokens of one sample) -> ln_post of the last num_token tokens -> @ proj.
+StyleAdapterModel::StyleAdapterModel(const gyre_b200_style_adapter_config& cfg) : cfg_(cfg) {
+  const int D = cfg.width;
+  layers_.resize(cfg.n_layers);
+  for (int i = 0; i < cfg.n_layers; ++i) {
+    ClipLayerW* l = &layers_[i];
+    const std::string p = "transformer_layes." + std::to_string(i);          // (sic)
+    reg_norm(p + ".ln_1", D, &l->ln1);
+    reg_norm(p + ".ln_2", D, &l->ln2);
+    l->qkv.N = 3 * D;
+    l->qkv.K = D;
+    l->qkv.w = static_cast<__half*>(dalloc(sizeof(__half) * 3 * static_cast<size_t>(D) * D));
+    l->qkv.bias = static_cast<float*>(dalloc(sizeof(float) * 3 * D));
+    reg(p + ".attn.in_proj_weight", P_LINEAR, l->qkv.w, {3 * D, D}, D);
+    reg(p + ".attn.in_proj_bias", P_F32, l->qkv.bias, {3 * D});
+    reg_linear(p + ".attn.out_proj", D, D, true, &l->out);
+    reg_linear(p + ".mlp.c_fc", 4 * D, D, true, &l->fc1);
+    reg_linear(p + ".mlp.c_proj", D, 4 * D, true, &l->fc2);
+  }
+  style_emb_ = static_cast<__half*>(dalloc(sizeof(__half) * static_cast<size_t>(cfg.num_token) * D));
+  reg("style_embedding", P_LINEAR, style_emb_, {cfg.num_token, D}, D);
+  reg_norm("ln_pre", D, &ln_pre_);
+  reg_norm("ln_post", D, &ln_post_);
+  proj_.N = cfg.context_dim;
+  proj_.K = D;
+  proj_.w = static_cast<__half*>(dalloc(sizeof(__half) * static_cast<size_t>(cfg.context_dim) * D));
+  reg("proj", P_LINEAR, proj_.w, {cfg.context_dim, D}, D);
+}
+
+int StyleAdapterModel::forward(Exec& ex, const __half* x, int B, int L, __half* out) {
+  GYRE_REQUIRE(B > 0 && L > 0, "style_adapter_forward: empty input");
+  if (!ex.dry) GYRE_TRY(ensure_device());
+  const int D = cfg_.width, T = cfg_.num_token, H = cfg_.num_head, F = 4 * D;
+  const int N = L + T, M = B * N, d = D / H;
+  const size_t n = static_cast<size_t>(M) * D;
+  const float eps = 1e-5f;
+  const float scale = 1.0f / sqrtf(static_cast<float>(d));
+  __half* cat = ex.p16(n);
+  __half* h = ex.p16(n);
+  __half* h2 = ex.p16(n);
+  __half* nrm = ex.p16(n);
+  __half* qkv = ex.p16(n * 3);
+  __half* att = ex.p16(n);
+  __half* mid = ex.p16(static_cast<size_t>(M) * F);
+  __half* tail = ex.p16(static_cast<size_t>(B) * T * D);
+  __half* tail_n = ex.p16(static_cast<size_t>(B) * T * D);
+  if (!ex.dry) {
+    const size_t row = static_cast<size_t>(D) * sizeof(__half);
+    GYRE_CHECK_CUDA(cudaMemcpy2DAsync(cat, N * row, x, L * row, L * row, B, cudaMemcpyDeviceToDevice, ex.st));
+    for (int b = 0; b < B; ++b)
+      GYRE_CHECK_CUDA(cudaMemcpyAsync(cat + (static_cast<size_t>(b) * N + L) * D, style_emb_, T * row, cudaMemcpyDeviceToDevice,
+                                      ex.st));
+  }
+  RUN(ex, layernorm_rows(cat, M, D, eps, ln_pre_.g, ln_pre_.b, h, ex.st));
+  for (int i = 0; i < cfg_.n_layers; ++i) {
+    const ClipLayerW& l = layers_[i];
+    RUN(ex, layernorm_rows(h, M, D, eps, l.ln1.g, l.ln1.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, D, l.qkv.w, D, M, 3 * D, D, ep_out(qkv, 3 * D, l.qkv.bias), ex.st));
+    RUN(ex, attention_f16(qkv, 3 * D, off(qkv, D), 3 * D, off(qkv, 2 * D), 3 * D, B, H, N, N, d, scale, att, D, ex.st));
+    RUN(ex, gemm_f16(att, D, l.out.w, D, M, D, D, ep_out(h2, D, l.out.bias, h, D), ex.st));
+    RUN(ex, layernorm_rows(h2, M, D, eps, l.ln2.g, l.ln2.b, nrm, ex.st));
+    RUN(ex, gemm_f16(nrm, D, l.fc1.w, D, M, F, D, ep_out(mid, F, l.fc1.bias, nullptr, 0, ACT_QUICKGELU), ex.st));
+    RUN(ex, gemm_f16(mid, F, l.fc2.w, F, M, D, F, ep_out(h, D, l.fc2.bias, h2, D), ex.st));
+  }
+  if (!ex.dry) {
+    const size_t row = static_cast<size_t>(D) * sizeof(__half);
+    GYRE_CHECK_CUDA(cudaMemcpy2DAsync(tail, T * row, h + static_cast<size_t>(L) * D, N * row, T * row, B, cudaMemcpyDeviceToDevice,
+                                      ex.st));
+  }
+  RUN(ex, layernorm_rows(tail, B * T, D, eps, ln_post_.g, ln_post_.b, tail_n, ex.st));
+  RUN(ex, gemm_f16(tail_n, D, proj_.w, D, B * T, cfg_.context_dim, D, ep_out(out, cfg_.context_dim), ex.st));
   EX_CHECK(ex);
   return 0;
 }

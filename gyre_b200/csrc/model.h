@@ -257,7 +257,10 @@ class ClipVisionModel : public Model {
   explicit ClipVisionModel(const gyre_b200_clip_vision_config& cfg);
   bool is_unet() const override { return false; }
   int kind() const override { return 4; }
-  int forward(Exec& ex, const __half* pixel_values, int B, __half* image_embeds, float* scores);
+  // hidden != nullptr: stop after (num_layers - skip_last) layers and hand out the hidden states [B, tokens, C]
+  int forward(Exec& ex, const __half* pixel_values, int B, __half* image_embeds, float* scores, __half* hidden = nullptr,
+              int skip_last = 0, bool hidden_only = false);
+  int tokens() const { return (cfg_.image_size / cfg_.patch_size) * (cfg_.image_size / cfg_.patch_size) + 1; }
 
  private:
   gyre_b200_clip_vision_config cfg_;
@@ -270,6 +273,22 @@ class ClipVisionModel : public Model {
   LinW proj_;                     // visual_projection [projection_dim, C]
   float* embeds_ = nullptr;       // [num_special + num_concepts, projection_dim]: special-care rows first
   float* thresholds_ = nullptr;   // [num_special + num_concepts] (kept for completeness; the host applies them)
+};
+
+// Style T2I-adapter (gyre/pipeline/t2i_adapter/adapter.py:173-199)
+class StyleAdapterModel : public Model {
+ public:
+  explicit StyleAdapterModel(const gyre_b200_style_adapter_config& cfg);
+  bool is_unet() const override { return false; }
+  int kind() const override { return 5; }
+  int forward(Exec& ex, const __half* x, int B, int L, __half* out);
+
+ private:
+  gyre_b200_style_adapter_config cfg_;
+  std::vector<ClipLayerW> layers_;
+  __half* style_emb_ = nullptr;   // [num_token, width]
+  NormW ln_pre_, ln_post_;
+  LinW proj_;                     // [context_dim, width] (the module's `proj` transposed)
 };
 
 // T2I-adapter encoder (gyre/pipeline/t2i_adapter/adapter.py:65-132)

@@ -263,8 +263,8 @@ typedef struct gyre_b200_clip_vision_config {
   int32_t num_heads;               /* 16                             */
   int32_t hidden_act;              /* 0 quick_gelu, 1 gelu (erf)     */
   float layer_norm_eps;            /* 1e-5                           */
-  int32_t projection_dim;          /* 768                            */
-  int32_t num_concepts;            /* 17                             */
+  int32_t projection_dim;          /* 768; 0: no visual projection (tower only)  */
+  int32_t num_concepts;            /* 17; 0: no concept embeddings (tower only)  */
   int32_t num_special;             /* 3                              */
 } gyre_b200_clip_vision_config;
 int gyre_b200_clip_vision_create(const gyre_b200_clip_vision_config* cfg, gyre_b200_handle* out);
@@ -278,6 +278,29 @@ int gyre_b200_safety_scores(gyre_b200_handle h, const void* pixel_values, int ba
  * src [n_outer, in_size, inner] -> dst [n_outer, out_size, inner] (bounds [out_size, 2] = first source index and tap
  * count, coeffs [out_size, ksize] 22-bit fixed point: built on the host with PIL's expressions), and the centre crop +
  * x 1/255 + (x - mean) / std of u8 NHWC [batch, H, W, 3] -> fp16 NCHW [batch, 3, S, S]. */
+/* The vision tower alone (CLIPModel.vision_model as the style T2I-adapter uses it, gyre/pipeline/unified_pipeline.py:941-958):
+ * hidden states [batch, tokens, hidden_size] fp16 after (num_layers - skip_last) encoder layers, before post_layernorm -
+ * skip_last = 0 is `last_hidden_state`, 1 is `hidden_states[-2]` ...  A handle made with num_concepts = 0 and
+ * projection_dim = 0 registers the tower's parameters only. */
+int gyre_b200_clip_vision_hidden(gyre_b200_handle h, const void* pixel_values, int batch, int skip_last, void* hidden,
+                                 void* workspace, size_t workspace_bytes, gyre_b200_stream stream);
+
+/* Style T2I-adapter (replaces StyleAdapter.forward, gyre/pipeline/t2i_adapter/adapter.py:173-199; T2iAdapter_style,
+ * models.py:146-160): x [batch, tokens, width] fp16 (CLIP vision hidden states) -> out [batch, num_token, context_dim] fp16,
+ * the extra context tokens of the guided side.  Parameter keys are the module's, with two reshapes done by the caller:
+ * "style_embedding" as [num_token, width] and "proj" TRANSPOSED to [context_dim, width]. */
+typedef struct gyre_b200_style_adapter_config {
+  int32_t width;        /* 1024 */
+  int32_t context_dim;  /* 768  */
+  int32_t num_head;     /* 8    */
+  int32_t n_layers;     /* 3    */
+  int32_t num_token;    /* 8    */
+} gyre_b200_style_adapter_config;
+int gyre_b200_style_adapter_create(const gyre_b200_style_adapter_config* cfg, gyre_b200_handle* out);
+int gyre_b200_style_adapter_workspace_bytes(gyre_b200_handle h, int batch, int tokens, size_t* bytes);
+int gyre_b200_style_adapter_forward(gyre_b200_handle h, const void* x, int batch, int tokens, void* out, void* workspace,
+                                    size_t workspace_bytes, gyre_b200_stream stream);
+
 int gyre_b200_resample_u8(const void* src, int64_t n_outer, int in_size, int inner, const int32_t* bounds,
                           const int32_t* coeffs, int ksize, int out_size, void* dst, gyre_b200_stream stream);
 int gyre_b200_clip_normalize(const void* src_u8_nhwc, int batch, int height, int width, int crop, const float* mean3,

@@ -118,8 +118,10 @@ def clip_preprocess(images_u8_nhwc: np.ndarray, size: int = 224, mean=CLIP_MEAN,
     return np.stack(out)
 
 
-def clip_vision_forward(P: dict, pixel_values, *, num_layers, num_heads, patch_size, hidden_act="quick_gelu", eps=1e-5):
-    """Returns (pooled_output [B, C], image_embeds [B, projection_dim])."""
+def clip_vision_forward(P: dict, pixel_values, *, num_layers, num_heads, patch_size, hidden_act="quick_gelu", eps=1e-5,
+                        return_hidden_states=False):
+    """Returns (pooled_output [B, C], image_embeds [B, projection_dim]); with return_hidden_states also the transformers
+    `hidden_states` tuple (entry k = output of k encoder layers, before post_layernorm; the last one is last_hidden_state)."""
     w = P["vision_model.embeddings.patch_embedding.weight"]
     x = F.conv2d(pixel_values, w, stride=patch_size).flatten(2).transpose(1, 2)             # [B, np, C]
     B, _, C = x.shape
@@ -128,6 +130,7 @@ def clip_vision_forward(P: dict, pixel_values, *, num_layers, num_heads, patch_s
     h = F.layer_norm(h, (C,), P["vision_model.pre_layrnorm.weight"], P["vision_model.pre_layrnorm.bias"], eps)
     N = h.shape[1]
     d = C // num_heads
+    hs = [h]
     for i in range(num_layers):
         p = f"vision_model.encoder.layers.{i}"
         n = F.layer_norm(h, (C,), P[f"{p}.layer_norm1.weight"], P[f"{p}.layer_norm1.bias"], eps)
@@ -142,8 +145,10 @@ def clip_vision_forward(P: dict, pixel_values, *, num_layers, num_heads, patch_s
         m = F.linear(n, P[f"{p}.mlp.fc1.weight"], P[f"{p}.mlp.fc1.bias"])
         m = m * torch.sigmoid(1.702 * m) if hidden_act == "quick_gelu" else F.gelu(m)
         h = h + F.linear(m, P[f"{p}.mlp.fc2.weight"], P[f"{p}.mlp.fc2.bias"])
+        hs.append(h)
     pooled = F.layer_norm(h[:, 0], (C,), P["vision_model.post_layernorm.weight"], P["vision_model.post_layernorm.bias"], eps)
-    return pooled, F.linear(pooled, P["visual_projection.weight"])
+    emb = F.linear(pooled, P["visual_projection.weight"]) if "visual_projection.weight" in P else None
+    return (pooled, emb, hs) if return_hidden_states else (pooled, emb)
 
 
 def cosine_scores(image_embeds, P):

@@ -7,6 +7,7 @@ use_conv False).  adapter.py is pure torch: scripts/make_golden.py imports it as
 Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may import this module."""
 from __future__ import annotations
 
+import torch
 import torch.nn.functional as F
 
 
@@ -93,3 +94,28 @@ def adapter_light_forward(P, x, channels=(320, 640, 1280, 1280), nums_rb=4):
         x = F.conv2d(x, P[f"{p}.out_conv.weight"], P[f"{p}.out_conv.bias"])
         feats.append(x)
     return feats
+
+
+def style_adapter_forward(P, x, num_head=8, num_token=8):
+    """StyleAdapter.forward (adapter.py:186-199) over ResidualAttentionBlock (:153-170; nn.MultiheadAttention written out:
+    packed in_proj, softmax(q k^T / sqrt d) v per head over the tokens of one sample, out_proj) and the fp32 LayerNorm
+    subclass (:135-142).  PINNED against the reference class (scripts/make_golden.py:pin_t2i_adapter)."""
+    B, L, D = x.shape
+    T = num_token
+    d = D // num_head
+
+    def ln(t, p):
+        return F.layer_norm(t.float(), (D,), P[f"{p}.weight"].float(), P[f"{p}.bias"].float(), 1e-5).to(t.dtype)
+    style = P["style_embedding"] + torch.zeros((B, T, D), device=x.device)
+    h = ln(torch.cat([x, style], dim=1), "ln_pre")
+    n_layers = 1 + max(int(k.split(".")[1]) for k in P if k.startswith("transformer_layes."))
+    for i in range(n_layers):
+        p = f"transformer_layes.{i}"
+        qkv = F.linear(ln(h, f"{p}.ln_1"), P[f"{p}.attn.in_proj_weight"], P[f"{p}.attn.in_proj_bias"])
+        q, k, v = (t.reshape(B, L + T, num_head, d).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
+        a = torch.softmax((q * d ** -0.5) @ k.transpose(-1, -2), dim=-1) @ v
+        a = a.permute(0, 2, 1, 3).reshape(B, L + T, D)
+        h = h + F.linear(a, P[f"{p}.attn.out_proj.weight"], P[f"{p}.attn.out_proj.bias"])
+        m = F.linear(ln(h, f"{p}.ln_2"), P[f"{p}.mlp.c_fc.weight"], P[f"{p}.mlp.c_fc.bias"])
+        h = h + F.linear(m * torch.sigmoid(1.702 * m), P[f"{p}.mlp.c_proj.weight"], P[f"{p}.mlp.c_proj.bias"])
+    return ln(h[:, -T:, :], "ln_post") @ P["proj"]

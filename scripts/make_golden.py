@@ -669,6 +669,26 @@ def pin_t2i_adapter():
         out["light_tiny"] = {"config": lkw, "state_dict": {k: v.half() for k, v in sd.items()}, "x": x.half(),
                              "features": oad.adapter_light_forward(sd16, x.half().float(), channels=lkw["channels"],
                                                                    nums_rb=lkw["nums_rb"])}
+    # StyleAdapter (`type: style`)
+    skw = dict(width=64, context_dim=48, num_head=4, n_layes=2, num_token=4)
+    torch.manual_seed(23)
+    m = ad.StyleAdapter(**skw).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g3 = torch.Generator().manual_seed(6)
+    for k in sd:
+        if k.endswith("bias") or "ln_" in k:
+            sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g3)
+    m.load_state_dict(sd)
+    xs = torch.randn(2, 17, skw["width"], generator=g3)
+    with torch.no_grad():
+        ref = m(xs)
+        mine = oad.style_adapter_forward(sd, xs, num_head=skw["num_head"], num_token=skw["num_token"])
+        err = (ref - mine).abs().max().item()
+        assert err < 2e-6, f"StyleAdapter.forward: {err}"
+        sd16 = {k: v.half().float() for k, v in sd.items()}
+        out["style_tiny"] = {"config": skw, "state_dict": {k: v.half() for k, v in sd.items()}, "x": xs.half(),
+                             "tokens": oad.style_adapter_forward(sd16, xs.half().float(), num_head=skw["num_head"],
+                                                                 num_token=skw["num_token"])}
     torch.save(out, os.path.join(GOLD, "t2i_adapter.pt"))
     print(f"t2i_adapter: {len(out)} configurations, oracle bit-exact against gyre/pipeline/t2i_adapter/adapter.py")
 
@@ -736,11 +756,17 @@ def pin_safety():
         m.load_state_dict(sd, strict=False)
         P = {k[len("vision_model."):] if k.startswith("vision_model.vision_model.") else k: v for k, v in sd.items()}
         with torch.no_grad():
-            pooled_ref = m.vision_model(x)[1]
+            vout = m.vision_model(x, output_hidden_states=True, return_dict=True)
+            pooled_ref = vout.pooler_output
             emb_ref = m.visual_projection(pooled_ref)
-            pooled, emb = osf.clip_vision_forward(P, x, num_layers=vis["num_hidden_layers"], num_heads=vis["num_attention_heads"],
-                                                  patch_size=vis["patch_size"], hidden_act=vis["hidden_act"])
+            pooled, emb, hs = osf.clip_vision_forward(P, x, num_layers=vis["num_hidden_layers"], num_heads=vis["num_attention_heads"],
+                                                      patch_size=vis["patch_size"], hidden_act=vis["hidden_act"],
+                                                      return_hidden_states=True)
             assert (pooled - pooled_ref).abs().max().item() < 2e-5 and (emb - emb_ref).abs().max().item() < 2e-5, name
+            assert len(hs) == len(vout.hidden_states)
+            for a_, b_ in zip(hs, vout.hidden_states):
+                assert (a_ - b_).abs().max().item() < 5e-5, name          # hidden states (the style adapter's input)
+            assert (hs[-1] - vout.last_hidden_state).abs().max().item() < 5e-5
             scores = osf.cosine_scores(emb_ref, P)
         print(f"  {name}: score spread across the batch (std per column, mean) {scores.std(0).mean().item():.3f}")
         # thresholds in the middle of the score distribution so the flags are mixed, special-care hits included, and no
@@ -775,6 +801,8 @@ def pin_safety():
         assert imgs_out is imgs and list(flags_ref) == list(flags), f"FlagOnlySafetyChecker.forward ({name}): {flags_ref} vs {flags}"
         sd = {k: (v.half() if torch.equal(v.half().float(), v) else v) for k, v in sd.items()}
         out["models"][name] = {"vision_config": vis, "projection_dim": proj, "state_dict": sd, "clip_input": x.half(),
+                               "hidden_last": hs[-1][:2].half() if name == "tiny" else None,
+                               "hidden_penultimate": hs[-2][:2].half() if name == "tiny" else None,
                                "image_embeds": emb_ref, "scores": scores, "flags": [bool(f) for f in flags],
                                "result": [{"special_scores": [float(v) for v in r["special_scores"].values()],
                                            "concept_scores": [float(v) for v in r["concept_scores"].values()],

@@ -88,3 +88,37 @@ def test_adapter_autoinvert_and_errors():
         plain(torch.zeros(1, 1, 64, 64).half().cuda())
     with pytest.raises(ValueError):
         plain(torch.zeros(1, 3, 60, 64).half().cuda())
+
+
+def test_style_adapter_vs_reference_vectors():
+    """`type: style` (StyleAdapter): tokens of the oracle pinned to the reference class (real nn.MultiheadAttention)."""
+    from gyre_b200.clip_vision import B200T2iStyleAdapter, style_adapter_param_shapes
+    v = torch.load(GOLD)["style_tiny"]
+    assert style_adapter_param_shapes(**v["config"]) == {k: tuple(t.shape) for k, t in v["state_dict"].items()}
+    ad = B200T2iStyleAdapter(**v["config"]).load_state_dict(v["state_dict"])
+    tok = ad(v["x"].cuda())
+    assert tuple(tok.shape) == tuple(v["tokens"].shape)
+    err = rel_err(tok.cpu(), v["tokens"])
+    print(f"style adapter: rel err {err:.2e}")
+    assert err < 5e-3
+    # one sample's tokens do not depend on its batch neighbour
+    assert torch.equal(ad(v["x"][1:].cuda()), tok[1:])
+
+
+def test_clip_vision_hidden_states_vs_transformers_fixture():
+    """B200CLIPVisionModel (`clip_model.vision_model(image, output_hidden_states=)`): last and penultimate hidden states against
+    the oracle pinned to transformers' CLIPVisionModel (tests/golden/safety.pt)."""
+    from gyre_b200.clip_vision import B200CLIPVisionModel
+    m = torch.load(os.path.join(os.path.dirname(__file__), "golden", "safety.pt"))["models"]["tiny"]
+    sd = {k[len("vision_model."):]: v for k, v in m["state_dict"].items() if k.startswith("vision_model.vision_model.")}
+    vm = B200CLIPVisionModel(m["vision_config"]).load_state_dict(sd)
+    out = vm.vision_model(m["clip_input"][:2].cuda(), output_hidden_states=True, return_dict=True)
+    for got, ref in ((out.last_hidden_state, m["hidden_last"]), (out.hidden_states[-1], m["hidden_last"]),
+                     (out.hidden_states[-2], m["hidden_penultimate"])):
+        err = (got.float().cpu() - ref.float()).abs().max().item()
+        assert err < 2e-2 * max(1.0, ref.float().abs().max().item()), err
+    assert len(out.hidden_states) == m["vision_config"]["num_hidden_layers"] + 1
+    with pytest.raises(Exception):
+        from gyre_b200 import _native as N
+        import ctypes as C
+        N.check(N.load().gyre_b200_safety_scores(vm._h, None, 1, None, None, None, 0, None), "safety_scores")   # tower-only handle
