@@ -64,6 +64,10 @@ class B200GuidedUNet:
         self.controlnets = [h for h in hints if isinstance(h, B200ControlnetHint)]
         t2i = [h for h in hints if isinstance(h, B200T2iHint)]
         self.t2i = UNetWithT2I(None, t2i) if t2i else None
+        if self.t2i is not None and self.t2i.style_states is not None:
+            # style tokens extend the context for the life of this wrapper (core.py:221-237): [uncond + its own tail ; cond +
+            # style tokens]; the UNet re-projects K / V for the longer context on first use
+            self.embeddings = self.t2i.styled_context(self.embeddings, "f").to(torch.float16).contiguous()
 
     def _hint_kwargs(self, x_in, t_i64, embeddings, cfg_meta):
         """UNetWithControlnet / UNetWithT2I (unet/core.py:38-64, 212-239) for one native UNet call."""

@@ -12,7 +12,9 @@ The models are `B200ControlNet` / `B200T2iAdapter`; their outputs go to the nati
 
 Hint masks (the alpha channel of an RGBA hint, or `mask=`) and ControlNets under the 9-channel inpaint UNets go through
 `gyre_b200.images.resize` (the lanczos3 ResizeRight call of gyre/images.py:324-340 on the device); the resized masks are
-cached per request - they do not change between steps.  Not built (raise): style adapters, co-adapters + fuser."""
+cached per request - they do not change between steps.  Style adapters (`style_call`, :941-975: the hint image through
+`images.rescale(.., "cover")`, the CLIP normalisation, the CLIP vision tower and `B200T2iStyleAdapter`) add context tokens to
+the guided side (core.py:221-237).  Not built (raise): co-adapters + fuser."""
 from __future__ import annotations
 
 from types import SimpleNamespace
@@ -150,11 +152,41 @@ class B200ControlnetHint:
         return SimpleNamespace(down_block_res_samples=down, mid_block_res_sample=mid)
 
 
-class B200T2iHint:
-    """UnifiedPipelineHint_T2i, standard (non-style) adapters (unified_pipeline.py:836-955)."""
+def normalise_clip_layer(clip_layer, default=None):
+    """gyre/pipeline/prompt_types.py:19-34."""
+    if clip_layer is None:
+        clip_layer = default
+    if isinstance(clip_layer, int):
+        clip_layer = abs(clip_layer)
+    if clip_layer in (0, 1, "final"):
+        return "final"
+    if clip_layer in (2, "penultimate"):
+        return "penultimate"
+    return clip_layer
 
-    def __init__(self, model, image, mask=None, weight=1.0, soft_injection=False, cfg_only=False):
+
+class B200T2iHint:
+    """UnifiedPipelineHint_T2i (unified_pipeline.py:836-955): standard adapters (a list of per-level states) and style
+    adapters (context tokens; needs `clip_model` = B200CLIPVisionModel and a feature extractor for mean / std / size)."""
+
+    def __init__(self, model, image, mask=None, weight=1.0, soft_injection=False, cfg_only=False, clip_model=None,
+                 feature_extractor=None, clip_layer=None):
         self.model = model
+        self.type = "style" if hasattr(model, "num_token") else "standard"
+        if self.type == "style":
+            # (masks and soft injection "don't make sense" for style adapters: ignored like the reference, :873-883)
+            if clip_model is None or feature_extractor is None:
+                raise ValueError("T2i Style model needs a clip model and feature extractor")
+            img, _ = _split_hint(image, None)
+            self.image = img.to(device=model.device, dtype=torch.float32).contiguous()
+            self.mask = None
+            self.weight, self.soft_injection, self.cfg_only = float(weight), False, bool(cfg_only)
+            self.clip_model, self.clip_layer, self.fuser = clip_model, clip_layer, None
+            self.image_mean = torch.tensor(feature_extractor.image_mean, device=model.device).view(1, 3, 1, 1)
+            self.image_std = torch.tensor(feature_extractor.image_std, device=model.device).view(1, 3, 1, 1)
+            size = feature_extractor.size
+            self.clip_size = size["shortest_edge"] if isinstance(size, dict) else size
+            return
         channels = model.cin // 64               # (`model.config.cin // 64`, unified_pipeline.py:869)
         img, mask = _split_hint(image, mask, channels=1 if channels == 1 else 3)
         self.image = img.to(device=model.device, dtype=torch.float16).contiguous()
@@ -171,7 +203,24 @@ class B200T2iHint:
     def coadapter_type(self):
         return False
 
+    def style_call(self):
+        """:941-975: rescale to the CLIP size ("cover"), normalise, vision tower hidden state of the chosen layer, adapter."""
+        from .images import rescale
+        layer = normalise_clip_layer(self.clip_layer, "final")
+        image = rescale(self.image, self.clip_size, self.clip_size, "cover")
+        image = (image - self.image_mean) / self.image_std
+        out = self.clip_model.vision_model(image, output_hidden_states=(layer != "final"), return_dict=True)
+        if layer == "final":
+            hidden = out.last_hidden_state
+        elif layer == "penultimate":
+            hidden = out.hidden_states[-2]
+        else:
+            hidden = out.hidden_states[-layer]
+        return self.model(hidden) * self.weight
+
     def __call__(self):
+        if self.type == "style":
+            return self.style_call()
         layer_weights = [1.0, 1.0, 1.0, 1.0]
         if self.soft_injection:
             layer_weights = torch.logspace(-0.25, 0, 4).tolist()
@@ -249,13 +298,18 @@ class UNetWithT2I:
         self.standard_states = None
         self.style_states = None
         standard = AdapterStateList()
+        style = []
         for adapter in t2i_adapters:
             if adapter.coadapter_type():
                 raise NotImplementedError("co-adapters need the fuser model: not built")
             state = adapter()
-            if not isinstance(state, list):
-                raise NotImplementedError("style adapters (token states) are not built")
-            standard.append(state, adapter.cfg_only)
+            if isinstance(state, list):
+                standard.append(state, adapter.cfg_only)
+            else:
+                style.append(state)              # style states always apply to the guided side only (core.py:99-100)
+        if style:
+            self.style_states = torch.cat(style, dim=1)
+            self.style_dim0, self.style_dim1 = self.style_states.shape[0], self.style_states.shape[1]
         g, u = list(standard.all), list(standard.either)
         if g:
             self.standard_states = {"u": _sum_lists(u), "g": _sum_lists(g)}
@@ -276,9 +330,33 @@ class UNetWithT2I:
             self.standard_states = dict(self.standard_states, **{cfg_meta: states})      # expanded once per request
         return states
 
+    def styled_context(self, hidden_states, cfg_meta):
+        """core.py:221-237: the guided side's context gets the style tokens appended; the unconditional side is padded to
+        the same length with its own last tokens."""
+        if self.style_states is None:
+            return hidden_states
+        if cfg_meta == "f":
+            uncond, cond = hidden_states.chunk(2)
+        elif cfg_meta == "u":
+            uncond, cond = hidden_states, None
+        else:
+            uncond, cond = None, hidden_states
+        res = []
+        if uncond is not None:
+            res.append(torch.cat([uncond, uncond[:, -self.style_dim1:, :]], dim=1))
+        if cond is not None:
+            style = self.style_states.to(cond.dtype)
+            if style.shape[0] == 1 and cond.shape[0] > 1:
+                style = style.expand(cond.shape[0], -1, -1)          # one hint image serves every sample of the request
+            res.append(torch.cat([cond, style], dim=1))
+        return torch.cat(res, dim=0)
+
     def __call__(self, latents, t, **kwargs):
-        is_f = kwargs["encoder_hidden_states"].shape[0] == self.standard_dim0 * 2
+        dim0 = self.standard_dim0 if self.standard_states is not None else self.style_dim0
+        is_f = kwargs["encoder_hidden_states"].shape[0] == dim0 * 2
         cfg_meta = kwargs.get("cfg_meta", "f" if is_f else "g")
         if self.standard_states is not None:
             kwargs["adapter_states"] = self.standard_states[cfg_meta]
+        if self.style_states is not None:
+            kwargs["encoder_hidden_states"] = self.styled_context(kwargs.pop("encoder_hidden_states"), cfg_meta)
         return self.unet(latents, t, **kwargs)

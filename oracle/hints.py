@@ -77,16 +77,37 @@ class ControlnetHint:
 
 
 class T2iHint:
-    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False, mask=None, channels=3):
+    def __init__(self, model, image, weight=1.0, soft_injection=False, cfg_only=False, mask=None, channels=3, style=None):
+        """style: None for standard adapters, else dict(vision=callable(image, output_hidden_states) -> object with
+        last_hidden_state / hidden_states, mean, std, size, clip_layer) - UnifiedPipelineHint_T2i.style_setup / style_call
+        (unified_pipeline.py:843-853, 941-975)."""
         self.model = model
-        self.image, self.mask = split_hint(image, mask, channels)
-        self.weight, self.soft_injection, self.cfg_only = weight, soft_injection, cfg_only
+        self.image, self.mask = split_hint(image, None if style else mask, channels)
+        self.weight, self.soft_injection, self.cfg_only = weight, (False if style else soft_injection), cfg_only
         self.fuser = None
+        self.style = style
 
     def coadapter_type(self):
         return False
 
+    def style_call(self):
+        from .hires import images_rescale
+        st = self.style
+        layer = st.get("clip_layer") or "final"
+        if isinstance(layer, int):
+            layer = abs(layer)
+        layer = "final" if layer in (0, 1, "final") else ("penultimate" if layer in (2, "penultimate") else layer)
+        image = images_rescale(self.image, st["size"], st["size"], "cover")
+        mean = torch.tensor(st["mean"]).view(1, 3, 1, 1)
+        std = torch.tensor(st["std"]).view(1, 3, 1, 1)
+        image = (image - mean) / std
+        out = st["vision"](image, output_hidden_states=(layer != "final"))
+        hidden = out.last_hidden_state if layer == "final" else (out.hidden_states[-2] if layer == "penultimate" else out.hidden_states[-layer])
+        return self.model(hidden) * self.weight
+
     def __call__(self):
+        if self.style:
+            return self.style_call()
         layer_weights = (1.0, 1.0, 1.0, 1.0)
         if self.soft_injection:
             layer_weights = torch.logspace(-0.25, 0, 4)
@@ -137,10 +158,19 @@ class UNetWithT2I:
     def __init__(self, unet, t2i_adapters):
         self.unet = unet
         self.standard_states = None
+        self.style_states = None
         standard = AdapterStateList()
+        style = []
         for adapter in t2i_adapters:
             assert not adapter.coadapter_type()
-            standard.append(adapter(), adapter.cfg_only)
+            state = adapter()
+            if isinstance(state, list):
+                standard.append(state, adapter.cfg_only)
+            else:
+                style.append(state)
+        if style:
+            self.style_states = torch.cat(style, dim=1)
+            self.style_dim0, self.style_dim1 = self.style_states.shape[0], self.style_states.shape[1]
         g, u = list(standard.all), list(standard.either)
         if g:
             self.standard_states = {"u": [sum(i) for i in zip(*u)], "g": [sum(i) for i in zip(*g)]}
@@ -152,6 +182,20 @@ class UNetWithT2I:
         cfg_meta = kwargs.get("cfg_meta", "f" if is_f else "g")
         if self.standard_states is not None:
             kwargs["adapter_states"] = self.standard_states[cfg_meta]
+        if self.style_states is not None:                      # core.py:221-237
+            hidden_states = kwargs.pop("encoder_hidden_states")
+            if cfg_meta == "f":
+                uncond, cond = hidden_states.chunk(2)
+            elif cfg_meta == "u":
+                uncond, cond = hidden_states, None
+            else:
+                uncond, cond = None, hidden_states
+            res = []
+            if uncond is not None:
+                res += [torch.cat([uncond, uncond[:, -self.style_dim1:, :]], dim=1)]
+            if cond is not None:
+                res += [torch.cat([cond, self.style_states], dim=1)]
+            kwargs["encoder_hidden_states"] = torch.cat(res, dim=0)
         return self.unet(latents, t, **kwargs)
 
 

@@ -479,3 +479,23 @@ def images_resize(tensor, factors, sharpness=1):
         ww = w.reshape(*w.shape, *([1] * (t.ndim - 1)))
         out = (t[idx] * ww).sum(1).transpose(0, d)
     return out.to(tensor.dtype).clamp(0, 1)
+
+
+def images_rescale(tensor, height, width=None, fit="cover", pad_mode="constant", sharpness=1):
+    """gyre/images.py:369-408 (pinned with images_resize: scripts/make_golden.py:pin_resize)."""
+    if width is None:
+        width = height
+    orig_h, orig_w = tensor.shape[-2], tensor.shape[-1]
+    scale_h, scale_w = height / orig_h, width / orig_w
+    if fit == "cover":
+        scale_h = scale_w = max(scale_h, scale_w)
+    elif fit == "contain":
+        scale_h = scale_w = min(scale_h, scale_w)
+    tensor = images_resize(tensor, (scale_h, scale_w), sharpness=sharpness)
+    res_h, res_w = tensor.shape[-2], tensor.shape[-1]
+    err_h, err_w = (height - res_h) // 2, (width - res_w) // 2
+    top, left = (-err_h if err_h < 0 else 0), (-err_w if err_w < 0 else 0)
+    tensor = tensor[:, :, top:top + height, left:left + width]
+    pad = [err_w, width - res_w - err_w] if err_w > 0 else [0, 0]
+    pad += [err_h, height - res_h - err_h] if err_h > 0 else [0, 0]
+    return torch.nn.functional.pad(tensor, pad, pad_mode)

@@ -871,6 +871,7 @@ def pin_hints():
     g = torch.Generator().manual_seed(41)
 
     from fakes import FakeHintAdapter as FakeAdapter, FakeHintControlnet as FakeControlnet, FakeHintUNet as FakeUNet
+    from fakes import FakeHintStyleAdapter as FakeStyle
     lat = torch.randn(2, 4, 8, 8, generator=g)
     t = torch.tensor([500, 500])
     ehs = torch.randn(2, 5, 6, generator=g)
@@ -899,6 +900,23 @@ def pin_hints():
                 for a_, b_ in zip(ref_w.standard_states[k], mine_w.standard_states[k]):
                     assert torch.equal(a_, b_)
             out["t2i"][f"{meta}/{''.join('c' if c else 'b' for c in combo)}"] = ref
+    # style adapters (context tokens for the guided side, core.py:221-237) next to a standard one
+    out["t2i_style"] = {}
+    for meta in ("f", "g", "u"):
+        for n_style in (1, 2):
+            ads = [FakeAdapter(1000, False)] + [FakeStyle(50 + i, tokens=2) for i in range(n_style)]
+            e = torch.cat([ehs[:1], ehs[1:2]]) if meta == "f" else ehs[:1]
+            l = torch.cat([lat[:1], lat[:1]]) if meta == "f" else lat[:1]
+            tt = t[:2] if meta == "f" else t[:1]
+
+            class CtxUNet(FakeUNet):          # the context must matter token by token here
+                def __call__(self, latents, t_, **kw):
+                    w = torch.arange(1, kw["encoder_hidden_states"].shape[1] + 1, dtype=torch.float32)[None, :, None]
+                    return super().__call__(latents, t_, **kw) + (kw["encoder_hidden_states"] * w).mean(dim=(1, 2))[:, None, None, None]
+            ref = core.UNetWithT2I(CtxUNet(), ads)(l, tt, encoder_hidden_states=e, cfg_meta=meta)
+            mine = oh.UNetWithT2I(CtxUNet(), ads)(l, tt, encoder_hidden_states=e, cfg_meta=meta)
+            assert torch.equal(ref, mine), ("UNetWithT2I style", meta, n_style)
+            out["t2i_style"][f"{meta}/{n_style}"] = ref
     rl, ml = core.AdapterStateList(), oh.AdapterStateList()
     for i, c in enumerate((False, True, False)):
         st = FakeAdapter(7 + i, c).state
@@ -908,7 +926,7 @@ def pin_hints():
         for a_, b_ in zip(getattr(rl, prop), getattr(ml, prop)):
             assert all(torch.equal(x_, y_) for x_, y_ in zip(a_, b_)), prop
     torch.save(out, os.path.join(GOLD, "hints.pt"))
-    print(f"hints: UNetWithControlnet ({len(out['controlnet'])} cases), UNetWithT2I ({len(out['t2i'])} cases), AdapterStateList "
+    print(f"hints: UNetWithControlnet ({len(out['controlnet'])} cases), UNetWithT2I ({len(out['t2i'])} + {len(out['t2i_style'])} style cases), AdapterStateList "
           "bit-exact against gyre/pipeline/unet/core.py")
 
 
@@ -1192,6 +1210,52 @@ def pin_hint_classes():
         print(f"  hints/{name}: rel diff {err:.2e}")
         assert err < 2e-5, name
         out[name] = ref
+    # a style adapter (`style_call`, unified_pipeline.py:941-975: images.rescale "cover", CLIP normalisation, the CLIP vision
+    # tower's hidden state of the chosen layer, StyleAdapter) next to a standard adapter (alone, the reference's UNetWithT2I
+    # reads an attribute it only sets for standard states, core.py:201, 214)
+    from oracle import safety as osf
+    sg = torch.load(os.path.join(GOLD, "safety.pt"))["models"]["tiny"]
+    vis = sg["vision_config"]
+    Pv = {k[len("vision_model."):]: v.float() for k, v in sg["state_dict"].items() if k.startswith("vision_model.vision_model.")}
+    skw = dict(width=vis["hidden_size"], context_dim=cfg.cross_attention_dim, num_head=4, n_layes=2, num_token=4)
+    from gyre_b200.clip_vision import style_adapter_param_shapes
+    Pst = synth_params(style_adapter_param_shapes(**skw), seed=47)
+
+    def vision(image, output_hidden_states=False, return_dict=True):
+        with torch.no_grad():
+            _, _, hs = osf.clip_vision_forward(Pv, image, num_layers=vis["num_hidden_layers"], num_heads=vis["num_attention_heads"],
+                                               patch_size=vis["patch_size"], hidden_act=vis["hidden_act"], return_hidden_states=True)
+        return SN(last_hidden_state=hs[-1], hidden_states=tuple(hs))
+
+    class ST(up.t2i_adapter.T2iAdapter_style):
+        config = _Cfg()
+        _coadapter_type = False
+
+        def __call__(self, x):
+            with torch.no_grad():
+                return oad.style_adapter_forward(Pst, x, num_head=skw["num_head"], num_token=skw["num_token"])
+    up.modeling_utils.get_parameter_dtype = lambda m_: torch.float32
+    fe = SN(image_mean=list(osf.CLIP_MEAN), image_std=list(osf.CLIP_STD), size={"shortest_edge": vis["image_size"]})
+    style_img = torch.rand(1, 3, 96, 128, generator=g).half().float()
+    out["style_image"] = style_img.half()
+    for name, layer in (("style final + t2i", None), ("style penultimate + t2i", "penultimate")):
+        rh = [up.UnifiedPipelineHint_T2i(AD(), img.expand(2, -1, -1, -1).clone(), None, None, None, None, 1.0, False, False, None),
+              up.UnifiedPipelineHint_T2i(ST(), style_img.expand(2, -1, -1, -1).clone(), SN(vision_model=vision), fe, None, None, 0.7,
+                                         False, True, layer)]
+        for h in rh:
+            h.to(torch.device("cpu"), torch.float32)
+        ref = _reference_segment(up, unet, None, unc, emb, kind="txt2img", sampler_fn=ksamp.sample_euler_ancestral, steps=4,
+                                 seeds=[420420420, 420420421], height=128, width=128, sample_size=16, hints=rh)
+        style = dict(vision=vision, mean=osf.CLIP_MEAN, std=osf.CLIP_STD, size=vis["image_size"], clip_layer=layer)
+        ohints = [oh.T2iHint(AD(), img.expand(2, -1, -1, -1)),
+                  oh.T2iHint(ST(), style_img.expand(2, -1, -1, -1), weight=0.7, cfg_only=True, style=style)]
+        with torch.no_grad():
+            mine = osamp.txt2img_latents(oh.guided_eps_unet(unet, unc, emb, 7.5, ohints), batch=2, in_channels=4, height=128,
+                                         width=128, sample_size=16, seeds=[420420420, 420420421], steps=4, sampler="euler_a")
+        err = (ref - mine).abs().max().item() / ref.abs().max().item()
+        print(f"  hints/{name}: rel diff {err:.2e}")
+        assert err < 2e-5, name
+        out[name] = ref
     seeds, steps = [420420420, 420420421], 5
     cases = [("controlnet", dict(weight=1.0, soft_injection=False, cfg_only=False), None, "parallel"),
              ("controlnet soft 0.7", dict(weight=0.7, soft_injection=True, cfg_only=False), None, "parallel"),
@@ -1225,7 +1289,7 @@ def pin_hint_classes():
         assert err < 2e-5, name
         out[name] = ref
     torch.save(out, os.path.join(GOLD, "hint_classes.pt"))
-    print(f"hint classes: {len([k for k in out if not k.startswith('r')])} runs of UnifiedPipelineHint_Controlnet / _T2i inside the reference's stack == oracle/hints.py")
+    print(f"hint classes: {len([k for k in out if not k.startswith('r') and k != 'style_image'])} runs of UnifiedPipelineHint_Controlnet / _T2i inside the reference's stack == oracle/hints.py")
 
 
 def _reference_call(up, *, unet, vae, unc, emb, sampler_fn, seeds, inpaint_unet=None, depth_unet=None, options=None,

@@ -68,3 +68,18 @@ class FakeHintUNet:
             out = out + (i + 1) * a.mean(dim=(1, 2, 3), keepdim=True)
         return out
 
+
+
+class FakeHintStyleAdapter:
+    """A style adapter as UNetWithT2I sees it: its state is a tensor of context tokens [1, T, C], not a list."""
+
+    def __init__(self, seed, tokens=3, dim=6):
+        self.state = torch.randn(1, tokens, dim, generator=torch.Generator().manual_seed(seed))
+        self.cfg_only = True
+        self.fuser = None
+
+    def coadapter_type(self):
+        return False
+
+    def __call__(self):
+        return self.state

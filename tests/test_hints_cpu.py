@@ -62,14 +62,38 @@ def test_t2i_states_expand_to_the_unet_batch():
 def test_unbuilt_hint_features_raise():
     from gyre_b200.hints import UNetWithT2I, _split_hint
 
-    class Style(FakeHintAdapter):
-        def __call__(self):
-            return torch.zeros(1, 8, 16)
+    class Co(FakeHintAdapter):
+        def coadapter_type(self):
+            return "sketch"
     with pytest.raises(NotImplementedError):
-        UNetWithT2I(None, [Style(1, False)])
+        UNetWithT2I(None, [Co(1, False)])
     # an RGBA hint carries its mask in the alpha channel; a mask of ones is dropped (unified_pipeline.py:758-771)
     rgba = torch.rand(1, 4, 8, 8)
     img, mask = _split_hint(rgba, None)
     assert torch.equal(img, rgba[:, :3]) and torch.equal(mask, rgba[:, 3:])
     assert _split_hint(torch.cat([rgba[:, :3], torch.ones(1, 1, 8, 8)], 1), None)[1] is None
     assert _split_hint(rgba[:, :1], None)[0].shape[1] == 3
+
+
+@pytest.mark.parametrize("impl", ["product", "oracle"])
+def test_unet_with_t2i_style_states_match_reference(impl):
+    """Style adapters: context tokens appended to the guided side, the unconditional side padded with its own tail
+    (core.py:221-237), next to a standard adapter."""
+    from fakes import FakeHintStyleAdapter
+    H = _impls()[impl]
+    G = torch.load(os.path.join(GOLD, "hints.pt"))
+    I = G["inputs"]
+    assert len(G["t2i_style"]) == 6
+
+    class CtxUNet(FakeHintUNet):
+        def __call__(self, latents, t_, **kw):
+            w = torch.arange(1, kw["encoder_hidden_states"].shape[1] + 1, dtype=torch.float32)[None, :, None]
+            return super().__call__(latents, t_, **kw) + (kw["encoder_hidden_states"] * w).mean(dim=(1, 2))[:, None, None, None]
+    for key, ref in G["t2i_style"].items():
+        meta, n_style = key.split("/")
+        ads = [FakeHintAdapter(1000, False)] + [FakeHintStyleAdapter(50 + i, tokens=2) for i in range(int(n_style))]
+        e = torch.cat([I["ehs"][:1], I["ehs"][1:2]]) if meta == "f" else I["ehs"][:1]
+        l = torch.cat([I["lat"][:1], I["lat"][:1]]) if meta == "f" else I["lat"][:1]
+        t = I["t"][:2] if meta == "f" else I["t"][:1]
+        got = H.UNetWithT2I(CtxUNet(), ads)(l, t, encoder_hidden_states=e, cfg_meta=meta)
+        assert torch.equal(got, ref), key

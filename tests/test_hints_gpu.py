@@ -182,3 +182,45 @@ def test_controlnet_under_inpaint_unet_vs_oracle(setup):
     err = (out.float().cpu() - ref).abs().max().item() / scale
     assert (plain - ref).abs().max().item() / scale > 0.02
     assert err < 1.4e-2, f"ControlNet under the inpaint UNet: rel err {err}"
+
+
+@pytest.mark.parametrize("layer,key", [(None, "style final + t2i"), ("penultimate", "style penultimate + t2i")])
+def test_style_adapter_hint_vs_reference_run(setup, layer, key):
+    """A style T2I-adapter hint (rescale "cover" -> CLIP normalisation -> native CLIP vision tower -> native StyleAdapter ->
+    context tokens on the guided side) next to a standard adapter, against what the REFERENCE's own UnifiedPipelineHint_T2i /
+    UNetWithT2I / scheduler returned over the oracle models (tests/golden/hint_classes.pt, pin_hint_classes)."""
+    import os
+    from oracle import hints as oh
+    from oracle import safety as osf
+    from oracle import sampling as osamp
+    from oracle.unet import synth_params
+    from gyre_b200.clip_vision import B200CLIPVisionModel, B200T2iStyleAdapter, style_adapter_param_shapes
+    from gyre_b200.hints import B200T2iHint
+    s = setup
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    G = torch.load(os.path.join(gold, "hint_classes.pt"))
+    sg = torch.load(os.path.join(gold, "safety.pt"))["models"]["tiny"]
+    vis = sg["vision_config"]
+    vm = B200CLIPVisionModel(vis).load_state_dict({k[len("vision_model."):]: v for k, v in sg["state_dict"].items()
+                                                   if k.startswith("vision_model.vision_model.")})
+    skw = dict(width=vis["hidden_size"], context_dim=s.cfg.cross_attention_dim, num_head=4, n_layes=2, num_token=4)
+    st = B200T2iStyleAdapter(**skw).load_state_dict(synth_params(style_adapter_param_shapes(**skw), seed=47))
+    fe = SimpleNamespace(image_mean=list(osf.CLIP_MEAN), image_std=list(osf.CLIP_STD), size={"shortest_edge": vis["image_size"]})
+    # (the fixture run used these embeddings / hint image: generator 11 like the `setup` fixture)
+    style_img = G["style_image"].float()
+    hints = [B200T2iHint(s.ad, s.img.cuda()),
+             B200T2iHint(st, style_img.cuda(), weight=0.7, cfg_only=True, clip_model=vm, feature_extractor=fe, clip_layer=layer)]
+    seeds, steps = [420420420, 420420421], 4
+    out = s.pipe(s.emb.cuda(), s.unc.cuda(), height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
+                 generator=[torch.Generator("cpu").manual_seed(x) for x in seeds], sampler="k_euler_ancestral", output_type="latent",
+                 latents_dtype=torch.float32, return_fp32_latents=True, hints=hints).latents
+    ref = G[key]
+    with torch.no_grad():
+        no_style = osamp.txt2img_latents(oh.guided_eps_unet(s.o_unet, s.unc, s.emb, 7.5, [oh.T2iHint(s.o_ad, s.img.expand(2, -1, -1, -1))]),
+                                         batch=2, in_channels=4, height=128, width=128, sample_size=16, seeds=seeds, steps=steps,
+                                         sampler="euler_a")
+    scale = ref.abs().max().item()
+    err = (out.float().cpu() - ref).abs().max().item() / scale
+    moved = (no_style - ref).abs().max().item() / scale
+    assert moved > 0.01, f"the style tokens did not change the result ({moved})"
+    assert err < 1.4e-2, f"style hint ({key}): rel err {err} (the style tokens move the latents by {moved})"

@@ -140,7 +140,7 @@ def test_hint_classes_match_reference_classes(models):
              "t2i soft cfg_only + controlnet": ([oh.ControlnetHint(cn, img, weight=0.5, soft_injection=False, cfg_only=False),
                                                  oh.T2iHint(ad, img.expand(2, -1, -1, -1), weight=0.9, soft_injection=True,
                                                             cfg_only=True)], True)}
-    assert set(cases) <= set(G) and len([k for k in G if not k.startswith('r')]) == 9
+    assert set(cases) <= set(G) and len([k for k in G if not k.startswith('r') and k != 'style_image']) == 11
     for key, (hints, parallel) in cases.items():
         eps = oh.guided_eps_unet(models["unet"], unc, emb, 7.5, hints, parallel=parallel)
         with torch.no_grad():
