@@ -113,6 +113,8 @@ SIGNATURES = {
     "gyre_b200_unet_forward_cond": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp]),
     "gyre_b200_controlnet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _i, _vp, _vp, _sz, _vp]),
     "gyre_b200_resample_f32": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "gyre_b200_webp_sizes": (_i, [_i, _i, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
+    "gyre_b200_webp_encode": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     "gyre_b200_png_sizes": (_i, [_i, _i, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
     "gyre_b200_png_encode": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     "gyre_b200_clip_vision_create": (_i, [C.POINTER(ClipVisionConfigC), C.POINTER(_vp)]),

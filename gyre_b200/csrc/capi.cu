@@ -246,6 +246,17 @@ int gyre_b200_png_encode(const void* images_u8_nhwc, int batch, int height, int 
                     out_stride, out_lengths, workspace, workspace_bytes, S(stream));
 }
 
+int gyre_b200_webp_sizes(int batch, int height, int width, int channels, size_t* workspace_bytes, size_t* out_stride) {
+  return webp_sizes(batch, height, width, channels, workspace_bytes, out_stride);
+}
+
+int gyre_b200_webp_encode(const void* images_u8_nhwc, int batch, int height, int width, int channels, void* out,
+                          size_t out_stride, int64_t* out_lengths, void* workspace, size_t workspace_bytes,
+                          gyre_b200_stream stream) {
+  return webp_encode(static_cast<const uint8_t*>(images_u8_nhwc), batch, height, width, channels, static_cast<uint8_t*>(out),
+                     out_stride, out_lengths, workspace, workspace_bytes, S(stream));
+}
+
 size_t gyre_b200_outpaint_scratch_bytes(void) { return outpaint_scratch_bytes(); }
 
 int gyre_b200_outpaint_match_histograms(const void* result, const void* source, const void* outmask, int batch, int64_t hw,

@@ -164,6 +164,10 @@ int resample_f32(const float* src, int64_t n_outer, int in_sz, int inner, const 
 int png_sizes(int B, int H, int W, int C, size_t* workspace_bytes, size_t* out_stride);
 int png_encode(const uint8_t* images, int B, int H, int W, int C, uint8_t* out, size_t out_stride, int64_t* out_len,
                void* workspace, size_t workspace_bytes, cudaStream_t st);
+// Lossless WebP (VP8L) encoder (webp.cu): u8 NHWC [B, H, W, C] (C = 3 RGB, 4 RGBA) -> one WebP file per image
+int webp_sizes(int B, int H, int W, int C, size_t* workspace_bytes, size_t* out_stride);
+int webp_encode(const uint8_t* images, int B, int H, int W, int C, uint8_t* out, size_t out_stride, int64_t* out_len,
+                void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t outpaint_scratch_bytes();
 int outpaint_match_histograms(const __half* result, const __half* source, const __half* mask, int B, int64_t hw, __half* out,
                               void* scratch, cudaStream_t st);

@@ -192,3 +192,63 @@ def rescale(tensor, height, width=None, fit="cover", pad_mode="constant", sharpn
     pad = [err_w, width - res_w - err_w] if err_w > 0 else [0, 0]
     pad += [err_h, height - res_h - err_h] if err_h > 0 else [0, 0]
     return torch.nn.functional.pad(tensor, pad, pad_mode)
+
+
+def encode_webp_u8(u8_nhwc):
+    """uint8 [B, H, W, 3 | 4] on the device -> (files [B, stride] uint8, lengths [B] int64): one lossless WebP per row."""
+    import ctypes as C
+    N.require_cuda(u8_nhwc)
+    if u8_nhwc.dtype != torch.uint8 or u8_nhwc.ndim != 4:
+        raise ValueError(f"encode_webp_u8: want uint8 [B, H, W, C], got {u8_nhwc.dtype} {tuple(u8_nhwc.shape)}")
+    x = u8_nhwc.contiguous()
+    B, H, W, Cc = x.shape
+    lib = N.load()
+    ws_bytes, stride = C.c_size_t(), C.c_size_t()
+    N.check(lib.gyre_b200_webp_sizes(B, H, W, Cc, C.byref(ws_bytes), C.byref(stride)), "webp_sizes")
+    ws = torch.empty((ws_bytes.value,), device=x.device, dtype=torch.uint8)
+    out = torch.empty((B, stride.value), device=x.device, dtype=torch.uint8)
+    lengths = torch.empty((B,), device=x.device, dtype=torch.int64)
+    with torch.cuda.device(x.device):
+        N.check(lib.gyre_b200_webp_encode(N.ptr(x), B, H, W, Cc, N.ptr(out), stride.value, N.ptr(lengths), N.ptr(ws),
+                                          ws.numel(), N.stream_ptr(x.device)), "webp_encode")
+    return out, lengths
+
+
+def to_webp_bytes(tensor):
+    """gyre/images.py:125-135 toWebpBytes (lossless): [B, C, H, W] / [C, H, W] float images in [0, 1], quantised
+    `(x.to(float32) * 255).round()` like toCV, 1 / 3 / 4 channels (grey is written as RGB) -> list of WebP files as bytes,
+    encoded on the device.  uint8 [B, H, W, C] input is taken as is."""
+    if tensor.dtype == torch.uint8:
+        u8 = tensor if tensor.ndim == 4 else tensor[None]
+    else:
+        t = tensor if tensor.ndim == 4 else tensor[None]
+        u8 = to_uint8_nhwc(t)
+    if u8.shape[-1] == 1:
+        u8 = u8.expand(-1, -1, -1, 3)
+    if not u8.is_cuda:
+        if not torch.cuda.is_available():
+            raise N.NativeError("to_webp_bytes needs a CUDA device: there is no CPU path")
+        u8 = u8.cuda()
+    files, lengths = encode_webp_u8(u8)
+    lens = lengths.cpu().tolist()
+    host = files[:, :max(lens)].cpu().numpy()
+    return [host[i, :n].tobytes() for i, n in enumerate(lens)]
+
+
+def add_text_chunk_to_webp_bytes(binary: bytes, info_fourcc: bytes, text: str) -> bytes:
+    """gyre/images.py:186-226 addTextChunkToWebpBytes: a simple lossless file becomes an extended one (VP8X header) with a
+    LIST / INFO chunk behind the image (host bytes in, host bytes out)."""
+    import struct
+    assert len(info_fourcc) == 4, f"{info_fourcc} needs to a be four byte FourCC"
+    body = text.encode("utf-8")
+    txt_chunk = (b"LIST" + struct.pack("<I", 4 + 4 + 4 + len(body)) + b"INFO" + info_fourcc + struct.pack("<I", len(body)) + body
+                 + bytes(len(body) % 2))
+    if binary[12:16] != b"VP8L":
+        raise NotImplementedError("Can only apply chunk to simple lossless webp")
+    remainder = binary[12:]
+    info = struct.unpack("<I", binary[21:25])[0]
+    width, height, alpha = (info & 0x3FFF) + 1, ((info >> 14) & 0x3FFF) + 1, bool((info >> 28) & 0x1)
+    header_chunk = (b"VP8X" + struct.pack("<I", 10) + bytes([0b10000 if alpha else 0, 0, 0, 0]) + struct.pack("<I", width - 1)[0:3]
+                    + struct.pack("<I", height - 1)[0:3])
+    total = 4 + len(header_chunk) + len(remainder) + len(txt_chunk)
+    return b"RIFF" + struct.pack("<I", total) + b"WEBP" + header_chunk + remainder + txt_chunk

@@ -320,6 +320,17 @@ int gyre_b200_png_encode(const void* images_u8_nhwc, int batch, int height, int 
                          size_t out_stride, int64_t* out_lengths, void* workspace, size_t workspace_bytes,
                          gyre_b200_stream stream);
 
+/* Lossless WebP  (replaces gyre/images.py:125-135 toWebpBytes -> cv.imencode(".webp", .., [IMWRITE_WEBP_QUALITY, 500]) on the
+ *   host, chosen by gyre/services/generate.py:73-76 for clients that accept image/webp)
+ * images u8 NHWC [batch, height, width, channels] (3 RGB | 4 RGBA) -> out [batch][out_stride] bytes, one simple-format VP8L
+ * file per image ("RIFF" .. "WEBP" "VP8L"), its length in out_lengths[i]; out must be 4-byte aligned, out_stride a multiple
+ * of 4 and at least what gyre_b200_webp_sizes returns.  Lossless: any WebP decoder returns the input pixels; the stream is
+ * this library's own (gradient predictor + per-image Huffman codes, no LZ77). */
+int gyre_b200_webp_sizes(int batch, int height, int width, int channels, size_t* workspace_bytes, size_t* out_stride);
+int gyre_b200_webp_encode(const void* images_u8_nhwc, int batch, int height, int width, int channels, void* out,
+                          size_t out_stride, int64_t* out_lengths, void* workspace, size_t workspace_bytes,
+                          gyre_b200_stream stream);
+
 int gyre_b200_destroy(gyre_b200_handle h);
 
 /* ------------------------------------------------------------------------------------------
