@@ -24,6 +24,7 @@ class Epilogue(C.Structure):
         ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t), ("sk_flags", C.c_void_p), ("sk_flags_count", C.c_int32),
         ("rowstat_out", C.c_void_p), ("ln_rowstat", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_parts", C.c_int32), ("ln_inv_c", C.c_float), ("ln_eps", C.c_float),
+        ("gn_out", C.c_void_p), ("gn_groups", C.c_int32), ("gn_nparts", C.c_int32),
     ]
 
 
@@ -169,6 +170,9 @@ SIGNATURES = {
     "gyre_b200_upconv2x": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(Epilogue), _vp]),
     "gyre_b200_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),
     "gyre_b200_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "gyre_b200_conv3x3_gn_parts": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "gyre_b200_groupnorm_pre_ok": (_i, [_i, _i, _i]),
+    "gyre_b200_groupnorm_pre": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "gyre_b200_layernorm": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "gyre_b200_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
 }
@@ -351,8 +355,9 @@ def pack_conv3x3(w):
 
 
 def conv3x3(x_nhwc, wp, cout, bias=None, residual=None, stride=1, pad=1, act=0, rowgroup_bias=None,
-            rows_per_group=1):
-    """x [B, H, W, Cin] fp16 NHWC -> [B, Ho, Wo, Cout] fp16 NHWC."""
+            rows_per_group=1, gn_groups=0):
+    """x [B, H, W, Cin] fp16 NHWC -> [B, Ho, Wo, Cout] fp16 NHWC.  gn_groups > 0: also returns the GroupNorm partials
+    [B, nparts, gn_groups, 2] fp32 the epilogue left for `groupnorm_pre` (None when the shape cannot produce them)."""
     require_cuda(x_nhwc, wp)
     B, H, W, Cin = x_nhwc.shape
     if stride == 1:
@@ -363,8 +368,16 @@ def conv3x3(x_nhwc, wp, cout, bias=None, residual=None, stride=1, pad=1, act=0, 
         Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
     out = torch.empty((B * Ho * Wo, cout), device=x_nhwc.device, dtype=torch.float16)
     e = _epilogue(out, bias, residual, act, rowgroup_bias, rows_per_group)
+    pre = None
+    if gn_groups > 0:
+        parts = load().gyre_b200_conv3x3_gn_parts(B, H, W, cout, stride, pad, gn_groups)
+        if parts > 0:
+            pre = torch.full((B, parts, gn_groups, 2), float("nan"), device=x_nhwc.device, dtype=torch.float32)
+            e.gn_out, e.gn_groups, e.gn_nparts = ptr(pre), gn_groups, parts
     check(load().gyre_b200_conv3x3(ptr(x_nhwc), Cin, B, H, W, Cin, ptr(wp), cout, stride, pad, C.byref(e),
                                    stream_ptr(x_nhwc.device)), "conv3x3")
+    if gn_groups > 0:
+        return out.view(B, Ho, Wo, cout), pre
     return out.view(B, Ho, Wo, cout)
 
 
@@ -400,6 +413,18 @@ def groupnorm(x1, gamma, beta, groups, eps, silu, x2=None):
                           dtype=torch.float32)
     check(load().gyre_b200_groupnorm(ptr(x1), C1, ptr(x2), C2, B, HW, groups, eps, ptr(gamma), ptr(beta),
                                      1 if silu else 0, ptr(out), ptr(scratch), stream_ptr(x1.device)), "groupnorm")
+    return out
+
+
+def groupnorm_pre(x, gamma, beta, groups, eps, silu, pre):
+    """GroupNorm of x [B, HW, C] fp16 from the partials `pre` [B, nparts, G, 2] its producing conv3x3 left."""
+    require_cuda(x, gamma, beta, pre)
+    B, HW, Cc = x.shape
+    out = torch.empty_like(x)
+    stats = torch.empty((B, groups, 2), device=x.device, dtype=torch.float32)
+    check(load().gyre_b200_groupnorm_pre(ptr(x), Cc, B, HW, groups, eps, ptr(gamma), ptr(beta), 1 if silu else 0,
+                                         ptr(out), ptr(pre), pre.shape[1], ptr(stats), stream_ptr(x.device)),
+          "groupnorm_pre")
     return out
 
 

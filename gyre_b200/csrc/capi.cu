@@ -35,6 +35,9 @@ int to_epilogue(const gyre_b200_epilogue* e, Epilogue* out) {
   out->ln_parts = e->ln_parts;
   out->ln_inv_c = e->ln_inv_c;
   out->ln_eps = e->ln_eps;
+  out->gn_out = e->gn_out;
+  out->gn_groups = e->gn_groups;
+  out->gn_nparts = e->gn_nparts;
   return 0;
 }
 }  // namespace
@@ -142,6 +145,19 @@ int gyre_b200_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, i
   GYRE_REQUIRE(x1 && gamma && beta && out && scratch, "groupnorm: null operand");
   return groupnorm_nhwc(static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, B, HW, G, eps, gamma,
                         beta, silu != 0, static_cast<__half*>(out), scratch, S(stream));
+}
+
+int gyre_b200_conv3x3_gn_parts(int B, int H, int W, int Cout, int stride, int pad, int groups) {
+  return conv3x3_gn_parts(B, H, W, Cout, stride, pad, groups);
+}
+
+int gyre_b200_groupnorm_pre_ok(int C, int HW, int G) { return groupnorm_pre_ok(C, HW, G) ? 1 : 0; }
+
+int gyre_b200_groupnorm_pre(const void* x, int C, int B, int HW, int G, float eps, const float* gamma, const float* beta,
+                            int silu, void* out, const float* pre, int nparts, float* stats, gyre_b200_stream stream) {
+  GYRE_REQUIRE(x && gamma && beta && out && pre, "groupnorm_pre: null operand");
+  return groupnorm_nhwc_pre(static_cast<const __half*>(x), C, B, HW, G, eps, gamma, beta, silu != 0,
+                            static_cast<__half*>(out), pre, nparts, stats, S(stream));
 }
 
 int gyre_b200_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,

@@ -48,6 +48,11 @@ struct GemmParams {
   int sk_maxp;        // partial-accumulator slots per stream-K tile
   float* sk_ws;       // [sk_tiles][sk_maxp][128][BN] fp32 partial accumulators
   int* sk_flags;      // [sk_tiles] partials delivered (zero between launches)
+  // GroupNorm statistics of the output (EPI 6; Epilogue::gn_out): per 32-column slice of a tile, bit i of gn_mask is set
+  // when a group ends behind column pair i of the slice, gn_g0 is the (tile-relative) group of the slice's first column
+  uint32_t gn_mask[8];
+  uint8_t gn_g0[8];
+  int gn_cpg;
   Epilogue ep;
 };
 
@@ -57,6 +62,7 @@ constexpr int kThreads = 320;        // TMA warp, MMA warp, 8 epilogue warps (2 
 constexpr int kEpiThreads = 256;
 constexpr int kSliceBytes = kBM * 32 * 2;   // one 128-row x 32-column fp16 epilogue slice (64-byte rows)
 constexpr int kMaxBiasGroups = 2;
+constexpr int kGnTileGroups = 32;    // groups one tile may span when it produces GroupNorm statistics (EPI 6)
 
 template <int BN, bool PAIR2 = false, int EPI = 1>
 struct GemmCfg {
@@ -66,7 +72,9 @@ struct GemmCfg {
   // epilogue staging: per column-half 2 output + 2 residual slices; per-tile column bias (double buffered)
   static constexpr int EPI_BYTES = 2 * 2 * 2 * kSliceBytes;
   static constexpr int BIAS_BYTES = 2 * kMaxBiasGroups * BN * 4;
-  static constexpr int FIXED = EPI_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  // EPI 6: [4 lane quadrants][kGnTileGroups][2 slice parities] float2 group totals of the tile in flight
+  static constexpr int GN_BYTES = EPI == 6 ? 4 * 32 * 2 * 8 : 0;
+  static constexpr int FIXED = EPI_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + GN_BYTES;
   static constexpr int STAGES_RAW = (227 * 1024 - FIXED) / (A_BYTES + B_BYTES);
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // two accumulator buffers so that the epilogue of tile i overlaps the main loop of tile i+1
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
   uint64_t* res_bar = tempty_bar + 2;               // [half][slot] residual slice landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+  float2* gn_tot = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + 512);   // EPI 6 only (Cfg::GN_BYTES)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -412,6 +421,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     constexpr bool kGegluCode = (EPI == 1 || EPI == 2 || EPI == 5);
     constexpr bool kPlainCode = (EPI != 2 && EPI != 5);
     constexpr bool kRowStat = (EPI == 3);
+    constexpr bool kGnStat = (EPI == 6);
+    if constexpr (kGnStat) {
+      for (int i = etid; i < 4 * kGnTileGroups * 2; i += kEpiThreads) gn_tot[i] = make_float2(0.f, 0.f);
+    }
     constexpr bool kLnConsume = (EPI == 4 || EPI == 5);
     const bool geglu = EPI == 2 || EPI == 5 || (EPI == 1 && ep.act == ACT_GEGLU);
     const int bn_out = geglu ? BN / 2 : BN;           // output columns per tile
@@ -726,12 +739,72 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               rq2 = __ffma2_rn(v2, v2, rq2);
             }
           }
+          if constexpr (kGnStat) {
+            // Statistics of the ROUNDED outputs (what the GroupNorm will read).  Per thread: (sum, sum of squares) of every
+            // group segment inside this slice of its row, parked in this warp's 32 rows of the still unused output slot
+            // [segment][lane]; then four lanes per segment add the 32 rows in a fixed order and the quad's total joins the
+            // tile's group totals.  Everything is warp-private up to the tile's last barrier: no atomics, fixed order.
+            uint32_t hw[16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            __align__(16) __half2 h[4];
+            for (int i = 0; i < 16; ++i) {
+              const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+              hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            float2* scratch = reinterpret_cast<float2*>(sOut + slot * kSliceBytes + q * (32 * 64));
+            const uint32_t mask = p.gn_mask[sl];
+            float2 a2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+            int k = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[u * 8 + 2 * i], v[u * 8 + 2 * i + 1]);
-            *reinterpret_cast<uint4*>(my_out_row + slot * kSliceBytes + ((u ^ swz) << 4)) = *reinterpret_cast<uint4*>(h);
+            for (int i = 0; i < 16; ++i) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+              a2 = __fadd2_rn(a2, f);
+              q2 = __ffma2_rn(f, f, q2);
+              if ((mask >> i) & 1u) {
+                scratch[k * 32 + lane] = make_float2(a2.x + a2.y, q2.x + q2.y);
+                ++k;
+                a2 = make_float2(0.f, 0.f);
+                q2 = make_float2(0.f, 0.f);
+              }
+            }
+            if (!((mask >> 15) & 1u)) {
+              scratch[k * 32 + lane] = make_float2(a2.x + a2.y, q2.x + q2.y);
+              ++k;
+            }
+            __syncwarp();
+            {
+              const int seg = lane >> 2, part = lane & 3;
+              float ts = 0.f, tq = 0.f;
+              if (seg < k) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 e = scratch[seg * 32 + part * 8 + ((i + lane) & 7)];
+                  ts += e.x;
+                  tq += e.y;
+                }
+              }
+              ts += __shfl_xor_sync(0xffffffffu, ts, 1);
+              tq += __shfl_xor_sync(0xffffffffu, tq, 1);
+              ts += __shfl_xor_sync(0xffffffffu, ts, 2);
+              tq += __shfl_xor_sync(0xffffffffu, tq, 2);
+              if (seg < k && part == 0) {
+                float2* t2 = gn_tot + ((q * kGnTileGroups + p.gn_g0[sl] + seg) * 2 + (sl & 1));
+                const float2 o = *t2;
+                *t2 = make_float2(o.x + ts, o.y + tq);
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(my_out_row + slot * kSliceBytes + ((u ^ swz) << 4)) =
+                  make_uint4(hw[4 * u], hw[4 * u + 1], hw[4 * u + 2], hw[4 * u + 3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              __align__(16) __half2 h[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[u * 8 + 2 * i], v[u * 8 + 2 * i + 1]);
+              *reinterpret_cast<uint4*>(my_out_row + slot * kSliceBytes + ((u ^ swz) << 4)) = *reinterpret_cast<uint4*>(h);
+            }
           }
           fence_proxy_async();
           named_bar_sync(2 + half, 128);
@@ -747,6 +820,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           if (valid)
             ep.rowstat_out[(static_cast<int64_t>(n_tile) * 2 + half) * (ep.rowstat_ld > 0 ? ep.rowstat_ld : p.M) + out_row] =
                 make_float2(rs2.x + rs2.y, rq2.x + rq2.y);
+        }
+        if constexpr (kGnStat) {
+          // every warp's slice totals are in: one thread per group of the tile adds the 4 quadrants x 2 slice parities in
+          // a fixed order, leaves the entries zero for the next tile and writes the tile's partial
+          named_bar_sync(1, kEpiThreads);
+          const int ntg = min(bn_out, n_out - col_base) / p.gn_cpg;
+          if (etid < ntg) {
+            float ts = 0.f, tq = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              // the two slice parities are added to each other first: which parity a straddling group's halves land in
+              // depends on the tile width, the sum of the pair does not (same partials at every BN)
+              float2* t2 = gn_tot + (qq * kGnTileGroups + etid) * 2;
+              ts += t2[0].x + t2[1].x;
+              tq += t2[0].y + t2[1].y;
+              t2[0] = make_float2(0.f, 0.f);
+              t2[1] = make_float2(0.f, 0.f);
+            }
+            const int per_sample = p.tiles_x * p.tiles_y;
+            const int chunk = m_tile % per_sample;
+            float* dst = ep.gn_out + ((static_cast<int64_t>(n0) * ep.gn_nparts + chunk) * ep.gn_groups +
+                                      col_base / p.gn_cpg + etid) * 2;
+            *reinterpret_cast<float2*>(dst) = make_float2(ts, tq);
+          }
         }
       } else if constexpr (EPI == 1) {
         // ================================================= direct path (fp32 out, unaligned pitches, tiny N)
@@ -863,6 +960,9 @@ static auto kernel_for(int epi) -> decltype(&gemm_tc_kernel<BN, CONV, PAIR2, 1>)
     if (epi == 3) return gemm_tc_kernel<BN, CONV, PAIR2, 3>;
     if (epi == 4) return gemm_tc_kernel<BN, CONV, PAIR2, 4>;
   }
+  if constexpr (BN >= 128 && CONV) {      // GroupNorm statistics of the output: conv only
+    if (epi == 6) return gemm_tc_kernel<BN, CONV, PAIR2, 6>;
+  }
   return gemm_tc_kernel<BN, CONV, PAIR2, 1>;
 }
 // shared-memory footprint / ring depth of an image
@@ -871,6 +971,9 @@ static void cfg_for(int epi, int* smem, int* stages) {
   if (epi == 1) {
     *smem = GemmCfg<BN, PAIR2, 1>::SMEM;
     *stages = GemmCfg<BN, PAIR2, 1>::STAGES;
+  } else if (epi == 6) {
+    *smem = GemmCfg<BN, PAIR2, 6>::SMEM;
+    *stages = GemmCfg<BN, PAIR2, 6>::STAGES;
   } else {
     *smem = GemmCfg<BN, PAIR2, 0>::SMEM;
     *stages = GemmCfg<BN, PAIR2, 0>::STAGES;
@@ -880,6 +983,7 @@ static int epi_class(const GemmParams& p) {
   if (!p.tma_epi) return 1;
   if (p.ep.ln_rowstat != nullptr) return p.ep.act == ACT_GEGLU ? 5 : 4;   // validated in gemm2_f16
   if (p.ep.rowstat_out != nullptr) return 3;
+  if (p.ep.gn_out != nullptr) return 6;                                   // validated in conv_impl
   if (p.ep.act == ACT_NONE) return 0;
   if (p.ep.act == ACT_GEGLU && p.fast_gelu && !p.conv) return 2;
   return 1;
@@ -893,19 +997,23 @@ static int prepare(int* max_clusters) {
   static bool done = false;
   static int clusters = 0;
   if (!done) {
-    for (int epi = 0; epi < 6; ++epi) {
+    for (int epi = 0; epi < 7; ++epi) {
       if ((epi == 2 || epi == 5) && BN != 256) continue;   // kernel_for aliases the all-variants image elsewhere
       if ((epi == 3 || epi == 4) && BN < 64) continue;
+      if (epi == 6 && BN < 128) continue;
       int smem = 0, stages = 0;
       cfg_for<BN, false>(epi, &smem, &stages);
-      GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, false, false>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem));
+      // (EPI 6 exists for the convolution only: the GEMM lookup would alias the all-variants image)
+      if (epi != 6)
+        GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, false, false>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem));
       GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, true, false>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            smem));
       if constexpr (BN >= 64) {
         cfg_for<BN, true>(epi, &smem, &stages);
-        GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, false, true>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             smem));
+        if (epi != 6)
+          GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, false, true>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               smem));
         GYRE_CHECK_CUDA(cudaFuncSetAttribute(kernel_for<BN, true, true>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              smem));
       }
@@ -1206,22 +1314,8 @@ static inline int pow2_ceil(int v) {
   return p;
 }
 
-// Geometry of one implicit-GEMM convolution launch: taps_h x taps_w taps whose (0, 0) tap reads input pixel
-// (x * stride + off_x, y * stride + off_y); output pixel (x, y) of the Ho x Wo grid is written to pixel
-// (x * out_step + out_ox, y * out_step + out_oy) of a [B, Ho*out_step, Wo*out_step, ldo] tensor.
-struct ConvGeom {
-  int taps_h = 3, taps_w = 3;
-  int off_x = -1, off_y = -1;
-  int Ho = 0, Wo = 0;
-  int out_step = 1, out_ox = 0, out_oy = 0;
-  double algo_flops = 0.0, algo_bytes = 0.0;
-};
-
-static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp, int Cout, int stride,
-                     const ConvGeom& gm, const Epilogue& ep, cudaStream_t st) {
-  const int Ho = gm.Ho, Wo = gm.Wo;
-  const int ntaps = gm.taps_h * gm.taps_w;
-  // choose the 128-pixel patch shape with the least padded work
+// The 128-pixel output patch (tile_w x tile_h pixels of tile_n images) with the least padded work.
+static bool conv_tile_shape(int Ho, int Wo, int B, int stride, int* tw_out, int* th_out, int* tn_out) {
   int best_w = 0, best_h = 0, best_n = 0;
   long long best_cost = -1;
   const int max_edge = stride == 2 ? 128 : 256;
@@ -1241,6 +1335,54 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
       }
     }
   }
+  *tw_out = best_w;
+  *th_out = best_h;
+  *tn_out = best_n;
+  return best_cost > 0;
+}
+
+static int conv_out_extent(int n, int stride, int pad) {
+  return (stride == 1) ? n : (pad == 1 ? (n - 1) / 2 + 1 : (n + 1 - 3) / 2 + 1);
+}
+
+// GroupNorm statistics in the epilogue (Epilogue::gn_out): tiles must partition each sample exactly (one image per tile,
+// no overhang - padded rows would carry the bias), group boundaries must coincide with tile boundaries, a slice may not
+// hold more than 8 group segments (cpg >= 4, even: column pairs never straddle a group).
+static int conv_gn_parts(int B, int Ho, int Wo, int Cout, int stride, int groups, int* bn_out) {
+  if (!tunable(TUNE_GN_FUSE) || groups <= 0 || Cout % groups != 0 || (Cout & 7) != 0) return 0;
+  const int cpg = Cout / groups;
+  if (cpg < 4 || (cpg & 1) != 0) return 0;
+  int tw = 0, th = 0, tn = 0;
+  if (!conv_tile_shape(Ho, Wo, B, stride, &tw, &th, &tn)) return 0;
+  if (tn != 1 || Wo % tw != 0 || Ho % th != 0) return 0;
+  const int m_tiles = (Wo / tw) * (Ho / th) * B;
+  const int bn = pick_bn(m_tiles, Cout, ACT_NONE);
+  if (bn < 128 || bn % cpg != 0 || bn / cpg > kGnTileGroups) return 0;
+  if (bn_out) *bn_out = bn;
+  return (Wo / tw) * (Ho / th);
+}
+
+int conv3x3_gn_parts(int B, int H, int W, int Cout, int stride, int pad, int groups) {
+  return conv_gn_parts(B, conv_out_extent(H, stride, pad), conv_out_extent(W, stride, pad), Cout, stride, groups, nullptr);
+}
+
+// Geometry of one implicit-GEMM convolution launch: taps_h x taps_w taps whose (0, 0) tap reads input pixel
+// (x * stride + off_x, y * stride + off_y); output pixel (x, y) of the Ho x Wo grid is written to pixel
+// (x * out_step + out_ox, y * out_step + out_oy) of a [B, Ho*out_step, Wo*out_step, ldo] tensor.
+struct ConvGeom {
+  int taps_h = 3, taps_w = 3;
+  int off_x = -1, off_y = -1;
+  int Ho = 0, Wo = 0;
+  int out_step = 1, out_ox = 0, out_oy = 0;
+  double algo_flops = 0.0, algo_bytes = 0.0;
+};
+
+static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, const __half* Wp, int Cout, int stride,
+                     const ConvGeom& gm, const Epilogue& ep, cudaStream_t st) {
+  const int Ho = gm.Ho, Wo = gm.Wo;
+  const int ntaps = gm.taps_h * gm.taps_w;
+  int best_w = 0, best_h = 0, best_n = 0;
+  const long long best_cost = conv_tile_shape(Ho, Wo, B, stride, &best_w, &best_h, &best_n) ? 1 : -1;
   GYRE_REQUIRE(best_cost > 0, "conv3x3: no tile shape for %dx%d", Ho, Wo);
   const int m_tiles = ((Wo + best_w - 1) / best_w) * ((Ho + best_h - 1) / best_h) * ((B + best_n - 1) / best_n);
   const int bn = pick_bn(m_tiles, Cout, ACT_NONE);
@@ -1275,6 +1417,22 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
   if (ep.rowgroup_bias != nullptr && ep.rows_per_group == Ho * Wo && best_n <= kMaxBiasGroups)
     p.rgb_rows = best_w * best_h;
   p.tma_epi = (tma_epilogue_ok(ep, Cout) && (ep.rowgroup_bias == nullptr || p.rgb_rows > 0)) ? 1 : 0;
+  if (ep.gn_out != nullptr) {
+    int bn_gn = 0;
+    const int parts = conv_gn_parts(B, Ho, Wo, Cout, stride, ep.gn_groups, &bn_gn);
+    GYRE_REQUIRE(parts > 0 && parts == ep.gn_nparts && bn_gn == bn && p.tma_epi && ep.act == ACT_NONE && gm.out_step == 1,
+                 "conv3x3: GroupNorm statistics cannot be produced here (%dx%d, Cout %d, %d groups, %d parts given)", Ho, Wo,
+                 Cout, ep.gn_groups, ep.gn_nparts);
+    const int cpg = Cout / ep.gn_groups;
+    p.gn_cpg = cpg;
+    for (int sl = 0; sl < 8; ++sl) {
+      const int c0 = sl * 32;                       // tile-relative first column of the slice (tiles start on a group)
+      uint32_t mask = 0;
+      for (int pos = cpg - c0 % cpg; pos <= 32; pos += cpg) mask |= 1u << (pos / 2 - 1);
+      p.gn_mask[sl] = mask;
+      p.gn_g0[sl] = static_cast<uint8_t>(c0 / cpg);
+    }
+  }
   GYRE_TRY(want_pair_mode(bn, m_tiles, p.k_iters, &p.mcast));
   {
     int max_clusters = 0;
@@ -1334,8 +1492,8 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "conv3x3: null output");
   ConvGeom gm;
   gm.off_x = gm.off_y = -pad;
-  gm.Ho = (stride == 1) ? H : (pad == 1 ? (H - 1) / 2 + 1 : (H + 1 - 3) / 2 + 1);
-  gm.Wo = (stride == 1) ? W : (pad == 1 ? (W - 1) / 2 + 1 : (W + 1 - 3) / 2 + 1);
+  gm.Ho = conv_out_extent(H, stride, pad);
+  gm.Wo = conv_out_extent(W, stride, pad);
   gm.algo_flops = 2.0 * 9 * Cin * Cout * static_cast<double>(B) * gm.Ho * gm.Wo;
   gm.algo_bytes = 2.0 * (static_cast<double>(B) * H * W * Cin + 9.0 * Cin * Cout +
                          static_cast<double>(B) * gm.Ho * gm.Wo * Cout * (ep.residual ? 2 : 1));

@@ -54,12 +54,16 @@ void* Exec::alloc_s(size_t bytes) {
 // ------------------------------------------------------------------------------------------ Model base
 constexpr size_t kStreamKBytes = 48u << 20;
 constexpr int kStreamKFlags = 256;
+constexpr size_t kGnPreFloats = 4u << 20;     // conv-produced GroupNorm partials (16 MB: 8 x 1024 x 1024 images in the VAE)
+constexpr size_t kGnPreStats = 16u << 10;
 
 Model::Model() {
   cudaGetDevice(&device_);
   sk_ws_ = dalloc(kStreamKBytes);
   sk_flags_ = static_cast<int*>(dalloc(kStreamKFlags * sizeof(int)));   // dalloc zero-fills
   sk_ws_bytes_ = sk_ws_ ? kStreamKBytes : 0;
+  gn_pre_buf_ = static_cast<float*>(dalloc((kGnPreFloats + kGnPreStats) * sizeof(float)));
+  gn_pre_floats_ = gn_pre_buf_ ? kGnPreFloats : 0;
 }
 
 Model::~Model() {
@@ -248,6 +252,35 @@ Epilogue Model::ep_out(__half* out, int ldo, const float* bias, const __half* re
   return e;
 }
 
+void Model::gn_offer(Epilogue& e, int B, int H, int W, int Cout, int stride, int pad) {
+  gn_pre_.x = nullptr;
+  if (gn_pre_buf_ == nullptr || e.out == nullptr || e.act != ACT_NONE || e.ldo != Cout) return;
+  const int parts = conv3x3_gn_parts(B, H, W, Cout, stride, pad, groups_);
+  if (parts <= 0) return;
+  const int Ho = stride == 1 ? H : (pad == 1 ? (H - 1) / 2 + 1 : (H + 1 - 3) / 2 + 1);
+  const int Wo = stride == 1 ? W : (pad == 1 ? (W - 1) / 2 + 1 : (W + 1 - 3) / 2 + 1);
+  if (!groupnorm_pre_ok(Cout, Ho * Wo, groups_)) return;
+  if (static_cast<size_t>(B) * parts * groups_ * 2 > gn_pre_floats_ || static_cast<size_t>(B) * groups_ * 2 > kGnPreStats) return;
+  e.gn_out = gn_pre_buf_;
+  e.gn_groups = groups_;
+  e.gn_nparts = parts;
+  gn_pre_ = GnPre{static_cast<const __half*>(e.out), B, Ho * Wo, Cout, parts};
+}
+
+int Model::gnorm(Exec& ex, const __half* x1, int C1, const __half* x2, int C2, int B, int HW, float eps, const NormW& n,
+                 bool silu, __half* out) {
+  const GnPre pre = gn_pre_;
+  gn_pre_.x = nullptr;
+  float* scratch = ex.s32(gn_partials_floats(B, HW, groups_));
+  if (!ex.dry && pre.x != nullptr && pre.x == x1 && C2 == 0 && pre.C == C1 && pre.B == B && pre.HW == HW) {
+    RUN(ex, groupnorm_nhwc_pre(x1, C1, B, HW, groups_, eps, n.g, n.b, silu, out, gn_pre_buf_, pre.nparts,
+                               gn_pre_buf_ + gn_pre_floats_, ex.st));
+    return 0;
+  }
+  RUN(ex, groupnorm_nhwc(x1, C1, x2, C2, B, HW, groups_, eps, n.g, n.b, silu, out, scratch, ex.st));
+  return 0;
+}
+
 // ResnetBlock2D: GN+SiLU -> conv3x3 (+bias +temb) -> GN+SiLU -> conv3x3 (+bias) + shortcut(x)
 // The input may be the channel concatenation x1 ++ x2 (UNet up path): GroupNorm and the 1x1 shortcut read
 // both sources directly, so the concatenation is never written to memory.
@@ -256,9 +289,8 @@ int Model::resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __
   const int HW = H * W;
   const size_t rows = static_cast<size_t>(B) * HW;
   GYRE_REQUIRE(C1 + C2 == r.cin, "resnet: input channels %d+%d != %d", C1, C2, r.cin);
-  float* gn_scratch = ex.s32(gn_partials_floats(B, HW, groups_));
   __half* t1 = ex.s16(rows * r.cin);
-  RUN(ex, groupnorm_nhwc(x1, C1, x2, C2, B, HW, groups_, eps, r.n1.g, r.n1.b, true, t1, gn_scratch, ex.st));
+  GYRE_TRY(gnorm(ex, x1, C1, x2, C2, B, HW, eps, r.n1, true, t1));
   __half* t2 = ex.s16(rows * r.cout);
   {
     Epilogue e = ep_out(t2, r.cout, r.c1.bias);
@@ -267,10 +299,11 @@ int Model::resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __
       e.rgb_ld = temb_ld;
       e.rows_per_group = HW;
     }
+    gn_offer(e, B, H, W, r.cout, 1, 1);
     RUN(ex, conv3x3_f16(t1, r.cin, B, H, W, r.cin, r.c1.wp, r.cout, 1, 1, e, ex.st));
   }
   __half* t3 = ex.s16(rows * r.cout);
-  RUN(ex, groupnorm_nhwc(t2, r.cout, nullptr, 0, B, HW, groups_, eps, r.n2.g, r.n2.b, true, t3, gn_scratch, ex.st));
+  GYRE_TRY(gnorm(ex, t2, r.cout, nullptr, 0, B, HW, eps, r.n2, true, t3));
   const __half* res = x1;
   if (r.has_sc) {
     __half* t4 = ex.s16(rows * r.cout);
@@ -282,6 +315,7 @@ int Model::resnet(Exec& ex, const ResnetW& r, const __half* x1, int C1, const __
   }
   {
     Epilogue e = ep_out(out, r.cout, r.c2.bias, res, r.cout);
+    gn_offer(e, B, H, W, r.cout, 1, 1);     // whoever normalises `out` next (a transformer's GroupNorm, the next resnet)
     RUN(ex, conv3x3_f16(t3, r.cout, B, H, W, r.cout, r.c2.wp, r.cout, 1, 1, e, ex.st));
   }
   return 0;
@@ -519,9 +553,8 @@ int UNetModel::transformer(Exec& ex, const TransformerW& t, const __half* x, int
   const size_t ns = static_cast<size_t>(Ms) * C;
   const int d = C / t.heads;
   const float scale = 1.0f / sqrtf(static_cast<float>(d));
-  float* gn_scratch = ex.s32(gn_partials_floats(B, HW, groups_));
   __half* tn = ex.s16(n);
-  RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, Bs, HW, groups_, 1e-6f, t.gn.g, t.gn.b, false, tn, gn_scratch, ex.st));
+  GYRE_TRY(gnorm(ex, x, C, nullptr, 0, Bs, HW, 1e-6f, t.gn, false, tn));
   __half* h = ex.s16(n);
   // LayerNorm folded into the GEMMs around it: the GEMM that PRODUCES a residual-stream tensor also emits
   // per-row (sum, sum of squares) partials; a tiny kernel turns them into (mean, rstd); the GEMM that CONSUMES the
@@ -700,6 +733,7 @@ int UNetModel::set_adapter_states(const __half* const* states, int n) {
 int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const __half* ctx, const __half* add_cond, int B,
                        int H, int W, int L, const int32_t* tome_r, __half* out, const ControlNetIO* cn) {
   GYRE_REQUIRE(B > 0 && H > 0 && W > 0 && L > 0, "unet_forward: empty problem");
+  gn_forget();
   GYRE_REQUIRE(ex.dry || (cfg_.controlnet != 0) == (cn != nullptr),
                "unet_forward: a ControlNet handle runs through gyre_b200_controlnet_forward (and only it)");
   if (!ex.dry)
@@ -788,8 +822,11 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
     GYRE_REQUIRE(eh == H && ew == W, "controlnet: the conditioning image must be 8x the latent size");
     cond_emb = ecur;
   }
-  RUN(ex, conv3x3_f16(x_nhwc, cin8, Bs, H, W, cin8, conv_in_.wp, ch[0], 1, 1,
-                      ep_out(hcur, ch[0], conv_in_.bias, cond_emb, cond_emb ? ch[0] : 0), ex.st));
+  {
+    Epilogue e = ep_out(hcur, ch[0], conv_in_.bias, cond_emb, cond_emb ? ch[0] : 0);
+    gn_offer(e, Bs, H, W, ch[0], 1, 1);      // the first resnet's norm1
+    RUN(ex, conv3x3_f16(x_nhwc, cin8, Bs, H, W, cin8, conv_in_.wp, ch[0], 1, 1, e, ex.st));
+  }
   if (share && !ex.dry) {
     // conv_in's output is also the first skip tensor, which the up path reads at the full batch: duplicate it
     const size_t half = static_cast<size_t>(Bs) * H * W * ch[0];
@@ -823,13 +860,19 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
       skips.push_back({hcur, ccur, h_ * w_});
     }
     // T2I-adapter: the block's last hidden state (== its last skip tensor) takes the level's state in place
-    if (!ex.dry && !adapter_.empty()) RUN(ex, add_nchw_to_nhwc_f16(hcur, adapter_[i], B, ccur, h_ * w_, ex.st));
+    if (!ex.dry && !adapter_.empty()) {
+      RUN(ex, add_nchw_to_nhwc_f16(hcur, adapter_[i], B, ccur, h_ * w_, ex.st));
+      gn_forget();   // the tensor a convolution left statistics for has just changed
+    }
     if (i < nl - 1) {
       ex.reset_scratch();
       const int ho = (h_ - 1) / 2 + 1, wo = (w_ - 1) / 2 + 1;
       __half* o = ex.p16(static_cast<size_t>(B) * ho * wo * ccur);
-      RUN(ex, conv3x3_f16(hcur, ccur, B, h_, w_, ccur, downs_[di].wp, ccur, 2, 1, ep_out(o, ccur, downs_[di].bias),
-                          ex.st));
+      {
+        Epilogue e = ep_out(o, ccur, downs_[di].bias);
+        gn_offer(e, B, h_, w_, ccur, 2, 1);   // the next level's first resnet
+        RUN(ex, conv3x3_f16(hcur, ccur, B, h_, w_, ccur, downs_[di].wp, ccur, 2, 1, e, ex.st));
+      }
       ++di;
       hcur = o;
       h_ = ho;
@@ -846,6 +889,7 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
       if (k + 1 == skips.size()) continue;
       RUN(ex, add_nchw_to_nhwc_f16(skips[k].p, ctrl_down_[k], B, skips[k].C, skips[k].hw, ex.st));
     }
+    gn_forget();
   }
   // ---- mid
   {
@@ -860,12 +904,16 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
     __half* o3 = ex.p16(static_cast<size_t>(B) * h_ * w_ * ccur);
     GYRE_TRY(resnet(ex, resnets_[ri++], o2, ccur, nullptr, 0, B, h_, w_, eps, temb_all, temb_total_, o3));
     hcur = o3;
-    if (!ex.dry && ctrl_mid_ != nullptr) RUN(ex, add_nchw_to_nhwc_f16(o3, ctrl_mid_, B, ccur, h_ * w_, ex.st));
+    if (!ex.dry && ctrl_mid_ != nullptr) {
+      RUN(ex, add_nchw_to_nhwc_f16(o3, ctrl_mid_, B, ccur, h_ * w_, ex.st));
+      gn_forget();
+    }
   }
   if (!ex.dry && !ctrl_down_.empty()) {
     // the deepest skip was the mid block's input: it takes its residual only now that the mid block has read it
     const Skip& ls = skips.back();
     RUN(ex, add_nchw_to_nhwc_f16(ls.p, ctrl_down_.back(), B, ls.C, ls.hw, ex.st));
+    gn_forget();
   }
   // residuals are per call (core.py passes them with every UNet invocation)
   if (!ex.dry) {
@@ -926,10 +974,8 @@ int UNetModel::forward(Exec& ex, const __half* sample, const int64_t* t, const _
   ex.reset_scratch();
   {
     const size_t rows = static_cast<size_t>(B) * h_ * w_;
-    float* gn_scratch = ex.s32(gn_partials_floats(B, h_ * w_, groups_));
     __half* tn = ex.s16(rows * ccur);
-    RUN(ex, groupnorm_nhwc(hcur, ccur, nullptr, 0, B, h_ * w_, groups_, eps, norm_out_.g, norm_out_.b, true, tn,
-                           gn_scratch, ex.st));
+    GYRE_TRY(gnorm(ex, hcur, ccur, nullptr, 0, B, h_ * w_, eps, norm_out_, true, tn));
     const int oc = cfg_.out_channels;
     __half* eps_nhwc = ex.s16(rows * oc);
     RUN(ex, conv3x3_f16(tn, ccur, B, h_, w_, ccur, conv_out_.wp, oc, 1, 1, ep_out(eps_nhwc, oc, conv_out_.bias),
@@ -1035,9 +1081,8 @@ int VAEModel::attn(Exec& ex, const VaeAttnW& a, const __half* x, int B, int HW, 
   const int C = a.C;
   const int M = B * HW;
   const size_t n = static_cast<size_t>(M) * C;
-  float* gn_scratch = ex.s32(gn_partials_floats(B, HW, groups_));
   __half* tn = ex.s16(n);
-  RUN(ex, groupnorm_nhwc(x, C, nullptr, 0, B, HW, groups_, 1e-6f, a.gn.g, a.gn.b, false, tn, gn_scratch, ex.st));
+  GYRE_TRY(gnorm(ex, x, C, nullptr, 0, B, HW, 1e-6f, a.gn, false, tn));
   __half* qk = ex.s16(n * 2);
   RUN(ex, gemm_f16(tn, C, a.qk.w, C, M, 2 * C, C, ep_out(qk, 2 * C, a.qk.bias), ex.st));
   __half* o = ex.s16(n);
@@ -1082,7 +1127,12 @@ int VAEModel::decode(Exec& ex, const __half* z, int B, int h, int w, bool postpr
   __half* z2 = ex.p16(px * zc8);
   RUN(ex, conv1x1_small(z_nhwc, static_cast<int64_t>(px), zc, post_quant_.w, post_quant_.bias, zc, z2, zc8, ex.st));
   __half* cur = ex.p16(px * top);
-  RUN(ex, conv3x3_f16(z2, zc8, B, h, w, zc8, dec_conv_in_.wp, top, 1, 1, ep_out(cur, top, dec_conv_in_.bias), ex.st));
+  gn_forget();
+  {
+    Epilogue e = ep_out(cur, top, dec_conv_in_.bias);
+    gn_offer(e, B, h, w, top, 1, 1);
+    RUN(ex, conv3x3_f16(z2, zc8, B, h, w, zc8, dec_conv_in_.wp, top, 1, 1, e, ex.st));
+  }
   int H = h, W = w, C = top;
   auto block_out = [&](size_t elems) { return ex.p16(elems); };
   {
@@ -1119,10 +1169,8 @@ int VAEModel::decode(Exec& ex, const __half* z, int B, int h, int w, bool postpr
   ex.reset_scratch();
   {
     const size_t rows = static_cast<size_t>(B) * H * W;
-    float* gn_scratch = ex.s32(gn_partials_floats(B, H * W, groups_));
     __half* tn = ex.s16(rows * C);
-    RUN(ex, groupnorm_nhwc(cur, C, nullptr, 0, B, H * W, groups_, eps, dec_norm_out_.g, dec_norm_out_.b, true, tn,
-                           gn_scratch, ex.st));
+    GYRE_TRY(gnorm(ex, cur, C, nullptr, 0, B, H * W, eps, dec_norm_out_, true, tn));
     const int oc = cfg_.out_channels;
     GYRE_REQUIRE(oc == 3, "vae_decode: out_channels must be 3");
     __half* rgb = ex.s16(rows * 4);
@@ -1147,7 +1195,12 @@ int VAEModel::encode(Exec& ex, const __half* img, int B, int H, int W, __half* m
   __half* x = ex.p16(static_cast<size_t>(B) * H * W * ic8);
   RUN(ex, nchw_to_nhwc_f16(img, B, ic, H, W, x, ic8, ex.st));
   __half* cur = ex.p16(static_cast<size_t>(B) * H * W * ch[0]);
-  RUN(ex, conv3x3_f16(x, ic8, B, H, W, ic8, enc_conv_in_.wp, ch[0], 1, 1, ep_out(cur, ch[0], enc_conv_in_.bias), ex.st));
+  gn_forget();
+  {
+    Epilogue e = ep_out(cur, ch[0], enc_conv_in_.bias);
+    gn_offer(e, B, H, W, ch[0], 1, 1);
+    RUN(ex, conv3x3_f16(x, ic8, B, H, W, ic8, enc_conv_in_.wp, ch[0], 1, 1, e, ex.st));
+  }
   int C = ch[0];
   size_t ri = 0;
   for (int i = 0; i < L; ++i) {
@@ -1164,7 +1217,11 @@ int VAEModel::encode(Exec& ex, const __half* img, int B, int H, int W, __half* m
       // TMA out-of-bounds fill on the right/bottom edge
       const int ho = (H + 1 - 3) / 2 + 1, wo = (W + 1 - 3) / 2 + 1;
       __half* o = ex.p16(static_cast<size_t>(B) * ho * wo * C);
-      RUN(ex, conv3x3_f16(cur, C, B, H, W, C, enc_downs_[i].wp, C, 2, 0, ep_out(o, C, enc_downs_[i].bias), ex.st));
+      {
+        Epilogue e = ep_out(o, C, enc_downs_[i].bias);
+        gn_offer(e, B, H, W, C, 2, 0);
+        RUN(ex, conv3x3_f16(cur, C, B, H, W, C, enc_downs_[i].wp, C, 2, 0, e, ex.st));
+      }
       cur = o;
       H = ho;
       W = wo;
@@ -1185,10 +1242,8 @@ int VAEModel::encode(Exec& ex, const __half* img, int B, int H, int W, __half* m
   ex.reset_scratch();
   {
     const size_t rows = static_cast<size_t>(B) * H * W;
-    float* gn_scratch = ex.s32(gn_partials_floats(B, H * W, groups_));
     __half* tn = ex.s16(rows * C);
-    RUN(ex, groupnorm_nhwc(cur, C, nullptr, 0, B, H * W, groups_, eps, enc_norm_out_.g, enc_norm_out_.b, true, tn,
-                           gn_scratch, ex.st));
+    GYRE_TRY(gnorm(ex, cur, C, nullptr, 0, B, H * W, eps, enc_norm_out_, true, tn));
     __half* m0 = ex.s16(rows * 2 * zc);
     RUN(ex, conv3x3_f16(tn, C, B, H, W, C, enc_conv_out_.wp, 2 * zc, 1, 1, ep_out(m0, 2 * zc, enc_conv_out_.bias),
                         ex.st));

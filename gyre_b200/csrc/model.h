@@ -117,6 +117,19 @@ class Model {
   Epilogue ep_out(__half* out, int ldo, const float* bias = nullptr, const __half* residual = nullptr, int ldr = 0,
                   int act = 0) const;
 
+  // GroupNorm statistics from the producing convolution (Epilogue::gn_out).  gn_offer() asks the conv that is about to
+  // write e.out for them when the shape allows it and remembers the tensor; gnorm() - every GroupNorm of the models goes
+  // through it - takes the one-pass path when its input is exactly that tensor, the two-pass kernels otherwise, and
+  // forgets the offer either way.  Anything that rewrites a tensor in place between the two must call gn_forget().
+  void gn_offer(Epilogue& e, int B, int H, int W, int Cout, int stride, int pad);
+  int gnorm(Exec& ex, const __half* x1, int C1, const __half* x2, int C2, int B, int HW, float eps, const NormW& n, bool silu,
+            __half* out);
+  void gn_forget() { gn_pre_.x = nullptr; }
+  struct GnPre { const __half* x = nullptr; int B = 0, HW = 0, C = 0, nparts = 0; };
+  GnPre gn_pre_;
+  float* gn_pre_buf_ = nullptr;     // partials [B][nparts][G][2], then kGnPreStats floats of folded (mean, rstd)
+  size_t gn_pre_floats_ = 0;        // capacity of the partials part
+
   std::unordered_map<std::string, ParamSlot> slots_;
   std::vector<void*> allocs_;
   int device_ = 0;

@@ -136,8 +136,11 @@ __global__ void gn_stats_kernel(const GnArgs a, float* __restrict__ partials) {
 // finalize launch - then normalises (+SiLU) its chunk.  The first batch of rows is requested BEFORE the fold so
 // the statistics latency hides under the loads.  Chunks and samples are walked in the REVERSE order of pass 1:
 // what pass 1 touched last is still in L2.
+// nparts: partials per sample behind `partials` (the statistics pass leaves one per chunk; a producing convolution one
+// per output tile); ready != 0: `partials` holds finished (mean, rstd) pairs [B][G][2] instead (gn_fold_kernel).
 __global__ void gn_apply_kernel(const GnArgs a, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                int silu, float eps, const float* __restrict__ partials, __half* __restrict__ out) {
+                                int silu, float eps, const float* __restrict__ partials, int nparts, int ready,
+                                __half* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
   const int C = a.C1 + a.C2;
@@ -170,12 +173,18 @@ __global__ void gn_apply_kernel(const GnArgs a, const float* __restrict__ gamma,
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
   int parts = static_cast<int>(blockDim.x) / a.G;
   if (parts > 8) parts = 8;
-  if (static_cast<int>(threadIdx.x) < parts * a.G) {
+  if (ready) {
+    if (static_cast<int>(threadIdx.x) < a.G) {
+      const float2 ms = *reinterpret_cast<const float2*>(partials + (static_cast<int64_t>(b) * a.G + threadIdx.x) * 2);
+      s_mean[threadIdx.x] = ms.x;
+      s_rstd[threadIdx.x] = ms.y;
+    }
+  } else if (static_cast<int>(threadIdx.x) < parts * a.G) {
     const int g = threadIdx.x % a.G;
     const int part = threadIdx.x / a.G;
-    const float* pp = partials + static_cast<int64_t>(b) * chunks * (2 * a.G) + 2 * g;
+    const float* pp = partials + static_cast<int64_t>(b) * nparts * (2 * a.G) + 2 * g;
     double s = 0.0, q = 0.0;
-    for (int c = part; c < chunks; c += parts) {
+    for (int c = part; c < nparts; c += parts) {
       const float2 t = *reinterpret_cast<const float2*>(pp + static_cast<int64_t>(c) * (2 * a.G));
       s += static_cast<double>(t.x);
       q += static_cast<double>(t.y);
@@ -184,7 +193,7 @@ __global__ void gn_apply_kernel(const GnArgs a, const float* __restrict__ gamma,
     sh_q[part][g] = q;
   }
   __syncthreads();
-  if (static_cast<int>(threadIdx.x) < a.G) {
+  if (!ready && static_cast<int>(threadIdx.x) < a.G) {
     const int g = threadIdx.x;
     double s = 0.0, q = 0.0;
     for (int t = 0; t < parts; ++t) {
@@ -333,6 +342,95 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const __half* __restrict_
   }
 }
 
+// Many partials per sample (VAE-sized maps: one per 128-pixel conv tile): one CTA per (group, sample) folds them in a
+// fixed order (per-thread strided sums, then a fixed tree in fp64) into (mean, rstd) -> stats [B][G][2].
+__global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ partials, int nparts, int G, double inv_n,
+                                                      float eps, float* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
+  const int g = blockIdx.x, b = blockIdx.y;
+  const float* pp = partials + static_cast<int64_t>(b) * nparts * (2 * G) + 2 * g;
+  double s = 0.0, q = 0.0;
+  for (int c = threadIdx.x; c < nparts; c += 256) {
+    const float2 t = *reinterpret_cast<const float2*>(pp + static_cast<int64_t>(c) * (2 * G));
+    s += static_cast<double>(t.x);
+    q += static_cast<double>(t.y);
+  }
+  __shared__ double sh_s[256], sh_q[256];
+  sh_s[threadIdx.x] = s;
+  sh_q[threadIdx.x] = q;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (static_cast<int>(threadIdx.x) < w) {
+      sh_s[threadIdx.x] += sh_s[threadIdx.x + w];
+      sh_q[threadIdx.x] += sh_q[threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = sh_s[0] * inv_n;
+    double var = sh_q[0] * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float* dst = stats + (static_cast<int64_t>(b) * G + g) * 2;
+    dst[0] = static_cast<float>(mean);
+    dst[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+static bool gn_small_path(int C, int HW, int G) {
+  const int cpg = C / G;
+  const size_t slab_bytes = static_cast<size_t>(HW) * cpg * sizeof(__half);
+  return (cpg & 1) == 0 && HW <= 256 && slab_bytes <= 40 * 1024;
+}
+
+// geometry of the two-pass kernels for a shape (shared by groupnorm_nhwc and groupnorm_nhwc_pre)
+static int gn_two_pass_args(const __half* x1, int C1, const __half* x2, int C2, int HW, int G, GnArgs* a, int* threads) {
+  const int C = C1 + C2;
+  const int nvec = C / 8;
+  GYRE_REQUIRE(nvec <= 1024, "groupnorm: C=%d too large", C);
+  int gn_threads = tunable(TUNE_GN_THREADS);          // CTA size target (a function of nothing but the tunable)
+  if (gn_threads < 64 || gn_threads > 1024) gn_threads = 256;
+  int rpar = gn_threads / nvec;
+  if (rpar < 1) rpar = 1;
+  *threads = nvec * rpar;
+  GYRE_REQUIRE(*threads >= 4 * G, "groupnorm: too few threads for %d groups", G);
+  a->x1 = x1;
+  a->x2 = x2;
+  a->C1 = C1;
+  a->C2 = C2;
+  a->HW = HW;
+  a->G = G;
+  a->rpar = rpar;
+  a->rows_per_cta = gn_rows_per_cta(HW);
+  return 0;
+}
+
+bool groupnorm_pre_ok(int C, int HW, int G) {
+  return G > 0 && G <= kMaxGroups && C % G == 0 && C % 8 == 0 && !gn_small_path(C, HW, G);
+}
+
+int groupnorm_nhwc_pre(const __half* x, int C, int B, int HW, int G, float eps, const float* gamma, const float* beta,
+                       bool silu, __half* out, const float* pre, int nparts, float* stats, cudaStream_t st) {
+  GYRE_REQUIRE(B > 0 && HW > 0 && C > 0 && nparts > 0 && pre != nullptr, "groupnorm_pre: empty input");
+  GYRE_REQUIRE(groupnorm_pre_ok(C, HW, G), "groupnorm_pre: C=%d HW=%d G=%d takes the single-pass kernel", C, HW, G);
+  GnArgs a;
+  int threads = 0;
+  GYRE_TRY(gn_two_pass_args(x, C, nullptr, 0, HW, G, &a, &threads));
+  const int chunks = (HW + a.rows_per_cta - 1) / a.rows_per_cta;
+  // one pass over the tensor: read + write
+  prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, nparts > 64 ? 2 : 1);
+  int ready = 0;
+  if (nparts > 64) {
+    GYRE_REQUIRE(stats != nullptr, "groupnorm_pre: %d partials per sample need the statistics scratch", nparts);
+    const double inv_n = 1.0 / (static_cast<double>(HW) * (C / G));
+    GYRE_TRY(launch_kernel(gn_fold_kernel, dim3(G, B), dim3(256), 0, st, pre, nparts, G, inv_n, eps, stats));
+    pre = stats;
+    ready = 1;
+  }
+  return launch_kernel(gn_apply_kernel, dim3(chunks, B), dim3(threads), 0, st, a, gamma, beta, silu ? 1 : 0, eps, pre,
+                       nparts, ready, out);
+}
+
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, int G, float eps,
                    const float* gamma, const float* beta, bool silu, __half* out, float* partials, cudaStream_t st) {
   const int C = C1 + C2;
@@ -340,41 +438,26 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   GYRE_REQUIRE(G > 0 && G <= kMaxGroups && C % G == 0, "groupnorm: C=%d not divisible into %d groups", C, G);
   GYRE_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "groupnorm: channel counts must be multiples of 8");
   GYRE_REQUIRE(x2 != nullptr || C2 == 0, "groupnorm: missing second source");
-  {
+  if (gn_small_path(C, HW, G)) {
     const int cpg = C / G;
     const size_t slab_bytes = static_cast<size_t>(HW) * cpg * sizeof(__half);
-    if ((cpg & 1) == 0 && HW <= 256 && slab_bytes <= 40 * 1024) {
-      prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 1);
-      // a vector must not straddle the x1 / x2 boundary or a group boundary: C1, cpg multiples of VEC
-      const int vec = (cpg % 8 == 0) ? 8 : (cpg % 4 == 0 ? 4 : 2);
-      const dim3 grid(G, B);
-      if (vec == 8)
-        return launch_kernel(gn_small_kernel<8>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
-                             silu ? 1 : 0, out);
-      if (vec == 4)
-        return launch_kernel(gn_small_kernel<4>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
-                             silu ? 1 : 0, out);
-      return launch_kernel(gn_small_kernel<2>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
+    prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 1);
+    // a vector must not straddle the x1 / x2 boundary or a group boundary: C1, cpg multiples of VEC
+    const int vec = (cpg % 8 == 0) ? 8 : (cpg % 4 == 0 ? 4 : 2);
+    const dim3 grid(G, B);
+    if (vec == 8)
+      return launch_kernel(gn_small_kernel<8>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
                            silu ? 1 : 0, out);
-    }
+    if (vec == 4)
+      return launch_kernel(gn_small_kernel<4>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
+                           silu ? 1 : 0, out);
+    return launch_kernel(gn_small_kernel<2>, grid, dim3(256), slab_bytes, st, x1, C1, x2, C2, HW, G, eps, gamma, beta,
+                         silu ? 1 : 0, out);
   }
-  const int nvec = C / 8;
-  GYRE_REQUIRE(nvec <= 1024, "groupnorm: C=%d too large", C);
-  int gn_threads = tunable(TUNE_GN_THREADS);          // CTA size target (a function of nothing but the tunable)
-  if (gn_threads < 64 || gn_threads > 1024) gn_threads = 256;
-  int rpar = gn_threads / nvec;
-  if (rpar < 1) rpar = 1;
-  const int threads = nvec * rpar;
-  GYRE_REQUIRE(threads >= 4 * G, "groupnorm: too few threads for %d groups", G);
   GnArgs a;
-  a.x1 = x1;
-  a.x2 = x2;
-  a.C1 = C1;
-  a.C2 = C2;
-  a.HW = HW;
-  a.G = G;
-  a.rpar = rpar;
-  a.rows_per_cta = gn_rows_per_cta(HW);
+  int threads = 0;
+  GYRE_TRY(gn_two_pass_args(x1, C1, x2, C2, HW, G, &a, &threads));
+  const int rpar = a.rpar;
   const int chunks = (HW + a.rows_per_cta - 1) / a.rows_per_cta;
   dim3 grid(chunks, B);
   prof::Scope ps(prof::F_GROUPNORM, 0.0, 2.0 * 2.0 * B * HW * C, st, 2);
@@ -384,7 +467,7 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
                            partials));
   if (phase != 1)
     GYRE_TRY(launch_kernel(gn_apply_kernel, grid, dim3(threads), 0, st, a, gamma, beta, silu ? 1 : 0, eps,
-                           static_cast<const float*>(partials), out));
+                           static_cast<const float*>(partials), chunks, 0, out));
   return 0;
 }
 

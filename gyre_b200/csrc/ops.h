@@ -44,6 +44,13 @@ struct Epilogue {
   int ln_parts = 0;
   float ln_inv_c = 0.f;
   float ln_eps = 1e-5f;
+  // GroupNorm statistics of the OUTPUT, produced by the 3x3 convolution that writes it (conv only, TMA epilogue):
+  // gn_out [B][gn_nparts][gn_groups][2] float = per output tile of a sample the (sum, sum of squares) of every group's
+  // fp16-rounded outputs, summed in a fixed order (batch-size independent); groupnorm_nhwc_pre consumes them in place of
+  // its own statistics pass.  gn_nparts must be what conv3x3_gn_parts() returns for the launch (0 = cannot be fused).
+  float* gn_out = nullptr;
+  int gn_groups = 0;
+  int gn_nparts = 0;
   // optional stream-K scratch (owned by the caller, reused by every launch on one stream): fp32 partial
   // accumulators + one int flag per tile of the partial wave (flags must be zero; the kernel leaves them zero)
   void* sk_ws = nullptr;
@@ -60,6 +67,9 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
 // shortcut without materialising the concatenation).  K1 must be a multiple of 64.
 int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int K2, const __half* W, int ldw, int M,
               int N, const Epilogue& ep, cudaStream_t st);
+// Partials per sample a stride-1/2 conv3x3 of this shape leaves in Epilogue::gn_out, or 0 when the statistics cannot be
+// produced there (tiles that span samples or overhang the image, group boundaries that do not fall on tile boundaries).
+int conv3x3_gn_parts(int B, int H, int W, int Cout, int stride, int pad, int groups);
 // number of (max, argmax) partials per row an ACT_ROWMAX GEMM of this shape writes
 int gemm_rowmax_partials(int M, int N);
 // number of float2 partials per row a GEMM of this shape writes to Epilogue::rowstat_out
@@ -89,6 +99,15 @@ int upconv2x_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const _
 size_t gn_partials_floats(int B, int HW, int G);
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, int G, float eps,
                    const float* gamma, const float* beta, bool silu, __half* out, float* partials, cudaStream_t st);
+
+// The same with the statistics already there: pre [B][nparts][G][2] float (sum, sum of squares) partials left by the
+// producing convolution (Epilogue::gn_out).  `stats` is fp32 scratch of >= 2 * B * G floats (used when nparts > 64: a
+// tiny launch folds the partials into (mean, rstd) first).  Whether a given x can take this path: groupnorm_pre_ok().
+int groupnorm_nhwc_pre(const __half* x, int C, int B, int HW, int G, float eps, const float* gamma, const float* beta,
+                       bool silu, __half* out, const float* pre, int nparts, float* stats, cudaStream_t st);
+// true when groupnorm_nhwc would run its two-pass kernels for this shape (the single-pass small-map kernel reads the
+// tensor once anyway and does not take precomputed statistics)
+bool groupnorm_pre_ok(int C, int HW, int G);
 
 // LayerNorm over the last dim of [rows, C] fp16 (fp32 statistics, affine).
 int layernorm_rows(const __half* x, int rows, int C, float eps, const float* gamma, const float* beta, __half* out,
@@ -218,7 +237,7 @@ int mma_bench(int n, int naccs, int a_tmem, int reps, int blocks, long long* out
 // ---- tunables: small integer knobs read on the host at launch time.  Each starts from the environment
 // variable GYRE_B200_<NAME> (if set) and can be changed through gyre_b200_set_tunable (A/B measurements).
 enum Tunable { TUNE_ATT_VARIANT = 0, TUNE_PDL = 1, TUNE_GELU_FAST = 2, TUNE_GN_CHUNKS = 3, TUNE_UPCONV_FOLD = 4,
-               TUNE_CTX_KV_CACHE = 5, TUNE_XATTN = 6, TUNE_GN_PHASE = 7, TUNE_MCAST = 8, TUNE_ATT_D128 = 9, TUNE_STREAMK = 10, TUNE_FORCE_BN = 11, TUNE_GEMM_STAGES = 12, TUNE_DEBUG = 13, TUNE_LN_SUB = 14, TUNE_GN_THREADS = 15, TUNE_LN_FUSE = 16, TUNE_CFG_SHARE = 17, TUNE_COUNT = 18 };
+               TUNE_CTX_KV_CACHE = 5, TUNE_XATTN = 6, TUNE_GN_PHASE = 7, TUNE_MCAST = 8, TUNE_ATT_D128 = 9, TUNE_STREAMK = 10, TUNE_FORCE_BN = 11, TUNE_GEMM_STAGES = 12, TUNE_DEBUG = 13, TUNE_LN_SUB = 14, TUNE_GN_THREADS = 15, TUNE_LN_FUSE = 16, TUNE_CFG_SHARE = 17, TUNE_GN_FUSE = 18, TUNE_COUNT = 19 };
 int tunable(int id);
 int set_tunable_by_name(const char* name, int value);
 int get_tunable_by_name(const char* name, int* value);

@@ -68,7 +68,8 @@ int gyre_b200_debug_attention_trace(long long* dev_buf, int capacity);
  * measurement bits: 1 no output stores, 2 no epilogue - both give WRONG results -, 4 all-variants image),
  * "LN_SUB" (LayerNorm: several rows per warp for C <= 320 [1, default] / <= 640 [2]), "GN_THREADS", "LN_FUSE"
  * (LayerNorm folded into the GEMMs around it; read when a UNet is created [derived weights] and at every forward),
- * "CFG_SHARE" (0: ignore gyre_b200_unet_set_cfg_duplicate).
+ * "CFG_SHARE" (0: ignore gyre_b200_unet_set_cfg_duplicate), "GN_FUSE" (GroupNorm statistics produced by the epilogue of
+ * the 3x3 convolution that writes the tensor [1, default] instead of a statistics pass over it).
  * Every knob also reads GYRE_B200_<NAME> from the environment at first use.  Results stay within the
  * documented tolerances for every setting except the DEBUG store / epilogue bits. */
 int gyre_b200_set_tunable(const char* name, int value);
@@ -521,6 +522,14 @@ typedef struct gyre_b200_epilogue {
   int32_t ln_parts;
   float ln_inv_c;
   float ln_eps;
+  /* GroupNorm statistics of the output, produced by the convolution that writes it (gyre_b200_conv3x3 only; NULL: off).
+   * Replaces the statistics half of the torch.nn.GroupNorm that follows a conv in diffusers' ResnetBlock2D / AttentionBlock
+   * (structure restated in SURVEY.md A.2): gn_out [B][gn_nparts][gn_groups][2] float = per output tile of a sample the
+   * (sum, sum of squares) of every group's fp16-rounded outputs, summed in a fixed order; gyre_b200_groupnorm_pre
+   * consumes them.  gn_nparts must be gyre_b200_conv3x3_gn_parts() of the launch (0: this shape cannot produce them). */
+  float* gn_out;
+  int32_t gn_groups;
+  int32_t gn_nparts;
 } gyre_b200_epilogue;
 
 /* out = epilogue([A | A2] @ W^T): A [M, K1] pitch lda, A2 [M, K2] pitch lda2 (may be NULL/0),
@@ -558,6 +567,13 @@ size_t gyre_b200_groupnorm_scratch_floats(int B, int HW, int G);
 int gyre_b200_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, int G, float eps,
                         const float* gamma, const float* beta, int silu, void* out, float* scratch,
                         gyre_b200_stream stream);
+/* The same from statistics a producing convolution left (gyre_b200_epilogue::gn_out): one pass over x.  pre
+ * [B][nparts][G][2] float; stats: fp32 scratch of >= 2 * B * G floats.  gyre_b200_groupnorm_pre_ok tells whether the
+ * shape takes this path at all (small maps are normalised by a single-pass kernel that needs no statistics). */
+int gyre_b200_conv3x3_gn_parts(int B, int H, int W, int Cout, int stride, int pad, int groups);
+int gyre_b200_groupnorm_pre_ok(int C, int HW, int G);
+int gyre_b200_groupnorm_pre(const void* x, int C, int B, int HW, int G, float eps, const float* gamma, const float* beta,
+                            int silu, void* out, const float* pre, int nparts, float* stats, gyre_b200_stream stream);
 int gyre_b200_layernorm(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                         gyre_b200_stream stream);
 /* softmax(Q K^T * scale) V per head, reading Q/K/V in place from token-major projections:

@@ -166,6 +166,25 @@ def test_unet_sd15_full_size():
     assert torch.isfinite(out).all()
     assert err < 4e-3          # measured 1.28e-3 (the fp16 evaluation of the oracle itself: 1.81e-3)
     assert err < 1.5 * floor
+    # GN_FUSE (default on): the 3x3 convs leave the GroupNorm statistics of their outputs, the statistics passes over those
+    # tensors do not run.  Off = the two-pass kernels everywhere: same result up to the summation order of the statistics.
+    from gyre_b200 import _native as N
+    assert N.get_tunable("GN_FUSE") == 1
+    n0 = N.launch_count()
+    unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda())
+    n_fused = N.launch_count() - n0
+    N.set_tunable("GN_FUSE", 0)
+    try:
+        n0 = N.launch_count()
+        plain = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample.clone()
+        n_plain = N.launch_count() - n0
+    finally:
+        N.set_tunable("GN_FUSE", 1)
+    print(f"launches per forward: {n_fused} with conv-produced GroupNorm statistics, {n_plain} without; "
+          f"rel diff of the outputs {rel_err(out, plain):.3e}, two-pass rel err {rel_err(plain, ref):.3e}")
+    assert n_fused < n_plain, "no GroupNorm took the statistics of its producing convolution"
+    assert rel_err(out, plain) < 3e-3      # measured 1.5e-3: two fp16 evaluations, each ~1.3e-3 from the fp32 oracle
+    assert rel_err(plain, ref) < 4e-3
 
 
 @pytest.fixture(scope="module")
@@ -399,13 +418,16 @@ def test_vae_sd_decode_batch8_full_size():
     print(f"batch 1 vs batch 8, stream-K on: max abs diff {d:.3e} (|img| max {img[3].abs().max().item():.2f})")
     assert d < 1.6e-2
     from gyre_b200 import _native
-    old = _native.get_tunable("STREAMK")
+    # (GN_FUSE: whether a conv can leave the GroupNorm statistics depends on its tile width, which follows the tile count)
+    old = _native.get_tunable("STREAMK"), _native.get_tunable("GN_FUSE")
     _native.set_tunable("STREAMK", 0)
+    _native.set_tunable("GN_FUSE", 0)
     try:
         a = vae.decode(z.cuda()).sample
         b = vae.decode(z[3:4].cuda()).sample
     finally:
-        _native.set_tunable("STREAMK", old)
+        _native.set_tunable("STREAMK", old[0])
+        _native.set_tunable("GN_FUSE", old[1])
     assert torch.equal(b[0], a[3]), "image 3 differs between batch 1 and batch 8 with stream-K off"
 
 
@@ -553,9 +575,10 @@ def test_cfg_shared_prefix_is_the_full_computation(variant):
     t = torch.tensor([900, 500, 30]).cuda()
     t2 = torch.cat([t, t]).contiguous()
     ctx = torch.randn(2 * B, 77, cfg.cross_attention_dim, generator=gen).half().cuda()
-    saved = {k: N.get_tunable(k) for k in ("STREAMK", "LN_FUSE")}
+    saved = {k: N.get_tunable(k) for k in ("STREAMK", "LN_FUSE", "GN_FUSE")}
     try:
         N.set_tunable("STREAMK", 0)
+        N.set_tunable("GN_FUSE", 0)
         if variant == "ln_kernels":
             N.set_tunable("LN_FUSE", 0)
         if variant == "tome":

@@ -269,6 +269,68 @@ def test_groupnorm(nat, B, HW, C1, C2, G, silu):
     assert_close(out, ref.permute(0, 2, 1), 2e-3, 2e-3, "groupnorm")
 
 
+# shapes: UNet levels 0 / 1 (cpg 10 / 20: groups straddle the 32-column epilogue slices), SDXL-like 1280 at 32x32 (cpg 40),
+# the stride-2 downsamplers, VAE widths (cpg 4 / 8 / 16; many partials -> the fold launch), stream-K and pair launches
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,pad,res,temb", [
+    (2, 64, 64, 320, 320, 1, 1, True, False), (8, 32, 32, 640, 640, 1, 1, False, True), (8, 32, 32, 320, 640, 1, 1, False, True),
+    (16, 32, 32, 128, 1280, 1, 1, True, False), (2, 128, 128, 320, 320, 2, 1, False, False), (16, 64, 64, 64, 640, 2, 1, False, False),
+    (1, 128, 128, 256, 256, 1, 1, False, False), (1, 64, 64, 512, 512, 1, 1, True, False),
+    (1, 256, 256, 128, 128, 1, 1, False, False), (16, 64, 64, 64, 320, 1, 1, False, True), (4, 128, 128, 64, 128, 2, 0, False, False)])
+def test_conv3x3_groupnorm_statistics(nat, B, H, W, Cin, Cout, stride, pad, res, temb):
+    """The conv epilogue's GroupNorm partials (Epilogue::gn_out) + groupnorm_pre against (a) fp64 statistics of the conv's own
+    fp16 output and (b) the two-pass GroupNorm kernels on that output."""
+    G = 32
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=1 / math.sqrt(9 * Cin))
+    bias = rnd(Cout, seed=3, dtype=torch.float32)
+    wp = nat.pack_conv3x3(w)
+    parts = nat.load().gyre_b200_conv3x3_gn_parts(B, H, W, Cout, stride, pad, G)
+    assert parts > 0, "this shape was chosen to take the fused path"
+    Ho, Wo = (H, W) if stride == 1 else (((H - 1) // 2 + 1, (W - 1) // 2 + 1) if pad == 1 else ((H - 2) // 2 + 1, (W - 2) // 2 + 1))
+    residual = (rnd(B * Ho * Wo, Cout, seed=4) + 0.25) if res else None
+    tvec = rnd(B, Cout, seed=5) if temb else None
+    kw = dict(bias=bias, residual=residual, stride=stride, pad=pad, rowgroup_bias=tvec, rows_per_group=Ho * Wo)
+    out, pre = nat.conv3x3(x, wp, Cout, gn_groups=G, **kw)
+    plain = nat.conv3x3(x, wp, Cout, **kw)
+    assert torch.equal(out, plain), "producing the statistics must not change the convolution's output"
+    assert pre.shape == (B, parts, G, 2) and torch.isfinite(pre).all(), "every (sample, tile, group) partial is written"
+    o64 = out.double().view(B, Ho * Wo, G, Cout // G)
+    tot = pre.double().sum(1)
+    n = Ho * Wo * (Cout // G)
+    assert_close(tot[..., 0] / n, o64.sum((1, 3)) / n, 1e-5, 1e-5, "group means")
+    assert_close(tot[..., 1] / n, (o64 * o64).sum((1, 3)) / n, 1e-5, 1e-5, "group second moments")
+    gamma = 1 + 0.1 * rnd(Cout, seed=6, dtype=torch.float32)
+    beta = 0.1 * rnd(Cout, seed=7, dtype=torch.float32)
+    assert nat.load().gyre_b200_groupnorm_pre_ok(Cout, Ho * Wo, G) == 1
+    flat = out.view(B, Ho * Wo, Cout)
+    for silu in (True, False):
+        fused = nat.groupnorm_pre(flat, gamma, beta, G, 1e-5, silu, pre)
+        two_pass = nat.groupnorm(flat, gamma, beta, G, 1e-5, silu)
+        ref = F.group_norm(flat.float().permute(0, 2, 1), G, gamma, beta, 1e-5)
+        ref = (F.silu(ref) if silu else ref).permute(0, 2, 1)
+        assert_close(fused, ref, 2e-3, 2e-3, "groupnorm from conv statistics")
+        assert (fused.float() - two_pass.float()).abs().max().item() <= 2e-3
+    # batch independence: a sample's partials (and so its normalised rows) are bit-identical at batch 1
+    one, pre1 = nat.conv3x3(x[B - 1:].contiguous(), wp, Cout, gn_groups=G, bias=bias, stride=stride, pad=pad,
+                            residual=residual[(B - 1) * Ho * Wo:].contiguous() if res else None,
+                            rowgroup_bias=tvec[B - 1:].contiguous() if temb else None, rows_per_group=Ho * Wo)
+    if pre1 is not None and torch.equal(one[0], out[B - 1]):      # (stream-K may change the conv's last bit with the batch)
+        assert torch.equal(pre1[0], pre[B - 1])
+
+
+def test_conv3x3_gn_parts_refuses_what_it_cannot_do(nat):
+    lib = nat.load()
+    assert lib.gyre_b200_conv3x3_gn_parts(2, 8, 8, 1280, 1, 1, 32) == 0       # a tile spans two samples
+    assert lib.gyre_b200_conv3x3_gn_parts(1, 12, 20, 320, 1, 1, 32) == 0      # tiles overhang the image
+    assert lib.gyre_b200_conv3x3_gn_parts(1, 64, 64, 96, 1, 1, 32) == 0       # odd-width groups (cpg 3)
+    assert lib.gyre_b200_conv3x3_gn_parts(1, 64, 64, 4, 1, 1, 32) == 0
+    assert lib.gyre_b200_conv3x3_gn_parts(2, 64, 64, 320, 1, 1, 32) == 32
+    x = rnd(1, 12, 20, 64, seed=1)
+    w = rnd(320, 64, 3, 3, seed=2, scale=0.05)
+    out, pre = nat.conv3x3(x, nat.pack_conv3x3(w), 320, gn_groups=32)
+    assert pre is None and out.shape == (1, 12, 20, 320)
+
+
 def test_groupnorm_batch_independent(nat):
     """Chunking depends on HW only: a sample's result is bit-identical at any batch size."""
     x = rnd(4, 4096, 320, seed=9)
