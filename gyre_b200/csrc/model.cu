@@ -1087,23 +1087,33 @@ int VAEModel::attn(Exec& ex, const VaeAttnW& a, const __half* x, int B, int HW, 
   RUN(ex, gemm_f16(tn, C, a.qk.w, C, M, 2 * C, C, ep_out(qk, 2 * C, a.qk.bias), ex.st));
   __half* o = ex.s16(n);
   __half* vt = ex.s16(static_cast<size_t>(C) * HW);
-  float* s = ex.s32(static_cast<size_t>(HW) * HW);
-  __half* p = ex.s16(static_cast<size_t>(HW) * HW);
+  // query rows per pass: the fp32 scores + fp16 probabilities of one pass stay under ~0.75 GB however large the image is
+  // (HW = 4096 at 512 x 512: one pass; 65536 at 2048 x 2048: 2048 rows per pass instead of a 26 GB score matrix)
+  int qc = HW;
+  {
+    const size_t budget_rows = (size_t(768) << 20) / (static_cast<size_t>(HW) * 6);
+    if (static_cast<size_t>(qc) > budget_rows) qc = static_cast<int>(budget_rows < 128 ? 128 : (budget_rows & ~size_t(127)));
+  }
+  float* s = ex.s32(static_cast<size_t>(qc) * HW);
+  __half* p = ex.s16(static_cast<size_t>(qc) * HW);
   const float scale = 1.0f / sqrtf(static_cast<float>(C));
   for (int b = 0; b < B; ++b) {
     const __half* tb = off(tn, static_cast<size_t>(b) * HW * C);
     const __half* qb = off(qk, static_cast<size_t>(b) * HW * 2 * C);
     RUN(ex, gemm_f16(a.v.w, C, tb, C, C, HW, C, ep_out(vt, HW), ex.st));                      // V^T [C, HW]
-    {
-      Epilogue e;
-      e.out = s;
-      e.ldo = HW;
-      e.out_mode = OUT_F32;
-      RUN(ex, gemm_f16(qb, 2 * C, off(qb, C), 2 * C, HW, HW, C, e, ex.st));                      // S = Q K^T
+    for (int q0 = 0; q0 < HW; q0 += qc) {
+      const int nq = HW - q0 < qc ? HW - q0 : qc;
+      {
+        Epilogue e;
+        e.out = s;
+        e.ldo = HW;
+        e.out_mode = OUT_F32;
+        RUN(ex, gemm_f16(off(qb, static_cast<size_t>(q0) * 2 * C), 2 * C, off(qb, C), 2 * C, nq, HW, C, e, ex.st));   // S = Q K^T
+      }
+      RUN(ex, softmax_rows_f32(s, nq, HW, scale, p, HW, ex.st));
+      RUN(ex, gemm_f16(p, HW, vt, HW, nq, C, HW,
+                       ep_out(off(o, (static_cast<size_t>(b) * HW + q0) * C), C, a.v_bias), ex.st));
     }
-    RUN(ex, softmax_rows_f32(s, HW, HW, scale, p, HW, ex.st));
-    RUN(ex, gemm_f16(p, HW, vt, HW, HW, C, HW, ep_out(off(o, static_cast<size_t>(b) * HW * C), C, a.v_bias),
-                     ex.st));
   }
   RUN(ex, gemm_f16(o, C, a.proj.w, C, M, C, C, ep_out(out, C, a.proj.bias, x, C), ex.st));
   return 0;

@@ -222,6 +222,23 @@ def test_vae_tiny_encode_vs_golden(tiny_vae):
     assert (s1.cpu().float() - ref).abs().max().item() < 2e-3
 
 
+def test_vae_decode_large_latent_attention_in_passes(tiny_vae):
+    """128 x 128 latent -> 1024 x 1024 image: the mid-block attention (16384 tokens) runs in two passes over the query rows
+    instead of materialising a 16384^2 score matrix at once, and the 1024^2 GroupNorms fold 8192 conv-produced partials."""
+    from oracle.vae import vae_decode
+    _no_tf32()
+    cfg, P, vae = tiny_vae
+    z = torch.randn(1, 4, 128, 128, generator=torch.Generator("cpu").manual_seed(5)).half()
+    Pc = {k: v.cuda() for k, v in P.items()}
+    with torch.no_grad():
+        ref = vae_decode(Pc, cfg, z.cuda().float())
+    img = vae.decode(z.cuda()).sample
+    err = rel_err(img, ref)
+    print(f"tiny VAE decode 1024x1024 rel err {err:.3e}")
+    assert torch.isfinite(img).all()
+    assert err < 5e-3
+
+
 def test_vae_sd_decode_full_size():
     """SD VAE decoder, 64x64 latent -> 512x512 image, batch 1, vs the fp32 oracle on the GPU."""
     from oracle.unet import synth_params
