@@ -46,7 +46,7 @@ struct GemmParams {
   int sk_first;       // first tile index handled by stream-K; tiles below it are dealt round-robin as whole tiles
   int sk_tiles;       // number of stream-K tiles (< grid size)
   int sk_maxp;        // partial-accumulator slots per stream-K tile
-  float* sk_ws;       // [sk_tiles][sk_maxp][128][BN] fp32 partial accumulators
+  float* sk_ws;       // [sk_tiles][sk_maxp][BN / 4][128] float4 partial accumulators (quad-major: coalesced per warp)
   int* sk_flags;      // [sk_tiles] partials delivered (zero between launches)
   // GroupNorm statistics of the output (EPI 6; Epilogue::gn_out): per 32-column slice of a tile, bit i of gn_mask is set
   // when a group ends behind column pair i of the slice, gn_g0 is the (tile-relative) group of the slice's first column
@@ -554,7 +554,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const float* sk_part = nullptr;                         // owner: slot 0 of this tile's partial accumulators
       if (wi.kind == 1) {
         // partial producer: dump the raw fp32 accumulator (all BN columns of my row) and raise the tile's flag
-        float* dst = p.sk_ws + (((static_cast<size_t>(sk_tt) * p.sk_maxp + wi.aux) * npr + rank) * kBM + r) * BN;
+        // slot layout [BN / 4 column quads][128 rows] float4: a warp's 32 rows of one quad are 512 contiguous bytes, so
+        // the dump and the owner's loads are fully coalesced (row-major slots cost 32 sectors per warp instruction)
+        float* dst = p.sk_ws + ((static_cast<size_t>(sk_tt) * p.sk_maxp + wi.aux) * npr + rank) * (kBM * BN) + r * 4;
         named_bar_sync(1, kEpiThreads);
         mbar_wait(&tfull_bar[buf], use & 1);
         tc_fence_after();
@@ -564,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            *reinterpret_cast<uint4*>(dst + sl * 32 + u * 4) = make_uint4(ra[4 * u], ra[4 * u + 1], ra[4 * u + 2], ra[4 * u + 3]);
+            *reinterpret_cast<uint4*>(dst + (sl * 8 + u) * (kBM * 4)) = make_uint4(ra[4 * u], ra[4 * u + 1], ra[4 * u + 2], ra[4 * u + 3]);
         }
         __threadfence();
         named_bar_sync(1, kEpiThreads);
@@ -588,15 +590,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           __threadfence();
         }
-        sk_part = p.sk_ws + (((static_cast<size_t>(sk_tt) * p.sk_maxp) * npr + rank) * kBM + r) * BN;
+        sk_part = p.sk_ws + ((static_cast<size_t>(sk_tt) * p.sk_maxp) * npr + rank) * (kBM * BN) + r * 4;
       }
       // adds the partial accumulators of this row, columns [c, c + 32), in slot order
       auto add_partials = [&](uint32_t (&acc)[32], int c) {
         for (int s2 = 0; s2 < wi.aux; ++s2) {
-          const float* src = sk_part + static_cast<size_t>(s2) * npr * kBM * BN + c;
+          const float* src = sk_part + static_cast<size_t>(s2) * npr * kBM * BN + (c >> 2) * (kBM * 4);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + u * 4));
+            const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + u * (kBM * 4)));
             acc[4 * u] = __float_as_uint(__uint_as_float(acc[4 * u]) + v4.x);
             acc[4 * u + 1] = __float_as_uint(__uint_as_float(acc[4 * u + 1]) + v4.y);
             acc[4 * u + 2] = __float_as_uint(__uint_as_float(acc[4 * u + 2]) + v4.z);
@@ -1078,7 +1080,7 @@ static void plan_stream_k(GemmParams* p, int bn, int max_clusters) {
   // The hand-off costs ~5-10 us of epilogue time per launch (partial dump + fence + flag, then latency-bound partial
   // loads in the owner's epilogue - measured on B200), so only tiles whose main loop runs for tens of us qualify:
   // the 3x3 convolutions at 32x32 and below, not the transformer GEMMs (their 3-15 us tiles got slower).
-  if (ep.act == ACT_ROWMAX || static_cast<long long>(p->k_iters) * bn < 14000) return;
+  if (ep.act == ACT_ROWMAX || static_cast<long long>(p->k_iters) * bn < tunable(TUNE_SK_MIN)) return;
   const long long T = static_cast<long long>(npr == 2 ? (p->m_tiles + 1) / 2 : p->m_tiles) * p->n_tiles;
   const int G = npr == 2 ? max_clusters : sm_count();
   if (G <= 0) return;
@@ -1186,6 +1188,23 @@ static int pick_bn(long long m_tiles, int N, int act) {
     }
   }
   return best;
+}
+
+// Tile width of a convolution.  Small maps with wide channels (the 8x8 / 16x16 levels: <= 32 M tiles, K in the thousands)
+// do not fill a wave of 128 x BN tiles whatever BN is, so with stream-K available - it cuts the K range of the tiles over
+// all SMs - the wave term of pick_bn is moot and the widest tile that divides N wins (fewest operand bytes per flop:
+// measured 16x8x8 1280->1280 45 -> 35 us, 16x16x16 1280->1280 95 -> 85 us, profiles/r02_ab_conv_smallmap.txt).
+static int pick_bn_conv(long long m_tiles, int N, int k_iters, bool streamk_avail) {
+  const int plain = pick_bn(m_tiles, N, ACT_NONE);
+  if (!streamk_avail || !tunable(TUNE_STREAMK) || tunable(TUNE_FORCE_BN) != 0 || tunable(TUNE_MCAST) < 2) return plain;
+  if (m_tiles < 4 || m_tiles > 32 || k_iters < 10) return plain;
+  const long long pairs = (m_tiles + 1) / 2;
+  int cand = 0;
+  if (pairs >= 8 && N % 256 == 0) cand = 256;
+  else if (N % 160 == 0) cand = 160;
+  else if (N % 128 == 0) cand = 128;
+  if (cand == 0 || static_cast<long long>(k_iters) * cand < tunable(TUNE_SK_MIN)) return plain;   // plan_stream_k's own floor
+  return cand;
 }
 
 static int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
@@ -1385,13 +1404,16 @@ static int conv_impl(const __half* X, int ldx, int B, int H, int W, int Cin, con
   const long long best_cost = conv_tile_shape(Ho, Wo, B, stride, &best_w, &best_h, &best_n) ? 1 : -1;
   GYRE_REQUIRE(best_cost > 0, "conv3x3: no tile shape for %dx%d", Ho, Wo);
   const int m_tiles = ((Wo + best_w - 1) / best_w) * ((Ho + best_h - 1) / best_h) * ((B + best_n - 1) / best_n);
-  const int bn = pick_bn(m_tiles, Cout, ACT_NONE);
   GemmParams p{};
   p.M = 0;
   p.N = Cout;
   p.cin_chunks = (Cin + kBK - 1) / kBK;
   p.cin_pad = p.cin_chunks * kBK;
   p.k_iters = ntaps * p.cin_chunks;
+  // (a launch that also produces GroupNorm statistics keeps the width conv3x3_gn_parts planned with)
+  const bool sk_avail = ep.sk_ws != nullptr && ep.sk_flags != nullptr && ep.gn_out == nullptr && ep.act != ACT_ROWMAX &&
+                        tma_epilogue_ok(ep, Cout);
+  const int bn = pick_bn_conv(m_tiles, Cout, p.k_iters, sk_avail);
   p.k1_iters = p.k_iters;
   p.n_tiles = (Cout + bn - 1) / bn;
   p.m_tiles = m_tiles;

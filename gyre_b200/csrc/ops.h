@@ -237,7 +237,7 @@ int mma_bench(int n, int naccs, int a_tmem, int reps, int blocks, long long* out
 // ---- tunables: small integer knobs read on the host at launch time.  Each starts from the environment
 // variable GYRE_B200_<NAME> (if set) and can be changed through gyre_b200_set_tunable (A/B measurements).
 enum Tunable { TUNE_ATT_VARIANT = 0, TUNE_PDL = 1, TUNE_GELU_FAST = 2, TUNE_GN_CHUNKS = 3, TUNE_UPCONV_FOLD = 4,
-               TUNE_CTX_KV_CACHE = 5, TUNE_XATTN = 6, TUNE_GN_PHASE = 7, TUNE_MCAST = 8, TUNE_ATT_D128 = 9, TUNE_STREAMK = 10, TUNE_FORCE_BN = 11, TUNE_GEMM_STAGES = 12, TUNE_DEBUG = 13, TUNE_LN_SUB = 14, TUNE_GN_THREADS = 15, TUNE_LN_FUSE = 16, TUNE_CFG_SHARE = 17, TUNE_GN_FUSE = 18, TUNE_COUNT = 19 };
+               TUNE_CTX_KV_CACHE = 5, TUNE_XATTN = 6, TUNE_GN_PHASE = 7, TUNE_MCAST = 8, TUNE_ATT_D128 = 9, TUNE_STREAMK = 10, TUNE_FORCE_BN = 11, TUNE_GEMM_STAGES = 12, TUNE_DEBUG = 13, TUNE_LN_SUB = 14, TUNE_GN_THREADS = 15, TUNE_LN_FUSE = 16, TUNE_CFG_SHARE = 17, TUNE_GN_FUSE = 18, TUNE_SK_MIN = 19, TUNE_COUNT = 20 };
 int tunable(int id);
 int set_tunable_by_name(const char* name, int value);
 int get_tunable_by_name(const char* name, int* value);

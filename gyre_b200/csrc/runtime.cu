@@ -78,9 +78,9 @@ int encode_tmap_f16_sw(CUtensorMap* out, const void* base, int rank, const uint6
 
 // ------------------------------------------------------------------ tunables
 static const char* kTunableNames[TUNE_COUNT] = {"ATT_VARIANT", "PDL", "GELU_FAST", "GN_CHUNKS", "UPCONV_FOLD",
-                                                "CTX_KV_CACHE", "XATTN", "GN_PHASE", "MCAST", "ATT_D128", "STREAMK", "FORCE_BN", "GEMM_STAGES", "DEBUG", "LN_SUB", "GN_THREADS", "LN_FUSE", "CFG_SHARE", "GN_FUSE"};
+                                                "CTX_KV_CACHE", "XATTN", "GN_PHASE", "MCAST", "ATT_D128", "STREAMK", "FORCE_BN", "GEMM_STAGES", "DEBUG", "LN_SUB", "GN_THREADS", "LN_FUSE", "CFG_SHARE", "GN_FUSE", "SK_MIN"};
 // defaults = the configuration measured fastest on B200 (profiles/); 0 restores the plain round-1 kernels
-static const int kTunableDefaults[TUNE_COUNT] = {2002, 1, 1, 32, 1, 1, 1, 0, 2, 1, 1, 0, 0, 0, 1, 256, 1, 1, 1};
+static const int kTunableDefaults[TUNE_COUNT] = {2002, 1, 1, 32, 1, 1, 1, 0, 2, 1, 1, 0, 0, 0, 1, 256, 1, 1, 1, 14000};
 static std::atomic<int> g_tunables[TUNE_COUNT];
 static std::once_flag g_tunables_once;
 

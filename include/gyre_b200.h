@@ -69,7 +69,8 @@ int gyre_b200_debug_attention_trace(long long* dev_buf, int capacity);
  * "LN_SUB" (LayerNorm: several rows per warp for C <= 320 [1, default] / <= 640 [2]), "GN_THREADS", "LN_FUSE"
  * (LayerNorm folded into the GEMMs around it; read when a UNet is created [derived weights] and at every forward),
  * "CFG_SHARE" (0: ignore gyre_b200_unet_set_cfg_duplicate), "GN_FUSE" (GroupNorm statistics produced by the epilogue of
- * the 3x3 convolution that writes the tensor [1, default] instead of a statistics pass over it).
+ * the 3x3 convolution that writes the tensor [1, default] instead of a statistics pass over it), "SK_MIN" (stream-K floor:
+ * k-iterations x tile width below which a launch keeps whole tiles [14000]).
  * Every knob also reads GYRE_B200_<NAME> from the environment at first use.  Results stay within the
  * documented tolerances for every setting except the DEBUG store / epilogue bits. */
 int gyre_b200_set_tunable(const char* name, int value);

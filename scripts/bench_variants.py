@@ -204,6 +204,38 @@ if "streamk" in what:
             rec("streamk", f"conv {B}x{H}x{H} {cin}->{cout} streamk={sk}", us, 2.0 * 9 * cin * cout * B * H * H)
         del x
 
+if "conv8" in what:
+    # the weight-heavy small-map convs (8x8 / 16x16 levels): tile width x stream-K x pair mode
+    for (B, H, cin, cout) in ((16, 8, 1280, 1280), (16, 8, 2560, 1280), (16, 16, 1280, 1280), (16, 16, 2560, 1280), (8, 8, 1280, 1280)):
+        x = [torch.randn(B, H, H, cin, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(cout, cin, 3, 3, device=dev).half() * (1 / math.sqrt(9 * cin))
+        wp = N.pack_conv3x3(w)
+        bias = torch.randn(cout, device=dev)
+        for sk in (1, 0):
+            for mc in (2, 0):
+                for bn in (0, 128, 160, 256):
+                    def run():
+                        return with_tunable("STREAMK", sk, lambda: with_tunable("MCAST", mc, lambda: with_tunable(
+                            "FORCE_BN", bn, lambda: graph_time(lambda i: N.conv3x3(x[i % ROT], wp, cout, bias=bias)))))
+                    rec("conv8", f"conv {B}x{H}x{H} {cin}->{cout} streamk={sk} mcast={mc} BN={bn or 'auto'}", run(),
+                        2.0 * 9 * cin * cout * B * H * H)
+        del x
+
+if "skgemm" in what:
+    # transformer GEMMs with the stream-K floor lowered (SK_MIN): does the coalesced hand-over pay below the conv sizes?
+    for (M, Nn, K, res) in ((4096, 1280, 1280, True), (4096, 1280, 5120, True), (4096, 3840, 1280, False), (16384, 640, 640, True),
+                            (16384, 640, 2560, True), (16384, 1920, 640, False), (65536, 320, 1280, True), (1024, 1280, 1280, True),
+                            (1024, 1280, 5120, True)):
+        a = [torch.randn(M, K, device=dev).half() for _ in range(ROT)]
+        w = torch.randn(Nn, K, device=dev).half() * (1 / math.sqrt(K))
+        bias = torch.randn(Nn, device=dev)
+        r = [torch.randn(M, Nn, device=dev).half() for _ in range(ROT)] if res else None
+        for skmin in (14000, 6000, 3000, 1000):
+            us = with_tunable("SK_MIN", skmin, lambda: graph_time(
+                lambda i: N.gemm(a[i % ROT], w, bias=bias, residual=r[i % ROT] if res else None)))
+            rec("skgemm", f"gemm M{M} N{Nn} K{K}{' +res' if res else ''} SK_MIN={skmin}", us, 2.0 * M * Nn * K)
+        del a, r
+
 if "bn" in what:
     for (M, Nn, K, res) in ((65536, 320, 320, False), (65536, 320, 320, True), (65536, 960, 320, False), (65536, 320, 1280, True),
                             (16384, 640, 640, True), (4096, 1280, 1280, True)):

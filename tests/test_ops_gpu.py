@@ -291,8 +291,15 @@ def test_conv3x3_groupnorm_statistics(nat, B, H, W, Cin, Cout, stride, pad, res,
     tvec = rnd(B, Cout, seed=5) if temb else None
     kw = dict(bias=bias, residual=residual, stride=stride, pad=pad, rowgroup_bias=tvec, rows_per_group=Ho * Wo)
     out, pre = nat.conv3x3(x, wp, Cout, gn_groups=G, **kw)
-    plain = nat.conv3x3(x, wp, Cout, **kw)
-    assert torch.equal(out, plain), "producing the statistics must not change the convolution's output"
+    # producing the statistics does not change the convolution's output: bitwise with stream-K off (with it on, the plain
+    # launch of a small map may take a wider, K-split tile, i.e. another fp32 summation order)
+    old_sk = nat.get_tunable("STREAMK")
+    nat.set_tunable("STREAMK", 0)
+    try:
+        assert torch.equal(nat.conv3x3(x, wp, Cout, gn_groups=G, **kw)[0], nat.conv3x3(x, wp, Cout, **kw))
+    finally:
+        nat.set_tunable("STREAMK", old_sk)
+    assert_close(out, nat.conv3x3(x, wp, Cout, **kw), 2e-3, 2e-3, "conv with / without statistics")
     assert pre.shape == (B, parts, G, 2) and torch.isfinite(pre).all(), "every (sample, tile, group) partial is written"
     o64 = out.double().view(B, Ho * Wo, G, Cout // G)
     tot = pre.double().sum(1)
