@@ -1360,7 +1360,7 @@ static bool conv_tile_shape(int Ho, int Wo, int B, int stride, int* tw_out, int*
   return best_cost > 0;
 }
 
-static int conv_out_extent(int n, int stride, int pad) {
+int conv3x3_out_extent(int n, int stride, int pad) {
   return (stride == 1) ? n : (pad == 1 ? (n - 1) / 2 + 1 : (n + 1 - 3) / 2 + 1);
 }
 
@@ -1382,7 +1382,7 @@ static int conv_gn_parts(int B, int Ho, int Wo, int Cout, int stride, int groups
 }
 
 int conv3x3_gn_parts(int B, int H, int W, int Cout, int stride, int pad, int groups) {
-  return conv_gn_parts(B, conv_out_extent(H, stride, pad), conv_out_extent(W, stride, pad), Cout, stride, groups, nullptr);
+  return conv_gn_parts(B, conv3x3_out_extent(H, stride, pad), conv3x3_out_extent(W, stride, pad), Cout, stride, groups, nullptr);
 }
 
 // Geometry of one implicit-GEMM convolution launch: taps_h x taps_w taps whose (0, 0) tap reads input pixel
@@ -1514,8 +1514,8 @@ int conv3x3_f16(const __half* X, int ldx, int B, int H, int W, int Cin, const __
   GYRE_REQUIRE(ep.out != nullptr && ep.ldo > 0, "conv3x3: null output");
   ConvGeom gm;
   gm.off_x = gm.off_y = -pad;
-  gm.Ho = conv_out_extent(H, stride, pad);
-  gm.Wo = conv_out_extent(W, stride, pad);
+  gm.Ho = conv3x3_out_extent(H, stride, pad);
+  gm.Wo = conv3x3_out_extent(W, stride, pad);
   gm.algo_flops = 2.0 * 9 * Cin * Cout * static_cast<double>(B) * gm.Ho * gm.Wo;
   gm.algo_bytes = 2.0 * (static_cast<double>(B) * H * W * Cin + 9.0 * Cin * Cout +
                          static_cast<double>(B) * gm.Ho * gm.Wo * Cout * (ep.residual ? 2 : 1));

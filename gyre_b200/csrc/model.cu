@@ -257,8 +257,7 @@ void Model::gn_offer(Epilogue& e, int B, int H, int W, int Cout, int stride, int
   if (gn_pre_buf_ == nullptr || e.out == nullptr || e.act != ACT_NONE || e.ldo != Cout) return;
   const int parts = conv3x3_gn_parts(B, H, W, Cout, stride, pad, groups_);
   if (parts <= 0) return;
-  const int Ho = stride == 1 ? H : (pad == 1 ? (H - 1) / 2 + 1 : (H + 1 - 3) / 2 + 1);
-  const int Wo = stride == 1 ? W : (pad == 1 ? (W - 1) / 2 + 1 : (W + 1 - 3) / 2 + 1);
+  const int Ho = conv3x3_out_extent(H, stride, pad), Wo = conv3x3_out_extent(W, stride, pad);
   if (!groupnorm_pre_ok(Cout, Ho * Wo, groups_)) return;
   if (static_cast<size_t>(B) * parts * groups_ * 2 > gn_pre_floats_ || static_cast<size_t>(B) * groups_ * 2 > kGnPreStats) return;
   e.gn_out = gn_pre_buf_;

@@ -70,6 +70,8 @@ int gemm2_f16(const __half* A, int lda, int K1, const __half* A2, int lda2, int 
 // Partials per sample a stride-1/2 conv3x3 of this shape leaves in Epilogue::gn_out, or 0 when the statistics cannot be
 // produced there (tiles that span samples or overhang the image, group boundaries that do not fall on tile boundaries).
 int conv3x3_gn_parts(int B, int H, int W, int Cout, int stride, int pad, int groups);
+// output extent of conv3x3_f16 along one axis (stride 1: n; stride 2: pad 1 -> (n - 1) / 2 + 1, pad 0 = F.pad(0, 1) -> (n - 2) / 2 + 1)
+int conv3x3_out_extent(int n, int stride, int pad);
 // number of (max, argmax) partials per row an ACT_ROWMAX GEMM of this shape writes
 int gemm_rowmax_partials(int M, int N);
 // number of float2 partials per row a GEMM of this shape writes to Epilogue::rowstat_out
