@@ -355,7 +355,7 @@ def pack_conv3x3(w):
 
 
 def conv3x3(x_nhwc, wp, cout, bias=None, residual=None, stride=1, pad=1, act=0, rowgroup_bias=None,
-            rows_per_group=1, gn_groups=0):
+            rows_per_group=1, gn_groups=0, gn_guard=False):
     """x [B, H, W, Cin] fp16 NHWC -> [B, Ho, Wo, Cout] fp16 NHWC.  gn_groups > 0: also returns the GroupNorm partials
     [B, nparts, gn_groups, 2] fp32 the epilogue left for `groupnorm_pre` (None when the shape cannot produce them)."""
     require_cuda(x_nhwc, wp)
@@ -372,7 +372,9 @@ def conv3x3(x_nhwc, wp, cout, bias=None, residual=None, stride=1, pad=1, act=0, 
     if gn_groups > 0:
         parts = load().gyre_b200_conv3x3_gn_parts(B, H, W, cout, stride, pad, gn_groups)
         if parts > 0:
-            pre = torch.full((B, parts, gn_groups, 2), float("nan"), device=x_nhwc.device, dtype=torch.float32)
+            # gn_guard (tests): one more sample's worth of NaNs behind the buffer, returned with it - nothing may write there
+            pre = torch.full((B + (1 if gn_guard else 0), parts, gn_groups, 2), float("nan"), device=x_nhwc.device,
+                             dtype=torch.float32)
             e.gn_out, e.gn_groups, e.gn_nparts = ptr(pre), gn_groups, parts
     check(load().gyre_b200_conv3x3(ptr(x_nhwc), Cin, B, H, W, Cin, ptr(wp), cout, stride, pad, C.byref(e),
                                    stream_ptr(x_nhwc.device)), "conv3x3")

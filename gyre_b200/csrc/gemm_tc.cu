@@ -828,6 +828,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           // a fixed order, leaves the entries zero for the next tile and writes the tile's partial
           named_bar_sync(1, kEpiThreads);
           const int ntg = min(bn_out, n_out - col_base) / p.gn_cpg;
+          // (n0 >= Bn: the phantom second tile of the last CTA pair when the tile count is odd - its entries are still reset)
+          const bool real_tile = n0 < p.Bn;
           if (etid < ntg) {
             float ts = 0.f, tq = 0.f;
 #pragma unroll
@@ -844,7 +846,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int chunk = m_tile % per_sample;
             float* dst = ep.gn_out + ((static_cast<int64_t>(n0) * ep.gn_nparts + chunk) * ep.gn_groups +
                                       col_base / p.gn_cpg + etid) * 2;
-            *reinterpret_cast<float2*>(dst) = make_float2(ts, tq);
+            if (real_tile) *reinterpret_cast<float2*>(dst) = make_float2(ts, tq);
           }
         }
       } else if constexpr (EPI == 1) {

@@ -325,6 +325,27 @@ def test_conv3x3_groupnorm_statistics(nat, B, H, W, Cin, Cout, stride, pad, res,
         assert torch.equal(pre1[0], pre[B - 1])
 
 
+def test_conv3x3_groupnorm_statistics_odd_tile_count(nat):
+    """9 M tiles (3 per sample, batch 3) under CTA pairs: the last pair's second tile does not exist - nothing may be written
+    for it (guard sample stays NaN), every real partial is written."""
+    B, H, W, Cin, Cout, G = 3, 16, 24, 128, 128, 32
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=1 / math.sqrt(9 * Cin))
+    wp = nat.pack_conv3x3(w)
+    old = nat.get_tunable("FORCE_BN")
+    nat.set_tunable("FORCE_BN", 128)        # (a problem this small would pick 64-wide tiles, which carry no statistics)
+    try:
+        assert nat.load().gyre_b200_conv3x3_gn_parts(B, H, W, Cout, 1, 1, G) == 3
+        out, pre = nat.conv3x3(x, wp, Cout, gn_groups=G, gn_guard=True)
+    finally:
+        nat.set_tunable("FORCE_BN", old)
+    assert pre.shape == (B + 1, 3, G, 2)
+    assert torch.isnan(pre[B]).all(), "the phantom tile of the last CTA pair wrote statistics"
+    assert torch.isfinite(pre[:B]).all()
+    o64 = out.double().view(B, H * W, G, Cout // G)
+    assert_close(pre[:B].double().sum(1)[..., 0], o64.sum((1, 3)), 1e-2, 1e-5, "group sums")
+
+
 def test_conv3x3_gn_parts_refuses_what_it_cannot_do(nat):
     lib = nat.load()
     assert lib.gyre_b200_conv3x3_gn_parts(2, 8, 8, 1280, 1, 1, 32) == 0       # a tile spans two samples
