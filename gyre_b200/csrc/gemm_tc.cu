@@ -1206,6 +1206,15 @@ static int pick_bn_conv(long long m_tiles, int N, int k_iters, bool streamk_avai
   else if (N % 160 == 0) cand = 160;
   else if (N % 128 == 0) cand = 128;
   if (cand == 0 || static_cast<long long>(k_iters) * cand < tunable(TUNE_SK_MIN)) return plain;   // plan_stream_k's own floor
+  // the wide tile only pays if plan_stream_k will really cut its partial wave: same conditions, evaluated up front
+  int G = 0;
+  if (gemm_max_clusters(cand, &G) != 0 || G < sm_count() / 4) return plain;
+  const long long T = pairs * (N / cand);
+  const long long R = T % G;
+  if (R != 0) {
+    const double without = static_cast<double>(T / G + 1), with = static_cast<double>(T) / G;
+    if ((without - with) / without < 0.10 || without > 4.0 || R * k_iters / G < 4) return plain;
+  }
   return cand;
 }
 
