@@ -55,3 +55,37 @@ def test_kernels_are_blackwell_native():
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, f"{mnemonic} not found in the SASS of libgyre_b200.so"
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path present"
+
+
+def test_groupnorm_statistics_planning_is_host_logic():
+    """gyre_b200_conv3x3_gn_parts / gyre_b200_groupnorm_pre_ok plan on the host (no launch): which convolutions of the
+    headline configuration leave GroupNorm statistics, and what is refused."""
+    from gyre_b200 import _native as N
+    lib = N.load()
+    G = 32
+    # SD1.5, CFG batch 16: the 64x64 and 32x32 levels (one partial per 128-pixel tile of a sample), downsamplers included
+    assert lib.gyre_b200_conv3x3_gn_parts(16, 64, 64, 320, 1, 1, G) == 32
+    assert lib.gyre_b200_conv3x3_gn_parts(16, 32, 32, 640, 1, 1, G) == 8
+    assert lib.gyre_b200_conv3x3_gn_parts(16, 64, 64, 320, 2, 1, G) == 8          # -> 32x32
+    assert lib.gyre_b200_conv3x3_gn_parts(8, 64, 64, 320, 1, 1, G) == 32           # the CFG shared prefix runs at half the batch
+    # VAE decoder widths at batch 8 (2048 partials per sample at 512x512: the fold launch)
+    assert lib.gyre_b200_conv3x3_gn_parts(8, 512, 512, 128, 1, 1, G) == 2048
+    assert lib.gyre_b200_conv3x3_gn_parts(8, 256, 256, 256, 1, 1, G) == 512
+    assert lib.gyre_b200_conv3x3_gn_parts(8, 64, 64, 512, 1, 1, G) == 32
+    # refused: a tile spans samples, tiles overhang the map, odd-width groups, too few channels
+    assert lib.gyre_b200_conv3x3_gn_parts(16, 8, 8, 1280, 1, 1, G) == 0
+    assert lib.gyre_b200_conv3x3_gn_parts(1, 12, 20, 320, 1, 1, G) == 0
+    assert lib.gyre_b200_conv3x3_gn_parts(16, 64, 64, 96, 1, 1, G) == 0
+    assert lib.gyre_b200_conv3x3_gn_parts(16, 64, 64, 4, 1, 1, G) == 0
+    # the tunable switches it off everywhere
+    old = N.get_tunable("GN_FUSE")
+    N.set_tunable("GN_FUSE", 0)
+    try:
+        assert lib.gyre_b200_conv3x3_gn_parts(16, 64, 64, 320, 1, 1, G) == 0
+    finally:
+        N.set_tunable("GN_FUSE", old)
+    # small maps are normalised by the single-pass kernel: no precomputed statistics there
+    assert lib.gyre_b200_groupnorm_pre_ok(320, 4096, G) == 1
+    assert lib.gyre_b200_groupnorm_pre_ok(1280, 256, G) == 0
+    assert lib.gyre_b200_groupnorm_pre_ok(1280, 64, G) == 0
+    assert lib.gyre_b200_groupnorm_pre_ok(100, 4096, G) == 0                       # C not divisible into 32 groups
