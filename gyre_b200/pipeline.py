@@ -25,8 +25,9 @@ from .randtools import batched_randn
 
 @dataclass
 class PipelineOutput:
-    images: object                   # [B, 3, H, W] in [0, 1] (output_type "pt"), uint8 NHWC ("uint8"), list of PNG files as
-                                     # bytes ("png": images.toPngBytes of the reference, encoded on the device), None ("latent")
+    images: object                   # [B, 3, H, W] in [0, 1] (output_type "pt"), uint8 NHWC ("uint8"), list of PNG / lossless
+                                     # WebP files as bytes ("png" / "webp": images.toPngBytes / toWebpBytes of the reference,
+                                     # encoded on the device), None ("latent")
     latents: torch.Tensor            # final latents (before the 1/0.18215 scaling)
     nsfw_content_detected: list | None = None   # per image, from the safety checker (unified_pipeline.py:2514-2524)
 
@@ -411,12 +412,12 @@ class B200Pipeline:
             return PipelineOutput(images=None, latents=latents)
         z = (1 / self.vae.config.scaling_factor * latents.float()).to(torch.float16)
         outpaint = image is not None and outmask_image is not None
-        img, u8 = self.vae.decode_raw(z.contiguous(), postprocess=True, want_u8=(output_type in ("uint8", "png") and not outpaint))
+        img, u8 = self.vae.decode_raw(z.contiguous(), postprocess=True, want_u8=(output_type in ("uint8", "png", "webp") and not outpaint))
         if outpaint:
             # unified_pipeline.py:2493-2510: histogram-match the result to the source around it, mix the source back in
             from .images import match_histograms_outpaint, to_uint8_nhwc
             img = match_histograms_outpaint(img, image, outmask_image)
-            u8 = to_uint8_nhwc(img) if output_type in ("uint8", "png") else None
+            u8 = to_uint8_nhwc(img) if output_type in ("uint8", "png", "webp") else None
         if run_safety_checker and self.safety_checker is not None:
             # unified_pipeline.py:2514-2522: the checker looks at the 8-bit image (numpy_to_pil's quantisation) through the
             # CLIP feature extractor; here both stay on the device and only the 20 scores per image come back
@@ -427,4 +428,7 @@ class B200Pipeline:
         if output_type == "png":
             from .images import to_png_bytes
             return PipelineOutput(images=to_png_bytes(u8), latents=latents, nsfw_content_detected=has_nsfw)
+        if output_type == "webp":      # what services/generate.py:73-76 picks when the client accepts image/webp
+            from .images import to_webp_bytes
+            return PipelineOutput(images=to_webp_bytes(u8), latents=latents, nsfw_content_detected=has_nsfw)
         return PipelineOutput(images=u8 if output_type == "uint8" else img, latents=latents, nsfw_content_detected=has_nsfw)

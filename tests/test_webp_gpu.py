@@ -75,3 +75,24 @@ def test_to_webp_bytes_mirrors_reference_signature():
     assert np.array_equal(_decode(to_webp_bytes(grey.cuda())[0], 3)[..., 0], (grey * 255).round().to(torch.uint8)[0, 0].numpy())
     tagged = add_text_chunk_to_webp_bytes(files[0], b"ICMT", "steps=50")
     assert np.array_equal(_decode(tagged, 3), u8[0])
+
+
+def test_pipeline_webp_output_decodes_to_uint8_output():
+    from oracle.unet import UNetConfig, synth_params, unet_param_shapes
+    from oracle.vae import VAEConfig, vae_param_shapes
+    from gyre_b200.pipeline import B200Pipeline
+    from gyre_b200.unet import B200UNet
+    from gyre_b200.vae import B200VAE
+    ucfg, vcfg = UNetConfig.tiny(), VAEConfig.tiny()
+    pipe = B200Pipeline(B200UNet(ucfg).load_state_dict(synth_params(unet_param_shapes(ucfg), seed=1234)),
+                        B200VAE(vcfg).load_state_dict(synth_params(vae_param_shapes(vcfg), seed=4321)))
+    pipe.unet_sample_size_override = 16
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 77, ucfg.cross_attention_dim, generator=g).half().cuda()
+    unc = torch.randn(2, 77, ucfg.cross_attention_dim, generator=g).half().cuda()
+    kw = dict(height=128, width=128, num_inference_steps=3, sampler="k_euler")
+    u8 = pipe(emb, unc, generator=[torch.Generator("cpu").manual_seed(s) for s in (5, 6)], output_type="uint8", **kw).images
+    webp = pipe(emb, unc, generator=[torch.Generator("cpu").manual_seed(s) for s in (5, 6)], output_type="webp", **kw).images
+    assert isinstance(webp, list) and len(webp) == 2 and all(isinstance(f, bytes) and f[8:12] == b"WEBP" for f in webp)
+    for f, ref in zip(webp, u8.cpu().numpy()):
+        assert np.array_equal(_decode(f, 3), ref)
